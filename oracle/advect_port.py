@@ -1,0 +1,292 @@
+"""ORACLE (test infrastructure, never the product path): NumPy/SciPy restatement of the
+reference's per-timestep advection hot path for geographic regular-grid readers.
+
+Each function cites the reference code it restates.  It keeps the reference's
+*algorithm and rounding points* (float32 block -> float64 bilinear per layer ->
+float32 -> float64 vertical lerp -> time lerp -> float32 environment -> float32
+azimuth/speed -> float64 WGS84 geodesic), including the per-layer loop over every
+block layer that dominates the reference's run time, so that it can stand in for the
+reference as the CPU baseline on the GPU box (where /root/reference does not exist).
+
+Pinned against the real reference (oracle/refrun.py, run in the build container) by
+tests/test_oracle_port.py on the committed fixtures tests/golden/ref_*.npz, which
+oracle/make_golden.py writes.
+"""
+from datetime import datetime, timedelta
+
+import numpy as np
+from scipy.ndimage import map_coordinates
+from scipy.interpolate import interp1d
+
+from . import geod_karney
+
+FALLBACK = {'x_sea_water_velocity': 0.0, 'y_sea_water_velocity': 0.0,
+            'upward_sea_water_velocity': 0.0, 'x_wind': 0.0, 'y_wind': 0.0,
+            'horizontal_diffusivity': 0.0,
+            'sea_surface_wave_stokes_drift_x_velocity': 0.0,
+            'sea_surface_wave_stokes_drift_y_velocity': 0.0}
+
+
+class GridReader:
+    """In-memory regular lon/lat(/z) reader: what reference StructuredReader subclasses
+    provide through get_variables() (opendrift/readers/basereader/structured.py:125-147),
+    always returning the full grid as one block (as reader_constant_2d.py:45-49)."""
+
+    def __init__(self, lon, lat, z, times, fields):
+        self.x = np.asarray(lon, dtype=np.float32)
+        self.y = np.asarray(lat, dtype=np.float32)
+        self.z = None if z is None else np.asarray(z, dtype=np.float64)
+        self.times = list(times)
+        self.fields = fields            # var -> (nt, [nz,] ny, nx) float32
+        self.variables = list(fields.keys())
+        self.xmin, self.xmax = float(self.x.min()), float(self.x.max())
+        self.ymin, self.ymax = float(self.y.min()), float(self.y.max())
+        self.start_time, self.end_time = self.times[0], self.times[-1]
+        self.time_step = (self.times[1] - self.times[0]) if len(self.times) > 1 else None
+
+    # opendrift/readers/basereader/variables.py:402-443 (constant time step branch == list lookup here)
+    def nearest_time(self, time):
+        if self.start_time == self.end_time:
+            return self.start_time, None, 0, 0
+        indx = (time - self.start_time).total_seconds() / self.time_step.total_seconds()
+        ib, ia = int(np.floor(indx)), int(np.ceil(indx))
+        return self.times[ib], self.times[ia], ib, ia
+
+
+def _linear2d(block2d, xi, yi):
+    """Linear2DInterpolator.__call__ without NaN holes
+    (opendrift/readers/interpolation/interpolators.py:113-139)."""
+    return map_coordinates(block2d, [yi, xi], cval=np.nan, order=1)
+
+
+def block_interpolate(reader, it, variables, x, y, z):
+    """ReaderBlock.interpolate (opendrift/readers/interpolation/structured.py:107-146) for the
+    default 'linearNDFast' horizontal + 'linear' vertical interpolators."""
+    xg, yg = reader.x, reader.y
+    # interpolators.py:107-111 (float32 grid end points, promoted to float64 by x)
+    xi = (x - xg[0]) / (xg[-1] - xg[0]) * (len(xg) - 1)
+    yi = (y - yg[0]) / (yg[-1] - yg[0]) * (len(yg) - 1)
+    out = {}
+    lin1d = None
+    for var in variables:
+        data = reader.fields[var][it]
+        if data.ndim == 2:
+            out[var] = _linear2d(data, xi, yi)              # float32 result
+            continue
+        if lin1d is None:
+            # Linear1DInterpolator.__init__ (interpolators.py:174-193); z is a float32 copy
+            zg = reader.z
+            zc = z.copy()
+            zc[zc < zg.min()] = zg.min()
+            zc[zc > zg.max()] = zg.max()
+            if zg[1] > zg[0]:
+                f = interp1d(zg, range(len(zg)))
+            else:
+                f = interp1d(zg[::-1], range(len(zg))[::-1])
+            interp_zi = f(zc)
+            ia = np.floor(interp_zi).astype(np.int8)
+            ia[ia < 0] = 0
+            ib = np.minimum(ia + 1, len(zg) - 1)
+            wa = 1 - (interp_zi - ia)
+            lin1d = (ia, ib, wa, np.arange(len(zc)))
+        # structured.py:148-163: every layer of the block, float32 results into a float64 array
+        nl = data.shape[0]
+        horiz = np.empty((nl, len(x)))
+        for layer in range(nl):
+            horiz[layer, :] = _linear2d(data[layer], xi, yi)
+        ia, ib, wa, rng = lin1d
+        out[var] = horiz[ia, rng] * wa + horiz[ib, rng] * (1 - wa)   # interpolators.py:195-197
+    return out
+
+
+def reader_interpolate(reader, variables, time, lon, lat, z):
+    """Variables.get_variables_interpolated -> get_variables_interpolated_xy ->
+    StructuredReader._get_variables_interpolated_ for a '+proj=latlong' reader
+    (opendrift/readers/basereader/variables.py:860-920, 709-858; structured.py:202-400)."""
+    lon = np.mod(lon, 360) if reader.xmin >= 0 else np.mod(lon + 180, 360) - 180   # variables.py:259-280
+    x, y = lon, lat
+    covered = np.where((x >= reader.xmin) & (x <= reader.xmax) &
+                       (y >= reader.ymin) & (y <= reader.ymax))[0]               # variables.py:229-257
+    n = len(x)
+    if len(covered) == 0:
+        return {v: np.full(n, np.nan) for v in variables}
+    xc, yc, zc = x[covered], y[covered], z.copy()[covered]
+    t_before, t_after, ib, ia = reader.nearest_time(time)
+    if time == t_before:
+        t_after = None
+    env_before = block_interpolate(reader, ib, variables, xc, yc, zc)
+    if t_after is not None:
+        env_after = block_interpolate(reader, ia, variables, xc, yc, zc)
+        w = (time - t_before).total_seconds() / (t_after - t_before).total_seconds()  # structured.py:353-364
+        env = {v: env_before[v] * (1 - w) + env_after[v] * w for v in variables}
+    else:
+        env = env_before
+    if len(covered) != n:                                                        # variables.py:841-853
+        for v in variables:
+            tmp = np.nan * np.ones(n)
+            tmp[covered] = env[v]
+            env[v] = tmp
+    return env
+
+
+def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, truncate_below=None):
+    """Environment.get_environment for one reader per variable group
+    (opendrift/models/basemodel/environment.py:499-923): float32 cast at :695-696,
+    fallback fill at :782-791."""
+    if truncate_below is not None:
+        z = z.copy()
+        z[z < -truncate_below] = -truncate_below
+    env = {}
+    remaining = list(variables)
+    for reader in readers:
+        group = [v for v in remaining if v in reader.variables]
+        if not group:
+            continue
+        tmp = reader_interpolate(reader, group, time, lon, lat, z)
+        for v in group:
+            env[v] = np.asarray(tmp[v]).astype(np.float32)
+            remaining.remove(v)
+    for v in remaining:
+        env[v] = np.full(len(lon), np.nan, dtype=np.float32)
+    for v in variables:
+        fb = fallback.get(v)
+        if fb is not None:
+            bad = ~np.isfinite(env[v])
+            env[v][bad] = fb
+    return env
+
+
+_GEOD = geod_karney.Geod()
+
+
+def update_positions(lon, lat, x_vel, y_vel, moving, dt):
+    """OpenDriftSimulation.update_positions (opendrift/models/basemodel/__init__.py:4630-4669)."""
+    azimuth = np.degrees(np.arctan2(x_vel, y_vel))
+    velocity = np.sqrt(x_vel ** 2 + y_vel ** 2)
+    velocity = velocity * moving
+    lon2, lat2, _ = _GEOD.fwd(lon, lat, azimuth, velocity * dt)
+    return lon2, lat2
+
+
+def advect_ocean_current(readers, scheme, time, dt, lon, lat, z, cdf, moving, env, factor=1,
+                         truncate_below=None):
+    """PhysicsMethods.advect_ocean_current (opendrift/models/physics_methods.py:611-691),
+    including the reference's RK4 stage-4 quirk (half step at :660-666, time t+dt at :669)."""
+    factor = factor * cdf
+    uv = ['x_sea_water_velocity', 'y_sea_water_velocity']
+    ts = timedelta(seconds=dt)
+    x_vel, y_vel = env[uv[0]], env[uv[1]]
+    if scheme == 'euler':
+        return update_positions(lon, lat, factor * x_vel, factor * y_vel, moving, dt)
+
+    def mid(xv, yv):
+        az = np.degrees(np.arctan2(xv, yv))
+        speed = np.sqrt(xv * xv + yv * yv)
+        dist = speed * dt * .5
+        lo, la, _ = _GEOD.fwd(lon, lat, az, dist, radians=False)
+        return lo, la
+
+    mlon, mlat = mid(x_vel, y_vel)
+    e2 = get_environment(readers, uv, time + ts / 2, mlon, mlat, z, truncate_below=truncate_below)
+    if scheme == 'runge-kutta':
+        return update_positions(lon, lat, factor * e2[uv[0]], factor * e2[uv[1]], moving, dt)
+    assert scheme == 'runge-kutta4'
+    lon2, lat2 = mid(e2[uv[0]], e2[uv[1]])
+    e3 = get_environment(readers, uv, time + ts / 2, lon2, lat2, z, truncate_below=truncate_below)
+    lon3, lat3 = mid(e3[uv[0]], e3[uv[1]])
+    e4 = get_environment(readers, uv, time + ts, lon3, lat3, z, truncate_below=truncate_below)
+    u4 = (x_vel + 2 * e2[uv[0]] + 2 * e3[uv[0]] + e4[uv[0]]) / 6.0
+    v4 = (y_vel + 2 * e2[uv[1]] + 2 * e3[uv[1]] + e4[uv[1]]) / 6.0
+    return update_positions(lon, lat, u4 * factor, v4 * factor, moving, dt)
+
+
+def advect_wind(lon, lat, z, wdf_in, env, moving, dt, wind_drift_depth=0.1, factor=1):
+    """PhysicsMethods.advect_wind (opendrift/models/physics_methods.py:712-791), relative_wind off."""
+    n = len(lon)
+    wind_drift_factor = wdf_in.copy()
+    if wind_drift_depth == 0:
+        surface_only = True
+        wdd = 0
+    else:
+        wdd = np.abs(wind_drift_depth) * np.ones(n)
+        surface_only = False
+    surface = z >= -wdd
+    if surface.sum() == 0:
+        return lon, lat
+    wdf = wind_drift_factor.copy()
+    wdf_air = wdf.copy()
+    if not surface_only:
+        wdf = wdf * (wdd + z) / wdd
+        wdf[z > 0] = wdf_air[z > 0]
+    wdf[~surface] = 0.0
+    x_wind, y_wind = env['x_wind'].copy(), env['y_wind'].copy()
+    speed = np.sqrt(x_wind[surface] * x_wind[surface] + y_wind[surface] * y_wind[surface])
+    if wdf[surface].max() == 0 or speed.max() == 0:
+        return lon, lat
+    return update_positions(lon, lat, x_wind * wdf * factor, y_wind * wdf * factor, moving, dt)
+
+
+def vertical_advection(z, w, moving, dt, at_surface=False):
+    """OceanDrift.vertical_advection (opendrift/models/oceandrift.py:315-350), no SSH correction."""
+    z = z.copy()
+    applicable = np.where(z <= 0)[0] if at_surface else np.where(z < 0)[0]
+    if len(applicable) > 0:
+        z[applicable] = np.minimum(0, z[applicable] + moving[applicable] * w[applicable] * dt)
+    return z
+
+
+def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
+    """OpenDriftSimulation.horizontal_diffusion (opendrift/models/basemodel/__init__.py:1746-1772):
+    two normal draws from the legacy global generator, x first."""
+    if len(D) == 0 or D.max() == 0:
+        return lon, lat
+    adt = np.abs(dt)
+    n = len(lon)
+    x_vel = moving * np.sqrt(2 * D / adt) * rng.normal(scale=1, size=n)
+    y_vel = moving * np.sqrt(2 * D / adt) * rng.normal(scale=1, size=n)
+    return update_positions(lon, lat, x_vel, y_vel, moving, dt)
+
+
+def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
+                   vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
+                   diffusivity=0.0, seed=0, truncate_below=None):
+    """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
+    OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
+    no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
+    np.random.seed(seed)                       # basemodel/__init__.py:326
+    n = len(lon)
+    # seeding casts to the declared element dtypes (opendrift/elements/elements.py:156-158)
+    lon = np.asarray(lon, dtype=np.float32)
+    lat = np.asarray(lat, dtype=np.float32)
+    z = np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
+    # Scalar element properties (defaults, or scalars given to seed_elements) become *float64*
+    # arrays when the scheduled elements are released: LagrangianArray.move_elements does
+    # ``self_var*np.ones(self_len)`` (opendrift/elements/elements.py:213-216).  Arrays given to
+    # seed_elements keep their declared dtype (float32 / int32).
+    def prop(v, dtype):
+        if np.ndim(v) == 0:
+            return dtype(v) * np.ones(n)
+        return np.asarray(v, dtype=dtype)
+    cdf = prop(cdf, np.float32)
+    wdf_arr = prop(wdf, np.float32)
+    moving = prop(1, np.int32)
+    variables = ['x_sea_water_velocity', 'y_sea_water_velocity']
+    if vertical_adv:
+        variables.append('upward_sea_water_velocity')
+    if wind:
+        variables += ['x_wind', 'y_wind']
+    time = start_time
+    for _ in range(steps):
+        env = get_environment(readers, variables, time, lon, lat, z, truncate_below=truncate_below)
+        lon0, lat0, z0 = lon, lat, z
+        lon, lat = advect_ocean_current(readers, scheme, time, dt, lon, lat, z, cdf, moving, env,
+                                        truncate_below=truncate_below)
+        if wind:
+            lon, lat = advect_wind(lon, lat, z, wdf_arr, env, moving, dt, wind_drift_depth)
+        if vertical_adv:
+            z = vertical_advection(z, env['upward_sea_water_velocity'], moving, dt)
+        if diffusivity > 0:
+            D = np.float32(diffusivity) * np.ones(n, dtype=np.float32)
+            lon, lat = horizontal_diffusion(lon, lat, D, moving, dt)
+        time = time + timedelta(seconds=dt)
+    return lon, lat, z

@@ -1,0 +1,120 @@
+"""ORACLE fixture generator: runs the UNMODIFIED reference (oracle/refrun.py, this container
+only) on small seeded cases and writes inputs + final positions to tests/golden/ref_*.npz.
+
+    python -m oracle.make_golden
+
+The fixtures travel to the GPU box; /root/reference does not.  Each fixture stores the
+complete forcing (float32 slabs), the seeded particles, the configuration and the
+reference's final lon/lat/z (float64/float64/float32).
+"""
+import json
+from datetime import timedelta
+import os
+
+import numpy as np
+
+from oracle import refrun
+from opendrift_b200 import synthetic as syn
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+CURRENT = ['x_sea_water_velocity', 'y_sea_water_velocity']
+
+
+def build_fields(g, n_slabs, with_w=False):
+    times = syn.slab_times(n_slabs)
+    U, V = [], []
+    for t in times:
+        u, v = syn.double_gyre_uv(g, (t - syn.T0).total_seconds(), three_d=g.z is not None)
+        U.append(u)
+        V.append(v)
+    f = {CURRENT[0]: np.stack(U), CURRENT[1]: np.stack(V)}
+    if with_w:
+        f['upward_sea_water_velocity'] = np.stack([syn.upward_w(g)] * n_slabs)
+    return times, f
+
+
+def build_wind(g, n_slabs):
+    times = syn.slab_times(n_slabs)
+    X, Y = [], []
+    for t in times:
+        wx, wy = syn.wind_xy(g, (t - syn.T0).total_seconds())
+        X.append(wx)
+        Y.append(wy)
+    return {'x_wind': np.stack(X), 'y_wind': np.stack(Y)}
+
+
+def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0):
+    n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
+    times, f3 = build_fields(g, n_slabs, with_w)
+    lon, lat, z = syn.particle_cloud(n, seed=seed + 1, three_d=g.z is not None)
+    # keep the cloud inside this (smaller) grid
+    lon = (g.lon[0] + (lon - 1.0) / 8.2 * g.Lx * 0.8 + 0.1 * g.Lx).astype(np.float32)
+    lat = (g.lat[0] + (lat - 55.5) / 4.1 * g.Ly * 0.8 + 0.1 * g.Ly).astype(np.float32)
+    if g.z is not None:
+        z = (z / 90.0 * abs(g.z.min()) * 1.1).astype(np.float32)     # some below the deepest level
+        z[: n // 20] = 0.0                                             # at the surface
+        z[n // 20: n // 10] = -0.05                                    # inside the wind-drift layer
+    if spill:
+        lon[: n // 10] += np.float32(g.Lx)                             # outside coverage -> fallback 0
+    readers = [refrun.make_grid_reader(g.lon, g.lat, g.z, times, f3, 'current')]
+    f2 = None
+    if wind:
+        f2 = build_wind(g, n_slabs)
+        readers.append(refrun.make_grid_reader(g.lon, g.lat, None, times, f2, 'wind'))
+    cfg = {'drift:advection_scheme': scheme, 'drift:vertical_advection': bool(with_w)}
+    if diffusivity:
+        cfg['environment:constant:horizontal_diffusivity'] = diffusivity
+    if wind_drift_depth is not None:
+        cfg['drift:wind_drift_depth'] = wind_drift_depth
+    seed_kwargs = {}
+    if cdf is not None:
+        seed_kwargs['current_drift_factor'] = cdf
+    start = syn.T0 + timedelta(seconds=start_offset_s)
+    if dt < 0:
+        start = times[-1]
+    o = refrun.run_oceandrift(readers, lon, lat, z, start, dt, steps, config=cfg,
+                              seed_kwargs=seed_kwargs, seed=seed)
+    meta = dict(name=name, steps=steps, dt=dt, scheme=scheme, with_w=with_w, wind=wind,
+                diffusivity=diffusivity, seed=seed, wind_drift_depth=wind_drift_depth,
+                start_offset_s=start_offset_s if dt > 0 else None,
+                start_index=None if dt > 0 else len(times) - 1,
+                slab_step_s=3600, cdf_is_array=cdf is not None)
+    out = dict(meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat,
+               grid_z=np.zeros(0) if g.z is None else g.z,
+               u=f3[CURRENT[0]], v=f3[CURRENT[1]], lon0=lon, lat0=lat, z0=z,
+               lon=np.asarray(o.elements.lon, dtype=np.float64),
+               lat=np.asarray(o.elements.lat, dtype=np.float64),
+               z=np.asarray(o.elements.z, dtype=np.float32))
+    if with_w:
+        out['w'] = f3['upward_sea_water_velocity']
+    if wind:
+        out['x_wind'], out['y_wind'] = f2['x_wind'], f2['y_wind']
+    if cdf is not None:
+        out['cdf'] = np.asarray(cdf, dtype=np.float32)
+    assert len(o.elements.lon) == n, 'reference deactivated particles in %s' % name
+    path = os.path.join(OUT, 'ref_%s.npz' % name)
+    np.savez_compressed(path, **out)
+    print('wrote', path, 'max |dlon|', np.abs(out['lon'] - lon).max())
+
+
+def main():
+    g3 = syn.GridSpec(nx=40, ny=36, nz=8, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03, dz=12.0)
+    g2 = syn.GridSpec(nx=40, ny=36, nz=1, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03)
+    n = 1500
+    run_case('rk4_3d', g3, n, 14, 600, 'runge-kutta4')
+    run_case('rk2_3d', g3, n, 14, 600, 'runge-kutta')
+    run_case('euler_3d', g3, n, 14, 600, 'euler')
+    run_case('rk4_2d', g2, n, 14, 600, 'runge-kutta4')
+    run_case('rk4_3d_offgrid', g3, n, 8, 900, 'runge-kutta4', spill=True, start_offset_s=450)
+    rng = np.random.default_rng(7)
+    run_case('rk4_3d_cdf32', g3, n, 8, 600, 'runge-kutta4',
+             cdf=rng.uniform(0.5, 1.0, n).astype(np.float32))
+    run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
+    run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
+    run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+
+
+if __name__ == '__main__':
+    main()

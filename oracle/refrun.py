@@ -1,0 +1,175 @@
+"""ORACLE (test infrastructure): import and run the UNMODIFIED reference Python from
+/root/reference in THIS container.
+
+The reference's own arithmetic for the hot path (OpenDriftSimulation.run ->
+Environment.get_environment -> StructuredReader/ReaderBlock -> Linear2DInterpolator
+-> PhysicsMethods.advect_ocean_current -> update_positions) is pure NumPy/SciPy and
+imports fine once the plotting / IO third-party packages that are absent from this
+image are replaced by MagicMock modules.  The single piece of missing *arithmetic*
+is ``pyproj.Geod.fwd``; a fake ``pyproj`` module backed by oracle/geod_karney.py
+(validated against mpmath, see oracle/geod_exact.py) is injected for it.
+
+This module cannot travel to the GPU box (no /root/reference there): it is used only
+by oracle/make_golden.py to write tests/golden/*.npz, and by the CPU tests that are
+skipped when /root/reference is absent.
+"""
+import os
+import sys
+import types
+import logging
+from unittest.mock import MagicMock
+from datetime import datetime, timedelta
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get('OPENDRIFT_REFERENCE', '/root/reference')
+
+_MOCKED = [
+    'xarray', 'netCDF4', 'matplotlib', 'matplotlib.pyplot', 'matplotlib.animation',
+    'matplotlib.patches', 'matplotlib.path', 'matplotlib.widgets', 'matplotlib.colors',
+    'matplotlib.tri', 'matplotlib.cm', 'matplotlib.dates', 'matplotlib.ticker',
+    'mpl_toolkits', 'mpl_toolkits.axes_grid1',
+    'cartopy', 'cartopy.crs', 'cartopy.feature', 'cartopy.io', 'cartopy.io.shapereader',
+    'cartopy.mpl', 'cartopy.mpl.gridliner', 'cartopy.mpl.ticker',
+    'geojson', 'roaring_landmask', 'cmocean', 'coloredlogs', 'copernicusmarine', 'dotenv',
+    'geopandas', 'shapely', 'shapely.geometry', 'shapely.ops', 'shapely.prepared',
+    'shapely.vectorized', 'shapely.strtree', 'utm', 'pynucos', 'nc_time_axis', 'pykdtree',
+    'pykdtree.kdtree', 'xhistogram', 'xhistogram.xarray', 'adios_db', 'cftime', 'trajan',
+    'dask', 'dask.array', 'h5py', 'pygrib', 'cfgrib', 'earthaccess', 'pyresample',
+]
+
+
+def _fake_pyproj():
+    from oracle.geod_karney import Geod
+
+    class _CRS:
+        def __init__(self, geographic=True, srs='+proj=latlong'):
+            self.is_geographic = geographic
+            self.srs = srs
+
+        def __eq__(self, other):
+            return isinstance(other, _CRS) and other.srs == self.srs
+
+        def __hash__(self):
+            return hash(self.srs)
+
+    class Proj:
+        """Identity projection: only '+proj=latlong' style CRSs are supported."""
+
+        def __init__(self, projparams=None, **kw):
+            s = str(projparams)
+            if 'latlong' not in s and 'longlat' not in s:
+                raise NotImplementedError('fake pyproj only supports latlong: ' + s)
+            self.srs = s
+            self.crs = _CRS(True, s)
+            self.definition_string = lambda: s
+
+        def __call__(self, x, y, inverse=False):
+            return x, y
+
+    m = types.ModuleType('pyproj')
+    m.Proj = Proj
+    m.Geod = Geod
+    m.CRS = MagicMock()
+    m.Transformer = MagicMock()
+    m.__version__ = '0.0-fake'
+    return m
+
+
+_ready = False
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'opendrift'))
+
+
+def setup():
+    """Install the stub modules and put the reference on sys.path (idempotent)."""
+    global _ready
+    if _ready:
+        return
+    if not available():
+        raise RuntimeError('reference tree not found at %s' % REFERENCE_ROOT)
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    for name in _MOCKED:
+        if name not in sys.modules:
+            sys.modules[name] = MagicMock()
+    sys.modules['pyproj'] = _fake_pyproj()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import opendrift.readers.basereader  # noqa: F401  (must precede interpolation.structured)
+    from opendrift.models.basemodel import OpenDriftSimulation
+    # xarray is mocked: the result buffer cannot be written. It is not on the hot path.
+    OpenDriftSimulation.state_to_buffer = lambda self, final=False: None
+    logging.getLogger('opendrift').setLevel(logging.CRITICAL)
+    _ready = True
+
+
+def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid'):
+    """A reference StructuredReader (subclass of the reference base class) serving
+    in-memory regular lon/lat(/z) slabs.  ``fields[var]`` has shape (nt, nz, ny, nx) or
+    (nt, ny, nx) float32.  get_variables returns the FULL grid block (like
+    reader_constant_2d.py:45-49) with float32 x/y (as reader_netCDF_CF_generic.py:586-587).
+    """
+    setup()
+    from opendrift.readers.basereader.structured import StructuredReader
+
+    class Reader(StructuredReader):
+        def __init__(self):
+            self.proj4 = '+proj=latlong'
+            self.lon = np.asarray(lon, dtype=np.float32)
+            self.lat = np.asarray(lat, dtype=np.float32)
+            self.zlev = None if z is None else np.asarray(z, dtype=np.float64)
+            self.xmin, self.xmax = float(self.lon.min()), float(self.lon.max())
+            self.ymin, self.ymax = float(self.lat.min()), float(self.lat.max())
+            self.delta_x = float(self.lon[1] - self.lon[0])
+            self.delta_y = float(self.lat[1] - self.lat[0])
+            self.numx, self.numy = len(self.lon), len(self.lat)
+            self.variables = list(fields.keys())
+            self.fields = fields
+            self.times = list(times)
+            self.start_time, self.end_time = times[0], times[-1]
+            self.time_step = (times[1] - times[0]) if len(times) > 1 else None
+            self.name = name
+            super().__init__()
+
+        def get_variables(self, requested_variables, time=None, x=None, y=None, z=None):
+            it = self.times.index(time)
+            out = {'x': self.lon, 'y': self.lat, 'time': time}
+            three_d = False
+            for v in requested_variables:
+                a = self.fields[v][it]
+                three_d |= a.ndim == 3
+                out[v] = np.array(a, dtype=np.float32, copy=True)
+            out['z'] = self.zlev if three_d else 0
+            return out
+
+    return Reader()
+
+
+def run_oceandrift(readers, lon, lat, z, start_time, time_step, steps, config=None,
+                   seed_kwargs=None, model='OceanDrift', seed=0):
+    """Run the reference model and return final (lon, lat, z, status-free) arrays."""
+    setup()
+    import tempfile
+    if model == 'OceanDrift':
+        from opendrift.models.oceandrift import OceanDrift as Model
+    elif model == 'Leeway':
+        from opendrift.models.leeway import Leeway as Model
+    else:
+        raise ValueError(model)
+    logfile = os.path.join(tempfile.gettempdir(), 'oracle_refrun.log')
+    o = Model(loglevel=50, logfile=logfile, seed=seed)
+    for r in readers:
+        o.add_reader(r)
+    cfg = {'general:use_auto_landmask': False,
+           'environment:constant:land_binary_mask': 0,
+           'general:coastline_action': 'none'}
+    cfg.update(config or {})
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    o.seed_elements(lon=lon, lat=lat, z=z, time=start_time, **(seed_kwargs or {}))
+    o.run(steps=steps, time_step=time_step, time_step_output=time_step)
+    return o
