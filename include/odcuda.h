@@ -1,0 +1,192 @@
+/* odcuda.h -- C-ABI of libodcuda.so: the B200 (sm_100a) particle-advection hot path behind
+ * OpenDrift's Python interface.
+ *
+ * The reference (OpenDrift 1.14.10, pure Python) has no FFI for this path; its extension API is
+ * Python subclassing.  Each entry point below replaces the *body* of a reference Python method and
+ * is bound from Python with ctypes (opendrift_b200/_lib.py).  Reference interface replaced, per call:
+ *
+ *   od_geod_fwd           pyproj.Geod(ellps='WGS84').fwd as called at
+ *                         opendrift/models/basemodel/__init__.py:4651-4657, physics_methods.py:632-635
+ *   od_update_positions   OpenDriftSimulation.update_positions   basemodel/__init__.py:4630-4669
+ *   od_field_* / od_interp  StructuredReader._get_variables_interpolated_ + ReaderBlock.interpolate
+ *                         readers/basereader/structured.py:202-400, readers/interpolation/structured.py:107-163,
+ *                         readers/interpolation/interpolators.py:105-139, 174-197; the float32 cast and
+ *                         fallback fill of Environment.get_environment  basemodel/environment.py:695-696, 782-791
+ *   od_advect_current     PhysicsMethods.advect_ocean_current    models/physics_methods.py:611-691
+ *   od_step_oceandrift    OceanDrift.update + horizontal_diffusion  models/oceandrift.py:185-211,
+ *                         basemodel/__init__.py:1746-1772 (current -> wind -> vertical advection -> diffusion)
+ *   od_sort_* / od_permute LagrangianArray element order (elements/elements.py:197-228) -- locality only
+ *
+ * Conventions: every pointer named d_* is a CUDA device pointer owned by the caller (PyTorch tensors are
+ * used only as allocators); h_* are host pointers.  All calls enqueue work on the context's stream and
+ * return immediately, except where stated.  Return value: 0 on success, negative od_status otherwise;
+ * od_last_error() gives the text.  Nothing throws or aborts.  A context is not thread-safe.
+ */
+#ifndef ODCUDA_H
+#define ODCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct od_ctx od_ctx;
+
+enum od_status {
+    OD_OK = 0,
+    OD_ERR_CUDA = -1,
+    OD_ERR_ARG = -2,
+    OD_ERR_STATE = -3,
+    OD_ERR_NOMEM = -4
+};
+
+enum od_scheme { OD_EULER = 0, OD_RK2 = 1, OD_RK4 = 2 };
+
+/* how a time sample combines the two slabs of a pair */
+enum od_time_mode {
+    OD_T_LERP = 0,     /* slab_a*(1-w) + slab_b*w                        (structured.py:353-364) */
+    OD_T_FIRST = 1,    /* slab_a only: time == time_before               (structured.py:224-229, 339) */
+    OD_T_SECOND = 2,   /* slab_b only */
+    OD_T_MISSING = 3   /* reader does not cover this time: every particle gets the fallback value
+                          (OutsideTemporalCoverageError -> NaN -> fallback, environment.py:642-654, 782-791) */
+};
+
+enum od_lon_mode { OD_LON_0_360 = 0, OD_LON_PM180 = 1 };
+
+#define OD_MAX_LEVELS 128
+#define OD_ABI_VERSION 1
+
+int od_abi_version(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int od_create(int device, od_ctx** out);
+void od_destroy(od_ctx* ctx);
+const char* od_last_error(od_ctx* ctx);
+/* use an existing CUDA stream (cudaStream_t passed as void*; NULL = legacy default stream) */
+int od_set_stream(od_ctx* ctx, void* cuda_stream);
+int od_sync(od_ctx* ctx);                        /* blocks until the stream is idle */
+int od_device_sm_count(od_ctx* ctx);
+
+/* ---- forcing fields ---------------------------------------------------------------------
+ * A field *group* is one reader block geometry carrying 1 or 2 components that are always
+ * sampled together (e.g. x/y_sea_water_velocity; upward_sea_water_velocity; x/y_wind).
+ * x0/xspan/y0/yspan follow Linear2DInterpolator: xi = (x - x0) / xspan * (nx - 1) with
+ * x0 = (double)xgrid[0], xspan = (double)(float)(xgrid[nx-1] - xgrid[0]) for float32 grids.
+ * xmin..ymax is the reader's coverage box (covers_positions_xy).  h_z_levels: nz level depths
+ * as the reader returns them (increasing or decreasing), ignored when nz == 1.
+ * fallback[c]: value used where the sample is not finite / not covered; NaN = none. */
+typedef struct od_group_desc {
+    int32_t ncomp;            /* 1 or 2 */
+    int32_t nx, ny, nz;
+    int32_t lon_mode;         /* od_lon_mode */
+    int32_t n_slots;          /* ring of time slabs kept on the device (>= 2) */
+    double x0, xspan, y0, yspan;
+    double xmin, xmax, ymin, ymax;
+    float fallback[2];
+} od_group_desc;
+
+int od_group_define(od_ctx* ctx, int group, const od_group_desc* desc, const double* h_z_levels);
+/* copy one time slab of one component ([nz][ny][nx] float32, C order) into ring slot `slot`;
+ * src may be host (pinned or pageable) or device memory */
+int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const float* src, int src_is_device);
+/* raw device pointer of a ring slot component, e.g. as the target of an NCCL broadcast */
+int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** d_out);
+/* tell the library a slot's contents changed behind its back (after a broadcast into od_group_slot_ptr) */
+int od_group_touch(od_ctx* ctx, int group, int slot);
+
+/* one time sample of a group: which two ring slots bracket it and how they combine */
+typedef struct od_time_sample {
+    int32_t slot_a, slot_b;
+    int32_t mode;             /* od_time_mode */
+    int32_t pad_;
+    double w;                 /* weight of slot_b for OD_T_LERP */
+} od_time_sample;
+
+/* get_variables_interpolated fast path: d_out[c] (float32[n]) for c < ncomp; d_out entries may be NULL.
+ * z may be NULL for nz == 1.  lon/lat float64.  pos_f32 != 0: the positions hold float32 values (the
+ * reference's element arrays are float32 from seeding until the first update_positions,
+ * elements/elements.py:156-158) and NumPy then does the index arithmetic of interpolators.py:110-111 in
+ * float32; the kernel reproduces that. */
+int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n,
+              const double* d_lon, const double* d_lat, const float* d_z, int pos_f32,
+              float* d_out0, float* d_out1);
+
+/* ---- geodesic --------------------------------------------------------------------------- */
+/* in place: (lon, lat) <- WGS84 direct(lon, lat, az_deg, dist_m); lon normalised to [-180, 180] */
+int od_geod_fwd(od_ctx* ctx, int64_t n, double* d_lon, double* d_lat,
+                const double* d_az_deg, const double* d_dist_m);
+
+/* update_positions: velocities float32 (vel_f64 = 0) or float64 (vel_f64 = 1) -- the reference's
+ * arithmetic follows the dtype of its inputs; moving may be NULL (all 1). */
+int od_update_positions(od_ctx* ctx, int64_t n, double* d_lon, double* d_lat,
+                        const void* d_xvel, const void* d_yvel, int vel_f64,
+                        const int32_t* d_moving, double dt);
+
+/* ---- fused advection -------------------------------------------------------------------- */
+typedef struct od_advect_args {
+    int32_t scheme;               /* od_scheme */
+    int32_t group_uv;             /* 2-component current group */
+    od_time_sample t_start;       /* time t        (stage 1; ignored when d_k1_u given) */
+    od_time_sample t_mid;         /* time t + dt/2 (stages 2, 3) */
+    od_time_sample t_end;         /* time t + dt   (stage 4) */
+    double dt;                    /* seconds, may be negative */
+    int64_t n;
+    double* d_lon;                /* in/out float64 */
+    double* d_lat;
+    const float* d_z;             /* float32 or NULL (2-D group) */
+    const void* d_factor;         /* factor * current_drift_factor per particle; NULL = 1 */
+    int32_t factor_f64;           /* dtype of d_factor: 0 float32, 1 float64 (reference promotes scalars
+                                     to float64 arrays, elements/elements.py:213-216) */
+    int32_t pos_f32;              /* lon/lat hold float32 values (first step after seeding), see od_interp */
+    const int32_t* d_moving;      /* elements.moving (0 = frozen); NULL = all moving */
+    const float* d_k1_u;          /* optional start-of-step environment (already sampled) */
+    const float* d_k1_v;
+    double truncate_below;        /* drift:truncate_ocean_model_below_m, <= 0 disables */
+    /* optional outputs: start-of-step sampled current (float32[n]) */
+    float* d_env_u;
+    float* d_env_v;
+} od_advect_args;
+
+int od_advect_current(od_ctx* ctx, const od_advect_args* a);
+
+typedef struct od_step_args {
+    od_advect_args cur;           /* current advection */
+    /* wind drift (advect_wind): group_wind < 0 disables */
+    int32_t group_wind;
+    int32_t wdf_f64;              /* dtype of d_wdf */
+    od_time_sample t_wind;        /* sampled at time t, start-of-step positions */
+    const void* d_wdf;            /* wind_drift_factor per particle */
+    double wind_drift_depth;      /* drift:wind_drift_depth (0 = surface only) */
+    /* vertical advection: group_w < 0 disables; z updated in place */
+    int32_t group_w;
+    int32_t w_at_surface;         /* drift:vertical_advection_at_surface */
+    od_time_sample t_w;
+    float* d_z_inout;
+    /* horizontal diffusion: d_rand_x NULL disables; standard normal draws (float64[n]) */
+    const double* d_rand_x;
+    const double* d_rand_y;
+    const float* d_diffusivity;   /* per particle float32, or NULL -> diffusivity_const */
+    float diffusivity_const;
+    int32_t pad2_;
+} od_step_args;
+
+int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
+
+/* ---- particle order (locality) ---------------------------------------------------------- */
+/* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by
+ * the grid cell (and level) of `group` they are in.  Stable counting sort. */
+int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* d_lon, const double* d_lat,
+                    const float* d_z, int32_t* d_perm_out);
+/* dst[k] = src[perm[k]] for an array of elem_size-byte elements (4 or 8) */
+int od_permute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);
+/* dst[perm[k]] = src[k] */
+int od_unpermute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);
+
+/* counters of the library's own kernel launches since creation (for bench.py's gpu_launches) */
+int64_t od_launch_count(od_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODCUDA_H */

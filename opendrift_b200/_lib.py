@@ -1,0 +1,99 @@
+"""ctypes binding of libodcuda.so (C-ABI declared in include/odcuda.h).
+
+The library is the product: there is no CPU fallback.  Importing this module without the
+built shared object raises immediately with build instructions.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libodcuda.so')
+
+OD_EULER, OD_RK2, OD_RK4 = 0, 1, 2
+OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
+OD_LON_0_360, OD_LON_PM180 = 0, 1
+OD_MAX_LEVELS = 128
+SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
+
+
+class GroupDesc(C.Structure):
+    _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
+                ('lon_mode', C.c_int32), ('n_slots', C.c_int32),
+                ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
+                ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
+                ('fallback', C.c_float * 2)]
+
+
+class TimeSample(C.Structure):
+    _fields_ = [('slot_a', C.c_int32), ('slot_b', C.c_int32), ('mode', C.c_int32), ('pad_', C.c_int32),
+                ('w', C.c_double)]
+
+
+class AdvectArgs(C.Structure):
+    _fields_ = [('scheme', C.c_int32), ('group_uv', C.c_int32),
+                ('t_start', TimeSample), ('t_mid', TimeSample), ('t_end', TimeSample),
+                ('dt', C.c_double), ('n', C.c_int64),
+                ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
+                ('d_factor', C.c_void_p), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32),
+                ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
+                ('truncate_below', C.c_double),
+                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [('cur', AdvectArgs),
+                ('group_wind', C.c_int32), ('wdf_f64', C.c_int32), ('t_wind', TimeSample),
+                ('d_wdf', C.c_void_p), ('wind_drift_depth', C.c_double),
+                ('group_w', C.c_int32), ('w_at_surface', C.c_int32), ('t_w', TimeSample),
+                ('d_z_inout', C.c_void_p),
+                ('d_rand_x', C.c_void_p), ('d_rand_y', C.c_void_p), ('d_diffusivity', C.c_void_p),
+                ('diffusivity_const', C.c_float), ('pad2_', C.c_int32)]
+
+
+# every symbol include/odcuda.h declares: (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    'od_abi_version': (C.c_int, []),
+    'od_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
+    'od_destroy': (None, [_P]),
+    'od_last_error': (C.c_char_p, [_P]),
+    'od_set_stream': (C.c_int, [_P, _P]),
+    'od_sync': (C.c_int, [_P]),
+    'od_device_sm_count': (C.c_int, [_P]),
+    'od_group_define': (C.c_int, [_P, C.c_int, C.POINTER(GroupDesc), C.POINTER(C.c_double)]),
+    'od_group_upload': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
+    'od_group_slot_ptr': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    'od_group_touch': (C.c_int, [_P, C.c_int, C.c_int]),
+    'od_interp': (C.c_int, [_P, C.c_int, C.POINTER(TimeSample), C.c_int64, _P, _P, _P, C.c_int, _P, _P]),
+    'od_geod_fwd': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+    'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
+    'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
+    'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
+    'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),
+    'od_unpermute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),
+    'od_launch_count': (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libodcuda.so (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'opendrift_b200: %s is missing. This package has no CPU fallback; build the CUDA '
+            'extension first:  python -c "import __graft_entry__ as g; g.build()"  '
+            '(or python -m opendrift_b200.build).' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.od_abi_version() != 1:
+        raise RuntimeError('libodcuda.so ABI version mismatch')
+    _lib = lib
+    return lib

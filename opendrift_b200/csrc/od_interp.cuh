@@ -1,0 +1,295 @@
+// od_interp.cuh -- regular-grid sampling of a forcing field group at one particle position.
+//
+// Restates, per particle, what the reference does per array:
+//   Variables.get_variables_interpolated[_xy]   opendrift/readers/basereader/variables.py:860-920, 709-858
+//     (longitude modulation :259-280, coverage test :229-257, NaN for uncovered :841-853)
+//   Linear2DInterpolator                        opendrift/readers/interpolation/interpolators.py:105-139
+//     (fractional index :110-111; scipy.ndimage.map_coordinates(order=1, cval=nan) :122)
+//   Linear1DInterpolator                        interpolators.py:174-197
+//   ReaderBlock._interpolate_horizontal_layers  opendrift/readers/interpolation/structured.py:148-163
+//     (float32 layer results stored into a float64 array, then the vertical lerp in float64)
+//   time interpolation                          opendrift/readers/basereader/structured.py:353-364
+//   float32 cast + fallback                     opendrift/models/basemodel/environment.py:695-696, 782-791
+//
+// Rounding points are reproduced exactly (no FMA contraction where NumPy/SciPy round twice).
+//
+// Device layout of a group ("pair texels"): for the two time slabs A, B that bracket a sample the library
+// keeps one interleaved array  tex[z][y][x][c0A, c1A, c0B, c1B]  (ncomp = 2, one 16-byte load per corner)
+// or tex[z][y][x][c0A, c0B] (ncomp = 1, one 8-byte load), so that one bilinear corner of both components
+// and both times is a single vector load.
+#pragma once
+#include "od_geod.cuh"
+
+namespace od {
+
+#if defined(__CUDA_ARCH__)
+#define OD_DMUL(a, b) __dmul_rn((a), (b))
+#define OD_DADD(a, b) __dadd_rn((a), (b))
+#define OD_DSUB(a, b) __dsub_rn((a), (b))
+#define OD_FMUL(a, b) __fmul_rn((a), (b))
+#define OD_FADD(a, b) __fadd_rn((a), (b))
+#else
+#define OD_DMUL(a, b) ((a) * (b))
+#define OD_DADD(a, b) ((a) + (b))
+#define OD_DSUB(a, b) ((a) - (b))
+#define OD_FMUL(a, b) ((a) * (b))
+#define OD_FADD(a, b) ((a) + (b))
+#endif
+
+struct GroupGeom {
+    int nx, ny, nz, ncomp;
+    int lon_mode;            // 0: np.mod(lon, 360); 1: np.mod(lon + 180, 360) - 180
+    int pad_;
+    double x0, xspan, y0, yspan;
+    double xmin, xmax, ymin, ymax;
+    double nxm1, nym1;
+    double zmin, zmax;       // min / max of the level depths
+    float fallback[2];
+    const double* zs;        // [nz] level depths in increasing order
+    const double* zy;        // [nz] layer index of zs[i] (as float64), what interp1d maps to
+};
+
+struct PairRef {
+    const float* tex;        // pair texels
+    int mode;                // od_time_mode (3 = reader does not cover the time: fallback)
+    int pad_;
+    double w;                // weight of B
+};
+
+struct VertW {
+    int ia, ib;
+    double wa;
+};
+
+// numpy's np.mod(x, 360.0)
+OD_HD double np_mod360(double x) {
+    double r = fmod(x, 360.0);
+    if (r != 0.0) {
+        if (r < 0.0) r += 360.0;
+    } else {
+        r = 0.0;
+    }
+    return r;
+}
+
+// Linear1DInterpolator.__init__ for one particle (z is the particle's float32 depth).
+template <typename ZPtr>
+OD_HD VertW vert_weights(const GroupGeom& g, ZPtr zs, ZPtr zy, float z) {
+    VertW v;
+    if (g.nz <= 1) {
+        v.ia = v.ib = 0;
+        v.wa = 1.0;
+        return v;
+    }
+    // z[z < zgrid.min()] = zgrid.min()  (float64 comparison, float32 store)
+    float zc = z;
+    if ((double)zc < g.zmin) zc = (float)g.zmin;
+    if ((double)zc > g.zmax) zc = (float)g.zmax;
+    const double xn = (double)zc;
+    // np.searchsorted(zs, xn) (side='left'), clipped to [1, nz-1]
+    int lo = 0, hi = g.nz;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (zs[mid] < xn) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo < 1 ? 1 : (lo > g.nz - 1 ? g.nz - 1 : lo);
+    const double x_lo = zs[idx - 1], x_hi = zs[idx], y_lo = zy[idx - 1], y_hi = zy[idx];
+    const double slope = (y_hi - y_lo) / (x_hi - x_lo);
+    const double yn = OD_DADD(OD_DMUL(slope, OD_DSUB(xn, x_lo)), y_lo);
+    double fl = floor(yn);
+    int ia = (int)fl;
+    if (!(fl >= 0.0)) ia = 0;                        // also NaN
+    if (ia > g.nz - 1) ia = g.nz - 1;
+    v.ia = ia;
+    v.ib = ia + 1 < g.nz - 1 ? ia + 1 : g.nz - 1;
+    v.wa = OD_DSUB(1.0, OD_DSUB(yn, (double)ia));
+    return v;
+}
+
+// bilinear weights of scipy's order-1 spline: w0 = 1 - frac, w1 = 1 - w0
+struct HorizW {
+    int i00, i01, i10, i11;     // texel offsets (in texels) of the four corners within one layer
+    double wy0, wy1, wx0, wx1;
+    bool valid;
+};
+
+// numpy's np.mod for float32 operands
+OD_HD float np_mod360f(float x) {
+    float r = fmodf(x, 360.0f);
+    if (r != 0.0f) {
+        if (r < 0.0f) r += 360.0f;
+    } else {
+        r = 0.0f;
+    }
+    return r;
+}
+
+// pos_f32: lon/lat carry float32 values (the reference's element arrays are float32 until the first
+// update_positions, opendrift/elements/elements.py:156-158), so NumPy does the longitude modulation and
+// the fractional-index arithmetic of interpolators.py:110-111 in float32.
+OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_f32) {
+    HorizW h;
+    double x, xi, yi;
+    const double y = lat;
+    if (pos_f32) {
+        const float xf = (g.lon_mode == 0) ? np_mod360f((float)lon) : OD_FADD(np_mod360f(OD_FADD((float)lon, 180.0f)), -180.0f);
+        x = (double)xf;
+        xi = (double)OD_FMUL(OD_FADD(xf, -(float)g.x0) / (float)g.xspan, (float)g.nxm1);
+        yi = (double)OD_FMUL(OD_FADD((float)lat, -(float)g.y0) / (float)g.yspan, (float)g.nym1);
+    } else {
+        x = (g.lon_mode == 0) ? np_mod360(lon) : OD_DSUB(np_mod360(OD_DADD(lon, 180.0)), 180.0);
+        xi = OD_DMUL(OD_DSUB(x, g.x0) / g.xspan, g.nxm1);
+        yi = OD_DMUL(OD_DSUB(y, g.y0) / g.yspan, g.nym1);
+    }
+    bool covered = (x >= g.xmin) && (x <= g.xmax) && (y >= g.ymin) && (y <= g.ymax);
+    covered = covered && (xi >= 0.0) && (xi <= g.nxm1) && (yi >= 0.0) && (yi <= g.nym1);
+    h.valid = covered;
+    if (!covered) {
+        h.i00 = h.i01 = h.i10 = h.i11 = 0;
+        h.wy0 = h.wy1 = h.wx0 = h.wx1 = 0.0;
+        return h;
+    }
+    const double fx = floor(xi), fy = floor(yi);
+    const int ix = (int)fx, iy = (int)fy;
+    const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1;
+    const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
+    h.wx0 = OD_DSUB(1.0, OD_DSUB(xi, fx));
+    h.wx1 = OD_DSUB(1.0, h.wx0);
+    h.wy0 = OD_DSUB(1.0, OD_DSUB(yi, fy));
+    h.wy1 = OD_DSUB(1.0, h.wy0);
+    h.i00 = iy * g.nx + ix;
+    h.i01 = iy * g.nx + ix1;
+    h.i10 = iy1 * g.nx + ix;
+    h.i11 = iy1 * g.nx + ix1;
+    return h;
+}
+
+// map_coordinates(order=1) accumulation order: (y0,x0), (y0,x1), (y1,x0), (y1,x1); result cast to float32
+OD_HD float bilin(const HorizW& h, float a00, float a01, float a10, float a11) {
+    double t = OD_DMUL(OD_DMUL((double)a00, h.wy0), h.wx0);
+    t = OD_DADD(t, OD_DMUL(OD_DMUL((double)a01, h.wy0), h.wx1));
+    t = OD_DADD(t, OD_DMUL(OD_DMUL((double)a10, h.wy1), h.wx0));
+    t = OD_DADD(t, OD_DMUL(OD_DMUL((double)a11, h.wy1), h.wx1));
+    return (float)t;
+}
+
+struct alignas(16) Tex4 { float x, y, z, w; };
+struct alignas(8) Tex2 { float x, y; };
+
+OD_HD Tex4 ld_tex4(const float* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    Tex4 r = {t.x, t.y, t.z, t.w};
+#else
+    Tex4 r = {p[0], p[1], p[2], p[3]};
+#endif
+    return r;
+}
+
+OD_HD Tex2 ld_tex2(const float* p) {
+#if defined(__CUDA_ARCH__)
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    Tex2 r = {t.x, t.y};
+#else
+    Tex2 r = {p[0], p[1]};
+#endif
+    return r;
+}
+
+OD_HD bool finite_f(float v) { return fabsf(v) <= 3.4028234663852886e38f; }   // false for NaN / inf
+
+// vertical + time combination of the four horizontal results (layer a/b x time A/B) of one component
+OD_HD float combine(const GroupGeom& g, const PairRef& pr, const VertW& vw,
+                    float haA, float hbA, float haB, float hbB) {
+    if (g.nz > 1) {
+        // horiz[ia]*wa + horiz[ib]*(1-wa) in float64 (interpolators.py:195-197)
+        const double omw = OD_DSUB(1.0, vw.wa);
+        const double vA = OD_DADD(OD_DMUL((double)haA, vw.wa), OD_DMUL((double)hbA, omw));
+        if (pr.mode == 1) return (float)vA;
+        const double vB = OD_DADD(OD_DMUL((double)haB, vw.wa), OD_DMUL((double)hbB, omw));
+        if (pr.mode == 2) return (float)vB;
+        // env_before*(1-w) + env_after*w in float64 (structured.py:353-364), then float32 (environment.py:695)
+        return (float)OD_DADD(OD_DMUL(vA, OD_DSUB(1.0, pr.w)), OD_DMUL(vB, pr.w));
+    }
+    if (pr.mode == 1) return haA;
+    if (pr.mode == 2) return haB;
+    // 2-D variables stay float32: float32 array * Python float -> float32 (NumPy weak scalars)
+    const float w1 = (float)pr.w, w0 = (float)OD_DSUB(1.0, pr.w);
+    return OD_FADD(OD_FMUL(haA, w0), OD_FMUL(haB, w1));
+}
+
+// Sample a 2-component group (e.g. x/y_sea_water_velocity) -> float32 u, v with fallback applied.
+OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
+                   float& u, float& v, bool pos_f32 = false) {
+    const HorizW h = horiz_weights(g, lon, lat, pos_f32);
+    float ru = NAN, rv = NAN;
+    if (h.valid && pr.mode != 3) {
+        const long long layer = (long long)g.nx * g.ny;
+        const float* ta = pr.tex + ((long long)vw.ia * layer) * 4;
+        const Tex4 a00 = ld_tex4(ta + 4ll * h.i00), a01 = ld_tex4(ta + 4ll * h.i01);
+        const Tex4 a10 = ld_tex4(ta + 4ll * h.i10), a11 = ld_tex4(ta + 4ll * h.i11);
+        Tex4 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
+        if (g.nz > 1) {
+            const float* tb = pr.tex + ((long long)vw.ib * layer) * 4;
+            b00 = ld_tex4(tb + 4ll * h.i00); b01 = ld_tex4(tb + 4ll * h.i01);
+            b10 = ld_tex4(tb + 4ll * h.i10); b11 = ld_tex4(tb + 4ll * h.i11);
+        }
+        float uaA = 0.f, ubA = 0.f, uaB = 0.f, ubB = 0.f, vaA = 0.f, vbA = 0.f, vaB = 0.f, vbB = 0.f;
+        if (pr.mode != 2) {
+            uaA = bilin(h, a00.x, a01.x, a10.x, a11.x);
+            vaA = bilin(h, a00.y, a01.y, a10.y, a11.y);
+            if (g.nz > 1) {
+                ubA = bilin(h, b00.x, b01.x, b10.x, b11.x);
+                vbA = bilin(h, b00.y, b01.y, b10.y, b11.y);
+            }
+        }
+        if (pr.mode != 1) {
+            uaB = bilin(h, a00.z, a01.z, a10.z, a11.z);
+            vaB = bilin(h, a00.w, a01.w, a10.w, a11.w);
+            if (g.nz > 1) {
+                ubB = bilin(h, b00.z, b01.z, b10.z, b11.z);
+                vbB = bilin(h, b00.w, b01.w, b10.w, b11.w);
+            }
+        }
+        ru = combine(g, pr, vw, uaA, ubA, uaB, ubB);
+        rv = combine(g, pr, vw, vaA, vbA, vaB, vbB);
+    }
+    // masked_invalid -> fallback (environment.py:782-791); fallback NaN = keep missing
+    if (!finite_f(ru)) ru = g.fallback[0];
+    if (!finite_f(rv)) rv = g.fallback[1];
+    u = ru;
+    v = rv;
+}
+
+// Sample a 1-component group (e.g. upward_sea_water_velocity).
+OD_HD float sample1(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
+                     bool pos_f32 = false) {
+    const HorizW h = horiz_weights(g, lon, lat, pos_f32);
+    float r = NAN;
+    if (h.valid && pr.mode != 3) {
+        const long long layer = (long long)g.nx * g.ny;
+        const float* ta = pr.tex + ((long long)vw.ia * layer) * 2;
+        const Tex2 a00 = ld_tex2(ta + 2ll * h.i00), a01 = ld_tex2(ta + 2ll * h.i01);
+        const Tex2 a10 = ld_tex2(ta + 2ll * h.i10), a11 = ld_tex2(ta + 2ll * h.i11);
+        Tex2 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
+        if (g.nz > 1) {
+            const float* tb = pr.tex + ((long long)vw.ib * layer) * 2;
+            b00 = ld_tex2(tb + 2ll * h.i00); b01 = ld_tex2(tb + 2ll * h.i01);
+            b10 = ld_tex2(tb + 2ll * h.i10); b11 = ld_tex2(tb + 2ll * h.i11);
+        }
+        float aA = 0.f, bA = 0.f, aB = 0.f, bB = 0.f;
+        if (pr.mode != 2) {
+            aA = bilin(h, a00.x, a01.x, a10.x, a11.x);
+            if (g.nz > 1) bA = bilin(h, b00.x, b01.x, b10.x, b11.x);
+        }
+        if (pr.mode != 1) {
+            aB = bilin(h, a00.y, a01.y, a10.y, a11.y);
+            if (g.nz > 1) bB = bilin(h, b00.y, b01.y, b10.y, b11.y);
+        }
+        r = combine(g, pr, vw, aA, bA, aB, bB);
+    }
+    if (!finite_f(r)) r = g.fallback[0];
+    return r;
+}
+
+}  // namespace od

@@ -1,0 +1,670 @@
+// od_kernels.cu -- libodcuda.so: CUDA kernels (sm_100a) and the C-ABI of include/odcuda.h.
+//
+// One thread per particle; particle state is SoA in HBM (float64 lon/lat, float32 z, per-particle
+// factors); forcing lives in "pair texel" arrays (see od_interp.cuh) so that a bilinear corner of both
+// velocity components and both bracketing time slabs is one 16-byte load.  The whole RK4 stage loop,
+// the four WGS84 geodesic moves and (in od_step_oceandrift) wind drift, vertical advection and the
+// horizontal random walk run in a single kernel launch per time step.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/odcuda.h"
+#include "od_advect.cuh"
+
+using namespace od;
+
+#define OD_MAX_GROUPS 16
+#define OD_PAIR_CACHE 4
+#define OD_BLOCK 256
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct PairEntry {
+    float* tex = nullptr;
+    int slot_a = -1, slot_b = -1;
+    uint64_t ver_a = 0, ver_b = 0;
+    uint64_t last_use = 0;
+};
+
+struct Group {
+    bool defined = false;
+    od_group_desc desc;
+    std::vector<float*> slots;          // [n_slots * ncomp] raw slabs [nz][ny][nx]
+    std::vector<uint64_t> version;      // [n_slots]
+    double* d_zs = nullptr;             // increasing level depths
+    double* d_zy = nullptr;             // their layer indices
+    double zmin = 0, zmax = 0;
+    PairEntry pairs[OD_PAIR_CACHE];
+    size_t cells() const { return (size_t)desc.nx * desc.ny * desc.nz; }
+};
+
+struct od_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    Group groups[OD_MAX_GROUPS];
+    int64_t launches = 0;
+    uint64_t tick = 0;
+    int sm_count = 0;
+    // sort scratch
+    int32_t* d_keys = nullptr;
+    int32_t* d_bins = nullptr;
+    int64_t keys_cap = 0, bins_cap = 0;
+};
+
+static int fail(od_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) return fail(ctx, OD_ERR_CUDA, #call, e_); \
+    } while (0)
+
+static inline int grid_for(int64_t n) { return (int)((n + OD_BLOCK - 1) / OD_BLOCK); }
+
+extern "C" int od_abi_version(void) { return OD_ABI_VERSION; }
+
+extern "C" int od_create(int device, od_ctx** out) {
+    if (!out) return OD_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return OD_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return OD_ERR_CUDA;
+    od_ctx* c = new od_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return OD_OK;
+}
+
+static void free_group(Group& g) {
+    for (float* p : g.slots) if (p) cudaFree(p);
+    g.slots.clear();
+    g.version.clear();
+    if (g.d_zs) cudaFree(g.d_zs);
+    if (g.d_zy) cudaFree(g.d_zy);
+    g.d_zs = g.d_zy = nullptr;
+    for (auto& p : g.pairs) {
+        if (p.tex) cudaFree(p.tex);
+        p = PairEntry();
+    }
+    g.defined = false;
+}
+
+extern "C" void od_destroy(od_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& g : ctx->groups) free_group(g);
+    if (ctx->d_keys) cudaFree(ctx->d_keys);
+    if (ctx->d_bins) cudaFree(ctx->d_bins);
+    delete ctx;
+}
+
+extern "C" const char* od_last_error(od_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int od_set_stream(od_ctx* ctx, void* s) {
+    if (!ctx) return OD_ERR_ARG;
+    ctx->stream = (cudaStream_t)s;
+    return OD_OK;
+}
+
+extern "C" int od_sync(od_ctx* ctx) {
+    if (!ctx) return OD_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return OD_OK;
+}
+
+extern "C" int od_device_sm_count(od_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t od_launch_count(od_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// field groups
+// ------------------------------------------------------------------------------------------------
+extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, const double* h_z) {
+    if (!ctx || !d || group < 0 || group >= OD_MAX_GROUPS) return fail(ctx, OD_ERR_ARG, "od_group_define: bad group");
+    if (d->ncomp < 1 || d->ncomp > 2 || d->nx < 2 || d->ny < 2 || d->nz < 1 || d->nz > OD_MAX_LEVELS ||
+        d->n_slots < 2 || d->n_slots > 64)
+        return fail(ctx, OD_ERR_ARG, "od_group_define: bad shape");
+    if (d->nz > 1 && !h_z) return fail(ctx, OD_ERR_ARG, "od_group_define: z levels missing");
+    if ((size_t)d->nx * d->ny * d->nz >= (1ull << 31)) return fail(ctx, OD_ERR_ARG, "od_group_define: block too large");
+    CK(cudaSetDevice(ctx->device));
+    Group& g = ctx->groups[group];
+    free_group(g);
+    g.desc = *d;
+    g.slots.assign((size_t)d->n_slots * d->ncomp, nullptr);
+    g.version.assign(d->n_slots, 0);
+    for (auto& p : g.slots) CK(cudaMalloc(&p, g.cells() * sizeof(float)));
+    if (d->nz > 1) {
+        std::vector<double> zs(d->nz), zy(d->nz);
+        bool inc = h_z[1] > h_z[0];
+        for (int i = 0; i < d->nz; ++i) {
+            int src = inc ? i : d->nz - 1 - i;
+            zs[i] = h_z[src];
+            zy[i] = (double)src;
+        }
+        for (int i = 1; i < d->nz; ++i)
+            if (!(zs[i] > zs[i - 1])) return fail(ctx, OD_ERR_ARG, "od_group_define: z levels not monotonic");
+        g.zmin = zs[0];
+        g.zmax = zs[d->nz - 1];
+        CK(cudaMalloc(&g.d_zs, d->nz * sizeof(double)));
+        CK(cudaMalloc(&g.d_zy, d->nz * sizeof(double)));
+        CK(cudaMemcpyAsync(g.d_zs, zs.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(g.d_zy, zy.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    g.defined = true;
+    return OD_OK;
+}
+
+static int check_slot(od_ctx* ctx, int group, int slot, int comp) {
+    if (!ctx || group < 0 || group >= OD_MAX_GROUPS || !ctx->groups[group].defined)
+        return fail(ctx, OD_ERR_STATE, "group not defined");
+    const Group& g = ctx->groups[group];
+    if (slot < 0 || slot >= g.desc.n_slots || comp < 0 || comp >= g.desc.ncomp)
+        return fail(ctx, OD_ERR_ARG, "bad slot/component");
+    return OD_OK;
+}
+
+extern "C" int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const float* src, int on_device) {
+    int rc = check_slot(ctx, group, slot, comp);
+    if (rc) return rc;
+    if (!src) return fail(ctx, OD_ERR_ARG, "od_group_upload: null source");
+    Group& g = ctx->groups[group];
+    CK(cudaMemcpyAsync(g.slots[(size_t)slot * g.desc.ncomp + comp], src, g.cells() * sizeof(float),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    g.version[slot] = ++ctx->tick;
+    return OD_OK;
+}
+
+extern "C" int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** out) {
+    int rc = check_slot(ctx, group, slot, comp);
+    if (rc) return rc;
+    if (!out) return fail(ctx, OD_ERR_ARG, "od_group_slot_ptr: null out");
+    Group& g = ctx->groups[group];
+    *out = g.slots[(size_t)slot * g.desc.ncomp + comp];
+    return OD_OK;
+}
+
+extern "C" int od_group_touch(od_ctx* ctx, int group, int slot) {
+    int rc = check_slot(ctx, group, slot, 0);
+    if (rc) return rc;
+    ctx->groups[group].version[slot] = ++ctx->tick;
+    return OD_OK;
+}
+
+// interleave two time slabs (and two components) into pair texels
+__global__ void __launch_bounds__(OD_BLOCK) pack_pair2_kernel(const float* __restrict__ a0, const float* __restrict__ a1,
+                                                               const float* __restrict__ b0, const float* __restrict__ b1,
+                                                               float4* __restrict__ tex, int64_t cells) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cells; i += stride) tex[i] = make_float4(a0[i], a1[i], b0[i], b1[i]);
+}
+
+__global__ void __launch_bounds__(OD_BLOCK) pack_pair1_kernel(const float* __restrict__ a0, const float* __restrict__ b0,
+                                                               float2* __restrict__ tex, int64_t cells) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cells; i += stride) tex[i] = make_float2(a0[i], b0[i]);
+}
+
+// Resolve a time sample to pair texels (building / reusing a cached pair).
+static int resolve_pair(od_ctx* ctx, int group, const od_time_sample& ts, PairRef* out) {
+    Group& g = ctx->groups[group];
+    const int nc = g.desc.ncomp;
+    if (ts.mode == OD_T_MISSING) {
+        out->tex = nullptr; out->mode = OD_T_MISSING; out->pad_ = 0; out->w = 0.0;
+        return OD_OK;
+    }
+    int sa = ts.slot_a, sb = ts.slot_b;
+    if (ts.mode == OD_T_FIRST) sb = (sb < 0 || sb >= g.desc.n_slots) ? sa : sb;
+    if (ts.mode == OD_T_SECOND) sa = (sa < 0 || sa >= g.desc.n_slots) ? sb : sa;
+    if (sa < 0 || sa >= g.desc.n_slots || sb < 0 || sb >= g.desc.n_slots || ts.mode < 0 || ts.mode > 2)
+        return fail(ctx, OD_ERR_ARG, "bad time sample");
+    out->w = ts.w;
+    out->pad_ = 0;
+    // a single-slab sample can be served by any cached pair that contains the slab
+    if (ts.mode != OD_T_LERP) {
+        const int need = ts.mode == OD_T_FIRST ? sa : sb;
+        for (auto& p : g.pairs) {
+            if (!p.tex) continue;
+            if (p.slot_a == need && p.ver_a == g.version[need]) { out->tex = p.tex; out->mode = OD_T_FIRST; p.last_use = ++ctx->tick; return OD_OK; }
+            if (p.slot_b == need && p.ver_b == g.version[need]) { out->tex = p.tex; out->mode = OD_T_SECOND; p.last_use = ++ctx->tick; return OD_OK; }
+        }
+    }
+    for (auto& p : g.pairs) {
+        if (p.tex && p.slot_a == sa && p.slot_b == sb && p.ver_a == g.version[sa] && p.ver_b == g.version[sb]) {
+            out->tex = p.tex;
+            out->mode = ts.mode;
+            p.last_use = ++ctx->tick;
+            return OD_OK;
+        }
+    }
+    // build into the least recently used entry
+    PairEntry* victim = &g.pairs[0];
+    for (auto& p : g.pairs) {
+        if (!p.tex) { victim = &p; break; }
+        if (p.last_use < victim->last_use) victim = &p;
+    }
+    if (!victim->tex) CK(cudaMalloc(&victim->tex, g.cells() * sizeof(float) * 2 * nc));
+    const int64_t cells = (int64_t)g.cells();
+    int blocks = (int)((cells + OD_BLOCK - 1) / OD_BLOCK);
+    const int cap = ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (nc == 2)
+        pack_pair2_kernel<<<blocks, OD_BLOCK, 0, ctx->stream>>>(g.slots[(size_t)sa * 2], g.slots[(size_t)sa * 2 + 1],
+                                                                g.slots[(size_t)sb * 2], g.slots[(size_t)sb * 2 + 1],
+                                                                (float4*)victim->tex, cells);
+    else
+        pack_pair1_kernel<<<blocks, OD_BLOCK, 0, ctx->stream>>>(g.slots[sa], g.slots[sb], (float2*)victim->tex, cells);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    victim->slot_a = sa;
+    victim->slot_b = sb;
+    victim->ver_a = g.version[sa];
+    victim->ver_b = g.version[sb];
+    victim->last_use = ++ctx->tick;
+    out->tex = victim->tex;
+    out->mode = ts.mode;
+    return OD_OK;
+}
+
+static GroupGeom make_geom(const Group& g) {
+    GroupGeom q;
+    memset(&q, 0, sizeof(q));
+    q.nx = g.desc.nx; q.ny = g.desc.ny; q.nz = g.desc.nz; q.ncomp = g.desc.ncomp;
+    q.lon_mode = g.desc.lon_mode;
+    q.x0 = g.desc.x0; q.xspan = g.desc.xspan; q.y0 = g.desc.y0; q.yspan = g.desc.yspan;
+    q.xmin = g.desc.xmin; q.xmax = g.desc.xmax; q.ymin = g.desc.ymin; q.ymax = g.desc.ymax;
+    q.nxm1 = (double)(g.desc.nx - 1); q.nym1 = (double)(g.desc.ny - 1);
+    q.zmin = g.zmin; q.zmax = g.zmax;
+    q.fallback[0] = g.desc.fallback[0]; q.fallback[1] = g.desc.fallback[1];
+    q.zs = g.d_zs; q.zy = g.d_zy;
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// Level table of a group staged in shared memory (the vertical search is data dependent).
+struct LevelsSmem {
+    double zs[OD_MAX_LEVELS];
+    double zy[OD_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void load_levels(LevelsSmem& s, const GroupGeom& g) {
+    for (int i = threadIdx.x; i < g.nz; i += blockDim.x) {
+        s.zs[i] = g.zs[i];
+        s.zy[i] = g.zy[i];
+    }
+}
+
+struct InterpParams {
+    GroupGeom g;
+    PairRef pr;
+    int64_t n;
+    const double* lon;
+    const double* lat;
+    const float* z;
+    float* out0;
+    float* out1;
+    int pos_f32;
+};
+
+__global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) {
+    __shared__ LevelsSmem lv;
+    if (p.g.nz > 1) load_levels(lv, p.g);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const float z = (p.z && p.g.nz > 1) ? p.z[i] : 0.0f;
+    const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, z);
+    if (p.g.ncomp == 2) {
+        float u, v;
+        sample2(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
+        if (p.out0) p.out0[i] = u;
+        if (p.out1) p.out1[i] = v;
+    } else {
+        const float r = sample1(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        if (p.out0) p.out0[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(OD_BLOCK) geod_fwd_kernel(int64_t n, double* __restrict__ lon, double* __restrict__ lat,
+                                                             const double* __restrict__ az, const double* __restrict__ dist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo, la;
+    geod_direct(lon[i], lat[i], az[i], dist[i], lo, la);
+    lon[i] = lo;
+    lat[i] = la;
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(OD_BLOCK) update_positions_kernel(int64_t n, double* __restrict__ lon, double* __restrict__ lat,
+                                                                     const void* __restrict__ xv, const void* __restrict__ yv,
+                                                                     const int32_t* __restrict__ moving, double dt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double lon0 = lon[i], lat0 = lat[i];
+    const double mv = moving ? (double)moving[i] : 1.0;
+    const GeodStart gs = geod_start(lat0);
+    double lo, la;
+    if (F64) final_move_f64(gs, lon0, ((const double*)xv)[i], ((const double*)yv)[i], mv, dt, lo, la);
+    else     final_move_f32(gs, lon0, ((const float*)xv)[i], ((const float*)yv)[i], mv, dt, lo, la);
+    lon[i] = lo;
+    lat[i] = la;
+}
+
+template <int SCHEME, bool F64, bool EXTRAS>
+__global__ void __launch_bounds__(OD_BLOCK) step_kernel(const StepParams p) {
+    __shared__ LevelsSmem lv;
+    __shared__ LevelsSmem lvw;
+    if (p.cs.g.nz > 1) load_levels(lv, p.cs.g);
+    if (EXTRAS && p.w_on && p.gw.nz > 1) load_levels(lvw, p.gw);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    step_particle<SCHEME, F64, EXTRAS>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+}
+
+// ---- particle ordering ---------------------------------------------------------------------------
+struct SortParams {
+    GroupGeom g;
+    int64_t n;
+    const double* lon;
+    const double* lat;
+    const float* z;
+    int tile, ntx, nty;
+};
+
+__global__ void __launch_bounds__(OD_BLOCK) cell_key_kernel(const SortParams p, int32_t* __restrict__ keys,
+                                                             int32_t* __restrict__ bins) {
+    __shared__ LevelsSmem lv;
+    if (p.g.nz > 1) load_levels(lv, p.g);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const HorizW h = horiz_weights(p.g, p.lon[i], p.lat[i], false);
+    int key = 0;
+    if (h.valid) {
+        const int iy = h.i00 / p.g.nx, ix = h.i00 - iy * p.g.nx;
+        const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, (p.z && p.g.nz > 1) ? p.z[i] : 0.0f);
+        key = 1 + (vw.ia * p.nty + iy / p.tile) * p.ntx + ix / p.tile;
+    }
+    keys[i] = key;
+    atomicAdd(&bins[key], 1);
+}
+
+// exclusive scan of the bin counts, one block (bins <= a few hundred thousand)
+__global__ void __launch_bounds__(1024) scan_bins_kernel(int32_t* __restrict__ bins, int nbins) {
+    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nbins; base += 1024) {
+        const int i = base + threadIdx.x;
+        int v = i < nbins ? bins[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int s = warp_sums[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (threadIdx.x >= o) s += y;
+            }
+            warp_sums[threadIdx.x] = s;
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+        const int incl = x + warp_off + carry;
+        if (i < nbins) bins[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(OD_BLOCK) scatter_perm_kernel(int64_t n, const int32_t* __restrict__ keys,
+                                                                 int32_t* __restrict__ bins, int32_t* __restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pos = atomicAdd(&bins[keys[i]], 1);
+    perm[pos] = (int32_t)i;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OD_BLOCK) permute_kernel(int64_t n, const int32_t* __restrict__ perm,
+                                                            const T* __restrict__ src, T* __restrict__ dst, int inverse) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (inverse) dst[perm[k]] = src[k];
+    else dst[k] = src[perm[k]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI entry points
+// ------------------------------------------------------------------------------------------------
+static int need_group(od_ctx* ctx, int group, int ncomp) {
+    if (!ctx) return OD_ERR_ARG;
+    if (group < 0 || group >= OD_MAX_GROUPS || !ctx->groups[group].defined) return fail(ctx, OD_ERR_STATE, "group not defined");
+    if (ncomp && ctx->groups[group].desc.ncomp != ncomp) return fail(ctx, OD_ERR_ARG, "group has wrong component count");
+    return OD_OK;
+}
+
+extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n, const double* lon, const double* lat,
+                         const float* z, int pos_f32, float* out0, float* out1) {
+    int rc = need_group(ctx, group, 0);
+    if (rc) return rc;
+    if (!ts || n < 0 || (n > 0 && (!lon || !lat))) return fail(ctx, OD_ERR_ARG, "od_interp: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    InterpParams p;
+    p.g = make_geom(ctx->groups[group]);
+    rc = resolve_pair(ctx, group, *ts, &p.pr);
+    if (rc) return rc;
+    p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = pos_f32;
+    interp_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+extern "C" int od_geod_fwd(od_ctx* ctx, int64_t n, double* lon, double* lat, const double* az, const double* dist) {
+    if (!ctx || n < 0 || (n > 0 && (!lon || !lat || !az || !dist))) return fail(ctx, OD_ERR_ARG, "od_geod_fwd: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    geod_fwd_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, lon, lat, az, dist);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+extern "C" int od_update_positions(od_ctx* ctx, int64_t n, double* lon, double* lat, const void* xv, const void* yv,
+                                   int vel_f64, const int32_t* moving, double dt) {
+    if (!ctx || n < 0 || (n > 0 && (!lon || !lat || !xv || !yv))) return fail(ctx, OD_ERR_ARG, "od_update_positions: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (vel_f64) update_positions_kernel<true><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, lon, lat, xv, yv, moving, dt);
+    else         update_positions_kernel<false><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, lon, lat, xv, yv, moving, dt);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
+    int rc = need_group(ctx, a->group_uv, 2);
+    if (rc) return rc;
+    if (a->scheme < 0 || a->scheme > 2) return fail(ctx, OD_ERR_ARG, "unknown advection scheme");
+    if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat))) return fail(ctx, OD_ERR_ARG, "null particle arrays");
+    const Group& g = ctx->groups[a->group_uv];
+    if (g.desc.nz > 1 && !a->d_z) return fail(ctx, OD_ERR_ARG, "3-D current group needs z");
+    if ((a->d_k1_u == nullptr) != (a->d_k1_v == nullptr)) return fail(ctx, OD_ERR_ARG, "k1 needs both components");
+    memset(p, 0, sizeof(*p));
+    p->cs.g = make_geom(g);
+    p->has_k1 = a->d_k1_u != nullptr;
+    if (!p->has_k1) {
+        rc = resolve_pair(ctx, a->group_uv, a->t_start, &p->cs.t_start);
+        if (rc) return rc;
+    }
+    if (a->scheme != OD_EULER) {
+        rc = resolve_pair(ctx, a->group_uv, a->t_mid, &p->cs.t_mid);
+        if (rc) return rc;
+    }
+    if (a->scheme == OD_RK4) {
+        rc = resolve_pair(ctx, a->group_uv, a->t_end, &p->cs.t_end);
+        if (rc) return rc;
+    }
+    p->dt = a->dt;
+    p->dt32 = (float)a->dt;
+    p->adt32 = (float)fabs(a->dt);
+    p->n = a->n;
+    p->lon = a->d_lon; p->lat = a->d_lat; p->z = a->d_z;
+    p->factor = a->d_factor; p->moving = a->d_moving;
+    p->k1u = a->d_k1_u; p->k1v = a->d_k1_v;
+    p->env_u = a->d_env_u; p->env_v = a->d_env_v;
+    p->truncate_below = a->truncate_below;
+    p->pos_f32 = a->pos_f32;
+    return OD_OK;
+}
+
+template <bool EXTRAS>
+static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
+    const int grid = grid_for(p.n);
+    cudaStream_t s = ctx->stream;
+#define OD_LAUNCH(S, F) step_kernel<S, F, EXTRAS><<<grid, OD_BLOCK, 0, s>>>(p)
+    if (scheme == OD_EULER) { if (f64) OD_LAUNCH(0, true); else OD_LAUNCH(0, false); }
+    else if (scheme == OD_RK2) { if (f64) OD_LAUNCH(1, true); else OD_LAUNCH(1, false); }
+    else { if (f64) OD_LAUNCH(2, true); else OD_LAUNCH(2, false); }
+#undef OD_LAUNCH
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_advect_current: null argument");
+    CK(cudaSetDevice(ctx->device));
+    StepParams p;
+    int rc = fill_current(ctx, a, &p);
+    if (rc) return rc;
+    if (a->n == 0) return OD_OK;
+    return launch_step<false>(ctx, a->scheme, a->factor_f64 != 0, p);
+}
+
+extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift: null argument");
+    CK(cudaSetDevice(ctx->device));
+    StepParams p;
+    int rc = fill_current(ctx, &a->cur, &p);
+    if (rc) return rc;
+    if (a->group_wind >= 0) {
+        rc = need_group(ctx, a->group_wind, 2);
+        if (rc) return rc;
+        if (!a->d_wdf) return fail(ctx, OD_ERR_ARG, "wind drift needs wind_drift_factor");
+        if (ctx->groups[a->group_wind].desc.nz != 1) return fail(ctx, OD_ERR_ARG, "wind group must be 2-D");
+        p.wind_on = 1;
+        p.wdf_f64 = a->wdf_f64;
+        p.gwind = make_geom(ctx->groups[a->group_wind]);
+        rc = resolve_pair(ctx, a->group_wind, a->t_wind, &p.pwind);
+        if (rc) return rc;
+        p.wdf = a->d_wdf;
+        p.wind_drift_depth = a->wind_drift_depth;
+    }
+    if (a->group_w >= 0) {
+        rc = need_group(ctx, a->group_w, 1);
+        if (rc) return rc;
+        if (!a->d_z_inout || !a->cur.d_z) return fail(ctx, OD_ERR_ARG, "vertical advection needs z");
+        p.w_on = 1;
+        p.w_at_surface = a->w_at_surface;
+        p.gw = make_geom(ctx->groups[a->group_w]);
+        rc = resolve_pair(ctx, a->group_w, a->t_w, &p.pw);
+        if (rc) return rc;
+        p.z_inout = a->d_z_inout;
+    }
+    if (a->d_rand_x) {
+        if (!a->d_rand_y) return fail(ctx, OD_ERR_ARG, "diffusion needs both random arrays");
+        p.diff_on = 1;
+        p.rand_x = a->d_rand_x; p.rand_y = a->d_rand_y;
+        p.diffusivity = a->d_diffusivity;
+        p.diffusivity_const = a->diffusivity_const;
+    }
+    if (a->cur.n == 0) return OD_OK;
+    return launch_step<true>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+}
+
+extern "C" int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* lon, const double* lat, const float* z,
+                               int32_t* perm) {
+    int rc = need_group(ctx, group, 0);
+    if (rc) return rc;
+    if (n < 0 || n >= (1ll << 31) || (n > 0 && (!lon || !lat || !perm))) return fail(ctx, OD_ERR_ARG, "od_sort_by_cell: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    const Group& g = ctx->groups[group];
+    SortParams p;
+    p.g = make_geom(g);
+    p.n = n; p.lon = lon; p.lat = lat; p.z = z;
+    p.tile = 4;
+    p.ntx = (g.desc.nx + p.tile - 1) / p.tile;
+    p.nty = (g.desc.ny + p.tile - 1) / p.tile;
+    const int64_t nbins = 1 + (int64_t)p.ntx * p.nty * g.desc.nz;
+    if (nbins >= (1ll << 30)) return fail(ctx, OD_ERR_ARG, "od_sort_by_cell: too many bins");
+    if (ctx->keys_cap < n) {
+        if (ctx->d_keys) cudaFree(ctx->d_keys);
+        ctx->d_keys = nullptr;
+        CK(cudaMalloc(&ctx->d_keys, n * sizeof(int32_t)));
+        ctx->keys_cap = n;
+    }
+    if (ctx->bins_cap < nbins) {
+        if (ctx->d_bins) cudaFree(ctx->d_bins);
+        ctx->d_bins = nullptr;
+        CK(cudaMalloc(&ctx->d_bins, nbins * sizeof(int32_t)));
+        ctx->bins_cap = nbins;
+    }
+    CK(cudaMemsetAsync(ctx->d_bins, 0, nbins * sizeof(int32_t), ctx->stream));
+    cell_key_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p, ctx->d_keys, ctx->d_bins);
+    scan_bins_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bins, (int)nbins);
+    scatter_perm_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, ctx->d_keys, ctx->d_bins, perm);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+    return OD_OK;
+}
+
+static int permute_impl(od_ctx* ctx, int64_t n, const int32_t* perm, const void* src, void* dst, int es, int inverse) {
+    if (!ctx || n < 0 || (n > 0 && (!perm || !src || !dst)) || src == dst) return fail(ctx, OD_ERR_ARG, "od_permute: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (es == 4) permute_kernel<uint32_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint32_t*)src, (uint32_t*)dst, inverse);
+    else if (es == 8) permute_kernel<uint64_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint64_t*)src, (uint64_t*)dst, inverse);
+    else return fail(ctx, OD_ERR_ARG, "od_permute: element size must be 4 or 8");
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+extern "C" int od_permute(od_ctx* ctx, int64_t n, const int32_t* perm, const void* src, void* dst, int es) {
+    return permute_impl(ctx, n, perm, src, dst, es, 0);
+}
+
+extern "C" int od_unpermute(od_ctx* ctx, int64_t n, const int32_t* perm, const void* src, void* dst, int es) {
+    return permute_impl(ctx, n, perm, src, dst, es, 1);
+}

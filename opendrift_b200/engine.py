@@ -1,0 +1,310 @@
+"""Thin Python owner of one od_ctx (one per GPU / process): field groups, slab residency and
+the kernel calls.  PyTorch is used only to allocate device buffers and to provide the CUDA
+stream; every computation happens in libodcuda.so.
+
+Host logic restated from the reference:
+  * which reader time slabs bracket a requested time, and the interpolation weight
+    (Variables.nearest_time, opendrift/readers/basereader/variables.py:402-443;
+    StructuredReader._get_variables_interpolated_, readers/basereader/structured.py:218-229, 353-356);
+  * the before/after block cache with swap-on-advance (structured.py:243-318) becomes a ring of
+    device-resident slabs per field group.
+"""
+import ctypes as C
+from bisect import bisect_left
+
+import numpy as np
+
+from . import _lib
+from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, OD_T_LERP, OD_T_FIRST,
+                   OD_T_MISSING, SCHEMES)
+
+
+def _seconds(t, t0):
+    return (t - t0).total_seconds() if hasattr(t - t0, 'total_seconds') else float(t - t0)
+
+
+def bracket(times, t):
+    """(index_before, index_after_or_None, weight_after) of time t in the sorted list `times`.
+
+    Follows Variables.nearest_time for readers with a `times` list (variables.py:414-430) and the
+    `time == time_before -> no after block` rule (structured.py:224-229); returns None when t is
+    outside the reader's time coverage (covers_time, variables.py:391-400)."""
+    if len(times) == 1:
+        return 0, None, 0.0
+    if t < times[0] or t > times[-1]:
+        return None
+    ib = max(0, bisect_left(times, t) - 1)
+    if times[ib + 1] == t:
+        ib += 1
+    tb = times[ib]
+    if t == tb:
+        return ib, None, 0.0
+    ia = min(ib + 1, len(times) - 1)
+    ta = times[ia]
+    w = _seconds(t, tb) / _seconds(ta, tb)
+    return ib, ia, w
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class FieldGroup:
+    """One od group: geometry + a ring of device slots filled on demand from a slab supplier."""
+
+    def __init__(self, engine, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3,
+                 names=None):
+        self.engine, self.gid, self.ncomp = engine, gid, ncomp
+        self.lon = np.asarray(lon, dtype=np.float32)
+        self.lat = np.asarray(lat, dtype=np.float32)
+        self.z = None if z is None else np.asarray(z, dtype=np.float64)
+        self.times = list(times)
+        self.supplier = supplier          # supplier(time_index, comp) -> float32 [nz,]ny,nx (NumPy or CUDA tensor)
+        self.names = names
+        self.n_slots = n_slots
+        self.resident = [None] * n_slots  # time index held by each ring slot
+        self.use = [0] * n_slots
+        self._tick = 0
+        d = GroupDesc()
+        d.ncomp, d.nx, d.ny = ncomp, len(self.lon), len(self.lat)
+        d.nz = 1 if self.z is None else len(self.z)
+        xmin, xmax = float(self.lon.min()), float(self.lon.max())
+        d.lon_mode = _lib.OD_LON_PM180 if xmin < 0 else _lib.OD_LON_0_360     # variables.py:259-280
+        d.n_slots = n_slots
+        # Linear2DInterpolator (interpolators.py:110-111): float32 end points, float32 difference
+        d.x0 = float(self.lon[0])
+        d.xspan = float(np.float32(self.lon[-1] - self.lon[0]))
+        d.y0 = float(self.lat[0])
+        d.yspan = float(np.float32(self.lat[-1] - self.lat[0]))
+        d.xmin, d.xmax = xmin, xmax
+        d.ymin, d.ymax = float(self.lat.min()), float(self.lat.max())
+        fb = list(fallback) + [float('nan')] * (2 - len(fallback))
+        d.fallback[0] = float('nan') if fb[0] is None else fb[0]
+        d.fallback[1] = float('nan') if fb[1] is None else fb[1]
+        self.desc = d
+        zl = None
+        if self.z is not None:
+            zl = (C.c_double * len(self.z))(*self.z)
+        engine._check(engine.lib.od_group_define(engine.ctx, gid, C.byref(d), zl))
+
+    # -- slab residency -------------------------------------------------------------------
+    def slot_of(self, ti, pinned=()):
+        """Ring slot holding time index ti, uploading it if necessary (never evicting `pinned`)."""
+        self._tick += 1
+        if ti in self.resident:
+            s = self.resident.index(ti)
+            self.use[s] = self._tick
+            return s
+        cand = [s for s in range(self.n_slots) if self.resident[s] not in pinned or self.resident[s] is None]
+        s = min(cand, key=lambda k: (self.resident[k] is not None, self.use[k]))
+        for c in range(self.ncomp):
+            self.engine.upload(self.gid, s, c, self.supplier(ti, c))
+        self.resident[s] = ti
+        self.use[s] = self._tick
+        return s
+
+    def sample(self, t, pinned=()):
+        """od_time_sample for time t (uploads slabs as needed)."""
+        ts = TimeSample()
+        br = bracket(self.times, t)
+        if br is None:
+            ts.mode = OD_T_MISSING
+            return ts, ()
+        ib, ia, w = br
+        if ia is None:
+            ts.slot_a = self.slot_of(ib, pinned)
+            ts.slot_b = -1
+            ts.mode = OD_T_FIRST
+            return ts, (ib,)
+        sa = self.slot_of(ib, tuple(pinned) + (ia,))
+        sb = self.slot_of(ia, tuple(pinned) + (ib,))
+        ts.slot_a, ts.slot_b, ts.mode, ts.w = sa, sb, OD_T_LERP, w
+        return ts, (ib, ia)
+
+
+class Engine:
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('opendrift_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', device)
+        torch.cuda.set_device(self.device)
+        ctx = C.c_void_p()
+        rc = self.lib.od_create(device, C.byref(ctx))
+        if rc != 0:
+            raise RuntimeError('od_create failed (%d)' % rc)
+        self.ctx = ctx
+        self.use_stream(torch.cuda.current_stream(self.device))
+        self._next_gid = 0
+        self.groups = {}
+
+    def close(self):
+        if getattr(self, 'ctx', None):
+            self.lib.od_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError('libodcuda: %s (status %d)' % (self.lib.od_last_error(self.ctx).decode(), rc))
+
+    def use_stream(self, stream):
+        self._check(self.lib.od_set_stream(self.ctx, C.c_void_p(stream.cuda_stream)))
+
+    def sync(self):
+        self._check(self.lib.od_sync(self.ctx))
+
+    def launches(self):
+        return int(self.lib.od_launch_count(self.ctx))
+
+    # -- buffers --------------------------------------------------------------------------
+    def to_device(self, a, dtype=None):
+        t = self.torch.as_tensor(np.ascontiguousarray(a))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def empty(self, n, dtype):
+        return self.torch.empty(n, dtype=dtype, device=self.device)
+
+    # -- groups ---------------------------------------------------------------------------
+    def add_group(self, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3, names=None):
+        gid = self._next_gid
+        self._next_gid += 1
+        g = FieldGroup(self, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots, names)
+        self.groups[gid] = g
+        return g
+
+    def upload(self, gid, slot, comp, data):
+        torch = self.torch
+        if isinstance(data, torch.Tensor):
+            assert data.dtype == torch.float32 and data.is_contiguous()
+            on_dev = 1 if data.is_cuda else 0
+            self._check(self.lib.od_group_upload(self.ctx, gid, slot, comp, C.c_void_p(data.data_ptr()), on_dev))
+            if not on_dev:
+                self.sync()          # pageable host memory may be reused by the caller
+        else:
+            a = np.ascontiguousarray(data, dtype=np.float32)
+            self._check(self.lib.od_group_upload(self.ctx, gid, slot, comp, a.ctypes.data_as(C.c_void_p), 0))
+            self.sync()
+
+    def slot_tensor(self, group, slot, comp):
+        """The ring slot as a CUDA tensor (e.g. the target of a torch.distributed broadcast)."""
+        p = C.c_void_p()
+        self._check(self.lib.od_group_slot_ptr(self.ctx, group.gid, slot, comp, C.byref(p)))
+        d = group.desc
+        n = d.nx * d.ny * d.nz
+        # wrap the raw pointer without copying
+        iface = {'shape': (n,), 'typestr': '<f4', 'data': (p.value, False), 'version': 3}
+
+        class _W:
+            __cuda_array_interface__ = iface
+        return self.torch.as_tensor(_W(), device=self.device)
+
+    # -- kernels --------------------------------------------------------------------------
+    def interp(self, group, t, lon, lat, z=None, pos_f32=False):
+        """get_variables_interpolated fast path on device tensors -> list of float32 tensors."""
+        n = lon.numel()
+        ts, _ = group.sample(t)
+        outs = [self.empty(n, self.torch.float32) for _ in range(group.ncomp)]
+        self._check(self.lib.od_interp(self.ctx, group.gid, C.byref(ts), n, _ptr(lon), _ptr(lat), _ptr(z),
+                                       1 if pos_f32 else 0, _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
+        return outs
+
+    def geod_fwd(self, lon, lat, az, dist):
+        self._check(self.lib.od_geod_fwd(self.ctx, lon.numel(), _ptr(lon), _ptr(lat), _ptr(az), _ptr(dist)))
+
+    def update_positions(self, lon, lat, xvel, yvel, moving, dt):
+        f64 = 1 if xvel.dtype == self.torch.float64 else 0
+        assert xvel.dtype == yvel.dtype
+        self._check(self.lib.od_update_positions(self.ctx, lon.numel(), _ptr(lon), _ptr(lat), _ptr(xvel),
+                                                 _ptr(yvel), f64, _ptr(moving), float(dt)))
+
+    def _advect_args(self, a, group, scheme, t, dt_seconds, half, full, lon, lat, z, factor, moving,
+                     k1=None, truncate_below=None, env_out=None, pos_f32=False):
+        a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
+        a.pos_f32 = 1 if pos_f32 else 0
+        a.group_uv = group.gid
+        pinned = ()
+        if k1 is None:
+            a.t_start, p = group.sample(t)
+            pinned += p
+        if a.scheme != _lib.OD_EULER:
+            a.t_mid, p = group.sample(half, pinned)
+            pinned += p
+        if a.scheme == _lib.OD_RK4:
+            a.t_end, p = group.sample(full, pinned)
+        a.dt = float(dt_seconds)
+        a.n = lon.numel()
+        a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
+        a.d_z = z.data_ptr() if z is not None else None
+        if factor is not None:
+            a.d_factor = factor.data_ptr()
+            a.factor_f64 = 1 if factor.dtype == self.torch.float64 else 0
+        else:
+            a.factor_f64 = 1
+        a.d_moving = moving.data_ptr() if moving is not None else None
+        if k1 is not None:
+            a.d_k1_u, a.d_k1_v = k1[0].data_ptr(), k1[1].data_ptr()
+        a.truncate_below = float(truncate_below) if truncate_below else 0.0
+        if env_out is not None:
+            a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
+
+    def advect_current(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None, k1=None,
+                       truncate_below=None, env_out=None, pos_f32=False):
+        """advect_ocean_current on device tensors (in place).  t is the reader-time object (datetime
+        or seconds), dt a timedelta-like or seconds."""
+        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        a = AdvectArgs()
+        self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving, k1,
+                          truncate_below, env_out, pos_f32)
+        self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
+
+    def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
+                        truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False):
+        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        s = StepArgs()
+        self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
+                          None, truncate_below, None, pos_f32)
+        s.group_wind = -1
+        s.group_w = -1
+        if wind is not None:
+            s.group_wind = wind.gid
+            s.t_wind, _ = wind.sample(t)
+            s.d_wdf = wdf.data_ptr()
+            s.wdf_f64 = 1 if wdf.dtype == self.torch.float64 else 0
+            s.wind_drift_depth = float(wind_drift_depth)
+        if w_group is not None:
+            s.group_w = w_group.gid
+            s.t_w, _ = w_group.sample(t)
+            s.w_at_surface = 1 if w_at_surface else 0
+            s.d_z_inout = z.data_ptr()
+        if rand is not None:
+            s.d_rand_x, s.d_rand_y = rand[0].data_ptr(), rand[1].data_ptr()
+            if hasattr(diffusivity, 'data_ptr'):
+                s.d_diffusivity = diffusivity.data_ptr()
+            else:
+                s.diffusivity_const = float(diffusivity)
+        self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
+
+    def sort_by_cell(self, group, lon, lat, z=None):
+        perm = self.empty(lon.numel(), self.torch.int32)
+        self._check(self.lib.od_sort_by_cell(self.ctx, group.gid, lon.numel(), _ptr(lon), _ptr(lat), _ptr(z),
+                                             _ptr(perm)))
+        return perm
+
+    def permute(self, perm, src, inverse=False):
+        dst = self.torch.empty_like(src)
+        fn = self.lib.od_unpermute if inverse else self.lib.od_permute
+        self._check(fn(self.ctx, src.numel(), _ptr(perm), _ptr(src), _ptr(dst), src.element_size()))
+        return dst

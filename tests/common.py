@@ -1,0 +1,245 @@
+"""Shared helpers of the test-suite: fixture loading and the three ways a fixture can be replayed
+(oracle port on CPU, host-compiled device math on CPU, CUDA library on the GPU)."""
+import ctypes as C
+import glob
+import json
+import os
+import subprocess
+import sys
+from datetime import timedelta
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from opendrift_b200 import synthetic as syn            # noqa: E402
+from opendrift_b200.engine import bracket              # noqa: E402  (pure-Python host logic)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+CUR = ['x_sea_water_velocity', 'y_sea_water_velocity']
+
+
+def fixtures():
+    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
+
+
+class Fixture:
+    def __init__(self, name):
+        d = np.load(os.path.join(GOLDEN, 'ref_%s.npz' % name))
+        self.name = name
+        self.meta = json.loads(str(d['meta']))
+        self.grid_lon, self.grid_lat = d['grid_lon'], d['grid_lat']
+        self.grid_z = d['grid_z'] if d['grid_z'].size else None
+        self.u, self.v = d['u'], d['v']
+        self.w = d['w'] if 'w' in d else None
+        self.x_wind = d['x_wind'] if 'x_wind' in d else None
+        self.y_wind = d['y_wind'] if 'y_wind' in d else None
+        self.cdf = d['cdf'] if 'cdf' in d else None
+        self.lon0, self.lat0, self.z0 = d['lon0'], d['lat0'], d['z0']
+        self.lon, self.lat, self.z = d['lon'], d['lat'], d['z']
+        m = self.meta
+        self.times = syn.slab_times(self.u.shape[0], m['slab_step_s'])
+        self.dt = m['dt']
+        self.steps = m['steps']
+        self.start = self.times[-1] if self.dt < 0 else syn.T0 + timedelta(seconds=m['start_offset_s'] or 0)
+        self.n = len(self.lon0)
+
+    def props(self):
+        """Element properties as the reference holds them after release (scalars -> float64 arrays,
+        opendrift/elements/elements.py:213-216)."""
+        n = self.n
+        cdf = self.cdf.astype(np.float32) if self.cdf is not None else np.float32(1) * np.ones(n)
+        wdf = np.float32(0.02) * np.ones(n)
+        moving = np.ones(n, dtype=np.int32)
+        return cdf, wdf, moving
+
+    def wind_drift_depth(self):
+        wdd = self.meta.get('wind_drift_depth')
+        return 0.1 if wdd is None else wdd          # OceanDrift default (oceandrift.py:149-152)
+
+
+def run_port(fx):
+    from oracle import advect_port as ap
+    readers = [ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times,
+                             dict({CUR[0]: fx.u, CUR[1]: fx.v},
+                                  **({'upward_sea_water_velocity': fx.w} if fx.w is not None else {})))]
+    if fx.x_wind is not None:
+        readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times,
+                                     {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}))
+    m = fx.meta
+    return ap.run_oceandrift(readers, fx.lon0, fx.lat0, fx.z0, fx.start, fx.dt, fx.steps, scheme=m['scheme'],
+                             vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
+                             cdf=fx.cdf if fx.cdf is not None else 1.0, diffusivity=m['diffusivity'],
+                             seed=m['seed'])
+
+
+# ---- host-compiled device math ---------------------------------------------------------------
+class HsGroup(C.Structure):
+    _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
+                ('lon_mode', C.c_int32), ('pad_', C.c_int32),
+                ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
+                ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
+                ('fallback', C.c_float * 2), ('z_levels', C.c_void_p)]
+
+
+class HsPair(C.Structure):
+    _fields_ = [('tex', C.c_void_p), ('mode', C.c_int32), ('pad_', C.c_int32), ('w', C.c_double)]
+
+
+class HsStepArgs(C.Structure):
+    _fields_ = [('scheme', C.c_int32), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32), ('pad0_', C.c_int32),
+                ('g_uv', HsGroup),
+                ('t_start', HsPair), ('t_mid', HsPair), ('t_end', HsPair),
+                ('dt', C.c_double), ('n', C.c_int64),
+                ('lon', C.c_void_p), ('lat', C.c_void_p), ('z', C.c_void_p),
+                ('factor', C.c_void_p), ('moving', C.c_void_p), ('truncate_below', C.c_double),
+                ('wind_on', C.c_int32), ('wdf_f64', C.c_int32), ('w_on', C.c_int32), ('w_at_surface', C.c_int32),
+                ('g_wind', HsGroup), ('t_wind', HsPair), ('wdf', C.c_void_p), ('wind_drift_depth', C.c_double),
+                ('g_w', HsGroup), ('t_w', HsPair), ('z_inout', C.c_void_p),
+                ('rand_x', C.c_void_p), ('rand_y', C.c_void_p), ('diffusivity', C.c_void_p),
+                ('diffusivity_const', C.c_float), ('pad_', C.c_int32)]
+
+
+_shim = None
+
+
+def hostshim():
+    """Build (once) and load tests/hostshim/libhostshim.so."""
+    global _shim
+    if _shim is None:
+        d = os.path.join(ROOT, 'tests', 'hostshim')
+        so, src = os.path.join(d, 'libhostshim.so'), os.path.join(d, 'hostshim.cpp')
+        hdrs = glob.glob(os.path.join(ROOT, 'opendrift_b200', 'csrc', '*.cuh'))
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
+            subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC',
+                                   '-o', so, src])
+        _shim = C.CDLL(so)
+        _shim.hs_step.restype = C.c_int
+    return _shim
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HsField:
+    """A field group for the host shim: builds pair texels with NumPy."""
+
+    def __init__(self, lon, lat, z, comps, times, fallback=(0.0, 0.0)):
+        self.lon, self.lat = np.asarray(lon, np.float32), np.asarray(lat, np.float32)
+        self.z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        self.comps, self.times = comps, times
+        g = HsGroup()
+        g.ncomp, g.nx, g.ny, g.nz = len(comps), len(self.lon), len(self.lat), 1 if self.z is None else len(self.z)
+        g.lon_mode = 1 if float(self.lon.min()) < 0 else 0
+        g.x0, g.xspan = float(self.lon[0]), float(np.float32(self.lon[-1] - self.lon[0]))
+        g.y0, g.yspan = float(self.lat[0]), float(np.float32(self.lat[-1] - self.lat[0]))
+        g.xmin, g.xmax = float(self.lon.min()), float(self.lon.max())
+        g.ymin, g.ymax = float(self.lat.min()), float(self.lat.max())
+        g.fallback[0], g.fallback[1] = fallback[0], fallback[-1]
+        g.z_levels = None if self.z is None else self.z.ctypes.data
+        self.g = g
+        self._keep = []
+
+    def pair(self, t):
+        pr = HsPair()
+        br = bracket(self.times, t)
+        if br is None:
+            pr.mode = 3
+            return pr
+        ib, ia, w = br
+        ja = ib if ia is None else ia
+        tex = np.ascontiguousarray(np.stack([c[ib] for c in self.comps] + [c[ja] for c in self.comps], axis=-1),
+                                   dtype=np.float32)
+        self._keep.append(tex)
+        pr.tex, pr.mode, pr.w = tex.ctypes.data, (1 if ia is None else 0), w
+        return pr
+
+
+def run_hostshim(fx):
+    lib = hostshim()
+    m = fx.meta
+    cur = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.u, fx.v], fx.times)
+    wind = HsField(fx.grid_lon, fx.grid_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
+    wfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.w], fx.times, (0.0,)) if m['with_w'] else None
+    cdf, wdf, moving = fx.props()
+    lon = fx.lon0.astype(np.float64)
+    lat = fx.lat0.astype(np.float64)
+    z = fx.z0.astype(np.float32).copy()
+    np.random.seed(m['seed'])
+    t = fx.start
+    dt = timedelta(seconds=fx.dt)
+    for istep in range(fx.steps):
+        a = HsStepArgs()
+        a.pos_f32 = 1 if istep == 0 else 0
+        a.scheme = {'euler': 0, 'runge-kutta': 1, 'runge-kutta4': 2}[m['scheme']]
+        a.factor_f64 = 1 if cdf.dtype == np.float64 else 0
+        a.g_uv = cur.g
+        a.t_start, a.t_mid, a.t_end = cur.pair(t), cur.pair(t + dt / 2), cur.pair(t + dt)
+        a.dt, a.n = float(fx.dt), fx.n
+        a.lon, a.lat, a.z = _p(lon), _p(lat), _p(z)
+        a.factor, a.moving = _p(cdf), _p(moving)
+        if wind is not None:
+            a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, 1, wind.g, wind.pair(t)
+            a.wdf, a.wind_drift_depth = _p(wdf), fx.wind_drift_depth()
+        if wfld is not None:
+            a.w_on, a.g_w, a.t_w, a.z_inout = 1, wfld.g, wfld.pair(t), _p(z)
+        if m['diffusivity']:
+            rx = np.random.normal(scale=1, size=fx.n)
+            ry = np.random.normal(scale=1, size=fx.n)
+            a.rand_x, a.rand_y, a.diffusivity_const = _p(rx), _p(ry), m['diffusivity']
+        assert lib.hs_step(C.byref(a)) == 0
+        t = t + dt
+    return lon, lat, z
+
+
+def run_engine(fx, fused=True, sort_every=0):
+    """Replay a fixture on the GPU through the product Engine."""
+    import torch
+    from opendrift_b200.engine import Engine
+    m = fx.meta
+    eng = Engine(0)
+    three_d = fx.grid_z is not None
+    cur = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 2, fx.times,
+                        lambda ti, c: (fx.u, fx.v)[c][ti], (0.0, 0.0))
+    wind = wgrp = None
+    if m['wind']:
+        wind = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times,
+                             lambda ti, c: (fx.x_wind, fx.y_wind)[c][ti], (0.0, 0.0))
+    if m['with_w']:
+        wgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.w[ti], (0.0,))
+    cdf, wdf, moving = fx.props()
+    lon = eng.to_device(fx.lon0.astype(np.float64))
+    lat = eng.to_device(fx.lat0.astype(np.float64))
+    z = eng.to_device(fx.z0.astype(np.float32)) if three_d or m['wind'] or m['with_w'] else None
+    d_cdf, d_wdf, d_mov = eng.to_device(cdf), eng.to_device(wdf), eng.to_device(moving)
+    np.random.seed(m['seed'])
+    t = fx.start
+    dt = timedelta(seconds=fx.dt)
+    for istep in range(fx.steps):
+        first = istep == 0          # element positions are float32 until the first update_positions
+        rand = None
+        if m['diffusivity']:
+            rand = (eng.to_device(np.random.normal(scale=1, size=fx.n)),
+                    eng.to_device(np.random.normal(scale=1, size=fx.n)))
+        if fused:
+            eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
+                                factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
+                                wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
+                                diffusivity=m['diffusivity'], pos_f32=first)
+        else:
+            assert not (m['wind'] or m['with_w'] or m['diffusivity'])
+            eng.advect_current(cur, m['scheme'], t, dt, lon, lat, z if three_d else None, factor=d_cdf,
+                               moving=d_mov, pos_f32=first)
+        t = t + dt
+    eng.sync()
+    out = lon.cpu().numpy(), lat.cpu().numpy(), (z.cpu().numpy() if z is not None else fx.z0)
+    eng.close()
+    return out
+
+
+def max_err_deg(lon, lat, rlon, rlat):
+    dlon = (lon - rlon + 180.0) % 360.0 - 180.0
+    return float(np.max(np.abs(dlon))), float(np.max(np.abs(lat - rlat)))

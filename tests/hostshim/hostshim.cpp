@@ -1,0 +1,139 @@
+// hostshim.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the per-particle device math of
+// opendrift_b200/csrc/*.cuh for the host (g++, -ffp-contract=off) so that the CPU test-suite can check
+// the arithmetic of the CUDA kernels against the oracle without a GPU.  Never loaded by the product
+// package (opendrift_b200/_lib.py only ever loads libodcuda.so and fails without it).
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "../../opendrift_b200/csrc/od_advect.cuh"
+
+using namespace od;
+
+extern "C" {
+
+struct hs_group {
+    int32_t ncomp, nx, ny, nz, lon_mode, pad_;
+    double x0, xspan, y0, yspan, xmin, xmax, ymin, ymax;
+    float fallback[2];
+    const double* z_levels;   // as the reader gives them
+};
+
+struct hs_pair {
+    const float* tex;
+    int32_t mode, pad_;
+    double w;
+};
+
+struct hs_levels {
+    std::vector<double> zs, zy;
+    double zmin = 0, zmax = 0;
+};
+
+static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
+    GroupGeom q;
+    memset(&q, 0, sizeof(q));
+    q.nx = d.nx; q.ny = d.ny; q.nz = d.nz; q.ncomp = d.ncomp; q.lon_mode = d.lon_mode;
+    q.x0 = d.x0; q.xspan = d.xspan; q.y0 = d.y0; q.yspan = d.yspan;
+    q.xmin = d.xmin; q.xmax = d.xmax; q.ymin = d.ymin; q.ymax = d.ymax;
+    q.nxm1 = (double)(d.nx - 1); q.nym1 = (double)(d.ny - 1);
+    q.fallback[0] = d.fallback[0]; q.fallback[1] = d.fallback[1];
+    if (d.nz > 1) {
+        lv.zs.resize(d.nz); lv.zy.resize(d.nz);
+        bool inc = d.z_levels[1] > d.z_levels[0];
+        for (int i = 0; i < d.nz; ++i) {
+            int src = inc ? i : d.nz - 1 - i;
+            lv.zs[i] = d.z_levels[src];
+            lv.zy[i] = (double)src;
+        }
+        q.zmin = lv.zs[0]; q.zmax = lv.zs[d.nz - 1];
+        q.zs = lv.zs.data(); q.zy = lv.zy.data();
+    }
+    return q;
+}
+
+static PairRef make_pair(const hs_pair& p) {
+    PairRef r;
+    r.tex = p.tex; r.mode = p.mode; r.pad_ = 0; r.w = p.w;
+    return r;
+}
+
+void hs_geod_direct(int64_t n, const double* lon, const double* lat, const double* az, const double* dist,
+                    double* lon2, double* lat2) {
+    for (int64_t i = 0; i < n; ++i) geod_direct(lon[i], lat[i], az[i], dist[i], lon2[i], lat2[i]);
+}
+
+void hs_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lon, const double* lat, const float* z,
+               int pos_f32, float* out0, float* out1) {
+    hs_levels lv;
+    GroupGeom q = make_geom(*g, lv);
+    PairRef p = make_pair(*pr);
+    for (int64_t i = 0; i < n; ++i) {
+        VertW vw = vert_weights(q, q.zs, q.zy, (z && q.nz > 1) ? z[i] : 0.0f);
+        if (q.ncomp == 2) {
+            float u, v;
+            sample2(q, p, vw, lon[i], lat[i], u, v, pos_f32 != 0);
+            out0[i] = u; out1[i] = v;
+        } else {
+            out0[i] = sample1(q, p, vw, lon[i], lat[i], pos_f32 != 0);
+        }
+    }
+}
+
+struct hs_step_args {
+    int32_t scheme, factor_f64, pos_f32, pad0_;
+    hs_group g_uv;
+    hs_pair t_start, t_mid, t_end;
+    double dt;
+    int64_t n;
+    double* lon; double* lat; const float* z;
+    const void* factor; const int32_t* moving;
+    double truncate_below;
+    // extras
+    int32_t wind_on, wdf_f64, w_on, w_at_surface;
+    hs_group g_wind; hs_pair t_wind; const void* wdf; double wind_drift_depth;
+    hs_group g_w; hs_pair t_w; float* z_inout;
+    const double* rand_x; const double* rand_y; const float* diffusivity; float diffusivity_const; int32_t pad_;
+};
+
+}  // extern "C"
+
+template <int S, bool F>
+static void run(const StepParams& p, const GroupGeom& gw) {
+    for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+}
+
+extern "C" {
+
+int hs_step(const hs_step_args* a) {
+    hs_levels l1, l2, l3;
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.cs.g = make_geom(a->g_uv, l1);
+    p.cs.t_start = make_pair(a->t_start); p.cs.t_mid = make_pair(a->t_mid); p.cs.t_end = make_pair(a->t_end);
+    p.dt = a->dt; p.dt32 = (float)a->dt; p.adt32 = (float)fabs(a->dt);
+    p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z = a->z; p.factor = a->factor; p.moving = a->moving;
+    p.truncate_below = a->truncate_below;
+    p.pos_f32 = a->pos_f32;
+    if (a->wind_on) {
+        p.wind_on = 1; p.wdf_f64 = a->wdf_f64; p.gwind = make_geom(a->g_wind, l2); p.pwind = make_pair(a->t_wind);
+        p.wdf = a->wdf; p.wind_drift_depth = a->wind_drift_depth;
+    }
+    if (a->w_on) {
+        p.w_on = 1; p.w_at_surface = a->w_at_surface; p.gw = make_geom(a->g_w, l3); p.pw = make_pair(a->t_w);
+        p.z_inout = a->z_inout;
+    }
+    if (a->rand_x) {
+        p.diff_on = 1; p.rand_x = a->rand_x; p.rand_y = a->rand_y; p.diffusivity = a->diffusivity;
+        p.diffusivity_const = a->diffusivity_const;
+    }
+    const bool f = a->factor_f64 != 0;
+    switch (a->scheme) {
+        case 0: f ? run<0, true>(p, p.gw) : run<0, false>(p, p.gw); break;
+        case 1: f ? run<1, true>(p, p.gw) : run<1, false>(p, p.gw); break;
+        case 2: f ? run<2, true>(p, p.gw) : run<2, false>(p, p.gw); break;
+        default: return -2;
+    }
+    return 0;
+}
+
+}  // extern "C"
