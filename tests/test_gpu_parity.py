@@ -105,8 +105,10 @@ def test_update_positions_vs_oracle(eng):
         dl, da = eng.to_device(lon), eng.to_device(lat)
         eng.update_positions(dl, da, eng.to_device(xv.astype(np.float32)), eng.to_device(yv.astype(np.float32)),
                              eng.to_device(moving), dt)
-        e = common.max_err_deg(dl.cpu().numpy(), da.cpu().numpy(), rl, ra)
-        assert max(e) < 5e-8, e
+        # an ulp or two of float32 azimuth (1.5e-5 deg) over <= 3.6 km; compare on the ground, not in
+        # longitude degrees (the cloud reaches 85 deg latitude)
+        dlon = ((dl.cpu().numpy() - rl + 180.0) % 360.0 - 180.0) * np.cos(np.radians(ra))
+        assert np.abs(dlon).max() < 5e-8 and np.abs(da.cpu().numpy() - ra).max() < 5e-8
     # frozen elements do not move
     frozen = moving == 0
     assert np.abs(da.cpu().numpy()[frozen] - lat[frozen]).max() < 1e-12
