@@ -1,0 +1,207 @@
+"""Reader base classes with the reference's public surface for geographic regular-grid readers.
+
+Mirrors, for `+proj=latlong` structured readers,
+  opendrift/readers/basereader/variables.py  (ReaderDomain/Variables: coverage, nearest_time,
+      get_variables_interpolated[_xy], valid-range check :630-668)
+  opendrift/readers/basereader/structured.py (StructuredReader: before/after block cache, time interpolation)
+  opendrift/readers/interpolation/structured.py + interpolators.py (ReaderBlock, linearNDFast + linear)
+but the arithmetic runs in libodcuda.so: a reader is *bound* to an Engine, its blocks become device-resident
+field groups (a ring of time slabs in HBM), and get_variables_interpolated() is a thin host wrapper around
+od_interp (host arrays in, host arrays out, as the reference returns NumPy).  The fused step kernels use
+the bound groups directly.
+
+Reader implementers keep the reference contract (basereader/structured.py:125-147): provide
+`get_variables(requested_variables, time, x, y, z)` returning {'x','y','z','time', var: ndarray[(z,)y,x]} and
+the attributes proj4, xmin/xmax/ymin/ymax, variables, start_time/end_time/time_step (or times), name.
+"""
+from datetime import timedelta
+
+import numpy as np
+
+from ..errors import (NotCoveredError, OutsideSpatialCoverageError,  # noqa: F401
+                      OutsideTemporalCoverageError, VariableNotCoveredError)
+
+# valid (but extreme) ranges, opendrift/readers/basereader/consts.py:2-21
+standard_names = {
+    'x_wind': (-50, 50), 'y_wind': (-50, 50),
+    'x_sea_water_velocity': (-15, 15), 'y_sea_water_velocity': (-15, 15),
+    'land_binary_mask': (0, 1), 'sea_floor_depth_below_sea_level': (-20, 12000),
+    'ocean_vertical_diffusivity': (0, 1)}
+
+# x/y vector pairs that are always sampled together (consts.py:26-36)
+vector_pairs_xy = [
+    ('x_wind', 'y_wind'),
+    ('sea_ice_x_velocity', 'sea_ice_y_velocity'),
+    ('x_sea_water_velocity', 'y_sea_water_velocity'),
+    ('sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity')]
+
+
+def check_variable_array(name, a):
+    """Variables.__check_variable_array__ (variables.py:630-668): masked -> NaN, out-of-range -> NaN."""
+    if isinstance(a, np.ma.MaskedArray):
+        a = a.astype(np.float32).filled(np.nan)
+    a = np.array(a, dtype=np.float32, copy=True)
+    if name in standard_names:
+        lo, hi = standard_names[name]
+        with np.errstate(invalid='ignore'):
+            bad = np.isfinite(a) & ((a < lo) | (a > hi))
+        if bad.any():
+            a[bad] = np.nan
+    return a
+
+
+def fill_nan_towards_seafloor(a):
+    """interpolators.py:204-212: copy layer i-1 into the NaNs of layer i."""
+    for i in range(1, a.shape[0]):
+        m = np.isnan(a[i])
+        if m.any():
+            a[i][m] = a[i - 1][m]
+    return a
+
+
+class StructuredReader:
+    """Regular lon/lat(/z) grid reader whose interpolation runs on the GPU."""
+
+    name = 'structured_reader'
+    proj4 = '+proj=latlong'
+    times = None
+    always_valid = False
+
+    def __init__(self):
+        p = str(getattr(self, 'proj4', '+proj=latlong'))
+        if 'latlong' not in p and 'longlat' not in p:
+            raise NotImplementedError('opendrift_b200 readers are geographic (+proj=latlong); got %s' % p)
+        if getattr(self, 'times', None) is None and getattr(self, 'start_time', None) is not None \
+                and getattr(self, 'time_step', None) is not None and self.end_time != self.start_time:
+            n = int(round((self.end_time - self.start_time).total_seconds() / self.time_step.total_seconds())) + 1
+            self.times = [self.start_time + i * self.time_step for i in range(n)]
+        elif getattr(self, 'times', None) is None:
+            self.times = [self.start_time]
+        self.zmin, self.zmax = -np.inf, np.inf
+        self._engine = None
+        self._groups = {}          # variable -> (FieldGroup, component)
+        self._block_geom = None
+        self.number_of_fails = 0
+
+    # -- coverage (variables.py:229-257, 391-400) ------------------------------------------------
+    def covers_time(self, time):
+        if self.start_time is None:
+            return True
+        return self.start_time <= time <= self.end_time
+
+    def modulate_longitude(self, lons):
+        lons = np.asarray(lons)
+        return np.mod(lons + 180, 360) - 180 if self.xmin < 0 else np.mod(lons, 360)
+
+    def covers_positions(self, lon, lat, z=0):
+        x = self.modulate_longitude(np.atleast_1d(lon))
+        y = np.atleast_1d(lat)
+        ind = np.where((x >= self.xmin) & (x <= self.xmax) & (y >= self.ymin) & (y <= self.ymax))[0]
+        return ind, x[ind], y[ind]
+
+    def nearest_time(self, time):
+        from ..engine import bracket
+        br = bracket(self.times, time)
+        if br is None:
+            return None, None, None, None, None, None
+        ib, ia, w = br
+        tb = self.times[ib]
+        ta = None if ia is None else self.times[ia]
+        near = tb if (ta is None or (time - tb) < (ta - time)) else ta
+        return near, tb, ta, self.times.index(near), ib, ia
+
+    # -- device binding --------------------------------------------------------------------------
+    def _fetch_block(self, names, ti):
+        """One reader block for time index ti via the reader's own get_variables()."""
+        t = self.times[ti]
+        blk = self.get_variables(list(names), time=t, x=None, y=None, z=None)
+        return blk
+
+    def bind(self, engine, fallback=None, n_slots=3):
+        """Create the device field groups of this reader on `engine` (idempotent)."""
+        if self._engine is engine:
+            return
+        self._engine = engine
+        self._groups = {}
+        fallback = fallback or {}
+        probe = self._fetch_block(self.variables, 0)
+        x = np.asarray(probe['x'], dtype=np.float32)      # __check_env_coordinates__ (variables.py:622-628)
+        y = np.asarray(probe['y'], dtype=np.float32)
+        done = set()
+        plan = []
+        for a, b in vector_pairs_xy:
+            if a in self.variables and b in self.variables:
+                plan.append((a, b))
+                done |= {a, b}
+        plan += [(v,) for v in self.variables if v not in done]
+        for names in plan:
+            three_d = np.ndim(probe[names[0]]) == 3
+            z = np.asarray(probe['z'], dtype=np.float64) if three_d else None
+            cache = {}
+
+            def supplier(ti, c, names=names, cache=cache):
+                if ti not in cache:
+                    cache.clear()
+                    blk = self._fetch_block(names, ti)
+                    arrs = []
+                    for nme in names:
+                        a = blk[nme]
+                        if hasattr(a, 'is_cuda'):           # already a device tensor: trusted, no host pass
+                            arrs.append(a)
+                            continue
+                        a = check_variable_array(nme, a)
+                        if a.ndim == 3:
+                            fill_nan_towards_seafloor(a)
+                        arrs.append(a)
+                    cache[ti] = arrs
+                return cache[ti][c]
+            fb = [fallback.get(nme) for nme in names]
+            g = engine.add_group(x, y, z, len(names), self.times, supplier, fb, n_slots=n_slots, names=names)
+            for c, nme in enumerate(names):
+                self._groups[nme] = (g, c)
+
+    def group_of(self, variable):
+        return self._groups[variable]
+
+    # -- the reference's public entry point (variables.py:860-920) -----------------------------------
+    def get_variables_interpolated(self, variables, profiles=None, profiles_depth=None, time=None,
+                                   lon=None, lat=None, z=None, rotate_to_proj=None):
+        if isinstance(variables, str):
+            variables = [variables]
+        assert set(variables).issubset(self.variables), f'{variables} is not subset of {self.variables}'
+        if profiles is not None:
+            raise NotImplementedError('vertical profiles are served by the vertical-mixing kernel, not by this call')
+        if not self.covers_time(time):
+            raise OutsideTemporalCoverageError('%s is outside time coverage (%s - %s) of %s'
+                                               % (time, self.start_time, self.end_time, self.name))
+        if self._engine is None:
+            from ..engine import default_engine
+            self.bind(default_engine())
+        eng = self._engine
+        lon_in, lat_in = np.atleast_1d(lon), np.atleast_1d(lat)
+        n = len(lon_in)
+        pos_f32 = lon_in.dtype == np.float32 and lat_in.dtype == np.float32
+        ind, _, _ = self.covers_positions(lon_in, lat_in)
+        if len(ind) == 0:
+            raise OutsideSpatialCoverageError('All %s particles are outside domain of %s' % (n, self.name))
+        zz = np.zeros(n, dtype=np.float32) if z is None else np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
+        d_lon = eng.to_device(lon_in.astype(np.float64))
+        d_lat = eng.to_device(lat_in.astype(np.float64))
+        d_z = eng.to_device(zz)
+        env = {}
+        for v in variables:
+            if v in env:
+                continue
+            g, c = self._groups[v]
+            # no fallback here: uncovered / missing samples are NaN-masked like the reference's reader output
+            outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True)
+            for nme, (gg, cc) in self._groups.items():
+                if gg is g and nme in variables:
+                    a = outs[cc].cpu().numpy()
+                    if g.desc.nz > 1 or True:
+                        env[nme] = np.ma.masked_invalid(a.astype(np.float64) if g.desc.nz > 1 else a)
+        return env, None
+
+    def __repr__(self):
+        return 'Reader: %s  [%s..%s] x [%s..%s], %s - %s, variables %s' % (
+            self.name, self.xmin, self.xmax, self.ymin, self.ymax, self.start_time, self.end_time, self.variables)
