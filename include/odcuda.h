@@ -54,6 +54,8 @@ enum od_time_mode {
 
 enum od_lon_mode { OD_LON_0_360 = 0, OD_LON_PM180 = 1 };
 
+enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2 };
+
 #define OD_MAX_LEVELS 128
 #define OD_ABI_VERSION 1
 
@@ -86,7 +88,10 @@ typedef struct od_group_desc {
     float fallback[2];
 } od_group_desc;
 
+#define OD_MAX_GROUPS 64
 int od_group_define(od_ctx* ctx, int group, const od_group_desc* desc, const double* h_z_levels);
+/* release the device memory of a group (its id can be defined again) */
+int od_group_free(od_ctx* ctx, int group);
 /* copy one time slab of one component ([nz][ny][nx] float32, C order) into ring slot `slot`;
  * src may be host (pinned or pageable) or device memory */
 int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const float* src, int src_is_device);
@@ -104,12 +109,14 @@ typedef struct od_time_sample {
 } od_time_sample;
 
 /* get_variables_interpolated fast path: d_out[c] (float32[n]) for c < ncomp; d_out entries may be NULL.
- * z may be NULL for nz == 1.  lon/lat float64.  pos_f32 != 0: the positions hold float32 values (the
+ * z may be NULL for nz == 1.  lon/lat float64.  flags: OD_INTERP_POS_F32 | OD_INTERP_NO_FALLBACK.
+ * OD_INTERP_NO_FALLBACK returns NaN where the reader has no data (what Reader.get_variables_interpolated
+ * hands to Environment, which applies the fallback itself).  OD_INTERP_POS_F32: the positions hold float32 values (the
  * reference's element arrays are float32 from seeding until the first update_positions,
  * elements/elements.py:156-158) and NumPy then does the index arithmetic of interpolators.py:110-111 in
  * float32; the kernel reproduces that. */
 int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n,
-              const double* d_lon, const double* d_lat, const float* d_z, int pos_f32,
+              const double* d_lon, const double* d_lat, const float* d_z, int flags,
               float* d_out0, float* d_out1);
 
 /* ---- geodesic --------------------------------------------------------------------------- */

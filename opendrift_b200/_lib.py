@@ -13,6 +13,7 @@ OD_EULER, OD_RK2, OD_RK4 = 0, 1, 2
 OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
 OD_LON_0_360, OD_LON_PM180 = 0, 1
 OD_MAX_LEVELS = 128
+OD_MAX_GROUPS = 64
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
 
 
@@ -61,6 +62,7 @@ SYMBOLS = {
     'od_sync': (C.c_int, [_P]),
     'od_device_sm_count': (C.c_int, [_P]),
     'od_group_define': (C.c_int, [_P, C.c_int, C.POINTER(GroupDesc), C.POINTER(C.c_double)]),
+    'od_group_free': (C.c_int, [_P, C.c_int]),
     'od_group_upload': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     'od_group_slot_ptr': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     'od_group_touch': (C.c_int, [_P, C.c_int, C.c_int]),

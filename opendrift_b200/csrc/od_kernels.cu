@@ -17,7 +17,6 @@
 
 using namespace od;
 
-#define OD_MAX_GROUPS 16
 #define OD_PAIR_CACHE 4
 #define OD_BLOCK 256
 
@@ -167,6 +166,14 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
         CK(cudaStreamSynchronize(ctx->stream));
     }
     g.defined = true;
+    return OD_OK;
+}
+
+extern "C" int od_group_free(od_ctx* ctx, int group) {
+    if (!ctx || group < 0 || group >= OD_MAX_GROUPS) return fail(ctx, OD_ERR_ARG, "od_group_free: bad group");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_group(ctx->groups[group]);
     return OD_OK;
 }
 
@@ -472,7 +479,7 @@ static int need_group(od_ctx* ctx, int group, int ncomp) {
 }
 
 extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n, const double* lon, const double* lat,
-                         const float* z, int pos_f32, float* out0, float* out1) {
+                         const float* z, int flags, float* out0, float* out1) {
     int rc = need_group(ctx, group, 0);
     if (rc) return rc;
     if (!ts || n < 0 || (n > 0 && (!lon || !lat))) return fail(ctx, OD_ERR_ARG, "od_interp: bad arguments");
@@ -482,7 +489,8 @@ extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64
     p.g = make_geom(ctx->groups[group]);
     rc = resolve_pair(ctx, group, *ts, &p.pr);
     if (rc) return rc;
-    p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = pos_f32;
+    p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = flags & OD_INTERP_POS_F32;
+    if (flags & OD_INTERP_NO_FALLBACK) p.g.fallback[0] = p.g.fallback[1] = NAN;
     interp_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;

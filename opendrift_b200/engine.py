@@ -10,6 +10,8 @@ Host logic restated from the reference:
     device-resident slabs per field group.
 """
 import ctypes as C
+import gc
+import weakref
 from bisect import bisect_left
 
 import numpy as np
@@ -64,6 +66,7 @@ class FieldGroup:
         self.supplier = supplier          # supplier(time_index, comp) -> float32 [nz,]ny,nx (NumPy or CUDA tensor)
         self.names = names
         self.n_slots = n_slots
+        self.freed = False
         self.resident = [None] * n_slots  # time index held by each ring slot
         self.use = [0] * n_slots
         self._tick = 0
@@ -88,6 +91,12 @@ class FieldGroup:
         if self.z is not None:
             zl = (C.c_double * len(self.z))(*self.z)
         engine._check(engine.lib.od_group_define(engine.ctx, gid, C.byref(d), zl))
+
+    def __del__(self):
+        try:
+            self.engine.free_group(self)
+        except Exception:
+            pass
 
     # -- slab residency -------------------------------------------------------------------
     def slot_of(self, ti, pinned=()):
@@ -124,6 +133,19 @@ class FieldGroup:
         return ts, (ib, ia)
 
 
+_default = {}
+
+
+def default_engine(device=None):
+    """Process-wide Engine for the current CUDA device (LOCAL_RANK under torchrun)."""
+    import os
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]
+
+
 class Engine:
     def __init__(self, device=0):
         import torch
@@ -139,8 +161,7 @@ class Engine:
             raise RuntimeError('od_create failed (%d)' % rc)
         self.ctx = ctx
         self.use_stream(torch.cuda.current_stream(self.device))
-        self._next_gid = 0
-        self.groups = {}
+        self.groups = weakref.WeakValueDictionary()     # gid -> FieldGroup (owned by the reader that bound it)
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -178,11 +199,24 @@ class Engine:
 
     # -- groups ---------------------------------------------------------------------------
     def add_group(self, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3, names=None):
-        gid = self._next_gid
-        self._next_gid += 1
+        free = [k for k in range(_lib.OD_MAX_GROUPS) if k not in self.groups]
+        if not free:
+            gc.collect()
+            free = [k for k in range(_lib.OD_MAX_GROUPS) if k not in self.groups]
+        if not free:
+            raise RuntimeError('all %d field groups of this engine are in use; release readers you no longer need'
+                               % _lib.OD_MAX_GROUPS)
+        gid = free[0]
         g = FieldGroup(self, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots, names)
         self.groups[gid] = g
         return g
+
+    def free_group(self, group):
+        """Release a group's device slabs (its id becomes reusable)."""
+        if self.ctx and self.groups.get(group.gid) in (group, None) and not group.freed:
+            group.freed = True
+            self._check(self.lib.od_group_free(self.ctx, group.gid))
+            self.groups.pop(group.gid, None)
 
     def upload(self, gid, slot, comp, data):
         torch = self.torch
@@ -211,13 +245,13 @@ class Engine:
         return self.torch.as_tensor(_W(), device=self.device)
 
     # -- kernels --------------------------------------------------------------------------
-    def interp(self, group, t, lon, lat, z=None, pos_f32=False):
+    def interp(self, group, t, lon, lat, z=None, pos_f32=False, raw=False):
         """get_variables_interpolated fast path on device tensors -> list of float32 tensors."""
         n = lon.numel()
         ts, _ = group.sample(t)
         outs = [self.empty(n, self.torch.float32) for _ in range(group.ncomp)]
         self._check(self.lib.od_interp(self.ctx, group.gid, C.byref(ts), n, _ptr(lon), _ptr(lat), _ptr(z),
-                                       1 if pos_f32 else 0, _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
+                                       (1 if pos_f32 else 0) | (2 if raw else 0), _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
         return outs
 
     def geod_fwd(self, lon, lat, az, dist):

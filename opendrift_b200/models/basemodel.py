@@ -1,0 +1,568 @@
+"""OpenDriftSimulation: the reference's run loop, seeding, configuration and element bookkeeping
+(opendrift/models/basemodel/__init__.py) with particle state resident in HBM and the per-step arithmetic in
+libodcuda.so.
+
+Same public surface as the reference for the advection path:
+  __init__(seed=0, loglevel=...), add_reader(), set_config()/get_config(), seed_elements(), run(time_step, steps,
+  duration, end_time, time_step_output), update() (abstract), update_positions(x_vel, y_vel),
+  horizontal_diffusion(), deactivate_elements(), elements / elements_deactivated / environment / time / time_step,
+  num_elements_active()/..., get_lonlats().
+Not rebuilt (out of scope): plotting/animation, netCDF/parquet export, landmask/coastline
+interaction, seafloor interaction, lazy readers, the xarray result Dataset (a NumPy history buffer stands in).
+
+Reference line numbers are cited at each method.
+"""
+import logging
+from datetime import datetime, timedelta
+
+import numpy as np
+
+from ..config import Configurable, CONFIG_LEVEL_ESSENTIAL, CONFIG_LEVEL_BASIC, CONFIG_LEVEL_ADVANCED
+from ..elements import LagrangianArray, DeviceElements
+from ..engine import default_engine
+from .environment import Environment
+from .physics_methods import PhysicsMethods
+
+logger = logging.getLogger('opendrift_b200')
+
+
+class EnvironmentView:
+    """self.environment: attribute access returns float32 NumPy arrays like the reference's recarray;
+    the data are device tensors sampled at the start of the step."""
+
+    def __init__(self, tensors):
+        object.__setattr__(self, '_t', tensors)
+        object.__setattr__(self, '_h', {})
+
+    def __getattr__(self, name):
+        t = object.__getattribute__(self, '_t')
+        h = object.__getattribute__(self, '_h')
+        if name in h:
+            return h[name]
+        if name in t:
+            h[name] = t[name].cpu().numpy()
+            t.pop(name)                # host copy is now authoritative (may be modified in place)
+            return h[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self._h[name] = np.asarray(value)
+        self._t.pop(name, None)
+
+    def dev(self, name, engine):
+        if name in self._h:
+            self._t[name] = engine.to_device(np.ascontiguousarray(self._h.pop(name)))
+        return self._t[name]
+
+    def __contains__(self, name):
+        return name in self._t or name in self._h
+
+
+class OpenDriftSimulation(PhysicsMethods, Configurable):
+    ElementType = LagrangianArray
+    required_variables = {}
+    status_categories = ['active']
+
+    def __init__(self, seed=0, loglevel=None, logfile=None, engine=None, **kwargs):
+        Configurable.__init__(self)
+        self.status_categories = ['active']
+        if seed is not None:
+            np.random.seed(seed)                      # basemodel/__init__.py:326: the legacy global generator
+        self._engine = engine
+        self.origin_marker = None
+        self.steps_calculation = 0
+        self.elements_deactivated = self.ElementType()
+        self.env = Environment(self.required_variables, self)
+        self.validity_domain = None
+        self.history = None
+        c = {
+            'general:time_step_minutes': {'type': 'float', 'min': .01, 'max': 1440, 'default': 60, 'units': 'minutes',
+                                          'level': CONFIG_LEVEL_BASIC, 'description': 'Calculation time step.'},
+            'general:time_step_output_minutes': {'type': 'float', 'min': 1, 'max': 1440, 'default': None,
+                                                 'units': 'minutes', 'level': CONFIG_LEVEL_BASIC,
+                                                 'description': 'Output time step.'},
+            'general:use_auto_landmask': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
+                                          'description': 'Accepted for script compatibility; no landmask on the GPU path.'},
+            'general:coastline_action': {'type': 'enum', 'enum': ['none', 'stranding', 'previous'], 'default': 'none',
+                                         'level': CONFIG_LEVEL_BASIC, 'description': 'Only "none" is implemented.'},
+            'seed:number': {'type': 'int', 'default': 1, 'min': 1, 'max': 100000000, 'units': 1,
+                            'level': CONFIG_LEVEL_BASIC, 'description': 'The number of elements for the simulation.'},
+            'drift:max_age_seconds': {'type': 'float', 'default': None, 'min': 0, 'max': np.inf, 'units': 'seconds',
+                                      'level': CONFIG_LEVEL_ADVANCED, 'description': 'Retire elements at this age.'},
+            'drift:advection_scheme': {'type': 'enum', 'enum': ['euler', 'runge-kutta', 'runge-kutta4'],
+                                       'default': 'euler', 'level': CONFIG_LEVEL_ADVANCED,
+                                       'description': 'Numerical advection scheme for ocean current advection'},
+            'drift:max_speed': {'type': 'float', 'default': 1, 'min': 0, 'max': np.inf, 'units': 'm/s',
+                                'level': CONFIG_LEVEL_ESSENTIAL, 'description': 'Maximum anticipated speed.'},
+            'drift:current_uncertainty': {'type': 'float', 'default': 0, 'min': 0, 'max': 5, 'units': 'm/s',
+                                          'level': CONFIG_LEVEL_ADVANCED, 'description': 'Not implemented on the GPU path (must be 0).'},
+            'drift:wind_uncertainty': {'type': 'float', 'default': 0, 'min': 0, 'max': 5, 'units': 'm/s',
+                                       'level': CONFIG_LEVEL_ADVANCED, 'description': 'Not implemented on the GPU path (must be 0).'},
+            'drift:relative_wind': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                    'description': 'Wind relative to the ocean current.'},
+            'drift:deactivate_north_of': {'type': 'float', 'default': None, 'min': -90, 'max': 90, 'units': 'degrees',
+                                          'level': CONFIG_LEVEL_ADVANCED, 'description': 'Deactivate north of.'},
+            'drift:deactivate_south_of': {'type': 'float', 'default': None, 'min': -90, 'max': 90, 'units': 'degrees',
+                                          'level': CONFIG_LEVEL_ADVANCED, 'description': 'Deactivate south of.'},
+            'drift:deactivate_east_of': {'type': 'float', 'default': None, 'min': -360, 'max': 360, 'units': 'degrees',
+                                         'level': CONFIG_LEVEL_ADVANCED, 'description': 'Deactivate east of.'},
+            'drift:deactivate_west_of': {'type': 'float', 'default': None, 'min': -360, 'max': 360, 'units': 'degrees',
+                                         'level': CONFIG_LEVEL_ADVANCED, 'description': 'Deactivate west of.'},
+            'gpu:sort_interval_steps': {'type': 'int', 'default': 20, 'min': 0, 'max': 1000000, 'units': 1,
+                                        'level': CONFIG_LEVEL_ADVANCED,
+                                        'description': 'Re-order the device particle arrays by grid cell every N steps (0 = never).'},
+        }
+        # environment:constant:<var> / environment:fallback:<var> per required variable (environment.py:41-76)
+        for v, spec in self.required_variables.items():
+            c['environment:constant:%s' % v] = {'type': 'float', 'min': None, 'max': None, 'units': '', 'default': None,
+                                                'level': CONFIG_LEVEL_BASIC, 'description': 'Constant value for %s' % v}
+            c['environment:fallback:%s' % v] = {'type': 'float', 'min': None, 'max': None, 'units': '',
+                                                'default': spec.get('fallback'), 'level': CONFIG_LEVEL_BASIC,
+                                                'description': 'Fallback value for %s' % v}
+        self._add_config(c)
+        # seed:<property> for element properties with a default (used by seed_elements)
+        for name, spec in self.ElementType.variables.items():
+            if spec.get('seed', True) and 'default' in spec and name not in ('z',):
+                self._add_config({'seed:%s' % name: {'type': 'float', 'min': None, 'max': None, 'units': '',
+                                                      'default': spec['default'], 'level': CONFIG_LEVEL_BASIC,
+                                                      'description': 'Seed property %s' % name}}, overwrite=False)
+
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = default_engine()
+        return self._engine
+
+    def add_reader(self, readers, variables=None, first=False):
+        self.env.add_reader(readers, variables, first)
+
+    def add_readers_from_list(self, *a, **k):
+        raise NotImplementedError('lazy readers are host-side IO, out of scope of the GPU hot path')
+
+    # -- counts (basemodel/__init__.py:841-866) ----------------------------------------------------------
+    def num_elements_active(self):
+        return len(self.elements) if hasattr(self, 'elements') else 0
+
+    def num_elements_scheduled(self):
+        return len(self.elements_scheduled) if hasattr(self, 'elements_scheduled') else 0
+
+    def num_elements_deactivated(self):
+        return len(self.elements_deactivated)
+
+    def num_elements_activated(self):
+        return self.num_elements_active() + self.num_elements_deactivated()
+
+    def num_elements_total(self):
+        return self.num_elements_activated() + self.num_elements_scheduled()
+
+    # -- seeding (basemodel/__init__.py:1033-1237, 869-907) ------------------------------------------------
+    def seed_elements(self, lon, lat, time, radius=0, number=None, number_per_point=None,
+                      radius_type='gaussian', **kwargs):
+        if self.origin_marker is None:
+            self.origin_marker = {}
+        kwargs.setdefault('origin_marker', len(self.origin_marker))
+        self.origin_marker[str(kwargs['origin_marker'])] = kwargs.pop('origin_marker_name',
+                                                                      'Seed %d' % len(self.origin_marker)).replace(' ', '_')
+        lon = np.atleast_1d(lon).ravel()
+        lat = np.atleast_1d(lat).ravel()
+        radius = np.atleast_1d(radius).ravel()
+        time = list(np.atleast_1d(time))
+        if lat.max() > 90 or lat.min() < -90:
+            raise ValueError('Latitude must be between -90 and 90 degrees')
+        if len(lon) != len(lat):
+            raise ValueError('Lon and lat must have same lengths')
+        if len(lon) > 1:
+            if number_per_point is not None:
+                if number is not None:
+                    raise ValueError('Both number and number_per_point is provided')
+                number = number_per_point * len(lon)
+            if number is not None:
+                if number % len(lon) != 0:
+                    raise ValueError('Lon and lat have length %s, but number is %s, which is not a multiple'
+                                     % (len(lon), number))
+                npp = int(number / len(lon))
+                if npp > 1:
+                    lon, lat = np.repeat(lon, npp), np.repeat(lat, npp)
+            number = len(lon)
+        else:
+            if number is None:
+                number = len(time) if len(time) > 2 else self.get_config('seed:number')
+            lon = lon * np.ones(number)
+            lat = lat * np.ones(number)
+        if len(time) != number and len(time) > 1:
+            if len(time) == 2:
+                td = (time[1] - time[0]) / (number - 1)
+                time = [time[0] + i * td for i in range(number)]
+            else:
+                raise ValueError('Time array has length %s, must be 1, 2 or %s' % (len(time), number))
+        if radius.max() > 0:
+            # same draws, same order as the reference (:1150-1166); the geodesic runs on the GPU
+            if radius_type == 'gaussian':
+                x = np.random.randn(number) * radius
+                y = np.random.randn(number) * radius
+                az = np.degrees(np.arctan2(x, y))
+                dist = np.sqrt(x * x + y * y)
+            elif radius_type == 'uniform':
+                az = np.random.rand(number) * 360
+                dist = np.sqrt(np.random.uniform(0, 1, number)) * radius
+            else:
+                raise ValueError('unknown radius_type ' + str(radius_type))
+            eng = self.engine
+            d_lon, d_lat = eng.to_device(lon.astype(np.float64)), eng.to_device(lat.astype(np.float64))
+            eng.geod_fwd(d_lon, d_lat, eng.to_device(az.astype(np.float64)), eng.to_device(dist.astype(np.float64)))
+            lon, lat = d_lon.cpu().numpy(), d_lat.cpu().numpy()
+        if isinstance(kwargs.get('z'), str):
+            raise NotImplementedError("z='seafloor' needs a bathymetry reader on the host path")
+        for key, spec in self.get_configspec('seed:').items():
+            prop = key.split(':')[-1]
+            if prop not in kwargs and prop in self.ElementType.variables:
+                kwargs[prop] = spec['value']
+        elements = self.ElementType(lon=lon, lat=lat, **kwargs)
+        return self.schedule_elements(elements, time)
+
+    def schedule_elements(self, elements, time):
+        if len(time) == 1 and len(elements) > 1:
+            time = time * len(elements)
+        if not hasattr(self, 'elements_scheduled'):
+            self.elements_scheduled = elements
+            self.elements_scheduled_time = np.array(time)
+            self.start_time = time[0]
+            self.elements_scheduled.ID = np.arange(0, len(elements))
+        else:
+            elements.ID = np.arange(self.num_elements_scheduled(), self.num_elements_scheduled() + len(elements))
+            self.elements_scheduled.extend(elements)
+            self.elements_scheduled_time = np.append(self.elements_scheduled_time, np.array(time))
+        self.start_time = min(self.start_time, min(time))
+        return elements.ID
+
+    def release_elements(self):
+        """:909-934 -- scheduled elements whose time falls inside this step move to the device arrays."""
+        if len(self.elements_scheduled) == 0:
+            return
+        t, dt = self.time, self.time_step
+        st = self.elements_scheduled_time
+        idx = (st >= t) & (st < t + dt) if dt.days >= 0 else (st <= t) & (st > t + dt)
+        if not idx.any():
+            return
+        first_release = len(self.elements) == 0
+        self.elements.append_host(self.elements_scheduled, idx)
+        keep = self.ElementType()
+        self.elements_scheduled.move_elements(keep, idx)      # drops the released ones from the schedule
+        self.elements_scheduled_time = st[~idx]
+        if not first_release:
+            self.elements.positions_f32 = False                # mixed ages: already float64 positions
+
+    # -- deactivation (:1774-1826) ---------------------------------------------------------------------------
+    def deactivate_elements(self, indices, reason='deactivated'):
+        torch = self.engine.torch
+        if isinstance(indices, np.ndarray):
+            if not indices.any():
+                return
+            indices = self.engine.to_device(indices.astype(bool))
+        if reason not in self.status_categories:
+            self.status_categories.append(reason)
+        code = self.status_categories.index(reason)
+        status = self.elements.dev('status')
+        moving = self.elements.dev('moving')
+        self.elements.set_dev('status', torch.where(indices & (status == 0), torch.full_like(status, code), status))
+        self.elements.set_dev('moving', torch.where(indices, torch.zeros_like(moving), moving))
+        self._maybe_deactivated = True
+
+    def remove_deactivated_elements(self):
+        if not getattr(self, '_maybe_deactivated', False) or len(self.elements) == 0:
+            return
+        self._maybe_deactivated = False
+        keep = self.elements.dev('status') == 0
+        if bool(keep.all()):
+            return
+        removed = self.elements.compact(keep)
+        tmp = self.ElementType(**{k: v for k, v in removed.items()})
+        for k, v in removed.items():                           # keep the dtypes the active arrays had
+            setattr(tmp, k, v)
+        sel = np.ones(len(tmp), dtype=bool)
+        tmp.move_elements(self.elements_deactivated, sel)
+        self._env_dev = None
+
+    def increase_age_and_retire(self):
+        """:2345-2356"""
+        age = self.elements.dev('age_seconds')
+        self.elements.set_dev('age_seconds', age + age.new_tensor(self.time_step.total_seconds()).to(age.dtype))
+        max_age = self.get_config('drift:max_age_seconds')
+        if max_age is not None:
+            self.deactivate_elements(self.elements.dev('age_seconds') >= max_age, reason='retired')
+
+    def deactivate_outside(self):
+        """:2358-2386"""
+        if self.validity_domain is None:
+            return
+        W, E, S, N = self.validity_domain
+        lon, lat = self.elements.dev('lon'), self.elements.dev('lat')
+        if W is not None:
+            self.deactivate_elements(lon < W, reason='outside')
+        if E is not None:
+            self.deactivate_elements(lon > E, reason='outside')
+        if S is not None:
+            self.deactivate_elements(lat < S, reason='outside')
+        if N is not None:
+            self.deactivate_elements(lat > N, reason='outside')
+
+    # -- environment ---------------------------------------------------------------------------------------
+    def _active_variables(self):
+        """Required variables after the skip_if conditionals (:1899-1924)."""
+        out = []
+        for v, spec in self.required_variables.items():
+            cond = spec.get('skip_if')
+            if cond is not None:
+                key, op, val = cond
+                cur = self.get_config(key)
+                if (op == 'is' and cur is val) or (op == 'in' and cur in val):
+                    continue
+            out.append(v)
+        return out
+
+    @property
+    def environment(self):
+        """Start-of-step environment (float32 per variable), sampled lazily on the device."""
+        if getattr(self, '_env_view', None) is None:
+            el = self.elements
+            d_env, missing = self.env.device_environment(self._env_variables, self.time, el.dev('lon', self.engine.torch.float64),
+                                                         el.dev('lat', self.engine.torch.float64), self._z_for_sampling(),
+                                                         pos_f32=el.positions_f32)
+            self._env_view = EnvironmentView(d_env)
+            self._env_missing = missing
+        return self._env_view
+
+    def _z_for_sampling(self):
+        z = self.elements.dev('z')
+        if z.dtype != self.engine.torch.float32:
+            z = z.to(self.engine.torch.float32)
+        return z
+
+    # -- positions (:4630-4669) ---------------------------------------------------------------------------------
+    def update_positions(self, x_vel, y_vel):
+        """Move particles with the given velocity components for one time step (WGS84 geodesic)."""
+        eng, el = self.engine, self.elements
+        torch = eng.torch
+        xv = x_vel if isinstance(x_vel, torch.Tensor) else eng.to_device(np.ascontiguousarray(x_vel))
+        yv = y_vel if isinstance(y_vel, torch.Tensor) else eng.to_device(np.ascontiguousarray(y_vel))
+        if xv.dtype != yv.dtype or xv.dtype not in (torch.float32, torch.float64):
+            xv, yv = xv.to(torch.float64), yv.to(torch.float64)
+        moving = el.dev('moving')
+        if moving.dtype != torch.int32:
+            moving = moving.to(torch.int32)
+        eng.update_positions(el.dev('lon', torch.float64), el.dev('lat', torch.float64), xv, yv, moving,
+                             self.time_step.total_seconds())
+        el.positions_f32 = False
+        lon, lat = el.dev('lon'), el.dev('lat')
+        # the reference aborts on invalid coordinates (:4661-4669); checked lazily at output steps here
+
+    def horizontal_diffusion(self):
+        """:1746-1772 -- two normal draws from the legacy global generator (x first), then update_positions."""
+        if 'horizontal_diffusivity' not in self.required_variables or self.num_elements_active() == 0:
+            return
+        D = self._constant_or_none('horizontal_diffusivity')
+        if D is None:
+            D_dev = self.environment.dev('horizontal_diffusivity', self.engine)
+            if float(D_dev.max()) == 0:
+                return
+        elif D == 0:
+            return
+        eng = self.engine
+        n = self.num_elements_active()
+        rx = eng.to_device(np.random.normal(scale=1, size=n))
+        ry = eng.to_device(np.random.normal(scale=1, size=n))
+        dt = abs(self.time_step.total_seconds())
+        torch = eng.torch
+        if D is None:
+            s = torch.sqrt(2 * D_dev / np.float32(dt))
+        else:
+            s = torch.full((n,), float(np.sqrt(np.float32(2) * np.float32(D) / np.float32(dt))), dtype=torch.float32,
+                           device=eng.device)
+        mv = self.elements.dev('moving').to(torch.float64)
+        self.update_positions(mv * s.to(torch.float64) * rx, mv * s.to(torch.float64) * ry)
+
+    def _constant_or_none(self, var):
+        """Value of a variable that no reader provides (constant, else fallback), or None if a reader does."""
+        c = self.env.constant(var)
+        if c is not None:
+            return c
+        if not self.env.priority_list.get(var):
+            return self.env.fallback(var)
+        return None
+
+    # -- the main loop (:1828-2340) -----------------------------------------------------------------------------
+    def update(self):
+        raise NotImplementedError('model subclasses implement update()')
+
+    def update_and_diffuse(self):
+        """One time step of the model physics (:2272-2280): update() then horizontal_diffusion()."""
+        _ = self.environment          # sample the start-of-step environment before anything moves (:2238-2246)
+        self.update()
+        self.horizontal_diffusion()
+
+    def prepare_run(self):
+        pass
+
+    def run(self, time_step=None, steps=None, time_step_output=None, duration=None, end_time=None,
+            outfile=None, export_variables=None, export_buffer_length=100, stop_on_error=False):
+        if outfile is not None:
+            raise NotImplementedError('file export is outside the GPU hot path; read o.history / o.elements')
+        if self.num_elements_scheduled() == 0:
+            raise ValueError('Please seed elements before starting a run.')
+        for k in ('drift:current_uncertainty', 'drift:wind_uncertainty'):
+            if self.get_config(k, 0):
+                raise NotImplementedError('%s needs the sequential legacy RNG per stage; not on the GPU path' % k)
+        if time_step is None:
+            time_step = timedelta(minutes=self.get_config('general:time_step_minutes'))
+        if not isinstance(time_step, timedelta):
+            time_step = timedelta(seconds=time_step)
+        self.time_step = time_step
+        if time_step_output is None:
+            tso = self.get_config('general:time_step_output_minutes')
+            self.time_step_output = self.time_step if tso is None else timedelta(minutes=tso)
+        else:
+            self.time_step_output = time_step_output if isinstance(time_step_output, timedelta) \
+                else timedelta(seconds=time_step_output)
+            if self.time_step_output.days >= 0 and self.time_step.days < 0:
+                self.time_step_output = -self.time_step_output
+        ratio = self.time_step_output.total_seconds() / self.time_step.total_seconds()
+        if ratio < 1:
+            raise ValueError('Output time step must be equal or larger than calculation time step.')
+        if not float(ratio).is_integer():
+            raise ValueError('Ratio of calculation and output time steps must be an integer - given ratio is %s' % ratio)
+        if time_step.days < 0:
+            self.start_time = self.elements_scheduled_time.max()
+        if sum(x is not None for x in (duration, end_time, steps)) > 1:
+            raise ValueError('Only one of "steps", "duration" and "end_time" may be provided simultaneously')
+        if duration is None and end_time is None:
+            if steps is not None:
+                duration = steps * self.time_step
+            else:
+                for r in self.env.readers.values():
+                    if getattr(r, 'end_time', None) is not None:
+                        end_time = r.end_time if end_time is None else min(end_time, r.end_time)
+        if duration is None:
+            duration = end_time - self.start_time
+        if time_step.days < 0 and duration.days >= 0:
+            duration = -duration
+        if np.sign(duration.total_seconds()) * np.sign(time_step.total_seconds()) < 0:
+            raise ValueError('Time step must be negative if duration is negative.')
+        r = duration / self.time_step_output
+        if not float(r).is_integer():
+            duration = np.ceil(r) * self.time_step_output
+        self.expected_steps_output = int(duration.total_seconds() / self.time_step_output.total_seconds() + 1)
+        self.expected_steps_calculation = int(duration.total_seconds() / self.time_step.total_seconds())
+        self.expected_end_time = self.start_time + self.expected_steps_calculation * self.time_step
+        W, E = self.get_config('drift:deactivate_west_of'), self.get_config('drift:deactivate_east_of')
+        S, N = self.get_config('drift:deactivate_south_of'), self.get_config('drift:deactivate_north_of')
+        self.validity_domain = None if all(v is None for v in (W, E, S, N)) else [W, E, S, N]
+
+        eng = self.engine
+        self.env.finalize(eng)
+        self._env_variables = [v for v in self._active_variables()
+                               if self.env.priority_list.get(v) or self.env.constant(v) is not None
+                               or self.env.fallback(v) is not None]
+        self.elements = DeviceElements(self.ElementType, eng)
+        self.time = self.start_time
+        self.steps_calculation = 0
+        self._maybe_deactivated = False
+        out_every = int(round(ratio))
+        n_total = self.num_elements_total()
+        self.history = {'time': [], 'lon': [], 'lat': [], 'z': [], 'status': []}
+        self._n_total = n_total
+        self.prepare_run()
+
+        for i in range(self.expected_steps_calculation):
+            self.release_elements()
+            if self.num_elements_active() == 0 and self.num_elements_scheduled() > 0:
+                self.steps_calculation += 1
+                self.time = self.time + self.time_step
+                continue
+            self._env_view = None
+            self.deactivate_outside()
+            if i % out_every == 0:
+                self.state_to_buffer()
+            self.increase_age_and_retire()
+            self.remove_deactivated_elements()
+            if self.num_elements_active() > 0:
+                self._maybe_sort()
+                self.update_and_diffuse()
+            elif self.num_elements_scheduled() == 0:
+                break
+            self.time = self.time + self.time_step
+            self.steps_calculation += 1
+        self._env_view = None
+        self._restore_id_order()
+        self.state_to_buffer()
+        self.remove_deactivated_elements()
+        eng.sync()
+        self._check_positions()
+        return self.history
+
+    def _check_positions(self):
+        """:4661-4669 -- the reference exits on invalid coordinates; raised here after the run."""
+        if self.num_elements_active() == 0:
+            return
+        lon, lat = self.elements.dev('lon'), self.elements.dev('lat')
+        if float(lon.min()) < -180 or float(lon.max()) > 360 or float(lat.min()) < -90 or float(lat.max()) > 90:
+            raise ValueError('Invalid new coordinates')
+
+    def _restore_id_order(self):
+        """Put the device arrays back in the reference's element order (increasing ID)."""
+        if not getattr(self, '_sorted', False) or self.num_elements_active() == 0:
+            return
+        ids = self.elements.dev('ID')
+        perm = self.engine.torch.argsort(ids.to(self.engine.torch.int64), stable=True).to(self.engine.torch.int32)
+        self.elements.permute(perm)
+        self._sorted = False
+
+    def _maybe_sort(self):
+        """Keep the device arrays ordered by grid cell (locality of the field gathers).  Element order is
+        an implementation detail of the device arrays: outputs are keyed by ID."""
+        k = self.get_config('gpu:sort_interval_steps')
+        if not k or self.steps_calculation % k != 0 or self.num_elements_active() < 100000:
+            return
+        if (self._constant_or_none('horizontal_diffusivity') or 0) != 0 or self._constant_or_none('horizontal_diffusivity') is None:
+            return        # the legacy RNG draws are consumed in element order: keep the reference's order
+        r = self.env.reader_for('x_sea_water_velocity', self.time)
+        if r is None or not hasattr(r, 'group_of'):
+            return
+        g, _ = r.group_of('x_sea_water_velocity')
+        el = self.elements
+        t = self.engine.torch
+        perm = self.engine.sort_by_cell(g, el.dev('lon', t.float64), el.dev('lat', t.float64), self._z_for_sampling())
+        el.permute(perm)
+        self._sorted = True
+        self._env_view = None
+
+    def state_to_buffer(self):
+        """History of lon/lat/z/status per element ID at output steps (stands in for :2384-2499)."""
+        h = self.history
+        lon = np.full(self._n_total, np.nan, dtype=np.float32)
+        lat = np.full(self._n_total, np.nan, dtype=np.float32)
+        z = np.full(self._n_total, np.nan, dtype=np.float32)
+        st = np.full(self._n_total, -1, dtype=np.int32)
+        if self.num_elements_active() > 0:
+            el = self.elements
+            ids = el.to_host_array('ID').astype(np.int64)
+            lon[ids] = el.to_host_array('lon')
+            lat[ids] = el.to_host_array('lat')
+            z[ids] = el.to_host_array('z')
+            st[ids] = el.to_host_array('status')
+        h['time'].append(self.time)
+        h['lon'].append(lon)
+        h['lat'].append(lat)
+        h['z'].append(z)
+        h['status'].append(st)
+
+    def get_lonlats(self):
+        return np.array(self.history['lon']).T, np.array(self.history['lat']).T
+
+    def elements_by_id(self):
+        """Active elements' lon/lat/z ordered by ID (the device arrays may be cell-sorted)."""
+        el = self.elements
+        ids = el.to_host_array('ID').astype(np.int64)
+        order = np.argsort(ids, kind='stable')
+        return (ids[order], el.to_host_array('lon')[order], el.to_host_array('lat')[order],
+                el.to_host_array('z')[order])

@@ -1,0 +1,137 @@
+"""Environment: reader registry and get_environment() with the reference's contract
+(opendrift/models/basemodel/environment.py:499-923): loop the variable groups over the readers in priority
+order on the still-missing particles, cast to float32, apply `environment:constant:*` /
+`environment:fallback:*`, return (recarray float32, env_profiles, missing mask).
+
+Two faces:
+  * get_environment(...)      NumPy in / NumPy out, for model code and user scripts (host copies);
+  * device_environment(...)   device tensors in / device tensors out, used by the step methods.
+Both run od_interp for the sampling.  The fused step kernels bypass this class entirely and read the bound
+field groups directly; fallback values are baked into the groups when readers are bound in finalize().
+"""
+import logging
+
+import numpy as np
+
+from ..errors import NotCoveredError
+
+logger = logging.getLogger('opendrift_b200')
+
+
+class Environment:
+    def __init__(self, required_variables, config):
+        self.required_variables = required_variables      # name -> spec dict
+        self._config = config
+        self.readers = {}
+        self.priority_list = {}
+        self.discarded_readers = {}
+        self.__finalized__ = False
+        self._engine = None
+
+    # -- registry (environment.py:267-330) -------------------------------------------------------
+    def add_reader(self, readers, variables=None, first=False):
+        if not isinstance(readers, (list, tuple)):
+            readers = [readers]
+        for r in readers:
+            name = getattr(r, 'name', type(r).__name__)
+            base, k = name, 1
+            while name in self.readers:
+                k += 1
+                name = '%s_%d' % (base, k)
+            r.name = name
+            self.readers[name] = r
+            for v in (variables or r.variables):
+                if v not in r.variables:
+                    continue
+                lst = self.priority_list.setdefault(v, [])
+                if first:
+                    lst.insert(0, name)
+                else:
+                    lst.append(name)
+
+    def finalize(self, engine):
+        self._engine = engine
+        for r in self.readers.values():
+            if hasattr(r, 'bind'):
+                r.bind(engine, fallback={v: self.fallback(v) for v in r.variables})
+        self.__finalized__ = True
+
+    def constant(self, var):
+        item = self._config._config.get('environment:constant:%s' % var)
+        return None if item is None else item['value']
+
+    def fallback(self, var):
+        item = self._config._config.get('environment:fallback:%s' % var)
+        return None if item is None else item['value']
+
+    def reader_for(self, var, time):
+        """First reader in priority order that provides `var` and covers `time` (or None)."""
+        if self.constant(var) is not None:
+            return None
+        for name in self.priority_list.get(var, []):
+            r = self.readers[name]
+            if r.covers_time(time):
+                return r
+        return None
+
+    # -- device face ---------------------------------------------------------------------------------
+    def device_environment(self, variables, time, d_lon, d_lat, d_z, pos_f32=False):
+        """dict var -> float32 device tensor, with constants / fallbacks applied, + missing mask tensor."""
+        eng = self._engine
+        torch = eng.torch
+        n = d_lon.numel()
+        out = {}
+        for v in variables:
+            if v in out:
+                continue
+            c = self.constant(v)
+            if c is not None:
+                out[v] = torch.full((n,), float(c), dtype=torch.float32, device=eng.device)
+                continue
+            res = None
+            for name in self.priority_list.get(v, []):
+                r = self.readers[name]
+                if not r.covers_time(time) or not hasattr(r, 'group_of'):
+                    continue
+                g, comp = r.group_of(v)
+                outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True)
+                if res is None:
+                    res = {nm: outs[cc] for nm, (gg, cc) in r._groups.items() if gg is g}
+                else:                                   # next reader fills what is still missing
+                    for nm, (gg, cc) in r._groups.items():
+                        if gg is g and nm in res:
+                            res[nm] = torch.where(torch.isfinite(res[nm]), res[nm], outs[cc])
+                if bool(torch.isfinite(res[v]).all()):
+                    break
+            if res is None:
+                res = {v: torch.full((n,), float('nan'), dtype=torch.float32, device=eng.device)}
+            for nm, t in res.items():
+                if nm in variables and nm not in out:
+                    fb = self.fallback(nm)
+                    if fb is not None:
+                        t = torch.where(torch.isfinite(t), t, torch.full_like(t, float(fb)))
+                    out[nm] = t
+        missing = torch.zeros(n, dtype=torch.bool, device=eng.device)
+        for v in variables:
+            missing |= ~torch.isfinite(out[v])
+        return out, missing
+
+    # -- host face (the reference signature) ---------------------------------------------------------
+    def get_environment(self, variables, time, lon, lat, z, profiles=None, profiles_depth=None, element_ID=None):
+        assert self.__finalized__ is True, 'The environment has not been finalized.'
+        eng = self._engine
+        lon, lat = np.atleast_1d(lon), np.atleast_1d(lat)
+        n = len(lon)
+        pos_f32 = lon.dtype == np.float32 and lat.dtype == np.float32
+        trunc = self._config.get_config('drift:truncate_ocean_model_below_m', None) \
+            if 'drift:truncate_ocean_model_below_m' in self._config._config else None
+        zz = np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
+        if trunc is not None:
+            zz = zz.copy()
+            zz[zz < -trunc] = -trunc
+        d_env, d_missing = self.device_environment(list(variables), time, eng.to_device(lon.astype(np.float64)),
+                                                   eng.to_device(lat.astype(np.float64)), eng.to_device(zz), pos_f32)
+        env = np.zeros(n, dtype=[(v, np.float32) for v in variables])
+        for v in variables:
+            env[v] = d_env[v].cpu().numpy()
+        return env.view(np.recarray), None, d_missing.cpu().numpy()

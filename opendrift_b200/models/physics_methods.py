@@ -1,0 +1,99 @@
+"""PhysicsMethods mixin -- the advection helpers model subclasses call from update(), with the
+reference's signatures (opendrift/models/physics_methods.py): advect_ocean_current(factor=1) :611-691,
+advect_wind(factor=1) :712-791.  Each call is one kernel launch on the device-resident elements; the
+start-of-step environment is the one sampled by the run loop (self.environment)."""
+import numpy as np
+
+
+class PhysicsMethods:
+
+    def _current_group(self, t):
+        r = self.env.reader_for('x_sea_water_velocity', t)
+        if r is None or not hasattr(r, 'group_of'):
+            return None
+        g, c = r.group_of('x_sea_water_velocity')
+        g2, c2 = r.group_of('y_sea_water_velocity')
+        assert g is g2 and (c, c2) == (0, 1), 'current components must come from one reader'
+        return g
+
+    def _device_factor(self, factor, name):
+        """factor * elements.<name> with NumPy's dtype rules (int/float scalar factors are weak)."""
+        eng, torch = self.engine, self.engine.torch
+        p = self.elements.dev(name)
+        if isinstance(factor, (int, float)) and factor == 1:
+            return p
+        if isinstance(factor, (int, float)):
+            return p * p.new_tensor(factor)
+        f = factor if isinstance(factor, torch.Tensor) else eng.to_device(np.ascontiguousarray(factor))
+        return f * p
+
+    def advect_ocean_current(self, factor=1):
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        scheme = self.get_config('drift:advection_scheme')
+        fac = self._device_factor(factor, 'current_drift_factor') if 'current_drift_factor' in el.variables else None
+        if fac is not None and fac.dtype not in (torch.float32, torch.float64):
+            fac = fac.to(torch.float64)
+        moving = el.dev('moving')
+        if moving.dtype != torch.int32:
+            moving = moving.to(torch.int32)
+        lon, lat = el.dev('lon', torch.float64), el.dev('lat', torch.float64)
+        g = self._current_group(self.time)
+        trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
+        if g is None:
+            # no gridded current reader: constant / fallback current -> plain update_positions (Euler == RK)
+            env = self.environment
+            u, v = env.dev('x_sea_water_velocity', eng), env.dev('y_sea_water_velocity', eng)
+            if fac is None:
+                self.update_positions(u, v)
+            else:
+                self.update_positions(fac * u if fac.dtype == u.dtype else fac.to(torch.float64) * u.to(torch.float64),
+                                      fac * v if fac.dtype == v.dtype else fac.to(torch.float64) * v.to(torch.float64))
+            return
+        # k1 is the start-of-step environment if somebody already materialised it (e.g. a subclass modified it)
+        k1 = None
+        view = getattr(self, '_env_view', None)
+        if view is not None and 'x_sea_water_velocity' in view:
+            k1 = (view.dev('x_sea_water_velocity', eng), view.dev('y_sea_water_velocity', eng))
+        eng.advect_current(g, scheme, self.time, self.time_step, lon, lat,
+                           self._z_for_sampling() if g.desc.nz > 1 else None, factor=fac, moving=moving, k1=k1,
+                           truncate_below=trunc, pos_f32=el.positions_f32)
+        el.positions_f32 = False
+
+    def advect_wind(self, factor=1):
+        """Wind drift of elements near the surface (:712-791): wind_drift_factor, linearly reduced to zero at
+        drift:wind_drift_depth; relative_wind optional."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        env = self.environment
+        if 'x_wind' not in env:
+            return
+        xw, yw = env.dev('x_wind', eng), env.dev('y_wind', eng)
+        wdf = el.dev('wind_drift_factor')
+        z = el.dev('z')
+        wdd = self.get_config('drift:wind_drift_depth', 0) or 0
+        surface = z >= -abs(wdd)
+        if wdd != 0:
+            wdd_t = torch.full_like(z, abs(wdd), dtype=torch.float64)
+            w = wdf.to(torch.float64) * (wdd_t + z.to(torch.float64)) / wdd_t
+            w = torch.where(z > 0, wdf.to(torch.float64), w)
+        else:
+            w = wdf.clone()
+        w = torch.where(surface, w, torch.zeros_like(w))
+        if self.get_config('drift:relative_wind', False):
+            xw = xw - env.dev('x_sea_water_velocity', eng)
+            yw = yw - env.dev('y_sea_water_velocity', eng)
+        if isinstance(factor, (int, float)) and factor == 1:
+            xv, yv = xw.to(w.dtype) * w, yw.to(w.dtype) * w
+        else:
+            f = factor if isinstance(factor, torch.Tensor) else (
+                eng.to_device(np.ascontiguousarray(factor)) if not isinstance(factor, (int, float)) else factor)
+            xv, yv = xw.to(w.dtype) * w * f, yw.to(w.dtype) * w * f
+        self.update_positions(xv, yv)
+
+    def stokes_drift(self, factor=1):
+        """:793-848.  Surface Stokes drift with a depth profile is a "next" row; with the
+        default fallback of 0 m/s the reference returns early, which is what happens here."""
+        if not self.get_config('drift:stokes_drift', False):
+            return
+        for v in ('sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity'):
+            if self.env.priority_list.get(v) or (self.env.constant(v) or 0) != 0:
+                raise NotImplementedError('Stokes drift profiles are not on the GPU path yet')

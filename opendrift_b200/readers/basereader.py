@@ -160,6 +160,23 @@ class StructuredReader:
             for c, nme in enumerate(names):
                 self._groups[nme] = (g, c)
 
+    def unbind(self):
+        """Release the device slabs of this reader."""
+        eng = self._engine
+        if eng is not None:
+            for g in {id(g): g for g, _ in self._groups.values()}.values():
+                try:
+                    eng.free_group(g)
+                except Exception:
+                    pass
+        self._engine, self._groups = None, {}
+
+    def __del__(self):
+        try:
+            self.unbind()
+        except Exception:
+            pass
+
     def group_of(self, variable):
         return self._groups[variable]
 

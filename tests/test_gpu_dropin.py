@@ -1,0 +1,144 @@
+"""The reference-facing Python surface (OceanDrift / readers / Environment) on the GPU path, driven the
+way the reference's own scripts and tests drive it, and compared with the UNMODIFIED reference's results
+(tests/golden/ref_*.npz)."""
+from datetime import timedelta
+
+import numpy as np
+import pytest
+
+import common
+from common import Fixture, fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(fx, **cfg):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    m = fx.meta
+    o = OceanDrift(loglevel=50, seed=m['seed'])
+    f3 = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
+    if fx.w is not None:
+        f3['upward_sea_water_velocity'] = fx.w
+    o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, name='current'))
+    if fx.x_wind is not None:
+        o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times,
+                                                {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind'))
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('general:coastline_action', 'none')
+    o.set_config('drift:advection_scheme', m['scheme'])
+    o.set_config('drift:vertical_advection', bool(m['with_w']))
+    if m['diffusivity']:
+        o.set_config('environment:constant:horizontal_diffusivity', m['diffusivity'])
+    if m.get('wind_drift_depth') is not None:
+        o.set_config('drift:wind_drift_depth', m['wind_drift_depth'])
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    kw = {}
+    if fx.cdf is not None:
+        kw['current_drift_factor'] = fx.cdf
+    o.seed_elements(lon=fx.lon0, lat=fx.lat0, z=fx.z0, time=fx.start, **kw)
+    return o
+
+
+@pytest.mark.parametrize('name', fixtures())
+def test_oceandrift_run_matches_reference(name):
+    fx = Fixture(name)
+    o = _model(fx)
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    assert o.num_elements_active() == fx.n
+    lon, lat, z = o.elements.lon, o.elements.lat, o.elements.z
+    assert lon.dtype == np.float64                       # float64 after the first update, as in the reference
+    e = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    assert max(e) < 5e-8, e
+    assert np.abs(z - fx.z).max() <= 1e-5
+    assert np.array_equal(o.elements.ID, np.arange(fx.n))
+    assert len(o.history['time']) == fx.steps + 1
+
+
+class HelperByHelper:
+    """A model subclass that overrides update() like the reference's own subclasses do: the helpers then
+    run as separate kernels and must give the same trajectories as the fused step."""
+
+
+def test_overridden_update_uses_helpers_and_matches():
+    from opendrift_b200.models.oceandrift import OceanDrift
+
+    class MyDrift(OceanDrift):
+        def update(self):
+            self.advect_ocean_current()
+            self.advect_wind()
+            self.vertical_advection()
+
+    for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32'):
+        fx = Fixture(name)
+        o = _model(fx)
+        o.__class__ = MyDrift
+        o.run(steps=fx.steps, time_step=fx.dt)
+        e = common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)
+        assert max(e) < 5e-8, (name, e)
+        assert np.abs(o.elements.z - fx.z).max() <= 1e-5
+
+
+def test_subclass_touching_numpy_state_still_works():
+    """Drop-in for model code that manipulates self.elements / self.environment as NumPy arrays."""
+    from opendrift_b200.models.oceandrift import OceanDrift
+
+    class Halver(OceanDrift):
+        def update(self):
+            u = self.environment.x_sea_water_velocity          # NumPy float32
+            assert isinstance(u, np.ndarray) and u.dtype == np.float32
+            self.update_positions(0.5 * u, 0.5 * self.environment.y_sea_water_velocity)
+            self.elements.z = self.elements.z - np.float32(0.25)
+
+    fx = Fixture('euler_3d')
+    o = _model(fx)
+    o.__class__ = Halver
+    o.run(steps=3, time_step=fx.dt)
+    assert np.allclose(o.elements.z, fx.z0 - 0.75, atol=1e-5)
+    assert np.abs(o.elements.lon - fx.lon0).max() > 1e-4
+
+
+def test_reader_get_variables_interpolated_and_environment():
+    from oracle import advect_port as ap
+    from opendrift_b200.readers import reader_regular_grid
+    from opendrift_b200.errors import OutsideTemporalCoverageError
+    fx = Fixture('rk4_3d_offgrid')
+    r = reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v})
+    ref = ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v})
+    t = fx.times[0] + timedelta(seconds=777)
+    lon, lat, z = fx.lon0.astype(np.float64), fx.lat0.astype(np.float64), fx.z0
+    env, prof = r.get_variables_interpolated(common.CUR, time=t, lon=lon, lat=lat, z=z)
+    want = ap.reader_interpolate(ref, common.CUR, t, lon, lat, z)
+    assert prof is None
+    for v in common.CUR:
+        got = np.ma.filled(env[v].astype(np.float32), np.nan)
+        exp = want[v].astype(np.float32)
+        assert np.array_equal(np.isnan(got), np.isnan(exp))
+        assert np.array_equal(got[~np.isnan(got)], exp[~np.isnan(exp)])
+        assert np.isnan(got).sum() > 50                      # uncovered points are masked, not filled
+    with pytest.raises(OutsideTemporalCoverageError):
+        r.get_variables_interpolated(common.CUR, time=fx.times[-1] + timedelta(days=1), lon=lon, lat=lat, z=z)
+
+
+def test_seeding_radius_and_deactivation():
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = Fixture('rk4_2d')
+    o = OceanDrift(loglevel=50, seed=3)
+    o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}))
+    clon, clat = float(fx.grid_lon.mean()), float(fx.grid_lat.mean())
+    o.seed_elements(lon=clon, lat=clat, time=fx.times[0], number=5000, radius=2000.0)
+    o.set_config('drift:advection_scheme', 'runge-kutta4')
+    o.set_config('drift:max_age_seconds', 4 * 600.0)
+    with pytest.raises(ValueError):
+        o.set_config('drift:advection_scheme', 'leapfrog')
+    o.run(steps=6, time_step=600)
+    # gaussian radius: sigma of 2 km in each direction
+    lon0, lat0 = np.array(o.history['lon'][0]), np.array(o.history['lat'][0])
+    sx = np.std((lon0 - clon) * 111e3 * np.cos(np.radians(clat)))
+    sy = np.std((lat0 - clat) * 111e3)
+    assert 1800 < sx < 2200 and 1800 < sy < 2200
+    # everybody retired at age 4 steps
+    assert o.num_elements_active() == 0 and o.num_elements_deactivated() == 5000
+    assert 'retired' in o.status_categories
