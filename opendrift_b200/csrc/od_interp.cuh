@@ -63,6 +63,7 @@ struct VertW {
 
 // numpy's np.mod(x, 360.0)
 OD_HD double np_mod360(double x) {
+    if (x >= 0.0 && x < 360.0) return x;          // fmod(x, 360) == x exactly
     double r = fmod(x, 360.0);
     if (r != 0.0) {
         if (r < 0.0) r += 360.0;
@@ -115,6 +116,7 @@ struct HorizW {
 
 // numpy's np.mod for float32 operands
 OD_HD float np_mod360f(float x) {
+    if (x >= 0.0f && x < 360.0f) return x;
     float r = fmodf(x, 360.0f);
     if (r != 0.0f) {
         if (r < 0.0f) r += 360.0f;

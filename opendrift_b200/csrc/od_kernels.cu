@@ -18,7 +18,14 @@
 using namespace od;
 
 #define OD_PAIR_CACHE 4
-#define OD_BLOCK 256
+// Launch shape of the step kernel, chosen by measurement on B200 (profiles/r1_tuning.md): 128-thread blocks,
+// registers capped at 80 (6 resident blocks = 24 warps/SM); 256x2 (90 registers, 16 warps) is 12% slower.
+#ifndef OD_BLOCK
+#define OD_BLOCK 128
+#endif
+#ifndef OD_STEP_MINB
+#define OD_STEP_MINB 6
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(OD_BLOCK) update_positions_kernel(int64_t n, d
 }
 
 template <int SCHEME, bool F64, bool EXTRAS>
-__global__ void __launch_bounds__(OD_BLOCK) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const StepParams p) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
     if (p.cs.g.nz > 1) load_levels(lv, p.cs.g);

@@ -1,0 +1,54 @@
+"""Component timings on the GPU box: od_geod_fwd, od_interp (one RK stage worth of sampling), od_update_positions,
+step_kernel<RK4>, sort/permute -- CUDA events, 10 M particles.  Also the target of `ncu --set full -k regex:...`."""
+import sys, os, json
+from datetime import timedelta
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from opendrift_b200 import synthetic as syn
+from opendrift_b200.engine import Engine
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+eng = Engine(0)
+g = syn.GridSpec()
+times = syn.slab_times(3)
+slabs = [tuple(torch.from_numpy(a).cuda() for a in syn.double_gyre_uv(g, (t - syn.T0).total_seconds())) for t in times]
+grp = eng.add_group(g.lon, g.lat, g.z, 2, times, lambda ti, c: slabs[ti][c], (0.0, 0.0))
+lon0, lat0, z0 = syn.particle_cloud(n, seed=5)
+lon, lat, z = eng.to_device(lon0.astype(np.float64)), eng.to_device(lat0.astype(np.float64)), eng.to_device(z0)
+perm = eng.sort_by_cell(grp, lon, lat, z)
+lon, lat, z = eng.permute(perm, lon), eng.permute(perm, lat), eng.permute(perm, z)
+az = torch.rand(n, device='cuda', dtype=torch.float64) * 360 - 180
+dist = torch.rand(n, device='cuda', dtype=torch.float64) * 600
+xv = torch.randn(n, device='cuda', dtype=torch.float32)
+yv = torch.randn(n, device='cuda', dtype=torch.float32)
+t = times[0] + timedelta(seconds=300)
+dt = timedelta(seconds=600)
+
+
+def timeit(fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return float(np.median(out))
+
+
+res = {}
+l2, a2 = lon.clone(), lat.clone()
+res['geod_fwd_ms'] = timeit(lambda: eng.geod_fwd(l2, a2, az, dist))
+res['interp_uv_ms'] = timeit(lambda: eng.interp(grp, t, lon, lat, z))
+l2, a2 = lon.clone(), lat.clone()
+res['update_positions_f32_ms'] = timeit(lambda: eng.update_positions(l2, a2, xv, yv, None, 600.0))
+l2, a2 = lon.clone(), lat.clone()
+res['step_rk4_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z))
+l2, a2 = lon.clone(), lat.clone()
+res['step_euler_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z))
+res['sort_by_cell_ms'] = timeit(lambda: eng.sort_by_cell(grp, lon, lat, z))
+res['permute_f64_ms'] = timeit(lambda: eng.permute(perm, lon))
+res['n'] = n
+print(json.dumps(res))
