@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from datetime import timedelta
 
@@ -47,50 +46,64 @@ def measured_peak_hbm():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (one `-lms 100` process)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.35)          # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
 
-    def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def stop(self, t_begin=None, t_end=None):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ''
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.strip().splitlines():
+            r = [c.strip() for c in line.split(',')]
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons),
-                'samples': len(sm)}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0}
+        # samples under load = those above the idle clock
+        load = [x for x in sm if x > 0.5 * max(mx)] or sm
+        return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm), 'samples_under_load': len(load), 'power_w_max': float(np.max(pw))}
 
 
-def field_slabs(grid, n_slabs):
-    times = syn.slab_times(n_slabs)
-    slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times]
-    return times, slabs
+PERIOD = 10      # the synthetic double gyre repeats every 36000 s = 10 hourly slabs
+
+
+class PeriodicSlabs:
+    """fields[var][time_index] for a field that is periodic in time: PERIOD distinct slabs serve any run length."""
+
+    def __init__(self, slabs, comp):
+        self.slabs, self.comp = slabs, comp
+
+    def __getitem__(self, ti):
+        return self.slabs[ti % PERIOD][self.comp]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -98,8 +111,9 @@ def cpu_port_rate(n, steps, seed=123):
     """Reference CPU algorithm (NumPy/SciPy port) on a bounded sample; returns (rate, seconds, threads)."""
     from oracle import advect_port as ap
     grid = syn.GridSpec()
-    times, slabs = field_slabs(grid, syn.n_slabs_for(steps, DT))
-    fields = {CUR[0]: np.stack([s[0] for s in slabs]), CUR[1]: np.stack([s[1] for s in slabs])}
+    times = syn.slab_times(syn.n_slabs_for(steps, DT))
+    slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times[:PERIOD]]
+    fields = {CUR[0]: PeriodicSlabs(slabs, 0), CUR[1]: PeriodicSlabs(slabs, 1)}
     reader = ap.GridReader(grid.lon, grid.lat, grid.z, times, fields)
     lon, lat, z = syn.particle_cloud(n, seed=seed)
     t0 = time.perf_counter()
@@ -109,25 +123,29 @@ def cpu_port_rate(n, steps, seed=123):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU algorithm (single process, as the reference runs) with each
+    step a bounded sample of the workload, sized so that K + W steps end within ~2 minutes."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n = args.ref_particles
-    rates = []
-    for _ in range(args.warmup):
-        cpu_port_rate(max(1000, n // 10), 1)
-    t0 = time.perf_counter()
+    if n <= 0:
+        budget = 3.0e6                                   # particle-steps (about 90 s at ~3.5e4 particle-steps/s)
+        n = int(min(100_000, max(2_000, budget / max(1, args.steps + args.warmup))))
+    if args.warmup:
+        cpu_port_rate(n, args.warmup)
     rate, secs, thr = cpu_port_rate(n, args.steps)
     ms = secs * 1e3 / args.steps
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'particle-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v, dt=600 s (configs[1]); '
-                               'CPU arm on a bounded sample of %d particles per step' % n},
+        'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, dt=600 s (BASELINE configs[1]); '
+                               'CPU arm: each step is a bounded sample of %d particles of that workload' % n},
         'cpu_baseline': {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': 'port',
-                         'sample': '%d particles x %d steps, NumPy/SciPy restatement of the reference path '
-                                   '(single process, as the reference runs)' % (n, args.steps)},
+                         'sample': '%d particles x %d steps; oracle/advect_port.py = NumPy/SciPy restatement of the reference '
+                                   'path, bit-identical to the reference on the committed fixtures; single process, single '
+                                   'thread, as the reference runs (/root/reference cannot travel to the GPU box)' % (n, args.steps)},
         'e2e': {'value': rate, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -148,37 +166,38 @@ def run_b200(args):
     eng = Engine(local)
     dev = eng.device
     n = args.particles
-    steps_total = args.warmup + args.steps
     grid = syn.GridSpec()
-    n_slabs = syn.n_slabs_for(2 * steps_total + 2, DT)
-    times = syn.slab_times(n_slabs)
+    n_times = syn.n_slabs_for(args.warmup + args.steps + 4, DT) + PERIOD
+    times = syn.slab_times(n_times)
 
-    # forcing slabs: rank 0 builds them on the host; other ranks receive them with an NCCL broadcast
-    # (the once-per-reader-time-step exchange of the multi-GPU design; replicated field, sharded particles)
-    host_slabs = []
-    dev_slabs = []
-    for ti in range(n_slabs):
+    # forcing slabs: rank 0 builds them on the host; the other ranks receive them with an NCCL broadcast over
+    # NVLink (the once-per-reader-time-step exchange of the multi-GPU design: replicated field, sharded particles)
+    host_slabs, dev_slabs = [], []
+    t_bcast = 0.0
+    for ti in range(PERIOD):
         if rank == 0:
             u, v = syn.double_gyre_uv(grid, (times[ti] - syn.T0).total_seconds())
             hu, hv = torch.from_numpy(u).pin_memory(), torch.from_numpy(v).pin_memory()
             du, dv = hu.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
         else:
-            hu = hv = None
             du = torch.empty((grid.nz, grid.ny, grid.nx), dtype=torch.float32, device=dev)
             dv = torch.empty_like(du)
         if world > 1:
+            torch.cuda.synchronize()
+            b0 = time.perf_counter()
             dist.broadcast(du, 0)
             dist.broadcast(dv, 0)
+            torch.cuda.synchronize()
+            t_bcast += time.perf_counter() - b0
             if rank != 0:
                 hu, hv = du.cpu().pin_memory(), dv.cpu().pin_memory()
         host_slabs.append((hu, hv))
         dev_slabs.append((du, dv))
     torch.cuda.synchronize()
-
     resident = {'on': True}
 
     def supplier(ti, c):
-        return dev_slabs[ti][c] if resident['on'] else host_slabs[ti][c]
+        return dev_slabs[ti % PERIOD][c] if resident['on'] else host_slabs[ti % PERIOD][c]
 
     grp = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, supplier, (0.0, 0.0), n_slots=3)
 
@@ -186,7 +205,7 @@ def run_b200(args):
     h_lon = torch.from_numpy(lon0.astype(np.float64)).pin_memory()
     h_lat = torch.from_numpy(lat0.astype(np.float64)).pin_memory()
     h_z = torch.from_numpy(z0).pin_memory()
-    lon, lat, z = h_lon.to(dev), h_lat.to(dev), h_z.to(dev)
+    st = {'lon': h_lon.to(dev), 'lat': h_lat.to(dev), 'z': h_z.to(dev), 't': times[0], 'k': 0}
     dt = timedelta(seconds=DT)
 
     def barrier():
@@ -194,22 +213,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # optional spatial ordering of the particle arrays (locality of the field gathers)
     def resort():
-        nonlocal lon, lat, z
-        perm = eng.sort_by_cell(grp, lon, lat, z)
-        lon, lat, z = eng.permute(perm, lon), eng.permute(perm, lat), eng.permute(perm, z)
-
-    state = {'t': times[0], 'k': 0}
+        # spatial ordering of the SoA particle arrays (locality of the field gathers); part of the step cost
+        perm = eng.sort_by_cell(grp, st['lon'], st['lat'], st['z'])
+        for k in ('lon', 'lat', 'z'):
+            st[k] = eng.permute(perm, st[k])
 
     def step():
-        if args.sort_every and state['k'] % args.sort_every == 0:
+        if args.sort_every and st['k'] % args.sort_every == 0:
             resort()
-        eng.advect_current(grp, 'runge-kutta4', state['t'], dt, lon, lat, z, pos_f32=(state['k'] == 0))
-        state['t'] += dt
-        state['k'] += 1
+        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, st['lon'], st['lat'], st['z'], pos_f32=(st['k'] == 0))
+        st['t'] += dt
+        st['k'] += 1
 
-    # ---- resident run ---------------------------------------------------------------------------
+    # ---- resident run: state and slabs in HBM -----------------------------------------------------------
     for _ in range(args.warmup):
         step()
     barrier()
@@ -218,7 +235,6 @@ def run_b200(args):
         sampler.start()
     l0 = eng.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -229,54 +245,45 @@ def run_b200(args):
     launches = eng.launches() - l0
     clocks = sampler.stop() if sampler else None
 
-    # dominant kernel alone (CUDA events around single launches of step_kernel<RK4>, no sort / pack)
-    for _ in range(3):
+    # dominant kernel alone: CUDA events around single launches of step_kernel<RK4> on the launching stream
+    kern_ms = []
+    for _ in range(5):
         ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tl, ta = lon.clone(), lat.clone()
+        tl, ta = st['lon'].clone(), st['lat'].clone()
         torch.cuda.synchronize()
         ka.record()
-        eng.advect_current(grp, 'runge-kutta4', state['t'], dt, tl, ta, z)
+        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
         kb.record()
         torch.cuda.synchronize()
         kern_ms.append(ka.elapsed_time(kb))
     kernel_ms = float(np.median(kern_ms))
 
-    # ---- end-to-end: host buffers, copies inside the timed region -----------------------------------
+    # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
-    grp.resident = [None] * grp.n_slots                     # slabs must come from the host again
-    o_lon = torch.empty_like(h_lon).pin_memory()
-    o_lat = torch.empty_like(h_lat).pin_memory()
+    grp.resident = [None] * grp.n_slots                     # forcing slabs come from pinned host memory again
+    o_lon, o_lat = torch.empty_like(h_lon).pin_memory(), torch.empty_like(h_lat).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
     t_e2e = times[0]
+    bufs = [(h_lon, h_lat), (o_lon, o_lat)]
 
-    def e2e_step(t):
-        lon.copy_(h_lon, non_blocking=True)
-        lat.copy_(h_lat, non_blocking=True)
-        z.copy_(h_z, non_blocking=True)
-        eng.advect_current(grp, 'runge-kutta4', t, dt, lon, lat, z)
-        o_lon.copy_(lon, non_blocking=True)
-        o_lat.copy_(lat, non_blocking=True)
-        h_lon.copy_(o_lon)            # host-side state advance (the caller owns the arrays)
-        h_lat.copy_(o_lat)
+    def e2e_step(i, t):
+        src, dst = bufs[i % 2], bufs[(i + 1) % 2]
+        eng.advect_current_host(grp, 'runge-kutta4', t, dt, src[0], src[1], h_z, dst[0], dst[1], chunks=args.e2e_chunks)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step(t_e2e)
-        torch.cuda.synchronize()
+    for i in range(2):
+        e2e_step(i, t_e2e)
         t_e2e += dt
     barrier()
-    w0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for _ in range(e2e_steps):
-        e2e_step(t_e2e)
-        torch.cuda.synchronize()
+    for i in range(e2e_steps):
+        e2e_step(i, t_e2e)
         t_e2e += dt
     g1.record()
     barrier()
-    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - w0) * 1e3 * 0)  # device clock
+    e2e_ms = g0.elapsed_time(g1)
 
-    # max over ranks
-    if world > 1:
+    if world > 1:       # device-timed, max over ranks
         tt = torch.tensor([ms_total, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total, e2e_ms, kernel_ms = [float(x) for x in tt.tolist()]
@@ -288,16 +295,24 @@ def run_b200(args):
     value = n * world * args.steps / (ms_total * 1e-3)
     e2e_value = n * world * e2e_steps / (e2e_ms * 1e-3)
     peak, peak_src = measured_peak_hbm()
-    field_bytes = 2 * 2 * grid.nx * grid.ny * grid.nz * 4           # two slabs x (u, v)
-    state_bytes = 44                                                  # lon,lat r/w (32) + z, moving, cdf (12)
-    b_alg = state_bytes * n + field_bytes                             # per launch
+    field_bytes = 2 * 2 * grid.nx * grid.ny * grid.nz * 4           # two time slabs x (u, v) float32
+    state_bytes = 44                                                  # lon, lat read + written (32), z, moving, factor (12)
+    b_alg = state_bytes * n + field_bytes                             # 65 B per particle-step at 10 M
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        except Exception:
+            pass
     cpu = None
     if not args.no_cpu:
         rate, secs, thr = cpu_port_rate(args.cpu_particles, args.cpu_steps)
         cpu = {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': 'port',
                'sample': '%d particles x %d steps (%.1f s) of the same workload through oracle/advect_port.py, the '
-                         'NumPy/SciPy restatement of the reference path' % (args.cpu_particles, args.cpu_steps, secs)}
+                         'NumPy/SciPy restatement of the reference path (bit-identical to the reference on the '
+                         'committed fixtures; single process like the reference)' % (args.cpu_particles, args.cpu_steps, secs)}
     line = {
         'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -305,17 +320,19 @@ def run_b200(args):
         'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, %d particles per GPU, '
                                'dt=600 s (BASELINE configs[1]%s)' % (n, '; configs[2] sharding' if world > 1 else ''),
                    'particles_per_gpu': n, 'field': '512x512x50 f32 u,v, hourly slabs', 'scheme': 'runge-kutta4',
-                   'sort_every': args.sort_every, 'parallelism': 'particle-index shards x%d, replicated field' % world,
+                   'sort_every': args.sort_every, 'mode': 'exact (bit-exact field sampling, float64 geodesic)',
+                   'parallelism': 'particle-index shards x%d, replicated field (NCCL broadcast of slabs: %.1f ms per slab pair)'
+                                  % (world, 1e3 * t_bcast / PERIOD) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 16,
-                'steps': e2e_steps},
+                'steps': e2e_steps, 'api': 'Engine.advect_current_host (pinned host arrays in/out, %d-chunk copy/compute pipeline)' % args.e2e_chunks},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms,
+                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms,
                      'algorithmic_bytes_per_launch': b_alg,
-                     'note': 'fp64 RK4 is bound by the FP64 pipe and gather latency, not by algorithmic HBM bytes '
-                             '(65 B per particle-step); see DESIGN.md'},
+                     'note': 'this float64 kernel is bound by the FP64 pipe (ncu: fp64 pipe ~45% of peak, issue slots ~51%), '
+                             'not by its 65 algorithmic bytes per particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
     }
     print(json.dumps(line))
@@ -326,15 +343,16 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--particles', type=int, default=10_000_000)
-    ap.add_argument('--sort-every', type=int, default=0)
+    ap.add_argument('--sort-every', type=int, default=20)
+    ap.add_argument('--e2e-chunks', type=int, default=8)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-particles', type=int, default=50_000)
     ap.add_argument('--cpu-steps', type=int, default=4)
-    ap.add_argument('--ref-particles', type=int, default=50_000)
+    ap.add_argument('--ref-particles', type=int, default=0, help='0 = sized from --steps')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

@@ -331,6 +331,65 @@ class Engine:
                 s.diffusivity_const = float(diffusivity)
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
 
+    def advect_current_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None,
+                            factor=None, moving=None, chunks=8, pos_f32=False):
+        """advect_ocean_current for HOST arrays (pinned torch tensors): the particle range is cut into chunks
+        whose host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the
+        PCIe transfers of neighbouring chunks overlap the kernel.  Results land in h_out_lon / h_out_lat
+        (default: in place).  Returns after everything has completed."""
+        torch = self.torch
+        n = h_lon.numel()
+        h_out_lon = h_lon if h_out_lon is None else h_out_lon
+        h_out_lat = h_lat if h_out_lat is None else h_out_lat
+        if not hasattr(self, '_hs'):
+            self._hs = {'streams': [torch.cuda.Stream(self.device) for _ in range(3)], 'buf': {}}
+        hs = self._hs
+        csz = (n + chunks - 1) // chunks
+        key = (csz, h_z is not None)
+        if key not in hs['buf']:
+            hs['buf'].clear()
+            hs['buf'][key] = [(self.empty(csz, torch.float64), self.empty(csz, torch.float64),
+                               self.empty(csz, torch.float32) if h_z is not None else None) for _ in range(3)]
+        bufs = hs['buf'][key]
+        main = torch.cuda.current_stream(self.device)
+        # resolve the time samples once (uploads / pair packing happen on the main stream)
+        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        a = AdvectArgs()
+        self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, bufs[0][0][:1], bufs[0][1][:1],
+                          bufs[0][2][:1] if h_z is not None else None, factor, moving, None, None, None, pos_f32)
+        a.n = 0
+        self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))     # n = 0: builds the pair texels only
+        ready = torch.cuda.Event()
+        ready.record(main)
+        done = []
+        for c in range(chunks):
+            lo, hi = c * csz, min(n, (c + 1) * csz)
+            if lo >= hi:
+                break
+            st = hs['streams'][c % 3]
+            d_lon, d_lat, d_z = bufs[c % 3]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                m = hi - lo
+                d_lon[:m].copy_(h_lon[lo:hi], non_blocking=True)
+                d_lat[:m].copy_(h_lat[lo:hi], non_blocking=True)
+                if d_z is not None:
+                    d_z[:m].copy_(h_z[lo:hi], non_blocking=True)
+                self.use_stream(st)
+                a.n = m
+                a.d_lon, a.d_lat = d_lon.data_ptr(), d_lat.data_ptr()
+                a.d_z = d_z.data_ptr() if d_z is not None else None
+                self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
+                h_out_lon[lo:hi].copy_(d_lon[:m], non_blocking=True)
+                h_out_lat[lo:hi].copy_(d_lat[:m], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        self.use_stream(main)
+        for ev in done:
+            main.wait_event(ev)
+        main.synchronize()
+
     def sort_by_cell(self, group, lon, lat, z=None):
         perm = self.empty(lon.numel(), self.torch.int32)
         self._check(self.lib.od_sort_by_cell(self.ctx, group.gid, lon.numel(), _ptr(lon), _ptr(lat), _ptr(z),
