@@ -54,7 +54,7 @@ enum od_time_mode {
 
 enum od_lon_mode { OD_LON_0_360 = 0, OD_LON_PM180 = 1 };
 
-enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2 };
+enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2, OD_INTERP_Z_F64 = 4 };
 
 #define OD_MAX_LEVELS 128
 #define OD_ABI_VERSION 1
@@ -116,7 +116,7 @@ typedef struct od_time_sample {
  * elements/elements.py:156-158) and NumPy then does the index arithmetic of interpolators.py:110-111 in
  * float32; the kernel reproduces that. */
 int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n,
-              const double* d_lon, const double* d_lat, const float* d_z, int flags,
+              const double* d_lon, const double* d_lat, const void* d_z, int flags,
               float* d_out0, float* d_out1);
 
 /* ---- geodesic --------------------------------------------------------------------------- */
@@ -141,7 +141,7 @@ typedef struct od_advect_args {
     int64_t n;
     double* d_lon;                /* in/out float64 */
     double* d_lat;
-    const float* d_z;             /* float32 or NULL (2-D group) */
+    const void* d_z;              /* float32 (or float64 when z_f64) or NULL (2-D group) */
     const void* d_factor;         /* factor * current_drift_factor per particle; NULL = 1 */
     int32_t factor_f64;           /* dtype of d_factor: 0 float32, 1 float64 (reference promotes scalars
                                      to float64 arrays, elements/elements.py:213-216) */
@@ -153,6 +153,9 @@ typedef struct od_advect_args {
     /* optional outputs: start-of-step sampled current (float32[n]) */
     float* d_env_u;
     float* d_env_v;
+    int32_t z_f64;                /* dtype of d_z (and d_z_inout): the reference's z is float32 until vertical mixing
+                                     makes it float64 (oceandrift.py:527) */
+    int32_t pad2_;
 } od_advect_args;
 
 int od_advect_current(od_ctx* ctx, const od_advect_args* a);
@@ -169,16 +172,48 @@ typedef struct od_step_args {
     int32_t group_w;
     int32_t w_at_surface;         /* drift:vertical_advection_at_surface */
     od_time_sample t_w;
-    float* d_z_inout;
+    void* d_z_inout;              /* depth to update (dtype per cur.z_f64); may differ from cur.d_z */
     /* horizontal diffusion: d_rand_x NULL disables; standard normal draws (float64[n]) */
     const double* d_rand_x;
     const double* d_rand_y;
     const float* d_diffusivity;   /* per particle float32, or NULL -> diffusivity_const */
     float diffusivity_const;
-    int32_t pad2_;
+    int32_t z_inout_f64;          /* dtype of d_z_inout: 0 float32, 1 float64 */
 } od_step_args;
 
 int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
+
+/* ---- vertical turbulent mixing ----------------------------------------------------------------
+ * OceanDrift.vertical_mixing (models/oceandrift.py:397-571) with diffusivity from the environment profiles of
+ * a 3-D one-component group: all int(dt/dt_mix) inner random-walk iterations in one launch.  Positions are
+ * the START-of-step positions (where the reference samples environment_profiles); z_out is float64 (the
+ * reference's z becomes float64 here) and may not alias z_in. */
+typedef struct od_mix_args {
+    int32_t group_k;              /* ocean_vertical_diffusivity group (1 component, nz > 1) */
+    int32_t ntimes;               /* abs(int(time_step / dt_mix)) */
+    od_time_sample t_k;
+    int64_t n;
+    const double* d_lon;
+    const double* d_lat;
+    const void* d_z_in;           /* float32, or float64 when z_in_f64 */
+    double* d_z_out;
+    const int32_t* d_moving;      /* NULL = all moving */
+    const void* d_terminal_velocity;   /* NULL = 0; float32, or float64 when tv_f64 */
+    const int32_t* d_ids;         /* element IDs keying the device generator; NULL = array index */
+    const double* d_rand;         /* [ntimes][n] draws of np.random.random (parity with the reference), or NULL:
+                                     Philox4x32-10 keyed by (seed, ID, step_index, iteration) */
+    const float* d_sea_floor;     /* per-particle sea_floor_depth_below_sea_level, or NULL -> sea_floor_const */
+    double dt_mix;                /* vertical_mixing:timestep with the sign of the time step */
+    double sea_floor_const;
+    uint64_t seed;
+    int32_t step_index;
+    int32_t z_in_f64, tv_f64;
+    int32_t mix_at_surface;       /* drift:vertical_mixing_at_surface */
+    int32_t pos_f32;              /* see od_interp */
+    int32_t pad_;
+} od_mix_args;
+
+int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a);
 
 /* ---- particle order (locality) ---------------------------------------------------------- */
 /* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by

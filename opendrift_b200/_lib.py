@@ -38,7 +38,7 @@ class AdvectArgs(C.Structure):
                 ('d_factor', C.c_void_p), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32),
                 ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
                 ('truncate_below', C.c_double),
-                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p)]
+                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('pad2_', C.c_int32)]
 
 
 class StepArgs(C.Structure):
@@ -48,7 +48,17 @@ class StepArgs(C.Structure):
                 ('group_w', C.c_int32), ('w_at_surface', C.c_int32), ('t_w', TimeSample),
                 ('d_z_inout', C.c_void_p),
                 ('d_rand_x', C.c_void_p), ('d_rand_y', C.c_void_p), ('d_diffusivity', C.c_void_p),
-                ('diffusivity_const', C.c_float), ('pad2_', C.c_int32)]
+                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32)]
+
+
+class MixArgs(C.Structure):
+    _fields_ = [('group_k', C.c_int32), ('ntimes', C.c_int32), ('t_k', TimeSample), ('n', C.c_int64),
+                ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z_in', C.c_void_p), ('d_z_out', C.c_void_p),
+                ('d_moving', C.c_void_p), ('d_terminal_velocity', C.c_void_p), ('d_ids', C.c_void_p),
+                ('d_rand', C.c_void_p), ('d_sea_floor', C.c_void_p), ('dt_mix', C.c_double),
+                ('sea_floor_const', C.c_double), ('seed', C.c_uint64), ('step_index', C.c_int32),
+                ('z_in_f64', C.c_int32), ('tv_f64', C.c_int32), ('mix_at_surface', C.c_int32),
+                ('pos_f32', C.c_int32), ('pad_', C.c_int32)]
 
 
 # every symbol include/odcuda.h declares: (restype, argtypes)
@@ -71,6 +81,7 @@ SYMBOLS = {
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
     'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
+    'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),
     'od_unpermute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),

@@ -94,11 +94,11 @@ struct StepParams {
     double dt;
     float dt32;
     int32_t has_k1;
-    int32_t pos_f32, pad0_;
+    int32_t pos_f32, z_f64;
     int64_t n;
     double* lon;
     double* lat;
-    const float* z;
+    const void* z;                // float32 or float64 (z_f64)
     const void* factor;
     const int32_t* moving;
     const float* k1u;
@@ -107,14 +107,14 @@ struct StepParams {
     float* env_v;
     double truncate_below;
     // extras (od_step_oceandrift)
-    int32_t wind_on, wdf_f64, w_on, w_at_surface, diff_on, pad_;
+    int32_t wind_on, wdf_f64, w_on, w_at_surface, diff_on, zio_f64;   // zio_f64: dtype of z_inout
     GroupGeom gwind;
     PairRef pwind;
     const void* wdf;
     double wind_drift_depth;
     GroupGeom gw;
     PairRef pw;
-    float* z_inout;
+    void* z_inout;                // dtype as z; may be a different buffer than z (after vertical mixing)
     const double* rand_x;
     const double* rand_y;
     const float* diffusivity;
@@ -129,10 +129,11 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
                          const double* zsw, const double* zyw) {
     const GroupGeom& g = p.cs.g;
     const double lon0 = p.lon[i], lat0 = p.lat[i];
-    const float z0 = p.z ? p.z[i] : 0.0f;
-    float zt = z0;
-    if (p.truncate_below > 0.0 && (double)zt < -p.truncate_below) zt = (float)(-p.truncate_below);
-    const VertW vw = vert_weights(g, zs, zy, zt);
+    const bool zf32 = p.z_f64 == 0;
+    const double z0 = p.z ? (zf32 ? (double)((const float*)p.z)[i] : ((const double*)p.z)[i]) : 0.0;
+    double zt = z0;                // drift:truncate_ocean_model_below_m (environment.py:554-562)
+    if (p.truncate_below > 0.0 && zt < -p.truncate_below) zt = zf32 ? (double)(float)(-p.truncate_below) : -p.truncate_below;
+    const VertW vw = vert_weights(g, zs, zy, zt, zf32);
     const double mv = p.moving ? (double)p.moving[i] : 1.0;
     const GeodStart gs = geod_start(lat0);
 
@@ -166,13 +167,13 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
             float xw, yw;
             sample2(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
             const double wdd = fabs(p.wind_drift_depth);
-            const bool surface = (double)z0 >= -wdd;
+            const bool surface = z0 >= -wdd;
             if (p.wdf_f64 || wdd != 0.0) {
                 double wdf = p.wdf_f64 ? ((const double*)p.wdf)[i] : (double)((const float*)p.wdf)[i];
                 if (wdd != 0.0) {
                     const double air = wdf;
-                    wdf = OD_DMUL(wdf, OD_DADD(wdd, (double)z0)) / wdd;
-                    if (z0 > 0.0f) wdf = air;
+                    wdf = OD_DMUL(wdf, OD_DADD(wdd, z0)) / wdd;
+                    if (z0 > 0.0) wdf = air;
                 }
                 if (!surface) wdf = 0.0;
                 const double xv = OD_DMUL((double)xw, wdf), yv = OD_DMUL((double)yw, wdf);
@@ -190,14 +191,18 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
                 }
             }
         }
-        // ---- vertical_advection (oceandrift.py:315-350): z = min(0, z + moving*w*dt)
+        // ---- vertical_advection (oceandrift.py:315-350): z = min(0, z + moving*w*dt); w sampled at the
+        // start-of-step depth, applied to the current depth (which vertical mixing may already have changed)
         if (p.w_on) {
-            const bool applicable = p.w_at_surface ? (z0 <= 0.0f) : (z0 < 0.0f);
+            const bool zio32 = p.zio_f64 == 0;
+            const double zc = zio32 ? (double)((const float*)p.z_inout)[i] : ((const double*)p.z_inout)[i];
+            const bool applicable = p.w_at_surface ? (zc <= 0.0) : (zc < 0.0);
             if (applicable) {
-                const VertW vww = vert_weights(p.gw, zsw, zyw, zt);
+                const VertW vww = vert_weights(p.gw, zsw, zyw, zt, zf32);
                 const float w = sample1(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
-                const double zn = OD_DADD((double)z0, OD_DMUL(OD_DMUL(mv, (double)w), p.dt));
-                p.z_inout[i] = (float)fmin(0.0, zn);
+                const double zn = fmin(0.0, OD_DADD(zc, OD_DMUL(OD_DMUL(mv, (double)w), p.dt)));
+                if (zio32) ((float*)p.z_inout)[i] = (float)zn;
+                else ((double*)p.z_inout)[i] = zn;
             }
         }
         // ---- horizontal_diffusion (basemodel/__init__.py:1746-1772)

@@ -73,20 +73,20 @@ OD_HD double np_mod360(double x) {
     return r;
 }
 
-// Linear1DInterpolator.__init__ for one particle (z is the particle's float32 depth).
+// Linear1DInterpolator.__init__ for one particle.  z is the particle depth; z_f32 tells whether the reference's
+// z array is float32 (element default) or float64 (after vertical mixing has touched it, oceandrift.py:527).
 template <typename ZPtr>
-OD_HD VertW vert_weights(const GroupGeom& g, ZPtr zs, ZPtr zy, float z) {
+OD_HD VertW vert_weights(const GroupGeom& g, ZPtr zs, ZPtr zy, double z, bool z_f32 = true) {
     VertW v;
     if (g.nz <= 1) {
         v.ia = v.ib = 0;
         v.wa = 1.0;
         return v;
     }
-    // z[z < zgrid.min()] = zgrid.min()  (float64 comparison, float32 store)
-    float zc = z;
-    if ((double)zc < g.zmin) zc = (float)g.zmin;
-    if ((double)zc > g.zmax) zc = (float)g.zmax;
-    const double xn = (double)zc;
+    // z[z < zgrid.min()] = zgrid.min()  (float64 comparison; the store rounds to the dtype of z)
+    double xn = z;
+    if (xn < g.zmin) xn = z_f32 ? (double)(float)g.zmin : g.zmin;
+    if (xn > g.zmax) xn = z_f32 ? (double)(float)g.zmax : g.zmax;
     // np.searchsorted(zs, xn) (side='left'), clipped to [1, nz-1]
     int lo = 0, hi = g.nz;
     while (lo < hi) {

@@ -14,6 +14,7 @@
 
 #include "../../include/odcuda.h"
 #include "od_advect.cuh"
+#include "od_mix.cuh"
 
 using namespace od;
 
@@ -44,6 +45,10 @@ struct Group {
     std::vector<uint64_t> version;      // [n_slots]
     double* d_zs = nullptr;             // increasing level depths
     double* d_zy = nullptr;             // their layer indices
+    double* d_zl = nullptr;             // levels as the reader gives them (mixing_z)
+    double* d_mxs = nullptr;            // -levels sorted increasing (interp1d of vertical mixing)
+    double* d_mxy = nullptr;            // their layer indices
+    std::vector<double> h_levels;
     double zmin = 0, zmax = 0;
     PairEntry pairs[OD_PAIR_CACHE];
     size_t cells() const { return (size_t)desc.nx * desc.ny * desc.nz; }
@@ -103,7 +108,11 @@ static void free_group(Group& g) {
     g.version.clear();
     if (g.d_zs) cudaFree(g.d_zs);
     if (g.d_zy) cudaFree(g.d_zy);
-    g.d_zs = g.d_zy = nullptr;
+    if (g.d_zl) cudaFree(g.d_zl);
+    if (g.d_mxs) cudaFree(g.d_mxs);
+    if (g.d_mxy) cudaFree(g.d_mxy);
+    g.d_zs = g.d_zy = g.d_zl = g.d_mxs = g.d_mxy = nullptr;
+    g.h_levels.clear();
     for (auto& p : g.pairs) {
         if (p.tex) cudaFree(p.tex);
         p = PairEntry();
@@ -170,6 +179,20 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
         CK(cudaMalloc(&g.d_zy, d->nz * sizeof(double)));
         CK(cudaMemcpyAsync(g.d_zs, zs.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(g.d_zy, zy.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // tables of the vertical-mixing index search: interp1d(-levels -> layer index), x sorted increasing
+        g.h_levels.assign(h_z, h_z + d->nz);
+        std::vector<double> mxs(d->nz), mxy(d->nz);
+        for (int i = 0; i < d->nz; ++i) {
+            int src = inc ? d->nz - 1 - i : i;          // -levels increasing <=> levels decreasing
+            mxs[i] = -h_z[src];
+            mxy[i] = (double)src;
+        }
+        CK(cudaMalloc(&g.d_zl, d->nz * sizeof(double)));
+        CK(cudaMalloc(&g.d_mxs, d->nz * sizeof(double)));
+        CK(cudaMalloc(&g.d_mxy, d->nz * sizeof(double)));
+        CK(cudaMemcpyAsync(g.d_zl, h_z, d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(g.d_mxs, mxs.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(g.d_mxy, mxy.data(), d->nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     g.defined = true;
@@ -333,10 +356,10 @@ struct InterpParams {
     int64_t n;
     const double* lon;
     const double* lat;
-    const float* z;
+    const void* z;
     float* out0;
     float* out1;
-    int pos_f32;
+    int pos_f32, z_f64;
 };
 
 __global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) {
@@ -345,8 +368,8 @@ __global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) 
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const float z = (p.z && p.g.nz > 1) ? p.z[i] : 0.0f;
-    const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, z);
+    const double z = (p.z && p.g.nz > 1) ? (p.z_f64 ? ((const double*)p.z)[i] : (double)((const float*)p.z)[i]) : 0.0;
+    const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, z, p.z_f64 == 0);
     if (p.g.ncomp == 2) {
         float u, v;
         sample2(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
@@ -396,6 +419,21 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const Step
     step_particle<SCHEME, F64, EXTRAS>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
+// ---- vertical mixing -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
+    __shared__ double xs[OD_MAX_LEVELS];
+    __shared__ double xy[OD_MAX_LEVELS];
+    for (int i = threadIdx.x; i < p.g.nz; i += blockDim.x) {
+        xs[i] = p.xs[i];
+        xy[i] = p.xy[i];
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double K[OD_MAX_LEVELS];
+    mix_particle(p, i, xs, xy, K);
+}
+
 // ---- particle ordering ---------------------------------------------------------------------------
 struct SortParams {
     GroupGeom g;
@@ -417,7 +455,7 @@ __global__ void __launch_bounds__(OD_BLOCK) cell_key_kernel(const SortParams p, 
     int key = 0;
     if (h.valid) {
         const int iy = h.i00 / p.g.nx, ix = h.i00 - iy * p.g.nx;
-        const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, (p.z && p.g.nz > 1) ? p.z[i] : 0.0f);
+        const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, (p.z && p.g.nz > 1) ? (double)p.z[i] : 0.0);
         key = 1 + (vw.ia * p.nty + iy / p.tile) * p.ntx + ix / p.tile;
     }
     keys[i] = key;
@@ -486,7 +524,7 @@ static int need_group(od_ctx* ctx, int group, int ncomp) {
 }
 
 extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n, const double* lon, const double* lat,
-                         const float* z, int flags, float* out0, float* out1) {
+                         const void* z, int flags, float* out0, float* out1) {
     int rc = need_group(ctx, group, 0);
     if (rc) return rc;
     if (!ts || n < 0 || (n > 0 && (!lon || !lat))) return fail(ctx, OD_ERR_ARG, "od_interp: bad arguments");
@@ -497,6 +535,7 @@ extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64
     rc = resolve_pair(ctx, group, *ts, &p.pr);
     if (rc) return rc;
     p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = flags & OD_INTERP_POS_F32;
+    p.z_f64 = (flags & OD_INTERP_Z_F64) ? 1 : 0;
     if (flags & OD_INTERP_NO_FALLBACK) p.g.fallback[0] = p.g.fallback[1] = NAN;
     interp_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
@@ -559,6 +598,7 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
     p->env_u = a->d_env_u; p->env_v = a->d_env_v;
     p->truncate_below = a->truncate_below;
     p->pos_f32 = a->pos_f32;
+    p->z_f64 = a->z_f64;
     return OD_OK;
 }
 
@@ -615,6 +655,7 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         rc = resolve_pair(ctx, a->group_w, a->t_w, &p.pw);
         if (rc) return rc;
         p.z_inout = a->d_z_inout;
+        p.zio_f64 = a->z_inout_f64;
     }
     if (a->d_rand_x) {
         if (!a->d_rand_y) return fail(ctx, OD_ERR_ARG, "diffusion needs both random arrays");
@@ -625,6 +666,38 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
     }
     if (a->cur.n == 0) return OD_OK;
     return launch_step<true>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+}
+
+extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: null argument");
+    int rc = need_group(ctx, a->group_k, 1);
+    if (rc) return rc;
+    const Group& g = ctx->groups[a->group_k];
+    if (g.desc.nz < 2) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: the diffusivity group must be 3-D");
+    if (a->n < 0 || a->ntimes < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_z_in || !a->d_z_out)))
+        return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: bad arguments");
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = make_geom(g);
+    rc = resolve_pair(ctx, a->group_k, a->t_k, &p.pr);
+    if (rc) return rc;
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z_in = a->d_z_in; p.z_out = a->d_z_out;
+    p.moving = a->d_moving; p.terminal_velocity = a->d_terminal_velocity; p.ids = a->d_ids; p.rand = a->d_rand;
+    p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.sea_floor = a->d_sea_floor;
+    p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
+    p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.zl = g.d_zl; p.xs = g.d_mxs; p.xy = g.d_mxy;
+    const std::vector<double>& lv = g.h_levels;
+    p.uniform_dz = 1;
+    p.dz0 = lv[1] - lv[0];
+    for (size_t k = 1; k + 1 < lv.size(); ++k)
+        if (lv[k + 1] - lv[k] != p.dz0) p.uniform_dz = 0;
+    mix_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
 }
 
 extern "C" int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* lon, const double* lat, const float* z,

@@ -1,0 +1,168 @@
+// od_mix.cuh -- vertical turbulent mixing of one particle (Visser random walk), all inner iterations fused.
+//
+// Restates OceanDrift.vertical_mixing (opendrift/models/oceandrift.py:397-571) for diffusivity taken from the
+// environment profiles, with the profile block exactly as Environment.get_environment hands it over
+// (opendrift/models/basemodel/environment.py:697-724): per block layer the float32 horizontal interpolation of
+// ReaderBlock (interpolation/structured.py:148-163), time-interpolated in float64 (basereader/structured.py:366-383),
+// then written back through a float32 cast for every layer but the last.  The reference materialises (nz, N)
+// profile arrays (1 GB per variable at 5 M particles x 50 layers) and loops dt/dt_mix times over N-sized NumPy
+// expressions; here each thread keeps its K column in local memory and runs the whole inner loop.
+//   gradK = -np.gradient(K, z)  thresholded at 1e-10            (:500-502)
+//   zi = round(interp1d(-z_levels -> index)(-z))  as uint16     (:513)
+//   z -= moving * (dKdz*dt_mix - R*sqrt(K*|dt_mix|*2/r)), R = 2*U(0,1)-1, r = 1/3   (:524-528)
+//   reflect at the surface (:531-533) and at the sea floor (:537-540), buoyancy w*dt_mix (:543),
+//   surface pinning (:548-549), surface_stick (:370-374).
+// Random numbers: either the caller's array (NumPy's legacy generator, for bit parity with the reference) or
+// Philox4x32-10 keyed by (seed, element ID, step, iteration) -- independent of the order of the particle arrays.
+#pragma once
+#include "od_interp.cuh"
+
+namespace od {
+
+// Philox4x32-10 (Salmon et al., SC'11), counter-based; philox_uniform2 returns two uniform doubles in [0, 1)
+OD_HD void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1;
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+OD_HD void philox_uniform2(unsigned long long seed, unsigned id, unsigned step, unsigned iter, double& u0, double& u1) {
+        unsigned c0 = id, c1 = step, c2 = iter, c3 = 0x6f647274u;
+        unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c0, c1, c2, c3, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        // 53-bit doubles like NumPy's random(): (a >> 5, b >> 6)
+        u0 = ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+        u1 = ((double)(c2 >> 5) * 67108864.0 + (double)(c3 >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+struct MixParams {
+    GroupGeom g;                 // 1-component 3-D group: ocean_vertical_diffusivity
+    PairRef pr;
+    int64_t n;
+    const double* lon;           // positions at the START of the step (where the environment profiles are sampled)
+    const double* lat;
+    const void* z_in;            // float32 or float64 (z_in_f64)
+    double* z_out;               // always float64: the reference's z becomes float64 here (:527)
+    const int32_t* moving;       // NULL = all moving
+    const void* terminal_velocity;   // NULL = 0; float32 or float64 (tv_f64)
+    const int32_t* ids;          // element IDs (Philox key); NULL = array index
+    const double* rand;          // [ntimes][n] uniform draws of the legacy generator, or NULL -> Philox
+    double dt_mix;               // signed like the time step
+    double zmin_const;           // -(sea_floor_depth + sea_surface_height) when no per-particle array is given
+    const float* sea_floor;      // optional per-particle sea_floor_depth_below_sea_level (float32)
+    unsigned long long seed;
+    int32_t ntimes, z_in_f64, tv_f64, mix_at_surface, pos_f32, step_index;
+    const double* zl;            // [nz] block level depths as the reader gives them (mixing_z)
+    const double* xs;            // [nz] -mixing_z sorted increasing
+    const double* xy;            // [nz] index of each xs entry
+    int32_t uniform_dz, pad_;
+    double dz0;                  // np.diff(mixing_z)[0] when the spacing is uniform
+};
+
+// -np.gradient(K, mixing_z)[l] with numpy's edge_order=1 formulas, |g| < 1e-10 -> 0
+OD_HD double neg_gradient(const MixParams& p, const double* K, int l) {
+    const int nz = p.g.nz;
+    double gr;
+    if (l == 0) {
+        gr = OD_DSUB(K[1], K[0]) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[1], p.zl[0]));
+    } else if (l == nz - 1) {
+        gr = OD_DSUB(K[nz - 1], K[nz - 2]) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[nz - 1], p.zl[nz - 2]));
+    } else if (p.uniform_dz) {
+        gr = OD_DSUB(K[l + 1], K[l - 1]) / OD_DMUL(2.0, p.dz0);
+    } else {
+        const double dx1 = OD_DSUB(p.zl[l], p.zl[l - 1]), dx2 = OD_DSUB(p.zl[l + 1], p.zl[l]);
+        const double a = -(dx2) / OD_DMUL(dx1, OD_DADD(dx1, dx2));
+        const double b = OD_DSUB(dx2, dx1) / OD_DMUL(dx1, dx2);
+        const double c = dx1 / OD_DMUL(dx2, OD_DADD(dx1, dx2));
+        gr = OD_DADD(OD_DADD(OD_DMUL(a, K[l - 1]), OD_DMUL(b, K[l])), OD_DMUL(c, K[l + 1]));
+    }
+    gr = -gr;
+    return fabs(gr) < 1e-10 ? 0.0 : gr;
+}
+
+// index of the nearest profile level: np.round(interp1d(-mixing_z, range(nz), fill_value=(0, nz-1))(-z))
+OD_HD int nearest_level(const MixParams& p, const double* xs, const double* xy, double x_new) {
+    const int nz = p.g.nz;
+    double y;
+    if (x_new < xs[0]) y = 0.0;
+    else if (x_new > xs[nz - 1]) y = (double)(nz - 1);
+    else {
+        int lo = 0, hi = nz;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xs[mid] < x_new) lo = mid + 1; else hi = mid;
+        }
+        const int idx = lo < 1 ? 1 : (lo > nz - 1 ? nz - 1 : lo);
+        const double slope = OD_DSUB(xy[idx], xy[idx - 1]) / OD_DSUB(xs[idx], xs[idx - 1]);
+        y = OD_DADD(OD_DMUL(slope, OD_DSUB(x_new, xs[idx - 1])), xy[idx - 1]);
+    }
+    int zi = (int)rint(y);
+    return zi < 0 ? 0 : (zi > nz - 1 ? nz - 1 : zi);
+}
+
+OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const double* xy, double* K) {
+    const GroupGeom& g = p.g;
+    const int nz = g.nz;
+    // ---- the particle's diffusivity column (environment profile) --------------------------------------------
+    const HorizW h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
+    const long long layer = (long long)g.nx * g.ny;
+    for (int l = 0; l < nz; ++l) {
+        double v = NAN;
+        if (h.valid && p.pr.mode != 3) {
+            const float* t = p.pr.tex + ((long long)l * layer) * 2;
+            const Tex2 a00 = ld_tex2(t + 2ll * h.i00), a01 = ld_tex2(t + 2ll * h.i01);
+            const Tex2 a10 = ld_tex2(t + 2ll * h.i10), a11 = ld_tex2(t + 2ll * h.i11);
+            const double hA = (double)bilin(h, a00.x, a01.x, a10.x, a11.x);
+            if (p.pr.mode == 1) v = hA;
+            else {
+                const double hB = (double)bilin(h, a00.y, a01.y, a10.y, a11.y);
+                v = p.pr.mode == 2 ? hB : OD_DADD(OD_DMUL(hA, OD_DSUB(1.0, p.pr.w)), OD_DMUL(hB, p.pr.w));
+            }
+        }
+        if (l < nz - 1) v = (double)(float)v;           // environment.py:706-713 (float32 write-back, all but the last layer)
+        K[l] = v;
+    }
+    if (nz > 1 && K[nz - 1] != K[nz - 1]) K[nz - 1] = K[nz - 2];        // environment.py:715-724
+    for (int l = 0; l < nz; ++l)
+        if (!(fabs(K[l]) <= 1.7976931348623157e308)) K[l] = (double)g.fallback[0];   // masked -> fallback (:803-806)
+
+    // ---- inner loop ---------------------------------------------------------------------------------------------
+    double z = p.z_in_f64 ? ((const double*)p.z_in)[i] : (double)((const float*)p.z_in)[i];
+    const double mv = p.moving ? (double)p.moving[i] : 1.0;
+    const double w = p.terminal_velocity ? (p.tv_f64 ? ((const double*)p.terminal_velocity)[i]
+                                                      : (double)((const float*)p.terminal_velocity)[i]) : 0.0;
+    const double zmin = p.sea_floor ? -(double)p.sea_floor[i] : p.zmin_const;
+    const double adt = fabs(p.dt_mix);
+    const double r = 1.0 / 3;
+    const unsigned id = p.ids ? (unsigned)p.ids[i] : (unsigned)i;
+    double spare = 0.0;
+    for (int it = 0; it < p.ntimes; ++it) {
+        const bool surface = z == 0.0;
+        const int zi = nearest_level(p, xs, xy, -z);
+        const double Kz = K[zi];
+        const double dKdz = neg_gradient(p, K, zi);
+        double U;
+        if (p.rand) {
+            U = p.rand[(int64_t)it * p.n + i];
+        } else if ((it & 1) == 0) {
+            philox_uniform2(p.seed, id, (unsigned)p.step_index, (unsigned)(it >> 1), U, spare);
+        } else {
+            U = spare;
+        }
+        const double R = OD_DSUB(OD_DMUL(2.0, U), 1.0);
+        const double walk = OD_DMUL(R, sqrt(OD_DMUL(OD_DMUL(Kz, adt), 2.0) / r));
+        z = OD_DSUB(z, OD_DMUL(mv, OD_DSUB(OD_DMUL(dKdz, p.dt_mix), walk)));
+        if (z >= 0.0) z = -z;                                         // reflect from the surface
+        if (z < zmin && mv == 1.0) z = OD_DSUB(OD_DMUL(2.0, zmin), z);    // reflect from the sea floor
+        z = OD_DADD(z, OD_DMUL(OD_DMUL(w, p.dt_mix), mv));           // buoyancy
+        if (!p.mix_at_surface && surface) z = 0.0;
+        if (z > 0.0) z = 0.0;                                          // surface_stick
+    }
+    p.z_out[i] = z;
+}
+
+}  // namespace od

@@ -17,7 +17,7 @@ from bisect import bisect_left
 import numpy as np
 
 from . import _lib
-from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, OD_T_LERP, OD_T_FIRST,
+from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, MixArgs, OD_T_LERP, OD_T_FIRST,
                    OD_T_MISSING, SCHEMES)
 
 
@@ -251,7 +251,8 @@ class Engine:
         ts, _ = group.sample(t)
         outs = [self.empty(n, self.torch.float32) for _ in range(group.ncomp)]
         self._check(self.lib.od_interp(self.ctx, group.gid, C.byref(ts), n, _ptr(lon), _ptr(lat), _ptr(z),
-                                       (1 if pos_f32 else 0) | (2 if raw else 0), _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
+                                       (1 if pos_f32 else 0) | (2 if raw else 0) | (4 if (z is not None and z.dtype == self.torch.float64) else 0),
+                                       _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
         return outs
 
     def geod_fwd(self, lon, lat, az, dist):
@@ -281,6 +282,7 @@ class Engine:
         a.n = lon.numel()
         a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
         a.d_z = z.data_ptr() if z is not None else None
+        a.z_f64 = 1 if (z is not None and z.dtype == self.torch.float64) else 0
         if factor is not None:
             a.d_factor = factor.data_ptr()
             a.factor_f64 = 1 if factor.dtype == self.torch.float64 else 0
@@ -305,7 +307,9 @@ class Engine:
 
     def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
                         truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
-                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False):
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None):
+        """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
+        array that vertical advection updates -- a different buffer after vertical mixing."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         s = StepArgs()
         self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
@@ -322,7 +326,9 @@ class Engine:
             s.group_w = w_group.gid
             s.t_w, _ = w_group.sample(t)
             s.w_at_surface = 1 if w_at_surface else 0
-            s.d_z_inout = z.data_ptr()
+            zu = z if z_update is None else z_update
+            s.d_z_inout = zu.data_ptr()
+            s.z_inout_f64 = 1 if zu.dtype == self.torch.float64 else 0
         if rand is not None:
             s.d_rand_x, s.d_rand_y = rand[0].data_ptr(), rand[1].data_ptr()
             if hasattr(diffusivity, 'data_ptr'):
@@ -390,7 +396,37 @@ class Engine:
             main.wait_event(ev)
         main.synchronize()
 
+    def vertical_mixing(self, group, t, lon, lat, z_in, dt_mix, ntimes, moving=None, terminal_velocity=None, ids=None,
+                        rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False):
+        """OceanDrift.vertical_mixing on device tensors; returns the new depth (float64 tensor)."""
+        torch = self.torch
+        n = lon.numel()
+        z_out = self.empty(n, torch.float64)
+        a = MixArgs()
+        a.group_k, a.ntimes = group.gid, int(ntimes)
+        a.t_k, _ = group.sample(t)
+        a.n = n
+        a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
+        a.d_z_in, a.z_in_f64 = z_in.data_ptr(), 1 if z_in.dtype == torch.float64 else 0
+        a.d_z_out = z_out.data_ptr()
+        a.d_moving = moving.data_ptr() if moving is not None else None
+        if terminal_velocity is not None:
+            a.d_terminal_velocity = terminal_velocity.data_ptr()
+            a.tv_f64 = 1 if terminal_velocity.dtype == torch.float64 else 0
+        a.d_ids = ids.data_ptr() if ids is not None else None
+        a.d_rand = rand.data_ptr() if rand is not None else None
+        if hasattr(sea_floor, 'data_ptr'):
+            a.d_sea_floor = sea_floor.data_ptr()
+        else:
+            a.sea_floor_const = float(sea_floor)
+        a.dt_mix, a.seed, a.step_index = float(dt_mix), int(seed), int(step_index)
+        a.mix_at_surface, a.pos_f32 = (1 if mix_at_surface else 0), (1 if pos_f32 else 0)
+        self._check(self.lib.od_vertical_mixing(self.ctx, C.byref(a)))
+        return z_out
+
     def sort_by_cell(self, group, lon, lat, z=None):
+        if z is not None and z.dtype != self.torch.float32:
+            z = z.to(self.torch.float32)          # ordering only
         perm = self.empty(lon.numel(), self.torch.int32)
         self._check(self.lib.od_sort_by_cell(self.ctx, group.gid, lon.numel(), _ptr(lon), _ptr(lat), _ptr(z),
                                              _ptr(perm)))

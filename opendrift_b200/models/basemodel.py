@@ -68,6 +68,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self.status_categories = ['active']
         if seed is not None:
             np.random.seed(seed)                      # basemodel/__init__.py:326: the legacy global generator
+        self._seed = 0 if seed is None else int(seed)
         self._engine = engine
         self.origin_marker = None
         self.steps_calculation = 0
@@ -334,9 +335,10 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         return self._env_view
 
     def _z_for_sampling(self):
+        """Depth tensor in the dtype the reference's array has: float32, or float64 after vertical mixing."""
         z = self.elements.dev('z')
-        if z.dtype != self.engine.torch.float32:
-            z = z.to(self.engine.torch.float32)
+        if z.dtype not in (self.engine.torch.float32, self.engine.torch.float64):
+            z = z.to(self.engine.torch.float64)
         return z
 
     # -- positions (:4630-4669) ---------------------------------------------------------------------------------

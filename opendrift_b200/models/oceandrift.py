@@ -6,7 +6,7 @@ element type, required variables, configuration keys and update() recipe for the
 
 When update() is not overridden by a subclass the whole recipe runs as ONE kernel launch per time step
 (od_step_oceandrift); a subclass that overrides update() gets the same helpers as separate launches.
-Vertical turbulent mixing (:397-571) is the next row of SURVEY.md 8(f) and not on this path yet.
+Vertical turbulent mixing (:397-571) runs as one extra launch per step (od_vertical_mixing, all inner iterations fused).
 """
 import numpy as np
 
@@ -52,7 +52,21 @@ class OceanDrift(OpenDriftSimulation):
             'drift:vertical_advection_at_surface': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
                                                     'description': 'Also advect elements at the surface vertically.'},
             'drift:vertical_mixing': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_BASIC,
-                                      'description': 'Vertical turbulent mixing (not on the GPU path yet).'},
+                                      'description': 'Activate vertical mixing scheme with inner loop'},
+            'drift:vertical_mixing_at_surface': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                                 'description': 'Surface elements (z=0) are only mixed if True.'},
+            'vertical_mixing:timestep': {'type': 'float', 'min': 0.1, 'max': 3600, 'default': 60, 'units': 'seconds',
+                                         'level': CONFIG_LEVEL_ADVANCED,
+                                         'description': 'Time step used for inner loop of vertical mixing.'},
+            'vertical_mixing:diffusivitymodel': {'type': 'enum', 'default': 'environment',
+                                                 'enum': ['environment', 'stepfunction', 'windspeed_Sundby1983',
+                                                          'windspeed_Large1994', 'constant'],
+                                                 'level': CONFIG_LEVEL_ADVANCED,
+                                                 'description': 'Source of the diffusivity profile; only "environment" '
+                                                                '(from a reader) runs on the GPU path.'},
+            'gpu:rng': {'type': 'enum', 'enum': ['numpy', 'philox'], 'default': 'numpy', 'level': CONFIG_LEVEL_ADVANCED,
+                        'description': 'numpy: draws of the legacy global generator made on the host in the reference\'s '
+                                       'order (bit parity); philox: counter-based generator on the device keyed by element ID.'},
             'drift:stokes_drift': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
                                    'description': 'Advection with Stokes drift.'},
             'drift:wind_drift_depth': {'type': 'float', 'default': 0.1, 'min': 0, 'max': 10, 'units': 'meters',
@@ -70,7 +84,7 @@ class OceanDrift(OpenDriftSimulation):
         self.advect_wind()
         self.stokes_drift()
         if self.get_config('drift:vertical_mixing'):
-            raise NotImplementedError('vertical mixing is not on the GPU path yet (SURVEY.md 8(f)1)')
+            self.vertical_mixing()
         self.vertical_advection()
 
     def vertical_advection(self):
@@ -88,10 +102,52 @@ class OceanDrift(OpenDriftSimulation):
         zn = torch.clamp(z.to(torch.float64) + mv * w.to(torch.float64) * self.time_step.total_seconds(), max=0.0)
         el.set_dev('z', torch.where(ok, zn.to(z.dtype), z))
 
+    # -- vertical mixing (oceandrift.py:397-571) --------------------------------------------------------------------
+    def _mixing_inputs(self):
+        if self.get_config('vertical_mixing:diffusivitymodel') != 'environment':
+            raise NotImplementedError('only vertical_mixing:diffusivitymodel = "environment" runs on the GPU path')
+        r = self.env.reader_for('ocean_vertical_diffusivity', self.time)
+        if r is None or not hasattr(r, 'group_of'):
+            raise NotImplementedError('vertical mixing needs a gridded ocean_vertical_diffusivity reader')
+        g, _ = r.group_of('ocean_vertical_diffusivity')
+        dt_mix = self.get_config('vertical_mixing:timestep') * np.sign(self.time_step.total_seconds())
+        ntimes = int(np.abs(int(self.time_step.total_seconds() / dt_mix)))
+        floor = self._constant_or_none('sea_floor_depth_below_sea_level')
+        if floor is None:
+            floor = self.environment.dev('sea_floor_depth_below_sea_level', self.engine)
+        return g, dt_mix, ntimes, floor
+
+    def _mix(self, lon0, lat0, z_in, pos_f32):
+        """Run the mixing kernel from start-of-step positions; returns the new float64 depth tensor."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        g, dt_mix, ntimes, floor = self._mixing_inputs()
+        n = len(el)
+        rand = None
+        if self.get_config('gpu:rng') == 'numpy':          # the reference's draws, in its order (:524)
+            rand = eng.to_device(np.ascontiguousarray(np.stack([np.random.random(n) for _ in range(ntimes)])))
+        moving = el.dev('moving')
+        if moving.dtype != torch.int32:
+            moving = moving.to(torch.int32)
+        tv = el.dev('terminal_velocity') if 'terminal_velocity' in el.variables else None
+        ids = el.dev('ID')
+        if ids.dtype != torch.int32:
+            ids = ids.to(torch.int32)
+        return eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, moving=moving, terminal_velocity=tv,
+                                   ids=ids, rand=rand, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation,
+                                   sea_floor=floor, mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'),
+                                   pos_f32=pos_f32)
+
+    def vertical_mixing(self, store_depths=False):
+        """Helper for subclasses that override update(): uses the start-of-step positions saved by the run loop."""
+        if self.get_config('drift:vertical_mixing') is False:
+            return
+        lon0, lat0, f32 = self._start_positions
+        self.elements.set_dev('z', self._mix(lon0, lat0, self._z_for_sampling(), f32))
+
     # -- fused path -----------------------------------------------------------------------------------------------
     def _fused_ok(self):
         return (type(self).update is OceanDrift.update and type(self).advect_ocean_current is OceanDrift.advect_ocean_current
-                and not self.get_config('drift:vertical_mixing') and not self.get_config('drift:relative_wind'))
+                and type(self).vertical_mixing is OceanDrift.vertical_mixing and not self.get_config('drift:relative_wind'))
 
     def run(self, *args, **kwargs):
         self._use_fused = None
@@ -126,13 +182,20 @@ class OceanDrift(OpenDriftSimulation):
         fac = el.dev('current_drift_factor')
         z = self._z_for_sampling()
         el.set_dev('z', z)
+        z_new = None
+        if self.get_config('drift:vertical_mixing'):
+            # mixing first: it reads the start-of-step positions and depth and writes a new depth buffer; the
+            # step kernel still samples with the old depth and applies vertical advection to the new one
+            z_new = self._mix(el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, el.positions_f32)
         eng.step_oceandrift(g, self.get_config('drift:advection_scheme'), t, self.time_step,
                             el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, factor=fac, moving=moving,
                             truncate_below=self.get_config('drift:truncate_ocean_model_below_m'),
                             wind=wind, wdf=el.dev('wind_drift_factor'),
                             wind_drift_depth=self.get_config('drift:wind_drift_depth'), w_group=wgrp,
                             w_at_surface=self.get_config('drift:vertical_advection_at_surface'), rand=rand,
-                            diffusivity=float(D), pos_f32=el.positions_f32)
+                            diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new)
+        if z_new is not None:
+            el.set_dev('z', z_new)
         el.positions_f32 = False
         return True
 
@@ -141,5 +204,9 @@ class OceanDrift(OpenDriftSimulation):
         if self._fused_ok() and self._step_fused():
             return
         _ = self.environment          # start-of-step environment, before anything moves
+        if self.get_config('drift:vertical_mixing'):
+            t64 = self.engine.torch.float64
+            self._start_positions = (self.elements.dev('lon', t64).clone(), self.elements.dev('lat', t64).clone(),
+                                     self.elements.positions_f32)
         self.update()
         OpenDriftSimulation.horizontal_diffusion(self)

@@ -53,6 +53,15 @@ def upward_w(grid):
     return w.astype(np.float32)
 
 
+def vertical_diffusivity(grid, t_seconds=0.0):
+    """K(z) slab (nz, ny, nx) float32: 0.01 exp(z / 20) with a horizontal and a slow temporal modulation (cfg 4)."""
+    X = 2.0 * (grid.lon.astype(np.float64) - float(grid.lon[0])) / grid.Lx
+    Y = (grid.lat.astype(np.float64) - float(grid.lat[0])) / grid.Ly
+    mod = 1.0 + 0.5 * np.sin(np.pi * X / 2)[None, :] * np.sin(np.pi * Y)[:, None]
+    amp = 0.01 * (1.0 + 0.2 * np.sin(2 * np.pi * t_seconds / 43200.0))
+    return (amp * np.exp(grid.z / 20.0)[:, None, None] * mod[None]).astype(np.float32)
+
+
 def wind_xy(grid, t_seconds, speed=10.0):
     """2-D wind slabs (ny, nx) float32: a slowly rotating, spatially modulated 10 m/s wind."""
     X = 2.0 * (grid.lon.astype(np.float64) - float(grid.lon[0])) / grid.Lx

@@ -22,7 +22,7 @@ from . import geod_karney
 
 FALLBACK = {'x_sea_water_velocity': 0.0, 'y_sea_water_velocity': 0.0,
             'upward_sea_water_velocity': 0.0, 'x_wind': 0.0, 'y_wind': 0.0,
-            'horizontal_diffusivity': 0.0,
+            'horizontal_diffusivity': 0.0, 'ocean_vertical_diffusivity': 0.0,
             'sea_surface_wave_stokes_drift_x_velocity': 0.0,
             'sea_surface_wave_stokes_drift_y_velocity': 0.0}
 
@@ -59,7 +59,7 @@ def _linear2d(block2d, xi, yi):
     return map_coordinates(block2d, [yi, xi], cval=np.nan, order=1)
 
 
-def block_interpolate(reader, it, variables, x, y, z):
+def block_interpolate(reader, it, variables, x, y, z, profiles=None):
     """ReaderBlock.interpolate (opendrift/readers/interpolation/structured.py:107-146) for the
     default 'linearNDFast' horizontal + 'linear' vertical interpolators."""
     xg, yg = reader.x, reader.y
@@ -67,6 +67,7 @@ def block_interpolate(reader, it, variables, x, y, z):
     xi = (x - xg[0]) / (xg[-1] - xg[0]) * (len(xg) - 1)
     yi = (y - yg[0]) / (yg[-1] - yg[0]) * (len(yg) - 1)
     out = {}
+    prof = {}
     lin1d = None
     for var in variables:
         data = reader.fields[var][it]
@@ -94,12 +95,16 @@ def block_interpolate(reader, it, variables, x, y, z):
         horiz = np.empty((nl, len(x)))
         for layer in range(nl):
             horiz[layer, :] = _linear2d(data[layer], xi, yi)
+        if profiles is not None and var in profiles:
+            prof[var] = horiz                                   # structured.py:137-138: not interpolated in z
         ia, ib, wa, rng = lin1d
         out[var] = horiz[ia, rng] * wa + horiz[ib, rng] * (1 - wa)   # interpolators.py:195-197
+    if profiles is not None:
+        return out, prof
     return out
 
 
-def reader_interpolate(reader, variables, time, lon, lat, z):
+def reader_interpolate(reader, variables, time, lon, lat, z, profiles=None):
     """Variables.get_variables_interpolated -> get_variables_interpolated_xy ->
     StructuredReader._get_variables_interpolated_ for a '+proj=latlong' reader
     (opendrift/readers/basereader/variables.py:860-920, 709-858; structured.py:202-400)."""
@@ -114,13 +119,29 @@ def reader_interpolate(reader, variables, time, lon, lat, z):
     t_before, t_after, ib, ia = reader.nearest_time(time)
     if time == t_before:
         t_after = None
-    env_before = block_interpolate(reader, ib, variables, xc, yc, zc)
+    if profiles is not None:
+        assert len(covered) == n, 'profiles are restated for fully covered particle sets only'
+        env_before, prof_before = block_interpolate(reader, ib, variables, xc, yc, zc, profiles)
+    else:
+        env_before = block_interpolate(reader, ib, variables, xc, yc, zc)
+    env_profiles = None
     if t_after is not None:
-        env_after = block_interpolate(reader, ia, variables, xc, yc, zc)
+        if profiles is not None:
+            env_after, prof_after = block_interpolate(reader, ia, variables, xc, yc, zc, profiles)
+        else:
+            env_after = block_interpolate(reader, ia, variables, xc, yc, zc)
         w = (time - t_before).total_seconds() / (t_after - t_before).total_seconds()  # structured.py:353-364
         env = {v: env_before[v] * (1 - w) + env_after[v] * w for v in variables}
+        if profiles is not None:                                                      # structured.py:366-383
+            env_profiles = {'z': reader.z}
+            for v in prof_before:
+                env_profiles[v] = prof_before[v] * (1 - w) + prof_after[v] * w
     else:
         env = env_before
+        if profiles is not None:
+            env_profiles = dict(prof_before, z=reader.z)
+    if profiles is not None:
+        return env, env_profiles
     if len(covered) != n:                                                        # variables.py:841-853
         for v in variables:
             tmp = np.nan * np.ones(n)
@@ -129,7 +150,7 @@ def reader_interpolate(reader, variables, time, lon, lat, z):
     return env
 
 
-def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, truncate_below=None):
+def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, truncate_below=None, profiles=None):
     """Environment.get_environment for one reader per variable group
     (opendrift/models/basemodel/environment.py:499-923): float32 cast at :695-696,
     fallback fill at :782-791."""
@@ -142,7 +163,25 @@ def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, tr
         group = [v for v in remaining if v in reader.variables]
         if not group:
             continue
-        tmp = reader_interpolate(reader, group, time, lon, lat, z)
+        env_profiles = None
+        if profiles is not None and set(group) & set(profiles):
+            tmp, env_profiles = reader_interpolate(reader, group, time, lon, lat, z, [p for p in profiles if p in group])
+            # environment.py:697-724: with a single reader the profile block is written back onto itself through
+            # a float32 cast for all layers but the last (z_ind = arange(len(z) - 1)); NaNs of the last layer are
+            # filled from the layer above.
+            prof = {}
+            for k, a in env_profiles.items():
+                a = np.array(a, dtype=np.float64)
+                if k != 'z':
+                    nl = a.shape[0]
+                    a[0:nl - 1] = a[0:nl - 1].astype(np.float32)
+                    if nl > 1:
+                        mb = np.isnan(a[-1])
+                        a[-1, mb] = a[-2, mb]
+                prof[k] = a
+            env['__profiles__'] = prof
+        else:
+            tmp = reader_interpolate(reader, group, time, lon, lat, z)
         for v in group:
             env[v] = np.asarray(tmp[v]).astype(np.float32)
             remaining.remove(v)
@@ -153,6 +192,8 @@ def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, tr
         if fb is not None:
             bad = ~np.isfinite(env[v])
             env[v][bad] = fb
+    if profiles is not None:
+        return env, env.pop('__profiles__', None)
     return env
 
 
@@ -235,6 +276,44 @@ def vertical_advection(z, w, moving, dt, at_surface=False):
     return z
 
 
+def vertical_mixing(z, moving, Kprofiles, mixing_z, dt, dt_mix=60.0, sea_floor_depth=10000.0, mix_at_surface=False,
+                    rng=np.random):
+    """OceanDrift.vertical_mixing (opendrift/models/oceandrift.py:397-571) with diffusivity from the environment
+    profiles, zero terminal velocity (update_terminal_velocity is a no-op in OceanDrift, :285-291) and the
+    stock surface_stick (:370-374).  Visser random walk, `int(dt/dt_mix)` inner iterations, one
+    np.random.random(N) draw each (:524)."""
+    n = len(z)
+    dt_mix = dt_mix * np.sign(dt)
+    Zmin = -1. * (np.float32(sea_floor_depth) * np.ones(n, dtype=np.float32) + np.zeros(n, dtype=np.float32))   # :420
+    z_i = range(mixing_z.shape[0])
+    z_index = interp1d(-mixing_z, z_i, bounds_error=False, fill_value=(0, len(z_i) - 1))    # :483-487
+    ntimes_mix = np.abs(int(dt / dt_mix))
+    gradK = -np.gradient(Kprofiles, mixing_z, axis=0)                                         # :500-502
+    gradK[np.abs(gradK) < 1e-10] = 0
+    w = np.float32(0) * np.ones(n)                                                            # terminal_velocity
+    for _ in range(ntimes_mix):
+        surface = z == 0
+        zi = np.round(z_index(-z)).astype(np.uint16)
+        Kz = Kprofiles[zi, range(Kprofiles.shape[1])]
+        dKdz = gradK[zi, range(Kprofiles.shape[1])]
+        R = 2 * rng.random(n) - 1
+        r = 1.0 / 3
+        z = z - moving * (dKdz * dt_mix - R * np.sqrt((Kz * np.abs(dt_mix) * 2 / r)))
+        reflect = np.where(z >= 0)
+        if len(reflect[0]) > 0:
+            z[reflect] = -z[reflect]
+        bottom = np.where(np.logical_and(z < Zmin, moving == 1))
+        if len(bottom[0]) > 0:
+            z[bottom] = 2 * Zmin[bottom] - z[bottom]
+        z = z + w * dt_mix * moving
+        if not mix_at_surface:
+            z[surface] = 0.
+        above = np.where(z > 0)                                                               # surface_stick
+        if len(above[0]) > 0:
+            z[above] = 0
+    return z
+
+
 def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
     """OpenDriftSimulation.horizontal_diffusion (opendrift/models/basemodel/__init__.py:1746-1772):
     two normal draws from the legacy global generator, x first."""
@@ -249,7 +328,7 @@ def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
 
 def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
                    vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
-                   diffusivity=0.0, seed=0, truncate_below=None):
+                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0):
     """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
     OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
@@ -275,14 +354,22 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
         variables.append('upward_sea_water_velocity')
     if wind:
         variables += ['x_wind', 'y_wind']
+    if mixing:
+        variables.append('ocean_vertical_diffusivity')
     time = start_time
     for _ in range(steps):
-        env = get_environment(readers, variables, time, lon, lat, z, truncate_below=truncate_below)
+        if mixing:
+            env, prof = get_environment(readers, variables, time, lon, lat, z, truncate_below=truncate_below,
+                                        profiles=['ocean_vertical_diffusivity'])
+        else:
+            env = get_environment(readers, variables, time, lon, lat, z, truncate_below=truncate_below)
         lon0, lat0, z0 = lon, lat, z
         lon, lat = advect_ocean_current(readers, scheme, time, dt, lon, lat, z, cdf, moving, env,
                                         truncate_below=truncate_below)
         if wind:
             lon, lat = advect_wind(lon, lat, z, wdf_arr, env, moving, dt, wind_drift_depth)
+        if mixing:
+            z = vertical_mixing(z, moving, prof['ocean_vertical_diffusivity'], prof['z'], dt, dt_mix)
         if vertical_adv:
             z = vertical_advection(z, env['upward_sea_water_velocity'], moving, dt)
         if diffusivity > 0:

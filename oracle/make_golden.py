@@ -21,7 +21,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'g
 CURRENT = ['x_sea_water_velocity', 'y_sea_water_velocity']
 
 
-def build_fields(g, n_slabs, with_w=False):
+def build_fields(g, n_slabs, with_w=False, mixing=False):
     times = syn.slab_times(n_slabs)
     U, V = [], []
     for t in times:
@@ -31,6 +31,8 @@ def build_fields(g, n_slabs, with_w=False):
     f = {CURRENT[0]: np.stack(U), CURRENT[1]: np.stack(V)}
     if with_w:
         f['upward_sea_water_velocity'] = np.stack([syn.upward_w(g)] * n_slabs)
+    if mixing:
+        f['ocean_vertical_diffusivity'] = np.stack([syn.vertical_diffusivity(g, (t - syn.T0).total_seconds()) for t in times])
     return times, f
 
 
@@ -45,9 +47,9 @@ def build_wind(g, n_slabs):
 
 
 def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
-             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0):
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0):
     n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
-    times, f3 = build_fields(g, n_slabs, with_w)
+    times, f3 = build_fields(g, n_slabs, with_w, mixing)
     lon, lat, z = syn.particle_cloud(n, seed=seed + 1, three_d=g.z is not None)
     # keep the cloud inside this (smaller) grid
     lon = (g.lon[0] + (lon - 1.0) / 8.2 * g.Lx * 0.8 + 0.1 * g.Lx).astype(np.float32)
@@ -68,6 +70,9 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
         cfg['environment:constant:horizontal_diffusivity'] = diffusivity
     if wind_drift_depth is not None:
         cfg['drift:wind_drift_depth'] = wind_drift_depth
+    if mixing:
+        cfg['drift:vertical_mixing'] = True
+        cfg['vertical_mixing:timestep'] = dt_mix
     seed_kwargs = {}
     if cdf is not None:
         seed_kwargs['current_drift_factor'] = cdf
@@ -80,15 +85,17 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
                 diffusivity=diffusivity, seed=seed, wind_drift_depth=wind_drift_depth,
                 start_offset_s=start_offset_s if dt > 0 else None,
                 start_index=None if dt > 0 else len(times) - 1,
-                slab_step_s=3600, cdf_is_array=cdf is not None)
+                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix)
     out = dict(meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat,
                grid_z=np.zeros(0) if g.z is None else g.z,
                u=f3[CURRENT[0]], v=f3[CURRENT[1]], lon0=lon, lat0=lat, z0=z,
                lon=np.asarray(o.elements.lon, dtype=np.float64),
                lat=np.asarray(o.elements.lat, dtype=np.float64),
-               z=np.asarray(o.elements.z, dtype=np.float32))
+               z=np.asarray(o.elements.z))      # float32, or float64 once vertical mixing has touched it
     if with_w:
         out['w'] = f3['upward_sea_water_velocity']
+    if mixing:
+        out['kdiff'] = f3['ocean_vertical_diffusivity']
     if wind:
         out['x_wind'], out['y_wind'] = f2['x_wind'], f2['y_wind']
     if cdf is not None:
@@ -114,6 +121,8 @@ def main():
     run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
     run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
     run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+    run_case('rk4_3d_mixing', g3, 600, 7, 600, 'runge-kutta4', mixing=True, dt_mix=60.0)
+    run_case('euler_3d_mixing_w', g3, 600, 4, 900, 'euler', mixing=True, dt_mix=100.0, with_w=True)
 
 
 if __name__ == '__main__':

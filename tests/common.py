@@ -37,6 +37,7 @@ class Fixture:
         self.x_wind = d['x_wind'] if 'x_wind' in d else None
         self.y_wind = d['y_wind'] if 'y_wind' in d else None
         self.cdf = d['cdf'] if 'cdf' in d else None
+        self.kdiff = d['kdiff'] if 'kdiff' in d else None
         self.lon0, self.lat0, self.z0 = d['lon0'], d['lat0'], d['z0']
         self.lon, self.lat, self.z = d['lon'], d['lat'], d['z']
         m = self.meta
@@ -62,9 +63,12 @@ class Fixture:
 
 def run_port(fx):
     from oracle import advect_port as ap
-    readers = [ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times,
-                             dict({CUR[0]: fx.u, CUR[1]: fx.v},
-                                  **({'upward_sea_water_velocity': fx.w} if fx.w is not None else {})))]
+    f3 = {CUR[0]: fx.u, CUR[1]: fx.v}
+    if fx.w is not None:
+        f3['upward_sea_water_velocity'] = fx.w
+    if fx.kdiff is not None:
+        f3['ocean_vertical_diffusivity'] = fx.kdiff
+    readers = [ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3)]
     if fx.x_wind is not None:
         readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times,
                                      {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}))
@@ -72,7 +76,7 @@ def run_port(fx):
     return ap.run_oceandrift(readers, fx.lon0, fx.lat0, fx.z0, fx.start, fx.dt, fx.steps, scheme=m['scheme'],
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
                              cdf=fx.cdf if fx.cdf is not None else 1.0, diffusivity=m['diffusivity'],
-                             seed=m['seed'])
+                             seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0))
 
 
 # ---- host-compiled device math ---------------------------------------------------------------
@@ -89,7 +93,7 @@ class HsPair(C.Structure):
 
 
 class HsStepArgs(C.Structure):
-    _fields_ = [('scheme', C.c_int32), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32), ('pad0_', C.c_int32),
+    _fields_ = [('scheme', C.c_int32), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32), ('z_f64', C.c_int32),
                 ('g_uv', HsGroup),
                 ('t_start', HsPair), ('t_mid', HsPair), ('t_end', HsPair),
                 ('dt', C.c_double), ('n', C.c_int64),
@@ -99,7 +103,15 @@ class HsStepArgs(C.Structure):
                 ('g_wind', HsGroup), ('t_wind', HsPair), ('wdf', C.c_void_p), ('wind_drift_depth', C.c_double),
                 ('g_w', HsGroup), ('t_w', HsPair), ('z_inout', C.c_void_p),
                 ('rand_x', C.c_void_p), ('rand_y', C.c_void_p), ('diffusivity', C.c_void_p),
-                ('diffusivity_const', C.c_float), ('pad_', C.c_int32)]
+                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32)]
+
+
+class HsMixArgs(C.Structure):
+    _fields_ = [('g', HsGroup), ('t_k', HsPair), ('n', C.c_int64), ('lon', C.c_void_p), ('lat', C.c_void_p),
+                ('z_in', C.c_void_p), ('z_out', C.c_void_p), ('moving', C.c_void_p), ('rand', C.c_void_p),
+                ('dt_mix', C.c_double), ('sea_floor_const', C.c_double), ('seed', C.c_uint64),
+                ('ntimes', C.c_int32), ('z_in_f64', C.c_int32), ('mix_at_surface', C.c_int32), ('pos_f32', C.c_int32),
+                ('step_index', C.c_int32), ('pad_', C.c_int32)]
 
 
 _shim = None
@@ -164,6 +176,7 @@ def run_hostshim(fx):
     cur = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.u, fx.v], fx.times)
     wind = HsField(fx.grid_lon, fx.grid_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
     wfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.w], fx.times, (0.0,)) if m['with_w'] else None
+    kfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.kdiff], fx.times, (0.0,)) if m.get('mixing') else None
     cdf, wdf, moving = fx.props()
     lon = fx.lon0.astype(np.float64)
     lat = fx.lat0.astype(np.float64)
@@ -172,8 +185,22 @@ def run_hostshim(fx):
     t = fx.start
     dt = timedelta(seconds=fx.dt)
     for istep in range(fx.steps):
+        z_new = None
+        if kfld is not None:                   # vertical mixing first: it needs the start-of-step positions
+            ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
+            rnd = np.ascontiguousarray(np.stack([np.random.random(fx.n) for _ in range(ntimes)]))
+            ma = HsMixArgs()
+            ma.g, ma.t_k, ma.n = kfld.g, kfld.pair(t), fx.n
+            z_new = np.empty(fx.n, dtype=np.float64)
+            ma.lon, ma.lat, ma.z_in, ma.z_out = _p(lon), _p(lat), _p(z), _p(z_new)
+            ma.moving, ma.rand = _p(moving), _p(rnd)
+            ma.dt_mix, ma.sea_floor_const = m['dt_mix'] * np.sign(fx.dt), 10000.0
+            ma.ntimes, ma.z_in_f64 = ntimes, 1 if z.dtype == np.float64 else 0
+            ma.pos_f32 = 1 if istep == 0 else 0
+            assert lib.hs_mix(C.byref(ma)) == 0
         a = HsStepArgs()
         a.pos_f32 = 1 if istep == 0 else 0
+        a.z_f64 = 1 if z.dtype == np.float64 else 0
         a.scheme = {'euler': 0, 'runge-kutta': 1, 'runge-kutta4': 2}[m['scheme']]
         a.factor_f64 = 1 if cdf.dtype == np.float64 else 0
         a.g_uv = cur.g
@@ -185,12 +212,16 @@ def run_hostshim(fx):
             a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, 1, wind.g, wind.pair(t)
             a.wdf, a.wind_drift_depth = _p(wdf), fx.wind_drift_depth()
         if wfld is not None:
-            a.w_on, a.g_w, a.t_w, a.z_inout = 1, wfld.g, wfld.pair(t), _p(z)
+            zu = z if z_new is None else z_new
+            a.w_on, a.g_w, a.t_w, a.z_inout = 1, wfld.g, wfld.pair(t), _p(zu)
+            a.z_inout_f64 = 1 if zu.dtype == np.float64 else 0
         if m['diffusivity']:
             rx = np.random.normal(scale=1, size=fx.n)
             ry = np.random.normal(scale=1, size=fx.n)
             a.rand_x, a.rand_y, a.diffusivity_const = _p(rx), _p(ry), m['diffusivity']
         assert lib.hs_step(C.byref(a)) == 0
+        if z_new is not None:
+            z = z_new
         t = t + dt
     return lon, lat, z
 
@@ -210,6 +241,9 @@ def run_engine(fx, fused=True, sort_every=0):
                              lambda ti, c: (fx.x_wind, fx.y_wind)[c][ti], (0.0, 0.0))
     if m['with_w']:
         wgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.w[ti], (0.0,))
+    kgrp = None
+    if m.get('mixing'):
+        kgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.kdiff[ti], (0.0,))
     cdf, wdf, moving = fx.props()
     lon = eng.to_device(fx.lon0.astype(np.float64))
     lat = eng.to_device(fx.lat0.astype(np.float64))
@@ -224,11 +258,19 @@ def run_engine(fx, fused=True, sort_every=0):
         if m['diffusivity']:
             rand = (eng.to_device(np.random.normal(scale=1, size=fx.n)),
                     eng.to_device(np.random.normal(scale=1, size=fx.n)))
+        z_new = None
+        if kgrp is not None:
+            ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
+            rnd = eng.to_device(np.ascontiguousarray(np.stack([np.random.random(fx.n) for _ in range(ntimes)])))
+            z_new = eng.vertical_mixing(kgrp, t, lon, lat, z, m['dt_mix'] * np.sign(fx.dt), ntimes, moving=d_mov,
+                                        rand=rnd, pos_f32=first)
         if fused:
             eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
-                                diffusivity=m['diffusivity'], pos_f32=first)
+                                diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new)
+            if z_new is not None:
+                z = z_new
         else:
             assert not (m['wind'] or m['with_w'] or m['diffusivity'])
             eng.advect_current(cur, m['scheme'], t, dt, lon, lat, z if three_d else None, factor=d_cdf,

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../../opendrift_b200/csrc/od_advect.cuh"
+#include "../../opendrift_b200/csrc/od_mix.cuh"
 
 using namespace od;
 
@@ -68,7 +69,7 @@ void hs_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lo
     GroupGeom q = make_geom(*g, lv);
     PairRef p = make_pair(*pr);
     for (int64_t i = 0; i < n; ++i) {
-        VertW vw = vert_weights(q, q.zs, q.zy, (z && q.nz > 1) ? z[i] : 0.0f);
+        VertW vw = vert_weights(q, q.zs, q.zy, (z && q.nz > 1) ? (double)z[i] : 0.0);
         if (q.ncomp == 2) {
             float u, v;
             sample2(q, p, vw, lon[i], lat[i], u, v, pos_f32 != 0);
@@ -80,19 +81,19 @@ void hs_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lo
 }
 
 struct hs_step_args {
-    int32_t scheme, factor_f64, pos_f32, pad0_;
+    int32_t scheme, factor_f64, pos_f32, z_f64;
     hs_group g_uv;
     hs_pair t_start, t_mid, t_end;
     double dt;
     int64_t n;
-    double* lon; double* lat; const float* z;
+    double* lon; double* lat; const void* z;
     const void* factor; const int32_t* moving;
     double truncate_below;
     // extras
     int32_t wind_on, wdf_f64, w_on, w_at_surface;
     hs_group g_wind; hs_pair t_wind; const void* wdf; double wind_drift_depth;
-    hs_group g_w; hs_pair t_w; float* z_inout;
-    const double* rand_x; const double* rand_y; const float* diffusivity; float diffusivity_const; int32_t pad_;
+    hs_group g_w; hs_pair t_w; void* z_inout;
+    const double* rand_x; const double* rand_y; const float* diffusivity; float diffusivity_const; int32_t z_inout_f64;
 };
 
 }  // extern "C"
@@ -114,6 +115,7 @@ int hs_step(const hs_step_args* a) {
     p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z = a->z; p.factor = a->factor; p.moving = a->moving;
     p.truncate_below = a->truncate_below;
     p.pos_f32 = a->pos_f32;
+    p.z_f64 = a->z_f64;
     if (a->wind_on) {
         p.wind_on = 1; p.wdf_f64 = a->wdf_f64; p.gwind = make_geom(a->g_wind, l2); p.pwind = make_pair(a->t_wind);
         p.wdf = a->wdf; p.wind_drift_depth = a->wind_drift_depth;
@@ -121,6 +123,7 @@ int hs_step(const hs_step_args* a) {
     if (a->w_on) {
         p.w_on = 1; p.w_at_surface = a->w_at_surface; p.gw = make_geom(a->g_w, l3); p.pw = make_pair(a->t_w);
         p.z_inout = a->z_inout;
+        p.zio_f64 = a->z_inout_f64;
     }
     if (a->rand_x) {
         p.diff_on = 1; p.rand_x = a->rand_x; p.rand_y = a->rand_y; p.diffusivity = a->diffusivity;
@@ -133,6 +136,34 @@ int hs_step(const hs_step_args* a) {
         case 2: f ? run<2, true>(p, p.gw) : run<2, false>(p, p.gw); break;
         default: return -2;
     }
+    return 0;
+}
+
+struct hs_mix_args {
+    hs_group g; hs_pair t_k;
+    int64_t n; const double* lon; const double* lat; const void* z_in; double* z_out;
+    const int32_t* moving; const double* rand; double dt_mix; double sea_floor_const;
+    unsigned long long seed; int32_t ntimes, z_in_f64, mix_at_surface, pos_f32, step_index, pad_;
+};
+
+int hs_mix(const hs_mix_args* a) {
+    hs_levels lv;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = make_geom(a->g, lv);
+    p.pr = make_pair(a->t_k);
+    const int nz = a->g.nz;
+    std::vector<double> xs(nz), xy(nz), zl(a->g.z_levels, a->g.z_levels + nz);
+    const bool inc = zl[1] > zl[0];
+    for (int i = 0; i < nz; ++i) { int src = inc ? nz - 1 - i : i; xs[i] = -zl[src]; xy[i] = (double)src; }
+    p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z_in = a->z_in; p.z_out = a->z_out; p.moving = a->moving;
+    p.rand = a->rand; p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.seed = a->seed;
+    p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32;
+    p.step_index = a->step_index; p.zl = zl.data(); p.xs = xs.data(); p.xy = xy.data();
+    p.uniform_dz = 1; p.dz0 = zl[1] - zl[0];
+    for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
+    std::vector<double> K(nz);
+    for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy, K.data());
     return 0;
 }
 

@@ -20,6 +20,8 @@ def _model(fx, **cfg):
     f3 = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
     if fx.w is not None:
         f3['upward_sea_water_velocity'] = fx.w
+    if fx.kdiff is not None:
+        f3['ocean_vertical_diffusivity'] = fx.kdiff
     o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, name='current'))
     if fx.x_wind is not None:
         o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times,
@@ -32,6 +34,9 @@ def _model(fx, **cfg):
         o.set_config('environment:constant:horizontal_diffusivity', m['diffusivity'])
     if m.get('wind_drift_depth') is not None:
         o.set_config('drift:wind_drift_depth', m['wind_drift_depth'])
+    if m.get('mixing'):
+        o.set_config('drift:vertical_mixing', True)
+        o.set_config('vertical_mixing:timestep', m['dt_mix'])
     for k, v in cfg.items():
         o.set_config(k, v)
     kw = {}
@@ -51,7 +56,8 @@ def test_oceandrift_run_matches_reference(name):
     assert lon.dtype == np.float64                       # float64 after the first update, as in the reference
     e = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     assert max(e) < 5e-8, e
-    assert np.abs(z - fx.z).max() <= 1e-5
+    assert np.abs(z - fx.z).max() <= (1e-9 if fx.meta.get('mixing') else 1e-5)
+    assert z.dtype == fx.z.dtype
     assert np.array_equal(o.elements.ID, np.arange(fx.n))
     assert len(o.history['time']) == fx.steps + 1
 
@@ -70,10 +76,16 @@ def test_overridden_update_uses_helpers_and_matches():
             self.advect_wind()
             self.vertical_advection()
 
-    for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32'):
+    class MyMixingDrift(OceanDrift):
+        def update(self):
+            self.advect_ocean_current()
+            self.vertical_mixing()
+            self.vertical_advection()
+
+    for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32', 'rk4_3d_mixing', 'euler_3d_mixing_w'):
         fx = Fixture(name)
         o = _model(fx)
-        o.__class__ = MyDrift
+        o.__class__ = MyMixingDrift if fx.meta.get('mixing') else MyDrift
         o.run(steps=fx.steps, time_step=fx.dt)
         e = common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)
         assert max(e) < 5e-8, (name, e)
