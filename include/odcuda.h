@@ -183,6 +183,34 @@ typedef struct od_step_args {
 
 int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
 
+/* ---- Stokes drift and reductions -----------------------------------------------------------------
+ * od_minmax_f32: min / max of a[i] (or a[i] + b[i] when d_b is given) with NaNs ignored, returned to the host
+ * (synchronises).  These are the collective decisions the reference takes with .max() / .min() on environment
+ * arrays (physics_methods.py:799-812, 899, 771-775; basemodel/__init__.py:1754). */
+int od_minmax_f32(od_ctx* ctx, int64_t n, const float* d_a, const float* d_b, float* h_min, float* h_max);
+
+/* PhysicsMethods.stokes_drift (models/physics_methods.py:793-848): depth-profiled Stokes velocity from the
+ * float32 environment samples and the geodesic move, in place. */
+typedef struct od_stokes_args {
+    int64_t n;
+    double* d_lon;
+    double* d_lat;
+    const void* d_z;              /* float32, or float64 when z_f64 */
+    const float* d_us;            /* sea_surface_wave_stokes_drift_x/y_velocity sampled at the start of the step */
+    const float* d_vs;
+    const float* d_hs;            /* sea_surface_wave_significant_height (hs_mode 0) */
+    const float* d_xwind;         /* wind (wave period, and Hs for hs_mode 1); NULL = no wind */
+    const float* d_ywind;
+    const int32_t* d_moving;
+    double dt;
+    int32_t z_f64;
+    int32_t hs_mode;              /* 0: Hs from d_hs; 1: 0.0246 |wind|^2; 2: Hs = 1 (no Hs and no wind anywhere) */
+    int32_t profile;              /* 0 monochromatic, 1 exponential, 2 Phillips */
+    int32_t pad_;
+} od_stokes_args;
+
+int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a);
+
 /* ---- vertical turbulent mixing ----------------------------------------------------------------
  * OceanDrift.vertical_mixing (models/oceandrift.py:397-571) with diffusivity from the environment profiles of
  * a 3-D one-component group: all int(dt/dt_mix) inner random-walk iterations in one launch.  Positions are

@@ -61,6 +61,13 @@ class MixArgs(C.Structure):
                 ('pos_f32', C.c_int32), ('pad_', C.c_int32)]
 
 
+class StokesArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
+                ('d_us', C.c_void_p), ('d_vs', C.c_void_p), ('d_hs', C.c_void_p), ('d_xwind', C.c_void_p),
+                ('d_ywind', C.c_void_p), ('d_moving', C.c_void_p), ('dt', C.c_double), ('z_f64', C.c_int32),
+                ('hs_mode', C.c_int32), ('profile', C.c_int32), ('pad_', C.c_int32)]
+
+
 # every symbol include/odcuda.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -81,6 +88,8 @@ SYMBOLS = {
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
     'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
+    'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    'od_stokes_drift': (C.c_int, [_P, C.POINTER(StokesArgs)]),
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),

@@ -15,6 +15,7 @@
 #include "../../include/odcuda.h"
 #include "od_advect.cuh"
 #include "od_mix.cuh"
+#include "od_stokes.cuh"
 
 using namespace od;
 
@@ -66,6 +67,7 @@ struct od_ctx {
     int32_t* d_keys = nullptr;
     int32_t* d_bins = nullptr;
     int64_t keys_cap = 0, bins_cap = 0;
+    unsigned* d_red = nullptr;          // reduction scratch
 };
 
 static int fail(od_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -126,6 +128,7 @@ extern "C" void od_destroy(od_ctx* ctx) {
     for (auto& g : ctx->groups) free_group(g);
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->d_bins) cudaFree(ctx->d_bins);
+    if (ctx->d_red) cudaFree(ctx->d_red);
     delete ctx;
 }
 
@@ -434,6 +437,46 @@ __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     mix_particle(p, i, xs, xy, K);
 }
 
+// ---- Stokes drift and reductions --------------------------------------------------------------------
+__global__ void __launch_bounds__(OD_BLOCK) stokes_kernel(const StokesParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) stokes_particle(p, i);
+}
+
+// order-preserving map float -> unsigned so that atomicMin/atomicMax work on floats
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float ord2f(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// min and max of a[i] (+ b[i]) over all i, NaNs ignored; grid-stride, warp shuffle, one atomic pair per warp
+__global__ void __launch_bounds__(256) minmax_kernel(int64_t n, const float* __restrict__ a, const float* __restrict__ b,
+                                                     unsigned* __restrict__ out) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = b ? __fadd_rn(a[i], b[i]) : a[i];
+        if (v == v) {
+            const unsigned o = f2ord(v);
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], lo);
+        atomicMax(&out[1], hi);
+    }
+}
+
 // ---- particle ordering ---------------------------------------------------------------------------
 struct SortParams {
     GroupGeom g;
@@ -666,6 +709,49 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
     }
     if (a->cur.n == 0) return OD_OK;
     return launch_step<true>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+}
+
+extern "C" int od_minmax_f32(od_ctx* ctx, int64_t n, const float* d_a, const float* d_b, float* h_min, float* h_max) {
+    if (!ctx || n < 0 || (n > 0 && !d_a) || !h_min || !h_max) return fail(ctx, OD_ERR_ARG, "od_minmax_f32: bad arguments");
+    *h_min = INFINITY;
+    *h_max = -INFINITY;
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_red) CK(cudaMalloc(&ctx->d_red, 2 * sizeof(unsigned)));
+    const unsigned init[2] = {0xffffffffu, 0u};
+    CK(cudaMemcpyAsync(ctx->d_red, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    minmax_kernel<<<blocks, 256, 0, ctx->stream>>>(n, d_a, d_b, ctx->d_red);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    unsigned res[2];
+    CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (res[0] != 0xffffffffu) {
+        *h_min = ord2f(res[0]);
+        *h_max = ord2f(res[1]);
+    }
+    return OD_OK;
+}
+
+extern "C" int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_stokes_drift: null argument");
+    if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_z || !a->d_us || !a->d_vs)))
+        return fail(ctx, OD_ERR_ARG, "od_stokes_drift: bad arguments");
+    if (a->hs_mode < 0 || a->hs_mode > 2 || a->profile < 0 || a->profile > 2 || (a->hs_mode == 0 && !a->d_hs))
+        return fail(ctx, OD_ERR_ARG, "od_stokes_drift: bad mode");
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    StokesParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.us = a->d_us; p.vs = a->d_vs; p.hs = a->d_hs;
+    p.xwind = a->d_xwind; p.ywind = a->d_ywind; p.moving = a->d_moving; p.dt = a->dt;
+    p.z_f64 = a->z_f64; p.hs_mode = a->hs_mode; p.profile = a->profile;
+    stokes_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
 }
 
 extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {

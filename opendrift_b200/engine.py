@@ -17,7 +17,7 @@ from bisect import bisect_left
 import numpy as np
 
 from . import _lib
-from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, MixArgs, OD_T_LERP, OD_T_FIRST,
+from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, MixArgs, StokesArgs, OD_T_LERP, OD_T_FIRST,
                    OD_T_MISSING, SCHEMES)
 
 
@@ -395,6 +395,27 @@ class Engine:
         for ev in done:
             main.wait_event(ev)
         main.synchronize()
+
+    def minmax(self, a, b=None):
+        """(min, max) of a (+ b) over a float32 device tensor, NaNs ignored (synchronises)."""
+        lo, hi = C.c_float(), C.c_float()
+        self._check(self.lib.od_minmax_f32(self.ctx, a.numel(), _ptr(a), _ptr(b), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2}
+
+    def stokes_drift(self, lon, lat, z, us, vs, hs, xwind, ywind, moving, dt, hs_mode, profile):
+        a = StokesArgs()
+        a.n = lon.numel()
+        a.d_lon, a.d_lat, a.d_z = lon.data_ptr(), lat.data_ptr(), z.data_ptr()
+        a.z_f64 = 1 if z.dtype == self.torch.float64 else 0
+        a.d_us, a.d_vs = us.data_ptr(), vs.data_ptr()
+        a.d_hs = hs.data_ptr() if hs is not None else None
+        a.d_xwind = xwind.data_ptr() if xwind is not None else None
+        a.d_ywind = ywind.data_ptr() if ywind is not None else None
+        a.d_moving = moving.data_ptr() if moving is not None else None
+        a.dt, a.hs_mode, a.profile = float(dt), int(hs_mode), self.PROFILES[profile]
+        self._check(self.lib.od_stokes_drift(self.ctx, C.byref(a)))
 
     def vertical_mixing(self, group, t, lon, lat, z_in, dt_mix, ntimes, moving=None, terminal_velocity=None, ids=None,
                         rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False):

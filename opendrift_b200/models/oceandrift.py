@@ -38,6 +38,7 @@ class OceanDrift(OpenDriftSimulation):
         'upward_sea_water_velocity': {'fallback': 0, 'skip_if': ['drift:vertical_advection', 'is', False]},
         'ocean_vertical_diffusivity': {'fallback': 0, 'skip_if': ['drift:vertical_mixing', 'is', False], 'profiles': True},
         'horizontal_diffusivity': {'fallback': 0},
+        'sea_surface_wave_significant_height': {'fallback': 0},
         'sea_surface_wave_stokes_drift_x_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
         'sea_surface_wave_stokes_drift_y_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
         'sea_floor_depth_below_sea_level': {'fallback': 10000},
@@ -68,7 +69,11 @@ class OceanDrift(OpenDriftSimulation):
                         'description': 'numpy: draws of the legacy global generator made on the host in the reference\'s '
                                        'order (bit parity); philox: counter-based generator on the device keyed by element ID.'},
             'drift:stokes_drift': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
-                                   'description': 'Advection with Stokes drift.'},
+                                   'description': 'Advection elements with Stokes drift (wave orbital motion).'},
+            'drift:stokes_drift_profile': {'type': 'enum', 'default': 'Phillips',
+                                           'enum': ['monochromatic', 'exponential', 'Phillips', 'windsea_swell'],
+                                           'level': CONFIG_LEVEL_ADVANCED,
+                                           'description': 'Algorithm to calculate Stokes drift at depth from surface value'},
             'drift:wind_drift_depth': {'type': 'float', 'default': 0.1, 'min': 0, 'max': 10, 'units': 'meters',
                                        'level': CONFIG_LEVEL_ADVANCED,
                                        'description': 'Wind drift decreases linearly to zero at this depth.'},
@@ -172,9 +177,17 @@ class OceanDrift(OpenDriftSimulation):
         D = self._constant_or_none('horizontal_diffusivity')
         if D is None:
             return False                                  # gridded diffusivity: helper path
+        # Stokes drift moves between wind drift and the random walk: when it is active its start-of-step samples
+        # are taken first, the fused kernel does current + wind (+ w), then the Stokes and diffusion launches follow
+        stokes_inp = None
+        if self.get_config('drift:stokes_drift') and any(
+                self.env.priority_list.get(v) or (self.env.constant(v) or 0) != 0
+                for v in ('sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity')):
+            stokes_inp = self._stokes_inputs()
+        split_diffusion = stokes_inp is not None and D != 0
         rand = None
         n = len(el)
-        if D != 0:
+        if D != 0 and not split_diffusion:
             rand = (eng.to_device(np.random.normal(scale=1, size=n)), eng.to_device(np.random.normal(scale=1, size=n)))
         moving = el.dev('moving')
         if moving.dtype != torch.int32:
@@ -194,9 +207,14 @@ class OceanDrift(OpenDriftSimulation):
                             wind_drift_depth=self.get_config('drift:wind_drift_depth'), w_group=wgrp,
                             w_at_surface=self.get_config('drift:vertical_advection_at_surface'), rand=rand,
                             diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new)
+        if stokes_inp is not None:
+            z_keep = el._dev.get('z')
+            self.stokes_drift(_inputs=stokes_inp)
         if z_new is not None:
             el.set_dev('z', z_new)
         el.positions_f32 = False
+        if split_diffusion:
+            OpenDriftSimulation.horizontal_diffusion(self)
         return True
 
     def update_and_diffuse(self):

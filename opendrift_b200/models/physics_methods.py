@@ -89,11 +89,48 @@ class PhysicsMethods:
             xv, yv = xw.to(w.dtype) * w * f, yw.to(w.dtype) * w * f
         self.update_positions(xv, yv)
 
-    def stokes_drift(self, factor=1):
-        """:793-848.  Surface Stokes drift with a depth profile is a "next" row; with the
-        default fallback of 0 m/s the reference returns early, which is what happens here."""
+    def _stokes_inputs(self):
+        """Start-of-step samples the Stokes move needs (device float32 tensors) + the reference's collective
+        decisions (:799-812, :893-906).  Returns None when the reference would return early."""
+        eng = self.engine
+        env = self.environment
+        sx, sy = 'sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity'
+        if sx not in env or sy not in env:
+            return None
+        us, vs = env.dev(sx, eng), env.dev(sy, eng)
+        if eng.minmax(us, vs)[1] == 0:
+            return None                                   # 'No Stokes drift velocity available'
+        hs = env.dev('sea_surface_wave_significant_height', eng) if 'sea_surface_wave_significant_height' in env else None
+        xw = env.dev('x_wind', eng) if 'x_wind' in env else None
+        yw = env.dev('y_wind', eng) if 'y_wind' in env else None
+        if hs is not None and eng.minmax(hs)[1] > 0:
+            mode = 0
+        else:
+            any_wind = False
+            for w in (xw, yw):
+                if w is not None:
+                    lo, hi = eng.minmax(w)
+                    any_wind |= (hi > 0 or lo < 0)
+            mode = 1 if any_wind else 2
+        return us, vs, hs, xw, yw, mode
+
+    def stokes_drift(self, factor=1, _inputs='sample'):
+        """Stokes drift with a depth profile (:793-848): monochromatic / exponential / Phillips (:332-416)."""
         if not self.get_config('drift:stokes_drift', False):
             return
-        for v in ('sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity'):
-            if self.env.priority_list.get(v) or (self.env.constant(v) or 0) != 0:
-                raise NotImplementedError('Stokes drift profiles are not on the GPU path yet')
+        if not (isinstance(factor, (int, float)) and factor == 1):
+            raise NotImplementedError('stokes_drift(factor != 1) is not on the GPU path')
+        profile = self.get_config('drift:stokes_drift_profile', default='monochromatic')
+        if profile == 'windsea_swell':
+            raise NotImplementedError('the windsea_swell Stokes profile is not on the GPU path')
+        inp = self._stokes_inputs() if _inputs == 'sample' else _inputs
+        if inp is None:
+            return
+        us, vs, hs, xw, yw, mode = inp
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        moving = el.dev('moving')
+        if moving.dtype != torch.int32:
+            moving = moving.to(torch.int32)
+        eng.stokes_drift(el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), us, vs, hs,
+                         xw, yw, moving, self.time_step.total_seconds(), mode, profile)
+        el.positions_f32 = False

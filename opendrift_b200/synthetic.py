@@ -71,6 +71,21 @@ def wind_xy(grid, t_seconds, speed=10.0):
     return (speed * np.cos(th) * mod).astype(np.float32), (speed * np.sin(th) * mod).astype(np.float32)
 
 
+def stokes_xy(grid, t_seconds, speed=0.12):
+    """Surface Stokes drift slabs (ny, nx) float32, roughly aligned with the synthetic wind."""
+    wx, wy = wind_xy(grid, t_seconds, speed=1.0)
+    X = 2.0 * (grid.lon.astype(np.float64) - float(grid.lon[0])) / grid.Lx
+    mod = (1.0 + 0.4 * np.cos(np.pi * X))[None, :]
+    return (speed * wx * mod).astype(np.float32), (speed * wy * mod).astype(np.float32)
+
+
+def wave_height(grid, t_seconds):
+    """Significant wave height slab (ny, nx) float32, 1-3 m."""
+    Y = (grid.lat.astype(np.float64) - float(grid.lat[0])) / grid.Ly
+    X = 2.0 * (grid.lon.astype(np.float64) - float(grid.lon[0])) / grid.Lx
+    return (2.0 + np.sin(np.pi * Y)[:, None] * np.cos(np.pi * X / 2)[None, :]).astype(np.float32)
+
+
 def slab_times(n_slabs, step_seconds=3600):
     return [T0 + timedelta(seconds=step_seconds * i) for i in range(n_slabs)]
 

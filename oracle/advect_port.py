@@ -24,7 +24,7 @@ FALLBACK = {'x_sea_water_velocity': 0.0, 'y_sea_water_velocity': 0.0,
             'upward_sea_water_velocity': 0.0, 'x_wind': 0.0, 'y_wind': 0.0,
             'horizontal_diffusivity': 0.0, 'ocean_vertical_diffusivity': 0.0,
             'sea_surface_wave_stokes_drift_x_velocity': 0.0,
-            'sea_surface_wave_stokes_drift_y_velocity': 0.0}
+            'sea_surface_wave_stokes_drift_y_velocity': 0.0, 'sea_surface_wave_significant_height': 0.0}
 
 
 class GridReader:
@@ -267,6 +267,48 @@ def advect_wind(lon, lat, z, wdf_in, env, moving, dt, wind_drift_depth=0.1, fact
     return update_positions(lon, lat, x_wind * wdf * factor, y_wind * wdf * factor, moving, dt)
 
 
+def stokes_drift(lon, lat, z, env, moving, dt, profile='Phillips', factor=1):
+    """PhysicsMethods.stokes_drift (opendrift/models/physics_methods.py:793-848) for the variables OceanDrift
+    requires: surface Stokes drift from a reader, Hs from a reader or else from wind (significant_wave_height,
+    :893-906), wave period from wind (wave_period / _wave_frequency, :908-943), profiles :332-416."""
+    import scipy.special
+    us = env['sea_surface_wave_stokes_drift_x_velocity']
+    vs = env['sea_surface_wave_stokes_drift_y_velocity']
+    if np.max(np.array(us + vs)) == 0:
+        return lon, lat
+    wind_speed = np.sqrt(env['x_wind'] ** 2 + env['y_wind'] ** 2)
+    hs_env = env['sea_surface_wave_significant_height']
+    wave_height = hs_env if hs_env.max() > 0 else 0.0246 * np.power(wind_speed, 2)
+    omega = 5 * np.ones(wind_speed.shape)
+    omega[wind_speed > 0] = 0.877 * 9.81 / (1.17 * wind_speed[wind_speed > 0])
+    wave_period = (2 * np.pi) / omega
+    if np.max(np.array(wave_height)) == 0:
+        wave_height = 1
+    if np.max(np.array(wave_period)) == 0:
+        wave_period = 8
+    speed = np.sqrt(us ** 2 + vs ** 2)
+    transport = (2. * np.pi / wave_period) * np.power(wave_height, 2) / 16
+    if profile == 'monochromatic':
+        km = speed / (2 * transport)
+        unit = np.exp(2 * km * z)
+    elif profile == 'exponential':
+        km = speed / (2 * transport)
+        ke = km / 3
+        unit = np.exp(2.0 * ke * z) / (1.0 - 8.0 * ke * z)
+    elif profile == 'Phillips':
+        beta = 1
+        km = speed * (1 - 2 * beta / 3) / (2 * transport)
+        unit = (np.exp(2 * km * z) - beta * np.sqrt(2 * np.pi * km * np.abs(z)) *
+                scipy.special.erfc(np.sqrt(2 * km * np.abs(z))))
+    else:
+        raise NotImplementedError(profile)
+    su, sv = us * unit, vs * unit
+    zero = speed == 0
+    su[zero] = 0
+    sv[zero] = 0
+    return update_positions(lon, lat, su * factor, sv * factor, moving, dt)
+
+
 def vertical_advection(z, w, moving, dt, at_surface=False):
     """OceanDrift.vertical_advection (opendrift/models/oceandrift.py:315-350), no SSH correction."""
     z = z.copy()
@@ -328,7 +370,7 @@ def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
 
 def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
                    vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
-                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0):
+                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None):
     """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
     OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
@@ -356,6 +398,11 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
         variables += ['x_wind', 'y_wind']
     if mixing:
         variables.append('ocean_vertical_diffusivity')
+    if stokes:
+        variables += ['sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity',
+                      'sea_surface_wave_significant_height']
+        if 'x_wind' not in variables:
+            variables += ['x_wind', 'y_wind']
     time = start_time
     for _ in range(steps):
         if mixing:
@@ -368,6 +415,8 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
                                         truncate_below=truncate_below)
         if wind:
             lon, lat = advect_wind(lon, lat, z, wdf_arr, env, moving, dt, wind_drift_depth)
+        if stokes:
+            lon, lat = stokes_drift(lon, lat, z, env, moving, dt, profile=stokes)
         if mixing:
             z = vertical_mixing(z, moving, prof['ocean_vertical_diffusivity'], prof['z'], dt, dt_mix)
         if vertical_adv:

@@ -36,6 +36,15 @@ def build_fields(g, n_slabs, with_w=False, mixing=False):
     return times, f
 
 
+def build_stokes(g, n_slabs, with_hs):
+    times = syn.slab_times(n_slabs)
+    sx, sy = zip(*[syn.stokes_xy(g, (t - syn.T0).total_seconds()) for t in times])
+    f = {'sea_surface_wave_stokes_drift_x_velocity': np.stack(sx), 'sea_surface_wave_stokes_drift_y_velocity': np.stack(sy)}
+    if with_hs:
+        f['sea_surface_wave_significant_height'] = np.stack([syn.wave_height(g, 0.0)] * n_slabs)
+    return f
+
+
 def build_wind(g, n_slabs):
     times = syn.slab_times(n_slabs)
     X, Y = [], []
@@ -47,7 +56,7 @@ def build_wind(g, n_slabs):
 
 
 def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
-             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0):
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True):
     n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
     times, f3 = build_fields(g, n_slabs, with_w, mixing)
     lon, lat, z = syn.particle_cloud(n, seed=seed + 1, three_d=g.z is not None)
@@ -65,7 +74,15 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
     if wind:
         f2 = build_wind(g, n_slabs)
         readers.append(refrun.make_grid_reader(g.lon, g.lat, None, times, f2, 'wind'))
+    fs = None
+    if stokes:
+        fs = build_stokes(g, n_slabs, stokes_hs)
+        readers.append(refrun.make_grid_reader(g.lon, g.lat, None, times, fs, 'waves'))
     cfg = {'drift:advection_scheme': scheme, 'drift:vertical_advection': bool(with_w)}
+    if stokes:
+        cfg['drift:stokes_drift_profile'] = stokes
+    else:
+        cfg['drift:stokes_drift'] = False
     if diffusivity:
         cfg['environment:constant:horizontal_diffusivity'] = diffusivity
     if wind_drift_depth is not None:
@@ -85,7 +102,7 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
                 diffusivity=diffusivity, seed=seed, wind_drift_depth=wind_drift_depth,
                 start_offset_s=start_offset_s if dt > 0 else None,
                 start_index=None if dt > 0 else len(times) - 1,
-                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix)
+                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix, stokes=stokes)
     out = dict(meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat,
                grid_z=np.zeros(0) if g.z is None else g.z,
                u=f3[CURRENT[0]], v=f3[CURRENT[1]], lon0=lon, lat0=lat, z0=z,
@@ -96,6 +113,9 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
         out['w'] = f3['upward_sea_water_velocity']
     if mixing:
         out['kdiff'] = f3['ocean_vertical_diffusivity']
+    if stokes:
+        for k, v in fs.items():
+            out['stokes__' + k] = v
     if wind:
         out['x_wind'], out['y_wind'] = f2['x_wind'], f2['y_wind']
     if cdf is not None:
@@ -121,6 +141,9 @@ def main():
     run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
     run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
     run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+    run_case('rk4_3d_stokes_phillips', g3, n, 6, 600, 'runge-kutta4', wind=True, stokes='Phillips')
+    run_case('euler_3d_stokes_mono_nohs', g3, n, 6, 600, 'euler', wind=True, stokes='monochromatic', stokes_hs=False)
+    run_case('rk2_3d_stokes_exp', g3, n, 5, 600, 'runge-kutta', wind=True, stokes='exponential')
     run_case('rk4_3d_mixing', g3, 600, 7, 600, 'runge-kutta4', mixing=True, dt_mix=60.0)
     run_case('euler_3d_mixing_w', g3, 600, 4, 900, 'euler', mixing=True, dt_mix=100.0, with_w=True)
 

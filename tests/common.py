@@ -38,6 +38,7 @@ class Fixture:
         self.y_wind = d['y_wind'] if 'y_wind' in d else None
         self.cdf = d['cdf'] if 'cdf' in d else None
         self.kdiff = d['kdiff'] if 'kdiff' in d else None
+        self.stokes = {k[len('stokes__'):]: d[k] for k in d.files if k.startswith('stokes__')} or None
         self.lon0, self.lat0, self.z0 = d['lon0'], d['lat0'], d['z0']
         self.lon, self.lat, self.z = d['lon'], d['lat'], d['z']
         m = self.meta
@@ -72,11 +73,14 @@ def run_port(fx):
     if fx.x_wind is not None:
         readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times,
                                      {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}))
+    if fx.stokes is not None:
+        readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, fx.stokes))
     m = fx.meta
     return ap.run_oceandrift(readers, fx.lon0, fx.lat0, fx.z0, fx.start, fx.dt, fx.steps, scheme=m['scheme'],
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
                              cdf=fx.cdf if fx.cdf is not None else 1.0, diffusivity=m['diffusivity'],
-                             seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0))
+                             seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0),
+                             stokes=m.get('stokes'))
 
 
 # ---- host-compiled device math ---------------------------------------------------------------
@@ -104,6 +108,27 @@ class HsStepArgs(C.Structure):
                 ('g_w', HsGroup), ('t_w', HsPair), ('z_inout', C.c_void_p),
                 ('rand_x', C.c_void_p), ('rand_y', C.c_void_p), ('diffusivity', C.c_void_p),
                 ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32)]
+
+
+class HsStokesArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('lon', C.c_void_p), ('lat', C.c_void_p), ('z', C.c_void_p), ('us', C.c_void_p),
+                ('vs', C.c_void_p), ('hs', C.c_void_p), ('xwind', C.c_void_p), ('ywind', C.c_void_p),
+                ('moving', C.c_void_p), ('dt', C.c_double), ('z_f64', C.c_int32), ('hs_mode', C.c_int32),
+                ('profile', C.c_int32), ('pad_', C.c_int32)]
+
+
+PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2}
+
+
+def stokes_hs_mode(us, vs, hs, xw, yw):
+    """The reference's collective decisions (physics_methods.py:799-812, 893-906): None = no Stokes drift at all,
+    else 0 (Hs from the environment), 1 (Hs from wind) or 2 (Hs = 1)."""
+    if np.max(np.array(us + vs)) == 0:
+        return None
+    if hs is not None and hs.max() > 0:
+        return 0
+    ws = np.sqrt(xw ** 2 + yw ** 2)
+    return 1 if ws.max() > 0 else 2
 
 
 class HsMixArgs(C.Structure):
@@ -155,6 +180,14 @@ class HsField:
         self.g = g
         self._keep = []
 
+    def sample(self, lib, t, lon, lat, z, pos_f32):
+        n = len(lon)
+        o0, o1 = np.empty(n, np.float32), np.empty(n, np.float32)
+        pr = self.pair(t)
+        lib.hs_interp(C.byref(self.g), C.byref(pr), C.c_int64(n), _p(lon), _p(lat), _p(z.astype(np.float32)),
+                      C.c_int(1 if pos_f32 else 0), _p(o0), _p(o1))
+        return o0, o1
+
     def pair(self, t):
         pr = HsPair()
         br = bracket(self.times, t)
@@ -177,6 +210,12 @@ def run_hostshim(fx):
     wind = HsField(fx.grid_lon, fx.grid_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
     wfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.w], fx.times, (0.0,)) if m['with_w'] else None
     kfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.kdiff], fx.times, (0.0,)) if m.get('mixing') else None
+    sfld = hfld = None
+    if m.get('stokes'):
+        sfld = HsField(fx.grid_lon, fx.grid_lat, None, [fx.stokes['sea_surface_wave_stokes_drift_x_velocity'],
+                                                         fx.stokes['sea_surface_wave_stokes_drift_y_velocity']], fx.times)
+        if 'sea_surface_wave_significant_height' in fx.stokes:
+            hfld = HsField(fx.grid_lon, fx.grid_lat, None, [fx.stokes['sea_surface_wave_significant_height']], fx.times, (0.0,))
     cdf, wdf, moving = fx.props()
     lon = fx.lon0.astype(np.float64)
     lat = fx.lat0.astype(np.float64)
@@ -198,6 +237,12 @@ def run_hostshim(fx):
             ma.ntimes, ma.z_in_f64 = ntimes, 1 if z.dtype == np.float64 else 0
             ma.pos_f32 = 1 if istep == 0 else 0
             assert lib.hs_mix(C.byref(ma)) == 0
+        senv = None
+        if sfld is not None:                   # start-of-step environment for the Stokes move
+            us, vs = sfld.sample(lib, t, lon, lat, z, istep == 0)
+            hs = hfld.sample(lib, t, lon, lat, z, istep == 0)[0] if hfld is not None else None
+            xw, yw = wind.sample(lib, t, lon, lat, z, istep == 0)
+            senv = (us, vs, hs, xw, yw)
         a = HsStepArgs()
         a.pos_f32 = 1 if istep == 0 else 0
         a.z_f64 = 1 if z.dtype == np.float64 else 0
@@ -220,6 +265,16 @@ def run_hostshim(fx):
             ry = np.random.normal(scale=1, size=fx.n)
             a.rand_x, a.rand_y, a.diffusivity_const = _p(rx), _p(ry), m['diffusivity']
         assert lib.hs_step(C.byref(a)) == 0
+        if senv is not None:
+            us, vs, hs, xw, yw = senv
+            mode = stokes_hs_mode(us, vs, hs, xw, yw)
+            if mode is not None:
+                sa = HsStokesArgs()
+                sa.n, sa.lon, sa.lat, sa.z = fx.n, _p(lon), _p(lat), _p(z)
+                sa.us, sa.vs, sa.hs, sa.xwind, sa.ywind = _p(us), _p(vs), _p(hs), _p(xw), _p(yw)
+                sa.moving, sa.dt, sa.z_f64 = _p(moving), float(fx.dt), 1 if z.dtype == np.float64 else 0
+                sa.hs_mode, sa.profile = mode, PROFILES[m['stokes']]
+                assert lib.hs_stokes(C.byref(sa)) == 0
         if z_new is not None:
             z = z_new
         t = t + dt
@@ -244,6 +299,13 @@ def run_engine(fx, fused=True, sort_every=0):
     kgrp = None
     if m.get('mixing'):
         kgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.kdiff[ti], (0.0,))
+    sgrp = hgrp = None
+    if m.get('stokes'):
+        sx, sy = fx.stokes['sea_surface_wave_stokes_drift_x_velocity'], fx.stokes['sea_surface_wave_stokes_drift_y_velocity']
+        sgrp = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times, lambda ti, c: (sx, sy)[c][ti], (0.0, 0.0))
+        if 'sea_surface_wave_significant_height' in fx.stokes:
+            hh = fx.stokes['sea_surface_wave_significant_height']
+            hgrp = eng.add_group(fx.grid_lon, fx.grid_lat, None, 1, fx.times, lambda ti, c: hh[ti], (0.0,))
     cdf, wdf, moving = fx.props()
     lon = eng.to_device(fx.lon0.astype(np.float64))
     lat = eng.to_device(fx.lat0.astype(np.float64))
@@ -258,6 +320,12 @@ def run_engine(fx, fused=True, sort_every=0):
         if m['diffusivity']:
             rand = (eng.to_device(np.random.normal(scale=1, size=fx.n)),
                     eng.to_device(np.random.normal(scale=1, size=fx.n)))
+        senv = None
+        if sgrp is not None:
+            us, vs = eng.interp(sgrp, t, lon, lat, z, pos_f32=first)
+            hs = eng.interp(hgrp, t, lon, lat, z, pos_f32=first)[0] if hgrp is not None else None
+            xw, yw = eng.interp(wind, t, lon, lat, z, pos_f32=first)
+            senv = (us, vs, hs, xw, yw)
         z_new = None
         if kgrp is not None:
             ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
@@ -269,6 +337,13 @@ def run_engine(fx, fused=True, sort_every=0):
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
                                 diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new)
+            if senv is not None:
+                us, vs, hs, xw, yw = senv
+                mode = None
+                if eng.minmax(us, vs)[1] != 0:
+                    mode = 0 if (hs is not None and eng.minmax(hs)[1] > 0) else (1 if max(eng.minmax(xw)[1], -eng.minmax(xw)[0], eng.minmax(yw)[1], -eng.minmax(yw)[0]) > 0 else 2)
+                if mode is not None:
+                    eng.stokes_drift(lon, lat, z, us, vs, hs, xw, yw, d_mov, fx.dt, mode, m['stokes'])
             if z_new is not None:
                 z = z_new
         else:

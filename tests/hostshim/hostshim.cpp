@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../opendrift_b200/csrc/od_advect.cuh"
 #include "../../opendrift_b200/csrc/od_mix.cuh"
+#include "../../opendrift_b200/csrc/od_stokes.cuh"
 
 using namespace od;
 
@@ -164,6 +165,21 @@ int hs_mix(const hs_mix_args* a) {
     for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
     std::vector<double> K(nz);
     for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy, K.data());
+    return 0;
+}
+
+struct hs_stokes_args {
+    int64_t n; double* lon; double* lat; const void* z; const float* us; const float* vs; const float* hs;
+    const float* xwind; const float* ywind; const int32_t* moving; double dt; int32_t z_f64, hs_mode, profile, pad_;
+};
+
+int hs_stokes(const hs_stokes_args* a) {
+    StokesParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z = a->z; p.us = a->us; p.vs = a->vs; p.hs = a->hs;
+    p.xwind = a->xwind; p.ywind = a->ywind; p.moving = a->moving; p.dt = a->dt; p.z_f64 = a->z_f64;
+    p.hs_mode = a->hs_mode; p.profile = a->profile;
+    for (int64_t i = 0; i < a->n; ++i) stokes_particle(p, i);
     return 0;
 }
 

@@ -26,6 +26,9 @@ def _model(fx, **cfg):
     if fx.x_wind is not None:
         o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times,
                                                 {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind'))
+    if fx.stokes is not None:
+        o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, dict(fx.stokes), name='waves'))
+        o.set_config('drift:stokes_drift_profile', m['stokes'])
     o.set_config('general:use_auto_landmask', False)
     o.set_config('general:coastline_action', 'none')
     o.set_config('drift:advection_scheme', m['scheme'])
@@ -76,16 +79,23 @@ def test_overridden_update_uses_helpers_and_matches():
             self.advect_wind()
             self.vertical_advection()
 
+    class MyStokesDrift(OceanDrift):
+        def update(self):
+            self.advect_ocean_current()
+            self.advect_wind()
+            self.stokes_drift()
+
     class MyMixingDrift(OceanDrift):
         def update(self):
             self.advect_ocean_current()
             self.vertical_mixing()
             self.vertical_advection()
 
-    for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32', 'rk4_3d_mixing', 'euler_3d_mixing_w'):
+    for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32', 'rk4_3d_mixing', 'euler_3d_mixing_w',
+                 'rk4_3d_stokes_phillips', 'euler_3d_stokes_mono_nohs'):
         fx = Fixture(name)
         o = _model(fx)
-        o.__class__ = MyMixingDrift if fx.meta.get('mixing') else MyDrift
+        o.__class__ = MyMixingDrift if fx.meta.get('mixing') else (MyStokesDrift if fx.meta.get('stokes') else MyDrift)
         o.run(steps=fx.steps, time_step=fx.dt)
         e = common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)
         assert max(e) < 5e-8, (name, e)
