@@ -257,6 +257,18 @@ def run_b200(args):
         torch.cuda.synchronize()
         kern_ms.append(ka.elapsed_time(kb))
     kernel_ms = float(np.median(kern_ms))
+    # the opt-in fast arithmetic (float32 sampling + mid-latitude moves on float64 positions), same launch
+    fast_ms = []
+    for _ in range(5):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tl, ta = st['lon'].clone(), st['lat'].clone()
+        torch.cuda.synchronize()
+        ka.record()
+        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'], fast=True)
+        kb.record()
+        torch.cuda.synchronize()
+        fast_ms.append(ka.elapsed_time(kb))
+    fast_kernel_ms = float(np.median(fast_ms))
 
     # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
@@ -334,6 +346,10 @@ def run_b200(args):
                      'note': 'this float64 kernel is bound by the FP64 pipe (ncu: fp64 pipe ~45% of peak, issue slots ~51%), '
                              'not by its 65 algorithmic bytes per particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
+        'fast_mode': {'kernel_ms': fast_kernel_ms, 'particle_steps_per_s_kernel': n / (fast_kernel_ms * 1e-3),
+                      'hbm_frac_algorithmic': b_alg / (fast_kernel_ms * 1e-3) / 1e9 / peak,
+                      'note': 'opt-in FastMath (float32 sampling, mid-latitude moves on float64 positions), <= 2e-8 deg from the '
+                              'reference on the fixtures; not the headline: value/e2e use the exact mode'},
     }
     print(json.dumps(line))
     if world > 1:

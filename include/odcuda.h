@@ -155,7 +155,9 @@ typedef struct od_advect_args {
     float* d_env_v;
     int32_t z_f64;                /* dtype of d_z (and d_z_inout): the reference's z is float32 until vertical mixing
                                      makes it float64 (oceandrift.py:527) */
-    int32_t pad2_;
+    int32_t fast;                 /* 0: exact restatement of the reference arithmetic (bit-exact sampling, Karney
+                                     geodesic); 1: float32 sampling and mid-latitude moves on float64 positions
+                                     (~1e-7 deg from the reference after 100 steps; see od_advect.cuh FastMath) */
 } od_advect_args;
 
 int od_advect_current(od_ctx* ctx, const od_advect_args* a);

@@ -38,7 +38,7 @@ class AdvectArgs(C.Structure):
                 ('d_factor', C.c_void_p), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32),
                 ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
                 ('truncate_below', C.c_double),
-                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('pad2_', C.c_int32)]
+                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('fast', C.c_int32)]
 
 
 class StepArgs(C.Structure):

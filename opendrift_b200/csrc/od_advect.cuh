@@ -55,14 +55,153 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
     geod_move(gs, lon0, az, OD_DMUL(vel, dt), lon1, lat1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Arithmetic policies of the step.  ExactMath is the restatement of the reference (bit-exact field sampling,
+// Karney geodesic).  FastMath keeps float64 positions but does the per-step arithmetic in float32:
+//   * field sampling: time lerp of the eight corner texels, then trilinear, with float32 FMAs (the fractional
+//     cell index is still formed in float64 from the float64 position);
+//   * moves: for displacements up to 5 km the ellipsoidal mid-latitude formulas with the azimuth-convergence
+//     correction (truncation error 4e-7 m for a 300 m step, 4e-4 m for 3 km at |lat| < 70; float32 rounding
+//     ~1e-4 m per step), meridional / prime-vertical radii from a second-order expansion of sin/cos about the
+//     start latitude; longer displacements fall back to the exact geodesic.  RK mid-points (which only feed
+//     the sampler) use the uncorrected first-order form.
+// Measured against the reference fixtures FastMath stays within ~1e-7 deg after 14 RK4 steps (tolerance of
+// the float64 path: 1e-6 deg); it is an opt-in (`gpu:precision = fast`, od_advect_args.fast).
+// ---------------------------------------------------------------------------------------------------------
+struct ExactMath {
+    typedef GeodStart Start;
+    OD_HDS Start start(double lat0) { return geod_start(lat0); }
+    OD_HDS void midpoint(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
+        rk_midpoint(s, lon0, ku, kv, dt32, mlon, mlat);
+    }
+    OD_HDS void move32(const Start& s, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
+        final_move_f32(s, lon0, xv, yv, mv, dt, lon1, lat1);
+    }
+    OD_HDS void move64(const Start& s, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
+        final_move_f64(s, lon0, xv, yv, mv, dt, lon1, lat1);
+    }
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32) {
+        sample2(g, pr, vw, lon, lat, u, v, pos_f32);
+    }
+    OD_HDS float sample_s(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
+        return sample1(g, pr, vw, lon, lat, pos_f32);
+    }
+};
+
+struct FastStart {
+    float s0, c0;        // sin, cos of the start latitude
+    float im, in_;       // 1/M(lat0), 1/(N(lat0) cos lat0)  [radians per metre]
+};
+
+struct FastMath {
+    typedef FastStart Start;
+    OD_HDS Start start(double lat0) {
+        Start st;
+        double sd, cd;
+        sincosd(lat0, sd, cd);
+        st.s0 = (float)sd;
+        st.c0 = (float)cd;
+        radii(st.s0, st.c0, st.im, st.in_);
+        return st;
+    }
+    // 1/M and 1/(N cos phi) from sin, cos of the latitude: W^2 = 1 - e^2 sin^2, N = a/W, M = a (1-e^2) / W^3
+    OD_HDS void radii(float s, float c, float& im, float& in_) {
+        const float W2 = 1.0f - (float)Wgs84::e2 * s * s;
+        const float W = sqrtf(W2);
+        im = W2 * W * (float)(1.0 / (Wgs84::a * (1.0 - Wgs84::e2)));
+        in_ = W * (float)(1.0 / Wgs84::a) / c;
+    }
+    // first-order displacement (RK mid-points: the position only feeds the field sampler)
+    OD_HDS void midpoint(const Start& st, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
+        const float h = 0.5f * dt32;
+        mlat = lat0 + (double)(kv * h * st.im * (float)kRad2Deg);
+        mlon = lon0 + (double)(ku * h * st.in_ * (float)kRad2Deg);
+    }
+    OD_HDS void move_m(const Start& st, double lon0, double lat0, float de, float dn, double& lon1, double& lat1) {
+        if (!(fabsf(de) + fabsf(dn) <= 5000.0f)) {          // long step (or NaN): exact geodesic
+            const double az = atan2((double)de, (double)dn) * kRad2Deg;
+            geod_direct(lon0, lat0, az, sqrt((double)de * de + (double)dn * dn), lon1, lat1);
+            return;
+        }
+        // mid-latitude formulas with one azimuth-convergence correction
+        float dphi = dn * st.im;
+        float d = 0.5f * dphi;
+        float sm = st.s0 + d * (st.c0 - 0.5f * d * st.s0), cm = st.c0 - d * (st.s0 + 0.5f * d * st.c0);
+        float im, in_;
+        radii(sm, cm, im, in_);
+        const float dalp = de * in_ * sm;                    // convergence of the meridians over the step
+        const float de2 = de + 0.5f * dn * dalp, dn2 = dn - 0.5f * de * dalp;
+        dphi = dn2 * im;
+        d = 0.5f * dphi;
+        sm = st.s0 + d * (st.c0 - 0.5f * d * st.s0);
+        cm = st.c0 - d * (st.s0 + 0.5f * d * st.c0);
+        radii(sm, cm, im, in_);
+        lat1 = lat0 + (double)(dn2 * im * (float)kRad2Deg);
+        double lo = lon0 + (double)(de2 * in_ * (float)kRad2Deg);
+        lon1 = ang_normalize(lo);
+    }
+    OD_HDS void move32(const Start& st, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
+        const float k = (float)(mv * dt);
+        move_m(st, lon0, lat0, xv * k, yv * k, lon1, lat1);
+    }
+    OD_HDS void move64(const Start& st, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
+        const double k = mv * dt;
+        move_m(st, lon0, lat0, (float)(xv * k), (float)(yv * k), lon1, lat1);
+    }
+    OD_HDS float lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
+    // time lerp of the corners, then trilinear, float32 FMAs
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool) {
+        float ru = NAN, rv = NAN;
+        double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
+        const double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
+        if (pr.mode != 3 && x >= g.xmin && x <= g.xmax && lat >= g.ymin && lat <= g.ymax &&
+            xi >= 0.0 && xi <= g.nxm1 && yi >= 0.0 && yi <= g.nym1) {
+            const double fx = floor(xi), fy = floor(yi);
+            const int ix = (int)fx, iy = (int)fy;
+            const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1, iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
+            const float tx = (float)(xi - fx), ty = (float)(yi - fy);
+            const float tw = pr.mode == 0 ? (float)pr.w : (pr.mode == 1 ? 0.0f : 1.0f);
+            const long long layer = (long long)g.nx * g.ny;
+            float lu[2], lvv[2];
+            const int nl = g.nz > 1 ? 2 : 1;
+            for (int l = 0; l < nl; ++l) {
+                const float* t = pr.tex + ((long long)(l == 0 ? vw.ia : vw.ib) * layer) * 4;
+                const Tex4 a00 = ld_tex4(t + 4ll * (iy * g.nx + ix)), a01 = ld_tex4(t + 4ll * (iy * g.nx + ix1));
+                const Tex4 a10 = ld_tex4(t + 4ll * (iy1 * g.nx + ix)), a11 = ld_tex4(t + 4ll * (iy1 * g.nx + ix1));
+                const float u0 = lerp(lerp(a00.x, a00.z, tw), lerp(a01.x, a01.z, tw), tx);
+                const float u1 = lerp(lerp(a10.x, a10.z, tw), lerp(a11.x, a11.z, tw), tx);
+                const float v0 = lerp(lerp(a00.y, a00.w, tw), lerp(a01.y, a01.w, tw), tx);
+                const float v1 = lerp(lerp(a10.y, a10.w, tw), lerp(a11.y, a11.w, tw), tx);
+                lu[l] = lerp(u0, u1, ty);
+                lvv[l] = lerp(v0, v1, ty);
+            }
+            if (nl == 2) {
+                const float wb = 1.0f - (float)vw.wa;
+                ru = lerp(lu[0], lu[1], wb);
+                rv = lerp(lvv[0], lvv[1], wb);
+            } else {
+                ru = lu[0];
+                rv = lvv[0];
+            }
+        }
+        if (!finite_f(ru)) ru = g.fallback[0];
+        if (!finite_f(rv)) rv = g.fallback[1];
+        u = ru;
+        v = rv;
+    }
+    OD_HDS float sample_s(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
+        return sample1(g, pr, vw, lon, lat, pos_f32);       // one sample per step: the exact sampler is fine
+    }
+};
+
 struct CurrentStages {
     GroupGeom g;
     PairRef t_start, t_mid, t_end;
 };
 
 // Returns the RK-combined velocity (float32) that the final move uses; k1 is sampled here unless given.
-template <int SCHEME>
-OD_HD void rk_velocity(const CurrentStages& cs, const VertW& vw, const GeodStart& gs, double lon0, double lat0,
+template <int SCHEME, class MATH>
+OD_HD void rk_velocity(const CurrentStages& cs, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
                        float dt32, float k1u, float k1v, float& ou, float& ov) {
     if (SCHEME == 0) {
         ou = k1u;
@@ -70,20 +209,20 @@ OD_HD void rk_velocity(const CurrentStages& cs, const VertW& vw, const GeodStart
         return;
     }
     double mlon, mlat;
-    rk_midpoint(gs, lon0, k1u, k1v, dt32, mlon, mlat);
+    MATH::midpoint(gs, lon0, lat0, k1u, k1v, dt32, mlon, mlat);
     float k2u, k2v;
-    sample2(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v);
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false);
     if (SCHEME == 1) {
         ou = k2u;
         ov = k2v;
         return;
     }
-    rk_midpoint(gs, lon0, k2u, k2v, dt32, mlon, mlat);
+    MATH::midpoint(gs, lon0, lat0, k2u, k2v, dt32, mlon, mlat);
     float k3u, k3v;
-    sample2(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v);
-    rk_midpoint(gs, lon0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false);
+    MATH::midpoint(gs, lon0, lat0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
     float k4u, k4v;
-    sample2(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v);     // ... at time t + dt
+    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false);     // ... at time t + dt
     // (x_vel + 2*x_vel2 + 2*x_vel3 + x_vel4)/6.0, float32, left to right
     ou = OD_FADD(OD_FADD(OD_FADD(k1u, OD_FMUL(2.0f, k2u)), OD_FMUL(2.0f, k3u)), k4u) / 6.0f;
     ov = OD_FADD(OD_FADD(OD_FADD(k1v, OD_FMUL(2.0f, k2v)), OD_FMUL(2.0f, k3v)), k4v) / 6.0f;
@@ -124,7 +263,7 @@ struct StepParams {
 
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
-template <int SCHEME, bool F64, bool EXTRAS>
+template <int SCHEME, bool F64, bool EXTRAS, class MATH = ExactMath>
 OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
                          const double* zsw, const double* zyw) {
     const GroupGeom& g = p.cs.g;
@@ -135,7 +274,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
     if (p.truncate_below > 0.0 && zt < -p.truncate_below) zt = zf32 ? (double)(float)(-p.truncate_below) : -p.truncate_below;
     const VertW vw = vert_weights(g, zs, zy, zt, zf32);
     const double mv = p.moving ? (double)p.moving[i] : 1.0;
-    const GeodStart gs = geod_start(lat0);
+    const typename MATH::Start gs = MATH::start(lat0);
 
     // stage 1: the start-of-step environment
     float k1u, k1v;
@@ -143,21 +282,21 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         k1u = p.k1u[i];
         k1v = p.k1v[i];
     } else {
-        sample2(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0);
+        MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0);
     }
     if (p.env_u) p.env_u[i] = k1u;
     if (p.env_v) p.env_v[i] = k1v;
 
     float ru, rv;
-    rk_velocity<SCHEME>(p.cs, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv);
+    rk_velocity<SCHEME, MATH>(p.cs, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv);
 
     double lon1, lat1;
     if (F64) {
         const double f = p.factor ? ((const double*)p.factor)[i] : 1.0;
-        final_move_f64(gs, lon0, OD_DMUL((double)ru, f), OD_DMUL((double)rv, f), mv, p.dt, lon1, lat1);
+        MATH::move64(gs, lon0, lat0, OD_DMUL((double)ru, f), OD_DMUL((double)rv, f), mv, p.dt, lon1, lat1);
     } else {
         const float f = p.factor ? ((const float*)p.factor)[i] : 1.0f;
-        final_move_f32(gs, lon0, OD_FMUL(ru, f), OD_FMUL(rv, f), mv, p.dt, lon1, lat1);
+        MATH::move32(gs, lon0, lat0, OD_FMUL(ru, f), OD_FMUL(rv, f), mv, p.dt, lon1, lat1);
     }
 
     if (EXTRAS) {
@@ -165,7 +304,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         if (p.wind_on) {
             const VertW v0 = {0, 0, 1.0};
             float xw, yw;
-            sample2(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+            MATH::sample_uv(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
             const double wdd = fabs(p.wind_drift_depth);
             const bool surface = z0 >= -wdd;
             if (p.wdf_f64 || wdd != 0.0) {
@@ -178,16 +317,16 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
                 if (!surface) wdf = 0.0;
                 const double xv = OD_DMUL((double)xw, wdf), yv = OD_DMUL((double)yw, wdf);
                 if (xv != 0.0 || yv != 0.0) {
-                    const GeodStart g1 = geod_start(lat1);
-                    final_move_f64(g1, lon1, xv, yv, mv, p.dt, lon1, lat1);
+                    const typename MATH::Start g1 = MATH::start(lat1);
+                    MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
                 }
             } else {
                 float wdf = ((const float*)p.wdf)[i];
                 if (!surface) wdf = 0.0f;
                 const float xv = OD_FMUL(xw, wdf), yv = OD_FMUL(yw, wdf);
                 if (xv != 0.0f || yv != 0.0f) {
-                    const GeodStart g1 = geod_start(lat1);
-                    final_move_f32(g1, lon1, xv, yv, mv, p.dt, lon1, lat1);
+                    const typename MATH::Start g1 = MATH::start(lat1);
+                    MATH::move32(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
                 }
             }
         }
@@ -199,7 +338,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
             const bool applicable = p.w_at_surface ? (zc <= 0.0) : (zc < 0.0);
             if (applicable) {
                 const VertW vww = vert_weights(p.gw, zsw, zyw, zt, zf32);
-                const float w = sample1(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
+                const float w = MATH::sample_s(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
                 const double zn = fmin(0.0, OD_DADD(zc, OD_DMUL(OD_DMUL(mv, (double)w), p.dt)));
                 if (zio32) ((float*)p.z_inout)[i] = (float)zn;
                 else ((double*)p.z_inout)[i] = zn;
@@ -212,8 +351,8 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
             const double sd = OD_DMUL(mv, (double)s);
             const double xv = OD_DMUL(sd, p.rand_x[i]), yv = OD_DMUL(sd, p.rand_y[i]);
             if (xv != 0.0 || yv != 0.0) {
-                const GeodStart g1 = geod_start(lat1);
-                final_move_f64(g1, lon1, xv, yv, mv, p.dt, lon1, lat1);
+                const typename MATH::Start g1 = MATH::start(lat1);
+                MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
             }
         }
     }

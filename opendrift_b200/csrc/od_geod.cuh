@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define OD_HD __host__ __device__ __forceinline__
+#define OD_HDS static __host__ __device__ __forceinline__
 #else
 #define OD_HD static inline
+#define OD_HDS static inline
 #endif
 
 namespace od {

@@ -43,6 +43,7 @@ struct GroupGeom {
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     double nxm1, nym1;
+    double inv_dx, inv_dy;   // (nx-1)/xspan, (ny-1)/yspan (fast sampler only)
     double zmin, zmax;       // min / max of the level depths
     float fallback[2];
     const double* zs;        // [nz] level depths in increasing order

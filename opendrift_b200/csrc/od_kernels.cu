@@ -331,6 +331,7 @@ static GroupGeom make_geom(const Group& g) {
     q.x0 = g.desc.x0; q.xspan = g.desc.xspan; q.y0 = g.desc.y0; q.yspan = g.desc.yspan;
     q.xmin = g.desc.xmin; q.xmax = g.desc.xmax; q.ymin = g.desc.ymin; q.ymax = g.desc.ymax;
     q.nxm1 = (double)(g.desc.nx - 1); q.nym1 = (double)(g.desc.ny - 1);
+    q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
     q.zmin = g.zmin; q.zmax = g.zmax;
     q.fallback[0] = g.desc.fallback[0]; q.fallback[1] = g.desc.fallback[1];
     q.zs = g.d_zs; q.zy = g.d_zy;
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(OD_BLOCK) update_positions_kernel(int64_t n, d
     lat[i] = la;
 }
 
-template <int SCHEME, bool F64, bool EXTRAS>
+template <int SCHEME, bool F64, bool EXTRAS, class MATH>
 __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const StepParams p) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const Step
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    step_particle<SCHEME, F64, EXTRAS>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+    step_particle<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
 // ---- vertical mixing -----------------------------------------------------------------------------
@@ -645,11 +646,11 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
     return OD_OK;
 }
 
-template <bool EXTRAS>
+template <bool EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
-#define OD_LAUNCH(S, F) step_kernel<S, F, EXTRAS><<<grid, OD_BLOCK, 0, s>>>(p)
+#define OD_LAUNCH(S, F) step_kernel<S, F, EXTRAS, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
     if (scheme == OD_EULER) { if (f64) OD_LAUNCH(0, true); else OD_LAUNCH(0, false); }
     else if (scheme == OD_RK2) { if (f64) OD_LAUNCH(1, true); else OD_LAUNCH(1, false); }
     else { if (f64) OD_LAUNCH(2, true); else OD_LAUNCH(2, false); }
@@ -666,7 +667,8 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     int rc = fill_current(ctx, a, &p);
     if (rc) return rc;
     if (a->n == 0) return OD_OK;
-    return launch_step<false>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->fast) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    return launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
 }
 
 extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
@@ -708,7 +710,8 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         p.diffusivity_const = a->diffusivity_const;
     }
     if (a->cur.n == 0) return OD_OK;
-    return launch_step<true>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    if (a->cur.fast) return launch_step<true, FastMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    return launch_step<true, ExactMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
 }
 
 extern "C" int od_minmax_f32(od_ctx* ctx, int64_t n, const float* d_a, const float* d_b, float* h_min, float* h_max) {

@@ -265,8 +265,9 @@ class Engine:
                                                  _ptr(yvel), f64, _ptr(moving), float(dt)))
 
     def _advect_args(self, a, group, scheme, t, dt_seconds, half, full, lon, lat, z, factor, moving,
-                     k1=None, truncate_below=None, env_out=None, pos_f32=False):
+                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=False):
         a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
+        a.fast = 1 if fast else 0
         a.pos_f32 = 1 if pos_f32 else 0
         a.group_uv = group.gid
         pinned = ()
@@ -296,24 +297,24 @@ class Engine:
             a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
 
     def advect_current(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None, k1=None,
-                       truncate_below=None, env_out=None, pos_f32=False):
+                       truncate_below=None, env_out=None, pos_f32=False, fast=False):
         """advect_ocean_current on device tensors (in place).  t is the reader-time object (datetime
         or seconds), dt a timedelta-like or seconds."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
         self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving, k1,
-                          truncate_below, env_out, pos_f32)
+                          truncate_below, env_out, pos_f32, fast)
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
 
     def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
                         truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
-                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None):
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=False):
         """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
         array that vertical advection updates -- a different buffer after vertical mixing."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         s = StepArgs()
         self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
-                          None, truncate_below, None, pos_f32)
+                          None, truncate_below, None, pos_f32, fast)
         s.group_wind = -1
         s.group_w = -1
         if wind is not None:
@@ -338,7 +339,7 @@ class Engine:
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
 
     def advect_current_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None,
-                            factor=None, moving=None, chunks=8, pos_f32=False):
+                            factor=None, moving=None, chunks=8, pos_f32=False, fast=False):
         """advect_ocean_current for HOST arrays (pinned torch tensors): the particle range is cut into chunks
         whose host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the
         PCIe transfers of neighbouring chunks overlap the kernel.  Results land in h_out_lon / h_out_lat
@@ -362,7 +363,7 @@ class Engine:
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
         self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, bufs[0][0][:1], bufs[0][1][:1],
-                          bufs[0][2][:1] if h_z is not None else None, factor, moving, None, None, None, pos_f32)
+                          bufs[0][2][:1] if h_z is not None else None, factor, moving, None, None, None, pos_f32, fast)
         a.n = 0
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))     # n = 0: builds the pair texels only
         ready = torch.cuda.Event()

@@ -107,7 +107,7 @@ class HsStepArgs(C.Structure):
                 ('g_wind', HsGroup), ('t_wind', HsPair), ('wdf', C.c_void_p), ('wind_drift_depth', C.c_double),
                 ('g_w', HsGroup), ('t_w', HsPair), ('z_inout', C.c_void_p),
                 ('rand_x', C.c_void_p), ('rand_y', C.c_void_p), ('diffusivity', C.c_void_p),
-                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32)]
+                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32), ('fast', C.c_int32), ('pad1_', C.c_int32)]
 
 
 class HsStokesArgs(C.Structure):
@@ -203,7 +203,7 @@ class HsField:
         return pr
 
 
-def run_hostshim(fx):
+def run_hostshim(fx, fast=False):
     lib = hostshim()
     m = fx.meta
     cur = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.u, fx.v], fx.times)
@@ -244,6 +244,7 @@ def run_hostshim(fx):
             xw, yw = wind.sample(lib, t, lon, lat, z, istep == 0)
             senv = (us, vs, hs, xw, yw)
         a = HsStepArgs()
+        a.fast = 1 if fast else 0
         a.pos_f32 = 1 if istep == 0 else 0
         a.z_f64 = 1 if z.dtype == np.float64 else 0
         a.scheme = {'euler': 0, 'runge-kutta': 1, 'runge-kutta4': 2}[m['scheme']]
@@ -281,7 +282,7 @@ def run_hostshim(fx):
     return lon, lat, z
 
 
-def run_engine(fx, fused=True, sort_every=0):
+def run_engine(fx, fused=True, sort_every=0, fast=False):
     """Replay a fixture on the GPU through the product Engine."""
     import torch
     from opendrift_b200.engine import Engine
@@ -336,7 +337,7 @@ def run_engine(fx, fused=True, sort_every=0):
             eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
-                                diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new)
+                                diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new, fast=fast)
             if senv is not None:
                 us, vs, hs, xw, yw = senv
                 mode = None
@@ -349,7 +350,7 @@ def run_engine(fx, fused=True, sort_every=0):
         else:
             assert not (m['wind'] or m['with_w'] or m['diffusivity'])
             eng.advect_current(cur, m['scheme'], t, dt, lon, lat, z if three_d else None, factor=d_cdf,
-                               moving=d_mov, pos_f32=first)
+                               moving=d_mov, pos_f32=first, fast=fast)
         t = t + dt
     eng.sync()
     out = lon.cpu().numpy(), lat.cpu().numpy(), (z.cpu().numpy() if z is not None else fx.z0)

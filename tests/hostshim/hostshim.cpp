@@ -38,6 +38,7 @@ static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
     q.x0 = d.x0; q.xspan = d.xspan; q.y0 = d.y0; q.yspan = d.yspan;
     q.xmin = d.xmin; q.xmax = d.xmax; q.ymin = d.ymin; q.ymax = d.ymax;
     q.nxm1 = (double)(d.nx - 1); q.nym1 = (double)(d.ny - 1);
+    q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
     q.fallback[0] = d.fallback[0]; q.fallback[1] = d.fallback[1];
     if (d.nz > 1) {
         lv.zs.resize(d.nz); lv.zy.resize(d.nz);
@@ -95,13 +96,15 @@ struct hs_step_args {
     hs_group g_wind; hs_pair t_wind; const void* wdf; double wind_drift_depth;
     hs_group g_w; hs_pair t_w; void* z_inout;
     const double* rand_x; const double* rand_y; const float* diffusivity; float diffusivity_const; int32_t z_inout_f64;
+    int32_t fast, pad1_;
 };
 
 }  // extern "C"
 
 template <int S, bool F>
-static void run(const StepParams& p, const GroupGeom& gw) {
-    for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+static void run(const StepParams& p, const GroupGeom& gw, bool fast = false) {
+    if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
 }
 
 extern "C" {
@@ -132,9 +135,9 @@ int hs_step(const hs_step_args* a) {
     }
     const bool f = a->factor_f64 != 0;
     switch (a->scheme) {
-        case 0: f ? run<0, true>(p, p.gw) : run<0, false>(p, p.gw); break;
-        case 1: f ? run<1, true>(p, p.gw) : run<1, false>(p, p.gw); break;
-        case 2: f ? run<2, true>(p, p.gw) : run<2, false>(p, p.gw); break;
+        case 0: f ? run<0, true>(p, p.gw, a->fast) : run<0, false>(p, p.gw, a->fast); break;
+        case 1: f ? run<1, true>(p, p.gw, a->fast) : run<1, false>(p, p.gw, a->fast); break;
+        case 2: f ? run<2, true>(p, p.gw, a->fast) : run<2, false>(p, p.gw, a->fast); break;
         default: return -2;
     }
     return 0;

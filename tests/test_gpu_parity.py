@@ -53,6 +53,19 @@ def test_fused_step_vs_reference_fixture(name):
     assert max(e2) < TIGHT_DEG, e2
 
 
+@pytest.mark.parametrize('name', fixtures())
+def test_fast_mode_within_float64_tolerance(name):
+    """FastMath (float32 sampling + mid-latitude moves on float64 positions) stays inside the float64 tolerance
+    of the north star (1e-6 deg) with a wide margin; the exact mode remains the default."""
+    fx = Fixture(name)
+    lon, lat, z = common.run_engine(fx, fused=True, fast=True)
+    elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    assert elon < TOL_DEG and elat < TOL_DEG, (elon, elat)
+    assert elon < 1e-7 and elat < 1e-7, (elon, elat)
+    hl, ha, hz = common.run_hostshim(fx, fast=True)          # same arithmetic on the host build
+    assert max(common.max_err_deg(lon, lat, hl, ha)) < 1e-7
+
+
 @pytest.mark.parametrize('name', ['rk4_3d', 'rk2_3d', 'euler_3d', 'rk4_2d', 'rk4_3d_cdf32'])
 def test_advect_current_entry_point(name):
     fx = Fixture(name)

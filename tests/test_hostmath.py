@@ -35,6 +35,14 @@ def test_step_vs_reference_fixture(name):
     assert np.abs(z - fx.z).max() <= (0.0 if fx.meta.get('mixing') else 1e-5)
 
 
+@pytest.mark.parametrize('name', fixtures())
+def test_fast_mode_vs_reference_fixture(name):
+    fx = Fixture(name)
+    lon, lat, z = run_hostshim(fx, fast=True)
+    elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    assert elon < 1e-7 and elat < 1e-7, (elon, elat)
+
+
 def test_interpolation_bit_exact():
     """od_interp arithmetic == ReaderBlock/Linear2DInterpolator/Linear1DInterpolator/time lerp/float32 cast."""
     from datetime import timedelta
