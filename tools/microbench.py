@@ -47,6 +47,9 @@ res['update_positions_f32_ms'] = timeit(lambda: eng.update_positions(l2, a2, xv,
 l2, a2 = lon.clone(), lat.clone()
 res['step_rk4_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z))
 l2, a2 = lon.clone(), lat.clone()
+l2, a2 = lon.clone(), lat.clone()
+res['step_rk4_fast_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=True))
+l2, a2 = lon.clone(), lat.clone()
 res['step_euler_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z))
 res['sort_by_cell_ms'] = timeit(lambda: eng.sort_by_cell(grp, lon, lat, z))
 res['permute_f64_ms'] = timeit(lambda: eng.permute(perm, lon))
