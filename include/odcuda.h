@@ -185,6 +185,37 @@ typedef struct od_step_args {
 
 int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
 
+/* ---- Leeway ------------------------------------------------------------------------------------------
+ * Leeway.update (models/leeway.py:430-494, capsizing excluded): leeway move + current move + jibing in one launch.
+ * Wind and current are 2-D two-component groups sampled at the start-of-step position.  Elements with a missing
+ * sample get status = missing_code (report_missing_variables) and do not move. */
+typedef struct od_leeway_args {
+    int32_t group_wind, group_cur;
+    od_time_sample t_wind, t_cur;
+    int64_t n;
+    double* d_lon;
+    double* d_lat;
+    const float* d_dw_slope;
+    const float* d_dw_offset;
+    const float* d_dw_eps;
+    float* d_cw_slope;            /* in/out: sign flips when an element jibes */
+    const float* d_cw_offset;
+    const float* d_cw_eps;
+    uint8_t* d_orientation;       /* in/out */
+    const uint8_t* d_capsized;    /* NULL = none */
+    const void* d_jibe_probability;   /* float32, or float64 when jp_f64 */
+    const int32_t* d_moving;
+    int32_t* d_status;            /* NULL = do not flag missing data */
+    const int32_t* d_ids;
+    const double* d_rand;         /* np.random.random(n) of this step (parity), or NULL: Philox keyed by (seed, ID, step) */
+    double dt;
+    uint64_t seed;
+    float capsize_fraction;       /* capsizing:leeway_fraction */
+    int32_t jp_f64, pos_f32, step_index, missing_code, pad_;
+} od_leeway_args;
+
+int od_leeway_step(od_ctx* ctx, const od_leeway_args* a);
+
 /* ---- Stokes drift and reductions -----------------------------------------------------------------
  * od_minmax_f32: min / max of a[i] (or a[i] + b[i] when d_b is given) with NaNs ignored, returned to the host
  * (synchronises).  These are the collective decisions the reference takes with .max() / .min() on environment
@@ -254,6 +285,11 @@ int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* d_lon, cons
 int od_permute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);
 /* dst[perm[k]] = src[k] */
 int od_unpermute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);
+
+/* Stable partition for remove_deactivated_elements (basemodel/__init__.py:1797-1826, elements.py:197-228):
+ * perm_out = [indices with status == 0, in order | indices with status != 0, in order]; *h_n_keep = number kept
+ * (synchronises).  Apply with od_permute to every element column. */
+int od_partition_active(od_ctx* ctx, int64_t n, const int32_t* d_status, int32_t* d_perm_out, int64_t* h_n_keep);
 
 /* counters of the library's own kernel launches since creation (for bench.py's gpu_launches) */
 int64_t od_launch_count(od_ctx* ctx);

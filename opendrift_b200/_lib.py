@@ -61,6 +61,17 @@ class MixArgs(C.Structure):
                 ('pos_f32', C.c_int32), ('pad_', C.c_int32)]
 
 
+class LeewayArgs(C.Structure):
+    _fields_ = [('group_wind', C.c_int32), ('group_cur', C.c_int32), ('t_wind', TimeSample), ('t_cur', TimeSample),
+                ('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_dw_slope', C.c_void_p),
+                ('d_dw_offset', C.c_void_p), ('d_dw_eps', C.c_void_p), ('d_cw_slope', C.c_void_p),
+                ('d_cw_offset', C.c_void_p), ('d_cw_eps', C.c_void_p), ('d_orientation', C.c_void_p),
+                ('d_capsized', C.c_void_p), ('d_jibe_probability', C.c_void_p), ('d_moving', C.c_void_p),
+                ('d_status', C.c_void_p), ('d_ids', C.c_void_p), ('d_rand', C.c_void_p), ('dt', C.c_double),
+                ('seed', C.c_uint64), ('capsize_fraction', C.c_float), ('jp_f64', C.c_int32), ('pos_f32', C.c_int32),
+                ('step_index', C.c_int32), ('missing_code', C.c_int32), ('pad_', C.c_int32)]
+
+
 class StokesArgs(C.Structure):
     _fields_ = [('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
                 ('d_us', C.c_void_p), ('d_vs', C.c_void_p), ('d_hs', C.c_void_p), ('d_xwind', C.c_void_p),
@@ -88,10 +99,12 @@ SYMBOLS = {
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
     'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
+    'od_leeway_step': (C.c_int, [_P, C.POINTER(LeewayArgs)]),
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'od_stokes_drift': (C.c_int, [_P, C.POINTER(StokesArgs)]),
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    'od_partition_active': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),
     'od_unpermute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),
     'od_launch_count': (C.c_int64, [_P]),

@@ -16,6 +16,7 @@
 #include "od_advect.cuh"
 #include "od_mix.cuh"
 #include "od_stokes.cuh"
+#include "od_leeway.cuh"
 
 using namespace od;
 
@@ -438,6 +439,12 @@ __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     mix_particle(p, i, xs, xy, K);
 }
 
+// ---- Leeway -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OD_BLOCK) leeway_kernel(const LeewayParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) leeway_particle(p, i);
+}
+
 // ---- Stokes drift and reductions --------------------------------------------------------------------
 __global__ void __launch_bounds__(OD_BLOCK) stokes_kernel(const StokesParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,6 +553,42 @@ __global__ void __launch_bounds__(OD_BLOCK) scatter_perm_kernel(int64_t n, const
     if (i >= n) return;
     const int pos = atomicAdd(&bins[keys[i]], 1);
     perm[pos] = (int32_t)i;
+}
+
+// ---- stable partition (deactivated-element compaction) ---------------------------------------------------
+// LagrangianArray.move_elements keeps the relative order of both the kept and the moved elements
+// (elements/elements.py:223-228).  Pass 1 counts the kept elements per block, a single-block scan turns the
+// counts into offsets, pass 2 writes perm = [kept indices in order | removed indices in order].
+#define OD_PART_BLOCK 256
+__global__ void __launch_bounds__(OD_PART_BLOCK) partition_count_kernel(int64_t n, const int32_t* __restrict__ status,
+                                                                        int32_t* __restrict__ block_keep) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int keep = (i < n && status[i] == 0) ? 1 : 0;
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_keep[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(OD_PART_BLOCK) partition_scatter_kernel(int64_t n, const int32_t* __restrict__ status,
+                                                                          const int32_t* __restrict__ block_keep_excl,
+                                                                          int64_t n_keep, int32_t* __restrict__ perm) {
+    __shared__ int warp_keep[OD_PART_BLOCK / 32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int keep = (valid && status[i] == 0) ? 1 : 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank_in_warp = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_keep[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_keep[w];
+    const int64_t keep_base = block_keep_excl[blockIdx.x];
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    if (!valid) return;
+    const int local_keep_rank = before + rank_in_warp;              // kept elements before me in this block
+    const int local_index = (int)(i - first);
+    if (keep) perm[keep_base + local_keep_rank] = (int32_t)i;
+    else perm[n_keep + (first - keep_base) + (local_index - local_keep_rank)] = (int32_t)i;
 }
 
 template <typename T>
@@ -714,6 +757,40 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
     return launch_step<true, ExactMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
 }
 
+extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_leeway_step: null argument");
+    int rc = need_group(ctx, a->group_wind, 2);
+    if (rc) return rc;
+    rc = need_group(ctx, a->group_cur, 2);
+    if (rc) return rc;
+    if (ctx->groups[a->group_wind].desc.nz != 1 || ctx->groups[a->group_cur].desc.nz != 1)
+        return fail(ctx, OD_ERR_ARG, "od_leeway_step: wind and surface current groups must be 2-D");
+    if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_dw_slope || !a->d_dw_offset || !a->d_dw_eps ||
+                                  !a->d_cw_slope || !a->d_cw_offset || !a->d_cw_eps || !a->d_orientation || !a->d_jibe_probability)))
+        return fail(ctx, OD_ERR_ARG, "od_leeway_step: bad arguments");
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    LeewayParams p;
+    memset(&p, 0, sizeof(p));
+    p.gwind = make_geom(ctx->groups[a->group_wind]);
+    p.gcur = make_geom(ctx->groups[a->group_cur]);
+    rc = resolve_pair(ctx, a->group_wind, a->t_wind, &p.pwind);
+    if (rc) return rc;
+    rc = resolve_pair(ctx, a->group_cur, a->t_cur, &p.pcur);
+    if (rc) return rc;
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat;
+    p.dw_slope = a->d_dw_slope; p.dw_offset = a->d_dw_offset; p.dw_eps = a->d_dw_eps;
+    p.cw_slope = a->d_cw_slope; p.cw_offset = a->d_cw_offset; p.cw_eps = a->d_cw_eps;
+    p.orientation = a->d_orientation; p.capsized = a->d_capsized; p.jibe_probability = a->d_jibe_probability;
+    p.moving = a->d_moving; p.status = a->d_status; p.ids = a->d_ids; p.rand = a->d_rand; p.dt = a->dt; p.seed = a->seed;
+    p.capsize_fraction = a->capsize_fraction; p.jp_f64 = a->jp_f64; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.missing_code = a->missing_code;
+    leeway_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
 extern "C" int od_minmax_f32(od_ctx* ctx, int64_t n, const float* d_a, const float* d_b, float* h_min, float* h_max) {
     if (!ctx || n < 0 || (n > 0 && !d_a) || !h_min || !h_max) return fail(ctx, OD_ERR_ARG, "od_minmax_f32: bad arguments");
     *h_min = INFINITY;
@@ -823,6 +900,32 @@ extern "C" int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* 
     scatter_perm_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, ctx->d_keys, ctx->d_bins, perm);
     CK(cudaGetLastError());
     ctx->launches += 3;
+    return OD_OK;
+}
+
+extern "C" int od_partition_active(od_ctx* ctx, int64_t n, const int32_t* d_status, int32_t* d_perm, int64_t* h_n_keep) {
+    if (!ctx || n < 0 || n >= (1ll << 31) || (n > 0 && (!d_status || !d_perm)) || !h_n_keep)
+        return fail(ctx, OD_ERR_ARG, "od_partition_active: bad arguments");
+    *h_n_keep = 0;
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int nblocks = (int)((n + OD_PART_BLOCK - 1) / OD_PART_BLOCK);
+    if (ctx->bins_cap < nblocks + 1) {
+        if (ctx->d_bins) cudaFree(ctx->d_bins);
+        ctx->d_bins = nullptr;
+        CK(cudaMalloc(&ctx->d_bins, (size_t)(nblocks + 1) * sizeof(int32_t)));
+        ctx->bins_cap = nblocks + 1;
+    }
+    CK(cudaMemsetAsync(ctx->d_bins + nblocks, 0, sizeof(int32_t), ctx->stream));
+    partition_count_kernel<<<nblocks, OD_PART_BLOCK, 0, ctx->stream>>>(n, d_status, ctx->d_bins);
+    scan_bins_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_bins, nblocks + 1);     // exclusive; last entry = total
+    int32_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_bins + nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    partition_scatter_kernel<<<nblocks, OD_PART_BLOCK, 0, ctx->stream>>>(n, d_status, ctx->d_bins, (int64_t)total, d_perm);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+    *h_n_keep = total;
     return OD_OK;
 }
 

@@ -193,15 +193,22 @@ class DeviceElements:
             self._host.pop(v, None)
         object.__setattr__(self, '_n', self._n + n_new)
 
-    def compact(self, keep_mask_dev):
-        """Keep the elements where keep_mask is True (stable); returns the removed ones as host arrays."""
+    def compact(self):
+        """Move the elements with status != 0 out (stable partition on the device, od_partition_active +
+        od_permute per column); returns the removed ones as host arrays, or None if nothing was removed."""
+        torch = self._engine.torch
+        status = self.dev('status')
+        if status.dtype != torch.int32:
+            status = status.to(torch.int32)
+        perm, n_keep = self._engine.partition_active(status)
+        if n_keep == self._n:
+            return None
         removed = {}
-        drop = ~keep_mask_dev
         for v in self.variables:
-            t = self.dev(v)
-            removed[v] = t[drop].cpu().numpy()
-            self._dev[v] = t[keep_mask_dev].contiguous()
-        object.__setattr__(self, '_n', int(keep_mask_dev.sum().item()))
+            t = self._engine.permute(perm, self.dev(v))
+            removed[v] = t[n_keep:].cpu().numpy()
+            self._dev[v] = t[:n_keep].clone()
+        object.__setattr__(self, '_n', n_keep)
         return removed
 
     def permute(self, perm):

@@ -17,7 +17,7 @@ from bisect import bisect_left
 import numpy as np
 
 from . import _lib
-from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, MixArgs, StokesArgs, OD_T_LERP, OD_T_FIRST,
+from ._lib import (GroupDesc, TimeSample, AdvectArgs, StepArgs, MixArgs, StokesArgs, LeewayArgs, OD_T_LERP, OD_T_FIRST,
                    OD_T_MISSING, SCHEMES)
 
 
@@ -397,6 +397,35 @@ class Engine:
             main.wait_event(ev)
         main.synchronize()
 
+    def leeway_step(self, wind, cur, t, dt, lon, lat, el, moving=None, status=None, ids=None, rand=None, seed=0,
+                    step_index=0, capsize_fraction=0.4, missing_code=1, pos_f32=False):
+        """Leeway.update on device tensors; el: dict of the per-element coefficient tensors."""
+        torch = self.torch
+        a = LeewayArgs()
+        a.group_wind, a.group_cur = wind.gid, cur.gid
+        a.t_wind, _ = wind.sample(t)
+        a.t_cur, _ = cur.sample(t)
+        a.n = lon.numel()
+        a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
+        for k in ('dw_slope', 'dw_offset', 'dw_eps', 'cw_slope', 'cw_offset', 'cw_eps'):
+            assert el[k].dtype == torch.float32
+            setattr(a, 'd_' + k, el[k].data_ptr())
+        assert el['orientation'].dtype == torch.uint8
+        a.d_orientation = el['orientation'].data_ptr()
+        if el.get('capsized') is not None:
+            assert el['capsized'].dtype == torch.uint8
+            a.d_capsized = el['capsized'].data_ptr()
+        jp = el['jibe_probability']
+        a.d_jibe_probability, a.jp_f64 = jp.data_ptr(), 1 if jp.dtype == torch.float64 else 0
+        a.d_moving = moving.data_ptr() if moving is not None else None
+        a.d_status = status.data_ptr() if status is not None else None
+        a.d_ids = ids.data_ptr() if ids is not None else None
+        a.d_rand = rand.data_ptr() if rand is not None else None
+        a.dt = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        a.seed, a.step_index, a.capsize_fraction = int(seed), int(step_index), float(capsize_fraction)
+        a.missing_code, a.pos_f32 = int(missing_code), 1 if pos_f32 else 0
+        self._check(self.lib.od_leeway_step(self.ctx, C.byref(a)))
+
     def minmax(self, a, b=None):
         """(min, max) of a (+ b) over a float32 device tensor, NaNs ignored (synchronises)."""
         lo, hi = C.c_float(), C.c_float()
@@ -453,6 +482,14 @@ class Engine:
         self._check(self.lib.od_sort_by_cell(self.ctx, group.gid, lon.numel(), _ptr(lon), _ptr(lat), _ptr(z),
                                              _ptr(perm)))
         return perm
+
+    def partition_active(self, status):
+        """(perm, n_keep): stable partition of the elements by status == 0 (kept first)."""
+        n = status.numel()
+        perm = self.empty(n, self.torch.int32)
+        nk = C.c_int64()
+        self._check(self.lib.od_partition_active(self.ctx, n, _ptr(status), _ptr(perm), C.byref(nk)))
+        return perm, int(nk.value)
 
     def permute(self, perm, src, inverse=False):
         dst = self.torch.empty_like(src)

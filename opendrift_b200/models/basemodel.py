@@ -274,10 +274,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if not getattr(self, '_maybe_deactivated', False) or len(self.elements) == 0:
             return
         self._maybe_deactivated = False
-        keep = self.elements.dev('status') == 0
-        if bool(keep.all()):
+        removed = self.elements.compact()
+        if removed is None:
             return
-        removed = self.elements.compact(keep)
         tmp = self.ElementType(**{k: v for k, v in removed.items()})
         for k, v in removed.items():                           # keep the dtypes the active arrays had
             setattr(tmp, k, v)

@@ -1,0 +1,181 @@
+"""Leeway (search-and-rescue drift) on the GPU path: the reference's model class (opendrift/models/leeway.py)
+with the same element type (LeewayObj :49-134), required variables (:144-171), seeding of the per-element leeway
+coefficients from the legacy generator (:292-400) and update() (:430-494), the latter as ONE kernel launch per time
+step (od_leeway_step: leeway move + current move + jibing).  Euler only, like the reference.
+
+Object categories: the reference reads ~85 categories from OBJECTPROP.DAT (Allen & Plourde 1999 / Allen 2005).  A
+path to such a file can be given as `Leeway(d=path)` exactly like the reference; without it the four person-in-water
+categories below are available.  Capsizing (`processes:capsizing`) is not on the GPU path.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+from ..config import CONFIG_LEVEL_ESSENTIAL, CONFIG_LEVEL_BASIC, CONFIG_LEVEL_ADVANCED
+from ..elements import LagrangianArray
+from .basemodel import OpenDriftSimulation
+
+RIGHT, LEFT = 0, 1
+
+_COLS = ('DWSLOPE', 'DWOFFSET', 'DWSTD', 'CWRSLOPE', 'CWROFFSET', 'CWRSTD', 'CWLSLOPE', 'CWLOFFSET', 'CWLSTD')
+# (key, description, downwind slope [%], offset [cm/s], std; crosswind right slope, offset, std; crosswind left ...)
+_BUILTIN = [
+    ('PIW-1', 'Person-in-water (PIW), unknown state (mean values)', 0.96, 0.00, 12.00, 0.54, 0.00, 9.40, -0.54, 0.00, 9.40),
+    ('PIW-2', '>PIW, vertical PFD type III conscious', 0.48, 0.00, 8.30, 0.15, 0.00, 6.70, -0.15, 0.00, 6.70),
+    ('PIW-3', '>PIW, sitting, PFD type I or II', 1.60, -3.98, 2.42, 0.13, 0.33, 2.11, -0.13, -0.33, 2.11),
+    ('PIW-4', '>PIW, survival suit (face up)', 1.71, 1.12, 3.93, 1.36, -3.30, 1.71, -0.13, -2.65, 1.62),
+]
+
+
+def read_object_properties(path=None):
+    """{number: {OBJKEY, Description, DWSLOPE, ...}} from an OBJECTPROP.DAT-style file (three lines per object:
+    key, description, nine numbers; leeway.py:186-209) or the built-in categories."""
+    props = OrderedDict()
+    if path is None:
+        for i, row in enumerate(_BUILTIN, start=1):
+            props[i] = dict(OBJKEY=row[0], Description=row[1], **dict(zip(_COLS, row[2:])))
+        return props
+    lines = open(path).readlines()
+    for i in range(len(lines) // 3 + 1):
+        if i * 3 >= len(lines) or not lines[i * 3].strip():
+            break
+        vals = [float(x) for x in lines[i * 3 + 2].split()]
+        props[i + 1] = dict(OBJKEY=lines[i * 3].split()[0].strip(), Description=lines[i * 3 + 1].strip(),
+                            **dict(zip(_COLS, vals)))
+    return props
+
+
+class LeewayObj(LagrangianArray):
+    variables = LagrangianArray.add_variables([
+        ('object_type', {'dtype': np.uint16, 'units': '1', 'seed': False, 'default': 0}),
+        ('orientation', {'dtype': np.uint8, 'units': '1', 'seed': False, 'default': 1,
+                         'description': '0/1 is left/right of downwind. Randomly chosen at seed time'}),
+        ('jibe_probability', {'dtype': np.float32, 'units': '1/h', 'default': 0.04,
+                              'description': 'Probability per hour that an object may change orientation (jibing)'}),
+        ('capsized', {'dtype': np.uint8, 'units': '1', 'seed': True, 'default': 0}),
+        ('downwind_slope', {'dtype': np.float32, 'units': '%', 'seed': False, 'default': 1}),
+        ('crosswind_slope', {'dtype': np.float32, 'units': '1', 'seed': False, 'default': 1}),
+        ('downwind_offset', {'dtype': np.float32, 'units': 'cm/s', 'seed': False, 'default': 0}),
+        ('crosswind_offset', {'dtype': np.float32, 'units': 'cm/s', 'seed': False, 'default': 0}),
+        ('downwind_eps', {'dtype': np.float32, 'units': 'cm/s', 'seed': False, 'default': 0}),
+        ('crosswind_eps', {'dtype': np.float32, 'units': 'cm/s', 'seed': False, 'default': 0}),
+        ('current_drift_factor', {'dtype': np.float32, 'units': '1', 'default': 1})])
+
+
+class Leeway(OpenDriftSimulation):
+    ElementType = LeewayObj
+
+    required_variables = {
+        'x_wind': {'fallback': None},
+        'y_wind': {'fallback': None},
+        'x_sea_water_velocity': {'fallback': None},
+        'y_sea_water_velocity': {'fallback': None},
+        'sea_surface_wave_stokes_drift_x_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
+        'sea_surface_wave_stokes_drift_y_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
+        'land_binary_mask': {'fallback': None},
+    }
+
+    def __init__(self, d=None, *args, **kwargs):
+        self.leewayprop = read_object_properties(d)
+        super().__init__(*args, **kwargs)
+        descriptions = [p['Description'] for p in self.leewayprop.values()]
+        self._add_config({
+            'seed:object_type': {'type': 'enum', 'enum': descriptions, 'default': descriptions[0],
+                                 'level': CONFIG_LEVEL_ESSENTIAL, 'description': 'Leeway object category for this simulation'},
+            'seed:jibe_probability': {'type': 'float', 'default': 0.04, 'min': 0, 'max': 1, 'units': 'probability',
+                                      'level': CONFIG_LEVEL_BASIC,
+                                      'description': 'Probability per hour for jibing (objects changing orientation)'},
+            'processes:capsizing': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_BASIC,
+                                    'description': 'Capsizing (not on the GPU path).'},
+            'capsizing:leeway_fraction': {'type': 'float', 'default': 0.4, 'min': 0, 'max': 1, 'units': 'fraction',
+                                          'level': CONFIG_LEVEL_BASIC,
+                                          'description': 'Leeway coefficients of capsized elements are multiplied by this factor'},
+            'drift:stokes_drift': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                   'description': 'Advection elements with surface Stokes drift.'},
+            'gpu:rng': {'type': 'enum', 'enum': ['numpy', 'philox'], 'default': 'numpy', 'level': CONFIG_LEVEL_ADVANCED,
+                        'description': 'numpy: jibing draws from the legacy generator on the host (bit parity); philox: on device.'},
+        })
+        self._set_config_default('general:time_step_minutes', 10)
+        self._set_config_default('general:time_step_output_minutes', 60)
+        self._set_config_default('drift:max_speed', 5)
+
+    def seed_elements(self, lon, lat, object_type=None, **kwargs):
+        """leeway.py:292-400 -- same draws from the legacy generator, in the same order."""
+        lon = np.atleast_1d(lon).ravel()
+        lat = np.atleast_1d(lat).ravel()
+        if kwargs.get('number') is not None:
+            number = kwargs['number']
+        elif len(lon) > 1:
+            number = len(lon)
+        else:
+            number = self.get_config('seed:number')
+        if object_type is None:
+            name = self.get_config('seed:object_type')
+            for object_type, p in self.leewayprop.items():
+                if name in (p['OBJKEY'], p['Description']):
+                    break
+            else:
+                raise ValueError('Object %s not available' % name)
+        prop = self.leewayprop[object_type]
+        orientation = np.r_[:number] % 2
+        ones = np.ones_like(orientation)
+        downwind_slope = ones * prop['DWSLOPE']
+        downwind_offset = ones * prop['DWOFFSET']
+        epsdw = np.zeros(number)
+        for i in range(number):                      # sequential on purpose: the draw count depends on the values
+            r = np.random.randn(1)[0]
+            epsdw[i] = r * prop['DWSTD']
+            while downwind_slope[i] + epsdw[i] / 20.0 < 0.0:
+                r = np.random.randn(1)[0]
+                epsdw[i] = r * prop['DWSTD']
+        rcw = np.random.randn(number)
+        right, left = orientation == RIGHT, orientation == LEFT
+        crosswind_slope = np.where(right, prop['CWRSLOPE'], prop['CWLSLOPE']).astype(float)
+        crosswind_offset = np.where(right, prop['CWROFFSET'], prop['CWLOFFSET']).astype(float)
+        crosswind_eps = np.where(right, rcw * prop['CWRSTD'], rcw * prop['CWLSTD'])
+        return super().seed_elements(lon, lat, orientation=orientation, object_type=object_type,
+                                     downwind_slope=downwind_slope, crosswind_slope=crosswind_slope,
+                                     downwind_offset=downwind_offset, crosswind_offset=crosswind_offset,
+                                     downwind_eps=epsdw, crosswind_eps=crosswind_eps, **kwargs)
+
+    def list_object_categories(self, substr=None):
+        for i, p in self.leewayprop.items():
+            if substr is None or substr.lower() in (p['Description'] + p['OBJKEY']).lower():
+                print('%i %s %s' % (i, p['OBJKEY'], p['Description']))
+
+    def update(self):
+        """leeway.py:430-494 as one launch."""
+        if self.get_config('processes:capsizing'):
+            raise NotImplementedError('processes:capsizing is not on the GPU path')
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        t = self.time
+        wr, cr = self.env.reader_for('x_wind', t), self.env.reader_for('x_sea_water_velocity', t)
+        if wr is None or cr is None or not hasattr(wr, 'group_of') or not hasattr(cr, 'group_of'):
+            raise NotImplementedError('Leeway on the GPU path needs gridded wind and current readers covering the run')
+        n = len(el)
+        rand = eng.to_device(np.random.random(n)) if self.get_config('gpu:rng') == 'numpy' else None
+        cols = {'dw_slope': 'downwind_slope', 'dw_offset': 'downwind_offset', 'dw_eps': 'downwind_eps',
+                'cw_slope': 'crosswind_slope', 'cw_offset': 'crosswind_offset', 'cw_eps': 'crosswind_eps'}
+        d = {k: el.dev(v, torch.float32) for k, v in cols.items()}
+        d['orientation'] = el.dev('orientation', torch.uint8)
+        d['capsized'] = el.dev('capsized', torch.uint8)
+        d['jibe_probability'] = el.dev('jibe_probability')
+        if d['jibe_probability'].dtype not in (torch.float32, torch.float64):
+            d['jibe_probability'] = d['jibe_probability'].to(torch.float64)
+        if 'missing_data' not in self.status_categories:
+            self.status_categories.append('missing_data')
+        eng.leeway_step(wr.group_of('x_wind')[0], cr.group_of('x_sea_water_velocity')[0], t, self.time_step,
+                        el.dev('lon', torch.float64), el.dev('lat', torch.float64), d,
+                        moving=el.dev('moving', torch.int32), status=el.dev('status', torch.int32),
+                        ids=el.dev('ID', torch.int32), rand=rand, seed=self._seed, step_index=self.steps_calculation,
+                        capsize_fraction=self.get_config('capsizing:leeway_fraction'),
+                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32)
+        el.positions_f32 = False
+        self._maybe_deactivated = True           # the kernel may have flagged elements with missing forcing
+        self.stokes_drift()
+
+    def update_and_diffuse(self):
+        if type(self).update is Leeway.update:
+            self.update()                        # stock recipe: no host-side environment needed
+        else:
+            super().update_and_diffuse()

@@ -126,6 +126,37 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
     print('wrote', path, 'max |dlon|', np.abs(out['lon'] - lon).max())
 
 
+def run_leeway_case(name, g, n, steps, dt, object_type=1, seed=0):
+    """Reference Leeway (opendrift/models/leeway.py) with 2-D current and wind readers."""
+    import tempfile
+    refrun.setup()
+    from opendrift.models.leeway import Leeway
+    n_slabs = syn.n_slabs_for(steps, dt)
+    times, fc = build_fields(g, n_slabs)
+    fw = build_wind(g, n_slabs)
+    lon, lat, _ = syn.particle_cloud(n, seed=seed + 1, three_d=False)
+    lon = (g.lon[0] + (lon - 1.0) / 8.2 * g.Lx * 0.8 + 0.1 * g.Lx).astype(np.float32)
+    lat = (g.lat[0] + (lat - 55.5) / 4.1 * g.Ly * 0.8 + 0.1 * g.Ly).astype(np.float32)
+    o = Leeway(loglevel=50, logfile=os.path.join(tempfile.gettempdir(), 'oracle_refrun.log'), seed=seed)
+    o.add_reader([refrun.make_grid_reader(g.lon, g.lat, None, times, fc, 'current'),
+                  refrun.make_grid_reader(g.lon, g.lat, None, times, fw, 'wind')])
+    for k, v in {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': 0,
+                 'general:coastline_action': 'none'}.items():
+        o.set_config(k, v)
+    o.seed_elements(lon=lon, lat=lat, time=syn.T0, object_type=object_type)
+    o.run(steps=steps, time_step=dt, time_step_output=dt)
+    assert len(o.elements.lon) == n
+    prop = {k: v for k, v in o.leewayprop[object_type].items() if k not in ('OBJKEY', 'Description')}
+    meta = dict(name=name, steps=steps, dt=dt, seed=seed, slab_step_s=3600, object_type=object_type, prop=prop, model='Leeway',
+                start_offset_s=0)
+    path = os.path.join(OUT, 'ref_%s.npz' % name)
+    np.savez_compressed(path, meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat, u=fc[CURRENT[0]], v=fc[CURRENT[1]],
+                        x_wind=fw['x_wind'], y_wind=fw['y_wind'], lon0=lon, lat0=lat,
+                        lon=np.asarray(o.elements.lon), lat=np.asarray(o.elements.lat),
+                        orientation=np.asarray(o.elements.orientation), crosswind_slope=np.asarray(o.elements.crosswind_slope))
+    print('wrote', path, 'max |dlon|', np.abs(o.elements.lon - lon).max(), 'jibed', int((o.elements.orientation != np.r_[:n] % 2).sum()))
+
+
 def main():
     g3 = syn.GridSpec(nx=40, ny=36, nz=8, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03, dz=12.0)
     g2 = syn.GridSpec(nx=40, ny=36, nz=1, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03)
@@ -141,6 +172,8 @@ def main():
     run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
     run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
     run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+    run_leeway_case('leeway_piw1', g2, 1200, 12, 600, object_type=1)
+    run_leeway_case('leeway_piw4', g2, 1200, 8, 900, object_type=4, seed=5)
     run_case('rk4_3d_stokes_phillips', g3, n, 6, 600, 'runge-kutta4', wind=True, stokes='Phillips')
     run_case('euler_3d_stokes_mono_nohs', g3, n, 6, 600, 'euler', wind=True, stokes='monochromatic', stokes_hs=False)
     run_case('rk2_3d_stokes_exp', g3, n, 5, 600, 'runge-kutta', wind=True, stokes='exponential')

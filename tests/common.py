@@ -22,7 +22,89 @@ CUR = ['x_sea_water_velocity', 'y_sea_water_velocity']
 
 
 def fixtures():
-    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
+    """OceanDrift fixtures."""
+    return sorted(n for n in (os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
+                  if not n.startswith('leeway'))
+
+
+def leeway_fixtures():
+    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, 'ref_leeway*.npz')))
+
+
+class LeewayFixture:
+    def __init__(self, name):
+        d = np.load(os.path.join(GOLDEN, 'ref_%s.npz' % name))
+        self.name, self.meta = name, json.loads(str(d['meta']))
+        for k in ('grid_lon', 'grid_lat', 'u', 'v', 'x_wind', 'y_wind', 'lon0', 'lat0', 'lon', 'lat', 'orientation',
+                  'crosswind_slope'):
+            setattr(self, k, d[k])
+        self.times = syn.slab_times(self.u.shape[0], self.meta['slab_step_s'])
+        self.dt, self.steps, self.n, self.start = self.meta['dt'], self.meta['steps'], len(self.lon0), syn.T0
+        self.prop = self.meta['prop']
+
+
+def run_leeway_port(fx):
+    from oracle import advect_port as ap, leeway_port as lp
+    rc = ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, {CUR[0]: fx.u, CUR[1]: fx.v})
+    rw = ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind})
+    return lp.run_leeway([rc, rw], fx.lon0, fx.lat0, fx.start, fx.dt, fx.steps, fx.prop, seed=fx.meta['seed'])
+
+
+def _leeway_elements(fx):
+    """Seed the per-element coefficients exactly as the reference does (same draws), via the oracle port."""
+    from oracle import leeway_port as lp
+    np.random.seed(fx.meta['seed'])
+    return lp.seed_coefficients(fx.n, fx.prop)
+
+
+def run_leeway_hostshim(fx):
+    lib = hostshim()
+    el = _leeway_elements(fx)
+    wind = HsField(fx.grid_lon, fx.grid_lat, None, [fx.x_wind, fx.y_wind], fx.times, (float('nan'), float('nan')))
+    cur = HsField(fx.grid_lon, fx.grid_lat, None, [fx.u, fx.v], fx.times, (float('nan'), float('nan')))
+    lon, lat = fx.lon0.astype(np.float64), fx.lat0.astype(np.float64)
+    moving = np.ones(fx.n, dtype=np.int32)
+    jp = np.float32(0.04) * np.ones(fx.n)
+    t, dt = fx.start, timedelta(seconds=fx.dt)
+    for istep in range(fx.steps):
+        a = HsLeewayArgs()
+        a.g_wind, a.g_cur, a.t_wind, a.t_cur = wind.g, cur.g, wind.pair(t), cur.pair(t)
+        a.n, a.lon, a.lat = fx.n, _p(lon), _p(lat)
+        a.dw_slope, a.dw_offset, a.dw_eps = _p(el['downwind_slope']), _p(el['downwind_offset']), _p(el['downwind_eps'])
+        a.cw_slope, a.cw_offset, a.cw_eps = _p(el['crosswind_slope']), _p(el['crosswind_offset']), _p(el['crosswind_eps'])
+        rnd = np.random.random(fx.n)
+        a.orientation, a.jibe_probability, a.moving, a.rand = _p(el['orientation']), _p(jp), _p(moving), _p(rnd)
+        a.dt, a.capsize_fraction, a.pos_f32 = float(fx.dt), 0.4, 1 if istep == 0 else 0
+        assert lib.hs_leeway(C.byref(a)) == 0
+        t = t + dt
+    return lon, lat, el
+
+
+def run_leeway_engine(fx, rng='numpy'):
+    from opendrift_b200.engine import Engine
+    import torch
+    eng = Engine(0)
+    el = _leeway_elements(fx)
+    nan = float('nan')
+    wind = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times, lambda ti, c: (fx.x_wind, fx.y_wind)[c][ti], (nan, nan))
+    cur = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times, lambda ti, c: (fx.u, fx.v)[c][ti], (nan, nan))
+    lon, lat = eng.to_device(fx.lon0.astype(np.float64)), eng.to_device(fx.lat0.astype(np.float64))
+    d = {'dw_slope': eng.to_device(el['downwind_slope']), 'dw_offset': eng.to_device(el['downwind_offset']),
+         'dw_eps': eng.to_device(el['downwind_eps']), 'cw_slope': eng.to_device(el['crosswind_slope']),
+         'cw_offset': eng.to_device(el['crosswind_offset']), 'cw_eps': eng.to_device(el['crosswind_eps']),
+         'orientation': eng.to_device(el['orientation']), 'capsized': None,
+         'jibe_probability': eng.to_device(np.float32(0.04) * np.ones(fx.n))}
+    ids = eng.to_device(np.arange(fx.n, dtype=np.int32))
+    t, dt = fx.start, timedelta(seconds=fx.dt)
+    for istep in range(fx.steps):
+        rand = eng.to_device(np.random.random(fx.n)) if rng == 'numpy' else None
+        eng.leeway_step(wind, cur, t, dt, lon, lat, d, ids=ids, rand=rand, seed=7, step_index=istep, pos_f32=istep == 0)
+        t = t + dt
+    eng.sync()
+    out = lon.cpu().numpy(), lat.cpu().numpy(), {'orientation': d['orientation'].cpu().numpy(),
+                                                  'crosswind_slope': d['cw_slope'].cpu().numpy()}
+    eng.close()
+    return out
 
 
 class Fixture:
@@ -94,6 +176,17 @@ class HsGroup(C.Structure):
 
 class HsPair(C.Structure):
     _fields_ = [('tex', C.c_void_p), ('mode', C.c_int32), ('pad_', C.c_int32), ('w', C.c_double)]
+
+
+class HsLeewayArgsReal(C.Structure):
+    _fields_ = [('g_wind', HsGroup), ('g_cur', HsGroup), ('t_wind', HsPair), ('t_cur', HsPair), ('n', C.c_int64),
+                ('lon', C.c_void_p), ('lat', C.c_void_p), ('dw_slope', C.c_void_p), ('dw_offset', C.c_void_p),
+                ('dw_eps', C.c_void_p), ('cw_slope', C.c_void_p), ('cw_offset', C.c_void_p), ('cw_eps', C.c_void_p),
+                ('orientation', C.c_void_p), ('jibe_probability', C.c_void_p), ('moving', C.c_void_p), ('rand', C.c_void_p),
+                ('dt', C.c_double), ('capsize_fraction', C.c_float), ('pos_f32', C.c_int32)]
+
+
+HsLeewayArgs = HsLeewayArgsReal
 
 
 class HsStepArgs(C.Structure):

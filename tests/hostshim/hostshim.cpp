@@ -8,6 +8,7 @@
 #include "../../opendrift_b200/csrc/od_advect.cuh"
 #include "../../opendrift_b200/csrc/od_mix.cuh"
 #include "../../opendrift_b200/csrc/od_stokes.cuh"
+#include "../../opendrift_b200/csrc/od_leeway.cuh"
 
 using namespace od;
 
@@ -183,6 +184,27 @@ int hs_stokes(const hs_stokes_args* a) {
     p.xwind = a->xwind; p.ywind = a->ywind; p.moving = a->moving; p.dt = a->dt; p.z_f64 = a->z_f64;
     p.hs_mode = a->hs_mode; p.profile = a->profile;
     for (int64_t i = 0; i < a->n; ++i) stokes_particle(p, i);
+    return 0;
+}
+
+struct hs_leeway_args {
+    hs_group g_wind, g_cur; hs_pair t_wind, t_cur;
+    int64_t n; double* lon; double* lat; const float* dw_slope; const float* dw_offset; const float* dw_eps;
+    float* cw_slope; const float* cw_offset; const float* cw_eps; uint8_t* orientation; const double* jibe_probability;
+    const int32_t* moving; const double* rand; double dt; float capsize_fraction; int32_t pos_f32;
+};
+
+int hs_leeway(const hs_leeway_args* a) {
+    hs_levels l1, l2;
+    LeewayParams p;
+    memset(&p, 0, sizeof(p));
+    p.gwind = make_geom(a->g_wind, l1); p.gcur = make_geom(a->g_cur, l2);
+    p.pwind = make_pair(a->t_wind); p.pcur = make_pair(a->t_cur);
+    p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.dw_slope = a->dw_slope; p.dw_offset = a->dw_offset; p.dw_eps = a->dw_eps;
+    p.cw_slope = a->cw_slope; p.cw_offset = a->cw_offset; p.cw_eps = a->cw_eps; p.orientation = a->orientation;
+    p.jibe_probability = a->jibe_probability; p.jp_f64 = 1; p.moving = a->moving; p.rand = a->rand; p.dt = a->dt;
+    p.capsize_fraction = a->capsize_fraction; p.pos_f32 = a->pos_f32;
+    for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);
     return 0;
 }
 

@@ -143,6 +143,40 @@ def test_reader_get_variables_interpolated_and_environment():
         r.get_variables_interpolated(common.CUR, time=fx.times[-1] + timedelta(days=1), lon=lon, lat=lat, z=z)
 
 
+@pytest.mark.parametrize('name', common.leeway_fixtures())
+def test_leeway_model_matches_reference(name):
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_regular_grid
+    fx = common.LeewayFixture(name)
+    o = Leeway(loglevel=50, seed=fx.meta['seed'])
+    o.add_reader([reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}, name='current'),
+                  reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind')])
+    o.set_config('general:use_auto_landmask', False)
+    o.seed_elements(lon=fx.lon0, lat=fx.lat0, time=fx.start, object_type=fx.meta['object_type'])
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    assert o.num_elements_active() == fx.n
+    e = common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)
+    assert max(e) < 5e-8, e
+    assert np.array_equal(o.elements.orientation, fx.orientation)
+    assert np.array_equal(o.elements.crosswind_slope, fx.crosswind_slope)
+
+
+def test_leeway_missing_forcing_deactivates():
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_regular_grid
+    fx = common.LeewayFixture('leeway_piw1')
+    o = Leeway(loglevel=50, seed=1)
+    o.add_reader([reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}),
+                  reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind})])
+    lon = fx.lon0.copy()
+    lon[:100] += np.float32(5.0)                      # outside the readers' coverage: no fallback in Leeway
+    o.seed_elements(lon=lon, lat=fx.lat0, time=fx.start, object_type=1)
+    o.run(steps=3, time_step=600)
+    assert o.num_elements_active() == fx.n - 100 and o.num_elements_deactivated() == 100
+    assert 'missing_data' in o.status_categories
+    assert np.array_equal(np.sort(o.elements_deactivated.ID), np.arange(100))
+
+
 def test_seeding_radius_and_deactivation():
     from opendrift_b200.models.oceandrift import OceanDrift
     from opendrift_b200.readers import reader_regular_grid

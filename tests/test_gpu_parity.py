@@ -152,6 +152,34 @@ def test_sort_and_permute_roundtrip(eng):
     assert (np.diff(xi[inside] // 4) < 0).sum() < 0.2 * n
 
 
+@pytest.mark.parametrize('name', common.leeway_fixtures())
+def test_leeway_step_vs_reference_fixture(name):
+    fx = common.LeewayFixture(name)
+    lon, lat, el = common.run_leeway_engine(fx)
+    e = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    assert max(e) < TIGHT_DEG, e
+    assert np.array_equal(el['orientation'], fx.orientation)
+    assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+    # device generator: same physics, different (but plausible) jibing history
+    lon2, lat2, el2 = common.run_leeway_engine(fx, rng='philox')
+    jibed = (el2['orientation'] != np.r_[:fx.n] % 2).mean()
+    p_expected = 1 - (1 - 0.04) ** (fx.steps * fx.dt / 3600.0)
+    assert abs(jibed - p_expected) < 0.03, (jibed, p_expected)
+    assert max(common.max_err_deg(lon2, lat2, fx.lon, fx.lat)) < 0.05
+
+
+def test_stable_partition(eng):
+    rng = np.random.default_rng(8)
+    for n in (1, 255, 256, 257, 100003):
+        status = (rng.uniform(size=n) < 0.3).astype(np.int32) * rng.integers(1, 4, n).astype(np.int32)
+        perm, nk = eng.partition_active(eng.to_device(status))
+        p = perm.cpu().numpy()
+        keep = np.where(status == 0)[0]
+        drop = np.where(status != 0)[0]
+        assert nk == len(keep)
+        assert np.array_equal(p[:nk], keep) and np.array_equal(p[nk:], drop)      # stable on both sides
+
+
 def test_sorted_order_does_not_change_results():
     """Particles are independent: advecting a cell-sorted copy and un-permuting gives identical bits."""
     import torch

@@ -43,6 +43,16 @@ def test_fast_mode_vs_reference_fixture(name):
     assert elon < 1e-7 and elat < 1e-7, (elon, elat)
 
 
+@pytest.mark.parametrize('name', common.leeway_fixtures())
+def test_leeway_step_vs_reference_fixture(name):
+    fx = common.LeewayFixture(name)
+    lon, lat, el = common.run_leeway_hostshim(fx)
+    e = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    assert max(e) < 5e-8, e                       # float32 sin / cos / arctan2 differ from NumPy's SIMD versions by an ulp
+    assert np.array_equal(el['orientation'], fx.orientation)
+    assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+
+
 def test_interpolation_bit_exact():
     """od_interp arithmetic == ReaderBlock/Linear2DInterpolator/Linear1DInterpolator/time lerp/float32 cast."""
     from datetime import timedelta

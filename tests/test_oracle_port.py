@@ -18,6 +18,15 @@ def test_port_matches_reference_fixture(name):
     assert np.abs(fx.lon - fx.lon0).max() > 1e-3        # the particles did move
 
 
+@pytest.mark.parametrize('name', common.leeway_fixtures())
+def test_leeway_port_matches_reference_fixture(name):
+    fx = common.LeewayFixture(name)
+    lon, lat, el = common.run_leeway_port(fx)
+    assert np.array_equal(lon, fx.lon) and np.array_equal(lat, fx.lat)
+    assert np.array_equal(el['orientation'], fx.orientation)
+    assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+
+
 def test_port_matches_live_reference():
     from oracle import refrun
     if not refrun.available():
