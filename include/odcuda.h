@@ -281,7 +281,7 @@ int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a);
  * the grid cell (and level) of `group` they are in.  Stable counting sort. */
 int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* d_lon, const double* d_lat,
                     const float* d_z, int32_t* d_perm_out);
-/* dst[k] = src[perm[k]] for an array of elem_size-byte elements (4 or 8) */
+/* dst[k] = src[perm[k]] for an array of elem_size-byte elements (1, 2, 4 or 8) */
 int od_permute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);
 /* dst[perm[k]] = src[k] */
 int od_unpermute(od_ctx* ctx, int64_t n, const int32_t* d_perm, const void* d_src, void* d_dst, int elem_size);

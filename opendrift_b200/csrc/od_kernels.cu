@@ -935,7 +935,9 @@ static int permute_impl(od_ctx* ctx, int64_t n, const int32_t* perm, const void*
     CK(cudaSetDevice(ctx->device));
     if (es == 4) permute_kernel<uint32_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint32_t*)src, (uint32_t*)dst, inverse);
     else if (es == 8) permute_kernel<uint64_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint64_t*)src, (uint64_t*)dst, inverse);
-    else return fail(ctx, OD_ERR_ARG, "od_permute: element size must be 4 or 8");
+    else if (es == 1) permute_kernel<uint8_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint8_t*)src, (uint8_t*)dst, inverse);
+    else if (es == 2) permute_kernel<uint16_t><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, perm, (const uint16_t*)src, (uint16_t*)dst, inverse);
+    else return fail(ctx, OD_ERR_ARG, "od_permute: element size must be 1, 2, 4 or 8");
     CK(cudaGetLastError());
     ctx->launches++;
     return OD_OK;
