@@ -95,6 +95,10 @@ int od_group_free(od_ctx* ctx, int group);
 /* copy one time slab of one component ([nz][ny][nx] float32, C order) into ring slot `slot`;
  * src may be host (pinned or pageable) or device memory */
 int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const float* src, int src_is_device);
+/* Fill non-finite cells of an uploaded slab from their finite 3x3 neighbours (maximum), layer by layer, up to
+ * max_iterations passes: the NaN handling of Linear2DInterpolator (readers/interpolation/interpolators.py:9-20,
+ * 121-139; the reference uses at most 10).  *h_remaining = cells still missing.  Synchronises. */
+int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining);
 /* raw device pointer of a ring slot component, e.g. as the target of an NCCL broadcast */
 int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** d_out);
 /* tell the library a slot's contents changed behind its back (after a broadcast into od_group_slot_ptr) */

@@ -92,6 +92,7 @@ SYMBOLS = {
     'od_group_define': (C.c_int, [_P, C.c_int, C.POINTER(GroupDesc), C.POINTER(C.c_double)]),
     'od_group_free': (C.c_int, [_P, C.c_int]),
     'od_group_upload': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
+    'od_group_fill_nan': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     'od_group_slot_ptr': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     'od_group_touch': (C.c_int, [_P, C.c_int, C.c_int]),
     'od_interp': (C.c_int, [_P, C.c_int, C.POINTER(TimeSample), C.c_int64, _P, _P, _P, C.c_int, _P, _P]),

@@ -231,6 +231,42 @@ extern "C" int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const
     return OD_OK;
 }
 
+__global__ void dilate_nan_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int64_t cells,
+                                  unsigned* __restrict__ counters);
+
+extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining) {
+    int rc = check_slot(ctx, group, slot, comp);
+    if (rc) return rc;
+    Group& g = ctx->groups[group];
+    CK(cudaSetDevice(ctx->device));
+    const int64_t cells = (int64_t)g.cells();
+    float* a = g.slots[(size_t)slot * g.desc.ncomp + comp];
+    if (!ctx->d_red) CK(cudaMalloc(&ctx->d_red, 2 * sizeof(unsigned)));
+    float* tmp = nullptr;
+    int64_t remaining = -1;
+    for (int it = 0; it < max_iterations; ++it) {
+        if (!tmp) CK(cudaMalloc(&tmp, cells * sizeof(float)));
+        CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
+        dilate_nan_kernel<<<(int)((cells + 255) / 256), 256, 0, ctx->stream>>>(a, tmp, g.desc.nx, g.desc.ny, cells, ctx->d_red);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        unsigned res[2];
+        CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        remaining = res[1];
+        if (res[0] == 0) break;                      // nothing could be filled (no holes, or unreachable ones)
+        CK(cudaMemcpyAsync(a, tmp, cells * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        g.version[slot] = ++ctx->tick;
+        if (remaining == 0) break;
+    }
+    if (tmp) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    if (h_remaining) *h_remaining = remaining < 0 ? 0 : remaining;
+    return OD_OK;
+}
+
 extern "C" int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** out) {
     int rc = check_slot(ctx, group, slot, comp);
     if (rc) return rc;
@@ -245,6 +281,41 @@ extern "C" int od_group_touch(od_ctx* ctx, int group, int slot) {
     if (rc) return rc;
     ctx->groups[group].version[slot] = ++ctx->tick;
     return OD_OK;
+}
+
+// ---- NaN holes (land) ---------------------------------------------------------------------------------
+// Linear2DInterpolator fills missing values by repeatedly replacing every non-finite cell with the maximum of
+// its finite 3x3 neighbours (expand_numpy_array: scipy grey_dilation(size=3), interpolators.py:9-20), as often
+// as some particle still interpolates to NaN, at most 10 times (:121-139); the mutation persists in the cached
+// block.  A filled cell never changes again and finite cells are never touched, so filling a block 10 times
+// when it is uploaded gives every particle inside the block the value the reference's lazy loop would give.
+__global__ void __launch_bounds__(256) dilate_nan_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny,
+                                                         int64_t cells, unsigned* __restrict__ counters) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const float v = src[i];
+    if (fabsf(v) <= 3.4028234663852886e38f) {        // finite: unchanged
+        dst[i] = v;
+        return;
+    }
+    const int64_t layer = (int64_t)nx * ny;
+    const int64_t base = (i / layer) * layer;
+    const int r = (int)((i - base) / nx), c = (int)((i - base) % nx);
+    float best = -INFINITY;
+    bool found = false;
+    for (int dr = -1; dr <= 1; ++dr) {
+        const int rr = min(max(r + dr, 0), ny - 1);
+        for (int dc = -1; dc <= 1; ++dc) {
+            const int cc = min(max(c + dc, 0), nx - 1);
+            const float w = src[base + (int64_t)rr * nx + cc];
+            if (fabsf(w) <= 3.4028234663852886e38f) {
+                best = fmaxf(best, w);
+                found = true;
+            }
+        }
+    }
+    dst[i] = found ? best : NAN;
+    atomicAdd(&counters[found ? 0 : 1], 1u);         // [0] filled in this pass, [1] still missing
 }
 
 // interleave two time slabs (and two components) into pair texels

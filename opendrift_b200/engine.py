@@ -67,6 +67,7 @@ class FieldGroup:
         self.names = names
         self.n_slots = n_slots
         self.freed = False
+        self.fill_nan = 10                # passes of the linearNDFast NaN fill applied to every uploaded slab (0 = off)
         self.resident = [None] * n_slots  # time index held by each ring slot
         self.use = [0] * n_slots
         self._tick = 0
@@ -110,6 +111,8 @@ class FieldGroup:
         s = min(cand, key=lambda k: (self.resident[k] is not None, self.use[k]))
         for c in range(self.ncomp):
             self.engine.upload(self.gid, s, c, self.supplier(ti, c))
+            if self.fill_nan:
+                self.engine.fill_nan(self.gid, s, c, self.fill_nan)
         self.resident[s] = ti
         self.use[s] = self._tick
         return s
@@ -230,6 +233,11 @@ class Engine:
             a = np.ascontiguousarray(data, dtype=np.float32)
             self._check(self.lib.od_group_upload(self.ctx, gid, slot, comp, a.ctypes.data_as(C.c_void_p), 0))
             self.sync()
+
+    def fill_nan(self, gid, slot, comp, iterations=10):
+        rem = C.c_int64()
+        self._check(self.lib.od_group_fill_nan(self.ctx, gid, slot, comp, iterations, C.byref(rem)))
+        return int(rem.value)
 
     def slot_tensor(self, group, slot, comp):
         """The ring slot as a CUDA tensor (e.g. the target of a torch.distributed broadcast)."""

@@ -43,6 +43,22 @@ class GridReader:
         self.ymin, self.ymax = float(self.y.min()), float(self.y.max())
         self.start_time, self.end_time = self.times[0], self.times[-1]
         self.time_step = (self.times[1] - self.times[0]) if len(self.times) > 1 else None
+        self._blocks = {}
+
+    def block(self, var, it):
+        """The ReaderBlock array of one variable and time: a private float32 copy (the NaN fill of
+        Linear2DInterpolator mutates it), NaNs filled towards the sea floor at block creation
+        (interpolation/structured.py:58-70, interpolators.py:204-212)."""
+        key = (var, it)
+        if key not in self._blocks:
+            a = np.array(self.fields[var][it], dtype=np.float32, copy=True)
+            if a.ndim == 3:
+                for i in range(1, a.shape[0]):
+                    m = np.isnan(a[i])
+                    if m.any():
+                        a[i][m] = a[i - 1][m]
+            self._blocks[key] = a
+        return self._blocks[key]
 
     # opendrift/readers/basereader/variables.py:402-443 (constant time step branch == list lookup here)
     def nearest_time(self, time):
@@ -53,10 +69,34 @@ class GridReader:
         return self.times[ib], self.times[ia], ib, ia
 
 
+def expand_numpy_array(data):
+    """interpolators.py:9-20: replace non-finite cells by the maximum of their 3x3 neighbourhood, in place."""
+    from scipy.ndimage import grey_dilation
+    if not np.isfinite(data).any():
+        return
+    mask = ~np.isfinite(data)
+    minval = np.finfo(data[mask].dtype).min
+    data[mask] = minval
+    data[mask] = grey_dilation(data, size=3)[mask]
+    data[data == minval] = np.nan
+
+
 def _linear2d(block2d, xi, yi):
-    """Linear2DInterpolator.__call__ without NaN holes
-    (opendrift/readers/interpolation/interpolators.py:113-139)."""
-    return map_coordinates(block2d, [yi, xi], cval=np.nan, order=1)
+    """Linear2DInterpolator.__call__ (opendrift/readers/interpolation/interpolators.py:113-139) including the
+    NaN loop: dilate the block IN PLACE and re-interpolate the missing points with mode='nearest', <= 10 times."""
+    if not np.isfinite(block2d).any():
+        return np.nan * np.ones(len(xi))
+    interp = map_coordinates(block2d, [yi, xi], cval=np.nan, order=1)
+    missing = np.where(~np.isfinite(interp))[0]
+    i = 0
+    while len(missing) > 0:
+        i += 1
+        if i > 10:
+            return interp
+        expand_numpy_array(block2d)
+        interp[missing] = map_coordinates(block2d, [yi[missing], xi[missing]], cval=np.nan, order=1, mode='nearest')
+        missing = np.where(~np.isfinite(interp))[0]
+    return interp
 
 
 def block_interpolate(reader, it, variables, x, y, z, profiles=None):
@@ -70,7 +110,7 @@ def block_interpolate(reader, it, variables, x, y, z, profiles=None):
     prof = {}
     lin1d = None
     for var in variables:
-        data = reader.fields[var][it]
+        data = reader.block(var, it)
         if data.ndim == 2:
             out[var] = _linear2d(data, xi, yi)              # float32 result
             continue

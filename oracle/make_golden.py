@@ -36,6 +36,21 @@ def build_fields(g, n_slabs, with_w=False, mixing=False):
     return times, f
 
 
+def punch_holes(g, fields):
+    """Land: an island (NaN in every layer), a 'coast' band and a shoaling sea floor (NaN in the deep layers)."""
+    iy, ix = np.meshgrid(np.arange(g.ny), np.arange(g.nx), indexing='ij')
+    island = (ix - 20) ** 2 + (iy - 18) ** 2 <= 10
+    coast = ix >= g.nx - 4
+    shoal = (ix - 9) ** 2 + (iy - 9) ** 2 <= 30
+    for k in (CURRENT[0], CURRENT[1]):
+        a = fields[k]
+        if a.ndim == 4:
+            a[:, :, island | coast] = np.nan
+            a[:, a.shape[1] - 3:, shoal] = np.nan
+        else:
+            a[:, island | coast] = np.nan
+
+
 def build_stokes(g, n_slabs, with_hs):
     times = syn.slab_times(n_slabs)
     sx, sy = zip(*[syn.stokes_xy(g, (t - syn.T0).total_seconds()) for t in times])
@@ -56,9 +71,11 @@ def build_wind(g, n_slabs):
 
 
 def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
-             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True):
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True, holes=False):
     n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
     times, f3 = build_fields(g, n_slabs, with_w, mixing)
+    if holes:
+        punch_holes(g, f3)
     lon, lat, z = syn.particle_cloud(n, seed=seed + 1, three_d=g.z is not None)
     # keep the cloud inside this (smaller) grid
     lon = (g.lon[0] + (lon - 1.0) / 8.2 * g.Lx * 0.8 + 0.1 * g.Lx).astype(np.float32)
@@ -172,6 +189,8 @@ def main():
     run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
     run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
     run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+    run_case('rk4_3d_land', g3, n, 10, 600, 'runge-kutta4', holes=True)
+    run_case('euler_2d_land', g2, n, 10, 600, 'euler', holes=True)
     run_leeway_case('leeway_piw1', g2, 1200, 12, 600, object_type=1)
     run_leeway_case('leeway_piw4', g2, 1200, 8, 900, object_type=4, seed=5)
     run_case('rk4_3d_stokes_phillips', g3, n, 6, 600, 'runge-kutta4', wind=True, stokes='Phillips')

@@ -254,6 +254,26 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def prep_block(a):
+    """What the product does to a reader block before sampling: fill towards the sea floor (host, at block creation)
+    and the 10-pass NaN fill (device, od_group_fill_nan) -- emulated here with the oracle's expand_numpy_array."""
+    from oracle.advect_port import expand_numpy_array
+    a = np.array(a, dtype=np.float32, copy=True)
+    if not np.isnan(a).any():
+        return a
+    if a.ndim == 3:
+        for i in range(1, a.shape[0]):
+            m = np.isnan(a[i])
+            a[i][m] = a[i - 1][m]
+    layers = a if a.ndim == 3 else a[None]
+    for lay in layers:
+        for _ in range(10):
+            if not np.isnan(lay).any():
+                break
+            expand_numpy_array(lay)
+    return a
+
+
 class HsField:
     """A field group for the host shim: builds pair texels with NumPy."""
 
@@ -289,8 +309,8 @@ class HsField:
             return pr
         ib, ia, w = br
         ja = ib if ia is None else ia
-        tex = np.ascontiguousarray(np.stack([c[ib] for c in self.comps] + [c[ja] for c in self.comps], axis=-1),
-                                   dtype=np.float32)
+        tex = np.ascontiguousarray(np.stack([prep_block(c[ib]) for c in self.comps] + [prep_block(c[ja]) for c in self.comps],
+                                            axis=-1), dtype=np.float32)
         self._keep.append(tex)
         pr.tex, pr.mode, pr.w = tex.ctypes.data, (1 if ia is None else 0), w
         return pr
@@ -382,8 +402,12 @@ def run_engine(fx, fused=True, sort_every=0, fast=False):
     m = fx.meta
     eng = Engine(0)
     three_d = fx.grid_z is not None
-    cur = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 2, fx.times,
-                        lambda ti, c: (fx.u, fx.v)[c][ti], (0.0, 0.0))
+    from opendrift_b200.readers.basereader import fill_nan_towards_seafloor
+
+    def cur_supplier(ti, c):                 # host-side block preparation, as StructuredReader.bind does
+        a = np.array((fx.u, fx.v)[c][ti], dtype=np.float32, copy=True)
+        return fill_nan_towards_seafloor(a) if a.ndim == 3 else a
+    cur = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 2, fx.times, cur_supplier, (0.0, 0.0))
     wind = wgrp = None
     if m['wind']:
         wind = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times,
