@@ -159,6 +159,11 @@ typedef struct od_advect_args {
     float* d_env_v;
     int32_t z_f64;                /* dtype of d_z (and d_z_inout): the reference's z is float32 until vertical mixing
                                      makes it float64 (oceandrift.py:527) */
+    int32_t pad3_;
+    const double* d_noise_cur;    /* drift:current_uncertainty[_uniform] (environment.py:869-885): scaled float64 draws
+                                     [stage 0..3][kind 0 normal, 1 uniform][component u, v][n], added to the float32
+                                     current of every stage as the reference does per get_environment call; NULL = none */
+    int32_t noise_kinds;          /* bit 0: normal draws present, bit 1: uniform draws present */
     int32_t fast;                 /* 0: exact restatement of the reference arithmetic (bit-exact sampling, Karney
                                      geodesic); 1: float32 sampling and mid-latitude moves on float64 positions
                                      (~1e-7 deg from the reference after 100 steps; see od_advect.cuh FastMath) */
@@ -185,6 +190,7 @@ typedef struct od_step_args {
     const float* d_diffusivity;   /* per particle float32, or NULL -> diffusivity_const */
     float diffusivity_const;
     int32_t z_inout_f64;          /* dtype of d_z_inout: 0 float32, 1 float64 */
+    const double* d_noise_wind;   /* drift:wind_uncertainty: [component][n] scaled normal draws, or NULL */
 } od_step_args;
 
 int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);

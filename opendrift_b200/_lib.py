@@ -38,7 +38,8 @@ class AdvectArgs(C.Structure):
                 ('d_factor', C.c_void_p), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32),
                 ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
                 ('truncate_below', C.c_double),
-                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('fast', C.c_int32)]
+                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('pad3_', C.c_int32), ('d_noise_cur', C.c_void_p), ('noise_kinds', C.c_int32),
+                ('fast', C.c_int32)]
 
 
 class StepArgs(C.Structure):
@@ -48,7 +49,7 @@ class StepArgs(C.Structure):
                 ('group_w', C.c_int32), ('w_at_surface', C.c_int32), ('t_w', TimeSample),
                 ('d_z_inout', C.c_void_p),
                 ('d_rand_x', C.c_void_p), ('d_rand_y', C.c_void_p), ('d_diffusivity', C.c_void_p),
-                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32)]
+                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32), ('d_noise_wind', C.c_void_p)]
 
 
 class MixArgs(C.Structure):

@@ -199,35 +199,6 @@ struct CurrentStages {
     PairRef t_start, t_mid, t_end;
 };
 
-// Returns the RK-combined velocity (float32) that the final move uses; k1 is sampled here unless given.
-template <int SCHEME, class MATH>
-OD_HD void rk_velocity(const CurrentStages& cs, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
-                       float dt32, float k1u, float k1v, float& ou, float& ov) {
-    if (SCHEME == 0) {
-        ou = k1u;
-        ov = k1v;
-        return;
-    }
-    double mlon, mlat;
-    MATH::midpoint(gs, lon0, lat0, k1u, k1v, dt32, mlon, mlat);
-    float k2u, k2v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false);
-    if (SCHEME == 1) {
-        ou = k2u;
-        ov = k2v;
-        return;
-    }
-    MATH::midpoint(gs, lon0, lat0, k2u, k2v, dt32, mlon, mlat);
-    float k3u, k3v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false);
-    MATH::midpoint(gs, lon0, lat0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
-    float k4u, k4v;
-    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false);     // ... at time t + dt
-    // (x_vel + 2*x_vel2 + 2*x_vel3 + x_vel4)/6.0, float32, left to right
-    ou = OD_FADD(OD_FADD(OD_FADD(k1u, OD_FMUL(2.0f, k2u)), OD_FMUL(2.0f, k3u)), k4u) / 6.0f;
-    ov = OD_FADD(OD_FADD(OD_FADD(k1v, OD_FMUL(2.0f, k2v)), OD_FMUL(2.0f, k3v)), k4v) / 6.0f;
-}
-
 struct StepParams {
     CurrentStages cs;
     double dt;
@@ -245,6 +216,13 @@ struct StepParams {
     float* env_u;
     float* env_v;
     double truncate_below;
+    // drift:current_uncertainty[_uniform] / drift:wind_uncertainty (environment.py:869-891): per get_environment
+    // call the reference adds N(0, std) and then U(-std, std) draws to the float32 current (and N(0, std) to the
+    // wind).  noise_cur: [stage 0..3][kind 0 normal, 1 uniform][component][n] float64 draws of the legacy generator
+    // (already scaled), or NULL; kinds present are flagged in noise_kinds (bit 0 normal, bit 1 uniform).
+    const double* noise_cur;
+    const double* noise_wind;     // [component][n] normal draws for the wind, or NULL
+    int32_t noise_kinds, pad1_;
     // extras (od_step_oceandrift)
     int32_t wind_on, wdf_f64, w_on, w_at_surface, diff_on, zio_f64;   // zio_f64: dtype of z_inout
     GroupGeom gwind;
@@ -260,6 +238,50 @@ struct StepParams {
     float diffusivity_const;
     float adt32;
 };
+
+// env[var] += draws  on a float32 array: float32(float64(k) + draw), normal first, then uniform
+OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u, float& v) {
+    if (!p.noise_cur) return;
+    for (int kind = 0; kind < 2; ++kind) {
+        if (!(p.noise_kinds & (1 << kind))) continue;
+        const double* base = p.noise_cur + ((int64_t)(stage * 2 + kind) * 2) * p.n;
+        u = (float)OD_DADD((double)u, base[i]);
+        v = (float)OD_DADD((double)v, base[p.n + i]);
+    }
+}
+
+// Returns the RK-combined velocity (float32) that the final move uses; k1 is sampled here unless given.
+template <int SCHEME, class MATH>
+OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
+                       float dt32, float k1u, float k1v, float& ou, float& ov) {
+    const CurrentStages& cs = p.cs;
+    if (SCHEME == 0) {
+        ou = k1u;
+        ov = k1v;
+        return;
+    }
+    double mlon, mlat;
+    MATH::midpoint(gs, lon0, lat0, k1u, k1v, dt32, mlon, mlat);
+    float k2u, k2v;
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false);
+    add_current_noise(p, 1, i, k2u, k2v);
+    if (SCHEME == 1) {
+        ou = k2u;
+        ov = k2v;
+        return;
+    }
+    MATH::midpoint(gs, lon0, lat0, k2u, k2v, dt32, mlon, mlat);
+    float k3u, k3v;
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false);
+    add_current_noise(p, 2, i, k3u, k3v);
+    MATH::midpoint(gs, lon0, lat0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
+    float k4u, k4v;
+    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false);     // ... at time t + dt
+    add_current_noise(p, 3, i, k4u, k4v);
+    // (x_vel + 2*x_vel2 + 2*x_vel3 + x_vel4)/6.0, float32, left to right
+    ou = OD_FADD(OD_FADD(OD_FADD(k1u, OD_FMUL(2.0f, k2u)), OD_FMUL(2.0f, k3u)), k4u) / 6.0f;
+    ov = OD_FADD(OD_FADD(OD_FADD(k1v, OD_FMUL(2.0f, k2v)), OD_FMUL(2.0f, k3v)), k4v) / 6.0f;
+}
 
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
@@ -283,12 +305,13 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         k1v = p.k1v[i];
     } else {
         MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0);
+        add_current_noise(p, 0, i, k1u, k1v);
     }
     if (p.env_u) p.env_u[i] = k1u;
     if (p.env_v) p.env_v[i] = k1v;
 
     float ru, rv;
-    rk_velocity<SCHEME, MATH>(p.cs, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv);
+    rk_velocity<SCHEME, MATH>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv);
 
     double lon1, lat1;
     if (F64) {
@@ -305,6 +328,10 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
             const VertW v0 = {0, 0, 1.0};
             float xw, yw;
             MATH::sample_uv(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+            if (p.noise_wind) {
+                xw = (float)OD_DADD((double)xw, p.noise_wind[i]);
+                yw = (float)OD_DADD((double)yw, p.noise_wind[p.n + i]);
+            }
             const double wdd = fabs(p.wind_drift_depth);
             const bool surface = z0 >= -wdd;
             if (p.wdf_f64 || wdd != 0.0) {

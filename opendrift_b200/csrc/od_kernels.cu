@@ -757,6 +757,9 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
     p->truncate_below = a->truncate_below;
     p->pos_f32 = a->pos_f32;
     p->z_f64 = a->z_f64;
+    p->noise_cur = a->noise_kinds ? a->d_noise_cur : nullptr;
+    p->noise_kinds = a->noise_kinds;
+    if (a->noise_kinds && !a->d_noise_cur) return fail(ctx, OD_ERR_ARG, "noise_kinds set without d_noise_cur");
     return OD_OK;
 }
 
@@ -803,6 +806,7 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         if (rc) return rc;
         p.wdf = a->d_wdf;
         p.wind_drift_depth = a->wind_drift_depth;
+        p.noise_wind = a->d_noise_wind;
     }
     if (a->group_w >= 0) {
         rc = need_group(ctx, a->group_w, 1);

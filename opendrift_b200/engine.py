@@ -47,6 +47,26 @@ def bracket(times, t):
     return ib, ia, w
 
 
+def draw_uncertainty(n, scheme, cur_std=0.0, cur_uniform=0.0, wind_std=0.0, with_wind=False):
+    """The uncertainty draws of one time step from NumPy's legacy global generator, in the reference's order
+    (environment.py:869-891, called once for the step's environment and once per Runge-Kutta stage):
+    returns (noise_cur [4][2][2][n] float64 or None, kinds bitmask, noise_wind [2][n] or None)."""
+    kinds = (1 if cur_std > 0 else 0) | (2 if cur_uniform > 0 else 0)
+    stages = {'euler': 1, 'runge-kutta': 2, 'runge-kutta4': 4}[scheme]
+    cur = np.zeros((4, 2, 2, n)) if kinds else None
+    wind = None
+    for st in range(stages):
+        if cur_std > 0:
+            cur[st, 0, 0] = np.random.normal(0, cur_std, n)
+            cur[st, 0, 1] = np.random.normal(0, cur_std, n)
+        if cur_uniform > 0:
+            cur[st, 1, 0] = np.random.uniform(-cur_uniform, cur_uniform, n)
+            cur[st, 1, 1] = np.random.uniform(-cur_uniform, cur_uniform, n)
+        if st == 0 and with_wind and wind_std > 0:
+            wind = np.stack([np.random.normal(0, wind_std, n), np.random.normal(0, wind_std, n)])
+    return cur, kinds, wind
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -273,8 +293,10 @@ class Engine:
                                                  _ptr(yvel), f64, _ptr(moving), float(dt)))
 
     def _advect_args(self, a, group, scheme, t, dt_seconds, half, full, lon, lat, z, factor, moving,
-                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=False):
+                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=False, noise=None, noise_kinds=0):
         a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
+        if noise is not None:
+            a.d_noise_cur, a.noise_kinds = noise.data_ptr(), int(noise_kinds)
         a.fast = 1 if fast else 0
         a.pos_f32 = 1 if pos_f32 else 0
         a.group_uv = group.gid
@@ -305,24 +327,25 @@ class Engine:
             a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
 
     def advect_current(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None, k1=None,
-                       truncate_below=None, env_out=None, pos_f32=False, fast=False):
+                       truncate_below=None, env_out=None, pos_f32=False, fast=False, noise=None, noise_kinds=0):
         """advect_ocean_current on device tensors (in place).  t is the reader-time object (datetime
         or seconds), dt a timedelta-like or seconds."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
         self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving, k1,
-                          truncate_below, env_out, pos_f32, fast)
+                          truncate_below, env_out, pos_f32, fast, noise, noise_kinds)
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
 
     def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
                         truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
-                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=False):
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=False, noise=None, noise_kinds=0,
+                        wind_noise=None):
         """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
         array that vertical advection updates -- a different buffer after vertical mixing."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         s = StepArgs()
         self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
-                          None, truncate_below, None, pos_f32, fast)
+                          None, truncate_below, None, pos_f32, fast, noise, noise_kinds)
         s.group_wind = -1
         s.group_w = -1
         if wind is not None:
@@ -331,6 +354,8 @@ class Engine:
             s.d_wdf = wdf.data_ptr()
             s.wdf_f64 = 1 if wdf.dtype == self.torch.float64 else 0
             s.wind_drift_depth = float(wind_drift_depth)
+            if wind_noise is not None:
+                s.d_noise_wind = wind_noise.data_ptr()
         if w_group is not None:
             s.group_w = w_group.gid
             s.t_w, _ = w_group.sample(t)

@@ -96,9 +96,14 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             'drift:max_speed': {'type': 'float', 'default': 1, 'min': 0, 'max': np.inf, 'units': 'm/s',
                                 'level': CONFIG_LEVEL_ESSENTIAL, 'description': 'Maximum anticipated speed.'},
             'drift:current_uncertainty': {'type': 'float', 'default': 0, 'min': 0, 'max': 5, 'units': 'm/s',
-                                          'level': CONFIG_LEVEL_ADVANCED, 'description': 'Not implemented on the GPU path (must be 0).'},
+                                          'level': CONFIG_LEVEL_ADVANCED,
+                                          'description': 'Add gaussian perturbation with this standard deviation to current components at each time step'},
+            'drift:current_uncertainty_uniform': {'type': 'float', 'default': 0, 'min': 0, 'max': 5, 'units': 'm/s',
+                                                  'level': CONFIG_LEVEL_ADVANCED,
+                                                  'description': 'Add gaussian perturbation with this magnitude to current components at each time step'},
             'drift:wind_uncertainty': {'type': 'float', 'default': 0, 'min': 0, 'max': 5, 'units': 'm/s',
-                                       'level': CONFIG_LEVEL_ADVANCED, 'description': 'Not implemented on the GPU path (must be 0).'},
+                                       'level': CONFIG_LEVEL_ADVANCED,
+                                       'description': 'Add gaussian perturbation with this standard deviation to wind components at each time step.'},
             'drift:relative_wind': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
                                     'description': 'Wind relative to the ocean current.'},
             'drift:deactivate_north_of': {'type': 'float', 'default': None, 'min': -90, 'max': 90, 'units': 'degrees',
@@ -329,9 +334,33 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             d_env, missing = self.env.device_environment(self._env_variables, self.time, el.dev('lon', self.engine.torch.float64),
                                                          el.dev('lat', self.engine.torch.float64), self._z_for_sampling(),
                                                          pos_f32=el.positions_f32)
+            self._add_uncertainty(d_env)
             self._env_view = EnvironmentView(d_env)
             self._env_missing = missing
         return self._env_view
+
+    def _uncertainty(self):
+        return (self.get_config('drift:current_uncertainty', 0) or 0, self.get_config('drift:current_uncertainty_uniform', 0) or 0,
+                self.get_config('drift:wind_uncertainty', 0) or 0)
+
+    def _add_uncertainty(self, d_env):
+        """environment.py:869-891 for the step's environment: env[var] += draw on float32 arrays."""
+        cu, cuu, wu = self._uncertainty()
+        eng, torch = self.engine, self.engine.torch
+        n = self.num_elements_active()
+
+        def add(var, draw):
+            d_env[var] = (d_env[var].to(torch.float64) + eng.to_device(draw)).to(torch.float32)
+        if 'x_sea_water_velocity' in d_env and 'y_sea_water_velocity' in d_env:
+            if cu > 0:
+                add('x_sea_water_velocity', np.random.normal(0, cu, n))
+                add('y_sea_water_velocity', np.random.normal(0, cu, n))
+            if cuu > 0:
+                add('x_sea_water_velocity', np.random.uniform(-cuu, cuu, n))
+                add('y_sea_water_velocity', np.random.uniform(-cuu, cuu, n))
+        if 'x_wind' in d_env and 'y_wind' in d_env and wu > 0:
+            add('x_wind', np.random.normal(0, wu, n))
+            add('y_wind', np.random.normal(0, wu, n))
 
     def _z_for_sampling(self):
         """Depth tensor in the dtype the reference's array has: float32, or float64 after vertical mixing."""
@@ -411,9 +440,6 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             raise NotImplementedError('file export is outside the GPU hot path; read o.history / o.elements')
         if self.num_elements_scheduled() == 0:
             raise ValueError('Please seed elements before starting a run.')
-        for k in ('drift:current_uncertainty', 'drift:wind_uncertainty'):
-            if self.get_config(k, 0):
-                raise NotImplementedError('%s needs the sequential legacy RNG per stage; not on the GPU path' % k)
         if time_step is None:
             time_step = timedelta(minutes=self.get_config('general:time_step_minutes'))
         if not isinstance(time_step, timedelta):

@@ -185,8 +185,16 @@ class OceanDrift(OpenDriftSimulation):
                 for v in ('sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity')):
             stokes_inp = self._stokes_inputs()
         split_diffusion = stokes_inp is not None and D != 0
-        rand = None
         n = len(el)
+        from ..engine import draw_uncertainty
+        cu, cuu, wu = self._uncertainty()
+        if stokes_inp is not None and (cu > 0 or cuu > 0 or wu > 0):
+            return False        # the step's environment (with its draws) is already materialised: helper path
+        ncur, nkinds, nwind = draw_uncertainty(n, self.get_config('drift:advection_scheme'), cu, cuu, wu,
+                                               with_wind=wind is not None)
+        d_ncur = eng.to_device(ncur) if ncur is not None else None
+        d_nwind = eng.to_device(nwind) if nwind is not None else None
+        rand = None
         if D != 0 and not split_diffusion:
             rand = (eng.to_device(np.random.normal(scale=1, size=n)), eng.to_device(np.random.normal(scale=1, size=n)))
         moving = el.dev('moving')
@@ -206,7 +214,8 @@ class OceanDrift(OpenDriftSimulation):
                             wind=wind, wdf=el.dev('wind_drift_factor'),
                             wind_drift_depth=self.get_config('drift:wind_drift_depth'), w_group=wgrp,
                             w_at_surface=self.get_config('drift:vertical_advection_at_surface'), rand=rand,
-                            diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new)
+                            diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new,
+                            noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind)
         if stokes_inp is not None:
             z_keep = el._dev.get('z')
             self.stokes_drift(_inputs=stokes_inp)

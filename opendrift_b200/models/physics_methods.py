@@ -54,9 +54,30 @@ class PhysicsMethods:
         view = getattr(self, '_env_view', None)
         if view is not None and 'x_sea_water_velocity' in view:
             k1 = (view.dev('x_sea_water_velocity', eng), view.dev('y_sea_water_velocity', eng))
+        noise, kinds = None, 0
+        cu, cuu, _ = self._uncertainty()
+        if cu > 0 or cuu > 0:
+            from ..engine import draw_uncertainty
+            if k1 is None:                    # the step's environment has not been drawn yet: stage 0 included
+                arr, kinds, _ = draw_uncertainty(lon.numel(), scheme, cu, cuu)
+            else:                             # stages 2..4 only (the step's environment already carries its draws)
+                sub = {'euler': None, 'runge-kutta': 'euler', 'runge-kutta4': 'runge-kutta4'}[scheme]
+                arr = None
+                if sub is not None:
+                    nst = 1 if scheme == 'runge-kutta' else 3
+                    arr = np.zeros((4, 2, 2, lon.numel()))
+                    kinds = (1 if cu > 0 else 0) | (2 if cuu > 0 else 0)
+                    for st in range(1, 1 + nst):
+                        if cu > 0:
+                            arr[st, 0, 0] = np.random.normal(0, cu, lon.numel())
+                            arr[st, 0, 1] = np.random.normal(0, cu, lon.numel())
+                        if cuu > 0:
+                            arr[st, 1, 0] = np.random.uniform(-cuu, cuu, lon.numel())
+                            arr[st, 1, 1] = np.random.uniform(-cuu, cuu, lon.numel())
+            noise = eng.to_device(arr) if arr is not None else None
         eng.advect_current(g, scheme, self.time, self.time_step, lon, lat,
                            self._z_for_sampling() if g.desc.nz > 1 else None, factor=fac, moving=moving, k1=k1,
-                           truncate_below=trunc, pos_f32=el.positions_f32)
+                           truncate_below=trunc, pos_f32=el.positions_f32, noise=noise, noise_kinds=kinds if noise is not None else 0)
         el.positions_f32 = False
 
     def advect_wind(self, factor=1):

@@ -190,6 +190,9 @@ def reader_interpolate(reader, variables, time, lon, lat, z, profiles=None):
     return env
 
 
+NOISE = {'current': 0.0, 'current_uniform': 0.0, 'wind': 0.0}     # drift:*_uncertainty of the run being restated
+
+
 def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, truncate_below=None, profiles=None):
     """Environment.get_environment for one reader per variable group
     (opendrift/models/basemodel/environment.py:499-923): float32 cast at :695-696,
@@ -232,6 +235,22 @@ def get_environment(readers, variables, time, lon, lat, z, fallback=FALLBACK, tr
         if fb is not None:
             bad = ~np.isfinite(env[v])
             env[v][bad] = fb
+    # environment.py:869-891: uncertainty draws from the legacy generator, per call, in this order
+    n = len(lon)
+    if 'x_sea_water_velocity' in variables and 'y_sea_water_velocity' in variables:
+        std = NOISE['current']
+        if std > 0:
+            env['x_sea_water_velocity'] += np.random.normal(0, std, n)
+            env['y_sea_water_velocity'] += np.random.normal(0, std, n)
+        std = NOISE['current_uniform']
+        if std > 0:
+            env['x_sea_water_velocity'] += np.random.uniform(-std, std, n)
+            env['y_sea_water_velocity'] += np.random.uniform(-std, std, n)
+    if 'x_wind' in variables and 'y_wind' in variables:
+        std = NOISE['wind']
+        if std > 0:
+            env['x_wind'] += np.random.normal(0, std, n)
+            env['y_wind'] += np.random.normal(0, std, n)
     if profiles is not None:
         return env, env.pop('__profiles__', None)
     return env
@@ -410,10 +429,12 @@ def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
 
 def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
                    vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
-                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None):
+                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None, noise=None):
     """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
     OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
+    NOISE.update({'current': 0.0, 'current_uniform': 0.0, 'wind': 0.0})
+    NOISE.update(noise or {})
     np.random.seed(seed)                       # basemodel/__init__.py:326
     n = len(lon)
     # seeding casts to the declared element dtypes (opendrift/elements/elements.py:156-158)

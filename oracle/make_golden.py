@@ -71,7 +71,7 @@ def build_wind(g, n_slabs):
 
 
 def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
-             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True, holes=False):
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True, holes=False, noise=None):
     n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
     times, f3 = build_fields(g, n_slabs, with_w, mixing)
     if holes:
@@ -104,6 +104,8 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
         cfg['environment:constant:horizontal_diffusivity'] = diffusivity
     if wind_drift_depth is not None:
         cfg['drift:wind_drift_depth'] = wind_drift_depth
+    for k, v in (noise or {}).items():
+        cfg['drift:%s_uncertainty' % k if k != 'current_uniform' else 'drift:current_uncertainty_uniform'] = v
     if mixing:
         cfg['drift:vertical_mixing'] = True
         cfg['vertical_mixing:timestep'] = dt_mix
@@ -119,7 +121,7 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
                 diffusivity=diffusivity, seed=seed, wind_drift_depth=wind_drift_depth,
                 start_offset_s=start_offset_s if dt > 0 else None,
                 start_index=None if dt > 0 else len(times) - 1,
-                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix, stokes=stokes)
+                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix, stokes=stokes, noise=noise)
     out = dict(meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat,
                grid_z=np.zeros(0) if g.z is None else g.z,
                u=f3[CURRENT[0]], v=f3[CURRENT[1]], lon0=lon, lat0=lat, z0=z,
@@ -189,6 +191,9 @@ def main():
     run_case('rk4_3d_backward', g3, n, 8, -600, 'runge-kutta4')
     run_case('rk4_3d_full', g3, n, 10, 600, 'runge-kutta4', with_w=True, wind=True, diffusivity=10.0)
     run_case('euler_2d_wind', g2, n, 10, 600, 'euler', wind=True, wind_drift_depth=0)
+    run_case('rk4_3d_noise', g3, 800, 6, 600, 'runge-kutta4', wind=True, diffusivity=5.0,
+             noise={'current': 0.1, 'current_uniform': 0.05, 'wind': 1.0})
+    run_case('rk2_3d_noise', g3, 800, 5, 600, 'runge-kutta', noise={'current': 0.2})
     run_case('rk4_3d_land', g3, n, 10, 600, 'runge-kutta4', holes=True)
     run_case('euler_2d_land', g2, n, 10, 600, 'euler', holes=True)
     run_leeway_case('leeway_piw1', g2, 1200, 12, 600, object_type=1)

@@ -15,7 +15,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from opendrift_b200 import synthetic as syn            # noqa: E402
-from opendrift_b200.engine import bracket              # noqa: E402  (pure-Python host logic)
+from opendrift_b200.engine import bracket, draw_uncertainty   # noqa: E402  (pure-Python host logic)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 CUR = ['x_sea_water_velocity', 'y_sea_water_velocity']
@@ -162,7 +162,7 @@ def run_port(fx):
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
                              cdf=fx.cdf if fx.cdf is not None else 1.0, diffusivity=m['diffusivity'],
                              seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0),
-                             stokes=m.get('stokes'))
+                             stokes=m.get('stokes'), noise=m.get('noise'))
 
 
 # ---- host-compiled device math ---------------------------------------------------------------
@@ -200,7 +200,8 @@ class HsStepArgs(C.Structure):
                 ('g_wind', HsGroup), ('t_wind', HsPair), ('wdf', C.c_void_p), ('wind_drift_depth', C.c_double),
                 ('g_w', HsGroup), ('t_w', HsPair), ('z_inout', C.c_void_p),
                 ('rand_x', C.c_void_p), ('rand_y', C.c_void_p), ('diffusivity', C.c_void_p),
-                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32), ('fast', C.c_int32), ('pad1_', C.c_int32)]
+                ('diffusivity_const', C.c_float), ('z_inout_f64', C.c_int32), ('fast', C.c_int32), ('noise_kinds', C.c_int32),
+                ('noise_cur', C.c_void_p), ('noise_wind', C.c_void_p)]
 
 
 class HsStokesArgs(C.Structure):
@@ -336,7 +337,10 @@ def run_hostshim(fx, fast=False):
     np.random.seed(m['seed'])
     t = fx.start
     dt = timedelta(seconds=fx.dt)
+    nz_ = m.get('noise') or {}
     for istep in range(fx.steps):
+        ncur, nkinds, nwind = draw_uncertainty(fx.n, m['scheme'], nz_.get('current', 0), nz_.get('current_uniform', 0),
+                                               nz_.get('wind', 0), with_wind=bool(m['wind']))
         z_new = None
         if kfld is not None:                   # vertical mixing first: it needs the start-of-step positions
             ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
@@ -357,6 +361,12 @@ def run_hostshim(fx, fast=False):
             xw, yw = wind.sample(lib, t, lon, lat, z, istep == 0)
             senv = (us, vs, hs, xw, yw)
         a = HsStepArgs()
+        if ncur is not None:
+            ncur = np.ascontiguousarray(ncur)
+            a.noise_cur, a.noise_kinds = _p(ncur), nkinds
+        if nwind is not None:
+            nwind = np.ascontiguousarray(nwind)
+            a.noise_wind = _p(nwind)
         a.fast = 1 if fast else 0
         a.pos_f32 = 1 if istep == 0 else 0
         a.z_f64 = 1 if z.dtype == np.float64 else 0
@@ -432,8 +442,13 @@ def run_engine(fx, fused=True, sort_every=0, fast=False):
     np.random.seed(m['seed'])
     t = fx.start
     dt = timedelta(seconds=fx.dt)
+    nz_ = m.get('noise') or {}
     for istep in range(fx.steps):
         first = istep == 0          # element positions are float32 until the first update_positions
+        ncur, nkinds, nwind = draw_uncertainty(fx.n, m['scheme'], nz_.get('current', 0), nz_.get('current_uniform', 0),
+                                               nz_.get('wind', 0), with_wind=bool(m['wind']))
+        d_ncur = eng.to_device(ncur) if ncur is not None else None
+        d_nwind = eng.to_device(nwind) if nwind is not None else None
         rand = None
         if m['diffusivity']:
             rand = (eng.to_device(np.random.normal(scale=1, size=fx.n)),
@@ -454,7 +469,8 @@ def run_engine(fx, fused=True, sort_every=0, fast=False):
             eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
-                                diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new, fast=fast)
+                                diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new, fast=fast,
+                                noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind)
             if senv is not None:
                 us, vs, hs, xw, yw = senv
                 mode = None
@@ -467,7 +483,7 @@ def run_engine(fx, fused=True, sort_every=0, fast=False):
         else:
             assert not (m['wind'] or m['with_w'] or m['diffusivity'])
             eng.advect_current(cur, m['scheme'], t, dt, lon, lat, z if three_d else None, factor=d_cdf,
-                               moving=d_mov, pos_f32=first, fast=fast)
+                               moving=d_mov, pos_f32=first, fast=fast, noise=d_ncur, noise_kinds=nkinds)
         t = t + dt
     eng.sync()
     out = lon.cpu().numpy(), lat.cpu().numpy(), (z.cpu().numpy() if z is not None else fx.z0)

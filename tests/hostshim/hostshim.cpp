@@ -97,7 +97,8 @@ struct hs_step_args {
     hs_group g_wind; hs_pair t_wind; const void* wdf; double wind_drift_depth;
     hs_group g_w; hs_pair t_w; void* z_inout;
     const double* rand_x; const double* rand_y; const float* diffusivity; float diffusivity_const; int32_t z_inout_f64;
-    int32_t fast, pad1_;
+    int32_t fast, noise_kinds;
+    const double* noise_cur; const double* noise_wind;
 };
 
 }  // extern "C"
@@ -121,6 +122,7 @@ int hs_step(const hs_step_args* a) {
     p.truncate_below = a->truncate_below;
     p.pos_f32 = a->pos_f32;
     p.z_f64 = a->z_f64;
+    p.noise_cur = a->noise_kinds ? a->noise_cur : nullptr; p.noise_kinds = a->noise_kinds; p.noise_wind = a->noise_wind;
     if (a->wind_on) {
         p.wind_on = 1; p.wdf_f64 = a->wdf_f64; p.gwind = make_geom(a->g_wind, l2); p.pwind = make_pair(a->t_wind);
         p.wdf = a->wdf; p.wind_drift_depth = a->wind_drift_depth;

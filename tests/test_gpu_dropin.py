@@ -37,6 +37,8 @@ def _model(fx, **cfg):
         o.set_config('environment:constant:horizontal_diffusivity', m['diffusivity'])
     if m.get('wind_drift_depth') is not None:
         o.set_config('drift:wind_drift_depth', m['wind_drift_depth'])
+    for k, v in (m.get('noise') or {}).items():
+        o.set_config('drift:current_uncertainty_uniform' if k == 'current_uniform' else 'drift:%s_uncertainty' % k, v)
     if m.get('mixing'):
         o.set_config('drift:vertical_mixing', True)
         o.set_config('vertical_mixing:timestep', m['dt_mix'])
@@ -92,7 +94,7 @@ def test_overridden_update_uses_helpers_and_matches():
             self.vertical_advection()
 
     for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32', 'rk4_3d_mixing', 'euler_3d_mixing_w',
-                 'rk4_3d_stokes_phillips', 'euler_3d_stokes_mono_nohs'):
+                 'rk4_3d_stokes_phillips', 'euler_3d_stokes_mono_nohs', 'rk4_3d_noise', 'rk2_3d_noise'):
         fx = Fixture(name)
         o = _model(fx)
         o.__class__ = MyMixingDrift if fx.meta.get('mixing') else (MyStokesDrift if fx.meta.get('stokes') else MyDrift)
