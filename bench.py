@@ -269,6 +269,20 @@ def run_b200(args):
         torch.cuda.synchronize()
         fast_ms.append(ka.elapsed_time(kb))
     fast_kernel_ms = float(np.median(fast_ms))
+    # the TMA-staged variant of the same kernel (shared-memory field boxes), bit-identical results
+    eng.set_tile(True)
+    tile_ms = []
+    for _ in range(5):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tl, ta = st['lon'].clone(), st['lat'].clone()
+        torch.cuda.synchronize()
+        ka.record()
+        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
+        kb.record()
+        torch.cuda.synchronize()
+        tile_ms.append(ka.elapsed_time(kb))
+    eng.set_tile(False)
+    tile_kernel_ms = float(np.median(tile_ms))
 
     # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
@@ -346,6 +360,8 @@ def run_b200(args):
                      'note': 'this float64 kernel is bound by the FP64 pipe (ncu: fp64 pipe ~45% of peak, issue slots ~51%), '
                              'not by its 65 algorithmic bytes per particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
+        'tma_tile': {'kernel_ms': tile_kernel_ms, 'note': 'opt-in OD_OPT_TILE: one cp.async.bulk.tensor.4d box per block; same bits; '
+                                                          'not faster than L1-served gathers on sorted particles (see DESIGN.md)'},
         'fast_mode': {'kernel_ms': fast_kernel_ms, 'particle_steps_per_s_kernel': n / (fast_kernel_ms * 1e-3),
                       'hbm_frac_algorithmic': b_alg / (fast_kernel_ms * 1e-3) / 1e9 / peak,
                       'note': 'opt-in FastMath (float32 sampling, mid-latitude moves on float64 positions), <= 2e-8 deg from the '

@@ -68,6 +68,11 @@ const char* od_last_error(od_ctx* ctx);
 /* use an existing CUDA stream (cudaStream_t passed as void*; NULL = legacy default stream) */
 int od_set_stream(od_ctx* ctx, void* cuda_stream);
 int od_sync(od_ctx* ctx);                        /* blocks until the stream is idle */
+/* OD_OPT_TILE: od_advect_current (RK schemes) stages a box of pair texels per thread block in shared memory with one
+ * TMA load (cp.async.bulk.tensor.4d) and serves the bilinear corners of all stages from it; pays off for cell-sorted
+ * particle arrays, results are bit-identical either way. */
+enum od_option { OD_OPT_TILE = 1 };
+int od_set_option(od_ctx* ctx, int option, int value);
 int od_device_sm_count(od_ctx* ctx);
 
 /* ---- forcing fields ---------------------------------------------------------------------

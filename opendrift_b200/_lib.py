@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('ODCUDA_LIB') or os.path.join(_HERE, 'libodcuda.so')  
 OD_EULER, OD_RK2, OD_RK4 = 0, 1, 2
 OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
 OD_LON_0_360, OD_LON_PM180 = 0, 1
+OD_OPT_TILE = 1
 OD_MAX_LEVELS = 128
 OD_MAX_GROUPS = 64
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
@@ -89,6 +90,7 @@ SYMBOLS = {
     'od_last_error': (C.c_char_p, [_P]),
     'od_set_stream': (C.c_int, [_P, _P]),
     'od_sync': (C.c_int, [_P]),
+    'od_set_option': (C.c_int, [_P, C.c_int, C.c_int]),
     'od_device_sm_count': (C.c_int, [_P]),
     'od_group_define': (C.c_int, [_P, C.c_int, C.POINTER(GroupDesc), C.POINTER(C.c_double)]),
     'od_group_free': (C.c_int, [_P, C.c_int]),

@@ -80,8 +80,9 @@ struct ExactMath {
     OD_HDS void move64(const Start& s, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
         final_move_f64(s, lon0, xv, yv, mv, dt, lon1, lat1);
     }
-    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32) {
-        sample2(g, pr, vw, lon, lat, u, v, pos_f32);
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
+                          const TileView& tv = TileView()) {
+        sample2(g, pr, vw, lon, lat, u, v, pos_f32, tv);
     }
     OD_HDS float sample_s(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
         return sample1(g, pr, vw, lon, lat, pos_f32);
@@ -150,7 +151,8 @@ struct FastMath {
     }
     OD_HDS float lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
     // time lerp of the corners, then trilinear, float32 FMAs
-    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool) {
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool,
+                          const TileView& tv = TileView()) {
         float ru = NAN, rv = NAN;
         double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
         const double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
@@ -161,13 +163,13 @@ struct FastMath {
             const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1, iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
             const float tx = (float)(xi - fx), ty = (float)(yi - fy);
             const float tw = pr.mode == 0 ? (float)pr.w : (pr.mode == 1 ? 0.0f : 1.0f);
-            const long long layer = (long long)g.nx * g.ny;
+            const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, ix, ix1, iy, iy1, vw.ia, g.nz > 1 ? vw.ib : vw.ia);
             float lu[2], lvv[2];
             const int nl = g.nz > 1 ? 2 : 1;
             for (int l = 0; l < nl; ++l) {
-                const float* t = pr.tex + ((long long)(l == 0 ? vw.ia : vw.ib) * layer) * 4;
-                const Tex4 a00 = ld_tex4(t + 4ll * (iy * g.nx + ix)), a01 = ld_tex4(t + 4ll * (iy * g.nx + ix1));
-                const Tex4 a10 = ld_tex4(t + 4ll * (iy1 * g.nx + ix)), a11 = ld_tex4(t + 4ll * (iy1 * g.nx + ix1));
+                const int lay = l == 0 ? vw.ia : vw.ib;
+                const Tex4 a00 = fetch4(ts, lay, iy, ix), a01 = fetch4(ts, lay, iy, ix1);
+                const Tex4 a10 = fetch4(ts, lay, iy1, ix), a11 = fetch4(ts, lay, iy1, ix1);
                 const float u0 = lerp(lerp(a00.x, a00.z, tw), lerp(a01.x, a01.z, tw), tx);
                 const float u1 = lerp(lerp(a10.x, a10.z, tw), lerp(a11.x, a11.z, tw), tx);
                 const float v0 = lerp(lerp(a00.y, a00.w, tw), lerp(a01.y, a01.w, tw), tx);
@@ -253,7 +255,7 @@ OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u
 // Returns the RK-combined velocity (float32) that the final move uses; k1 is sampled here unless given.
 template <int SCHEME, class MATH>
 OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
-                       float dt32, float k1u, float k1v, float& ou, float& ov) {
+                       float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv) {
     const CurrentStages& cs = p.cs;
     if (SCHEME == 0) {
         ou = k1u;
@@ -263,7 +265,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
     double mlon, mlat;
     MATH::midpoint(gs, lon0, lat0, k1u, k1v, dt32, mlon, mlat);
     float k2u, k2v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false);
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false, tv);
     add_current_noise(p, 1, i, k2u, k2v);
     if (SCHEME == 1) {
         ou = k2u;
@@ -272,11 +274,11 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
     }
     MATH::midpoint(gs, lon0, lat0, k2u, k2v, dt32, mlon, mlat);
     float k3u, k3v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false);
+    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false, tv);
     add_current_noise(p, 2, i, k3u, k3v);
     MATH::midpoint(gs, lon0, lat0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
     float k4u, k4v;
-    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false);     // ... at time t + dt
+    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false, tv);     // ... at time t + dt
     add_current_noise(p, 3, i, k4u, k4v);
     // (x_vel + 2*x_vel2 + 2*x_vel3 + x_vel4)/6.0, float32, left to right
     ou = OD_FADD(OD_FADD(OD_FADD(k1u, OD_FMUL(2.0f, k2u)), OD_FMUL(2.0f, k3u)), k4u) / 6.0f;
@@ -287,7 +289,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
 template <int SCHEME, bool F64, bool EXTRAS, class MATH = ExactMath>
 OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
-                         const double* zsw, const double* zyw) {
+                         const double* zsw, const double* zyw, const TileView& tv = TileView()) {
     const GroupGeom& g = p.cs.g;
     const double lon0 = p.lon[i], lat0 = p.lat[i];
     const bool zf32 = p.z_f64 == 0;
@@ -304,14 +306,14 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         k1u = p.k1u[i];
         k1v = p.k1v[i];
     } else {
-        MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0);
+        MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0, tv);
         add_current_noise(p, 0, i, k1u, k1v);
     }
     if (p.env_u) p.env_u[i] = k1u;
     if (p.env_v) p.env_v[i] = k1v;
 
     float ru, rv;
-    rk_velocity<SCHEME, MATH>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv);
+    rk_velocity<SCHEME, MATH>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv);
 
     double lon1, lat1;
     if (F64) {

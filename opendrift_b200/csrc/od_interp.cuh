@@ -111,6 +111,7 @@ OD_HD VertW vert_weights(const GroupGeom& g, ZPtr zs, ZPtr zy, double z, bool z_
 // bilinear weights of scipy's order-1 spline: w0 = 1 - frac, w1 = 1 - w0
 struct HorizW {
     int i00, i01, i10, i11;     // texel offsets (in texels) of the four corners within one layer
+    int ix, iy, ix1, iy1;       // cell indices of the corners
     double wy0, wy1, wx0, wx1;
     bool valid;
 };
@@ -149,6 +150,7 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
     h.valid = covered;
     if (!covered) {
         h.i00 = h.i01 = h.i10 = h.i11 = 0;
+        h.ix = h.iy = h.ix1 = h.iy1 = 0;
         h.wy0 = h.wy1 = h.wx0 = h.wx1 = 0.0;
         return h;
     }
@@ -160,6 +162,7 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
     h.wx1 = OD_DSUB(1.0, h.wx0);
     h.wy0 = OD_DSUB(1.0, OD_DSUB(yi, fy));
     h.wy1 = OD_DSUB(1.0, h.wy0);
+    h.ix = ix; h.iy = iy; h.ix1 = ix1; h.iy1 = iy1;
     h.i00 = iy * g.nx + ix;
     h.i01 = iy * g.nx + ix1;
     h.i10 = iy1 * g.nx + ix;
@@ -199,6 +202,52 @@ OD_HD Tex2 ld_tex2(const float* p) {
     return r;
 }
 
+// A box of pair texels staged in shared memory by TMA (cp.async.bulk.tensor) for the particles of one thread
+// block; texels outside the box (or of another pair buffer) are fetched from global memory.
+struct TileView {
+    const float* smem;        // [bz][by][bx][4] floats, or nullptr when the block has no tile
+    const float* tex;         // the pair-texel buffer the tile mirrors
+    int x0, y0, z0;           // box origin (cell indices, layer)
+    int bx, by, bz;           // box extents
+};
+
+// Where the eight corners of one sample live: either all inside the staged box (shared memory, box strides) or in
+// the global pair-texel buffer.  One test per sample; the loads then go through a generic pointer.
+struct TexelSource {
+    const float* base;        // such that texel (layer, iy, ix) is at base + 4 * ((layer * ly + iy) * lx + ix)
+    long long lx, ly;
+};
+
+OD_HD TexelSource texel_source(const float* tex, const TileView& tv, int nx, int ny, int ix, int ix1, int iy, int iy1,
+                               int ia, int ib) {
+    TexelSource t;
+#if defined(__CUDA_ARCH__)
+    if (tv.smem && tex == tv.tex && ix >= tv.x0 && ix1 < tv.x0 + tv.bx && iy >= tv.y0 && iy1 < tv.y0 + tv.by &&
+        ia >= tv.z0 && ib < tv.z0 + tv.bz) {
+        t.base = tv.smem - 4 * ((tv.z0 * tv.by + tv.y0) * tv.bx + tv.x0);
+        t.lx = tv.bx;
+        t.ly = tv.by;
+        return t;
+    }
+#endif
+    t.base = tex;
+    t.lx = nx;
+    t.ly = ny;
+    return t;
+}
+
+OD_HD Tex4 fetch4(const TexelSource& t, int layer, int iy, int ix) {
+    const float* p = t.base + 4ll * (((long long)layer * t.ly + iy) * t.lx + ix);
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    Tex4 r = {v.x, v.y, v.z, v.w};
+    return r;
+#else
+    Tex4 r = {p[0], p[1], p[2], p[3]};
+    return r;
+#endif
+}
+
 OD_HD bool finite_f(float v) { return fabsf(v) <= 3.4028234663852886e38f; }   // false for NaN / inf
 
 // vertical + time combination of the four horizontal results (layer a/b x time A/B) of one component
@@ -223,19 +272,17 @@ OD_HD float combine(const GroupGeom& g, const PairRef& pr, const VertW& vw,
 
 // Sample a 2-component group (e.g. x/y_sea_water_velocity) -> float32 u, v with fallback applied.
 OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
-                   float& u, float& v, bool pos_f32 = false) {
+                   float& u, float& v, bool pos_f32 = false, const TileView& tv = TileView()) {
     const HorizW h = horiz_weights(g, lon, lat, pos_f32);
     float ru = NAN, rv = NAN;
     if (h.valid && pr.mode != 3) {
-        const long long layer = (long long)g.nx * g.ny;
-        const float* ta = pr.tex + ((long long)vw.ia * layer) * 4;
-        const Tex4 a00 = ld_tex4(ta + 4ll * h.i00), a01 = ld_tex4(ta + 4ll * h.i01);
-        const Tex4 a10 = ld_tex4(ta + 4ll * h.i10), a11 = ld_tex4(ta + 4ll * h.i11);
+        const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
+        const Tex4 a00 = fetch4(ts, vw.ia, h.iy, h.ix), a01 = fetch4(ts, vw.ia, h.iy, h.ix1);
+        const Tex4 a10 = fetch4(ts, vw.ia, h.iy1, h.ix), a11 = fetch4(ts, vw.ia, h.iy1, h.ix1);
         Tex4 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
         if (g.nz > 1) {
-            const float* tb = pr.tex + ((long long)vw.ib * layer) * 4;
-            b00 = ld_tex4(tb + 4ll * h.i00); b01 = ld_tex4(tb + 4ll * h.i01);
-            b10 = ld_tex4(tb + 4ll * h.i10); b11 = ld_tex4(tb + 4ll * h.i11);
+            b00 = fetch4(ts, vw.ib, h.iy, h.ix); b01 = fetch4(ts, vw.ib, h.iy, h.ix1);
+            b10 = fetch4(ts, vw.ib, h.iy1, h.ix); b11 = fetch4(ts, vw.ib, h.iy1, h.ix1);
         }
         float uaA = 0.f, ubA = 0.f, uaB = 0.f, ubB = 0.f, vaA = 0.f, vbA = 0.f, vaB = 0.f, vbB = 0.f;
         if (pr.mode != 2) {

@@ -5,6 +5,7 @@
 // velocity components and both bracketing time slabs is one 16-byte load.  The whole RK4 stage loop,
 // the four WGS84 geodesic moves and (in od_step_oceandrift) wind drift, vertical advection and the
 // horizontal random walk run in a single kernel launch per time step.
+#include <cuda.h>            // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -33,7 +34,17 @@ using namespace od;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// Box of pair texels one thread block stages in shared memory (TMA).  Particles are sorted by (layer, 4x4-cell
+// tile), so the 128 particles of a block typically sit in ~10 neighbouring tiles of one tile row: 48 x 8 cells
+// (4-cell tile + 2-cell halo on each side for the RK stage excursions) x 2 layers = 12 KB.
+#define OD_TILE_BX 48
+#define OD_TILE_BY 8
+#define OD_TILE_BZ 2
+#define OD_TILE_HALO 2
+
 struct PairEntry {
+    CUtensorMap tmap;            // 4-D tiled view {4 floats, nx, ny, nz} of tex (valid when tmap_ok)
+    bool tmap_ok = false;
     float* tex = nullptr;
     int slot_a = -1, slot_b = -1;
     uint64_t ver_a = 0, ver_b = 0;
@@ -69,6 +80,7 @@ struct od_ctx {
     int32_t* d_bins = nullptr;
     int64_t keys_cap = 0, bins_cap = 0;
     unsigned* d_red = nullptr;          // reduction scratch
+    int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
 };
 
 static int fail(od_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -139,6 +151,12 @@ extern "C" int od_set_stream(od_ctx* ctx, void* s) {
     if (!ctx) return OD_ERR_ARG;
     ctx->stream = (cudaStream_t)s;
     return OD_OK;
+}
+
+extern "C" int od_set_option(od_ctx* ctx, int option, int value) {
+    if (!ctx) return OD_ERR_ARG;
+    if (option == OD_OPT_TILE) { ctx->tile = value ? 1 : 0; return OD_OK; }
+    return fail(ctx, OD_ERR_ARG, "od_set_option: unknown option");
 }
 
 extern "C" int od_sync(od_ctx* ctx) {
@@ -334,6 +352,37 @@ __global__ void __launch_bounds__(OD_BLOCK) pack_pair1_kernel(const float* __res
     for (; i < cells; i += stride) tex[i] = make_float2(a0[i], b0[i]);
 }
 
+typedef CUresult (*od_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static od_encode_tiled_fn tensor_map_encoder() {
+    static od_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (od_encode_tiled_fn)f;
+    }
+    return fn;
+}
+
+// tensor map of a two-component pair-texel buffer: dims {4, nx, ny, nz} float32, box {4, BX, BY, min(BZ, nz)}
+static bool make_tensor_map(const Group& g, float* tex, CUtensorMap* out) {
+    od_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc || g.desc.ncomp != 2) return false;
+    const cuuint64_t dims[4] = {4, (cuuint64_t)g.desc.nx, (cuuint64_t)g.desc.ny, (cuuint64_t)g.desc.nz};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)g.desc.nx * 16, (cuuint64_t)g.desc.nx * g.desc.ny * 16};
+    const cuuint32_t box[4] = {4, OD_TILE_BX, OD_TILE_BY, (cuuint32_t)(g.desc.nz < OD_TILE_BZ ? g.desc.nz : OD_TILE_BZ)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (g.desc.nx < OD_TILE_BX || g.desc.ny < OD_TILE_BY) return false;
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, tex, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Resolve a time sample to pair texels (building / reusing a cached pair).
 static int resolve_pair(od_ctx* ctx, int group, const od_time_sample& ts, PairRef* out) {
     Group& g = ctx->groups[group];
@@ -372,7 +421,10 @@ static int resolve_pair(od_ctx* ctx, int group, const od_time_sample& ts, PairRe
         if (!p.tex) { victim = &p; break; }
         if (p.last_use < victim->last_use) victim = &p;
     }
-    if (!victim->tex) CK(cudaMalloc(&victim->tex, g.cells() * sizeof(float) * 2 * nc));
+    if (!victim->tex) {
+        CK(cudaMalloc(&victim->tex, g.cells() * sizeof(float) * 2 * nc));
+        victim->tmap_ok = make_tensor_map(g, victim->tex, &victim->tmap);
+    }
     const int64_t cells = (int64_t)g.cells();
     int blocks = (int)((cells + OD_BLOCK - 1) / OD_BLOCK);
     const int cap = ctx->sm_count * 8;
@@ -763,6 +815,112 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
     return OD_OK;
 }
 
+// ---- TMA-staged variant -----------------------------------------------------------------------------------
+// One elected thread computes nothing itself: the block first reduces the bounding box of its particles' stage-1
+// cells; if the box (plus halo) fits the tensor map's box, thread 0 issues ONE cp.async.bulk.tensor.4d load of
+// {4 floats, BX, BY, BZ} pair texels into shared memory and the block waits on the mbarrier; all bilinear
+// corners of all RK stages that fall inside the box are then served from shared memory (fetch4), the rest and
+// blocks whose particles are too spread out (unsorted input, tile-row wrap) go to global memory as before.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int SCHEME, bool F64, bool EXTRAS, class MATH>
+__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_tiled_kernel(const StepParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                            const float* tile_tex) {
+    __shared__ LevelsSmem lv;
+    __shared__ LevelsSmem lvw;
+    __shared__ alignas(128) float tile[OD_TILE_BZ * OD_TILE_BY * OD_TILE_BX * 4];
+    __shared__ alignas(8) unsigned long long mbar;
+    __shared__ int bbox[6 * (OD_BLOCK / 32)];
+    __shared__ int tile_org[4];                 // x0, y0, z0, ok
+    const GroupGeom& g = p.cs.g;
+    if (g.nz > 1) load_levels(lv, g);
+    if (EXTRAS && p.w_on && p.gw.nz > 1) load_levels(lvw, p.gw);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < p.n;
+    // bounding box of the stage-1 corners of this block's particles
+    int mnx = 1 << 30, mxx = -1, mny = 1 << 30, mxy = -1, mnz = 1 << 30, mxz = -1;
+    if (active) {
+        const HorizW h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        if (h.valid) {
+            const bool zf32 = p.z_f64 == 0;
+            double z0 = p.z ? (zf32 ? (double)((const float*)p.z)[i] : ((const double*)p.z)[i]) : 0.0;
+            if (p.truncate_below > 0.0 && z0 < -p.truncate_below) z0 = zf32 ? (double)(float)(-p.truncate_below) : -p.truncate_below;
+            const VertW vw = vert_weights(g, (const double*)lv.zs, (const double*)lv.zy, z0, zf32);
+            mnx = h.ix; mxx = h.ix1; mny = h.iy; mxy = h.iy1; mnz = vw.ia; mxz = vw.ib;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mnz = min(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxz = max(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        bbox[warp * 6 + 0] = mnx; bbox[warp * 6 + 1] = mxx; bbox[warp * 6 + 2] = mny;
+        bbox[warp * 6 + 3] = mxy; bbox[warp * 6 + 4] = mnz; bbox[warp * 6 + 5] = mxz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < OD_BLOCK / 32; ++w) {
+            mnx = min(mnx, bbox[w * 6 + 0]); mxx = max(mxx, bbox[w * 6 + 1]); mny = min(mny, bbox[w * 6 + 2]);
+            mxy = max(mxy, bbox[w * 6 + 3]); mnz = min(mnz, bbox[w * 6 + 4]); mxz = max(mxz, bbox[w * 6 + 5]);
+        }
+        const int bz = g.nz < OD_TILE_BZ ? g.nz : OD_TILE_BZ;
+        const int x0 = max(0, mnx - OD_TILE_HALO), y0 = max(0, mny - OD_TILE_HALO);
+        const bool ok = mxx >= 0 && (mxx + OD_TILE_HALO - x0) < OD_TILE_BX && (mxy + OD_TILE_HALO - y0) < OD_TILE_BY &&
+                        (mxz - mnz) < bz;
+        tile_org[0] = x0; tile_org[1] = y0; tile_org[2] = ok ? mnz : 0; tile_org[3] = ok ? 1 : 0;
+        if (ok) {
+            const unsigned bytes = (unsigned)(bz * OD_TILE_BY * OD_TILE_BX * 16);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(tile)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(smem_u32(&mbar)),
+                  "r"(0), "r"(x0), "r"(y0), "r"(mnz) : "memory");
+        }
+    }
+    __syncthreads();
+    TileView tv;
+    tv.smem = nullptr; tv.tex = tile_tex;
+    tv.x0 = tile_org[0]; tv.y0 = tile_org[1]; tv.z0 = tile_org[2];
+    tv.bx = OD_TILE_BX; tv.by = OD_TILE_BY; tv.bz = g.nz < OD_TILE_BZ ? g.nz : OD_TILE_BZ;
+    if (tile_org[3]) {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0) : "memory");
+        }
+        tv.smem = tile;
+    }
+    if (!active) return;
+    step_particle<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy, tv);
+}
+
+static const PairEntry* find_tmap(const Group& g, const float* tex) {
+    for (const auto& pe : g.pairs)
+        if (pe.tex == tex && pe.tmap_ok) return &pe;
+    return nullptr;
+}
+
+template <bool EXTRAS, class MATH>
+static int launch_step_tiled(od_ctx* ctx, int scheme, bool f64, const StepParams& p, const PairEntry* pe) {
+    const int grid = grid_for(p.n);
+    cudaStream_t s = ctx->stream;
+#define OD_LAUNCHT(S, F) step_tiled_kernel<S, F, EXTRAS, MATH><<<grid, OD_BLOCK, 0, s>>>(p, pe->tmap, pe->tex)
+    if (scheme == OD_EULER) { if (f64) OD_LAUNCHT(0, true); else OD_LAUNCHT(0, false); }
+    else if (scheme == OD_RK2) { if (f64) OD_LAUNCHT(1, true); else OD_LAUNCHT(1, false); }
+    else { if (f64) OD_LAUNCHT(2, true); else OD_LAUNCHT(2, false); }
+#undef OD_LAUNCHT
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
 template <bool EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
@@ -784,6 +942,13 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     int rc = fill_current(ctx, a, &p);
     if (rc) return rc;
     if (a->n == 0) return OD_OK;
+    const PairEntry* pe = nullptr;
+    if (ctx->tile && a->scheme != OD_EULER)          // tile the pair the RK stages sample (t_mid)
+        pe = find_tmap(ctx->groups[a->group_uv], p.cs.t_mid.tex);
+    if (pe) {
+        if (a->fast) return launch_step_tiled<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        return launch_step_tiled<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+    }
     if (a->fast) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     return launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
 }

@@ -204,6 +204,10 @@ class Engine:
     def use_stream(self, stream):
         self._check(self.lib.od_set_stream(self.ctx, C.c_void_p(stream.cuda_stream)))
 
+    def set_tile(self, on):
+        """TMA-staged field boxes in shared memory for the RK kernels (cell-sorted particle arrays)."""
+        self._check(self.lib.od_set_option(self.ctx, _lib.OD_OPT_TILE, 1 if on else 0))
+
     def sync(self):
         self._check(self.lib.od_sync(self.ctx))
 

@@ -49,6 +49,12 @@ res['step_rk4_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, d
 l2, a2 = lon.clone(), lat.clone()
 l2, a2 = lon.clone(), lat.clone()
 res['step_rk4_fast_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=True))
+eng.set_tile(True)
+l2, a2 = lon.clone(), lat.clone()
+res['step_rk4_tile_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z))
+l2, a2 = lon.clone(), lat.clone()
+res['step_rk4_fast_tile_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=True))
+eng.set_tile(False)
 l2, a2 = lon.clone(), lat.clone()
 res['step_euler_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z))
 res['sort_by_cell_ms'] = timeit(lambda: eng.sort_by_cell(grp, lon, lat, z))
