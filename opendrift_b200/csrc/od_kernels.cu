@@ -80,6 +80,8 @@ struct od_ctx {
     int32_t* d_bins = nullptr;
     int64_t keys_cap = 0, bins_cap = 0;
     unsigned* d_red = nullptr;          // reduction scratch
+    float* d_fill = nullptr;            // scratch slab of the NaN fill
+    int64_t fill_cap = 0;
     int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
 };
 
@@ -142,6 +144,7 @@ extern "C" void od_destroy(od_ctx* ctx) {
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->d_bins) cudaFree(ctx->d_bins);
     if (ctx->d_red) cudaFree(ctx->d_red);
+    if (ctx->d_fill) cudaFree(ctx->d_fill);
     delete ctx;
 }
 
@@ -251,6 +254,7 @@ extern "C" int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const
 
 __global__ void dilate_nan_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int64_t cells,
                                   unsigned* __restrict__ counters);
+__global__ void count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters);
 
 extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining) {
     int rc = check_slot(ctx, group, slot, comp);
@@ -260,28 +264,42 @@ extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int
     const int64_t cells = (int64_t)g.cells();
     float* a = g.slots[(size_t)slot * g.desc.ncomp + comp];
     if (!ctx->d_red) CK(cudaMalloc(&ctx->d_red, 2 * sizeof(unsigned)));
-    float* tmp = nullptr;
-    int64_t remaining = -1;
-    for (int it = 0; it < max_iterations; ++it) {
-        if (!tmp) CK(cudaMalloc(&tmp, cells * sizeof(float)));
-        CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
-        dilate_nan_kernel<<<(int)((cells + 255) / 256), 256, 0, ctx->stream>>>(a, tmp, g.desc.nx, g.desc.ny, cells, ctx->d_red);
+    // cheap first look: is there any non-finite cell at all? (one read pass, no scratch)
+    unsigned res[2] = {0, 0};
+    CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
+    {
+        int blocks = (int)((cells + 255) / 256);
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        count_nonfinite_kernel<<<blocks, 256, 0, ctx->stream>>>(a, cells, ctx->d_red);
         CK(cudaGetLastError());
         ctx->launches++;
-        unsigned res[2];
-        CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        remaining = res[1];
-        if (res[0] == 0) break;                      // nothing could be filled (no holes, or unreachable ones)
-        CK(cudaMemcpyAsync(a, tmp, cells * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-        g.version[slot] = ++ctx->tick;
-        if (remaining == 0) break;
     }
-    if (tmp) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
+    CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int64_t remaining = res[0];
+    if (remaining > 0 && max_iterations > 0) {
+        if (ctx->fill_cap < cells) {                 // grow-only scratch slab
+            if (ctx->d_fill) cudaFree(ctx->d_fill);
+            ctx->d_fill = nullptr;
+            CK(cudaMalloc(&ctx->d_fill, cells * sizeof(float)));
+            ctx->fill_cap = cells;
+        }
+        float* tmp = ctx->d_fill;
+        for (int it = 0; it < max_iterations; ++it) {
+            CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
+            dilate_nan_kernel<<<(int)((cells + 255) / 256), 256, 0, ctx->stream>>>(a, tmp, g.desc.nx, g.desc.ny, cells, ctx->d_red);
+            CK(cudaGetLastError());
+            ctx->launches++;
+            CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            remaining = res[1];
+            if (res[0] == 0) break;                  // nothing could be filled (unreachable holes)
+            CK(cudaMemcpyAsync(a, tmp, cells * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            g.version[slot] = ++ctx->tick;
+            if (remaining == 0) break;
+        }
     }
-    if (h_remaining) *h_remaining = remaining < 0 ? 0 : remaining;
+    if (h_remaining) *h_remaining = remaining;
     return OD_OK;
 }
 
@@ -334,6 +352,14 @@ __global__ void __launch_bounds__(256) dilate_nan_kernel(const float* __restrict
     }
     dst[i] = found ? best : NAN;
     atomicAdd(&counters[found ? 0 : 1], 1u);         // [0] filled in this pass, [1] still missing
+}
+
+__global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters) {
+    unsigned c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
+        c += !(fabsf(a[i]) <= 3.4028234663852886e38f);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[0], c);
 }
 
 // interleave two time slabs (and two components) into pair texels
@@ -558,8 +584,7 @@ __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    double K[OD_MAX_LEVELS];
-    mix_particle(p, i, xs, xy, K);
+    mix_particle(p, i, xs, xy);
 }
 
 // ---- Leeway -------------------------------------------------------------------------------------------

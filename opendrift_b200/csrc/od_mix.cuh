@@ -6,7 +6,8 @@
 // ReaderBlock (interpolation/structured.py:148-163), time-interpolated in float64 (basereader/structured.py:366-383),
 // then written back through a float32 cast for every layer but the last.  The reference materialises (nz, N)
 // profile arrays (1 GB per variable at 5 M particles x 50 layers) and loops dt/dt_mix times over N-sized NumPy
-// expressions; here each thread keeps its K column in local memory and runs the whole inner loop.
+// expressions; here each thread evaluates the levels of its K column it actually visits (a sliding window held in registers)
+// and runs the whole inner loop.
 //   gradK = -np.gradient(K, z)  thresholded at 1e-10            (:500-502)
 //   zi = round(interp1d(-z_levels -> index)(-z))  as uint16     (:513)
 //   z -= moving * (dKdz*dt_mix - R*sqrt(K*|dt_mix|*2/r)), R = 2*U(0,1)-1, r = 1/3   (:524-528)
@@ -63,22 +64,72 @@ struct MixParams {
     double dz0;                  // np.diff(mixing_z)[0] when the spacing is uniform
 };
 
+// One level of the particle's diffusivity column (environment profile), on demand.
+OD_HD double k_level_raw(const MixParams& p, const HorizW& h, int l) {
+    double v = NAN;
+    if (h.valid && p.pr.mode != 3) {
+        const long long layer = (long long)p.g.nx * p.g.ny;
+        const float* t = p.pr.tex + ((long long)l * layer) * 2;
+        const Tex2 a00 = ld_tex2(t + 2ll * h.i00), a01 = ld_tex2(t + 2ll * h.i01);
+        const Tex2 a10 = ld_tex2(t + 2ll * h.i10), a11 = ld_tex2(t + 2ll * h.i11);
+        const double hA = (double)bilin(h, a00.x, a01.x, a10.x, a11.x);
+        if (p.pr.mode == 1) v = hA;
+        else {
+            const double hB = (double)bilin(h, a00.y, a01.y, a10.y, a11.y);
+            v = p.pr.mode == 2 ? hB : OD_DADD(OD_DMUL(hA, OD_DSUB(1.0, p.pr.w)), OD_DMUL(hB, p.pr.w));
+        }
+    }
+    if (l < p.g.nz - 1) v = (double)(float)v;      // environment.py:706-713 (float32 write-back, all but the last layer)
+    return v;
+}
+
+OD_HD double k_level(const MixParams& p, const HorizW& h, int l) {
+    double v = k_level_raw(p, h, l);
+    if (l == p.g.nz - 1 && p.g.nz > 1 && v != v) v = k_level_raw(p, h, l - 1);       // environment.py:715-724
+    if (!(fabs(v) <= 1.7976931348623157e308)) v = (double)p.g.fallback[0];          // masked -> fallback (:803-806)
+    return v;
+}
+
+// A window of OD_MIX_WINDOW consecutive levels of the column, recentred (and recomputed) when the particle
+// leaves it: a random-walk step is a fraction of a level, so one window serves a whole time step almost always.
+#define OD_MIX_WINDOW 8
+struct KWindow {
+    double v[OD_MIX_WINDOW];
+    int lo;
+};
+
+OD_HD void k_window_fill(const MixParams& p, const HorizW& h, KWindow& w, int centre) {
+    const int nz = p.g.nz;
+    int lo = centre - OD_MIX_WINDOW / 2;
+    if (lo > nz - OD_MIX_WINDOW) lo = nz - OD_MIX_WINDOW;
+    if (lo < 0) lo = 0;
+    w.lo = lo;
+    for (int k = 0; k < OD_MIX_WINDOW; ++k) w.v[k] = (lo + k < nz) ? k_level(p, h, lo + k) : 0.0;
+}
+
+OD_HD double k_get(const MixParams& p, const HorizW& h, KWindow& w, int l) {
+    if (l < w.lo || l >= w.lo + OD_MIX_WINDOW) k_window_fill(p, h, w, l);
+    double r = w.v[0];
+    for (int k = 1; k < OD_MIX_WINDOW; ++k) r = (l - w.lo == k) ? w.v[k] : r;     // register select, no local memory
+    return r;
+}
+
 // -np.gradient(K, mixing_z)[l] with numpy's edge_order=1 formulas, |g| < 1e-10 -> 0
-OD_HD double neg_gradient(const MixParams& p, const double* K, int l) {
+OD_HD double neg_gradient(const MixParams& p, const HorizW& h, KWindow& w, int l) {
     const int nz = p.g.nz;
     double gr;
     if (l == 0) {
-        gr = OD_DSUB(K[1], K[0]) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[1], p.zl[0]));
+        gr = OD_DSUB(k_get(p, h, w, 1), k_get(p, h, w, 0)) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[1], p.zl[0]));
     } else if (l == nz - 1) {
-        gr = OD_DSUB(K[nz - 1], K[nz - 2]) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[nz - 1], p.zl[nz - 2]));
+        gr = OD_DSUB(k_get(p, h, w, nz - 1), k_get(p, h, w, nz - 2)) / (p.uniform_dz ? p.dz0 : OD_DSUB(p.zl[nz - 1], p.zl[nz - 2]));
     } else if (p.uniform_dz) {
-        gr = OD_DSUB(K[l + 1], K[l - 1]) / OD_DMUL(2.0, p.dz0);
+        gr = OD_DSUB(k_get(p, h, w, l + 1), k_get(p, h, w, l - 1)) / OD_DMUL(2.0, p.dz0);
     } else {
         const double dx1 = OD_DSUB(p.zl[l], p.zl[l - 1]), dx2 = OD_DSUB(p.zl[l + 1], p.zl[l]);
         const double a = -(dx2) / OD_DMUL(dx1, OD_DADD(dx1, dx2));
         const double b = OD_DSUB(dx2, dx1) / OD_DMUL(dx1, dx2);
         const double c = dx1 / OD_DMUL(dx2, OD_DADD(dx1, dx2));
-        gr = OD_DADD(OD_DADD(OD_DMUL(a, K[l - 1]), OD_DMUL(b, K[l])), OD_DMUL(c, K[l + 1]));
+        gr = OD_DADD(OD_DADD(OD_DMUL(a, k_get(p, h, w, l - 1)), OD_DMUL(b, k_get(p, h, w, l))), OD_DMUL(c, k_get(p, h, w, l + 1)));
     }
     gr = -gr;
     return fabs(gr) < 1e-10 ? 0.0 : gr;
@@ -104,31 +155,12 @@ OD_HD int nearest_level(const MixParams& p, const double* xs, const double* xy, 
     return zi < 0 ? 0 : (zi > nz - 1 ? nz - 1 : zi);
 }
 
-OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const double* xy, double* K) {
+OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const double* xy) {
     const GroupGeom& g = p.g;
-    const int nz = g.nz;
-    // ---- the particle's diffusivity column (environment profile) --------------------------------------------
+    // the particle's diffusivity column (environment profile) is evaluated lazily, a window of levels at a time
     const HorizW h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
-    const long long layer = (long long)g.nx * g.ny;
-    for (int l = 0; l < nz; ++l) {
-        double v = NAN;
-        if (h.valid && p.pr.mode != 3) {
-            const float* t = p.pr.tex + ((long long)l * layer) * 2;
-            const Tex2 a00 = ld_tex2(t + 2ll * h.i00), a01 = ld_tex2(t + 2ll * h.i01);
-            const Tex2 a10 = ld_tex2(t + 2ll * h.i10), a11 = ld_tex2(t + 2ll * h.i11);
-            const double hA = (double)bilin(h, a00.x, a01.x, a10.x, a11.x);
-            if (p.pr.mode == 1) v = hA;
-            else {
-                const double hB = (double)bilin(h, a00.y, a01.y, a10.y, a11.y);
-                v = p.pr.mode == 2 ? hB : OD_DADD(OD_DMUL(hA, OD_DSUB(1.0, p.pr.w)), OD_DMUL(hB, p.pr.w));
-            }
-        }
-        if (l < nz - 1) v = (double)(float)v;           // environment.py:706-713 (float32 write-back, all but the last layer)
-        K[l] = v;
-    }
-    if (nz > 1 && K[nz - 1] != K[nz - 1]) K[nz - 1] = K[nz - 2];        // environment.py:715-724
-    for (int l = 0; l < nz; ++l)
-        if (!(fabs(K[l]) <= 1.7976931348623157e308)) K[l] = (double)g.fallback[0];   // masked -> fallback (:803-806)
+    KWindow kw;
+    kw.lo = -(1 << 20);
 
     // ---- inner loop ---------------------------------------------------------------------------------------------
     double z = p.z_in_f64 ? ((const double*)p.z_in)[i] : (double)((const float*)p.z_in)[i];
@@ -143,8 +175,8 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
     for (int it = 0; it < p.ntimes; ++it) {
         const bool surface = z == 0.0;
         const int zi = nearest_level(p, xs, xy, -z);
-        const double Kz = K[zi];
-        const double dKdz = neg_gradient(p, K, zi);
+        const double Kz = k_get(p, h, kw, zi);
+        const double dKdz = neg_gradient(p, h, kw, zi);
         double U;
         if (p.rand) {
             U = p.rand[(int64_t)it * p.n + i];

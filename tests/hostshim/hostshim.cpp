@@ -169,8 +169,7 @@ int hs_mix(const hs_mix_args* a) {
     p.step_index = a->step_index; p.zl = zl.data(); p.xs = xs.data(); p.xy = xy.data();
     p.uniform_dz = 1; p.dz0 = zl[1] - zl[0];
     for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
-    std::vector<double> K(nz);
-    for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy, K.data());
+    for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);
     return 0;
 }
 

@@ -57,6 +57,24 @@ res['step_rk4_fast_tile_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kut
 eng.set_tile(False)
 l2, a2 = lon.clone(), lat.clone()
 res['step_euler_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z))
+# cfg 4: vertical mixing, 50-level diffusivity column, dt/dt_mix = 10 inner iterations, Philox draws
+kslabs = [torch.from_numpy(syn.vertical_diffusivity(g, (tt - syn.T0).total_seconds())).cuda() for tt in times]
+kgrp = eng.add_group(g.lon, g.lat, g.z, 1, times, lambda ti, c: kslabs[ti], (0.0,))
+ids = torch.arange(n, device='cuda', dtype=torch.int32)
+res['vertical_mixing_10it_ms'] = timeit(lambda: eng.vertical_mixing(kgrp, t, lon, lat, z, 60.0, 10, ids=ids, seed=1))
+res['vertical_mixing_60it_ms'] = timeit(lambda: eng.vertical_mixing(kgrp, t, lon, lat, z, 60.0, 60, ids=ids, seed=1))
+# cfg 5: Leeway step (2-D wind + current, Euler)
+g2 = syn.GridSpec(nz=1)
+wsl = [tuple(torch.from_numpy(a).cuda() for a in syn.wind_xy(g2, (tt - syn.T0).total_seconds())) for tt in times]
+csl = [tuple(torch.from_numpy(a).cuda() for a in syn.double_gyre_uv(g2, (tt - syn.T0).total_seconds(), three_d=False)) for tt in times]
+wg = eng.add_group(g2.lon, g2.lat, None, 2, times, lambda ti, c: wsl[ti][c], (float('nan'),) * 2)
+cg = eng.add_group(g2.lon, g2.lat, None, 2, times, lambda ti, c: csl[ti][c], (float('nan'),) * 2)
+el = {k: torch.rand(n, device='cuda', dtype=torch.float32) for k in ('dw_slope', 'dw_offset', 'dw_eps', 'cw_slope', 'cw_offset', 'cw_eps')}
+el['orientation'] = (torch.arange(n, device='cuda') % 2).to(torch.uint8)
+el['capsized'] = None
+el['jibe_probability'] = torch.full((n,), 0.04, device='cuda', dtype=torch.float64)
+l2, a2 = lon.clone(), lat.clone()
+res['leeway_step_ms'] = timeit(lambda: eng.leeway_step(wg, cg, t, dt, l2, a2, el, ids=ids, seed=3))
 res['sort_by_cell_ms'] = timeit(lambda: eng.sort_by_cell(grp, lon, lat, z))
 res['permute_f64_ms'] = timeit(lambda: eng.permute(perm, lon))
 res['n'] = n
