@@ -200,6 +200,8 @@ def run_b200(args):
         return dev_slabs[ti % PERIOD][c] if resident['on'] else host_slabs[ti % PERIOD][c]
 
     grp = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, supplier, (0.0, 0.0), n_slots=3)
+    if os.environ.get('OD_BENCH_NOFILL'):
+        grp.fill_nan = 0
 
     lon0, lat0, z0 = syn.particle_cloud(n, seed=1000 + rank)
     h_lon = torch.from_numpy(lon0.astype(np.float64)).pin_memory()
@@ -219,14 +221,34 @@ def run_b200(args):
         for k in ('lon', 'lat', 'z'):
             st[k] = eng.permute(perm, st[k])
 
-    def step():
+    step_events = []
+    host_us = []
+
+    def step(record=False):
         if args.sort_every and st['k'] % args.sort_every == 0:
             resort()
+        if record:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            h0 = time.perf_counter()
         eng.advect_current(grp, 'runge-kutta4', st['t'], dt, st['lon'], st['lat'], st['z'], pos_f32=(st['k'] == 0))
+        if record:
+            host_us.append((time.perf_counter() - h0) * 1e6)
+            eb.record()
+            step_events.append((ea, eb))
         st['t'] += dt
         st['k'] += 1
 
     # ---- resident run: state and slabs in HBM -----------------------------------------------------------
+    # clock ramp: a fresh process on an idle GPU runs its first second ~20 % slow (power state / clock ramp), far
+    # longer than W steps of 2 ms; spin the same kernel on scratch copies (simulation state untouched) first
+    ramp_t0 = time.perf_counter()
+    tl, ta = st['lon'].clone(), st['lat'].clone()
+    while time.perf_counter() - ramp_t0 < args.ramp_seconds:
+        for _ in range(20):
+            eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
+        torch.cuda.synchronize()
+    del tl, ta
     for _ in range(args.warmup):
         step()
     barrier()
@@ -238,11 +260,12 @@ def run_b200(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step()
+        step(record=True)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launches() - l0
+    loop_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))   # includes slab upload / pair packing
     clocks = sampler.stop() if sampler else None
 
     # dominant kernel alone: CUDA events around single launches of step_kernel<RK4> on the launching stream
@@ -257,6 +280,15 @@ def run_b200(args):
         torch.cuda.synchronize()
         kern_ms.append(ka.elapsed_time(kb))
     kernel_ms = float(np.median(kern_ms))
+    sort_ms = None
+    if args.sort_every:
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sa.record()
+        resort()
+        sb.record()
+        torch.cuda.synchronize()
+        sort_ms = sa.elapsed_time(sb)
     # the opt-in fast arithmetic (float32 sampling + mid-latitude moves on float64 positions), same launch
     fast_ms = []
     for _ in range(5):
@@ -346,7 +378,7 @@ def run_b200(args):
         'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, %d particles per GPU, '
                                'dt=600 s (BASELINE configs[1]%s)' % (n, '; configs[2] sharding' if world > 1 else ''),
                    'particles_per_gpu': n, 'field': '512x512x50 f32 u,v, hourly slabs', 'scheme': 'runge-kutta4',
-                   'sort_every': args.sort_every, 'mode': 'exact (bit-exact field sampling, float64 geodesic)',
+                   'sort_every': args.sort_every, 'sort_ms': sort_ms, 'clock_ramp_s': args.ramp_seconds, 'mode': 'exact (bit-exact field sampling, float64 geodesic)',
                    'parallelism': 'particle-index shards x%d, replicated field (NCCL broadcast of slabs: %.1f ms per slab pair)'
                                   % (world, 1e3 * t_bcast / PERIOD) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
@@ -355,7 +387,8 @@ def run_b200(args):
                 'steps': e2e_steps, 'api': 'Engine.advect_current_host (pinned host arrays in/out, %d-chunk copy/compute pipeline)' % args.e2e_chunks},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms,
+                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
+                     'host_us_per_launch_median': float(np.median(host_us)), 'host_us_per_launch_max': float(np.max(host_us)),
                      'algorithmic_bytes_per_launch': b_alg,
                      'note': 'this float64 kernel is bound by the FP64 pipe (ncu: fp64 pipe ~45% of peak, issue slots ~51%), '
                              'not by its 65 algorithmic bytes per particle-step; see DESIGN.md and profiles/'},
@@ -381,6 +414,7 @@ def main():
     ap.add_argument('--particles', type=int, default=10_000_000)
     ap.add_argument('--sort-every', type=int, default=20)
     ap.add_argument('--e2e-chunks', type=int, default=8)
+    ap.add_argument('--ramp-seconds', type=float, default=1.5)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-particles', type=int, default=50_000)
     ap.add_argument('--cpu-steps', type=int, default=4)

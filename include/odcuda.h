@@ -102,7 +102,9 @@ int od_group_free(od_ctx* ctx, int group);
 int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const float* src, int src_is_device);
 /* Fill non-finite cells of an uploaded slab from their finite 3x3 neighbours (maximum), layer by layer, up to
  * max_iterations passes: the NaN handling of Linear2DInterpolator (readers/interpolation/interpolators.py:9-20,
- * 121-139; the reference uses at most 10).  *h_remaining = cells still missing.  Synchronises. */
+ * 121-139; the reference uses at most 10, the library accepts up to 16).  Enqueued without a host round trip: a slab
+ * without holes costs one read pass.  h_remaining may be NULL; if given it receives the number of cells still missing
+ * (and the call synchronises). */
 int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining);
 /* raw device pointer of a ring slot component, e.g. as the target of an NCCL broadcast */
 int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** d_out);

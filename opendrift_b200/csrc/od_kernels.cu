@@ -81,6 +81,7 @@ struct od_ctx {
     int64_t keys_cap = 0, bins_cap = 0;
     unsigned* d_red = nullptr;          // reduction scratch
     float* d_fill = nullptr;            // scratch slab of the NaN fill
+    unsigned* d_fillcnt = nullptr;      // per-pass missing-cell counters
     int64_t fill_cap = 0;
     int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
 };
@@ -145,6 +146,7 @@ extern "C" void od_destroy(od_ctx* ctx) {
     if (ctx->d_bins) cudaFree(ctx->d_bins);
     if (ctx->d_red) cudaFree(ctx->d_red);
     if (ctx->d_fill) cudaFree(ctx->d_fill);
+    if (ctx->d_fillcnt) cudaFree(ctx->d_fillcnt);
     delete ctx;
 }
 
@@ -252,54 +254,49 @@ extern "C" int od_group_upload(od_ctx* ctx, int group, int slot, int comp, const
     return OD_OK;
 }
 
+#define OD_FILL_MAX_IT 16
 __global__ void dilate_nan_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, int64_t cells,
-                                  unsigned* __restrict__ counters);
+                                  const unsigned* __restrict__ missing_before, unsigned* __restrict__ missing_after);
+__global__ void dilate_commit_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t cells,
+                                     const unsigned* __restrict__ missing_before);
 __global__ void count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters);
 
 extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining) {
     int rc = check_slot(ctx, group, slot, comp);
     if (rc) return rc;
+    if (max_iterations < 0 || max_iterations > OD_FILL_MAX_IT) return fail(ctx, OD_ERR_ARG, "od_group_fill_nan: bad iteration count");
     Group& g = ctx->groups[group];
     CK(cudaSetDevice(ctx->device));
     const int64_t cells = (int64_t)g.cells();
     float* a = g.slots[(size_t)slot * g.desc.ncomp + comp];
-    if (!ctx->d_red) CK(cudaMalloc(&ctx->d_red, 2 * sizeof(unsigned)));
-    // cheap first look: is there any non-finite cell at all? (one read pass, no scratch)
-    unsigned res[2] = {0, 0};
-    CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
-    {
-        int blocks = (int)((cells + 255) / 256);
-        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-        count_nonfinite_kernel<<<blocks, 256, 0, ctx->stream>>>(a, cells, ctx->d_red);
-        CK(cudaGetLastError());
-        ctx->launches++;
+    if (!ctx->d_fillcnt) CK(cudaMalloc(&ctx->d_fillcnt, (OD_FILL_MAX_IT + 2) * sizeof(unsigned)));
+    if (ctx->fill_cap < cells) {                     // grow-only scratch slab (allocated once per context)
+        if (ctx->d_fill) cudaFree(ctx->d_fill);
+        ctx->d_fill = nullptr;
+        CK(cudaMalloc(&ctx->d_fill, cells * sizeof(float)));
+        ctx->fill_cap = cells;
     }
-    CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    int64_t remaining = res[0];
-    if (remaining > 0 && max_iterations > 0) {
-        if (ctx->fill_cap < cells) {                 // grow-only scratch slab
-            if (ctx->d_fill) cudaFree(ctx->d_fill);
-            ctx->d_fill = nullptr;
-            CK(cudaMalloc(&ctx->d_fill, cells * sizeof(float)));
-            ctx->fill_cap = cells;
-        }
-        float* tmp = ctx->d_fill;
-        for (int it = 0; it < max_iterations; ++it) {
-            CK(cudaMemsetAsync(ctx->d_red, 0, 2 * sizeof(unsigned), ctx->stream));
-            dilate_nan_kernel<<<(int)((cells + 255) / 256), 256, 0, ctx->stream>>>(a, tmp, g.desc.nx, g.desc.ny, cells, ctx->d_red);
-            CK(cudaGetLastError());
-            ctx->launches++;
-            CK(cudaMemcpyAsync(res, ctx->d_red, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            remaining = res[1];
-            if (res[0] == 0) break;                  // nothing could be filled (unreachable holes)
-            CK(cudaMemcpyAsync(a, tmp, cells * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-            g.version[slot] = ++ctx->tick;
-            if (remaining == 0) break;
-        }
+    // Everything below is enqueued without a host round trip: counters[it] = cells still missing before pass `it`;
+    // a pass whose counter is zero returns at once, so a slab without holes costs one read pass.
+    unsigned* cnt = ctx->d_fillcnt;
+    CK(cudaMemsetAsync(cnt, 0, (OD_FILL_MAX_IT + 2) * sizeof(unsigned), ctx->stream));
+    int blocks = (int)((cells + 255) / 256);
+    const int capped = blocks > ctx->sm_count * 16 ? ctx->sm_count * 16 : blocks;
+    count_nonfinite_kernel<<<capped, 256, 0, ctx->stream>>>(a, cells, cnt);
+    ctx->launches++;
+    for (int it = 0; it < max_iterations; ++it) {
+        dilate_nan_kernel<<<capped, 256, 0, ctx->stream>>>(a, ctx->d_fill, g.desc.nx, g.desc.ny, cells, cnt + it, cnt + it + 1);
+        dilate_commit_kernel<<<capped, 256, 0, ctx->stream>>>(ctx->d_fill, a, cells, cnt + it);
+        ctx->launches += 2;
     }
-    if (h_remaining) *h_remaining = remaining;
+    CK(cudaGetLastError());
+    g.version[slot] = ++ctx->tick;
+    if (h_remaining) {                               // optional: the caller asks how many cells stayed missing (synchronises)
+        unsigned res = 0;
+        CK(cudaMemcpyAsync(&res, cnt + max_iterations, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *h_remaining = res;
+    }
     return OD_OK;
 }
 
@@ -326,32 +323,42 @@ extern "C" int od_group_touch(od_ctx* ctx, int group, int slot) {
 // block.  A filled cell never changes again and finite cells are never touched, so filling a block 10 times
 // when it is uploaded gives every particle inside the block the value the reference's lazy loop would give.
 __global__ void __launch_bounds__(256) dilate_nan_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny,
-                                                         int64_t cells, unsigned* __restrict__ counters) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cells) return;
-    const float v = src[i];
-    if (fabsf(v) <= 3.4028234663852886e38f) {        // finite: unchanged
-        dst[i] = v;
-        return;
-    }
+                                                         int64_t cells, const unsigned* __restrict__ missing_before,
+                                                         unsigned* __restrict__ missing_after) {
+    if (*missing_before == 0) return;                // nothing left to fill: this pass is a no-op
     const int64_t layer = (int64_t)nx * ny;
-    const int64_t base = (i / layer) * layer;
-    const int r = (int)((i - base) / nx), c = (int)((i - base) % nx);
-    float best = -INFINITY;
-    bool found = false;
-    for (int dr = -1; dr <= 1; ++dr) {
-        const int rr = min(max(r + dr, 0), ny - 1);
-        for (int dc = -1; dc <= 1; ++dc) {
-            const int cc = min(max(c + dc, 0), nx - 1);
-            const float w = src[base + (int64_t)rr * nx + cc];
-            if (fabsf(w) <= 3.4028234663852886e38f) {
-                best = fmaxf(best, w);
-                found = true;
+    unsigned still = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        if (fabsf(v) <= 3.4028234663852886e38f) {    // finite: unchanged
+            dst[i] = v;
+            continue;
+        }
+        const int64_t base = (i / layer) * layer;
+        const int r = (int)((i - base) / nx), c = (int)((i - base) % nx);
+        float best = -INFINITY;
+        bool found = false;
+        for (int dr = -1; dr <= 1; ++dr) {
+            const int rr = min(max(r + dr, 0), ny - 1);
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int cc = min(max(c + dc, 0), nx - 1);
+                const float w = src[base + (int64_t)rr * nx + cc];
+                if (fabsf(w) <= 3.4028234663852886e38f) {
+                    best = fmaxf(best, w);
+                    found = true;
+                }
             }
         }
+        dst[i] = found ? best : NAN;
+        still += found ? 0u : 1u;
     }
-    dst[i] = found ? best : NAN;
-    atomicAdd(&counters[found ? 0 : 1], 1u);         // [0] filled in this pass, [1] still missing
+    if (still) atomicAdd(missing_after, still);
+}
+
+__global__ void __launch_bounds__(256) dilate_commit_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t cells,
+                                                            const unsigned* __restrict__ missing_before) {
+    if (*missing_before == 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters) {

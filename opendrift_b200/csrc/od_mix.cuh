@@ -6,7 +6,7 @@
 // ReaderBlock (interpolation/structured.py:148-163), time-interpolated in float64 (basereader/structured.py:366-383),
 // then written back through a float32 cast for every layer but the last.  The reference materialises (nz, N)
 // profile arrays (1 GB per variable at 5 M particles x 50 layers) and loops dt/dt_mix times over N-sized NumPy
-// expressions; here each thread evaluates the levels of its K column it actually visits (a sliding window held in registers)
+// expressions; here each thread evaluates the levels of its K column it actually visits (a sliding 8-level window)
 // and runs the whole inner loop.
 //   gradK = -np.gradient(K, z)  thresholded at 1e-10            (:500-502)
 //   zi = round(interp1d(-z_levels -> index)(-z))  as uint16     (:513)
@@ -109,9 +109,7 @@ OD_HD void k_window_fill(const MixParams& p, const HorizW& h, KWindow& w, int ce
 
 OD_HD double k_get(const MixParams& p, const HorizW& h, KWindow& w, int l) {
     if (l < w.lo || l >= w.lo + OD_MIX_WINDOW) k_window_fill(p, h, w, l);
-    double r = w.v[0];
-    for (int k = 1; k < OD_MIX_WINDOW; ++k) r = (l - w.lo == k) ? w.v[k] : r;     // register select, no local memory
-    return r;
+    return w.v[l - w.lo];            // dynamically indexed: 64 bytes of (L1-resident) local memory per thread
 }
 
 // -np.gradient(K, mixing_z)[l] with numpy's edge_order=1 formulas, |g| < 1e-10 -> 0

@@ -251,17 +251,20 @@ class Engine:
             assert data.dtype == torch.float32 and data.is_contiguous()
             on_dev = 1 if data.is_cuda else 0
             self._check(self.lib.od_group_upload(self.ctx, gid, slot, comp, C.c_void_p(data.data_ptr()), on_dev))
-            if not on_dev:
-                self.sync()          # pageable host memory may be reused by the caller
+            if not on_dev and not data.is_pinned():
+                self.sync()          # pageable host memory may be reused by the caller; pinned slabs are the caller's to keep
         else:
             a = np.ascontiguousarray(data, dtype=np.float32)
             self._check(self.lib.od_group_upload(self.ctx, gid, slot, comp, a.ctypes.data_as(C.c_void_p), 0))
             self.sync()
 
-    def fill_nan(self, gid, slot, comp, iterations=10):
-        rem = C.c_int64()
-        self._check(self.lib.od_group_fill_nan(self.ctx, gid, slot, comp, iterations, C.byref(rem)))
-        return int(rem.value)
+    def fill_nan(self, gid, slot, comp, iterations=10, report=False):
+        """linearNDFast NaN fill of an uploaded slab (asynchronous unless report=True)."""
+        if report:
+            rem = C.c_int64()
+            self._check(self.lib.od_group_fill_nan(self.ctx, gid, slot, comp, iterations, C.byref(rem)))
+            return int(rem.value)
+        self._check(self.lib.od_group_fill_nan(self.ctx, gid, slot, comp, iterations, None))
 
     def slot_tensor(self, group, slot, comp):
         """The ring slot as a CUDA tensor (e.g. the target of a torch.distributed broadcast)."""
