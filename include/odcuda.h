@@ -142,6 +142,10 @@ int od_update_positions(od_ctx* ctx, int64_t n, double* d_lon, double* d_lat,
                         const int32_t* d_moving, double dt);
 
 /* ---- fused advection -------------------------------------------------------------------- */
+#define OD_MATH_EXACT 0
+#define OD_MATH_FAST 1
+#define OD_MATH_SERIES 2
+
 typedef struct od_advect_args {
     int32_t scheme;               /* od_scheme */
     int32_t group_uv;             /* 2-component current group */
@@ -171,9 +175,16 @@ typedef struct od_advect_args {
                                      [stage 0..3][kind 0 normal, 1 uniform][component u, v][n], added to the float32
                                      current of every stage as the reference does per get_environment call; NULL = none */
     int32_t noise_kinds;          /* bit 0: normal draws present, bit 1: uniform draws present */
-    int32_t fast;                 /* 0: exact restatement of the reference arithmetic (bit-exact sampling, Karney
-                                     geodesic); 1: float32 sampling and mid-latitude moves on float64 positions
-                                     (~1e-7 deg from the reference after 100 steps; see od_advect.cuh FastMath) */
+    int32_t fast;                 /* arithmetic mode (OD_MATH_*):
+                                     0 EXACT : restatement of the reference arithmetic, operation by operation
+                                               (bit-exact field sampling, float32 mid-point azimuths, full Karney geodesic);
+                                     2 SERIES: the same bit-exact sampling; every move by the fifth-order short-arc
+                                               series of the direct geodesic (<= 1e-13 deg from the full solution, which
+                                               it falls back to for long steps and near the poles); mid-points skip the
+                                               float32 azimuth rounding (od_advect.cuh SeriesMath).  ~1e-9 deg from
+                                               EXACT per step, the size of the reference's own float32 arctan2 noise;
+                                     1 FAST  : float32 sampling and mid-latitude moves on float64 positions
+                                               (~1e-7 deg from the reference after 100 steps; od_advect.cuh FastMath) */
 } od_advect_args;
 
 int od_advect_current(od_ctx* ctx, const od_advect_args* a);

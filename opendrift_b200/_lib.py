@@ -13,6 +13,7 @@ OD_EULER, OD_RK2, OD_RK4 = 0, 1, 2
 OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
 OD_LON_0_360, OD_LON_PM180 = 0, 1
 OD_OPT_TILE = 1
+OD_MATH_EXACT, OD_MATH_FAST, OD_MATH_SERIES = 0, 1, 2
 OD_MAX_LEVELS = 128
 OD_MAX_GROUPS = 64
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}

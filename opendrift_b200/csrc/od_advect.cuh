@@ -89,6 +89,36 @@ struct ExactMath {
     }
 };
 
+// SeriesMath: the reference's field sampling bit for bit (ExactMath's sampler) with every move evaluated by the
+// fifth-order short-arc series of the direct geodesic (od_geod.cuh: series_move) -- the same positions as the full
+// solution to <= 1e-13 deg, at a tenth of its FP64 instructions.  Differences from ExactMath:
+//   * RK mid-points take the displacement components (0.5 dt ku, 0.5 dt kv) directly instead of the reference's
+//     float32 azimuth / float32 distance (physics_methods.py:629-631); the rounding this skips moves a mid-point by
+//     <= 2e-5 m, which changes a sampled float32 velocity in the last bit at most (positions: ~1e-10 deg, below the
+//     ~1e-9 deg/step that NumPy's own non-reproducible float32 arctan2 puts on the reference);
+//   * float64 final moves (the default dtype flow) take (dt xv, dt yv) directly: closer to the reference's
+//     float64 arctan2 -> geodesic chain than any re-implementation of that chain;
+//   * float32 final moves keep the float32 azimuth and speed of update_positions (basemodel/__init__.py:4643-4650).
+struct SeriesMath : ExactMath {
+    typedef SeriesStart Start;
+    OD_HDS Start start(double lat0) { return series_start(lat0); }
+    OD_HDS void midpoint(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
+        const double h = OD_DMUL((double)dt32, 0.5);
+        geod_move_ne(s, lon0, OD_DMUL((double)kv, h), OD_DMUL((double)ku, h), mlon, mlat);
+    }
+    OD_HDS void move32(const Start& s, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
+        const float az = az_f32(xv, yv);
+        const double dist = OD_DMUL(OD_DMUL((double)speed_f32(xv, yv), mv), dt);
+        double sa, ca;
+        sincosd(ang_round(ang_normalize((double)az)), sa, ca);
+        geod_move_ne(s, lon0, OD_DMUL(dist, ca), OD_DMUL(dist, sa), lon1, lat1);
+    }
+    OD_HDS void move64(const Start& s, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
+        const double k = OD_DMUL(mv, dt);
+        geod_move_ne(s, lon0, OD_DMUL(yv, k), OD_DMUL(xv, k), lon1, lat1);
+    }
+};
+
 struct FastStart {
     float s0, c0;        // sin, cos of the start latitude
     float im, in_;       // 1/M(lat0), 1/(N(lat0) cos lat0)  [radians per metre]
@@ -253,6 +283,11 @@ OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u
 }
 
 // Returns the RK-combined velocity (float32) that the final move uses; k1 is sampled here unless given.
+// The stages run as one rolled loop (a single copy of the move and of the sampler in the instruction stream: the
+// unrolled form exceeded the SM's instruction cache and spent a fifth of its issue slots waiting for fetches).
+//   stage 1..3: position x0 (+) 0.5*dt*k_{stage}; pair t_mid, t_mid, t_end (the reference's stage-4 quirk: half
+//   step, end time); RK2 stops after stage 1 and returns k2; RK4 returns (k1 + 2 k2 + 2 k3 + k4) / 6 in float32,
+//   accumulated left to right as the reference writes it.
 template <int SCHEME, class MATH>
 OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
                        float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv) {
@@ -262,27 +297,34 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
         ov = k1v;
         return;
     }
-    double mlon, mlat;
-    MATH::midpoint(gs, lon0, lat0, k1u, k1v, dt32, mlon, mlat);
-    float k2u, k2v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k2u, k2v, false, tv);
-    add_current_noise(p, 1, i, k2u, k2v);
+    float ku = k1u, kv = k1v;           // velocity of the previous stage
+    float su = k1u, sv = k1v;           // running RK4 sum
+    const int last = SCHEME == 1 ? 1 : 3;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int st = 1; st <= last; ++st) {
+        double mlon, mlat;
+        MATH::midpoint(gs, lon0, lat0, ku, kv, dt32, mlon, mlat);
+        const PairRef& pr = st == 3 ? cs.t_end : cs.t_mid;
+        MATH::sample_uv(cs.g, pr, vw, mlon, mlat, ku, kv, false, tv);
+        add_current_noise(p, st, i, ku, kv);
+        if (st < 3) {
+            su = OD_FADD(su, OD_FMUL(2.0f, ku));
+            sv = OD_FADD(sv, OD_FMUL(2.0f, kv));
+        } else {
+            su = OD_FADD(su, ku);
+            sv = OD_FADD(sv, kv);
+        }
+    }
     if (SCHEME == 1) {
-        ou = k2u;
-        ov = k2v;
+        ou = ku;
+        ov = kv;
         return;
     }
-    MATH::midpoint(gs, lon0, lat0, k2u, k2v, dt32, mlon, mlat);
-    float k3u, k3v;
-    MATH::sample_uv(cs.g, cs.t_mid, vw, mlon, mlat, k3u, k3v, false, tv);
-    add_current_noise(p, 2, i, k3u, k3v);
-    MATH::midpoint(gs, lon0, lat0, k3u, k3v, dt32, mlon, mlat);     // half step (reference quirk) ...
-    float k4u, k4v;
-    MATH::sample_uv(cs.g, cs.t_end, vw, mlon, mlat, k4u, k4v, false, tv);     // ... at time t + dt
-    add_current_noise(p, 3, i, k4u, k4v);
     // (x_vel + 2*x_vel2 + 2*x_vel3 + x_vel4)/6.0, float32, left to right
-    ou = OD_FADD(OD_FADD(OD_FADD(k1u, OD_FMUL(2.0f, k2u)), OD_FMUL(2.0f, k3u)), k4u) / 6.0f;
-    ov = OD_FADD(OD_FADD(OD_FADD(k1v, OD_FMUL(2.0f, k2v)), OD_FMUL(2.0f, k3v)), k4v) / 6.0f;
+    ou = su / 6.0f;
+    ov = sv / 6.0f;
 }
 
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).

@@ -52,7 +52,7 @@ constexpr double kPio4 = 0.78539816339744830962;
 
 // Every constant with a long mantissa that the geodesic needs.
 struct GeodK {
-    double ep2, f1, neg_f, inv_b, deg, rad2deg, inv90, inv360;
+    double ep2, f1, neg_f, inv_b, inv_c, deg, rad2deg, inv90, inv360;
     double S[6], C[6];        // sin / cos minimax kernels on [-pi/4, pi/4]
     double c1[6][3];          // C1[l]  / eps^l : polynomial in eps^2 (highest power first), pre-divided
     double c1p[6][3];         // C1'[l] / eps^l
@@ -66,6 +66,7 @@ constexpr GeodK make_geodk() {
     GeodK k = {};
     const double n = Wgs84::n;
     k.ep2 = Wgs84::ep2; k.f1 = Wgs84::f1; k.neg_f = -Wgs84::f; k.inv_b = 1.0 / Wgs84::b;
+    k.inv_c = Wgs84::b / (Wgs84::a * Wgs84::a);
     k.deg = kDeg; k.rad2deg = kRad2Deg; k.inv90 = 1.0 / 90.0; k.inv360 = 1.0 / 360.0;
     // minimax kernels of sin and cos on [-pi/4, pi/4] (the classic fdlibm k_sin / k_cos coefficients)
     k.S[0] = -1.66666666666666324348e-01; k.S[1] = 8.33333333332248946124e-03; k.S[2] = -1.98412698298579493134e-04;
@@ -366,6 +367,84 @@ OD_HD void geod_move(const GeodStart& p, double lon1, double azi1, double s12, d
 OD_HD void geod_direct(double lon1, double lat1, double azi1, double s12, double& lon2, double& lat2) {
     GeodStart p = geod_start(lat1);
     geod_move(p, lon1, azi1, s12, lon2, lat2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Short-arc direct problem: Taylor series of the geodesic in the northward / eastward displacement.
+//
+// Along a geodesic  dphi/ds = cos(alpha) V^3/c,  dlambda/ds = sin(alpha) V/(c cos phi),  dalpha/ds = sin(alpha) t V/c
+// (c = a^2/b, V^2 = 1 + e'^2 cos^2 phi, t = tan phi).  Differentiating along the line gives phi2 - phi1 and
+// lambda2 - lambda1 as polynomials in X = s cos(alpha)/N, Y = s sin(alpha)/N whose coefficients are polynomials in
+// V^2 and t at the start point (the classical Legendre series; tools/gen_geod_series.py derives them with SymPy to
+// fifth order and writes od_geod_series.inc).  No azimuth, no trigonometric function of the move: the displacement
+// components dt*v, dt*u enter directly.  With r = (|X| + |Y|) max(1, |t|) the measured difference from the full
+// solution is at double round-off (<= 5e-14 deg) for r <= 4e-3, 1.5e-13 for r <= 5e-3, 2.4e-12 for r <= 8e-3
+// (sixth-order truncation).  kSeriesMaxR = 4e-3 admits every move of <= 10 km at 60N, <= 3 km at 80N; the caller
+// hands longer or more polar moves (and NaN) to geod_move (tests/test_hostmath.py::test_series_*,
+// tools/gen_geod_series.py --check).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef OD_SERIES_MAX_R
+#define OD_SERIES_MAX_R 4.0e-3
+#endif
+constexpr double kSeriesMaxR = OD_SERIES_MAX_R;
+
+struct SeriesStart {
+    double lat1;        // degrees
+    double t, W;        // tan(phi1), V^2 = 1 + e'^2 cos^2(phi1)
+    double vc;          // V / c = 1 / N(phi1)                      [1/m]
+    double icd;         // (180/pi) / cos(phi1)
+};
+
+OD_HD SeriesStart series_start(double lat1) {
+    SeriesStart p;
+    if (fabs(lat1) > 90.0) lat1 = NAN;
+    double sp, cp;
+    sincosd(lat1, sp, cp);
+    const double ic = 1.0 / cp;
+    p.lat1 = lat1;
+    p.t = sp * ic;
+    p.W = 1.0 + OD_GK.ep2 * (cp * cp);
+    p.vc = sqrt(p.W) * OD_GK.inv_c;
+    p.icd = ic * OD_GK.rad2deg;
+    return p;
+}
+
+// Position after moving xn metres north and ye metres east along the geodesic that starts with that direction.
+// Returns false (lon2/lat2 untouched) when the move is outside the series' range (long steps, near the poles, NaN).
+OD_HD bool series_move(const SeriesStart& p, double lon1, double xn, double ye, double& lon2, double& lat2) {
+    const double X = xn * p.vc, Y = ye * p.vc;
+    const double r = (fabs(X) + fabs(Y)) * fmax(1.0, fabs(p.t));
+    if (!(r <= kSeriesMaxR)) return false;
+    const double t = p.t, T = t * t, W = p.W;
+#include "od_geod_series.inc"
+    const double X2 = X * X, Y2 = Y * Y, XY2 = X2 * Y2, X4 = X2 * X2, Y4 = Y2 * Y2;
+    const double Pe = (p12 * Y2 + p30 * X2) + (p14 * Y4 + p32 * XY2 + p50 * X4);          // even in t, times X
+    const double Po = (p02 * Y2 + p20 * X2) + (p04 * Y4 + p22 * XY2 + p40 * X4);          // odd in t
+    const double P = X + (X * Pe + t * Po);
+    const double Qe = (q03 * Y2 + q21 * X2) + (q05 * Y4 + q23 * XY2 + q41 * X4);
+    const double Qo = X * (1.0 + (q13 * Y2 + q31 * X2));
+    const double Q = Y + Y * (Qe + t * Qo);
+    (void)p10; (void)q01; (void)q11;
+    lat2 = p.lat1 + (W * P) * OD_GK.rad2deg;
+    lon2 = ang_normalize(ang_normalize(lon1) + Q * p.icd);
+    return true;
+}
+
+// the rarely taken full solution, kept out of line so that the callers stay small
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+void geod_direct_ne(double lon1, double lat1, double xn, double ye, double* lon2, double* lat2) {
+    const double az = atan2(ye, xn) * OD_GK.rad2deg;
+    geod_direct(lon1, lat1, az, sqrt(xn * xn + ye * ye), *lon2, *lat2);
+}
+
+// (north, east) displacement in metres -> position, series first, full solution otherwise
+OD_HD void geod_move_ne(const SeriesStart& p, double lon1, double xn, double ye, double& lon2, double& lat2) {
+    if (series_move(p, lon1, xn, ye, lon2, lat2)) return;
+    geod_direct_ne(lon1, p.lat1, xn, ye, &lon2, &lat2);
 }
 
 }  // namespace od

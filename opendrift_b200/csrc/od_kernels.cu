@@ -977,11 +977,14 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     const PairEntry* pe = nullptr;
     if (ctx->tile && a->scheme != OD_EULER)          // tile the pair the RK stages sample (t_mid)
         pe = find_tmap(ctx->groups[a->group_uv], p.cs.t_mid.tex);
+    if (a->fast < 0 || a->fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_advect_current: unknown arithmetic mode");
     if (pe) {
-        if (a->fast) return launch_step_tiled<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        if (a->fast == OD_MATH_FAST) return launch_step_tiled<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        if (a->fast == OD_MATH_SERIES) return launch_step_tiled<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
         return launch_step_tiled<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
     }
-    if (a->fast) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->fast == OD_MATH_FAST) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->fast == OD_MATH_SERIES) return launch_step<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     return launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
 }
 
@@ -1025,7 +1028,9 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         p.diffusivity_const = a->diffusivity_const;
     }
     if (a->cur.n == 0) return OD_OK;
-    if (a->cur.fast) return launch_step<true, FastMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    if (a->cur.fast < 0 || a->cur.fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift: unknown arithmetic mode");
+    if (a->cur.fast == OD_MATH_FAST) return launch_step<true, FastMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    if (a->cur.fast == OD_MATH_SERIES) return launch_step<true, SeriesMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
     return launch_step<true, ExactMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
 }
 

@@ -185,6 +185,9 @@ class Engine:
         self.ctx = ctx
         self.use_stream(torch.cuda.current_stream(self.device))
         self.groups = weakref.WeakValueDictionary()     # gid -> FieldGroup (owned by the reader that bound it)
+        # arithmetic of the step kernels when a call does not say (include/odcuda.h OD_MATH_*): bit-exact sampling +
+        # short-arc series geodesic; MATH_EXACT replays the reference operation by operation, MATH_FAST is float32
+        self.math_mode = _lib.OD_MATH_SERIES
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -300,11 +303,11 @@ class Engine:
                                                  _ptr(yvel), f64, _ptr(moving), float(dt)))
 
     def _advect_args(self, a, group, scheme, t, dt_seconds, half, full, lon, lat, z, factor, moving,
-                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=False, noise=None, noise_kinds=0):
+                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0):
         a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
         if noise is not None:
             a.d_noise_cur, a.noise_kinds = noise.data_ptr(), int(noise_kinds)
-        a.fast = 1 if fast else 0
+        a.fast = self.math_mode if fast is None else int(fast)      # OD_MATH_EXACT 0 / FAST 1 (True) / SERIES 2
         a.pos_f32 = 1 if pos_f32 else 0
         a.group_uv = group.gid
         pinned = ()
@@ -334,7 +337,7 @@ class Engine:
             a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
 
     def advect_current(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None, k1=None,
-                       truncate_below=None, env_out=None, pos_f32=False, fast=False, noise=None, noise_kinds=0):
+                       truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0):
         """advect_ocean_current on device tensors (in place).  t is the reader-time object (datetime
         or seconds), dt a timedelta-like or seconds."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
@@ -345,7 +348,7 @@ class Engine:
 
     def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
                         truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
-                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=False, noise=None, noise_kinds=0,
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=None, noise=None, noise_kinds=0,
                         wind_noise=None):
         """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
         array that vertical advection updates -- a different buffer after vertical mixing."""
@@ -379,7 +382,7 @@ class Engine:
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
 
     def advect_current_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None,
-                            factor=None, moving=None, chunks=8, pos_f32=False, fast=False):
+                            factor=None, moving=None, chunks=8, pos_f32=False, fast=None):
         """advect_ocean_current for HOST arrays (pinned torch tensors): the particle range is cut into chunks
         whose host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the
         PCIe transfers of neighbouring chunks overlap the kernel.  Results land in h_out_lon / h_out_lat

@@ -242,7 +242,7 @@ def hostshim():
     if _shim is None:
         d = os.path.join(ROOT, 'tests', 'hostshim')
         so, src = os.path.join(d, 'libhostshim.so'), os.path.join(d, 'hostshim.cpp')
-        hdrs = glob.glob(os.path.join(ROOT, 'opendrift_b200', 'csrc', '*.cuh'))
+        hdrs = glob.glob(os.path.join(ROOT, 'opendrift_b200', 'csrc', '*.cuh')) + glob.glob(os.path.join(ROOT, 'opendrift_b200', 'csrc', '*.inc'))
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC',
                                    '-o', so, src])
@@ -367,7 +367,7 @@ def run_hostshim(fx, fast=False):
         if nwind is not None:
             nwind = np.ascontiguousarray(nwind)
             a.noise_wind = _p(nwind)
-        a.fast = 1 if fast else 0
+        a.fast = int(fast)
         a.pos_f32 = 1 if istep == 0 else 0
         a.z_f64 = 1 if z.dtype == np.float64 else 0
         a.scheme = {'euler': 0, 'runge-kutta': 1, 'runge-kutta4': 2}[m['scheme']]
@@ -405,8 +405,8 @@ def run_hostshim(fx, fast=False):
     return lon, lat, z
 
 
-def run_engine(fx, fused=True, sort_every=0, fast=False):
-    """Replay a fixture on the GPU through the product Engine."""
+def run_engine(fx, fused=True, sort_every=0, fast=None):
+    """Replay a fixture on the GPU through the product Engine (fast=None: the engine's default arithmetic)."""
     import torch
     from opendrift_b200.engine import Engine
     m = fx.meta

@@ -66,6 +66,16 @@ void hs_geod_direct(int64_t n, const double* lon, const double* lat, const doubl
     for (int64_t i = 0; i < n; ++i) geod_direct(lon[i], lat[i], az[i], dist[i], lon2[i], lat2[i]);
 }
 
+// series_move on (north, east) displacements; used[i] = 1 where the series applied (else the full solution ran)
+void hs_geod_series(int64_t n, const double* lon, const double* lat, const double* xn, const double* ye,
+                    double* lon2, double* lat2, int32_t* used) {
+    for (int64_t i = 0; i < n; ++i) {
+        const SeriesStart st = series_start(lat[i]);
+        used[i] = series_move(st, lon[i], xn[i], ye[i], lon2[i], lat2[i]) ? 1 : 0;
+        if (!used[i]) geod_move_ne(st, lon[i], xn[i], ye[i], lon2[i], lat2[i]);
+    }
+}
+
 void hs_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lon, const double* lat, const float* z,
                int pos_f32, float* out0, float* out1) {
     hs_levels lv;
@@ -104,8 +114,9 @@ struct hs_step_args {
 }  // extern "C"
 
 template <int S, bool F>
-static void run(const StepParams& p, const GroupGeom& gw, bool fast = false) {
-    if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+static void run(const StepParams& p, const GroupGeom& gw, int fast = 0) {
+    if (fast == 2) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, SeriesMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
     else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
 }
 

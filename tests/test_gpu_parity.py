@@ -39,16 +39,19 @@ def test_geodesic_vs_exact_integrals(eng):
     assert np.abs(dlon * np.cos(np.radians(g['lat2']))).max() < 1e-12
 
 
+@pytest.mark.parametrize('mode', ['default', 'exact'])
 @pytest.mark.parametrize('name', fixtures())
-def test_fused_step_vs_reference_fixture(name):
+def test_fused_step_vs_reference_fixture(name, mode):
+    """default = the engine's arithmetic (OD_MATH_SERIES: bit-exact sampling + short-arc series geodesic);
+    exact = OD_MATH_EXACT, the operation-by-operation replay of the reference."""
     fx = Fixture(name)
-    lon, lat, z = common.run_engine(fx, fused=True)
+    lon, lat, z = common.run_engine(fx, fused=True, fast=None if mode == 'default' else 0)
     elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     assert elon < TOL_DEG and elat < TOL_DEG, (elon, elat)
     assert elon < TIGHT_DEG and elat < TIGHT_DEG, (elon, elat)
     assert np.abs(z - fx.z).max() <= (1e-9 if fx.meta.get('mixing') else 1e-5)
     # and against the host-compiled device math: same arithmetic on both sides of the PCIe bus
-    hl, ha, hz = common.run_hostshim(fx)
+    hl, ha, hz = common.run_hostshim(fx, fast=2 if mode == 'default' else 0)
     e2 = common.max_err_deg(lon, lat, hl, ha)
     assert max(e2) < TIGHT_DEG, e2
 
@@ -56,7 +59,7 @@ def test_fused_step_vs_reference_fixture(name):
 @pytest.mark.parametrize('name', fixtures())
 def test_fast_mode_within_float64_tolerance(name):
     """FastMath (float32 sampling + mid-latitude moves on float64 positions) stays inside the float64 tolerance
-    of the north star (1e-6 deg) with a wide margin; the exact mode remains the default."""
+    of the north star (1e-6 deg) with a wide margin; it is an opt-in."""
     fx = Fixture(name)
     lon, lat, z = common.run_engine(fx, fused=True, fast=True)
     elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)

@@ -36,6 +36,70 @@ def test_step_vs_reference_fixture(name):
 
 
 @pytest.mark.parametrize('name', fixtures())
+def test_series_mode_vs_reference_fixture(name):
+    """OD_MATH_SERIES (the engine's default): same tolerance as the exact replay."""
+    fx = Fixture(name)
+    lon, lat, z = run_hostshim(fx, fast=2)
+    elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
+    tol = 1e-11 if fx.meta['scheme'] == 'euler' and fx.cdf is None else 2e-8
+    assert elon < tol and elat < tol, (elon, elat)
+    assert np.abs(z - fx.z).max() <= (0.0 if fx.meta.get('mixing') else 1e-5)
+
+
+def _wrap(d):
+    return d - 360.0 * np.round(d / 360.0)
+
+
+def test_series_geodesic_vs_exact_integrals():
+    """The short-arc series against the mpmath evaluation of the geodesic integrals, where it applies."""
+    lib = hostshim()
+    g = np.load(os.path.join(GOLDEN, 'geod_mpmath.npz'))
+    n = len(g['lon1'])
+    xn = g['s12'] * np.cos(np.radians(g['azi1']))
+    ye = g['s12'] * np.sin(np.radians(g['azi1']))
+    lo, la, used = np.empty(n), np.empty(n), np.zeros(n, dtype=np.int32)
+    lib.hs_geod_series(C.c_int64(n), _p(g['lon1']), _p(g['lat1']), _p(xn), _p(ye), _p(lo), _p(la), _p(used))
+    m = used == 1
+    assert m.sum() > 300                      # the golden set holds many step-sized cases
+    err_lon = np.abs(_wrap(lo - g['lon2']) * np.cos(np.radians(g['lat2'])))
+    assert np.abs(la - g['lat2'])[m].max() < 1e-13 and err_lon[m].max() < 1e-13
+    assert np.abs(la - g['lat2']).max() < 1e-12 and err_lon.max() < 1e-12       # fallback = the full solution
+
+
+def test_series_geodesic_vs_karney_random():
+    """Series vs the oracle's full Karney solution on random step-sized moves; the series must take every move of
+    an ordinary drift step (<= 10 km below 80 degrees of latitude) and hand long or polar moves to the full solution."""
+    from oracle import geod_karney as gk
+    lib = hostshim()
+    rng = np.random.default_rng(11)
+    n = 200000
+    lon = rng.uniform(-180, 180, n)
+    az = rng.uniform(-180, 180, n)
+    for lat_max, s_max, all_series in ((60.0, 10000.0, True), (80.0, 3000.0, True), (89.99, 50000.0, False)):
+        lat = rng.uniform(-lat_max, lat_max, n)
+        s = rng.uniform(0.0, s_max, n)
+        xn, ye = s * np.cos(np.radians(az)), s * np.sin(np.radians(az))
+        lo, la, used = np.empty(n), np.empty(n), np.zeros(n, dtype=np.int32)
+        lib.hs_geod_series(C.c_int64(n), _p(lon), _p(lat), _p(xn), _p(ye), _p(lo), _p(la), _p(used))
+        l2, a2 = gk.direct(lon, lat, az, s)
+        assert np.abs(la - a2).max() < 1e-13
+        assert np.abs(_wrap(lo - l2) * np.cos(np.radians(a2))).max() < 1e-13
+        if all_series:
+            assert used.all()
+        else:
+            assert 0 < used.sum() < n
+    # degenerate inputs: zero-length move returns the start point; NaN propagates; a pole start falls back
+    lon1 = np.array([10.0, 10.0, 10.0, -179.9999999]); lat1 = np.array([60.0, 60.0, 90.0, 0.0])
+    xn = np.array([0.0, np.nan, -100.0, 0.0]); ye = np.array([0.0, 1.0, 0.0, -50.0])
+    lo, la, used = np.empty(4), np.empty(4), np.zeros(4, dtype=np.int32)
+    lib.hs_geod_series(C.c_int64(4), _p(lon1), _p(lat1), _p(xn), _p(ye), _p(lo), _p(la), _p(used))
+    assert lo[0] == 10.0 and la[0] == 60.0 and used[0] == 1
+    assert np.isnan(lo[1]) and np.isnan(la[1]) and used[1] == 0
+    assert used[2] == 0 and abs(la[2] - (90.0 - 100.0 / 111693.9)) < 1e-6
+    assert used[3] == 1 and 179.999 < lo[3] <= 180.0 and la[3] == 0.0       # crosses the date line westwards
+
+
+@pytest.mark.parametrize('name', fixtures())
 def test_fast_mode_vs_reference_fixture(name):
     fx = Fixture(name)
     lon, lat, z = run_hostshim(fx, fast=True)

@@ -45,8 +45,11 @@ res['interp_uv_ms'] = timeit(lambda: eng.interp(grp, t, lon, lat, z))
 l2, a2 = lon.clone(), lat.clone()
 res['update_positions_f32_ms'] = timeit(lambda: eng.update_positions(l2, a2, xv, yv, None, 600.0))
 l2, a2 = lon.clone(), lat.clone()
-res['step_rk4_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z))
+res['step_rk4_exact_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=0))
 l2, a2 = lon.clone(), lat.clone()
+res['step_rk4_series_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=2))
+l2, a2 = lon.clone(), lat.clone()
+res['step_euler_series_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z, fast=2))
 l2, a2 = lon.clone(), lat.clone()
 res['step_rk4_fast_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=True))
 eng.set_tile(True)
@@ -56,7 +59,7 @@ l2, a2 = lon.clone(), lat.clone()
 res['step_rk4_fast_tile_ms'] = timeit(lambda: eng.advect_current(grp, 'runge-kutta4', t, dt, l2, a2, z, fast=True))
 eng.set_tile(False)
 l2, a2 = lon.clone(), lat.clone()
-res['step_euler_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z))
+res['step_euler_exact_ms'] = timeit(lambda: eng.advect_current(grp, 'euler', t, dt, l2, a2, z, fast=0))
 # cfg 4: vertical mixing, 50-level diffusivity column, dt/dt_mix = 10 inner iterations, Philox draws
 kslabs = [torch.from_numpy(syn.vertical_diffusivity(g, (tt - syn.T0).total_seconds())).cuda() for tt in times]
 kgrp = eng.add_group(g.lon, g.lat, g.z, 1, times, lambda ti, c: kslabs[ti], (0.0,))
