@@ -47,8 +47,9 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (one `-lms 100` process)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+    """nvidia-smi clocks / throttle reasons during the timed region (one `-lms 100` process, started before the
+    warm-up so that the GPU never idles between warm-up and the timed steps; samples are filtered by timestamp)."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -67,22 +68,28 @@ class ClockSampler:
     def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        from datetime import datetime as _dt
         time.sleep(0.15)
         self.proc.terminate()
         try:
             out = self.proc.communicate(timeout=5)[0]
         except Exception:
             out = ''
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             r = [c.strip() for c in line.split(',')]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                pw.append(float(r[3]))
+                rows.append((_dt.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f'), float(r[1]), float(r[2]), float(r[3]), r[5:9]))
             except Exception:
                 continue
-            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[5:9]):
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        window = 'timed region' if inside else 'whole run (no sample fell inside the timed region)'
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, a, b, c, flags in (inside or rows):
+            sm.append(a)
+            mx.append(b)
+            pw.append(c)
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], flags):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         if not sm:
@@ -90,7 +97,7 @@ class ClockSampler:
         # samples under load = those above the idle clock
         load = [x for x in sm if x > 0.5 * max(mx)] or sm
         return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons),
-                'samples': len(sm), 'samples_under_load': len(load), 'power_w_max': float(np.max(pw))}
+                'samples': len(sm), 'samples_under_load': len(load), 'power_w_max': float(np.max(pw)), 'window': window}
 
 
 PERIOD = 10      # the synthetic double gyre repeats every 36000 s = 10 hourly slabs
@@ -242,6 +249,9 @@ def run_b200(args):
     # ---- resident run: state and slabs in HBM -----------------------------------------------------------
     # clock ramp: a fresh process on an idle GPU runs its first second ~20 % slow (power state / clock ramp), far
     # longer than W steps of 2 ms; spin the same kernel on scratch copies (simulation state untouched) first
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get('OD_BENCH_NOSMI') else None
+    if sampler:
+        sampler.start()
     ramp_t0 = time.perf_counter()
     tl, ta = st['lon'].clone(), st['lat'].clone()
     while time.perf_counter() - ramp_t0 < args.ramp_seconds:
@@ -252,21 +262,26 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     l0 = eng.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    from datetime import datetime as _dt
+    import gc
+    gc.collect()
+    gc.disable()                       # no collector pauses between launches of the timed steps
+    wall0 = _dt.now()
     e0.record()
     for _ in range(args.steps):
         step(record=True)
     e1.record()
     barrier()
+    gc.enable()
+    wall1 = _dt.now()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launches() - l0
     loop_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))   # includes slab upload / pair packing
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    per_step = np.array([a.elapsed_time(b) for a, b in step_events])
 
     # dominant kernel alone: CUDA events around single launches of step_kernel<RK4> on the launching stream
     kern_ms = []
@@ -289,6 +304,18 @@ def run_b200(args):
         sb.record()
         torch.cuda.synchronize()
         sort_ms = sa.elapsed_time(sb)
+    # the operation-by-operation replay of the reference (float32 mid-point azimuths, full Karney geodesic), same launch
+    exact_ms = []
+    for _ in range(5):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tl, ta = st['lon'].clone(), st['lat'].clone()
+        torch.cuda.synchronize()
+        ka.record()
+        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'], fast=0)
+        kb.record()
+        torch.cuda.synchronize()
+        exact_ms.append(ka.elapsed_time(kb))
+    exact_kernel_ms = float(np.median(exact_ms))
     # the opt-in fast arithmetic (float32 sampling + mid-latitude moves on float64 positions), same launch
     fast_ms = []
     for _ in range(5):
@@ -378,27 +405,36 @@ def run_b200(args):
         'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, %d particles per GPU, '
                                'dt=600 s (BASELINE configs[1]%s)' % (n, '; configs[2] sharding' if world > 1 else ''),
                    'particles_per_gpu': n, 'field': '512x512x50 f32 u,v, hourly slabs', 'scheme': 'runge-kutta4',
-                   'sort_every': args.sort_every, 'sort_ms': sort_ms, 'clock_ramp_s': args.ramp_seconds, 'mode': 'exact (bit-exact field sampling, float64 geodesic)',
+                   'sort_every': args.sort_every, 'sort_ms': sort_ms, 'clock_ramp_s': args.ramp_seconds, 'mode': 'default arithmetic OD_MATH_SERIES: bit-exact field sampling (float64 index and weight arithmetic of the reference), '
+                           'float64 short-arc series geodesic (round-off accurate, full Karney solution beyond its range)',
                    'parallelism': 'particle-index shards x%d, replicated field (NCCL broadcast of slabs: %.1f ms per slab pair)'
                                   % (world, 1e3 * t_bcast / PERIOD) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 16,
-                'steps': e2e_steps, 'api': 'Engine.advect_current_host (pinned host arrays in/out, %d-chunk copy/compute pipeline)' % args.e2e_chunks},
+                'steps': e2e_steps, 'api': 'od_advect_current_host through Engine.advect_current_host (pinned host arrays in/out, %d-chunk '
+                       'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
+                'pcie_ceiling': 'this box moves 20 B in + 16 B out per particle concurrently at 2.5e9 particles/s (tools/pcie_probe.py)'},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
-                     'host_us_per_launch_median': float(np.median(host_us)), 'host_us_per_launch_max': float(np.max(host_us)),
+                     'loop_ms_p50': float(np.median(per_step)), 'loop_ms_p95': float(np.percentile(per_step, 95)),
+                     'loop_ms_first20_mean': float(per_step[:20].mean()), 'host_us_per_launch_median': float(np.median(host_us)), 'host_us_per_launch_max': float(np.max(host_us)),
                      'algorithmic_bytes_per_launch': b_alg,
-                     'note': 'this float64 kernel is bound by the FP64 pipe (ncu: fp64 pipe ~45% of peak, issue slots ~51%), '
-                             'not by its 65 algorithmic bytes per particle-step; see DESIGN.md and profiles/'},
+                     'note': 'this float64 kernel is bound by FP64 issue (the reference samples its float32 fields with float64 '
+                             'index and weight arithmetic, reproduced bit for bit), not by its 65 algorithmic bytes per '
+                             'particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
         'tma_tile': {'kernel_ms': tile_kernel_ms, 'note': 'opt-in OD_OPT_TILE: one cp.async.bulk.tensor.4d box per block; same bits; '
                                                           'not faster than L1-served gathers on sorted particles (see DESIGN.md)'},
+        'exact_replay_mode': {'kernel_ms': exact_kernel_ms, 'particle_steps_per_s_kernel': n / (exact_kernel_ms * 1e-3),
+                              'note': 'OD_MATH_EXACT: the reference arithmetic operation by operation (float32 mid-point azimuth and '
+                                      'distance, order-6 Karney geodesic for every move); ~1e-9 deg per step from the default, the size '
+                                      'of the reference\'s own float32 arctan2 noise'},
         'fast_mode': {'kernel_ms': fast_kernel_ms, 'particle_steps_per_s_kernel': n / (fast_kernel_ms * 1e-3),
                       'hbm_frac_algorithmic': b_alg / (fast_kernel_ms * 1e-3) / 1e9 / peak,
                       'note': 'opt-in FastMath (float32 sampling, mid-latitude moves on float64 positions), <= 2e-8 deg from the '
-                              'reference on the fixtures; not the headline: value/e2e use the exact mode'},
+                              'reference on the fixtures; not the headline: value/e2e use the default mode'},
     }
     print(json.dumps(line))
     if world > 1:
@@ -413,7 +449,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--particles', type=int, default=10_000_000)
     ap.add_argument('--sort-every', type=int, default=20)
-    ap.add_argument('--e2e-chunks', type=int, default=8)
+    ap.add_argument('--e2e-chunks', type=int, default=12)
     ap.add_argument('--ramp-seconds', type=float, default=1.5)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-particles', type=int, default=50_000)

@@ -189,6 +189,25 @@ typedef struct od_advect_args {
 
 int od_advect_current(od_ctx* ctx, const od_advect_args* a);
 
+/* The same step for particle arrays that live in HOST memory -- what a caller that keeps the reference's NumPy element
+ * arrays (opendrift/elements/elements.py) hands over: a->n particles at h_lon / h_lat / h_z, results to h_out_lon /
+ * h_out_lat (may alias the inputs).  a->d_lon, d_lat, d_z are ignored; d_factor / d_moving (device, optional) are
+ * indexed like the host arrays; k1 / env / noise arrays are not supported here.  The range is cut into `chunks` pieces
+ * (0 = default 12; first and last half size) whose host->device copies, kernel and device->host copies are pipelined
+ * on three internal streams behind the work already enqueued on the context's stream.  Host memory should be pinned
+ * (cudaHostAlloc / cudaHostRegister) for the copies to overlap.  Returns after the results have landed. */
+typedef struct od_host_io {
+    const double* h_lon;
+    const double* h_lat;
+    const void* h_z;              /* float32, or float64 when a->z_f64; NULL for a 2-D group */
+    double* h_out_lon;
+    double* h_out_lat;
+    int32_t chunks;
+    int32_t pad_;
+} od_host_io;
+
+int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, const od_host_io* io);
+
 typedef struct od_step_args {
     od_advect_args cur;           /* current advection */
     /* wind drift (advect_wind): group_wind < 0 disables */

@@ -32,6 +32,11 @@ class TimeSample(C.Structure):
                 ('w', C.c_double)]
 
 
+class HostIO(C.Structure):
+    _fields_ = [('h_lon', C.c_void_p), ('h_lat', C.c_void_p), ('h_z', C.c_void_p),
+                ('h_out_lon', C.c_void_p), ('h_out_lat', C.c_void_p), ('chunks', C.c_int32), ('pad_', C.c_int32)]
+
+
 class AdvectArgs(C.Structure):
     _fields_ = [('scheme', C.c_int32), ('group_uv', C.c_int32),
                 ('t_start', TimeSample), ('t_mid', TimeSample), ('t_end', TimeSample),
@@ -103,6 +108,7 @@ SYMBOLS = {
     'od_geod_fwd': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
     'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
+    'od_advect_current_host': (C.c_int, [_P, C.POINTER(AdvectArgs), C.POINTER(HostIO)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
     'od_leeway_step': (C.c_int, [_P, C.POINTER(LeewayArgs)]),
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

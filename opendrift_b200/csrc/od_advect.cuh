@@ -198,8 +198,10 @@ struct FastMath {
             const int nl = g.nz > 1 ? 2 : 1;
             for (int l = 0; l < nl; ++l) {
                 const int lay = l == 0 ? vw.ia : vw.ib;
-                const Tex4 a00 = fetch4(ts, lay, iy, ix), a01 = fetch4(ts, lay, iy, ix1);
-                const Tex4 a10 = fetch4(ts, lay, iy1, ix), a11 = fetch4(ts, lay, iy1, ix1);
+                const float* lp = layer_ptr(ts, lay);
+                const int r0 = 4 * iy * ts.lx, r1 = 4 * iy1 * ts.lx;
+                const Tex4 a00 = fetch4(lp, r0 + 4 * ix), a01 = fetch4(lp, r0 + 4 * ix1);
+                const Tex4 a10 = fetch4(lp, r1 + 4 * ix), a11 = fetch4(lp, r1 + 4 * ix1);
                 const float u0 = lerp(lerp(a00.x, a00.z, tw), lerp(a01.x, a01.z, tw), tx);
                 const float u1 = lerp(lerp(a10.x, a10.z, tw), lerp(a11.x, a11.z, tw), tx);
                 const float v0 = lerp(lerp(a00.y, a00.w, tw), lerp(a01.y, a01.w, tw), tx);

@@ -215,7 +215,8 @@ struct TileView {
 // the global pair-texel buffer.  One test per sample; the loads then go through a generic pointer.
 struct TexelSource {
     const float* base;        // such that texel (layer, iy, ix) is at base + 4 * ((layer * ly + iy) * lx + ix)
-    long long lx, ly;
+    int lx;                   // row stride in texels
+    long long plane;          // layer stride in floats (4 * lx * ly)
 };
 
 OD_HD TexelSource texel_source(const float* tex, const TileView& tv, int nx, int ny, int ix, int ix1, int iy, int iy1,
@@ -226,18 +227,22 @@ OD_HD TexelSource texel_source(const float* tex, const TileView& tv, int nx, int
         ia >= tv.z0 && ib < tv.z0 + tv.bz) {
         t.base = tv.smem - 4 * ((tv.z0 * tv.by + tv.y0) * tv.bx + tv.x0);
         t.lx = tv.bx;
-        t.ly = tv.by;
+        t.plane = 4ll * tv.bx * tv.by;
         return t;
     }
 #endif
     t.base = tex;
     t.lx = nx;
-    t.ly = ny;
+    t.plane = 4ll * nx * ny;
     return t;
 }
 
-OD_HD Tex4 fetch4(const TexelSource& t, int layer, int iy, int ix) {
-    const float* p = t.base + 4ll * (((long long)layer * t.ly + iy) * t.lx + ix);
+// first texel of a layer; corners are then addressed with 32-bit offsets 4 * (iy * lx + ix) (a layer holds fewer
+// than 2^29 texels: od_group_define checks)
+OD_HD const float* layer_ptr(const TexelSource& t, int layer) { return t.base + (long long)layer * t.plane; }
+
+OD_HD Tex4 fetch4(const float* layer, int off) {
+    const float* p = layer + off;
 #if defined(__CUDA_ARCH__)
     const float4 v = *reinterpret_cast<const float4*>(p);
     Tex4 r = {v.x, v.y, v.z, v.w};
@@ -277,12 +282,14 @@ OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, doubl
     float ru = NAN, rv = NAN;
     if (h.valid && pr.mode != 3) {
         const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
-        const Tex4 a00 = fetch4(ts, vw.ia, h.iy, h.ix), a01 = fetch4(ts, vw.ia, h.iy, h.ix1);
-        const Tex4 a10 = fetch4(ts, vw.ia, h.iy1, h.ix), a11 = fetch4(ts, vw.ia, h.iy1, h.ix1);
+        const int r0 = 4 * h.iy * ts.lx, r1 = 4 * h.iy1 * ts.lx;
+        const int o00 = r0 + 4 * h.ix, o01 = r0 + 4 * h.ix1, o10 = r1 + 4 * h.ix, o11 = r1 + 4 * h.ix1;
+        const float* la = layer_ptr(ts, vw.ia);
+        const Tex4 a00 = fetch4(la, o00), a01 = fetch4(la, o01), a10 = fetch4(la, o10), a11 = fetch4(la, o11);
         Tex4 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
         if (g.nz > 1) {
-            b00 = fetch4(ts, vw.ib, h.iy, h.ix); b01 = fetch4(ts, vw.ib, h.iy, h.ix1);
-            b10 = fetch4(ts, vw.ib, h.iy1, h.ix); b11 = fetch4(ts, vw.ib, h.iy1, h.ix1);
+            const float* lb = layer_ptr(ts, vw.ib);
+            b00 = fetch4(lb, o00); b01 = fetch4(lb, o01); b10 = fetch4(lb, o10); b11 = fetch4(lb, o11);
         }
         float uaA = 0.f, ubA = 0.f, uaB = 0.f, ubB = 0.f, vaA = 0.f, vbA = 0.f, vaB = 0.f, vbB = 0.f;
         if (pr.mode != 2) {

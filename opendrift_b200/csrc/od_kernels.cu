@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -28,7 +29,7 @@ using namespace od;
 #define OD_BLOCK 128
 #endif
 #ifndef OD_STEP_MINB
-#define OD_STEP_MINB 6
+#define OD_STEP_MINB 8
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -84,6 +85,11 @@ struct od_ctx {
     unsigned* d_fillcnt = nullptr;      // per-pass missing-cell counters
     int64_t fill_cap = 0;
     int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
+    // host-array pipeline (od_advect_current_host): three streams, three staging buffers
+    cudaStream_t hstream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t hready = nullptr;
+    char* hbuf[3] = {nullptr, nullptr, nullptr};
+    int64_t hbuf_cap = 0;               // particles per staging buffer
 };
 
 static int fail(od_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -147,6 +153,11 @@ extern "C" void od_destroy(od_ctx* ctx) {
     if (ctx->d_red) cudaFree(ctx->d_red);
     if (ctx->d_fill) cudaFree(ctx->d_fill);
     if (ctx->d_fillcnt) cudaFree(ctx->d_fillcnt);
+    for (int k = 0; k < 3; ++k) {
+        if (ctx->hbuf[k]) cudaFree(ctx->hbuf[k]);
+        if (ctx->hstream[k]) cudaStreamDestroy(ctx->hstream[k]);
+    }
+    if (ctx->hready) cudaEventDestroy(ctx->hready);
     delete ctx;
 }
 
@@ -183,6 +194,7 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
         return fail(ctx, OD_ERR_ARG, "od_group_define: bad shape");
     if (d->nz > 1 && !h_z) return fail(ctx, OD_ERR_ARG, "od_group_define: z levels missing");
     if ((size_t)d->nx * d->ny * d->nz >= (1ull << 31)) return fail(ctx, OD_ERR_ARG, "od_group_define: block too large");
+    if ((size_t)d->nx * d->ny >= (1ull << 28)) return fail(ctx, OD_ERR_ARG, "od_group_define: layer too large (32-bit corner offsets)");
     CK(cudaSetDevice(ctx->device));
     Group& g = ctx->groups[group];
     free_group(g);
@@ -455,8 +467,19 @@ static int resolve_pair(od_ctx* ctx, int group, const od_time_sample& ts, PairRe
         if (p.last_use < victim->last_use) victim = &p;
     }
     if (!victim->tex) {
+        // first pair of this group: allocate the whole cache now, so that no later step pays for a cudaMalloc
+        // (tens of milliseconds for a 200 MB block on a cold device, and an implicit device synchronisation)
         CK(cudaMalloc(&victim->tex, g.cells() * sizeof(float) * 2 * nc));
         victim->tmap_ok = make_tensor_map(g, victim->tex, &victim->tmap);
+        for (auto& p : g.pairs) {
+            if (p.tex) continue;
+            if (cudaMalloc(&p.tex, g.cells() * sizeof(float) * 2 * nc) != cudaSuccess) {   // best effort: a smaller cache still works
+                p.tex = nullptr;
+                cudaGetLastError();
+                break;
+            }
+            p.tmap_ok = make_tensor_map(g, p.tex, &p.tmap);
+        }
     }
     const int64_t cells = (int64_t)g.cells();
     int blocks = (int)((cells + OD_BLOCK - 1) / OD_BLOCK);
@@ -986,6 +1009,124 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     if (a->fast == OD_MATH_FAST) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     if (a->fast == OD_MATH_SERIES) return launch_step<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     return launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+}
+
+// advect_ocean_current on HOST arrays: the particle range is cut into chunks; each chunk's host->device copies, kernel
+// and device->host copies go to one of three streams (and staging buffers), so the PCIe transfers of neighbouring
+// chunks overlap each other (both directions) and the kernel.  The first and last chunks are half size: the pipeline
+// fills and drains faster.  Pinned host memory is needed for the copies to overlap.  Returns when the results are in
+// h_out_lon / h_out_lat.
+extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, const od_host_io* io) {
+    if (!ctx || !a || !io) return fail(ctx, OD_ERR_ARG, "od_advect_current_host: null argument");
+    const int64_t n = a->n;
+    if (n < 0 || (n > 0 && (!io->h_lon || !io->h_lat || !io->h_out_lon || !io->h_out_lat)))
+        return fail(ctx, OD_ERR_ARG, "od_advect_current_host: null host arrays");
+    if (a->d_k1_u || a->d_k1_v || a->d_env_u || a->d_env_v || a->d_noise_cur)
+        return fail(ctx, OD_ERR_ARG, "od_advect_current_host: k1 / env / noise arrays are not supported on the host path");
+    CK(cudaSetDevice(ctx->device));
+    const Group* gp = (a->group_uv >= 0 && a->group_uv < OD_MAX_GROUPS) ? &ctx->groups[a->group_uv] : nullptr;
+    const bool has_z = io->h_z != nullptr;
+    if (gp && gp->defined && gp->desc.nz > 1 && !has_z) return fail(ctx, OD_ERR_ARG, "3-D current group needs z");
+    // resolve the pairs once, on the caller's stream (uploads / pair packing were enqueued there)
+    od_advect_args b = *a;
+    StepParams p;
+    double dummy = 0.0;
+    b.n = 0;
+    b.d_lon = b.d_lat = &dummy;
+    b.d_z = has_z ? (const void*)&dummy : nullptr;
+    int rc = fill_current(ctx, &b, &p);
+    if (rc) return rc;
+    if (n == 0) return OD_OK;
+    if (a->fast < 0 || a->fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_advect_current_host: unknown arithmetic mode");
+    if (!ctx->hready) {
+        CK(cudaEventCreateWithFlags(&ctx->hready, cudaEventDisableTiming));
+        for (int k = 0; k < 3; ++k) CK(cudaStreamCreateWithFlags(&ctx->hstream[k], cudaStreamNonBlocking));
+    }
+    int chunks = io->chunks > 0 ? io->chunks : 12;
+    if (chunks > n) chunks = (int)n;
+    // chunk boundaries: weights 1/2, 1, ..., 1, 1/2
+    const double unit = chunks > 2 ? (double)n / (chunks - 1) : (double)n / chunks;
+    const int64_t cap = (int64_t)unit + 2;
+    const size_t zsz = a->z_f64 ? 8 : 4;
+    if (ctx->hbuf_cap < cap) {
+        for (int k = 0; k < 3; ++k) {
+            if (ctx->hbuf[k]) cudaFree(ctx->hbuf[k]);
+            ctx->hbuf[k] = nullptr;
+        }
+        ctx->hbuf_cap = 0;
+        for (int k = 0; k < 3; ++k) CK(cudaMalloc(&ctx->hbuf[k], (size_t)cap * 24));      // lon, lat (float64), z (<= 8 B)
+        ctx->hbuf_cap = cap;
+    }
+    CK(cudaEventRecord(ctx->hready, ctx->stream));
+    static const bool trace = getenv("OD_HOST_TRACE") != nullptr;       // debugging aid: per-chunk timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t0 = nullptr;
+    if (trace) {
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, ctx->stream);
+    }
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    const size_t fsz = a->factor_f64 ? 8 : 4;
+    cudaStream_t caller = ctx->stream;
+    int64_t lo = 0;
+    rc = OD_OK;
+    for (int c = 0; c < chunks && rc == OD_OK; ++c) {
+        int64_t hi;
+        if (c == chunks - 1) hi = n;
+        else if (chunks > 2) hi = (int64_t)(unit * (c + 0.5));
+        else hi = (int64_t)(unit * (c + 1));
+        if (hi > n) hi = n;
+        const int64_t m = hi - lo;
+        if (m <= 0) continue;
+        const int k = c % 3;
+        cudaStream_t st = ctx->hstream[k];
+        double* d_lon = (double*)ctx->hbuf[k];
+        double* d_lat = d_lon + ctx->hbuf_cap;
+        char* d_z = (char*)(d_lat + ctx->hbuf_cap);
+        if (c < 3) CK(cudaStreamWaitEvent(st, ctx->hready, 0));
+        mark(st);
+        CK(cudaMemcpyAsync(d_lon, io->h_lon + lo, m * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_lat, io->h_lat + lo, m * 8, cudaMemcpyHostToDevice, st));
+        if (has_z) CK(cudaMemcpyAsync(d_z, (const char*)io->h_z + lo * zsz, m * zsz, cudaMemcpyHostToDevice, st));
+        mark(st);
+        StepParams q = p;
+        q.n = m;
+        q.lon = d_lon; q.lat = d_lat; q.z = has_z ? (const void*)d_z : nullptr;
+        q.factor = a->d_factor ? (const void*)((const char*)a->d_factor + lo * fsz) : nullptr;
+        q.moving = a->d_moving ? a->d_moving + lo : nullptr;
+        ctx->stream = st;
+        if (a->fast == OD_MATH_FAST) rc = launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, q);
+        else if (a->fast == OD_MATH_SERIES) rc = launch_step<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, q);
+        else rc = launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, q);
+        ctx->stream = caller;
+        if (rc) break;
+        mark(st);
+        CK(cudaMemcpyAsync(io->h_out_lon + lo, d_lon, m * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(io->h_out_lat + lo, d_lat, m * 8, cudaMemcpyDeviceToHost, st));
+        mark(st);
+        lo = hi;
+    }
+    for (int k = 0; k < 3; ++k) {
+        cudaError_t e = cudaStreamSynchronize(ctx->hstream[k]);
+        if (e != cudaSuccess && rc == OD_OK) rc = fail(ctx, OD_ERR_CUDA, "od_advect_current_host", e);
+    }
+    if (trace) {
+        fprintf(stderr, "od_advect_current_host timeline (ms after the caller's stream reached the call): chunk: h2d-start h2d-end kernel-end d2h-end\n");
+        for (size_t k = 0; k + 3 < tev.size() + 0; k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], t0, tev[k + j]);
+            fprintf(stderr, "  %2zu: %7.3f %7.3f %7.3f %7.3f\n", k / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t0);
+    }
+    return rc;
 }
 
 extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {

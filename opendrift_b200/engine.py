@@ -382,63 +382,40 @@ class Engine:
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
 
     def advect_current_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None,
-                            factor=None, moving=None, chunks=8, pos_f32=False, fast=None):
-        """advect_ocean_current for HOST arrays (pinned torch tensors): the particle range is cut into chunks
-        whose host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the
-        PCIe transfers of neighbouring chunks overlap the kernel.  Results land in h_out_lon / h_out_lat
+                            factor=None, moving=None, chunks=0, pos_f32=False, fast=None):
+        """advect_ocean_current for HOST arrays (float64 lon / lat, float32 or float64 z; NumPy arrays or CPU torch
+        tensors, pinned for full speed): od_advect_current_host cuts the particle range into chunks whose
+        host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the PCIe
+        transfers of neighbouring chunks overlap each other and the kernel.  Results land in h_out_lon / h_out_lat
         (default: in place).  Returns after everything has completed."""
         torch = self.torch
-        n = h_lon.numel()
-        h_out_lon = h_lon if h_out_lon is None else h_out_lon
-        h_out_lat = h_lat if h_out_lat is None else h_out_lat
-        if not hasattr(self, '_hs'):
-            self._hs = {'streams': [torch.cuda.Stream(self.device) for _ in range(3)], 'buf': {}}
-        hs = self._hs
-        csz = (n + chunks - 1) // chunks
-        key = (csz, h_z is not None)
-        if key not in hs['buf']:
-            hs['buf'].clear()
-            hs['buf'][key] = [(self.empty(csz, torch.float64), self.empty(csz, torch.float64),
-                               self.empty(csz, torch.float32) if h_z is not None else None) for _ in range(3)]
-        bufs = hs['buf'][key]
-        main = torch.cuda.current_stream(self.device)
-        # resolve the time samples once (uploads / pair packing happen on the main stream)
+
+        def host_ptr(x, dtypes):
+            if x is None:
+                return None, None
+            if isinstance(x, np.ndarray):
+                assert x.dtype in [np.dtype(d) for d in dtypes] and x.flags['C_CONTIGUOUS']
+                return x.ctypes.data, x.dtype.itemsize
+            assert not x.is_cuda and x.is_contiguous() and x.element_size() in [np.dtype(d).itemsize for d in dtypes]
+            return x.data_ptr(), x.element_size()
+        n = int(h_lon.shape[0])
+        io = _lib.HostIO()
+        io.h_lon, _ = host_ptr(h_lon, ['f8'])
+        io.h_lat, _ = host_ptr(h_lat, ['f8'])
+        io.h_z, zsz = host_ptr(h_z, ['f4', 'f8'])
+        io.h_out_lon, _ = host_ptr(h_lon if h_out_lon is None else h_out_lon, ['f8'])
+        io.h_out_lat, _ = host_ptr(h_lat if h_out_lat is None else h_out_lat, ['f8'])
+        io.chunks = int(chunks)
+        if not hasattr(self, '_host_dummy'):
+            self._host_dummy = (self.empty(1, torch.float64), self.empty(1, torch.float64), self.empty(1, torch.float32),
+                                self.empty(1, torch.float64))
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
-        self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, bufs[0][0][:1], bufs[0][1][:1],
-                          bufs[0][2][:1] if h_z is not None else None, factor, moving, None, None, None, pos_f32, fast)
-        a.n = 0
-        self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))     # n = 0: builds the pair texels only
-        ready = torch.cuda.Event()
-        ready.record(main)
-        done = []
-        for c in range(chunks):
-            lo, hi = c * csz, min(n, (c + 1) * csz)
-            if lo >= hi:
-                break
-            st = hs['streams'][c % 3]
-            d_lon, d_lat, d_z = bufs[c % 3]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                m = hi - lo
-                d_lon[:m].copy_(h_lon[lo:hi], non_blocking=True)
-                d_lat[:m].copy_(h_lat[lo:hi], non_blocking=True)
-                if d_z is not None:
-                    d_z[:m].copy_(h_z[lo:hi], non_blocking=True)
-                self.use_stream(st)
-                a.n = m
-                a.d_lon, a.d_lat = d_lon.data_ptr(), d_lat.data_ptr()
-                a.d_z = d_z.data_ptr() if d_z is not None else None
-                self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
-                h_out_lon[lo:hi].copy_(d_lon[:m], non_blocking=True)
-                h_out_lat[lo:hi].copy_(d_lat[:m], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(st)
-                done.append(ev)
-        self.use_stream(main)
-        for ev in done:
-            main.wait_event(ev)
-        main.synchronize()
+        dz = None if h_z is None else (self._host_dummy[3] if zsz == 8 else self._host_dummy[2])
+        self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, self._host_dummy[0], self._host_dummy[1], dz,
+                          factor, moving, None, None, None, pos_f32, fast)
+        a.n = n
+        self._check(self.lib.od_advect_current_host(self.ctx, C.byref(a), C.byref(io)))
 
     def leeway_step(self, wind, cur, t, dt, lon, lat, el, moving=None, status=None, ids=None, rand=None, seed=0,
                     step_index=0, capsize_fraction=0.4, missing_code=1, pos_f32=False):

@@ -282,3 +282,45 @@ def test_full_size_properties(eng):
         t -= dt
     e = common.max_err_deg(lon.cpu().numpy(), lat.cpu().numpy(), lon0.astype(np.float64), lat0.astype(np.float64))
     assert max(e) < 1e-4, e            # RK4 (with the reference's stage-4 quirk) is not exactly reversible
+
+
+@pytest.mark.parametrize('chunks', [0, 1, 2, 3, 7, 40])
+def test_host_array_entry_point_matches_device_path(eng, chunks):
+    """od_advect_current_host (chunked copy/compute pipeline on host arrays) == od_advect_current on device arrays,
+    bit for bit, for every chunking, with per-particle factor / moving arrays, in place and out of place."""
+    import torch
+    from opendrift_b200 import synthetic as syn
+    grid = syn.GridSpec(nx=64, ny=48, nz=12)
+    times = syn.slab_times(3)
+    slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times]
+    grp = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, lambda ti, c: slabs[ti][c], (0.0, 0.0))
+    rng = np.random.default_rng(chunks)
+    n = 100003
+    lon = rng.uniform(0.05, 1.2, n)
+    lat = rng.uniform(55.02, 55.45, n)
+    z = rng.uniform(-20.0, 0.0, n).astype(np.float32)
+    factor = eng.to_device(rng.uniform(0.5, 1.5, n))
+    moving = eng.to_device((rng.uniform(size=n) > 0.1).astype(np.int32))
+    t, dt = times[0] + timedelta(seconds=1700), timedelta(seconds=900)
+    for scheme in ('runge-kutta4', 'euler'):
+        dl, da = eng.to_device(lon), eng.to_device(lat)
+        eng.advect_current(grp, scheme, t, dt, dl, da, eng.to_device(z), factor=factor, moving=moving)
+        ref_lon, ref_lat = dl.cpu().numpy(), da.cpu().numpy()
+        # NumPy arrays (pageable), out of place
+        o_lon, o_lat = np.empty(n), np.empty(n)
+        eng.advect_current_host(grp, scheme, t, dt, lon.copy(), lat.copy(), z, o_lon, o_lat, factor=factor, moving=moving,
+                                chunks=chunks)
+        assert np.array_equal(o_lon, ref_lon) and np.array_equal(o_lat, ref_lat)
+        # pinned tensors, in place
+        p_lon, p_lat = torch.from_numpy(lon.copy()).pin_memory(), torch.from_numpy(lat.copy()).pin_memory()
+        eng.advect_current_host(grp, scheme, t, dt, p_lon, p_lat, torch.from_numpy(z).pin_memory(), factor=factor,
+                                moving=moving, chunks=chunks)
+        assert np.array_equal(p_lon.numpy(), ref_lon) and np.array_equal(p_lat.numpy(), ref_lat)
+    assert np.abs(ref_lon - lon).max() > 1e-4
+    # float64 depths (after vertical mixing) and an empty call
+    dl, da = eng.to_device(lon), eng.to_device(lat)
+    eng.advect_current(grp, 'runge-kutta', t, dt, dl, da, eng.to_device(z.astype(np.float64)))
+    o_lon, o_lat = lon.copy(), lat.copy()
+    eng.advect_current_host(grp, 'runge-kutta', t, dt, o_lon, o_lat, z.astype(np.float64), chunks=chunks)
+    assert np.array_equal(o_lon, dl.cpu().numpy()) and np.array_equal(o_lat, da.cpu().numpy())
+    eng.advect_current_host(grp, 'runge-kutta', t, dt, np.empty(0), np.empty(0), np.empty(0, dtype=np.float32), chunks=chunks)
