@@ -368,6 +368,39 @@ def run_b200(args):
     barrier()
     e2e_ms = g0.elapsed_time(g1)
 
+    # the link the end-to-end number lives on: this step's bytes (20 B in, 16 B out per particle) as two plain pinned
+    # copies running concurrently on two streams
+    pcie = None
+    if rank == 0:
+        try:
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            d_in, d_out = torch.empty_like(h_lon, device=dev), torch.empty_like(h_lat, device=dev)
+            d_in2, d_z2 = torch.empty_like(h_lat, device=dev), torch.empty_like(h_z, device=dev)
+            torch.cuda.synchronize()
+            pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 4
+            pa.record()
+            for _ in range(reps):
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(pa)
+                    d_in.copy_(h_lon, non_blocking=True)
+                    d_in2.copy_(h_lat, non_blocking=True)
+                    d_z2.copy_(h_z, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(pa)
+                    o_lon.copy_(d_out, non_blocking=True)
+                    o_lat.copy_(d_in, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s_in)
+            torch.cuda.current_stream().wait_stream(s_out)
+            pb.record()
+            torch.cuda.synchronize()
+            pms = pa.elapsed_time(pb) / reps
+            pcie = {'ms_per_step_copies_only': pms, 'particle_steps_per_s_ceiling': n / (pms * 1e-3),
+                    'GBps_both_directions': n * 36 / pms / 1e6}
+            del d_in, d_out, d_in2, d_z2
+        except Exception as exc:        # the probe is informative only
+            pcie = {'error': str(exc)}
+
     if world > 1:       # device-timed, max over ranks
         tt = torch.tensor([ms_total, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -414,7 +447,7 @@ def run_b200(args):
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 16,
                 'steps': e2e_steps, 'api': 'od_advect_current_host through Engine.advect_current_host (pinned host arrays in/out, %d-chunk '
                        'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
-                'pcie_ceiling': 'this box moves 20 B in + 16 B out per particle concurrently at 2.5e9 particles/s (tools/pcie_probe.py)'},
+                'pcie_probe': pcie},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,

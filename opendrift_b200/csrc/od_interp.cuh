@@ -44,6 +44,7 @@ struct GroupGeom {
     double xmin, xmax, ymin, ymax;
     double nxm1, nym1;
     double inv_dx, inv_dy;   // (nx-1)/xspan, (ny-1)/yspan (fast sampler only)
+    double rxspan, ryspan;   // RN(1/xspan), RN(1/yspan), or 0 when div_rn() must use a true division
     double zmin, zmax;       // min / max of the level depths
     float fallback[2];
     const double* zs;        // [nz] level depths in increasing order
@@ -131,6 +132,32 @@ OD_HD float np_mod360f(float x) {
 // pos_f32: lon/lat carry float32 values (the reference's element arrays are float32 until the first
 // update_positions, opendrift/elements/elements.py:156-158), so NumPy does the longitude modulation and
 // the fractional-index arithmetic of interpolators.py:110-111 in float32.
+// Correctly rounded d / s from the correctly rounded reciprocal r = RN(1/s) (Markstein 1990: q0 = RN(d r),
+// e = d - q0 s exactly (FMA), q = RN(q0 + e r) equals RN(d/s) whenever the significand of s is not all ones --
+// make_geom() passes r = 0 in that case and for spans outside the normal range, which selects the true division).
+// NaN stays NaN; an infinite d gives NaN instead of infinity, and both fail the coverage test that follows.
+OD_HD double div_rn(double d, double s, double r) {
+#if defined(__CUDA_ARCH__)
+    if (r == 0.0 || (fabs(d) < 1e-250 && d != 0.0)) return d / s;      // tiny numerators: the residual would underflow
+    const double q0 = __dmul_rn(d, r);
+    const double e = __fma_rn(-q0, s, d);
+    return __fma_rn(e, r, q0);
+#else
+    (void)r;
+    return d / s;
+#endif
+}
+
+// r for div_rn: RN(1/s) if the shortcut is valid for this divisor, else 0
+static inline double div_rn_reciprocal(double s) {
+    union { double d; unsigned long long u; } c;
+    c.d = s;
+    const unsigned long long mant = c.u & 0xFFFFFFFFFFFFFull;
+    const int ex = (int)((c.u >> 52) & 0x7FF);
+    if (!(s == s) || ex < 100 || ex > 1900 || mant == 0xFFFFFFFFFFFFFull) return 0.0;
+    return 1.0 / s;
+}
+
 OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_f32) {
     HorizW h;
     double x, xi, yi;
@@ -142,8 +169,8 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
         yi = (double)OD_FMUL(OD_FADD((float)lat, -(float)g.y0) / (float)g.yspan, (float)g.nym1);
     } else {
         x = (g.lon_mode == 0) ? np_mod360(lon) : OD_DSUB(np_mod360(OD_DADD(lon, 180.0)), 180.0);
-        xi = OD_DMUL(OD_DSUB(x, g.x0) / g.xspan, g.nxm1);
-        yi = OD_DMUL(OD_DSUB(y, g.y0) / g.yspan, g.nym1);
+        xi = OD_DMUL(div_rn(OD_DSUB(x, g.x0), g.xspan, g.rxspan), g.nxm1);
+        yi = OD_DMUL(div_rn(OD_DSUB(y, g.y0), g.yspan, g.ryspan), g.nym1);
     }
     bool covered = (x >= g.xmin) && (x <= g.xmax) && (y >= g.ymin) && (y <= g.ymax);
     covered = covered && (xi >= 0.0) && (xi <= g.nxm1) && (yi >= 0.0) && (yi <= g.nym1);

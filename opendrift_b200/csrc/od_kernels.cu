@@ -7,6 +7,7 @@
 // horizontal random walk run in a single kernel launch per time step.
 #include <cuda.h>            // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,6 +84,7 @@ struct od_ctx {
     unsigned* d_red = nullptr;          // reduction scratch
     float* d_fill = nullptr;            // scratch slab of the NaN fill
     unsigned* d_fillcnt = nullptr;      // per-pass missing-cell counters
+    int coop_fill_blocks = -1;          // co-resident grid of fill_nan_coop_kernel (0: no cooperative launch)
     int64_t fill_cap = 0;
     int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
     // host-array pipeline (od_advect_current_host): three streams, three staging buffers
@@ -272,6 +274,7 @@ __global__ void dilate_nan_kernel(const float* __restrict__ src, float* __restri
 __global__ void dilate_commit_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t cells,
                                      const unsigned* __restrict__ missing_before);
 __global__ void count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters);
+__global__ void fill_nan_coop_kernel(float* a, float* tmp, int nx, int ny, int64_t cells, int max_iterations, unsigned* cnt);
 
 extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterations, int64_t* h_remaining) {
     int rc = check_slot(ctx, group, slot, comp);
@@ -294,12 +297,32 @@ extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int
     CK(cudaMemsetAsync(cnt, 0, (OD_FILL_MAX_IT + 2) * sizeof(unsigned), ctx->stream));
     int blocks = (int)((cells + 255) / 256);
     const int capped = blocks > ctx->sm_count * 16 ? ctx->sm_count * 16 : blocks;
-    count_nonfinite_kernel<<<capped, 256, 0, ctx->stream>>>(a, cells, cnt);
-    ctx->launches++;
-    for (int it = 0; it < max_iterations; ++it) {
-        dilate_nan_kernel<<<capped, 256, 0, ctx->stream>>>(a, ctx->d_fill, g.desc.nx, g.desc.ny, cells, cnt + it, cnt + it + 1);
-        dilate_commit_kernel<<<capped, 256, 0, ctx->stream>>>(ctx->d_fill, a, cells, cnt + it);
-        ctx->launches += 2;
+    if (ctx->coop_fill_blocks < 0) {                 // once: can the whole grid be co-resident (cooperative launch)?
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_nan_coop_kernel, 256, 0) == cudaSuccess && per_sm > 0)
+            ctx->coop_fill_blocks = per_sm * ctx->sm_count;
+        else
+            ctx->coop_fill_blocks = 0;
+        cudaGetLastError();
+    }
+    if (ctx->coop_fill_blocks > 0) {
+        int gridc = blocks < ctx->coop_fill_blocks ? blocks : ctx->coop_fill_blocks;
+        float* tmp = ctx->d_fill;
+        int nx = g.desc.nx, ny = g.desc.ny;
+        int64_t ncells = cells;
+        int mit = max_iterations;
+        void* args[] = {&a, &tmp, &nx, &ny, &ncells, &mit, &cnt};
+        CK(cudaLaunchCooperativeKernel((const void*)fill_nan_coop_kernel, dim3(gridc), dim3(256), args, 0, ctx->stream));
+        ctx->launches++;
+    } else {
+        count_nonfinite_kernel<<<capped, 256, 0, ctx->stream>>>(a, cells, cnt);
+        ctx->launches++;
+        for (int it = 0; it < max_iterations; ++it) {
+            dilate_nan_kernel<<<capped, 256, 0, ctx->stream>>>(a, ctx->d_fill, g.desc.nx, g.desc.ny, cells, cnt + it, cnt + it + 1);
+            dilate_commit_kernel<<<capped, 256, 0, ctx->stream>>>(ctx->d_fill, a, cells, cnt + it);
+            ctx->launches += 2;
+        }
     }
     CK(cudaGetLastError());
     g.version[slot] = ++ctx->tick;
@@ -371,6 +394,52 @@ __global__ void __launch_bounds__(256) dilate_commit_kernel(const float* __restr
                                                             const unsigned* __restrict__ missing_before) {
     if (*missing_before == 0) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// All passes of the fill in one cooperative launch: count, then (dilate, commit) until nothing is missing or
+// max_iterations passes ran.  A slab without holes costs one read pass and one grid barrier.
+__global__ void __launch_bounds__(256) fill_nan_coop_kernel(float* a, float* tmp, int nx, int ny,
+                                                            int64_t cells, int max_iterations, unsigned* cnt) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t layer = (int64_t)nx * ny;
+    unsigned c = 0;
+    for (int64_t i = first; i < cells; i += stride) c += !(fabsf(a[i]) <= 3.4028234663852886e38f);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[0], c);
+    grid.sync();
+    for (int it = 0; it < max_iterations; ++it) {
+        if (*((volatile unsigned*)&cnt[it]) == 0) break;          // uniform across the grid (read after the barrier)
+        unsigned still = 0;
+        for (int64_t i = first; i < cells; i += stride) {
+            const float v = a[i];
+            if (fabsf(v) <= 3.4028234663852886e38f) {
+                tmp[i] = v;
+                continue;
+            }
+            const int64_t base = (i / layer) * layer;
+            const int r = (int)((i - base) / nx), cc0 = (int)((i - base) % nx);
+            float best = -INFINITY;
+            bool found = false;
+            for (int dr = -1; dr <= 1; ++dr) {
+                const int rr = min(max(r + dr, 0), ny - 1);
+                for (int dc = -1; dc <= 1; ++dc) {
+                    const int cc = min(max(cc0 + dc, 0), nx - 1);
+                    const float w = a[base + (int64_t)rr * nx + cc];
+                    if (fabsf(w) <= 3.4028234663852886e38f) {
+                        best = fmaxf(best, w);
+                        found = true;
+                    }
+                }
+            }
+            tmp[i] = found ? best : NAN;
+            still += found ? 0u : 1u;
+        }
+        if (still) atomicAdd(&cnt[it + 1], still);
+        grid.sync();
+        for (int64_t i = first; i < cells; i += stride) a[i] = tmp[i];
+        grid.sync();
+    }
 }
 
 __global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __restrict__ a, int64_t cells, unsigned* __restrict__ counters) {
@@ -512,6 +581,7 @@ static GroupGeom make_geom(const Group& g) {
     q.xmin = g.desc.xmin; q.xmax = g.desc.xmax; q.ymin = g.desc.ymin; q.ymax = g.desc.ymax;
     q.nxm1 = (double)(g.desc.nx - 1); q.nym1 = (double)(g.desc.ny - 1);
     q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
+    q.rxspan = div_rn_reciprocal(q.xspan); q.ryspan = div_rn_reciprocal(q.yspan);
     q.zmin = g.zmin; q.zmax = g.zmax;
     q.fallback[0] = g.desc.fallback[0]; q.fallback[1] = g.desc.fallback[1];
     q.zs = g.d_zs; q.zy = g.d_zy;

@@ -40,6 +40,7 @@ static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
     q.xmin = d.xmin; q.xmax = d.xmax; q.ymin = d.ymin; q.ymax = d.ymax;
     q.nxm1 = (double)(d.nx - 1); q.nym1 = (double)(d.ny - 1);
     q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
+    q.rxspan = div_rn_reciprocal(q.xspan); q.ryspan = div_rn_reciprocal(q.yspan);
     q.fallback[0] = d.fallback[0]; q.fallback[1] = d.fallback[1];
     if (d.nz > 1) {
         lv.zs.resize(d.nz); lv.zy.resize(d.nz);

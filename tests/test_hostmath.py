@@ -144,3 +144,28 @@ def test_interpolation_bit_exact():
         assert np.array_equal(o0, env[common.CUR[0]]), (off, pos32)
         assert np.array_equal(o1, env[common.CUR[1]]), (off, pos32)
         assert (o0 == 0).sum() > 100          # some samples fell outside coverage -> fallback 0
+
+
+def test_reciprocal_division_is_correctly_rounded():
+    """The device forms (x - x0) / xspan as q0 = RN(d r), e = fma(-q0, s, d), q = fma(e, r, q0) with r = RN(1/s)
+    (od_interp.cuh div_rn).  Emulate the three correctly rounded operations with exact rationals and compare with the
+    IEEE quotient the reference computes, for the spans of the bench grid, of the fixtures and for random spans."""
+    from fractions import Fraction
+    from opendrift_b200 import synthetic as syn
+    rng = np.random.default_rng(21)
+    g = syn.GridSpec()
+    spans = [float(np.float32(g.lon[-1] - g.lon[0])), float(np.float32(g.lat[-1] - g.lat[0]))]
+    fx = Fixture('rk4_3d')
+    spans += [float(np.float32(fx.grid_lon[-1] - fx.grid_lon[0])), float(np.float32(fx.grid_lat[-1] - fx.grid_lat[0]))]
+    spans += [float(np.float32(s)) for s in rng.uniform(0.01, 360.0, 20)] + list(rng.uniform(1e-3, 400.0, 20))
+    bad = 0
+    for s in spans:
+        r = 1.0 / s
+        fs, fr = Fraction(s), Fraction(r)
+        for d in np.concatenate([rng.uniform(-1.0, 1.2, 1500) * s, rng.uniform(-400, 400, 500), [0.0, s, -s, 1e-249, -3e-200]]):            # |d| < 1e-250 takes the true division
+            d = float(d)
+            q0 = d * r
+            e = float(Fraction(d) - Fraction(q0) * fs)            # exact: the FMA rounds once, and this residual is representable
+            q = float(Fraction(q0) + Fraction(e) * fr)
+            bad += q != d / s
+    assert bad == 0
