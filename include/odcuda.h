@@ -82,12 +82,19 @@ int od_device_sm_count(od_ctx* ctx);
  * x0 = (double)xgrid[0], xspan = (double)(float)(xgrid[nx-1] - xgrid[0]) for float32 grids.
  * xmin..ymax is the reader's coverage box (covers_positions_xy).  h_z_levels: nz level depths
  * as the reader returns them (increasing or decreasing), ignored when nz == 1.
- * fallback[c]: value used where the sample is not finite / not covered; NaN = none. */
+ * fallback[c]: value used where the sample is not finite / not covered; NaN = none.
+ * wrap_x: the grid covers the globe east-west (reference: Variables.global_coverage, readers/basereader/variables.py:289-301)
+ * and is periodic: the block the sampler sees is the nx stored columns plus one virtual column that repeats column 0 at
+ * xgrid[nx-1] + dx (what a reference reader hands to ReaderBlock(wrap_x=True) so that the seam cell is covered,
+ * readers/interpolation/structured.py:35-48, reader_netCDF_CF_generic.py:452-463).  Then xspan = (double)(float)(xgrid[nx-1] + dx -
+ * xgrid[0]), the index scale is nx instead of nx - 1, and the east-west coverage test is skipped (variables.py:239-242). */
 typedef struct od_group_desc {
     int32_t ncomp;            /* 1 or 2 */
     int32_t nx, ny, nz;
     int32_t lon_mode;         /* od_lon_mode */
     int32_t n_slots;          /* ring of time slabs kept on the device (>= 2) */
+    int32_t wrap_x;           /* 0 / 1, see above */
+    int32_t pad_;
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     float fallback[2];

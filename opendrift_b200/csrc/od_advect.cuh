@@ -60,11 +60,8 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
 // Karney geodesic).  FastMath keeps float64 positions but does the per-step arithmetic in float32:
 //   * field sampling: time lerp of the eight corner texels, then trilinear, with float32 FMAs (the fractional
 //     cell index is still formed in float64 from the float64 position);
-//   * moves: for displacements up to 5 km the ellipsoidal mid-latitude formulas with the azimuth-convergence
-//     correction (truncation error 4e-7 m for a 300 m step, 4e-4 m for 3 km at |lat| < 70; float32 rounding
-//     ~1e-4 m per step), meridional / prime-vertical radii from a second-order expansion of sin/cos about the
-//     start latitude; longer displacements fall back to the exact geodesic.  RK mid-points (which only feed
-//     the sampler) use the uncorrected first-order form.
+//   * RK mid-points (which only feed the sampler): first-order displacement with float32 radii of curvature;
+//     the move that is kept: the float64 short-arc series of SeriesMath.
 // Measured against the reference fixtures FastMath stays within ~1e-7 deg after 14 RK4 steps (tolerance of
 // the float64 path: 1e-6 deg); it is an opt-in (`gpu:precision = fast`, od_advect_args.fast).
 // ---------------------------------------------------------------------------------------------------------
@@ -148,49 +145,41 @@ struct FastMath {
         mlat = lat0 + (double)(kv * h * st.im * (float)kRad2Deg);
         mlon = lon0 + (double)(ku * h * st.in_ * (float)kRad2Deg);
     }
-    OD_HDS void move_m(const Start& st, double lon0, double lat0, float de, float dn, double& lon1, double& lat1) {
-        if (!(fabsf(de) + fabsf(dn) <= 5000.0f)) {          // long step (or NaN): exact geodesic
-            const double az = atan2((double)de, (double)dn) * kRad2Deg;
-            geod_direct(lon0, lat0, az, sqrt((double)de * de + (double)dn * dn), lon1, lat1);
-            return;
-        }
-        // mid-latitude formulas with one azimuth-convergence correction
-        float dphi = dn * st.im;
-        float d = 0.5f * dphi;
-        float sm = st.s0 + d * (st.c0 - 0.5f * d * st.s0), cm = st.c0 - d * (st.s0 + 0.5f * d * st.c0);
-        float im, in_;
-        radii(sm, cm, im, in_);
-        const float dalp = de * in_ * sm;                    // convergence of the meridians over the step
-        const float de2 = de + 0.5f * dn * dalp, dn2 = dn - 0.5f * de * dalp;
-        dphi = dn2 * im;
-        d = 0.5f * dphi;
-        sm = st.s0 + d * (st.c0 - 0.5f * d * st.s0);
-        cm = st.c0 - d * (st.s0 + 0.5f * d * st.c0);
-        radii(sm, cm, im, in_);
-        lat1 = lat0 + (double)(dn2 * im * (float)kRad2Deg);
-        double lo = lon0 + (double)(de2 * in_ * (float)kRad2Deg);
-        lon1 = ang_normalize(lo);
+    // the move that is kept: float64 short-arc series (round-off accurate at every latitude; the float32 mid-latitude
+    // formulas this replaced lost 5e-6 deg per 3.6 km step at 77N)
+    OD_HDS void move_m(const Start& st, double lon0, double lat0, double de, double dn, double& lon1, double& lat1) {
+        const SeriesStart ss = series_start(lat0);
+        geod_move_ne(ss, lon0, dn, de, lon1, lat1);
     }
     OD_HDS void move32(const Start& st, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
-        const float k = (float)(mv * dt);
-        move_m(st, lon0, lat0, xv * k, yv * k, lon1, lat1);
+        const double k = mv * dt;
+        move_m(st, lon0, lat0, (double)xv * k, (double)yv * k, lon1, lat1);
     }
     OD_HDS void move64(const Start& st, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
         const double k = mv * dt;
-        move_m(st, lon0, lat0, (float)(xv * k), (float)(yv * k), lon1, lat1);
+        move_m(st, lon0, lat0, xv * k, yv * k, lon1, lat1);
     }
     OD_HDS float lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
     // time lerp of the corners, then trilinear, float32 FMAs
-    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool,
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
                           const TileView& tv = TileView()) {
+        if (pos_f32) {       // first step after seeding: the reference forms the cell index in float32 (ulp 3e-5 at lon 359);
+            sample2(g, pr, vw, lon, lat, u, v, true, tv);     // in a strong gradient that is visible, so replay it exactly
+            return;
+        }
         float ru = NAN, rv = NAN;
         double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
         const double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
-        if (pr.mode != 3 && x >= g.xmin && x <= g.xmax && lat >= g.ymin && lat <= g.ymax &&
+        if (pr.mode != 3 && (g.wrap != 0 || (x >= g.xmin && x <= g.xmax)) && lat >= g.ymin && lat <= g.ymax &&
             xi >= 0.0 && xi <= g.nxm1 && yi >= 0.0 && yi <= g.nym1) {
             const double fx = floor(xi), fy = floor(yi);
-            const int ix = (int)fx, iy = (int)fy;
-            const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1, iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
+            int ix = (int)fx;
+            const int iy = (int)fy;
+            const int nxv = g.nx + g.wrap;
+            int ix1 = ix + 1 < nxv ? ix + 1 : nxv - 1;
+            if (ix >= g.nx) ix -= g.nx;
+            if (ix1 >= g.nx) ix1 -= g.nx;
+            const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
             const float tx = (float)(xi - fx), ty = (float)(yi - fy);
             const float tw = pr.mode == 0 ? (float)pr.w : (pr.mode == 1 ? 0.0f : 1.0f);
             const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, ix, ix1, iy, iy1, vw.ia, g.nz > 1 ? vw.ib : vw.ia);

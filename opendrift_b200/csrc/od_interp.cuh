@@ -39,7 +39,7 @@ namespace od {
 struct GroupGeom {
     int nx, ny, nz, ncomp;
     int lon_mode;            // 0: np.mod(lon, 360); 1: np.mod(lon + 180, 360) - 180
-    int pad_;
+    int wrap;                // 1: periodic east-west; one virtual column (= column 0) follows the nx stored ones
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     double nxm1, nym1;
@@ -172,7 +172,8 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
         xi = OD_DMUL(div_rn(OD_DSUB(x, g.x0), g.xspan, g.rxspan), g.nxm1);
         yi = OD_DMUL(div_rn(OD_DSUB(y, g.y0), g.yspan, g.ryspan), g.nym1);
     }
-    bool covered = (x >= g.xmin) && (x <= g.xmax) && (y >= g.ymin) && (y <= g.ymax);
+    // global readers are tested north-south only (variables.py:239-242)
+    bool covered = (g.wrap != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (y >= g.ymin) && (y <= g.ymax);
     covered = covered && (xi >= 0.0) && (xi <= g.nxm1) && (yi >= 0.0) && (yi <= g.nym1);
     h.valid = covered;
     if (!covered) {
@@ -182,8 +183,12 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
         return h;
     }
     const double fx = floor(xi), fy = floor(yi);
-    const int ix = (int)fx, iy = (int)fy;
-    const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1;
+    int ix = (int)fx;
+    const int iy = (int)fy;
+    const int nxv = g.nx + g.wrap;                       // columns of the block incl. the virtual one
+    int ix1 = ix + 1 < nxv ? ix + 1 : nxv - 1;
+    if (ix >= g.nx) ix -= g.nx;                          // the virtual column is column 0
+    if (ix1 >= g.nx) ix1 -= g.nx;
     const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
     h.wx0 = OD_DSUB(1.0, OD_DSUB(xi, fx));
     h.wx1 = OD_DSUB(1.0, h.wx0);
@@ -250,7 +255,7 @@ OD_HD TexelSource texel_source(const float* tex, const TileView& tv, int nx, int
                                int ia, int ib) {
     TexelSource t;
 #if defined(__CUDA_ARCH__)
-    if (tv.smem && tex == tv.tex && ix >= tv.x0 && ix1 < tv.x0 + tv.bx && iy >= tv.y0 && iy1 < tv.y0 + tv.by &&
+    if (tv.smem && tex == tv.tex && ix1 >= ix && ix >= tv.x0 && ix1 < tv.x0 + tv.bx && iy >= tv.y0 && iy1 < tv.y0 + tv.by &&
         ia >= tv.z0 && ib < tv.z0 + tv.bz) {
         t.base = tv.smem - 4 * ((tv.z0 * tv.by + tv.y0) * tv.bx + tv.x0);
         t.lx = tv.bx;

@@ -580,9 +580,10 @@ static GroupGeom make_geom(const Group& g) {
     memset(&q, 0, sizeof(q));
     q.nx = g.desc.nx; q.ny = g.desc.ny; q.nz = g.desc.nz; q.ncomp = g.desc.ncomp;
     q.lon_mode = g.desc.lon_mode;
+    q.wrap = g.desc.wrap_x ? 1 : 0;
     q.x0 = g.desc.x0; q.xspan = g.desc.xspan; q.y0 = g.desc.y0; q.yspan = g.desc.yspan;
     q.xmin = g.desc.xmin; q.xmax = g.desc.xmax; q.ymin = g.desc.ymin; q.ymax = g.desc.ymax;
-    q.nxm1 = (double)(g.desc.nx - 1); q.nym1 = (double)(g.desc.ny - 1);
+    q.nxm1 = (double)(g.desc.nx - 1 + q.wrap); q.nym1 = (double)(g.desc.ny - 1);
     q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
     q.rxspan = div_rn_reciprocal(q.xspan); q.ryspan = div_rn_reciprocal(q.yspan);
     q.zmin = g.zmin; q.zmax = g.zmax;

@@ -73,6 +73,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def grid_geometry(lon, lat):
+    """What the sampler needs to know about a regular float32 lon/lat grid, following the reference:
+    * Linear2DInterpolator (interpolators.py:110-111): xi = (x - xg[0]) / (xg[-1] - xg[0]) * (nx - 1), float32 end points and
+      float32 difference;
+    * longitude convention of the reader (variables.py:259-280): [-180, 180) when the grid starts west of 0, else [0, 360);
+    * east-west global coverage (variables.py:289-301).  A global grid that is exactly periodic (nx * dx == 360) is sampled
+      as the block 'all columns + column 0 again at lon[-1] + dx' (include/odcuda.h: wrap_x), which covers the seam cell."""
+    lon = np.asarray(lon, dtype=np.float32)
+    lat = np.asarray(lat, dtype=np.float32)
+    xmin, xmax = float(lon.min()), float(lon.max())
+    dx = float(lon[1] - lon[0])
+    glob = (xmin - 2 * dx <= 0 and xmax + 2 * dx >= 360) or (xmin - 2 * dx <= -180 and xmax + 2 * dx >= 180)
+    periodic = bool(glob) and abs(len(lon) * dx - 360.0) < 1e-3 * dx
+    x_last = np.float32(lon[-1] + np.float32(dx)) if periodic else lon[-1]
+    return {'lon_mode': _lib.OD_LON_PM180 if xmin < 0 else _lib.OD_LON_0_360, 'wrap_x': 1 if periodic else 0,
+            'global_coverage': bool(glob),
+            'x0': float(lon[0]), 'xspan': float(np.float32(x_last - lon[0])),
+            'y0': float(lat[0]), 'yspan': float(np.float32(lat[-1] - lat[0])),
+            'xmin': xmin, 'xmax': xmax, 'ymin': float(lat.min()), 'ymax': float(lat.max())}
+
+
 class FieldGroup:
     """One od group: geometry + a ring of device slots filled on demand from a slab supplier."""
 
@@ -94,16 +115,12 @@ class FieldGroup:
         d = GroupDesc()
         d.ncomp, d.nx, d.ny = ncomp, len(self.lon), len(self.lat)
         d.nz = 1 if self.z is None else len(self.z)
-        xmin, xmax = float(self.lon.min()), float(self.lon.max())
-        d.lon_mode = _lib.OD_LON_PM180 if xmin < 0 else _lib.OD_LON_0_360     # variables.py:259-280
         d.n_slots = n_slots
-        # Linear2DInterpolator (interpolators.py:110-111): float32 end points, float32 difference
-        d.x0 = float(self.lon[0])
-        d.xspan = float(np.float32(self.lon[-1] - self.lon[0]))
-        d.y0 = float(self.lat[0])
-        d.yspan = float(np.float32(self.lat[-1] - self.lat[0]))
-        d.xmin, d.xmax = xmin, xmax
-        d.ymin, d.ymax = float(self.lat.min()), float(self.lat.max())
+        geo = grid_geometry(self.lon, self.lat)
+        d.lon_mode, d.wrap_x = geo['lon_mode'], geo['wrap_x']
+        d.x0, d.xspan, d.y0, d.yspan = geo['x0'], geo['xspan'], geo['y0'], geo['yspan']
+        d.xmin, d.xmax, d.ymin, d.ymax = geo['xmin'], geo['xmax'], geo['ymin'], geo['ymax']
+        self.global_coverage, self.periodic = geo['global_coverage'], bool(geo['wrap_x'])
         fb = list(fallback) + [float('nan')] * (2 - len(fallback))
         d.fallback[0] = float('nan') if fb[0] is None else fb[0]
         d.fallback[1] = float('nan') if fb[1] is None else fb[1]

@@ -93,10 +93,24 @@ class StructuredReader:
         lons = np.asarray(lons)
         return np.mod(lons + 180, 360) - 180 if self.xmin < 0 else np.mod(lons, 360)
 
+    def global_coverage(self):
+        """True if the reader covers the globe east-west (variables.py:289-301)."""
+        dx = getattr(self, 'delta_x', None) or 0
+        return bool((self.xmin - 2 * dx <= 0 and self.xmax + 2 * dx >= 360) or
+                    (self.xmin - 2 * dx <= -180 and self.xmax + 2 * dx >= 180))
+
+    def lon_range(self):
+        if not self.global_coverage():
+            raise ValueError('Only valid for readers with global coverage')
+        return '-180to180' if self.xmin < 0 else '0to360'
+
     def covers_positions(self, lon, lat, z=0):
         x = self.modulate_longitude(np.atleast_1d(lon))
         y = np.atleast_1d(lat)
-        ind = np.where((x >= self.xmin) & (x <= self.xmax) & (y >= self.ymin) & (y <= self.ymax))[0]
+        if self.global_coverage():             # north-south only (variables.py:239-242)
+            ind = np.where((y >= self.ymin) & (y <= self.ymax))[0]
+        else:
+            ind = np.where((x >= self.xmin) & (x <= self.xmax) & (y >= self.ymin) & (y <= self.ymax))[0]
         return ind, x[ind], y[ind]
 
     def nearest_time(self, time):

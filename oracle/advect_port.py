@@ -44,6 +44,15 @@ class GridReader:
         self.start_time, self.end_time = self.times[0], self.times[-1]
         self.time_step = (self.times[1] - self.times[0]) if len(self.times) > 1 else None
         self._blocks = {}
+        # east-west global coverage (variables.py:289-301) of an exactly periodic grid: the block is the full circle
+        # plus one wrapped column (see oracle/refrun.py:make_grid_reader)
+        dx = float(self.x[1] - self.x[0])
+        self.global_coverage = (self.xmin - 2 * dx <= 0 and self.xmax + 2 * dx >= 360) or \
+                               (self.xmin - 2 * dx <= -180 and self.xmax + 2 * dx >= 180)
+        self.periodic = bool(self.global_coverage) and abs(len(self.x) * dx - 360.0) < 1e-3 * dx
+        self.block_x = self.x
+        if self.periodic:
+            self.block_x = np.append(self.x, np.float32(self.x[-1] + np.float32(dx))).astype(np.float32)
 
     def block(self, var, it):
         """The ReaderBlock array of one variable and time: a private float32 copy (the NaN fill of
@@ -52,6 +61,8 @@ class GridReader:
         key = (var, it)
         if key not in self._blocks:
             a = np.array(self.fields[var][it], dtype=np.float32, copy=True)
+            if self.periodic:
+                a = np.concatenate([a, a[..., :1]], axis=-1)
             if a.ndim == 3:
                 for i in range(1, a.shape[0]):
                     m = np.isnan(a[i])
@@ -102,7 +113,7 @@ def _linear2d(block2d, xi, yi):
 def block_interpolate(reader, it, variables, x, y, z, profiles=None):
     """ReaderBlock.interpolate (opendrift/readers/interpolation/structured.py:107-146) for the
     default 'linearNDFast' horizontal + 'linear' vertical interpolators."""
-    xg, yg = reader.x, reader.y
+    xg, yg = reader.block_x, reader.y
     # interpolators.py:107-111 (float32 grid end points, promoted to float64 by x)
     xi = (x - xg[0]) / (xg[-1] - xg[0]) * (len(xg) - 1)
     yi = (y - yg[0]) / (yg[-1] - yg[0]) * (len(yg) - 1)
@@ -148,10 +159,13 @@ def reader_interpolate(reader, variables, time, lon, lat, z, profiles=None):
     """Variables.get_variables_interpolated -> get_variables_interpolated_xy ->
     StructuredReader._get_variables_interpolated_ for a '+proj=latlong' reader
     (opendrift/readers/basereader/variables.py:860-920, 709-858; structured.py:202-400)."""
-    lon = np.mod(lon, 360) if reader.xmin >= 0 else np.mod(lon + 180, 360) - 180   # variables.py:259-280
+    lon = np.mod(lon, 360) if reader.xmin >= 0 else np.mod(lon + 180, 360) - 180   # variables.py:259-280, structured.py:205-215
     x, y = lon, lat
-    covered = np.where((x >= reader.xmin) & (x <= reader.xmax) &
-                       (y >= reader.ymin) & (y <= reader.ymax))[0]               # variables.py:229-257
+    if reader.global_coverage:                                                   # variables.py:239-242: north-south only
+        covered = np.where((y >= reader.ymin) & (y <= reader.ymax))[0]
+    else:
+        covered = np.where((x >= reader.xmin) & (x <= reader.xmax) &
+                           (y >= reader.ymin) & (y <= reader.ymax))[0]           # variables.py:229-257
     n = len(x)
     if len(covered) == 0:
         return {v: np.full(n, np.nan) for v in variables}

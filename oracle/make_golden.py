@@ -176,6 +176,66 @@ def run_leeway_case(name, g, n, steps, dt, object_type=1, seed=0):
     print('wrote', path, 'max |dlon|', np.abs(o.elements.lon - lon).max(), 'jibed', int((o.elements.orientation != np.r_[:n] % 2).sum()))
 
 
+def run_dateline_case(name, field, seeds_lon, seeds_lat, steps, dt, scheme='euler', wdf=0.1):
+    """The reference's tests/readers/test_interpolation.py:43-148 (test_dateline) with in-memory readers: a current
+    reader on lon 0..359 (global, 0-360 convention) and a wind reader on lon -180..179 (global, -180-180 convention),
+    lat -88..88, daily slabs.  field='piecewise' are the test's own fields (u = +1 east of 0, -1 west; wind v = +1 on
+    the western half of its grid, -1 on the eastern); 'smooth' varies with lon / lat so that the seam cells matter."""
+    lat = np.arange(-88, 89).astype(np.float32)
+    lon_c = np.arange(0, 360).astype(np.float32)
+    lon_w = np.arange(-180, 180).astype(np.float32)
+    times = syn.slab_times(3, 86400)
+    ny = len(lat)
+    if field == 'piecewise':
+        u = np.zeros((3, ny, 360), np.float32); v = np.zeros_like(u)
+        u[:, :, 0:180] = 1
+        u[:, :, 180:] = -1
+        xw = np.zeros((3, ny, 360), np.float32); yw = np.zeros_like(xw)
+        yw[:, :, 0:180] = 1
+        yw[:, :, 180:] = -1
+    else:
+        lo_c, la = np.meshgrid(np.radians(lon_c.astype(np.float64)), np.radians(lat.astype(np.float64)))
+        lo_w, _ = np.meshgrid(np.radians(lon_w.astype(np.float64)), np.radians(lat.astype(np.float64)))
+        u = np.stack([(0.8 * np.cos(la) * np.sin(2 * lo_c + 0.3 * k) + 0.2 * np.cos(lo_c)) for k in range(3)]).astype(np.float32)
+        v = np.stack([(0.3 * np.sin(3 * lo_c) * np.cos(la) * (1 + 0.1 * k)) for k in range(3)]).astype(np.float32)
+        xw = np.stack([(8.0 * np.cos(lo_w + 0.2 * k) * np.cos(la)) for k in range(3)]).astype(np.float32)
+        yw = np.stack([(5.0 * np.sin(2 * lo_w) + 1.0 * k) for k in range(3)]).astype(np.float32)
+    lon0 = np.asarray(seeds_lon, dtype=np.float32)
+    lat0 = np.asarray(seeds_lat, dtype=np.float32)
+    n = len(lon0)
+    z0 = np.zeros(n, dtype=np.float32)
+    readers = [refrun.make_grid_reader(lon_c, lat, None, times, {CURRENT[0]: u, CURRENT[1]: v}, 'current'),
+               refrun.make_grid_reader(lon_w, lat, None, times, {'x_wind': xw, 'y_wind': yw}, 'wind')]
+    assert readers[0].periodic and readers[1].periodic
+    cfg = {'drift:advection_scheme': scheme, 'drift:vertical_advection': False, 'drift:stokes_drift': False}
+    o = refrun.run_oceandrift(readers, lon0, lat0, z0, syn.T0, dt, steps, config=cfg, seed_kwargs={'wind_drift_factor': wdf})
+    assert len(o.elements.lon) == n, 'reference deactivated particles in %s' % name
+    meta = dict(name=name, steps=steps, dt=dt, scheme=scheme, with_w=False, wind=True, diffusivity=0.0, seed=0,
+                wind_drift_depth=None, start_offset_s=0, start_index=None, slab_step_s=86400, cdf_is_array=False,
+                mixing=False, dt_mix=60.0, stokes=None, noise=None, wdf=wdf, field=field)
+    path = os.path.join(OUT, 'ref_%s.npz' % name)
+    np.savez_compressed(path, meta=json.dumps(meta), grid_lon=lon_c, grid_lat=lat, grid_z=np.zeros(0), u=u, v=v,
+                        x_wind=xw, y_wind=yw, wind_lon=lon_w, wind_lat=lat, lon0=lon0, lat0=lat0, z0=z0,
+                        lon=np.asarray(o.elements.lon, dtype=np.float64), lat=np.asarray(o.elements.lat, dtype=np.float64),
+                        z=np.asarray(o.elements.z))
+    print('wrote', path, 'first four', np.asarray(o.elements.lon)[:4], np.asarray(o.elements.lat)[:4])
+
+
+def dateline_cases():
+    rng = np.random.default_rng(42)
+    near = np.concatenate([rng.uniform(-1.5, 1.5, 150), rng.uniform(178.5, 181.5, 150)])
+    near = (near + 180.0) % 360.0 - 180.0
+    lon_a = np.concatenate([[-2, 2, -175, 175], near])
+    lat_a = np.concatenate([[60, 60, 60, 60], rng.uniform(-80, 80, 300)])
+    run_dateline_case('dateline_piecewise_euler', 'piecewise', lon_a, lat_a, 2, 3600)
+    lons, lats = np.meshgrid(np.arange(-180, 181, 20), np.arange(-80, 81, 20))
+    run_dateline_case('dateline_piecewise_spread', 'piecewise', lons.ravel(), lats.ravel(), 2, 3600 * 12)
+    lon_c = np.concatenate([near, rng.uniform(-180, 180, 400)])
+    lat_c = rng.uniform(-85, 85, len(lon_c))
+    run_dateline_case('dateline_smooth_rk4', 'smooth', lon_c, lat_c, 6, 3600, scheme='runge-kutta4')
+    run_dateline_case('dateline_smooth_euler', 'smooth', lon_c, lat_c, 4, 7200, scheme='euler', wdf=0.03)
+
+
 def main():
     g3 = syn.GridSpec(nx=40, ny=36, nz=8, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03, dz=12.0)
     g2 = syn.GridSpec(nx=40, ny=36, nz=1, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03)
@@ -203,6 +263,7 @@ def main():
     run_case('rk2_3d_stokes_exp', g3, n, 5, 600, 'runge-kutta', wind=True, stokes='exponential')
     run_case('rk4_3d_mixing', g3, 600, 7, 600, 'runge-kutta4', mixing=True, dt_mix=60.0)
     run_case('euler_3d_mixing_w', g3, 600, 4, 900, 'euler', mixing=True, dt_mix=100.0, with_w=True)
+    dateline_cases()
 
 
 if __name__ == '__main__':

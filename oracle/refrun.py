@@ -112,6 +112,12 @@ def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid'):
     in-memory regular lon/lat(/z) slabs.  ``fields[var]`` has shape (nt, nz, ny, nx) or
     (nt, ny, nx) float32.  get_variables returns the FULL grid block (like
     reader_constant_2d.py:45-49) with float32 x/y (as reader_netCDF_CF_generic.py:586-587).
+
+    A grid that is global east-west by the reference's rule (variables.py:289-301) and exactly periodic
+    (nx * dx == 360) returns the full circle plus ONE wrapped column (x = lon[-1] + dx, values of column 0), so that the
+    block is monotonic, stays inside [-180, 360] as ReaderBlock demands (interpolation/structured.py:35-48) and covers
+    the seam cell between the last and the first column -- what reader_netCDF_CF_generic assembles from two parts when
+    the particle cloud straddles its longitude border (reader_netCDF_CF_generic.py:452-463).
     """
     setup()
     from opendrift.readers.basereader.structured import StructuredReader
@@ -134,15 +140,22 @@ def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid'):
             self.time_step = (times[1] - times[0]) if len(times) > 1 else None
             self.name = name
             super().__init__()
+            self.periodic = bool(self.global_coverage()) and abs(self.numx * self.delta_x - 360.0) < 1e-3 * self.delta_x
+            self.block_x = self.lon
+            if self.periodic:
+                self.block_x = np.append(self.lon, np.float32(self.lon[-1] + np.float32(self.delta_x))).astype(np.float32)
 
         def get_variables(self, requested_variables, time=None, x=None, y=None, z=None):
             it = self.times.index(time)
-            out = {'x': self.lon, 'y': self.lat, 'time': time}
+            out = {'x': self.block_x, 'y': self.lat, 'time': time}
             three_d = False
             for v in requested_variables:
                 a = self.fields[v][it]
                 three_d |= a.ndim == 3
-                out[v] = np.array(a, dtype=np.float32, copy=True)
+                a = np.array(a, dtype=np.float32, copy=True)
+                if self.periodic:
+                    a = np.concatenate([a, a[..., :1]], axis=-1)
+                out[v] = a
             out['z'] = self.zlev if three_d else 0
             return out
 

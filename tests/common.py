@@ -118,6 +118,8 @@ class Fixture:
         self.w = d['w'] if 'w' in d else None
         self.x_wind = d['x_wind'] if 'x_wind' in d else None
         self.y_wind = d['y_wind'] if 'y_wind' in d else None
+        self.wind_lon = d['wind_lon'] if 'wind_lon' in d else self.grid_lon      # the wind reader may have its own grid
+        self.wind_lat = d['wind_lat'] if 'wind_lat' in d else self.grid_lat
         self.cdf = d['cdf'] if 'cdf' in d else None
         self.kdiff = d['kdiff'] if 'kdiff' in d else None
         self.stokes = {k[len('stokes__'):]: d[k] for k in d.files if k.startswith('stokes__')} or None
@@ -135,7 +137,7 @@ class Fixture:
         opendrift/elements/elements.py:213-216)."""
         n = self.n
         cdf = self.cdf.astype(np.float32) if self.cdf is not None else np.float32(1) * np.ones(n)
-        wdf = np.float32(0.02) * np.ones(n)
+        wdf = np.float32(self.meta.get('wdf', 0.02)) * np.ones(n)
         moving = np.ones(n, dtype=np.int32)
         return cdf, wdf, moving
 
@@ -153,14 +155,14 @@ def run_port(fx):
         f3['ocean_vertical_diffusivity'] = fx.kdiff
     readers = [ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3)]
     if fx.x_wind is not None:
-        readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times,
+        readers.append(ap.GridReader(fx.wind_lon, fx.wind_lat, None, fx.times,
                                      {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}))
     if fx.stokes is not None:
         readers.append(ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, fx.stokes))
     m = fx.meta
     return ap.run_oceandrift(readers, fx.lon0, fx.lat0, fx.z0, fx.start, fx.dt, fx.steps, scheme=m['scheme'],
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
-                             cdf=fx.cdf if fx.cdf is not None else 1.0, diffusivity=m['diffusivity'],
+                             cdf=fx.cdf if fx.cdf is not None else 1.0, wdf=m.get('wdf', 0.02), diffusivity=m['diffusivity'],
                              seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0),
                              stokes=m.get('stokes'), noise=m.get('noise'))
 
@@ -168,7 +170,7 @@ def run_port(fx):
 # ---- host-compiled device math ---------------------------------------------------------------
 class HsGroup(C.Structure):
     _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
-                ('lon_mode', C.c_int32), ('pad_', C.c_int32),
+                ('lon_mode', C.c_int32), ('wrap_x', C.c_int32),
                 ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
                 ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
                 ('fallback', C.c_float * 2), ('z_levels', C.c_void_p)]
@@ -284,11 +286,11 @@ class HsField:
         self.comps, self.times = comps, times
         g = HsGroup()
         g.ncomp, g.nx, g.ny, g.nz = len(comps), len(self.lon), len(self.lat), 1 if self.z is None else len(self.z)
-        g.lon_mode = 1 if float(self.lon.min()) < 0 else 0
-        g.x0, g.xspan = float(self.lon[0]), float(np.float32(self.lon[-1] - self.lon[0]))
-        g.y0, g.yspan = float(self.lat[0]), float(np.float32(self.lat[-1] - self.lat[0]))
-        g.xmin, g.xmax = float(self.lon.min()), float(self.lon.max())
-        g.ymin, g.ymax = float(self.lat.min()), float(self.lat.max())
+        from opendrift_b200.engine import grid_geometry
+        geo = grid_geometry(self.lon, self.lat)
+        g.lon_mode, g.wrap_x = geo['lon_mode'], geo['wrap_x']
+        g.x0, g.xspan, g.y0, g.yspan = geo['x0'], geo['xspan'], geo['y0'], geo['yspan']
+        g.xmin, g.xmax, g.ymin, g.ymax = geo['xmin'], geo['xmax'], geo['ymin'], geo['ymax']
         g.fallback[0], g.fallback[1] = fallback[0], fallback[-1]
         g.z_levels = None if self.z is None else self.z.ctypes.data
         self.g = g
@@ -321,7 +323,7 @@ def run_hostshim(fx, fast=False):
     lib = hostshim()
     m = fx.meta
     cur = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.u, fx.v], fx.times)
-    wind = HsField(fx.grid_lon, fx.grid_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
+    wind = HsField(fx.wind_lon, fx.wind_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
     wfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.w], fx.times, (0.0,)) if m['with_w'] else None
     kfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.kdiff], fx.times, (0.0,)) if m.get('mixing') else None
     sfld = hfld = None
@@ -420,7 +422,7 @@ def run_engine(fx, fused=True, sort_every=0, fast=None):
     cur = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 2, fx.times, cur_supplier, (0.0, 0.0))
     wind = wgrp = None
     if m['wind']:
-        wind = eng.add_group(fx.grid_lon, fx.grid_lat, None, 2, fx.times,
+        wind = eng.add_group(fx.wind_lon, fx.wind_lat, None, 2, fx.times,
                              lambda ti, c: (fx.x_wind, fx.y_wind)[c][ti], (0.0, 0.0))
     if m['with_w']:
         wgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.w[ti], (0.0,))

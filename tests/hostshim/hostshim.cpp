@@ -15,7 +15,7 @@ using namespace od;
 extern "C" {
 
 struct hs_group {
-    int32_t ncomp, nx, ny, nz, lon_mode, pad_;
+    int32_t ncomp, nx, ny, nz, lon_mode, wrap_x;
     double x0, xspan, y0, yspan, xmin, xmax, ymin, ymax;
     float fallback[2];
     const double* z_levels;   // as the reader gives them
@@ -35,10 +35,10 @@ struct hs_levels {
 static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
     GroupGeom q;
     memset(&q, 0, sizeof(q));
-    q.nx = d.nx; q.ny = d.ny; q.nz = d.nz; q.ncomp = d.ncomp; q.lon_mode = d.lon_mode;
+    q.nx = d.nx; q.ny = d.ny; q.nz = d.nz; q.ncomp = d.ncomp; q.lon_mode = d.lon_mode; q.wrap = d.wrap_x ? 1 : 0;
     q.x0 = d.x0; q.xspan = d.xspan; q.y0 = d.y0; q.yspan = d.yspan;
     q.xmin = d.xmin; q.xmax = d.xmax; q.ymin = d.ymin; q.ymax = d.ymax;
-    q.nxm1 = (double)(d.nx - 1); q.nym1 = (double)(d.ny - 1);
+    q.nxm1 = (double)(d.nx - 1 + q.wrap); q.nym1 = (double)(d.ny - 1);
     q.inv_dx = q.nxm1 / q.xspan; q.inv_dy = q.nym1 / q.yspan;
     q.rxspan = div_rn_reciprocal(q.xspan); q.ryspan = div_rn_reciprocal(q.yspan);
     q.fallback[0] = d.fallback[0]; q.fallback[1] = d.fallback[1];

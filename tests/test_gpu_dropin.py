@@ -24,7 +24,7 @@ def _model(fx, **cfg):
         f3['ocean_vertical_diffusivity'] = fx.kdiff
     o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, name='current'))
     if fx.x_wind is not None:
-        o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times,
+        o.add_reader(reader_regular_grid.Reader(fx.wind_lon, fx.wind_lat, None, fx.times,
                                                 {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind'))
     if fx.stokes is not None:
         o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, dict(fx.stokes), name='waves'))
@@ -47,6 +47,8 @@ def _model(fx, **cfg):
     kw = {}
     if fx.cdf is not None:
         kw['current_drift_factor'] = fx.cdf
+    if 'wdf' in m:
+        kw['wind_drift_factor'] = m['wdf']
     o.seed_elements(lon=fx.lon0, lat=fx.lat0, z=fx.z0, time=fx.start, **kw)
     return o
 
