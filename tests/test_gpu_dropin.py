@@ -202,3 +202,39 @@ def test_seeding_radius_and_deactivation():
     # everybody retired at age 4 steps
     assert o.num_elements_active() == 0 and o.num_elements_deactivated() == 5000
     assert 'retired' in o.status_categories
+
+
+def test_reference_known_answers_with_constant_environment():
+    """The reference's own model-level known answers for this path, as its tests write them:
+    tests/models/test_models.py:44-64 (test_wind_and_current_drift_factor) and
+    tests/models/test_environment.py:30-41 (test_previous, coastline_action 'none')."""
+    from datetime import datetime
+    from opendrift_b200.models.oceandrift import OceanDrift
+    lat, lon = 60, 4
+    o = OceanDrift(loglevel=50)
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('environment:constant:land_binary_mask', 0)
+    o.set_config('environment:constant:x_wind', 5)
+    o.set_config('environment:constant:y_sea_water_velocity', 1)
+    o.seed_elements(lon=lon, lat=lat, time=datetime.now(), wind_drift_factor=0, current_drift_factor=1)
+    o.run(duration=timedelta(hours=2))
+    o2 = OceanDrift(loglevel=50)
+    o2.set_config('general:use_auto_landmask', False)
+    o2.set_config('environment:constant:land_binary_mask', 0)
+    o2.set_config('environment:constant:x_wind', 5)
+    o2.set_config('environment:constant:y_sea_water_velocity', 1)
+    o2.seed_elements(lon=lon, lat=lat, time=datetime.now(), wind_drift_factor=0.02, current_drift_factor=.3)
+    o2.run(duration=timedelta(hours=2))
+    assert abs(o.elements.lat[0] - (lat + 0.0646)) < 5e-4
+    assert abs(o.elements.lon[0] - lon) < 5e-8
+    assert abs(o2.elements.lat[0] - (lat + 0.0646 * .3)) < 5e-4
+    assert abs(o2.elements.lon[0] - (lon + 0.0129)) < 5e-4
+
+    o = OceanDrift(loglevel=50)
+    o.set_config('general:coastline_action', 'none')
+    o.set_config('drift:vertical_advection', False)
+    o.set_config('environment:constant:land_binary_mask', 0)
+    o.set_config('environment:constant:x_sea_water_velocity', 1)
+    o.seed_elements(lon=3, lat=60, time=datetime.now())
+    o.run(steps=1)
+    assert o.elements.lon == pytest.approx(3.0645, .001)
