@@ -149,9 +149,8 @@ class Leeway(OpenDriftSimulation):
             raise NotImplementedError('processes:capsizing is not on the GPU path')
         eng, el, torch = self.engine, self.elements, self.engine.torch
         t = self.time
-        wr, cr = self.env.reader_for('x_wind', t), self.env.reader_for('x_sea_water_velocity', t)
-        if wr is None or cr is None or not hasattr(wr, 'group_of') or not hasattr(cr, 'group_of'):
-            raise NotImplementedError('Leeway on the GPU path needs gridded wind and current readers covering the run')
+        gw = self._pair_group('x_wind', 'y_wind', t)
+        gc = self._pair_group('x_sea_water_velocity', 'y_sea_water_velocity', t)
         n = len(el)
         rand = eng.to_device(np.random.random(n)) if self.get_config('gpu:rng') == 'numpy' else None
         cols = {'dw_slope': 'downwind_slope', 'dw_offset': 'downwind_offset', 'dw_eps': 'downwind_eps',
@@ -164,7 +163,7 @@ class Leeway(OpenDriftSimulation):
             d['jibe_probability'] = d['jibe_probability'].to(torch.float64)
         if 'missing_data' not in self.status_categories:
             self.status_categories.append('missing_data')
-        eng.leeway_step(wr.group_of('x_wind')[0], cr.group_of('x_sea_water_velocity')[0], t, self.time_step,
+        eng.leeway_step(gw, gc, t, self.time_step,
                         el.dev('lon', torch.float64), el.dev('lat', torch.float64), d,
                         moving=el.dev('moving', torch.int32), status=el.dev('status', torch.int32),
                         ids=el.dev('ID', torch.int32), rand=rand, seed=self._seed, step_index=self.steps_calculation,
@@ -173,6 +172,32 @@ class Leeway(OpenDriftSimulation):
         el.positions_f32 = False
         self._maybe_deactivated = True           # the kernel may have flagged elements with missing forcing
         self.stokes_drift()
+
+    def _pair_group(self, xname, yname, t):
+        """Device field group serving a vector pair at time t: the first reader that covers t, or -- when the pair comes
+        from `environment:constant:*` / `environment:fallback:*` only (environment.py:499-923 applies them per
+        variable) -- a uniform 2 x 2 global group holding those values."""
+        r = self.env.reader_for(xname, t)
+        if r is not None:
+            if not hasattr(r, 'group_of'):
+                raise NotImplementedError('Leeway on the GPU path needs gridded readers (got %r)' % r)
+            return r.group_of(xname)[0]
+        vals = []
+        for nme in (xname, yname):
+            v = self.env.constant(nme)
+            if v is None:
+                v = self.env.fallback(nme)
+            if v is None:
+                raise ValueError('No reader, constant or fallback value for %s at %s' % (nme, t))
+            vals.append(float(v))
+        key = (xname, tuple(vals))
+        cache = self.__dict__.setdefault('_uniform_groups', {})
+        if key not in cache:
+            lon = np.array([-180.0, 180.0], dtype=np.float32)
+            lat = np.array([-90.0, 90.0], dtype=np.float32)
+            slab = [np.full((2, 2), v, dtype=np.float32) for v in vals]
+            cache[key] = self.engine.add_group(lon, lat, None, 2, [t], lambda ti, c: slab[c], tuple(vals))
+        return cache[key]
 
     def update_and_diffuse(self):
         if type(self).update is Leeway.update:

@@ -69,7 +69,7 @@ class StructuredReader:
 
     def __init__(self):
         p = str(getattr(self, 'proj4', '+proj=latlong'))
-        if 'latlong' not in p and 'longlat' not in p:
+        if not any(k in p for k in ('latlong', 'longlat', 'lonlat', 'latlon')):      # PROJ's aliases of the geographic CRS
             raise NotImplementedError('opendrift_b200 readers are geographic (+proj=latlong); got %s' % p)
         if getattr(self, 'times', None) is None and getattr(self, 'start_time', None) is not None \
                 and getattr(self, 'time_step', None) is not None and self.end_time != self.start_time:

@@ -183,3 +183,58 @@ def test_gpu_sampler_on_a_north_to_south_grid_is_bit_exact():
     o = eng.interp(grp, t, eng.to_device(plon), eng.to_device(plat), eng.to_device(pz))
     assert np.array_equal(o[0].cpu().numpy(), env[common.CUR[0]]) and np.array_equal(o[1].cpu().numpy(), env[common.CUR[1]])
     eng.close()
+
+
+def test_modulate_longitude_known_answers():
+    """tests/readers/test_variables.py:31-90 (test_modulate_longitude_360 / _180) on the product's reader base class."""
+    from opendrift_b200.readers.basereader import StructuredReader
+
+    class R(StructuredReader):
+        def __init__(self, xmin, xmax):
+            self.proj4 = '+proj=lonlat +ellps=WGS84'
+            self.xmin, self.xmax, self.ymin, self.ymax = xmin, xmax, -80, 80
+            self.variables = []
+            self.name = 'domain'
+            self.start_time = self.end_time = self.time_step = None
+            super().__init__()
+
+    r = R(0, 340)
+    lons = np.linspace(0, 300, 100)
+    assert (r.modulate_longitude(lons) == lons).all()
+    assert (r.modulate_longitude(np.array([-180, -90])) == np.array([360 - 180, 360 - 90])).all()
+    assert (r.modulate_longitude(np.array([0, 90])) == np.array([0, 90])).all()
+    assert (r.modulate_longitude(np.array([100, 180])) == np.array([100, 180])).all()
+    assert (r.modulate_longitude(np.array([240, 350])) == np.array([240, 350])).all()
+    r = R(-150, 180)
+    lons = np.linspace(-180, 150, 100)
+    assert (r.modulate_longitude(lons) == lons).all()
+    assert (r.modulate_longitude(np.array([-180, -90])) == np.array([-180, -90])).all()
+    assert (r.modulate_longitude(np.array([0, 90])) == np.array([0, 90])).all()
+    assert (r.modulate_longitude(np.array([100, 180])) == np.array([100, -180])).all()
+    assert (r.modulate_longitude(np.array([240])) == np.array([-120])).all()
+
+
+@pytest.mark.gpu
+def test_leeway_forward_backward_symmetry():
+    """tests/models/test_basemodel.py:96-146 (test_simulation_matches_forw_backward) without the automatic landmask:
+    a forward run and a backward run with mirrored forcing end at the same positions.  (The reference test seeds
+    FISHING-VESSEL-1 from its OBJECTPROP.DAT; the product ships the four PIW categories only, so PIW-4 stands in.)"""
+    from opendrift_b200.models.leeway import Leeway
+
+    def run(sign):
+        lee = Leeway(loglevel=50)
+        lee.set_config('general:use_auto_landmask', False)
+        lee.set_config('environment:constant:land_binary_mask', 0)
+        lee.set_config('environment:fallback:x_wind', -1.5 * sign)
+        lee.set_config('environment:fallback:y_wind', -10 * sign)
+        lee.set_config('environment:fallback:x_sea_water_velocity', -1.5 * sign)
+        lee.set_config('environment:fallback:y_sea_water_velocity', 0)
+        lee.seed_elements(lon=4.5, lat=60, number=100, object_type=4, time=datetime(2015, 1, 1))
+        lee.run(steps=2, time_step=sign * 10 * 3600, time_step_output=sign * 10 * 3600)
+        return lee
+    leef, leeb = run(1), run(-1)
+    assert leef.num_elements_active() == leeb.num_elements_active() == 100
+    assert leef.num_elements_deactivated() == leeb.num_elements_deactivated()
+    np.testing.assert_array_almost_equal(np.sort(leef.elements.lon), np.sort(leeb.elements.lon))
+    np.testing.assert_array_almost_equal(np.sort(leef.elements.lat), np.sort(leeb.elements.lat), decimal=5)
+    assert np.abs(leef.elements.lon - 4.5).max() > 0.05
