@@ -120,11 +120,13 @@ def cpu_port_rate(n, steps, seed=123):
     grid = syn.GridSpec()
     times = syn.slab_times(syn.n_slabs_for(steps, DT))
     slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times[:PERIOD]]
-    fields = {CUR[0]: PeriodicSlabs(slabs, 0), CUR[1]: PeriodicSlabs(slabs, 1)}
+    w = syn.upward_w(grid)
+    fields = {CUR[0]: PeriodicSlabs(slabs, 0), CUR[1]: PeriodicSlabs(slabs, 1),
+              'upward_sea_water_velocity': PeriodicSlabs([(w,)] * PERIOD, 0)}
     reader = ap.GridReader(grid.lon, grid.lat, grid.z, times, fields)
     lon, lat, z = syn.particle_cloud(n, seed=seed)
     t0 = time.perf_counter()
-    ap.run_oceandrift([reader], lon, lat, z, syn.T0, DT, steps, scheme='runge-kutta4')
+    ap.run_oceandrift([reader], lon, lat, z, syn.T0, DT, steps, scheme='runge-kutta4', vertical_adv=True)
     dt = time.perf_counter() - t0
     return n * steps / dt, dt, 1
 
@@ -147,7 +149,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'particle-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, dt=600 s (BASELINE configs[1]); '
+        'config': {'workload': 'OceanDrift RK4 + vertical advection, synthetic 512x512x50 double-gyre u/v/w reader, dt=600 s (BASELINE configs[1]); '
                                'CPU arm: each step is a bounded sample of %d particles of that workload' % n},
         'cpu_baseline': {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': 'port',
                          'sample': '%d particles x %d steps; oracle/advect_port.py = NumPy/SciPy restatement of the reference '
@@ -209,6 +211,10 @@ def run_b200(args):
     grp = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, supplier, (0.0, 0.0), n_slots=3)
     if os.environ.get('OD_BENCH_NOFILL'):
         grp.fill_nan = 0
+    # upward_sea_water_velocity of the u/v/w reader (static in time; every rank builds it from the same formula)
+    h_w = torch.from_numpy(syn.upward_w(grid)).pin_memory()
+    d_w = h_w.to(dev)
+    wgrp = eng.add_group(grid.lon, grid.lat, grid.z, 1, times, lambda ti, c: d_w if resident['on'] else h_w, (0.0,), n_slots=3)
 
     lon0, lat0, z0 = syn.particle_cloud(n, seed=1000 + rank)
     h_lon = torch.from_numpy(lon0.astype(np.float64)).pin_memory()
@@ -238,7 +244,7 @@ def run_b200(args):
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ea.record()
             h0 = time.perf_counter()
-        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, st['lon'], st['lat'], st['z'], pos_f32=(st['k'] == 0))
+        eng.step_oceandrift(grp, 'runge-kutta4', st['t'], dt, st['lon'], st['lat'], st['z'], w_group=wgrp, pos_f32=(st['k'] == 0))
         if record:
             host_us.append((time.perf_counter() - h0) * 1e6)
             eb.record()
@@ -253,12 +259,12 @@ def run_b200(args):
     if sampler:
         sampler.start()
     ramp_t0 = time.perf_counter()
-    tl, ta = st['lon'].clone(), st['lat'].clone()
+    tl, ta, tz = st['lon'].clone(), st['lat'].clone(), st['z'].clone()
     while time.perf_counter() - ramp_t0 < args.ramp_seconds:
         for _ in range(20):
-            eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
+            eng.step_oceandrift(grp, 'runge-kutta4', st['t'], dt, tl, ta, tz, w_group=wgrp)
         torch.cuda.synchronize()
-    del tl, ta
+    del tl, ta, tz
     for _ in range(args.warmup):
         step()
     barrier()
@@ -283,18 +289,22 @@ def run_b200(args):
     clocks = sampler.stop(wall0, wall1) if sampler else None
     per_step = np.array([a.elapsed_time(b) for a, b in step_events])
 
-    # dominant kernel alone: CUDA events around single launches of step_kernel<RK4> on the launching stream
-    kern_ms = []
-    for _ in range(5):
-        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tl, ta = st['lon'].clone(), st['lat'].clone()
-        torch.cuda.synchronize()
-        ka.record()
-        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
-        kb.record()
-        torch.cuda.synchronize()
-        kern_ms.append(ka.elapsed_time(kb))
-    kernel_ms = float(np.median(kern_ms))
+    # dominant kernel alone: CUDA events around single launches of the step kernel on the launching stream
+    def kernel_alone(fn):
+        out = []
+        for _ in range(5):
+            ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tl, ta, tz = st['lon'].clone(), st['lat'].clone(), st['z'].clone()
+            torch.cuda.synchronize()
+            ka.record()
+            fn(tl, ta, tz)
+            kb.record()
+            torch.cuda.synchronize()
+            out.append(ka.elapsed_time(kb))
+        return float(np.median(out))
+
+    t_now = st['t']
+    kernel_ms = kernel_alone(lambda tl, ta, tz: eng.step_oceandrift(grp, 'runge-kutta4', t_now, dt, tl, ta, tz, w_group=wgrp))
     sort_ms = None
     if args.sort_every:
         sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,55 +315,28 @@ def run_b200(args):
         torch.cuda.synchronize()
         sort_ms = sa.elapsed_time(sb)
     # the operation-by-operation replay of the reference (float32 mid-point azimuths, full Karney geodesic), same launch
-    exact_ms = []
-    for _ in range(5):
-        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tl, ta = st['lon'].clone(), st['lat'].clone()
-        torch.cuda.synchronize()
-        ka.record()
-        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'], fast=0)
-        kb.record()
-        torch.cuda.synchronize()
-        exact_ms.append(ka.elapsed_time(kb))
-    exact_kernel_ms = float(np.median(exact_ms))
-    # the opt-in fast arithmetic (float32 sampling + mid-latitude moves on float64 positions), same launch
-    fast_ms = []
-    for _ in range(5):
-        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tl, ta = st['lon'].clone(), st['lat'].clone()
-        torch.cuda.synchronize()
-        ka.record()
-        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'], fast=True)
-        kb.record()
-        torch.cuda.synchronize()
-        fast_ms.append(ka.elapsed_time(kb))
-    fast_kernel_ms = float(np.median(fast_ms))
-    # the TMA-staged variant of the same kernel (shared-memory field boxes), bit-identical results
+    exact_kernel_ms = kernel_alone(lambda tl, ta, tz: eng.step_oceandrift(grp, 'runge-kutta4', t_now, dt, tl, ta, tz, w_group=wgrp, fast=0))
+    # the opt-in fast arithmetic (float32 sampling, first-order mid-points), same launch
+    fast_kernel_ms = kernel_alone(lambda tl, ta, tz: eng.step_oceandrift(grp, 'runge-kutta4', t_now, dt, tl, ta, tz, w_group=wgrp, fast=1))
+    # current advection only (no vertical advection): the plain kernel and its TMA-staged variant (shared-memory field boxes)
+    uv_kernel_ms = kernel_alone(lambda tl, ta, tz: eng.advect_current(grp, 'runge-kutta4', t_now, dt, tl, ta, tz))
     eng.set_tile(True)
-    tile_ms = []
-    for _ in range(5):
-        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tl, ta = st['lon'].clone(), st['lat'].clone()
-        torch.cuda.synchronize()
-        ka.record()
-        eng.advect_current(grp, 'runge-kutta4', st['t'], dt, tl, ta, st['z'])
-        kb.record()
-        torch.cuda.synchronize()
-        tile_ms.append(ka.elapsed_time(kb))
+    tile_kernel_ms = kernel_alone(lambda tl, ta, tz: eng.advect_current(grp, 'runge-kutta4', t_now, dt, tl, ta, tz))
     eng.set_tile(False)
-    tile_kernel_ms = float(np.median(tile_ms))
 
     # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
     grp.resident = [None] * grp.n_slots                     # forcing slabs come from pinned host memory again
-    o_lon, o_lat = torch.empty_like(h_lon).pin_memory(), torch.empty_like(h_lat).pin_memory()
+    wgrp.resident = [None] * wgrp.n_slots
+    o_lon, o_lat, o_z = torch.empty_like(h_lon).pin_memory(), torch.empty_like(h_lat).pin_memory(), torch.empty_like(h_z).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     t_e2e = times[0]
-    bufs = [(h_lon, h_lat), (o_lon, o_lat)]
+    bufs = [(h_lon, h_lat, h_z), (o_lon, o_lat, o_z)]
 
     def e2e_step(i, t):
         src, dst = bufs[i % 2], bufs[(i + 1) % 2]
-        eng.advect_current_host(grp, 'runge-kutta4', t, dt, src[0], src[1], h_z, dst[0], dst[1], chunks=args.e2e_chunks)
+        eng.step_oceandrift_host(grp, 'runge-kutta4', t, dt, src[0], src[1], src[2], dst[0], dst[1], dst[2], w_group=wgrp,
+                                 chunks=args.e2e_chunks)
 
     for i in range(2):
         e2e_step(i, t_e2e)
@@ -368,7 +351,7 @@ def run_b200(args):
     barrier()
     e2e_ms = g0.elapsed_time(g1)
 
-    # the link the end-to-end number lives on: this step's bytes (20 B in, 16 B out per particle) as two plain pinned
+    # the link the end-to-end number lives on: this step's bytes (20 B in, 20 B out per particle) as two plain pinned
     # copies running concurrently on two streams
     pcie = None
     if rank == 0:
@@ -390,13 +373,14 @@ def run_b200(args):
                     s_out.wait_event(pa)
                     o_lon.copy_(d_out, non_blocking=True)
                     o_lat.copy_(d_in, non_blocking=True)
+                    o_z.copy_(d_z2, non_blocking=True)
             torch.cuda.current_stream().wait_stream(s_in)
             torch.cuda.current_stream().wait_stream(s_out)
             pb.record()
             torch.cuda.synchronize()
             pms = pa.elapsed_time(pb) / reps
             pcie = {'ms_per_step_copies_only': pms, 'particle_steps_per_s_ceiling': n / (pms * 1e-3),
-                    'GBps_both_directions': n * 36 / pms / 1e6}
+                    'GBps_both_directions': n * 40 / pms / 1e6}
             del d_in, d_out, d_in2, d_z2
         except Exception as exc:        # the probe is informative only
             pcie = {'error': str(exc)}
@@ -413,9 +397,9 @@ def run_b200(args):
     value = n * world * args.steps / (ms_total * 1e-3)
     e2e_value = n * world * e2e_steps / (e2e_ms * 1e-3)
     peak, peak_src = measured_peak_hbm()
-    field_bytes = 2 * 2 * grid.nx * grid.ny * grid.nz * 4           # two time slabs x (u, v) float32
-    state_bytes = 44                                                  # lon, lat read + written (32), z, moving, factor (12)
-    b_alg = state_bytes * n + field_bytes                             # 65 B per particle-step at 10 M
+    field_bytes = 2 * 3 * grid.nx * grid.ny * grid.nz * 4           # two time slabs x (u, v, w) float32
+    state_bytes = 52                                                  # lon, lat read + written (32), z, moving, factor (12), z updated (8)
+    b_alg = state_bytes * n + field_bytes                             # 83.5 B per particle-step at 10 M with w
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
@@ -435,22 +419,22 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'OceanDrift RK4, synthetic 512x512x50 double-gyre u/v reader, %d particles per GPU, '
+        'config': {'workload': 'OceanDrift RK4 + vertical advection, synthetic 512x512x50 double-gyre u/v/w reader, %d particles per GPU, '
                                'dt=600 s (BASELINE configs[1]%s)' % (n, '; configs[2] sharding' if world > 1 else ''),
-                   'particles_per_gpu': n, 'field': '512x512x50 f32 u,v, hourly slabs', 'scheme': 'runge-kutta4',
+                   'particles_per_gpu': n, 'field': '512x512x50 f32 u,v (hourly slabs) + w', 'scheme': 'runge-kutta4',
                    'sort_every': args.sort_every, 'sort_ms': sort_ms, 'clock_ramp_s': args.ramp_seconds, 'mode': 'default arithmetic OD_MATH_SERIES: bit-exact field sampling (float64 index and weight arithmetic of the reference), '
                            'float64 short-arc series geodesic (round-off accurate, full Karney solution beyond its range)',
                    'parallelism': 'particle-index shards x%d, replicated field (NCCL broadcast of slabs: %.1f ms per slab pair)'
                                   % (world, 1e3 * t_bcast / PERIOD) if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 16,
-                'steps': e2e_steps, 'api': 'od_advect_current_host through Engine.advect_current_host (pinned host arrays in/out, %d-chunk '
+        'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 20,
+                'steps': e2e_steps, 'api': 'od_step_oceandrift_host through Engine.step_oceandrift_host (pinned host lon/lat/z in and out, %d-chunk '
                        'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
                 'pcie_probe': pcie},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4>', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
+                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4, extras> (current advection + vertical advection in one launch)', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
                      'loop_ms_p50': float(np.median(per_step)), 'loop_ms_p95': float(np.percentile(per_step, 95)),
                      'loop_ms_first20_mean': float(per_step[:20].mean()), 'host_us_per_launch_median': float(np.median(host_us)), 'host_us_per_launch_max': float(np.max(host_us)),
                      'algorithmic_bytes_per_launch': b_alg,
@@ -458,7 +442,9 @@ def run_b200(args):
                              'index and weight arithmetic, reproduced bit for bit), not by its 65 algorithmic bytes per '
                              'particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
-        'tma_tile': {'kernel_ms': tile_kernel_ms, 'note': 'opt-in OD_OPT_TILE: one cp.async.bulk.tensor.4d box per block; same bits; '
+        'current_only': {'kernel_ms': uv_kernel_ms, 'particle_steps_per_s_kernel': n / (uv_kernel_ms * 1e-3),
+                         'note': 'od_advect_current alone (u/v sampling and moves, no vertical advection), same particles'},
+        'tma_tile': {'kernel_ms': tile_kernel_ms, 'note': 'opt-in OD_OPT_TILE for current_only: one cp.async.bulk.tensor.4d box per block; same bits; '
                                                           'not faster than L1-served gathers on sorted particles (see DESIGN.md)'},
         'exact_replay_mode': {'kernel_ms': exact_kernel_ms, 'particle_steps_per_s_kernel': n / (exact_kernel_ms * 1e-3),
                               'note': 'OD_MATH_EXACT: the reference arithmetic operation by operation (float32 mid-point azimuth and '

@@ -211,6 +211,7 @@ typedef struct od_host_io {
     double* h_out_lat;
     int32_t chunks;
     int32_t pad_;
+    void* h_out_z;                /* od_step_oceandrift_host with vertical advection: updated depths (dtype as h_z; may alias h_z) */
 } od_host_io;
 
 int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, const od_host_io* io);
@@ -238,6 +239,10 @@ typedef struct od_step_args {
 } od_step_args;
 
 int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
+/* the fused step for HOST particle arrays (od_host_io above): a->cur.d_lon / d_lat / d_z and a->d_z_inout are ignored; the
+ * per-particle device arrays (d_factor, d_moving, d_wdf, d_diffusivity, d_rand_x / y) are indexed like the host arrays;
+ * the wind-noise array is not supported here. */
+int od_step_oceandrift_host(od_ctx* ctx, const od_step_args* a, const od_host_io* io);
 
 /* ---- Leeway ------------------------------------------------------------------------------------------
  * Leeway.update (models/leeway.py:430-494, capsizing excluded): leeway move + current move + jibing in one launch.

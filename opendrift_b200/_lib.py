@@ -34,7 +34,8 @@ class TimeSample(C.Structure):
 
 class HostIO(C.Structure):
     _fields_ = [('h_lon', C.c_void_p), ('h_lat', C.c_void_p), ('h_z', C.c_void_p),
-                ('h_out_lon', C.c_void_p), ('h_out_lat', C.c_void_p), ('chunks', C.c_int32), ('pad_', C.c_int32)]
+                ('h_out_lon', C.c_void_p), ('h_out_lat', C.c_void_p), ('chunks', C.c_int32), ('pad_', C.c_int32),
+                ('h_out_z', C.c_void_p)]
 
 
 class AdvectArgs(C.Structure):
@@ -109,6 +110,7 @@ SYMBOLS = {
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),
     'od_advect_current': (C.c_int, [_P, C.POINTER(AdvectArgs)]),
     'od_advect_current_host': (C.c_int, [_P, C.POINTER(AdvectArgs), C.POINTER(HostIO)]),
+    'od_step_oceandrift_host': (C.c_int, [_P, C.POINTER(StepArgs), C.POINTER(HostIO)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
     'od_leeway_step': (C.c_int, [_P, C.POINTER(LeewayArgs)]),
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -67,6 +67,7 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
 // ---------------------------------------------------------------------------------------------------------
 struct ExactMath {
     typedef GeodStart Start;
+    static constexpr bool kExactSampler = true;      // sample_uv == sample2: the horizontal weights can be shared
     OD_HDS Start start(double lat0) { return geod_start(lat0); }
     OD_HDS void midpoint(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
         rk_midpoint(s, lon0, ku, kv, dt32, mlon, mlat);
@@ -123,6 +124,7 @@ struct FastStart {
 
 struct FastMath {
     typedef FastStart Start;
+    static constexpr bool kExactSampler = false;
     OD_HDS Start start(double lat0) {
         Start st;
         double sd, cd;
@@ -245,7 +247,8 @@ struct StepParams {
     // (already scaled), or NULL; kinds present are flagged in noise_kinds (bit 0 normal, bit 1 uniform).
     const double* noise_cur;
     const double* noise_wind;     // [component][n] normal draws for the wind, or NULL
-    int32_t noise_kinds, pad1_;
+    int32_t noise_kinds;
+    int32_t w_same_grid;          // the vertical-velocity group has the geometry and levels of the current group: share index arithmetic
     // extras (od_step_oceandrift)
     int32_t wind_on, wdf_f64, w_on, w_at_surface, diff_on, zio_f64;   // zio_f64: dtype of z_inout
     GroupGeom gwind;
@@ -318,9 +321,79 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
     ov = sv / 6.0f;
 }
 
+// The wind move and the diffusion move of the fused step.  (Measured: making them __noinline__ to keep their code out of
+// the hot loop's instruction stream costs far more than it saves -- the calls give the kernel a 1.2 KB stack frame and
+// double its run time -- so they are inlined.)
+#if defined(__CUDACC__)
+#define OD_COLD static __host__ __device__ __forceinline__
+#else
+#define OD_COLD static
+#endif
+
+template <class MATH>
+OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, double lon0, double lat0,
+                         double* plon1, double* plat1) {
+    double lon1 = *plon1, lat1 = *plat1;
+    // ---- advect_wind (physics_methods.py:712-791): wind sampled at the start-of-step position
+    {
+        const VertW v0 = {0, 0, 1.0};
+        float xw, yw;
+        MATH::sample_uv(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+        if (p.noise_wind) {
+            xw = (float)OD_DADD((double)xw, p.noise_wind[i]);
+            yw = (float)OD_DADD((double)yw, p.noise_wind[p.n + i]);
+        }
+        const double wdd = fabs(p.wind_drift_depth);
+        const bool surface = z0 >= -wdd;
+        if (p.wdf_f64 || wdd != 0.0) {
+            double wdf = p.wdf_f64 ? ((const double*)p.wdf)[i] : (double)((const float*)p.wdf)[i];
+            if (wdd != 0.0) {
+                const double air = wdf;
+                wdf = OD_DMUL(wdf, OD_DADD(wdd, z0)) / wdd;
+                if (z0 > 0.0) wdf = air;
+            }
+            if (!surface) wdf = 0.0;
+            const double xv = OD_DMUL((double)xw, wdf), yv = OD_DMUL((double)yw, wdf);
+            if (xv != 0.0 || yv != 0.0) {
+                const typename MATH::Start g1 = MATH::start(lat1);
+                MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+            }
+        } else {
+            float wdf = ((const float*)p.wdf)[i];
+            if (!surface) wdf = 0.0f;
+            const float xv = OD_FMUL(xw, wdf), yv = OD_FMUL(yw, wdf);
+            if (xv != 0.0f || yv != 0.0f) {
+                const typename MATH::Start g1 = MATH::start(lat1);
+                MATH::move32(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+            }
+        }
+    }
+    *plon1 = lon1;
+    *plat1 = lat1;
+}
+
+template <class MATH>
+OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double* plon1, double* plat1) {
+    double lon1 = *plon1, lat1 = *plat1;
+    // ---- horizontal_diffusion (basemodel/__init__.py:1746-1772)
+    {
+        const float D = p.diffusivity ? p.diffusivity[i] : p.diffusivity_const;
+        const float s = sqrtf(OD_FMUL(2.0f, D) / p.adt32);
+        const double sd = OD_DMUL(mv, (double)s);
+        const double xv = OD_DMUL(sd, p.rand_x[i]), yv = OD_DMUL(sd, p.rand_y[i]);
+        if (xv != 0.0 || yv != 0.0) {
+            const typename MATH::Start g1 = MATH::start(lat1);
+            MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+        }
+    }
+    *plon1 = lon1;
+    *plat1 = lat1;
+}
+
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
-template <int SCHEME, bool F64, bool EXTRAS, class MATH = ExactMath>
+// EXTRAS: 0 current advection only; 1 all extras (wind move, vertical advection, diffusion move); 2 vertical advection only
+template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath>
 OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
                          const double* zsw, const double* zyw, const TileView& tv = TileView()) {
     const GroupGeom& g = p.cs.g;
@@ -335,15 +408,42 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
 
     // stage 1: the start-of-step environment
     float k1u, k1v;
+    HorizW h0;                     // horizontal cell / weights of the start-of-step position (exact samplers)
+    const bool share_h0 = EXTRAS != 0 && MATH::kExactSampler && p.w_on && p.w_same_grid;
+    if (share_h0 || (MATH::kExactSampler && !p.has_k1)) h0 = horiz_weights(g, lon0, lat0, p.pos_f32 != 0);
     if (p.has_k1) {
         k1u = p.k1u[i];
         k1v = p.k1v[i];
     } else {
-        MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0, tv);
+        if (MATH::kExactSampler) sample2_h(g, p.cs.t_start, vw, h0, k1u, k1v, tv);
+        else MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0, tv);
         add_current_noise(p, 0, i, k1u, k1v);
     }
     if (p.env_u) p.env_u[i] = k1u;
     if (p.env_v) p.env_v[i] = k1v;
+
+    if (EXTRAS) {
+        // (done here, next to the stage-1 sample whose cell and weights it can share; it only touches z)
+        // ---- vertical_advection (oceandrift.py:315-350): z = min(0, z + moving*w*dt); w sampled at the
+        // start-of-step depth, applied to the current depth (which vertical mixing may already have changed)
+        if (p.w_on) {
+            const bool zio32 = p.zio_f64 == 0;
+            const double zc = zio32 ? (double)((const float*)p.z_inout)[i] : ((const double*)p.z_inout)[i];
+            const bool applicable = p.w_at_surface ? (zc <= 0.0) : (zc < 0.0);
+            if (applicable) {
+                float w;
+                if (share_h0) {
+                    w = sample1_h(p.gw, p.pw, vw, h0);
+                } else {
+                    const VertW vww = vert_weights(p.gw, zsw, zyw, zt, zf32);
+                    w = MATH::sample_s(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
+                }
+                const double zn = fmin(0.0, OD_DADD(zc, OD_DMUL(OD_DMUL(mv, (double)w), p.dt)));
+                if (zio32) ((float*)p.z_inout)[i] = (float)zn;
+                else ((double*)p.z_inout)[i] = zn;
+            }
+        }
+    }
 
     float ru, rv;
     rk_velocity<SCHEME, MATH>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv);
@@ -357,66 +457,9 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         MATH::move32(gs, lon0, lat0, OD_FMUL(ru, f), OD_FMUL(rv, f), mv, p.dt, lon1, lat1);
     }
 
-    if (EXTRAS) {
-        // ---- advect_wind (physics_methods.py:712-791): wind sampled at the start-of-step position
-        if (p.wind_on) {
-            const VertW v0 = {0, 0, 1.0};
-            float xw, yw;
-            MATH::sample_uv(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
-            if (p.noise_wind) {
-                xw = (float)OD_DADD((double)xw, p.noise_wind[i]);
-                yw = (float)OD_DADD((double)yw, p.noise_wind[p.n + i]);
-            }
-            const double wdd = fabs(p.wind_drift_depth);
-            const bool surface = z0 >= -wdd;
-            if (p.wdf_f64 || wdd != 0.0) {
-                double wdf = p.wdf_f64 ? ((const double*)p.wdf)[i] : (double)((const float*)p.wdf)[i];
-                if (wdd != 0.0) {
-                    const double air = wdf;
-                    wdf = OD_DMUL(wdf, OD_DADD(wdd, z0)) / wdd;
-                    if (z0 > 0.0) wdf = air;
-                }
-                if (!surface) wdf = 0.0;
-                const double xv = OD_DMUL((double)xw, wdf), yv = OD_DMUL((double)yw, wdf);
-                if (xv != 0.0 || yv != 0.0) {
-                    const typename MATH::Start g1 = MATH::start(lat1);
-                    MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
-                }
-            } else {
-                float wdf = ((const float*)p.wdf)[i];
-                if (!surface) wdf = 0.0f;
-                const float xv = OD_FMUL(xw, wdf), yv = OD_FMUL(yw, wdf);
-                if (xv != 0.0f || yv != 0.0f) {
-                    const typename MATH::Start g1 = MATH::start(lat1);
-                    MATH::move32(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
-                }
-            }
-        }
-        // ---- vertical_advection (oceandrift.py:315-350): z = min(0, z + moving*w*dt); w sampled at the
-        // start-of-step depth, applied to the current depth (which vertical mixing may already have changed)
-        if (p.w_on) {
-            const bool zio32 = p.zio_f64 == 0;
-            const double zc = zio32 ? (double)((const float*)p.z_inout)[i] : ((const double*)p.z_inout)[i];
-            const bool applicable = p.w_at_surface ? (zc <= 0.0) : (zc < 0.0);
-            if (applicable) {
-                const VertW vww = vert_weights(p.gw, zsw, zyw, zt, zf32);
-                const float w = MATH::sample_s(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
-                const double zn = fmin(0.0, OD_DADD(zc, OD_DMUL(OD_DMUL(mv, (double)w), p.dt)));
-                if (zio32) ((float*)p.z_inout)[i] = (float)zn;
-                else ((double*)p.z_inout)[i] = zn;
-            }
-        }
-        // ---- horizontal_diffusion (basemodel/__init__.py:1746-1772)
-        if (p.diff_on) {
-            const float D = p.diffusivity ? p.diffusivity[i] : p.diffusivity_const;
-            const float s = sqrtf(OD_FMUL(2.0f, D) / p.adt32);
-            const double sd = OD_DMUL(mv, (double)s);
-            const double xv = OD_DMUL(sd, p.rand_x[i]), yv = OD_DMUL(sd, p.rand_y[i]);
-            if (xv != 0.0 || yv != 0.0) {
-                const typename MATH::Start g1 = MATH::start(lat1);
-                MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
-            }
-        }
+    if (EXTRAS == 1) {
+        if (p.wind_on) extras_wind<MATH>(p, i, z0, mv, lon0, lat0, &lon1, &lat1);
+        if (p.diff_on) extras_diffusion<MATH>(p, i, mv, &lon1, &lat1);
     }
     p.lon[i] = lon1;
     p.lat[i] = lat1;

@@ -308,9 +308,9 @@ OD_HD float combine(const GroupGeom& g, const PairRef& pr, const VertW& vw,
 }
 
 // Sample a 2-component group (e.g. x/y_sea_water_velocity) -> float32 u, v with fallback applied.
-OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
-                   float& u, float& v, bool pos_f32 = false, const TileView& tv = TileView()) {
-    const HorizW h = horiz_weights(g, lon, lat, pos_f32);
+// (the part after the horizontal index / weight arithmetic, so that groups on the same grid can share it)
+OD_HD void sample2_h(const GroupGeom& g, const PairRef& pr, const VertW& vw, const HorizW& h,
+                     float& u, float& v, const TileView& tv = TileView()) {
     float ru = NAN, rv = NAN;
     if (h.valid && pr.mode != 3) {
         const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
@@ -350,10 +350,14 @@ OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, doubl
     v = rv;
 }
 
-// Sample a 1-component group (e.g. upward_sea_water_velocity).
-OD_HD float sample1(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
-                     bool pos_f32 = false) {
+OD_HD void sample2(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
+                   float& u, float& v, bool pos_f32 = false, const TileView& tv = TileView()) {
     const HorizW h = horiz_weights(g, lon, lat, pos_f32);
+    sample2_h(g, pr, vw, h, u, v, tv);
+}
+
+// Sample a 1-component group (e.g. upward_sea_water_velocity).
+OD_HD float sample1_h(const GroupGeom& g, const PairRef& pr, const VertW& vw, const HorizW& h) {
     float r = NAN;
     if (h.valid && pr.mode != 3) {
         const long long layer = (long long)g.nx * g.ny;
@@ -379,6 +383,12 @@ OD_HD float sample1(const GroupGeom& g, const PairRef& pr, const VertW& vw, doub
     }
     if (!finite_f(r)) r = g.fallback[0];
     return r;
+}
+
+OD_HD float sample1(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat,
+                     bool pos_f32 = false) {
+    const HorizW h = horiz_weights(g, lon, lat, pos_f32);
+    return sample1_h(g, pr, vw, h);
 }
 
 }  // namespace od

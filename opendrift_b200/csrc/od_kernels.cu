@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(OD_BLOCK) update_positions_kernel(int64_t n, d
     lat[i] = la;
 }
 
-template <int SCHEME, bool F64, bool EXTRAS, class MATH>
+template <int SCHEME, bool F64, int EXTRAS, class MATH>
 __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const StepParams p) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
@@ -1016,7 +1016,7 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
 // blocks whose particles are too spread out (unsorted input, tile-row wrap) go to global memory as before.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int SCHEME, bool F64, bool EXTRAS, class MATH>
+template <int SCHEME, bool F64, int EXTRAS, class MATH>
 __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_tiled_kernel(const StepParams p, const __grid_constant__ CUtensorMap tmap,
                                                                             const float* tile_tex) {
     __shared__ LevelsSmem lv;
@@ -1100,7 +1100,7 @@ static const PairEntry* find_tmap(const Group& g, const float* tex) {
     return nullptr;
 }
 
-template <bool EXTRAS, class MATH>
+template <int EXTRAS, class MATH>
 static int launch_step_tiled(od_ctx* ctx, int scheme, bool f64, const StepParams& p, const PairEntry* pe) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
@@ -1114,7 +1114,7 @@ static int launch_step_tiled(od_ctx* ctx, int scheme, bool f64, const StepParams
     return OD_OK;
 }
 
-template <bool EXTRAS, class MATH>
+template <int EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
@@ -1140,13 +1140,13 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
         pe = find_tmap(ctx->groups[a->group_uv], p.cs.t_mid.tex);
     if (a->fast < 0 || a->fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_advect_current: unknown arithmetic mode");
     if (pe) {
-        if (a->fast == OD_MATH_FAST) return launch_step_tiled<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
-        if (a->fast == OD_MATH_SERIES) return launch_step_tiled<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
-        return launch_step_tiled<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        if (a->fast == OD_MATH_FAST) return launch_step_tiled<0, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        if (a->fast == OD_MATH_SERIES) return launch_step_tiled<0, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
+        return launch_step_tiled<0, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
     }
-    if (a->fast == OD_MATH_FAST) return launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
-    if (a->fast == OD_MATH_SERIES) return launch_step<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
-    return launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->fast == OD_MATH_FAST) return launch_step<0, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->fast == OD_MATH_SERIES) return launch_step<0, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    return launch_step<0, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
 }
 
 // advect_ocean_current on HOST arrays: the particle range is cut into chunks; each chunk's host->device copies, kernel
@@ -1154,8 +1154,11 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
 // chunks overlap each other (both directions) and the kernel.  The first and last chunks are half size: the pipeline
 // fills and drains faster.  Pinned host memory is needed for the copies to overlap.  Returns when the results are in
 // h_out_lon / h_out_lat.
-extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, const od_host_io* io) {
-    if (!ctx || !a || !io) return fail(ctx, OD_ERR_ARG, "od_advect_current_host: null argument");
+static int fill_step(od_ctx* ctx, const od_step_args* a, StepParams* pp);
+template <int EXTRAS>
+static int launch_step_mode(od_ctx* ctx, int mode, int scheme, bool f64, const StepParams& p);
+
+static int host_pipeline(od_ctx* ctx, const od_advect_args* a, const od_step_args* step, const od_host_io* io) {
     const int64_t n = a->n;
     if (n < 0 || (n > 0 && (!io->h_lon || !io->h_lat || !io->h_out_lon || !io->h_out_lat)))
         return fail(ctx, OD_ERR_ARG, "od_advect_current_host: null host arrays");
@@ -1166,13 +1169,23 @@ extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, cons
     const bool has_z = io->h_z != nullptr;
     if (gp && gp->defined && gp->desc.nz > 1 && !has_z) return fail(ctx, OD_ERR_ARG, "3-D current group needs z");
     // resolve the pairs once, on the caller's stream (uploads / pair packing were enqueued there)
-    od_advect_args b = *a;
     StepParams p;
     double dummy = 0.0;
-    b.n = 0;
-    b.d_lon = b.d_lat = &dummy;
-    b.d_z = has_z ? (const void*)&dummy : nullptr;
-    int rc = fill_current(ctx, &b, &p);
+    int rc;
+    if (step) {
+        od_step_args b = *step;
+        b.cur.n = 0;
+        b.cur.d_lon = b.cur.d_lat = &dummy;
+        b.cur.d_z = has_z ? (const void*)&dummy : nullptr;
+        if (b.group_w >= 0) b.d_z_inout = &dummy;
+        rc = fill_step(ctx, &b, &p);
+    } else {
+        od_advect_args b = *a;
+        b.n = 0;
+        b.d_lon = b.d_lat = &dummy;
+        b.d_z = has_z ? (const void*)&dummy : nullptr;
+        rc = fill_current(ctx, &b, &p);
+    }
     if (rc) return rc;
     if (n == 0) return OD_OK;
     if (a->fast < 0 || a->fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_advect_current_host: unknown arithmetic mode");
@@ -1238,15 +1251,24 @@ extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, cons
         q.lon = d_lon; q.lat = d_lat; q.z = has_z ? (const void*)d_z : nullptr;
         q.factor = a->d_factor ? (const void*)((const char*)a->d_factor + lo * fsz) : nullptr;
         q.moving = a->d_moving ? a->d_moving + lo : nullptr;
+        if (step) {
+            if (q.wind_on) q.wdf = (const char*)step->d_wdf + lo * (step->wdf_f64 ? 8 : 4);
+            if (q.w_on) { q.z_inout = d_z; q.zio_f64 = a->z_f64; }
+            if (q.diff_on) {
+                q.rand_x = step->d_rand_x + lo; q.rand_y = step->d_rand_y + lo;
+                if (step->d_diffusivity) q.diffusivity = step->d_diffusivity + lo;
+            }
+        }
         ctx->stream = st;
-        if (a->fast == OD_MATH_FAST) rc = launch_step<false, FastMath>(ctx, a->scheme, a->factor_f64 != 0, q);
-        else if (a->fast == OD_MATH_SERIES) rc = launch_step<false, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, q);
-        else rc = launch_step<false, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, q);
+        rc = !step ? launch_step_mode<0>(ctx, a->fast, a->scheme, a->factor_f64 != 0, q)
+                   : (!q.wind_on && !q.diff_on) ? launch_step_mode<2>(ctx, a->fast, a->scheme, a->factor_f64 != 0, q)
+                                                : launch_step_mode<1>(ctx, a->fast, a->scheme, a->factor_f64 != 0, q);
         ctx->stream = caller;
         if (rc) break;
         mark(st);
         CK(cudaMemcpyAsync(io->h_out_lon + lo, d_lon, m * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(io->h_out_lat + lo, d_lat, m * 8, cudaMemcpyDeviceToHost, st));
+        if (step && q.w_on) CK(cudaMemcpyAsync((char*)io->h_out_z + lo * zsz, d_z, m * zsz, cudaMemcpyDeviceToHost, st));
         mark(st);
         lo = hi;
     }
@@ -1267,10 +1289,14 @@ extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, cons
     return rc;
 }
 
-extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
-    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift: null argument");
-    CK(cudaSetDevice(ctx->device));
-    StepParams p;
+extern "C" int od_advect_current_host(od_ctx* ctx, const od_advect_args* a, const od_host_io* io) {
+    if (!ctx || !a || !io) return fail(ctx, OD_ERR_ARG, "od_advect_current_host: null argument");
+    return host_pipeline(ctx, a, nullptr, io);
+}
+
+// extras of the fused OceanDrift step (wind move, vertical advection, horizontal diffusion) into StepParams
+static int fill_step(od_ctx* ctx, const od_step_args* a, StepParams* pp) {
+    StepParams& p = *pp;
     int rc = fill_current(ctx, &a->cur, &p);
     if (rc) return rc;
     if (a->group_wind >= 0) {
@@ -1298,6 +1324,13 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         if (rc) return rc;
         p.z_inout = a->d_z_inout;
         p.zio_f64 = a->z_inout_f64;
+        // same reader block as the current (one grid, one level table): the kernel reuses the cell and the weights
+        const Group& gu = ctx->groups[a->cur.group_uv];
+        const Group& gw = ctx->groups[a->group_w];
+        const od_group_desc &du = gu.desc, &dw = gw.desc;
+        p.w_same_grid = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x &&
+                        du.x0 == dw.x0 && du.xspan == dw.xspan && du.y0 == dw.y0 && du.yspan == dw.yspan && du.xmin == dw.xmin &&
+                        du.xmax == dw.xmax && du.ymin == dw.ymin && du.ymax == dw.ymax && gu.h_levels == gw.h_levels;
     }
     if (a->d_rand_x) {
         if (!a->d_rand_y) return fail(ctx, OD_ERR_ARG, "diffusion needs both random arrays");
@@ -1306,11 +1339,37 @@ extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
         p.diffusivity = a->d_diffusivity;
         p.diffusivity_const = a->diffusivity_const;
     }
+    return OD_OK;
+}
+
+template <int EXTRAS>
+static int launch_step_mode(od_ctx* ctx, int mode, int scheme, bool f64, const StepParams& p) {
+    if (mode == OD_MATH_FAST) return launch_step<EXTRAS, FastMath>(ctx, scheme, f64, p);
+    if (mode == OD_MATH_SERIES) return launch_step<EXTRAS, SeriesMath>(ctx, scheme, f64, p);
+    return launch_step<EXTRAS, ExactMath>(ctx, scheme, f64, p);
+}
+
+extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift: null argument");
+    CK(cudaSetDevice(ctx->device));
+    StepParams p;
+    int rc = fill_step(ctx, a, &p);
+    if (rc) return rc;
     if (a->cur.n == 0) return OD_OK;
     if (a->cur.fast < 0 || a->cur.fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift: unknown arithmetic mode");
-    if (a->cur.fast == OD_MATH_FAST) return launch_step<true, FastMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
-    if (a->cur.fast == OD_MATH_SERIES) return launch_step<true, SeriesMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
-    return launch_step<true, ExactMath>(ctx, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    // vertical advection only: the kernel variant without the wind / diffusion code (smaller instruction footprint)
+    if (!p.wind_on && !p.diff_on) return launch_step_mode<2>(ctx, a->cur.fast, a->cur.scheme, a->cur.factor_f64 != 0, p);
+    return launch_step_mode<1>(ctx, a->cur.fast, a->cur.scheme, a->cur.factor_f64 != 0, p);
+}
+
+// The fused step on HOST arrays (see od_advect_current_host): lon / lat / z in, lon / lat (/ z when vertical advection is
+// on) out.  Per-particle device arrays of the step (factor, moving, wdf, diffusivity, random draws) are indexed like
+// the host arrays.
+extern "C" int od_step_oceandrift_host(od_ctx* ctx, const od_step_args* a, const od_host_io* io) {
+    if (!ctx || !a || !io) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift_host: null argument");
+    if (a->d_noise_wind) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift_host: noise arrays are not supported on the host path");
+    if (a->group_w >= 0 && (!io->h_z || !io->h_out_z)) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift_host: vertical advection needs h_z and h_out_z");
+    return host_pipeline(ctx, &a->cur, a, io);
 }
 
 extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {

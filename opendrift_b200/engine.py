@@ -363,14 +363,9 @@ class Engine:
                           truncate_below, env_out, pos_f32, fast, noise, noise_kinds)
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
 
-    def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
-                        truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
-                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=None, noise=None, noise_kinds=0,
-                        wind_noise=None):
-        """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
-        array that vertical advection updates -- a different buffer after vertical mixing."""
-        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
-        s = StepArgs()
+    def _step_args(self, s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf,
+                   wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds,
+                   wind_noise):
         self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
                           None, truncate_below, None, pos_f32, fast, noise, noise_kinds)
         s.group_wind = -1
@@ -396,7 +391,59 @@ class Engine:
                 s.d_diffusivity = diffusivity.data_ptr()
             else:
                 s.diffusivity_const = float(diffusivity)
+
+    def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
+                        truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
+                        w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=None, noise=None, noise_kinds=0,
+                        wind_noise=None):
+        """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
+        array that vertical advection updates -- a different buffer after vertical mixing."""
+        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        s = StepArgs()
+        self._step_args(s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf, wind_drift_depth,
+                        w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds, wind_noise)
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
+
+    @staticmethod
+    def _host_ptr(x, dtypes):
+        if x is None:
+            return None, None
+        if isinstance(x, np.ndarray):
+            assert x.dtype in [np.dtype(d) for d in dtypes] and x.flags['C_CONTIGUOUS']
+            return x.ctypes.data, x.dtype.itemsize
+        assert not x.is_cuda and x.is_contiguous() and x.element_size() in [np.dtype(d).itemsize for d in dtypes]
+        return x.data_ptr(), x.element_size()
+
+    def _host_io(self, h_lon, h_lat, h_z, h_out_lon, h_out_lat, h_out_z, chunks):
+        io = _lib.HostIO()
+        io.h_lon, _ = self._host_ptr(h_lon, ['f8'])
+        io.h_lat, _ = self._host_ptr(h_lat, ['f8'])
+        io.h_z, zsz = self._host_ptr(h_z, ['f4', 'f8'])
+        io.h_out_lon, _ = self._host_ptr(h_lon if h_out_lon is None else h_out_lon, ['f8'])
+        io.h_out_lat, _ = self._host_ptr(h_lat if h_out_lat is None else h_out_lat, ['f8'])
+        io.h_out_z, zo = self._host_ptr(h_z if h_out_z is None else h_out_z, ['f4', 'f8'])
+        assert zo == zsz
+        io.chunks = int(chunks)
+        torch = self.torch
+        if not hasattr(self, '_host_dummy'):
+            self._host_dummy = (self.empty(1, torch.float64), self.empty(1, torch.float64), self.empty(1, torch.float32),
+                                self.empty(1, torch.float64))
+        dz = None if h_z is None else (self._host_dummy[3] if zsz == 8 else self._host_dummy[2])
+        return io, dz
+
+    def step_oceandrift_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None, h_out_z=None,
+                             factor=None, moving=None, truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1,
+                             w_group=None, w_at_surface=False, rand=None, diffusivity=None, chunks=0, pos_f32=False, fast=None):
+        """The fused OceanDrift step for HOST arrays (od_step_oceandrift_host): positions and depths in, positions (and
+        depths, when vertical advection is on) out, pipelined in chunks like advect_current_host."""
+        io, dz = self._host_io(h_lon, h_lat, h_z, h_out_lon, h_out_lat, h_out_z, chunks)
+        dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
+        s = StepArgs()
+        self._step_args(s, group, scheme, t, dts, dt, self._host_dummy[0], self._host_dummy[1], dz, factor, moving,
+                        truncate_below, wind, wdf, wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, None,
+                        fast, None, 0, None)
+        s.cur.n = int(h_lon.shape[0])
+        self._check(self.lib.od_step_oceandrift_host(self.ctx, C.byref(s), C.byref(io)))
 
     def advect_current_host(self, group, scheme, t, dt, h_lon, h_lat, h_z=None, h_out_lon=None, h_out_lat=None,
                             factor=None, moving=None, chunks=0, pos_f32=False, fast=None):
@@ -405,33 +452,12 @@ class Engine:
         host->device copy, kernel and device->host copy are pipelined on three CUDA streams, so that the PCIe
         transfers of neighbouring chunks overlap each other and the kernel.  Results land in h_out_lon / h_out_lat
         (default: in place).  Returns after everything has completed."""
-        torch = self.torch
-
-        def host_ptr(x, dtypes):
-            if x is None:
-                return None, None
-            if isinstance(x, np.ndarray):
-                assert x.dtype in [np.dtype(d) for d in dtypes] and x.flags['C_CONTIGUOUS']
-                return x.ctypes.data, x.dtype.itemsize
-            assert not x.is_cuda and x.is_contiguous() and x.element_size() in [np.dtype(d).itemsize for d in dtypes]
-            return x.data_ptr(), x.element_size()
-        n = int(h_lon.shape[0])
-        io = _lib.HostIO()
-        io.h_lon, _ = host_ptr(h_lon, ['f8'])
-        io.h_lat, _ = host_ptr(h_lat, ['f8'])
-        io.h_z, zsz = host_ptr(h_z, ['f4', 'f8'])
-        io.h_out_lon, _ = host_ptr(h_lon if h_out_lon is None else h_out_lon, ['f8'])
-        io.h_out_lat, _ = host_ptr(h_lat if h_out_lat is None else h_out_lat, ['f8'])
-        io.chunks = int(chunks)
-        if not hasattr(self, '_host_dummy'):
-            self._host_dummy = (self.empty(1, torch.float64), self.empty(1, torch.float64), self.empty(1, torch.float32),
-                                self.empty(1, torch.float64))
+        io, dz = self._host_io(h_lon, h_lat, h_z, h_out_lon, h_out_lat, None, chunks)
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
-        dz = None if h_z is None else (self._host_dummy[3] if zsz == 8 else self._host_dummy[2])
         self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, self._host_dummy[0], self._host_dummy[1], dz,
                           factor, moving, None, None, None, pos_f32, fast)
-        a.n = n
+        a.n = int(h_lon.shape[0])
         self._check(self.lib.od_advect_current_host(self.ctx, C.byref(a), C.byref(io)))
 
     def leeway_step(self, wind, cur, t, dt, lon, lat, el, moving=None, status=None, ids=None, rand=None, seed=0,

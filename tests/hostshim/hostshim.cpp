@@ -116,9 +116,9 @@ struct hs_step_args {
 
 template <int S, bool F>
 static void run(const StepParams& p, const GroupGeom& gw, int fast = 0) {
-    if (fast == 2) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, SeriesMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
-    else if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
-    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, true, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    if (fast == 2) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, SeriesMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
 }
 
 extern "C" {
@@ -143,6 +143,12 @@ int hs_step(const hs_step_args* a) {
         p.w_on = 1; p.w_at_surface = a->w_at_surface; p.gw = make_geom(a->g_w, l3); p.pw = make_pair(a->t_w);
         p.z_inout = a->z_inout;
         p.zio_f64 = a->z_inout_f64;
+        const hs_group &du = a->g_uv, &dw = a->g_w;
+        bool same = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x &&
+                    du.x0 == dw.x0 && du.xspan == dw.xspan && du.y0 == dw.y0 && du.yspan == dw.yspan && du.xmin == dw.xmin &&
+                    du.xmax == dw.xmax && du.ymin == dw.ymin && du.ymax == dw.ymax;
+        for (int k = 0; same && du.nz > 1 && k < du.nz; ++k) same = du.z_levels[k] == dw.z_levels[k];
+        p.w_same_grid = same ? 1 : 0;
     }
     if (a->rand_x) {
         p.diff_on = 1; p.rand_x = a->rand_x; p.rand_y = a->rand_y; p.diffusivity = a->diffusivity;

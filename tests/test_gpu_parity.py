@@ -324,3 +324,36 @@ def test_host_array_entry_point_matches_device_path(eng, chunks):
     eng.advect_current_host(grp, 'runge-kutta', t, dt, o_lon, o_lat, z.astype(np.float64), chunks=chunks)
     assert np.array_equal(o_lon, dl.cpu().numpy()) and np.array_equal(o_lat, da.cpu().numpy())
     eng.advect_current_host(grp, 'runge-kutta', t, dt, np.empty(0), np.empty(0), np.empty(0, dtype=np.float32), chunks=chunks)
+
+
+@pytest.mark.parametrize('chunks', [0, 1, 5])
+def test_fused_step_host_entry_point_matches_device_path(eng, chunks):
+    """od_step_oceandrift_host == od_step_oceandrift (wind move, vertical advection, horizontal diffusion), bit for bit,
+    including the updated depths."""
+    from opendrift_b200 import synthetic as syn
+    grid = syn.GridSpec(nx=64, ny=48, nz=12)
+    g2 = syn.GridSpec(nx=64, ny=48, nz=1)
+    times = syn.slab_times(3)
+    uv = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times]
+    wnd = [syn.wind_xy(g2, (t - syn.T0).total_seconds()) for t in times]
+    wv = syn.upward_w(grid)
+    cur = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, lambda ti, c: uv[ti][c], (0.0, 0.0))
+    wind = eng.add_group(grid.lon, grid.lat, None, 2, times, lambda ti, c: wnd[ti][c], (0.0, 0.0))
+    wgrp = eng.add_group(grid.lon, grid.lat, grid.z, 1, times, lambda ti, c: wv, (0.0,))
+    rng = np.random.default_rng(10 + chunks)
+    n = 60001
+    lon = rng.uniform(0.05, 1.2, n)
+    lat = rng.uniform(55.02, 55.45, n)
+    z = rng.uniform(-20.0, 0.0, n).astype(np.float32)
+    z[:5000] = 0.0
+    wdf = eng.to_device(np.float32(0.02) * np.ones(n))
+    moving = eng.to_device((rng.uniform(size=n) > 0.1).astype(np.int32))
+    rand = (eng.to_device(rng.normal(size=n)), eng.to_device(rng.normal(size=n)))
+    t, dt = times[0] + timedelta(seconds=900), timedelta(seconds=600)
+    kw = dict(moving=moving, wind=wind, wdf=wdf, wind_drift_depth=0.1, w_group=wgrp, rand=rand, diffusivity=5.0)
+    dl, da, dz = eng.to_device(lon), eng.to_device(lat), eng.to_device(z)
+    eng.step_oceandrift(cur, 'runge-kutta4', t, dt, dl, da, dz, **kw)
+    o_lon, o_lat, o_z = np.empty(n), np.empty(n), np.empty(n, np.float32)
+    eng.step_oceandrift_host(cur, 'runge-kutta4', t, dt, lon.copy(), lat.copy(), z.copy(), o_lon, o_lat, o_z, chunks=chunks, **kw)
+    assert np.array_equal(o_lon, dl.cpu().numpy()) and np.array_equal(o_lat, da.cpu().numpy())
+    assert np.array_equal(o_z, dz.cpu().numpy()) and np.abs(o_z - z).max() > 1e-3
