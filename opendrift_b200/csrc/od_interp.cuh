@@ -309,6 +309,23 @@ OD_HD float combine(const GroupGeom& g, const PairRef& pr, const VertW& vw,
 
 // Sample a 2-component group (e.g. x/y_sea_water_velocity) -> float32 u, v with fallback applied.
 // (the part after the horizontal index / weight arithmetic, so that groups on the same grid can share it)
+// the four horizontal results (component u, v x time A, B) of one layer: four corner texels, four bilinears
+struct LayerVals { float uA, vA, uB, vB; };
+
+OD_HD LayerVals layer_bilin(const HorizW& h, const float* lp, int o00, int o01, int o10, int o11, int mode) {
+    const Tex4 a00 = fetch4(lp, o00), a01 = fetch4(lp, o01), a10 = fetch4(lp, o10), a11 = fetch4(lp, o11);
+    LayerVals r = {0.f, 0.f, 0.f, 0.f};
+    if (mode != 2) {
+        r.uA = bilin(h, a00.x, a01.x, a10.x, a11.x);
+        r.vA = bilin(h, a00.y, a01.y, a10.y, a11.y);
+    }
+    if (mode != 1) {
+        r.uB = bilin(h, a00.z, a01.z, a10.z, a11.z);
+        r.vB = bilin(h, a00.w, a01.w, a10.w, a11.w);
+    }
+    return r;
+}
+
 OD_HD void sample2_h(const GroupGeom& g, const PairRef& pr, const VertW& vw, const HorizW& h,
                      float& u, float& v, const TileView& tv = TileView()) {
     float ru = NAN, rv = NAN;
@@ -316,32 +333,17 @@ OD_HD void sample2_h(const GroupGeom& g, const PairRef& pr, const VertW& vw, con
         const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
         const int r0 = 4 * h.iy * ts.lx, r1 = 4 * h.iy1 * ts.lx;
         const int o00 = r0 + 4 * h.ix, o01 = r0 + 4 * h.ix1, o10 = r1 + 4 * h.ix, o11 = r1 + 4 * h.ix1;
-        const float* la = layer_ptr(ts, vw.ia);
-        const Tex4 a00 = fetch4(la, o00), a01 = fetch4(la, o01), a10 = fetch4(la, o10), a11 = fetch4(la, o11);
-        Tex4 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
+        // one layer at a time: four texels live instead of eight (the kernel runs at 64 registers per thread)
+        const LayerVals A = layer_bilin(h, layer_ptr(ts, vw.ia), o00, o01, o10, o11, pr.mode);
+        LayerVals B = A;
         if (g.nz > 1) {
-            const float* lb = layer_ptr(ts, vw.ib);
-            b00 = fetch4(lb, o00); b01 = fetch4(lb, o01); b10 = fetch4(lb, o10); b11 = fetch4(lb, o11);
+#if defined(__CUDA_ARCH__) && defined(OD_LAYER_FENCE)
+            asm volatile("" ::: "memory");
+#endif
+            B = layer_bilin(h, layer_ptr(ts, vw.ib), o00, o01, o10, o11, pr.mode);
         }
-        float uaA = 0.f, ubA = 0.f, uaB = 0.f, ubB = 0.f, vaA = 0.f, vbA = 0.f, vaB = 0.f, vbB = 0.f;
-        if (pr.mode != 2) {
-            uaA = bilin(h, a00.x, a01.x, a10.x, a11.x);
-            vaA = bilin(h, a00.y, a01.y, a10.y, a11.y);
-            if (g.nz > 1) {
-                ubA = bilin(h, b00.x, b01.x, b10.x, b11.x);
-                vbA = bilin(h, b00.y, b01.y, b10.y, b11.y);
-            }
-        }
-        if (pr.mode != 1) {
-            uaB = bilin(h, a00.z, a01.z, a10.z, a11.z);
-            vaB = bilin(h, a00.w, a01.w, a10.w, a11.w);
-            if (g.nz > 1) {
-                ubB = bilin(h, b00.z, b01.z, b10.z, b11.z);
-                vbB = bilin(h, b00.w, b01.w, b10.w, b11.w);
-            }
-        }
-        ru = combine(g, pr, vw, uaA, ubA, uaB, ubB);
-        rv = combine(g, pr, vw, vaA, vbA, vaB, vbB);
+        ru = combine(g, pr, vw, A.uA, B.uA, A.uB, B.uB);
+        rv = combine(g, pr, vw, A.vA, B.vA, A.vB, B.vB);
     }
     // masked_invalid -> fallback (environment.py:782-791); fallback NaN = keep missing
     if (!finite_f(ru)) ru = g.fallback[0];
