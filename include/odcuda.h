@@ -330,8 +330,22 @@ typedef struct od_mix_args {
     int32_t z_in_f64, tv_f64;
     int32_t mix_at_surface;       /* drift:vertical_mixing_at_surface */
     int32_t pos_f32;              /* see od_interp */
+    int32_t model;                /* vertical_mixing:diffusivitymodel as the reference resolves it (oceandrift.py:429-453):
+                                     0 OD_MIX_ENVIRONMENT: the profile of group_k;  otherwise group_k is ignored and the
+                                     column is analytical on 1 m levels mixing_z = -arange(nlev):
+                                     1 OD_MIX_LARGE1994, 2 OD_MIX_SUNDBY1983 (physics_methods.py:203-249), 3 OD_MIX_CONSTANT */
+    int32_t nlev;                 /* analytical models: len(-arange(0, max(MLD) + 2)) */
     int32_t pad_;
+    const float* d_wind_speed;    /* [n] float32 sqrt(x_wind^2 + y_wind^2) at the start of the step (models 1, 2) */
+    const float* d_mld;           /* [n] float32 ocean_mixed_layer_thickness, or NULL -> mld_const */
+    double mld_const;
+    double background;            /* vertical_mixing:background_diffusivity */
+    double k_const;               /* model 3: the constant diffusivity */
 } od_mix_args;
+#define OD_MIX_ENVIRONMENT 0
+#define OD_MIX_LARGE1994 1
+#define OD_MIX_SUNDBY1983 2
+#define OD_MIX_CONSTANT 3
 
 int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a);
 

@@ -14,6 +14,7 @@ OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
 OD_LON_0_360, OD_LON_PM180 = 0, 1
 OD_OPT_TILE = 1
 OD_MATH_EXACT, OD_MATH_FAST, OD_MATH_SERIES = 0, 1, 2
+OD_MIX_ENVIRONMENT, OD_MIX_LARGE1994, OD_MIX_SUNDBY1983, OD_MIX_CONSTANT = 0, 1, 2, 3
 OD_MAX_LEVELS = 128
 OD_MAX_GROUPS = 64
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
@@ -67,7 +68,9 @@ class MixArgs(C.Structure):
                 ('d_rand', C.c_void_p), ('d_sea_floor', C.c_void_p), ('dt_mix', C.c_double),
                 ('sea_floor_const', C.c_double), ('seed', C.c_uint64), ('step_index', C.c_int32),
                 ('z_in_f64', C.c_int32), ('tv_f64', C.c_int32), ('mix_at_surface', C.c_int32),
-                ('pos_f32', C.c_int32), ('pad_', C.c_int32)]
+                ('pos_f32', C.c_int32), ('model', C.c_int32), ('nlev', C.c_int32), ('pad_', C.c_int32),
+                ('d_wind_speed', C.c_void_p), ('d_mld', C.c_void_p), ('mld_const', C.c_double),
+                ('background', C.c_double), ('k_const', C.c_double)]
 
 
 class LeewayArgs(C.Structure):

@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const Step
 __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     __shared__ double xs[OD_MAX_LEVELS];
     __shared__ double xy[OD_MAX_LEVELS];
-    for (int i = threadIdx.x; i < p.g.nz; i += blockDim.x) {
+    for (int i = threadIdx.x; p.model == 0 && i < p.g.nz; i += blockDim.x) {
         xs[i] = p.xs[i];
         xy[i] = p.xy[i];
     }
@@ -1451,30 +1451,44 @@ extern "C" int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a) {
 
 extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {
     if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: null argument");
-    int rc = need_group(ctx, a->group_k, 1);
-    if (rc) return rc;
-    const Group& g = ctx->groups[a->group_k];
-    if (g.desc.nz < 2) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: the diffusivity group must be 3-D");
     if (a->n < 0 || a->ntimes < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_z_in || !a->d_z_out)))
         return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: bad arguments");
-    if (a->n == 0) return OD_OK;
-    CK(cudaSetDevice(ctx->device));
+    if (a->model < OD_MIX_ENVIRONMENT || a->model > OD_MIX_CONSTANT) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: unknown diffusivity model");
     MixParams p;
     memset(&p, 0, sizeof(p));
-    p.g = make_geom(g);
-    rc = resolve_pair(ctx, a->group_k, a->t_k, &p.pr);
-    if (rc) return rc;
+    if (a->model == OD_MIX_ENVIRONMENT) {
+        int rc = need_group(ctx, a->group_k, 1);
+        if (rc) return rc;
+        const Group& g = ctx->groups[a->group_k];
+        if (g.desc.nz < 2) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: the diffusivity group must be 3-D");
+        if (a->n == 0) return OD_OK;
+        CK(cudaSetDevice(ctx->device));
+        p.g = make_geom(g);
+        rc = resolve_pair(ctx, a->group_k, a->t_k, &p.pr);
+        if (rc) return rc;
+        p.zl = g.d_zl; p.xs = g.d_mxs; p.xy = g.d_mxy;
+        const std::vector<double>& lv = g.h_levels;
+        p.uniform_dz = 1;
+        p.dz0 = lv[1] - lv[0];
+        for (size_t k = 1; k + 1 < lv.size(); ++k)
+            if (lv[k + 1] - lv[k] != p.dz0) p.uniform_dz = 0;
+    } else {
+        if (a->nlev < 2 || a->nlev > 65535) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: analytical models need 2 <= nlev <= 65535");
+        if (a->model != OD_MIX_CONSTANT && !a->d_wind_speed) return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: wind speed array missing");
+        if (a->n == 0) return OD_OK;
+        CK(cudaSetDevice(ctx->device));
+        p.g.nz = a->nlev;
+        p.uniform_dz = 1;
+        p.dz0 = -1.0;                       // mixing_z = -arange(nlev)
+        p.wind_speed = a->d_wind_speed; p.mld = a->d_mld; p.mld_const = (float)a->mld_const;
+        p.background = a->background; p.k_const = a->k_const;
+    }
+    p.model = a->model;
     p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z_in = a->d_z_in; p.z_out = a->d_z_out;
     p.moving = a->d_moving; p.terminal_velocity = a->d_terminal_velocity; p.ids = a->d_ids; p.rand = a->d_rand;
     p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.sea_floor = a->d_sea_floor;
     p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
     p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
-    p.zl = g.d_zl; p.xs = g.d_mxs; p.xy = g.d_mxy;
-    const std::vector<double>& lv = g.h_levels;
-    p.uniform_dz = 1;
-    p.dz0 = lv[1] - lv[0];
-    for (size_t k = 1; k + 1 < lv.size(); ++k)
-        if (lv[k + 1] - lv[k] != p.dz0) p.uniform_dz = 0;
     mix_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;

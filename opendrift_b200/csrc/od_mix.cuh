@@ -60,9 +60,38 @@ struct MixParams {
     const double* zl;            // [nz] block level depths as the reader gives them (mixing_z)
     const double* xs;            // [nz] -mixing_z sorted increasing
     const double* xy;            // [nz] index of each xs entry
-    int32_t uniform_dz, pad_;
+    int32_t uniform_dz;
+    // Analytical diffusivity (vertical_mixing:diffusivitymodel other than a usable ocean-model field, oceandrift.py:429-453):
+    // 1 m levels mixing_z = -arange(nlev), nlev = int(ceil(max(MLD) + 2)); K from the wind speed and the mixed layer depth.
+    int32_t model;               // 0 environment profile, 1 windspeed_Large1994, 2 windspeed_Sundby1983, 3 constant
     double dz0;                  // np.diff(mixing_z)[0] when the spacing is uniform
+    const float* wind_speed;     // [n] float32 sqrt(x_wind^2 + y_wind^2) at the start of the step
+    const float* mld;            // [n] float32 ocean_mixed_layer_thickness, or NULL -> mld_const
+    float mld_const, pad2_;
+    double background;           // vertical_mixing:background_diffusivity
+    double k_const;              // model 3
 };
+
+// physics_methods.py:217-249 (Large et al. 1994) and :203-215 (Sundby 1983) for one level (depth d metres) of one
+// particle, in NumPy's dtype flow: float32 wind stress and MLD factors, float64 depth ratio.
+OD_HD double k_analytic(const MixParams& p, float ws, float m, int l) {
+    const double d = (double)l, bg = p.background;
+    if (p.model == 3) return p.k_const;
+    if (p.model == 2) {
+        double K = OD_DADD(76.1e-4, (double)OD_FMUL(OD_FMUL((float)2.26e-4, ws), ws));
+        if (d > (double)OD_FADD(m, -1.0f)) K = OD_DADD(K, bg) / 2.0;
+        if (d >= (double)m) K = bg;
+        return K;
+    }
+    const float stress = OD_FMUL(OD_FMUL(OD_FMUL(ws, ws), (float)1.25e-3), (float)1.22);
+    const double sigma = d / (double)m;
+    double G = OD_DADD(OD_DADD(sigma, OD_DMUL(-2.0, OD_DMUL(sigma, sigma))), pow(sigma, 3.0));
+    if (G >= 1.0) G = OD_DMUL(G, 0.0);
+    const float c = OD_FMUL(OD_FMUL(m, (float)0.2), (float)0.4);
+    double K = OD_DADD(OD_DMUL(OD_DMUL((double)c, G), (double)stress), OD_DMUL(sigma, bg));
+    if (d >= (double)m) K = bg;
+    return K;
+}
 
 // One level of the particle's diffusivity column (environment profile), on demand.
 OD_HD double k_level_raw(const MixParams& p, const HorizW& h, int l) {
@@ -96,6 +125,7 @@ OD_HD double k_level(const MixParams& p, const HorizW& h, int l) {
 struct KWindow {
     double v[OD_MIX_WINDOW];
     int lo;
+    float ws, mld;               // analytical models: this particle's wind speed and mixed layer depth
 };
 
 OD_HD void k_window_fill(const MixParams& p, const HorizW& h, KWindow& w, int centre) {
@@ -104,7 +134,8 @@ OD_HD void k_window_fill(const MixParams& p, const HorizW& h, KWindow& w, int ce
     if (lo > nz - OD_MIX_WINDOW) lo = nz - OD_MIX_WINDOW;
     if (lo < 0) lo = 0;
     w.lo = lo;
-    for (int k = 0; k < OD_MIX_WINDOW; ++k) w.v[k] = (lo + k < nz) ? k_level(p, h, lo + k) : 0.0;
+    for (int k = 0; k < OD_MIX_WINDOW; ++k)
+        w.v[k] = (lo + k < nz) ? (p.model ? k_analytic(p, w.ws, w.mld, lo + k) : k_level(p, h, lo + k)) : 0.0;
 }
 
 OD_HD double k_get(const MixParams& p, const HorizW& h, KWindow& w, int l) {
@@ -137,9 +168,16 @@ OD_HD double neg_gradient(const MixParams& p, const HorizW& h, KWindow& w, int l
 OD_HD int nearest_level(const MixParams& p, const double* xs, const double* xy, double x_new) {
     const int nz = p.g.nz;
     double y;
-    if (x_new < xs[0]) y = 0.0;
-    else if (x_new > xs[nz - 1]) y = (double)(nz - 1);
-    else {
+    const double x_first = p.model ? 0.0 : xs[0], x_last = p.model ? (double)(nz - 1) : xs[nz - 1];
+    if (x_new < x_first) y = 0.0;
+    else if (x_new > x_last) y = (double)(nz - 1);
+    else if (p.model) {                      // levels 0, 1, 2, ...: the table is its own index
+        const int lo = (int)ceil(x_new);      // searchsorted(side='left')
+        const int idx = lo < 1 ? 1 : (lo > nz - 1 ? nz - 1 : lo);
+        const double x0 = (double)(idx - 1);
+        const double slope = OD_DSUB((double)idx, x0) / OD_DSUB((double)idx, x0);
+        y = OD_DADD(OD_DMUL(slope, OD_DSUB(x_new, x0)), x0);
+    } else {
         int lo = 0, hi = nz;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -156,9 +194,17 @@ OD_HD int nearest_level(const MixParams& p, const double* xs, const double* xy, 
 OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const double* xy) {
     const GroupGeom& g = p.g;
     // the particle's diffusivity column (environment profile) is evaluated lazily, a window of levels at a time
-    const HorizW h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
+    HorizW h;
     KWindow kw;
     kw.lo = -(1 << 20);
+    kw.ws = kw.mld = 0.0f;
+    if (p.model) {
+        h.valid = false;
+        kw.ws = p.wind_speed ? p.wind_speed[i] : 0.0f;
+        kw.mld = p.mld ? p.mld[i] : p.mld_const;
+    } else {
+        h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
+    }
 
     // ---- inner loop ---------------------------------------------------------------------------------------------
     double z = p.z_in_f64 ? ((const double*)p.z_in)[i] : (double)((const float*)p.z_in)[i];

@@ -510,15 +510,39 @@ class Engine:
         a.dt, a.hs_mode, a.profile = float(dt), int(hs_mode), self.PROFILES[profile]
         self._check(self.lib.od_stokes_drift(self.ctx, C.byref(a)))
 
+    MIX_MODELS = {'environment': _lib.OD_MIX_ENVIRONMENT, 'windspeed_Large1994': _lib.OD_MIX_LARGE1994,
+                  'windspeed_Sundby1983': _lib.OD_MIX_SUNDBY1983, 'constant': _lib.OD_MIX_CONSTANT}
+
     def vertical_mixing(self, group, t, lon, lat, z_in, dt_mix, ntimes, moving=None, terminal_velocity=None, ids=None,
-                        rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False):
-        """OceanDrift.vertical_mixing on device tensors; returns the new depth (float64 tensor)."""
+                        rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False,
+                        model='environment', wind_speed=None, mld=50.0, background=1.2e-5, k_const=0.0):
+        """OceanDrift.vertical_mixing on device tensors; returns the new depth (float64 tensor).
+        model 'environment' takes the diffusivity column from `group`; 'windspeed_Large1994' / 'windspeed_Sundby1983' /
+        'constant' build it analytically on 1 m levels from wind_speed (float32 tensor) and the mixed layer depth mld
+        (float32 tensor or scalar), as oceandrift.py:429-453 does when no ocean-model diffusivity is available."""
         torch = self.torch
         n = lon.numel()
         z_out = self.empty(n, torch.float64)
         a = MixArgs()
-        a.group_k, a.ntimes = group.gid, int(ntimes)
-        a.t_k, _ = group.sample(t)
+        a.ntimes = int(ntimes)
+        a.model = self.MIX_MODELS[model]
+        if a.model == _lib.OD_MIX_ENVIRONMENT:
+            a.group_k = group.gid
+            a.t_k, _ = group.sample(t)
+        else:
+            a.group_k = -1
+            if hasattr(mld, 'data_ptr'):
+                assert mld.dtype == torch.float32
+                a.d_mld = mld.data_ptr()
+                mld_max = float(self.minmax(mld)[1])
+            else:
+                a.mld_const = float(np.float32(mld))
+                mld_max = float(np.float32(mld))
+            a.nlev = len(np.arange(0, np.float32(mld_max) + 2))          # mixing_z = -np.arange(0, MLD.max() + 2)
+            if wind_speed is not None:
+                assert wind_speed.dtype == torch.float32
+                a.d_wind_speed = wind_speed.data_ptr()
+            a.background, a.k_const = float(background), float(k_const)
         a.n = n
         a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
         a.d_z_in, a.z_in_f64 = z_in.data_ptr(), 1 if z_in.dtype == torch.float64 else 0

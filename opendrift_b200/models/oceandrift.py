@@ -41,6 +41,7 @@ class OceanDrift(OpenDriftSimulation):
         'sea_surface_wave_significant_height': {'fallback': 0},
         'sea_surface_wave_stokes_drift_x_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
         'sea_surface_wave_stokes_drift_y_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
+        'ocean_mixed_layer_thickness': {'fallback': 50, 'skip_if': ['drift:vertical_mixing', 'is', False]},
         'sea_floor_depth_below_sea_level': {'fallback': 10000},
         'land_binary_mask': {'fallback': None},
     }
@@ -63,8 +64,12 @@ class OceanDrift(OpenDriftSimulation):
                                                  'enum': ['environment', 'stepfunction', 'windspeed_Sundby1983',
                                                           'windspeed_Large1994', 'constant'],
                                                  'level': CONFIG_LEVEL_ADVANCED,
-                                                 'description': 'Source of the diffusivity profile; only "environment" '
-                                                                '(from a reader) runs on the GPU path.'},
+                                                 'description': 'Algorithm/source used for profile of vertical diffusivity. '
+                                                                'Environment means that diffusivity is aquired from '
+                                                                'readers or environment constants/fallback.'},
+            'vertical_mixing:background_diffusivity': {'type': 'float', 'min': 0, 'max': 1, 'default': 1.2e-5,
+                                                       'level': CONFIG_LEVEL_ADVANCED, 'units': 'm2s-1', 'description':
+                                                       'Background diffusivity used below mixed layer for wind parameterisations.'},
             'gpu:rng': {'type': 'enum', 'enum': ['numpy', 'philox'], 'default': 'numpy', 'level': CONFIG_LEVEL_ADVANCED,
                         'description': 'numpy: draws of the legacy global generator made on the host in the reference\'s '
                                        'order (bit parity); philox: counter-based generator on the device keyed by element ID.'},
@@ -109,23 +114,40 @@ class OceanDrift(OpenDriftSimulation):
 
     # -- vertical mixing (oceandrift.py:397-571) --------------------------------------------------------------------
     def _mixing_inputs(self):
-        if self.get_config('vertical_mixing:diffusivitymodel') != 'environment':
-            raise NotImplementedError('only vertical_mixing:diffusivitymodel = "environment" runs on the GPU path')
-        r = self.env.reader_for('ocean_vertical_diffusivity', self.time)
-        if r is None or not hasattr(r, 'group_of'):
-            raise NotImplementedError('vertical mixing needs a gridded ocean_vertical_diffusivity reader')
-        g, _ = r.group_of('ocean_vertical_diffusivity')
+        """Which diffusivity column the reference would use (oceandrift.py:425-453): the ocean-model profile when a
+        gridded ocean_vertical_diffusivity reader serves this time, else Large et al. (1994) from the wind; or the
+        analytical / constant model the configuration names."""
+        model = self.get_config('vertical_mixing:diffusivitymodel')
+        g = None
+        if model == 'environment':
+            r = self.env.reader_for('ocean_vertical_diffusivity', self.time)
+            if r is not None and hasattr(r, 'group_of'):
+                g, _ = r.group_of('ocean_vertical_diffusivity')
+            else:
+                model = 'windspeed_Large1994'
+        elif model not in ('windspeed_Large1994', 'windspeed_Sundby1983', 'constant'):
+            raise NotImplementedError('vertical_mixing:diffusivitymodel = %r is not on the GPU path' % model)
         dt_mix = self.get_config('vertical_mixing:timestep') * np.sign(self.time_step.total_seconds())
         ntimes = int(np.abs(int(self.time_step.total_seconds() / dt_mix)))
         floor = self._constant_or_none('sea_floor_depth_below_sea_level')
         if floor is None:
             floor = self.environment.dev('sea_floor_depth_below_sea_level', self.engine)
-        return g, dt_mix, ntimes, floor
+        return g, model, dt_mix, ntimes, floor
+
+    def _env_scalar_or_tensor(self, var, default):
+        """A float (constant / fallback with no reader) or the start-of-step float32 device tensor of an environment variable."""
+        c = self._constant_or_none(var)
+        if c is not None:
+            return float(c)
+        if self.env.reader_for(var, self.time) is None:
+            fb = self.env.fallback(var)
+            return float(default if fb is None else fb)
+        return self.environment.dev(var, self.engine)
 
     def _mix(self, lon0, lat0, z_in, pos_f32):
         """Run the mixing kernel from start-of-step positions; returns the new float64 depth tensor."""
         eng, el, torch = self.engine, self.elements, self.engine.torch
-        g, dt_mix, ntimes, floor = self._mixing_inputs()
+        g, model, dt_mix, ntimes, floor = self._mixing_inputs()
         n = len(el)
         rand = None
         if self.get_config('gpu:rng') == 'numpy':          # the reference's draws, in its order (:524)
@@ -137,10 +159,22 @@ class OceanDrift(OpenDriftSimulation):
         ids = el.dev('ID')
         if ids.dtype != torch.int32:
             ids = ids.to(torch.int32)
+        kw = {}
+        if model != 'environment':
+            env = self.environment
+            if 'x_wind' in env and 'y_wind' in env:
+                xw, yw = env.dev('x_wind', eng), env.dev('y_wind', eng)
+                ws = torch.sqrt(xw * xw + yw * yw)                                       # PhysicsMethods.wind_speed (:885-887)
+            else:
+                ws = torch.zeros(n, dtype=torch.float32, device=eng.device)
+            kw = dict(model=model, wind_speed=ws,
+                      mld=self._env_scalar_or_tensor('ocean_mixed_layer_thickness', 50.0),
+                      background=self.get_config('vertical_mixing:background_diffusivity'),
+                      k_const=float(self.env.fallback('ocean_vertical_diffusivity') or 0.0))
         return eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, moving=moving, terminal_velocity=tv,
                                    ids=ids, rand=rand, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation,
                                    sea_floor=floor, mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'),
-                                   pos_f32=pos_f32)
+                                   pos_f32=pos_f32, **kw)
 
     def vertical_mixing(self, store_depths=False):
         """Helper for subclasses that override update(): uses the start-of-step positions saved by the run loop."""

@@ -429,6 +429,34 @@ def vertical_mixing(z, moving, Kprofiles, mixing_z, dt, dt_mix=60.0, sea_floor_d
     return z
 
 
+def diffusivity_profiles(model, wind_speed, mld, background=0.0):
+    """Analytical eddy-diffusivity columns on 1 m levels, as OceanDrift.vertical_mixing builds them when the diffusivity
+    does not come from an ocean model (opendrift/models/oceandrift.py:429-453, get_diffusivity_profile :385-395):
+    mixing_z = -arange(0, max(MLD) + 2); K from the wind speed with Large et al. (1994) or Sundby (1983)
+    (opendrift/models/physics_methods.py:203-249).  wind_speed and mld are the float32 environment arrays; the dtype
+    flow (float32 wind stress, float64 depth ratio) is NumPy's own since the same expressions are evaluated."""
+    mixing_z = -np.arange(0, mld.max() + 2)
+    wind, depth = np.meshgrid(wind_speed, np.abs(mixing_z))
+    if model == 'windspeed_Large1994':
+        depth = np.abs(depth)
+        windstress = wind * wind * 1.25e-3 * 1.22                      # cd (Kara et al. 2007) * air density
+        sigma = depth / mld
+
+        def shape(s):                                                    # vertical shape function of the eddy diffusivity
+            g = 1. * s + (-2) * s**2 + 1 * s**3
+            g[np.where(g >= 1)] = g[np.where(g >= 1)] * 0.
+            return g
+        K = mld * 0.2 * 0.4 * shape(sigma) * windstress + sigma * background     # 0.2: the stability function
+        K[depth >= mld] = background
+    elif model == 'windspeed_Sundby1983':
+        K = 76.1e-4 + 2.26e-4 * wind * wind * np.ones(np.atleast_1d(depth.shape))
+        K[depth > mld - 1] = (K[depth > mld - 1] + background) / 2
+        K[depth >= mld] = background
+    else:
+        raise ValueError('Unknown diffusivity model: ' + model)
+    return K, mixing_z
+
+
 def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
     """OpenDriftSimulation.horizontal_diffusion (opendrift/models/basemodel/__init__.py:1746-1772):
     two normal draws from the legacy global generator, x first."""
@@ -443,7 +471,8 @@ def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
 
 def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
                    vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
-                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None, noise=None):
+                   diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None, noise=None,
+                   w_at_surface=False, diffusivity_model=None, mld=50.0, background_diffusivity=1.2e-5):
     """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
     OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
@@ -471,8 +500,11 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
         variables.append('upward_sea_water_velocity')
     if wind:
         variables += ['x_wind', 'y_wind']
-    if mixing:
+    analytic = mixing and diffusivity_model not in (None, 'environment')
+    if mixing and not analytic:
         variables.append('ocean_vertical_diffusivity')
+    if analytic and 'x_wind' not in variables:
+        variables += ['x_wind', 'y_wind']          # OceanDrift always requires the wind (fallback 0)
     if stokes:
         variables += ['sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity',
                       'sea_surface_wave_significant_height']
@@ -480,7 +512,7 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
             variables += ['x_wind', 'y_wind']
     time = start_time
     for _ in range(steps):
-        if mixing:
+        if mixing and not analytic:
             env, prof = get_environment(readers, variables, time, lon, lat, z, truncate_below=truncate_below,
                                         profiles=['ocean_vertical_diffusivity'])
         else:
@@ -492,10 +524,15 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
             lon, lat = advect_wind(lon, lat, z, wdf_arr, env, moving, dt, wind_drift_depth)
         if stokes:
             lon, lat = stokes_drift(lon, lat, z, env, moving, dt, profile=stokes)
-        if mixing:
+        if analytic:
+            wind_speed = np.sqrt(env['x_wind']**2 + env['y_wind']**2)                # PhysicsMethods.wind_speed
+            Kp, mz = diffusivity_profiles(diffusivity_model, wind_speed, np.float32(mld) * np.ones(n, dtype=np.float32),
+                                          background_diffusivity)
+            z = vertical_mixing(z, moving, Kp, mz, dt, dt_mix)
+        elif mixing:
             z = vertical_mixing(z, moving, prof['ocean_vertical_diffusivity'], prof['z'], dt, dt_mix)
         if vertical_adv:
-            z = vertical_advection(z, env['upward_sea_water_velocity'], moving, dt)
+            z = vertical_advection(z, env['upward_sea_water_velocity'], moving, dt, at_surface=w_at_surface)
         if diffusivity > 0:
             D = np.float32(diffusivity) * np.ones(n, dtype=np.float32)
             lon, lat = horizontal_diffusion(lon, lat, D, moving, dt)

@@ -71,9 +71,10 @@ def build_wind(g, n_slabs):
 
 
 def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivity=0.0,
-             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True, holes=False, noise=None):
+             cdf=None, spill=False, seed=0, wind_drift_depth=None, start_offset_s=0, mixing=False, dt_mix=60.0, stokes=None, stokes_hs=True, holes=False, noise=None,
+             truncate=None, w_at_surface=False, diffusivity_model=None, background_diffusivity=None):
     n_slabs = syn.n_slabs_for(steps, dt) + (1 if start_offset_s else 0)
-    times, f3 = build_fields(g, n_slabs, with_w, mixing)
+    times, f3 = build_fields(g, n_slabs, with_w, mixing and diffusivity_model in (None, 'environment'))
     if holes:
         punch_holes(g, f3)
     lon, lat, z = syn.particle_cloud(n, seed=seed + 1, three_d=g.z is not None)
@@ -109,6 +110,14 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
     if mixing:
         cfg['drift:vertical_mixing'] = True
         cfg['vertical_mixing:timestep'] = dt_mix
+    if diffusivity_model is not None and diffusivity_model != 'environment_no_reader':
+        cfg['vertical_mixing:diffusivitymodel'] = diffusivity_model
+    if background_diffusivity is not None:
+        cfg['vertical_mixing:background_diffusivity'] = background_diffusivity
+    if truncate is not None:
+        cfg['drift:truncate_ocean_model_below_m'] = truncate
+    if w_at_surface:
+        cfg['drift:vertical_advection_at_surface'] = True
     seed_kwargs = {}
     if cdf is not None:
         seed_kwargs['current_drift_factor'] = cdf
@@ -121,7 +130,9 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
                 diffusivity=diffusivity, seed=seed, wind_drift_depth=wind_drift_depth,
                 start_offset_s=start_offset_s if dt > 0 else None,
                 start_index=None if dt > 0 else len(times) - 1,
-                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix, stokes=stokes, noise=noise)
+                slab_step_s=3600, cdf_is_array=cdf is not None, mixing=mixing, dt_mix=dt_mix, stokes=stokes, noise=noise,
+                truncate=truncate, w_at_surface=w_at_surface, diffusivity_model=diffusivity_model,
+                background_diffusivity=background_diffusivity)
     out = dict(meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat,
                grid_z=np.zeros(0) if g.z is None else g.z,
                u=f3[CURRENT[0]], v=f3[CURRENT[1]], lon0=lon, lat0=lat, z0=z,
@@ -130,7 +141,7 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
                z=np.asarray(o.elements.z))      # float32, or float64 once vertical mixing has touched it
     if with_w:
         out['w'] = f3['upward_sea_water_velocity']
-    if mixing:
+    if mixing and 'ocean_vertical_diffusivity' in f3:
         out['kdiff'] = f3['ocean_vertical_diffusivity']
     if stokes:
         for k, v in fs.items():
@@ -264,6 +275,14 @@ def main():
     run_case('rk4_3d_mixing', g3, 600, 7, 600, 'runge-kutta4', mixing=True, dt_mix=60.0)
     run_case('euler_3d_mixing_w', g3, 600, 4, 900, 'euler', mixing=True, dt_mix=100.0, with_w=True)
     dateline_cases()
+    run_case('rk4_3d_truncate_wsurf', g3, n, 8, 600, 'runge-kutta4', with_w=True, wind=True, truncate=40.0, w_at_surface=True)
+    run_case('rk2_3d_truncate', g3, n, 6, 900, 'runge-kutta', truncate=25.0)
+    run_case('rk4_3d_mixing_large1994', g3, 600, 5, 600, 'runge-kutta4', mixing=True, dt_mix=60.0, wind=True,
+             diffusivity_model='windspeed_Large1994')
+    run_case('euler_3d_mixing_sundby1983', g3, 600, 4, 900, 'euler', mixing=True, dt_mix=100.0, wind=True,
+             diffusivity_model='windspeed_Sundby1983', background_diffusivity=1e-4)
+    run_case('rk2_3d_mixing_env_fallback', g3, 600, 4, 600, 'runge-kutta', mixing=True, dt_mix=60.0, wind=True,
+             diffusivity_model='environment_no_reader')
 
 
 if __name__ == '__main__':

@@ -164,7 +164,10 @@ def run_port(fx):
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
                              cdf=fx.cdf if fx.cdf is not None else 1.0, wdf=m.get('wdf', 0.02), diffusivity=m['diffusivity'],
                              seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0),
-                             stokes=m.get('stokes'), noise=m.get('noise'))
+                             stokes=m.get('stokes'), noise=m.get('noise'), truncate_below=m.get('truncate'),
+                             w_at_surface=bool(m.get('w_at_surface')),
+                             diffusivity_model={'environment_no_reader': 'windspeed_Large1994'}.get(m.get('diffusivity_model'), m.get('diffusivity_model')),
+                             background_diffusivity=1.2e-5 if m.get('background_diffusivity') is None else m['background_diffusivity'])
 
 
 # ---- host-compiled device math ---------------------------------------------------------------
@@ -232,7 +235,32 @@ class HsMixArgs(C.Structure):
                 ('z_in', C.c_void_p), ('z_out', C.c_void_p), ('moving', C.c_void_p), ('rand', C.c_void_p),
                 ('dt_mix', C.c_double), ('sea_floor_const', C.c_double), ('seed', C.c_uint64),
                 ('ntimes', C.c_int32), ('z_in_f64', C.c_int32), ('mix_at_surface', C.c_int32), ('pos_f32', C.c_int32),
-                ('step_index', C.c_int32), ('pad_', C.c_int32)]
+                ('step_index', C.c_int32), ('model', C.c_int32), ('nlev', C.c_int32), ('pad_', C.c_int32),
+                ('wind_speed', C.c_void_p), ('mld_const', C.c_double), ('background', C.c_double), ('k_const', C.c_double)]
+
+
+MIX_MODEL_IDS = {'windspeed_Large1994': 1, 'environment_no_reader': 1, 'windspeed_Sundby1983': 2}
+
+
+def mix_model(meta):
+    """(id, name) of the analytical diffusivity model of a fixture, or (0, 'environment')."""
+    dm = meta.get('diffusivity_model')
+    if meta.get('mixing') and dm in MIX_MODEL_IDS:
+        return MIX_MODEL_IDS[dm], ('windspeed_Large1994' if dm == 'environment_no_reader' else dm)
+    return 0, 'environment'
+
+
+def z_tolerance(meta, exact=0.0):
+    """Depth tolerance of a fixture: `exact` (default: bit for bit) for vertical mixing on profiles that are evaluated with
+    elementary arithmetic only; 1e-12 m where the column comes from Large et al. (1994), whose sigma**3 NumPy evaluates
+    with its own SIMD pow (an ulp from libm's / CUDA's); 1e-5 m for float32 depths."""
+    if not meta.get('mixing'):
+        return 1e-5
+    return max(exact, 1e-12) if mix_model(meta)[0] == 1 else exact
+
+
+def mix_background(meta):
+    return 1.2e-5 if meta.get('background_diffusivity') is None else meta['background_diffusivity']
 
 
 _shim = None
@@ -344,11 +372,19 @@ def run_hostshim(fx, fast=False):
         ncur, nkinds, nwind = draw_uncertainty(fx.n, m['scheme'], nz_.get('current', 0), nz_.get('current_uniform', 0),
                                                nz_.get('wind', 0), with_wind=bool(m['wind']))
         z_new = None
-        if kfld is not None:                   # vertical mixing first: it needs the start-of-step positions
+        mix_id, _ = mix_model(m)
+        if kfld is not None or mix_id:         # vertical mixing first: it needs the start-of-step positions
             ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
             rnd = np.ascontiguousarray(np.stack([np.random.random(fx.n) for _ in range(ntimes)]))
             ma = HsMixArgs()
-            ma.g, ma.t_k, ma.n = kfld.g, kfld.pair(t), fx.n
+            ma.n = fx.n
+            if mix_id:
+                xw0, yw0 = wind.sample(lib, t, lon, lat, z, istep == 0)
+                ws = np.sqrt(xw0**2 + yw0**2)                                   # PhysicsMethods.wind_speed, float32
+                ma.model, ma.nlev, ma.wind_speed = mix_id, len(np.arange(0, np.float32(50) + 2)), _p(ws)
+                ma.mld_const, ma.background = 50.0, mix_background(m)
+            else:
+                ma.g, ma.t_k = kfld.g, kfld.pair(t)
             z_new = np.empty(fx.n, dtype=np.float64)
             ma.lon, ma.lat, ma.z_in, ma.z_out = _p(lon), _p(lat), _p(z), _p(z_new)
             ma.moving, ma.rand = _p(moving), _p(rnd)
@@ -379,12 +415,14 @@ def run_hostshim(fx, fast=False):
         a.dt, a.n = float(fx.dt), fx.n
         a.lon, a.lat, a.z = _p(lon), _p(lat), _p(z)
         a.factor, a.moving = _p(cdf), _p(moving)
+        a.truncate_below = float(m.get('truncate') or 0.0)
         if wind is not None:
             a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, 1, wind.g, wind.pair(t)
             a.wdf, a.wind_drift_depth = _p(wdf), fx.wind_drift_depth()
         if wfld is not None:
             zu = z if z_new is None else z_new
             a.w_on, a.g_w, a.t_w, a.z_inout = 1, wfld.g, wfld.pair(t), _p(zu)
+            a.w_at_surface = 1 if m.get('w_at_surface') else 0
             a.z_inout_f64 = 1 if zu.dtype == np.float64 else 0
         if m['diffusivity']:
             rx = np.random.normal(scale=1, size=fx.n)
@@ -462,15 +500,21 @@ def run_engine(fx, fused=True, sort_every=0, fast=None):
             xw, yw = eng.interp(wind, t, lon, lat, z, pos_f32=first)
             senv = (us, vs, hs, xw, yw)
         z_new = None
-        if kgrp is not None:
+        mix_id, mix_name = mix_model(m)
+        if kgrp is not None or mix_id:
             ntimes = abs(int(fx.dt / (m['dt_mix'] * np.sign(fx.dt))))
             rnd = eng.to_device(np.ascontiguousarray(np.stack([np.random.random(fx.n) for _ in range(ntimes)])))
+            kw = {}
+            if mix_id:
+                xw0, yw0 = eng.interp(wind, t, lon, lat, z, pos_f32=first)
+                kw = dict(model=mix_name, wind_speed=torch.sqrt(xw0 * xw0 + yw0 * yw0), mld=50.0, background=mix_background(m))
             z_new = eng.vertical_mixing(kgrp, t, lon, lat, z, m['dt_mix'] * np.sign(fx.dt), ntimes, moving=d_mov,
-                                        rand=rnd, pos_f32=first)
+                                        rand=rnd, pos_f32=first, **kw)
         if fused:
             eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
+                                w_at_surface=bool(m.get('w_at_surface')), truncate_below=m.get('truncate'),
                                 diffusivity=m['diffusivity'], pos_f32=first, z_update=z_new, fast=fast,
                                 noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind)
             if senv is not None:
@@ -485,7 +529,8 @@ def run_engine(fx, fused=True, sort_every=0, fast=None):
         else:
             assert not (m['wind'] or m['with_w'] or m['diffusivity'])
             eng.advect_current(cur, m['scheme'], t, dt, lon, lat, z if three_d else None, factor=d_cdf,
-                               moving=d_mov, pos_f32=first, fast=fast, noise=d_ncur, noise_kinds=nkinds)
+                               moving=d_mov, pos_f32=first, fast=fast, noise=d_ncur, noise_kinds=nkinds,
+                               truncate_below=m.get('truncate'))
         t = t + dt
     eng.sync()
     out = lon.cpu().numpy(), lat.cpu().numpy(), (z.cpu().numpy() if z is not None else fx.z0)

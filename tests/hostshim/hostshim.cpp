@@ -168,25 +168,35 @@ struct hs_mix_args {
     hs_group g; hs_pair t_k;
     int64_t n; const double* lon; const double* lat; const void* z_in; double* z_out;
     const int32_t* moving; const double* rand; double dt_mix; double sea_floor_const;
-    unsigned long long seed; int32_t ntimes, z_in_f64, mix_at_surface, pos_f32, step_index, pad_;
+    unsigned long long seed; int32_t ntimes, z_in_f64, mix_at_surface, pos_f32, step_index, model;
+    int32_t nlev, pad_; const float* wind_speed; double mld_const, background, k_const;
 };
 
 int hs_mix(const hs_mix_args* a) {
     hs_levels lv;
     MixParams p;
     memset(&p, 0, sizeof(p));
-    p.g = make_geom(a->g, lv);
-    p.pr = make_pair(a->t_k);
-    const int nz = a->g.nz;
-    std::vector<double> xs(nz), xy(nz), zl(a->g.z_levels, a->g.z_levels + nz);
-    const bool inc = zl[1] > zl[0];
-    for (int i = 0; i < nz; ++i) { int src = inc ? nz - 1 - i : i; xs[i] = -zl[src]; xy[i] = (double)src; }
+    std::vector<double> xs, xy, zl;
+    if (a->model == 0) {
+        p.g = make_geom(a->g, lv);
+        p.pr = make_pair(a->t_k);
+        const int nz = a->g.nz;
+        xs.resize(nz); xy.resize(nz); zl.assign(a->g.z_levels, a->g.z_levels + nz);
+        const bool inc = zl[1] > zl[0];
+        for (int i = 0; i < nz; ++i) { int src = inc ? nz - 1 - i : i; xs[i] = -zl[src]; xy[i] = (double)src; }
+        p.zl = zl.data(); p.xs = xs.data(); p.xy = xy.data();
+        p.uniform_dz = 1; p.dz0 = zl[1] - zl[0];
+        for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
+    } else {
+        p.g.nz = a->nlev;
+        p.uniform_dz = 1; p.dz0 = -1.0;
+        p.wind_speed = a->wind_speed; p.mld_const = (float)a->mld_const; p.background = a->background; p.k_const = a->k_const;
+    }
+    p.model = a->model;
     p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z_in = a->z_in; p.z_out = a->z_out; p.moving = a->moving;
     p.rand = a->rand; p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.seed = a->seed;
     p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32;
-    p.step_index = a->step_index; p.zl = zl.data(); p.xs = xs.data(); p.xy = xy.data();
-    p.uniform_dz = 1; p.dz0 = zl[1] - zl[0];
-    for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
+    p.step_index = a->step_index;
     for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);
     return 0;
 }

@@ -39,6 +39,14 @@ def _model(fx, **cfg):
         o.set_config('drift:wind_drift_depth', m['wind_drift_depth'])
     for k, v in (m.get('noise') or {}).items():
         o.set_config('drift:current_uncertainty_uniform' if k == 'current_uniform' else 'drift:%s_uncertainty' % k, v)
+    if m.get('truncate') is not None:
+        o.set_config('drift:truncate_ocean_model_below_m', m['truncate'])
+    if m.get('w_at_surface'):
+        o.set_config('drift:vertical_advection_at_surface', True)
+    if m.get('diffusivity_model') not in (None, 'environment_no_reader'):
+        o.set_config('vertical_mixing:diffusivitymodel', m['diffusivity_model'])
+    if m.get('background_diffusivity') is not None:
+        o.set_config('vertical_mixing:background_diffusivity', m['background_diffusivity'])
     if m.get('mixing'):
         o.set_config('drift:vertical_mixing', True)
         o.set_config('vertical_mixing:timestep', m['dt_mix'])
@@ -63,7 +71,7 @@ def test_oceandrift_run_matches_reference(name):
     assert lon.dtype == np.float64                       # float64 after the first update, as in the reference
     e = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     assert max(e) < 5e-8, e
-    assert np.abs(z - fx.z).max() <= (1e-9 if fx.meta.get('mixing') else 1e-5)
+    assert np.abs(z - fx.z).max() <= common.z_tolerance(fx.meta, exact=1e-9)
     assert z.dtype == fx.z.dtype
     assert np.array_equal(o.elements.ID, np.arange(fx.n))
     assert len(o.history['time']) == fx.steps + 1

@@ -49,7 +49,7 @@ def test_fused_step_vs_reference_fixture(name, mode):
     elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     assert elon < TOL_DEG and elat < TOL_DEG, (elon, elat)
     assert elon < TIGHT_DEG and elat < TIGHT_DEG, (elon, elat)
-    assert np.abs(z - fx.z).max() <= (1e-9 if fx.meta.get('mixing') else 1e-5)
+    assert np.abs(z - fx.z).max() <= common.z_tolerance(fx.meta, exact=1e-9)
     # and against the host-compiled device math: same arithmetic on both sides of the PCIe bus
     hl, ha, hz = common.run_hostshim(fx, fast=2 if mode == 'default' else 0)
     e2 = common.max_err_deg(lon, lat, hl, ha)

@@ -32,7 +32,7 @@ def test_step_vs_reference_fixture(name):
     elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     tol = 1e-11 if fx.meta['scheme'] == 'euler' and fx.cdf is None else 2e-8
     assert elon < tol and elat < tol, (elon, elat)
-    assert np.abs(z - fx.z).max() <= (0.0 if fx.meta.get('mixing') else 1e-5)
+    assert np.abs(z - fx.z).max() <= common.z_tolerance(fx.meta)
 
 
 @pytest.mark.parametrize('name', fixtures())
@@ -43,7 +43,7 @@ def test_series_mode_vs_reference_fixture(name):
     elon, elat = common.max_err_deg(lon, lat, fx.lon, fx.lat)
     tol = 1e-11 if fx.meta['scheme'] == 'euler' and fx.cdf is None else 2e-8
     assert elon < tol and elat < tol, (elon, elat)
-    assert np.abs(z - fx.z).max() <= (0.0 if fx.meta.get('mixing') else 1e-5)
+    assert np.abs(z - fx.z).max() <= common.z_tolerance(fx.meta)
 
 
 def _wrap(d):
