@@ -63,7 +63,7 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
 //   * RK mid-points (which only feed the sampler): first-order displacement with float32 radii of curvature;
 //     the move that is kept: the float64 short-arc series of SeriesMath.
 // Measured against the reference fixtures FastMath stays within ~1e-7 deg after 14 RK4 steps (tolerance of
-// the float64 path: 1e-6 deg); it is an opt-in (`gpu:precision = fast`, od_advect_args.fast).
+// the float64 path: 1e-6 deg); it is an opt-in (od_advect_args.fast = OD_MATH_FAST, Engine.math_mode).
 // ---------------------------------------------------------------------------------------------------------
 struct ExactMath {
     typedef GeodStart Start;

@@ -117,6 +117,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             'gpu:sort_interval_steps': {'type': 'int', 'default': 20, 'min': 0, 'max': 1000000, 'units': 1,
                                         'level': CONFIG_LEVEL_ADVANCED,
                                         'description': 'Re-order the device particle arrays by grid cell every N steps (0 = never).'},
+            'gpu:arithmetic': {'type': 'enum', 'enum': ['series', 'exact', 'fast'], 'default': 'series', 'level': CONFIG_LEVEL_ADVANCED,
+                               'description': 'Arithmetic of the step kernels (include/odcuda.h OD_MATH_*): series = bit-exact field '
+                                              'sampling + short-arc series geodesic (round-off accurate); exact = the reference\'s '
+                                              'arithmetic operation by operation (full Karney geodesic, float32 mid-point azimuths); '
+                                              'fast = float32 sampling (within ~3e-8 deg of the reference on the fixtures).'},
         }
         # environment:constant:<var> / environment:fallback:<var> per required variable (environment.py:41-76)
         for v, spec in self.required_variables.items():
@@ -440,6 +445,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             raise NotImplementedError('file export is outside the GPU hot path; read o.history / o.elements')
         if self.num_elements_scheduled() == 0:
             raise ValueError('Please seed elements before starting a run.')
+        from .. import _lib
+        self.engine.math_mode = {'series': _lib.OD_MATH_SERIES, 'exact': _lib.OD_MATH_EXACT,
+                                 'fast': _lib.OD_MATH_FAST}[self.get_config('gpu:arithmetic')]
         if time_step is None:
             time_step = timedelta(minutes=self.get_config('general:time_step_minutes'))
         if not isinstance(time_step, timedelta):

@@ -246,3 +246,16 @@ def test_reference_known_answers_with_constant_environment():
     o.seed_elements(lon=3, lat=60, time=datetime.now())
     o.run(steps=1)
     assert o.elements.lon == pytest.approx(3.0645, .001)
+
+
+@pytest.mark.parametrize('arith,tol', [('exact', 5e-8), ('fast', 1e-7)])
+def test_arithmetic_config_selects_the_kernel_policy(arith, tol):
+    """gpu:arithmetic = exact / fast run the same model through the other arithmetic policies of the step kernels."""
+    fx = Fixture('rk4_3d_full')
+    o = _model(fx, **{'gpu:arithmetic': arith})
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    e = common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)
+    assert max(e) < tol, e
+    from opendrift_b200 import _lib
+    assert o.engine.math_mode == {'exact': _lib.OD_MATH_EXACT, 'fast': _lib.OD_MATH_FAST}[arith]
+    o.engine.math_mode = _lib.OD_MATH_SERIES
