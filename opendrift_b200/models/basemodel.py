@@ -392,6 +392,22 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         lon, lat = el.dev('lon'), el.dev('lat')
         # the reference aborts on invalid coordinates (:4661-4669); checked lazily at output steps here
 
+    def _device_normals(self, n, k=2, salt=0):
+        """k float64 device tensors of n standard-normal draws for the active elements.
+        gpu:rng = numpy (default): np.random.normal of the legacy global generator, in the reference's order -- parity.
+        gpu:rng = philox: drawn on the device from a generator keyed by (seed, step, salt) and indexed by element ID, so
+        the draws do not depend on the order of the device arrays (which may then be re-sorted by cell) and nothing
+        crosses the PCIe bus."""
+        eng = self.engine
+        torch = eng.torch
+        if self.get_config('gpu:rng', 'numpy') != 'philox':
+            return [eng.to_device(np.random.normal(scale=1, size=n)) for _ in range(k)]
+        gen = torch.Generator(device=eng.device)
+        gen.manual_seed((int(self._seed) * 1000003 + int(self.steps_calculation)) * 16 + int(salt))
+        ids = self.elements.dev('ID').to(torch.int64)
+        base = torch.randn((k, int(self._n_total)), dtype=torch.float64, device=eng.device, generator=gen)
+        return [base[j][ids] for j in range(k)]
+
     def horizontal_diffusion(self):
         """:1746-1772 -- two normal draws from the legacy global generator (x first), then update_positions."""
         if 'horizontal_diffusivity' not in self.required_variables or self.num_elements_active() == 0:
@@ -405,8 +421,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         eng = self.engine
         n = self.num_elements_active()
-        rx = eng.to_device(np.random.normal(scale=1, size=n))
-        ry = eng.to_device(np.random.normal(scale=1, size=n))
+        rx, ry = self._device_normals(n, 2, salt=1)
         dt = abs(self.time_step.total_seconds())
         torch = eng.torch
         if D is None:
@@ -558,7 +573,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         k = self.get_config('gpu:sort_interval_steps')
         if not k or self.steps_calculation % k != 0 or self.num_elements_active() < 100000:
             return
-        if (self._constant_or_none('horizontal_diffusivity') or 0) != 0 or self._constant_or_none('horizontal_diffusivity') is None:
+        if self.get_config('gpu:rng', 'numpy') != 'philox' and (
+                (self._constant_or_none('horizontal_diffusivity') or 0) != 0 or self._constant_or_none('horizontal_diffusivity') is None):
             return        # the legacy RNG draws are consumed in element order: keep the reference's order
         r = self.env.reader_for('x_sea_water_velocity', self.time)
         if r is None or not hasattr(r, 'group_of'):

@@ -230,7 +230,7 @@ class OceanDrift(OpenDriftSimulation):
         d_nwind = eng.to_device(nwind) if nwind is not None else None
         rand = None
         if D != 0 and not split_diffusion:
-            rand = (eng.to_device(np.random.normal(scale=1, size=n)), eng.to_device(np.random.normal(scale=1, size=n)))
+            rand = tuple(self._device_normals(n, 2, salt=1))
         moving = el.dev('moving')
         if moving.dtype != torch.int32:
             moving = moving.to(torch.int32)

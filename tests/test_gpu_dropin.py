@@ -259,3 +259,38 @@ def test_arithmetic_config_selects_the_kernel_policy(arith, tol):
     from opendrift_b200 import _lib
     assert o.engine.math_mode == {'exact': _lib.OD_MATH_EXACT, 'fast': _lib.OD_MATH_FAST}[arith]
     o.engine.math_mode = _lib.OD_MATH_SERIES
+
+
+def test_device_rng_for_diffusion_is_order_independent():
+    """gpu:rng = philox: the random-walk draws are made on the device, keyed by element ID -- re-sorting the device arrays
+    every step gives the same trajectories as never sorting, and the spread matches sqrt(2 D dt) per step."""
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = Fixture('rk4_2d')
+    n = 120000
+    rng = np.random.default_rng(4)
+    lon = rng.uniform(fx.grid_lon[4], fx.grid_lon[-5], n)
+    lat = rng.uniform(fx.grid_lat[4], fx.grid_lat[-5], n)
+    D, dt, steps = 20.0, 600, 3
+    out = []
+    for sort_every in (0, 1):
+        o = OceanDrift(loglevel=50, seed=11)
+        zero = {k: np.zeros_like(v) for k, v in {common.CUR[0]: fx.u, common.CUR[1]: fx.v}.items()}
+        o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, zero, name='still_water'))
+        o.set_config('general:use_auto_landmask', False)
+        o.set_config('general:coastline_action', 'none')
+        o.set_config('drift:advection_scheme', 'euler')
+        o.set_config('drift:vertical_advection', False)
+        o.set_config('environment:constant:horizontal_diffusivity', D)
+        o.set_config('gpu:rng', 'philox')
+        o.set_config('gpu:sort_interval_steps', sort_every)
+        o.seed_elements(lon=lon, lat=lat, time=fx.start)
+        o.run(steps=steps, time_step=dt, time_step_output=dt)
+        assert o.num_elements_active() == n
+        ids = np.asarray(o.elements.ID)
+        order = np.argsort(ids)
+        out.append((np.asarray(o.elements.lon)[order], np.asarray(o.elements.lat)[order]))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    dy = (out[0][1] - lat.astype(np.float32)) * 111194.9                       # metres north (float32 seeding rounding is < 1 m)
+    expected = np.sqrt(2 * D * dt * steps)
+    assert abs(dy.std() / expected - 1.0) < 0.03 and abs(dy.mean()) < 0.02 * expected
