@@ -245,7 +245,7 @@ int od_step_oceandrift(od_ctx* ctx, const od_step_args* a);
 int od_step_oceandrift_host(od_ctx* ctx, const od_step_args* a, const od_host_io* io);
 
 /* ---- Leeway ------------------------------------------------------------------------------------------
- * Leeway.update (models/leeway.py:430-494, capsizing excluded): leeway move + current move + jibing in one launch.
+ * Leeway.update (models/leeway.py:430-494): optional capsizing, leeway move + current move + jibing in one launch.
  * Wind and current are 2-D two-component groups sampled at the start-of-step position.  Elements with a missing
  * sample get status = missing_code (report_missing_variables) and do not move. */
 typedef struct od_leeway_args {
@@ -261,7 +261,7 @@ typedef struct od_leeway_args {
     const float* d_cw_offset;
     const float* d_cw_eps;
     uint8_t* d_orientation;       /* in/out */
-    const uint8_t* d_capsized;    /* NULL = none */
+    uint8_t* d_capsized;          /* NULL = none; in/out when capsize_on */
     const void* d_jibe_probability;   /* float32, or float64 when jp_f64 */
     const int32_t* d_moving;
     int32_t* d_status;            /* NULL = do not flag missing data */
@@ -271,6 +271,12 @@ typedef struct od_leeway_args {
     uint64_t seed;
     float capsize_fraction;       /* capsizing:leeway_fraction */
     int32_t jp_f64, pos_f32, step_index, missing_code, pad_;
+    /* processes:capsizing (leeway.py:438-454): elements with capsized == capsize_from (0 in forward, 1 in backward runs) flip
+     * with probability (0.5 + 0.5 tanh((wind - wind_threshold) / wind_sigma)) |dt| / 3600 */
+    int32_t capsize_on, capsize_from;
+    float wind_threshold, wind_sigma;      /* capsizing:wind_threshold, capsizing:wind_threshold_sigma */
+    const double* d_rand_capsize; /* [n] the reference's np.random.rand(len(eligible)) draws scattered to the eligible elements (parity),
+                                     or NULL: Philox keyed by (seed, ID, step) */
 } od_leeway_args;
 
 int od_leeway_step(od_ctx* ctx, const od_leeway_args* a);

@@ -81,7 +81,9 @@ class LeewayArgs(C.Structure):
                 ('d_capsized', C.c_void_p), ('d_jibe_probability', C.c_void_p), ('d_moving', C.c_void_p),
                 ('d_status', C.c_void_p), ('d_ids', C.c_void_p), ('d_rand', C.c_void_p), ('dt', C.c_double),
                 ('seed', C.c_uint64), ('capsize_fraction', C.c_float), ('jp_f64', C.c_int32), ('pos_f32', C.c_int32),
-                ('step_index', C.c_int32), ('missing_code', C.c_int32), ('pad_', C.c_int32)]
+                ('step_index', C.c_int32), ('missing_code', C.c_int32), ('pad_', C.c_int32),
+                ('capsize_on', C.c_int32), ('capsize_from', C.c_int32), ('wind_threshold', C.c_float),
+                ('wind_sigma', C.c_float), ('d_rand_capsize', C.c_void_p)]
 
 
 class StokesArgs(C.Structure):

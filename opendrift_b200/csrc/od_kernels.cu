@@ -1399,6 +1399,9 @@ extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {
     p.orientation = a->d_orientation; p.capsized = a->d_capsized; p.jibe_probability = a->d_jibe_probability;
     p.moving = a->d_moving; p.status = a->d_status; p.ids = a->d_ids; p.rand = a->d_rand; p.dt = a->dt; p.seed = a->seed;
     p.capsize_fraction = a->capsize_fraction; p.jp_f64 = a->jp_f64; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from; p.wind_threshold = a->wind_threshold;
+    p.wind_sigma = a->wind_sigma; p.rand_capsize = a->d_rand_capsize;
+    if (a->capsize_on && !a->d_capsized) return fail(ctx, OD_ERR_ARG, "od_leeway_step: capsizing needs the capsized array");
     p.missing_code = a->missing_code;
     leeway_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());

@@ -1,6 +1,6 @@
 // od_leeway.cuh -- one Leeway time step of one drifting object.
 //
-// Restates Leeway.update (opendrift/models/leeway.py:430-494) without capsizing: wind speed and direction from the
+// Restates Leeway.update (opendrift/models/leeway.py:430-494): optional capsizing (:438-454), wind speed and direction from the
 // float32 environment, down- and cross-wind leeway from the per-element coefficients (float32, as NumPy computes
 // them), the leeway move and then the current move (two sequential update_positions, basemodel/__init__.py:4630),
 // both sampled at the START-of-step position, and the random jibing (crosswind_slope -> -crosswind_slope,
@@ -21,7 +21,7 @@ struct LeewayParams {
     const float* dw_slope; const float* dw_offset; const float* dw_eps;
     float* cw_slope; const float* cw_offset; const float* cw_eps;
     uint8_t* orientation;
-    const uint8_t* capsized;          // NULL = none capsized
+    uint8_t* capsized;                // NULL = none capsized; toggled when processes:capsizing is on
     const void* jibe_probability;     // float32 or float64 (jp_f64)
     const int32_t* moving;
     int32_t* status;                  // may be NULL
@@ -30,7 +30,12 @@ struct LeewayParams {
     double dt;
     unsigned long long seed;
     float capsize_fraction;
-    int32_t jp_f64, pos_f32, step_index, missing_code, pad_;
+    int32_t jp_f64, pos_f32, step_index, missing_code;
+    // processes:capsizing (:438-454): an eligible element (capsized == capsize_from: 0 in forward runs, 1 in backward runs)
+    // flips with probability (0.5 + 0.5 tanh((wind - threshold) / sigma)) |dt| / 3600
+    int32_t capsize_on, capsize_from;
+    float wind_threshold, wind_sigma;
+    const double* rand_capsize;       // [n] np.random.rand draws laid out per element (entries of ineligible elements unused), or NULL -> Philox
 };
 
 OD_HD void leeway_particle(const LeewayParams& p, int64_t i) {
@@ -53,6 +58,15 @@ OD_HD void leeway_particle(const LeewayParams& p, int64_t i) {
     const float sinth = sinf(wd), costh = cosf(wd);
     float yl = OD_FADD(OD_FMUL(dl, costh), OD_FMUL(cl, sinth));
     float xl = OD_FADD(OD_FMUL(-dl, sinth), OD_FMUL(cl, costh));
+    if (p.capsize_on && p.capsized && p.capsized[i] == (uint8_t)p.capsize_from) {
+        // float32 probability per hour, promoted to float64 by np.abs(dt) (a NumPy float64 scalar)
+        const float ph = OD_FADD(0.5f, OD_FMUL(0.5f, tanhf(OD_FADD(ws, -p.wind_threshold) / p.wind_sigma)));
+        const double prob = OD_DMUL((double)ph, fabs(p.dt)) / 3600;
+        double Uc, spare_c;
+        if (p.rand_capsize) Uc = p.rand_capsize[i];
+        else philox_uniform2(p.seed, p.ids ? (unsigned)p.ids[i] : (unsigned)i, (unsigned)p.step_index, 0x43415053u, Uc, spare_c);
+        if (Uc < prob) p.capsized[i] = (uint8_t)(1 - p.capsized[i]);
+    }
     if (p.capsized && p.capsized[i] == 1) {
         xl = OD_FMUL(xl, p.capsize_fraction);
         yl = OD_FMUL(yl, p.capsize_fraction);

@@ -5,7 +5,7 @@ step (od_leeway_step: leeway move + current move + jibing).  Euler only, like th
 
 Object categories: the reference reads ~85 categories from OBJECTPROP.DAT (Allen & Plourde 1999 / Allen 2005).  A
 path to such a file can be given as `Leeway(d=path)` exactly like the reference; without it the four person-in-water
-categories below are available.  Capsizing (`processes:capsizing`) is not on the GPU path.
+categories below are available.  Capsizing (`processes:capsizing`, :438-454) runs inside the same launch.
 """
 from collections import OrderedDict
 
@@ -86,7 +86,14 @@ class Leeway(OpenDriftSimulation):
                                       'level': CONFIG_LEVEL_BASIC,
                                       'description': 'Probability per hour for jibing (objects changing orientation)'},
             'processes:capsizing': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_BASIC,
-                                    'description': 'Capsizing (not on the GPU path).'},
+                                    'description': 'If True, elements can be capsized when wind exceeds threshold given by '
+                                                   'config item capsize:wind_threshold'},
+            'capsizing:wind_threshold': {'type': 'float', 'default': 30, 'min': 0, 'max': 50, 'units': 'm/s',
+                                         'level': CONFIG_LEVEL_BASIC, 'description':
+                                         'Probability of capsizing per hour is: 0.5 + 0.5tanh((windspeed-wind_threshold)/wind_threshold_sigma)'},
+            'capsizing:wind_threshold_sigma': {'type': 'float', 'default': 5, 'min': 0, 'max': 20, 'units': 'm/s',
+                                               'level': CONFIG_LEVEL_BASIC,
+                                               'description': 'Sigma parameter in parameterization of capsize probability'},
             'capsizing:leeway_fraction': {'type': 'float', 'default': 0.4, 'min': 0, 'max': 1, 'units': 'fraction',
                                           'level': CONFIG_LEVEL_BASIC,
                                           'description': 'Leeway coefficients of capsized elements are multiplied by this factor'},
@@ -145,13 +152,23 @@ class Leeway(OpenDriftSimulation):
 
     def update(self):
         """leeway.py:430-494 as one launch."""
-        if self.get_config('processes:capsizing'):
-            raise NotImplementedError('processes:capsizing is not on the GPU path')
         eng, el, torch = self.engine, self.elements, self.engine.torch
         t = self.time
         gw = self._pair_group('x_wind', 'y_wind', t)
         gc = self._pair_group('x_sea_water_velocity', 'y_sea_water_velocity', t)
         n = len(el)
+        caps_kw = {}
+        if self.get_config('processes:capsizing'):
+            caps_kw['capsizing'] = (self.get_config('capsizing:wind_threshold'), self.get_config('capsizing:wind_threshold_sigma'))
+            if self.get_config('gpu:rng') == 'numpy':
+                # the reference draws np.random.rand(len(eligible)) BEFORE the jibing draws (:443-451): eligible = not yet
+                # capsized in forward runs, capsized in backward runs; laid out per element for the kernel
+                capsized = el.dev('capsized', torch.uint8).cpu().numpy()
+                can = np.where(capsized == (0 if self.time_step.total_seconds() >= 0 else 1))[0]
+                draws = np.full(n, 2.0)
+                if len(can) > 0:
+                    draws[can] = np.random.rand(len(can))
+                caps_kw['rand_capsize'] = eng.to_device(draws)
         rand = eng.to_device(np.random.random(n)) if self.get_config('gpu:rng') == 'numpy' else None
         cols = {'dw_slope': 'downwind_slope', 'dw_offset': 'downwind_offset', 'dw_eps': 'downwind_eps',
                 'cw_slope': 'crosswind_slope', 'cw_offset': 'crosswind_offset', 'cw_eps': 'crosswind_eps'}
@@ -168,7 +185,7 @@ class Leeway(OpenDriftSimulation):
                         moving=el.dev('moving', torch.int32), status=el.dev('status', torch.int32),
                         ids=el.dev('ID', torch.int32), rand=rand, seed=self._seed, step_index=self.steps_calculation,
                         capsize_fraction=self.get_config('capsizing:leeway_fraction'),
-                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32)
+                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32, **caps_kw)
         el.positions_f32 = False
         self._maybe_deactivated = True           # the kernel may have flagged elements with missing forcing
         self.stokes_drift()

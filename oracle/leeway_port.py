@@ -42,7 +42,9 @@ def seed_coefficients(number, prop):
                 crosswind_eps=f32(crosswind_eps))
 
 
-def run_leeway(readers, lon, lat, start_time, dt, steps, prop, seed=0, jibe_probability=0.04, capsize_fraction=0.4):
+def run_leeway(readers, lon, lat, start_time, dt, steps, prop, seed=0, jibe_probability=0.04, capsize_fraction=0.4,
+               capsizing=None):
+    """capsizing: None (processes:capsizing off) or (wind_threshold, wind_threshold_sigma) (leeway.py:438-454)."""
     np.random.seed(seed)
     n = len(lon)
     lon = np.asarray(lon, dtype=np.float32)
@@ -60,6 +62,13 @@ def run_leeway(readers, lon, lat, start_time, dt, steps, prop, seed=0, jibe_prob
         # Leeway.update (:430-494)
         windspeed = np.sqrt(env['x_wind'] ** 2 + env['y_wind'] ** 2)
         winddir = np.arctan2(env['x_wind'], env['y_wind'])
+        if capsizing is not None:
+            thr, sig = capsizing
+            can = np.where(capsized == (0 if dt >= 0 else 1))[0]          # forward runs capsize, backward runs un-capsize
+            if len(can) > 0:
+                prob = (.5 + .5 * np.tanh((windspeed[can] - thr) / sig)) * np.abs(float(dt)) / 3600
+                flip = can[np.where(np.random.rand(len(can)) < prob)[0]]
+                capsized[flip] = 1 - capsized[flip]
         downwind = ((el['downwind_slope'] + el['downwind_eps'] / 20.0) * windspeed + el['downwind_offset'] +
                     el['downwind_eps'] / 2.0) * .01
         crosswind = ((el['crosswind_slope'] + el['crosswind_eps'] / 20.0) * windspeed + el['crosswind_offset'] +
@@ -77,4 +86,5 @@ def run_leeway(readers, lon, lat, start_time, dt, steps, prop, seed=0, jibe_prob
         el['crosswind_slope'][jib] = -el['crosswind_slope'][jib]
         el['orientation'][jib] = 1 - el['orientation'][jib]
         time = time + timedelta(seconds=dt)
+    el['capsized'] = capsized
     return lon, lat, el

@@ -156,7 +156,7 @@ def run_case(name, g, n, steps, dt, scheme, with_w=False, wind=False, diffusivit
     print('wrote', path, 'max |dlon|', np.abs(out['lon'] - lon).max())
 
 
-def run_leeway_case(name, g, n, steps, dt, object_type=1, seed=0):
+def run_leeway_case(name, g, n, steps, dt, object_type=1, seed=0, capsizing=None):
     """Reference Leeway (opendrift/models/leeway.py) with 2-D current and wind readers."""
     import tempfile
     refrun.setup()
@@ -173,17 +173,23 @@ def run_leeway_case(name, g, n, steps, dt, object_type=1, seed=0):
     for k, v in {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': 0,
                  'general:coastline_action': 'none'}.items():
         o.set_config(k, v)
-    o.seed_elements(lon=lon, lat=lat, time=syn.T0, object_type=object_type)
+    if capsizing is not None:            # (wind_threshold, wind_threshold_sigma)
+        o.set_config('processes:capsizing', True)
+        o.set_config('capsizing:wind_threshold', capsizing[0])
+        o.set_config('capsizing:wind_threshold_sigma', capsizing[1])
+    o.seed_elements(lon=lon, lat=lat, time=syn.T0 if dt > 0 else times[-1], object_type=object_type,
+                    **({'capsized': 1} if (capsizing is not None and dt < 0) else {}))
     o.run(steps=steps, time_step=dt, time_step_output=dt)
     assert len(o.elements.lon) == n
     prop = {k: v for k, v in o.leewayprop[object_type].items() if k not in ('OBJKEY', 'Description')}
     meta = dict(name=name, steps=steps, dt=dt, seed=seed, slab_step_s=3600, object_type=object_type, prop=prop, model='Leeway',
-                start_offset_s=0)
+                start_offset_s=0, capsizing=list(capsizing) if capsizing is not None else None)
     path = os.path.join(OUT, 'ref_%s.npz' % name)
     np.savez_compressed(path, meta=json.dumps(meta), grid_lon=g.lon, grid_lat=g.lat, u=fc[CURRENT[0]], v=fc[CURRENT[1]],
                         x_wind=fw['x_wind'], y_wind=fw['y_wind'], lon0=lon, lat0=lat,
                         lon=np.asarray(o.elements.lon), lat=np.asarray(o.elements.lat),
-                        orientation=np.asarray(o.elements.orientation), crosswind_slope=np.asarray(o.elements.crosswind_slope))
+                        orientation=np.asarray(o.elements.orientation), crosswind_slope=np.asarray(o.elements.crosswind_slope),
+                        capsized=np.asarray(o.elements.capsized))
     print('wrote', path, 'max |dlon|', np.abs(o.elements.lon - lon).max(), 'jibed', int((o.elements.orientation != np.r_[:n] % 2).sum()))
 
 
@@ -269,6 +275,7 @@ def main():
     run_case('euler_2d_land', g2, n, 10, 600, 'euler', holes=True)
     run_leeway_case('leeway_piw1', g2, 1200, 12, 600, object_type=1)
     run_leeway_case('leeway_piw4', g2, 1200, 8, 900, object_type=4, seed=5)
+    run_leeway_case('leeway_piw1_capsizing', g2, 1200, 10, 600, object_type=1, seed=2, capsizing=(8.0, 5.0))
     run_case('rk4_3d_stokes_phillips', g3, n, 6, 600, 'runge-kutta4', wind=True, stokes='Phillips')
     run_case('euler_3d_stokes_mono_nohs', g3, n, 6, 600, 'euler', wind=True, stokes='monochromatic', stokes_hs=False)
     run_case('rk2_3d_stokes_exp', g3, n, 5, 600, 'runge-kutta', wind=True, stokes='exponential')

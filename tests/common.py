@@ -38,6 +38,7 @@ class LeewayFixture:
         for k in ('grid_lon', 'grid_lat', 'u', 'v', 'x_wind', 'y_wind', 'lon0', 'lat0', 'lon', 'lat', 'orientation',
                   'crosswind_slope'):
             setattr(self, k, d[k])
+        self.capsized = d['capsized'] if 'capsized' in d else None
         self.times = syn.slab_times(self.u.shape[0], self.meta['slab_step_s'])
         self.dt, self.steps, self.n, self.start = self.meta['dt'], self.meta['steps'], len(self.lon0), syn.T0
         self.prop = self.meta['prop']
@@ -47,7 +48,9 @@ def run_leeway_port(fx):
     from oracle import advect_port as ap, leeway_port as lp
     rc = ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, {CUR[0]: fx.u, CUR[1]: fx.v})
     rw = ap.GridReader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind})
-    return lp.run_leeway([rc, rw], fx.lon0, fx.lat0, fx.start, fx.dt, fx.steps, fx.prop, seed=fx.meta['seed'])
+    caps = fx.meta.get('capsizing')
+    return lp.run_leeway([rc, rw], fx.lon0, fx.lat0, fx.start, fx.dt, fx.steps, fx.prop, seed=fx.meta['seed'],
+                         capsizing=tuple(caps) if caps else None)
 
 
 def _leeway_elements(fx):
@@ -65,6 +68,7 @@ def run_leeway_hostshim(fx):
     lon, lat = fx.lon0.astype(np.float64), fx.lat0.astype(np.float64)
     moving = np.ones(fx.n, dtype=np.int32)
     jp = np.float32(0.04) * np.ones(fx.n)
+    capsized = np.zeros(fx.n, dtype=np.uint8)
     t, dt = fx.start, timedelta(seconds=fx.dt)
     for istep in range(fx.steps):
         a = HsLeewayArgs()
@@ -72,11 +76,17 @@ def run_leeway_hostshim(fx):
         a.n, a.lon, a.lat = fx.n, _p(lon), _p(lat)
         a.dw_slope, a.dw_offset, a.dw_eps = _p(el['downwind_slope']), _p(el['downwind_offset']), _p(el['downwind_eps'])
         a.cw_slope, a.cw_offset, a.cw_eps = _p(el['crosswind_slope']), _p(el['crosswind_offset']), _p(el['crosswind_eps'])
+        caps = fx.meta.get('capsizing')
+        if caps:
+            rc, frm = capsize_draws(fx.meta, capsized, fx.dt)                 # drawn before the jibing draws, as the reference does
+            a.capsized, a.rand_capsize, a.capsize_on, a.capsize_from = _p(capsized), _p(rc), 1, frm
+            a.wind_threshold, a.wind_sigma = caps[0], caps[1]
         rnd = np.random.random(fx.n)
         a.orientation, a.jibe_probability, a.moving, a.rand = _p(el['orientation']), _p(jp), _p(moving), _p(rnd)
         a.dt, a.capsize_fraction, a.pos_f32 = float(fx.dt), 0.4, 1 if istep == 0 else 0
         assert lib.hs_leeway(C.byref(a)) == 0
         t = t + dt
+    el['capsized'] = capsized
     return lon, lat, el
 
 
@@ -92,17 +102,26 @@ def run_leeway_engine(fx, rng='numpy'):
     d = {'dw_slope': eng.to_device(el['downwind_slope']), 'dw_offset': eng.to_device(el['downwind_offset']),
          'dw_eps': eng.to_device(el['downwind_eps']), 'cw_slope': eng.to_device(el['crosswind_slope']),
          'cw_offset': eng.to_device(el['crosswind_offset']), 'cw_eps': eng.to_device(el['crosswind_eps']),
-         'orientation': eng.to_device(el['orientation']), 'capsized': None,
+         'orientation': eng.to_device(el['orientation']),
+         'capsized': eng.to_device(np.zeros(fx.n, dtype=np.uint8)) if fx.meta.get('capsizing') else None,
          'jibe_probability': eng.to_device(np.float32(0.04) * np.ones(fx.n))}
     ids = eng.to_device(np.arange(fx.n, dtype=np.int32))
     t, dt = fx.start, timedelta(seconds=fx.dt)
     for istep in range(fx.steps):
+        kw = {}
+        caps = fx.meta.get('capsizing')
+        if caps:
+            kw = dict(capsizing=(caps[0], caps[1]))
+            if rng == 'numpy':
+                rc, _ = capsize_draws(fx.meta, d['capsized'].cpu().numpy(), fx.dt)
+                kw['rand_capsize'] = eng.to_device(rc)
         rand = eng.to_device(np.random.random(fx.n)) if rng == 'numpy' else None
-        eng.leeway_step(wind, cur, t, dt, lon, lat, d, ids=ids, rand=rand, seed=7, step_index=istep, pos_f32=istep == 0)
+        eng.leeway_step(wind, cur, t, dt, lon, lat, d, ids=ids, rand=rand, seed=7, step_index=istep, pos_f32=istep == 0, **kw)
         t = t + dt
     eng.sync()
     out = lon.cpu().numpy(), lat.cpu().numpy(), {'orientation': d['orientation'].cpu().numpy(),
-                                                  'crosswind_slope': d['cw_slope'].cpu().numpy()}
+                                                  'crosswind_slope': d['cw_slope'].cpu().numpy(),
+                                                  'capsized': None if d['capsized'] is None else d['capsized'].cpu().numpy()}
     eng.close()
     return out
 
@@ -188,10 +207,23 @@ class HsLeewayArgsReal(C.Structure):
                 ('lon', C.c_void_p), ('lat', C.c_void_p), ('dw_slope', C.c_void_p), ('dw_offset', C.c_void_p),
                 ('dw_eps', C.c_void_p), ('cw_slope', C.c_void_p), ('cw_offset', C.c_void_p), ('cw_eps', C.c_void_p),
                 ('orientation', C.c_void_p), ('jibe_probability', C.c_void_p), ('moving', C.c_void_p), ('rand', C.c_void_p),
-                ('dt', C.c_double), ('capsize_fraction', C.c_float), ('pos_f32', C.c_int32)]
+                ('dt', C.c_double), ('capsize_fraction', C.c_float), ('pos_f32', C.c_int32),
+                ('capsized', C.c_void_p), ('rand_capsize', C.c_void_p), ('capsize_on', C.c_int32), ('capsize_from', C.c_int32),
+                ('wind_threshold', C.c_float), ('wind_sigma', C.c_float)]
 
 
 HsLeewayArgs = HsLeewayArgsReal
+
+
+def capsize_draws(meta, capsized, dt):
+    """The reference's capsizing draws of one step (leeway.py:443-451) laid out per element: np.random.rand(len(eligible))
+    scattered to the eligible elements (capsized == 0 in forward runs, == 1 in backward runs); 2.0 (never selected) elsewhere."""
+    frm = 0 if dt >= 0 else 1
+    can = np.where(capsized == frm)[0]
+    full = np.full(len(capsized), 2.0)
+    if len(can) > 0:
+        full[can] = np.random.rand(len(can))
+    return full, frm
 
 
 class HsStepArgs(C.Structure):

@@ -221,6 +221,7 @@ struct hs_leeway_args {
     int64_t n; double* lon; double* lat; const float* dw_slope; const float* dw_offset; const float* dw_eps;
     float* cw_slope; const float* cw_offset; const float* cw_eps; uint8_t* orientation; const double* jibe_probability;
     const int32_t* moving; const double* rand; double dt; float capsize_fraction; int32_t pos_f32;
+    uint8_t* capsized; const double* rand_capsize; int32_t capsize_on, capsize_from; float wind_threshold, wind_sigma;
 };
 
 int hs_leeway(const hs_leeway_args* a) {
@@ -233,6 +234,8 @@ int hs_leeway(const hs_leeway_args* a) {
     p.cw_slope = a->cw_slope; p.cw_offset = a->cw_offset; p.cw_eps = a->cw_eps; p.orientation = a->orientation;
     p.jibe_probability = a->jibe_probability; p.jp_f64 = 1; p.moving = a->moving; p.rand = a->rand; p.dt = a->dt;
     p.capsize_fraction = a->capsize_fraction; p.pos_f32 = a->pos_f32;
+    p.capsized = a->capsized; p.rand_capsize = a->rand_capsize; p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from;
+    p.wind_threshold = a->wind_threshold; p.wind_sigma = a->wind_sigma;
     for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);
     return 0;
 }

@@ -164,6 +164,10 @@ def test_leeway_model_matches_reference(name):
     o.add_reader([reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}, name='current'),
                   reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind')])
     o.set_config('general:use_auto_landmask', False)
+    if fx.meta.get('capsizing'):
+        o.set_config('processes:capsizing', True)
+        o.set_config('capsizing:wind_threshold', fx.meta['capsizing'][0])
+        o.set_config('capsizing:wind_threshold_sigma', fx.meta['capsizing'][1])
     o.seed_elements(lon=fx.lon0, lat=fx.lat0, time=fx.start, object_type=fx.meta['object_type'])
     o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
     assert o.num_elements_active() == fx.n
@@ -171,6 +175,8 @@ def test_leeway_model_matches_reference(name):
     assert max(e) < 5e-8, e
     assert np.array_equal(o.elements.orientation, fx.orientation)
     assert np.array_equal(o.elements.crosswind_slope, fx.crosswind_slope)
+    if fx.capsized is not None:
+        assert np.array_equal(np.asarray(o.elements.capsized, dtype=np.float64), fx.capsized)
 
 
 def test_leeway_missing_forcing_deactivates():

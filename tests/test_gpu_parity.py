@@ -163,6 +163,8 @@ def test_leeway_step_vs_reference_fixture(name):
     assert max(e) < TIGHT_DEG, e
     assert np.array_equal(el['orientation'], fx.orientation)
     assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+    if fx.capsized is not None:                   # processes:capsizing: the same elements capsized
+        assert np.array_equal(np.asarray(el['capsized'], dtype=np.float64), fx.capsized) and fx.capsized.sum() > 100
     # device generator: same physics, different (but plausible) jibing history
     lon2, lat2, el2 = common.run_leeway_engine(fx, rng='philox')
     jibed = (el2['orientation'] != np.r_[:fx.n] % 2).mean()

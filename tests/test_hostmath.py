@@ -115,6 +115,8 @@ def test_leeway_step_vs_reference_fixture(name):
     assert max(e) < 5e-8, e                       # float32 sin / cos / arctan2 differ from NumPy's SIMD versions by an ulp
     assert np.array_equal(el['orientation'], fx.orientation)
     assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+    if fx.capsized is not None:                   # processes:capsizing: the same elements capsized
+        assert np.array_equal(np.asarray(el['capsized'], dtype=np.float64), fx.capsized) and fx.capsized.sum() > 100
 
 
 def test_interpolation_bit_exact():

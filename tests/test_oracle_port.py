@@ -25,6 +25,8 @@ def test_leeway_port_matches_reference_fixture(name):
     assert np.array_equal(lon, fx.lon) and np.array_equal(lat, fx.lat)
     assert np.array_equal(el['orientation'], fx.orientation)
     assert np.array_equal(el['crosswind_slope'], fx.crosswind_slope)
+    if fx.capsized is not None:                   # processes:capsizing: the same elements capsized
+        assert np.array_equal(np.asarray(el['capsized'], dtype=np.float64), fx.capsized) and fx.capsized.sum() > 100
 
 
 def test_port_matches_live_reference():
