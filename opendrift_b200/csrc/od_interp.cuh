@@ -97,8 +97,17 @@ OD_HD VertW vert_weights(const GroupGeom& g, ZPtr zs, ZPtr zy, double z, bool z_
     }
     int idx = lo < 1 ? 1 : (lo > g.nz - 1 ? g.nz - 1 : lo);
     const double x_lo = zs[idx - 1], x_hi = zs[idx], y_lo = zy[idx - 1], y_hi = zy[idx];
-    const double slope = (y_hi - y_lo) / (x_hi - x_lo);
-    const double yn = OD_DADD(OD_DMUL(slope, OD_DSUB(xn, x_lo)), y_lo);
+    // SciPy's interp1d(kind='linear') hands 1-D float64 tables to np.interp, which returns the table value itself at a
+    // knot (and at the last point) and the slope form slope * (x - xp[j]) + fp[j] in between -- at a knot the slope form
+    // can be off by an ulp, which would put 1e-16 of the neighbouring layer into a particle that sits exactly on a level
+    // (every surface particle when the first level is z = 0).
+    double yn;
+    if (xn == x_hi) yn = y_hi;
+    else if (xn == x_lo) yn = y_lo;
+    else {
+        const double slope = (y_hi - y_lo) / (x_hi - x_lo);
+        yn = OD_DADD(OD_DMUL(slope, OD_DSUB(xn, x_lo)), y_lo);
+    }
     double fl = floor(yn);
     int ia = (int)fl;
     if (!(fl >= 0.0)) ia = 0;                        // also NaN
@@ -173,8 +182,16 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
         yi = OD_DMUL(div_rn(OD_DSUB(y, g.y0), g.yspan, g.ryspan), g.nym1);
     }
     // global readers are tested north-south only (variables.py:239-242)
-    bool covered = (g.wrap != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (y >= g.ymin) && (y <= g.ymax);
-    covered = covered && (xi >= 0.0) && (xi <= g.nxm1) && (yi >= 0.0) && (yi <= g.nym1);
+    const bool covered = (g.wrap != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (y >= g.ymin) && (y <= g.ymax) &&
+                         (xi == xi) && (yi == yi);          // (a NaN position is not covered)
+    // A covered point whose fractional index falls outside [0, n-1] -- the float32 span of the block makes that happen
+    // by up to 1e-7 of the grid length on the last row / column -- first comes back NaN from map_coordinates
+    // (mode='constant', cval=nan) and is then re-interpolated by the NaN loop of Linear2DInterpolator with
+    // mode='nearest' (interpolators.py:121-139): the edge value.  Clamping the index gives the same number.
+    if (covered) {
+        xi = xi < 0.0 ? 0.0 : (xi > g.nxm1 ? g.nxm1 : xi);
+        yi = yi < 0.0 ? 0.0 : (yi > g.nym1 ? g.nym1 : yi);
+    }
     h.valid = covered;
     if (!covered) {
         h.i00 = h.i01 = h.i10 = h.i11 = 0;

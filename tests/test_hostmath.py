@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 
 import common
+from datetime import timedelta
+
 from common import Fixture, fixtures, run_hostshim, hostshim, _p, GOLDEN
 
 
@@ -171,3 +173,57 @@ def test_reciprocal_division_is_correctly_rounded():
             q = float(Fraction(q0) + Fraction(e) * fr)
             bad += q != d / s
     assert bad == 0
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_interpolation_bit_exact_on_random_geometries(seed):
+    """The sampler against the port on random block geometries: grid sizes down to 2 x 2 x 2, ascending and descending
+    longitude / latitude / depth axes, irregular depth levels, longitude conventions on both sides of Greenwich and
+    east-west periodic grids, 1- and 2-component groups, float64 and float32 positions, particles on and off the grid."""
+    from oracle import advect_port as ap
+    lib = hostshim()
+    rng = np.random.default_rng(1000 + seed)
+    nx, ny = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+    nz = int(rng.choice([1, 2, 3, 7, 12]))
+    periodic = seed % 4 == 3
+    if periodic:
+        nx = int(rng.choice([36, 72, 90]))
+        dx = 360.0 / nx
+        lon = (rng.choice([0.0, -180.0]) + dx * np.arange(nx)).astype(np.float32)
+    else:
+        x0 = rng.uniform(-170, 170) if seed % 2 else rng.uniform(1, 300)
+        dx = rng.uniform(0.01, 0.5)
+        lon = (x0 + dx * np.arange(nx)).astype(np.float32)
+        if rng.uniform() < 0.3:
+            lon = lon[::-1].copy()
+    lat = (rng.uniform(-80, 60) + rng.uniform(0.01, 0.4) * np.arange(ny)).astype(np.float32)
+    if rng.uniform() < 0.4:
+        lat = lat[::-1].copy()
+    z = None
+    if nz > 1:
+        # levels representable in float32: the reference clamps a float32 copy of z to the float64 level range and scipy's
+        # interp1d raises when the rounded value lands outside it (interpolators.py:176-183), so such grids cannot be replayed
+        z = (-np.cumsum(rng.uniform(0.5, 20.0, nz)) + rng.uniform(0, 3)).astype(np.float32).astype(np.float64)
+        if rng.uniform() < 0.5:
+            z = z[::-1].copy()
+    times = [common.syn.T0 + timedelta(hours=i) for i in range(3)]
+    shape = (3, nz, ny, nx) if nz > 1 else (3, ny, nx)
+    ncomp = 1 if seed % 3 == 0 else 2
+    names = ['upward_sea_water_velocity'] if ncomp == 1 else list(common.CUR)
+    fields = [rng.normal(size=shape).astype(np.float32) for _ in range(ncomp)]
+    r = ap.GridReader(lon, lat, z, times, dict(zip(names, fields)))
+    f = common.HsField(lon, lat, z, fields, times, tuple([0.0] * ncomp))
+    assert bool(f.g.wrap_x) == periodic
+    n = 4000
+    plon = rng.uniform(float(lon.min()) - 2 * abs(dx), float(lon.max()) + 2 * abs(dx), n)
+    plat = rng.uniform(float(lat.min()) - 0.3, float(lat.max()) + 0.3, n)
+    plon[:20], plat[20:40] = float(lon[-1]), float(lat[-1])             # on the last column / row
+    plon[40:60], plat[60:80] = float(lon[0]), float(lat[0])
+    pz = (rng.uniform(float(z.min()) - 5, 3.0, n) if z is not None else np.zeros(n)).astype(np.float32)
+    for off, pos32 in ((0, 0), (1800, 0), (4321, 0), (4321, 1)):
+        t = times[0] + timedelta(seconds=off)
+        lo, la = (plon.astype(np.float32), plat.astype(np.float32)) if pos32 else (plon, plat)
+        env = ap.get_environment([r], names, t, lo, la, pz)
+        outs = f.sample(lib, t, lo.astype(np.float64), la.astype(np.float64), pz, bool(pos32))
+        for k, nme in enumerate(names):
+            assert np.array_equal(outs[k], env[nme]), (seed, off, pos32, nme)
