@@ -12,6 +12,7 @@ import pytest
 
 import common
 from datetime import timedelta
+from opendrift_b200 import synthetic as syn
 
 from common import Fixture, fixtures, run_hostshim, hostshim, _p, GOLDEN
 
@@ -227,3 +228,74 @@ def test_interpolation_bit_exact_on_random_geometries(seed):
         outs = f.sample(lib, t, lo.astype(np.float64), la.astype(np.float64), pz, bool(pos32))
         for k, nme in enumerate(names):
             assert np.array_equal(outs[k], env[nme]), (seed, off, pos32, nme)
+
+
+# ---- random whole-step scenarios: the device math (host build) against the port ---------------------------------------
+class _Fx:
+    pass
+
+def _random_scenario(seed):
+    rng=np.random.default_rng(5000+seed)
+    fx=_Fx()
+    nx, ny = int(rng.integers(8, 40)), int(rng.integers(8, 40))
+    nz = int(rng.choice([1, 3, 7]))
+    periodic = seed % 5 == 4
+    if periodic:
+        nx = 72; dx=5.0
+        lon=(rng.choice([0.0,-180.0]) + dx*np.arange(nx)).astype(np.float32)
+        lat=(rng.uniform(-60,20)+0.5*np.arange(ny)).astype(np.float32)
+    else:
+        dx=rng.uniform(0.02,0.2)
+        lon=(rng.uniform(-170,150)+dx*np.arange(nx)).astype(np.float32)
+        lat=(rng.uniform(-70,60)+rng.uniform(0.02,0.1)*np.arange(ny)).astype(np.float32)
+        if rng.uniform()<0.3: lon=lon[::-1].copy()
+    if rng.uniform()<0.4: lat=lat[::-1].copy()
+    z=None
+    if nz>1:
+        z=(-np.cumsum(rng.uniform(1,15,nz))+rng.uniform(0,1)).astype(np.float32).astype(np.float64)
+        z[0]=0.0 if rng.uniform()<0.5 else z[0]
+        if rng.uniform()<0.5: z=z[::-1].copy()
+    steps=int(rng.integers(3,7)); dt=int(rng.choice([300,600,900,-600]))
+    nsl=syn.n_slabs_for(steps,dt)+1
+    shape=(nsl,nz,ny,nx) if nz>1 else (nsl,ny,nx)
+    amp=0.5
+    fx.u=(amp*rng.normal(size=shape)).astype(np.float32); fx.v=(amp*rng.normal(size=shape)).astype(np.float32)
+    with_w = nz>1 and rng.uniform()<0.5
+    fx.w=(1e-3*rng.normal(size=shape)).astype(np.float32) if with_w else None
+    wind = rng.uniform()<0.5
+    fx.x_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32) if wind else None
+    fx.y_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32) if wind else None
+    fx.wind_lon, fx.wind_lat = lon, lat
+    fx.grid_lon, fx.grid_lat, fx.grid_z = lon, lat, z
+    fx.cdf=None; fx.kdiff=None; fx.stokes=None
+    n=800
+    fx.lon0=rng.uniform(float(lon.min())-abs(dx), float(lon.max())+abs(dx), n).astype(np.float32)
+    fx.lat0=rng.uniform(float(lat.min())-0.05, float(lat.max())+0.05, n).astype(np.float32)
+    fx.z0=(rng.uniform((z.min()-3) if z is not None else -1, 0.5, n)).astype(np.float32)
+    fx.z0[fx.z0>0]=0
+    if z is None: fx.z0[:]=0
+    fx.times=syn.slab_times(nsl,3600)
+    fx.dt=dt; fx.steps=steps; fx.n=n
+    fx.start=fx.times[-1] if dt<0 else syn.T0+timedelta(seconds=int(rng.choice([0,450])))
+    scheme=str(rng.choice(['euler','runge-kutta','runge-kutta4']))
+    fx.meta=dict(scheme=scheme,with_w=with_w,wind=wind,diffusivity=0.0,seed=0,wind_drift_depth=None,mixing=False,dt_mix=60.0,stokes=None,noise=None,start_offset_s=0)
+    fx.props=lambda: (np.float32(1)*np.ones(n), np.float32(0.02)*np.ones(n), np.ones(n,dtype=np.int32))
+    fx.wind_drift_depth=lambda: 0.1
+    return fx
+
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_random_step_scenarios_vs_port(seed):
+    """Random block geometry (ascending / descending axes, periodic grids, a level at z = 0 or not), scheme, time step
+    (also backward), start offset, wind drift and vertical advection; particles inside and outside the block: the device
+    math must follow the port (= the reference) to the same 2e-8 deg as on the fixtures, in both float64 arithmetic modes."""
+    fx = _random_scenario(seed)
+    pl, pa, pz = common.run_port(fx)
+    for mode in (0, 2):
+        hl, ha, hz = run_hostshim(fx, fast=mode)
+        assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+        m = np.isfinite(pl)
+        e = common.max_err_deg(hl[m], ha[m], pl[m], pa[m])
+        assert max(e) < 2e-8, (seed, mode, e)
+        assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
