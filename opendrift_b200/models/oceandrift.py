@@ -242,6 +242,10 @@ class OceanDrift(OpenDriftSimulation):
             # mixing first: it reads the start-of-step positions and depth and writes a new depth buffer; the
             # step kernel still samples with the old depth and applies vertical advection to the new one
             z_new = self._mix(el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, el.positions_f32)
+        elif stokes_inp is not None and wgrp is not None:
+            # update() moves with the Stokes drift BEFORE vertical advection (oceandrift.py:196-205): the Stokes profile
+            # must see the start-of-step depth, so vertical advection writes into a copy that replaces z afterwards
+            z_new = z.clone()
         eng.step_oceandrift(g, self.get_config('drift:advection_scheme'), t, self.time_step,
                             el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, factor=fac, moving=moving,
                             truncate_below=self.get_config('drift:truncate_ocean_model_below_m'),

@@ -284,6 +284,7 @@ def main():
     dateline_cases()
     run_case('rk4_3d_truncate_wsurf', g3, n, 8, 600, 'runge-kutta4', with_w=True, wind=True, truncate=40.0, w_at_surface=True)
     run_case('rk2_3d_truncate', g3, n, 6, 900, 'runge-kutta', truncate=25.0)
+    run_case('rk2_3d_stokes_w', g3, 900, 5, 600, 'runge-kutta', wind=True, stokes='Phillips', with_w=True)
     run_case('rk4_3d_cfg4', g3, 600, 5, 600, 'runge-kutta4', wind=True, stokes='Phillips', mixing=True, dt_mix=60.0, with_w=True)
     run_case('rk4_3d_mixing_large1994', g3, 600, 5, 600, 'runge-kutta4', mixing=True, dt_mix=60.0, wind=True,
              diffusivity_model='windspeed_Large1994')

@@ -452,6 +452,8 @@ def run_hostshim(fx, fast=False):
             a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, 1, wind.g, wind.pair(t)
             a.wdf, a.wind_drift_depth = _p(wdf), fx.wind_drift_depth()
         if wfld is not None:
+            if z_new is None and senv is not None:
+                z_new = z.copy()          # the Stokes move (after this launch) still needs the start-of-step depth
             zu = z if z_new is None else z_new
             a.w_on, a.g_w, a.t_w, a.z_inout = 1, wfld.g, wfld.pair(t), _p(zu)
             a.w_at_surface = 1 if m.get('w_at_surface') else 0
@@ -543,6 +545,8 @@ def run_engine(fx, fused=True, sort_every=0, fast=None):
             z_new = eng.vertical_mixing(kgrp, t, lon, lat, z, m['dt_mix'] * np.sign(fx.dt), ntimes, moving=d_mov,
                                         rand=rnd, pos_f32=first, **kw)
         if fused:
+            if z_new is None and senv is not None and wgrp is not None:
+                z_new = z.clone()         # the Stokes move (after this launch) still needs the start-of-step depth
             eng.step_oceandrift(cur, m['scheme'], t, dt, lon, lat, z if three_d or wind or wgrp else None,
                                 factor=d_cdf, moving=d_mov, wind=wind, wdf=d_wdf,
                                 wind_drift_depth=fx.wind_drift_depth(), w_group=wgrp, rand=rand,
