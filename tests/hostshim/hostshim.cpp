@@ -201,6 +201,19 @@ int hs_mix(const hs_mix_args* a) {
     return 0;
 }
 
+// the diffusivity column a particle sees (k_level of od_mix.cuh), all levels: out[n][nz]
+void hs_kcolumn(const hs_group* g, const hs_pair* pr, int64_t n, const double* lon, const double* lat, int pos_f32, double* out) {
+    hs_levels lv;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = make_geom(*g, lv);
+    p.pr = make_pair(*pr);
+    for (int64_t i = 0; i < n; ++i) {
+        const HorizW h = horiz_weights(p.g, lon[i], lat[i], pos_f32 != 0);
+        for (int l = 0; l < p.g.nz; ++l) out[i * p.g.nz + l] = k_level(p, h, l);
+    }
+}
+
 struct hs_stokes_args {
     int64_t n; double* lon; double* lat; const void* z; const float* us; const float* vs; const float* hs;
     const float* xwind; const float* ywind; const int32_t* moving; double dt; int32_t z_f64, hs_mode, profile, pad_;

@@ -299,3 +299,89 @@ def test_random_step_scenarios_vs_port(seed):
         e = common.max_err_deg(hl[m], ha[m], pl[m], pa[m])
         assert max(e) < 2e-8, (seed, mode, e)
         assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
+
+
+def _random_physics_scenario(seed):
+    rng=np.random.default_rng(9000+seed)
+    fx=_random_scenario(seed+1000)
+    n=fx.n
+    three_d = fx.grid_z is not None
+    nsl=fx.u.shape[0]; ny,nx=len(fx.grid_lat),len(fx.grid_lon)
+    m=fx.meta
+    if fx.dt<0:
+        return None
+    # always wind for stokes / analytic mixing
+    if fx.x_wind is None:
+        fx.x_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32); fx.y_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32)
+    m['wind']=True
+    choice=seed%4
+    if choice==0 and three_d:      # env mixing
+        nz=len(fx.grid_z)
+        fx.kdiff=(0.01*rng.uniform(0.1,1.0,size=(nsl,nz,ny,nx))).astype(np.float32)
+        m['mixing']=True; m['dt_mix']=float(rng.choice([60.0,100.0]))
+    elif choice==1:                # analytic mixing
+        m['mixing']=True; m['dt_mix']=60.0; m['diffusivity_model']=str(rng.choice(['windspeed_Large1994','windspeed_Sundby1983'])); m['background_diffusivity']=float(rng.choice([1.2e-5,1e-4]))
+    elif choice==2:                # stokes
+        prof=str(rng.choice(['Phillips','monochromatic','exponential']))
+        fx.stokes={'sea_surface_wave_stokes_drift_x_velocity':(0.1*rng.normal(size=(nsl,ny,nx))).astype(np.float32),
+                   'sea_surface_wave_stokes_drift_y_velocity':(0.1*rng.normal(size=(nsl,ny,nx))).astype(np.float32)}
+        if rng.uniform()<0.5:
+            fx.stokes['sea_surface_wave_significant_height']=(1+rng.uniform(size=(nsl,ny,nx))).astype(np.float32)
+        m['stokes']=prof
+    else:
+        m['diffusivity']=float(rng.choice([1.0,10.0]))
+    return fx
+
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3, 5, 6, 7, 18, 42, 46])
+def test_random_physics_scenarios_vs_port(seed):
+    """As above with the analytical mixing models, a Stokes profile (with vertical advection in the same step: the Stokes
+    move must see the start-of-step depth) or horizontal diffusion switched on."""
+    fx = _random_physics_scenario(seed)
+    if fx is None:
+        pytest.skip('backward run or 2-D block drawn for this seed')
+    pl, pa, pz = common.run_port(fx)
+    for mode in (0, 2):
+        hl, ha, hz = run_hostshim(fx, fast=mode)
+        assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+        m = np.isfinite(pl)
+        assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 2e-8, (seed, mode)
+        assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= (1e-6 if fx.meta.get('mixing') else 1e-5)
+
+
+class _L:
+    pass
+def _random_leeway_scenario(seed):
+    rng=np.random.default_rng(20000+seed)
+    b=_random_scenario(seed+7000)
+    fx=_L()
+    fx.grid_lon,fx.grid_lat=b.grid_lon,b.grid_lat
+    nsl=b.u.shape[0]; ny,nx=len(b.grid_lat),len(b.grid_lon)
+    fx.u=(0.3*rng.normal(size=(nsl,ny,nx))).astype(np.float32); fx.v=(0.3*rng.normal(size=(nsl,ny,nx))).astype(np.float32)
+    fx.x_wind=(8*rng.normal(size=(nsl,ny,nx))).astype(np.float32); fx.y_wind=(8*rng.normal(size=(nsl,ny,nx))).astype(np.float32)
+    n=600
+    lo,hi=float(fx.grid_lon.min()),float(fx.grid_lon.max()); la0,la1=float(fx.grid_lat.min()),float(fx.grid_lat.max())
+    fx.lon0=rng.uniform(lo+0.2*(hi-lo), hi-0.2*(hi-lo), n).astype(np.float32)
+    fx.lat0=rng.uniform(la0+0.2*(la1-la0), la1-0.2*(la1-la0), n).astype(np.float32)
+    fx.times=b.times; fx.dt=abs(b.dt); fx.steps=b.steps; fx.n=n; fx.start=syn.T0
+    caps = [8.0,5.0] if seed%2 else None
+    from opendrift_b200.models.leeway import read_object_properties
+    prop=read_object_properties()[int(rng.choice([1,2,3,4]))]
+    fx.prop={k:v for k,v in prop.items() if k not in('OBJKEY','Description')}
+    fx.meta=dict(seed=int(seed),capsizing=caps)
+    fx.capsized=None
+    return fx
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_random_leeway_scenarios_vs_port(seed):
+    fx = _random_leeway_scenario(seed)
+    pl, pa, pel = common.run_leeway_port(fx)
+    hl, ha, hel = common.run_leeway_hostshim(fx)
+    assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+    m = np.isfinite(pl)
+    assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 5e-8
+    assert np.array_equal(hel['orientation'], pel['orientation']) and np.array_equal(hel['crosswind_slope'], pel['crosswind_slope'])
+    if fx.meta['capsizing'] is not None:
+        assert np.array_equal(np.asarray(hel['capsized'], dtype=np.float64), pel['capsized'])
