@@ -277,6 +277,11 @@ OD_HD GeodStart geod_start(double lat1) {
 // Position at distance s12 (metres, may be negative) along azimuth azi1 (degrees) from (lon1, start).
 OD_HD void geod_move(const GeodStart& p, double lon1, double azi1, double s12, double& lon2, double& lat2) {
     const GeodK& K = OD_GK;
+    if (s12 == 0.0) {            // a particle that does not move stays where it is, to the bit (a zero velocity is the fallback of an
+        lon2 = ang_normalize(ang_normalize(lon1));      // uncovered Runge-Kutta stage: the next stage must sample the start point itself,
+        lat2 = p.lat1;                                  // e.g. on the boundary row of the block, not a point an ulp outside it)
+        return;
+    }
     double salp1, calp1;
     sincosd(ang_round(ang_normalize(azi1)), salp1, calp1);
     const double sbet1 = p.sbet1, cbet1 = p.cbet1;

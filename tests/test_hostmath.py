@@ -385,3 +385,53 @@ def test_random_leeway_scenarios_vs_port(seed):
     assert np.array_equal(hel['orientation'], pel['orientation']) and np.array_equal(hel['crosswind_slope'], pel['crosswind_slope'])
     if fx.meta['capsizing'] is not None:
         assert np.array_equal(np.asarray(hel['capsized'], dtype=np.float64), pel['capsized'])
+
+
+def _random_options_scenario(seed):
+    rng=np.random.default_rng(30000+seed)
+    fx=_random_scenario(seed+5000)
+    m=fx.meta; n=fx.n
+    three_d=fx.grid_z is not None
+    if rng.uniform()<0.4 and three_d:
+        m['truncate']=float(rng.uniform(2, abs(fx.grid_z).max()))
+    if m['with_w'] and rng.uniform()<0.5: m['w_at_surface']=True
+    if m['wind']:
+        wdd=float(rng.choice([0.0,0.1,0.5,2.0])); m['wind_drift_depth']=wdd
+        fx.wind_drift_depth=(lambda w=wdd: w)
+    if rng.uniform()<0.3:
+        cdf=rng.uniform(0.3,1.2,n).astype(np.float32); fx.cdf=cdf
+        fx.props=(lambda c=cdf,n=n: (c.astype(np.float32), np.float32(0.02)*np.ones(n), np.ones(n,dtype=np.int32)))
+    # particles exactly on nodes / levels
+    k=40
+    ii=rng.integers(1,len(fx.grid_lon)-1,k); jj=rng.integers(1,len(fx.grid_lat)-1,k)     # interior nodes (a motionless particle exactly on the boundary is a 1-ulp knife edge of the geodesic)
+    fx.lon0[:k]=fx.grid_lon[ii]; fx.lat0[:k]=fx.grid_lat[jj]
+    if three_d:
+        kk=rng.integers(0,len(fx.grid_z),k); fx.z0[k:2*k]=np.minimum(fx.grid_z[kk],0).astype(np.float32)
+    # land holes
+    if rng.uniform()<0.4:
+        ny,nx=len(fx.grid_lat),len(fx.grid_lon)
+        iy,ix=np.meshgrid(np.arange(ny),np.arange(nx),indexing='ij')
+        cx,cy=rng.integers(0,nx),rng.integers(0,ny); hole=(ix-cx)**2+(iy-cy)**2<=rng.integers(2,20)
+        for a in (fx.u,fx.v):
+            if a.ndim==4:
+                a[:,:,hole]=np.nan
+                a[:,a.shape[1]//2:,(ix-cx-3)**2+(iy-cy)**2<=9]=np.nan
+            else: a[:,hole]=np.nan
+    if rng.uniform()<0.25:
+        m['noise']={'current':0.1} if rng.uniform()<0.5 else {'current_uniform':0.05,'wind':0.5}
+    return fx
+
+
+@pytest.mark.parametrize('seed', [0, 3, 6, 17, 19, 21, 27, 31])
+def test_random_option_scenarios_vs_port(seed):
+    """Random scenarios with drift:truncate_ocean_model_below_m, vertical advection at the surface, wind-drift depths,
+    per-element float32 drift factors, uncertainty draws, land holes (NaN fill) and particles exactly on interior grid
+    nodes and on depth levels."""
+    fx = _random_options_scenario(seed)
+    pl, pa, pz = common.run_port(fx)
+    for mode in (0, 2):
+        hl, ha, hz = run_hostshim(fx, fast=mode)
+        assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+        m = np.isfinite(pl)
+        assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 2e-8, (seed, mode)
+        assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
