@@ -94,7 +94,9 @@ typedef struct od_group_desc {
     int32_t lon_mode;         /* od_lon_mode */
     int32_t n_slots;          /* ring of time slabs kept on the device (>= 2) */
     int32_t wrap_x;           /* 0 / 1, see above */
-    int32_t pad_;
+    int32_t global_x;         /* 0 / 1: east-west global coverage by the reference's rule (variables.py:289-301), periodic or not: the
+                                 coverage test is north-south only (variables.py:239-242); points in the east-west gap of a global grid
+                                 that is not periodic get the edge value (the NaN loop of Linear2DInterpolator) */
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     float fallback[2];

@@ -22,7 +22,7 @@ SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
 
 class GroupDesc(C.Structure):
     _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
-                ('lon_mode', C.c_int32), ('n_slots', C.c_int32), ('wrap_x', C.c_int32), ('pad_', C.c_int32),
+                ('lon_mode', C.c_int32), ('n_slots', C.c_int32), ('wrap_x', C.c_int32), ('global_x', C.c_int32),
                 ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
                 ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
                 ('fallback', C.c_float * 2)]

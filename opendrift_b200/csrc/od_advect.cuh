@@ -172,7 +172,7 @@ struct FastMath {
         float ru = NAN, rv = NAN;
         double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
         double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
-        if (pr.mode != 3 && (g.wrap != 0 || (x >= g.xmin && x <= g.xmax)) && lat >= g.ymin && lat <= g.ymax &&
+        if (pr.mode != 3 && (g.glob != 0 || (x >= g.xmin && x <= g.xmax)) && lat >= g.ymin && lat <= g.ymax &&
             xi == xi && yi == yi) {
             xi = xi < 0.0 ? 0.0 : (xi > g.nxm1 ? g.nxm1 : xi);       // covered: edge value (see horiz_weights)
             yi = yi < 0.0 ? 0.0 : (yi > g.nym1 ? g.nym1 : yi);

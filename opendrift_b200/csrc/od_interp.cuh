@@ -40,6 +40,7 @@ struct GroupGeom {
     int nx, ny, nz, ncomp;
     int lon_mode;            // 0: np.mod(lon, 360); 1: np.mod(lon + 180, 360) - 180
     int wrap;                // 1: periodic east-west; one virtual column (= column 0) follows the nx stored ones
+    int glob;                // 1: east-west global coverage (periodic or not): no east-west coverage test
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     double nxm1, nym1;
@@ -182,7 +183,7 @@ OD_HD HorizW horiz_weights(const GroupGeom& g, double lon, double lat, bool pos_
         yi = OD_DMUL(div_rn(OD_DSUB(y, g.y0), g.yspan, g.ryspan), g.nym1);
     }
     // global readers are tested north-south only (variables.py:239-242)
-    const bool covered = (g.wrap != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (y >= g.ymin) && (y <= g.ymax) &&
+    const bool covered = (g.glob != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (y >= g.ymin) && (y <= g.ymax) &&
                          (xi == xi) && (yi == yi);          // (a NaN position is not covered)
     // A covered point whose fractional index falls outside [0, n-1] -- the float32 span of the block makes that happen
     // by up to 1e-7 of the grid length on the last row / column -- first comes back NaN from map_coordinates

@@ -581,6 +581,7 @@ static GroupGeom make_geom(const Group& g) {
     q.nx = g.desc.nx; q.ny = g.desc.ny; q.nz = g.desc.nz; q.ncomp = g.desc.ncomp;
     q.lon_mode = g.desc.lon_mode;
     q.wrap = g.desc.wrap_x ? 1 : 0;
+    q.glob = (g.desc.global_x || g.desc.wrap_x) ? 1 : 0;
     q.x0 = g.desc.x0; q.xspan = g.desc.xspan; q.y0 = g.desc.y0; q.yspan = g.desc.yspan;
     q.xmin = g.desc.xmin; q.xmax = g.desc.xmax; q.ymin = g.desc.ymin; q.ymax = g.desc.ymax;
     q.nxm1 = (double)(g.desc.nx - 1 + q.wrap); q.nym1 = (double)(g.desc.ny - 1);
@@ -1328,7 +1329,7 @@ static int fill_step(od_ctx* ctx, const od_step_args* a, StepParams* pp) {
         const Group& gu = ctx->groups[a->cur.group_uv];
         const Group& gw = ctx->groups[a->group_w];
         const od_group_desc &du = gu.desc, &dw = gw.desc;
-        p.w_same_grid = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x &&
+        p.w_same_grid = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x && du.global_x == dw.global_x &&
                         du.x0 == dw.x0 && du.xspan == dw.xspan && du.y0 == dw.y0 && du.yspan == dw.yspan && du.xmin == dw.xmin &&
                         du.xmax == dw.xmax && du.ymin == dw.ymin && du.ymax == dw.ymax && gu.h_levels == gw.h_levels;
     }

@@ -87,7 +87,7 @@ def grid_geometry(lon, lat):
     glob = (xmin - 2 * dx <= 0 and xmax + 2 * dx >= 360) or (xmin - 2 * dx <= -180 and xmax + 2 * dx >= 180)
     periodic = bool(glob) and abs(len(lon) * dx - 360.0) < 1e-3 * dx
     x_last = np.float32(lon[-1] + np.float32(dx)) if periodic else lon[-1]
-    return {'lon_mode': _lib.OD_LON_PM180 if xmin < 0 else _lib.OD_LON_0_360, 'wrap_x': 1 if periodic else 0,
+    return {'lon_mode': _lib.OD_LON_PM180 if xmin < 0 else _lib.OD_LON_0_360, 'wrap_x': 1 if periodic else 0, 'global_x': 1 if glob else 0,
             'global_coverage': bool(glob),
             'x0': float(lon[0]), 'xspan': float(np.float32(x_last - lon[0])),
             'y0': float(lat[0]), 'yspan': float(np.float32(lat[-1] - lat[0])),
@@ -117,7 +117,7 @@ class FieldGroup:
         d.nz = 1 if self.z is None else len(self.z)
         d.n_slots = n_slots
         geo = grid_geometry(self.lon, self.lat)
-        d.lon_mode, d.wrap_x = geo['lon_mode'], geo['wrap_x']
+        d.lon_mode, d.wrap_x, d.global_x = geo['lon_mode'], geo['wrap_x'], geo['global_x']
         d.x0, d.xspan, d.y0, d.yspan = geo['x0'], geo['xspan'], geo['y0'], geo['yspan']
         d.xmin, d.xmax, d.ymin, d.ymax = geo['xmin'], geo['xmax'], geo['ymin'], geo['ymax']
         self.global_coverage, self.periodic = geo['global_coverage'], bool(geo['wrap_x'])

@@ -168,11 +168,14 @@ class Fixture:
 def run_port(fx):
     from oracle import advect_port as ap
     f3 = {CUR[0]: fx.u, CUR[1]: fx.v}
-    if fx.w is not None:
+    w_own_grid = getattr(fx, 'w_lon', None) is not None          # upward velocity from a reader of its own
+    if fx.w is not None and not w_own_grid:
         f3['upward_sea_water_velocity'] = fx.w
     if fx.kdiff is not None:
         f3['ocean_vertical_diffusivity'] = fx.kdiff
     readers = [ap.GridReader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3)]
+    if fx.w is not None and w_own_grid:
+        readers.append(ap.GridReader(fx.w_lon, fx.w_lat, fx.w_z, fx.times, {'upward_sea_water_velocity': fx.w}))
     if fx.x_wind is not None:
         readers.append(ap.GridReader(fx.wind_lon, fx.wind_lat, None, fx.times,
                                      {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}))
@@ -192,7 +195,7 @@ def run_port(fx):
 # ---- host-compiled device math ---------------------------------------------------------------
 class HsGroup(C.Structure):
     _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
-                ('lon_mode', C.c_int32), ('wrap_x', C.c_int32),
+                ('lon_mode', C.c_int32), ('wrap_x', C.c_int32), ('global_x', C.c_int32), ('pad_', C.c_int32),
                 ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
                 ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
                 ('fallback', C.c_float * 2), ('z_levels', C.c_void_p)]
@@ -348,7 +351,7 @@ class HsField:
         g.ncomp, g.nx, g.ny, g.nz = len(comps), len(self.lon), len(self.lat), 1 if self.z is None else len(self.z)
         from opendrift_b200.engine import grid_geometry
         geo = grid_geometry(self.lon, self.lat)
-        g.lon_mode, g.wrap_x = geo['lon_mode'], geo['wrap_x']
+        g.lon_mode, g.wrap_x, g.global_x = geo['lon_mode'], geo['wrap_x'], geo['global_x']
         g.x0, g.xspan, g.y0, g.yspan = geo['x0'], geo['xspan'], geo['y0'], geo['yspan']
         g.xmin, g.xmax, g.ymin, g.ymax = geo['xmin'], geo['xmax'], geo['ymin'], geo['ymax']
         g.fallback[0], g.fallback[1] = fallback[0], fallback[-1]
@@ -384,7 +387,8 @@ def run_hostshim(fx, fast=False):
     m = fx.meta
     cur = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.u, fx.v], fx.times)
     wind = HsField(fx.wind_lon, fx.wind_lat, None, [fx.x_wind, fx.y_wind], fx.times) if m['wind'] else None
-    wfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.w], fx.times, (0.0,)) if m['with_w'] else None
+    wg = (fx.w_lon, fx.w_lat, fx.w_z) if getattr(fx, 'w_lon', None) is not None else (fx.grid_lon, fx.grid_lat, fx.grid_z)
+    wfld = HsField(wg[0], wg[1], wg[2], [fx.w], fx.times, (0.0,)) if m['with_w'] else None
     kfld = HsField(fx.grid_lon, fx.grid_lat, fx.grid_z, [fx.kdiff], fx.times, (0.0,)) if m.get('mixing') else None
     sfld = hfld = None
     if m.get('stokes'):
@@ -497,7 +501,8 @@ def run_engine(fx, fused=True, sort_every=0, fast=None):
         wind = eng.add_group(fx.wind_lon, fx.wind_lat, None, 2, fx.times,
                              lambda ti, c: (fx.x_wind, fx.y_wind)[c][ti], (0.0, 0.0))
     if m['with_w']:
-        wgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.w[ti], (0.0,))
+        wg = (fx.w_lon, fx.w_lat, fx.w_z) if getattr(fx, 'w_lon', None) is not None else (fx.grid_lon, fx.grid_lat, fx.grid_z)
+        wgrp = eng.add_group(wg[0], wg[1], wg[2], 1, fx.times, lambda ti, c: fx.w[ti], (0.0,))
     kgrp = None
     if m.get('mixing'):
         kgrp = eng.add_group(fx.grid_lon, fx.grid_lat, fx.grid_z, 1, fx.times, lambda ti, c: fx.kdiff[ti], (0.0,))

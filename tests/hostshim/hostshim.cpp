@@ -15,7 +15,7 @@ using namespace od;
 extern "C" {
 
 struct hs_group {
-    int32_t ncomp, nx, ny, nz, lon_mode, wrap_x;
+    int32_t ncomp, nx, ny, nz, lon_mode, wrap_x, global_x, pad_;
     double x0, xspan, y0, yspan, xmin, xmax, ymin, ymax;
     float fallback[2];
     const double* z_levels;   // as the reader gives them
@@ -35,7 +35,7 @@ struct hs_levels {
 static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
     GroupGeom q;
     memset(&q, 0, sizeof(q));
-    q.nx = d.nx; q.ny = d.ny; q.nz = d.nz; q.ncomp = d.ncomp; q.lon_mode = d.lon_mode; q.wrap = d.wrap_x ? 1 : 0;
+    q.nx = d.nx; q.ny = d.ny; q.nz = d.nz; q.ncomp = d.ncomp; q.lon_mode = d.lon_mode; q.wrap = d.wrap_x ? 1 : 0; q.glob = (d.global_x || d.wrap_x) ? 1 : 0;
     q.x0 = d.x0; q.xspan = d.xspan; q.y0 = d.y0; q.yspan = d.yspan;
     q.xmin = d.xmin; q.xmax = d.xmax; q.ymin = d.ymin; q.ymax = d.ymax;
     q.nxm1 = (double)(d.nx - 1 + q.wrap); q.nym1 = (double)(d.ny - 1);
@@ -144,7 +144,7 @@ int hs_step(const hs_step_args* a) {
         p.z_inout = a->z_inout;
         p.zio_f64 = a->z_inout_f64;
         const hs_group &du = a->g_uv, &dw = a->g_w;
-        bool same = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x &&
+        bool same = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x && du.global_x == dw.global_x &&
                     du.x0 == dw.x0 && du.xspan == dw.xspan && du.y0 == dw.y0 && du.yspan == dw.yspan && du.xmin == dw.xmin &&
                     du.xmax == dw.xmax && du.ymin == dw.ymin && du.ymax == dw.ymax;
         for (int k = 0; same && du.nz > 1 && k < du.nz; ++k) same = du.z_levels[k] == dw.z_levels[k];

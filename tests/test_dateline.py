@@ -49,9 +49,11 @@ def test_geometry_of_global_grids():
     g = grid_geometry(np.arange(-180, 180), lat)
     assert g['wrap_x'] == 1 and g['xspan'] == 360.0 and g['x0'] == -180.0
     g = grid_geometry(np.arange(160, 280), lat)                       # the Pacific wind reader of the reference test
-    assert g['wrap_x'] == 0 and not g['global_coverage'] and g['xspan'] == 119.0
+    assert g['wrap_x'] == 0 and g['global_x'] == 0 and not g['global_coverage'] and g['xspan'] == 119.0
     g = grid_geometry(np.arange(0, 361), lat)                         # global with a duplicated end column: no virtual column
-    assert g['wrap_x'] == 0 and g['global_coverage']
+    assert g['wrap_x'] == 0 and g['global_coverage'] and g['global_x'] == 1
+    g = grid_geometry(np.linspace(-180.01, 175.01, 9), lat)           # global by the reference's rule (xmin - 2 dx <= -180 ...), not periodic
+    assert g['wrap_x'] == 0 and g['global_x'] == 1
     g = grid_geometry(np.arange(0.25, 360, 0.5), lat)
     assert g['wrap_x'] == 1 and abs(g['xspan'] - 360.0) < 1e-4
 

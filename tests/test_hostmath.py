@@ -435,3 +435,44 @@ def test_random_option_scenarios_vs_port(seed):
         m = np.isfinite(pl)
         assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 2e-8, (seed, mode)
         assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
+
+
+def _random_readers_scenario(seed):
+    rng=np.random.default_rng(50000+seed)
+    fx=_random_scenario(seed+11000)
+    if fx.grid_z is None or fx.dt<0: return None
+    nsl=fx.u.shape[0]
+    # w on its own (coarser / finer, differently ordered) grid covering the same box, different levels
+    lo,hi=float(fx.grid_lon.min()),float(fx.grid_lon.max()); la0,la1=float(fx.grid_lat.min()),float(fx.grid_lat.max())
+    nxw,nyw,nzw=int(rng.integers(5,30)),int(rng.integers(5,30)),int(rng.choice([2,4,9]))
+    fx.w_lon=np.linspace(lo-0.01,hi+0.01,nxw).astype(np.float32); fx.w_lat=np.linspace(la0-0.01,la1+0.01,nyw).astype(np.float32)
+    if rng.uniform()<0.5: fx.w_lat=fx.w_lat[::-1].copy()
+    zmin=float(fx.grid_z.min())
+    fx.w_z=np.linspace(0.0,zmin*rng.uniform(0.6,1.2),nzw).astype(np.float32).astype(np.float64)
+    if rng.uniform()<0.5: fx.w_z=fx.w_z[::-1].copy()
+    fx.w=(2e-3*rng.normal(size=(nsl,nzw,nyw,nxw))).astype(np.float32)
+    fx.meta['with_w']=True
+    if rng.uniform()<0.5: fx.meta['w_at_surface']=True
+    # wind on a global periodic grid
+    if seed%2:
+        fx.wind_lon=(rng.choice([0.0,-180.0])+5.0*np.arange(72)).astype(np.float32); fx.wind_lat=np.linspace(-88,88,45).astype(np.float32)
+        fx.x_wind=(6*rng.normal(size=(nsl,45,72))).astype(np.float32); fx.y_wind=(6*rng.normal(size=(nsl,45,72))).astype(np.float32)
+        fx.meta['wind']=True
+    return fx
+
+
+@pytest.mark.parametrize('seed', [0, 1, 4, 9, 14, 19])
+def test_random_reader_combinations_vs_port(seed):
+    """The vertical velocity from a reader of its own (another grid, other levels: the kernel cannot share the cell and
+    weights of the current sample), the wind from a global periodic grid over a regional current, grids that are global by
+    the reference's rule without being periodic (north-south coverage test only, edge value in the east-west gap)."""
+    fx = _random_readers_scenario(seed)
+    if fx is None:
+        pytest.skip('backward run or 2-D block drawn for this seed')
+    pl, pa, pz = common.run_port(fx)
+    for mode in (0, 2):
+        hl, ha, hz = run_hostshim(fx, fast=mode)
+        assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+        m = np.isfinite(pl)
+        assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 2e-8, (seed, mode)
+        assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
