@@ -184,7 +184,9 @@ def run_port(fx):
     m = fx.meta
     return ap.run_oceandrift(readers, fx.lon0, fx.lat0, fx.z0, fx.start, fx.dt, fx.steps, scheme=m['scheme'],
                              vertical_adv=m['with_w'], wind=m['wind'], wind_drift_depth=fx.wind_drift_depth(),
-                             cdf=fx.cdf if fx.cdf is not None else 1.0, wdf=m.get('wdf', 0.02), diffusivity=m['diffusivity'],
+                             cdf=fx.cdf if fx.cdf is not None else 1.0,
+                             wdf=fx.wdf_array if getattr(fx, 'wdf_array', None) is not None else m.get('wdf', 0.02),
+                             diffusivity=m['diffusivity'],
                              seed=m['seed'], mixing=m.get('mixing', False), dt_mix=m.get('dt_mix', 60.0),
                              stokes=m.get('stokes'), noise=m.get('noise'), truncate_below=m.get('truncate'),
                              w_at_surface=bool(m.get('w_at_surface')),
@@ -453,7 +455,7 @@ def run_hostshim(fx, fast=False):
         a.factor, a.moving = _p(cdf), _p(moving)
         a.truncate_below = float(m.get('truncate') or 0.0)
         if wind is not None:
-            a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, 1, wind.g, wind.pair(t)
+            a.wind_on, a.wdf_f64, a.g_wind, a.t_wind = 1, (1 if wdf.dtype == np.float64 else 0), wind.g, wind.pair(t)
             a.wdf, a.wind_drift_depth = _p(wdf), fx.wind_drift_depth()
         if wfld is not None:
             if z_new is None and senv is not None:

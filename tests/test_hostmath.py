@@ -476,3 +476,33 @@ def test_random_reader_combinations_vs_port(seed):
         m = np.isfinite(pl)
         assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 2e-8, (seed, mode)
         assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
+
+
+def _random_wdf_scenario(seed):
+    rng=np.random.default_rng(70000+seed)
+    fx=_random_scenario(seed+15000)
+    n=fx.n
+    nsl=fx.u.shape[0]; ny,nx=len(fx.grid_lat),len(fx.grid_lon)
+    if fx.x_wind is None:
+        fx.x_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32); fx.y_wind=(5*rng.normal(size=(nsl,ny,nx))).astype(np.float32)
+    fx.meta['wind']=True
+    wdf=rng.uniform(0.0,0.05,n).astype(np.float32); wdf[:50]=0
+    fx.wdf_array=wdf
+    cdf=(rng.uniform(0.5,1.0,n).astype(np.float32)) if seed%2 else None
+    fx.cdf=cdf
+    fx.props=(lambda c=cdf,w=wdf,n=n: ((c if c is not None else np.float32(1)*np.ones(n)), w, np.ones(n,dtype=np.int32)))
+    wdd=float(rng.choice([0.0,0.1,1.0])); fx.meta['wind_drift_depth']=wdd; fx.wind_drift_depth=(lambda w=wdd: w)
+    return fx
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_random_float32_drift_factor_arrays_vs_port(seed):
+    """Per-element float32 wind_drift_factor (and current_drift_factor) arrays: the wind move and the final move then run in
+    float32 azimuth / speed (update_positions, basemodel/__init__.py:4643-4650), with the surface taper of drift:wind_drift_depth."""
+    fx = _random_wdf_scenario(seed)
+    pl, pa, pz = common.run_port(fx)
+    for mode in (0, 2):
+        hl, ha, hz = run_hostshim(fx, fast=mode)
+        assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
+        m = np.isfinite(pl)
+        assert max(common.max_err_deg(hl[m], ha[m], pl[m], pa[m])) < 5e-8, (seed, mode)
