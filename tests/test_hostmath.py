@@ -445,7 +445,7 @@ def _random_readers_scenario(seed):
     # w on its own (coarser / finer, differently ordered) grid covering the same box, different levels
     lo,hi=float(fx.grid_lon.min()),float(fx.grid_lon.max()); la0,la1=float(fx.grid_lat.min()),float(fx.grid_lat.max())
     nxw,nyw,nzw=int(rng.integers(5,30)),int(rng.integers(5,30)),int(rng.choice([2,4,9]))
-    fx.w_lon=np.linspace(lo-0.01,hi+0.01,nxw).astype(np.float32); fx.w_lat=np.linspace(la0-0.01,la1+0.01,nyw).astype(np.float32)
+    fx.w_lon=np.linspace(lo+0.01,hi-0.01,nxw).astype(np.float32); fx.w_lat=np.linspace(la0-0.01,la1+0.01,nyw).astype(np.float32)
     if rng.uniform()<0.5: fx.w_lat=fx.w_lat[::-1].copy()
     zmin=float(fx.grid_z.min())
     fx.w_z=np.linspace(0.0,zmin*rng.uniform(0.6,1.2),nzw).astype(np.float32).astype(np.float64)
