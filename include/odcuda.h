@@ -357,6 +357,58 @@ typedef struct od_mix_args {
 
 int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a);
 
+/* ---- analytical readers on a projected plane ---------------------------------------------------------
+ * BASELINE configs[0]: opendrift/readers/reader_double_gyre.py (a ContinuousReader, basereader/continuous.py:9-48) on the
+ * spherical stereographic plane its constructor asks pyproj for (reader_double_gyre.py:27-31).  The reader chain of
+ * Variables.get_variables_interpolated (basereader/variables.py:860-920: modulate_longitude, Proj forward, coverage,
+ * get_variables, rotate_vectors :59-109, NaN for uncovered) is evaluated per particle on the device. */
+#define OD_PROJ_STERE_SPHERE 1
+typedef struct od_proj_desc {
+    int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0) */
+    int32_t has_lat_ts;           /* +lat_ts given (polar aspects only) */
+    double a;                     /* sphere radius, m */
+    double lat_0, lon_0, lat_ts;  /* degrees */
+    double k_0, x_0, y_0;
+} od_proj_desc;
+
+#define OD_ANALYTIC_DOUBLE_GYRE 1
+typedef struct od_analytic_desc {
+    int32_t kind;                 /* OD_ANALYTIC_DOUBLE_GYRE */
+    int32_t lon_mode;             /* modulate_longitude: 0 np.mod(lon, 360), 1 np.mod(lon + 180, 360) - 180 */
+    od_proj_desc proj;
+    double xmin, xmax, ymin, ymax;   /* coverage in the reader's plane (reader attributes of the same names) */
+    double par[4];                /* double gyre: A, epsilon, omega (reader_double_gyre.py:27-28), unused */
+    double rot_delta;             /* length of the y-axis line of rotate_vectors: 10 (m) for a projected plane */
+    float fallback[2];            /* environment:fallback:x/y_sea_water_velocity, NaN = none */
+} od_analytic_desc;
+
+/* Reader.get_variables_interpolated(['x_sea_water_velocity', 'y_sea_water_velocity'], time, lon, lat): float32 east /
+ * north velocity, NaN where the reader does not cover the position (no fallback).  t_seconds = (time - initial_time)
+ * .total_seconds().  flags: OD_INTERP_POS_F32. */
+int od_analytic_interp(od_ctx* ctx, const od_analytic_desc* r, double t_seconds, int64_t n, const double* d_lon,
+                       const double* d_lat, int flags, float* d_u, float* d_v);
+
+/* PhysicsMethods.advect_ocean_current (models/physics_methods.py:611-691) with the analytical reader as the current:
+ * Euler / RK2 / RK4 stage loop + WGS84 moves in one launch.  Times are seconds since the reader's initial_time. */
+typedef struct od_analytic_advect_args {
+    int32_t scheme;               /* od_scheme */
+    int32_t math;                 /* OD_MATH_* */
+    int32_t factor_f64, pos_f32;
+    double t_start, t_mid, t_end; /* t, t + dt/2, t + dt */
+    double dt;
+    int64_t n;
+    double* d_lon;                /* in/out float64 */
+    double* d_lat;
+    const void* d_factor;         /* factor * current_drift_factor per particle, or NULL */
+    const int32_t* d_moving;      /* or NULL */
+    const float* d_k1_u;          /* optional start-of-step environment */
+    const float* d_k1_v;
+    float* d_env_u;               /* optional outputs: start-of-step sampled current */
+    float* d_env_v;
+} od_analytic_advect_args;
+
+int od_analytic_advect(od_ctx* ctx, const od_analytic_desc* r, const od_analytic_advect_args* a);
+
 /* ---- particle order (locality) ---------------------------------------------------------- */
 /* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by
  * the grid cell (and level) of `group` they are in.  Stable counting sort. */

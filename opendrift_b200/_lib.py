@@ -93,6 +93,28 @@ class StokesArgs(C.Structure):
                 ('hs_mode', C.c_int32), ('profile', C.c_int32), ('pad_', C.c_int32)]
 
 
+class ProjDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('has_lat_ts', C.c_int32), ('a', C.c_double), ('lat_0', C.c_double),
+                ('lon_0', C.c_double), ('lat_ts', C.c_double), ('k_0', C.c_double), ('x_0', C.c_double), ('y_0', C.c_double)]
+
+
+class AnalyticDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('lon_mode', C.c_int32), ('proj', ProjDesc),
+                ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
+                ('par', C.c_double * 4), ('rot_delta', C.c_double), ('fallback', C.c_float * 2)]
+
+
+class AnalyticAdvectArgs(C.Structure):
+    _fields_ = [('scheme', C.c_int32), ('math', C.c_int32), ('factor_f64', C.c_int32), ('pos_f32', C.c_int32),
+                ('t_start', C.c_double), ('t_mid', C.c_double), ('t_end', C.c_double), ('dt', C.c_double),
+                ('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_factor', C.c_void_p),
+                ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
+                ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p)]
+
+
+OD_PROJ_STERE_SPHERE = 1
+OD_ANALYTIC_DOUBLE_GYRE = 1
+
 # every symbol include/odcuda.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -118,6 +140,8 @@ SYMBOLS = {
     'od_step_oceandrift_host': (C.c_int, [_P, C.POINTER(StepArgs), C.POINTER(HostIO)]),
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
     'od_leeway_step': (C.c_int, [_P, C.POINTER(LeewayArgs)]),
+    'od_analytic_interp': (C.c_int, [_P, C.POINTER(AnalyticDesc), C.c_double, C.c_int64, _P, _P, C.c_int, _P, _P]),
+    'od_analytic_advect': (C.c_int, [_P, C.POINTER(AnalyticDesc), C.POINTER(AnalyticAdvectArgs)]),
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'od_stokes_drift': (C.c_int, [_P, C.POINTER(StokesArgs)]),
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),

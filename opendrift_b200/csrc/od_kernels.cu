@@ -20,6 +20,7 @@
 #include "od_mix.cuh"
 #include "od_stokes.cuh"
 #include "od_leeway.cuh"
+#include "od_analytic.cuh"
 
 using namespace od;
 
@@ -1371,6 +1372,90 @@ extern "C" int od_step_oceandrift_host(od_ctx* ctx, const od_step_args* a, const
     if (a->d_noise_wind) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift_host: noise arrays are not supported on the host path");
     if (a->group_w >= 0 && (!io->h_z || !io->h_out_z)) return fail(ctx, OD_ERR_ARG, "od_step_oceandrift_host: vertical advection needs h_z and h_out_z");
     return host_pipeline(ctx, &a->cur, a, io);
+}
+
+// ---- analytical reader on a projected plane (od_analytic.cuh) ---------------------------------------------
+__global__ void __launch_bounds__(OD_BLOCK) analytic_interp_kernel(AnalyticReader R, double t, int64_t n, const double* __restrict__ lon,
+                                                                  const double* __restrict__ lat, int pos_f32,
+                                                                  float* __restrict__ u, float* __restrict__ v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a, b;
+    analytic_sample_raw(R, t, lon[i], lat[i], pos_f32 != 0, a, b);
+    if (u) u[i] = a;
+    if (v) v[i] = b;
+}
+
+template <int SCHEME, bool F64, class MATH>
+__global__ void __launch_bounds__(OD_BLOCK) analytic_step_kernel(const __grid_constant__ AnalyticStepParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    analytic_step_particle<SCHEME, F64, MATH>(p, i);
+}
+
+static int make_analytic(od_ctx* ctx, const od_analytic_desc* r, AnalyticReader* R) {
+    switch (analytic_from_desc(r, R)) {
+        case 0: return OD_OK;
+        case 1: return fail(ctx, OD_ERR_ARG, "unknown analytical reader kind");
+        case 2: return fail(ctx, OD_ERR_ARG, "unknown projection kind");
+        default: return fail(ctx, OD_ERR_ARG, "projection needs a > 0 and k_0 > 0");
+    }
+}
+
+extern "C" int od_analytic_interp(od_ctx* ctx, const od_analytic_desc* r, double t_seconds, int64_t n, const double* lon,
+                                  const double* lat, int flags, float* u, float* v) {
+    if (!ctx || !r || n < 0 || (n > 0 && (!lon || !lat))) return fail(ctx, OD_ERR_ARG, "od_analytic_interp: bad arguments");
+    AnalyticReader R;
+    int rc = make_analytic(ctx, r, &R);
+    if (rc) return rc;
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    analytic_interp_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(R, t_seconds, n, lon, lat, flags & OD_INTERP_POS_F32, u, v);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+template <class MATH>
+static int launch_analytic(od_ctx* ctx, int scheme, bool f64, const AnalyticStepParams& p) {
+    const int grid = grid_for(p.n);
+    cudaStream_t s = ctx->stream;
+#define OD_LAUNCHA(S, F) analytic_step_kernel<S, F, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
+    if (scheme == OD_EULER) { if (f64) OD_LAUNCHA(0, true); else OD_LAUNCHA(0, false); }
+    else if (scheme == OD_RK2) { if (f64) OD_LAUNCHA(1, true); else OD_LAUNCHA(1, false); }
+    else { if (f64) OD_LAUNCHA(2, true); else OD_LAUNCHA(2, false); }
+#undef OD_LAUNCHA
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+}
+
+extern "C" int od_analytic_advect(od_ctx* ctx, const od_analytic_desc* r, const od_analytic_advect_args* a) {
+    if (!ctx || !r || !a) return fail(ctx, OD_ERR_ARG, "od_analytic_advect: null argument");
+    if (a->scheme < 0 || a->scheme > 2) return fail(ctx, OD_ERR_ARG, "unknown advection scheme");
+    if (a->math < 0 || a->math > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_analytic_advect: unknown arithmetic mode");
+    if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat))) return fail(ctx, OD_ERR_ARG, "null particle arrays");
+    if ((a->d_k1_u == nullptr) != (a->d_k1_v == nullptr)) return fail(ctx, OD_ERR_ARG, "k1 needs both components");
+    AnalyticStepParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_analytic(ctx, r, &p.R);
+    if (rc) return rc;
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    p.t_start = a->t_start; p.t_mid = a->t_mid; p.t_end = a->t_end;
+    p.dt = a->dt;
+    p.dt32 = (float)a->dt;
+    p.has_k1 = a->d_k1_u != nullptr;
+    p.pos_f32 = a->pos_f32;
+    p.n = a->n;
+    p.lon = a->d_lon; p.lat = a->d_lat;
+    p.factor = a->d_factor; p.moving = a->d_moving;
+    p.k1u = a->d_k1_u; p.k1v = a->d_k1_v;
+    p.env_u = a->d_env_u; p.env_v = a->d_env_v;
+    // the analytical sampler has no float32 variant: OD_MATH_FAST keeps its float32 mid-point moves only
+    if (a->math == OD_MATH_FAST) return launch_analytic<FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    if (a->math == OD_MATH_SERIES) return launch_analytic<SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    return launch_analytic<ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
 }
 
 extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {

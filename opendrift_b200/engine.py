@@ -363,6 +363,39 @@ class Engine:
                           truncate_below, env_out, pos_f32, fast, noise, noise_kinds)
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
 
+    # -- analytical reader on a projected plane (od_analytic_*) ----------------------------------------------
+    def analytic_interp(self, desc, t_seconds, lon, lat, pos_f32=False):
+        """Reader chain of an analytical projected reader on device tensors -> (u, v) float32, NaN where uncovered."""
+        n = lon.numel()
+        u, v = self.empty(n, self.torch.float32), self.empty(n, self.torch.float32)
+        self._check(self.lib.od_analytic_interp(self.ctx, C.byref(desc), float(t_seconds), n, _ptr(lon), _ptr(lat),
+                                                1 if pos_f32 else 0, _ptr(u), _ptr(v)))
+        return u, v
+
+    def analytic_advect(self, desc, scheme, t_seconds, dt_seconds, lon, lat, factor=None, moving=None, k1=None,
+                        env_out=None, pos_f32=False, fast=None):
+        """advect_ocean_current with an analytical reader as the current (in place).  t_seconds = (t, t + dt/2, t + dt)
+        in seconds since the reader's initial_time."""
+        a = _lib.AnalyticAdvectArgs()
+        a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
+        a.math = self.math_mode if fast is None else int(fast)
+        a.pos_f32 = 1 if pos_f32 else 0
+        a.t_start, a.t_mid, a.t_end = (float(x) for x in t_seconds)
+        a.dt = float(dt_seconds)
+        a.n = lon.numel()
+        a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
+        if factor is not None:
+            a.d_factor = factor.data_ptr()
+            a.factor_f64 = 1 if factor.dtype == self.torch.float64 else 0
+        else:
+            a.factor_f64 = 1
+        a.d_moving = moving.data_ptr() if moving is not None else None
+        if k1 is not None:
+            a.d_k1_u, a.d_k1_v = k1[0].data_ptr(), k1[1].data_ptr()
+        if env_out is not None:
+            a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
+        self._check(self.lib.od_analytic_advect(self.ctx, C.byref(desc), C.byref(a)))
+
     def _step_args(self, s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf,
                    wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds,
                    wind_noise):

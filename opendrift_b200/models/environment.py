@@ -91,6 +91,17 @@ class Environment:
             res = None
             for name in self.priority_list.get(v, []):
                 r = self.readers[name]
+                if r.covers_time(time) and hasattr(r, 'device_sample'):      # analytical reader (no field group)
+                    smp = r.device_sample(eng, time, d_lon, d_lat, pos_f32)
+                    if res is None:
+                        res = dict(smp)
+                    else:
+                        for nm, t_ in smp.items():
+                            if nm in res:
+                                res[nm] = torch.where(torch.isfinite(res[nm]), res[nm], t_)
+                    if bool(torch.isfinite(res[v]).all()):
+                        break
+                    continue
                 if not r.covers_time(time) or not hasattr(r, 'group_of'):
                     continue
                 g, comp = r.group_of(v)

@@ -39,6 +39,20 @@ class PhysicsMethods:
         lon, lat = el.dev('lon', torch.float64), el.dev('lat', torch.float64)
         g = self._current_group(self.time)
         trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
+        ra = self.env.reader_for('x_sea_water_velocity', self.time)
+        if g is None and ra is not None and hasattr(ra, 'analytic_desc'):
+            # analytical reader on a projected plane: the stage loop samples it on the device (od_analytic_advect)
+            if any(x > 0 for x in self._uncertainty()[:2]):
+                raise NotImplementedError('drift:current_uncertainty with an analytical reader is not on the GPU path')
+            k1 = None
+            view = getattr(self, '_env_view', None)
+            if view is not None and 'x_sea_water_velocity' in view:
+                k1 = (view.dev('x_sea_water_velocity', eng), view.dev('y_sea_water_velocity', eng))
+            t, dt = self.time, self.time_step
+            eng.analytic_advect(ra.analytic_desc(), scheme, (ra.seconds(t), ra.seconds(t + dt / 2), ra.seconds(t + dt)),
+                                dt.total_seconds(), lon, lat, factor=fac, moving=moving, k1=k1, pos_f32=el.positions_f32)
+            el.positions_f32 = False
+            return
         if g is None:
             # no gridded current reader: constant / fallback current -> plain update_positions (Euler == RK)
             env = self.environment

@@ -159,6 +159,9 @@ def reader_interpolate(reader, variables, time, lon, lat, z, profiles=None):
     """Variables.get_variables_interpolated -> get_variables_interpolated_xy ->
     StructuredReader._get_variables_interpolated_ for a '+proj=latlong' reader
     (opendrift/readers/basereader/variables.py:860-920, 709-858; structured.py:202-400)."""
+    if hasattr(reader, 'interpolate'):          # analytical reader on a projected plane (oracle/gyre_port.py)
+        assert profiles is None
+        return reader.interpolate(variables, time, lon, lat, z)
     lon = np.mod(lon, 360) if reader.xmin >= 0 else np.mod(lon + 180, 360) - 180   # variables.py:259-280, structured.py:205-215
     x, y = lon, lat
     if reader.global_coverage:                                                   # variables.py:239-242: north-south only
@@ -490,6 +493,8 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
     # seed_elements keep their declared dtype (float32 / int32).
     def prop(v, dtype):
         if np.ndim(v) == 0:
+            if n == 1:                  # a single element is not "shorter than the array": no promotion (elements.py:213)
+                return np.full(1, v, dtype=dtype)
             return dtype(v) * np.ones(n)
         return np.asarray(v, dtype=dtype)
     cdf = prop(cdf, np.float32)

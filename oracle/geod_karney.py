@@ -237,6 +237,60 @@ def direct(lon1, lat1, azi1, s12, ell=WGS84, return_azi2=False):
     return lon2, lat2
 
 
+def inverse_short(lon1, lat1, lon2, lat2, ell=WGS84, iterations=4):
+    """Inverse geodesic problem for SHORT lines (up to a few hundred km, away from the poles): forward azimuth at
+    point 1 (degrees) and distance (m).
+
+    The reference needs it in one place on this path: BaseReader.rotate_vectors (readers/basereader/variables.py:59-109)
+    asks ``Geod.inv`` for the azimuth of a 10 m (projected readers) or 0.1 deg (rotated-pole readers) line along the
+    reader's y axis.  PROJ solves the general inverse problem with Karney's Newton iteration on the azimuth; for a short
+    line the same solution is reached by inverting the pinned direct solution (``direct`` above): start from the
+    mid-latitude metric, then correct the (north, east) displacement with the miss of the direct solution until it
+    vanishes (the miss shrinks by (s/a)^2 per pass; 2 passes reach double round-off for the lines used here).
+    """
+    lon1 = np.asarray(lon1, dtype=np.float64)
+    lat1 = np.asarray(lat1, dtype=np.float64)
+    lon2 = np.asarray(lon2, dtype=np.float64)
+    lat2 = np.asarray(lat2, dtype=np.float64)
+
+    def metric(lat):
+        sp = np.sin(lat * _DEG)
+        w2 = 1.0 - ell.e2 * sp * sp
+        w = np.sqrt(w2)
+        return ell.a * (1.0 - ell.e2) / (w2 * w), ell.a / w * np.cos(lat * _DEG)
+
+    def wrap(d):
+        return d - 360.0 * np.round(d / 360.0)
+
+    dlat = lat2 - lat1
+    dlon = wrap(lon2 - lon1)
+    m_mid, n_mid = metric(0.5 * (lat1 + lat2))
+    north = m_mid * dlat * _DEG
+    east = n_mid * dlon * _DEG
+    # azimuth at point 1 = azimuth at the mid-point minus half the meridian convergence
+    conv = dlon * _DEG * np.sin(0.5 * (lat1 + lat2) * _DEG)
+    az_mid = np.arctan2(east, north)
+    s = np.hypot(east, north)
+    az = az_mid - 0.5 * conv
+    north, east = s * np.cos(az), s * np.sin(az)
+    m2, n2 = metric(lat2)
+    for _ in range(iterations):
+        s = np.hypot(east, north)
+        az = np.arctan2(east, north)
+        lo, la, az2 = direct(lon1, lat1, az / _DEG, s, ell, return_azi2=True)
+        # miss at point 2, expressed in the local frame there and turned back to the frame of point 1
+        rn = m2 * (lat2 - la) * _DEG
+        re = n2 * wrap(lon2 - lo) * _DEG
+        turn = (az2 * _DEG) - az
+        c, sn = np.cos(turn), np.sin(turn)
+        north = north + (rn * c + re * sn)
+        east = east + (-rn * sn + re * c)
+    s = np.hypot(east, north)
+    az = np.arctan2(east, north)
+    lo, la, az2 = direct(lon1, lat1, az / _DEG, s, ell, return_azi2=True)
+    return az / _DEG, az2, s
+
+
 class Geod:
     """Minimal stand-in for ``pyproj.Geod`` (fwd only + short-line inv) used when the
     reference is imported in this container (oracle/refrun.py)."""
@@ -261,3 +315,17 @@ class Geod:
         if scalar:
             return float(lon2), float(lat2), float(back)
         return lon2, lat2, back
+
+    def inv(self, lons1, lats1, lons2, lats2, radians=False):
+        """Forward azimuth, back azimuth, distance (pyproj.Geod.inv) -- short lines only, see inverse_short."""
+        scalar = np.isscalar(lons1)
+        a = [np.asarray(v, dtype=np.float64) for v in (lons1, lats1, lons2, lats2)]
+        if radians:
+            a = [np.degrees(v) for v in a]
+        az1, az2, s = inverse_short(*a, ell=self.ell)
+        back = np.where(az2 > 0, az2 - 180.0, az2 + 180.0)
+        if radians:
+            az1, back = np.radians(az1), np.radians(back)
+        if scalar:
+            return float(az1), float(back), float(s)
+        return az1, back, s

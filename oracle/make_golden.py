@@ -253,7 +253,60 @@ def dateline_cases():
     run_dateline_case('dateline_smooth_euler', 'smooth', lon_c, lat_c, 4, 7200, scheme='euler', wdf=0.03)
 
 
+def run_gyre_case(name, n, steps, dt, scheme, seed=0, epsilon=0.25, omega=0.628, A=0.25, cdf=None, example=False):
+    """BASELINE configs[0]: the reference's analytical double-gyre reader on its stereographic plane
+    (examples/example_double_gyre_advection_schemes.py; reader_double_gyre.py), unmodified reference, with
+    oracle/proj_stere.py + oracle/geod_karney.py standing in for pyproj."""
+    refrun.setup()
+    from opendrift.readers import reader_double_gyre
+    from opendrift.models.oceandrift import OceanDrift
+    rng = np.random.default_rng(seed)
+    dg = reader_double_gyre.Reader(epsilon=epsilon, omega=omega, A=A)
+    if example:
+        x, y = np.array([.6]), np.array([.3])                 # the example's seed point
+    else:
+        x = rng.uniform(-0.03, 2.03, n)                       # a few per cent start outside the box (fallback 0)
+        y = rng.uniform(-0.03, 1.03, n)
+    lon, lat = dg.xy2lonlat(x, y)
+    o = OceanDrift(loglevel=50, logfile='/tmp/od_gyre.log')
+    o.set_config('environment:fallback:land_binary_mask', 0)
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:advection_scheme', scheme)
+    o.add_reader(dg)
+    kw = {}
+    if cdf is not None:
+        kw['current_drift_factor'] = cdf
+    o.seed_elements(lon, lat, time=dg.initial_time, **kw)
+    o.run(steps=steps, time_step=dt)
+    assert len(o.elements.lon) == len(lon)
+    meta = dict(kind='double_gyre', scheme=scheme, dt=dt, steps=steps, epsilon=epsilon, omega=omega, A=A,
+                proj4=dg.proj4, initial_time=dg.initial_time.isoformat())
+    out = dict(seed_lon=np.asarray(lon, dtype=np.float64), seed_lat=np.asarray(lat, dtype=np.float64),
+               lon=np.asarray(o.elements.lon, dtype=np.float64), lat=np.asarray(o.elements.lat, dtype=np.float64),
+               meta=json.dumps(meta))
+    if cdf is not None:
+        out['cdf'] = np.asarray(cdf, dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, 'ref_%s.npz' % name), **out)
+    fx, fy = dg.lonlat2xy(o.elements.lon, o.elements.lat)
+    print('wrote', name, len(lon), 'x range %.3f..%.3f' % (fx.min(), fx.max()))
+
+
+def gyre_cases():
+    rng = np.random.default_rng(7)
+    run_gyre_case('gyre_rk4', 600, 60, 0.1, 'runge-kutta4', seed=1)
+    run_gyre_case('gyre_rk2', 600, 40, 0.1, 'runge-kutta', seed=2)
+    run_gyre_case('gyre_euler', 600, 40, 0.01, 'euler', seed=3)
+    run_gyre_case('gyre_rk4_back_cdf32', 400, 30, -0.1, 'runge-kutta4', seed=4, epsilon=0.1,
+                  cdf=rng.uniform(0.5, 1.0, 400).astype(np.float32))
+    for scheme, tag in (('euler', 'euler'), ('runge-kutta', 'rk2'), ('runge-kutta4', 'rk4')):
+        for dt, dtag in ((0.01, 'dt001'), (0.1, 'dt01')):          # the six runs of the example (duration 6 s)
+            run_gyre_case('gyre_example_%s_%s' % (tag, dtag), 1, int(round(6 / dt)), dt, scheme, example=True)
+
+
 def main():
+    import sys
+    if 'gyre' in sys.argv[1:]:
+        return gyre_cases()
     g3 = syn.GridSpec(nx=40, ny=36, nz=8, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03, dz=12.0)
     g2 = syn.GridSpec(nx=40, ny=36, nz=1, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03)
     n = 1500
@@ -292,6 +345,7 @@ def main():
              diffusivity_model='windspeed_Sundby1983', background_diffusivity=1e-4)
     run_case('rk2_3d_mixing_env_fallback', g3, 600, 4, 600, 'runge-kutta', mixing=True, dt_mix=60.0, wind=True,
              diffusivity_model='environment_no_reader')
+    gyre_cases()
 
 
 if __name__ == '__main__':

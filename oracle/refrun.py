@@ -54,24 +54,54 @@ def _fake_pyproj():
             return hash(self.srs)
 
     class Proj:
-        """Identity projection: only '+proj=latlong' style CRSs are supported."""
+        """'+proj=latlong' style CRSs (identity) and the spherical stereographic projection of
+        reader_double_gyre.py (oracle/proj_stere.py)."""
 
         def __init__(self, projparams=None, **kw):
             s = str(projparams)
-            if 'latlong' not in s and 'longlat' not in s:
-                raise NotImplementedError('fake pyproj only supports latlong: ' + s)
             self.srs = s
-            self.crs = _CRS(True, s)
             self.definition_string = lambda: s
+            if any(k in s for k in ('latlong', 'longlat', 'lonlat', 'latlon')):
+                self.impl = None
+                self.crs = _CRS(True, s)
+            elif '+proj=stere' in s:
+                from oracle.proj_stere import Stere
+                self.impl = Stere(s)
+                self.crs = _CRS(False, s)
+            else:
+                raise NotImplementedError('fake pyproj supports latlong and spherical stere only: ' + s)
 
         def __call__(self, x, y, inverse=False):
-            return x, y
+            if self.impl is None:
+                return x, y
+            scalar = np.isscalar(x)
+            a, b = (self.impl.inverse if inverse else self.impl.forward)(x, y)
+            if scalar:
+                return float(a), float(b)
+            return a, b
+
+    class Transformer:
+        """Transformer.from_proj(a, b).transform(x, y): through geographic coordinates, no datum shift (PROJ applies
+        none between a sphere-based projection without datum and a latlong CRS: 'ballpark' transformation)."""
+
+        def __init__(self, pf, pt):
+            self.pf, self.pt = pf, pt
+
+        @classmethod
+        def from_proj(cls, proj_from, proj_to, **kw):
+            pf = proj_from if isinstance(proj_from, Proj) else Proj(proj_from)
+            pt = proj_to if isinstance(proj_to, Proj) else Proj(proj_to)
+            return cls(pf, pt)
+
+        def transform(self, x, y):
+            lon, lat = self.pf(x, y, inverse=True)
+            return self.pt(lon, lat)
 
     m = types.ModuleType('pyproj')
     m.Proj = Proj
     m.Geod = Geod
     m.CRS = MagicMock()
-    m.Transformer = MagicMock()
+    m.Transformer = Transformer
     m.__version__ = '0.0-fake'
     return m
 

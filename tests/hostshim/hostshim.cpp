@@ -9,6 +9,7 @@
 #include "../../opendrift_b200/csrc/od_mix.cuh"
 #include "../../opendrift_b200/csrc/od_stokes.cuh"
 #include "../../opendrift_b200/csrc/od_leeway.cuh"
+#include "../../opendrift_b200/csrc/od_analytic.cuh"
 
 using namespace od;
 
@@ -250,6 +251,87 @@ int hs_leeway(const hs_leeway_args* a) {
     p.capsized = a->capsized; p.rand_capsize = a->rand_capsize; p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from;
     p.wind_threshold = a->wind_threshold; p.wind_sigma = a->wind_sigma;
     for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);
+    return 0;
+}
+
+// analytical reader on a projected plane (od_analytic.cuh), same descriptor and argument structs as the C-ABI
+int hs_analytic_interp(const od_analytic_desc* r, double t, int64_t n, const double* lon, const double* lat, int flags,
+                       float* u, float* v) {
+    AnalyticReader R;
+    int rc = analytic_from_desc(r, &R);
+    if (rc) return -rc;
+    for (int64_t i = 0; i < n; ++i) analytic_sample_raw(R, t, lon[i], lat[i], (flags & 1) != 0, u[i], v[i]);
+    return 0;
+}
+
+void hs_stere(const od_analytic_desc* r, int inverse, int64_t n, const double* a, const double* b, double* oa, double* ob) {
+    AnalyticReader R;
+    if (analytic_from_desc(r, &R)) return;
+    for (int64_t i = 0; i < n; ++i) {
+        if (inverse) stere_inverse(R.proj, a[i], b[i], oa[i], ob[i]);
+        else if (!stere_forward(R.proj, a[i], b[i], oa[i], ob[i])) oa[i] = ob[i] = INFINITY;
+    }
+}
+
+// od_update_positions (update_positions_kernel of od_kernels.cu): the full Karney move with float32 or float64 velocities
+void hs_update_positions(int64_t n, double* lon, double* lat, const void* xv, const void* yv, int vel_f64, const int32_t* moving,
+                         double dt) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double lon0 = lon[i], lat0 = lat[i];
+        const double mv = moving ? (double)moving[i] : 1.0;
+        const GeodStart gs = geod_start(lat0);
+        double lo, la;
+        if (vel_f64) final_move_f64(gs, lon0, ((const double*)xv)[i], ((const double*)yv)[i], mv, dt, lo, la);
+        else final_move_f32(gs, lon0, ((const float*)xv)[i], ((const float*)yv)[i], mv, dt, lo, la);
+        lon[i] = lo;
+        lat[i] = la;
+    }
+}
+
+void hs_minmax_f32(int64_t n, const float* a, const float* b, float* lo, float* hi) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) {
+        const float v = b ? a[i] + b[i] : a[i];
+        if (v != v) continue;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    if (mn <= mx) {         // untouched when every value is NaN, like od_minmax_f32
+        *lo = mn;
+        *hi = mx;
+    }
+}
+
+void hs_inverse_azimuth(int64_t n, const double* lon1, const double* lat1, const double* lon2, const double* lat2, double* az) {
+    for (int64_t i = 0; i < n; ++i) az[i] = inverse_azimuth_short(lon1[i], lat1[i], lon2[i], lat2[i]);
+}
+
+}  // extern "C"
+
+template <class MATH>
+static void run_analytic(const AnalyticStepParams& p, int scheme, bool f64) {
+    for (int64_t i = 0; i < p.n; ++i) {
+        if (scheme == 0) { if (f64) analytic_step_particle<0, true, MATH>(p, i); else analytic_step_particle<0, false, MATH>(p, i); }
+        else if (scheme == 1) { if (f64) analytic_step_particle<1, true, MATH>(p, i); else analytic_step_particle<1, false, MATH>(p, i); }
+        else { if (f64) analytic_step_particle<2, true, MATH>(p, i); else analytic_step_particle<2, false, MATH>(p, i); }
+    }
+}
+
+extern "C" {
+
+int hs_analytic_advect(const od_analytic_desc* r, const od_analytic_advect_args* a) {
+    AnalyticStepParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = analytic_from_desc(r, &p.R);
+    if (rc) return -rc;
+    p.t_start = a->t_start; p.t_mid = a->t_mid; p.t_end = a->t_end;
+    p.dt = a->dt; p.dt32 = (float)a->dt;
+    p.has_k1 = a->d_k1_u != nullptr; p.pos_f32 = a->pos_f32; p.n = a->n;
+    p.lon = a->d_lon; p.lat = a->d_lat; p.factor = a->d_factor; p.moving = a->d_moving;
+    p.k1u = a->d_k1_u; p.k1v = a->d_k1_v; p.env_u = a->d_env_u; p.env_v = a->d_env_v;
+    if (a->math == OD_MATH_FAST) run_analytic<FastMath>(p, a->scheme, a->factor_f64 != 0);
+    else if (a->math == OD_MATH_SERIES) run_analytic<SeriesMath>(p, a->scheme, a->factor_f64 != 0);
+    else run_analytic<ExactMath>(p, a->scheme, a->factor_f64 != 0);
     return 0;
 }
 
