@@ -161,6 +161,51 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+
+def configs0_double_gyre(eng, torch, n=10_000_000):
+    """BASELINE configs[0] -- the reference's analytical double gyre on its stereographic plane -- as one more measured
+    kernel: RK4 launches of od_analytic_advect over n particles (CUDA events, median of 5), one step of a subsample
+    checked against the oracle port, and the port's own rate on this host.  Guarded by the caller: it never affects the
+    headline line."""
+    import time
+    from datetime import datetime
+    from opendrift_b200.readers import reader_double_gyre
+    from oracle import advect_port as ap, gyre_port
+    t0 = datetime(2000, 1, 1)
+    rd = reader_double_gyre.Reader(initial_time=t0, epsilon=0.25, omega=0.628, A=0.25)
+    rd.bind(eng, {v: 0.0 for v in rd.variables})
+    d = rd.analytic_desc()
+    rng = np.random.default_rng(0)
+    lon, lat = rd.xy2lonlat(rng.uniform(0.0, 2.0, n), rng.uniform(0.0, 1.0, n))
+    dl0, da0 = eng.to_device(lon), eng.to_device(lat)
+    out = []
+    for _ in range(5):
+        tl, ta = dl0.clone(), da0.clone()
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ka.record()
+        eng.analytic_advect(d, 'runge-kutta4', (0.0, 0.05, 0.1), 0.1, tl, ta)
+        kb.record()
+        torch.cuda.synchronize()
+        out.append(ka.elapsed_time(kb))
+    ms = float(np.median(out))
+    m = 20000
+    pr = gyre_port.DoubleGyreReader(t0, epsilon=0.25, omega=0.628, A=0.25)
+    c0 = time.perf_counter()
+    env = ap.get_environment([pr], ['x_sea_water_velocity', 'y_sea_water_velocity'], t0, lon[:m], lat[:m], np.zeros(m))
+    pl, pa = ap.advect_ocean_current([pr], 'runge-kutta4', t0, 0.1, lon[:m], lat[:m], np.zeros(m), np.ones(m),
+                                     np.ones(m, dtype=np.int32), env)
+    cpu_s = time.perf_counter() - c0
+    k = 6.371e6 * np.pi / 180
+    err = float(np.max(np.hypot((tl[:m].cpu().numpy() - pl) * k, (ta[:m].cpu().numpy() - pa) * k)))
+    return {'workload': 'reader_double_gyre on +proj=stere sphere, RK4, dt=0.1 s, %d particles (examples/example_double_gyre_advection_schemes.py at scale)' % n,
+            'kernel': 'analytic_step_kernel<RK4, F64, SeriesMath>', 'kernel_ms': ms, 'particle_steps_per_s_kernel': n / (ms * 1e-3),
+            'algorithmic_bytes_per_launch': 32 * n, 'hbm_GBps_algorithmic': 32 * n / (ms * 1e-3) / 1e9,
+            'bound': 'FP64 / transcendental issue (projection, closed-form field and vector rotation evaluated per stage; no field traffic)',
+            'max_err_m_vs_port_one_step': err, 'parity_ok': bool(err < 1e-7),
+            'cpu_port_particle_steps_per_s': m / cpu_s, 'cpu_cores': 1}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -415,6 +460,12 @@ def run_b200(args):
                'sample': '%d particles x %d steps (%.1f s) of the same workload through oracle/advect_port.py, the '
                          'NumPy/SciPy restatement of the reference path (bit-identical to the reference on the '
                          'committed fixtures; single process like the reference)' % (args.cpu_particles, args.cpu_steps, secs)}
+    gyre = None
+    if world == 1 and not os.environ.get('OD_BENCH_NO_GYRE'):
+        try:
+            gyre = configs0_double_gyre(eng, torch, min(n, 10_000_000))
+        except Exception as ex:          # never let the extra measurement touch the headline
+            gyre = {'error': repr(ex)[:300]}
     line = {
         'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -442,6 +493,7 @@ def run_b200(args):
                              'index and weight arithmetic, reproduced bit for bit), not by its 65 algorithmic bytes per '
                              'particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
+        'configs0_double_gyre': gyre,
         'current_only': {'kernel_ms': uv_kernel_ms, 'particle_steps_per_s_kernel': n / (uv_kernel_ms * 1e-3),
                          'note': 'od_advect_current alone (u/v sampling and moves, no vertical advection), same particles'},
         'tma_tile': {'kernel_ms': tile_kernel_ms, 'note': 'opt-in OD_OPT_TILE for current_only: one cp.async.bulk.tensor.4d box per block; same bits; '
