@@ -125,3 +125,35 @@ def run_model(fx, arithmetic=None):
     o.seed_elements(fx.seed_lon, fx.seed_lat, time=rd.initial_time, **kw)
     o.run(steps=fx.steps, time_step=fx.dt)
     return np.asarray(o.elements.lon), np.asarray(o.elements.lat)
+
+
+ASPECTS = ['+proj=stere +lat_0=60 +lon_0=10 +R=6371000 +x_0=0.3 +y_0=-0.2 +units=m +no_defs',
+           '+proj=stere +lat_0=-35 +lon_0=170 +R=6371000 +x_0=-1 +y_0=-0.5 +units=m +no_defs',
+           '+proj=stere +lat_0=90 +lon_0=70 +lat_ts=60 +R=6371000 +x_0=-1500000 +y_0=-1000000 +units=m +no_defs',
+           '+proj=stere +lat_0=-90 +lon_0=-30 +R=6371000 +x_0=800000 +y_0=-1200000 +units=m +no_defs',
+           '+proj=stere +lat_0=0 +lon_0=-179.99999 +R=6371000 +x_0=-1 +units=m +no_defs']
+
+
+class AspectCase:
+    """The double gyre on another stereographic plane (the reader takes any proj4, reader_double_gyre.py:29-31): a
+    fixture-like object whose reference result is the port's (checked against the live reference in tests/test_gyre.py)."""
+
+    def __init__(self, proj4, n=200, steps=30, dt=0.1, scheme='runge-kutta4'):
+        from oracle import advect_port as ap, gyre_port
+        from oracle.proj_stere import Stere
+        self.proj4, self.n, self.steps, self.dt, self.scheme, self.cdf = proj4, n, steps, dt, scheme, None
+        self.t0 = datetime(2000, 1, 1)
+        self.par = dict(epsilon=.25, omega=.628, A=.25)
+        rng = np.random.default_rng(len(proj4))
+        self.seed_lon, self.seed_lat = self.product_reader().xy2lonlat(rng.uniform(0.05, 1.95, n), rng.uniform(0.05, 0.95, n))
+        self.plane = Stere(proj4)
+        pr = gyre_port.DoubleGyreReader(self.t0, proj4=proj4, **self.par)
+        self.lon, self.lat, _ = ap.run_oceandrift([pr], self.seed_lon, self.seed_lat, np.zeros(n), self.t0, dt, steps, scheme=scheme)
+
+    def product_reader(self):
+        return reader_double_gyre.Reader(initial_time=self.t0, proj4=self.proj4, **self.par)
+
+    def error_m(self, lon, lat):
+        x, y = self.plane.forward(lon, lat)
+        rx, ry = self.plane.forward(self.lon, self.lat)
+        return float(np.max(np.hypot(x - rx, y - ry)))

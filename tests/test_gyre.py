@@ -297,3 +297,38 @@ def test_reader_and_environment_calls_on_host_engine():
         ref[np.isnan(ref)] = 0.0
         assert np.array_equal(renv[k], ref)
     assert not missing.any()
+
+
+# ---- the other aspects of the projection (oblique, north / south polar) in a whole run -----------------------------------
+@pytest.mark.parametrize('proj4', gc.ASPECTS)
+def test_other_projection_aspects_whole_run(proj4):
+    """The double gyre placed on oblique and polar stereographic planes and across the dateline: host-compiled device
+    code against the port, and the port against the live reference when it is present.  (At these latitudes the float32
+    seed arrays of the reference quantise the 2 m box to a few distinct positions -- parity is what is checked, not
+    oceanography.  Readers north of 89 deg are discarded by the reference's simulation extent,
+    basemodel/__init__.py:2026-2034, hence the offsets.)"""
+    from oracle import refrun
+    fx = gc.AspectCase(proj4)
+    sx, sy = fx.plane.forward(fx.seed_lon.astype(np.float32).astype(np.float64), fx.seed_lat.astype(np.float32).astype(np.float64))
+    px, py = fx.plane.forward(fx.lon, fx.lat)
+    assert np.hypot(px - sx, py - sy).max() > 0.3                # the particles really travelled
+    hl, ha = gc.run_hostshim(fx)
+    assert fx.error_m(hl, ha) < 1e-5
+    from hostengine import HostEngine
+    o, _ = _model(fx, HostEngine())                              # the drop-in classes on the host build
+    o.run(steps=fx.steps, time_step=fx.dt)
+    assert np.array_equal(np.asarray(o.elements.lon), hl) and np.array_equal(np.asarray(o.elements.lat), ha)
+    if refrun.available():
+        refrun.setup()
+        from opendrift.readers import reader_double_gyre
+        from opendrift.models.oceandrift import OceanDrift
+        dg = reader_double_gyre.Reader(initial_time=fx.t0, proj4=proj4, **fx.par)
+        o = OceanDrift(loglevel=50, logfile='/tmp/od_gyre_test.log')
+        o.set_config('environment:fallback:land_binary_mask', 0)
+        o.set_config('general:use_auto_landmask', False)
+        o.set_config('drift:advection_scheme', fx.scheme)
+        o.add_reader(dg)
+        o.seed_elements(fx.seed_lon, fx.seed_lat, time=fx.t0)
+        o.run(steps=fx.steps, time_step=fx.dt)
+        assert o.steps_calculation == fx.steps
+        assert np.array_equal(fx.lon, o.elements.lon) and np.array_equal(fx.lat, o.elements.lat)

@@ -96,3 +96,13 @@ def test_large_particle_count_and_errors():
     bad.proj.a = -1.0
     with pytest.raises(RuntimeError, match='a > 0'):
         eng.analytic_interp(bad, 0.0, dl, da)
+
+
+@pytest.mark.parametrize('proj4', gc.ASPECTS)
+def test_other_projection_aspects_on_gpu(proj4):
+    """Oblique / polar aspects and a plane across the dateline: C-ABI and drop-in classes against the port."""
+    fx = gc.AspectCase(proj4)
+    lon, lat = gc.run_engine(fx)
+    assert fx.error_m(lon, lat) < 1e-5
+    lon, lat = gc.run_model(fx)
+    assert fx.error_m(lon, lat) < 1e-5
