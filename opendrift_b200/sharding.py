@@ -2,6 +2,11 @@
 forcing, so they are sharded by contiguous index ranges over the ranks (one process per GPU) and the forcing
 slabs are replicated; the only exchange is the broadcast of each new reader time slab from the rank that read
 it (NCCL over NVLink on the GPU box, gloo in the CPU tests) and a small all-reduce of run statistics.
+
+Optional spatial-tile mode (BASELINE configs[2] wording: "field broadcast + particle all-to-all"; needed only when the
+forcing is too large to replicate): the domain is cut into one longitude strip per rank (`strip_owner`), and after a step
+the particles that left their strip travel to the new owner as packed SoA records in ONE all-to-all (`exchange_particles`:
+counts first, then a single `all_to_all_single` of [n, record_bytes] rows).  Element identity travels in the ID column.
 """
 import numpy as np
 
@@ -42,3 +47,68 @@ def allreduce_stats(count_active, lon_min, lon_max, lat_min, lat_max):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt)
     return int(cnt.item()), -float(mx[2]), float(mx[0]), -float(mx[3]), float(mx[1])
+
+
+def strip_bounds(lon_min, lon_max, world):
+    """Edges of `world` equal-width longitude strips covering [lon_min, lon_max]."""
+    return np.linspace(float(lon_min), float(lon_max), world + 1)
+
+
+def strip_owner(lon, bounds):
+    """Owner rank of each particle: the strip its longitude falls in (particles outside the domain go to the edge strips).
+    lon: 1-D tensor (any device); returns int64 tensor."""
+    import torch
+    world = len(bounds) - 1
+    inner = torch.as_tensor(np.asarray(bounds[1:-1], dtype=np.float64), device=lon.device)
+    owner = torch.bucketize(lon.to(torch.float64), inner, right=True)
+    return owner.clamp_(0, world - 1)
+
+
+def _pack(columns, order):
+    """SoA columns -> [n, record_bytes] uint8 rows in `order` (one record per particle)."""
+    import torch
+    parts, layout = [], []
+    for name, t in columns.items():
+        t = t[order].contiguous()
+        width = t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64))
+        parts.append(t.view(torch.uint8).reshape(t.shape[0], width))
+        layout.append((name, t.dtype, tuple(t.shape[1:]), width))
+    rec = torch.cat(parts, dim=1) if parts else torch.empty((len(order), 0), dtype=torch.uint8)
+    return rec.contiguous(), layout
+
+
+def _unpack(rec, layout):
+    out, off = {}, 0
+    for name, dtype, tail, width in layout:
+        col = rec[:, off:off + width].contiguous().view(dtype)
+        out[name] = col.reshape((rec.shape[0],) + tail)
+        off += width
+    return out
+
+
+def exchange_particles(columns, owner, group=None):
+    """Send every particle to its owner rank; returns the columns of the particles this rank now owns (those it kept
+    first, in their previous relative order, then the arrivals by source rank).
+
+    columns: dict name -> tensor with leading dimension n (same device, any dtypes); owner: int64 tensor [n].
+    Two collectives: the per-destination counts (world int64 each way) and ONE all_to_all_single of the packed records.
+    With world size 1 (or no process group) the input is returned unchanged."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(columns)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    owner = owner.to(torch.int64)
+    order = torch.argsort(owner, stable=True)
+    send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    rec, layout = _pack(columns, order)
+    n_recv = int(recv_counts.sum().item())
+    out = torch.empty((n_recv, rec.shape[1]), dtype=torch.uint8, device=rec.device)
+    dist.all_to_all_single(out, rec, output_split_sizes=recv_counts.tolist(), input_split_sizes=send_counts.tolist(), group=group)
+    # own particles first (they did not travel), then the arrivals in rank order
+    offs = np.concatenate([[0], np.cumsum(recv_counts.tolist())])
+    mine = out[offs[rank]:offs[rank + 1]]
+    others = [out[offs[r]:offs[r + 1]] for r in range(world) if r != rank]
+    return _unpack(torch.cat([mine] + others, dim=0), layout)
