@@ -13,7 +13,7 @@ interaction, seafloor interaction, lazy readers, the xarray result Dataset (a Nu
 Reference line numbers are cited at each method.
 """
 import logging
-from datetime import datetime, timedelta
+from datetime import timedelta
 
 import numpy as np
 

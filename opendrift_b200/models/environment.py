@@ -13,8 +13,6 @@ import logging
 
 import numpy as np
 
-from ..errors import NotCoveredError
-
 logger = logging.getLogger('opendrift_b200')
 
 

@@ -255,7 +255,6 @@ class OceanDrift(OpenDriftSimulation):
                             diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new,
                             noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind)
         if stokes_inp is not None:
-            z_keep = el._dev.get('z')
             self.stokes_drift(_inputs=stokes_inp)
         if z_new is not None:
             el.set_dev('z', z_new)

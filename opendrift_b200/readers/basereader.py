@@ -14,8 +14,6 @@ Reader implementers keep the reference contract (basereader/structured.py:125-14
 `get_variables(requested_variables, time, x, y, z)` returning {'x','y','z','time', var: ndarray[(z,)y,x]} and
 the attributes proj4, xmin/xmax/ymin/ymax, variables, start_time/end_time/time_step (or times), name.
 """
-from datetime import timedelta
-
 import numpy as np
 
 from ..errors import (NotCoveredError, OutsideSpatialCoverageError,  # noqa: F401
@@ -229,8 +227,8 @@ class StructuredReader:
             for nme, (gg, cc) in self._groups.items():
                 if gg is g and nme in variables:
                     a = outs[cc].cpu().numpy()
-                    if g.desc.nz > 1 or True:
-                        env[nme] = np.ma.masked_invalid(a.astype(np.float64) if g.desc.nz > 1 else a)
+                    # the reference returns float64 for 3-D blocks (vertical lerp in float64) and float32 for 2-D blocks
+                    env[nme] = np.ma.masked_invalid(a.astype(np.float64) if g.desc.nz > 1 else a)
         return env, None
 
     def __repr__(self):

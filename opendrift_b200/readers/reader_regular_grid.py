@@ -1,8 +1,6 @@
 """In-memory regular lon/lat(/z) grid reader: the role the reference's reader_netCDF_CF_generic (block
 supplier, opendrift/readers/reader_netCDF_CF_generic.py:404-626) and reader_constant_2d play for gridded
 forcing -- `get_variables()` hands out full-grid blocks, float32 coordinates (:586-587)."""
-from datetime import timedelta
-
 import numpy as np
 
 from .basereader import StructuredReader
