@@ -409,6 +409,28 @@ typedef struct od_analytic_advect_args {
 
 int od_analytic_advect(od_ctx* ctx, const od_analytic_desc* r, const od_analytic_advect_args* a);
 
+/* ---- output buffer ------------------------------------------------------------------------------------------
+ * OpenDriftSimulation.state_to_buffer (models/basemodel/__init__.py:2384-2499): lon / lat / z / status of the active
+ * elements into column `col` of device-resident [n_total][ncols] arrays addressed by element ID (float32 positions and
+ * depth, as the reference's result arrays; rows of elements that are not active keep their fill value). */
+typedef struct od_history_args {
+    int64_t n;                    /* active elements */
+    int64_t n_total;              /* rows of the buffers (all seeded elements) */
+    int32_t col, ncols;
+    int32_t z_f64, pad_;
+    const int32_t* d_ids;         /* [n] element IDs = row indices */
+    const double* d_lon;
+    const double* d_lat;
+    const void* d_z;              /* float32, or float64 when z_f64 */
+    const int32_t* d_status;
+    float* d_buf_lon;             /* [n_total][ncols] */
+    float* d_buf_lat;
+    float* d_buf_z;
+    int32_t* d_buf_status;
+} od_history_args;
+
+int od_history_scatter(od_ctx* ctx, const od_history_args* a);
+
 /* ---- particle order (locality) ---------------------------------------------------------- */
 /* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by
  * the grid cell (and level) of `group` they are in.  Stable counting sort. */

@@ -112,6 +112,13 @@ class AnalyticAdvectArgs(C.Structure):
                 ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p)]
 
 
+class HistoryArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('n_total', C.c_int64), ('col', C.c_int32), ('ncols', C.c_int32),
+                ('z_f64', C.c_int32), ('pad_', C.c_int32), ('d_ids', C.c_void_p), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p),
+                ('d_z', C.c_void_p), ('d_status', C.c_void_p), ('d_buf_lon', C.c_void_p), ('d_buf_lat', C.c_void_p),
+                ('d_buf_z', C.c_void_p), ('d_buf_status', C.c_void_p)]
+
+
 OD_PROJ_STERE_SPHERE = 1
 OD_ANALYTIC_DOUBLE_GYRE = 1
 
@@ -141,6 +148,7 @@ SYMBOLS = {
     'od_step_oceandrift': (C.c_int, [_P, C.POINTER(StepArgs)]),
     'od_leeway_step': (C.c_int, [_P, C.POINTER(LeewayArgs)]),
     'od_analytic_interp': (C.c_int, [_P, C.POINTER(AnalyticDesc), C.c_double, C.c_int64, _P, _P, C.c_int, _P, _P]),
+    'od_history_scatter': (C.c_int, [_P, C.POINTER(HistoryArgs)]),
     'od_analytic_advect': (C.c_int, [_P, C.POINTER(AnalyticDesc), C.POINTER(AnalyticAdvectArgs)]),
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'od_stokes_drift': (C.c_int, [_P, C.POINTER(StokesArgs)]),

@@ -21,6 +21,7 @@
 #include "od_stokes.cuh"
 #include "od_leeway.cuh"
 #include "od_analytic.cuh"
+#include "od_history.cuh"
 
 using namespace od;
 
@@ -1456,6 +1457,32 @@ extern "C" int od_analytic_advect(od_ctx* ctx, const od_analytic_desc* r, const 
     if (a->math == OD_MATH_FAST) return launch_analytic<FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     if (a->math == OD_MATH_SERIES) return launch_analytic<SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     return launch_analytic<ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+}
+
+// ---- output buffer on the device (od_history.cuh) -----------------------------------------------------------
+__global__ void __launch_bounds__(OD_BLOCK) history_scatter_kernel(const HistoryParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    history_scatter_one(p, i);
+}
+
+extern "C" int od_history_scatter(od_ctx* ctx, const od_history_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_history_scatter: null argument");
+    if (a->n < 0 || a->n_total < 0 || a->ncols <= 0 || a->col < 0 || a->col >= a->ncols)
+        return fail(ctx, OD_ERR_ARG, "od_history_scatter: bad sizes");
+    if (a->n > 0 && (!a->d_ids || !a->d_lon || !a->d_lat || !a->d_z || !a->d_status || !a->d_buf_lon || !a->d_buf_lat ||
+                     !a->d_buf_z || !a->d_buf_status))
+        return fail(ctx, OD_ERR_ARG, "od_history_scatter: null arrays");
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    HistoryParams p;
+    p.n = a->n; p.n_total = a->n_total; p.col = a->col; p.ncols = a->ncols; p.z_f64 = a->z_f64; p.pad_ = 0;
+    p.ids = a->d_ids; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.status = a->d_status;
+    p.blon = a->d_buf_lon; p.blat = a->d_buf_lat; p.bz = a->d_buf_z; p.bstatus = a->d_buf_status;
+    history_scatter_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
 }
 
 extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {

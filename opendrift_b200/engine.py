@@ -396,6 +396,20 @@ class Engine:
             a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
         self._check(self.lib.od_analytic_advect(self.ctx, C.byref(desc), C.byref(a)))
 
+    # -- output buffer on the device (od_history_scatter) ------------------------------------------------------
+    def history_scatter(self, ids, lon, lat, z, status, bufs, col):
+        """state_to_buffer: scatter lon / lat / z / status of the active elements into column `col` of the
+        [n_total, ncols] device buffers bufs = (lon f32, lat f32, z f32, status i32), rows addressed by element ID."""
+        torch = self.torch
+        a = _lib.HistoryArgs()
+        a.n, a.n_total, a.col, a.ncols = ids.numel(), bufs[0].shape[0], int(col), bufs[0].shape[1]
+        assert ids.dtype == torch.int32 and status.dtype == torch.int32 and lon.dtype == torch.float64 and lat.dtype == torch.float64
+        assert z.dtype in (torch.float32, torch.float64) and all(b.is_contiguous() for b in bufs)
+        a.z_f64 = 1 if z.dtype == torch.float64 else 0
+        a.d_ids, a.d_lon, a.d_lat, a.d_z, a.d_status = ids.data_ptr(), lon.data_ptr(), lat.data_ptr(), z.data_ptr(), status.data_ptr()
+        a.d_buf_lon, a.d_buf_lat, a.d_buf_z, a.d_buf_status = (b.data_ptr() for b in bufs)
+        self._check(self.lib.od_history_scatter(self.ctx, C.byref(a)))
+
     def _step_args(self, s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf,
                    wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds,
                    wind_noise):

@@ -117,6 +117,10 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             'gpu:sort_interval_steps': {'type': 'int', 'default': 20, 'min': 0, 'max': 1000000, 'units': 1,
                                         'level': CONFIG_LEVEL_ADVANCED,
                                         'description': 'Re-order the device particle arrays by grid cell every N steps (0 = never).'},
+            'gpu:history': {'type': 'enum', 'enum': ['host', 'device'], 'default': 'host', 'level': CONFIG_LEVEL_ADVANCED,
+                            'description': 'Where the output buffer of state_to_buffer lives between flushes: host = four device-to-host '
+                                           'copies per output step; device = [trajectory, time] arrays in HBM filled by one scatter launch '
+                                           'per output step and read back once per export_buffer_length steps.'},
             'gpu:arithmetic': {'type': 'enum', 'enum': ['series', 'exact', 'fast'], 'default': 'series', 'level': CONFIG_LEVEL_ADVANCED,
                                'description': 'Arithmetic of the step kernels (include/odcuda.h OD_MATH_*): series = bit-exact field '
                                               'sampling + short-arc series geodesic (round-off accurate); exact = the reference\'s '
@@ -520,6 +524,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         out_every = int(round(ratio))
         n_total = self.num_elements_total()
         self.history = {'time': [], 'lon': [], 'lat': [], 'z': [], 'status': []}
+        self._hist_dev, self._hist_col, self._hist_times = None, 0, []
+        self._hist_len = max(1, int(export_buffer_length))
         self._n_total = n_total
         self.prepare_run()
 
@@ -545,6 +551,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._env_view = None
         self._restore_id_order()
         self.state_to_buffer()
+        self._flush_history()
         self.remove_deactivated_elements()
         eng.sync()
         self._check_positions()
@@ -589,6 +596,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
 
     def state_to_buffer(self):
         """History of lon/lat/z/status per element ID at output steps (stands in for :2384-2499)."""
+        if self.get_config('gpu:history', 'host') == 'device':
+            return self._state_to_device_buffer()
         h = self.history
         lon = np.full(self._n_total, np.nan, dtype=np.float32)
         lat = np.full(self._n_total, np.nan, dtype=np.float32)
@@ -606,6 +615,47 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         h['lat'].append(lat)
         h['z'].append(z)
         h['status'].append(st)
+
+    def _state_to_device_buffer(self):
+        """state_to_buffer with the [trajectory, time] block resident in HBM: one scatter launch per output step
+        (od_history_scatter), one read-back per export_buffer_length output steps (_flush_history)."""
+        eng, torch = self.engine, self.engine.torch
+        if self._hist_dev is None:
+            shape = (int(self._n_total), self._hist_len)
+            self._hist_dev = tuple(torch.full(shape, float('nan'), dtype=torch.float32, device=eng.device) for _ in range(3)) + (
+                torch.full(shape, -1, dtype=torch.int32, device=eng.device),)
+        if self.num_elements_active() > 0:
+            el = self.elements
+            ids, status = el.dev('ID'), el.dev('status')
+            if ids.dtype != torch.int32:
+                ids = ids.to(torch.int32)
+            if status.dtype != torch.int32:
+                status = status.to(torch.int32)
+            eng.history_scatter(ids, el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), status,
+                                self._hist_dev, self._hist_col)
+        self._hist_times.append(self.time)
+        self._hist_col += 1
+        if self._hist_col == self._hist_len:
+            self._flush_history()
+
+    def _flush_history(self):
+        """Read the filled columns of the device block back (one copy per array) and append them to self.history."""
+        if self._hist_dev is None or self._hist_col == 0:
+            return
+        k = self._hist_col
+        # [k, n_total] each; .copy(): a host tensor (tests) would otherwise share its memory with the block that is reset below
+        cols = [b[:, :k].t().contiguous().cpu().numpy().copy() for b in self._hist_dev]
+        h = self.history
+        for j in range(k):
+            h['time'].append(self._hist_times[j])
+            h['lon'].append(cols[0][j])
+            h['lat'].append(cols[1][j])
+            h['z'].append(cols[2][j])
+            h['status'].append(cols[3][j])
+        for b in self._hist_dev[:3]:
+            b.fill_(float('nan'))
+        self._hist_dev[3].fill_(-1)
+        self._hist_col, self._hist_times = 0, []
 
     def get_lonlats(self):
         return np.array(self.history['lon']).T, np.array(self.history['lat']).T

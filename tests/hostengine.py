@@ -27,6 +27,8 @@ class _HostLib:
         shim.hs_analytic_advect.argtypes = [C.POINTER(_lib.AnalyticDesc), C.POINTER(_lib.AnalyticAdvectArgs)]
         shim.hs_update_positions.restype = None
         shim.hs_update_positions.argtypes = [C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]
+        shim.hs_history_scatter.restype = C.c_int
+        shim.hs_history_scatter.argtypes = [C.POINTER(_lib.HistoryArgs)]
         shim.hs_minmax_f32.restype = None
         shim.hs_minmax_f32.argtypes = [C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
 
@@ -47,6 +49,10 @@ class _HostLib:
         self.calls.append('od_minmax_f32')
         self.shim.hs_minmax_f32(n, a, b, lo, hi)
         return 0
+
+    def od_history_scatter(self, ctx, args):
+        self.calls.append('od_history_scatter')
+        return self.shim.hs_history_scatter(args)
 
     def od_last_error(self, ctx):
         return b'hostshim call failed'
@@ -74,3 +80,4 @@ class HostEngine:
     analytic_advect = Engine.analytic_advect
     update_positions = Engine.update_positions
     minmax = Engine.minmax
+    history_scatter = Engine.history_scatter

@@ -10,6 +10,7 @@
 #include "../../opendrift_b200/csrc/od_stokes.cuh"
 #include "../../opendrift_b200/csrc/od_leeway.cuh"
 #include "../../opendrift_b200/csrc/od_analytic.cuh"
+#include "../../opendrift_b200/csrc/od_history.cuh"
 
 using namespace od;
 
@@ -300,6 +301,16 @@ void hs_minmax_f32(int64_t n, const float* a, const float* b, float* lo, float* 
         *lo = mn;
         *hi = mx;
     }
+}
+
+int hs_history_scatter(const od_history_args* a) {
+    HistoryParams p;
+    p.n = a->n; p.n_total = a->n_total; p.col = a->col; p.ncols = a->ncols; p.z_f64 = a->z_f64; p.pad_ = 0;
+    p.ids = a->d_ids; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.status = a->d_status;
+    p.blon = a->d_buf_lon; p.blat = a->d_buf_lat; p.bz = a->d_buf_z; p.bstatus = a->d_buf_status;
+    if (a->ncols <= 0 || a->col < 0 || a->col >= a->ncols) return -1;
+    for (int64_t i = 0; i < p.n; ++i) history_scatter_one(p, i);
+    return 0;
 }
 
 void hs_inverse_azimuth(int64_t n, const double* lon1, const double* lat1, const double* lon2, const double* lat2, double* az) {
