@@ -332,3 +332,25 @@ def test_other_projection_aspects_whole_run(proj4):
         o.run(steps=fx.steps, time_step=fx.dt)
         assert o.steps_calculation == fx.steps
         assert np.array_equal(fx.lon, o.elements.lon) and np.array_equal(fx.lat, o.elements.lat)
+
+
+def test_bench_extra_measurement_runs_on_host_engine():
+    """bench.py's guarded configs[0] measurement (timing aside): same code with the host engine and a stub for the CUDA events."""
+    import time
+    import types
+    import bench
+    from hostengine import HostEngine
+
+    class Ev:
+        def __init__(self, enable_timing=True):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+    fake = types.SimpleNamespace(cuda=types.SimpleNamespace(Event=Ev, synchronize=lambda: None))
+    r = bench.configs0_double_gyre(HostEngine(), fake, 20000)
+    assert r['parity_ok'] and r['max_err_m_vs_port_one_step'] < 1e-7
+    assert r['kernel_ms'] > 0 and r['algorithmic_bytes_per_launch'] == 32 * 20000 and r['cpu_port_particle_steps_per_s'] > 0
