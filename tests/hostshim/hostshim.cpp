@@ -347,3 +347,173 @@ int hs_analytic_advect(const od_analytic_desc* r, const od_analytic_advect_args*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hs2_*: the library's own argument structs (include/odcuda.h) + the field groups / time pairs they name, resolved by
+// the caller (tests/hostengine.py keeps the slab ring and builds the pair texels).  The parameter blocks are filled the
+// way od_kernels.cu fills them (fill_current / fill_step / od_vertical_mixing / od_leeway_step), so that the drop-in
+// classes can run end to end on the host build.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hs2_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lon, const double* lat, const void* z, int flags,
+               float* out0, float* out1) {
+    hs_levels lv;
+    GroupGeom q = make_geom(*g, lv);
+    if (flags & OD_INTERP_NO_FALLBACK) q.fallback[0] = q.fallback[1] = NAN;
+    const PairRef p = make_pair(*pr);
+    const bool z64 = (flags & OD_INTERP_Z_F64) != 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double zz = (z && q.nz > 1) ? (z64 ? ((const double*)z)[i] : (double)((const float*)z)[i]) : 0.0;
+        const VertW vw = vert_weights(q, q.zs, q.zy, zz, !z64);
+        if (q.ncomp == 2) {
+            float u, v;
+            sample2(q, p, vw, lon[i], lat[i], u, v, (flags & OD_INTERP_POS_F32) != 0);
+            if (out0) out0[i] = u;
+            if (out1) out1[i] = v;
+        } else {
+            const float r = sample1(q, p, vw, lon[i], lat[i], (flags & OD_INTERP_POS_F32) != 0);
+            if (out0) out0[i] = r;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+static bool same_grid(const hs_group& du, const hs_group& dw) {
+    bool same = du.nx == dw.nx && du.ny == dw.ny && du.nz == dw.nz && du.lon_mode == dw.lon_mode && du.wrap_x == dw.wrap_x &&
+                du.global_x == dw.global_x && du.x0 == dw.x0 && du.xspan == dw.xspan && du.y0 == dw.y0 && du.yspan == dw.yspan &&
+                du.xmin == dw.xmin && du.xmax == dw.xmax && du.ymin == dw.ymin && du.ymax == dw.ymax;
+    for (int k = 0; same && du.nz > 1 && k < du.nz; ++k) same = du.z_levels[k] == dw.z_levels[k];
+    return same;
+}
+
+static int fill_current2(const od_advect_args* a, const hs_group* g, const hs_pair* t3, StepParams* p, hs_levels& lv) {
+    if (a->scheme < 0 || a->scheme > 2) return -2;
+    if (g->nz > 1 && !a->d_z) return -3;
+    memset(p, 0, sizeof(*p));
+    p->cs.g = make_geom(*g, lv);
+    p->has_k1 = a->d_k1_u != nullptr;
+    if (!p->has_k1) p->cs.t_start = make_pair(t3[0]);
+    if (a->scheme != 0) p->cs.t_mid = make_pair(t3[1]);
+    if (a->scheme == 2) p->cs.t_end = make_pair(t3[2]);
+    p->dt = a->dt; p->dt32 = (float)a->dt; p->adt32 = (float)fabs(a->dt);
+    p->n = a->n; p->lon = a->d_lon; p->lat = a->d_lat; p->z = a->d_z;
+    p->factor = a->d_factor; p->moving = a->d_moving;
+    p->k1u = a->d_k1_u; p->k1v = a->d_k1_v; p->env_u = a->d_env_u; p->env_v = a->d_env_v;
+    p->truncate_below = a->truncate_below; p->pos_f32 = a->pos_f32; p->z_f64 = a->z_f64;
+    p->noise_cur = a->noise_kinds ? a->d_noise_cur : nullptr;
+    p->noise_kinds = a->d_noise_cur ? a->noise_kinds : 0;
+    return 0;
+}
+
+template <int S, bool F, int E>
+static void run2(const StepParams& p, int mode) {
+    const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
+    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, ExactMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+}
+
+template <int E>
+static int launch2(const StepParams& p, int scheme, bool f, int mode) {
+    switch (scheme) {
+        case 0: f ? run2<0, true, E>(p, mode) : run2<0, false, E>(p, mode); return 0;
+        case 1: f ? run2<1, true, E>(p, mode) : run2<1, false, E>(p, mode); return 0;
+        case 2: f ? run2<2, true, E>(p, mode) : run2<2, false, E>(p, mode); return 0;
+    }
+    return -2;
+}
+
+extern "C" {
+
+int hs2_advect(const od_advect_args* a, const hs_group* g, const hs_pair* t3) {
+    hs_levels lv;
+    StepParams p;
+    int rc = fill_current2(a, g, t3, &p, lv);
+    if (rc) return rc;
+    return launch2<0>(p, a->scheme, a->factor_f64 != 0, a->fast);
+}
+
+int hs2_step(const od_step_args* a, const hs_group* g_uv, const hs_pair* t3, const hs_group* g_wind, const hs_pair* t_wind,
+             const hs_group* g_w, const hs_pair* t_w) {
+    hs_levels l1, l2, l3;
+    StepParams p;
+    int rc = fill_current2(&a->cur, g_uv, t3, &p, l1);
+    if (rc) return rc;
+    if (a->group_wind >= 0) {
+        if (!a->d_wdf || !g_wind || g_wind->nz != 1) return -4;
+        p.wind_on = 1; p.wdf_f64 = a->wdf_f64; p.gwind = make_geom(*g_wind, l2); p.pwind = make_pair(*t_wind);
+        p.wdf = a->d_wdf; p.wind_drift_depth = a->wind_drift_depth; p.noise_wind = a->d_noise_wind;
+    }
+    if (a->group_w >= 0) {
+        if (!a->d_z_inout || !a->cur.d_z || !g_w) return -5;
+        p.w_on = 1; p.w_at_surface = a->w_at_surface; p.gw = make_geom(*g_w, l3); p.pw = make_pair(*t_w);
+        p.z_inout = a->d_z_inout; p.zio_f64 = a->z_inout_f64;
+        p.w_same_grid = same_grid(*g_uv, *g_w) ? 1 : 0;
+    }
+    if (a->d_rand_x) {
+        if (!a->d_rand_y) return -6;
+        p.diff_on = 1; p.rand_x = a->d_rand_x; p.rand_y = a->d_rand_y; p.diffusivity = a->d_diffusivity;
+        p.diffusivity_const = a->diffusivity_const;
+    }
+    if (!p.wind_on && !p.diff_on) return launch2<2>(p, a->cur.scheme, a->cur.factor_f64 != 0, a->cur.fast);
+    return launch2<1>(p, a->cur.scheme, a->cur.factor_f64 != 0, a->cur.fast);
+}
+
+int hs2_mix(const od_mix_args* a, const hs_group* g, const hs_pair* pr) {
+    hs_levels lv;
+    MixParams p;
+    memset(&p, 0, sizeof(p));
+    std::vector<double> xs, xy, zl;
+    if (a->model == OD_MIX_ENVIRONMENT) {
+        if (!g || g->nz < 2) return -2;
+        p.g = make_geom(*g, lv);
+        p.pr = make_pair(*pr);
+        const int nz = g->nz;
+        xs.resize(nz); xy.resize(nz); zl.assign(g->z_levels, g->z_levels + nz);
+        const bool inc = zl[1] > zl[0];
+        for (int i = 0; i < nz; ++i) { int src = inc ? nz - 1 - i : i; xs[i] = -zl[src]; xy[i] = (double)src; }
+        p.zl = zl.data(); p.xs = xs.data(); p.xy = xy.data();
+        p.uniform_dz = 1; p.dz0 = zl[1] - zl[0];
+        for (int k = 1; k + 1 < nz; ++k) if (zl[k + 1] - zl[k] != p.dz0) p.uniform_dz = 0;
+    } else {
+        if (a->nlev < 2 || a->nlev > 65535) return -3;
+        if (a->model != OD_MIX_CONSTANT && !a->d_wind_speed) return -4;
+        p.g.nz = a->nlev; p.uniform_dz = 1; p.dz0 = -1.0;
+        p.wind_speed = a->d_wind_speed; p.mld = a->d_mld; p.mld_const = (float)a->mld_const;
+        p.background = a->background; p.k_const = a->k_const;
+    }
+    p.model = a->model;
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z_in = a->d_z_in; p.z_out = a->d_z_out;
+    p.moving = a->d_moving; p.terminal_velocity = a->d_terminal_velocity; p.ids = a->d_ids; p.rand = a->d_rand;
+    p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.sea_floor = a->d_sea_floor;
+    p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
+    p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);
+    return 0;
+}
+
+int hs2_leeway(const od_leeway_args* a, const hs_group* g_wind, const hs_pair* t_wind, const hs_group* g_cur, const hs_pair* t_cur) {
+    hs_levels l1, l2;
+    LeewayParams p;
+    memset(&p, 0, sizeof(p));
+    if (g_wind->nz != 1 || g_cur->nz != 1) return -2;
+    p.gwind = make_geom(*g_wind, l1); p.gcur = make_geom(*g_cur, l2);
+    p.pwind = make_pair(*t_wind); p.pcur = make_pair(*t_cur);
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat;
+    p.dw_slope = a->d_dw_slope; p.dw_offset = a->d_dw_offset; p.dw_eps = a->d_dw_eps;
+    p.cw_slope = a->d_cw_slope; p.cw_offset = a->d_cw_offset; p.cw_eps = a->d_cw_eps;
+    p.orientation = a->d_orientation; p.capsized = a->d_capsized; p.jibe_probability = a->d_jibe_probability;
+    p.moving = a->d_moving; p.status = a->d_status; p.ids = a->d_ids; p.rand = a->d_rand; p.dt = a->dt; p.seed = a->seed;
+    p.capsize_fraction = a->capsize_fraction; p.jp_f64 = a->jp_f64; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from; p.wind_threshold = a->wind_threshold;
+    p.wind_sigma = a->wind_sigma; p.rand_capsize = a->d_rand_capsize;
+    if (a->capsize_on && !a->d_capsized) return -3;
+    p.missing_code = a->missing_code;
+    for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);
+    return 0;
+}
+
+}  // extern "C"

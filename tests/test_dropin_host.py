@@ -1,0 +1,67 @@
+"""The reference-facing Python surface (OceanDrift / Leeway / readers / Environment) end to end WITHOUT a GPU: the tests of
+tests/test_gpu_dropin.py (and the drop-in replay of the reference's test_dateline) re-run with the engine swapped for
+tests/hostengine.py -- Engine's own methods and ctypes argument structs, with the library replaced by the host build of
+the same device sources (tests/hostshim).  What runs here is the host logic of the product: seeding, release, the run
+loop, Environment, reader binding and the slab ring, the fused / helper step recipes, draws and their order, compaction.
+
+One difference from the GPU is known and allowed for: torch's CPU float32 sqrt is not correctly rounded (0.7 % of values are
+an ulp off; CUDA's sqrt.rn is IEEE), so the wind speed that feeds the analytical diffusivity models can differ by an ulp and
+depths of those three fixtures move by up to ~2e-6 m."""
+import numpy as np
+import pytest
+
+import common
+import test_gpu_dropin as T
+import test_dateline as TD
+from hostengine import HostEngine
+
+
+@pytest.fixture(autouse=True)
+def host_engine(monkeypatch):
+    eng = HostEngine()
+    import opendrift_b200.engine as E
+    import opendrift_b200.models.basemodel as B
+    monkeypatch.setattr(E, 'default_engine', lambda device=None: eng)
+    monkeypatch.setattr(B, 'default_engine', lambda device=None: eng)
+    yield eng
+
+
+ANALYTIC_MIXING = ('euler_3d_mixing_sundby1983', 'rk4_3d_mixing_large1994', 'rk2_3d_mixing_env_fallback')
+
+
+@pytest.mark.parametrize('name', common.fixtures())
+def test_oceandrift_run_matches_reference(name, host_engine):
+    fx = common.Fixture(name)
+    o = T._model(fx)
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    assert o.num_elements_active() == fx.n
+    lon, lat, z = o.elements.lon, o.elements.lat, o.elements.z
+    assert lon.dtype == np.float64 and z.dtype == fx.z.dtype
+    assert max(common.max_err_deg(lon, lat, fx.lon, fx.lat)) < 5e-8
+    ztol = 1e-5 if name in ANALYTIC_MIXING else common.z_tolerance(fx.meta, exact=1e-9)
+    assert np.abs(z - fx.z).max() <= ztol
+    assert np.array_equal(o.elements.ID, np.arange(fx.n)) and len(o.history['time']) == fx.steps + 1
+    if name not in ANALYTIC_MIXING:
+        # the same steps driven through the bare argument structs (tests/common.py:run_hostshim): bit for bit
+        hl, ha, hz = common.run_hostshim(fx, fast=2)
+        assert np.array_equal(lon, hl) and np.array_equal(lat, ha) and np.array_equal(z, hz)
+    assert 'od_step_oceandrift' in host_engine.lib.calls            # the fused recipe, one launch per step
+
+
+# the remaining drop-in tests as they are written for the GPU
+test_overridden_update_uses_helpers_and_matches = T.test_overridden_update_uses_helpers_and_matches
+test_subclass_touching_numpy_state_still_works = T.test_subclass_touching_numpy_state_still_works
+test_reader_get_variables_interpolated_and_environment = T.test_reader_get_variables_interpolated_and_environment
+test_leeway_model_matches_reference = T.test_leeway_model_matches_reference
+test_leeway_missing_forcing_deactivates = T.test_leeway_missing_forcing_deactivates
+test_seeding_radius_and_deactivation = T.test_seeding_radius_and_deactivation
+test_reference_known_answers_with_constant_environment = T.test_reference_known_answers_with_constant_environment
+test_arithmetic_config_selects_the_kernel_policy = T.test_arithmetic_config_selects_the_kernel_policy
+
+
+def test_dropin_model_replays_the_reference_dateline_test():
+    TD.test_gpu_dropin_model_replays_the_reference_test()
+
+
+def test_device_rng_for_diffusion_is_order_independent():
+    T.test_device_rng_for_diffusion_is_order_independent()
