@@ -228,9 +228,6 @@ class OceanDrift(OpenDriftSimulation):
                                                with_wind=wind is not None)
         d_ncur = eng.to_device(ncur) if ncur is not None else None
         d_nwind = eng.to_device(nwind) if nwind is not None else None
-        rand = None
-        if D != 0 and not split_diffusion:
-            rand = tuple(self._device_normals(n, 2, salt=1))
         moving = el.dev('moving')
         if moving.dtype != torch.int32:
             moving = moving.to(torch.int32)
@@ -246,6 +243,11 @@ class OceanDrift(OpenDriftSimulation):
             # update() moves with the Stokes drift BEFORE vertical advection (oceandrift.py:196-205): the Stokes profile
             # must see the start-of-step depth, so vertical advection writes into a copy that replaces z afterwards
             z_new = z.clone()
+        # the random-walk draws come last, after the mixing loop's (update() runs before horizontal_diffusion(),
+        # basemodel/__init__.py:2272-2280): the legacy generator is shared, so the order of the calls is part of the result
+        rand = None
+        if D != 0 and not split_diffusion:
+            rand = tuple(self._device_normals(n, 2, salt=1))
         eng.step_oceandrift(g, self.get_config('drift:advection_scheme'), t, self.time_step,
                             el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, factor=fac, moving=moving,
                             truncate_below=self.get_config('drift:truncate_ocean_model_below_m'),

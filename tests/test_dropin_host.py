@@ -65,3 +65,38 @@ def test_dropin_model_replays_the_reference_dateline_test():
 
 def test_device_rng_for_diffusion_is_order_independent():
     T.test_device_rng_for_diffusion_is_order_independent()
+
+
+def test_draw_order_with_mixing_and_horizontal_diffusion():
+    """The legacy generator is shared: update() (mixing loop draws) runs before horizontal_diffusion() (two normal
+    draws), basemodel/__init__.py:2272-2280.  The fused recipe once drew in the other order (found with this harness)."""
+    fx = common.Fixture('rk4_3d_mixing')
+    fx.meta['diffusivity'] = 5.0                      # a combination no reference fixture has
+    pl, pa, pz = common.run_port(fx)
+    o = T._model(fx)
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    assert max(common.max_err_deg(o.elements.lon, o.elements.lat, pl, pa)) < 5e-8
+    assert np.abs(o.elements.z - pz).max() < 1e-7
+
+
+@pytest.mark.parametrize('family,seed', [('basic', 1), ('basic', 9), ('physics', 2), ('physics', 7), ('physics', 13), ('options', 3),
+                                         ('options', 11), ('options', 21), ('readers', 3), ('readers', 4), ('readers', 14),
+                                         ('wdf', 17), ('wdf', 21), ('wdf', 24)])
+def test_random_scenarios_through_the_model_classes(family, seed):
+    """The randomised whole-run scenarios of tests/test_hostmath.py (which drive the bare step loop) through
+    OceanDrift.run(): readers on their own grids, global / periodic grids, drift-factor arrays, truncation, noise, Stokes,
+    mixing.  Must equal the bare loop bit for bit and the port within the position tolerance."""
+    import test_hostmath as th
+    fx = {'basic': th._random_scenario, 'physics': th._random_physics_scenario, 'options': th._random_options_scenario,
+          'readers': th._random_readers_scenario, 'wdf': th._random_wdf_scenario}[family](seed)
+    if fx is None:
+        pytest.skip('scenario not applicable for this seed')
+    o = T._model(fx)
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    lon, lat, z = o.elements.lon, o.elements.lat, np.asarray(o.elements.z)
+    hl, ha, hz = common.run_hostshim(fx, fast=2)
+    analytic = fx.meta.get('mixing') and fx.meta.get('diffusivity_model') not in (None, 'environment')
+    if not analytic:                                   # (torch's CPU sqrt, see the module docstring)
+        assert np.array_equal(lon, hl) and np.array_equal(lat, ha) and np.array_equal(z, np.asarray(hz))
+    pl, pa, pz = common.run_port(fx)
+    assert max(common.max_err_deg(lon, lat, pl, pa)) < 5e-8

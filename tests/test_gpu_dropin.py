@@ -18,11 +18,14 @@ def _model(fx, **cfg):
     m = fx.meta
     o = OceanDrift(loglevel=50, seed=m['seed'])
     f3 = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
-    if fx.w is not None:
+    w_own_grid = getattr(fx, 'w_lon', None) is not None          # random scenarios: upward velocity from a reader of its own
+    if fx.w is not None and not w_own_grid:
         f3['upward_sea_water_velocity'] = fx.w
     if fx.kdiff is not None:
         f3['ocean_vertical_diffusivity'] = fx.kdiff
     o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, name='current'))
+    if fx.w is not None and w_own_grid:
+        o.add_reader(reader_regular_grid.Reader(fx.w_lon, fx.w_lat, fx.w_z, fx.times, {'upward_sea_water_velocity': fx.w}, name='w'))
     if fx.x_wind is not None:
         o.add_reader(reader_regular_grid.Reader(fx.wind_lon, fx.wind_lat, None, fx.times,
                                                 {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind'))
@@ -55,7 +58,9 @@ def _model(fx, **cfg):
     kw = {}
     if fx.cdf is not None:
         kw['current_drift_factor'] = fx.cdf
-    if 'wdf' in m:
+    if getattr(fx, 'wdf_array', None) is not None:
+        kw['wind_drift_factor'] = fx.wdf_array
+    elif 'wdf' in m:
         kw['wind_drift_factor'] = m['wdf']
     o.seed_elements(lon=fx.lon0, lat=fx.lat0, z=fx.z0, time=fx.start, **kw)
     return o
