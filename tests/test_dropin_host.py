@@ -100,3 +100,15 @@ def test_random_scenarios_through_the_model_classes(family, seed):
         assert np.array_equal(lon, hl) and np.array_equal(lat, ha) and np.array_equal(z, np.asarray(hz))
     pl, pa, pz = common.run_port(fx)
     assert max(common.max_err_deg(lon, lat, pl, pa)) < 5e-8
+
+
+@pytest.mark.parametrize('case', __import__('bookkeeping').CASES)
+def test_run_loop_bookkeeping_matches_reference(case):
+    """Release over several steps, per-element release times, retirement by age, deactivate_north_of and the order of
+    the deactivated elements, against the unmodified reference's results (tests/golden/bookkeeping_ref.npz)."""
+    import bookkeeping as bk
+    o = bk.run_product(common.Fixture('rk4_3d'), case)
+    n_act, n_deact = bk.check(o, case)
+    assert n_act + n_deact == bk.N
+    if case in ('release_max_age', 'release_deactivate_north'):
+        assert n_deact > 100

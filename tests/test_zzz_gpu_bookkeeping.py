@@ -1,0 +1,29 @@
+"""GPU: run-loop bookkeeping of the drop-in classes (release over several steps, per-element release times, retirement by
+age, deactivate_north_of, order of the deactivated elements) against the unmodified reference's results
+(tests/golden/bookkeeping_ref.npz; cases and checks in tests/bookkeeping.py, host-verified in tests/test_dropin_host.py)."""
+import pytest
+
+import bookkeeping as bk
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('case', bk.CASES)
+def test_run_loop_bookkeeping_matches_reference_on_gpu(case):
+    o = bk.run_product(common.Fixture('rk4_3d'), case)
+    n_act, n_deact = bk.check(o, case)
+    assert n_act + n_deact == bk.N
+
+
+def test_draw_order_with_mixing_and_horizontal_diffusion_on_gpu():
+    """(see tests/test_dropin_host.py) the diffusion draws come after the mixing loop's"""
+    import numpy as np
+    from test_gpu_dropin import _model
+    fx = common.Fixture('rk4_3d_mixing')
+    fx.meta['diffusivity'] = 5.0
+    pl, pa, pz = common.run_port(fx)
+    o = _model(fx)
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+    assert max(common.max_err_deg(o.elements.lon, o.elements.lat, pl, pa)) < 5e-8
+    assert np.abs(o.elements.z - pz).max() < 1e-7
