@@ -72,6 +72,13 @@ class Environment:
                 return r
         return None
 
+    def readers_for(self, var, time):
+        """All readers, in priority order, that provide `var` and cover `time` (the reference loops over them on the
+        still-missing elements, environment.py:613-780)."""
+        if self.constant(var) is not None:
+            return []
+        return [self.readers[name] for name in self.priority_list.get(var, []) if self.readers[name].covers_time(time)]
+
     # -- device face ---------------------------------------------------------------------------------
     def device_environment(self, variables, time, d_lon, d_lat, d_z, pos_f32=False):
         """dict var -> float32 device tensor, with constants / fallbacks applied, + missing mask tensor."""

@@ -195,6 +195,11 @@ class Leeway(OpenDriftSimulation):
         from `environment:constant:*` / `environment:fallback:*` only (environment.py:499-923 applies them per
         variable) -- a uniform 2 x 2 global group holding those values."""
         r = self.env.reader_for(xname, t)
+        if len(self.env.readers_for(xname, t)) > 1:
+            # the fused Leeway launch samples one reader per vector pair; the reference would fill the elements the first
+            # reader does not cover from the next one (environment.py:613-780) -- refuse rather than be silently wrong
+            raise NotImplementedError('Leeway on the GPU path: several readers provide %s at %s; merge them into one '
+                                      'reader (priority lists of readers are only followed by OceanDrift)' % (xname, t))
         if r is not None:
             if not hasattr(r, 'group_of'):
                 raise NotImplementedError('Leeway on the GPU path needs gridded readers (got %r)' % r)

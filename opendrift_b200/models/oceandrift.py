@@ -121,6 +121,9 @@ class OceanDrift(OpenDriftSimulation):
         g = None
         if model == 'environment':
             r = self.env.reader_for('ocean_vertical_diffusivity', self.time)
+            if len(self.env.readers_for('ocean_vertical_diffusivity', self.time)) > 1:
+                raise NotImplementedError('vertical mixing on the GPU path takes its diffusivity profile from one reader; '
+                                          'several readers provide ocean_vertical_diffusivity at %s' % self.time)
             if r is not None and hasattr(r, 'group_of'):
                 g, _ = r.group_of('ocean_vertical_diffusivity')
             else:
@@ -198,6 +201,8 @@ class OceanDrift(OpenDriftSimulation):
         if g is None:
             return False
         t = self.time
+        if any(len(self.env.readers_for(v, t)) > 1 for v in ('x_sea_water_velocity', 'x_wind', 'upward_sea_water_velocity')):
+            return False                                  # several readers for one variable: the helpers loop over them
         wind_r = self.env.reader_for('x_wind', t)
         wind = wind_r.group_of('x_wind')[0] if wind_r is not None and hasattr(wind_r, 'group_of') else None
         if wind is None and (self._constant_or_none('x_wind') or 0) != 0:

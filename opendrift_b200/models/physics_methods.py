@@ -40,6 +40,10 @@ class PhysicsMethods:
         g = self._current_group(self.time)
         trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
         ra = self.env.reader_for('x_sea_water_velocity', self.time)
+        if len(self.env.readers_for('x_sea_water_velocity', self.time)) > 1:
+            # several current readers in priority order (e.g. a nested model inside a coarser one): every stage needs the
+            # reference's reader loop on the still-missing elements, which the single-group kernels do not do
+            return self._advect_ocean_current_staged(scheme, fac, moving, lon, lat)
         if g is None and ra is not None and hasattr(ra, 'analytic_desc'):
             # analytical reader on a projected plane: the stage loop samples it on the device (od_analytic_advect)
             if any(x > 0 for x in self._uncertainty()[:2]):
@@ -93,6 +97,50 @@ class PhysicsMethods:
                            self._z_for_sampling() if g.desc.nz > 1 else None, factor=fac, moving=moving, k1=k1,
                            truncate_below=trunc, pos_f32=el.positions_f32, noise=noise, noise_kinds=kinds if noise is not None else 0)
         el.positions_f32 = False
+
+    def _advect_ocean_current_staged(self, scheme, fac, moving, lon, lat):
+        """advect_ocean_current (:611-691) stage by stage for a current that comes from several readers: each stage
+        velocity is a full Environment.device_environment call (reader priority loop, fallback), mid-points and the final
+        move are geodesic launches.  Slower than the fused kernels (8 launches per RK4 step instead of 1); only used when
+        more than one reader provides the current."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        uv = ['x_sea_water_velocity', 'y_sea_water_velocity']
+        env = self.environment                       # start-of-step environment (with its uncertainty draws)
+        k1u, k1v = env.dev(uv[0], eng), env.dev(uv[1], eng)
+        t, dt = self.time, self.time_step
+        dts = np.float32(dt.total_seconds())
+        z = self._z_for_sampling()
+        trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
+        if trunc is not None:
+            z = torch.where(z < -trunc, torch.full_like(z, -trunc), z)
+
+        def stage(ku, kv, when):
+            # x0 (+) 0.5 dt k with the reference's float32 azimuth / speed / distance (:629-635)
+            az = torch.rad2deg(torch.atan2(ku, kv))
+            dist = torch.sqrt(ku * ku + kv * kv) * dts * np.float32(0.5)
+            mlon, mlat = lon.clone(), lat.clone()
+            eng.geod_fwd(mlon, mlat, az.to(torch.float64), dist.to(torch.float64))
+            d_env, _ = self.env.device_environment(uv, when, mlon, mlat, z, pos_f32=False)
+            self._add_uncertainty(d_env)
+            return d_env[uv[0]], d_env[uv[1]]
+
+        if scheme == 'euler':
+            ru, rv = k1u, k1v
+        else:
+            k2u, k2v = stage(k1u, k1v, t + dt / 2)
+            if scheme == 'runge-kutta':
+                ru, rv = k2u, k2v
+            else:
+                k3u, k3v = stage(k2u, k2v, t + dt / 2)
+                k4u, k4v = stage(k3u, k3v, t + dt)                       # half step, end time (:660-670)
+                ru = (k1u + 2 * k2u + 2 * k3u + k4u) / 6.0
+                rv = (k1v + 2 * k2v + 2 * k3v + k4v) / 6.0
+        if fac is None:
+            self.update_positions(ru, rv)
+        elif fac.dtype == ru.dtype:
+            self.update_positions(ru * fac, rv * fac)
+        else:
+            self.update_positions(ru.to(torch.float64) * fac.to(torch.float64), rv.to(torch.float64) * fac.to(torch.float64))
 
     def advect_wind(self, factor=1):
         """Wind drift of elements near the surface (:712-791): wind_drift_factor, linearly reduced to zero at

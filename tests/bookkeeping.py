@@ -71,10 +71,57 @@ def check(o, case):
     return len(got['id']), len(got['d_id'])
 
 
+# ---- several readers for one variable (a nested model inside a coarser one): environment.py:613-780 -----------------------
+MULTI_SCHEMES = ['euler', 'runge-kutta', 'runge-kutta4']
+MULTI_STEPS = 6
+
+
+def multireader_fields(fx):
+    """Reader A (first in priority): the western half of the fixture's grid; reader B: the whole grid, different values;
+    a band in the north is NaN in both (fallback 0)."""
+    h = len(fx.grid_lon) // 2
+    a = dict(lon=fx.grid_lon[:h], lat=fx.grid_lat, u=fx.u[..., :h].copy(), v=fx.v[..., :h].copy())
+    b = dict(lon=fx.grid_lon, lat=fx.grid_lat, u=(0.5 * fx.u).astype(np.float32), v=(-0.7 * fx.v).astype(np.float32))
+    return a, b
+
+
+def run_product_multireader(fx, scheme, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    a, b = multireader_fields(fx)
+    o = OceanDrift(loglevel=50, **model_kw)
+    o.add_reader([reader_regular_grid.Reader(r['lon'], r['lat'], None, fx.times, {common.CUR[0]: r['u'], common.CUR[1]: r['v']}, name=nm)
+                  for nm, r in (('A', a), ('B', b))])
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:advection_scheme', scheme)
+    o.set_config('drift:vertical_advection', False)
+    o.seed_elements(lon=fx.lon0, lat=fx.lat0, z=fx.z0, time=fx.start)
+    o.run(steps=MULTI_STEPS, time_step=fx.dt, time_step_output=fx.dt)
+    return o
+
+
+def check_multireader(o, scheme):
+    ref = np.load(GOLDEN)
+    rl, ra = ref['multireader_%s__lon' % scheme], ref['multireader_%s__lat' % scheme]
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), rl, ra)) < 5e-8
+    # the two readers really disagree: using only the first one (+ fallback) is off by ~1e-2 deg
+    return rl, ra
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
+    f2 = common.Fixture('rk4_2d')
+    a, b = multireader_fields(f2)
+    for scheme in MULTI_SCHEMES:
+        rds = [refrun.make_grid_reader(r['lon'], r['lat'], None, f2.times, {common.CUR[0]: r['u'], common.CUR[1]: r['v']}, name=nm)
+               for nm, r in (('A', a), ('B', b))]
+        ro = refrun.run_oceandrift(rds, f2.lon0, f2.lat0, f2.z0, f2.start, f2.dt, MULTI_STEPS,
+                                   config={'drift:advection_scheme': scheme, 'drift:vertical_advection': False})
+        out['multireader_%s__lon' % scheme] = np.asarray(ro.elements.lon, dtype=np.float64)
+        out['multireader_%s__lat' % scheme] = np.asarray(ro.elements.lat, dtype=np.float64)
+        print('multireader', scheme, len(ro.elements.lon))
     for case in CASES:
         t, cfg = case_setup(fx, case)
         rd = refrun.make_grid_reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v})

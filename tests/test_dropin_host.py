@@ -112,3 +112,30 @@ def test_run_loop_bookkeeping_matches_reference(case):
     assert n_act + n_deact == bk.N
     if case in ('release_max_age', 'release_deactivate_north'):
         assert n_deact > 100
+
+
+@pytest.mark.parametrize('scheme', __import__('bookkeeping').MULTI_SCHEMES)
+def test_two_prioritised_current_readers_match_reference(scheme, host_engine):
+    """A nested reader inside a coarser one (the reference loops over the readers on the still-missing elements at every
+    get_environment call, environment.py:613-780).  The single-group kernels cannot do that: the model falls back to the
+    staged recipe.  Found with this harness against the live reference; results pinned in tests/golden/bookkeeping_ref.npz."""
+    import bookkeeping as bk
+    o = bk.run_product_multireader(common.Fixture('rk4_2d'), scheme)
+    bk.check_multireader(o, scheme)
+    assert 'od_step_oceandrift' not in host_engine.lib.calls and 'od_advect_current' not in host_engine.lib.calls
+
+
+def test_models_refuse_reader_lists_they_cannot_follow():
+    """Leeway's fused launch and the mixing kernel sample one reader per variable: with several candidates they raise
+    instead of silently ignoring all but the first."""
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_regular_grid
+    fx = common.LeewayFixture('leeway_piw1')
+    o = Leeway(loglevel=50, seed=1)
+    cur = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
+    o.add_reader([reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, cur, name='c1'),
+                  reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, cur, name='c2'),
+                  reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind})])
+    o.seed_elements(lon=fx.lon0[:10], lat=fx.lat0[:10], time=fx.start, object_type=1)
+    with pytest.raises(NotImplementedError, match='several readers'):
+        o.run(steps=2, time_step=600)

@@ -27,3 +27,9 @@ def test_draw_order_with_mixing_and_horizontal_diffusion_on_gpu():
     o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
     assert max(common.max_err_deg(o.elements.lon, o.elements.lat, pl, pa)) < 5e-8
     assert np.abs(o.elements.z - pz).max() < 1e-7
+
+
+@pytest.mark.parametrize('scheme', bk.MULTI_SCHEMES)
+def test_two_prioritised_current_readers_match_reference_on_gpu(scheme):
+    o = bk.run_product_multireader(common.Fixture('rk4_2d'), scheme)
+    bk.check_multireader(o, scheme)
