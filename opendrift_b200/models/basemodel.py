@@ -341,7 +341,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if getattr(self, '_env_view', None) is None:
             el = self.elements
             d_env, missing = self.env.device_environment(self._env_variables, self.time, el.dev('lon', self.engine.torch.float64),
-                                                         el.dev('lat', self.engine.torch.float64), self._z_for_sampling(),
+                                                         el.dev('lat', self.engine.torch.float64), self._z_truncated(),
                                                          pos_f32=el.positions_f32)
             self._add_uncertainty(d_env)
             self._env_view = EnvironmentView(d_env)
@@ -377,6 +377,17 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if z.dtype not in (self.engine.torch.float32, self.engine.torch.float64):
             z = z.to(self.engine.torch.float64)
         return z
+
+    def _z_truncated(self):
+        """The depth the readers are asked at: drift:truncate_ocean_model_below_m (environment.py:554-562) clips a copy of z
+        in its own dtype; the element depths themselves are untouched."""
+        z = self._z_for_sampling()
+        trunc = self.get_config('drift:truncate_ocean_model_below_m', None) \
+            if 'drift:truncate_ocean_model_below_m' in self._config else None
+        if trunc is None:
+            return z
+        torch = self.engine.torch
+        return torch.where(z < -trunc, torch.full_like(z, -trunc), z)
 
     # -- positions (:4630-4669) ---------------------------------------------------------------------------------
     def update_positions(self, x_vel, y_vel):

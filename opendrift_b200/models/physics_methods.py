@@ -109,10 +109,7 @@ class PhysicsMethods:
         k1u, k1v = env.dev(uv[0], eng), env.dev(uv[1], eng)
         t, dt = self.time, self.time_step
         dts = np.float32(dt.total_seconds())
-        z = self._z_for_sampling()
-        trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
-        if trunc is not None:
-            z = torch.where(z < -trunc, torch.full_like(z, -trunc), z)
+        z = self._z_truncated()
 
         def stage(ku, kv, when):
             # x0 (+) 0.5 dt k with the reference's float32 azimuth / speed / distance (:629-635)

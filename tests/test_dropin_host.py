@@ -139,3 +139,26 @@ def test_models_refuse_reader_lists_they_cannot_follow():
     o.seed_elements(lon=fx.lon0[:10], lat=fx.lat0[:10], time=fx.start, object_type=1)
     with pytest.raises(NotImplementedError, match='several readers'):
         o.run(steps=2, time_step=600)
+
+
+@pytest.mark.parametrize('name', common.fixtures())
+def test_every_fixture_through_the_helper_recipe(name):
+    """A subclass that overrides update() with the reference's own recipe (oceandrift.py:185-211) gets the helpers as
+    separate launches; they must give the fixture's result like the fused launch does (this found the start-of-step
+    environment ignoring drift:truncate_ocean_model_below_m on that path)."""
+    from opendrift_b200.models.oceandrift import OceanDrift
+
+    class Recipe(OceanDrift):
+        def update(self):
+            self.advect_ocean_current()
+            self.advect_wind()
+            self.stokes_drift()
+            if self.get_config('drift:vertical_mixing'):
+                self.vertical_mixing()
+            self.vertical_advection()
+    fx = common.Fixture(name)
+    o = T._model(fx)
+    o.__class__ = Recipe
+    o.run(steps=fx.steps, time_step=fx.dt)
+    assert max(common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)) < 5e-8
+    assert np.abs(o.elements.z - fx.z).max() <= 1e-5

@@ -109,7 +109,8 @@ def test_overridden_update_uses_helpers_and_matches():
             self.vertical_advection()
 
     for name in ('rk4_3d_full', 'euler_2d_wind', 'rk4_3d_cdf32', 'rk4_3d_mixing', 'euler_3d_mixing_w',
-                 'rk4_3d_stokes_phillips', 'euler_3d_stokes_mono_nohs', 'rk4_3d_noise', 'rk2_3d_noise'):
+                 'rk4_3d_stokes_phillips', 'euler_3d_stokes_mono_nohs', 'rk4_3d_noise', 'rk2_3d_noise', 'rk2_3d_truncate',
+                 'rk4_3d_truncate_wsurf'):
         fx = Fixture(name)
         o = _model(fx)
         o.__class__ = MyMixingDrift if fx.meta.get('mixing') else (MyStokesDrift if fx.meta.get('stokes') else MyDrift)
