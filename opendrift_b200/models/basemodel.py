@@ -261,6 +261,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if not idx.any():
             return
         first_release = len(self.elements) == 0
+        ids = np.asarray(self.elements_scheduled.ID)[idx].astype(np.int64)
+        self._release_rank[ids] = np.arange(self._released, self._released + len(ids))     # the reference's array order
+        self._released += len(ids)
         self.elements.append_host(self.elements_scheduled, idx)
         keep = self.ElementType()
         self.elements_scheduled.move_elements(keep, idx)      # drops the released ones from the schedule
@@ -530,6 +533,12 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                                or self.env.fallback(v) is not None]
         self.elements = DeviceElements(self.ElementType, eng)
         self.time = self.start_time
+        if self.time_step.days < 0:
+            # 'Flipping ID array, so that lowest IDs are released first' (:2056-2062): in a backward run the element that
+            # was scheduled last becomes ID 0 (IDs label the trajectories of the result)
+            self.elements_scheduled.ID = np.flipud(np.asarray(self.elements_scheduled.ID))
+        self._release_rank = np.full(int(self.num_elements_total()), -1, dtype=np.int64)
+        self._released = 0
         self.steps_calculation = 0
         self._maybe_deactivated = False
         out_every = int(round(ratio))
@@ -577,11 +586,15 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             raise ValueError('Invalid new coordinates')
 
     def _restore_id_order(self):
-        """Put the device arrays back in the reference's element order (increasing ID)."""
+        """Put the device arrays back in the reference's element order: the order of release (elements are appended as
+        they are released and compaction is stable, elements.py:197-228), which is increasing ID only when the release
+        times are monotonic in the seeding order of a forward run."""
         if not getattr(self, '_sorted', False) or self.num_elements_active() == 0:
             return
-        ids = self.elements.dev('ID')
-        perm = self.engine.torch.argsort(ids.to(self.engine.torch.int64), stable=True).to(self.engine.torch.int32)
+        torch = self.engine.torch
+        ids = self.elements.dev('ID').to(torch.int64)
+        key = self.engine.to_device(self._release_rank)[ids]
+        perm = torch.argsort(key, stable=True).to(torch.int32)
         self.elements.permute(perm)
         self._sorted = False
 

@@ -62,10 +62,26 @@ class Environment:
         item = self._config._config.get('environment:fallback:%s' % var)
         return None if item is None else item['value']
 
+    def discard_ended_readers(self, time):
+        """Environment.discard_reader_if_not_relevant (environment.py:418-432), the rule that matters while a run is under
+        way: a reader whose end_time lies before the requested time is discarded FOR GOOD ('ends before simulation is
+        finished').  In a forward run that is indistinguishable from not covering the time any more; in a backward run that
+        starts after the reader's end the reference never uses the reader again -- mirrored here."""
+        for name, r in list(self.readers.items()):
+            if getattr(r, 'start_time', None) is None or getattr(r, 'always_valid', False) or time is None:
+                continue
+            if r.end_time < time:
+                self.discarded_readers[name] = 'ends before simuation is finished'
+                del self.readers[name]
+                for lst in self.priority_list.values():
+                    if name in lst:
+                        lst.remove(name)
+
     def reader_for(self, var, time):
         """First reader in priority order that provides `var` and covers `time` (or None)."""
         if self.constant(var) is not None:
             return None
+        self.discard_ended_readers(time)
         for name in self.priority_list.get(var, []):
             r = self.readers[name]
             if r.covers_time(time):
@@ -77,6 +93,7 @@ class Environment:
         still-missing elements, environment.py:613-780)."""
         if self.constant(var) is not None:
             return []
+        self.discard_ended_readers(time)
         return [self.readers[name] for name in self.priority_list.get(var, []) if self.readers[name].covers_time(time)]
 
     # -- device face ---------------------------------------------------------------------------------
@@ -86,6 +103,7 @@ class Environment:
         torch = eng.torch
         n = d_lon.numel()
         out = {}
+        self.discard_ended_readers(time)
         for v in variables:
             if v in out:
                 continue

@@ -10,7 +10,7 @@ import common
 
 GOLDEN = os.path.join(common.GOLDEN, 'bookkeeping_ref.npz')
 N, STEPS = 300, 8
-CASES = ['linear_release', 'release_max_age', 'release_deactivate_north', 'per_element_times']
+CASES = ['linear_release', 'release_max_age', 'release_deactivate_north', 'per_element_times', 'backward_release', 'backward_release_past_reader_end']
 
 
 def case_setup(fx, case):
@@ -24,9 +24,19 @@ def case_setup(fx, case):
     elif case == 'per_element_times':
         rng = np.random.default_rng(1)
         t = [fx.start + timedelta(seconds=float(fx.dt * k)) for k in rng.integers(0, 5, N)]
+    elif case == 'backward_release':          # a backward run: released from the last time backwards, IDs flipped (:2056-2062)
+        t = [fx.times[-1] - timedelta(seconds=4 * fx.dt), fx.times[-1] - timedelta(seconds=fx.dt)]
+    elif case == 'backward_release_past_reader_end':
+        # the interpolated release times end 33 microseconds after the reader's last slab: the reference discards the reader
+        # for good at the first step (environment.py:430-432) and the elements never move
+        t = [fx.times[-1] - timedelta(seconds=3 * fx.dt), fx.times[-1]]
     cfg = {'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': False}
     cfg.update(extra)
     return t, cfg
+
+
+def case_dt(fx, case):
+    return -fx.dt if case.startswith('backward_release') else fx.dt
 
 
 def run_product(fx, case, **model_kw):
@@ -40,7 +50,7 @@ def run_product(fx, case, **model_kw):
     for k, v in cfg.items():
         o.set_config(k, v)
     o.seed_elements(lon=fx.lon0[:N], lat=fx.lat0[:N], z=fx.z0[:N], time=t)
-    o.run(steps=STEPS, time_step=fx.dt, time_step_output=fx.dt)
+    o.run(steps=STEPS, time_step=case_dt(fx, case), time_step_output=case_dt(fx, case))
     return o
 
 
@@ -125,7 +135,7 @@ if __name__ == '__main__':
     for case in CASES:
         t, cfg = case_setup(fx, case)
         rd = refrun.make_grid_reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v})
-        ro = refrun.run_oceandrift([rd], fx.lon0[:N], fx.lat0[:N], fx.z0[:N], t, fx.dt, STEPS, config=cfg)
+        ro = refrun.run_oceandrift([rd], fx.lon0[:N], fx.lat0[:N], fx.z0[:N], t, case_dt(fx, case), STEPS, config=cfg)
         s = summary(ro, len(ro.elements_deactivated))
         for k, v in s.items():
             out['%s__%s' % (case, k)] = v
