@@ -123,6 +123,10 @@ class Leeway(OpenDriftSimulation):
                     break
             else:
                 raise ValueError('Object %s not available' % name)
+        if object_type not in self.leewayprop:
+            raise ValueError('Leeway object type %r is not in the property table (%d built-in categories: %s). Pass the full '
+                             'table as the reference does: Leeway(d="<path to an OBJECTPROP.DAT>").'
+                             % (object_type, len(self.leewayprop), ', '.join(p['OBJKEY'] for p in self.leewayprop.values())))
         prop = self.leewayprop[object_type]
         orientation = np.r_[:number] % 2
         ones = np.ones_like(orientation)

@@ -118,10 +118,69 @@ def check_multireader(o, scheme):
     return rl, ra
 
 
+# ---- Leeway: staggered release, backward runs with capsizing (leeway.py:430-494) -------------------------------------------------
+LEEWAY_CASES = {
+    'leeway_staggered': ({}, 1, 'interval', 7, 600),
+    'leeway_backward': ({}, 2, 'end', 6, -600),
+    'leeway_backward_capsizing': ({'processes:capsizing': True, 'capsizing:wind_threshold': 8.0, 'capsizing:wind_threshold_sigma': 5.0},
+                                  1, 'end', 6, -600),
+    'leeway_capsizing_staggered': ({'processes:capsizing': True, 'capsizing:wind_threshold': 6.0, 'capsizing:wind_threshold_sigma': 3.0},
+                                   3, 'interval', 7, 600),
+}
+LEEWAY_N = 400
+
+
+def leeway_seed(fx, case):
+    cfg, object_type, when, steps, dt = LEEWAY_CASES[case]
+    t = [fx.start, fx.start + timedelta(seconds=2400)] if when == 'interval' else fx.times[-1] - timedelta(seconds=600)
+    kw = dict(lon=fx.lon0[:LEEWAY_N], lat=fx.lat0[:LEEWAY_N], time=t, object_type=object_type)
+    if case == 'leeway_backward_capsizing':
+        kw['capsized'] = 1                      # a backward run 'un-capsizes' (leeway.py:443-454)
+    return cfg, kw, steps, dt
+
+
+def run_product_leeway(fx, case, **model_kw):
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_regular_grid
+    cfg, seedkw, steps, dt = leeway_seed(fx, case)
+    o = Leeway(loglevel=50, seed=0, **model_kw)
+    o.add_reader([reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}, name='current'),
+                  reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind')])
+    o.set_config('general:use_auto_landmask', False)
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    o.seed_elements(**seedkw)
+    o.run(steps=steps, time_step=dt, time_step_output=dt)
+    return o
+
+
+def check_leeway(o, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['%s__%s' % (case, k)]                      # noqa: E731
+    assert np.array_equal(np.asarray(o.elements.ID, dtype=np.int64), g('id'))
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+    assert np.array_equal(np.asarray(o.elements.orientation, dtype=np.int64), g('orientation'))
+    assert np.array_equal(np.asarray(o.elements.capsized, dtype=np.int64), g('capsized'))
+    assert np.array_equal(np.asarray(o.elements.crosswind_slope, dtype=np.float64), g('crosswind_slope'))
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
+    lf = common.LeewayFixture('leeway_piw1')
+    for case in LEEWAY_CASES:
+        cfg, seedkw, steps, dt = leeway_seed(lf, case)
+        rds = [refrun.make_grid_reader(lf.grid_lon, lf.grid_lat, None, lf.times, {common.CUR[0]: lf.u, common.CUR[1]: lf.v}, name='current'),
+               refrun.make_grid_reader(lf.grid_lon, lf.grid_lat, None, lf.times, {'x_wind': lf.x_wind, 'y_wind': lf.y_wind}, name='wind')]
+        ro = refrun.run_oceandrift(rds, seedkw['lon'], seedkw['lat'], 0, seedkw['time'], dt, steps, config=cfg,
+                                   seed_kwargs={k: v for k, v in seedkw.items() if k not in ('lon', 'lat', 'time')}, model='Leeway', seed=0)
+        el = ro.elements
+        out.update({case + '__id': np.asarray(el.ID, dtype=np.int64), case + '__lon': np.asarray(el.lon, dtype=np.float64),
+                    case + '__lat': np.asarray(el.lat, dtype=np.float64), case + '__orientation': np.asarray(el.orientation, dtype=np.int64),
+                    case + '__capsized': np.asarray(el.capsized, dtype=np.int64),
+                    case + '__crosswind_slope': np.asarray(el.crosswind_slope, dtype=np.float64)})
+        print(case, len(el.ID), 'capsized', int(np.sum(el.capsized)))
     f2 = common.Fixture('rk4_2d')
     a, b = multireader_fields(f2)
     for scheme in MULTI_SCHEMES:

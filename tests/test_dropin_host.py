@@ -163,3 +163,11 @@ def test_every_fixture_through_the_helper_recipe(name):
     o.run(steps=fx.steps, time_step=fx.dt)
     assert max(common.max_err_deg(o.elements.lon, o.elements.lat, fx.lon, fx.lat)) < 5e-8
     assert np.abs(o.elements.z - fx.z).max() <= 1e-5
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').LEEWAY_CASES))
+def test_leeway_release_and_backward_cases_match_reference(case):
+    """Leeway with a release interval, backward runs, capsizing in both directions: the unmodified reference's final
+    positions, orientation, capsized flags and (jibed) crosswind slopes (tests/golden/bookkeeping_ref.npz)."""
+    import bookkeeping as bk
+    bk.check_leeway(bk.run_product_leeway(common.LeewayFixture('leeway_piw1'), case), case)

@@ -33,3 +33,8 @@ def test_draw_order_with_mixing_and_horizontal_diffusion_on_gpu():
 def test_two_prioritised_current_readers_match_reference_on_gpu(scheme):
     o = bk.run_product_multireader(common.Fixture('rk4_2d'), scheme)
     bk.check_multireader(o, scheme)
+
+
+@pytest.mark.parametrize('case', list(bk.LEEWAY_CASES))
+def test_leeway_release_and_backward_cases_match_reference_on_gpu(case):
+    bk.check_leeway(bk.run_product_leeway(common.LeewayFixture('leeway_piw1'), case), case)
