@@ -164,10 +164,106 @@ def check_leeway(o, case):
     assert np.array_equal(np.asarray(o.elements.crosswind_slope, dtype=np.float64), g('crosswind_slope'))
 
 
+
+# ---- OceanDrift option combinations the fixtures do not have (compared with the live reference through the model classes) ------
+OD_N = 400
+
+
+def od_cases():
+    """name -> (fixture, readers, config, seed overrides, steps, dt).  readers: 'cur' (u, v, w), 'cur_k' (u, v, K), 'cur_short'
+    (u, v on the first two slabs only), 'wind'."""
+    full = common.Fixture('rk4_3d_full')
+    mix = common.Fixture('rk4_3d_mixing')
+    n = OD_N
+    idx = np.arange(n)
+    rk4, rk2 = {'drift:advection_scheme': 'runge-kutta4'}, {'drift:advection_scheme': 'runge-kutta'}
+    mixing = {'drift:vertical_mixing': True, 'drift:vertical_advection': False}
+    return {
+        'reader_ends_mid_run': (full, ['cur_short'], {**rk4, 'drift:vertical_advection': False}, {}, 9, 600),
+        'constant_wind_gridded_current': (full, ['cur'], {**rk2, 'environment:constant:x_wind': 7.0, 'environment:constant:y_wind': -3.0}, {'z': 0.0}, 5, 600),
+        'gridded_wind_constant_current': (full, ['wind'], {**rk4, 'environment:constant:x_sea_water_velocity': 0.3,
+                                                            'environment:constant:y_sea_water_velocity': 0.1}, {'z': 0.0}, 5, 600),
+        'wind_drift_depth_2_and_z_profile': (full, ['cur', 'wind'], {'drift:wind_drift_depth': 2.0}, {'z': np.linspace(-3, 0, n)}, 5, 600),
+        'diffusion_and_uniform_current_uncertainty': (full, ['cur', 'wind'], {**rk2, 'environment:constant:horizontal_diffusivity': 10.0,
+                                                                              'drift:current_uncertainty_uniform': 0.1}, {}, 4, 600),
+        'wdf_array_cdf_scalar': (full, ['cur', 'wind'], rk4, {'z': 0.0, 'wind_drift_factor': np.linspace(0, 0.05, n).astype(np.float32),
+                                                              'current_drift_factor': 0.8}, 5, 600),
+        'relative_wind': (full, ['cur', 'wind'], {**rk2, 'drift:relative_wind': True}, {'z': 0.0}, 4, 600),
+        'relative_wind_with_wind_uncertainty': (full, ['cur', 'wind'], {'drift:relative_wind': True, 'drift:wind_uncertainty': 2.0}, {'z': 0.0}, 4, 600),
+        'vertical_advection_at_surface': (full, ['cur'], {'drift:vertical_advection_at_surface': True}, {'z': 0.0}, 5, 600),
+        'all_noise_and_diffusion_rk4': (full, ['cur', 'wind'], {**rk4, 'drift:current_uncertainty': 0.2, 'drift:wind_uncertainty': 1.0,
+                                                                'environment:constant:horizontal_diffusivity': 3.0}, {}, 4, 600),
+        'positive_z_seeds': (full, ['cur', 'wind'], {}, {'z': np.linspace(-1, 0.5, n)}, 3, 600),
+        'mixing_terminal_velocity': (mix, ['cur_k'], mixing, {'terminal_velocity': 0.002}, 4, 600),
+        'mixing_sinking_array': (mix, ['cur_k'], mixing, {'terminal_velocity': np.linspace(-0.003, 0.0, n).astype(np.float32)}, 4, 600),
+        'mixing_at_surface': (mix, ['cur_k'], {**mixing, 'drift:vertical_mixing_at_surface': True}, {'z': np.where(idx % 3 == 0, 0.0, mix.z0[:n])}, 4, 600),
+        'mixing_shallow_sea_floor': (mix, ['cur_k'], {**mixing, 'environment:constant:sea_floor_depth_below_sea_level': 30.0},
+                                     {'z': np.clip(mix.z0[:n], -29, 0)}, 4, 600),
+        'mixing_dt_45': (mix, ['cur_k'], {**mixing, 'vertical_mixing:timestep': 45.0}, {}, 4, 600),
+        'mixing_constant_model': (mix, ['cur'], {**mixing, 'vertical_mixing:diffusivitymodel': 'constant',
+                                                 'environment:fallback:ocean_vertical_diffusivity': 0.01}, {}, 4, 600),
+        'mixing_backward': (mix, ['cur_k'], mixing, {'time': mix.times[-1]}, 4, -600),
+    }
+
+
+def od_readers(fx, which, make):
+    out = []
+    cur = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
+    if 'cur' in which:
+        f = dict(cur)
+        if fx.w is not None:
+            f['upward_sea_water_velocity'] = fx.w
+        out.append(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f, 'cur'))
+    if 'cur_k' in which:
+        out.append(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, dict(cur, ocean_vertical_diffusivity=fx.kdiff), 'cur'))
+    if 'cur_short' in which:
+        out.append(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times[:2], {k: v[:2] for k, v in cur.items()}, 'cur'))
+    if 'wind' in which:
+        out.append(make(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
+    return out
+
+
+def od_seed(fx, over):
+    kw = dict(lon=fx.lon0[:OD_N], lat=fx.lat0[:OD_N], z=fx.z0[:OD_N], time=fx.start)
+    kw.update(over)
+    return kw
+
+
+def run_product_od(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx, which, cfg, over, steps, dt = od_cases()[case]
+    o = OceanDrift(loglevel=50, seed=0, **model_kw)
+    for r in od_readers(fx, which, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name)):
+        o.add_reader(r)
+    o.set_config('general:use_auto_landmask', False)
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    o.seed_elements(**od_seed(fx, over))
+    o.run(steps=steps, time_step=dt, time_step_output=dt)
+    return o
+
+
+def check_od(o, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['od_%s__%s' % (case, k)]                   # noqa: E731
+    assert np.array_equal(np.asarray(o.elements.ID, dtype=np.int64), g('id'))
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+    assert np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max() <= (1e-9 if case.startswith('mixing') else 1e-5)
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
+    for case, (cfx, which, cfg, over, steps, dt) in od_cases().items():
+        rds = od_readers(cfx, which, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name))
+        kw = od_seed(cfx, over)
+        ro = refrun.run_oceandrift(rds, kw['lon'], kw['lat'], kw['z'], kw['time'], dt, steps, config=cfg,
+                                   seed_kwargs={k: v for k, v in kw.items() if k not in ('lon', 'lat', 'z', 'time')}, seed=0)
+        out.update({'od_%s__id' % case: np.asarray(ro.elements.ID, dtype=np.int64), 'od_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64),
+                    'od_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64), 'od_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64)})
+        print('od', case, len(ro.elements.ID))
     lf = common.LeewayFixture('leeway_piw1')
     for case in LEEWAY_CASES:
         cfg, seedkw, steps, dt = leeway_seed(lf, case)

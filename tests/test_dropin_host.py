@@ -171,3 +171,13 @@ def test_leeway_release_and_backward_cases_match_reference(case):
     positions, orientation, capsized flags and (jibed) crosswind slopes (tests/golden/bookkeeping_ref.npz)."""
     import bookkeeping as bk
     bk.check_leeway(bk.run_product_leeway(common.LeewayFixture('leeway_piw1'), case), case)
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').od_cases()))
+def test_option_combinations_match_reference(case):
+    """OceanDrift option combinations no fixture has -- constant / fallback forcing next to gridded readers, a reader that
+    ends mid-run, relative wind, wind-drift depth, uncertainty + diffusion, drift-factor arrays, and the vertical-mixing variants
+    (terminal velocity, mixing at the surface, shallow sea floor, non-divisor inner step, constant model, backward) -- against
+    results of the unmodified reference driven through its own model class (tests/golden/bookkeeping_ref.npz)."""
+    import bookkeeping as bk
+    bk.check_od(bk.run_product_od(case), case)

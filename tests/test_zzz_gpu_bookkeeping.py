@@ -38,3 +38,8 @@ def test_two_prioritised_current_readers_match_reference_on_gpu(scheme):
 @pytest.mark.parametrize('case', list(bk.LEEWAY_CASES))
 def test_leeway_release_and_backward_cases_match_reference_on_gpu(case):
     bk.check_leeway(bk.run_product_leeway(common.LeewayFixture('leeway_piw1'), case), case)
+
+
+@pytest.mark.parametrize('case', list(bk.od_cases()))
+def test_option_combinations_match_reference_on_gpu(case):
+    bk.check_od(bk.run_product_od(case), case)
