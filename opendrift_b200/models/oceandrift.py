@@ -201,10 +201,13 @@ class OceanDrift(OpenDriftSimulation):
         if g is None:
             return False
         t = self.time
-        if any(len(self.env.readers_for(v, t)) > 1 for v in ('x_sea_water_velocity', 'x_wind', 'upward_sea_water_velocity')):
+        if self._current_needs_reader_loop(t) or any(len(self.env.readers_for(v, t)) > 1 for v in
+                                                     ('x_wind', 'y_wind', 'upward_sea_water_velocity')):
             return False                                  # several readers for one variable: the helpers loop over them
         wind_r = self.env.reader_for('x_wind', t)
         wind = wind_r.group_of('x_wind')[0] if wind_r is not None and hasattr(wind_r, 'group_of') else None
+        if wind is not None and (wind.ncomp != 2 or self.env.reader_for('y_wind', t) is not wind_r):
+            return False                                  # wind components from different sources: helper path
         if wind is None and (self._constant_or_none('x_wind') or 0) != 0:
             return False                                  # constant non-zero wind: helper path
         wgrp = None

@@ -11,10 +11,20 @@ class PhysicsMethods:
         r = self.env.reader_for('x_sea_water_velocity', t)
         if r is None or not hasattr(r, 'group_of'):
             return None
+        if 'y_sea_water_velocity' not in r.variables:
+            return None                              # the components come from different sources: staged recipe
         g, c = r.group_of('x_sea_water_velocity')
         g2, c2 = r.group_of('y_sea_water_velocity')
         assert g is g2 and (c, c2) == (0, 1), 'current components must come from one reader'
         return g
+
+    def _current_needs_reader_loop(self, t):
+        """True when the current cannot be sampled from ONE two-component field group: several readers in priority order,
+        or x and y components from different readers (the reference resolves every variable on its own, environment.py:613-780)."""
+        rx, ry = self.env.readers_for('x_sea_water_velocity', t), self.env.readers_for('y_sea_water_velocity', t)
+        if len(rx) > 1 or len(ry) > 1:
+            return True
+        return len(rx) + len(ry) > 0 and (len(rx) != len(ry) or rx[0] is not ry[0])
 
     def _device_factor(self, factor, name):
         """factor * elements.<name> with NumPy's dtype rules (int/float scalar factors are weak)."""
@@ -40,7 +50,7 @@ class PhysicsMethods:
         g = self._current_group(self.time)
         trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
         ra = self.env.reader_for('x_sea_water_velocity', self.time)
-        if len(self.env.readers_for('x_sea_water_velocity', self.time)) > 1:
+        if self._current_needs_reader_loop(self.time):
             # several current readers in priority order (e.g. a nested model inside a coarser one): every stage needs the
             # reference's reader loop on the still-missing elements, which the single-group kernels do not do
             return self._advect_ocean_current_staged(scheme, fac, moving, lon, lat)

@@ -181,3 +181,30 @@ def test_option_combinations_match_reference(case):
     results of the unmodified reference driven through its own model class (tests/golden/bookkeeping_ref.npz)."""
     import bookkeeping as bk
     bk.check_od(bk.run_product_od(case), case)
+
+
+def test_constant_reader_replays_the_reference_known_answers():
+    """opendrift/readers/reader_constant.py on the drop-in classes: the reference's tests/readers/test_variables.py:107-128
+    (wind from speed + direction, 15 one-hour steps, default wind drift factor) as the reference writes it, and constant
+    current / wind readers next to each other (values from a run of the unmodified reference)."""
+    from datetime import datetime, timedelta
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_constant
+    for direction, lon, lat in ((225, 3.932, 59.966), (45, 4.068, 60.034)):
+        r = reader_constant.Reader({'wind_speed': 5, 'wind_to_direction': direction, 'land_binary_mask': 0})
+        o = OceanDrift(loglevel=50)
+        o.set_config('general:use_auto_landmask', False)
+        o.add_reader(r)
+        o.seed_elements(lon=4, lat=60, time=datetime.now())
+        o.run(steps=15)
+        np.testing.assert_almost_equal(o.elements.lon, lon, 3)
+        np.testing.assert_almost_equal(o.elements.lat, lat, 3)
+    o = OceanDrift(loglevel=50)
+    o.set_config('general:use_auto_landmask', False)
+    o.add_reader([reader_constant.Reader({'x_sea_water_velocity': 1, 'y_sea_water_velocity': 0, 'x_wind': 10, 'y_wind': 0})])
+    o.seed_elements(lon=4.0, lat=60.0, time=datetime(2026, 1, 1), current_drift_factor=0.3, wind_drift_factor=0.02)
+    o.run(steps=2, time_step=3600)
+    assert o.elements.lon[0] == pytest.approx(4.064516123645828, abs=1e-12)       # the unmodified reference, same script
+    assert o.elements.lat[0] == pytest.approx(59.99999590372567, abs=1e-12)
+    with pytest.raises(NotImplementedError):
+        reader_constant.Reader({'x_wind': np.arange(3.0), 'element_ID': np.arange(3)})

@@ -43,3 +43,19 @@ def test_leeway_release_and_backward_cases_match_reference_on_gpu(case):
 @pytest.mark.parametrize('case', list(bk.od_cases()))
 def test_option_combinations_match_reference_on_gpu(case):
     bk.check_od(bk.run_product_od(case), case)
+
+
+def test_constant_reader_known_answers_on_gpu():
+    """reader_constant on the GPU: tests/readers/test_variables.py:107-128 of the reference, as it is written there."""
+    from datetime import datetime
+    import numpy as np
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_constant
+    for direction, lon, lat in ((225, 3.932, 59.966), (45, 4.068, 60.034)):
+        o = OceanDrift(loglevel=50)
+        o.set_config('general:use_auto_landmask', False)
+        o.add_reader(reader_constant.Reader({'wind_speed': 5, 'wind_to_direction': direction, 'land_binary_mask': 0}))
+        o.seed_elements(lon=4, lat=60, time=datetime.now())
+        o.run(steps=15)
+        np.testing.assert_almost_equal(o.elements.lon, lon, 3)
+        np.testing.assert_almost_equal(o.elements.lat, lat, 3)
