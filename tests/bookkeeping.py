@@ -118,6 +118,57 @@ def check_multireader(o, scheme):
     return rl, ra
 
 
+
+# ---- run() argument variants (basemodel/__init__.py:1829-2060: duration / end_time / steps, output step, config time steps) -----
+RUN_N = 200
+
+
+def run_cases():
+    fx = common.Fixture('rk4_2d')
+    n = RUN_N
+    s = dict(lon=fx.lon0[:n], lat=fx.lat0[:n], time=fx.start)
+    m = timedelta(minutes=1)
+    return fx, {
+        'duration_50min': (s, dict(duration=50 * m, time_step=600), {}),
+        'duration_not_a_multiple': (s, dict(duration=55 * m, time_step=600), {}),
+        'end_time': (s, dict(end_time=fx.start + 70 * m, time_step=600), {}),
+        'output_every_third_step': (s, dict(steps=9, time_step=600, time_step_output=1800), {}),
+        'until_reader_end': (s, dict(time_step=900), {}),
+        'timedelta_time_step': (s, dict(steps=5, time_step=7 * m), {}),
+        'backward_duration': ({**s, 'time': fx.times[-1]}, dict(duration=40 * m, time_step=-600), {}),
+        'config_time_steps': (s, dict(steps=4), {'general:time_step_minutes': 12, 'general:time_step_output_minutes': 24}),
+        'number_per_point_radius': ({'lon': [3.0, 3.5], 'lat': [57.0, 57.2], 'number_per_point': 30, 'radius': 500, 'time': fx.start},
+                                    dict(steps=4, time_step=600), {}),
+        'deactivate_west_and_south': (s, dict(steps=8, time_step=600),
+                                      {'drift:deactivate_west_of': float(np.median(fx.lon0[:n])),
+                                       'drift:deactivate_south_of': float(np.percentile(fx.lat0[:n], 20))}),
+    }
+
+
+def run_product_runcase(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx, cases = run_cases()
+    seedkw, runkw, cfg = cases[case]
+    o = OceanDrift(loglevel=50, seed=0, **model_kw)
+    o.add_reader(reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}))
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:advection_scheme', 'runge-kutta')
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    o.seed_elements(**seedkw)
+    o.run(**runkw)
+    return o
+
+
+def check_runcase(o, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['run_%s__%s' % (case, k)]                  # noqa: E731
+    assert o.steps_calculation == int(g('steps')) and np.array_equal(np.asarray(o.elements.ID, dtype=np.int64), g('id'))
+    assert (o.time - run_cases()[0].start).total_seconds() == float(g('elapsed'))
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+
+
 # ---- Leeway: staggered release, backward runs with capsizing (leeway.py:430-494) -------------------------------------------------
 LEEWAY_CASES = {
     'leeway_staggered': ({}, 1, 'interval', 7, 600),
@@ -264,6 +315,20 @@ if __name__ == '__main__':
         out.update({'od_%s__id' % case: np.asarray(ro.elements.ID, dtype=np.int64), 'od_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64),
                     'od_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64), 'od_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64)})
         print('od', case, len(ro.elements.ID))
+    rfx, rcases = run_cases()
+    for case, (seedkw, runkw, cfg) in rcases.items():
+        from opendrift.models.oceandrift import OceanDrift as RefOceanDrift
+        ro = RefOceanDrift(loglevel=50, logfile='/tmp/od_bk.log', seed=0)
+        ro.add_reader(refrun.make_grid_reader(rfx.grid_lon, rfx.grid_lat, None, rfx.times, {common.CUR[0]: rfx.u, common.CUR[1]: rfx.v}))
+        for k, v in {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': 0, 'general:coastline_action': 'none',
+                     'drift:advection_scheme': 'runge-kutta', **cfg}.items():
+            ro.set_config(k, v)
+        ro.seed_elements(**seedkw)
+        ro.run(**runkw)
+        out.update({'run_%s__id' % case: np.asarray(ro.elements.ID, dtype=np.int64), 'run_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64),
+                    'run_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64), 'run_%s__steps' % case: np.int64(ro.steps_calculation),
+                    'run_%s__elapsed' % case: np.float64((ro.time - rfx.start).total_seconds())})
+        print('run', case, ro.steps_calculation, len(ro.elements.ID))
     lf = common.LeewayFixture('leeway_piw1')
     for case in LEEWAY_CASES:
         cfg, seedkw, steps, dt = leeway_seed(lf, case)

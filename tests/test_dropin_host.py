@@ -208,3 +208,12 @@ def test_constant_reader_replays_the_reference_known_answers():
     assert o.elements.lat[0] == pytest.approx(59.99999590372567, abs=1e-12)
     with pytest.raises(NotImplementedError):
         reader_constant.Reader({'x_wind': np.arange(3.0), 'element_ID': np.arange(3)})
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').run_cases()[1]))
+def test_run_argument_variants_match_reference(case):
+    """run(duration= / end_time= / steps=, time_step_output=, timedelta steps, config time steps, backward duration),
+    number_per_point seeding with a radius, deactivate_west/south_of: step count, end time, surviving IDs and positions of
+    the unmodified reference."""
+    import bookkeeping as bk
+    bk.check_runcase(bk.run_product_runcase(case), case)

@@ -59,3 +59,8 @@ def test_constant_reader_known_answers_on_gpu():
         o.run(steps=15)
         np.testing.assert_almost_equal(o.elements.lon, lon, 3)
         np.testing.assert_almost_equal(o.elements.lat, lat, 3)
+
+
+@pytest.mark.parametrize('case', list(bk.run_cases()[1]))
+def test_run_argument_variants_match_reference_on_gpu(case):
+    bk.check_runcase(bk.run_product_runcase(case), case)
