@@ -7,6 +7,8 @@ Optional spatial-tile mode (BASELINE configs[2] wording: "field broadcast + part
 forcing is too large to replicate): the domain is cut into one longitude strip per rank (`strip_owner`), and after a step
 the particles that left their strip travel to the new owner as packed SoA records in ONE all-to-all (`exchange_particles`:
 counts first, then a single `all_to_all_single` of [n, record_bytes] rows).  Element identity travels in the ID column.
+The field side: `strip_columns` gives every rank the columns of its strip plus a halo wide enough for the Runge-Kutta
+excursions of one step, `scatter_field_tiles` / `receive_field_tile` move each new time slab's tiles from the rank that read it.
 """
 import numpy as np
 
@@ -112,3 +114,51 @@ def exchange_particles(columns, owner, group=None):
     mine = out[offs[rank]:offs[rank + 1]]
     others = [out[offs[r]:offs[r + 1]] for r in range(world) if r != rank]
     return _unpack(torch.cat([mine] + others, dim=0), layout)
+
+
+def strip_columns(lon, bounds, halo_cells):
+    """Column range [i0, i1) of the global grid each rank holds in spatial-tile mode: the cells of its longitude strip plus
+    `halo_cells` on either side -- the reference's own block rule, buffer = ceil(max_speed * dt / pixel size) + 2 cells
+    around the particles (basereader/variables.py:616-617), so that every Runge-Kutta stage of a particle that starts the
+    step inside the strip finds its corners in the tile."""
+    lon = np.asarray(lon, dtype=np.float64)
+    nx = len(lon)
+    out = []
+    for r in range(len(bounds) - 1):
+        inside = np.where((lon >= bounds[r]) & (lon <= bounds[r + 1]))[0]
+        lo = (inside[0] if len(inside) else int(np.searchsorted(lon, bounds[r]))) - 1 - int(halo_cells)
+        hi = (inside[-1] if len(inside) else int(np.searchsorted(lon, bounds[r + 1]))) + 2 + int(halo_cells)
+        out.append((max(0, lo), min(nx, hi)))
+    return out
+
+
+def scatter_field_tiles(slab, columns, src=0, group=None):
+    """One time slab [..., ny, nx] on `src` -> every rank's tile slab[..., i0:i1] (point-to-point sends of the tiles; the
+    other ranks pass slab=None and the leading shape / dtype of the slab as `like`).  Returns this rank's tile."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        i0, i1 = columns[0]
+        return slab[..., i0:i1].contiguous()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if rank == src:
+        mine = None
+        for r in range(world):
+            i0, i1 = columns[r]
+            tile = slab[..., i0:i1].contiguous()
+            if r == src:
+                mine = tile
+            else:
+                dist.send(tile, r, group=group)
+        return mine
+    raise RuntimeError('receivers call receive_field_tile')
+
+
+def receive_field_tile(shape_prefix, columns, dtype, device='cpu', src=0, group=None):
+    """The receiving side of scatter_field_tiles: allocates [*shape_prefix, i1 - i0] and receives this rank's tile."""
+    import torch
+    import torch.distributed as dist
+    i0, i1 = columns[dist.get_rank(group)]
+    tile = torch.empty(tuple(shape_prefix) + (i1 - i0,), dtype=dtype, device=device)
+    dist.recv(tile, src, group=group)
+    return tile

@@ -146,3 +146,87 @@ def test_exchange_is_identity_without_process_group():
     assert all(torch.equal(back[k], cols[k].flip(0)) for k in cols)
     b = sharding.strip_bounds(0.0, 8.0, 4)
     assert sharding.strip_owner(torch.tensor([-3.0, 0.0, 1.99, 2.0, 7.9, 8.0, 11.0]), b).tolist() == [0, 0, 0, 1, 3, 3, 3]
+
+
+def _tiled_field_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, common.ROOT)
+    from datetime import timedelta
+    from oracle import advect_port as ap
+    fx = common.Fixture('rk4_2d')
+    bounds = sharding.strip_bounds(fx.grid_lon.min(), fx.grid_lon.max(), world)
+    # halo: the reference's block buffer, ceil(max_speed * dt / pixel) + 2 cells (variables.py:616-617)
+    dx_m = float(fx.grid_lon[1] - fx.grid_lon[0]) * 111e3 * np.cos(np.radians(float(fx.grid_lat.max())))
+    vmax = float(max(np.nanmax(np.abs(fx.u)), np.nanmax(np.abs(fx.v))))
+    halo = int(np.ceil(vmax * abs(fx.dt) / dx_m)) + 2
+    cols = sharding.strip_columns(fx.grid_lon, bounds, halo)
+    # rank 0 read the forcing; every rank receives only its tile of every slab
+    tiles = {}
+    for name, full in ((common.CUR[0], fx.u), (common.CUR[1], fx.v)):
+        if rank == 0:
+            tiles[name] = sharding.scatter_field_tiles(torch.from_numpy(full.copy()), cols, 0).numpy()
+        else:
+            tiles[name] = sharding.receive_field_tile(full.shape[:-1], cols, torch.float32, src=0).numpy()
+    i0, i1 = cols[rank]
+    ok = np.array_equal(tiles[common.CUR[0]], fx.u[..., i0:i1]) and (i1 - i0) < len(fx.grid_lon)       # a real sub-grid
+    reader = ap.GridReader(fx.grid_lon[i0:i1], fx.grid_lat, None, fx.times, tiles)
+    lo, hi = sharding.shard_range(fx.n, rank, world)
+    cols_p = {'ID': torch.arange(lo, hi, dtype=torch.int32),
+              'lon': torch.from_numpy(fx.lon0[lo:hi].astype(np.float32).astype(np.float64)),
+              'lat': torch.from_numpy(fx.lat0[lo:hi].astype(np.float32).astype(np.float64)),
+              'first': torch.ones(hi - lo, dtype=torch.uint8)}
+    t = fx.start
+    for k in range(fx.steps):
+        cols_p = sharding.exchange_particles(cols_p, sharding.strip_owner(cols_p['lon'], bounds))
+        n = len(cols_p['ID'])
+        if n:
+            lon, lat = cols_p['lon'].numpy(), cols_p['lat'].numpy()
+            first = cols_p['first'].numpy().astype(bool)
+            if first.all():
+                lon, lat = lon.astype(np.float32), lat.astype(np.float32)
+            z = np.zeros(n, dtype=np.float32)
+            env = ap.get_environment([reader], common.CUR, t, lon, lat, z, fallback={})        # no fallback: a miss must show
+            ok &= bool(np.isfinite(env[common.CUR[0]]).all())
+            lon, lat = ap.advect_ocean_current([reader], fx.meta['scheme'], t, fx.dt, lon, lat, z, np.ones(n),
+                                               np.ones(n, dtype=np.int32), env)
+            cols_p['lon'], cols_p['lat'] = torch.from_numpy(np.asarray(lon, dtype=np.float64)), torch.from_numpy(np.asarray(lat, dtype=np.float64))
+            cols_p['first'] = torch.zeros(n, dtype=torch.uint8)
+        t = t + timedelta(seconds=fx.dt)
+    ids = cols_p['ID'].numpy().astype(np.int64)
+    full_lon = sharding.gather_by_id(ids, cols_p['lon'].numpy(), fx.n)
+    full_lat = sharding.gather_by_id(ids, cols_p['lat'].numpy(), fx.n)
+    # the tiles have their own float32 end points, like the reference's own sub-blocks: index arithmetic differs in the last bits
+    e = common.max_err_deg(full_lon, full_lat, fx.lon, fx.lat)
+    ok &= max(e) < 5e-8
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_field_tiles_with_halo_and_particle_exchange():
+    """BASELINE configs[2] wording end to end on gloo: every rank holds only its longitude strip of the field (+ halo), new
+    slabs arrive as tiles from the rank that read them, particles move to their owner in one all-to-all per step; the result is
+    the unsharded reference run's."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tiled_field_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)], res
+
+
+def test_strip_columns_cover_their_strips():
+    lon = np.linspace(2.0, 3.95, 40)
+    b = sharding.strip_bounds(lon.min(), lon.max(), 4)
+    cols = sharding.strip_columns(lon, b, 2)
+    for r, (i0, i1) in enumerate(cols):
+        assert 0 <= i0 < i1 <= 40
+        inside = np.where((lon >= b[r]) & (lon <= b[r + 1]))[0]
+        assert i0 <= max(0, inside[0] - 3) and i1 >= min(40, inside[-1] + 4)
+    assert cols[0][0] == 0 and cols[-1][1] == 40
+    assert sharding.scatter_field_tiles(torch.arange(12.0).reshape(3, 4), [(1, 3)]).tolist() == [[1.0, 2.0], [5.0, 6.0], [9.0, 10.0]]
