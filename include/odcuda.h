@@ -194,7 +194,16 @@ typedef struct od_advect_args {
                                                EXACT per step, the size of the reference's own float32 arctan2 noise;
                                      1 FAST  : float32 sampling and mid-latitude moves on float64 positions
                                                (~1e-7 deg from the reference after 100 steps; od_advect.cuh FastMath) */
+    /* Reader priority list for the current (Environment.get_environment loops over the readers of a variable on the
+     * still-missing elements, environment.py:613-780 -- e.g. a nested model inside a coarser one): up to OD_MAX_CHAIN further
+     * two-component groups, sampled in order wherever the groups before them return NaN; the fallback values of
+     * group_uv apply after the last one. */
+    int32_t n_chain;
+    int32_t chain_group[2];
+    int32_t pad4_;
+    od_time_sample chain_t[2][3]; /* per chained group: time t, t + dt/2, t + dt */
 } od_advect_args;
+#define OD_MAX_CHAIN 2
 
 int od_advect_current(od_ctx* ctx, const od_advect_args* a);
 

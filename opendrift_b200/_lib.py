@@ -17,6 +17,7 @@ OD_MATH_EXACT, OD_MATH_FAST, OD_MATH_SERIES = 0, 1, 2
 OD_MIX_ENVIRONMENT, OD_MIX_LARGE1994, OD_MIX_SUNDBY1983, OD_MIX_CONSTANT = 0, 1, 2, 3
 OD_MAX_LEVELS = 128
 OD_MAX_GROUPS = 64
+OD_MAX_CHAIN = 2
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
 
 
@@ -48,7 +49,8 @@ class AdvectArgs(C.Structure):
                 ('d_moving', C.c_void_p), ('d_k1_u', C.c_void_p), ('d_k1_v', C.c_void_p),
                 ('truncate_below', C.c_double),
                 ('d_env_u', C.c_void_p), ('d_env_v', C.c_void_p), ('z_f64', C.c_int32), ('pad3_', C.c_int32), ('d_noise_cur', C.c_void_p), ('noise_kinds', C.c_int32),
-                ('fast', C.c_int32)]
+                ('fast', C.c_int32),
+                ('n_chain', C.c_int32), ('chain_group', C.c_int32 * 2), ('pad4_', C.c_int32), ('chain_t', (TimeSample * 3) * 2)]
 
 
 class StepArgs(C.Structure):

@@ -221,6 +221,10 @@ struct FastMath {
     }
 };
 
+#ifndef OD_MAX_CHAIN
+#define OD_MAX_CHAIN 2
+#endif
+
 struct CurrentStages {
     GroupGeom g;
     PairRef t_start, t_mid, t_end;
@@ -265,7 +269,29 @@ struct StepParams {
     const float* diffusivity;
     float diffusivity_const;
     float adt32;
+    // Reader priority list for the current (environment.py:613-780): where the first group gives NaN the next one is
+    // sampled, and so on; the environment fallback applies after the last.  Only read by the CHAIN instantiations.
+    int32_t n_chain, pad_chain_;
+    GroupGeom cg[OD_MAX_CHAIN];           // their fallback fields are NaN
+    PairRef ct[OD_MAX_CHAIN][3];          // pairs at t, t + dt/2, t + dt
+    float chain_fallback[2];
 };
+
+// fill what the groups so far left missing from the next readers of the priority list
+template <class MATH>
+OD_HD void chain_fill(const StepParams& p, int which, double zt, bool zf32, double lon, double lat, bool pos_f32, float& u, float& v) {
+    for (int k = 0; k < p.n_chain; ++k) {
+        if (finite_f(u) && finite_f(v)) break;
+        const GroupGeom& g = p.cg[k];
+        const VertW vw = vert_weights(g, g.zs, g.zy, zt, zf32);
+        float a, b;
+        MATH::sample_uv(g, p.ct[k][which], vw, lon, lat, a, b, pos_f32);
+        if (!finite_f(u)) u = a;
+        if (!finite_f(v)) v = b;
+    }
+    if (!finite_f(u)) u = p.chain_fallback[0];
+    if (!finite_f(v)) v = p.chain_fallback[1];
+}
 
 // env[var] += draws  on a float32 array: float32(float64(k) + draw), normal first, then uniform
 OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u, float& v) {
@@ -284,9 +310,9 @@ OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u
 //   stage 1..3: position x0 (+) 0.5*dt*k_{stage}; pair t_mid, t_mid, t_end (the reference's stage-4 quirk: half
 //   step, end time); RK2 stops after stage 1 and returns k2; RK4 returns (k1 + 2 k2 + 2 k3 + k4) / 6 in float32,
 //   accumulated left to right as the reference writes it.
-template <int SCHEME, class MATH>
+template <int SCHEME, class MATH, bool CHAIN = false>
 OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
-                       float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv) {
+                       float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv, double zt = 0.0, bool zf32 = true) {
     const CurrentStages& cs = p.cs;
     if (SCHEME == 0) {
         ou = k1u;
@@ -304,6 +330,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
         MATH::midpoint(gs, lon0, lat0, ku, kv, dt32, mlon, mlat);
         const PairRef& pr = st == 3 ? cs.t_end : cs.t_mid;
         MATH::sample_uv(cs.g, pr, vw, mlon, mlat, ku, kv, false, tv);
+        if (CHAIN) chain_fill<MATH>(p, st == 3 ? 2 : 1, zt, zf32, mlon, mlat, false, ku, kv);
         add_current_noise(p, st, i, ku, kv);
         if (st < 3) {
             su = OD_FADD(su, OD_FMUL(2.0f, ku));
@@ -395,7 +422,7 @@ OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double*
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
 // EXTRAS: 0 current advection only; 1 all extras (wind move, vertical advection, diffusion move); 2 vertical advection only
-template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath>
+template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath, bool CHAIN = false>
 OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
                          const double* zsw, const double* zyw, const TileView& tv = TileView()) {
     const GroupGeom& g = p.cs.g;
@@ -419,6 +446,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
     } else {
         if (MATH::kExactSampler) sample2_h(g, p.cs.t_start, vw, h0, k1u, k1v, tv);
         else MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0, tv);
+        if (CHAIN) chain_fill<MATH>(p, 0, zt, zf32, lon0, lat0, p.pos_f32 != 0, k1u, k1v);
         add_current_noise(p, 0, i, k1u, k1v);
     }
     if (p.env_u) p.env_u[i] = k1u;
@@ -448,7 +476,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
     }
 
     float ru, rv;
-    rk_velocity<SCHEME, MATH>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv);
+    rk_velocity<SCHEME, MATH, CHAIN>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv, zt, zf32);
 
     double lon1, lat1;
     if (F64) {

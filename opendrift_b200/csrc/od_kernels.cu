@@ -680,6 +680,20 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const Step
     step_particle<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
+// The same step with a reader priority list for the current (StepParams::cg): a separate kernel so that the default one is
+// not touched by it.  EXTRAS is 0 or 1 here (1 also serves vertical advection only).
+template <int SCHEME, bool F64, int EXTRAS, class MATH>
+__global__ void __launch_bounds__(OD_BLOCK) step_chain_kernel(const __grid_constant__ StepParams p) {
+    __shared__ LevelsSmem lv;
+    __shared__ LevelsSmem lvw;
+    if (p.cs.g.nz > 1) load_levels(lv, p.cs.g);
+    if (EXTRAS && p.w_on && p.gw.nz > 1) load_levels(lvw, p.gw);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    step_particle<SCHEME, F64, EXTRAS, MATH, true>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+}
+
 // ---- vertical mixing -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     __shared__ double xs[OD_MAX_LEVELS];
@@ -994,6 +1008,33 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
         rc = resolve_pair(ctx, a->group_uv, a->t_end, &p->cs.t_end);
         if (rc) return rc;
     }
+    if (a->n_chain < 0 || a->n_chain > OD_MAX_CHAIN) return fail(ctx, OD_ERR_ARG, "reader chain longer than OD_MAX_CHAIN");
+    p->n_chain = a->n_chain;
+    for (int k = 0; k < a->n_chain; ++k) {
+        rc = need_group(ctx, a->chain_group[k], 2);
+        if (rc) return rc;
+        const Group& gk = ctx->groups[a->chain_group[k]];
+        if (gk.desc.nz > 1 && !a->d_z) return fail(ctx, OD_ERR_ARG, "3-D current group needs z");
+        p->cg[k] = make_geom(gk);
+        p->cg[k].fallback[0] = p->cg[k].fallback[1] = NAN;
+        if (!p->has_k1) {
+            rc = resolve_pair(ctx, a->chain_group[k], a->chain_t[k][0], &p->ct[k][0]);
+            if (rc) return rc;
+        }
+        if (a->scheme != OD_EULER) {
+            rc = resolve_pair(ctx, a->chain_group[k], a->chain_t[k][1], &p->ct[k][1]);
+            if (rc) return rc;
+        }
+        if (a->scheme == OD_RK4) {
+            rc = resolve_pair(ctx, a->chain_group[k], a->chain_t[k][2], &p->ct[k][2]);
+            if (rc) return rc;
+        }
+    }
+    if (a->n_chain > 0) {          // the environment fallback applies after the last reader of the list
+        p->chain_fallback[0] = p->cs.g.fallback[0];
+        p->chain_fallback[1] = p->cs.g.fallback[1];
+        p->cs.g.fallback[0] = p->cs.g.fallback[1] = NAN;
+    }
     p->dt = a->dt;
     p->dt32 = (float)a->dt;
     p->adt32 = (float)fabs(a->dt);
@@ -1121,6 +1162,17 @@ template <int EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
+    if (p.n_chain > 0) {
+        constexpr int E = EXTRAS == 0 ? 0 : 1;
+#define OD_LAUNCHC(S, F) step_chain_kernel<S, F, E, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
+        if (scheme == OD_EULER) { if (f64) OD_LAUNCHC(0, true); else OD_LAUNCHC(0, false); }
+        else if (scheme == OD_RK2) { if (f64) OD_LAUNCHC(1, true); else OD_LAUNCHC(1, false); }
+        else { if (f64) OD_LAUNCHC(2, true); else OD_LAUNCHC(2, false); }
+#undef OD_LAUNCHC
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return OD_OK;
+    }
 #define OD_LAUNCH(S, F) step_kernel<S, F, EXTRAS, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
     if (scheme == OD_EULER) { if (f64) OD_LAUNCH(0, true); else OD_LAUNCH(0, false); }
     else if (scheme == OD_RK2) { if (f64) OD_LAUNCH(1, true); else OD_LAUNCH(1, false); }
@@ -1139,7 +1191,7 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     if (rc) return rc;
     if (a->n == 0) return OD_OK;
     const PairEntry* pe = nullptr;
-    if (ctx->tile && a->scheme != OD_EULER)          // tile the pair the RK stages sample (t_mid)
+    if (ctx->tile && a->scheme != OD_EULER && a->n_chain == 0)          // tile the pair the RK stages sample (t_mid)
         pe = find_tmap(ctx->groups[a->group_uv], p.cs.t_mid.tex);
     if (a->fast < 0 || a->fast > OD_MATH_SERIES) return fail(ctx, OD_ERR_ARG, "od_advect_current: unknown arithmetic mode");
     if (pe) {

@@ -320,7 +320,7 @@ class Engine:
                                                  _ptr(yvel), f64, _ptr(moving), float(dt)))
 
     def _advect_args(self, a, group, scheme, t, dt_seconds, half, full, lon, lat, z, factor, moving,
-                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0):
+                     k1=None, truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0, chain=()):
         a.scheme = SCHEMES[scheme] if isinstance(scheme, str) else scheme
         if noise is not None:
             a.d_noise_cur, a.noise_kinds = noise.data_ptr(), int(noise_kinds)
@@ -336,6 +336,21 @@ class Engine:
             pinned += p
         if a.scheme == _lib.OD_RK4:
             a.t_end, p = group.sample(full, pinned)
+        # further current groups in reader priority order (sampled where the ones before them give NaN)
+        if len(chain) > _lib.OD_MAX_CHAIN:
+            raise ValueError('at most %d chained current readers' % _lib.OD_MAX_CHAIN)
+        a.n_chain = len(chain)
+        for k, cg in enumerate(chain):
+            a.chain_group[k] = cg.gid
+            held = ()                      # slabs the earlier samples of this group refer to must stay in their ring slots
+            if k1 is None:
+                a.chain_t[k][0], q = cg.sample(t)
+                held += q
+            if a.scheme != _lib.OD_EULER:
+                a.chain_t[k][1], q = cg.sample(half, held)
+                held += q
+            if a.scheme == _lib.OD_RK4:
+                a.chain_t[k][2], q = cg.sample(full, held)
         a.dt = float(dt_seconds)
         a.n = lon.numel()
         a.d_lon, a.d_lat = lon.data_ptr(), lat.data_ptr()
@@ -354,13 +369,13 @@ class Engine:
             a.d_env_u, a.d_env_v = env_out[0].data_ptr(), env_out[1].data_ptr()
 
     def advect_current(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None, k1=None,
-                       truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0):
+                       truncate_below=None, env_out=None, pos_f32=False, fast=None, noise=None, noise_kinds=0, chain=()):
         """advect_ocean_current on device tensors (in place).  t is the reader-time object (datetime
         or seconds), dt a timedelta-like or seconds."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a = AdvectArgs()
         self._advect_args(a, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving, k1,
-                          truncate_below, env_out, pos_f32, fast, noise, noise_kinds)
+                          truncate_below, env_out, pos_f32, fast, noise, noise_kinds, chain)
         self._check(self.lib.od_advect_current(self.ctx, C.byref(a)))
 
     # -- analytical reader on a projected plane (od_analytic_*) ----------------------------------------------
@@ -412,9 +427,9 @@ class Engine:
 
     def _step_args(self, s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf,
                    wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds,
-                   wind_noise):
+                   wind_noise, chain=()):
         self._advect_args(s.cur, group, scheme, t, dts, t + dt / 2, t + dt, lon, lat, z, factor, moving,
-                          None, truncate_below, None, pos_f32, fast, noise, noise_kinds)
+                          None, truncate_below, None, pos_f32, fast, noise, noise_kinds, chain)
         s.group_wind = -1
         s.group_w = -1
         if wind is not None:
@@ -442,13 +457,14 @@ class Engine:
     def step_oceandrift(self, group, scheme, t, dt, lon, lat, z=None, factor=None, moving=None,
                         truncate_below=None, wind=None, wdf=None, wind_drift_depth=0.1, w_group=None,
                         w_at_surface=False, rand=None, diffusivity=None, pos_f32=False, z_update=None, fast=None, noise=None, noise_kinds=0,
-                        wind_noise=None):
+                        wind_noise=None, chain=()):
         """One fused OceanDrift step.  z is the depth used for sampling; z_update (default: z itself) is the depth
-        array that vertical advection updates -- a different buffer after vertical mixing."""
+        array that vertical advection updates -- a different buffer after vertical mixing.  chain: further current groups
+        in reader priority order."""
         dts = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         s = StepArgs()
         self._step_args(s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf, wind_drift_depth,
-                        w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds, wind_noise)
+                        w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds, wind_noise, chain)
         self._check(self.lib.od_step_oceandrift(self.ctx, C.byref(s)))
 
     @staticmethod

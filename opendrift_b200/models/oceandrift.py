@@ -201,8 +201,13 @@ class OceanDrift(OpenDriftSimulation):
         if g is None:
             return False
         t = self.time
-        if self._current_needs_reader_loop(t) or any(len(self.env.readers_for(v, t)) > 1 for v in
-                                                     ('x_wind', 'y_wind', 'upward_sea_water_velocity')):
+        chain = ()
+        if self._current_needs_reader_loop(t):
+            groups = self._current_chain(t)               # reader priority list inside the kernel, when it can be
+            if groups is None:
+                return False
+            g, chain = groups[0], tuple(groups[1:])
+        if any(len(self.env.readers_for(v, t)) > 1 for v in ('x_wind', 'y_wind', 'upward_sea_water_velocity')):
             return False                                  # several readers for one variable: the helpers loop over them
         wind_r = self.env.reader_for('x_wind', t)
         wind = wind_r.group_of('x_wind')[0] if wind_r is not None and hasattr(wind_r, 'group_of') else None
@@ -263,7 +268,7 @@ class OceanDrift(OpenDriftSimulation):
                             wind_drift_depth=self.get_config('drift:wind_drift_depth'), w_group=wgrp,
                             w_at_surface=self.get_config('drift:vertical_advection_at_surface'), rand=rand,
                             diffusivity=float(D), pos_f32=el.positions_f32, z_update=z_new,
-                            noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind)
+                            noise=d_ncur, noise_kinds=nkinds, wind_noise=d_nwind, chain=chain)
         if stokes_inp is not None:
             self.stokes_drift(_inputs=stokes_inp)
         if z_new is not None:

@@ -18,6 +18,25 @@ class PhysicsMethods:
         assert g is g2 and (c, c2) == (0, 1), 'current components must come from one reader'
         return g
 
+    def _current_chain(self, t):
+        """[primary group, further groups ...] when the current's reader priority list can run inside the step kernels: every
+        reader of the list is gridded, serves both components as one two-component group, and the list is short enough
+        (include/odcuda.h: OD_MAX_CHAIN further groups).  None otherwise (staged recipe)."""
+        from .. import _lib
+        rx, ry = self.env.readers_for('x_sea_water_velocity', t), self.env.readers_for('y_sea_water_velocity', t)
+        if len(rx) < 2 or len(rx) != len(ry) or any(a is not b for a, b in zip(rx, ry)) or len(rx) > 1 + _lib.OD_MAX_CHAIN:
+            return None
+        groups = []
+        for r in rx:
+            if not hasattr(r, 'group_of'):
+                return None
+            g, c = r.group_of('x_sea_water_velocity')
+            g2, c2 = r.group_of('y_sea_water_velocity')
+            if g is not g2 or (c, c2) != (0, 1):
+                return None
+            groups.append(g)
+        return groups
+
     def _current_needs_reader_loop(self, t):
         """True when the current cannot be sampled from ONE two-component field group: several readers in priority order,
         or x and y components from different readers (the reference resolves every variable on its own, environment.py:613-780)."""
@@ -50,10 +69,15 @@ class PhysicsMethods:
         g = self._current_group(self.time)
         trunc = self.get_config('drift:truncate_ocean_model_below_m', None)
         ra = self.env.reader_for('x_sea_water_velocity', self.time)
+        chain = ()
         if self._current_needs_reader_loop(self.time):
             # several current readers in priority order (e.g. a nested model inside a coarser one): every stage needs the
-            # reference's reader loop on the still-missing elements, which the single-group kernels do not do
-            return self._advect_ocean_current_staged(scheme, fac, moving, lon, lat)
+            # reference's reader loop on the still-missing elements -- inside the kernel when the list is made of gridded
+            # two-component groups (reader chain), else stage by stage
+            groups = self._current_chain(self.time)
+            if groups is None:
+                return self._advect_ocean_current_staged(scheme, fac, moving, lon, lat)
+            g, chain = groups[0], tuple(groups[1:])
         if g is None and ra is not None and hasattr(ra, 'analytic_desc'):
             # analytical reader on a projected plane: the stage loop samples it on the device (od_analytic_advect)
             if any(x > 0 for x in self._uncertainty()[:2]):
@@ -105,7 +129,8 @@ class PhysicsMethods:
             noise = eng.to_device(arr) if arr is not None else None
         eng.advect_current(g, scheme, self.time, self.time_step, lon, lat,
                            self._z_for_sampling() if g.desc.nz > 1 else None, factor=fac, moving=moving, k1=k1,
-                           truncate_below=trunc, pos_f32=el.positions_f32, noise=noise, noise_kinds=kinds if noise is not None else 0)
+                           truncate_below=trunc, pos_f32=el.positions_f32, noise=noise, noise_kinds=kinds if noise is not None else 0,
+                           chain=chain)
         el.positions_f32 = False
 
     def _advect_ocean_current_staged(self, scheme, fac, moving, lon, lat):

@@ -95,11 +95,11 @@ def multireader_fields(fx):
     return a, b
 
 
-def run_product_multireader(fx, scheme, **model_kw):
+def run_product_multireader(fx, scheme, cls=None, **model_kw):
     from opendrift_b200.models.oceandrift import OceanDrift
     from opendrift_b200.readers import reader_regular_grid
     a, b = multireader_fields(fx)
-    o = OceanDrift(loglevel=50, **model_kw)
+    o = (cls or OceanDrift)(loglevel=50, **model_kw)
     o.add_reader([reader_regular_grid.Reader(r['lon'], r['lat'], None, fx.times, {common.CUR[0]: r['u'], common.CUR[1]: r['v']}, name=nm)
                   for nm, r in (('A', a), ('B', b))])
     o.set_config('general:use_auto_landmask', False)
@@ -167,6 +167,49 @@ def check_runcase(o, case):
     assert o.steps_calculation == int(g('steps')) and np.array_equal(np.asarray(o.elements.ID, dtype=np.int64), g('id'))
     assert (o.time - run_cases()[0].start).total_seconds() == float(g('elapsed'))
     assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+
+
+
+# ---- three current readers with different extents and level tables + w, wind, noise, diffusion (reader chain, 3-D) ------------
+CHAIN3D_N, CHAIN3D_STEPS = 500, 6
+CHAIN3D_CFG = {'drift:advection_scheme': 'runge-kutta4', 'environment:constant:horizontal_diffusivity': 5.0,
+               'drift:current_uncertainty': 0.05}
+
+
+def chain3d_readers(fx, make):
+    """A: western third on every second level; B: southern half on all levels, other values; C: everywhere, surface only;
+    plus the vertical velocity and the wind on readers of their own."""
+    nx, ny = len(fx.grid_lon), len(fx.grid_lat)
+    cur = common.CUR
+    specs = [('A', fx.grid_lon[:nx // 3], fx.grid_lat, fx.grid_z[::2], fx.u[:, ::2, :, :nx // 3].copy(), fx.v[:, ::2, :, :nx // 3].copy()),
+             ('B', fx.grid_lon, fx.grid_lat[:ny // 2], fx.grid_z, (0.6 * fx.u[:, :, :ny // 2, :]).astype(np.float32),
+              (-0.5 * fx.v[:, :, :ny // 2, :]).astype(np.float32)),
+             ('C', fx.grid_lon, fx.grid_lat, None, (0.3 * fx.u[:, 0]).astype(np.float32), (0.9 * fx.v[:, 0]).astype(np.float32))]
+    out = [make(lon, lat, z, fx.times, {cur[0]: u, cur[1]: v}, nm) for nm, lon, lat, z, u, v in specs]
+    out.append(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {'upward_sea_water_velocity': fx.w}, 'w'))
+    out.append(make(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
+    return out
+
+
+def run_product_chain3d(cls=None, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = common.Fixture('rk4_3d_full')
+    o = (cls or OceanDrift)(loglevel=50, seed=0, **model_kw)
+    o.add_reader(chain3d_readers(fx, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name)))
+    o.set_config('general:use_auto_landmask', False)
+    for k, v in CHAIN3D_CFG.items():
+        o.set_config(k, v)
+    n = CHAIN3D_N
+    o.seed_elements(lon=fx.lon0[:n], lat=fx.lat0[:n], z=fx.z0[:n], time=fx.start)
+    o.run(steps=CHAIN3D_STEPS, time_step=fx.dt, time_step_output=fx.dt)
+    return o
+
+
+def check_chain3d(o):
+    ref = np.load(GOLDEN)
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), ref['chain3d__lon'], ref['chain3d__lat'])) < 5e-8
+    assert np.abs(np.asarray(o.elements.z, dtype=np.float64) - ref['chain3d__z']).max() <= 1e-5
 
 
 # ---- Leeway: staggered release, backward runs with capsizing (leeway.py:430-494) -------------------------------------------------
@@ -315,6 +358,13 @@ if __name__ == '__main__':
         out.update({'od_%s__id' % case: np.asarray(ro.elements.ID, dtype=np.int64), 'od_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64),
                     'od_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64), 'od_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64)})
         print('od', case, len(ro.elements.ID))
+    cfx = common.Fixture('rk4_3d_full')
+    ro = refrun.run_oceandrift(chain3d_readers(cfx, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name)),
+                               cfx.lon0[:CHAIN3D_N], cfx.lat0[:CHAIN3D_N], cfx.z0[:CHAIN3D_N], cfx.start, cfx.dt, CHAIN3D_STEPS,
+                               config=CHAIN3D_CFG, seed=0)
+    out.update({'chain3d__lon': np.asarray(ro.elements.lon, dtype=np.float64), 'chain3d__lat': np.asarray(ro.elements.lat, dtype=np.float64),
+                'chain3d__z': np.asarray(ro.elements.z, dtype=np.float64)})
+    print('chain3d', len(ro.elements.lon))
     rfx, rcases = run_cases()
     for case, (seedkw, runkw, cfg) in rcases.items():
         from opendrift.models.oceandrift import OceanDrift as RefOceanDrift

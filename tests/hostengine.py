@@ -24,6 +24,10 @@ def _np_from_ptr(ptr, n, dtype):
     return np.frombuffer(buf, dtype=dtype, count=n)
 
 
+class _HsChain(C.Structure):
+    _fields_ = [('g', C.POINTER(HsGroup) * _lib.OD_MAX_CHAIN), ('t', (HsPair * 3) * _lib.OD_MAX_CHAIN)]
+
+
 class _HostGroup:
     """The library's field group on the host: geometry, level table, the ring of raw slabs, pair texels on demand."""
 
@@ -81,9 +85,9 @@ class _HostLib:
         shim.hs2_interp.restype = C.c_int
         shim.hs2_interp.argtypes = [HG, HP, C.c_int64, _P, _P, _P, C.c_int, _P, _P]
         shim.hs2_advect.restype = C.c_int
-        shim.hs2_advect.argtypes = [C.POINTER(_lib.AdvectArgs), HG, HP]
+        shim.hs2_advect.argtypes = [C.POINTER(_lib.AdvectArgs), HG, HP, C.POINTER(_HsChain)]
         shim.hs2_step.restype = C.c_int
-        shim.hs2_step.argtypes = [C.POINTER(_lib.StepArgs), HG, HP, HG, HP, HG, HP]
+        shim.hs2_step.argtypes = [C.POINTER(_lib.StepArgs), HG, HP, HG, HP, HG, HP, C.POINTER(_HsChain)]
         shim.hs2_mix.restype = C.c_int
         shim.hs2_mix.argtypes = [C.POINTER(_lib.MixArgs), HG, HP]
         shim.hs2_leeway.restype = C.c_int
@@ -149,11 +153,24 @@ class _HostLib:
             arr[2] = g.pair(a.t_end)
         return arr
 
+    def _chain(self, a):
+        ch = _HsChain()
+        for k in range(a.n_chain):
+            g = self.groups[a.chain_group[k]]
+            ch.g[k] = C.pointer(g.hs)
+            if not a.d_k1_u:
+                ch.t[k][0] = g.pair(a.chain_t[k][0])
+            if a.scheme != _lib.OD_EULER:
+                ch.t[k][1] = g.pair(a.chain_t[k][1])
+            if a.scheme == _lib.OD_RK4:
+                ch.t[k][2] = g.pair(a.chain_t[k][2])
+        return ch
+
     def od_advect_current(self, ctx, args):
         self.calls.append('od_advect_current')
         a = args._obj
         t3 = self._t3(a.group_uv, a)
-        return self.shim.hs2_advect(args, C.byref(self.groups[a.group_uv].hs), t3)
+        return self.shim.hs2_advect(args, C.byref(self.groups[a.group_uv].hs), t3, C.byref(self._chain(a)))
 
     def od_step_oceandrift(self, ctx, args):
         self.calls.append('od_step_oceandrift')
@@ -166,7 +183,7 @@ class _HostLib:
         if a.group_w >= 0:
             gz, tz_ = self._gp(a.group_w, a.t_w)
             tz = C.byref(tz_)
-        return self.shim.hs2_step(args, C.byref(self.groups[a.cur.group_uv].hs), t3, gw, tw, gz, tz)
+        return self.shim.hs2_step(args, C.byref(self.groups[a.cur.group_uv].hs), t3, gw, tw, gz, tz, C.byref(self._chain(a.cur)))
 
     def od_vertical_mixing(self, ctx, args):
         self.calls.append('od_vertical_mixing')

@@ -389,6 +389,25 @@ static bool same_grid(const hs_group& du, const hs_group& dw) {
     return same;
 }
 
+struct hs_chain {             // the chained current groups of od_advect_args (resolved by the caller)
+    const hs_group* g[OD_MAX_CHAIN];
+    hs_pair t[OD_MAX_CHAIN][3];
+};
+
+static void fill_chain2(const od_advect_args* a, const hs_chain* c, StepParams* p, hs_levels* lv) {
+    p->n_chain = a->n_chain;
+    for (int k = 0; k < a->n_chain; ++k) {
+        p->cg[k] = make_geom(*c->g[k], lv[k]);
+        p->cg[k].fallback[0] = p->cg[k].fallback[1] = NAN;
+        for (int w = 0; w < 3; ++w) p->ct[k][w] = make_pair(c->t[k][w]);
+    }
+    if (a->n_chain > 0) {
+        p->chain_fallback[0] = p->cs.g.fallback[0];
+        p->chain_fallback[1] = p->cs.g.fallback[1];
+        p->cs.g.fallback[0] = p->cs.g.fallback[1] = NAN;
+    }
+}
+
 static int fill_current2(const od_advect_args* a, const hs_group* g, const hs_pair* t3, StepParams* p, hs_levels& lv) {
     if (a->scheme < 0 || a->scheme > 2) return -2;
     if (g->nz > 1 && !a->d_z) return -3;
@@ -409,7 +428,16 @@ static int fill_current2(const od_advect_args* a, const hs_group* g, const hs_pa
 }
 
 template <int S, bool F, int E>
+static void run2c(const StepParams& p, int mode) {          // step_chain_kernel
+    const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
+    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, SeriesMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, FastMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, ExactMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+}
+
+template <int S, bool F, int E>
 static void run2(const StepParams& p, int mode) {
+    if (p.n_chain > 0) { run2c<S, F, (E == 0 ? 0 : 1)>(p, mode); return; }
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
     if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
     else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
@@ -428,20 +456,22 @@ static int launch2(const StepParams& p, int scheme, bool f, int mode) {
 
 extern "C" {
 
-int hs2_advect(const od_advect_args* a, const hs_group* g, const hs_pair* t3) {
-    hs_levels lv;
+int hs2_advect(const od_advect_args* a, const hs_group* g, const hs_pair* t3, const hs_chain* chain) {
+    hs_levels lv, lc[OD_MAX_CHAIN];
     StepParams p;
     int rc = fill_current2(a, g, t3, &p, lv);
     if (rc) return rc;
+    if (a->n_chain > 0) fill_chain2(a, chain, &p, lc);
     return launch2<0>(p, a->scheme, a->factor_f64 != 0, a->fast);
 }
 
 int hs2_step(const od_step_args* a, const hs_group* g_uv, const hs_pair* t3, const hs_group* g_wind, const hs_pair* t_wind,
-             const hs_group* g_w, const hs_pair* t_w) {
-    hs_levels l1, l2, l3;
+             const hs_group* g_w, const hs_pair* t_w, const hs_chain* chain) {
+    hs_levels l1, l2, l3, lc[OD_MAX_CHAIN];
     StepParams p;
     int rc = fill_current2(&a->cur, g_uv, t3, &p, l1);
     if (rc) return rc;
+    if (a->cur.n_chain > 0) fill_chain2(&a->cur, chain, &p, lc);
     if (a->group_wind >= 0) {
         if (!a->d_wdf || !g_wind || g_wind->nz != 1) return -4;
         p.wind_on = 1; p.wdf_f64 = a->wdf_f64; p.gwind = make_geom(*g_wind, l2); p.pwind = make_pair(*t_wind);

@@ -118,12 +118,32 @@ def test_run_loop_bookkeeping_matches_reference(case):
 @pytest.mark.parametrize('scheme', __import__('bookkeeping').MULTI_SCHEMES)
 def test_two_prioritised_current_readers_match_reference(scheme, host_engine):
     """A nested reader inside a coarser one (the reference loops over the readers on the still-missing elements at every
-    get_environment call, environment.py:613-780).  The single-group kernels cannot do that: the model falls back to the
-    staged recipe.  Found with this harness against the live reference; results pinned in tests/golden/bookkeeping_ref.npz."""
+    get_environment call, environment.py:613-780).  Found with this harness against the live reference (the fused launch
+    once sampled the first reader only); results pinned in tests/golden/bookkeeping_ref.npz.  Three ways through the product:
+    the reader chain inside the fused kernel, the chain inside od_advect_current (helper recipe), and the staged recipe."""
     import bookkeeping as bk
-    o = bk.run_product_multireader(common.Fixture('rk4_2d'), scheme)
+    from opendrift_b200.models.oceandrift import OceanDrift
+    fx = common.Fixture('rk4_2d')
+    o = bk.run_product_multireader(fx, scheme)
     bk.check_multireader(o, scheme)
-    assert 'od_step_oceandrift' not in host_engine.lib.calls and 'od_advect_current' not in host_engine.lib.calls
+    assert host_engine.lib.calls.count('od_step_oceandrift') == bk.MULTI_STEPS          # one launch per step, chain inside
+
+    class Recipe(OceanDrift):
+        def update(self):
+            self.advect_ocean_current()
+            self.advect_wind()
+    host_engine.lib.calls.clear()
+    o = bk.run_product_multireader(fx, scheme, cls=Recipe)
+    bk.check_multireader(o, scheme)
+    assert host_engine.lib.calls.count('od_advect_current') == bk.MULTI_STEPS and 'od_step_oceandrift' not in host_engine.lib.calls
+
+    class Staged(Recipe):
+        def _current_chain(self, t):
+            return None
+    host_engine.lib.calls.clear()
+    o = bk.run_product_multireader(fx, scheme, cls=Staged)
+    bk.check_multireader(o, scheme)
+    assert 'od_advect_current' not in host_engine.lib.calls and 'od_step_oceandrift' not in host_engine.lib.calls
 
 
 def test_models_refuse_reader_lists_they_cannot_follow():
@@ -217,3 +237,20 @@ def test_run_argument_variants_match_reference(case):
     the unmodified reference."""
     import bookkeeping as bk
     bk.check_runcase(bk.run_product_runcase(case), case)
+
+
+def test_three_reader_chain_3d_with_everything_on(host_engine):
+    """Three current readers with different extents and level tables (one of them 2-D), vertical velocity and wind on
+    readers of their own, current uncertainty and horizontal diffusion, RK4: the reader chain inside the fused launch and
+    the staged recipe against the unmodified reference."""
+    import bookkeeping as bk
+    from opendrift_b200.models.oceandrift import OceanDrift
+    bk.check_chain3d(bk.run_product_chain3d())
+    assert host_engine.lib.calls.count('od_step_oceandrift') == bk.CHAIN3D_STEPS
+
+    class Staged(OceanDrift):
+        def _current_chain(self, t):
+            return None
+    host_engine.lib.calls.clear()
+    bk.check_chain3d(bk.run_product_chain3d(cls=Staged))
+    assert 'od_step_oceandrift' not in host_engine.lib.calls

@@ -64,3 +64,8 @@ def test_constant_reader_known_answers_on_gpu():
 @pytest.mark.parametrize('case', list(bk.run_cases()[1]))
 def test_run_argument_variants_match_reference_on_gpu(case):
     bk.check_runcase(bk.run_product_runcase(case), case)
+
+
+def test_three_reader_chain_3d_on_gpu():
+    """step_chain_kernel: three current readers (different extents / level tables), w and wind readers, noise, diffusion."""
+    bk.check_chain3d(bk.run_product_chain3d())
