@@ -254,3 +254,44 @@ def test_three_reader_chain_3d_with_everything_on(host_engine):
     host_engine.lib.calls.clear()
     bk.check_chain3d(bk.run_product_chain3d(cls=Staged))
     assert 'od_step_oceandrift' not in host_engine.lib.calls
+
+
+@pytest.mark.parametrize('seed', [2, 4, 10, 15, 19])
+def test_random_reader_chains_fused_equals_staged(seed):
+    """A random sub-box reader in front of a surface-only reader over the whole (possibly periodic / descending-axis) grid of a
+    random scenario, forward or backward: the reader chain inside the fused launch against the staged recipe -- two
+    independent implementations of the reference's reader loop (24 seeds during development)."""
+    import test_hostmath as th
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = th._random_scenario(seed)
+    rng = np.random.default_rng(seed)
+    nx, ny = len(fx.grid_lon), len(fx.grid_lat)
+    i0, i1 = sorted(rng.choice(np.arange(2, nx - 2), 2, replace=False))
+    j0, j1 = sorted(rng.choice(np.arange(2, ny - 2), 2, replace=False))
+    i1, j1 = max(i1, min(nx, i0 + 3)), max(j1, min(ny, j0 + 3))
+    three_d = fx.grid_z is not None
+    cur = common.CUR
+
+    def run(staged):
+        class M(OceanDrift):
+            pass
+        if staged:
+            M._current_chain = lambda self, t: None
+        eng = HostEngine()
+        o = M(loglevel=50, seed=0, engine=eng)
+        o.add_reader([reader_regular_grid.Reader(fx.grid_lon[i0:i1], fx.grid_lat[j0:j1], fx.grid_z, fx.times,
+                                                 {cur[0]: fx.u[..., j0:j1, i0:i1].copy(), cur[1]: fx.v[..., j0:j1, i0:i1].copy()}, name='A'),
+                      reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times,
+                                                 {cur[0]: (0.5 * (fx.u[:, 0] if three_d else fx.u)).astype(np.float32),
+                                                  cur[1]: (-0.8 * (fx.v[:, 0] if three_d else fx.v)).astype(np.float32)}, name='B')])
+        o.set_config('general:use_auto_landmask', False)
+        o.set_config('drift:advection_scheme', fx.meta['scheme'])
+        o.set_config('drift:vertical_advection', False)
+        o.seed_elements(lon=fx.lon0, lat=fx.lat0, z=fx.z0, time=fx.start)
+        o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt)
+        return np.asarray(o.elements.lon), np.asarray(o.elements.lat), eng.lib.calls
+    fl, fa, fcalls = run(False)
+    sl, sa, scalls = run(True)
+    assert 'od_step_oceandrift' in fcalls and 'od_step_oceandrift' not in scalls
+    assert max(common.max_err_deg(fl, fa, sl, sa)) < 5e-8
