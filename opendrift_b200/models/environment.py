@@ -96,6 +96,16 @@ class Environment:
         self.discard_ended_readers(time)
         return [self.readers[name] for name in self.priority_list.get(var, []) if self.readers[name].covers_time(time)]
 
+    def readers_for_times(self, var, times):
+        """Readers, in priority order, that provide `var` and cover at least ONE of `times` -- the stage times of a
+        Runge-Kutta step (t, t + dt/2, t + dt): every get_environment call of the reference picks its readers for its own
+        time, so a step that straddles the hand-over between two readers that follow each other in time uses both."""
+        if self.constant(var) is not None:
+            return []
+        self.discard_ended_readers(times[0])       # the step's own time comes first; later stage times cannot add discards that matter
+        return [self.readers[name] for name in self.priority_list.get(var, [])
+                if any(self.readers[name].covers_time(t) for t in times)]
+
     # -- device face ---------------------------------------------------------------------------------
     def device_environment(self, variables, time, d_lon, d_lat, d_z, pos_f32=False):
         """dict var -> float32 device tensor, with constants / fallbacks applied, + missing mask tensor."""

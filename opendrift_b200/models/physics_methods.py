@@ -8,7 +8,10 @@ import numpy as np
 class PhysicsMethods:
 
     def _current_group(self, t):
-        r = self.env.reader_for('x_sea_water_velocity', t)
+        # the first reader that covers any stage time of the step that starts at t (a reader whose coverage begins inside
+        # the step serves the later stages; the stages before it get the fallback, as in the reference)
+        rx = self._current_readers(t)[0]
+        r = rx[0] if rx else None
         if r is None or not hasattr(r, 'group_of'):
             return None
         if 'y_sea_water_velocity' not in r.variables:
@@ -18,12 +21,21 @@ class PhysicsMethods:
         assert g is g2 and (c, c2) == (0, 1), 'current components must come from one reader'
         return g
 
+    def _stage_times(self, t):
+        """Times at which advect_ocean_current samples the current (:611-691)."""
+        scheme, dt = self.get_config('drift:advection_scheme'), self.time_step
+        return [t] if scheme == 'euler' else ([t, t + dt / 2] if scheme == 'runge-kutta' else [t, t + dt / 2, t + dt])
+
+    def _current_readers(self, t):
+        ts = self._stage_times(t)
+        return (self.env.readers_for_times('x_sea_water_velocity', ts), self.env.readers_for_times('y_sea_water_velocity', ts))
+
     def _current_chain(self, t):
         """[primary group, further groups ...] when the current's reader priority list can run inside the step kernels: every
         reader of the list is gridded, serves both components as one two-component group, and the list is short enough
         (include/odcuda.h: OD_MAX_CHAIN further groups).  None otherwise (staged recipe)."""
         from .. import _lib
-        rx, ry = self.env.readers_for('x_sea_water_velocity', t), self.env.readers_for('y_sea_water_velocity', t)
+        rx, ry = self._current_readers(t)
         if len(rx) < 2 or len(rx) != len(ry) or any(a is not b for a, b in zip(rx, ry)) or len(rx) > 1 + _lib.OD_MAX_CHAIN:
             return None
         groups = []
@@ -40,7 +52,7 @@ class PhysicsMethods:
     def _current_needs_reader_loop(self, t):
         """True when the current cannot be sampled from ONE two-component field group: several readers in priority order,
         or x and y components from different readers (the reference resolves every variable on its own, environment.py:613-780)."""
-        rx, ry = self.env.readers_for('x_sea_water_velocity', t), self.env.readers_for('y_sea_water_velocity', t)
+        rx, ry = self._current_readers(t)
         if len(rx) > 1 or len(ry) > 1:
             return True
         return len(rx) + len(ry) > 0 and (len(rx) != len(ry) or rx[0] is not ry[0])

@@ -212,6 +212,45 @@ def check_chain3d(o):
     assert np.abs(np.asarray(o.elements.z, dtype=np.float64) - ref['chain3d__z']).max() <= 1e-5
 
 
+
+# ---- readers that follow each other in time: a step that straddles the hand-over samples both (one get_environment per stage) -----
+HANDOVER_CASES = [('two_readers', 'runge-kutta'), ('two_readers', 'runge-kutta4'), ('late_reader', 'runge-kutta'), ('late_reader', 'runge-kutta4')]
+HANDOVER_N, HANDOVER_STEPS, HANDOVER_DT = 300, 8, 840          # 14-minute steps over hourly slabs
+
+
+def handover_readers(fx, kind, make):
+    t, cur = fx.times, common.CUR
+    out = []
+    if kind == 'two_readers':           # A: the first hour; B: from the first hour on, other values
+        out.append(make(fx.grid_lon, fx.grid_lat, None, t[:2], {cur[0]: fx.u[:2], cur[1]: fx.v[:2]}, 'A'))
+        out.append(make(fx.grid_lon, fx.grid_lat, None, t[1:], {cur[0]: (0.5 * fx.u[1:]).astype(np.float32),
+                                                                 cur[1]: (-0.5 * fx.v[1:]).astype(np.float32)}, 'B'))
+    else:                               # nothing before the first hour: the stages before it get the fallback
+        out.append(make(fx.grid_lon, fx.grid_lat, None, t[1:], {cur[0]: fx.u[1:], cur[1]: fx.v[1:]}, 'B'))
+    return out
+
+
+def run_product_handover(kind, scheme, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = common.Fixture('rk4_2d')
+    o = OceanDrift(loglevel=50, seed=0, **model_kw)
+    o.add_reader(handover_readers(fx, kind, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name)))
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:advection_scheme', scheme)
+    o.set_config('drift:vertical_advection', False)
+    n = HANDOVER_N
+    o.seed_elements(lon=fx.lon0[:n], lat=fx.lat0[:n], z=0.0, time=fx.start)
+    o.run(steps=HANDOVER_STEPS, time_step=HANDOVER_DT, time_step_output=HANDOVER_DT)
+    return o
+
+
+def check_handover(o, kind, scheme):
+    ref = np.load(GOLDEN)
+    k = 'handover_%s_%s' % (kind, scheme)
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), ref[k + '__lon'], ref[k + '__lat'])) < 5e-8
+
+
 # ---- Leeway: staggered release, backward runs with capsizing (leeway.py:430-494) -------------------------------------------------
 LEEWAY_CASES = {
     'leeway_staggered': ({}, 1, 'interval', 7, 600),
@@ -365,6 +404,14 @@ if __name__ == '__main__':
     out.update({'chain3d__lon': np.asarray(ro.elements.lon, dtype=np.float64), 'chain3d__lat': np.asarray(ro.elements.lat, dtype=np.float64),
                 'chain3d__z': np.asarray(ro.elements.z, dtype=np.float64)})
     print('chain3d', len(ro.elements.lon))
+    hfx = common.Fixture('rk4_2d')
+    for kind, scheme in HANDOVER_CASES:
+        ro = refrun.run_oceandrift(handover_readers(hfx, kind, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name)),
+                                   hfx.lon0[:HANDOVER_N], hfx.lat0[:HANDOVER_N], 0.0, hfx.start, HANDOVER_DT, HANDOVER_STEPS,
+                                   config={'drift:advection_scheme': scheme, 'drift:vertical_advection': False}, seed=0)
+        k = 'handover_%s_%s' % (kind, scheme)
+        out.update({k + '__lon': np.asarray(ro.elements.lon, dtype=np.float64), k + '__lat': np.asarray(ro.elements.lat, dtype=np.float64)})
+        print('handover', kind, scheme)
     rfx, rcases = run_cases()
     for case, (seedkw, runkw, cfg) in rcases.items():
         from opendrift.models.oceandrift import OceanDrift as RefOceanDrift

@@ -295,3 +295,13 @@ def test_random_reader_chains_fused_equals_staged(seed):
     sl, sa, scalls = run(True)
     assert 'od_step_oceandrift' in fcalls and 'od_step_oceandrift' not in scalls
     assert max(common.max_err_deg(fl, fa, sl, sa)) < 5e-8
+
+
+@pytest.mark.parametrize('kind,scheme', __import__('bookkeeping').HANDOVER_CASES)
+def test_step_straddling_a_reader_hand_over(kind, scheme):
+    """Readers that follow each other in time (daily files as separate readers): the reference makes one get_environment call
+    per Runge-Kutta stage, each picking the readers that cover ITS time, so a step that starts in one reader's coverage and
+    ends in the next one's samples both; a reader whose coverage begins inside a step serves the later stages.  Found against
+    the live reference with this harness (the stage after the hand-over once got the fallback)."""
+    import bookkeeping as bk
+    bk.check_handover(bk.run_product_handover(kind, scheme), kind, scheme)

@@ -69,3 +69,8 @@ def test_run_argument_variants_match_reference_on_gpu(case):
 def test_three_reader_chain_3d_on_gpu():
     """step_chain_kernel: three current readers (different extents / level tables), w and wind readers, noise, diffusion."""
     bk.check_chain3d(bk.run_product_chain3d())
+
+
+@pytest.mark.parametrize('kind,scheme', bk.HANDOVER_CASES)
+def test_step_straddling_a_reader_hand_over_on_gpu(kind, scheme):
+    bk.check_handover(bk.run_product_handover(kind, scheme), kind, scheme)
