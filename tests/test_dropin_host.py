@@ -255,6 +255,16 @@ def test_three_reader_chain_3d_with_everything_on(host_engine):
     bk.check_chain3d(bk.run_product_chain3d(cls=Staged))
     assert 'od_step_oceandrift' not in host_engine.lib.calls
 
+    class Recipe(OceanDrift):                      # helper recipe: the chain (and the per-stage noise) inside od_advect_current
+        def update(self):
+            self.advect_ocean_current()
+            self.advect_wind()
+            self.stokes_drift()
+            self.vertical_advection()
+    host_engine.lib.calls.clear()
+    bk.check_chain3d(bk.run_product_chain3d(cls=Recipe))
+    assert host_engine.lib.calls.count('od_advect_current') == bk.CHAIN3D_STEPS and 'od_step_oceandrift' not in host_engine.lib.calls
+
 
 @pytest.mark.parametrize('seed', [2, 4, 10, 15, 19])
 def test_random_reader_chains_fused_equals_staged(seed):
