@@ -88,6 +88,26 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                                          'level': CONFIG_LEVEL_BASIC, 'description': 'Only "none" is implemented.'},
             'seed:number': {'type': 'int', 'default': 1, 'min': 1, 'max': 100000000, 'units': 1,
                             'level': CONFIG_LEVEL_BASIC, 'description': 'The number of elements for the simulation.'},
+            # keys the reference's scripts set that concern subsystems outside the GPU path: accepted with the reference's
+            # defaults so that set_config does not raise; values that would change the physics are refused at run()
+            'general:simulation_name': {'type': 'str', 'min_length': 0, 'max_length': 64, 'default': '', 'level': CONFIG_LEVEL_BASIC,
+                                        'description': 'Name of simulation'},
+            'general:coastline_approximation_precision': {'type': 'float', 'default': 0.001, 'min': 0.0001, 'max': 0.005, 'units': 'degrees',
+                                                          'level': CONFIG_LEVEL_ADVANCED,
+                                                          'description': 'Accepted for script compatibility (no coastline interaction on the GPU path).'},
+            'general:seafloor_action': {'type': 'enum', 'enum': ['none', 'lift_to_seafloor', 'deactivate', 'previous'],
+                                        'default': 'lift_to_seafloor', 'level': CONFIG_LEVEL_ADVANCED,
+                                        'description': 'Accepted for script compatibility: seafloor interaction needs a bathymetry reader '
+                                                       '(outside the GPU path); with the 10 km fallback depth no element ever reaches it.'},
+            'readers:max_number_of_fails': {'type': 'int', 'default': 1, 'min': 0, 'max': 1e6, 'units': 'number', 'level': CONFIG_LEVEL_ADVANCED,
+                                            'description': 'Accepted for script compatibility (in-memory readers do not fail).'},
+            'drift:profiles_depth': {'type': 'float', 'default': 50, 'min': 0, 'max': None, 'units': 'meters', 'level': CONFIG_LEVEL_ADVANCED,
+                                     'description': 'Accepted for script compatibility: the mixing kernel reads the whole column of the block.'},
+            'seed:ocean_only': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ESSENTIAL,
+                                'description': 'Accepted for script compatibility: moving elements seeded on land to the closest '
+                                               'ocean point needs a landmask, which is outside the GPU path.'},
+            'seed:seafloor': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ESSENTIAL,
+                              'description': 'Elements are seeded at seafloor (needs a bathymetry reader: not on the GPU path).'},
             'drift:max_age_seconds': {'type': 'float', 'default': None, 'min': 0, 'max': np.inf, 'units': 'seconds',
                                       'level': CONFIG_LEVEL_ADVANCED, 'description': 'Retire elements at this age.'},
             'drift:advection_scheme': {'type': 'enum', 'enum': ['euler', 'runge-kutta', 'runge-kutta4'],
@@ -137,7 +157,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._add_config(c)
         # seed:<property> for element properties with a default (used by seed_elements)
         for name, spec in self.ElementType.variables.items():
-            if spec.get('seed', True) and 'default' in spec and name not in ('z',):
+            if spec.get('seed', True) and 'default' in spec:
                 self._add_config({'seed:%s' % name: {'type': 'float', 'min': None, 'max': None, 'units': '',
                                                       'default': spec['default'], 'level': CONFIG_LEVEL_BASIC,
                                                       'description': 'Seed property %s' % name}}, overwrite=False)
@@ -227,8 +247,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             d_lon, d_lat = eng.to_device(lon.astype(np.float64)), eng.to_device(lat.astype(np.float64))
             eng.geod_fwd(d_lon, d_lat, eng.to_device(az.astype(np.float64)), eng.to_device(dist.astype(np.float64)))
             lon, lat = d_lon.cpu().numpy(), d_lat.cpu().numpy()
-        if isinstance(kwargs.get('z'), str):
-            raise NotImplementedError("z='seafloor' needs a bathymetry reader on the host path")
+        if isinstance(kwargs.get('z'), str) or (kwargs.get('z') is None and self.get_config('seed:seafloor', False)):
+            raise NotImplementedError("z='seafloor' / seed:seafloor needs a bathymetry reader, which is outside the GPU path")
         for key, spec in self.get_configspec('seed:').items():
             prop = key.split(':')[-1]
             if prop not in kwargs and prop in self.ElementType.variables:
@@ -478,6 +498,12 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             raise NotImplementedError('file export is outside the GPU hot path; read o.history / o.elements')
         if self.num_elements_scheduled() == 0:
             raise ValueError('Please seed elements before starting a run.')
+        for key in ('drift:water_column_stretching', 'drift:use_tabularised_stokes_drift', 'drift:vertical_advection_correction',
+                    'vertical_mixing:TSprofiles'):
+            if key in self._config and self.get_config(key):
+                raise NotImplementedError('%s = True is not on the GPU path' % key)
+        if self.env.priority_list.get('sea_surface_height') or (self.env.constant('sea_surface_height') or 0) != 0:
+            raise NotImplementedError('a varying sea_surface_height (sea-level correction of depths) is not on the GPU path')
         from .. import _lib
         self.engine.math_mode = {'series': _lib.OD_MATH_SERIES, 'exact': _lib.OD_MATH_EXACT,
                                  'fast': _lib.OD_MATH_FAST}[self.get_config('gpu:arithmetic')]

@@ -43,6 +43,7 @@ class OceanDrift(OpenDriftSimulation):
         'sea_surface_wave_stokes_drift_y_velocity': {'fallback': 0, 'skip_if': ['drift:stokes_drift', 'is', False]},
         'ocean_mixed_layer_thickness': {'fallback': 50, 'skip_if': ['drift:vertical_mixing', 'is', False]},
         'sea_floor_depth_below_sea_level': {'fallback': 10000},
+        'sea_surface_height': {'fallback': 0},           # only its fallback is used: a reader for it is refused at run()
         'land_binary_mask': {'fallback': None},
     }
 
@@ -70,6 +71,16 @@ class OceanDrift(OpenDriftSimulation):
             'vertical_mixing:background_diffusivity': {'type': 'float', 'min': 0, 'max': 1, 'default': 1.2e-5,
                                                        'level': CONFIG_LEVEL_ADVANCED, 'units': 'm2s-1', 'description':
                                                        'Background diffusivity used below mixed layer for wind parameterisations.'},
+            'drift:water_column_stretching': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                              'description': 'Accepted with the reference\'s default; True is refused at run().'},
+            'drift:vertical_advection_correction': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                                    'description': 'Accepted with the reference\'s default; True is refused at run().'},
+            'drift:use_tabularised_stokes_drift': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_BASIC,
+                                                   'description': 'Accepted with the reference\'s default; True is refused at run().'},
+            'drift:tabularised_stokes_drift_fetch': {'type': 'enum', 'enum': ['5000', '25000', '50000'], 'default': '25000',
+                                                     'level': CONFIG_LEVEL_ADVANCED, 'description': 'Only used with tabularised Stokes drift.'},
+            'vertical_mixing:TSprofiles': {'type': 'bool', 'default': False, 'level': CONFIG_LEVEL_ADVANCED,
+                                           'description': 'Accepted with the reference\'s default; True is refused at run().'},
             'gpu:rng': {'type': 'enum', 'enum': ['numpy', 'philox'], 'default': 'numpy', 'level': CONFIG_LEVEL_ADVANCED,
                         'description': 'numpy: draws of the legacy global generator made on the host in the reference\'s '
                                        'order (bit parity); philox: counter-based generator on the device keyed by element ID.'},

@@ -185,3 +185,36 @@ def test_field_group_ring_residency():
     assert len(eng.fills) == nf                                                    # fill switched off
     tsm, usedm = g.sample(times[-1] + timedelta(hours=1))
     assert tsm.mode == _lib.OD_T_MISSING and usedm == ()
+
+
+def test_config_keys_match_the_reference_model_classes():
+    """set_config / get_config of a script written for the reference must not raise here: OceanDrift and Leeway expose the
+    reference's configuration keys (plus gpu:*), with its defaults except general:coastline_action (no landmask on the GPU
+    path: 'none')."""
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip('reference tree not present (GPU box)')
+    refrun.setup()
+    import opendrift.models.oceandrift as ro
+    import opendrift.models.leeway as rl
+    import opendrift_b200.models.oceandrift as po
+    import opendrift_b200.models.leeway as pl
+
+    class NoEngine:
+        pass
+    for R, P, extra in ((ro.OceanDrift, po.OceanDrift, set()), (rl.Leeway, pl.Leeway, {'general:seafloor_action', 'seed:seafloor'})):
+        r, p = R(loglevel=50, logfile='/tmp/od_cfg_test.log'), P(loglevel=50, engine=NoEngine())
+        rk, pk = set(r._config), set(p._config)
+        assert rk - pk == set(), sorted(rk - pk)
+        assert {k for k in pk - rk if not k.startswith('gpu:')} == extra
+        for k in rk & pk:
+            if k != 'general:coastline_action':
+                assert r._config[k].get('default') == p._config[k].get('default'), k
+    o = po.OceanDrift(loglevel=50, engine=NoEngine())
+    o.set_config('general:simulation_name', 'my run')
+    o.set_config('seed:z', -5)
+    o.set_config('drift:water_column_stretching', True)            # accepted by set_config, refused when the run starts
+    o.seed_elements(lon=4, lat=60, time=__import__('datetime').datetime(2026, 1, 1))
+    assert o.elements_scheduled.z == -5
+    with pytest.raises(NotImplementedError, match='water_column_stretching'):
+        o.run(steps=1)
