@@ -186,6 +186,17 @@ class PhysicsMethods:
         else:
             self.update_positions(ru.to(torch.float64) * fac.to(torch.float64), rv.to(torch.float64) * fac.to(torch.float64))
 
+    # -- small helpers model subclasses call from update() (physics_methods.py:885-891, basemodel/__init__.py:4524-4529) -----------
+    def wind_speed(self):
+        return np.sqrt(self.environment.x_wind**2 + self.environment.y_wind**2)
+
+    def current_speed(self):
+        return np.sqrt(self.environment.x_sea_water_velocity**2 + self.environment.y_sea_water_velocity**2)
+
+    def simulation_direction(self):
+        """1 for a forward simulation, -1 for a backward simulation"""
+        return -1 if self.time_step.days < 0 else 1
+
     def advect_wind(self, factor=1):
         """Wind drift of elements near the surface (:712-791): wind_drift_factor, linearly reduced to zero at
         drift:wind_drift_depth; relative_wind optional."""

@@ -315,3 +315,23 @@ def test_step_straddling_a_reader_hand_over(kind, scheme):
     the live reference with this harness (the stage after the hand-over once got the fallback)."""
     import bookkeeping as bk
     bk.check_handover(bk.run_product_handover(kind, scheme), kind, scheme)
+
+
+def test_subclass_helpers_wind_speed_current_speed_direction():
+    """wind_speed() / current_speed() / simulation_direction(): what model subclasses read inside update()."""
+    from opendrift_b200.models.oceandrift import OceanDrift
+    seen = {}
+
+    class Probe(OceanDrift):
+        def update(self):
+            seen['w'], seen['c'], seen['d'] = self.wind_speed(), self.current_speed(), self.simulation_direction()
+            self.advect_ocean_current()
+    fx = common.Fixture('rk4_3d_full')
+    o = T._model(fx)
+    o.__class__ = Probe
+    o.run(steps=1, time_step=fx.dt)
+    assert seen['d'] == 1 and seen['w'].dtype == np.float32 and seen['w'].shape == (fx.n,) and seen['c'].max() > 0
+    lib = common.hostshim()
+    wind = common.HsField(fx.wind_lon, fx.wind_lat, None, [fx.x_wind, fx.y_wind], fx.times)
+    xw, yw = wind.sample(lib, fx.start, fx.lon0.astype(np.float64), fx.lat0.astype(np.float64), fx.z0, True)
+    assert np.array_equal(seen['w'], np.sqrt(xw**2 + yw**2))
