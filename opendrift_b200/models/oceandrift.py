@@ -148,6 +148,18 @@ class OceanDrift(OpenDriftSimulation):
             floor = self.environment.dev('sea_floor_depth_below_sea_level', self.engine)
         return g, model, dt_mix, ntimes, floor
 
+    def _mixing_reads_environment(self):
+        """True when the mixing launch needs start-of-step environment samples (wind for the analytical diffusivity models, a
+        mixed-layer or sea-floor depth that comes from a reader) in addition to the diffusivity profile itself."""
+        model = self.get_config('vertical_mixing:diffusivitymodel')
+        if model == 'environment':
+            r = self.env.reader_for('ocean_vertical_diffusivity', self.time)
+            if r is None or not hasattr(r, 'group_of'):
+                return True                           # falls back to Large et al. (1994): wind speed
+        else:
+            return True
+        return self._constant_or_none('sea_floor_depth_below_sea_level') is None
+
     def _env_scalar_or_tensor(self, var, default):
         """A float (constant / fallback with no reader) or the start-of-step float32 device tensor of an environment variable."""
         c = self._constant_or_none(var)
@@ -248,6 +260,8 @@ class OceanDrift(OpenDriftSimulation):
         cu, cuu, wu = self._uncertainty()
         if stokes_inp is not None and (cu > 0 or cuu > 0 or wu > 0):
             return False        # the step's environment (with its draws) is already materialised: helper path
+        if (cu > 0 or cuu > 0 or wu > 0) and self.get_config('drift:vertical_mixing') and self._mixing_reads_environment():
+            return False        # the mixing launch would materialise the environment and draw its uncertainty a second time
         ncur, nkinds, nwind = draw_uncertainty(n, self.get_config('drift:advection_scheme'), cu, cuu, wu,
                                                with_wind=wind is not None)
         d_ncur = eng.to_device(ncur) if ncur is not None else None

@@ -336,6 +336,10 @@ def od_cases():
         'mixing_constant_model': (mix, ['cur'], {**mixing, 'vertical_mixing:diffusivitymodel': 'constant',
                                                  'environment:fallback:ocean_vertical_diffusivity': 0.01}, {}, 4, 600),
         'mixing_backward': (mix, ['cur_k'], mixing, {'time': mix.times[-1]}, 4, -600),
+        # analytical diffusivity model + uncertainty: the mixing launch reads the environment, whose draws must not be made twice
+        'mixing_constant_model_with_uncertainty': (mix, ['cur'], {**mixing, **rk4, 'vertical_mixing:diffusivitymodel': 'constant',
+                                                                  'environment:fallback:ocean_vertical_diffusivity': 0.01,
+                                                                  'drift:current_uncertainty': 0.1}, {}, 4, 600),
     }
 
 
