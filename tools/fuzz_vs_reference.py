@@ -1,0 +1,113 @@
+"""Fuzzer (build container only: needs /root/reference): draws random OceanDrift option sets -- scheme, forward / backward, release
+interval, wind, Stokes profile, vertical advection, mixing model, diffusion, the three uncertainty settings, truncation, wind-drift
+depth, relative wind, drift-factor arrays, terminal velocity, a nested current reader -- and runs the UNMODIFIED reference
+(oracle/refrun.py) and the drop-in classes (on tests/hostengine.py, the host build of the device code) side by side.
+
+    python tools/fuzz_vs_reference.py FIRST_SEED LAST_SEED
+
+Prints one line per configuration; BAD lines carry the option set.  75 configurations were run in round 1; it found the double
+uncertainty draw with analytical diffusivity models."""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT)
+import numpy as np, common, traceback
+from datetime import timedelta
+from oracle import refrun
+refrun.setup()
+from hostengine import HostEngine
+from opendrift_b200.readers import reader_regular_grid
+CUR = common.CUR
+full = common.Fixture('rk4_3d_cfg4')      # u, v, w, K, wind, stokes
+def build(kind, c):
+    fx = full
+    mk = (lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name)) if kind == 'ref' else \
+         (lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name))
+    if kind == 'ref':
+        from opendrift.models.oceandrift import OceanDrift as M
+        o = M(loglevel=50, logfile='/tmp/x.log', seed=c['seed'])
+        base = {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': 0, 'general:coastline_action': 'none'}
+    else:
+        from opendrift_b200.models.oceandrift import OceanDrift as M
+        o = M(loglevel=50, seed=c['seed'], engine=HostEngine())
+        base = {'general:use_auto_landmask': False}
+    nx = len(fx.grid_lon)
+    f3 = {CUR[0]: fx.u, CUR[1]: fx.v}
+    if c['w']: f3['upward_sea_water_velocity'] = fx.w
+    if c['mixing'] == 'environment': f3['ocean_vertical_diffusivity'] = fx.kdiff
+    if c['chain']:
+        h = nx // 2
+        o.add_reader(mk(fx.grid_lon[:h], fx.grid_lat, fx.grid_z, fx.times, {CUR[0]: (1.3*fx.u[..., :h]).astype(np.float32), CUR[1]: (0.7*fx.v[..., :h]).astype(np.float32)}, 'nested'))
+    o.add_reader(mk(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, 'cur'))
+    if c['wind']: o.add_reader(mk(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
+    if c['stokes']: o.add_reader(mk(fx.grid_lon, fx.grid_lat, None, fx.times, dict(fx.stokes), 'waves'))
+    cfg = dict(base)
+    cfg['drift:advection_scheme'] = c['scheme']
+    cfg['drift:vertical_advection'] = bool(c['w'])
+    cfg['drift:stokes_drift'] = bool(c['stokes'])
+    if c['stokes']: cfg['drift:stokes_drift_profile'] = c['stokes']
+    if c['mixing']:
+        cfg['drift:vertical_mixing'] = True
+        cfg['vertical_mixing:timestep'] = c['dt_mix']
+        cfg['vertical_mixing:diffusivitymodel'] = c['mixing']
+    if c['D']: cfg['environment:constant:horizontal_diffusivity'] = c['D']
+    for k in ('current_uncertainty', 'current_uncertainty_uniform', 'wind_uncertainty'):
+        if c.get(k): cfg['drift:' + k] = c[k]
+    if c['truncate']: cfg['drift:truncate_ocean_model_below_m'] = c['truncate']
+    if c['wdd'] is not None: cfg['drift:wind_drift_depth'] = c['wdd']
+    if c['relative_wind']: cfg['drift:relative_wind'] = True
+    for k, v in cfg.items(): o.set_config(k, v)
+    n = c['n']
+    dt = c['dt']
+    t = fx.start if dt > 0 else fx.times[-1] - timedelta(seconds=600)
+    if c['release']:
+        t = [t, t + timedelta(seconds=abs(dt) * 3)] if dt > 0 else [t - timedelta(seconds=abs(dt) * 3), t]
+    kw = dict(lon=fx.lon0[:n], lat=fx.lat0[:n], z=c['z'](fx, n), time=t)
+    if c['cdf'] is not None: kw['current_drift_factor'] = c['cdf']
+    if c['wdf'] is not None: kw['wind_drift_factor'] = c['wdf']
+    if c['tv'] is not None: kw['terminal_velocity'] = c['tv']
+    np.random.seed(c['seed'])
+    o.seed_elements(**kw)
+    o.run(steps=c['steps'], time_step=dt, time_step_output=dt)
+    return o
+def draw(seed):
+    r = np.random.default_rng(seed)
+    n = 250
+    c = dict(seed=int(seed), n=n, scheme=r.choice(['euler', 'runge-kutta', 'runge-kutta4']), w=bool(r.integers(2)), wind=bool(r.integers(2)),
+             stokes=r.choice([None, None, 'Phillips', 'exponential', 'monochromatic']), mixing=r.choice([None, None, 'environment', 'windspeed_Sundby1983', 'constant']),
+             dt_mix=float(r.choice([60.0, 100.0, 45.0])), D=float(r.choice([0, 0, 5.0])), truncate=r.choice([None, None, 30.0]),
+             wdd=r.choice([None, 0, 0.5]), relative_wind=bool(r.integers(4) == 0), chain=bool(r.integers(3) == 0), release=bool(r.integers(3) == 0),
+             dt=float(r.choice([600, 900, -600])), steps=int(r.integers(3, 7)))
+    if r.integers(3) == 0: c['current_uncertainty'] = 0.1
+    if r.integers(4) == 0: c['current_uncertainty_uniform'] = 0.05
+    if c['wind'] and r.integers(4) == 0: c['wind_uncertainty'] = 1.0
+    if not c['wind']: c['relative_wind'] = False
+    if c['stokes'] and not c['wind']: c['wind'] = True
+    if c['mixing'] == 'windspeed_Sundby1983': c['mixing'] = 'constant'      # (torch CPU sqrt artefact on the host engine)
+    zsel = int(r.integers(3))
+    c['z'] = (lambda fx, n: fx.z0[:n]) if zsel == 0 else ((lambda fx, n: 0.0) if zsel == 1 else (lambda fx, n: np.where(np.arange(n) % 2 == 0, 0.0, fx.z0[:n])))
+    c['cdf'] = None if r.integers(3) else np.linspace(0.5, 1.0, n).astype(np.float32)
+    c['wdf'] = None if r.integers(3) else (0.03 if r.integers(2) else np.linspace(0, 0.04, n).astype(np.float32))
+    c['tv'] = None if (not c['mixing'] or r.integers(2)) else 0.001
+    return c
+bad = 0
+for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+    c = draw(seed)
+    desc = {k: (v if not callable(v) and np.ndim(v) == 0 else '...') for k, v in c.items() if k not in ('seed', 'n')}
+    try:
+        r = build('ref', c)
+    except BaseException as ex:
+        print(seed, 'ref failed', repr(ex)[:120]); continue
+    try:
+        p = build('prod', c)
+        rid, pid = np.asarray(r.elements.ID), np.asarray(p.elements.ID)
+        if not np.array_equal(rid, pid): bad += 1; print(seed, 'BAD ids', len(rid), len(pid), desc); continue
+        e = max(common.max_err_deg(p.elements.lon, p.elements.lat, r.elements.lon, r.elements.lat)) if len(rid) else 0
+        ez = np.abs(np.asarray(p.elements.z, float) - np.asarray(r.elements.z, float)).max() if len(rid) else 0
+        ok = e < 5e-8 and ez < 1e-5
+        bad += not ok
+        print(seed, 'OK ' if ok else 'BAD', 'err %.1e z %.1e' % (e, ez), '' if ok else desc)
+    except BaseException as ex:
+        bad += 1; print(seed, 'EXC', repr(ex)[:200], desc); traceback.print_exc(limit=3)
+print('bad', bad)
