@@ -1,0 +1,59 @@
+"""Leeway fuzzer (build container only: needs /root/reference): random object type, capsizing settings, forward / backward, release
+interval, positions or radius seeding, jibe probability -- the UNMODIFIED reference and the drop-in Leeway class (host build of
+the device code) side by side: IDs, positions, orientation, capsized flags.
+
+    python tools/fuzz_leeway_vs_reference.py FIRST_SEED LAST_SEED      (30 configurations were run in round 1: all equal)"""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT)
+import numpy as np, common, traceback
+from datetime import timedelta
+from oracle import refrun
+refrun.setup()
+from hostengine import HostEngine
+from opendrift_b200.readers import reader_regular_grid
+from opendrift_b200.models.leeway import Leeway
+fx = common.LeewayFixture('leeway_piw1')
+def mk(kind):
+    f = (lambda *a, **k: refrun.make_grid_reader(*a, **k)) if kind == 'ref' else (lambda lon, lat, z, t, fl, name: reader_regular_grid.Reader(lon, lat, z, t, fl, name=name))
+    return [f(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}, name='current'),
+            f(fx.grid_lon, fx.grid_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, name='wind')]
+bad = 0
+for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+    r = np.random.default_rng(1000 + seed)
+    n = 200
+    dt = float(r.choice([600, 900, -600]))
+    cfg = {}
+    if r.integers(2): cfg.update({'processes:capsizing': True, 'capsizing:wind_threshold': float(r.uniform(4, 10)), 'capsizing:wind_threshold_sigma': float(r.uniform(2, 6))})
+    if r.integers(3) == 0: cfg['capsizing:leeway_fraction'] = 0.6
+    t0 = fx.start if dt > 0 else fx.times[-1] - timedelta(seconds=600)
+    t = t0
+    if r.integers(3) == 0: t = [t0, t0 + timedelta(seconds=1800)] if dt > 0 else [t0 - timedelta(seconds=1800), t0]
+    kw = dict(time=t, object_type=int(r.integers(1, 5)))
+    if r.integers(2):
+        kw.update(lon=fx.lon0[:n], lat=fx.lat0[:n])
+    else:
+        kw.update(lon=float(np.mean(fx.lon0)), lat=float(np.mean(fx.lat0)), radius=float(r.uniform(500, 5000)), number=n)
+    if r.integers(3) == 0: kw['jibe_probability'] = float(r.uniform(0.05, 0.5))
+    if dt < 0 and cfg.get('processes:capsizing') and r.integers(2): kw['capsized'] = 1
+    steps = int(r.integers(3, 8))
+    try:
+        np.random.seed(seed)
+        ro = refrun.run_oceandrift(mk('ref'), kw['lon'], kw['lat'], 0, kw['time'], dt, steps, config=cfg, seed_kwargs={k: v for k, v in kw.items() if k not in ('lon', 'lat', 'time')}, model='Leeway', seed=seed)
+        o = Leeway(loglevel=50, seed=seed, engine=HostEngine())
+        o.add_reader(mk('prod')); o.set_config('general:use_auto_landmask', False)
+        for k, v in cfg.items(): o.set_config(k, v)
+        np.random.seed(seed)
+        o.seed_elements(**kw)
+        o.run(steps=steps, time_step=dt, time_step_output=dt)
+        rid, pid = np.asarray(ro.elements.ID), np.asarray(o.elements.ID)
+        ok = np.array_equal(rid, pid)
+        e = max(common.max_err_deg(o.elements.lon, o.elements.lat, ro.elements.lon, ro.elements.lat)) if ok and len(rid) else -1
+        ok = ok and e < 5e-8 and np.array_equal(np.asarray(o.elements.orientation), np.asarray(ro.elements.orientation)) and np.array_equal(np.asarray(o.elements.capsized, float), np.asarray(ro.elements.capsized, float))
+        bad += not ok
+        print(seed, 'OK ' if ok else 'BAD', 'err %.1e' % e, '' if ok else (cfg, {k: v for k, v in kw.items() if np.ndim(v) == 0}, dt, steps))
+    except BaseException as ex:
+        bad += 1; print(seed, 'EXC', repr(ex)[:200]); traceback.print_exc(limit=3)
+print('bad', bad)
