@@ -47,7 +47,7 @@ def bracket(times, t):
     return ib, ia, w
 
 
-def draw_uncertainty(n, scheme, cur_std=0.0, cur_uniform=0.0, wind_std=0.0, with_wind=False):
+def draw_uncertainty(n, scheme, cur_std=0.0, cur_uniform=0.0, wind_std=0.0, with_wind=False, stage0=None):
     """The uncertainty draws of one time step from NumPy's legacy global generator, in the reference's order
     (environment.py:869-891, called once for the step's environment and once per Runge-Kutta stage):
     returns (noise_cur [4][2][2][n] float64 or None, kinds bitmask, noise_wind [2][n] or None)."""
@@ -56,6 +56,16 @@ def draw_uncertainty(n, scheme, cur_std=0.0, cur_uniform=0.0, wind_std=0.0, with
     cur = np.zeros((4, 2, 2, n)) if kinds else None
     wind = None
     for st in range(stages):
+        if st == 0 and stage0 is not None:
+            # the step's own environment was drawn when the reference draws it: before this step's deactivations and
+            # removals (basemodel/__init__.py:2238-2262), for the elements that were active then
+            if cur_std > 0:
+                cur[0, 0, 0], cur[0, 0, 1] = stage0['cur_n']
+            if cur_uniform > 0:
+                cur[0, 1, 0], cur[0, 1, 1] = stage0['cur_u']
+            if with_wind and wind_std > 0:
+                wind = np.stack(stage0['wind'])
+            continue
         if cur_std > 0:
             cur[st, 0, 0] = np.random.normal(0, cur_std, n)
             cur[st, 0, 1] = np.random.normal(0, cur_std, n)

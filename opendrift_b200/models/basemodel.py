@@ -311,7 +311,14 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if not getattr(self, '_maybe_deactivated', False) or len(self.elements) == 0:
             return
         self._maybe_deactivated = False
+        pre = getattr(self, '_noise0', None)
+        keep = None
+        if pre:
+            keep = (self.elements.dev('status') == 0).cpu().numpy()
         removed = self.elements.compact()
+        if pre and removed is not None:
+            for k in pre:
+                pre[k] = [a[keep] for a in pre[k]]
         if removed is None:
             return
         tmp = self.ElementType(**{k: v for k, v in removed.items()})
@@ -366,7 +373,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             d_env, missing = self.env.device_environment(self._env_variables, self.time, el.dev('lon', self.engine.torch.float64),
                                                          el.dev('lat', self.engine.torch.float64), self._z_truncated(),
                                                          pos_f32=el.positions_f32)
-            self._add_uncertainty(d_env)
+            self._add_uncertainty(d_env, stage0=True)
             self._env_view = EnvironmentView(d_env)
             self._env_missing = missing
         return self._env_view
@@ -375,11 +382,43 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         return (self.get_config('drift:current_uncertainty', 0) or 0, self.get_config('drift:current_uncertainty_uniform', 0) or 0,
                 self.get_config('drift:wind_uncertainty', 0) or 0)
 
-    def _add_uncertainty(self, d_env):
-        """environment.py:869-891 for the step's environment: env[var] += draw on float32 arrays."""
+    def _predraw_step_uncertainty(self):
+        """The reference samples the step's environment -- and draws its uncertainty -- for every element that is active at the
+        top of the loop, BEFORE deactivate_outside / retirement / removal (basemodel/__init__.py:2238-2262).  The draws of the
+        legacy generator are therefore made here, for that element count, and follow the elements through the compaction."""
+        self._noise0 = None
+        cu, cuu, wu = self._uncertainty()
+        n = self.num_elements_active()
+        if n == 0 or not (cu > 0 or cuu > 0 or wu > 0):
+            return
+        d = {}
+        if cu > 0:
+            d['cur_n'] = [np.random.normal(0, cu, n), np.random.normal(0, cu, n)]
+        if cuu > 0:
+            d['cur_u'] = [np.random.uniform(-cuu, cuu, n), np.random.uniform(-cuu, cuu, n)]
+        if wu > 0 and 'x_wind' in self._env_variables and 'y_wind' in self._env_variables:
+            d['wind'] = [np.random.normal(0, wu, n), np.random.normal(0, wu, n)]
+        self._noise0 = d
+
+    def _add_uncertainty(self, d_env, stage0=False):
+        """environment.py:869-891: env[var] += draw on float32 arrays.  stage0: the step's own environment, whose draws were
+        made at the top of the loop (_predraw_step_uncertainty); otherwise (a Runge-Kutta stage) fresh draws."""
         cu, cuu, wu = self._uncertainty()
         eng, torch = self.engine, self.engine.torch
         n = self.num_elements_active()
+        pre = getattr(self, '_noise0', None) if stage0 else None
+        if pre is not None:
+            def addp(var, draw):
+                d_env[var] = (d_env[var].to(torch.float64) + eng.to_device(draw)).to(torch.float32)
+            if 'x_sea_water_velocity' in d_env and 'y_sea_water_velocity' in d_env:
+                for key in ('cur_n', 'cur_u'):
+                    if key in pre:
+                        addp('x_sea_water_velocity', pre[key][0])
+                        addp('y_sea_water_velocity', pre[key][1])
+            if 'x_wind' in d_env and 'y_wind' in d_env and 'wind' in pre:
+                addp('x_wind', pre['wind'][0])
+                addp('y_wind', pre['wind'][1])
+            return
 
         def add(var, draw):
             d_env[var] = (d_env[var].to(torch.float64) + eng.to_device(draw)).to(torch.float32)
@@ -582,6 +621,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                 self.time = self.time + self.time_step
                 continue
             self._env_view = None
+            self._predraw_step_uncertainty()
             self.deactivate_outside()
             if i % out_every == 0:
                 self.state_to_buffer()
@@ -633,6 +673,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if self.get_config('gpu:rng', 'numpy') != 'philox' and (
                 (self._constant_or_none('horizontal_diffusivity') or 0) != 0 or self._constant_or_none('horizontal_diffusivity') is None):
             return        # the legacy RNG draws are consumed in element order: keep the reference's order
+        if any(x > 0 for x in self._uncertainty()):
+            return        # so are the uncertainty draws (always the legacy generator)
         r = self.env.reader_for('x_sea_water_velocity', self.time)
         if r is None or not hasattr(r, 'group_of'):
             return

@@ -260,10 +260,12 @@ class OceanDrift(OpenDriftSimulation):
         cu, cuu, wu = self._uncertainty()
         if stokes_inp is not None and (cu > 0 or cuu > 0 or wu > 0):
             return False        # the step's environment (with its draws) is already materialised: helper path
+        if wu > 0 and wind is None:
+            return False        # the reference adds the wind uncertainty to the fallback wind too: helper path
         if (cu > 0 or cuu > 0 or wu > 0) and self.get_config('drift:vertical_mixing') and self._mixing_reads_environment():
             return False        # the mixing launch would materialise the environment and draw its uncertainty a second time
         ncur, nkinds, nwind = draw_uncertainty(n, self.get_config('drift:advection_scheme'), cu, cuu, wu,
-                                               with_wind=wind is not None)
+                                               with_wind=wind is not None, stage0=getattr(self, '_noise0', None))
         d_ncur = eng.to_device(ncur) if ncur is not None else None
         d_nwind = eng.to_device(nwind) if nwind is not None else None
         moving = el.dev('moving')

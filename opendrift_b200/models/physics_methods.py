@@ -123,7 +123,7 @@ class PhysicsMethods:
         if cu > 0 or cuu > 0:
             from ..engine import draw_uncertainty
             if k1 is None:                    # the step's environment has not been drawn yet: stage 0 included
-                arr, kinds, _ = draw_uncertainty(lon.numel(), scheme, cu, cuu)
+                arr, kinds, _ = draw_uncertainty(lon.numel(), scheme, cu, cuu, stage0=getattr(self, '_noise0', None))
             else:                             # stages 2..4 only (the step's environment already carries its draws)
                 sub = {'euler': None, 'runge-kutta': 'euler', 'runge-kutta4': 'runge-kutta4'}[scheme]
                 arr = None

@@ -481,6 +481,8 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
     NOISE.update({'current': 0.0, 'current_uniform': 0.0, 'wind': 0.0})
     NOISE.update(noise or {})
+    if NOISE['wind'] > 0:
+        wind = True        # OceanDrift always requests the wind: its uncertainty is added to the fallback wind (0) too, and drifts
     np.random.seed(seed)                       # basemodel/__init__.py:326
     n = len(lon)
     # seeding casts to the declared element dtypes (opendrift/elements/elements.py:156-158)

@@ -336,6 +336,13 @@ def od_cases():
         'mixing_constant_model': (mix, ['cur'], {**mixing, 'vertical_mixing:diffusivitymodel': 'constant',
                                                  'environment:fallback:ocean_vertical_diffusivity': 0.01}, {}, 4, 600),
         'mixing_backward': (mix, ['cur_k'], mixing, {'time': mix.times[-1]}, 4, -600),
+        # the step's uncertainty is drawn for the elements active at the top of the loop, before this step's deactivations
+        # (basemodel/__init__.py:2238-2262): the generator stays in step with the reference while elements leave
+        'uncertainty_with_deactivation': (full, ['cur', 'wind'], {**rk4, 'drift:current_uncertainty': 0.1, 'drift:wind_uncertainty': 1.0,
+                                                                  'drift:deactivate_east_of': float(np.percentile(full.lon0[:n], 70)),
+                                                                  }, {'z': 0.0}, 6, 600),
+        # the wind uncertainty is added to the fallback wind (0) too, and the elements drift with it
+        'wind_uncertainty_without_wind_reader': (full, ['cur'], {'drift:wind_uncertainty': 0.5, 'drift:vertical_advection': False}, {'z': 0.0}, 4, 600),
         # analytical diffusivity model + uncertainty: the mixing launch reads the environment, whose draws must not be made twice
         'mixing_constant_model_with_uncertainty': (mix, ['cur'], {**mixing, **rk4, 'vertical_mixing:diffusivitymodel': 'constant',
                                                                   'environment:fallback:ocean_vertical_diffusivity': 0.01,
