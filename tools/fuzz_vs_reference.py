@@ -36,11 +36,16 @@ def build(kind, c):
     f3 = {CUR[0]: fx.u, CUR[1]: fx.v}
     if c['w']: f3['upward_sea_water_velocity'] = fx.w
     if c['mixing'] == 'environment': f3['ocean_vertical_diffusivity'] = fx.kdiff
-    if c['chain']:
+    if c['chain'] == 'nested':
         h = nx // 2
         o.add_reader(mk(fx.grid_lon[:h], fx.grid_lat, fx.grid_z, fx.times, {CUR[0]: (1.3*fx.u[..., :h]).astype(np.float32), CUR[1]: (0.7*fx.v[..., :h]).astype(np.float32)}, 'nested'))
+    elif c['chain'] == 'handover':          # a reader that covers only the first hour (forward) / the last hour (backward), in front
+        sl = slice(0, 2) if c['dt'] > 0 else slice(len(fx.times) - 2, len(fx.times))
+        o.add_reader(mk(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times[sl], {CUR[0]: (1.3*fx.u[sl]).astype(np.float32), CUR[1]: (0.7*fx.v[sl]).astype(np.float32)}, 'first_hour'))
     o.add_reader(mk(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, f3, 'cur'))
-    if c['wind']: o.add_reader(mk(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
+    if c['wind'] == 'constant':
+        base = dict(base, **{'environment:constant:x_wind': 6.0, 'environment:constant:y_wind': -4.0})
+    elif c['wind']: o.add_reader(mk(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
     if c['stokes']: o.add_reader(mk(fx.grid_lon, fx.grid_lat, None, fx.times, dict(fx.stokes), 'waves'))
     cfg = dict(base)
     cfg['drift:advection_scheme'] = c['scheme']
@@ -79,12 +84,13 @@ def draw(seed):
     c = dict(seed=int(seed), n=n, scheme=r.choice(['euler', 'runge-kutta', 'runge-kutta4']), w=bool(r.integers(2)), wind=bool(r.integers(2)),
              stokes=r.choice([None, None, 'Phillips', 'exponential', 'monochromatic']), mixing=r.choice([None, None, 'environment', 'windspeed_Sundby1983', 'windspeed_Large1994', 'constant']),
              dt_mix=float(r.choice([60.0, 100.0, 45.0])), D=float(r.choice([0, 0, 5.0])), truncate=r.choice([None, None, 30.0]),
-             wdd=r.choice([None, 0, 0.5]), relative_wind=bool(r.integers(4) == 0), chain=bool(r.integers(3) == 0), release=bool(r.integers(3) == 0),
+             wdd=r.choice([None, 0, 0.5]), relative_wind=bool(r.integers(4) == 0), chain=r.choice([None, None, 'nested', 'handover']), release=bool(r.integers(3) == 0),
              dt=float(r.choice([600, 900, -600])), steps=int(r.integers(3, 7)))
     if r.integers(3) == 0: c['current_uncertainty'] = 0.1
     if r.integers(4) == 0: c['current_uncertainty_uniform'] = 0.05
     if c['wind'] and r.integers(4) == 0: c['wind_uncertainty'] = 1.0
     if not c['wind']: c['relative_wind'] = False
+    if c['wind'] and r.integers(5) == 0: c['wind'] = 'constant'
     if c['stokes'] and not c['wind']: c['wind'] = True
     if c['mixing'] in ('windspeed_Sundby1983', 'windspeed_Large1994') and not c['wind']: c['wind'] = True
     if r.integers(5) == 0: c['max_age'] = float(abs(c['dt']) * 2.5)
