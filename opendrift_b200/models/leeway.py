@@ -158,6 +158,9 @@ class Leeway(OpenDriftSimulation):
         """leeway.py:430-494 as one launch."""
         eng, el, torch = self.engine, self.elements, self.engine.torch
         t = self.time
+        if any(x > 0 for x in self._uncertainty()):
+            raise NotImplementedError('drift:current_uncertainty / drift:wind_uncertainty with Leeway are not on the GPU path '
+                                      '(the fused Leeway launch samples its forcing inside the kernel)')
         gw = self._pair_group('x_wind', 'y_wind', t)
         gc = self._pair_group('x_sea_water_velocity', 'y_sea_water_velocity', t)
         n = len(el)

@@ -338,3 +338,14 @@ def test_subclass_helpers_wind_speed_current_speed_direction():
     wind = common.HsField(fx.wind_lon, fx.wind_lat, None, [fx.x_wind, fx.y_wind], fx.times)
     xw, yw = wind.sample(lib, fx.start, fx.lon0.astype(np.float64), fx.lat0.astype(np.float64), fx.z0, True)
     assert np.array_equal(seen['w'], np.sqrt(xw**2 + yw**2))
+
+
+def test_leeway_refuses_uncertainty_settings_it_would_ignore():
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_constant
+    o = Leeway(loglevel=50, seed=1)
+    o.add_reader(reader_constant.Reader({'x_wind': 5, 'y_wind': 0, 'x_sea_water_velocity': 0.1, 'y_sea_water_velocity': 0}))
+    o.set_config('drift:wind_uncertainty', 2.0)
+    o.seed_elements(lon=4, lat=60, number=10, time=__import__('datetime').datetime(2026, 1, 1), object_type=1)
+    with pytest.raises(NotImplementedError, match='uncertainty'):
+        o.run(steps=2, time_step=600)
