@@ -440,6 +440,60 @@ typedef struct od_history_args {
 
 int od_history_scatter(od_ctx* ctx, const od_history_args* a);
 
+/* ---- per-element housekeeping (csrc/od_bookkeep.cuh) ----------------------------------------------------
+ * od_vertical_buoyancy replaces OceanDrift.vertical_buoyancy (models/oceandrift.py:352-367): the buoyancy move of the
+ * depth, z[z < 0] = min(0, z + terminal_velocity * dt), and -- when d_sea_floor is given -- the sea-floor interaction it
+ * ends with (OpenDriftSimulation.interact_with_seafloor, models/basemodel/__init__.py:748-783: 'lift_to_seafloor', or
+ * 'deactivate' when seafloor_code != 0).  Out of place (d_z_out may alias d_z_in); NumPy's dtype rules. */
+typedef struct od_buoyancy_args {
+    int64_t n;
+    const void* d_z_in;           /* float32, or float64 when z_f64 */
+    void* d_z_out;                /* same dtype */
+    const void* d_terminal_velocity;   /* float32 / float64 (tv_f64); NULL: sea-floor interaction only */
+    const float* d_sea_floor;     /* sea_floor_depth_below_sea_level sampled at the elements; NULL: no sea-floor interaction */
+    int32_t* d_status;            /* updated for seafloor_code != 0 */
+    int32_t* d_moving;
+    double dt;
+    float sea_surface_height;
+    int32_t z_f64, tv_f64;
+    int32_t seafloor_code;        /* status number of 'seafloor' for general:seafloor_action = deactivate, else 0 */
+    int64_t* h_n_deactivated;     /* optional: number of elements deactivated by this call (synchronises) */
+} od_buoyancy_args;
+
+int od_vertical_buoyancy(od_ctx* ctx, const od_buoyancy_args* a);
+
+/* od_bookkeeping replaces, in one pass over the active elements, what OpenDriftSimulation.run does between
+ * get_environment and update() (models/basemodel/__init__.py:2249-2270): deactivate_outside (:2358-2386),
+ * state_to_buffer (:2384-2403, into column `col` of the device output block of od_history_scatter; d_buf_lon NULL = not an
+ * output step) and increase_age_and_retire (:2345-2356), with deactivate_elements' rule (:1774-1795: an already deactivated
+ * element keeps its status, moving = 0).  h_counts[0..2] = elements newly 'outside', newly 'retired', with status != 0
+ * after the pass (synchronises when h_counts is given). */
+typedef struct od_bookkeep_args {
+    int64_t n;
+    const double* d_lon;
+    const double* d_lat;
+    const void* d_z;              /* float32 / float64 (z_f64): only for the output block */
+    void* d_age;                  /* age_seconds, float32 / float64 (age_f64), updated in place */
+    int32_t* d_status;
+    int32_t* d_moving;
+    const int32_t* d_ids;
+    double dt_age;                /* time_step.total_seconds() */
+    double max_age;               /* drift:max_age_seconds; NaN = none */
+    double west, east, south, north;   /* drift:deactivate_*_of; NaN = none */
+    int32_t outside_code, retired_code;
+    int32_t z_f64, age_f64;
+    int32_t pos_f32, pad_;
+    int64_t n_total;
+    int32_t col, ncols;
+    float* d_buf_lon;
+    float* d_buf_lat;
+    float* d_buf_z;
+    int32_t* d_buf_status;
+    int64_t* h_counts;            /* [3] or NULL */
+} od_bookkeep_args;
+
+int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a);
+
 /* ---- particle order (locality) ---------------------------------------------------------- */
 /* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by
  * the grid cell (and level) of `group` they are in.  Stable counting sort. */

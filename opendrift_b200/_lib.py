@@ -121,6 +121,23 @@ class HistoryArgs(C.Structure):
                 ('d_buf_z', C.c_void_p), ('d_buf_status', C.c_void_p)]
 
 
+class BuoyancyArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_z_in', C.c_void_p), ('d_z_out', C.c_void_p), ('d_terminal_velocity', C.c_void_p),
+                ('d_sea_floor', C.c_void_p), ('d_status', C.c_void_p), ('d_moving', C.c_void_p), ('dt', C.c_double),
+                ('sea_surface_height', C.c_float), ('z_f64', C.c_int32), ('tv_f64', C.c_int32), ('seafloor_code', C.c_int32),
+                ('h_n_deactivated', C.POINTER(C.c_int64))]
+
+
+class BookkeepArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p), ('d_age', C.c_void_p),
+                ('d_status', C.c_void_p), ('d_moving', C.c_void_p), ('d_ids', C.c_void_p), ('dt_age', C.c_double),
+                ('max_age', C.c_double), ('west', C.c_double), ('east', C.c_double), ('south', C.c_double), ('north', C.c_double),
+                ('outside_code', C.c_int32), ('retired_code', C.c_int32), ('z_f64', C.c_int32), ('age_f64', C.c_int32),
+                ('pos_f32', C.c_int32), ('pad_', C.c_int32), ('n_total', C.c_int64), ('col', C.c_int32), ('ncols', C.c_int32),
+                ('d_buf_lon', C.c_void_p), ('d_buf_lat', C.c_void_p), ('d_buf_z', C.c_void_p), ('d_buf_status', C.c_void_p),
+                ('h_counts', C.POINTER(C.c_int64))]
+
+
 OD_PROJ_STERE_SPHERE = 1
 OD_ANALYTIC_DOUBLE_GYRE = 1
 
@@ -155,6 +172,8 @@ SYMBOLS = {
     'od_minmax_f32': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'od_stokes_drift': (C.c_int, [_P, C.POINTER(StokesArgs)]),
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
+    'od_vertical_buoyancy': (C.c_int, [_P, C.POINTER(BuoyancyArgs)]),
+    'od_bookkeeping': (C.c_int, [_P, C.POINTER(BookkeepArgs)]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     'od_partition_active': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),

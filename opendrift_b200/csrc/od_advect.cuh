@@ -68,6 +68,7 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
 struct ExactMath {
     typedef GeodStart Start;
     static constexpr bool kExactSampler = true;      // sample_uv == sample2: the horizontal weights can be shared
+    static constexpr bool kDefer = false;            // moves outside the short-arc series' range are solved in place
     OD_HDS Start start(double lat0) { return geod_start(lat0); }
     OD_HDS void midpoint(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
         rk_midpoint(s, lon0, ku, kv, dt32, mlon, mlat);
@@ -102,7 +103,9 @@ struct SeriesMath : ExactMath {
     OD_HDS Start start(double lat0) { return series_start(lat0); }
     OD_HDS void midpoint(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
         const double h = OD_DMUL((double)dt32, 0.5);
-        geod_move_ne(s, lon0, OD_DMUL((double)kv, h), OD_DMUL((double)ku, h), mlon, mlat);
+        const double xn = OD_DMUL((double)kv, h), ye = OD_DMUL((double)ku, h);
+        if (series_move3(s, lon0, xn, ye, mlon, mlat)) return;      // (same arithmetic as SeriesHot: a redone particle repeats its mid-points to the bit)
+        geod_move_ne(s, lon0, xn, ye, mlon, mlat);
     }
     OD_HDS void move32(const Start& s, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
         const float az = az_f32(xv, yv);
@@ -117,6 +120,48 @@ struct SeriesMath : ExactMath {
     }
 };
 
+// SeriesHot: SeriesMath for the hot path of the step kernels.  A move outside the range of the short-arc series (long steps,
+// the polar caps, NaN) is not solved where it occurs -- the out-of-line call to the full solution there made the compiler
+// save and restore the live registers of the Runge-Kutta loop around it on EVERY pass (ABI call inside the loop: 170 local
+// loads and 90 local stores per particle-step, two thirds of the kernel's L1 traffic) -- but flagged: the particle finishes the
+// step with the move skipped, writes nothing, and is then redone from its untouched start state by the full SeriesMath path
+// in one out-of-line call at the very end of the thread (step_kernel), where nothing is live any more.
+struct SeriesHot : SeriesMath {
+    static constexpr bool kDefer = true;
+    OD_HDS void midpoint_d(const Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat, bool& bad) {
+        const double h = OD_DMUL((double)dt32, 0.5);
+        if (!series_move3(s, lon0, OD_DMUL((double)kv, h), OD_DMUL((double)ku, h), mlon, mlat)) { bad = true; mlon = lon0; mlat = lat0; }
+    }
+    OD_HDS void move32_d(const Start& s, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1, bool& bad) {
+        const float az = az_f32(xv, yv);
+        const double dist = OD_DMUL(OD_DMUL((double)speed_f32(xv, yv), mv), dt);
+        double sa, ca;
+        sincosd(ang_round(ang_normalize((double)az)), sa, ca);
+        if (!series_move(s, lon0, OD_DMUL(dist, ca), OD_DMUL(dist, sa), lon1, lat1)) { bad = true; lon1 = lon0; lat1 = lat0; }
+    }
+    OD_HDS void move64_d(const Start& s, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1, bool& bad) {
+        const double k = OD_DMUL(mv, dt);
+        if (!series_move(s, lon0, OD_DMUL(yv, k), OD_DMUL(xv, k), lon1, lat1)) { bad = true; lon1 = lon0; lat1 = lat0; }
+    }
+};
+
+// the three moves of a step through the policy, deferring variant when the policy has one
+template <class MATH>
+OD_HD void do_midpoint(const typename MATH::Start& s, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat, bool& bad) {
+    if constexpr (MATH::kDefer) MATH::midpoint_d(s, lon0, lat0, ku, kv, dt32, mlon, mlat, bad);
+    else MATH::midpoint(s, lon0, lat0, ku, kv, dt32, mlon, mlat);
+}
+template <class MATH>
+OD_HD void do_move32(const typename MATH::Start& s, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1, bool& bad) {
+    if constexpr (MATH::kDefer) MATH::move32_d(s, lon0, lat0, xv, yv, mv, dt, lon1, lat1, bad);
+    else MATH::move32(s, lon0, lat0, xv, yv, mv, dt, lon1, lat1);
+}
+template <class MATH>
+OD_HD void do_move64(const typename MATH::Start& s, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1, bool& bad) {
+    if constexpr (MATH::kDefer) MATH::move64_d(s, lon0, lat0, xv, yv, mv, dt, lon1, lat1, bad);
+    else MATH::move64(s, lon0, lat0, xv, yv, mv, dt, lon1, lat1);
+}
+
 struct FastStart {
     float s0, c0;        // sin, cos of the start latitude
     float im, in_;       // 1/M(lat0), 1/(N(lat0) cos lat0)  [radians per metre]
@@ -125,6 +170,7 @@ struct FastStart {
 struct FastMath {
     typedef FastStart Start;
     static constexpr bool kExactSampler = false;
+    static constexpr bool kDefer = false;
     OD_HDS Start start(double lat0) {
         Start st;
         double sd, cd;
@@ -312,7 +358,7 @@ OD_HD void add_current_noise(const StepParams& p, int stage, int64_t i, float& u
 //   accumulated left to right as the reference writes it.
 template <int SCHEME, class MATH, bool CHAIN = false>
 OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const typename MATH::Start& gs, double lon0, double lat0,
-                       float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv, double zt = 0.0, bool zf32 = true) {
+                       float dt32, float k1u, float k1v, float& ou, float& ov, const TileView& tv, bool& bad, double zt = 0.0, bool zf32 = true) {
     const CurrentStages& cs = p.cs;
     if (SCHEME == 0) {
         ou = k1u;
@@ -327,7 +373,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
 #endif
     for (int st = 1; st <= last; ++st) {
         double mlon, mlat;
-        MATH::midpoint(gs, lon0, lat0, ku, kv, dt32, mlon, mlat);
+        do_midpoint<MATH>(gs, lon0, lat0, ku, kv, dt32, mlon, mlat, bad);
         const PairRef& pr = st == 3 ? cs.t_end : cs.t_mid;
         MATH::sample_uv(cs.g, pr, vw, mlon, mlat, ku, kv, false, tv);
         if (CHAIN) chain_fill<MATH>(p, st == 3 ? 2 : 1, zt, zf32, mlon, mlat, false, ku, kv);
@@ -361,7 +407,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
 
 template <class MATH>
 OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, double lon0, double lat0,
-                         double* plon1, double* plat1) {
+                         double* plon1, double* plat1, bool& bad) {
     double lon1 = *plon1, lat1 = *plat1;
     // ---- advect_wind (physics_methods.py:712-791): wind sampled at the start-of-step position
     {
@@ -385,7 +431,7 @@ OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, d
             const double xv = OD_DMUL((double)xw, wdf), yv = OD_DMUL((double)yw, wdf);
             if (xv != 0.0 || yv != 0.0) {
                 const typename MATH::Start g1 = MATH::start(lat1);
-                MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+                do_move64<MATH>(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1, bad);
             }
         } else {
             float wdf = ((const float*)p.wdf)[i];
@@ -393,7 +439,7 @@ OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, d
             const float xv = OD_FMUL(xw, wdf), yv = OD_FMUL(yw, wdf);
             if (xv != 0.0f || yv != 0.0f) {
                 const typename MATH::Start g1 = MATH::start(lat1);
-                MATH::move32(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+                do_move32<MATH>(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1, bad);
             }
         }
     }
@@ -402,7 +448,7 @@ OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, d
 }
 
 template <class MATH>
-OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double* plon1, double* plat1) {
+OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double* plon1, double* plat1, bool& bad) {
     double lon1 = *plon1, lat1 = *plat1;
     // ---- horizontal_diffusion (basemodel/__init__.py:1746-1772)
     {
@@ -412,7 +458,7 @@ OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double*
         const double xv = OD_DMUL(sd, p.rand_x[i]), yv = OD_DMUL(sd, p.rand_y[i]);
         if (xv != 0.0 || yv != 0.0) {
             const typename MATH::Start g1 = MATH::start(lat1);
-            MATH::move64(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1);
+            do_move64<MATH>(g1, lon1, lat1, xv, yv, mv, p.dt, lon1, lat1, bad);
         }
     }
     *plon1 = lon1;
@@ -422,9 +468,12 @@ OD_COLD void extras_diffusion(const StepParams& p, int64_t i, double mv, double*
 // One particle, one step (the body of step_kernel; also compiled for the host by tests/hostshim).
 // zs/zy and zsw/zyw are the level tables of the current and the vertical-velocity group.
 // EXTRAS: 0 current advection only; 1 all extras (wind move, vertical advection, diffusion move); 2 vertical advection only
+// Returns true when the particle is done.  false (deferring policies only, MATH::kDefer): one of its moves was outside the
+// range of the hot path's geodesic; lon / lat have not been written and the caller redoes the particle with the full policy
+// and redo = true (the depth update of vertical advection, which does not depend on the moves, is not applied twice).
 template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath, bool CHAIN = false>
-OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
-                         const double* zsw, const double* zyw, const TileView& tv = TileView()) {
+OD_HD bool step_particle(const StepParams& p, int64_t i, const double* zs, const double* zy,
+                         const double* zsw, const double* zyw, const TileView& tv = TileView(), bool redo = false) {
     const GroupGeom& g = p.cs.g;
     const double lon0 = p.lon[i], lat0 = p.lat[i];
     const bool zf32 = p.z_f64 == 0;
@@ -456,7 +505,7 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
         // (done here, next to the stage-1 sample whose cell and weights it can share; it only touches z)
         // ---- vertical_advection (oceandrift.py:315-350): z = min(0, z + moving*w*dt); w sampled at the
         // start-of-step depth, applied to the current depth (which vertical mixing may already have changed)
-        if (p.w_on) {
+        if (p.w_on && !redo) {
             const bool zio32 = p.zio_f64 == 0;
             const double zc = zio32 ? (double)((const float*)p.z_inout)[i] : ((const double*)p.z_inout)[i];
             const bool applicable = p.w_at_surface ? (zc <= 0.0) : (zc < 0.0);
@@ -476,23 +525,50 @@ OD_HD void step_particle(const StepParams& p, int64_t i, const double* zs, const
     }
 
     float ru, rv;
-    rk_velocity<SCHEME, MATH, CHAIN>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv, zt, zf32);
+    bool bad = false;
+    rk_velocity<SCHEME, MATH, CHAIN>(p, i, vw, gs, lon0, lat0, p.dt32, k1u, k1v, ru, rv, tv, bad, zt, zf32);
 
     double lon1, lat1;
     if (F64) {
         const double f = p.factor ? ((const double*)p.factor)[i] : 1.0;
-        MATH::move64(gs, lon0, lat0, OD_DMUL((double)ru, f), OD_DMUL((double)rv, f), mv, p.dt, lon1, lat1);
+        do_move64<MATH>(gs, lon0, lat0, OD_DMUL((double)ru, f), OD_DMUL((double)rv, f), mv, p.dt, lon1, lat1, bad);
     } else {
         const float f = p.factor ? ((const float*)p.factor)[i] : 1.0f;
-        MATH::move32(gs, lon0, lat0, OD_FMUL(ru, f), OD_FMUL(rv, f), mv, p.dt, lon1, lat1);
+        do_move32<MATH>(gs, lon0, lat0, OD_FMUL(ru, f), OD_FMUL(rv, f), mv, p.dt, lon1, lat1, bad);
     }
 
     if (EXTRAS == 1) {
-        if (p.wind_on) extras_wind<MATH>(p, i, z0, mv, lon0, lat0, &lon1, &lat1);
-        if (p.diff_on) extras_diffusion<MATH>(p, i, mv, &lon1, &lat1);
+        if (p.wind_on) extras_wind<MATH>(p, i, z0, mv, lon0, lat0, &lon1, &lat1, bad);
+        if (p.diff_on) extras_diffusion<MATH>(p, i, mv, &lon1, &lat1, bad);
     }
+    if (MATH::kDefer && bad) return false;
     p.lon[i] = lon1;
     p.lat[i] = lat1;
+    return true;
+}
+
+// The step as the kernels run it: the hot policy first (SeriesHot for SeriesMath, the policy itself otherwise); a particle
+// whose step contained a move the hot path does not solve is redone with the full policy, out of line.
+template <class MATH> struct HotPolicy { typedef MATH type; };
+template <> struct HotPolicy<SeriesMath> { typedef SeriesHot type; };
+
+#if defined(__CUDACC__)
+#define OD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define OD_NOINLINE static
+#endif
+
+template <int SCHEME, bool F64, int EXTRAS, class MATH, bool CHAIN>
+OD_NOINLINE void step_particle_redo(const StepParams* p, int64_t i, const double* zs, const double* zy, const double* zsw, const double* zyw) {
+    step_particle<SCHEME, F64, EXTRAS, MATH, CHAIN>(*p, i, zs, zy, zsw, zyw, TileView(), true);
+}
+
+template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath, bool CHAIN = false>
+OD_HD void step_particle_full(const StepParams& p, int64_t i, const double* zs, const double* zy,
+                              const double* zsw, const double* zyw, const TileView& tv = TileView()) {
+    typedef typename HotPolicy<MATH>::type HOT;
+    if (!step_particle<SCHEME, F64, EXTRAS, HOT, CHAIN>(p, i, zs, zy, zsw, zyw, tv))
+        step_particle_redo<SCHEME, F64, EXTRAS, MATH, CHAIN>(&p, i, zs, zy, zsw, zyw);
 }
 
 }  // namespace od

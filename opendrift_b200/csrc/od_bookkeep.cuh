@@ -1,0 +1,168 @@
+// od_bookkeep.cuh -- per-element housekeeping of the run loop and of OceanDrift.update() that is not a move.
+//
+//   buoyancy_one      OceanDrift.vertical_buoyancy (opendrift/models/oceandrift.py:352-357):
+//                       z[z < 0] = np.minimum(0, z + terminal_velocity * dt)
+//                     and the 'lift_to_seafloor' / 'deactivate' branches of OpenDriftSimulation.interact_with_seafloor
+//                     (opendrift/models/basemodel/__init__.py:748-783) that the same method reaches through
+//                     bottom_interaction (:359-367): z < -(sea_floor_depth + sea_surface_height) -> z = -(...).
+//   bookkeep_one      one pass over the active elements for what the run loop does between get_environment and update()
+//                     (basemodel/__init__.py:2249-2270):
+//                       deactivate_outside       (:2358-2386)  lon / lat against the validity domain -> status 'outside'
+//                       state_to_buffer          (:2384-2403)  lon / lat / z / status of the element into column `col`
+//                                                               of the [trajectory, time] output block (optional)
+//                       increase_age_and_retire  (:2345-2356)  age_seconds += dt; age >= max_age -> status 'retired'
+//                     deactivate_elements (:1774-1795) semantics: the status of an element that is already deactivated is
+//                     kept, `moving` becomes 0.  The reference numbers a status category when it first occurs
+//                     (status_categories.append at the first deactivate_elements call that selects an element), so the
+//                     kernel writes the codes the host hands it -- provisional ones until the category has a number --
+//                     and counts, per launch, the elements it put into 'outside' / 'retired' and those whose status is
+//                     non-zero after the pass (one atomic per warp and counter): the host numbers new categories in the
+//                     reference's order and skips the compaction when nothing left.
+// NumPy dtype rules are kept: the dtypes of z / terminal_velocity / age_seconds are whatever the reference's arrays have
+// (float32 as seeded arrays, float64 once a scalar property was broadcast on release, elements/elements.py:213-216).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define OD_BK_HD __host__ __device__ __forceinline__
+#else
+#define OD_BK_HD static inline
+#endif
+
+namespace od {
+
+struct BuoyancyParams {
+    int64_t n;
+    const void* z_in;            // float32 / float64 (z_f64)
+    void* z_out;                 // same dtype as z_in; may alias it
+    const void* tv;              // terminal_velocity float32 / float64 (tv_f64); NULL = no buoyancy move (sea floor only)
+    const float* sea_floor;      // sea_floor_depth_below_sea_level at the elements, or NULL
+    int32_t* status;             // with seafloor_action 'deactivate': status / moving of the elements that hit the floor
+    int32_t* moving;
+    unsigned* counter;           // += elements deactivated here
+    double dt;
+    float ssh;                   // sea_surface_height (its fallback: a reader for it is refused at run())
+    int32_t z_f64, tv_f64;
+    int32_t seafloor_code;       // status code of 'seafloor' when seafloor_action == 'deactivate', else 0
+};
+
+OD_BK_HD bool buoyancy_one(const BuoyancyParams& p, int64_t i) {
+    bool deact = false;
+    if (p.z_f64) {
+        double z = ((const double*)p.z_in)[i];
+        if (p.tv && z < 0.0) {
+            // float32 * Python float stays float32 (weak scalar); the sum with a float64 z is float64
+            const double d = p.tv_f64 ? ((const double*)p.tv)[i] * p.dt : (double)(((const float*)p.tv)[i] * (float)p.dt);
+            z = fmin(0.0, z + d);
+        }
+        if (p.sea_floor) {
+            const float zmin = -(p.sea_floor[i] + p.ssh);       // float32 environment arithmetic
+            if (z < (double)zmin) {
+                z = (double)zmin;
+                deact = p.seafloor_code != 0;
+            }
+        }
+        ((double*)p.z_out)[i] = z;
+    } else {
+        float z = ((const float*)p.z_in)[i];
+        if (p.tv && z < 0.0f) {
+            if (p.tv_f64) z = (float)fmin(0.0, (double)z + ((const double*)p.tv)[i] * p.dt);    // float64 sum, stored into the float32 array
+            else z = fminf(0.0f, z + ((const float*)p.tv)[i] * (float)p.dt);
+        }
+        if (p.sea_floor) {
+            const float zmin = -(p.sea_floor[i] + p.ssh);
+            if (z < zmin) {
+                z = zmin;
+                deact = p.seafloor_code != 0;
+            }
+        }
+        ((float*)p.z_out)[i] = z;
+    }
+    if (deact && p.status) {
+        if (p.status[i] == 0) p.status[i] = p.seafloor_code;
+        if (p.moving) p.moving[i] = 0;
+    }
+    return deact;
+}
+
+struct BookkeepParams {
+    int64_t n;
+    const double* lon;
+    const double* lat;
+    const void* z;               // float32 / float64 (z_f64); only read for the output block
+    void* age;                   // age_seconds float32 / float64 (age_f64), updated in place
+    int32_t* status;
+    int32_t* moving;
+    const int32_t* ids;          // element IDs (rows of the output block)
+    unsigned* counters;          // [0] += newly 'outside', [1] += newly 'retired', [2] += status != 0 after the pass
+    double dt_age;               // seconds added to age_seconds
+    double max_age;              // drift:max_age_seconds, or NaN = no retirement
+    double west, east, south, north;    // validity domain, NaN = no limit (east > 180: longitudes < 0 are compared as lon + 360, :2362-2376)
+    int32_t outside_code, retired_code;
+    int32_t z_f64, age_f64;
+    int32_t pos_f32, pad_;       // lon / lat still carry float32 values: NumPy compares them with the limits in float32
+    // output block [n_total][ncols], or blon == NULL when this is not an output step
+    int64_t n_total;
+    int32_t col, ncols;
+    float* blon;
+    float* blat;
+    float* bz;
+    int32_t* bstatus;
+};
+
+// returns bit 0: newly 'outside', bit 1: newly 'retired', bit 2: status non-zero after the pass
+OD_BK_HD int bookkeep_one(const BookkeepParams& p, int64_t i) {
+    int st = p.status[i];
+    int flags = 0;
+    bool off = false;
+    const double lon = p.lon[i], lat = p.lat[i];
+    // deactivate_outside: four separate deactivate_elements calls (west, east, south, north), all with the same reason
+    bool out;
+    if (p.pos_f32) {         // float32 array against a Python float: the scalar is cast to float32 (NumPy weak scalars)
+        const float lf = (float)lon, af = (float)lat;
+        const float lc = (p.east == p.east && p.east > 180.0 && lf < 0.0f) ? lf + 360.0f : lf;
+        out = (p.west == p.west && lc < (float)p.west) || (p.east == p.east && lc > (float)p.east) ||
+              (p.south == p.south && af < (float)p.south) || (p.north == p.north && af > (float)p.north);
+    } else {
+        const double lonc = (p.east == p.east && p.east > 180.0 && lon < 0.0) ? lon + 360.0 : lon;
+        out = (p.west == p.west && lonc < p.west) || (p.east == p.east && lonc > p.east) ||
+              (p.south == p.south && lat < p.south) || (p.north == p.north && lat > p.north);
+    }
+    if (out) {
+        if (st == 0) { st = p.outside_code; flags |= 1; }
+        off = true;
+    }
+    if (p.blon) {
+        const int64_t id = p.ids[i];
+        if (id >= 0 && id < p.n_total) {
+            const int64_t o = id * p.ncols + p.col;
+            p.blon[o] = (float)lon;
+            p.blat[o] = (float)lat;
+            p.bz[o] = p.z_f64 ? (float)((const double*)p.z)[i] : ((const float*)p.z)[i];
+            p.bstatus[o] = st;
+        }
+    }
+    // age_seconds += time_step.total_seconds()  (in place: the array keeps its dtype)
+    bool old;
+    if (p.age_f64) {
+        const double a = ((double*)p.age)[i] + p.dt_age;
+        ((double*)p.age)[i] = a;
+        old = a >= p.max_age;
+    } else {
+        const float a = ((float*)p.age)[i] + (float)p.dt_age;
+        ((float*)p.age)[i] = a;
+        old = a >= (float)p.max_age;
+    }
+    if (p.max_age == p.max_age && old) {
+        if (st == 0) { st = p.retired_code; flags |= 2; }
+        off = true;
+    }
+    if (off) {
+        p.status[i] = st;
+        p.moving[i] = 0;
+    }
+    return flags | (st != 0 ? 4 : 0);
+}
+
+}  // namespace od

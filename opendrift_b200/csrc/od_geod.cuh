@@ -435,6 +435,34 @@ OD_HD bool series_move(const SeriesStart& p, double lon1, double xn, double ye, 
     return true;
 }
 
+// Third-order truncation of the same series, for positions that only feed the field sampler (Runge-Kutta mid-points).
+// Neglected: the fourth- and fifth-order terms, bounded by ~3 r^4 radians with r as above: 2e-9 m for a 300 m half step at
+// 60N (r = 8e-5), 2e-5 m at r = kSeries3MaxR = 1e-3 -- the size of the float32 azimuth / distance rounding of the
+// reference's mid-points that SeriesMath skips anyway (od_advect.cuh).  Five coefficients instead of eighteen: what the
+// Runge-Kutta loop keeps live fits in registers.  Returns false beyond kSeries3MaxR (the caller then takes series_move).
+#ifndef OD_SERIES3_MAX_R
+#define OD_SERIES3_MAX_R 1.0e-3
+#endif
+constexpr double kSeries3MaxR = OD_SERIES3_MAX_R;
+
+OD_HD bool series_move3(const SeriesStart& p, double lon1, double xn, double ye, double& lon2, double& lat2) {
+    const double X = xn * p.vc, Y = ye * p.vc;
+    const double r = (fabs(X) + fabs(Y)) * fmax(1.0, fabs(p.t));
+    if (!(r <= kSeries3MaxR)) return false;
+    const double t = p.t, T = t * t, W = p.W;
+    const double p20 = 1.5 - 1.5 * W;                                               // times t  (p02 = -1/2)
+    const double p12 = -2.0 * T + W * (1.5 * T - 1.0 / 6.0);
+    const double p30 = 2.0 * T + W * (-4.5 * T + W * (2.5 * T - 0.5) + 0.5);
+    const double q03 = (-1.0 / 3.0) * T;
+    const double q21 = T + (1.0 / 3.0) * W;
+    const double X2 = X * X, Y2 = Y * Y;
+    const double P = X + (X * (p12 * Y2 + p30 * X2) + t * (p20 * X2 - 0.5 * Y2));
+    const double Q = Y + Y * ((q03 * Y2 + q21 * X2) + t * X);
+    lat2 = p.lat1 + (W * P) * OD_GK.rad2deg;
+    lon2 = ang_normalize(ang_normalize(lon1) + Q * p.icd);
+    return true;
+}
+
 // the rarely taken full solution, kept out of line so that the callers stay small
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__

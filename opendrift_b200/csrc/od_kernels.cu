@@ -22,6 +22,7 @@
 #include "od_leeway.cuh"
 #include "od_analytic.cuh"
 #include "od_history.cuh"
+#include "od_bookkeep.cuh"
 
 using namespace od;
 
@@ -86,6 +87,7 @@ struct od_ctx {
     int32_t* d_tilesums = nullptr;      // tile totals of the two-level scan
     int tiles_cap = 0;
     unsigned* d_red = nullptr;          // reduction scratch
+    unsigned* d_cnt = nullptr;          // counters of the housekeeping kernels
     float* d_fill = nullptr;            // scratch slab of the NaN fill
     unsigned* d_fillcnt = nullptr;      // per-pass missing-cell counters
     int coop_fill_blocks = -1;          // co-resident grid of fill_nan_coop_kernel (0: no cooperative launch)
@@ -157,6 +159,7 @@ extern "C" void od_destroy(od_ctx* ctx) {
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->d_bins) cudaFree(ctx->d_bins);
     if (ctx->d_red) cudaFree(ctx->d_red);
+    if (ctx->d_cnt) cudaFree(ctx->d_cnt);
     if (ctx->d_fill) cudaFree(ctx->d_fill);
     if (ctx->d_fillcnt) cudaFree(ctx->d_fillcnt);
     if (ctx->d_tilesums) cudaFree(ctx->d_tilesums);
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(OD_BLOCK) update_positions_kernel(int64_t n, d
 }
 
 template <int SCHEME, bool F64, int EXTRAS, class MATH>
-__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const __grid_constant__ StepParams p) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
     if (p.cs.g.nz > 1) load_levels(lv, p.cs.g);
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const Step
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    step_particle<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+    step_particle_full<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
 // The same step with a reader priority list for the current (StepParams::cg): a separate kernel so that the default one is
@@ -691,7 +694,7 @@ __global__ void __launch_bounds__(OD_BLOCK) step_chain_kernel(const __grid_const
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    step_particle<SCHEME, F64, EXTRAS, MATH, true>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+    step_particle_full<SCHEME, F64, EXTRAS, MATH, true>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
 // ---- vertical mixing -----------------------------------------------------------------------------
@@ -1061,7 +1064,7 @@ static int fill_current(od_ctx* ctx, const od_advect_args* a, StepParams* p) {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int SCHEME, bool F64, int EXTRAS, class MATH>
-__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_tiled_kernel(const StepParams p, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_tiled_kernel(const __grid_constant__ StepParams p, const __grid_constant__ CUtensorMap tmap,
                                                                             const float* tile_tex) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
@@ -1135,7 +1138,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_tiled_kernel(cons
         tv.smem = tile;
     }
     if (!active) return;
-    step_particle<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy, tv);
+    step_particle_full<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy, tv);
 }
 
 static const PairEntry* find_tmap(const Group& g, const float* tex) {
@@ -1149,9 +1152,13 @@ static int launch_step_tiled(od_ctx* ctx, int scheme, bool f64, const StepParams
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
 #define OD_LAUNCHT(S, F) step_tiled_kernel<S, F, EXTRAS, MATH><<<grid, OD_BLOCK, 0, s>>>(p, pe->tmap, pe->tex)
+#ifdef OD_SLIM
+    return fail(ctx, OD_ERR_ARG, "tuning build (OD_SLIM): tiled kernels not compiled");
+#else
     if (scheme == OD_EULER) { if (f64) OD_LAUNCHT(0, true); else OD_LAUNCHT(0, false); }
     else if (scheme == OD_RK2) { if (f64) OD_LAUNCHT(1, true); else OD_LAUNCHT(1, false); }
     else { if (f64) OD_LAUNCHT(2, true); else OD_LAUNCHT(2, false); }
+#endif
 #undef OD_LAUNCHT
     CK(cudaGetLastError());
     ctx->launches++;
@@ -1162,6 +1169,14 @@ template <int EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
+#ifdef OD_SLIM
+    // tuning builds: only the bench's instantiations (RK4, float64 factor, no reader chain) are compiled
+    if (p.n_chain > 0 || scheme != OD_RK4 || !f64) return fail(ctx, OD_ERR_ARG, "tuning build (OD_SLIM): kernel variant not compiled");
+    step_kernel<2, true, EXTRAS, MATH><<<grid, OD_BLOCK, 0, s>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
+#else
     if (p.n_chain > 0) {
         constexpr int E = EXTRAS == 0 ? 0 : 1;
 #define OD_LAUNCHC(S, F) step_chain_kernel<S, F, E, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
@@ -1181,7 +1196,11 @@ static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     CK(cudaGetLastError());
     ctx->launches++;
     return OD_OK;
+#endif
 }
+
+template <int EXTRAS>
+static int launch_step_mode(od_ctx* ctx, int mode, int scheme, bool f64, const StepParams& p);
 
 extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
     if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_advect_current: null argument");
@@ -1199,9 +1218,7 @@ extern "C" int od_advect_current(od_ctx* ctx, const od_advect_args* a) {
         if (a->fast == OD_MATH_SERIES) return launch_step_tiled<0, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
         return launch_step_tiled<0, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p, pe);
     }
-    if (a->fast == OD_MATH_FAST) return launch_step<0, FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
-    if (a->fast == OD_MATH_SERIES) return launch_step<0, SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
-    return launch_step<0, ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+    return launch_step_mode<0>(ctx, a->fast, a->scheme, a->factor_f64 != 0, p);
 }
 
 // advect_ocean_current on HOST arrays: the particle range is cut into chunks; each chunk's host->device copies, kernel
@@ -1401,7 +1418,11 @@ template <int EXTRAS>
 static int launch_step_mode(od_ctx* ctx, int mode, int scheme, bool f64, const StepParams& p) {
     if (mode == OD_MATH_FAST) return launch_step<EXTRAS, FastMath>(ctx, scheme, f64, p);
     if (mode == OD_MATH_SERIES) return launch_step<EXTRAS, SeriesMath>(ctx, scheme, f64, p);
+#ifdef OD_SLIM
+    return fail(ctx, OD_ERR_ARG, "tuning build (OD_SLIM): exact replay not compiled");
+#else
     return launch_step<EXTRAS, ExactMath>(ctx, scheme, f64, p);
+#endif
 }
 
 extern "C" int od_step_oceandrift(od_ctx* ctx, const od_step_args* a) {
@@ -1474,9 +1495,14 @@ static int launch_analytic(od_ctx* ctx, int scheme, bool f64, const AnalyticStep
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
 #define OD_LAUNCHA(S, F) analytic_step_kernel<S, F, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
+#ifdef OD_SLIM
+    if (scheme != OD_RK4 || !f64) return fail(ctx, OD_ERR_ARG, "tuning build (OD_SLIM): kernel variant not compiled");
+    OD_LAUNCHA(2, true);
+#else
     if (scheme == OD_EULER) { if (f64) OD_LAUNCHA(0, true); else OD_LAUNCHA(0, false); }
     else if (scheme == OD_RK2) { if (f64) OD_LAUNCHA(1, true); else OD_LAUNCHA(1, false); }
     else { if (f64) OD_LAUNCHA(2, true); else OD_LAUNCHA(2, false); }
+#endif
 #undef OD_LAUNCHA
     CK(cudaGetLastError());
     ctx->launches++;
@@ -1507,8 +1533,12 @@ extern "C" int od_analytic_advect(od_ctx* ctx, const od_analytic_desc* r, const 
     p.env_u = a->d_env_u; p.env_v = a->d_env_v;
     // the analytical sampler has no float32 variant: OD_MATH_FAST keeps its float32 mid-point moves only
     if (a->math == OD_MATH_FAST) return launch_analytic<FastMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+#ifdef OD_SLIM
+    return launch_analytic<SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+#else
     if (a->math == OD_MATH_SERIES) return launch_analytic<SeriesMath>(ctx, a->scheme, a->factor_f64 != 0, p);
     return launch_analytic<ExactMath>(ctx, a->scheme, a->factor_f64 != 0, p);
+#endif
 }
 
 // ---- output buffer on the device (od_history.cuh) -----------------------------------------------------------
@@ -1534,6 +1564,88 @@ extern "C" int od_history_scatter(od_ctx* ctx, const od_history_args* a) {
     history_scatter_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;
+    return OD_OK;
+}
+
+// ---- housekeeping (od_bookkeep.cuh) --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) buoyancy_kernel(const BuoyancyParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool d = i < p.n && buoyancy_one(p, i);
+    const unsigned m = __ballot_sync(0xffffffffu, d);
+    if (m && (threadIdx.x & 31) == 0 && p.counter) atomicAdd(p.counter, (unsigned)__popc(m));
+}
+
+__global__ void __launch_bounds__(256) bookkeep_kernel(const BookkeepParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = i < p.n ? bookkeep_one(p, i) : 0;
+    const unsigned m0 = __ballot_sync(0xffffffffu, f & 1), m1 = __ballot_sync(0xffffffffu, f & 2), m2 = __ballot_sync(0xffffffffu, f & 4);
+    if ((threadIdx.x & 31) == 0) {
+        if (m0) atomicAdd(&p.counters[0], (unsigned)__popc(m0));
+        if (m1) atomicAdd(&p.counters[1], (unsigned)__popc(m1));
+        if (m2) atomicAdd(&p.counters[2], (unsigned)__popc(m2));
+    }
+}
+
+static int counters(od_ctx* ctx) {
+    if (!ctx->d_cnt) CK(cudaMalloc(&ctx->d_cnt, 4 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(ctx->d_cnt, 0, 4 * sizeof(unsigned), ctx->stream));
+    return OD_OK;
+}
+
+extern "C" int od_vertical_buoyancy(od_ctx* ctx, const od_buoyancy_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_vertical_buoyancy: null argument");
+    if (a->n < 0 || (a->n > 0 && (!a->d_z_in || !a->d_z_out))) return fail(ctx, OD_ERR_ARG, "od_vertical_buoyancy: bad arguments");
+    if (a->seafloor_code != 0 && (!a->d_status || !a->d_moving)) return fail(ctx, OD_ERR_ARG, "od_vertical_buoyancy: deactivation needs status and moving");
+    if (a->h_n_deactivated) *a->h_n_deactivated = 0;
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = counters(ctx);
+    if (rc) return rc;
+    BuoyancyParams p;
+    p.n = a->n; p.z_in = a->d_z_in; p.z_out = a->d_z_out; p.tv = a->d_terminal_velocity; p.sea_floor = a->d_sea_floor;
+    p.status = a->d_status; p.moving = a->d_moving; p.counter = ctx->d_cnt; p.dt = a->dt; p.ssh = a->sea_surface_height;
+    p.z_f64 = a->z_f64; p.tv_f64 = a->tv_f64; p.seafloor_code = a->seafloor_code;
+    buoyancy_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (a->h_n_deactivated) {
+        unsigned c = 0;
+        CK(cudaMemcpyAsync(&c, ctx->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *a->h_n_deactivated = c;
+    }
+    return OD_OK;
+}
+
+extern "C" int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_bookkeeping: null argument");
+    if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_age || !a->d_status || !a->d_moving)))
+        return fail(ctx, OD_ERR_ARG, "od_bookkeeping: bad arguments");
+    if (a->d_buf_lon && (!a->d_buf_lat || !a->d_buf_z || !a->d_buf_status || !a->d_ids || !a->d_z || a->ncols <= 0 || a->col < 0 ||
+                         a->col >= a->ncols || a->n_total < 0))
+        return fail(ctx, OD_ERR_ARG, "od_bookkeeping: bad output block");
+    if (a->h_counts) a->h_counts[0] = a->h_counts[1] = a->h_counts[2] = 0;
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = counters(ctx);
+    if (rc) return rc;
+    BookkeepParams p;
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status; p.moving = a->d_moving;
+    p.ids = a->d_ids; p.counters = ctx->d_cnt; p.dt_age = a->dt_age; p.max_age = a->max_age;
+    p.west = a->west; p.east = a->east; p.south = a->south; p.north = a->north;
+    p.outside_code = a->outside_code; p.retired_code = a->retired_code; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
+    p.pos_f32 = a->pos_f32; p.pad_ = 0;
+    p.n_total = a->n_total; p.col = a->col; p.ncols = a->ncols;
+    p.blon = a->d_buf_lon; p.blat = a->d_buf_lat; p.bz = a->d_buf_z; p.bstatus = a->d_buf_status;
+    bookkeep_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (a->h_counts) {
+        unsigned c[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(c, ctx->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 3; ++k) a->h_counts[k] = c[k];
+    }
     return OD_OK;
 }
 

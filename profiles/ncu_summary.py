@@ -15,7 +15,11 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'launch__registers_per_thread',
         'launch__occupancy_limit_registers', 'smsp__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct',
-        'lts__t_sector_hit_rate.pct', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
+        'lts__t_sector_hit_rate.pct', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_ld.sum',
+        'l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_st.sum', 'l1tex__m_l1tex2xbar_write_bytes.sum',
+        'launch__occupancy_limit_warps', 'sm__maximum_warps_per_active_cycle_pct']
 
 
 def main(path):

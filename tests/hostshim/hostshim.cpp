@@ -118,9 +118,9 @@ struct hs_step_args {
 
 template <int S, bool F>
 static void run(const StepParams& p, const GroupGeom& gw, int fast = 0) {
-    if (fast == 2) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, SeriesMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
-    else if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
-    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, 1, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    if (fast == 2) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, 1, SeriesMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else if (fast) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, 1, FastMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, 1, ExactMath>(p, i, p.cs.g.zs, p.cs.g.zy, gw.zs, gw.zy);
 }
 
 extern "C" {
@@ -430,18 +430,18 @@ static int fill_current2(const od_advect_args* a, const hs_group* g, const hs_pa
 template <int S, bool F, int E>
 static void run2c(const StepParams& p, int mode) {          // step_chain_kernel
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
-    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, SeriesMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
-    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, FastMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
-    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, ExactMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, SeriesMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, FastMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, ExactMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
 }
 
 template <int S, bool F, int E>
 static void run2(const StepParams& p, int mode) {
     if (p.n_chain > 0) { run2c<S, F, (E == 0 ? 0 : 1)>(p, mode); return; }
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
-    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
-    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
-    else for (int64_t i = 0; i < p.n; ++i) step_particle<S, F, E, ExactMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+    else for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, ExactMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
 }
 
 template <int E>
