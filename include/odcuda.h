@@ -119,6 +119,9 @@ int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterat
 int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** d_out);
 /* tell the library a slot's contents changed behind its back (after a broadcast into od_group_slot_ptr) */
 int od_group_touch(od_ctx* ctx, int group, int slot);
+/* environment:fallback:* of the group's variables (Environment.get_environment, models/basemodel/environment.py:782-801): the
+ * values are read at every launch, so that a reader bound once serves models / runs with different fallbacks. NaN = none. */
+int od_group_set_fallback(od_ctx* ctx, int group, float fallback0, float fallback1);
 
 /* one time sample of a group: which two ring slots bracket it and how they combine */
 typedef struct od_time_sample {
@@ -352,12 +355,19 @@ typedef struct od_mix_args {
                                      column is analytical on 1 m levels mixing_z = -arange(nlev):
                                      1 OD_MIX_LARGE1994, 2 OD_MIX_SUNDBY1983 (physics_methods.py:203-249), 3 OD_MIX_CONSTANT */
     int32_t nlev;                 /* analytical models: len(-arange(0, max(MLD) + 2)) */
-    int32_t pad_;
+    int32_t seafloor_action;      /* what 'Let particles stick to bottom' (oceandrift.py:559-564) does at the end of an iteration to an
+                                     element below the sea floor: 0 nothing (no reader provides the depth: interact_with_seafloor
+                                     returns at once, basemodel/__init__.py:752-753), 1 lift_to_seafloor, 2 deactivate (lifted,
+                                     status = seafloor_code unless already set, moving = 0 for the remaining iterations) */
     const float* d_wind_speed;    /* [n] float32 sqrt(x_wind^2 + y_wind^2) at the start of the step (models 1, 2) */
     const float* d_mld;           /* [n] float32 ocean_mixed_layer_thickness, or NULL -> mld_const */
     double mld_const;
     double background;            /* vertical_mixing:background_diffusivity */
     double k_const;               /* model 3: the constant diffusivity */
+    int32_t* d_status;            /* seafloor_action 2 */
+    int32_t* d_moving_out;        /* seafloor_action 2: the array d_moving points to, writable */
+    int32_t seafloor_code, pad2_;
+    int64_t* h_n_deactivated;     /* seafloor_action 2, optional: elements deactivated by this call (synchronises) */
 } od_mix_args;
 #define OD_MIX_ENVIRONMENT 0
 #define OD_MIX_LARGE1994 1
@@ -464,8 +474,8 @@ int od_vertical_buoyancy(od_ctx* ctx, const od_buoyancy_args* a);
 
 /* od_bookkeeping replaces, in one pass over the active elements, what OpenDriftSimulation.run does between
  * get_environment and update() (models/basemodel/__init__.py:2249-2270): deactivate_outside (:2358-2386),
- * state_to_buffer (:2384-2403, into column `col` of the device output block of od_history_scatter; d_buf_lon NULL = not an
- * output step) and increase_age_and_retire (:2345-2356), with deactivate_elements' rule (:1774-1795: an already deactivated
+ * state_to_buffer (:2384-2403, into column `col` of the device output block of od_history_scatter; d_buf_lon NULL = nothing
+ * is written) and increase_age_and_retire (:2345-2356), with deactivate_elements' rule (:1774-1795: an already deactivated
  * element keeps its status, moving = 0).  h_counts[0..2] = elements newly 'outside', newly 'retired', with status != 0
  * after the pass (synchronises when h_counts is given). */
 typedef struct od_bookkeep_args {
@@ -482,7 +492,8 @@ typedef struct od_bookkeep_args {
     double west, east, south, north;   /* drift:deactivate_*_of; NaN = none */
     int32_t outside_code, retired_code;
     int32_t z_f64, age_f64;
-    int32_t pos_f32, pad_;
+    int32_t pos_f32;
+    int32_t only_deactivated;     /* sub-step between output times: write only the elements with status != 0 (into the next output column) */
     int64_t n_total;
     int32_t col, ncols;
     float* d_buf_lon;

@@ -70,9 +70,10 @@ class MixArgs(C.Structure):
                 ('d_rand', C.c_void_p), ('d_sea_floor', C.c_void_p), ('dt_mix', C.c_double),
                 ('sea_floor_const', C.c_double), ('seed', C.c_uint64), ('step_index', C.c_int32),
                 ('z_in_f64', C.c_int32), ('tv_f64', C.c_int32), ('mix_at_surface', C.c_int32),
-                ('pos_f32', C.c_int32), ('model', C.c_int32), ('nlev', C.c_int32), ('pad_', C.c_int32),
+                ('pos_f32', C.c_int32), ('model', C.c_int32), ('nlev', C.c_int32), ('seafloor_action', C.c_int32),
                 ('d_wind_speed', C.c_void_p), ('d_mld', C.c_void_p), ('mld_const', C.c_double),
-                ('background', C.c_double), ('k_const', C.c_double)]
+                ('background', C.c_double), ('k_const', C.c_double), ('d_status', C.c_void_p), ('d_moving_out', C.c_void_p),
+                ('seafloor_code', C.c_int32), ('pad2_', C.c_int32), ('h_n_deactivated', C.POINTER(C.c_int64))]
 
 
 class LeewayArgs(C.Structure):
@@ -133,7 +134,7 @@ class BookkeepArgs(C.Structure):
                 ('d_status', C.c_void_p), ('d_moving', C.c_void_p), ('d_ids', C.c_void_p), ('dt_age', C.c_double),
                 ('max_age', C.c_double), ('west', C.c_double), ('east', C.c_double), ('south', C.c_double), ('north', C.c_double),
                 ('outside_code', C.c_int32), ('retired_code', C.c_int32), ('z_f64', C.c_int32), ('age_f64', C.c_int32),
-                ('pos_f32', C.c_int32), ('pad_', C.c_int32), ('n_total', C.c_int64), ('col', C.c_int32), ('ncols', C.c_int32),
+                ('pos_f32', C.c_int32), ('only_deactivated', C.c_int32), ('n_total', C.c_int64), ('col', C.c_int32), ('ncols', C.c_int32),
                 ('d_buf_lon', C.c_void_p), ('d_buf_lat', C.c_void_p), ('d_buf_z', C.c_void_p), ('d_buf_status', C.c_void_p),
                 ('h_counts', C.POINTER(C.c_int64))]
 
@@ -158,6 +159,7 @@ SYMBOLS = {
     'od_group_fill_nan': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     'od_group_slot_ptr': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     'od_group_touch': (C.c_int, [_P, C.c_int, C.c_int]),
+    'od_group_set_fallback': (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     'od_interp': (C.c_int, [_P, C.c_int, C.POINTER(TimeSample), C.c_int64, _P, _P, _P, C.c_int, _P, _P]),
     'od_geod_fwd': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     'od_update_positions': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, C.c_double]),

@@ -101,7 +101,8 @@ struct BookkeepParams {
     double west, east, south, north;    // validity domain, NaN = no limit (east > 180: longitudes < 0 are compared as lon + 360, :2362-2376)
     int32_t outside_code, retired_code;
     int32_t z_f64, age_f64;
-    int32_t pos_f32, pad_;       // lon / lat still carry float32 values: NumPy compares them with the limits in float32
+    int32_t pos_f32;             // lon / lat still carry float32 values: NumPy compares them with the limits in float32
+    int32_t only_deactivated;    // not an output time: only elements with status != 0 are written, into the NEXT output column (:2390-2396, 'backfill')
     // output block [n_total][ncols], or blon == NULL when this is not an output step
     int64_t n_total;
     int32_t col, ncols;
@@ -133,7 +134,7 @@ OD_BK_HD int bookkeep_one(const BookkeepParams& p, int64_t i) {
         if (st == 0) { st = p.outside_code; flags |= 1; }
         off = true;
     }
-    if (p.blon) {
+    if (p.blon && (!p.only_deactivated || st != 0)) {
         const int64_t id = p.ids[i];
         if (id >= 0 && id < p.n_total) {
             const int64_t o = id * p.ncols + p.col;

@@ -359,6 +359,14 @@ extern "C" int od_group_touch(od_ctx* ctx, int group, int slot) {
     return OD_OK;
 }
 
+extern "C" int od_group_set_fallback(od_ctx* ctx, int group, float fallback0, float fallback1) {
+    int rc = check_slot(ctx, group, 0, 0);
+    if (rc) return rc;
+    ctx->groups[group].desc.fallback[0] = fallback0;
+    ctx->groups[group].desc.fallback[1] = fallback1;
+    return OD_OK;
+}
+
 // ---- NaN holes (land) ---------------------------------------------------------------------------------
 // Linear2DInterpolator fills missing values by repeatedly replacing every non-finite cell with the maximum of
 // its finite 3x3 neighbours (expand_numpy_array: scipy grey_dilation(size=3), interpolators.py:9-20), as often
@@ -1634,7 +1642,7 @@ extern "C" int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a) {
     p.ids = a->d_ids; p.counters = ctx->d_cnt; p.dt_age = a->dt_age; p.max_age = a->max_age;
     p.west = a->west; p.east = a->east; p.south = a->south; p.north = a->north;
     p.outside_code = a->outside_code; p.retired_code = a->retired_code; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
-    p.pos_f32 = a->pos_f32; p.pad_ = 0;
+    p.pos_f32 = a->pos_f32; p.only_deactivated = a->only_deactivated;
     p.n_total = a->n_total; p.col = a->col; p.ncols = a->ncols;
     p.blon = a->d_buf_lon; p.blat = a->d_buf_lat; p.bz = a->d_buf_z; p.bstatus = a->d_buf_status;
     bookkeep_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, ctx->stream>>>(p);
@@ -1769,9 +1777,24 @@ extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {
     p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.sea_floor = a->d_sea_floor;
     p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
     p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.seafloor_action = a->seafloor_action; p.seafloor_code = a->seafloor_code; p.status = a->d_status; p.moving_out = a->d_moving_out;
+    if (a->h_n_deactivated) *a->h_n_deactivated = 0;
+    if (a->seafloor_action < 0 || a->seafloor_action > 2 || (a->seafloor_action == 2 && (!a->d_status || !a->d_moving_out)))
+        return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: bad sea-floor action");
+    if (a->seafloor_action == 2) {
+        int rc = counters(ctx);
+        if (rc) return rc;
+        p.counter = ctx->d_cnt;
+    }
     mix_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;
+    if (a->seafloor_action == 2 && a->h_n_deactivated) {
+        unsigned c = 0;
+        CK(cudaMemcpyAsync(&c, ctx->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *a->h_n_deactivated = c;
+    }
     return OD_OK;
 }
 

@@ -70,6 +70,12 @@ struct MixParams {
     float mld_const, pad2_;
     double background;           // vertical_mixing:background_diffusivity
     double k_const;              // model 3
+    // 'Let particles stick to bottom' (oceandrift.py:559-564 -> interact_with_seafloor, basemodel/__init__.py:748-783)
+    int32_t seafloor_action;     // 0 none, 1 lift_to_seafloor, 2 deactivate
+    int32_t seafloor_code;
+    int32_t* status;
+    int32_t* moving_out;
+    unsigned* counter;
 };
 
 // physics_methods.py:217-249 (Large et al. 1994) and :203-215 (Sundby 1983) for one level (depth d metres) of one
@@ -208,7 +214,8 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
 
     // ---- inner loop ---------------------------------------------------------------------------------------------
     double z = p.z_in_f64 ? ((const double*)p.z_in)[i] : (double)((const float*)p.z_in)[i];
-    const double mv = p.moving ? (double)p.moving[i] : 1.0;
+    double mv = p.moving ? (double)p.moving[i] : 1.0;
+    bool deactivated = false;
     const double w = p.terminal_velocity ? (p.tv_f64 ? ((const double*)p.terminal_velocity)[i]
                                                       : (double)((const float*)p.terminal_velocity)[i]) : 0.0;
     const double zmin = p.sea_floor ? -(double)p.sea_floor[i] : p.zmin_const;
@@ -237,8 +244,24 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
         z = OD_DADD(z, OD_DMUL(OD_DMUL(w, p.dt_mix), mv));           // buoyancy
         if (!p.mix_at_surface && surface) z = 0.0;
         if (z > 0.0) z = 0.0;                                          // surface_stick
+        if (p.seafloor_action && z < zmin) {                           // stick to the bottom
+            z = zmin;
+            if (p.seafloor_action == 2) {                              // deactivate_elements: moving = 0 from here on
+                mv = 0.0;
+                deactivated = true;
+            }
+        }
     }
     p.z_out[i] = z;
+    if (deactivated) {
+        if (p.status[i] == 0) p.status[i] = p.seafloor_code;
+        p.moving_out[i] = 0;
+#if defined(__CUDA_ARCH__)
+        if (p.counter) atomicAdd(p.counter, 1u);
+#else
+        if (p.counter) *p.counter += 1u;
+#endif
+    }
 }
 
 }  // namespace od

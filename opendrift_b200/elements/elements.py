@@ -113,7 +113,7 @@ def _torch_dtype(torch, npdt):
 class DeviceElements:
     """Active elements: SoA device buffers with NumPy-returning attribute access."""
 
-    _own = ('variables', '_engine', '_dev', '_host', '_n', 'dtype', 'positions_f32')
+    _own = ('variables', '_engine', '_dev', '_host', '_n', 'dtype', 'positions_f32', 'status_touched')
 
     def __init__(self, element_type, engine):
         object.__setattr__(self, 'variables', copy.deepcopy(element_type.variables))
@@ -124,6 +124,8 @@ class DeviceElements:
         object.__setattr__(self, 'dtype', np.dtype([(v, s['dtype']) for v, s in self.variables.items()]))
         # lon/lat still carry float32 values (no update_positions yet): selects NumPy's float32 index arithmetic
         object.__setattr__(self, 'positions_f32', True)
+        # elements.status was handed out as / assigned from a host array: a subclass may have deactivated elements through it
+        object.__setattr__(self, 'status_touched', False)
 
     def __len__(self):
         return self._n
@@ -134,6 +136,8 @@ class DeviceElements:
         if name not in variables:
             raise AttributeError(name)
         host = object.__getattribute__(self, '_host')
+        if name == 'status':
+            object.__setattr__(self, 'status_touched', True)
         if name not in host:
             dev = object.__getattribute__(self, '_dev')
             host[name] = dev[name].cpu().numpy() if name in dev else np.zeros(0, dtype=variables[name]['dtype'])
@@ -147,6 +151,8 @@ class DeviceElements:
         value = np.asarray(value)
         if value.ndim == 0:
             value = value * np.ones(self._n)
+        if name == 'status':
+            object.__setattr__(self, 'status_touched', True)
         self._host[name] = value
         self._dev.pop(name, None)
 

@@ -140,6 +140,14 @@ class FieldGroup:
             zl = (C.c_double * len(self.z))(*self.z)
         engine._check(engine.lib.od_group_define(engine.ctx, gid, C.byref(d), zl))
 
+    def set_fallback(self, fallback):
+        """environment:fallback:* of this group's variables; read by the kernels at every launch, so that a reader that was
+        bound earlier (a direct get_variables_interpolated call, another model instance) follows the current run's values."""
+        fb = list(fallback) + [None] * (2 - len(fallback))
+        fb = [float('nan') if v is None else float(v) for v in fb]
+        self.desc.fallback[0], self.desc.fallback[1] = fb[0], fb[1]
+        self.engine._check(self.engine.lib.od_group_set_fallback(self.engine.ctx, self.gid, fb[0], fb[1]))
+
     def __del__(self):
         try:
             self.engine.free_group(self)
@@ -435,6 +443,60 @@ class Engine:
         a.d_buf_lon, a.d_buf_lat, a.d_buf_z, a.d_buf_status = (b.data_ptr() for b in bufs)
         self._check(self.lib.od_history_scatter(self.ctx, C.byref(a)))
 
+    def bookkeeping(self, lon, lat, z, age, status, moving, ids, dt_age, max_age=None, domain=None, outside_code=0,
+                    retired_code=0, pos_f32=False, buf=None, only_deactivated=False, counts=True):
+        """deactivate_outside + state_to_buffer + increase_age_and_retire in one pass (od_bookkeeping).  buf: the four
+        [n_total] float32 / float32 / float32 / int32 device tensors of the output column to fill (or None).
+        Returns (newly outside, newly retired, elements with status != 0) when counts (synchronises), else None."""
+        torch = self.torch
+        a = _lib.BookkeepArgs()
+        a.n = lon.numel()
+        assert lon.dtype == torch.float64 and lat.dtype == torch.float64 and status.dtype == torch.int32 and moving.dtype == torch.int32
+        assert age.dtype in (torch.float32, torch.float64)
+        a.d_lon, a.d_lat, a.d_age, a.d_status, a.d_moving = lon.data_ptr(), lat.data_ptr(), age.data_ptr(), status.data_ptr(), moving.data_ptr()
+        a.age_f64 = 1 if age.dtype == torch.float64 else 0
+        a.dt_age = float(dt_age)
+        a.max_age = float('nan') if max_age is None else float(max_age)
+        W, E, S, N = domain if domain is not None else (None, None, None, None)
+        a.west, a.east, a.south, a.north = (float('nan') if v is None else float(v) for v in (W, E, S, N))
+        a.outside_code, a.retired_code = int(outside_code), int(retired_code)
+        a.pos_f32 = 1 if pos_f32 else 0
+        a.only_deactivated = 1 if only_deactivated else 0
+        if buf is not None:
+            assert ids.dtype == torch.int32 and z.dtype in (torch.float32, torch.float64)
+            a.d_ids, a.d_z, a.z_f64 = ids.data_ptr(), z.data_ptr(), 1 if z.dtype == torch.float64 else 0
+            a.n_total, a.col, a.ncols = buf[0].numel(), 0, 1
+            a.d_buf_lon, a.d_buf_lat, a.d_buf_z, a.d_buf_status = (b.data_ptr() for b in buf)
+        c = (C.c_int64 * 3)()
+        if counts:
+            a.h_counts = c
+        self._check(self.lib.od_bookkeeping(self.ctx, C.byref(a)))
+        return (int(c[0]), int(c[1]), int(c[2])) if counts else None
+
+    def vertical_buoyancy(self, z_in, z_out, terminal_velocity, dt, sea_floor=None, sea_surface_height=0.0, status=None, moving=None,
+                          seafloor_code=0, count=False):
+        """OceanDrift.vertical_buoyancy / interact_with_seafloor on device tensors (od_vertical_buoyancy); z_out may be z_in."""
+        torch = self.torch
+        a = _lib.BuoyancyArgs()
+        a.n = z_in.numel()
+        assert z_in.dtype == z_out.dtype and z_in.dtype in (torch.float32, torch.float64)
+        a.d_z_in, a.d_z_out, a.z_f64 = z_in.data_ptr(), z_out.data_ptr(), 1 if z_in.dtype == torch.float64 else 0
+        if terminal_velocity is not None:
+            assert terminal_velocity.dtype in (torch.float32, torch.float64)
+            a.d_terminal_velocity, a.tv_f64 = terminal_velocity.data_ptr(), 1 if terminal_velocity.dtype == torch.float64 else 0
+        if sea_floor is not None:
+            assert sea_floor.dtype == torch.float32
+            a.d_sea_floor = sea_floor.data_ptr()
+        a.dt, a.sea_surface_height, a.seafloor_code = float(dt), float(sea_surface_height), int(seafloor_code)
+        if status is not None:
+            assert status.dtype == torch.int32 and moving.dtype == torch.int32
+            a.d_status, a.d_moving = status.data_ptr(), moving.data_ptr()
+        c = C.c_int64(0)
+        if count:
+            a.h_n_deactivated = C.pointer(c)
+        self._check(self.lib.od_vertical_buoyancy(self.ctx, C.byref(a)))
+        return int(c.value) if count else None
+
     def _step_args(self, s, group, scheme, t, dts, dt, lon, lat, z, factor, moving, truncate_below, wind, wdf,
                    wind_drift_depth, w_group, w_at_surface, rand, diffusivity, pos_f32, z_update, fast, noise, noise_kinds,
                    wind_noise, chain=()):
@@ -593,7 +655,8 @@ class Engine:
 
     def vertical_mixing(self, group, t, lon, lat, z_in, dt_mix, ntimes, moving=None, terminal_velocity=None, ids=None,
                         rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False,
-                        model='environment', wind_speed=None, mld=50.0, background=1.2e-5, k_const=0.0):
+                        model='environment', wind_speed=None, mld=50.0, background=1.2e-5, k_const=0.0, seafloor_action=0,
+                        status=None, seafloor_code=0):
         """OceanDrift.vertical_mixing on device tensors; returns the new depth (float64 tensor).
         model 'environment' takes the diffusivity column from `group`; 'windspeed_Large1994' / 'windspeed_Sundby1983' /
         'constant' build it analytically on 1 m levels from wind_speed (float32 tensor) and the mixed layer depth mld
@@ -637,7 +700,14 @@ class Engine:
             a.sea_floor_const = float(sea_floor)
         a.dt_mix, a.seed, a.step_index = float(dt_mix), int(seed), int(step_index)
         a.mix_at_surface, a.pos_f32 = (1 if mix_at_surface else 0), (1 if pos_f32 else 0)
+        a.seafloor_action = int(seafloor_action)          # 'stick to bottom' with a sea-floor reader: 1 lift, 2 deactivate
+        nd = C.c_int64(0)
+        if a.seafloor_action == 2:
+            assert status is not None and moving is not None and status.dtype == torch.int32
+            a.d_status, a.d_moving_out, a.seafloor_code = status.data_ptr(), moving.data_ptr(), int(seafloor_code)
+            a.h_n_deactivated = C.pointer(nd)
         self._check(self.lib.od_vertical_mixing(self.ctx, C.byref(a)))
+        self.last_mix_deactivated = int(nd.value)
         return z_out
 
     def sort_by_cell(self, group, lon, lat, z=None):

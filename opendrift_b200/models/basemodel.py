@@ -57,6 +57,72 @@ class EnvironmentView:
     def __contains__(self, name):
         return name in self._t or name in self._h
 
+    def select(self, keep):
+        """Keep the rows of the elements selected by the boolean device tensor `keep`."""
+        t, h = object.__getattribute__(self, '_t'), object.__getattribute__(self, '_h')
+        for k in list(t):
+            t[k] = t[k][keep]
+        if h:
+            kh = keep.cpu().numpy()
+            for k in list(h):
+                h[k] = h[k][kh]
+
+
+class ResultVariable:
+    """result.<var>: `.values` is the [trajectory, time] array of the reference's xr.DataArray."""
+
+    def __init__(self, rows, name):
+        self._rows, self.name = rows, name
+
+    @property
+    def values(self):
+        if self.name == 'time':
+            return np.array(self._rows)
+        return np.array(self._rows).T if len(self._rows) else np.zeros((0, 0), dtype=np.float32)
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.values
+        return v if dtype is None else v.astype(dtype)
+
+    def isel(self, time=None, trajectory=None):
+        v = self.values
+        if self.name == 'time':
+            return v if time is None else v[time]
+        if trajectory is not None:
+            v = v[trajectory]
+        if time is not None:
+            v = v[..., time]
+        return v
+
+    def min(self):
+        return np.nanmin(self.values)
+
+    def max(self):
+        return np.nanmax(self.values)
+
+
+class Result(dict):
+    """What run() returns and o.result holds.  The reference returns an xr.Dataset with lon / lat / z / status [trajectory, time]
+    (basemodel/__init__.py:2100-2135, 2340); xarray is outside this package's dependencies, so the same data come as a dict of
+    per-output-time rows -- result['lon'][k] is the float32 [trajectory] array of output time result['time'][k], NaN (status -1)
+    where the element does not exist -- with the Dataset's access pattern on top: result.lon.values is [trajectory, time],
+    result.time.values the time axis, result.sizes, result.status_categories (the flag_meanings of the status variable)."""
+
+    status_categories = ()
+
+    def __getattr__(self, name):
+        if name in self:
+            return ResultVariable(self[name], name)
+        raise AttributeError(name)
+
+    @property
+    def sizes(self):
+        return {'time': len(self['time']), 'trajectory': len(self['lon'][0]) if self['lon'] else 0}
+
+    @property
+    def data_vars(self):
+        return [k for k in self if k != 'time']
+
 
 class OpenDriftSimulation(PhysicsMethods, Configurable):
     ElementType = LagrangianArray
@@ -137,10 +203,13 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             'gpu:sort_interval_steps': {'type': 'int', 'default': 20, 'min': 0, 'max': 1000000, 'units': 1,
                                         'level': CONFIG_LEVEL_ADVANCED,
                                         'description': 'Re-order the device particle arrays by grid cell every N steps (0 = never).'},
-            'gpu:history': {'type': 'enum', 'enum': ['host', 'device'], 'default': 'host', 'level': CONFIG_LEVEL_ADVANCED,
-                            'description': 'Where the output buffer of state_to_buffer lives between flushes: host = four device-to-host '
-                                           'copies per output step; device = [trajectory, time] arrays in HBM filled by one scatter launch '
-                                           'per output step and read back once per export_buffer_length steps.'},
+            'gpu:history': {'type': 'enum', 'enum': ['host', 'device'], 'default': 'device', 'level': CONFIG_LEVEL_ADVANCED,
+                            'description': 'Where the output buffer of state_to_buffer lives between flushes: device = a block of output '
+                                           'columns in HBM, filled by the per-step bookkeeping launch and read back once per '
+                                           'export_buffer_length output steps; host = a block of one column (read back every output step).'},
+            'gpu:history_block_bytes': {'type': 'int', 'default': 2 ** 31, 'min': 1, 'max': 2 ** 40, 'units': 'bytes',
+                                        'level': CONFIG_LEVEL_ADVANCED,
+                                        'description': 'Upper bound of the device block of output columns (16 bytes per element and column).'},
             'gpu:arithmetic': {'type': 'enum', 'enum': ['series', 'exact', 'fast'], 'default': 'series', 'level': CONFIG_LEVEL_ADVANCED,
                                'description': 'Arithmetic of the step kernels (include/odcuda.h OD_MATH_*): series = bit-exact field '
                                               'sampling + short-arc series geodesic (round-off accurate); exact = the reference\'s '
@@ -298,6 +367,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             if not indices.any():
                 return
             indices = self.engine.to_device(indices.astype(bool))
+        elif not bool(indices.any()):
+            return
         if reason not in self.status_categories:
             self.status_categories.append(reason)
         code = self.status_categories.index(reason)
@@ -312,13 +383,18 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         self._maybe_deactivated = False
         pre = getattr(self, '_noise0', None)
-        keep = None
-        if pre:
-            keep = (self.elements.dev('status') == 0).cpu().numpy()
+        view = getattr(self, '_env_view', None)
+        keep = keep_dev = None
+        if pre or view is not None:
+            keep_dev = self.elements.dev('status') == 0
+            if pre:
+                keep = keep_dev.cpu().numpy()
         removed = self.elements.compact()
         if pre and removed is not None:
             for k in pre:
                 pre[k] = [a[keep] for a in pre[k]]
+        if view is not None and removed is not None:       # self.environment = self.environment[~indices] (:1812-1813)
+            view.select(keep_dev)
         if removed is None:
             return
         tmp = self.ElementType(**{k: v for k, v in removed.items()})
@@ -328,28 +404,84 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         tmp.move_elements(self.elements_deactivated, sel)
         self._env_dev = None
 
+    # -- per-step housekeeping: one launch (od_bookkeeping) ------------------------------------------------------
+    def _bookkeep(self, outside=True, buffer_col=None, only_deactivated=False, age=True):
+        """deactivate_outside (:2358-2386) -> state_to_buffer (:2384-2403) -> increase_age_and_retire (:2345-2356) for the
+        active elements, in the reference's order, as ONE kernel launch.  The host is only synchronised (a 12-byte read of the
+        kernel's counters) when something CAN have been deactivated: a validity domain or a maximum age is configured, or an
+        earlier launch / a subclass flagged elements; the compaction is skipped when nothing was."""
+        n = self.num_elements_active()
+        if n == 0:
+            return
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        cats = self.status_categories
+        domain = self.validity_domain if outside else None
+        max_age = self.get_config('drift:max_age_seconds') if age else None
+        new_out = domain is not None and 'outside' not in cats
+        oc = cats.index('outside') if 'outside' in cats else len(cats)
+        rc = cats.index('retired') if 'retired' in cats else len(cats) + (1 if new_out else 0)
+        if getattr(el, 'status_touched', False):          # a subclass assigned / was handed elements.status (host view)
+            self._maybe_deactivated = True
+            el.status_touched = False
+        counts = domain is not None or max_age is not None or self._maybe_deactivated
+        agev = el.dev('age_seconds')
+        if agev.dtype not in (torch.float32, torch.float64):
+            agev = el.dev('age_seconds', torch.float64)
+        buf = None
+        if buffer_col is not None:
+            buf = self._hist_column(buffer_col)
+        res = eng.bookkeeping(el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), agev,
+                              el.dev('status', torch.int32), el.dev('moving', torch.int32), el.dev('ID', torch.int32),
+                              self.time_step.total_seconds() if age else 0.0, max_age, domain, oc, rc,
+                              pos_f32=el.positions_f32, buf=buf, only_deactivated=only_deactivated, counts=counts)
+        if res is None:
+            return
+        n_out, n_ret, n_off = res
+        if new_out and n_out > 0:                          # a category is numbered when it first occurs (:1778-1780)
+            cats.append('outside')
+        if n_ret > 0 and 'retired' not in cats:
+            cats.append('retired')
+            real = cats.index('retired')
+            if real != rc:                                 # 'outside' was provisionally numbered before it and did not occur
+                st = el.dev('status')
+                el.set_dev('status', torch.where(st == rc, torch.full_like(st, real), st))
+        self._maybe_deactivated = n_off > 0
+
     def increase_age_and_retire(self):
         """:2345-2356"""
-        age = self.elements.dev('age_seconds')
-        self.elements.set_dev('age_seconds', age + age.new_tensor(self.time_step.total_seconds()).to(age.dtype))
-        max_age = self.get_config('drift:max_age_seconds')
-        if max_age is not None:
-            self.deactivate_elements(self.elements.dev('age_seconds') >= max_age, reason='retired')
+        self._bookkeep(outside=False, age=True)
 
     def deactivate_outside(self):
         """:2358-2386"""
-        if self.validity_domain is None:
+        if self.validity_domain is not None:
+            self._bookkeep(outside=True, age=False)
+
+    def interact_with_seafloor(self):
+        """:748-783 -- elements below the sea floor (sea_floor_depth_below_sea_level from a reader + sea_surface_height) are lifted
+        to it, or lifted and deactivated ('seafloor'), as general:seafloor_action says; a no-op unless a reader provides the depth."""
+        if self.num_elements_active() == 0 or not self.env.priority_list.get('sea_floor_depth_below_sea_level'):
             return
-        W, E, S, N = self.validity_domain
-        lon, lat = self.elements.dev('lon'), self.elements.dev('lat')
-        if W is not None:
-            self.deactivate_elements(lon < W, reason='outside')
-        if E is not None:
-            self.deactivate_elements(lon > E, reason='outside')
-        if S is not None:
-            self.deactivate_elements(lat < S, reason='outside')
-        if N is not None:
-            self.deactivate_elements(lat > N, reason='outside')
+        action = self.get_config('general:seafloor_action')
+        if action == 'none':
+            return
+        if action == 'previous':
+            raise NotImplementedError("general:seafloor_action = 'previous' (positions of the previous step) is not on the GPU path")
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        floor = self._start_of_step_sample('sea_floor_depth_below_sea_level')
+        ssh = float(self.env.constant('sea_surface_height') or self.env.fallback('sea_surface_height') or 0.0) \
+            if 'sea_surface_height' in self.required_variables else 0.0
+        z = self._z_for_sampling()
+        code = 0
+        if action == 'deactivate':
+            # the category is numbered when the first element hits the floor; until then a provisional number is handed down
+            code = self.status_categories.index('seafloor') if 'seafloor' in self.status_categories else len(self.status_categories)
+        nd = eng.vertical_buoyancy(z, z, None, 0.0, sea_floor=floor, sea_surface_height=ssh, status=el.dev('status', torch.int32),
+                                   moving=el.dev('moving', torch.int32), seafloor_code=code, count=code != 0)
+        el.set_dev('z', z)
+        if nd:
+            if 'seafloor' not in self.status_categories:
+                self.status_categories.append('seafloor')
+            self._maybe_deactivated = True
 
     # -- environment ---------------------------------------------------------------------------------------
     def _active_variables(self):
@@ -377,6 +509,16 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             self._env_view = EnvironmentView(d_env)
             self._env_missing = missing
         return self._env_view
+
+    def _start_of_step_sample(self, var):
+        """float32 device tensor of ONE environment variable at the elements' current positions: from the step's environment when
+        it has been materialised, else sampled on its own (the fused step never materialises the full environment)."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        if getattr(self, '_env_view', None) is not None and var in self._env_view:
+            return self._env_view.dev(var, eng)
+        d_env, _ = self.env.device_environment([var], self.time, el.dev('lon', torch.float64), el.dev('lat', torch.float64),
+                                               self._z_truncated(), pos_f32=el.positions_f32)
+        return d_env[var]
 
     def _uncertainty(self):
         return (self.get_config('drift:current_uncertainty', 0) or 0, self.get_config('drift:current_uncertainty_uniform', 0) or 0,
@@ -608,39 +750,44 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._maybe_deactivated = False
         out_every = int(round(ratio))
         n_total = self.num_elements_total()
-        self.history = {'time': [], 'lon': [], 'lat': [], 'z': [], 'status': []}
-        self._hist_dev, self._hist_col, self._hist_times = None, 0, []
-        self._hist_len = max(1, int(export_buffer_length))
         self._n_total = n_total
+        self._out_every = out_every
+        self._init_history(export_buffer_length)
         self.prepare_run()
 
+        i = 0
         for i in range(self.expected_steps_calculation):
             self.release_elements()
             if self.num_elements_active() == 0 and self.num_elements_scheduled() > 0:
-                self.steps_calculation += 1
+                self.steps_calculation += 1                # (state_to_buffer with no elements: the column keeps its fill values)
                 self.time = self.time + self.time_step
                 continue
             self._env_view = None
             self._predraw_step_uncertainty()
-            self.deactivate_outside()
-            if i % out_every == 0:
-                self.state_to_buffer()
-            self.increase_age_and_retire()
+            # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
+            col, only_deact = self._column_of_step(i)
+            if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                _ = self.environment                       # sampled before the lift, as the reference does (:2238-2256)
+                self._bookkeep(outside=True, age=False)
+                self.interact_with_seafloor()
+                self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
+            else:
+                self._bookkeep(outside=True, buffer_col=col, only_deactivated=only_deact, age=True)
             self.remove_deactivated_elements()
             if self.num_elements_active() > 0:
                 self._maybe_sort()
                 self.update_and_diffuse()
             elif self.num_elements_scheduled() == 0:
-                break
+                break                                      # 'No more active or scheduled elements' (:2276-2278): time is not advanced
             self.time = self.time + self.time_step
             self.steps_calculation += 1
         self._env_view = None
         self._restore_id_order()
-        self.state_to_buffer()
-        self._flush_history()
+        self.state_to_buffer(final=True)
         self.remove_deactivated_elements()
         eng.sync()
         self._check_positions()
+        self.result = self.history
         return self.history
 
     def _check_positions(self):
@@ -648,7 +795,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if self.num_elements_active() == 0:
             return
         lon, lat = self.elements.dev('lon'), self.elements.dev('lat')
-        if float(lon.min()) < -180 or float(lon.max()) > 360 or float(lat.min()) < -90 or float(lat.max()) > 90:
+        lo, hi, ao, ai = float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max())
+        # (NaN compares False with everything: test for the valid range, not for the invalid one)
+        if not (lo >= -180 and hi <= 360 and ao >= -90 and ai <= 90):
             raise ValueError('Invalid new coordinates')
 
     def _restore_id_order(self):
@@ -686,68 +835,79 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._sorted = True
         self._env_view = None
 
-    def state_to_buffer(self):
-        """History of lon/lat/z/status per element ID at output steps (stands in for :2384-2499)."""
-        if self.get_config('gpu:history', 'host') == 'device':
-            return self._state_to_device_buffer()
-        h = self.history
-        lon = np.full(self._n_total, np.nan, dtype=np.float32)
-        lat = np.full(self._n_total, np.nan, dtype=np.float32)
-        z = np.full(self._n_total, np.nan, dtype=np.float32)
-        st = np.full(self._n_total, -1, dtype=np.int32)
-        if self.num_elements_active() > 0:
-            el = self.elements
-            ids = el.to_host_array('ID').astype(np.int64)
-            lon[ids] = el.to_host_array('lon')
-            lat[ids] = el.to_host_array('lat')
-            z[ids] = el.to_host_array('z')
-            st[ids] = el.to_host_array('status')
-        h['time'].append(self.time)
-        h['lon'].append(lon)
-        h['lat'].append(lat)
-        h['z'].append(z)
-        h['status'].append(st)
+    # -- the output buffer (:2100-2135, 2384-2499) -----------------------------------------------------------------------
+    # The reference pre-allocates result[var][trajectory, time] for the expected output times, NaN-filled; output steps write
+    # every active element into the column of their time, sub-steps between output times write only the elements that were
+    # deactivated, into the NEXT output column ('backfill'); the final state is written the same way and the time axis is cut at
+    # the last time reached.  Here a block of columns [time][trajectory] lives in HBM (bounded: export_buffer_length columns and
+    # gpu:history_block_bytes), filled by the bookkeeping launch and read back -- one contiguous copy per variable -- when the
+    # next column falls outside the block.
+    def _init_history(self, export_buffer_length):
+        n_out = int(self.expected_steps_output)
+        self._out_times = [self.start_time + k * self.time_step_output for k in range(n_out)]
+        self.history = Result({'time': [], 'lon': [], 'lat': [], 'z': [], 'status': []})
+        self.history.status_categories = self.status_categories
+        per_col = 16 * max(1, int(self._n_total))
+        cap = max(1, int(self.get_config('gpu:history_block_bytes')) // per_col)
+        length = n_out if export_buffer_length is None else max(1, int(export_buffer_length))
+        if self.get_config('gpu:history') == 'host':
+            length = 1                                     # every output column goes to the host as soon as the next one starts
+        self._hist_ncols = max(1, min(length, n_out, cap))
+        self._hist_base = 0
+        self._hist_dev = None
+        self._hist_hi = -1                                 # highest column written so far
 
-    def _state_to_device_buffer(self):
-        """state_to_buffer with the [trajectory, time] block resident in HBM: one scatter launch per output step
-        (od_history_scatter), one read-back per export_buffer_length output steps (_flush_history)."""
+    def _column_of_step(self, i):
+        """(output column, only_deactivated) of calculation step i: its own column on output steps, else the next one."""
+        if i % self._out_every == 0:
+            return i // self._out_every, False
+        return i // self._out_every + 1, True
+
+    def _hist_column(self, k):
+        """The four device arrays [n_total] of output column k (flushing the block to the host when k lies beyond it)."""
         eng, torch = self.engine, self.engine.torch
         if self._hist_dev is None:
-            shape = (int(self._n_total), self._hist_len)
+            shape = (self._hist_ncols, int(self._n_total))
             self._hist_dev = tuple(torch.full(shape, float('nan'), dtype=torch.float32, device=eng.device) for _ in range(3)) + (
                 torch.full(shape, -1, dtype=torch.int32, device=eng.device),)
-        if self.num_elements_active() > 0:
-            el = self.elements
-            ids, status = el.dev('ID'), el.dev('status')
-            if ids.dtype != torch.int32:
-                ids = ids.to(torch.int32)
-            if status.dtype != torch.int32:
-                status = status.to(torch.int32)
-            eng.history_scatter(ids, el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), status,
-                                self._hist_dev, self._hist_col)
-        self._hist_times.append(self.time)
-        self._hist_col += 1
-        if self._hist_col == self._hist_len:
-            self._flush_history()
+        while k >= self._hist_base + self._hist_ncols:
+            self._flush_history(self._hist_ncols)
+        self._hist_hi = max(self._hist_hi, k)
+        return tuple(b[k - self._hist_base] for b in self._hist_dev)
 
-    def _flush_history(self):
-        """Read the filled columns of the device block back (one copy per array) and append them to self.history."""
-        if self._hist_dev is None or self._hist_col == 0:
+    def _flush_history(self, ncols):
+        """Move the first ncols columns of the device block to self.history (one device-to-host copy per variable)."""
+        if ncols <= 0:
             return
-        k = self._hist_col
-        # [k, n_total] each; .copy(): a host tensor (tests) would otherwise share its memory with the block that is reset below
-        cols = [b[:, :k].t().contiguous().cpu().numpy().copy() for b in self._hist_dev]
         h = self.history
-        for j in range(k):
-            h['time'].append(self._hist_times[j])
-            h['lon'].append(cols[0][j])
-            h['lat'].append(cols[1][j])
-            h['z'].append(cols[2][j])
-            h['status'].append(cols[3][j])
-        for b in self._hist_dev[:3]:
-            b.fill_(float('nan'))
-        self._hist_dev[3].fill_(-1)
-        self._hist_col, self._hist_times = 0, []
+        if self._hist_dev is None:
+            cols = [np.full((ncols, int(self._n_total)), np.nan, dtype=np.float32) for _ in range(3)] + [
+                np.full((ncols, int(self._n_total)), -1, dtype=np.int32)]
+        else:
+            cols = [b[:ncols].cpu().numpy().copy() for b in self._hist_dev]
+            for b in self._hist_dev[:3]:
+                b.fill_(float('nan'))
+            self._hist_dev[3].fill_(-1)
+        for j in range(ncols):
+            h['time'].append(self._out_times[self._hist_base + j])
+            for key, c in zip(('lon', 'lat', 'z', 'status'), cols):
+                h[key].append(c[j])
+        self._hist_base += ncols
+
+    def state_to_buffer(self, final=False):
+        """:2384-2403 for the current time; with final=True also the cut of the time axis at the time reached (:2425-2430)."""
+        i = self.steps_calculation
+        if self.num_elements_active() > 0:
+            col, only_deact = self._column_of_step(i)
+            if col < len(self._out_times):
+                self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=False)
+        if final:
+            n_keep = i // self._out_every + 1              # output times <= the time reached
+            while self._hist_base < n_keep:
+                self._flush_history(min(self._hist_ncols, n_keep - self._hist_base))
+            for key in self.history:
+                del self.history[key][n_keep:]
+            self._hist_dev = None
 
     def get_lonlats(self):
         return np.array(self.history['lon']).T, np.array(self.history['lat']).T

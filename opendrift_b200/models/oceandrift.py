@@ -104,9 +104,54 @@ class OceanDrift(OpenDriftSimulation):
         self.advect_ocean_current()
         self.advect_wind()
         self.stokes_drift()
+        self.update_terminal_velocity()
         if self.get_config('drift:vertical_mixing'):
             self.vertical_mixing()
+        else:
+            self.vertical_buoyancy()
         self.vertical_advection()
+
+    def update_terminal_velocity(self, *args, **kwargs):
+        """oceandrift.py:213-222: a hook for subclasses (plankton, oil droplets ...); the stock model keeps the seeded values."""
+        pass
+
+    def _buoyancy_inputs(self):
+        """(sea floor tensor or None, sea_surface_height, status code for 'deactivate' or 0): the sea-floor part of
+        vertical_buoyancy only acts when a reader provides the depth (interact_with_seafloor, basemodel/__init__.py:752-753)."""
+        if not self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            return None, 0.0, 0
+        action = self.get_config('general:seafloor_action')
+        if action == 'none':
+            return None, 0.0, 0
+        if action == 'previous':
+            raise NotImplementedError("general:seafloor_action = 'previous' is not on the GPU path")
+        floor = self._start_of_step_sample('sea_floor_depth_below_sea_level')
+        ssh = float(self.env.constant('sea_surface_height') or self.env.fallback('sea_surface_height') or 0.0)
+        code = 0
+        if action == 'deactivate':
+            code = self.status_categories.index('seafloor') if 'seafloor' in self.status_categories else len(self.status_categories)
+        return floor, ssh, code
+
+    def _buoyancy(self, z_in):
+        """oceandrift.py:352-367 on the device (od_vertical_buoyancy): returns the new depth tensor (dtype of z_in)."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        tv = el.dev('terminal_velocity')
+        if tv.dtype not in (torch.float32, torch.float64):
+            tv = el.dev('terminal_velocity', torch.float64)
+        floor, ssh, code = self._buoyancy_inputs()
+        z_out = torch.empty_like(z_in)
+        nd = eng.vertical_buoyancy(z_in, z_out, tv, self.time_step.total_seconds(), sea_floor=floor, sea_surface_height=ssh,
+                                   status=el.dev('status', torch.int32), moving=el.dev('moving', torch.int32),
+                                   seafloor_code=code, count=code != 0)
+        if nd:
+            if 'seafloor' not in self.status_categories:
+                self.status_categories.append('seafloor')
+            self._maybe_deactivated = True
+        return z_out
+
+    def vertical_buoyancy(self):
+        """oceandrift.py:352-367: z[z < 0] = min(0, z + terminal_velocity * dt), then the sea floor."""
+        self.elements.set_dev('z', self._buoyancy(self._z_for_sampling()))
 
     def vertical_advection(self):
         """oceandrift.py:315-350: z = min(0, z + moving*w*dt) below (or at) the surface."""
@@ -197,10 +242,27 @@ class OceanDrift(OpenDriftSimulation):
                       mld=self._env_scalar_or_tensor('ocean_mixed_layer_thickness', 50.0),
                       background=self.get_config('vertical_mixing:background_diffusivity'),
                       k_const=float(self.env.fallback('ocean_vertical_diffusivity') or 0.0))
-        return eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, moving=moving, terminal_velocity=tv,
-                                   ids=ids, rand=rand, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation,
-                                   sea_floor=floor, mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'),
-                                   pos_f32=pos_f32, **kw)
+        # 'Let particles stick to bottom' (oceandrift.py:559-564) only acts when a reader provides the sea floor
+        action, code, status = 0, 0, None
+        if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            cfg = self.get_config('general:seafloor_action')
+            if cfg == 'previous':
+                raise NotImplementedError("general:seafloor_action = 'previous' is not on the GPU path")
+            action = {'none': 0, 'lift_to_seafloor': 1, 'deactivate': 2}[cfg]
+            if action == 2:
+                cats = self.status_categories
+                code = cats.index('seafloor') if 'seafloor' in cats else len(cats)
+                status = el.dev('status', torch.int32)
+                moving = el.dev('moving', torch.int32)
+        z_out = eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, moving=moving, terminal_velocity=tv,
+                                    ids=ids, rand=rand, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation,
+                                    sea_floor=floor, mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'),
+                                    pos_f32=pos_f32, seafloor_action=action, status=status, seafloor_code=code, **kw)
+        if action == 2 and getattr(eng, 'last_mix_deactivated', 0):
+            if 'seafloor' not in self.status_categories:
+                self.status_categories.append('seafloor')
+            self._maybe_deactivated = True
+        return z_out
 
     def vertical_mixing(self, store_depths=False):
         """Helper for subclasses that override update(): uses the start-of-step positions saved by the run loop."""
@@ -211,17 +273,29 @@ class OceanDrift(OpenDriftSimulation):
 
     # -- fused path -----------------------------------------------------------------------------------------------
     def _fused_ok(self):
-        return (type(self).update is OceanDrift.update and type(self).advect_ocean_current is OceanDrift.advect_ocean_current
-                and type(self).vertical_mixing is OceanDrift.vertical_mixing and not self.get_config('drift:relative_wind'))
+        t = type(self)
+        return (t.update is OceanDrift.update and t.advect_ocean_current is OceanDrift.advect_ocean_current
+                and t.vertical_mixing is OceanDrift.vertical_mixing and t.vertical_buoyancy is OceanDrift.vertical_buoyancy
+                and t.update_terminal_velocity is OceanDrift.update_terminal_velocity
+                and not self.get_config('drift:relative_wind'))
 
     def run(self, *args, **kwargs):
         self._use_fused = None
+        # does any element that this run will release have a buoyancy?  (decides whether the fused step needs the extra launch)
+        self._tv_nonzero = False
+        if hasattr(self, 'elements_scheduled') and 'terminal_velocity' in self.ElementType.variables:
+            self._tv_nonzero = bool(np.any(np.atleast_1d(self.elements_scheduled.terminal_velocity) != 0))
         return super().run(*args, **kwargs)
 
     def _step_fused(self):
         eng, el, torch = self.engine, self.elements, self.engine.torch
         g = self._current_group(self.time)
         if g is None:
+            return False
+        if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            # A reader for the sea floor: elements below it are lifted at the top of the loop, AFTER the step's environment was
+            # sampled (basemodel/__init__.py:2238-2256) -- the first Runge-Kutta stage and w see the depth before the lift, the
+            # later stages the depth after it.  The helper recipe does exactly that with the materialised environment.
             return False
         t = self.time
         chain = ()
@@ -279,6 +353,10 @@ class OceanDrift(OpenDriftSimulation):
             # mixing first: it reads the start-of-step positions and depth and writes a new depth buffer; the
             # step kernel still samples with the old depth and applies vertical advection to the new one
             z_new = self._mix(el.dev('lon', torch.float64), el.dev('lat', torch.float64), z, el.positions_f32)
+        elif self._tv_nonzero:
+            # no mixing: the buoyancy move (oceandrift.py:201-205), after the moves of this step have read the start-of-step depth
+            # and before vertical advection, which the step kernel applies to this new buffer
+            z_new = self._buoyancy(z)
         elif stokes_inp is not None and wgrp is not None:
             # update() moves with the Stokes drift BEFORE vertical advection (oceandrift.py:196-205): the Stokes profile
             # must see the start-of-step depth, so vertical advection writes into a copy that replaces z afterwards

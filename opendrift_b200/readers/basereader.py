@@ -132,6 +132,9 @@ class StructuredReader:
     def bind(self, engine, fallback=None, n_slots=3):
         """Create the device field groups of this reader on `engine` (idempotent)."""
         if self._engine is engine:
+            if fallback is not None:          # already bound (an earlier query, another model): follow this run's fallbacks
+                for g in {id(g): g for g, _ in self._groups.values()}.values():
+                    g.set_fallback([fallback.get(nme) for nme in g.names])
             return
         self._engine = engine
         self._groups = {}

@@ -303,10 +303,76 @@ def gyre_cases():
             run_gyre_case('gyre_example_%s_%s' % (tag, dtag), 1, int(round(6 / dt)), dt, scheme, example=True)
 
 
+# ---- the BENCHMARKED configurations at 1e5 particles (BASELINE.json configs[1], [3], [4]) ---------------------------------------
+# The forcing is syn.* on the full 512 x 512 x 50 grid: it is regenerated by the tests from the same formulas, so the fixtures hold
+# only the configuration and the reference's final state (seeds: syn.particle_cloud(n, seed)).
+BIG_N = 100_000
+
+
+def big_fields(kind, n_slabs):
+    g = syn.GridSpec() if kind != 'cfg5' else syn.GridSpec(nz=1)
+    times = syn.slab_times(n_slabs)
+    secs = [(t - syn.T0).total_seconds() for t in times]
+    uv = [syn.double_gyre_uv(g, s, three_d=g.z is not None) for s in secs]
+    out = {'current': {CURRENT[0]: np.stack([a for a, _ in uv]), CURRENT[1]: np.stack([b for _, b in uv])}}
+    if kind in ('cfg2', 'cfg4'):
+        out['current']['upward_sea_water_velocity'] = np.stack([syn.upward_w(g)] * n_slabs)
+    if kind == 'cfg4':
+        out['current']['ocean_vertical_diffusivity'] = np.stack([syn.vertical_diffusivity(g, s) for s in secs])
+    if kind in ('cfg4', 'cfg5'):
+        w = [syn.wind_xy(g, s) for s in secs]
+        out['wind'] = {'x_wind': np.stack([a for a, _ in w]), 'y_wind': np.stack([b for _, b in w])}
+    if kind == 'cfg4':
+        st = [syn.stokes_xy(g, s) for s in secs]
+        out['waves'] = {'sea_surface_wave_stokes_drift_x_velocity': np.stack([a for a, _ in st]),
+                        'sea_surface_wave_stokes_drift_y_velocity': np.stack([b for _, b in st]),
+                        'sea_surface_wave_significant_height': np.stack([syn.wave_height(g, 0.0)] * n_slabs)}
+    return g, times, out
+
+
+BIG = {
+    # OceanDrift RK4 + vertical advection on the u/v/w reader (the bench's workload); starts half an hour in, so that the
+    # run crosses a reader time step (new slab pair) after three steps
+    'cfg2': dict(model='OceanDrift', steps=8, dt=600, start_offset_s=1800, seed=11,
+                 config={'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': True, 'drift:stokes_drift': False}),
+    # 'OpenOil3D' forcing set: 3-D current + w + K, wind, Stokes drift; vertical mixing + RK4
+    'cfg4': dict(model='OceanDrift', steps=4, dt=600, start_offset_s=2400, seed=12,
+                 config={'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': True, 'drift:vertical_mixing': True,
+                         'vertical_mixing:timestep': 60.0, 'drift:stokes_drift_profile': 'Phillips'}),
+    # Leeway, Euler, 2-D current + wind
+    'cfg5': dict(model='Leeway', steps=8, dt=600, start_offset_s=1800, seed=13, config={}, object_type=1),
+}
+
+
+def run_big_case(kind):
+    c = BIG[kind]
+    n_slabs = syn.n_slabs_for(c['steps'], c['dt']) + 1
+    g, times, fields = big_fields(kind, n_slabs)
+    lon, lat, z = syn.particle_cloud(BIG_N, seed=c['seed'], three_d=g.z is not None)
+    readers = [refrun.make_grid_reader(g.lon, g.lat, g.z if nm == 'current' else None, times, f, nm) for nm, f in fields.items()]
+    start = syn.T0 + timedelta(seconds=c['start_offset_s'])
+    kw = {'object_type': c['object_type']} if c['model'] == 'Leeway' else {}
+    o = refrun.run_oceandrift(readers, lon, lat, z if c['model'] != 'Leeway' else 0, start, c['dt'], c['steps'], config=c['config'],
+                              seed_kwargs=kw, model=c['model'], seed=0)
+    assert len(o.elements.lon) == BIG_N, 'reference deactivated particles in %s' % kind
+    out = dict(meta=json.dumps(dict(kind=kind, n=BIG_N, n_slabs=n_slabs, **{k: v for k, v in c.items()})),
+               lon=np.asarray(o.elements.lon, dtype=np.float64), lat=np.asarray(o.elements.lat, dtype=np.float64))
+    if c['model'] == 'Leeway':
+        out['orientation'] = np.asarray(o.elements.orientation).astype(np.int8)
+    else:
+        out['z'] = np.asarray(o.elements.z)
+    np.savez_compressed(os.path.join(OUT, 'ref_big_%s.npz' % kind), **out)
+    print('wrote ref_big_%s' % kind, 'max |dlon|', np.abs(out['lon'] - lon).max(), 'z dtype', out.get('z', np.zeros(0)).dtype)
+
+
 def main():
     import sys
     if 'gyre' in sys.argv[1:]:
         return gyre_cases()
+    if 'big' in sys.argv[1:]:
+        for kind in [a for a in sys.argv[1:] if a in BIG] or list(BIG):
+            run_big_case(kind)
+        return
     g3 = syn.GridSpec(nx=40, ny=36, nz=8, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03, dz=12.0)
     g2 = syn.GridSpec(nx=40, ny=36, nz=1, lon0=2.0, dlon=0.05, lat0=56.0, dlat=0.03)
     n = 1500

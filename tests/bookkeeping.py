@@ -344,6 +344,17 @@ def od_cases():
         # the wind uncertainty is added to the fallback wind (0) too, and the elements drift with it
         'wind_uncertainty_without_wind_reader': (full, ['cur'], {'drift:wind_uncertainty': 0.5, 'drift:vertical_advection': False}, {'z': 0.0}, 4, 600),
         # analytical diffusivity model + uncertainty: the mixing launch reads the environment, whose draws must not be made twice
+        # no vertical mixing: update() moves the depth with the terminal velocity instead (vertical_buoyancy, oceandrift.py:201-205,
+        # 352-367), before vertical advection; float32 / float64 combinations of z and terminal_velocity
+        'buoyancy_rising_scalar_tv': (full, ['cur', 'wind'], rk2, {'terminal_velocity': 0.003}, 5, 600),
+        'buoyancy_array_tv_scalar_z': (full, ['cur'], rk4, {'z': -5.0, 'terminal_velocity': np.linspace(-0.004, 0.004, n).astype(np.float32)}, 5, 600),
+        'buoyancy_array_tv_no_w': (full, ['cur', 'wind'], {'drift:vertical_advection': False},
+                                   {'terminal_velocity': np.linspace(-0.01, 0.01, n).astype(np.float32)}, 4, 600),
+        # a reader for the sea floor: interact_with_seafloor at the top of the loop and at the end of vertical_buoyancy
+        # (basemodel/__init__.py:748-783)
+        'seafloor_reader_lift': (full, ['cur', 'floor'], rk2, {'terminal_velocity': -0.01}, 5, 600),
+        'seafloor_reader_deactivate': (full, ['cur', 'floor'], {**rk2, 'general:seafloor_action': 'deactivate'}, {'terminal_velocity': -0.01}, 5, 600),
+        'seafloor_reader_with_mixing': (mix, ['cur_k', 'floor'], mixing, {'terminal_velocity': -0.002}, 4, 600),
         'mixing_constant_model_with_uncertainty': (mix, ['cur'], {**mixing, **rk4, 'vertical_mixing:diffusivitymodel': 'constant',
                                                                   'environment:fallback:ocean_vertical_diffusivity': 0.01,
                                                                   'drift:current_uncertainty': 0.1}, {}, 4, 600),
@@ -364,6 +375,9 @@ def od_readers(fx, which, make):
         out.append(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times[:2], {k: v[:2] for k, v in cur.items()}, 'cur'))
     if 'wind' in which:
         out.append(make(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'))
+    if 'floor' in which:        # a sloping sea floor, 8 m in the west to 60 m in the east, shallower than the deepest seeds
+        depth = np.broadcast_to(np.linspace(8, 60, len(fx.grid_lon), dtype=np.float32), (len(fx.times), len(fx.grid_lat), len(fx.grid_lon)))
+        out.append(make(fx.grid_lon, fx.grid_lat, None, fx.times, {'sea_floor_depth_below_sea_level': np.ascontiguousarray(depth)}, 'floor'))
     return out
 
 

@@ -129,6 +129,12 @@ class _HostLib:
             h_remaining._obj.value = int(np.isnan(a).sum())
         return 0
 
+    def od_group_set_fallback(self, ctx, gid, f0, f1):
+        g = self.groups[gid]
+        g.desc.fallback[0], g.desc.fallback[1] = f0, f1
+        g.hs.fallback[0], g.hs.fallback[1] = f0, f1
+        return 0
+
     def od_group_touch(self, ctx, gid, slot):
         self.groups[gid].version[slot] = self.groups[gid].version.get(slot, 0) + 1
         return 0
@@ -270,6 +276,14 @@ class _HostLib:
         self.calls.append('od_history_scatter')
         return self.shim.hs_history_scatter(args)
 
+    def od_bookkeeping(self, ctx, args):
+        self.calls.append('od_bookkeeping')
+        return self.shim.hs_bookkeeping(args)
+
+    def od_vertical_buoyancy(self, ctx, args):
+        self.calls.append('od_vertical_buoyancy')
+        return self.shim.hs_vertical_buoyancy(args)
+
     def od_last_error(self, ctx):
         return b'hostshim call failed'
 
@@ -298,6 +312,8 @@ class HostEngine:
     update_positions = Engine.update_positions
     minmax = Engine.minmax
     history_scatter = Engine.history_scatter
+    bookkeeping = Engine.bookkeeping
+    vertical_buoyancy = Engine.vertical_buoyancy
     # gridded readers: Engine's own group management and call wrappers
     add_group = Engine.add_group
     free_group = Engine.free_group

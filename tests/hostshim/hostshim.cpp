@@ -11,6 +11,7 @@
 #include "../../opendrift_b200/csrc/od_leeway.cuh"
 #include "../../opendrift_b200/csrc/od_analytic.cuh"
 #include "../../opendrift_b200/csrc/od_history.cuh"
+#include "../../opendrift_b200/csrc/od_bookkeep.cuh"
 
 using namespace od;
 
@@ -313,6 +314,35 @@ int hs_history_scatter(const od_history_args* a) {
     return 0;
 }
 
+int hs_vertical_buoyancy(const od_buoyancy_args* a) {
+    BuoyancyParams p;
+    p.n = a->n; p.z_in = a->d_z_in; p.z_out = a->d_z_out; p.tv = a->d_terminal_velocity; p.sea_floor = a->d_sea_floor;
+    p.status = a->d_status; p.moving = a->d_moving; p.counter = nullptr; p.dt = a->dt; p.ssh = a->sea_surface_height;
+    p.z_f64 = a->z_f64; p.tv_f64 = a->tv_f64; p.seafloor_code = a->seafloor_code;
+    int64_t c = 0;
+    for (int64_t i = 0; i < p.n; ++i) c += buoyancy_one(p, i) ? 1 : 0;
+    if (a->h_n_deactivated) *a->h_n_deactivated = c;
+    return 0;
+}
+
+int hs_bookkeeping(const od_bookkeep_args* a) {
+    BookkeepParams p;
+    p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status; p.moving = a->d_moving;
+    p.ids = a->d_ids; p.counters = nullptr; p.dt_age = a->dt_age; p.max_age = a->max_age;
+    p.west = a->west; p.east = a->east; p.south = a->south; p.north = a->north;
+    p.outside_code = a->outside_code; p.retired_code = a->retired_code; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
+    p.pos_f32 = a->pos_f32; p.only_deactivated = a->only_deactivated;
+    p.n_total = a->n_total; p.col = a->col; p.ncols = a->ncols;
+    p.blon = a->d_buf_lon; p.blat = a->d_buf_lat; p.bz = a->d_buf_z; p.bstatus = a->d_buf_status;
+    int64_t c[3] = {0, 0, 0};
+    for (int64_t i = 0; i < p.n; ++i) {
+        const int f = bookkeep_one(p, i);
+        c[0] += f & 1; c[1] += (f >> 1) & 1; c[2] += (f >> 2) & 1;
+    }
+    if (a->h_counts) for (int k = 0; k < 3; ++k) a->h_counts[k] = c[k];
+    return 0;
+}
+
 void hs_inverse_azimuth(int64_t n, const double* lon1, const double* lat1, const double* lon2, const double* lat2, double* az) {
     for (int64_t i = 0; i < n; ++i) az[i] = inverse_azimuth_short(lon1[i], lat1[i], lon2[i], lat2[i]);
 }
@@ -521,7 +551,11 @@ int hs2_mix(const od_mix_args* a, const hs_group* g, const hs_pair* pr) {
     p.dt_mix = a->dt_mix; p.zmin_const = -(double)(float)a->sea_floor_const; p.sea_floor = a->d_sea_floor;
     p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
     p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
+    p.seafloor_action = a->seafloor_action; p.seafloor_code = a->seafloor_code; p.status = a->d_status; p.moving_out = a->d_moving_out;
+    unsigned cnt = 0;
+    p.counter = &cnt;
     for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);
+    if (a->h_n_deactivated) *a->h_n_deactivated = cnt;
     return 0;
 }
 

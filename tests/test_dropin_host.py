@@ -58,6 +58,9 @@ test_leeway_missing_forcing_deactivates = T.test_leeway_missing_forcing_deactiva
 test_seeding_radius_and_deactivation = T.test_seeding_radius_and_deactivation
 test_reference_known_answers_with_constant_environment = T.test_reference_known_answers_with_constant_environment
 test_arithmetic_config_selects_the_kernel_policy = T.test_arithmetic_config_selects_the_kernel_policy
+test_fallback_follows_the_run_not_the_first_binding = T.test_fallback_follows_the_run_not_the_first_binding
+test_output_buffer_has_the_reference_time_axis_and_backfill = T.test_output_buffer_has_the_reference_time_axis_and_backfill
+test_status_set_by_a_subclass_through_the_host_view_is_honoured = T.test_status_set_by_a_subclass_through_the_host_view_is_honoured
 
 
 def test_dropin_model_replays_the_reference_dateline_test():

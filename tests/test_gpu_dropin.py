@@ -307,3 +307,98 @@ def test_device_rng_for_diffusion_is_order_independent():
     dy = (out[0][1] - lat.astype(np.float32)) * 111194.9                       # metres north (float32 seeding rounding is < 1 m)
     expected = np.sqrt(2 * D * dt * steps)
     assert abs(dy.std() / expected - 1.0) < 0.03 and abs(dy.mean()) < 0.02 * expected
+
+
+# ---- run-loop semantics that round 1's review found wrong -------------------------------------------------------
+def _small_model(n=60, **cfg):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx = Fixture('rk4_2d')
+    o = OceanDrift(loglevel=50, seed=0)
+    rd = reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, None, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v}, name='current')
+    o.add_reader(rd)
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:vertical_advection', False)
+    for k, v in cfg.items():
+        o.set_config(k, v)
+    return o, fx, rd
+
+
+def test_fallback_follows_the_run_not_the_first_binding():
+    """A reader queried before run() is bound without fallbacks; the run's environment:fallback:* must still reach the
+    kernels (od_group_set_fallback): an element outside the reader's domain stays where it is instead of becoming NaN."""
+    o, fx, rd = _small_model()
+    rd.get_variables_interpolated(list(common.CUR), time=fx.start, lon=fx.lon0[:3], lat=fx.lat0[:3], z=np.zeros(3))   # auto-bind
+    lon = np.append(fx.lon0[:5], fx.grid_lon[-1] + 3.0)          # the last element is outside the grid
+    lat = np.append(fx.lat0[:5], fx.lat0[0])
+    o.seed_elements(lon=lon, lat=lat, time=fx.start)
+    o.run(steps=3, time_step=600)
+    assert np.isfinite(o.elements.lon).all() and np.isfinite(o.elements.lat).all()
+    assert abs(o.elements.lon[-1] - np.float32(lon[-1])) < 1e-12 and abs(o.elements.lat[-1] - np.float32(lat[-1])) < 1e-12
+    # a second model with another fallback on the same bound reader
+    o2, _, _ = _small_model()
+    o2.env.readers.clear(), o2.env.priority_list.clear()
+    o2.add_reader(rd)
+    o2.set_config('environment:fallback:x_sea_water_velocity', 0.5)
+    o2.seed_elements(lon=lon, lat=lat, time=fx.start)
+    o2.run(steps=3, time_step=600)
+    assert o2.elements.lon[-1] - np.float32(lon[-1]) > 0.01      # drifted east with the fallback current
+
+
+def test_output_buffer_has_the_reference_time_axis_and_backfill():
+    """state_to_buffer (basemodel/__init__.py:2384-2403): a fixed axis of output times; elements deactivated on a sub-step between
+    output times are written, with their status, into the NEXT output column; the axis is cut at the time reached."""
+    o, fx, rd = _small_model(**{'drift:deactivate_east_of': 0.0})
+    n = 40
+    lon0, lat0 = fx.lon0[:n].astype(np.float64), fx.lat0[:n]
+    o.set_config('drift:deactivate_east_of', float(np.median(lon0)))     # half of the elements start outside -> leave at step 0
+    o.set_config('drift:max_age_seconds', 1500)
+    o.seed_elements(lon=lon0, lat=lat0, time=fx.start)
+    res = o.run(steps=6, time_step=600, time_step_output=1800)
+    east = np.float32(lon0) > np.float32(np.median(lon0))
+    # step 0 is an output step: everybody is written there, the eastern half already with status 'outside'
+    assert o.status_categories[:3] == ['active', 'outside', 'retired']
+    st0 = res['status'][0]
+    assert np.array_equal(st0 == 1, east) and np.array_equal(st0 == 0, ~east)
+    # the others retire on the third step (age 1800 >= 1500) and nothing is left: the loop stops at 00:20 and the axis is cut
+    # at the last output time reached (00:00); the retired elements were removed before any further state_to_buffer
+    assert o.steps_calculation == 2 and len(res['time']) == 1 and res['time'][0] == fx.start
+    assert res.lon.values.shape == (n, 1) and res.sizes == {'time': 1, 'trajectory': n}
+    assert o.num_elements_active() == 0 and o.num_elements_deactivated() == n
+    # without retirement: elements that cross the limit on a sub-step land in the next output column with status 'outside'
+    o, fx, rd = _small_model()
+    o.set_config('drift:deactivate_north_of', float(np.percentile(lat0, 60)) + 0.002)
+    o.seed_elements(lon=lon0, lat=lat0, time=fx.start)
+    res = o.run(steps=6, time_step=600, time_step_output=1800)
+    assert [t for t in res['time']] == [fx.start + timedelta(seconds=1800 * k) for k in range(3)]     # 00:00, 00:30, 01:00
+    status = res.status.values                                                      # [trajectory, time]
+    gone = np.asarray(o.elements_deactivated.ID, dtype=np.int64)
+    assert len(gone) > 0 and o.num_elements_active() + len(gone) == n
+    for i in gone:                # a deactivated element ends with status 'outside' in the last column it appears in
+        cols = np.where(status[i] >= 0)[0]
+        assert status[i, cols[-1]] == o.status_categories.index('outside') and (status[i, cols[:-1]] == 0).all()
+    alive = np.asarray(o.elements.ID, dtype=np.int64)
+    assert (status[alive] == 0).all() and np.isfinite(res.lon.values[alive]).all()
+
+
+def test_status_set_by_a_subclass_through_the_host_view_is_honoured():
+    """A subclass may deactivate by writing elements.status directly (the reference tests status != 0 every step)."""
+    from opendrift_b200.models.oceandrift import OceanDrift
+
+    class Picky(OceanDrift):
+        def update(self):
+            super().update()
+            if self.steps_calculation == 1:
+                st = self.elements.status
+                st[::2] = 5
+                self.elements.status = st
+
+    o, fx, rd = _small_model()
+    p = Picky(loglevel=50, seed=0)
+    p.add_reader(rd)
+    p.set_config('general:use_auto_landmask', False)
+    p.set_config('drift:vertical_advection', False)
+    p.seed_elements(lon=fx.lon0[:20], lat=fx.lat0[:20], time=fx.start)
+    p.run(steps=4, time_step=600)
+    assert p.num_elements_active() == 10 and p.num_elements_deactivated() == 10
+    assert np.array_equal(np.asarray(p.elements.ID), np.arange(1, 20, 2))

@@ -61,8 +61,8 @@ def test_device_history_equals_host_history(length):
         o.seed_elements(fx.seed_lon[half:], fx.seed_lat[half:], time=rd.initial_time + timedelta(seconds=1))
         o.run(steps=20, time_step=fx.dt, time_step_output=2 * fx.dt, export_buffer_length=length)
         hist[mode] = o.history
-        n_scatter = eng.lib.calls.count('od_history_scatter')
-        assert n_scatter == (0 if mode == 'host' else 11)
+        # one housekeeping launch per calculation step (outside + output column + age in one pass) and one for the final state
+        assert eng.lib.calls.count('od_bookkeeping') == 21 and eng.lib.calls.count('od_history_scatter') == 0
     h, d = hist['host'], hist['device']
     assert h['time'] == d['time'] and len(h['time']) == 11
     for k in ('lon', 'lat', 'z', 'status'):
