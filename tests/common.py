@@ -24,7 +24,7 @@ CUR = ['x_sea_water_velocity', 'y_sea_water_velocity']
 def fixtures():
     """OceanDrift fixtures."""
     return sorted(n for n in (os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, 'ref_*.npz')))
-                  if not n.startswith('leeway') and not n.startswith('gyre'))
+                  if not n.startswith('leeway') and not n.startswith('gyre') and not n.startswith('big_'))
 
 
 def leeway_fixtures():
