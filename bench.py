@@ -131,6 +131,112 @@ def cpu_port_rate(n, steps, seed=123):
     return n * steps / dt, dt, 1
 
 
+def port_reader(n_steps_ahead):
+    from oracle import advect_port as ap
+    grid = syn.GridSpec()
+    times = syn.slab_times(n_steps_ahead)
+    slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times[:PERIOD]]
+    w = syn.upward_w(grid)
+    fields = {CUR[0]: PeriodicSlabs(slabs, 0), CUR[1]: PeriodicSlabs(slabs, 1),
+              'upward_sea_water_velocity': PeriodicSlabs([(w,)] * PERIOD, 0)}
+    return ap.GridReader(grid.lon, grid.lat, grid.z, times, fields)
+
+
+def by_id(torch, state, ids_wanted):
+    """(lon, lat, z) NumPy arrays of the elements `ids_wanted` from a device state whose arrays are in cell-sorted order."""
+    ids = state['ids'].to(torch.int64)
+    inv = torch.empty_like(ids)
+    inv[ids] = torch.arange(ids.numel(), device=ids.device)
+    pos = inv[torch.as_tensor(ids_wanted, device=ids.device)]
+    return tuple(state[k][pos].cpu().numpy() for k in ('lon', 'lat', 'z'))
+
+
+def parity_of_timed_run(eng, torch, st, snap, par_steps, step, args):
+    """(a) the last `par_steps` TIMED steps: a subsample of the snapshot taken inside the timed region is advanced by the CPU
+    oracle (oracle/advect_port.py, bit-identical to the reference on the committed fixtures) and compared with the positions
+    the timed loop produced; (b) 1e5 particles through `--parity-extra` further steps of the same loop (untimed)."""
+    from oracle import advect_port as ap
+    n = st['ids'].numel()
+    rng = np.random.default_rng(2026)
+    out = {'tolerance_deg': 1e-6, 'test_bar_deg': 5e-8}
+    n_ahead = syn.n_slabs_for(st['k'] + args.parity_extra + 4, DT) + PERIOD
+    rd = port_reader(n_ahead)
+
+    def compare(ids, state0, t0, steps, state1, first):
+        l0, a0, z0 = by_id(torch, state0, ids)
+        c0 = time.perf_counter()
+        pl, pa, pz = ap.run_oceandrift([rd], l0, a0, z0, t0, DT, steps, scheme='runge-kutta4', vertical_adv=True, resume=not first)
+        secs = time.perf_counter() - c0
+        l1, a1, z1 = by_id(torch, state1, ids)
+        moved = float(max(np.abs(l1 - l0).max(), np.abs(a1 - a0).max()))
+        return {'particles': len(ids), 'steps': steps, 'max_err_deg': float(max(np.abs(l1 - pl).max(), np.abs(a1 - pa).max())),
+                'max_err_z_m': float(np.abs(z1.astype(np.float64) - pz.astype(np.float64)).max()), 'max_displacement_deg': moved,
+                'cpu_s': secs}
+    if snap is not None:
+        state0, t0, k0 = snap
+        ids = np.sort(rng.choice(n, size=min(n, args.parity_particles), replace=False))
+        out['timed_steps'] = compare(ids, state0, t0, par_steps, st, first=(k0 == 0))
+        out['timed_steps']['which'] = 'timed steps %d..%d of %d' % (args.steps - par_steps + 1, args.steps, args.steps)
+        del state0
+    if args.parity_extra > 0:
+        state0 = {k: st[k].clone() for k in ('lon', 'lat', 'z', 'ids')}
+        t0, k0 = st['t'], st['k']
+        for _ in range(args.parity_extra):
+            step()
+        ids = np.sort(rng.choice(n, size=min(n, 100000), replace=False))
+        out['continued_steps'] = compare(ids, state0, t0, args.parity_extra, st, first=(k0 == 0))
+        out['continued_steps']['which'] = '%d further steps of the same loop after the timed region' % args.parity_extra
+    legs = [out[k] for k in ('timed_steps', 'continued_steps') if k in out]
+    out['max_err_deg'] = max(l['max_err_deg'] for l in legs)
+    out['max_err_z_m'] = max(l['max_err_z_m'] for l in legs)
+    out['ok'] = bool(out['max_err_deg'] < 5e-8 and out['max_err_z_m'] <= 1e-5)
+    out['against'] = 'oracle/advect_port.py: NumPy/SciPy restatement of the reference path, bit-identical to the unmodified reference on the committed fixtures (incl. this geometry: tests/golden/ref_big_cfg2.npz)'
+    return out
+
+
+def cpu_reference_rate(n, steps, seed=123):
+    """The UNMODIFIED reference (oracle/_ref: a byte-for-byte copy of /root/reference/opendrift made by oracle/build_ref.py, or
+    /root/reference itself in the build container) on a bounded sample: OceanDrift.run() of the reference, its own readers base
+    class, interpolators and physics; only the third-party packages this image lacks are stubbed (plotting / IO as MagicMock, pyproj by
+    oracle/geod_karney.py).  Returns (rate, seconds, threads) or None when the reference package is not there."""
+    import tempfile
+    from oracle import refrun
+    if not refrun.available():
+        return None
+    refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as RefOceanDrift
+    grid = syn.GridSpec()
+    times = syn.slab_times(syn.n_slabs_for(steps, DT))
+    slabs = [syn.double_gyre_uv(grid, (t - syn.T0).total_seconds()) for t in times[:PERIOD]]
+    w = syn.upward_w(grid)
+    fields = {CUR[0]: PeriodicSlabs(slabs, 0), CUR[1]: PeriodicSlabs(slabs, 1),
+              'upward_sea_water_velocity': PeriodicSlabs([(w,)] * PERIOD, 0)}
+    reader = refrun.make_grid_reader(grid.lon, grid.lat, grid.z, times, fields)
+    lon, lat, z = syn.particle_cloud(n, seed=seed)
+    o = RefOceanDrift(loglevel=50, logfile=os.path.join(tempfile.gettempdir(), 'bench_reference.log'), seed=0)
+    o.add_reader(reader)
+    for k, v in {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': 0, 'general:coastline_action': 'none',
+                 'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': True, 'drift:stokes_drift': False}.items():
+        o.set_config(k, v)
+    o.seed_elements(lon=lon, lat=lat, z=z, time=syn.T0)
+    t0 = time.perf_counter()
+    o.run(steps=steps, time_step=DT, time_step_output=DT)
+    dt = time.perf_counter() - t0
+    assert o.steps_calculation == steps and len(o.elements.lon) == n
+    return n * steps / dt, dt, 1
+
+
+def cpu_rate(n, steps):
+    """(rate, seconds, threads, kind, description): the unmodified reference when its package is present, else the port."""
+    r = cpu_reference_rate(n, steps)
+    if r is not None:
+        return r + ('reference', 'OceanDrift.run() of the UNMODIFIED reference package (oracle/_ref, copied byte for byte from '
+                                 '/root/reference/opendrift by oracle/build_ref.py; plotting / IO packages stubbed, pyproj.Geod by '
+                                 'oracle/geod_karney.py); single process, single thread, as the reference runs')
+    return cpu_port_rate(n, steps) + ('port', 'oracle/advect_port.py = NumPy/SciPy restatement of the reference path, bit-identical to the '
+                                              'reference on the committed fixtures (the reference package oracle/_ref is not present)')
+
+
 def run_reference(args):
     """The reference arm: the reference's own CPU algorithm (single process, as the reference runs) with each
     step a bounded sample of the workload, sized so that K + W steps end within ~2 minutes."""
@@ -139,11 +245,11 @@ def run_reference(args):
         return
     n = args.ref_particles
     if n <= 0:
-        budget = 3.0e6                                   # particle-steps (about 90 s at ~3.5e4 particle-steps/s)
+        budget = 1.2e6                                   # particle-steps (about 90 s at the ~1.3e4 particle-steps/s of the unmodified reference)
         n = int(min(100_000, max(2_000, budget / max(1, args.steps + args.warmup))))
     if args.warmup:
-        cpu_port_rate(n, args.warmup)
-    rate, secs, thr = cpu_port_rate(n, args.steps)
+        cpu_rate(n, args.warmup)
+    rate, secs, thr, kind, what = cpu_rate(n, args.steps)
     ms = secs * 1e3 / args.steps
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'particle-steps/s', 'n_gpus': args.gpus,
@@ -151,10 +257,8 @@ def run_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'OceanDrift RK4 + vertical advection, synthetic 512x512x50 double-gyre u/v/w reader, dt=600 s (BASELINE configs[1]); '
                                'CPU arm: each step is a bounded sample of %d particles of that workload' % n},
-        'cpu_baseline': {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': 'port',
-                         'sample': '%d particles x %d steps; oracle/advect_port.py = NumPy/SciPy restatement of the reference '
-                                   'path, bit-identical to the reference on the committed fixtures; single process, single '
-                                   'thread, as the reference runs (/root/reference cannot travel to the GPU box)' % (n, args.steps)},
+        'cpu_baseline': {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': kind,
+                         'sample': '%d particles x %d steps; %s' % (n, args.steps, what)},
         'e2e': {'value': rate, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -214,6 +318,8 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    from opendrift_b200.engine import bind_process_to_gpu_numa
+    numa = bind_process_to_gpu_numa(local) if not os.environ.get('OD_BENCH_NONUMA') else {'bound': False, 'off': True}
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -224,48 +330,62 @@ def run_b200(args):
     n_times = syn.n_slabs_for(args.warmup + args.steps + 4, DT) + PERIOD
     times = syn.slab_times(n_times)
 
-    # forcing slabs: rank 0 builds them on the host; the other ranks receive them with an NCCL broadcast over
-    # NVLink (the once-per-reader-time-step exchange of the multi-GPU design: replicated field, sharded particles)
+    # Forcing: rank 0 "reads" the slabs (builds them on the host, keeps them pinned and resident); in a distributed run the other
+    # ranks hold NO copy of the data: every new reader time slab reaches their device ring by an NCCL broadcast over NVLink, issued by
+    # the field group itself (FieldGroup._load) on the copy stream one slab ahead of the run -- inside the timed loop.
+    if world > 1:
+        eng.enable_distributed(src=0)
     host_slabs, dev_slabs = [], []
-    t_bcast = 0.0
-    for ti in range(PERIOD):
-        if rank == 0:
+    if rank == 0:
+        for ti in range(PERIOD):
             u, v = syn.double_gyre_uv(grid, (times[ti] - syn.T0).total_seconds())
             hu, hv = torch.from_numpy(u).pin_memory(), torch.from_numpy(v).pin_memory()
-            du, dv = hu.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
-        else:
-            du = torch.empty((grid.nz, grid.ny, grid.nx), dtype=torch.float32, device=dev)
-            dv = torch.empty_like(du)
-        if world > 1:
-            torch.cuda.synchronize()
-            b0 = time.perf_counter()
-            dist.broadcast(du, 0)
-            dist.broadcast(dv, 0)
-            torch.cuda.synchronize()
-            t_bcast += time.perf_counter() - b0
-            if rank != 0:
-                hu, hv = du.cpu().pin_memory(), dv.cpu().pin_memory()
-        host_slabs.append((hu, hv))
-        dev_slabs.append((du, dv))
+            host_slabs.append((hu, hv))
+            dev_slabs.append((hu.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)))
     torch.cuda.synchronize()
     resident = {'on': True}
 
-    def supplier(ti, c):
+    def supplier(ti, c):          # only ever called on the rank that reads
         return dev_slabs[ti % PERIOD][c] if resident['on'] else host_slabs[ti % PERIOD][c]
 
     grp = eng.add_group(grid.lon, grid.lat, grid.z, 2, times, supplier, (0.0, 0.0), n_slots=3)
     if os.environ.get('OD_BENCH_NOFILL'):
         grp.fill_nan = 0
-    # upward_sea_water_velocity of the u/v/w reader (static in time; every rank builds it from the same formula)
-    h_w = torch.from_numpy(syn.upward_w(grid)).pin_memory()
-    d_w = h_w.to(dev)
+    if os.environ.get('OD_BENCH_NOPREFETCH'):
+        grp.prefetch_on = False
+    # upward_sea_water_velocity of the u/v/w reader (static in time)
+    h_w = torch.from_numpy(syn.upward_w(grid)).pin_memory() if rank == 0 else None
+    d_w = h_w.to(dev) if rank == 0 else None
     wgrp = eng.add_group(grid.lon, grid.lat, grid.z, 1, times, lambda ti, c: d_w if resident['on'] else h_w, (0.0,), n_slots=3)
+
+    # warm cost of the one collective of the design: a slab pair (u, v of one reader time) broadcast from rank 0
+    bcast = None
+    if world > 1:
+        sa = torch.zeros((grid.nz, grid.ny, grid.nx), dtype=torch.float32, device=dev)
+        sb = torch.zeros_like(sa)
+        for _ in range(3):
+            dist.broadcast(sa, 0)
+            dist.broadcast(sb, 0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(5):
+            dist.broadcast(sa, 0)
+            dist.broadcast(sb, 0)
+        b1.record()
+        torch.cuda.synchronize()
+        ms_pair = b0.elapsed_time(b1) / 5
+        bcast = {'ms_per_slab_pair_warm': ms_pair, 'bytes_per_slab_pair': 2 * sa.numel() * 4,
+                 'GBps': 2 * sa.numel() * 4 / ms_pair / 1e6}
+        del sa, sb
 
     lon0, lat0, z0 = syn.particle_cloud(n, seed=1000 + rank)
     h_lon = torch.from_numpy(lon0.astype(np.float64)).pin_memory()
     h_lat = torch.from_numpy(lat0.astype(np.float64)).pin_memory()
     h_z = torch.from_numpy(z0).pin_memory()
-    st = {'lon': h_lon.to(dev), 'lat': h_lat.to(dev), 'z': h_z.to(dev), 't': times[0], 'k': 0}
+    st = {'lon': h_lon.to(dev), 'lat': h_lat.to(dev), 'z': h_z.to(dev), 't': times[0], 'k': 0,
+          'ids': torch.arange(n, dtype=torch.int32, device=dev)}        # element identity travels with the cell sort, as in run()
     dt = timedelta(seconds=DT)
 
     def barrier():
@@ -276,7 +396,7 @@ def run_b200(args):
     def resort():
         # spatial ordering of the SoA particle arrays (locality of the field gathers); part of the step cost
         perm = eng.sort_by_cell(grp, st['lon'], st['lat'], st['z'])
-        for k in ('lon', 'lat', 'z'):
+        for k in ('lon', 'lat', 'z', 'ids'):
             st[k] = eng.permute(perm, st[k])
 
     step_events = []
@@ -314,15 +434,26 @@ def run_b200(args):
         step()
     barrier()
     l0 = eng.launches()
+    bc0 = eng.dist.slabs_broadcast if eng.dist is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     from datetime import datetime as _dt
     import gc
     gc.collect()
     gc.disable()                       # no collector pauses between launches of the timed steps
+    # parity of the TIMED run: the state of every particle at the start of the last `par_steps` timed steps is kept (three
+    # device-to-device copies; before the timed region when it covers all K steps) and a subsample is replayed by the CPU oracle
+    par_steps = min(args.steps, args.parity_steps)
+    snap_at = args.steps - par_steps
+
+    def snapshot():
+        return {k: st[k].clone() for k in ('lon', 'lat', 'z', 'ids')}, st['t'], st['k']
+    snap = snapshot() if snap_at == 0 and not args.no_parity else None
     wall0 = _dt.now()
     e0.record()
-    for _ in range(args.steps):
+    for j in range(args.steps):
+        if j == snap_at and j > 0 and not args.no_parity:
+            snap = snapshot()
         step(record=True)
     e1.record()
     barrier()
@@ -330,6 +461,7 @@ def run_b200(args):
     wall1 = _dt.now()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launches() - l0
+    slabs_bcast = (eng.dist.slabs_broadcast - bc0) if eng.dist is not None else 0
     loop_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))   # includes slab upload / pair packing
     clocks = sampler.stop(wall0, wall1) if sampler else None
     per_step = np.array([a.elapsed_time(b) for a, b in step_events])
@@ -369,10 +501,23 @@ def run_b200(args):
     tile_kernel_ms = kernel_alone(lambda tl, ta, tz: eng.advect_current(grp, 'runge-kutta4', t_now, dt, tl, ta, tz))
     eng.set_tile(False)
 
+    # ---- parity of what was timed (rank 0; the other ranks wait at the next barrier) ------------------------------------
+    parity = None
+    if not args.no_parity:
+        if rank == 0:
+            try:
+                parity = parity_of_timed_run(eng, torch, st, snap, par_steps, step, args)
+            except Exception as ex:
+                parity = {'error': repr(ex)[:300], 'ok': False}
+        else:               # the continued steps load new slabs (collectives): every rank takes them, rank 0 alone compares
+            for _ in range(args.parity_extra):
+                step()
+
     # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
-    grp.resident = [None] * grp.n_slots                     # forcing slabs come from pinned host memory again
-    wgrp.resident = [None] * wgrp.n_slots
+    torch.cuda.synchronize()
+    for g_ in (grp, wgrp):                                  # forcing slabs come from pinned host memory again
+        g_.resident, g_.ready = [None] * g_.n_slots, [None] * g_.n_slots
     o_lon, o_lat, o_z = torch.empty_like(h_lon).pin_memory(), torch.empty_like(h_lat).pin_memory(), torch.empty_like(h_z).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     t_e2e = times[0]
@@ -455,11 +600,26 @@ def run_b200(args):
             pass
     cpu = None
     if not args.no_cpu:
-        rate, secs, thr = cpu_port_rate(args.cpu_particles, args.cpu_steps)
-        cpu = {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': 'port',
-               'sample': '%d particles x %d steps (%.1f s) of the same workload through oracle/advect_port.py, the '
-                         'NumPy/SciPy restatement of the reference path (bit-identical to the reference on the '
-                         'committed fixtures; single process like the reference)' % (args.cpu_particles, args.cpu_steps, secs)}
+        rate, secs, thr, kind, what = cpu_rate(args.cpu_particles, args.cpu_steps)
+        cpu = {'value': rate, 'unit': 'particle-steps/s', 'cores': thr, 'kind': kind,
+               'sample': '%d particles x %d steps (%.1f s) of the same workload: %s' % (args.cpu_particles, args.cpu_steps, secs, what)}
+        if kind == 'reference':          # the port beside it, for continuity with round 1
+            prate, psecs, _ = cpu_port_rate(args.cpu_particles, 2)
+            cpu['port_value'] = prate
+    extra = {}
+    if world == 1 and not args.no_legs:
+        import bench_legs as bl
+        for key, fn in (('api', lambda: bl.leg_api(eng, torch, n, max(8, min(args.steps, 200)),
+                                                   {'current': {CUR[0]: [d[0] for d in dev_slabs], CUR[1]: [d[1] for d in dev_slabs],
+                                                                'upward_sea_water_velocity': [d_w] * PERIOD}}, grid, peak)),
+                        ('cfg4_mixing_wind_stokes', lambda: bl.leg_cfg4(eng, torch, args.cfg4_particles, 12, peak)),
+                        ('cfg5_leeway', lambda: bl.leg_cfg5(eng, torch, args.cfg5_particles, 30, peak))):
+            try:
+                torch.cuda.empty_cache()
+                extra[key] = fn()
+            except Exception as ex:          # never let a secondary leg touch the headline
+                import traceback
+                extra[key] = {'error': repr(ex)[:300], 'where': traceback.format_exc()[-400:]}
     gyre = None
     if world == 1 and not os.environ.get('OD_BENCH_NO_GYRE'):
         try:
@@ -475,10 +635,13 @@ def run_b200(args):
                    'particles_per_gpu': n, 'field': '512x512x50 f32 u,v (hourly slabs) + w', 'scheme': 'runge-kutta4',
                    'sort_every': args.sort_every, 'sort_ms': sort_ms, 'clock_ramp_s': args.ramp_seconds, 'mode': 'default arithmetic OD_MATH_SERIES: bit-exact field sampling (float64 index and weight arithmetic of the reference), '
                            'float64 short-arc series geodesic (round-off accurate, full Karney solution beyond its range)',
-                   'parallelism': 'particle-index shards x%d, replicated field (NCCL broadcast of slabs: %.1f ms per slab pair)'
-                                  % (world, 1e3 * t_bcast / PERIOD) if world > 1 else 'single GPU',
+                   'parallelism': ('particle-index shards x%d, forcing read by rank 0 only and broadcast (NCCL) into the other ranks\' device '
+                                   'ring on the copy stream, one slab ahead of the run: %d slab broadcasts INSIDE the timed region; warm cost '
+                                   '%.2f ms per 210 MB slab pair = %.0f GB/s' % (world, slabs_bcast, bcast['ms_per_slab_pair_warm'], bcast['GBps']))
+                                  if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
         'clocks': clocks,
+        'comm': {'slab_broadcasts_in_timed_region': slabs_bcast, 'broadcast': bcast, 'numa': numa} if world > 1 else {'numa': numa},
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 20,
                 'steps': e2e_steps, 'api': 'od_step_oceandrift_host through Engine.step_oceandrift_host (pinned host lon/lat/z in and out, %d-chunk '
                        'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
@@ -493,6 +656,10 @@ def run_b200(args):
                              'index and weight arithmetic, reproduced bit for bit), not by its 65 algorithmic bytes per '
                              'particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
+        'parity': parity,
+        'api': extra.get('api'),
+        'cfg4_mixing_wind_stokes': extra.get('cfg4_mixing_wind_stokes'),
+        'cfg5_leeway': extra.get('cfg5_leeway'),
         'configs0_double_gyre': gyre,
         'current_only': {'kernel_ms': uv_kernel_ms, 'particle_steps_per_s_kernel': n / (uv_kernel_ms * 1e-3),
                          'note': 'od_advect_current alone (u/v sampling and moves, no vertical advection), same particles'},
@@ -526,6 +693,13 @@ def main():
     ap.add_argument('--cpu-particles', type=int, default=50_000)
     ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--ref-particles', type=int, default=0, help='0 = sized from --steps')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--parity-steps', type=int, default=20, help='timed steps replayed by the CPU oracle (the last ones)')
+    ap.add_argument('--parity-particles', type=int, default=20000)
+    ap.add_argument('--parity-extra', type=int, default=5, help='further steps after the timed region, replayed for 1e5 particles')
+    ap.add_argument('--no-legs', action='store_true', help='skip the api / cfg 4 / cfg 5 legs')
+    ap.add_argument('--cfg4-particles', type=int, default=5_000_000)
+    ap.add_argument('--cfg5-particles', type=int, default=20_000_000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

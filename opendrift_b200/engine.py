@@ -121,6 +121,8 @@ class FieldGroup:
         self.fill_nan = 10                # passes of the linearNDFast NaN fill applied to every uploaded slab (0 = off)
         self.resident = [None] * n_slots  # time index held by each ring slot
         self.use = [0] * n_slots
+        self.ready = [None] * n_slots     # event of a slab that was put into its slot on the copy stream (prefetch), until first use
+        self.prefetch_on = True
         self._tick = 0
         d = GroupDesc()
         d.ncomp, d.nx, d.ny = ncomp, len(self.lon), len(self.lat)
@@ -155,22 +157,71 @@ class FieldGroup:
             pass
 
     # -- slab residency -------------------------------------------------------------------
+    def _victim(self, pinned):
+        cand = [s for s in range(self.n_slots) if self.resident[s] not in pinned or self.resident[s] is None]
+        if not cand:
+            return None
+        return min(cand, key=lambda k: (self.resident[k] is not None, self.use[k]))
+
+    def _load(self, ti, s):
+        """Bring the slab of time index ti into ring slot s on the engine's CURRENT stream: the rank that reads (every rank when
+        the run is not distributed) uploads it from the supplier and fills its NaN holes; in a distributed run the other ranks
+        receive it by a broadcast straight into their ring slot (NCCL over NVLink on the GPU box)."""
+        eng = self.engine
+        d = eng.dist
+        eng.order_after_copies()       # the NaN fill's scratch buffers are per context: never two loads in flight on two streams
+        if d is None or d.rank == d.src:
+            for c in range(self.ncomp):
+                eng.upload(self.gid, s, c, self.supplier(ti, c))
+                if self.fill_nan:
+                    eng.fill_nan(self.gid, s, c, self.fill_nan)
+        if d is not None:
+            for c in range(self.ncomp):
+                d.broadcast(eng.slot_tensor(self, s, c))
+            if d.rank != d.src:
+                eng.touch(self.gid, s)
+            d.slabs_broadcast += 1
+
     def slot_of(self, ti, pinned=()):
-        """Ring slot holding time index ti, uploading it if necessary (never evicting `pinned`)."""
+        """Ring slot holding time index ti, loading it if necessary (never evicting `pinned`)."""
         self._tick += 1
         if ti in self.resident:
             s = self.resident.index(ti)
             self.use[s] = self._tick
+            if self.ready[s] is not None:                 # prefetched on the copy stream: order the compute stream behind it
+                self.engine.wait_event(self.ready[s])
+                self.ready[s] = None
             return s
-        cand = [s for s in range(self.n_slots) if self.resident[s] not in pinned or self.resident[s] is None]
-        s = min(cand, key=lambda k: (self.resident[k] is not None, self.use[k]))
-        for c in range(self.ncomp):
-            self.engine.upload(self.gid, s, c, self.supplier(ti, c))
-            if self.fill_nan:
-                self.engine.fill_nan(self.gid, s, c, self.fill_nan)
+        s = self._victim(pinned)
+        assert s is not None, 'no free ring slot'
+        self._load(ti, s)
         self.resident[s] = ti
+        self.ready[s] = None
         self.use[s] = self._tick
         return s
+
+    def prefetch(self, ti, pinned=()):
+        """Start loading the slab of time index ti into a free ring slot on the engine's COPY stream, so that the upload (and,
+        in a distributed run, its broadcast) overlaps the steps that still use the current pair -- the double-buffered block
+        supplier of StructuredReader's before / after cache (readers/basereader/structured.py:243-318).  The copy stream
+        first waits for the work already queued on the compute stream (kernels that may still read the slot being replaced)."""
+        if not self.prefetch_on or ti < 0 or ti >= len(self.times) or ti in self.resident:
+            return False
+        s = self._victim(pinned)
+        if s is None or self.resident[s] in pinned:
+            return False
+        eng = self.engine
+        if not eng.begin_copy_stream():
+            return False
+        try:
+            self._load(ti, s)
+            self.ready[s] = eng.end_copy_stream()
+        except Exception:
+            eng.end_copy_stream()
+            raise
+        self.resident[s] = ti
+        self.use[s] = 0                                   # least recently used until somebody asks for it
+        return True
 
     def sample(self, t, pinned=()):
         """od_time_sample for time t (uploads slabs as needed)."""
@@ -188,7 +239,58 @@ class FieldGroup:
         sa = self.slot_of(ib, tuple(pinned) + (ia,))
         sb = self.slot_of(ia, tuple(pinned) + (ib,))
         ts.slot_a, ts.slot_b, ts.mode, ts.w = sa, sb, OD_T_LERP, w
+        if self.n_slots > 2 and len(self.times) > 2:
+            # the slab the run needs next: after the pair in a forward run, before it in a backward run
+            nxt = ia + 1 if self.engine.direction >= 0 else ib - 1
+            self.prefetch(nxt, tuple(pinned) + (ib, ia))
         return ts, (ib, ia)
+
+
+def bind_process_to_gpu_numa(device_index):
+    """Pin this process (and, by first touch, the pinned host buffers it allocates afterwards) to the CPUs of the NUMA node the
+    GPU hangs off: one process per GPU, host staging memory on the GPU's own socket -- otherwise half of the ranks of an 8-GPU
+    box push their PCIe traffic through the inter-socket link.  Returns a dict describing what was done (never raises)."""
+    import os
+    import subprocess
+    info = {'device': int(device_index), 'bound': False}
+    try:
+        bus = subprocess.run(['nvidia-smi', '-i', str(device_index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return info
+        if len(bus.split(':')[0]) == 8:          # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        node_path = '/sys/bus/pci/devices/%s/numa_node' % bus
+        node = int(open(node_path).read().strip())
+        info['pci_bus_id'], info['numa_node'] = bus, node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info['bound'], info['cpus'] = True, len(cpus)
+    except Exception as ex:
+        info['error'] = repr(ex)[:120]
+    return info
+
+
+class DistContext:
+    """The torch.distributed job of a sharded run: particle-index shards, replicated forcing."""
+
+    def __init__(self, dist, rank, world, src=0, group=None):
+        self.dist, self.rank, self.world, self.src, self.group = dist, rank, world, src, group
+        self.slabs_broadcast = 0
+
+    def broadcast(self, tensor):
+        self.dist.broadcast(tensor, self.src, group=self.group)
+
+    def shard(self, n_total):
+        from .sharding import shard_range
+        return shard_range(n_total, self.rank, self.world)
 
 
 _default = {}
@@ -223,6 +325,58 @@ class Engine:
         # arithmetic of the step kernels when a call does not say (include/odcuda.h OD_MATH_*): bit-exact sampling +
         # short-arc series geodesic; MATH_EXACT replays the reference operation by operation, MATH_FAST is float32
         self.math_mode = _lib.OD_MATH_SERIES
+        self.dist = None               # DistContext of a distributed run (one process per GPU), else None
+        self.direction = 1             # +1 forward run, -1 backward run (which slab to prefetch)
+        self._main_stream = torch.cuda.current_stream(self.device)
+        self._copy_stream = None
+        self._in_copy = False
+
+    # -- streams: compute stream + one copy stream for slab prefetch ----------------------------------------------------
+    def wait_event(self, ev):
+        self.torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def order_after_copies(self):
+        """Make the current stream wait for whatever the copy stream still has queued (no-op while on the copy stream)."""
+        ev = getattr(self, '_last_copy_event', None)
+        if ev is not None and not self._in_copy:
+            self.wait_event(ev)
+            self._last_copy_event = None
+
+    def begin_copy_stream(self):
+        """Route the library's launches and copies (and torch's, e.g. a broadcast) to the copy stream; False when nested."""
+        if self._in_copy:
+            return False
+        torch = self.torch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._main_stream = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(self._main_stream)       # slots being replaced may still be read by queued kernels
+        self._ctx_mgr = torch.cuda.stream(self._copy_stream)
+        self._ctx_mgr.__enter__()
+        self.use_stream(self._copy_stream)
+        self._in_copy = True
+        return True
+
+    def end_copy_stream(self):
+        """Back to the compute stream; returns an event that marks the end of what was queued on the copy stream."""
+        ev = self.torch.cuda.Event()
+        ev.record(self._copy_stream)
+        self._ctx_mgr.__exit__(None, None, None)
+        self.use_stream(self._main_stream)
+        self._in_copy = False
+        self._last_copy_event = ev
+        return ev
+
+    def enable_distributed(self, src=0, group=None):
+        """Join the torch.distributed job this process belongs to (torchrun: one process per GPU): forcing slabs are read by
+        rank `src` and broadcast into the other ranks' ring slots.  A no-op for a single process."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self.dist = DistContext(dist, dist.get_rank(group), dist.get_world_size(group), src, group)
+        return self.dist
+
+    def touch(self, gid, slot):
+        self._check(self.lib.od_group_touch(self.ctx, gid, slot))
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -444,7 +598,7 @@ class Engine:
         self._check(self.lib.od_history_scatter(self.ctx, C.byref(a)))
 
     def bookkeeping(self, lon, lat, z, age, status, moving, ids, dt_age, max_age=None, domain=None, outside_code=0,
-                    retired_code=0, pos_f32=False, buf=None, only_deactivated=False, counts=True):
+                    retired_code=0, pos_f32=False, buf=None, only_deactivated=False, counts=True, id_base=0):
         """deactivate_outside + state_to_buffer + increase_age_and_retire in one pass (od_bookkeeping).  buf: the four
         [n_total] float32 / float32 / float32 / int32 device tensors of the output column to fill (or None).
         Returns (newly outside, newly retired, elements with status != 0) when counts (synchronises), else None."""
@@ -465,8 +619,9 @@ class Engine:
         if buf is not None:
             assert ids.dtype == torch.int32 and z.dtype in (torch.float32, torch.float64)
             a.d_ids, a.d_z, a.z_f64 = ids.data_ptr(), z.data_ptr(), 1 if z.dtype == torch.float64 else 0
-            a.n_total, a.col, a.ncols = buf[0].numel(), 0, 1
-            a.d_buf_lon, a.d_buf_lat, a.d_buf_z, a.d_buf_status = (b.data_ptr() for b in buf)
+            # rows are addressed by element ID; a shard of a distributed run holds the IDs id_base .. id_base + rows - 1
+            a.n_total, a.col, a.ncols = buf[0].numel() + int(id_base), 0, 1
+            a.d_buf_lon, a.d_buf_lat, a.d_buf_z, a.d_buf_status = (b.data_ptr() - 4 * int(id_base) for b in buf)
         c = (C.c_int64 * 3)()
         if counts:
             a.h_counts = c

@@ -207,6 +207,12 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                             'description': 'Where the output buffer of state_to_buffer lives between flushes: device = a block of output '
                                            'columns in HBM, filled by the per-step bookkeeping launch and read back once per '
                                            'export_buffer_length output steps; host = a block of one column (read back every output step).'},
+            'gpu:distributed': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
+                                'description': 'Under torchrun (torch.distributed initialised, one process per GPU): rank 0 reads the forcing '
+                                               'slabs and broadcasts them into the other ranks\' device ring; ranks step in lockstep.'},
+            'gpu:shard': {'type': 'enum', 'enum': ['index', 'none'], 'default': 'index', 'level': CONFIG_LEVEL_ADVANCED,
+                          'description': 'Distributed runs: index = every rank seeded all elements (same script) and keeps a contiguous '
+                                         'index range of them; none = the script seeded only this rank\'s elements.'},
             'gpu:history_block_bytes': {'type': 'int', 'default': 2 ** 31, 'min': 1, 'max': 2 ** 40, 'units': 'bytes',
                                         'level': CONFIG_LEVEL_ADVANCED,
                                         'description': 'Upper bound of the device block of output columns (16 bytes per element and column).'},
@@ -351,7 +357,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         first_release = len(self.elements) == 0
         ids = np.asarray(self.elements_scheduled.ID)[idx].astype(np.int64)
-        self._release_rank[ids] = np.arange(self._released, self._released + len(ids))     # the reference's array order
+        self._release_rank[ids - self._id_base] = np.arange(self._released, self._released + len(ids))     # the reference's array order
         self._released += len(ids)
         self.elements.append_host(self.elements_scheduled, idx)
         keep = self.ElementType()
@@ -433,7 +439,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         res = eng.bookkeeping(el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), agev,
                               el.dev('status', torch.int32), el.dev('moving', torch.int32), el.dev('ID', torch.int32),
                               self.time_step.total_seconds() if age else 0.0, max_age, domain, oc, rc,
-                              pos_f32=el.positions_f32, buf=buf, only_deactivated=only_deactivated, counts=counts)
+                              pos_f32=el.positions_f32, buf=buf, only_deactivated=only_deactivated, counts=counts,
+                              id_base=self._id_base)
         if res is None:
             return
         n_out, n_ret, n_off = res
@@ -624,7 +631,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         gen = torch.Generator(device=eng.device)
         gen.manual_seed((int(self._seed) * 1000003 + int(self.steps_calculation)) * 16 + int(salt))
         ids = self.elements.dev('ID').to(torch.int64)
-        base = torch.randn((k, int(self._n_total)), dtype=torch.float64, device=eng.device, generator=gen)
+        # (one value per element ID of the whole job, so that the draws do not depend on how the elements are sharded)
+        n_ids = int(self.shard[2]) if getattr(self, 'shard', None) else int(self._id_base + self._n_total)
+        base = torch.randn((k, n_ids), dtype=torch.float64, device=eng.device, generator=gen)
         return [base[j][ids] for j in range(k)]
 
     def horizontal_diffusion(self):
@@ -744,21 +753,44 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             # 'Flipping ID array, so that lowest IDs are released first' (:2056-2062): in a backward run the element that
             # was scheduled last becomes ID 0 (IDs label the trajectories of the result)
             self.elements_scheduled.ID = np.flipud(np.asarray(self.elements_scheduled.ID))
-        self._release_rank = np.full(int(self.num_elements_total()), -1, dtype=np.int64)
+        # A distributed run (torchrun, one process per GPU): every rank ran the same script and scheduled the same elements; each
+        # keeps a contiguous index range of them (particle-index shards, replicated forcing).  Element IDs stay
+        # global.  gpu:shard = none: the script seeded only this rank's elements itself.
+        eng = self.engine
+        eng.direction = -1 if self.time_step.days < 0 else 1
+        if getattr(eng, 'dist', None) is None and self.get_config('gpu:distributed') and hasattr(eng, 'enable_distributed'):
+            eng.enable_distributed()
+        self._dist = getattr(eng, 'dist', None)
+        self.shard = None
+        if self._dist is not None and self.get_config('gpu:shard') == 'index':
+            n_all = int(self.num_elements_total())
+            lo, hi = self._dist.shard(n_all)
+            drop = np.ones(n_all, dtype=bool)
+            drop[lo:hi] = False
+            self.elements_scheduled.move_elements(self.ElementType(), drop)
+            self.elements_scheduled_time = self.elements_scheduled_time[~drop]
+            self.shard = (lo, hi, n_all)
+        ids_all = np.atleast_1d(np.asarray(self.elements_scheduled.ID))
+        self._id_base = int(ids_all.min()) if len(ids_all) else 0         # rows of the output block / rank table: ID - _id_base
+        self._release_rank = np.full(int(ids_all.max()) - self._id_base + 1 if len(ids_all) else 0, -1, dtype=np.int64)
         self._released = 0
         self.steps_calculation = 0
         self._maybe_deactivated = False
         out_every = int(round(ratio))
-        n_total = self.num_elements_total()
+        n_total = len(self._release_rank)
         self._n_total = n_total
         self._out_every = out_every
         self._init_history(export_buffer_length)
         self.prepare_run()
 
         i = 0
+        dist_run = self._dist is not None
         for i in range(self.expected_steps_calculation):
             self.release_elements()
-            if self.num_elements_active() == 0 and self.num_elements_scheduled() > 0:
+            if dist_run:
+                # the slab collectives of this step, on every rank alike (also one that holds no elements right now)
+                self.env.touch_slabs(self._stage_times(self.time))
+            if self.num_elements_active() == 0 and (self.num_elements_scheduled() > 0 or dist_run):
                 self.steps_calculation += 1                # (state_to_buffer with no elements: the column keeps its fill values)
                 self.time = self.time + self.time_step
                 continue
@@ -777,7 +809,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             if self.num_elements_active() > 0:
                 self._maybe_sort()
                 self.update_and_diffuse()
-            elif self.num_elements_scheduled() == 0:
+            elif self.num_elements_scheduled() == 0 and not dist_run:
                 break                                      # 'No more active or scheduled elements' (:2276-2278): time is not advanced
             self.time = self.time + self.time_step
             self.steps_calculation += 1
@@ -808,7 +840,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         torch = self.engine.torch
         ids = self.elements.dev('ID').to(torch.int64)
-        key = self.engine.to_device(self._release_rank)[ids]
+        key = self.engine.to_device(self._release_rank)[ids - self._id_base]
         perm = torch.argsort(key, stable=True).to(torch.int32)
         self.elements.permute(perm)
         self._sorted = False

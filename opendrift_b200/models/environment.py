@@ -54,6 +54,24 @@ class Environment:
                 r.bind(engine, fallback={v: self.fallback(v) for v in r.variables})
         self.__finalized__ = True
 
+    def touch_slabs(self, times):
+        """Make every bound reader's slabs for the given times resident -- in a fixed order (readers as added, groups as bound,
+        times as given).  In a distributed run this is where the slab collectives happen: every rank calls it at every step,
+        whether it holds elements or not, so the ranks stay in lockstep; the step launches then find the slabs in place."""
+        for r in self.readers.values():
+            if not hasattr(r, '_groups'):
+                continue
+            seen = []
+            for g, _ in r._groups.values():
+                if any(g is x for x in seen):
+                    continue
+                seen.append(g)
+                held = ()
+                for t in times:
+                    if r.covers_time(t):
+                        _, q = g.sample(t, held)
+                        held += q
+
     def constant(self, var):
         item = self._config._config.get('environment:constant:%s' % var)
         return None if item is None else item['value']

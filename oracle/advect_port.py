@@ -475,7 +475,7 @@ def horizontal_diffusion(lon, lat, D, moving, dt, rng=np.random):
 def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-kutta4',
                    vertical_adv=False, wind=False, wind_drift_depth=0.1, wdf=0.02, cdf=1.0,
                    diffusivity=0.0, seed=0, truncate_below=None, mixing=False, dt_mix=60.0, stokes=None, noise=None,
-                   w_at_surface=False, diffusivity_model=None, mld=50.0, background_diffusivity=1.2e-5):
+                   w_at_surface=False, diffusivity_model=None, mld=50.0, background_diffusivity=1.2e-5, resume=False):
     """OpenDriftSimulation.run main loop (opendrift/models/basemodel/__init__.py:2193-2304) +
     OceanDrift.update (opendrift/models/oceandrift.py:185-211), restricted to the hot path:
     no stranding, no deactivation (the synthetic box has no normal flow), Stokes off."""
@@ -486,9 +486,13 @@ def run_oceandrift(readers, lon, lat, z, start_time, dt, steps, scheme='runge-ku
     np.random.seed(seed)                       # basemodel/__init__.py:326
     n = len(lon)
     # seeding casts to the declared element dtypes (opendrift/elements/elements.py:156-158)
-    lon = np.asarray(lon, dtype=np.float32)
-    lat = np.asarray(lat, dtype=np.float32)
-    z = np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
+    if resume:          # continue a run from a state after its first update: float64 positions (bench.py's parity legs)
+        lon, lat = np.asarray(lon, dtype=np.float64), np.asarray(lat, dtype=np.float64)
+        z = np.asarray(z)
+    else:
+        lon = np.asarray(lon, dtype=np.float32)
+        lat = np.asarray(lat, dtype=np.float32)
+        z = np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
     # Scalar element properties (defaults, or scalars given to seed_elements) become *float64*
     # arrays when the scheduled elements are released: LagrangianArray.move_elements does
     # ``self_var*np.ones(self_len)`` (opendrift/elements/elements.py:213-216).  Arrays given to

@@ -23,6 +23,9 @@ from datetime import datetime, timedelta
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get('OPENDRIFT_REFERENCE', '/root/reference')
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, 'opendrift')):
+    # the GPU box: the byte-for-byte copy that oracle/build_ref.py made in the build container (oracle/_ref, git-ignored)
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
 
 _MOCKED = [
     'xarray', 'netCDF4', 'matplotlib', 'matplotlib.pyplot', 'matplotlib.animation',

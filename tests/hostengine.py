@@ -297,6 +297,29 @@ class HostEngine:
         self.ctx = 1               # truthy: Engine.free_group checks it
         self.math_mode = _lib.OD_MATH_SERIES
         self.groups = weakref.WeakValueDictionary()
+        self.dist = None
+        self.direction = 1
+
+    # no streams on the host: no prefetch
+    def begin_copy_stream(self):
+        return False
+
+    def order_after_copies(self):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    enable_distributed = Engine.enable_distributed
+    touch = Engine.touch
+
+    def slot_tensor(self, group, slot, comp):
+        """The host slab of a ring slot as a torch tensor that shares its memory (target of a gloo broadcast)."""
+        g = self.lib.groups[group.gid]
+        d = g.desc
+        if (slot, comp) not in g.slabs:
+            g.slabs[(slot, comp)] = np.zeros((d.nz, d.ny, d.nx), dtype=np.float32)
+        return self.torch.from_numpy(g.slabs[(slot, comp)].reshape(-1))
 
     def sync(self):
         pass

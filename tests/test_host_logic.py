@@ -142,14 +142,33 @@ class _FakeLib:
 class _FakeEngine:
     """Records what FieldGroup asks of the engine; no CUDA involved."""
 
-    def __init__(self):
+    def __init__(self, copy_stream=False):
         self.lib, self.ctx, self.uploads, self.fills = _FakeLib(), None, [], []
+        self.dist, self.direction, self.has_copy, self.in_copy, self.on_copy, self.waited = None, 1, copy_stream, False, [], []
 
     def _check(self, rc):
         assert rc == 0
 
+    def order_after_copies(self):
+        pass
+
+    def begin_copy_stream(self):
+        if not self.has_copy:
+            return False
+        self.in_copy = True
+        return True
+
+    def end_copy_stream(self):
+        self.in_copy = False
+        return 'event%d' % len(self.on_copy)
+
+    def wait_event(self, ev):
+        self.waited.append(ev)
+
     def upload(self, gid, slot, comp, data):
         self.uploads.append((slot, comp, int(data[0, 0])))
+        if self.in_copy:
+            self.on_copy.append((slot, comp, int(data[0, 0])))
 
     def fill_nan(self, gid, slot, comp, passes):
         self.fills.append((slot, comp, passes))
@@ -185,6 +204,39 @@ def test_field_group_ring_residency():
     assert len(eng.fills) == nf                                                    # fill switched off
     tsm, usedm = g.sample(times[-1] + timedelta(hours=1))
     assert tsm.mode == _lib.OD_T_MISSING and usedm == ()
+
+
+def test_field_group_prefetches_the_next_slab_on_the_copy_stream():
+    """With a copy stream the slab after the current pair is loaded ahead of time into the free ring slot (backward runs: the
+    slab before it); when the run reaches it nothing is uploaded any more, the compute stream just waits for the copy's event."""
+    from opendrift_b200.engine import FieldGroup
+    eng = _FakeEngine(copy_stream=True)
+    times = [T0 + timedelta(hours=i) for i in range(6)]
+    g = FieldGroup(eng, 0, np.arange(4, dtype=np.float32), np.arange(3, dtype=np.float32), None, 1, times,
+                   lambda ti, c: np.full((3, 4), ti, np.float32), (0.0,), n_slots=3)
+    ts, _ = g.sample(T0 + timedelta(minutes=10))
+    assert [u[2] for u in eng.uploads] == [0, 1, 2] and [u[2] for u in eng.on_copy] == [2]      # pair on the compute stream, slab 2 ahead
+    assert eng.waited == []
+    g.sample(T0 + timedelta(minutes=50))
+    assert len(eng.uploads) == 3                                                                 # nothing new inside the bracket
+    ts2, _ = g.sample(T0 + timedelta(minutes=70))                                                # next bracket: slab 2 is already there
+    assert [u[2] for u in eng.uploads] == [0, 1, 2, 3] and [u[2] for u in eng.on_copy] == [2, 3]
+    assert eng.waited == ['event1'] and ts2.slot_a == ts.slot_b
+    # a step that straddles two brackets pins three slabs: no slot is free, nothing is prefetched, nothing is lost
+    g.sample(T0 + timedelta(minutes=110))
+    n = len(eng.uploads)
+    g.sample(T0 + timedelta(minutes=130), pinned=(1, 2))
+    assert len(eng.uploads) == n and g.resident.count(None) == 0
+    # backward
+    eng2 = _FakeEngine(copy_stream=True)
+    eng2.direction = -1
+    g2 = FieldGroup(eng2, 0, np.arange(4, dtype=np.float32), np.arange(3, dtype=np.float32), None, 1, times,
+                    lambda ti, c: np.full((3, 4), ti, np.float32), (0.0,), n_slots=3)
+    g2.sample(T0 + timedelta(minutes=250))
+    assert [u[2] for u in eng2.on_copy] == [3]
+    g2.prefetch_on = False
+    g2.sample(T0 + timedelta(minutes=190))
+    assert [u[2] for u in eng2.on_copy] == [3] and len(eng2.uploads) == 3
 
 
 def test_config_keys_match_the_reference_model_classes():

@@ -230,3 +230,75 @@ def test_strip_columns_cover_their_strips():
         assert i0 <= max(0, inside[0] - 3) and i1 >= min(40, inside[-1] + 4)
     assert cols[0][0] == 0 and cols[-1][1] == 40
     assert sharding.scatter_field_tiles(torch.arange(12.0).reshape(3, 4), [(1, 3)]).tolist() == [[1.0, 2.0], [5.0, 6.0], [9.0, 10.0]]
+
+
+# ---- OceanDrift.run() under a torch.distributed job: index shards, slabs read by rank 0 and broadcast into the ring -------------
+def _run_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, common.ROOT)
+    sys.path.insert(0, os.path.join(common.ROOT, 'tests'))
+    from hostengine import HostEngine
+    import test_gpu_dropin as T
+    import opendrift_b200.engine as E
+    import opendrift_b200.models.basemodel as B
+    eng = HostEngine()
+    E.default_engine = B.default_engine = lambda device=None: eng
+    fx = common.Fixture('rk4_3d_full')
+    fx.meta['diffusivity'] = 0.0            # (the legacy generator's draws are per process: parity mode is single-process)
+    reads = {'n': 0}
+    o = T._model(fx, **{'drift:max_age_seconds': 4000})
+    if rank != 0:                            # only rank 0 may touch the data: the other ranks' suppliers must never be called
+        for r in o.env.readers.values():
+            orig = r.get_variables
+
+            def guarded(requested_variables, time=None, x=None, y=None, z=None, orig=orig, r=r):
+                if time != r.times[0]:      # (the geometry probe at bind() reads the first block)
+                    reads['n'] += 1
+                return orig(requested_variables, time=time, x=x, y=y, z=z)
+            r.get_variables = guarded
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=2 * fx.dt)
+    lo, hi, n_all = o.shard
+    ids = np.concatenate([np.asarray(o.elements.ID, dtype=np.int64), np.asarray(o.elements_deactivated.ID, dtype=np.int64)])
+    lon = np.concatenate([np.asarray(o.elements.lon), np.asarray(o.elements_deactivated.lon)])
+    lat = np.concatenate([np.asarray(o.elements.lat), np.asarray(o.elements_deactivated.lat)])
+    full_lon = sharding.gather_by_id(ids, lon, n_all)
+    full_lat = sharding.gather_by_id(ids, lat, n_all)
+    hist_rows = o.history.lon.values.shape
+    q.put((rank, (lo, hi, n_all), full_lon, full_lat, reads['n'], eng.dist.slabs_broadcast, hist_rows, sorted(ids.tolist()) == list(range(lo, hi))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_model_run_shards_elements_and_broadcasts_slabs():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    # the unsharded run of the same model in this process
+    from hostengine import HostEngine
+    import test_gpu_dropin as T
+    fx = common.Fixture('rk4_3d_full')
+    fx.meta['diffusivity'] = 0.0
+    o = T._model(fx, **{'drift:max_age_seconds': 4000})
+    o._engine = HostEngine()
+    o.run(steps=fx.steps, time_step=fx.dt, time_step_output=2 * fx.dt)
+    ids = np.concatenate([np.asarray(o.elements.ID, dtype=np.int64), np.asarray(o.elements_deactivated.ID, dtype=np.int64)])
+    ref_lon, ref_lat = np.zeros(fx.n), np.zeros(fx.n)
+    ref_lon[ids] = np.concatenate([np.asarray(o.elements.lon), np.asarray(o.elements_deactivated.lon)])
+    ref_lat[ids] = np.concatenate([np.asarray(o.elements.lat), np.asarray(o.elements_deactivated.lat)])
+    n_cols = len(o.history['time'])
+    for rank, (lo, hi, n_all), lon, lat, foreign_reads, n_bcast, hist_shape, ids_ok in res:
+        assert n_all == fx.n and (lo, hi) == sharding.shard_range(fx.n, rank, 2) and ids_ok
+        assert np.array_equal(lon, ref_lon) and np.array_equal(lat, ref_lat)          # bit-identical to the unsharded run
+        # every rank buffers its own trajectories only; a distributed run keeps stepping (idle) to the requested end so that the
+        # ranks stay in lockstep, where the single process stops when its last element has retired
+        assert hist_shape[0] == hi - lo and hist_shape[1] >= n_cols
+        assert n_bcast > 0
+        if rank != 0:
+            assert foreign_reads == 0                                                  # forcing arrived by broadcast only
