@@ -317,8 +317,18 @@ typedef struct od_stokes_args {
     double dt;
     int32_t z_f64;
     int32_t hs_mode;              /* 0: Hs from d_hs; 1: 0.0246 |wind|^2; 2: Hs = 1 (no Hs and no wind anywhere) */
-    int32_t profile;              /* 0 monochromatic, 1 exponential, 2 Phillips */
+    int32_t profile;              /* 0 monochromatic, 1 exponential, 2 Phillips, 3 windsea_swell (models/physics_methods.py:418-455) */
     int32_t pad_;
+    double factor;                /* stokes_drift(factor): the velocities are multiplied by it (models/physics_methods.py:843) ... */
+    const void* d_factor;         /* ... or by this per-element array (float32, or float64 when factor_f64); NULL = the scalar */
+    int32_t factor_f64, pad2_;
+    /* profile 3: swell and wind-sea direction ('to', degrees), period and significant height at the elements (float32) */
+    const float* d_swell_dir;
+    const float* d_swell_period;
+    const float* d_swell_hs;
+    const float* d_windsea_dir;
+    const float* d_windsea_period;
+    const float* d_windsea_hs;
 } od_stokes_args;
 
 int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a);

@@ -93,7 +93,9 @@ class StokesArgs(C.Structure):
     _fields_ = [('n', C.c_int64), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
                 ('d_us', C.c_void_p), ('d_vs', C.c_void_p), ('d_hs', C.c_void_p), ('d_xwind', C.c_void_p),
                 ('d_ywind', C.c_void_p), ('d_moving', C.c_void_p), ('dt', C.c_double), ('z_f64', C.c_int32),
-                ('hs_mode', C.c_int32), ('profile', C.c_int32), ('pad_', C.c_int32)]
+                ('hs_mode', C.c_int32), ('profile', C.c_int32), ('pad_', C.c_int32), ('factor', C.c_double), ('d_factor', C.c_void_p),
+                ('factor_f64', C.c_int32), ('pad2_', C.c_int32), ('d_swell_dir', C.c_void_p), ('d_swell_period', C.c_void_p),
+                ('d_swell_hs', C.c_void_p), ('d_windsea_dir', C.c_void_p), ('d_windsea_period', C.c_void_p), ('d_windsea_hs', C.c_void_p)]
 
 
 class ProjDesc(C.Structure):

@@ -57,13 +57,8 @@ OD_HD void final_move_f64(const GeodStart& gs, double lon0, double xv, double yv
 
 // ---------------------------------------------------------------------------------------------------------
 // Arithmetic policies of the step.  ExactMath is the restatement of the reference (bit-exact field sampling,
-// Karney geodesic).  FastMath keeps float64 positions but does the per-step arithmetic in float32:
-//   * field sampling: time lerp of the eight corner texels, then trilinear, with float32 FMAs (the fractional
-//     cell index is still formed in float64 from the float64 position);
-//   * RK mid-points (which only feed the sampler): first-order displacement with float32 radii of curvature;
-//     the move that is kept: the float64 short-arc series of SeriesMath.
-// Measured against the reference fixtures FastMath stays within ~1e-7 deg after 14 RK4 steps (tolerance of
-// the float64 path: 1e-6 deg); it is an opt-in (od_advect_args.fast = OD_MATH_FAST, Engine.math_mode).
+// Karney geodesic); SeriesMath (the default) keeps the bit-exact sampling and evaluates the moves with the short-arc
+// series; FastMath (opt-in) is SeriesMath with the field sampled in float32 (below).
 // ---------------------------------------------------------------------------------------------------------
 struct ExactMath {
     typedef GeodStart Start;
@@ -162,108 +157,84 @@ OD_HD void do_move64(const typename MATH::Start& s, double lon0, double lat0, do
     else MATH::move64(s, lon0, lat0, xv, yv, mv, dt, lon1, lat1);
 }
 
-struct FastStart {
-    float s0, c0;        // sin, cos of the start latitude
-    float im, in_;       // 1/M(lat0), 1/(N(lat0) cos lat0)  [radians per metre]
-};
+// FastMath (opt-in, od_advect_args.fast = OD_MATH_FAST): SeriesMath's moves -- float64 positions, every mid-point and every kept
+// move the round-off-accurate short-arc series -- with the field sampled in float32: the time lerp of the eight corner texels, then
+// the trilinear interpolation, with float32 FMAs (the fractional cell index is still formed in float64 from the float64
+// position).  What it gives up against the reference is the float64 accumulation order of scipy's map_coordinates: a sampled
+// velocity differs in its last float32 bits (relative 1e-7), positions by ~1e-9 deg per step.  (Round 1's FastMath also took
+// first-order mid-points; they neglected the convergence of the meridians -- 5e-6 deg at 80-86 N in the randomised replays --
+// and are gone.)
+OD_HD float lerp_f32(float a, float b, float t) { return fmaf(t, b - a, a); }
 
-struct FastMath {
-    typedef FastStart Start;
+// time lerp of the corners, then trilinear, float32 FMAs
+OD_HD void fast_sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
+                          const TileView& tv) {
+    if (pos_f32) {       // first step after seeding: the reference forms the cell index in float32 (ulp 3e-5 at lon 359);
+        sample2(g, pr, vw, lon, lat, u, v, true, tv);     // in a strong gradient that is visible, so replay it exactly
+        return;
+    }
+    float ru = NAN, rv = NAN;
+    double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
+    double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
+    if (pr.mode != 3 && (g.glob != 0 || (x >= g.xmin && x <= g.xmax)) && lat >= g.ymin && lat <= g.ymax &&
+        xi == xi && yi == yi) {
+        xi = xi < 0.0 ? 0.0 : (xi > g.nxm1 ? g.nxm1 : xi);       // covered: edge value (see horiz_weights)
+        yi = yi < 0.0 ? 0.0 : (yi > g.nym1 ? g.nym1 : yi);
+        const double fx = floor(xi), fy = floor(yi);
+        int ix = (int)fx;
+        const int iy = (int)fy;
+        const int nxv = g.nx + g.wrap;
+        int ix1 = ix + 1 < nxv ? ix + 1 : nxv - 1;
+        if (ix >= g.nx) ix -= g.nx;
+        if (ix1 >= g.nx) ix1 -= g.nx;
+        const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
+        const float tx = (float)(xi - fx), ty = (float)(yi - fy);
+        const float tw = pr.mode == 0 ? (float)pr.w : (pr.mode == 1 ? 0.0f : 1.0f);
+        const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, ix, ix1, iy, iy1, vw.ia, g.nz > 1 ? vw.ib : vw.ia);
+        float lu[2], lvv[2];
+        const int nl = g.nz > 1 ? 2 : 1;
+        for (int l = 0; l < nl; ++l) {
+            const int lay = l == 0 ? vw.ia : vw.ib;
+            const float* lp = layer_ptr(ts, lay);
+            const int r0 = 4 * iy * ts.lx, r1 = 4 * iy1 * ts.lx;
+            const Tex4 a00 = fetch4(lp, r0 + 4 * ix), a01 = fetch4(lp, r0 + 4 * ix1);
+            const Tex4 a10 = fetch4(lp, r1 + 4 * ix), a11 = fetch4(lp, r1 + 4 * ix1);
+            const float u0 = lerp_f32(lerp_f32(a00.x, a00.z, tw), lerp_f32(a01.x, a01.z, tw), tx);
+            const float u1 = lerp_f32(lerp_f32(a10.x, a10.z, tw), lerp_f32(a11.x, a11.z, tw), tx);
+            const float v0 = lerp_f32(lerp_f32(a00.y, a00.w, tw), lerp_f32(a01.y, a01.w, tw), tx);
+            const float v1 = lerp_f32(lerp_f32(a10.y, a10.w, tw), lerp_f32(a11.y, a11.w, tw), tx);
+            lu[l] = lerp_f32(u0, u1, ty);
+            lvv[l] = lerp_f32(v0, v1, ty);
+        }
+        if (nl == 2) {
+            const float wb = 1.0f - (float)vw.wa;
+            ru = lerp_f32(lu[0], lu[1], wb);
+            rv = lerp_f32(lvv[0], lvv[1], wb);
+        } else {
+            ru = lu[0];
+            rv = lvv[0];
+        }
+    }
+    if (!finite_f(ru)) ru = g.fallback[0];
+    if (!finite_f(rv)) rv = g.fallback[1];
+    u = ru;
+    v = rv;
+}
+
+struct FastMath : SeriesMath {
     static constexpr bool kExactSampler = false;
-    static constexpr bool kDefer = false;
-    OD_HDS Start start(double lat0) {
-        Start st;
-        double sd, cd;
-        sincosd(lat0, sd, cd);
-        st.s0 = (float)sd;
-        st.c0 = (float)cd;
-        radii(st.s0, st.c0, st.im, st.in_);
-        return st;
-    }
-    // 1/M and 1/(N cos phi) from sin, cos of the latitude: W^2 = 1 - e^2 sin^2, N = a/W, M = a (1-e^2) / W^3
-    OD_HDS void radii(float s, float c, float& im, float& in_) {
-        const float W2 = 1.0f - (float)Wgs84::e2 * s * s;
-        const float W = sqrtf(W2);
-        im = W2 * W * (float)(1.0 / (Wgs84::a * (1.0 - Wgs84::e2)));
-        in_ = W * (float)(1.0 / Wgs84::a) / c;
-    }
-    // first-order displacement (RK mid-points: the position only feeds the field sampler)
-    OD_HDS void midpoint(const Start& st, double lon0, double lat0, float ku, float kv, float dt32, double& mlon, double& mlat) {
-        const float h = 0.5f * dt32;
-        mlat = lat0 + (double)(kv * h * st.im * (float)kRad2Deg);
-        mlon = lon0 + (double)(ku * h * st.in_ * (float)kRad2Deg);
-    }
-    // the move that is kept: float64 short-arc series (round-off accurate at every latitude; the float32 mid-latitude
-    // formulas this replaced lost 5e-6 deg per 3.6 km step at 77N)
-    OD_HDS void move_m(const Start& st, double lon0, double lat0, double de, double dn, double& lon1, double& lat1) {
-        const SeriesStart ss = series_start(lat0);
-        geod_move_ne(ss, lon0, dn, de, lon1, lat1);
-    }
-    OD_HDS void move32(const Start& st, double lon0, double lat0, float xv, float yv, double mv, double dt, double& lon1, double& lat1) {
-        const double k = mv * dt;
-        move_m(st, lon0, lat0, (double)xv * k, (double)yv * k, lon1, lat1);
-    }
-    OD_HDS void move64(const Start& st, double lon0, double lat0, double xv, double yv, double mv, double dt, double& lon1, double& lat1) {
-        const double k = mv * dt;
-        move_m(st, lon0, lat0, xv * k, yv * k, lon1, lat1);
-    }
-    OD_HDS float lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
-    // time lerp of the corners, then trilinear, float32 FMAs
     OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
                           const TileView& tv = TileView()) {
-        if (pos_f32) {       // first step after seeding: the reference forms the cell index in float32 (ulp 3e-5 at lon 359);
-            sample2(g, pr, vw, lon, lat, u, v, true, tv);     // in a strong gradient that is visible, so replay it exactly
-            return;
-        }
-        float ru = NAN, rv = NAN;
-        double x = (g.lon_mode == 0) ? np_mod360(lon) : np_mod360(lon + 180.0) - 180.0;
-        double xi = (x - g.x0) * g.inv_dx, yi = (lat - g.y0) * g.inv_dy;
-        if (pr.mode != 3 && (g.glob != 0 || (x >= g.xmin && x <= g.xmax)) && lat >= g.ymin && lat <= g.ymax &&
-            xi == xi && yi == yi) {
-            xi = xi < 0.0 ? 0.0 : (xi > g.nxm1 ? g.nxm1 : xi);       // covered: edge value (see horiz_weights)
-            yi = yi < 0.0 ? 0.0 : (yi > g.nym1 ? g.nym1 : yi);
-            const double fx = floor(xi), fy = floor(yi);
-            int ix = (int)fx;
-            const int iy = (int)fy;
-            const int nxv = g.nx + g.wrap;
-            int ix1 = ix + 1 < nxv ? ix + 1 : nxv - 1;
-            if (ix >= g.nx) ix -= g.nx;
-            if (ix1 >= g.nx) ix1 -= g.nx;
-            const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
-            const float tx = (float)(xi - fx), ty = (float)(yi - fy);
-            const float tw = pr.mode == 0 ? (float)pr.w : (pr.mode == 1 ? 0.0f : 1.0f);
-            const TexelSource ts = texel_source(pr.tex, tv, g.nx, g.ny, ix, ix1, iy, iy1, vw.ia, g.nz > 1 ? vw.ib : vw.ia);
-            float lu[2], lvv[2];
-            const int nl = g.nz > 1 ? 2 : 1;
-            for (int l = 0; l < nl; ++l) {
-                const int lay = l == 0 ? vw.ia : vw.ib;
-                const float* lp = layer_ptr(ts, lay);
-                const int r0 = 4 * iy * ts.lx, r1 = 4 * iy1 * ts.lx;
-                const Tex4 a00 = fetch4(lp, r0 + 4 * ix), a01 = fetch4(lp, r0 + 4 * ix1);
-                const Tex4 a10 = fetch4(lp, r1 + 4 * ix), a11 = fetch4(lp, r1 + 4 * ix1);
-                const float u0 = lerp(lerp(a00.x, a00.z, tw), lerp(a01.x, a01.z, tw), tx);
-                const float u1 = lerp(lerp(a10.x, a10.z, tw), lerp(a11.x, a11.z, tw), tx);
-                const float v0 = lerp(lerp(a00.y, a00.w, tw), lerp(a01.y, a01.w, tw), tx);
-                const float v1 = lerp(lerp(a10.y, a10.w, tw), lerp(a11.y, a11.w, tw), tx);
-                lu[l] = lerp(u0, u1, ty);
-                lvv[l] = lerp(v0, v1, ty);
-            }
-            if (nl == 2) {
-                const float wb = 1.0f - (float)vw.wa;
-                ru = lerp(lu[0], lu[1], wb);
-                rv = lerp(lvv[0], lvv[1], wb);
-            } else {
-                ru = lu[0];
-                rv = lvv[0];
-            }
-        }
-        if (!finite_f(ru)) ru = g.fallback[0];
-        if (!finite_f(rv)) rv = g.fallback[1];
-        u = ru;
-        v = rv;
+        fast_sample_uv(g, pr, vw, lon, lat, u, v, pos_f32, tv);
     }
-    OD_HDS float sample_s(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
-        return sample1(g, pr, vw, lon, lat, pos_f32);       // one sample per step: the exact sampler is fine
+};
+
+// FastMath for the hot path of the step kernels: SeriesHot's deferring moves (see there)
+struct FastHot : SeriesHot {
+    static constexpr bool kExactSampler = false;
+    OD_HDS void sample_uv(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
+                          const TileView& tv = TileView()) {
+        fast_sample_uv(g, pr, vw, lon, lat, u, v, pos_f32, tv);
     }
 };
 
@@ -551,6 +522,7 @@ OD_HD bool step_particle(const StepParams& p, int64_t i, const double* zs, const
 // whose step contained a move the hot path does not solve is redone with the full policy, out of line.
 template <class MATH> struct HotPolicy { typedef MATH type; };
 template <> struct HotPolicy<SeriesMath> { typedef SeriesHot type; };
+template <> struct HotPolicy<FastMath> { typedef FastHot type; };
 
 #if defined(__CUDACC__)
 #define OD_NOINLINE static __host__ __device__ __noinline__

@@ -1722,8 +1722,11 @@ extern "C" int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a) {
     if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_stokes_drift: null argument");
     if (a->n < 0 || (a->n > 0 && (!a->d_lon || !a->d_lat || !a->d_z || !a->d_us || !a->d_vs)))
         return fail(ctx, OD_ERR_ARG, "od_stokes_drift: bad arguments");
-    if (a->hs_mode < 0 || a->hs_mode > 2 || a->profile < 0 || a->profile > 2 || (a->hs_mode == 0 && !a->d_hs))
+    if (a->hs_mode < 0 || a->hs_mode > 2 || a->profile < 0 || a->profile > 3 || (a->hs_mode == 0 && !a->d_hs && a->profile != 3))
         return fail(ctx, OD_ERR_ARG, "od_stokes_drift: bad mode");
+    if (a->profile == 3 && (!a->d_swell_dir || !a->d_swell_period || !a->d_swell_hs || !a->d_windsea_dir || !a->d_windsea_period ||
+                            !a->d_windsea_hs))
+        return fail(ctx, OD_ERR_ARG, "od_stokes_drift: the windsea_swell profile needs the six swell / wind-sea arrays");
     if (a->n == 0) return OD_OK;
     CK(cudaSetDevice(ctx->device));
     StokesParams p;
@@ -1731,6 +1734,9 @@ extern "C" int od_stokes_drift(od_ctx* ctx, const od_stokes_args* a) {
     p.n = a->n; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.us = a->d_us; p.vs = a->d_vs; p.hs = a->d_hs;
     p.xwind = a->d_xwind; p.ywind = a->d_ywind; p.moving = a->d_moving; p.dt = a->dt;
     p.z_f64 = a->z_f64; p.hs_mode = a->hs_mode; p.profile = a->profile;
+    p.factor = a->factor; p.factor_arr = a->d_factor; p.factor_f64 = a->factor_f64;
+    p.sw_dir = a->d_swell_dir; p.sw_period = a->d_swell_period; p.sw_hs = a->d_swell_hs;
+    p.ws_dir = a->d_windsea_dir; p.ws_period = a->d_windsea_period; p.ws_hs = a->d_windsea_hs;
     stokes_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;

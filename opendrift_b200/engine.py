@@ -790,10 +790,22 @@ class Engine:
         self._check(self.lib.od_minmax_f32(self.ctx, a.numel(), _ptr(a), _ptr(b), C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
-    PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2}
+    PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2, 'windsea_swell': 3}
 
-    def stokes_drift(self, lon, lat, z, us, vs, hs, xwind, ywind, moving, dt, hs_mode, profile):
+    def stokes_drift(self, lon, lat, z, us, vs, hs, xwind, ywind, moving, dt, hs_mode, profile, factor=1, windsea_swell=None):
+        """factor: Python scalar or a float32 / float64 device tensor; windsea_swell: the six float32 tensors (swell direction,
+        period, height, wind-sea direction, period, height) of the combined profile."""
         a = StokesArgs()
+        a.factor = 1.0
+        if hasattr(factor, 'data_ptr'):
+            assert factor.dtype in (self.torch.float32, self.torch.float64)
+            a.d_factor, a.factor_f64 = factor.data_ptr(), 1 if factor.dtype == self.torch.float64 else 0
+        else:
+            a.factor = float(factor)
+        if windsea_swell is not None:
+            assert all(t.dtype == self.torch.float32 for t in windsea_swell)
+            (a.d_swell_dir, a.d_swell_period, a.d_swell_hs, a.d_windsea_dir, a.d_windsea_period,
+             a.d_windsea_hs) = (t.data_ptr() for t in windsea_swell)
         a.n = lon.numel()
         a.d_lon, a.d_lat, a.d_z = lon.data_ptr(), lat.data_ptr(), z.data_ptr()
         a.z_f64 = 1 if z.dtype == self.torch.float64 else 0

@@ -197,6 +197,33 @@ class PhysicsMethods:
         """1 for a forward simulation, -1 for a backward simulation"""
         return -1 if self.time_step.days < 0 else 1
 
+    def advect_with_sea_ice(self, factor=1):
+        """physics_methods.py:693-710: drift with the sea ice -- its velocity from a reader, else Nordam's rule of thumb
+        (current + 1.5 % of the wind) -- times `factor` (OpenOil: the ice coverage factor k_ice, a float32 array)."""
+        eng, torch = self.engine, self.engine.torch
+        env = self.environment
+        if 'sea_ice_x_velocity' in env:
+            u, v = env.dev('sea_ice_x_velocity', eng), env.dev('sea_ice_y_velocity', eng)
+        else:
+            if 'x_sea_water_velocity' not in env:
+                return
+            u, v = env.dev('x_sea_water_velocity', eng), env.dev('y_sea_water_velocity', eng)
+            if 'x_wind' in env:
+                # float32 + (Python float * float32): float32 arithmetic
+                c = u.new_tensor(0.015)
+                u, v = u + c * env.dev('x_wind', eng), v + c * env.dev('y_wind', eng)
+        if isinstance(factor, (int, float)):
+            if factor != 1:
+                f = u.new_tensor(factor)                  # weak scalar: the products stay float32
+                u, v = f * u, f * v
+        else:
+            f = factor if isinstance(factor, torch.Tensor) else eng.to_device(np.ascontiguousarray(factor))
+            if f.dtype != u.dtype:                        # NumPy's promotion
+                rt = torch.promote_types(f.dtype, u.dtype)
+                f, u, v = f.to(rt), u.to(rt), v.to(rt)
+            u, v = f * u, f * v
+        self.update_positions(u, v)
+
     def advect_wind(self, factor=1):
         """Wind drift of elements near the surface (:712-791): wind_drift_factor, linearly reduced to zero at
         drift:wind_drift_depth; relative_wind optional."""
@@ -256,19 +283,31 @@ class PhysicsMethods:
         """Stokes drift with a depth profile (:793-848): monochromatic / exponential / Phillips (:332-416)."""
         if not self.get_config('drift:stokes_drift', False):
             return
-        if not (isinstance(factor, (int, float)) and factor == 1):
-            raise NotImplementedError('stokes_drift(factor != 1) is not on the GPU path')
         profile = self.get_config('drift:stokes_drift_profile', default='monochromatic')
-        if profile == 'windsea_swell':
-            raise NotImplementedError('the windsea_swell Stokes profile is not on the GPU path')
         inp = self._stokes_inputs() if _inputs == 'sample' else _inputs
         if inp is None:
             return
         us, vs, hs, xw, yw, mode = inp
         eng, el, torch = self.engine, self.elements, self.engine.torch
+        ww = None
+        if profile == 'windsea_swell':
+            # the swell / wind-sea partition of the wave field (:418-455); the model must have declared these variables
+            env = self.environment
+            names = ('sea_surface_swell_wave_to_direction', 'sea_surface_swell_wave_peak_period_from_variance_spectral_density',
+                     'sea_surface_swell_wave_significant_height', 'sea_surface_wind_wave_to_direction',
+                     'sea_surface_wind_wave_mean_period', 'sea_surface_wind_wave_significant_height')
+            missing = [v for v in names if v not in env]
+            if missing:
+                raise AttributeError('the windsea_swell Stokes profile needs the environment variables %s '
+                                     '(add them to required_variables)' % missing)
+            ww = tuple(env.dev(v, eng) for v in names)
+        if not isinstance(factor, (int, float)):
+            factor = factor if isinstance(factor, torch.Tensor) else eng.to_device(np.ascontiguousarray(factor))
+            if factor.dtype not in (torch.float32, torch.float64):
+                factor = factor.to(torch.float64)
         moving = el.dev('moving')
         if moving.dtype != torch.int32:
             moving = moving.to(torch.int32)
         eng.stokes_drift(el.dev('lon', torch.float64), el.dev('lat', torch.float64), self._z_for_sampling(), us, vs, hs,
-                         xw, yw, moving, self.time_step.total_seconds(), mode, profile)
+                         xw, yw, moving, self.time_step.total_seconds(), mode, profile, factor=factor, windsea_swell=ww)
         el.positions_f32 = False

@@ -410,10 +410,120 @@ def check_od(o, case):
     assert np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max() <= (1e-9 if case.startswith('mixing') else 1e-5)
 
 
+# ---- subclass recipes on the helpers: drift in sea ice (OpenOil's advect_oil, openoil.py:1179-1216) and the combined swell / wind-sea
+#      Stokes profile (physics_methods.py:418-455) -- the same subclass body runs on the reference's OceanDrift and on the product's ----
+WAVE_VARS = {'sea_surface_swell_wave_to_direction': 250.0, 'sea_surface_swell_wave_peak_period_from_variance_spectral_density': 11.0,
+             'sea_surface_swell_wave_significant_height': 1.4, 'sea_surface_wind_wave_to_direction': 40.0,
+             'sea_surface_wind_wave_mean_period': 4.5, 'sea_surface_wind_wave_significant_height': 1.1}
+
+
+def ice_model_class(Base, ice_velocity):
+    extra = {'sea_ice_area_fraction': {'fallback': 0}}
+    if ice_velocity:
+        extra.update({'sea_ice_x_velocity': {'fallback': 0}, 'sea_ice_y_velocity': {'fallback': 0}})
+
+    class IceDrift(Base):
+        required_variables = dict(Base.required_variables, **extra)
+
+        def update(self):
+            A = self.environment.sea_ice_area_fraction
+            k_ice = (A - 0.3) / (0.8 - 0.3)             # Nordam et al. (2019): drift with the ice above 80 % cover, with the water below 30 %
+            k_ice[A < 0.3] = 0
+            k_ice[A > 0.8] = 1
+            factor_stokes = (0.7 - A) / 0.7             # Arneborg (2017): waves are damped by the ice
+            factor_stokes[A > 0.7] = 0
+            self.advect_ocean_current(factor=1 - k_ice)
+            self.advect_wind(factor=1 - k_ice)
+            self.stokes_drift(factor_stokes)
+            self.advect_with_sea_ice(factor=k_ice)
+            self.vertical_advection()
+    return IceDrift
+
+
+def wave_model_class(Base):
+    class WaveDrift(Base):
+        required_variables = dict(Base.required_variables, **{v: {'fallback': 0} for v in WAVE_VARS})
+    return WaveDrift
+
+
+SUBCLASS_CASES = {
+    'ice_with_ice_velocity': ('ice', True, {'drift:advection_scheme': 'runge-kutta'}, {'z': 0.0}),
+    'ice_rule_of_thumb': ('ice', False, {'drift:advection_scheme': 'euler', 'drift:stokes_drift_profile': 'exponential'}, {}),
+    'windsea_swell_z_float64': ('wave', None, {'drift:stokes_drift_profile': 'windsea_swell', 'drift:vertical_advection': False}, {'z': -0.5}),
+    'windsea_swell_z_float32': ('wave', None, {'drift:stokes_drift_profile': 'windsea_swell', 'drift:advection_scheme': 'runge-kutta4',
+                                              'drift:vertical_advection': False}, {}),
+}
+SUB_N, SUB_STEPS = 400, 4
+
+
+def subclass_readers(fx, kind, ice_velocity, make, constant):
+    st = common.Fixture('rk4_3d_stokes_phillips')
+    nt, ny, nx = len(fx.times), len(fx.grid_lat), len(fx.grid_lon)
+    out = [make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v, 'upward_sea_water_velocity': fx.w}, 'cur'),
+           make(fx.wind_lon, fx.wind_lat, None, fx.times, {'x_wind': fx.x_wind, 'y_wind': fx.y_wind}, 'wind'),
+           make(st.grid_lon, st.grid_lat, None, st.times, dict(st.stokes), 'waves')]
+    if kind == 'ice':
+        X, Y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+        A = np.clip(0.5 + 0.7 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y), 0, 1).astype(np.float32)
+        f = {'sea_ice_area_fraction': np.ascontiguousarray(np.broadcast_to(A, (nt, ny, nx)))}
+        if ice_velocity:
+            f['sea_ice_x_velocity'] = np.ascontiguousarray(np.broadcast_to((0.2 * np.cos(np.pi * Y)).astype(np.float32), (nt, ny, nx)))
+            f['sea_ice_y_velocity'] = np.ascontiguousarray(np.broadcast_to((-0.1 * np.sin(np.pi * X)).astype(np.float32), (nt, ny, nx)))
+        out.append(make(fx.grid_lon, fx.grid_lat, None, fx.times, f, 'ice'))
+    else:
+        out.append(constant(dict(WAVE_VARS)))
+    return out
+
+
+def run_subclass_case(case, Base, make, constant, **model_kw):
+    kind, ice_velocity, cfg, over = SUBCLASS_CASES[case]
+    fx = common.Fixture('rk4_3d_full')
+    Model = ice_model_class(Base, ice_velocity) if kind == 'ice' else wave_model_class(Base)
+    o = Model(loglevel=50, seed=0, **model_kw)
+    for r in subclass_readers(fx, kind, ice_velocity, make, constant):
+        o.add_reader(r)
+    for k, v in {'general:use_auto_landmask': False, 'general:coastline_action': 'none', **cfg}.items():
+        o.set_config(k, v)
+    if 'environment:constant:land_binary_mask' in getattr(o, '_config', {}):
+        o.set_config('environment:constant:land_binary_mask', 0)
+    kw = dict(lon=fx.lon0[:SUB_N], lat=fx.lat0[:SUB_N], z=np.clip(fx.z0[:SUB_N], -3, 0), time=fx.start)
+    kw.update(over)
+    o.seed_elements(**kw)
+    o.run(steps=SUB_STEPS, time_step=600, time_step_output=600)
+    return o
+
+
+def run_product_subclass(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid, reader_constant
+    return run_subclass_case(case, OceanDrift, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name),
+                             lambda m: reader_constant.Reader(m), **model_kw)
+
+
+def check_subclass(o, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['sub_%s__%s' % (case, k)]                  # noqa: E731
+    assert np.array_equal(np.asarray(o.elements.ID, dtype=np.int64), g('id'))
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+    assert np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max() <= 1e-5
+    return float(np.abs(np.asarray(o.elements.lon) - g('lon0')).max())
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
+    refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as _RefOD
+    from opendrift.readers import reader_constant as _ref_constant
+    for case in SUBCLASS_CASES:
+        ro = run_subclass_case(case, _RefOD, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name),
+                               lambda m: _ref_constant.Reader(m), logfile='/tmp/od_bk.log')
+        sfx = common.Fixture('rk4_3d_full')
+        out.update({'sub_%s__id' % case: np.asarray(ro.elements.ID, dtype=np.int64), 'sub_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64),
+                    'sub_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64), 'sub_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64),
+                    'sub_%s__lon0' % case: sfx.lon0[:SUB_N].astype(np.float64)})
+        print('subclass', case, len(ro.elements.ID), 'moved', np.abs(np.asarray(ro.elements.lon) - sfx.lon0[:SUB_N]).max())
     for case, (cfx, which, cfg, over, steps, dt) in od_cases().items():
         rds = od_readers(cfx, which, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name))
         kw = od_seed(cfx, over)

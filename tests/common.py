@@ -250,10 +250,16 @@ class HsStokesArgs(C.Structure):
     _fields_ = [('n', C.c_int64), ('lon', C.c_void_p), ('lat', C.c_void_p), ('z', C.c_void_p), ('us', C.c_void_p),
                 ('vs', C.c_void_p), ('hs', C.c_void_p), ('xwind', C.c_void_p), ('ywind', C.c_void_p),
                 ('moving', C.c_void_p), ('dt', C.c_double), ('z_f64', C.c_int32), ('hs_mode', C.c_int32),
-                ('profile', C.c_int32), ('pad_', C.c_int32)]
+                ('profile', C.c_int32), ('pad_', C.c_int32), ('factor', C.c_double), ('d_factor', C.c_void_p), ('factor_f64', C.c_int32),
+                ('pad2_', C.c_int32), ('sw_dir', C.c_void_p), ('sw_period', C.c_void_p), ('sw_hs', C.c_void_p), ('ws_dir', C.c_void_p),
+                ('ws_period', C.c_void_p), ('ws_hs', C.c_void_p)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.factor = 1.0
 
 
-PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2}
+PROFILES = {'monochromatic': 0, 'exponential': 1, 'Phillips': 2, 'windsea_swell': 3}
 
 
 def stokes_hs_mode(us, vs, hs, xw, yw):

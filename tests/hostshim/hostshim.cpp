@@ -220,6 +220,8 @@ void hs_kcolumn(const hs_group* g, const hs_pair* pr, int64_t n, const double* l
 struct hs_stokes_args {
     int64_t n; double* lon; double* lat; const void* z; const float* us; const float* vs; const float* hs;
     const float* xwind; const float* ywind; const int32_t* moving; double dt; int32_t z_f64, hs_mode, profile, pad_;
+    double factor; const void* d_factor; int32_t factor_f64, pad2_;
+    const float* sw_dir; const float* sw_period; const float* sw_hs; const float* ws_dir; const float* ws_period; const float* ws_hs;
 };
 
 int hs_stokes(const hs_stokes_args* a) {
@@ -228,6 +230,8 @@ int hs_stokes(const hs_stokes_args* a) {
     p.n = a->n; p.lon = a->lon; p.lat = a->lat; p.z = a->z; p.us = a->us; p.vs = a->vs; p.hs = a->hs;
     p.xwind = a->xwind; p.ywind = a->ywind; p.moving = a->moving; p.dt = a->dt; p.z_f64 = a->z_f64;
     p.hs_mode = a->hs_mode; p.profile = a->profile;
+    p.factor = a->factor; p.factor_arr = a->d_factor; p.factor_f64 = a->factor_f64;
+    p.sw_dir = a->sw_dir; p.sw_period = a->sw_period; p.sw_hs = a->sw_hs; p.ws_dir = a->ws_dir; p.ws_period = a->ws_period; p.ws_hs = a->ws_hs;
     for (int64_t i = 0; i < a->n; ++i) stokes_particle(p, i);
     return 0;
 }

@@ -352,3 +352,13 @@ def test_leeway_refuses_uncertainty_settings_it_would_ignore():
     o.seed_elements(lon=4, lat=60, number=10, time=__import__('datetime').datetime(2026, 1, 1), object_type=1)
     with pytest.raises(NotImplementedError, match='uncertainty'):
         o.run(steps=2, time_step=600)
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').SUBCLASS_CASES))
+def test_subclass_recipes_on_the_helpers_match_reference(case):
+    """Subclasses that drive the helpers with per-element factors -- drift in sea ice as OpenOil's advect_oil does it
+    (advect_ocean_current / advect_wind with 1 - k_ice, stokes_drift(factor array), advect_with_sea_ice) -- and the combined
+    swell / wind-sea Stokes profile, against the same subclass body on the unmodified reference."""
+    import bookkeeping as bk
+    o = bk.run_product_subclass(case)
+    assert bk.check_subclass(o, case) > 0.01

@@ -292,12 +292,12 @@ def test_random_step_scenarios_vs_port(seed):
     math must follow the port (= the reference) to the same 2e-8 deg as on the fixtures, in both float64 arithmetic modes."""
     fx = _random_scenario(seed)
     pl, pa, pz = common.run_port(fx)
-    for mode in (0, 2):
+    for mode in (0, 2, 1):          # exact replay, default (series), fast (float32 sampling + series moves)
         hl, ha, hz = run_hostshim(fx, fast=mode)
         assert np.array_equal(np.isfinite(pl), np.isfinite(hl))
         m = np.isfinite(pl)
         e = common.max_err_deg(hl[m], ha[m], pl[m], pa[m])
-        assert max(e) < 2e-8, (seed, mode, e)
+        assert max(e) < (1e-7 if mode == 1 else 2e-8), (seed, mode, e)     # (measured: fast <= 9e-9 over 120 scenarios up to 86 N)
         assert np.nanmax(np.abs(hz.astype(float) - pz.astype(float))) <= 1e-5
 
 

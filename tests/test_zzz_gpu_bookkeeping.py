@@ -74,3 +74,9 @@ def test_three_reader_chain_3d_on_gpu():
 @pytest.mark.parametrize('kind,scheme', bk.HANDOVER_CASES)
 def test_step_straddling_a_reader_hand_over_on_gpu(kind, scheme):
     bk.check_handover(bk.run_product_handover(kind, scheme), kind, scheme)
+
+
+@pytest.mark.parametrize('case', list(bk.SUBCLASS_CASES))
+def test_subclass_recipes_on_the_helpers_on_gpu(case):
+    """Drift in sea ice (per-element factors on every helper, advect_with_sea_ice) and the windsea_swell Stokes profile."""
+    assert bk.check_subclass(bk.run_product_subclass(case), case) > 0.01
