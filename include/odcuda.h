@@ -119,6 +119,15 @@ int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int max_iterat
 int od_group_slot_ptr(od_ctx* ctx, int group, int slot, int comp, float** d_out);
 /* tell the library a slot's contents changed behind its back (after a broadcast into od_group_slot_ptr) */
 int od_group_touch(od_ctx* ctx, int group, int slot);
+/* Sub-block readers: the blocks a reader hands out cover the elements plus a buffer (StructuredReader block cache,
+ * readers/basereader/structured.py:243-318; block supplier readers/reader_netCDF_CF_generic.py:404-626).  The group keeps the slots
+ * it was defined with (capacity = its full grid); this call replaces nx, ny and the block-relative index geometry (the block's own
+ * float32 axes, as ReaderBlock's interpolator sees them: interpolation/interpolators.py:110-111) by those of a window of the
+ * grid and invalidates the ring; slabs are then uploaded densely for the window.  ncomp, nz, n_slots must be unchanged. */
+int od_group_set_window(od_ctx* ctx, int group, const od_group_desc* window);
+/* bounding box of the elements (what the block request is made for): h_out4 = lon min, lon max, lat min, lat max; NaNs ignored;
+ * synchronises */
+int od_bbox(od_ctx* ctx, int64_t n, const double* d_lon, const double* d_lat, double* h_out4);
 /* environment:fallback:* of the group's variables (Environment.get_environment, models/basemodel/environment.py:782-801): the
  * values are read at every launch, so that a reader bound once serves models / runs with different fallbacks. NaN = none. */
 int od_group_set_fallback(od_ctx* ctx, int group, float fallback0, float fallback1);

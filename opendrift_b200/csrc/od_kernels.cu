@@ -69,6 +69,7 @@ struct Group {
     std::vector<double> h_levels;
     double zmin = 0, zmax = 0;
     PairEntry pairs[OD_PAIR_CACHE];
+    size_t capacity = 0;                // cells every slot was allocated for (the group's full grid)
     size_t cells() const { return (size_t)desc.nx * desc.ny * desc.nz; }
 };
 
@@ -87,6 +88,7 @@ struct od_ctx {
     int32_t* d_tilesums = nullptr;      // tile totals of the two-level scan
     int tiles_cap = 0;
     unsigned* d_red = nullptr;          // reduction scratch
+    unsigned long long* d_bbox = nullptr;   // od_bbox's four extrema
     unsigned* d_cnt = nullptr;          // counters of the housekeeping kernels
     float* d_fill = nullptr;            // scratch slab of the NaN fill
     unsigned* d_fillcnt = nullptr;      // per-pass missing-cell counters
@@ -159,6 +161,7 @@ extern "C" void od_destroy(od_ctx* ctx) {
     if (ctx->d_keys) cudaFree(ctx->d_keys);
     if (ctx->d_bins) cudaFree(ctx->d_bins);
     if (ctx->d_red) cudaFree(ctx->d_red);
+    if (ctx->d_bbox) cudaFree(ctx->d_bbox);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
     if (ctx->d_fill) cudaFree(ctx->d_fill);
     if (ctx->d_fillcnt) cudaFree(ctx->d_fillcnt);
@@ -211,6 +214,7 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
     g.desc = *d;
     g.slots.assign((size_t)d->n_slots * d->ncomp, nullptr);
     g.version.assign(d->n_slots, 0);
+    g.capacity = g.cells();
     for (auto& p : g.slots) CK(cudaMalloc(&p, g.cells() * sizeof(float)));
     if (d->nz > 1) {
         std::vector<double> zs(d->nz), zy(d->nz);
@@ -356,6 +360,80 @@ extern "C" int od_group_touch(od_ctx* ctx, int group, int slot) {
     int rc = check_slot(ctx, group, slot, 0);
     if (rc) return rc;
     ctx->groups[group].version[slot] = ++ctx->tick;
+    return OD_OK;
+}
+
+// Sub-block readers (readers/basereader/structured.py:243-318, reader_netCDF_CF_generic.py:404-626): the blocks a reader hands
+// out cover the elements plus a buffer, not its whole grid.  The group keeps the slots it was defined with (capacity = the full
+// grid) and the blocks in them share ONE window of it: nx, ny and the block-relative index geometry (x0, xspan, ... of the block's
+// own float32 axes, as ReaderBlock's interpolator sees them) are replaced here, the ring is invalidated, and the caller uploads
+// the window's slabs densely ([nz][ny][nx] of the window).
+extern "C" int od_group_set_window(od_ctx* ctx, int group, const od_group_desc* d) {
+    int rc = check_slot(ctx, group, 0, 0);
+    if (rc) return rc;
+    if (!d) return fail(ctx, OD_ERR_ARG, "od_group_set_window: null descriptor");
+    Group& g = ctx->groups[group];
+    if (d->ncomp != g.desc.ncomp || d->nz != g.desc.nz || d->n_slots != g.desc.n_slots || d->nx < 2 || d->ny < 2 ||
+        (size_t)d->nx * d->ny * d->nz > g.capacity)
+        return fail(ctx, OD_ERR_ARG, "od_group_set_window: the window must keep ncomp / nz / n_slots and fit the group's slots");
+    float fb0 = g.desc.fallback[0], fb1 = g.desc.fallback[1];
+    g.desc = *d;
+    g.desc.fallback[0] = fb0; g.desc.fallback[1] = fb1;
+    CK(cudaStreamSynchronize(ctx->stream));          // launches that still read the old window's texels
+    for (auto& v : g.version) v = ++ctx->tick;       // every slot's contents are stale now
+    for (auto& p : g.pairs) {                        // and so are the pair texels (their tensor maps encode the old shape)
+        p.slot_a = p.slot_b = -1;
+        p.tmap_ok = false;
+    }
+    return OD_OK;
+}
+
+// bounding box (xmin, xmax, ymin, ymax) of the elements' positions, NaNs ignored; longitudes as they are stored
+__global__ void __launch_bounds__(256) bbox_kernel(int64_t n, const double* __restrict__ lon, const double* __restrict__ lat,
+                                                   unsigned long long* __restrict__ out) {
+    // order-preserving map of a double onto an unsigned integer
+    auto enc = [](double v) { unsigned long long u = (unsigned long long)__double_as_longlong(v);
+                              return (u >> 63) ? ~u : (u | 0x8000000000000000ull); };
+    unsigned long long lo_x = ~0ull, hi_x = 0, lo_y = ~0ull, hi_y = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = lon[i], y = lat[i];
+        if (x == x) { const unsigned long long e = enc(x); lo_x = min(lo_x, e); hi_x = max(hi_x, e); }
+        if (y == y) { const unsigned long long e = enc(y); lo_y = min(lo_y, e); hi_y = max(hi_y, e); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], lo_x); atomicMax(&out[1], hi_x); atomicMin(&out[2], lo_y); atomicMax(&out[3], hi_y);
+    }
+}
+
+extern "C" int od_bbox(od_ctx* ctx, int64_t n, const double* d_lon, const double* d_lat, double* h_out4) {
+    if (!ctx || !h_out4 || n < 0 || (n > 0 && (!d_lon || !d_lat))) return fail(ctx, OD_ERR_ARG, "od_bbox: bad arguments");
+    for (int k = 0; k < 4; ++k) h_out4[k] = NAN;
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_bbox) CK(cudaMalloc(&ctx->d_bbox, 4 * sizeof(unsigned long long)));
+    unsigned long long* d = ctx->d_bbox;
+    const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
+    CK(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int blocks = (int)((n + 255) / 256 < (int64_t)ctx->sm_count * 8 ? (n + 255) / 256 : (int64_t)ctx->sm_count * 8);
+    bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(n, d_lon, d_lat, d);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    unsigned long long r[4];
+    CK(cudaMemcpyAsync(r, d, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) {
+        const bool empty = (k & 1) ? r[k] == 0ull : r[k] == ~0ull;
+        if (empty) continue;
+        const unsigned long long u = (r[k] >> 63) ? (r[k] & 0x7fffffffffffffffull) : ~r[k];
+        long long bits = (long long)u;
+        double v;
+        memcpy(&v, &bits, sizeof(v));
+        h_out4[k] = v;
+    }
     return OD_OK;
 }
 

@@ -142,6 +142,22 @@ class FieldGroup:
             zl = (C.c_double * len(self.z))(*self.z)
         engine._check(engine.lib.od_group_define(engine.ctx, gid, C.byref(d), zl))
 
+    def set_window(self, lon, lat):
+        """The blocks of this group now cover the window of the reader's grid with the axes lon, lat (float32, as the reader's
+        block hands them out): block-relative index geometry as ReaderBlock's interpolator would form it, every ring slot
+        invalidated.  The reader's own coverage (xmin .. ymax of the descriptor) is unchanged: an element inside the reader's domain
+        but outside the block gets the block's edge value, as the reference's NaN loop gives it (interpolators.py:121-139)."""
+        lon = np.asarray(lon, dtype=np.float32)
+        lat = np.asarray(lat, dtype=np.float32)
+        d = self.desc
+        d.nx, d.ny = len(lon), len(lat)
+        d.x0, d.xspan = float(lon[0]), float(np.float32(lon[-1] - lon[0]))
+        d.y0, d.yspan = float(lat[0]), float(np.float32(lat[-1] - lat[0]))
+        self.lon, self.lat = lon, lat
+        self.engine._check(self.engine.lib.od_group_set_window(self.engine.ctx, self.gid, C.byref(d)))
+        self.resident = [None] * self.n_slots
+        self.ready = [None] * self.n_slots
+
     def set_fallback(self, fallback):
         """environment:fallback:* of this group's variables; read by the kernels at every launch, so that a reader that was
         bound earlier (a direct get_variables_interpolated call, another model instance) follows the current run's values."""
@@ -287,6 +303,18 @@ class DistContext:
 
     def broadcast(self, tensor):
         self.dist.broadcast(tensor, self.src, group=self.group)
+
+    def allreduce_bbox(self, eng, bbox):
+        """(min, max, min, max) over all ranks; a rank without elements contributes nothing (NaN)."""
+        torch = eng.torch
+        big = 1e300
+        v = [(-bbox[0] if bbox[0] == bbox[0] else -big), (bbox[1] if bbox[1] == bbox[1] else -big),
+             (-bbox[2] if bbox[2] == bbox[2] else -big), (bbox[3] if bbox[3] == bbox[3] else -big)]
+        t = torch.tensor(v, dtype=torch.float64, device=eng.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        r = t.cpu().tolist()
+        out = (-r[0], r[1], -r[2], r[3])
+        return tuple(float('nan') if abs(x) >= big else x for x in out)
 
     def shard(self, n_total):
         from .sharding import shard_range
@@ -783,6 +811,12 @@ class Engine:
             a.wind_threshold, a.wind_sigma = float(capsizing[0]), float(capsizing[1])
             a.d_rand_capsize = rand_capsize.data_ptr() if rand_capsize is not None else None
         self._check(self.lib.od_leeway_step(self.ctx, C.byref(a)))
+
+    def bbox(self, lon, lat):
+        """(lon min, lon max, lat min, lat max) of float64 device tensors, NaNs ignored (synchronises)."""
+        out = (C.c_double * 4)()
+        self._check(self.lib.od_bbox(self.ctx, lon.numel(), _ptr(lon), _ptr(lat), out))
+        return tuple(out)
 
     def minmax(self, a, b=None):
         """(min, max) of a (+ b) over a float32 device tensor, NaNs ignored (synchronises)."""

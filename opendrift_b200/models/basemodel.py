@@ -517,6 +517,22 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             self._env_missing = missing
         return self._env_view
 
+    def _cover_elements_with_blocks(self):
+        """Readers that hand out sub-blocks (reader_netCDF_CF_generic.py:404-626) are asked for the block around the elements, as
+        StructuredReader does with the positions it is called with (structured.py:275-318): bounding box of the active elements
+        (one reduction launch + a 32-byte read), grown by what an element can travel in one step at drift:max_speed.  The block is
+        only replaced when the box has left the current one."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        bbox = eng.bbox(el.dev('lon', torch.float64), el.dev('lat', torch.float64))
+        d = getattr(self, '_dist', None)
+        if d is not None:                    # every rank must use the same window: the slabs are broadcast window-shaped
+            bbox = d.allreduce_bbox(eng, bbox)
+        lat_max = min(89.0, max(abs(bbox[2]), abs(bbox[3]))) if np.all(np.isfinite(bbox)) else 0.0
+        margin = (self.get_config('drift:max_speed') * abs(self.time_step.total_seconds()) / (111000.0 * np.cos(np.radians(lat_max)))
+                  + 1e-6)
+        if any(self.env.ensure_windows(bbox, margin)):
+            self._env_view = None
+
     def _start_of_step_sample(self, var):
         """float32 device tensor of ONE environment variable at the elements' current positions: from the step's environment when
         it has been materialised, else sampled on its own (the fused step never materialises the full environment)."""
@@ -785,6 +801,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
 
         i = 0
         dist_run = self._dist is not None
+        self._has_subblock_readers = bool(self.env.subblock_readers())
         for i in range(self.expected_steps_calculation):
             self.release_elements()
             if dist_run:
@@ -795,6 +812,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                 self.time = self.time + self.time_step
                 continue
             self._env_view = None
+            if self._has_subblock_readers:
+                self._cover_elements_with_blocks()
             self._predraw_step_uncertainty()
             # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
             col, only_deact = self._column_of_step(i)

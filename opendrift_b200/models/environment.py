@@ -49,10 +49,20 @@ class Environment:
 
     def finalize(self, engine):
         self._engine = engine
+        ms = self._config._config.get('drift:max_speed')
         for r in self.readers.values():
+            if hasattr(r, 'set_buffer_size') and ms is not None:
+                r.set_buffer_size(max_speed=ms['value'])             # environment.py:402
             if hasattr(r, 'bind'):
                 r.bind(engine, fallback={v: self.fallback(v) for v in r.variables})
         self.__finalized__ = True
+
+    def subblock_readers(self):
+        return [r for r in self.readers.values() if getattr(r, 'subblocks', False)]
+
+    def ensure_windows(self, bbox, margin_deg):
+        """Sub-block readers: their device blocks must cover the elements (bounding box + how far they can travel)."""
+        return [r.ensure_window(bbox, margin_deg) for r in self.subblock_readers()]
 
     def touch_slabs(self, times):
         """Make every bound reader's slabs for the given times resident -- in a fixed order (readers as added, groups as bound,

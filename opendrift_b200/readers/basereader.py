@@ -64,6 +64,11 @@ class StructuredReader:
     proj4 = '+proj=latlong'
     times = None
     always_valid = False
+    # True: get_variables(variables, time, x, y, z) is asked for the positions to cover (the corners of the elements' bounding
+    # box) and returns a SUB-BLOCK of the grid around them, with its own x / y axes (reader_netCDF_CF_generic.py:404-626);
+    # needs numx / numy (the full grid: capacity of the device slots).  False: the reader hands out its whole grid.
+    subblocks = False
+    buffer = 0
 
     def __init__(self):
         p = str(getattr(self, 'proj4', '+proj=latlong'))
@@ -80,6 +85,10 @@ class StructuredReader:
         self._groups = {}          # variable -> (FieldGroup, component)
         self._block_geom = None
         self.number_of_fails = 0
+        self._request = None       # sub-block readers: (x, y) corner positions of the current block request
+        self._window = None        # ... and the extent (xmin, xmax, ymin, ymax) of the block that came back
+        self._block_caches = []
+        self.windows_set = 0
 
     # -- coverage (variables.py:229-257, 391-400) ------------------------------------------------
     def covers_time(self, time):
@@ -122,12 +131,58 @@ class StructuredReader:
         near = tb if (ta is None or (time - tb) < (ta - time)) else ta
         return near, tb, ta, self.times.index(near), ib, ia
 
+    # -- block size (variables.py:154-165, 588-620) ---------------------------------------------------
+    def pixel_size(self):
+        dx = getattr(self, 'delta_x', None)
+        return None if dx is None else dx * 111000           # degrees -> metres (geographic readers)
+
+    def set_buffer_size(self, max_speed, time_coverage=None):
+        """Cells added around the requested positions so that the block still covers the elements at the end of the
+        reader's time step: ceil(max_speed * time_step / pixel) + 2."""
+        self.buffer = 0
+        px = self.pixel_size()
+        if px is not None:
+            ts = getattr(self, 'time_step', None)
+            secs = ts.total_seconds() if ts is not None else (3600 if time_coverage is None else time_coverage.total_seconds())
+            self.buffer = int(np.ceil(max_speed * abs(secs) / px)) + 2
+
     # -- device binding --------------------------------------------------------------------------
     def _fetch_block(self, names, ti):
-        """One reader block for time index ti via the reader's own get_variables()."""
+        """One reader block for time index ti via the reader's own get_variables(): the whole grid, or -- sub-block readers --
+        the block around the current request (the corners of the elements' bounding box)."""
         t = self.times[ti]
-        blk = self.get_variables(list(names), time=t, x=None, y=None, z=None)
-        return blk
+        if self.subblocks and self._request is not None:
+            x, y = self._request
+            return self.get_variables(list(names), time=t, x=x, y=y, z=None)
+        return self.get_variables(list(names), time=t, x=None, y=None, z=None)
+
+    def ensure_window(self, bbox, margin_deg):
+        """Sub-block readers: make the device blocks cover the elements' bounding box (lon min, lon max, lat min, lat max) grown
+        by margin_deg (how far an element can travel before the next check).  When the current window does not, a new block is
+        requested for the box -- the reader adds its own buffer (set_buffer_size) -- and its axes become the groups' index
+        geometry; the ring refills on demand, the next slab ahead of time on the copy stream.  Returns True when re-windowed."""
+        if not self.subblocks or self._engine is None or not np.all(np.isfinite(bbox)):
+            return False
+        x0, x1 = self.modulate_longitude(np.array([bbox[0], bbox[1]], dtype=np.float64))
+        if x1 < x0:                                            # the box straddles the reader's longitude seam: whole rows
+            x0, x1 = self.xmin, self.xmax
+        y0, y1 = bbox[2], bbox[3]
+        w = self._window
+        inside = w is not None and (max(x0 - margin_deg, self.xmin) >= w[0] and min(x1 + margin_deg, self.xmax) <= w[1] and
+                                    max(y0 - margin_deg, self.ymin) >= w[2] and min(y1 + margin_deg, self.ymax) <= w[3])
+        if inside:
+            return False
+        self._request = (np.array([np.clip(x0, self.xmin, self.xmax), np.clip(x1, self.xmin, self.xmax)]),
+                         np.array([np.clip(y0, self.ymin, self.ymax), np.clip(y1, self.ymin, self.ymax)]))
+        for cache in self._block_caches:
+            cache.clear()
+        probe = self._fetch_block(self.variables[:1], 0)
+        bx, by = np.asarray(probe['x'], dtype=np.float32), np.asarray(probe['y'], dtype=np.float32)
+        self._window = (float(bx.min()), float(bx.max()), float(by.min()), float(by.max()))
+        for g in {id(g): g for g, _ in self._groups.values()}.values():
+            g.set_window(bx, by)
+        self.windows_set += 1
+        return True
 
     def bind(self, engine, fallback=None, n_slots=3):
         """Create the device field groups of this reader on `engine` (idempotent)."""
@@ -139,9 +194,21 @@ class StructuredReader:
         self._engine = engine
         self._groups = {}
         fallback = fallback or {}
+        if self.subblocks:
+            # the slots are sized for the whole grid (numx x numy: any window fits); the first probe only asks for one corner --
+            # vertical levels and dimensionality of the variables -- the first real window comes with ensure_window()
+            self._request = (np.array([self.xmin, self.xmin]), np.array([self.ymin, self.ymin]))
+            self._window = None
         probe = self._fetch_block(self.variables, 0)
         x = np.asarray(probe['x'], dtype=np.float32)      # __check_env_coordinates__ (variables.py:622-628)
         y = np.asarray(probe['y'], dtype=np.float32)
+        if self.subblocks:
+            # the reader's full axes (only their length and end points matter here: capacity, longitude convention, coverage)
+            fx, fy = getattr(self, 'lon', None), getattr(self, 'lat', None)
+            x = np.asarray(fx, dtype=np.float32) if fx is not None and np.ndim(fx) == 1 and len(fx) == self.numx else \
+                (self.xmin + self.delta_x * np.arange(self.numx)).astype(np.float32)
+            y = np.asarray(fy, dtype=np.float32) if fy is not None and np.ndim(fy) == 1 and len(fy) == self.numy else \
+                (self.ymin + self.delta_y * np.arange(self.numy)).astype(np.float32)
         done = set()
         plan = []
         for a, b in vector_pairs_xy:
@@ -153,6 +220,7 @@ class StructuredReader:
             three_d = np.ndim(probe[names[0]]) == 3
             z = np.asarray(probe['z'], dtype=np.float64) if three_d else None
             cache = {}
+            self._block_caches.append(cache)
 
             def supplier(ti, c, names=names, cache=cache):
                 if ti not in cache:

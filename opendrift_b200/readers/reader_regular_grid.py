@@ -7,9 +7,11 @@ from .basereader import StructuredReader
 
 
 class Reader(StructuredReader):
-    def __init__(self, lon, lat, z=None, times=None, fields=None, name='regular_grid'):
+    def __init__(self, lon, lat, z=None, times=None, fields=None, name='regular_grid', subblocks=False):
         """fields: dict variable -> array (nt, [nz,] ny, nx) float32 (NumPy or CUDA tensors), or a callable
-        fields[var](time_index) -> ([nz,] ny, nx)."""
+        fields[var](time_index) -> ([nz,] ny, nx).  subblocks: hand out only the part of the grid around the requested
+        positions plus `buffer` cells, like a file reader does (reader_netCDF_CF_generic.py:436-466)."""
+        self.subblocks = bool(subblocks)
         self.proj4 = '+proj=latlong'
         self.lon = np.asarray(lon, dtype=np.float32)
         self.lat = np.asarray(lat, dtype=np.float32)
@@ -29,12 +31,28 @@ class Reader(StructuredReader):
 
     def get_variables(self, requested_variables, time=None, x=None, y=None, z=None):
         ti = self.times.index(time) if time is not None else 0
-        out = {'x': self.lon, 'y': self.lat, 'time': time}
+        sx = sy = slice(None)
+        if self.subblocks and x is not None and y is not None:
+            # the cells the positions fall in, widened by the buffer on every side
+            ix = np.floor(np.abs(np.asarray(x, dtype=np.float64) - float(self.lon[0])) / self.delta_x).astype(int)
+            iy = np.floor(np.abs(np.asarray(y, dtype=np.float64) - float(self.lat[0])) / self.delta_y).astype(int)
+            b = int(self.buffer)
+            sx = slice(max(0, int(ix.min()) - b), min(int(ix.max()) + b + 1, self.numx))
+            sy = slice(max(0, int(iy.min()) - b), min(int(iy.max()) + b + 1, self.numy))
+            if sx.stop - sx.start < 2:
+                sx = slice(max(0, sx.start - 1), min(sx.start + 2, self.numx))
+            if sy.stop - sy.start < 2:
+                sy = slice(max(0, sy.start - 1), min(sy.start + 2, self.numy))
+            self.blocks_served = getattr(self, 'blocks_served', 0) + 1
+        out = {'x': self.lon[sx], 'y': self.lat[sy], 'time': time}
         three_d = False
         for v in requested_variables:
             f = self.fields[v]
             a = f(ti) if callable(f) else f[ti]
             three_d |= getattr(a, 'ndim', 2) == 3
+            if sx != slice(None) or sy != slice(None):
+                a = a[..., sy, sx]
+                a = a.contiguous() if hasattr(a, 'is_cuda') else np.ascontiguousarray(a)
             out[v] = a
         out['z'] = self.zlev if three_d else 0
         return out

@@ -140,7 +140,7 @@ def setup():
     _ready = True
 
 
-def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid'):
+def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid', subblocks=False):
     """A reference StructuredReader (subclass of the reference base class) serving
     in-memory regular lon/lat(/z) slabs.  ``fields[var]`` has shape (nt, nz, ny, nx) or
     (nt, ny, nx) float32.  get_variables returns the FULL grid block (like
@@ -180,12 +180,23 @@ def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid'):
 
         def get_variables(self, requested_variables, time=None, x=None, y=None, z=None):
             it = self.times.index(time)
-            out = {'x': self.block_x, 'y': self.lat, 'time': time}
+            sx = sy = slice(None)
+            if subblocks and x is not None and y is not None and not self.periodic:
+                # a sub-block around the requested positions, widened by self.buffer cells (the role of
+                # reader_netCDF_CF_generic.py:436-466; self.buffer is set by the reference's set_buffer_size)
+                ix = np.floor(np.abs(np.asarray(x, dtype=np.float64) - float(self.lon[0])) / self.delta_x).astype(int)
+                iy = np.floor(np.abs(np.asarray(y, dtype=np.float64) - float(self.lat[0])) / self.delta_y).astype(int)
+                b = int(self.buffer)
+                sx = slice(max(0, int(ix.min()) - b), min(int(ix.max()) + b + 1, self.numx))
+                sy = slice(max(0, int(iy.min()) - b), min(int(iy.max()) + b + 1, self.numy))
+                self.blocks_served = getattr(self, 'blocks_served', 0) + 1
+                self.block_shapes = getattr(self, 'block_shapes', []) + [(sy.stop - sy.start, sx.stop - sx.start)]
+            out = {'x': self.block_x[sx], 'y': self.lat[sy], 'time': time}
             three_d = False
             for v in requested_variables:
                 a = self.fields[v][it]
                 three_d |= a.ndim == 3
-                a = np.array(a, dtype=np.float32, copy=True)
+                a = np.array(a[..., sy, sx], dtype=np.float32, copy=True)
                 if self.periodic:
                     a = np.concatenate([a, a[..., :1]], axis=-1)
                 out[v] = a

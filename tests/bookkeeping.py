@@ -509,11 +509,83 @@ def check_subclass(o, case):
     return float(np.abs(np.asarray(o.elements.lon) - g('lon0')).max())
 
 
+# ---- readers that hand out sub-blocks around the elements (reader_netCDF_CF_generic.py:404-626; structured.py:243-318) -----------
+SUBBLOCK_CASES = {
+    # the elements sit in a corner of the grid: an 11 x 11 block of the 36 x 40 grid serves the whole run
+    'corner_cluster': dict(spread=0.15, steps=10, dt=600, cfg={'drift:advection_scheme': 'runge-kutta4', 'drift:max_speed': 0.6}),
+    # long steps and a small anticipated speed: the elements outrun the buffer and the block is replaced under way
+    'outrun_the_buffer': dict(spread=0.08, steps=10, dt=1800, cfg={'drift:advection_scheme': 'runge-kutta', 'drift:max_speed': 0.05}),
+}
+SUBBLOCK_N = 300
+
+
+def subblock_setup(case):
+    c = SUBBLOCK_CASES[case]
+    fx = common.Fixture('rk4_3d_full')
+    n = SUBBLOCK_N
+    lon0 = (fx.grid_lon[3] + (fx.lon0[:n] - fx.lon0[:n].min()) * c['spread']).astype(np.float32)
+    lat0 = (fx.grid_lat[3] + (fx.lat0[:n] - fx.lat0[:n].min()) * c['spread']).astype(np.float32)
+    fields = {common.CUR[0]: fx.u, common.CUR[1]: fx.v, 'upward_sea_water_velocity': fx.w}
+    return fx, c, lon0, lat0, fx.z0[:n], fields
+
+
+def run_product_subblock(case, subblocks=True, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx, c, lon0, lat0, z0, fields = subblock_setup(case)
+    o = OceanDrift(loglevel=50, seed=0, **model_kw)
+    rd = reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, fields, name='cur', subblocks=subblocks)
+    o.add_reader(rd)
+    o.set_config('general:use_auto_landmask', False)
+    for k, v in c['cfg'].items():
+        o.set_config(k, v)
+    o.seed_elements(lon=lon0, lat=lat0, z=z0, time=fx.start)
+    o.run(steps=c['steps'], time_step=c['dt'], time_step_output=c['dt'])
+    return o, rd
+
+
+def run_product_rewindow(subblocks, **model_kw):
+    """A day-long drift (the fixture's four slabs repeated): the elements leave the first block and the reader is asked for new
+    ones under way."""
+    from datetime import timedelta as _td
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    fx, c, lon0, lat0, z0, fields = subblock_setup('corner_cluster')
+    nt = fx.u.shape[0]
+    times = [fx.start + _td(hours=k) for k in range(26)]
+    per = {v: (lambda ti, a=a: a[ti % nt]) for v, a in fields.items()}
+    o = OceanDrift(loglevel=50, seed=0, **model_kw)
+    rd = reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, times, per, name='cur', subblocks=subblocks)
+    o.add_reader(rd)
+    o.set_config('general:use_auto_landmask', False)
+    o.set_config('drift:advection_scheme', 'runge-kutta')
+    o.set_config('drift:max_speed', 1.0)           # buffer: ceil(1 m/s * 3600 s / 5.5 km) + 2 = 3 cells around the elements
+    o.seed_elements(lon=lon0, lat=lat0, z=z0, time=fx.start)
+    o.run(steps=24, time_step=3600, time_step_output=3600 * 24)
+    return o, rd
+
+
+def check_subblock(o, rd, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['subblock_%s__%s' % (case, k)]             # noqa: E731
+    e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat')))
+    dz = float(np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max())
+    grp = rd.group_of(common.CUR[0])[0]
+    return e, dz, (grp.desc.ny, grp.desc.nx), rd.windows_set
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
     refrun.setup()
+    for case in SUBBLOCK_CASES:
+        sfx, c, lon0, lat0, z0, fields = subblock_setup(case)
+        rd = refrun.make_grid_reader(sfx.grid_lon, sfx.grid_lat, sfx.grid_z, sfx.times, fields, 'cur', subblocks=True)
+        ro = refrun.run_oceandrift([rd], lon0, lat0, z0, sfx.start, c['dt'], c['steps'], config=c['cfg'])
+        out.update({'subblock_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64), 'subblock_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64),
+                    'subblock_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64)})
+        print('subblock', case, 'blocks', rd.blocks_served, sorted(set(rd.block_shapes)), 'buffer', rd.buffer)
     from opendrift.models.oceandrift import OceanDrift as _RefOD
     from opendrift.readers import reader_constant as _ref_constant
     for case in SUBCLASS_CASES:

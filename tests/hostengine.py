@@ -129,6 +129,20 @@ class _HostLib:
             h_remaining._obj.value = int(np.isnan(a).sum())
         return 0
 
+    def od_group_set_window(self, ctx, gid, desc):
+        d = desc._obj if hasattr(desc, '_obj') else desc
+        old = self.groups[gid]
+        assert (d.ncomp, d.nz, d.n_slots) == (old.desc.ncomp, old.desc.nz, old.desc.n_slots)
+        g = _HostGroup(d, old.levels)
+        g.version = dict(old.version)            # slot contents are stale: the product re-uploads before it samples
+        self.groups[gid] = g
+        return 0
+
+    def od_bbox(self, ctx, n, lon, lat, out):
+        x, y = _np_from_ptr(lon, n, np.float64), _np_from_ptr(lat, n, np.float64)
+        out[0], out[1], out[2], out[3] = np.nanmin(x), np.nanmax(x), np.nanmin(y), np.nanmax(y)
+        return 0
+
     def od_group_set_fallback(self, ctx, gid, f0, f1):
         g = self.groups[gid]
         g.desc.fallback[0], g.desc.fallback[1] = f0, f1
@@ -336,6 +350,7 @@ class HostEngine:
     minmax = Engine.minmax
     history_scatter = Engine.history_scatter
     bookkeeping = Engine.bookkeeping
+    bbox = Engine.bbox
     vertical_buoyancy = Engine.vertical_buoyancy
     # gridded readers: Engine's own group management and call wrappers
     add_group = Engine.add_group

@@ -362,3 +362,28 @@ def test_subclass_recipes_on_the_helpers_match_reference(case):
     import bookkeeping as bk
     o = bk.run_product_subclass(case)
     assert bk.check_subclass(o, case) > 0.01
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').SUBBLOCK_CASES))
+def test_subblock_reader_matches_reference(case):
+    """A reader that hands out sub-blocks around the elements: the device blocks take the block's own index geometry
+    (od_group_set_window), as the reference's ReaderBlock does; compared with the unmodified reference run on the same kind of
+    reader.  (With the whole grid instead of the block the first, float32-position step differs by ~4e-8 deg.)"""
+    import bookkeeping as bk
+    o, rd = bk.run_product_subblock(case)
+    e, dz, window, n_windows = bk.check_subblock(o, rd, case)
+    full = (len(common.Fixture('rk4_3d_full').grid_lat), len(common.Fixture('rk4_3d_full').grid_lon))
+    assert window[0] < full[0] and window[1] < full[1] and n_windows >= 1
+    assert e < 2e-9 and dz == 0.0, (e, dz)     # the reference's block, the reference's index arithmetic
+
+
+def test_subblock_reader_is_asked_for_new_blocks_when_the_elements_leave():
+    import bookkeeping as bk
+    o, rd = bk.run_product_rewindow(True)
+    f, rf = bk.run_product_rewindow(False)
+    assert rd.windows_set >= 2 and rf.windows_set == 0
+    g = rd.group_of(common.CUR[0])[0]
+    assert g.desc.nx < 40 and g.desc.ny < 36                 # a window, not the 36 x 40 grid
+    e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), np.asarray(f.elements.lon), np.asarray(f.elements.lat)))
+    # block-relative against whole-grid index arithmetic (float32 on the first step), grown over 24 one-hour steps: 2e-7 deg
+    assert e < 1e-6, e

@@ -80,3 +80,21 @@ def test_step_straddling_a_reader_hand_over_on_gpu(kind, scheme):
 def test_subclass_recipes_on_the_helpers_on_gpu(case):
     """Drift in sea ice (per-element factors on every helper, advect_with_sea_ice) and the windsea_swell Stokes profile."""
     assert bk.check_subclass(bk.run_product_subclass(case), case) > 0.01
+
+
+@pytest.mark.parametrize('case', list(bk.SUBBLOCK_CASES))
+def test_subblock_reader_on_gpu(case):
+    """Sub-block readers: od_group_set_window + od_bbox on the device, blocks replaced under way, prefetch on the copy stream."""
+    o, rd = bk.run_product_subblock(case)
+    e, dz, window, n_windows = bk.check_subblock(o, rd, case)
+    assert e < 5e-8 and dz <= 1e-5 and n_windows >= 1, (e, dz, window, n_windows)
+
+
+def test_subblock_rewindow_on_gpu():
+    o, rd = bk.run_product_rewindow(True)
+    f, rf = bk.run_product_rewindow(False)
+    assert rd.windows_set >= 2
+    import common
+    import numpy as np
+    e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), np.asarray(f.elements.lon), np.asarray(f.elements.lat)))
+    assert e < 1e-6, e

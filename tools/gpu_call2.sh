@@ -1,5 +1,7 @@
 set -x
 mkdir -p gpurun_out
+# the library must match the sources of this snapshot (rebuilds only when a source is newer than the .so)
+python -c 'from opendrift_b200 import build; build.build()' || exit 1
 python -m pytest tests -m gpu -x -q -s > gpurun_out/t2_gputests.log 2>&1
 tail -5 gpurun_out/t2_gputests.log
 grep -h "cfg[245]" gpurun_out/t2_gputests.log | head -20
