@@ -864,17 +864,24 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self.elements.permute(perm)
         self._sorted = False
 
+    def _draws_follow_element_order(self):
+        """True when this step consumes draws of NumPy's legacy generator element by element (parity mode): the device arrays
+        must then stay in the reference's order.  Model classes add their own draws (vertical mixing, Leeway's jibing)."""
+        if any(x > 0 for x in self._uncertainty()):
+            return True   # the uncertainty draws are always the legacy generator's
+        if self.get_config('gpu:rng', 'numpy') == 'philox':
+            return False
+        D = self._constant_or_none('horizontal_diffusivity') if 'horizontal_diffusivity' in self.required_variables else 0
+        return D is None or D != 0
+
     def _maybe_sort(self):
         """Keep the device arrays ordered by grid cell (locality of the field gathers).  Element order is
         an implementation detail of the device arrays: outputs are keyed by ID."""
         k = self.get_config('gpu:sort_interval_steps')
         if not k or self.steps_calculation % k != 0 or self.num_elements_active() < 100000:
             return
-        if self.get_config('gpu:rng', 'numpy') != 'philox' and (
-                (self._constant_or_none('horizontal_diffusivity') or 0) != 0 or self._constant_or_none('horizontal_diffusivity') is None):
-            return        # the legacy RNG draws are consumed in element order: keep the reference's order
-        if any(x > 0 for x in self._uncertainty()):
-            return        # so are the uncertainty draws (always the legacy generator)
+        if self._draws_follow_element_order():
+            return        # the legacy generator's draws are consumed in element order: keep the reference's order
         r = self.env.reader_for('x_sea_water_velocity', self.time)
         if r is None or not hasattr(r, 'group_of'):
             return

@@ -249,6 +249,10 @@ class Leeway(OpenDriftSimulation):
             cache[key] = self.engine.add_group(lon, lat, None, 2, [t], lambda ti, c: slab[c], tuple(vals))
         return cache[key]
 
+    def _draws_follow_element_order(self):
+        # jibing (and capsizing) draw np.random.random(n) in element order (leeway.py:443-451, 483-487)
+        return self.get_config('gpu:rng') == 'numpy' or super()._draws_follow_element_order()
+
     def update_and_diffuse(self):
         if type(self).update is Leeway.update:
             self.update()                        # stock recipe: no host-side environment needed

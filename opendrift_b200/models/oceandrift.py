@@ -271,6 +271,12 @@ class OceanDrift(OpenDriftSimulation):
         lon0, lat0, f32 = self._start_positions
         self.elements.set_dev('z', self._mix(lon0, lat0, self._z_for_sampling(), f32))
 
+    def _draws_follow_element_order(self):
+        if super()._draws_follow_element_order():
+            return True
+        # the mixing loop draws np.random.random(n) per inner iteration (oceandrift.py:524)
+        return bool(self.get_config('drift:vertical_mixing')) and self.get_config('gpu:rng') == 'numpy'
+
     # -- fused path -----------------------------------------------------------------------------------------------
     def _fused_ok(self):
         t = type(self)

@@ -31,7 +31,7 @@ def _case(kind):
     return _cases[kind]
 
 
-@pytest.mark.parametrize('kind,sort,ztol', [('cfg2', 20, 0.0), ('cfg2', 0, 0.0), ('cfg5', 20, 0.0), ('cfg4', 0, 1e-9)])
+@pytest.mark.parametrize('kind,sort,ztol', [('cfg2', 20, 0.0), ('cfg2', 0, 0.0), ('cfg5', 20, 0.0), ('cfg4', 0, 1e-9), ('cfg4', 20, 1e-9)])
 def test_benchmarked_configuration_on_the_host_build(kind, sort, ztol, host_engine):
     c = _case(kind)
     o = c.model(**{'gpu:sort_interval_steps': sort})
