@@ -524,6 +524,33 @@ typedef struct od_bookkeep_args {
 
 int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a);
 
+/* ---- particle exchange of the spatial-tile mode --------------------------------------------------------------
+ * BASELINE configs[2]: every rank owns one longitude strip of the domain (and holds only that part of the forcing, plus a halo);
+ * after a step the elements that left their strip travel to the new owner in ONE all-to-all.  od_pack_by_owner groups the
+ * elements by the strip their longitude falls in (h_bounds[0..world]: strip r = [bounds[r], bounds[r+1]), the edge strips
+ * open-ended) -- stable, elements of one owner keep their order -- and packs them as fixed-size records: the given SoA columns
+ * side by side, column c at byte offset sum(col_bytes[:c]).  h_counts[r] = elements for rank r (synchronises): the split sizes of
+ * the all_to_all_single over d_records.  od_unpack_records is the inverse on the receiving side.  (There is no reference
+ * counterpart: the reference is a single process.) */
+#define OD_PACK_MAX_COLS 16
+#define OD_PACK_MAX_WORLD 64
+typedef struct od_pack_args {
+    int64_t n;
+    const double* d_lon;                       /* decides the owner */
+    const double* h_bounds;                    /* [world + 1] strip edges (host) */
+    int32_t world, ncols;
+    const void* d_cols[OD_PACK_MAX_COLS];      /* SoA columns, n elements each */
+    int32_t col_bytes[OD_PACK_MAX_COLS];       /* bytes per element of each column */
+    int32_t rec_bytes, pad_;                   /* = sum(col_bytes) */
+    void* d_records;                           /* out: [n][rec_bytes] */
+    int32_t* d_perm;                           /* out, optional: perm[row] = index of the element packed into that row */
+    int64_t* h_counts;                         /* out: [world] (host) */
+} od_pack_args;
+
+int od_pack_by_owner(od_ctx* ctx, const od_pack_args* a);
+int od_unpack_records(od_ctx* ctx, int64_t n, const void* d_records, int32_t ncols, void* const* d_cols, const int32_t* col_bytes,
+                      int32_t rec_bytes);
+
 /* ---- particle order (locality) ---------------------------------------------------------- */
 /* d_perm_out[k] = index of the particle that should sit at position k when particles are ordered by
  * the grid cell (and level) of `group` they are in.  Stable counting sort. */

@@ -141,6 +141,15 @@ class BookkeepArgs(C.Structure):
                 ('h_counts', C.POINTER(C.c_int64))]
 
 
+OD_PACK_MAX_COLS, OD_PACK_MAX_WORLD = 16, 64
+
+
+class PackArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_lon', C.c_void_p), ('h_bounds', C.POINTER(C.c_double)), ('world', C.c_int32), ('ncols', C.c_int32),
+                ('d_cols', C.c_void_p * OD_PACK_MAX_COLS), ('col_bytes', C.c_int32 * OD_PACK_MAX_COLS), ('rec_bytes', C.c_int32),
+                ('pad_', C.c_int32), ('d_records', C.c_void_p), ('d_perm', C.c_void_p), ('h_counts', C.POINTER(C.c_int64))]
+
+
 OD_PROJ_STERE_SPHERE = 1
 OD_ANALYTIC_DOUBLE_GYRE = 1
 
@@ -180,6 +189,8 @@ SYMBOLS = {
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
     'od_vertical_buoyancy': (C.c_int, [_P, C.POINTER(BuoyancyArgs)]),
     'od_bookkeeping': (C.c_int, [_P, C.POINTER(BookkeepArgs)]),
+    'od_pack_by_owner': (C.c_int, [_P, C.POINTER(PackArgs)]),
+    'od_unpack_records': (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),
     'od_partition_active': (C.c_int, [_P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     'od_permute': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int]),

@@ -1022,6 +1022,98 @@ __global__ void __launch_bounds__(OD_BLOCK) permute_kernel(int64_t n, const int3
     else dst[k] = src[perm[k]];
 }
 
+// ---- particle exchange of the spatial-tile mode (BASELINE configs[2]: "halo particles that cross tile boundaries are
+// exchanged with a single all-to-all") -------------------------------------------------------------------------------------
+// Every rank owns one longitude strip.  After a step the elements are grouped by the rank that owns their new position and
+// packed as fixed-size records (one row per element, the SoA columns side by side) so that ONE all_to_all_single moves them:
+//   pass 1  owner of every element (search in the strip bounds) + per-block histogram, written owner-major [owner][block]
+//   scan    exclusive scan of that table = first output row of every (owner, block) pair (stable: blocks in order)
+//   pass 2  rank of the element among its block's elements with the same owner (warp match + per-warp counts) -> row;
+//           the element's columns are copied into its record
+// The receiving side scatters the records back into SoA columns (unpack_records_kernel).
+#define OD_PACK_BLOCK 256
+#define OD_PACK_MAX_COLS 16
+#define OD_PACK_MAX_WORLD 64
+
+struct PackParams {
+    int64_t n;
+    const double* lon;
+    int world, ncols, rec_bytes, nblocks;
+    double bounds[OD_PACK_MAX_WORLD + 1];
+    const unsigned char* cols[OD_PACK_MAX_COLS];
+    int col_bytes[OD_PACK_MAX_COLS];
+    int col_off[OD_PACK_MAX_COLS];
+};
+
+__device__ __forceinline__ int strip_of(const PackParams& p, double x) {
+    // torch.bucketize(lon, inner_bounds, right=True) clamped: number of inner bounds <= x  (NaN -> last strip, like bucketize)
+    int o = 0;
+    for (int k = 1; k < p.world; ++k) o += (x >= p.bounds[k]) ? 1 : 0;
+    if (!(x == x)) o = p.world - 1;
+    return o;
+}
+
+__global__ void __launch_bounds__(OD_PACK_BLOCK) owner_count_kernel(const __grid_constant__ PackParams p, int32_t* __restrict__ table) {
+    __shared__ int hist[OD_PACK_MAX_WORLD];
+    for (int k = threadIdx.x; k < p.world; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) atomicAdd(&hist[strip_of(p, p.lon[i])], 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.world; k += blockDim.x) table[(int64_t)k * p.nblocks + blockIdx.x] = hist[k];
+}
+
+__global__ void __launch_bounds__(OD_PACK_BLOCK) owner_pack_kernel(const __grid_constant__ PackParams p, const int32_t* __restrict__ table,
+                                                                   unsigned char* __restrict__ records, int32_t* __restrict__ perm) {
+    __shared__ int warp_cnt[OD_PACK_BLOCK / 32][OD_PACK_MAX_WORLD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < (OD_PACK_BLOCK / 32) * OD_PACK_MAX_WORLD; k += blockDim.x) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
+    const int owner = valid ? strip_of(p, p.lon[i]) : -1;
+    const unsigned same = __match_any_sync(0xffffffffu, owner);
+    const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0) warp_cnt[warp][owner] = __popc(same);
+    __syncthreads();
+    if (!valid) return;
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_cnt[w][owner];
+    const int64_t row = (int64_t)table[(int64_t)owner * p.nblocks + blockIdx.x] + before + rank_in_warp;
+    if (perm) perm[row] = (int32_t)i;
+    unsigned char* rec = records + row * p.rec_bytes;
+    for (int c = 0; c < p.ncols; ++c) {
+        const int b = p.col_bytes[c];
+        const unsigned char* src = p.cols[c] + i * b;
+        unsigned char* dst = rec + p.col_off[c];
+        if (b == 8 && ((p.col_off[c] | p.rec_bytes) & 7) == 0) *reinterpret_cast<uint64_t*>(dst) = *reinterpret_cast<const uint64_t*>(src);
+        else if (b == 4 && ((p.col_off[c] | p.rec_bytes) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+        else for (int k = 0; k < b; ++k) dst[k] = src[k];
+    }
+}
+
+struct UnpackParams {
+    int64_t n;
+    int ncols, rec_bytes;
+    unsigned char* cols[OD_PACK_MAX_COLS];
+    int col_bytes[OD_PACK_MAX_COLS];
+    int col_off[OD_PACK_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(OD_PACK_BLOCK) unpack_records_kernel(const __grid_constant__ UnpackParams p, const unsigned char* __restrict__ records) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const unsigned char* rec = records + i * p.rec_bytes;
+    for (int c = 0; c < p.ncols; ++c) {
+        const int b = p.col_bytes[c];
+        const unsigned char* src = rec + p.col_off[c];
+        unsigned char* dst = p.cols[c] + i * b;
+        if (b == 8 && ((p.col_off[c] | p.rec_bytes) & 7) == 0) *reinterpret_cast<uint64_t*>(dst) = *reinterpret_cast<const uint64_t*>(src);
+        else if (b == 4 && ((p.col_off[c] | p.rec_bytes) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+        else for (int k = 0; k < b; ++k) dst[k] = src[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI entry points
 // ------------------------------------------------------------------------------------------------
@@ -1967,4 +2059,83 @@ extern "C" int od_permute(od_ctx* ctx, int64_t n, const int32_t* perm, const voi
 
 extern "C" int od_unpermute(od_ctx* ctx, int64_t n, const int32_t* perm, const void* src, void* dst, int es) {
     return permute_impl(ctx, n, perm, src, dst, es, 1);
+}
+
+
+// ---- od_pack_by_owner / od_unpack_records --------------------------------------------------------------------------------------
+static int pack_layout(int ncols, const int32_t* col_bytes, int* off, int* rec_bytes) {
+    int o = 0;
+    for (int c = 0; c < ncols; ++c) {
+        if (col_bytes[c] < 1 || col_bytes[c] > 64) return -1;
+        off[c] = o;
+        o += col_bytes[c];
+    }
+    *rec_bytes = o;
+    return 0;
+}
+
+extern "C" int od_pack_by_owner(od_ctx* ctx, const od_pack_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_pack_by_owner: null argument");
+    if (a->n < 0 || a->n >= (1ll << 31) || a->world < 1 || a->world > OD_PACK_MAX_WORLD || a->ncols < 1 || a->ncols > OD_PACK_MAX_COLS ||
+        !a->h_bounds || !a->h_counts || (a->n > 0 && (!a->d_lon || !a->d_records)))
+        return fail(ctx, OD_ERR_ARG, "od_pack_by_owner: bad arguments");
+    PackParams p;
+    memset(&p, 0, sizeof(p));
+    if (pack_layout(a->ncols, a->col_bytes, p.col_off, &p.rec_bytes) || p.rec_bytes != a->rec_bytes)
+        return fail(ctx, OD_ERR_ARG, "od_pack_by_owner: record layout does not match the column widths");
+    for (int r = 0; r < a->world; ++r) a->h_counts[r] = 0;
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    p.n = a->n; p.lon = a->d_lon; p.world = a->world; p.ncols = a->ncols;
+    for (int k = 0; k <= a->world; ++k) p.bounds[k] = a->h_bounds[k];
+    for (int c = 0; c < a->ncols; ++c) {
+        if (!a->d_cols[c]) return fail(ctx, OD_ERR_ARG, "od_pack_by_owner: null column");
+        p.cols[c] = (const unsigned char*)a->d_cols[c];
+        p.col_bytes[c] = a->col_bytes[c];
+    }
+    p.nblocks = (int)((a->n + OD_PACK_BLOCK - 1) / OD_PACK_BLOCK);
+    const int64_t nbins = (int64_t)p.nblocks * a->world + 1;           // (+1: the grand total lands behind the table)
+    if (ctx->bins_cap < nbins) {
+        if (ctx->d_bins) cudaFree(ctx->d_bins);
+        ctx->d_bins = nullptr;
+        CK(cudaMalloc(&ctx->d_bins, nbins * sizeof(int32_t)));
+        ctx->bins_cap = nbins;
+    }
+    CK(cudaMemsetAsync(ctx->d_bins + (nbins - 1), 0, sizeof(int32_t), ctx->stream));
+    owner_count_kernel<<<p.nblocks, OD_PACK_BLOCK, 0, ctx->stream>>>(p, ctx->d_bins);
+    ctx->launches++;
+    int rc = scan_exclusive(ctx, ctx->d_bins, (int)nbins);
+    if (rc) return rc;
+    owner_pack_kernel<<<p.nblocks, OD_PACK_BLOCK, 0, ctx->stream>>>(p, ctx->d_bins, (unsigned char*)a->d_records, a->d_perm);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    // first row of every owner (+ the total) -> counts
+    std::vector<int32_t> first(a->world + 1);
+    for (int r = 0; r <= a->world; ++r)
+        CK(cudaMemcpyAsync(&first[r], ctx->d_bins + (int64_t)r * p.nblocks, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < a->world; ++r) a->h_counts[r] = (int64_t)first[r + 1] - first[r];
+    return OD_OK;
+}
+
+extern "C" int od_unpack_records(od_ctx* ctx, int64_t n, const void* d_records, int32_t ncols, void* const* d_cols, const int32_t* col_bytes,
+                                 int32_t rec_bytes) {
+    if (!ctx || n < 0 || ncols < 1 || ncols > OD_PACK_MAX_COLS || !d_cols || !col_bytes || (n > 0 && !d_records))
+        return fail(ctx, OD_ERR_ARG, "od_unpack_records: bad arguments");
+    UnpackParams p;
+    memset(&p, 0, sizeof(p));
+    if (pack_layout(ncols, col_bytes, p.col_off, &p.rec_bytes) || p.rec_bytes != rec_bytes)
+        return fail(ctx, OD_ERR_ARG, "od_unpack_records: record layout does not match the column widths");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    p.n = n; p.ncols = ncols;
+    for (int c = 0; c < ncols; ++c) {
+        if (!d_cols[c]) return fail(ctx, OD_ERR_ARG, "od_unpack_records: null column");
+        p.cols[c] = (unsigned char*)d_cols[c];
+        p.col_bytes[c] = col_bytes[c];
+    }
+    unpack_records_kernel<<<(unsigned)((n + OD_PACK_BLOCK - 1) / OD_PACK_BLOCK), OD_PACK_BLOCK, 0, ctx->stream>>>(p, (const unsigned char*)d_records);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return OD_OK;
 }

@@ -911,6 +911,46 @@ class Engine:
         self.last_mix_deactivated = int(nd.value)
         return z_out
 
+    # -- particle exchange of the spatial-tile mode (od_pack_by_owner / od_unpack_records) --------------------------------------
+    def pack_by_owner(self, lon, bounds, columns, want_perm=False):
+        """Group the elements by the longitude strip that owns them and pack them as records (one row per element, the
+        columns side by side).  columns: dict name -> 1-D device tensor (n elements).  Returns (records uint8 [n, rec_bytes],
+        counts per owner, layout, perm or None); layout = [(name, dtype, bytes), ...] for unpack_records."""
+        torch = self.torch
+        n = lon.numel()
+        assert lon.dtype == torch.float64 and len(columns) <= _lib.OD_PACK_MAX_COLS and len(bounds) - 1 <= _lib.OD_PACK_MAX_WORLD
+        a = _lib.PackArgs()
+        a.n, a.d_lon, a.world, a.ncols = n, lon.data_ptr(), len(bounds) - 1, len(columns)
+        hb = (C.c_double * len(bounds))(*[float(b) for b in bounds])
+        a.h_bounds = hb
+        layout, rec = [], 0
+        for k, (name, t) in enumerate(columns.items()):
+            assert t.is_contiguous() and t.dim() == 1 and t.numel() == n and t.device == lon.device
+            a.d_cols[k], a.col_bytes[k] = t.data_ptr(), t.element_size()
+            layout.append((name, t.dtype, t.element_size()))
+            rec += t.element_size()
+        a.rec_bytes = rec
+        records = torch.empty((n, rec), dtype=torch.uint8, device=lon.device)
+        a.d_records = records.data_ptr()
+        perm = self.empty(n, torch.int32) if want_perm else None
+        if perm is not None:
+            a.d_perm = perm.data_ptr()
+        counts = (C.c_int64 * (len(bounds) - 1))()
+        a.h_counts = counts
+        self._check(self.lib.od_pack_by_owner(self.ctx, C.byref(a)))
+        return records, [int(c) for c in counts], layout, perm
+
+    def unpack_records(self, records, layout):
+        """records uint8 [n, rec_bytes] -> dict name -> tensor (the inverse of pack_by_owner's packing)."""
+        torch = self.torch
+        n = records.shape[0]
+        out = {name: torch.empty(n, dtype=dt, device=records.device) for name, dt, _ in layout}
+        ptrs = (C.c_void_p * len(layout))(*[out[name].data_ptr() for name, _, _ in layout])
+        widths = (C.c_int32 * len(layout))(*[b for _, _, b in layout])
+        self._check(self.lib.od_unpack_records(self.ctx, n, C.c_void_p(records.data_ptr()), len(layout), ptrs, widths,
+                                               sum(b for _, _, b in layout)))
+        return out
+
     def sort_by_cell(self, group, lon, lat, z=None):
         if z is not None and z.dtype != self.torch.float32:
             z = z.to(self.torch.float32)          # ordering only

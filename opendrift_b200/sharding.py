@@ -116,6 +116,25 @@ def exchange_particles(columns, owner, group=None):
     return _unpack(torch.cat([mine] + others, dim=0), layout)
 
 
+def exchange_particles_device(eng, columns, bounds, group=None):
+    """exchange_particles with the packing done by the library on the device: od_pack_by_owner groups the elements by the strip
+    their 'lon' column falls in and packs them as records, ONE all_to_all_single (after the counts) moves them over NCCL,
+    od_unpack_records restores the SoA columns.  columns: dict name -> 1-D device tensor incl. 'lon' (float64).  Returns the
+    columns of the elements this rank owns now (segments in source-rank order; identity is in the ID column)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(columns)
+    rec, counts, layout, _ = eng.pack_by_owner(columns['lon'], bounds, columns)
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=rec.device)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    recv = recv_counts.tolist()
+    out = torch.empty((int(sum(recv)), rec.shape[1]), dtype=torch.uint8, device=rec.device)
+    dist.all_to_all_single(out, rec, output_split_sizes=recv, input_split_sizes=counts, group=group)
+    return eng.unpack_records(out, layout)
+
+
 def strip_columns(lon, bounds, halo_cells):
     """Column range [i0, i1) of the global grid each rank holds in spatial-tile mode: the cells of its longitude strip plus
     `halo_cells` on either side -- the reference's own block rule, buffer = ceil(max_speed * dt / pixel size) + 2 cells
