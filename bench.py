@@ -609,11 +609,11 @@ def run_b200(args):
     extra = {}
     if world == 1 and not args.no_legs:
         import bench_legs as bl
-        for key, fn in (('api', lambda: bl.leg_api(eng, torch, n, max(8, min(args.steps, 200)),
+        for key, fn in (('api', lambda: bl.leg_api(eng, torch, n, args.api_steps,
                                                    {'current': {CUR[0]: [d[0] for d in dev_slabs], CUR[1]: [d[1] for d in dev_slabs],
                                                                 'upward_sea_water_velocity': [d_w] * PERIOD}}, grid, peak)),
-                        ('cfg4_mixing_wind_stokes', lambda: bl.leg_cfg4(eng, torch, args.cfg4_particles, 12, peak)),
-                        ('cfg5_leeway', lambda: bl.leg_cfg5(eng, torch, args.cfg5_particles, 30, peak))):
+                        ('cfg4_mixing_wind_stokes', lambda: bl.leg_cfg4(eng, torch, args.cfg4_particles, 40, peak)),
+                        ('cfg5_leeway', lambda: bl.leg_cfg5(eng, torch, args.cfg5_particles, 60, peak))):
             try:
                 torch.cuda.empty_cache()
                 extra[key] = fn()
@@ -698,6 +698,7 @@ def main():
     ap.add_argument('--parity-particles', type=int, default=20000)
     ap.add_argument('--parity-extra', type=int, default=5, help='further steps after the timed region, replayed for 1e5 particles')
     ap.add_argument('--no-legs', action='store_true', help='skip the api / cfg 4 / cfg 5 legs')
+    ap.add_argument('--api-steps', type=int, default=120, help='steps of the OceanDrift.run() leg')
     ap.add_argument('--cfg4-particles', type=int, default=5_000_000)
     ap.add_argument('--cfg5-particles', type=int, default=20_000_000)
     args = ap.parse_args()

@@ -84,10 +84,13 @@ def port_readers(g, fields, n_times):
 
 class StepTimer:
     """CUDA events around the steady-state steps of a model run: wraps one Engine method (the step launch of the model) and
-    records an event before call number `first` and after the last call.  Pure instrumentation: the wrapped call is unchanged."""
+    records an event right before call number `first` and right before the LAST call (`total` calls are expected).  The interval
+    holds total - 1 - first complete steps of run() -- step launch, the next step's housekeeping launch, cell sorts, slab
+    changes, output columns -- and none of the work run() does once after the last step (restoring the element order, reading the
+    output block back).  Pure instrumentation: the wrapped call is unchanged."""
 
-    def __init__(self, eng, torch, method, first):
-        self.eng, self.torch, self.method, self.first = eng, torch, method, first
+    def __init__(self, eng, torch, method, first, total):
+        self.eng, self.torch, self.method, self.first, self.total = eng, torch, method, first, total
         self.calls = 0
         self.e0 = torch.cuda.Event(enable_timing=True)
         self.e1 = torch.cuda.Event(enable_timing=True)
@@ -97,23 +100,26 @@ class StepTimer:
         def wrapped(*a, **k):
             if self.calls == self.first:
                 self.e0.record()
-                self.t0 = time.perf_counter()
+            if self.calls == self.total - 1:
+                self.e1.record()
+                self.t_last = time.perf_counter()
             self.calls += 1
             return self.orig(*a, **k)
         setattr(self.eng, self.method, wrapped)
         return self
 
     def __exit__(self, *exc):
-        self.e1.record()
         self.torch.cuda.synchronize()
         self.t1 = time.perf_counter()
         delattr(self.eng, self.method)           # the instance attribute shadows the class method
         return False
 
     def ms_per_step(self):
-        """Mean time of a steady-state step: from the launch of step `first` to the end of the run's last step, bookkeeping,
-        sorting and output included -- divided by the steps in between."""
-        return self.e0.elapsed_time(self.e1) / max(1, self.calls - self.first)
+        return self.e0.elapsed_time(self.e1) / max(1, self.total - 1 - self.first)
+
+    def tail_s(self):
+        """Wall time from the launch of the last step to the return of run(): last step + final state + read-back."""
+        return self.t1 - self.t_last
 
 
 def events(torch, fn, reps=5):
@@ -151,24 +157,28 @@ def leg_api(eng, torch, n, steps, dev_fields, grid, peak):
     n_times = syn.n_slabs_for(steps + 2, DT) + 1
     out = {}
     for name, every in (('output_at_end', steps), ('output_every_step', 1)):
-        k = steps if every != 1 else min(steps, 27)
+        k = steps if every != 1 else min(steps, 40)
         o = _oceandrift(eng, product_readers(grid, dev_fields, n_times), cfg)
         w0 = time.perf_counter()
         o.seed_elements(lon=lon0, lat=lat0, z=z0, time=syn.T0)
         w1 = time.perf_counter()
-        first = min(3, k - 1)
-        with StepTimer(eng, torch, 'step_oceandrift', first) as st:
+        first = min(3, k - 2)
+        l0 = eng.launches()
+        with StepTimer(eng, torch, 'step_oceandrift', first, k) as st:
             o.run(steps=k, time_step=DT, time_step_output=every * DT)
         wall = st.t1 - w1
         ms = st.ms_per_step()
         out[name] = {'steps': k, 'ms_per_step_steady': ms, 'particle_steps_per_s_steady': n / (ms * 1e-3),
-                     'run_wall_s': wall, 'seed_elements_s': w1 - w0, 'particle_steps_per_s_whole_run': n * k / wall,
-                     'output_columns': len(o.history['time']), 'launches_per_step': None}
+                     'run_wall_s': wall, 'seed_elements_s': w1 - w0, 'after_last_step_s': st.tail_s(),
+                     'particle_steps_per_s_whole_run': n * k / wall,
+                     'output_columns': len(o.history['time']), 'gpu_launches_per_step': (eng.launches() - l0) / k}
         assert o.num_elements_active() == n and st.calls == k
         del o
-    out['note'] = ('steady = CUDA events from the launch of step 3 to the end of the last step of run() (housekeeping launch, cell sort '
-                   'every 20 steps, fused step launch, output columns and their read-back); whole_run = wall clock of run() incl. the '
-                   'release of the seeded elements to the device and the final read-back')
+    out['note'] = ('steady = CUDA events from the launch of step 3 to the launch of the last step inside run(): per step the housekeeping '
+                   'launch (outside / output column / age), the fused step launch, the cell sort every 20 steps, slab changes with their '
+                   'prefetch, and -- output_every_step -- the read-back of full output blocks; whole_run = wall clock of run() incl. the '
+                   'release of the seeded elements to the device (host arrays -> HBM) and, after the last step, the restoring of the element '
+                   'order and the read-back of the output block (after_last_step_s)')
     return out
 
 
@@ -204,7 +214,7 @@ def leg_cfg4(eng, torch, n, steps, peak):
     o = _oceandrift(eng, product_readers(grid, dev, n_times), dict(cfg, **{'gpu:rng': 'philox'}))
     o.seed_elements(lon=lon0, lat=lat0, z=z0, time=syn.T0)
     l0 = eng.launches()
-    with StepTimer(eng, torch, 'step_oceandrift', min(3, steps - 1)) as st:
+    with StepTimer(eng, torch, 'step_oceandrift', min(3, steps - 2), steps) as st:
         o.run(steps=steps, time_step=DT, time_step_output=steps * DT)
     launches = eng.launches() - l0
     ms = st.ms_per_step()
@@ -271,7 +281,7 @@ def leg_cfg5(eng, torch, n, steps, peak):
     o.seed_elements(lon=lon0, lat=lat0, time=syn.T0, object_type=1)
     seed_s = time.perf_counter() - w0
     l0 = eng.launches()
-    with StepTimer(eng, torch, 'leeway_step', min(3, steps - 1)) as st:
+    with StepTimer(eng, torch, 'leeway_step', min(3, steps - 2), steps) as st:
         o.run(steps=steps, time_step=DT, time_step_output=steps * DT)
     launches = eng.launches() - l0
     ms = st.ms_per_step()
