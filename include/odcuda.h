@@ -385,8 +385,14 @@ typedef struct od_mix_args {
     double k_const;               /* model 3: the constant diffusivity */
     int32_t* d_status;            /* seafloor_action 2 */
     int32_t* d_moving_out;        /* seafloor_action 2: the array d_moving points to, writable */
-    int32_t seafloor_code, pad2_;
+    int32_t seafloor_code;
+    int32_t iter0;                /* index of this call's first inner iteration within the time step: a subclass that overrides the
+                                     per-iteration hooks of the loop (surface_stick, surface_wave_mixing, bottom_interaction,
+                                     update_terminal_velocity: oceandrift.py:369-379, 553-564) gets one launch per iteration (ntimes = 1)
+                                     with the device generator continuing where the fused loop would be */
     int64_t* h_n_deactivated;     /* seafloor_action 2, optional: elements deactivated by this call (synchronises) */
+    int32_t skip_surface_stick;   /* the model overrides surface_stick(): the launch leaves elements above the surface alone */
+    int32_t pad3_;
 } od_mix_args;
 #define OD_MIX_ENVIRONMENT 0
 #define OD_MIX_LARGE1994 1

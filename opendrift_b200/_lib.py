@@ -73,7 +73,8 @@ class MixArgs(C.Structure):
                 ('pos_f32', C.c_int32), ('model', C.c_int32), ('nlev', C.c_int32), ('seafloor_action', C.c_int32),
                 ('d_wind_speed', C.c_void_p), ('d_mld', C.c_void_p), ('mld_const', C.c_double),
                 ('background', C.c_double), ('k_const', C.c_double), ('d_status', C.c_void_p), ('d_moving_out', C.c_void_p),
-                ('seafloor_code', C.c_int32), ('pad2_', C.c_int32), ('h_n_deactivated', C.POINTER(C.c_int64))]
+                ('seafloor_code', C.c_int32), ('iter0', C.c_int32), ('h_n_deactivated', C.POINTER(C.c_int64)),
+                ('skip_surface_stick', C.c_int32), ('pad3_', C.c_int32)]
 
 
 class LeewayArgs(C.Structure):

@@ -1954,6 +1954,7 @@ extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {
     p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
     p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
     p.seafloor_action = a->seafloor_action; p.seafloor_code = a->seafloor_code; p.status = a->d_status; p.moving_out = a->d_moving_out;
+    p.iter0 = a->iter0; p.skip_surface_stick = a->skip_surface_stick;
     if (a->h_n_deactivated) *a->h_n_deactivated = 0;
     if (a->seafloor_action < 0 || a->seafloor_action > 2 || (a->seafloor_action == 2 && (!a->d_status || !a->d_moving_out)))
         return fail(ctx, OD_ERR_ARG, "od_vertical_mixing: bad sea-floor action");

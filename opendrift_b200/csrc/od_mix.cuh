@@ -73,6 +73,8 @@ struct MixParams {
     // 'Let particles stick to bottom' (oceandrift.py:559-564 -> interact_with_seafloor, basemodel/__init__.py:748-783)
     int32_t seafloor_action;     // 0 none, 1 lift_to_seafloor, 2 deactivate
     int32_t seafloor_code;
+    int32_t iter0;               // first inner iteration of this launch within the step (per-iteration launches for hook overrides)
+    int32_t skip_surface_stick;
     int32_t* status;
     int32_t* moving_out;
     unsigned* counter;
@@ -231,10 +233,17 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
         double U;
         if (p.rand) {
             U = p.rand[(int64_t)it * p.n + i];
-        } else if ((it & 1) == 0) {
-            philox_uniform2(p.seed, id, (unsigned)p.step_index, (unsigned)(it >> 1), U, spare);
         } else {
-            U = spare;
+            // one Philox block serves two iterations; a launch that starts on an odd iteration regenerates its block
+            const int git = p.iter0 + it;
+            if ((git & 1) == 0 || it == 0) {
+                double a, b;
+                philox_uniform2(p.seed, id, (unsigned)p.step_index, (unsigned)(git >> 1), a, b);
+                U = (git & 1) ? b : a;
+                spare = b;
+            } else {
+                U = spare;
+            }
         }
         const double R = OD_DSUB(OD_DMUL(2.0, U), 1.0);
         const double walk = OD_DMUL(R, sqrt(OD_DMUL(OD_DMUL(Kz, adt), 2.0) / r));
@@ -243,7 +252,7 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
         if (z < zmin && mv == 1.0) z = OD_DSUB(OD_DMUL(2.0, zmin), z);    // reflect from the sea floor
         z = OD_DADD(z, OD_DMUL(OD_DMUL(w, p.dt_mix), mv));           // buoyancy
         if (!p.mix_at_surface && surface) z = 0.0;
-        if (z > 0.0) z = 0.0;                                          // surface_stick
+        if (z > 0.0 && !p.skip_surface_stick) z = 0.0;                 // surface_stick
         if (p.seafloor_action && z < zmin) {                           // stick to the bottom
             z = zmin;
             if (p.seafloor_action == 2) {                              // deactivate_elements: moving = 0 from here on

@@ -857,7 +857,7 @@ class Engine:
     def vertical_mixing(self, group, t, lon, lat, z_in, dt_mix, ntimes, moving=None, terminal_velocity=None, ids=None,
                         rand=None, seed=0, step_index=0, sea_floor=10000.0, mix_at_surface=False, pos_f32=False,
                         model='environment', wind_speed=None, mld=50.0, background=1.2e-5, k_const=0.0, seafloor_action=0,
-                        status=None, seafloor_code=0):
+                        status=None, seafloor_code=0, iter0=0, skip_surface_stick=False):
         """OceanDrift.vertical_mixing on device tensors; returns the new depth (float64 tensor).
         model 'environment' takes the diffusivity column from `group`; 'windspeed_Large1994' / 'windspeed_Sundby1983' /
         'constant' build it analytically on 1 m levels from wind_speed (float32 tensor) and the mixed layer depth mld
@@ -901,6 +901,7 @@ class Engine:
             a.sea_floor_const = float(sea_floor)
         a.dt_mix, a.seed, a.step_index = float(dt_mix), int(seed), int(step_index)
         a.mix_at_surface, a.pos_f32 = (1 if mix_at_surface else 0), (1 if pos_f32 else 0)
+        a.iter0, a.skip_surface_stick = int(iter0), 1 if skip_surface_stick else 0
         a.seafloor_action = int(seafloor_action)          # 'stick to bottom' with a sea-floor reader: 1 lift, 2 deactivate
         nd = C.c_int64(0)
         if a.seafloor_action == 2:

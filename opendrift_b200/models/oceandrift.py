@@ -115,6 +115,27 @@ class OceanDrift(OpenDriftSimulation):
         """oceandrift.py:213-222: a hook for subclasses (plankton, oil droplets ...); the stock model keeps the seeded values."""
         pass
 
+    # -- per-iteration hooks of the mixing loop (oceandrift.py:369-379): no-ops here, overridden by e.g. oil and plankton models --
+    def prepare_vertical_mixing(self):
+        pass
+
+    def surface_stick(self):
+        """Elements above the surface are put back onto it (the mixing launch does this itself unless a subclass overrides it)."""
+        el, torch = self.elements, self.engine.torch
+        z = self._z_for_sampling()
+        el.set_dev('z', torch.clamp(z, max=0.0))
+
+    def bottom_interaction(self, Zmin=None):
+        pass
+
+    def surface_wave_mixing(self, time_step_seconds):
+        pass
+
+    MIXING_HOOKS = ('prepare_vertical_mixing', 'update_terminal_velocity', 'surface_stick', 'surface_wave_mixing', 'bottom_interaction')
+
+    def _overridden_mixing_hooks(self):
+        return [h for h in self.MIXING_HOOKS if getattr(type(self), h) is not getattr(OceanDrift, h)]
+
     def _buoyancy_inputs(self):
         """(sea floor tensor or None, sea_surface_height, status code for 'deactivate' or 0): the sea-floor part of
         vertical_buoyancy only acts when a reader provides the depth (interact_with_seafloor, basemodel/__init__.py:752-753)."""
@@ -220,9 +241,6 @@ class OceanDrift(OpenDriftSimulation):
         eng, el, torch = self.engine, self.elements, self.engine.torch
         g, model, dt_mix, ntimes, floor = self._mixing_inputs()
         n = len(el)
-        rand = None
-        if self.get_config('gpu:rng') == 'numpy':          # the reference's draws, in its order (:524)
-            rand = eng.to_device(np.ascontiguousarray(np.stack([np.random.random(n) for _ in range(ntimes)])))
         moving = el.dev('moving')
         if moving.dtype != torch.int32:
             moving = moving.to(torch.int32)
@@ -254,15 +272,64 @@ class OceanDrift(OpenDriftSimulation):
                 code = cats.index('seafloor') if 'seafloor' in cats else len(cats)
                 status = el.dev('status', torch.int32)
                 moving = el.dev('moving', torch.int32)
-        z_out = eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, moving=moving, terminal_velocity=tv,
-                                    ids=ids, rand=rand, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation,
-                                    sea_floor=floor, mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'),
-                                    pos_f32=pos_f32, seafloor_action=action, status=status, seafloor_code=code, **kw)
-        if action == 2 and getattr(eng, 'last_mix_deactivated', 0):
+        common = dict(moving=moving, ids=ids, seed=getattr(self, '_seed', 0), step_index=self.steps_calculation, sea_floor=floor,
+                      mix_at_surface=self.get_config('drift:vertical_mixing_at_surface'), pos_f32=pos_f32, **kw)
+        hooks = self._overridden_mixing_hooks()
+        if not hooks:
+            # the whole inner loop in one launch
+            rand = None
+            if self.get_config('gpu:rng') == 'numpy':          # the reference's draws, in its order (:524)
+                rand = eng.to_device(np.ascontiguousarray(np.stack([np.random.random(n) for _ in range(ntimes)])))
+            z_out = eng.vertical_mixing(g, self.time, lon0, lat0, z_in, dt_mix, ntimes, terminal_velocity=tv, rand=rand,
+                                        seafloor_action=action, status=status, seafloor_code=code, **common)
+            if action == 2 and getattr(eng, 'last_mix_deactivated', 0):
+                if 'seafloor' not in self.status_categories:
+                    self.status_categories.append('seafloor')
+                self._maybe_deactivated = True
+            return z_out
+        # A subclass overrides a per-iteration hook: one launch per inner iteration, the hooks in between, in the reference's
+        # order (:515-564): [update_terminal_velocity] random walk + reflections + buoyancy [surface_stick] [surface_wave_mixing]
+        # sea floor [bottom_interaction].  The draws of the legacy generator are made iteration by iteration, as the reference does
+        # (a hook may draw too); the device generator continues its per-step stream (iter0).
+        self.prepare_vertical_mixing()
+        z = z_in
+        numpy_rng = self.get_config('gpu:rng') == 'numpy'
+        for it in range(ntimes):
+            if 'update_terminal_velocity' in hooks:
+                el.set_dev('z', z)
+                self.update_terminal_velocity(Tprofiles=None, Sprofiles=None, z_index=None)
+                tv = el.dev('terminal_velocity')
+            r = eng.to_device(np.ascontiguousarray(np.random.random(n)[None])) if numpy_rng else None
+            z = eng.vertical_mixing(g, self.time, lon0, lat0, z, dt_mix, 1, terminal_velocity=tv, rand=r, iter0=it,
+                                    skip_surface_stick='surface_stick' in hooks, **common)
+            el.set_dev('z', z)
+            if 'surface_stick' in hooks:
+                self.surface_stick()
+            if 'surface_wave_mixing' in hooks:
+                self.surface_wave_mixing(abs(dt_mix))
+            if action:
+                self._stick_to_bottom(floor, action, code)
+            if 'bottom_interaction' in hooks:
+                zmin = -(self.environment.sea_floor_depth_below_sea_level + self.environment.sea_surface_height) \
+                    if 'sea_surface_height' in self.environment else -self.environment.sea_floor_depth_below_sea_level
+                if (np.asarray(el.z) < zmin).any():
+                    self.bottom_interaction(zmin)
+            z = self._z_for_sampling()
+        return z
+
+    def _stick_to_bottom(self, floor, action, code):
+        """interact_with_seafloor at the end of a mixing iteration (:559-563)."""
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        z = self._z_for_sampling()
+        if not hasattr(floor, 'data_ptr'):
+            return
+        nd = eng.vertical_buoyancy(z, z, None, 0.0, sea_floor=floor, status=el.dev('status', torch.int32),
+                                   moving=el.dev('moving', torch.int32), seafloor_code=code if action == 2 else 0, count=action == 2)
+        el.set_dev('z', z)
+        if nd:
             if 'seafloor' not in self.status_categories:
                 self.status_categories.append('seafloor')
             self._maybe_deactivated = True
-        return z_out
 
     def vertical_mixing(self, store_depths=False):
         """Helper for subclasses that override update(): uses the start-of-step positions saved by the run loop."""
@@ -284,6 +351,7 @@ class OceanDrift(OpenDriftSimulation):
                 and t.vertical_mixing is OceanDrift.vertical_mixing and t.vertical_buoyancy is OceanDrift.vertical_buoyancy
                 and t.update_terminal_velocity is OceanDrift.update_terminal_velocity
                 and not self.get_config('drift:relative_wind'))
+        # (overridden mixing hooks are served inside _mix: one launch per inner iteration)
 
     def run(self, *args, **kwargs):
         self._use_fused = None

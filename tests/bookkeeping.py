@@ -574,11 +574,73 @@ def check_subblock(o, rd, case):
     return e, dz, (grp.desc.ny, grp.desc.nx), rd.windows_set
 
 
+# ---- subclasses that override the per-iteration hooks of the mixing loop (oceandrift.py:369-379, 515-564) -----------------------
+def hook_model_class(Base, which):
+    class Hooked(Base):
+        if which in ('same_stick', 'all'):
+            def surface_stick(self):                       # the stock behaviour, spelled out by the subclass
+                z = self.elements.z
+                z[z > 0] = 0
+                self.elements.z = z
+        if which in ('wave_mixing', 'all'):
+            def surface_wave_mixing(self, time_step_seconds):      # surfaced elements are pushed down by breaking waves (draws!)
+                z = self.elements.z
+                surf = np.where(z == 0)[0]
+                if len(surf):
+                    z[surf] = -0.5 * np.random.random(len(surf)) * time_step_seconds / 60.0
+                    self.elements.z = z
+        if which == 'all':
+            def update_terminal_velocity(self, Tprofiles=None, Sprofiles=None, z_index=None):
+                self.elements.terminal_velocity = 0.002 * np.exp(np.asarray(self.elements.z, dtype=np.float64) / 20.0)
+
+            def prepare_vertical_mixing(self):
+                self.prepared = getattr(self, 'prepared', 0) + 1
+    return Hooked
+
+
+HOOK_CASES = ['same_stick', 'wave_mixing', 'all']
+
+
+def run_hook_case(which, Base, make, **model_kw):
+    fx = common.Fixture('rk4_3d_mixing')
+    o = hook_model_class(Base, which)(loglevel=50, seed=0, **model_kw)
+    o.add_reader(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: fx.u, common.CUR[1]: fx.v, 'ocean_vertical_diffusivity': fx.kdiff}, 'cur'))
+    for k, v in {'general:use_auto_landmask': False, 'general:coastline_action': 'none', 'drift:vertical_mixing': True,
+                 'drift:vertical_advection': False, 'vertical_mixing:timestep': 60.0, 'drift:advection_scheme': 'runge-kutta'}.items():
+        o.set_config(k, v)
+    if 'environment:constant:land_binary_mask' in getattr(o, '_config', {}):
+        o.set_config('environment:constant:land_binary_mask', 0)
+    n = 300
+    z0 = np.where(np.arange(n) % 4 == 0, 0.0, fx.z0[:n]).astype(np.float32)
+    o.seed_elements(lon=fx.lon0[:n], lat=fx.lat0[:n], z=z0, time=fx.start, terminal_velocity=0.001)
+    o.run(steps=3, time_step=600, time_step_output=600)
+    return o
+
+
+def run_product_hooks(which, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    return run_hook_case(which, OceanDrift, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name), **model_kw)
+
+
+def check_hooks(o, which):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['hook_%s__%s' % (which, k)]               # noqa: E731
+    assert max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat'))) < 5e-8
+    return float(np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max())
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
     refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as _RefOD0
+    for which in HOOK_CASES:
+        ro = run_hook_case(which, _RefOD0, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name), logfile='/tmp/od_bk.log')
+        out.update({'hook_%s__lon' % which: np.asarray(ro.elements.lon, dtype=np.float64), 'hook_%s__lat' % which: np.asarray(ro.elements.lat, dtype=np.float64),
+                    'hook_%s__z' % which: np.asarray(ro.elements.z, dtype=np.float64)})
+        print('hooks', which, 'z range', float(np.min(ro.elements.z)), float(np.max(ro.elements.z)))
     for case in SUBBLOCK_CASES:
         sfx, c, lon0, lat0, z0, fields = subblock_setup(case)
         rd = refrun.make_grid_reader(sfx.grid_lon, sfx.grid_lat, sfx.grid_z, sfx.times, fields, 'cur', subblocks=True)

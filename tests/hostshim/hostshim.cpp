@@ -556,6 +556,7 @@ int hs2_mix(const od_mix_args* a, const hs_group* g, const hs_pair* pr) {
     p.seed = a->seed; p.ntimes = a->ntimes; p.z_in_f64 = a->z_in_f64; p.tv_f64 = a->tv_f64;
     p.mix_at_surface = a->mix_at_surface; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
     p.seafloor_action = a->seafloor_action; p.seafloor_code = a->seafloor_code; p.status = a->d_status; p.moving_out = a->d_moving_out;
+    p.iter0 = a->iter0; p.skip_surface_stick = a->skip_surface_stick;
     unsigned cnt = 0;
     p.counter = &cnt;
     for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);

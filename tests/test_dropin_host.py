@@ -387,3 +387,37 @@ def test_subblock_reader_is_asked_for_new_blocks_when_the_elements_leave():
     e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), np.asarray(f.elements.lon), np.asarray(f.elements.lat)))
     # block-relative against whole-grid index arithmetic (float32 on the first step), grown over 24 one-hour steps: 2e-7 deg
     assert e < 1e-6, e
+
+
+@pytest.mark.parametrize('which', __import__('bookkeeping').HOOK_CASES)
+def test_mixing_loop_hooks_of_a_subclass_match_reference(which, host_engine):
+    """A subclass that overrides surface_stick / surface_wave_mixing / update_terminal_velocity / prepare_vertical_mixing gets the
+    inner loop one launch per iteration with its hooks in between, in the reference's order, the legacy generator's draws
+    interleaved as the reference interleaves them; compared with the same subclass body on the unmodified reference."""
+    import bookkeeping as bk
+    o = bk.run_product_hooks(which)
+    dz = bk.check_hooks(o, which)
+    assert dz <= 1e-9, dz
+    n_mix = host_engine.lib.calls.count('od_vertical_mixing')
+    assert n_mix == 3 * 10                                  # 3 steps x 10 inner iterations, one launch each
+    if which == 'all':
+        assert o.prepared == 3
+
+
+def test_per_iteration_mixing_launches_continue_the_device_generator(host_engine):
+    """gpu:rng = philox: ten launches of one inner iteration each (a subclass with a hook) draw what the fused ten-iteration
+    launch draws -- the depths are the same bit for bit."""
+    import bookkeeping as bk
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    make = lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name)     # noqa: E731
+
+    class Philox(OceanDrift):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.set_config('gpu:rng', 'philox')
+    hooked = bk.run_hook_case('same_stick', Philox, make)
+    plain = bk.run_hook_case('none', Philox, make)
+    assert host_engine.lib.calls.count('od_vertical_mixing') == 30 + 3
+    assert np.array_equal(np.asarray(hooked.elements.z), np.asarray(plain.elements.z))
+    assert np.array_equal(np.asarray(hooked.elements.lon), np.asarray(plain.elements.lon))

@@ -98,3 +98,8 @@ def test_subblock_rewindow_on_gpu():
     import numpy as np
     e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), np.asarray(f.elements.lon), np.asarray(f.elements.lat)))
     assert e < 1e-6, e
+
+
+@pytest.mark.parametrize('which', bk.HOOK_CASES)
+def test_mixing_loop_hooks_on_gpu(which):
+    assert bk.check_hooks(bk.run_product_hooks(which), which) <= 1e-9
