@@ -29,6 +29,18 @@
 #else
 #define OD_BK_HD static inline
 #endif
+// NumPy rounds every product and every sum: no fused multiply-add (nvcc contracts a * b + c by default)
+#if defined(__CUDA_ARCH__)
+#define OD_BK_MUL_F(a, b) __fmul_rn((a), (b))
+#define OD_BK_ADD_F(a, b) __fadd_rn((a), (b))
+#define OD_BK_MUL_D(a, b) __dmul_rn((a), (b))
+#define OD_BK_ADD_D(a, b) __dadd_rn((a), (b))
+#else
+#define OD_BK_MUL_F(a, b) ((a) * (b))
+#define OD_BK_ADD_F(a, b) ((a) + (b))
+#define OD_BK_MUL_D(a, b) ((a) * (b))
+#define OD_BK_ADD_D(a, b) ((a) + (b))
+#endif
 
 namespace od {
 
@@ -53,8 +65,9 @@ OD_BK_HD bool buoyancy_one(const BuoyancyParams& p, int64_t i) {
         double z = ((const double*)p.z_in)[i];
         if (p.tv && z < 0.0) {
             // float32 * Python float stays float32 (weak scalar); the sum with a float64 z is float64
-            const double d = p.tv_f64 ? ((const double*)p.tv)[i] * p.dt : (double)(((const float*)p.tv)[i] * (float)p.dt);
-            z = fmin(0.0, z + d);
+            // (the product is rounded on its own -- float32 for a float32 terminal velocity -- before the float64 sum)
+            const double d = p.tv_f64 ? OD_BK_MUL_D(((const double*)p.tv)[i], p.dt) : (double)OD_BK_MUL_F(((const float*)p.tv)[i], (float)p.dt);
+            z = fmin(0.0, OD_BK_ADD_D(z, d));
         }
         if (p.sea_floor) {
             const float zmin = -(p.sea_floor[i] + p.ssh);       // float32 environment arithmetic
@@ -67,8 +80,8 @@ OD_BK_HD bool buoyancy_one(const BuoyancyParams& p, int64_t i) {
     } else {
         float z = ((const float*)p.z_in)[i];
         if (p.tv && z < 0.0f) {
-            if (p.tv_f64) z = (float)fmin(0.0, (double)z + ((const double*)p.tv)[i] * p.dt);    // float64 sum, stored into the float32 array
-            else z = fminf(0.0f, z + ((const float*)p.tv)[i] * (float)p.dt);
+            if (p.tv_f64) z = (float)fmin(0.0, OD_BK_ADD_D((double)z, OD_BK_MUL_D(((const double*)p.tv)[i], p.dt)));    // float64 sum, stored into the float32 array
+            else z = fminf(0.0f, OD_BK_ADD_F(z, OD_BK_MUL_F(((const float*)p.tv)[i], (float)p.dt)));
         }
         if (p.sea_floor) {
             const float zmin = -(p.sea_floor[i] + p.ssh);

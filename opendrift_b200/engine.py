@@ -154,6 +154,7 @@ class FieldGroup:
         d.x0, d.xspan = float(lon[0]), float(np.float32(lon[-1] - lon[0]))
         d.y0, d.yspan = float(lat[0]), float(np.float32(lat[-1] - lat[0]))
         self.lon, self.lat = lon, lat
+        self.engine.order_after_copies()          # a prefetch into one of the slots may still be in flight on the copy stream
         self.engine._check(self.engine.lib.od_group_set_window(self.engine.ctx, self.gid, C.byref(d)))
         self.resident = [None] * self.n_slots
         self.ready = [None] * self.n_slots
