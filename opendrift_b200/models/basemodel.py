@@ -207,6 +207,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                             'description': 'Where the output buffer of state_to_buffer lives between flushes: device = a block of output '
                                            'columns in HBM, filled by the per-step bookkeeping launch and read back once per '
                                            'export_buffer_length output steps; host = a block of one column (read back every output step).'},
+            'gpu:history_pinned_bytes': {'type': 'int', 'default': 16 * 2 ** 30, 'min': 0, 'max': 2 ** 44, 'units': 'bytes',
+                                         'level': CONFIG_LEVEL_ADVANCED,
+                                         'description': 'Outputs with more columns than one device block: the host side of the output buffer is '
+                                                        'page-locked memory (full blocks then travel asynchronously on the copy stream) when the '
+                                                        'whole time axis fits this many bytes; 0 = always pageable.'},
             'gpu:distributed': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
                                 'description': 'Under torchrun (torch.distributed initialised, one process per GPU): rank 0 reads the forcing '
                                                'slabs and broadcasts them into the other ranks\' device ring; ranks step in lockstep.'},
@@ -914,6 +919,19 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._hist_base = 0
         self._hist_dev = None
         self._hist_hi = -1                                 # highest column written so far
+        # Long outputs (more columns than one device block): the host side of the buffer is page-locked memory for the whole
+        # time axis, the device side two blocks used in turn, and a full block travels on the copy stream -- straight into its
+        # final rows, no staging, no host copies -- while the steps go on writing the other block.
+        eng = self.engine
+        self._hist_pinned = None
+        total = per_col * n_out
+        if (n_out > self._hist_ncols and getattr(eng.device, 'type', 'cpu') == 'cuda' and total <= int(self.get_config('gpu:history_pinned_bytes'))
+                and hasattr(eng, 'begin_copy_stream')):
+            torch = eng.torch
+            shape = (n_out, int(self._n_total))
+            self._hist_pinned = tuple(torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(3)) + (
+                torch.empty(shape, dtype=torch.int32, pin_memory=True),)
+            self._hist_other, self._hist_other_ready = None, None
 
     def _column_of_step(self, i):
         """(output column, only_deactivated) of calculation step i: its own column on output steps, else the next one."""
@@ -921,30 +939,69 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return i // self._out_every, False
         return i // self._out_every + 1, True
 
+    def _new_hist_block(self):
+        eng, torch = self.engine, self.engine.torch
+        shape = (self._hist_ncols, int(self._n_total))
+        return tuple(torch.full(shape, float('nan'), dtype=torch.float32, device=eng.device) for _ in range(3)) + (
+            torch.full(shape, -1, dtype=torch.int32, device=eng.device),)
+
     def _hist_column(self, k):
         """The four device arrays [n_total] of output column k (flushing the block to the host when k lies beyond it)."""
-        eng, torch = self.engine, self.engine.torch
         if self._hist_dev is None:
-            shape = (self._hist_ncols, int(self._n_total))
-            self._hist_dev = tuple(torch.full(shape, float('nan'), dtype=torch.float32, device=eng.device) for _ in range(3)) + (
-                torch.full(shape, -1, dtype=torch.int32, device=eng.device),)
+            self._hist_dev = self._new_hist_block()
         while k >= self._hist_base + self._hist_ncols:
             self._flush_history(self._hist_ncols)
         self._hist_hi = max(self._hist_hi, k)
         return tuple(b[k - self._hist_base] for b in self._hist_dev)
 
     def _flush_history(self, ncols):
-        """Move the first ncols columns of the device block to self.history (one device-to-host copy per variable)."""
+        """Move the first ncols columns of the device block to the host side of the buffer."""
         if ncols <= 0:
             return
         h = self.history
+        eng = self.engine
+        if self._hist_pinned is not None and self._hist_dev is not None:
+            # asynchronous: the block is copied into its rows of the page-locked buffer on the copy stream (which first waits for
+            # the launches that filled it), reset there, and becomes the spare block; the steps continue on the other one
+            base = self._hist_base
+            if eng.begin_copy_stream():
+                try:
+                    for src, dst in zip(self._hist_dev, self._hist_pinned):
+                        dst[base:base + ncols].copy_(src[:ncols], non_blocking=True)
+                    for bq in self._hist_dev[:3]:
+                        bq.fill_(float('nan'))
+                    self._hist_dev[3].fill_(-1)
+                finally:
+                    ready = eng.end_copy_stream()
+                spare, spare_ready = self._hist_other, self._hist_other_ready
+                self._hist_other, self._hist_other_ready = self._hist_dev, ready
+                if spare is None:
+                    spare = self._new_hist_block()
+                elif spare_ready is not None:
+                    eng.wait_event(spare_ready)            # (a copy that finished long ago)
+                self._hist_dev = spare
+                for j in range(ncols):
+                    h['time'].append(self._out_times[base + j])
+                    for key, c in zip(('lon', 'lat', 'z', 'status'), self._hist_pinned):
+                        h[key].append(c[base + j].numpy())     # (valid once the run has synchronised: run() does before it returns)
+                self._hist_base += ncols
+                return
         if self._hist_dev is None:
             cols = [np.full((ncols, int(self._n_total)), np.nan, dtype=np.float32) for _ in range(3)] + [
                 np.full((ncols, int(self._n_total)), -1, dtype=np.int32)]
+        elif self._hist_pinned is not None:
+            base = self._hist_base
+            for src, dst in zip(self._hist_dev, self._hist_pinned):
+                dst[base:base + ncols].copy_(src[:ncols])
+            cols = [c[base:base + ncols].numpy() for c in self._hist_pinned]
+            for bq in self._hist_dev[:3]:
+                bq.fill_(float('nan'))
+            self._hist_dev[3].fill_(-1)
         else:
-            cols = [b[:ncols].cpu().numpy().copy() for b in self._hist_dev]
-            for b in self._hist_dev[:3]:
-                b.fill_(float('nan'))
+            # one device-to-host copy per variable (a host tensor -- the CPU tests -- shares its memory with the block: clone)
+            cols = [(bq[:ncols].cpu() if bq.is_cuda else bq[:ncols].clone()).numpy() for bq in self._hist_dev]
+            for bq in self._hist_dev[:3]:
+                bq.fill_(float('nan'))
             self._hist_dev[3].fill_(-1)
         for j in range(ncols):
             h['time'].append(self._out_times[self._hist_base + j])
@@ -966,6 +1023,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             for key in self.history:
                 del self.history[key][n_keep:]
             self._hist_dev = None
+            if self._hist_pinned is not None:
+                self.engine.order_after_copies()
+                self._hist_other = None
 
     def get_lonlats(self):
         return np.array(self.history['lon']).T, np.array(self.history['lat']).T

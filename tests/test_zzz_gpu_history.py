@@ -59,3 +59,22 @@ def test_device_history_double_gyre_and_errors():
         torch.zeros((4, 2), dtype=torch.int32, device=eng.device),)
     with pytest.raises(RuntimeError, match='bad sizes'):
         eng.history_scatter(ids, pos, pos, z, ids, bufs, 2)
+
+
+def test_page_locked_output_buffer_equals_the_pageable_one():
+    """More output columns than one device block: blocks travel asynchronously into a page-locked buffer, two device blocks in
+    turn; the result is what the synchronous, pageable path gives."""
+    from test_gpu_dropin import _model
+    fx = common.Fixture('rk4_3d_full')
+    out = {}
+    for name, pinned in (('pinned', 16 * 2 ** 30), ('pageable', 0)):
+        o = _model(fx)
+        o.set_config('gpu:history_pinned_bytes', pinned)
+        o.run(steps=fx.steps, time_step=fx.dt, time_step_output=fx.dt, export_buffer_length=3)
+        assert (o._hist_pinned is not None) == (name == 'pinned')
+        out[name] = o.history
+    a, b = out['pinned'], out['pageable']
+    assert a['time'] == b['time'] and len(a['time']) == fx.steps + 1
+    for k in ('lon', 'lat', 'z', 'status'):
+        assert np.array_equal(np.array(a[k]), np.array(b[k]), equal_nan=True), k
+    assert np.isfinite(np.array(a['lon'])).all()
