@@ -300,6 +300,11 @@ typedef struct od_leeway_args {
     float wind_threshold, wind_sigma;      /* capsizing:wind_threshold, capsizing:wind_threshold_sigma */
     const double* d_rand_capsize; /* [n] the reference's np.random.rand(len(eligible)) draws scattered to the eligible elements (parity),
                                      or NULL: Philox keyed by (seed, ID, step) */
+    /* drift:current_uncertainty[_uniform] / drift:wind_uncertainty (environment.py:869-891): the step's draws, added to the float32
+     * samples as the reference adds them (float32(float64(value) + draw), normal first, then uniform) */
+    const double* d_noise_cur;    /* [kind 0 normal, 1 uniform][component][n] for the kinds flagged in noise_kinds, or NULL */
+    const double* d_noise_wind;   /* [component][n], or NULL */
+    int32_t noise_kinds, pad2_;
 } od_leeway_args;
 
 int od_leeway_step(od_ctx* ctx, const od_leeway_args* a);

@@ -87,7 +87,8 @@ class LeewayArgs(C.Structure):
                 ('seed', C.c_uint64), ('capsize_fraction', C.c_float), ('jp_f64', C.c_int32), ('pos_f32', C.c_int32),
                 ('step_index', C.c_int32), ('missing_code', C.c_int32), ('pad_', C.c_int32),
                 ('capsize_on', C.c_int32), ('capsize_from', C.c_int32), ('wind_threshold', C.c_float),
-                ('wind_sigma', C.c_float), ('d_rand_capsize', C.c_void_p)]
+                ('wind_sigma', C.c_float), ('d_rand_capsize', C.c_void_p),
+                ('d_noise_cur', C.c_void_p), ('d_noise_wind', C.c_void_p), ('noise_kinds', C.c_int32), ('pad2_', C.c_int32)]
 
 
 class StokesArgs(C.Structure):

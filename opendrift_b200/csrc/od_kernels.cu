@@ -632,11 +632,12 @@ static int resolve_pair(od_ctx* ctx, int group, const od_time_sample& ts, PairRe
     if (!victim->tex) {
         // first pair of this group: allocate the whole cache now, so that no later step pays for a cudaMalloc
         // (tens of milliseconds for a 200 MB block on a cold device, and an implicit device synchronisation)
-        CK(cudaMalloc(&victim->tex, g.cells() * sizeof(float) * 2 * nc));
+        // (sized for the group's full grid: a sub-block reader's windows vary in size, od_group_set_window)
+        CK(cudaMalloc(&victim->tex, g.capacity * sizeof(float) * 2 * nc));
         victim->tmap_ok = make_tensor_map(g, victim->tex, &victim->tmap);
         for (auto& p : g.pairs) {
             if (p.tex) continue;
-            if (cudaMalloc(&p.tex, g.cells() * sizeof(float) * 2 * nc) != cudaSuccess) {   // best effort: a smaller cache still works
+            if (cudaMalloc(&p.tex, g.capacity * sizeof(float) * 2 * nc) != cudaSuccess) {   // best effort: a smaller cache still works
                 p.tex = nullptr;
                 cudaGetLastError();
                 break;
@@ -1856,6 +1857,7 @@ extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {
     p.capsize_fraction = a->capsize_fraction; p.jp_f64 = a->jp_f64; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
     p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from; p.wind_threshold = a->wind_threshold;
     p.wind_sigma = a->wind_sigma; p.rand_capsize = a->d_rand_capsize;
+    p.noise_cur = a->d_noise_cur; p.noise_wind = a->d_noise_wind; p.noise_kinds = a->noise_kinds;
     if (a->capsize_on && !a->d_capsized) return fail(ctx, OD_ERR_ARG, "od_leeway_step: capsizing needs the capsized array");
     p.missing_code = a->missing_code;
     leeway_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);

@@ -36,6 +36,9 @@ struct LeewayParams {
     int32_t capsize_on, capsize_from;
     float wind_threshold, wind_sigma;
     const double* rand_capsize;       // [n] np.random.rand draws laid out per element (entries of ineligible elements unused), or NULL -> Philox
+    const double* noise_cur;          // uncertainty draws of the step (environment.py:869-891), see od_leeway_args
+    const double* noise_wind;
+    int32_t noise_kinds, pad2_;
 };
 
 OD_HD void leeway_particle(const LeewayParams& p, int64_t i) {
@@ -44,6 +47,18 @@ OD_HD void leeway_particle(const LeewayParams& p, int64_t i) {
     float xw, yw, cu, cv;
     sample2(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
     sample2(p.gcur, p.pcur, v0, lon0, lat0, cu, cv, p.pos_f32 != 0);
+    if (p.noise_cur) {                                   // env[var] += draw on float32 arrays: normal first, then uniform
+        for (int kind = 0; kind < 2; ++kind) {
+            if (!(p.noise_kinds & (1 << kind))) continue;
+            const double* base = p.noise_cur + (int64_t)(kind * 2) * p.n;
+            cu = (float)OD_DADD((double)cu, base[i]);
+            cv = (float)OD_DADD((double)cv, base[p.n + i]);
+        }
+    }
+    if (p.noise_wind) {
+        xw = (float)OD_DADD((double)xw, p.noise_wind[i]);
+        yw = (float)OD_DADD((double)yw, p.noise_wind[p.n + i]);
+    }
     if (!(finite_f(xw) && finite_f(yw) && finite_f(cu) && finite_f(cv))) {
         if (p.status && p.status[i] == 0) p.status[i] = p.missing_code;
         return;

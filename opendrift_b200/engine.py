@@ -780,7 +780,8 @@ class Engine:
         self._check(self.lib.od_advect_current_host(self.ctx, C.byref(a), C.byref(io)))
 
     def leeway_step(self, wind, cur, t, dt, lon, lat, el, moving=None, status=None, ids=None, rand=None, seed=0,
-                    step_index=0, capsize_fraction=0.4, missing_code=1, pos_f32=False, capsizing=None, rand_capsize=None):
+                    step_index=0, capsize_fraction=0.4, missing_code=1, pos_f32=False, capsizing=None, rand_capsize=None,
+                    noise_cur=None, noise_kinds=0, noise_wind=None):
         """Leeway.update on device tensors; el: dict of the per-element coefficient tensors."""
         torch = self.torch
         a = LeewayArgs()
@@ -806,6 +807,10 @@ class Engine:
         a.dt = dt.total_seconds() if hasattr(dt, 'total_seconds') else float(dt)
         a.seed, a.step_index, a.capsize_fraction = int(seed), int(step_index), float(capsize_fraction)
         a.missing_code, a.pos_f32 = int(missing_code), 1 if pos_f32 else 0
+        if noise_cur is not None:      # the step's uncertainty draws: float64 [kind][component][n] / [component][n]
+            a.d_noise_cur, a.noise_kinds = noise_cur.data_ptr(), int(noise_kinds)
+        if noise_wind is not None:
+            a.d_noise_wind = noise_wind.data_ptr()
         if capsizing is not None:        # processes:capsizing: (wind_threshold, wind_threshold_sigma); el['capsized'] is updated in place
             assert el.get('capsized') is not None
             a.capsize_on, a.capsize_from = 1, (0 if a.dt >= 0 else 1)

@@ -179,9 +179,22 @@ class Leeway(OpenDriftSimulation):
         """leeway.py:430-494 as one launch."""
         eng, el, torch = self.engine, self.elements, self.engine.torch
         t = self.time
-        if any(x > 0 for x in self._uncertainty()):
-            raise NotImplementedError('drift:current_uncertainty / drift:wind_uncertainty with Leeway are not on the GPU path '
-                                      '(the fused Leeway launch samples its forcing inside the kernel)')
+        # drift:current_uncertainty[_uniform] / drift:wind_uncertainty: the draws of this step's environment, made at the top of the
+        # loop for the elements active then (_predraw_step_uncertainty), are added inside the launch
+        noise_kw = {}
+        pre = getattr(self, '_noise0', None)
+        if pre:
+            cu, cuu, wu = self._uncertainty()
+            kinds = (1 if cu > 0 else 0) | (2 if cuu > 0 else 0)
+            if kinds:
+                arr = np.zeros((2, 2, len(el)))
+                if 'cur_n' in pre:
+                    arr[0, 0], arr[0, 1] = pre['cur_n']
+                if 'cur_u' in pre:
+                    arr[1, 0], arr[1, 1] = pre['cur_u']
+                noise_kw.update(noise_cur=eng.to_device(arr), noise_kinds=kinds)
+            if 'wind' in pre:
+                noise_kw['noise_wind'] = eng.to_device(np.stack(pre['wind']))
         gw = self._pair_group('x_wind', 'y_wind', t)
         gc = self._pair_group('x_sea_water_velocity', 'y_sea_water_velocity', t)
         n = len(el)
@@ -213,7 +226,7 @@ class Leeway(OpenDriftSimulation):
                         moving=el.dev('moving', torch.int32), status=el.dev('status', torch.int32),
                         ids=el.dev('ID', torch.int32), rand=rand, seed=self._seed, step_index=self.steps_calculation,
                         capsize_fraction=self.get_config('capsizing:leeway_fraction'),
-                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32, **caps_kw)
+                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32, **caps_kw, **noise_kw)
         el.positions_f32 = False
         self._maybe_deactivated = True           # the kernel may have flagged elements with missing forcing
         self.stokes_drift()

@@ -257,6 +257,11 @@ LEEWAY_CASES = {
     'leeway_backward': ({}, 2, 'end', 6, -600),
     'leeway_backward_capsizing': ({'processes:capsizing': True, 'capsizing:wind_threshold': 8.0, 'capsizing:wind_threshold_sigma': 5.0},
                                   1, 'end', 6, -600),
+    # uncertainty of current and wind: one set of draws per step, made before capsizing / jibing draw theirs
+    'leeway_uncertainty': ({'drift:current_uncertainty': 0.1, 'drift:current_uncertainty_uniform': 0.05, 'drift:wind_uncertainty': 1.5},
+                           1, 'interval', 7, 600),
+    'leeway_uncertainty_capsizing': ({'drift:wind_uncertainty': 2.0, 'processes:capsizing': True, 'capsizing:wind_threshold': 6.0,
+                                      'capsizing:wind_threshold_sigma': 3.0}, 3, 'interval', 6, 600),
     'leeway_capsizing_staggered': ({'processes:capsizing': True, 'capsizing:wind_threshold': 6.0, 'capsizing:wind_threshold_sigma': 3.0},
                                    3, 'interval', 7, 600),
 }

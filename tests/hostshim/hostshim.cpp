@@ -579,6 +579,7 @@ int hs2_leeway(const od_leeway_args* a, const hs_group* g_wind, const hs_pair* t
     p.capsize_fraction = a->capsize_fraction; p.jp_f64 = a->jp_f64; p.pos_f32 = a->pos_f32; p.step_index = a->step_index;
     p.capsize_on = a->capsize_on; p.capsize_from = a->capsize_from; p.wind_threshold = a->wind_threshold;
     p.wind_sigma = a->wind_sigma; p.rand_capsize = a->d_rand_capsize;
+    p.noise_cur = a->d_noise_cur; p.noise_wind = a->d_noise_wind; p.noise_kinds = a->noise_kinds;
     if (a->capsize_on && !a->d_capsized) return -3;
     p.missing_code = a->missing_code;
     for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);

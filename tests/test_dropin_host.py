@@ -343,15 +343,20 @@ def test_subclass_helpers_wind_speed_current_speed_direction():
     assert np.array_equal(seen['w'], np.sqrt(xw**2 + yw**2))
 
 
-def test_leeway_refuses_uncertainty_settings_it_would_ignore():
+def test_leeway_with_wind_uncertainty_scatters_the_elements():
+    """drift:wind_uncertainty reaches the fused Leeway launch (it was refused until the launch learnt to add the step's draws): the
+    same seed drifts elsewhere with it."""
     from opendrift_b200.models.leeway import Leeway
     from opendrift_b200.readers import reader_constant
-    o = Leeway(loglevel=50, seed=1)
-    o.add_reader(reader_constant.Reader({'x_wind': 5, 'y_wind': 0, 'x_sea_water_velocity': 0.1, 'y_sea_water_velocity': 0}))
-    o.set_config('drift:wind_uncertainty', 2.0)
-    o.seed_elements(lon=4, lat=60, number=10, time=__import__('datetime').datetime(2026, 1, 1), object_type=1)
-    with pytest.raises(NotImplementedError, match='uncertainty'):
+    lons = {}
+    for wu in (0.0, 2.0):
+        o = Leeway(loglevel=50, seed=1)
+        o.add_reader(reader_constant.Reader({'x_wind': 5, 'y_wind': 0, 'x_sea_water_velocity': 0.1, 'y_sea_water_velocity': 0}))
+        o.set_config('drift:wind_uncertainty', wu)
+        o.seed_elements(lon=4, lat=60, number=10, time=__import__('datetime').datetime(2026, 1, 1), object_type=1)
         o.run(steps=2, time_step=600)
+        lons[wu] = np.asarray(o.elements.lon).copy()
+    assert np.abs(lons[2.0] - lons[0.0]).max() > 1e-4         # (the runs with the reference's draws are in tests/bookkeeping.py)
 
 
 @pytest.mark.parametrize('case', list(__import__('bookkeeping').SUBCLASS_CASES))
