@@ -465,6 +465,12 @@ def run_b200(args):
     loop_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in step_events]))   # includes slab upload / pair packing
     clocks = sampler.stop(wall0, wall1) if sampler else None
     per_step = np.array([a.elapsed_time(b) for a, b in step_events])
+    if os.environ.get('OD_BENCH_DEBUG'):          # per-step device times and the gaps between steps, every rank
+        gaps = [step_events[k][1].elapsed_time(step_events[k + 1][0]) for k in range(len(step_events) - 1)]
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump({'rank': rank, 'ms_total': ms_total, 'step_ms': [round(float(x), 3) for x in per_step], 'gap_ms': [round(float(x), 3) for x in gaps],
+                   'host_us': [round(float(x), 1) for x in host_us]},
+                  open(os.path.join(ROOT, 'gpurun_out', 'steps_n%d_rank%d%s.json' % (world, rank, os.environ.get('OD_BENCH_TAG', ''))), 'w'))
 
     # dominant kernel alone: CUDA events around single launches of the step kernel on the launching stream
     def kernel_alone(fn):

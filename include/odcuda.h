@@ -54,7 +54,8 @@ enum od_time_mode {
 
 enum od_lon_mode { OD_LON_0_360 = 0, OD_LON_PM180 = 1 };
 
-enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2, OD_INTERP_Z_F64 = 4 };
+enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2, OD_INTERP_Z_F64 = 4,
+                       OD_INTERP_NO_ROTATE = 8 /* projected vector pairs stay along the grid's axes (rotate_to_proj=None) */ };
 
 #define OD_MAX_LEVELS 128
 #define OD_ABI_VERSION 1
@@ -87,7 +88,21 @@ int od_device_sm_count(od_ctx* ctx);
  * and is periodic: the block the sampler sees is the nx stored columns plus one virtual column that repeats column 0 at
  * xgrid[nx-1] + dx (what a reference reader hands to ReaderBlock(wrap_x=True) so that the seam cell is covered,
  * readers/interpolation/structured.py:35-48, reader_netCDF_CF_generic.py:452-463).  Then xspan = (double)(float)(xgrid[nx-1] + dx -
- * xgrid[0]), the index scale is nx instead of nx - 1, and the east-west coverage test is skipped (variables.py:239-242). */
+ * xgrid[0]), the index scale is nx instead of nx - 1, and the east-west coverage test is skipped (variables.py:239-242).
+ * proj: a reader whose grid lies on a projected plane (proj.kind != 0; its x / y axes, x0 .. ymax, are metres in that plane):
+ * positions are projected before the index arithmetic (Variables.lonlat2xy, readers/basereader/variables.py:129-143; the
+ * longitude is modulated first as lon_mode says, :259-280) and, with rotate_vectors, the two components of the group are
+ * rotated from the plane's axes to east / north after the interpolation (rotate_vectors, :59-109, :799-837).  Sampled by the
+ * general kernels (od_interp, the reader-chain family of step kernels, mixing, Leeway); kind 0 = geographic (+proj=latlong). */
+#define OD_PROJ_STERE_SPHERE 1
+typedef struct od_proj_desc {
+    int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0) */
+    int32_t has_lat_ts;           /* +lat_ts given (polar aspects only) */
+    double a;                     /* sphere radius, m */
+    double lat_0, lon_0, lat_ts;  /* degrees */
+    double k_0, x_0, y_0;
+} od_proj_desc;
+
 typedef struct od_group_desc {
     int32_t ncomp;            /* 1 or 2 */
     int32_t nx, ny, nz;
@@ -100,6 +115,9 @@ typedef struct od_group_desc {
     double x0, xspan, y0, yspan;
     double xmin, xmax, ymin, ymax;
     float fallback[2];
+    od_proj_desc proj;        /* kind 0: geographic */
+    int32_t rotate_vectors;   /* the group's two components are an x / y vector pair to be rotated to east / north */
+    int32_t pad_;
 } od_group_desc;
 
 #define OD_MAX_GROUPS 64
@@ -411,14 +429,6 @@ int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a);
  * spherical stereographic plane its constructor asks pyproj for (reader_double_gyre.py:27-31).  The reader chain of
  * Variables.get_variables_interpolated (basereader/variables.py:860-920: modulate_longitude, Proj forward, coverage,
  * get_variables, rotate_vectors :59-109, NaN for uncovered) is evaluated per particle on the device. */
-#define OD_PROJ_STERE_SPHERE 1
-typedef struct od_proj_desc {
-    int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0) */
-    int32_t has_lat_ts;           /* +lat_ts given (polar aspects only) */
-    double a;                     /* sphere radius, m */
-    double lat_0, lon_0, lat_ts;  /* degrees */
-    double k_0, x_0, y_0;
-} od_proj_desc;
 
 #define OD_ANALYTIC_DOUBLE_GYRE 1
 typedef struct od_analytic_desc {

@@ -21,12 +21,17 @@ OD_MAX_CHAIN = 2
 SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
 
 
+class ProjDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('has_lat_ts', C.c_int32), ('a', C.c_double), ('lat_0', C.c_double),
+                ('lon_0', C.c_double), ('lat_ts', C.c_double), ('k_0', C.c_double), ('x_0', C.c_double), ('y_0', C.c_double)]
+
+
 class GroupDesc(C.Structure):
     _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
                 ('lon_mode', C.c_int32), ('n_slots', C.c_int32), ('wrap_x', C.c_int32), ('global_x', C.c_int32),
                 ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
                 ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
-                ('fallback', C.c_float * 2)]
+                ('fallback', C.c_float * 2), ('proj', ProjDesc), ('rotate_vectors', C.c_int32), ('pad_', C.c_int32)]
 
 
 class TimeSample(C.Structure):
@@ -98,11 +103,6 @@ class StokesArgs(C.Structure):
                 ('hs_mode', C.c_int32), ('profile', C.c_int32), ('pad_', C.c_int32), ('factor', C.c_double), ('d_factor', C.c_void_p),
                 ('factor_f64', C.c_int32), ('pad2_', C.c_int32), ('d_swell_dir', C.c_void_p), ('d_swell_period', C.c_void_p),
                 ('d_swell_hs', C.c_void_p), ('d_windsea_dir', C.c_void_p), ('d_windsea_period', C.c_void_p), ('d_windsea_hs', C.c_void_p)]
-
-
-class ProjDesc(C.Structure):
-    _fields_ = [('kind', C.c_int32), ('has_lat_ts', C.c_int32), ('a', C.c_double), ('lat_0', C.c_double),
-                ('lon_0', C.c_double), ('lat_ts', C.c_double), ('k_0', C.c_double), ('x_0', C.c_double), ('y_0', C.c_double)]
 
 
 class AnalyticDesc(C.Structure):

@@ -294,6 +294,18 @@ struct StepParams {
     float chain_fallback[2];
 };
 
+// The current sample of a stage.  GENERAL (the reader chain family of kernels) also serves groups on a projected plane
+// (od_interp.cuh: sample2_any, exact sampler + vector rotation); the default kernels are only launched for geographic groups.
+template <class MATH, bool GENERAL>
+OD_HD void sample_cur(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32,
+                      const TileView& tv) {
+    if (GENERAL && g.proj_kind) {
+        sample2_any(g, pr, vw, lon, lat, u, v, pos_f32);
+        return;
+    }
+    MATH::sample_uv(g, pr, vw, lon, lat, u, v, pos_f32, tv);
+}
+
 // fill what the groups so far left missing from the next readers of the priority list
 template <class MATH>
 OD_HD void chain_fill(const StepParams& p, int which, double zt, bool zf32, double lon, double lat, bool pos_f32, float& u, float& v) {
@@ -302,7 +314,7 @@ OD_HD void chain_fill(const StepParams& p, int which, double zt, bool zf32, doub
         const GroupGeom& g = p.cg[k];
         const VertW vw = vert_weights(g, g.zs, g.zy, zt, zf32);
         float a, b;
-        MATH::sample_uv(g, p.ct[k][which], vw, lon, lat, a, b, pos_f32);
+        sample_cur<MATH, true>(g, p.ct[k][which], vw, lon, lat, a, b, pos_f32, TileView());
         if (!finite_f(u)) u = a;
         if (!finite_f(v)) v = b;
     }
@@ -346,7 +358,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
         double mlon, mlat;
         do_midpoint<MATH>(gs, lon0, lat0, ku, kv, dt32, mlon, mlat, bad);
         const PairRef& pr = st == 3 ? cs.t_end : cs.t_mid;
-        MATH::sample_uv(cs.g, pr, vw, mlon, mlat, ku, kv, false, tv);
+        sample_cur<MATH, CHAIN>(cs.g, pr, vw, mlon, mlat, ku, kv, false, tv);
         if (CHAIN) chain_fill<MATH>(p, st == 3 ? 2 : 1, zt, zf32, mlon, mlat, false, ku, kv);
         add_current_noise(p, st, i, ku, kv);
         if (st < 3) {
@@ -376,7 +388,7 @@ OD_HD void rk_velocity(const StepParams& p, int64_t i, const VertW& vw, const ty
 #define OD_COLD static
 #endif
 
-template <class MATH>
+template <class MATH, bool GENERAL = false>
 OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, double lon0, double lat0,
                          double* plon1, double* plat1, bool& bad) {
     double lon1 = *plon1, lat1 = *plat1;
@@ -384,7 +396,7 @@ OD_COLD void extras_wind(const StepParams& p, int64_t i, double z0, double mv, d
     {
         const VertW v0 = {0, 0, 1.0};
         float xw, yw;
-        MATH::sample_uv(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+        sample_cur<MATH, GENERAL>(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0, TileView());
         if (p.noise_wind) {
             xw = (float)OD_DADD((double)xw, p.noise_wind[i]);
             yw = (float)OD_DADD((double)yw, p.noise_wind[p.n + i]);
@@ -458,13 +470,15 @@ OD_HD bool step_particle(const StepParams& p, int64_t i, const double* zs, const
     // stage 1: the start-of-step environment
     float k1u, k1v;
     HorizW h0;                     // horizontal cell / weights of the start-of-step position (exact samplers)
-    const bool share_h0 = EXTRAS != 0 && MATH::kExactSampler && p.w_on && p.w_same_grid;
-    if (share_h0 || (MATH::kExactSampler && !p.has_k1)) h0 = horiz_weights(g, lon0, lat0, p.pos_f32 != 0);
+    const bool projected = CHAIN && g.proj_kind != 0;          // (general kernels only)
+    const bool share_h0 = EXTRAS != 0 && MATH::kExactSampler && p.w_on && p.w_same_grid && !projected;
+    if (share_h0 || (MATH::kExactSampler && !p.has_k1 && !projected)) h0 = horiz_weights(g, lon0, lat0, p.pos_f32 != 0);
     if (p.has_k1) {
         k1u = p.k1u[i];
         k1v = p.k1v[i];
     } else {
-        if (MATH::kExactSampler) sample2_h(g, p.cs.t_start, vw, h0, k1u, k1v, tv);
+        if (projected) sample2_any(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0);
+        else if (MATH::kExactSampler) sample2_h(g, p.cs.t_start, vw, h0, k1u, k1v, tv);
         else MATH::sample_uv(g, p.cs.t_start, vw, lon0, lat0, k1u, k1v, p.pos_f32 != 0, tv);
         if (CHAIN) chain_fill<MATH>(p, 0, zt, zf32, lon0, lat0, p.pos_f32 != 0, k1u, k1v);
         add_current_noise(p, 0, i, k1u, k1v);
@@ -486,7 +500,8 @@ OD_HD bool step_particle(const StepParams& p, int64_t i, const double* zs, const
                     w = sample1_h(p.gw, p.pw, vw, h0);
                 } else {
                     const VertW vww = vert_weights(p.gw, zsw, zyw, zt, zf32);
-                    w = MATH::sample_s(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
+                    w = CHAIN ? sample1_any(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0)
+                              : MATH::sample_s(p.gw, p.pw, vww, lon0, lat0, p.pos_f32 != 0);
                 }
                 const double zn = fmin(0.0, OD_DADD(zc, OD_DMUL(OD_DMUL(mv, (double)w), p.dt)));
                 if (zio32) ((float*)p.z_inout)[i] = (float)zn;
@@ -509,7 +524,7 @@ OD_HD bool step_particle(const StepParams& p, int64_t i, const double* zs, const
     }
 
     if (EXTRAS == 1) {
-        if (p.wind_on) extras_wind<MATH>(p, i, z0, mv, lon0, lat0, &lon1, &lat1, bad);
+        if (p.wind_on) extras_wind<MATH, CHAIN>(p, i, z0, mv, lon0, lat0, &lon1, &lat1, bad);
         if (p.diff_on) extras_diffusion<MATH>(p, i, mv, &lon1, &lat1, bad);
     }
     if (MATH::kDefer && bad) return false;

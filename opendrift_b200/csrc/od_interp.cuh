@@ -19,6 +19,7 @@
 // and both times is a single vector load.
 #pragma once
 #include "od_geod.cuh"
+#include "od_proj.cuh"
 
 namespace od {
 
@@ -50,6 +51,14 @@ struct GroupGeom {
     float fallback[2];
     const double* zs;        // [nz] level depths in increasing order
     const double* zy;        // [nz] layer index of zs[i] (as float64), what interp1d maps to
+    // Readers on a projected plane (x0 .. ymax are then metres in that plane): positions are projected before the index
+    // arithmetic (Variables.lonlat2xy, variables.py:129-143) and the components of a vector pair are rotated from the plane's
+    // axes to east / north (rotate_vectors, :59-109).  Only the general kernels (reader chain family, od_interp, mixing,
+    // Leeway, sorting) look at these; the default step kernels are launched for geographic groups only.
+    int proj_kind;           // 0 geographic, else OD_PROJ_*
+    int rotate;              // 2-component group whose components are an x / y vector pair
+    double rot_delta;        // length of the line along the plane's y axis that defines the rotation (10 m)
+    ProjStere proj;
 };
 
 struct PairRef {
@@ -409,6 +418,121 @@ OD_HD float sample1(const GroupGeom& g, const PairRef& pr, const VertW& vw, doub
                      bool pos_f32 = false) {
     const HorizW h = horiz_weights(g, lon, lat, pos_f32);
     return sample1_h(g, pr, vw, h);
+}
+
+// ---- groups on a projected plane ------------------------------------------------------------------------------------------------
+struct HorizWP {
+    HorizW h;
+    double px, py;           // position in the reader's plane (for the rotation of vector components)
+};
+
+// horiz_weights for any group: geographic groups as above; projected groups project first, then the same index arithmetic in
+// float64 on the plane coordinates (pyproj returns float64 whatever the dtype of the positions; the longitude is modulated
+// first -- in float32 while the element arrays are float32 -- as Variables.get_variables_interpolated does, :912-913)
+OD_HD HorizWP horiz_weights_any(const GroupGeom& g, double lon, double lat, bool pos_f32) {
+    HorizWP r;
+    r.px = r.py = 0.0;
+    if (!g.proj_kind) {
+        r.h = horiz_weights(g, lon, lat, pos_f32);
+        return r;
+    }
+    HorizW& h = r.h;
+    h.valid = false;
+    h.i00 = h.i01 = h.i10 = h.i11 = 0;
+    h.ix = h.iy = h.ix1 = h.iy1 = 0;
+    h.wy0 = h.wy1 = h.wx0 = h.wx1 = 0.0;
+    double xl;
+    if (pos_f32) {
+        const float xf = (g.lon_mode == 0) ? np_mod360f((float)lon) : OD_FADD(np_mod360f(OD_FADD((float)lon, 180.0f)), -180.0f);
+        xl = (double)xf;
+    } else {
+        xl = (g.lon_mode == 0) ? np_mod360(lon) : OD_DSUB(np_mod360(OD_DADD(lon, 180.0)), 180.0);
+    }
+    double px, py;
+    if (!stere_forward(g.proj, xl, lat, px, py)) return r;
+    r.px = px;
+    r.py = py;
+    if (!(px >= g.xmin && px <= g.xmax && py >= g.ymin && py <= g.ymax)) return r;
+    double xi = OD_DMUL(div_rn(OD_DSUB(px, g.x0), g.xspan, g.rxspan), g.nxm1);
+    double yi = OD_DMUL(div_rn(OD_DSUB(py, g.y0), g.yspan, g.ryspan), g.nym1);
+    if (!(xi == xi) || !(yi == yi)) return r;
+    xi = xi < 0.0 ? 0.0 : (xi > g.nxm1 ? g.nxm1 : xi);
+    yi = yi < 0.0 ? 0.0 : (yi > g.nym1 ? g.nym1 : yi);
+    const double fx = floor(xi), fy = floor(yi);
+    const int ix = (int)fx, iy = (int)fy;
+    const int ix1 = ix + 1 < g.nx ? ix + 1 : g.nx - 1;
+    const int iy1 = iy + 1 < g.ny ? iy + 1 : g.ny - 1;
+    h.wx0 = OD_DSUB(1.0, OD_DSUB(xi, fx));
+    h.wx1 = OD_DSUB(1.0, h.wx0);
+    h.wy0 = OD_DSUB(1.0, OD_DSUB(yi, fy));
+    h.wy1 = OD_DSUB(1.0, h.wy0);
+    h.ix = ix; h.iy = iy; h.ix1 = ix1; h.iy1 = iy1;
+    h.i00 = iy * g.nx + ix;
+    h.i01 = iy * g.nx + ix1;
+    h.i10 = iy1 * g.nx + ix;
+    h.i11 = iy1 * g.nx + ix1;
+    h.valid = true;
+    return r;
+}
+
+// vertical + time combination without the final float32 rounding: what the reader hands to rotate_vectors (float64 for 3-D
+// blocks, float32 values for 2-D ones)
+OD_HD double combine_d(const GroupGeom& g, const PairRef& pr, const VertW& vw, float haA, float hbA, float haB, float hbB) {
+    if (g.nz > 1) {
+        const double omw = OD_DSUB(1.0, vw.wa);
+        const double vA = OD_DADD(OD_DMUL((double)haA, vw.wa), OD_DMUL((double)hbA, omw));
+        if (pr.mode == 1) return vA;
+        const double vB = OD_DADD(OD_DMUL((double)haB, vw.wa), OD_DMUL((double)hbB, omw));
+        if (pr.mode == 2) return vB;
+        return OD_DADD(OD_DMUL(vA, OD_DSUB(1.0, pr.w)), OD_DMUL(vB, pr.w));
+    }
+    return (double)combine(g, pr, vw, haA, hbA, haB, hbB);
+}
+
+// sample2 for any group: a projected vector pair is rotated to east / north in float64 and then becomes float32.
+// (Kernels that may meet projected groups are compiled twice -- template parameter PROJ -- because the projection / rotation code
+// raises their register count, 72 -> 106 for Leeway, also when the groups they serve are geographic.)
+OD_HD void sample2_any(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, float& u, float& v, bool pos_f32) {
+    if (!g.proj_kind) {
+        sample2(g, pr, vw, lon, lat, u, v, pos_f32);
+        return;
+    }
+    const HorizWP hp = horiz_weights_any(g, lon, lat, pos_f32);
+    const HorizW& h = hp.h;
+    float ru = NAN, rv = NAN;
+    if (h.valid && pr.mode != 3) {
+        const TexelSource ts = texel_source(pr.tex, TileView(), g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
+        const int r0 = 4 * h.iy * ts.lx, r1 = 4 * h.iy1 * ts.lx;
+        const int o00 = r0 + 4 * h.ix, o01 = r0 + 4 * h.ix1, o10 = r1 + 4 * h.ix, o11 = r1 + 4 * h.ix1;
+        const LayerVals A = layer_bilin(h, layer_ptr(ts, vw.ia), o00, o01, o10, o11, pr.mode);
+        LayerVals B = A;
+        if (g.nz > 1) B = layer_bilin(h, layer_ptr(ts, vw.ib), o00, o01, o10, o11, pr.mode);
+        const double du = combine_d(g, pr, vw, A.uA, B.uA, A.uB, B.uB);
+        const double dv = combine_d(g, pr, vw, A.vA, B.vA, A.vB, B.vB);
+        if (g.rotate) {
+            double sr, cr;
+            sincos(rotation_to_geographic(g.proj, hp.px, hp.py, g.rot_delta), &sr, &cr);
+            ru = (float)OD_DSUB(OD_DMUL(du, cr), OD_DMUL(dv, sr));
+            rv = (float)OD_DADD(OD_DMUL(du, sr), OD_DMUL(dv, cr));
+        } else {
+            ru = (float)du;
+            rv = (float)dv;
+        }
+    }
+    if (!finite_f(ru)) ru = g.fallback[0];
+    if (!finite_f(rv)) rv = g.fallback[1];
+    u = ru;
+    v = rv;
+}
+
+// horizontal weights only (scalar groups: the mixing column, the sort key, vertical velocity)
+OD_HD HorizW horiz_weights_h(const GroupGeom& g, double lon, double lat, bool pos_f32) {
+    return horiz_weights_any(g, lon, lat, pos_f32).h;
+}
+
+OD_HD float sample1_any(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
+    if (!g.proj_kind) return sample1(g, pr, vw, lon, lat, pos_f32);
+    return sample1_h(g, pr, vw, horiz_weights_h(g, lon, lat, pos_f32));
 }
 
 }  // namespace od

@@ -206,6 +206,11 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
         d->n_slots < 2 || d->n_slots > 64)
         return fail(ctx, OD_ERR_ARG, "od_group_define: bad shape");
     if (d->nz > 1 && !h_z) return fail(ctx, OD_ERR_ARG, "od_group_define: z levels missing");
+    if (d->proj.kind != 0) {
+        ProjStere tmp;
+        if (proj_from_desc(&d->proj, &tmp) != 0) return fail(ctx, OD_ERR_ARG, "od_group_define: unsupported projection (spherical +proj=stere)");
+        if (d->wrap_x || d->global_x) return fail(ctx, OD_ERR_ARG, "od_group_define: a projected group cannot be periodic / global in x");
+    }
     if ((size_t)d->nx * d->ny * d->nz >= (1ull << 31)) return fail(ctx, OD_ERR_ARG, "od_group_define: block too large");
     if ((size_t)d->nx * d->ny >= (1ull << 28)) return fail(ctx, OD_ERR_ARG, "od_group_define: layer too large (32-bit corner offsets)");
     CK(cudaSetDevice(ctx->device));
@@ -682,6 +687,11 @@ static GroupGeom make_geom(const Group& g) {
     q.zmin = g.zmin; q.zmax = g.zmax;
     q.fallback[0] = g.desc.fallback[0]; q.fallback[1] = g.desc.fallback[1];
     q.zs = g.d_zs; q.zy = g.d_zy;
+    if (g.desc.proj.kind != 0 && proj_from_desc(&g.desc.proj, &q.proj) == 0) {
+        q.proj_kind = g.desc.proj.kind;
+        q.rotate = g.desc.rotate_vectors ? 1 : 0;
+        q.rot_delta = 10.0;                        // rotate_vectors: 10 m along the y axis of a projected plane (variables.py:79-82)
+    }
     return q;
 }
 
@@ -713,6 +723,7 @@ struct InterpParams {
     int pos_f32, z_f64;
 };
 
+template <bool PROJ>
 __global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) {
     __shared__ LevelsSmem lv;
     if (p.g.nz > 1) load_levels(lv, p.g);
@@ -723,11 +734,12 @@ __global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) 
     const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, z, p.z_f64 == 0);
     if (p.g.ncomp == 2) {
         float u, v;
-        sample2(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
+        if (PROJ) sample2_any(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
+        else sample2(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
         if (p.out0) p.out0[i] = u;
         if (p.out1) p.out1[i] = v;
     } else {
-        const float r = sample1(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        const float r = PROJ ? sample1_any(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0) : sample1(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0);
         if (p.out0) p.out0[i] = r;
     }
 }
@@ -785,6 +797,7 @@ __global__ void __launch_bounds__(OD_BLOCK) step_chain_kernel(const __grid_const
 }
 
 // ---- vertical mixing -----------------------------------------------------------------------------
+template <bool PROJ>
 __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     __shared__ double xs[OD_MAX_LEVELS];
     __shared__ double xy[OD_MAX_LEVELS];
@@ -795,13 +808,14 @@ __global__ void __launch_bounds__(OD_BLOCK) mix_kernel(const MixParams p) {
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    mix_particle(p, i, xs, xy);
+    mix_particle<PROJ>(p, i, xs, xy);
 }
 
 // ---- Leeway -------------------------------------------------------------------------------------------
+template <bool PROJ>
 __global__ void __launch_bounds__(OD_BLOCK) leeway_kernel(const LeewayParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p.n) leeway_particle(p, i);
+    if (i < p.n) leeway_particle<PROJ>(p, i);
 }
 
 // ---- Stokes drift and reductions --------------------------------------------------------------------
@@ -854,6 +868,7 @@ struct SortParams {
     int tile, ntx, nty;
 };
 
+template <bool PROJ>
 __global__ void __launch_bounds__(OD_BLOCK) cell_key_kernel(const SortParams p, int32_t* __restrict__ keys,
                                                              int32_t* __restrict__ bins) {
     __shared__ LevelsSmem lv;
@@ -861,7 +876,7 @@ __global__ void __launch_bounds__(OD_BLOCK) cell_key_kernel(const SortParams p, 
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const HorizW h = horiz_weights(p.g, p.lon[i], p.lat[i], false);
+    const HorizW h = PROJ ? horiz_weights_h(p.g, p.lon[i], p.lat[i], false) : horiz_weights(p.g, p.lon[i], p.lat[i], false);
     int key = 0;
     if (h.valid) {
         const int iy = h.i00 / p.g.nx, ix = h.i00 - iy * p.g.nx;
@@ -1139,7 +1154,9 @@ extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64
     p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = flags & OD_INTERP_POS_F32;
     p.z_f64 = (flags & OD_INTERP_Z_F64) ? 1 : 0;
     if (flags & OD_INTERP_NO_FALLBACK) p.g.fallback[0] = p.g.fallback[1] = NAN;
-    interp_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
+    if (flags & OD_INTERP_NO_ROTATE) p.g.rotate = 0;
+    if (p.g.proj_kind) interp_kernel<true><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
+    else interp_kernel<false><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;
     return OD_OK;
@@ -1356,7 +1373,8 @@ static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     ctx->launches++;
     return OD_OK;
 #else
-    if (p.n_chain > 0) {
+    const bool general = p.n_chain > 0 || p.cs.g.proj_kind != 0 || (EXTRAS != 0 && ((p.wind_on && p.gwind.proj_kind != 0) || (p.w_on && p.gw.proj_kind != 0)));
+    if (general) {
         constexpr int E = EXTRAS == 0 ? 0 : 1;
 #define OD_LAUNCHC(S, F) step_chain_kernel<S, F, E, MATH><<<grid, OD_BLOCK, 0, s>>>(p)
         if (scheme == OD_EULER) { if (f64) OD_LAUNCHC(0, true); else OD_LAUNCHC(0, false); }
@@ -1860,7 +1878,8 @@ extern "C" int od_leeway_step(od_ctx* ctx, const od_leeway_args* a) {
     p.noise_cur = a->d_noise_cur; p.noise_wind = a->d_noise_wind; p.noise_kinds = a->noise_kinds;
     if (a->capsize_on && !a->d_capsized) return fail(ctx, OD_ERR_ARG, "od_leeway_step: capsizing needs the capsized array");
     p.missing_code = a->missing_code;
-    leeway_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    if (p.gwind.proj_kind || p.gcur.proj_kind) leeway_kernel<true><<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    else leeway_kernel<false><<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;
     return OD_OK;
@@ -1965,7 +1984,8 @@ extern "C" int od_vertical_mixing(od_ctx* ctx, const od_mix_args* a) {
         if (rc) return rc;
         p.counter = ctx->d_cnt;
     }
-    mix_kernel<<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    if (p.g.proj_kind) mix_kernel<true><<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
+    else mix_kernel<false><<<grid_for(a->n), OD_BLOCK, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     ctx->launches++;
     if (a->seafloor_action == 2 && a->h_n_deactivated) {
@@ -2006,7 +2026,8 @@ extern "C" int od_sort_by_cell(od_ctx* ctx, int group, int64_t n, const double* 
         ctx->bins_cap = nbins;
     }
     CK(cudaMemsetAsync(ctx->d_bins, 0, nbins * sizeof(int32_t), ctx->stream));
-    cell_key_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p, ctx->d_keys, ctx->d_bins);
+    if (p.g.proj_kind) cell_key_kernel<true><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p, ctx->d_keys, ctx->d_bins);
+    else cell_key_kernel<false><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p, ctx->d_keys, ctx->d_bins);
     rc = scan_exclusive(ctx, ctx->d_bins, (int)nbins);
     if (rc) return rc;
     scatter_perm_kernel<<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(n, ctx->d_keys, ctx->d_bins, perm);

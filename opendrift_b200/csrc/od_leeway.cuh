@@ -41,12 +41,18 @@ struct LeewayParams {
     int32_t noise_kinds, pad2_;
 };
 
+template <bool PROJ = false>
 OD_HD void leeway_particle(const LeewayParams& p, int64_t i) {
     const double lon0 = p.lon[i], lat0 = p.lat[i];
     const VertW v0 = {0, 0, 1.0};
     float xw, yw, cu, cv;
-    sample2(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
-    sample2(p.gcur, p.pcur, v0, lon0, lat0, cu, cv, p.pos_f32 != 0);
+    if (PROJ) {
+        sample2_any(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+        sample2_any(p.gcur, p.pcur, v0, lon0, lat0, cu, cv, p.pos_f32 != 0);
+    } else {
+        sample2(p.gwind, p.pwind, v0, lon0, lat0, xw, yw, p.pos_f32 != 0);
+        sample2(p.gcur, p.pcur, v0, lon0, lat0, cu, cv, p.pos_f32 != 0);
+    }
     if (p.noise_cur) {                                   // env[var] += draw on float32 arrays: normal first, then uniform
         for (int kind = 0; kind < 2; ++kind) {
             if (!(p.noise_kinds & (1 << kind))) continue;

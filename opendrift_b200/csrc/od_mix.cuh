@@ -199,6 +199,7 @@ OD_HD int nearest_level(const MixParams& p, const double* xs, const double* xy, 
     return zi < 0 ? 0 : (zi > nz - 1 ? nz - 1 : zi);
 }
 
+template <bool PROJ = false>
 OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const double* xy) {
     const GroupGeom& g = p.g;
     // the particle's diffusivity column (environment profile) is evaluated lazily, a window of levels at a time
@@ -211,7 +212,7 @@ OD_HD void mix_particle(const MixParams& p, int64_t i, const double* xs, const d
         kw.ws = p.wind_speed ? p.wind_speed[i] : 0.0f;
         kw.mld = p.mld ? p.mld[i] : p.mld_const;
     } else {
-        h = horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        h = PROJ ? horiz_weights_h(g, p.lon[i], p.lat[i], p.pos_f32 != 0) : horiz_weights(g, p.lon[i], p.lat[i], p.pos_f32 != 0);
     }
 
     // ---- inner loop ---------------------------------------------------------------------------------------------

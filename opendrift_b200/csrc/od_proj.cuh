@@ -1,0 +1,153 @@
+// od_proj.cuh -- map projections of readers whose grid is not geographic, and the rotation of their vector components.
+//
+// The reference hands every position to pyproj (Variables.lonlat2xy, readers/basereader/variables.py:129-143) before it indexes a
+// projected reader's block, and rotates x / y vector components from the grid's axes to east / north afterwards
+// (rotate_vectors, :59-109: inverse projection of (x, y) and (x, y + 10 m), Geod.inv azimuth of that line, rotation by minus
+// that azimuth).  Both run per particle inside the kernels here.
+//
+// Projection: spherical stereographic, the four aspects PROJ's stere.cpp distinguishes (Snyder 1987, eqs. 21-2..21-4,
+// 20-14, 20-15, 20-18, 21-15), wrapped in PROJ's generic steps (lam = lon - lon_0 reduced to [-pi, pi], x = a x' + x_0).
+// Geod.inv: only the forward azimuth of a short line is needed; it is obtained by inverting the direct solution
+// (mid-latitude first guess, one correction with the miss of the direct series move) -- the miss shrinks by
+// (s/a)^2 ~ 2e-12 per pass for the 10 m line.
+#pragma once
+#include "../../include/odcuda.h"
+#include "od_geod.cuh"
+
+namespace od {
+
+enum { PROJ_EQUIT = 0, PROJ_OBLIQ = 1, PROJ_N_POLE = 2, PROJ_S_POLE = 3 };
+
+struct ProjStere {
+    int mode;
+    double a, ra, akm1, sinX1, cosX1, phi0, lam0, x0, y0;
+};
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kHalfPi = 1.57079632679489661923;
+
+// PROJ adjlon: reduce to [-pi, pi]; values already inside are left untouched
+OD_HD double adjlon(double lam) {
+    if (fabs(lam) <= kPi) return lam;
+    double t = lam + kPi;
+    t = t - 2.0 * kPi * floor(t / (2.0 * kPi));
+    return t - kPi;
+}
+
+// lon, lat in degrees -> x, y in metres; returns false where the projection is undefined (antipode)
+OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, double& y) {
+    const double lam = adjlon(lon * kDeg - P.lam0);
+    double phi = lat * kDeg;
+    double sinphi, cosphi, sinlam, coslam;
+    sincos(phi, &sinphi, &cosphi);
+    sincos(lam, &sinlam, &coslam);
+    double px, py;
+    if (P.mode == PROJ_EQUIT || P.mode == PROJ_OBLIQ) {
+        const double d = P.mode == PROJ_EQUIT ? 1.0 + cosphi * coslam : 1.0 + P.sinX1 * sinphi + P.cosX1 * cosphi * coslam;
+        if (!(d > 1e-10)) return false;
+        const double k = P.akm1 / d;
+        px = k * cosphi * sinlam;
+        py = P.mode == PROJ_EQUIT ? k * sinphi : k * (P.cosX1 * sinphi - P.sinX1 * cosphi * coslam);
+    } else {
+        if (P.mode == PROJ_N_POLE) {
+            coslam = -coslam;
+            phi = -phi;
+        }
+        if (fabs(phi - kHalfPi) < 1e-8) return false;
+        py = P.akm1 * tan(kPio4 + 0.5 * phi);
+        px = sinlam * py;
+        py = py * coslam;
+    }
+    x = P.a * px + P.x0;
+    y = P.a * py + P.y0;
+    return true;
+}
+
+// x, y in metres -> lon, lat in degrees
+OD_HD void stere_inverse(const ProjStere& P, double x, double y, double& lon, double& lat) {
+    x = (x - P.x0) * P.ra;
+    y = (y - P.y0) * P.ra;
+    const double rh = hypot(x, y);
+    const double c = 2.0 * atan(rh / P.akm1);
+    double sinc, cosc;
+    sincos(c, &sinc, &cosc);
+    const bool small = fabs(rh) <= 1e-10;
+    double phi, lam = 0.0;
+    if (P.mode == PROJ_EQUIT) {
+        phi = small ? 0.0 : asin(fmin(1.0, fmax(-1.0, y * sinc / rh)));
+        if (cosc != 0.0 || x != 0.0) lam = atan2(x * sinc, cosc * rh);
+    } else if (P.mode == PROJ_OBLIQ) {
+        phi = small ? P.phi0 : asin(fmin(1.0, fmax(-1.0, cosc * P.sinX1 + y * sinc * P.cosX1 / rh)));
+        const double cc = cosc - P.sinX1 * sin(phi);
+        if (cc != 0.0 || x != 0.0) lam = atan2(x * sinc * P.cosX1, cc * rh);
+    } else {
+        if (P.mode == PROJ_N_POLE) y = -y;
+        phi = small ? P.phi0 : asin(P.mode == PROJ_S_POLE ? -cosc : cosc);
+        lam = (x == 0.0 && y == 0.0) ? 0.0 : atan2(x, y);
+    }
+    lon = adjlon(lam + P.lam0) * kRad2Deg;
+    lat = phi * kRad2Deg;
+}
+
+OD_HD double wrap180(double d) { return d - 360.0 * rint(d * (1.0 / 360.0)); }
+
+// Forward azimuth (radians) at point 1 of the short WGS84 geodesic to point 2 (what rotate_vectors takes from Geod.inv)
+OD_HD double inverse_azimuth_short(double lon1, double lat1, double lon2, double lat2) {
+    double sm, cm;
+    sincos(0.5 * (lat1 + lat2) * kDeg, &sm, &cm);
+    const double w2 = 1.0 - Wgs84::e2 * sm * sm;
+    const double w = sqrt(w2);
+    const double M = Wgs84::a * (1.0 - Wgs84::e2) / (w2 * w);        // meridional radius of curvature
+    const double Nc = Wgs84::a / w * cm;                              // radius of the parallel
+    const double dlon = wrap180(lon2 - lon1);
+    double north = M * (lat2 - lat1) * kDeg;
+    double east = Nc * dlon * kDeg;
+    // azimuth at point 1 = azimuth at the mid-point minus half the meridian convergence
+    const double az = atan2(east, north) - 0.5 * dlon * kDeg * sm;
+    const double s = hypot(east, north);
+    double sa, ca;
+    sincos(az, &sa, &ca);
+    north = s * ca;
+    east = s * sa;
+    // one correction with the miss of the direct solution
+    const SeriesStart ss = series_start(lat1);
+    double lo, la;
+    geod_move_ne(ss, lon1, north, east, lo, la);
+    north += M * (lat2 - la) * kDeg;
+    east += Nc * wrap180(lon2 - lo) * kDeg;
+    return atan2(east, north);
+}
+
+// od_proj_desc (include/odcuda.h) -> the per-launch constants; the aspect and scale constant are chosen as PROJ's stere
+// setup does for a sphere.  Returns 0, or 2 unknown projection, 3 bad radius / scale.
+static inline int proj_from_desc(const od_proj_desc* d, ProjStere* Pp) {
+    if (d->kind != OD_PROJ_STERE_SPHERE) return 2;
+    if (!(d->a > 0.0) || !(d->k_0 > 0.0)) return 3;
+    ProjStere& P = *Pp;
+    P.a = d->a;
+    P.ra = 1.0 / d->a;
+    P.phi0 = d->lat_0 * kDeg;
+    P.lam0 = d->lon_0 * kDeg;
+    P.x0 = d->x_0;
+    P.y0 = d->y_0;
+    const double t = fabs(P.phi0);
+    if (fabs(t - kHalfPi) < 1e-10) P.mode = P.phi0 < 0 ? PROJ_S_POLE : PROJ_N_POLE;
+    else P.mode = t > 1e-10 ? PROJ_OBLIQ : PROJ_EQUIT;
+    P.sinX1 = sin(P.phi0);
+    P.cosX1 = cos(P.phi0);
+    const double phits = fabs(d->has_lat_ts ? d->lat_ts * kDeg : kHalfPi);
+    if (P.mode == PROJ_OBLIQ || P.mode == PROJ_EQUIT) P.akm1 = 2.0 * d->k_0;
+    else P.akm1 = fabs(phits - kHalfPi) >= 1e-10 ? cos(phits) / tan(kPio4 - 0.5 * phits) : 2.0 * d->k_0;
+    return 0;
+}
+
+// rotate_vectors (variables.py:59-109): angle (radians) by which components along the plane's x / y axes at (px, py) are
+// rotated to become east / north components
+OD_HD double rotation_to_geographic(const ProjStere& P, double px, double py, double delta) {
+    double lon1, lat1, lon2, lat2;
+    stere_inverse(P, px, py, lon1, lat1);
+    stere_inverse(P, px, py + delta, lon2, lat2);
+    return -inverse_azimuth_short(lon1, lat1, lon2, lat2);
+}
+
+}  // namespace od

@@ -108,7 +108,7 @@ class FieldGroup:
     """One od group: geometry + a ring of device slots filled on demand from a slab supplier."""
 
     def __init__(self, engine, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3,
-                 names=None):
+                 names=None, proj=None, lon_0to360=False, rotate=False):
         self.engine, self.gid, self.ncomp = engine, gid, ncomp
         self.lon = np.asarray(lon, dtype=np.float32)
         self.lat = np.asarray(lat, dtype=np.float32)
@@ -129,6 +129,12 @@ class FieldGroup:
         d.nz = 1 if self.z is None else len(self.z)
         d.n_slots = n_slots
         geo = grid_geometry(self.lon, self.lat)
+        if proj is not None:
+            # the axes are metres in a projected plane: no longitude conventions of the axes, no periodicity; the longitude of
+            # the positions is modulated as the reader's corner longitudes say, then projected (od_group_desc.proj)
+            geo.update(lon_mode=_lib.OD_LON_0_360 if lon_0to360 else _lib.OD_LON_PM180, wrap_x=0, global_x=0, global_coverage=False)
+            d.proj = proj
+            d.rotate_vectors = 1 if (rotate and ncomp == 2) else 0
         d.lon_mode, d.wrap_x, d.global_x = geo['lon_mode'], geo['wrap_x'], geo['global_x']
         d.x0, d.xspan, d.y0, d.yspan = geo['x0'], geo['xspan'], geo['y0'], geo['yspan']
         d.xmin, d.xmax, d.ymin, d.ymax = geo['xmin'], geo['xmax'], geo['ymin'], geo['ymax']
@@ -446,7 +452,7 @@ class Engine:
         return self.torch.empty(n, dtype=dtype, device=self.device)
 
     # -- groups ---------------------------------------------------------------------------
-    def add_group(self, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3, names=None):
+    def add_group(self, lon, lat, z, ncomp, times, supplier, fallback, n_slots=3, names=None, **proj_kw):
         free = [k for k in range(_lib.OD_MAX_GROUPS) if k not in self.groups]
         if not free:
             gc.collect()
@@ -455,7 +461,7 @@ class Engine:
             raise RuntimeError('all %d field groups of this engine are in use; release readers you no longer need'
                                % _lib.OD_MAX_GROUPS)
         gid = free[0]
-        g = FieldGroup(self, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots, names)
+        g = FieldGroup(self, gid, lon, lat, z, ncomp, times, supplier, fallback, n_slots, names, **proj_kw)
         self.groups[gid] = g
         return g
 
@@ -501,13 +507,14 @@ class Engine:
         return self.torch.as_tensor(_W(), device=self.device)
 
     # -- kernels --------------------------------------------------------------------------
-    def interp(self, group, t, lon, lat, z=None, pos_f32=False, raw=False):
+    def interp(self, group, t, lon, lat, z=None, pos_f32=False, raw=False, rotate=True):
         """get_variables_interpolated fast path on device tensors -> list of float32 tensors."""
         n = lon.numel()
         ts, _ = group.sample(t)
         outs = [self.empty(n, self.torch.float32) for _ in range(group.ncomp)]
         self._check(self.lib.od_interp(self.ctx, group.gid, C.byref(ts), n, _ptr(lon), _ptr(lat), _ptr(z),
-                                       (1 if pos_f32 else 0) | (2 if raw else 0) | (4 if (z is not None and z.dtype == self.torch.float64) else 0),
+                                       (1 if pos_f32 else 0) | (2 if raw else 0) | (4 if (z is not None and z.dtype == self.torch.float64) else 0)
+                                       | (0 if rotate else 8),
                                        _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
         return outs
 

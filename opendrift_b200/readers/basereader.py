@@ -72,8 +72,16 @@ class StructuredReader:
 
     def __init__(self):
         p = str(getattr(self, 'proj4', '+proj=latlong'))
+        self.proj = None               # a projected plane (spherical +proj=stere): x / y axes and xmin .. ymax are metres in it
         if not any(k in p for k in ('latlong', 'longlat', 'lonlat', 'latlon')):      # PROJ's aliases of the geographic CRS
-            raise NotImplementedError('opendrift_b200 readers are geographic (+proj=latlong); got %s' % p)
+            from .projection import SphericalStereographic
+            self.proj = SphericalStereographic(p)      # raises for what the device code does not project
+            if self.subblocks:
+                raise NotImplementedError('sub-block readers on a projected plane are not on the GPU path')
+            # modulate_longitude (variables.py:259-280): the longitude convention follows the corner longitudes
+            exlons, _ = self.proj(np.array([self.xmin, self.xmin, self.xmax, self.xmax], dtype=np.float64),
+                                  np.array([self.ymin, self.ymax, self.ymax, self.ymin], dtype=np.float64), inverse=True)
+            self._lon_0to360 = not (np.min(exlons) < 0)
         if getattr(self, 'times', None) is None and getattr(self, 'start_time', None) is not None \
                 and getattr(self, 'time_step', None) is not None and self.end_time != self.start_time:
             n = int(round((self.end_time - self.start_time).total_seconds() / self.time_step.total_seconds())) + 1
@@ -98,10 +106,22 @@ class StructuredReader:
 
     def modulate_longitude(self, lons):
         lons = np.asarray(lons)
+        if self.proj is not None:
+            return np.mod(lons, 360) if self._lon_0to360 else np.mod(lons + 180, 360) - 180
         return np.mod(lons + 180, 360) - 180 if self.xmin < 0 else np.mod(lons, 360)
+
+    def lonlat2xy(self, lon, lat):
+        """variables.py:129-143"""
+        return (lon, lat) if self.proj is None else self.proj(lon, lat, inverse=False)
+
+    def xy2lonlat(self, x, y):
+        """variables.py:114-127"""
+        return (x, y) if self.proj is None else self.proj(x, y, inverse=True)
 
     def global_coverage(self):
         """True if the reader covers the globe east-west (variables.py:289-301)."""
+        if self.proj is not None:
+            return False
         dx = getattr(self, 'delta_x', None) or 0
         return bool((self.xmin - 2 * dx <= 0 and self.xmax + 2 * dx >= 360) or
                     (self.xmin - 2 * dx <= -180 and self.xmax + 2 * dx >= 180))
@@ -114,6 +134,8 @@ class StructuredReader:
     def covers_positions(self, lon, lat, z=0):
         x = self.modulate_longitude(np.atleast_1d(lon))
         y = np.atleast_1d(lat)
+        if self.proj is not None:
+            x, y = self.lonlat2xy(x, y)
         if self.global_coverage():             # north-south only (variables.py:239-242)
             ind = np.where((y >= self.ymin) & (y <= self.ymax))[0]
         else:
@@ -134,7 +156,9 @@ class StructuredReader:
     # -- block size (variables.py:154-165, 588-620) ---------------------------------------------------
     def pixel_size(self):
         dx = getattr(self, 'delta_x', None)
-        return None if dx is None else dx * 111000           # degrees -> metres (geographic readers)
+        if dx is None:
+            return None
+        return dx if self.proj is not None else dx * 111000   # degrees -> metres for geographic readers
 
     def set_buffer_size(self, max_speed, time_coverage=None):
         """Cells added around the requested positions so that the block still covers the elements at the end of the
@@ -239,7 +263,10 @@ class StructuredReader:
                     cache[ti] = arrs
                 return cache[ti][c]
             fb = [fallback.get(nme) for nme in names]
-            g = engine.add_group(x, y, z, len(names), self.times, supplier, fb, n_slots=n_slots, names=names)
+            pk = {}
+            if self.proj is not None:       # the block's axes are metres in the reader's plane; vector pairs get rotated
+                pk = dict(proj=self.proj.desc(), lon_0to360=self._lon_0to360, rotate=len(names) == 2)
+            g = engine.add_group(x, y, z, len(names), self.times, supplier, fb, n_slots=n_slots, names=names, **pk)
             for c, nme in enumerate(names):
                 self._groups[nme] = (g, c)
 
@@ -294,7 +321,9 @@ class StructuredReader:
                 continue
             g, c = self._groups[v]
             # no fallback here: uncovered / missing samples are NaN-masked like the reference's reader output
-            outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True)
+            # (a projected reader's vector pairs are rotated to east / north when the caller names the target CRS, as
+            # Environment does with rotate_to_proj = '+proj=latlong'; without it the components stay along the grid's axes)
+            outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None)
             for nme, (gg, cc) in self._groups.items():
                 if gg is g and nme in variables:
                     a = outs[cc].cpu().numpy()

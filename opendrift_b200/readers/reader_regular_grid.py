@@ -7,12 +7,12 @@ from .basereader import StructuredReader
 
 
 class Reader(StructuredReader):
-    def __init__(self, lon, lat, z=None, times=None, fields=None, name='regular_grid', subblocks=False):
+    def __init__(self, lon, lat, z=None, times=None, fields=None, name='regular_grid', subblocks=False, proj4='+proj=latlong'):
         """fields: dict variable -> array (nt, [nz,] ny, nx) float32 (NumPy or CUDA tensors), or a callable
         fields[var](time_index) -> ([nz,] ny, nx).  subblocks: hand out only the part of the grid around the requested
         positions plus `buffer` cells, like a file reader does (reader_netCDF_CF_generic.py:436-466)."""
         self.subblocks = bool(subblocks)
-        self.proj4 = '+proj=latlong'
+        self.proj4 = proj4              # a projected plane (spherical +proj=stere): lon / lat are then its x / y axes in metres
         self.lon = np.asarray(lon, dtype=np.float32)
         self.lat = np.asarray(lat, dtype=np.float32)
         self.zlev = None if z is None else np.asarray(z, dtype=np.float64)

@@ -28,6 +28,15 @@ def broadcast_slab(tensor, src=0):
     return tensor
 
 
+def _collective_device():
+    """Where the tensors of a collective must live: the GPU for NCCL, the host for gloo."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
 def gather_by_id(local_ids, local_values, n_total, dtype=np.float64):
     """Assemble a full-length array keyed by element ID from per-rank pieces (all ranks get the result)."""
     import torch
@@ -35,7 +44,9 @@ def gather_by_id(local_ids, local_values, n_total, dtype=np.float64):
     out = torch.zeros(n_total, dtype=torch.float64)
     out[torch.as_tensor(np.asarray(local_ids, dtype=np.int64))] = torch.as_tensor(np.asarray(local_values, dtype=np.float64))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        out = out.to(_collective_device())
         dist.all_reduce(out)
+        out = out.cpu()
     return out.numpy().astype(dtype)
 
 
@@ -46,8 +57,10 @@ def allreduce_stats(count_active, lon_min, lon_max, lat_min, lat_max):
     mx = torch.tensor([lon_max, lat_max, -lon_min, -lat_min], dtype=torch.float64)
     cnt = torch.tensor([float(count_active)], dtype=torch.float64)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        mx, cnt = mx.to(_collective_device()), cnt.to(_collective_device())
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt)
+        mx, cnt = mx.cpu(), cnt.cpu()
     return int(cnt.item()), -float(mx[2]), float(mx[0]), -float(mx[3]), float(mx[1])
 
 

@@ -140,7 +140,7 @@ def setup():
     _ready = True
 
 
-def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid', subblocks=False):
+def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid', subblocks=False, proj4='+proj=latlong'):
     """A reference StructuredReader (subclass of the reference base class) serving
     in-memory regular lon/lat(/z) slabs.  ``fields[var]`` has shape (nt, nz, ny, nx) or
     (nt, ny, nx) float32.  get_variables returns the FULL grid block (like
@@ -157,7 +157,7 @@ def make_grid_reader(lon, lat, z, times, fields, name='synthetic_grid', subblock
 
     class Reader(StructuredReader):
         def __init__(self):
-            self.proj4 = '+proj=latlong'
+            self.proj4 = proj4              # a projected plane: lon / lat are then the x / y axes in metres
             self.lon = np.asarray(lon, dtype=np.float32)
             self.lat = np.asarray(lat, dtype=np.float32)
             self.zlev = None if z is None else np.asarray(z, dtype=np.float64)

@@ -635,11 +635,104 @@ def check_hooks(o, which):
     return float(np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max())
 
 
+# ---- readers on a projected plane (spherical +proj=stere): lonlat2xy before the index arithmetic, vector pairs rotated to
+#      east / north afterwards (readers/basereader/variables.py:129-143, 59-109, 799-837) -----------------------------------------
+PROJ_POLAR = '+proj=stere +lat_0=90 +lon_0=10 +lat_ts=60 +R=6371000 +units=m +no_defs'
+PROJ_OBLIQUE = '+proj=stere +lat_0=58 +lon_0=3 +k_0=0.9996 +x_0=50000 +y_0=-20000 +R=6370997 +units=m +no_defs'
+PROJ_CASES = {
+    'stere_polar_rk4_3d_w': dict(proj4=PROJ_POLAR, model='OceanDrift', readers=('cur3d',), steps=8, dt=600,
+                                 cfg={'drift:advection_scheme': 'runge-kutta4'}),
+    'stere_oblique_rk2_wind': dict(proj4=PROJ_OBLIQUE, model='OceanDrift', readers=('cur2d', 'wind'), steps=6, dt=900,
+                                   cfg={'drift:advection_scheme': 'runge-kutta', 'drift:vertical_advection': False}, seed={'z': 0.0}),
+    'stere_polar_mixing': dict(proj4=PROJ_POLAR, model='OceanDrift', readers=('cur3d_k',), steps=3, dt=600,
+                               cfg={'drift:vertical_mixing': True, 'drift:vertical_advection': False, 'vertical_mixing:timestep': 60.0}),
+    'stere_polar_leeway': dict(proj4=PROJ_POLAR, model='Leeway', readers=('cur2d', 'wind'), steps=6, dt=600, cfg={}),
+}
+PROJ_N = 400
+
+
+def proj_setup(case):
+    from oracle.proj_stere import Stere
+    c = PROJ_CASES[case]
+    P = Stere(c['proj4'])
+    cx, cy = P.forward(np.array([4.0]), np.array([60.0]))
+    nx, ny, nz, nt = 44, 38, 6, 4
+    xs = (cx[0] + 4000.0 * (np.arange(nx) - nx // 2)).astype(np.float32)
+    ys = (cy[0] + 4000.0 * (np.arange(ny) - ny // 2)).astype(np.float32)
+    zs = -10.0 * np.arange(nz)
+    times = common.syn.slab_times(nt)
+    X, Y = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny))
+    lay = lambda fn: np.stack([[fn(k, z) for z in zs] for k in range(nt)]).astype(np.float32)      # noqa: E731
+    flat = lambda fn: np.stack([fn(k) for k in range(nt)]).astype(np.float32)                      # noqa: E731
+    U3 = lay(lambda k, z: 0.5 * np.sin(2 * np.pi * X + 0.3 * k) * np.cos(np.pi * Y) * np.exp(z / 40))
+    V3 = lay(lambda k, z: 0.4 * np.cos(2 * np.pi * Y + 0.2 * k) * np.sin(np.pi * X) * np.exp(z / 40))
+    fields = {
+        'cur3d': {common.CUR[0]: U3, common.CUR[1]: V3,
+                  'upward_sea_water_velocity': lay(lambda k, z: 1e-3 * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * z / zs.min()))},
+        'cur3d_k': {common.CUR[0]: U3, common.CUR[1]: V3,
+                    'ocean_vertical_diffusivity': lay(lambda k, z: 0.01 * np.exp(z / 20) * (1 + 0.5 * np.sin(np.pi * X) * np.sin(np.pi * Y)))},
+        'cur2d': {common.CUR[0]: U3[:, 0].copy(), common.CUR[1]: V3[:, 0].copy()},
+        'wind': {'x_wind': flat(lambda k: 8 * np.cos(0.4 * k) * (1 + 0.3 * np.sin(np.pi * X))),
+                 'y_wind': flat(lambda k: 8 * np.sin(0.4 * k) * (1 + 0.3 * np.cos(np.pi * Y)))},
+    }
+    rng = np.random.default_rng(3)
+    px, py = rng.uniform(xs[3], xs[-4], PROJ_N), rng.uniform(ys[3], ys[-4], PROJ_N)
+    lon0, lat0 = P.inverse(px, py)
+    z0 = rng.uniform(-55, 0, PROJ_N).astype(np.float32)
+    return c, xs, ys, zs, times, fields, lon0.astype(np.float32), lat0.astype(np.float32), z0
+
+
+def run_proj_case(case, classes, make, **model_kw):
+    c, xs, ys, zs, times, fields, lon0, lat0, z0 = proj_setup(case)
+    o = classes[c['model']](loglevel=50, seed=0, **model_kw)
+    for nm in c['readers']:
+        three_d = nm.startswith('cur3d')
+        o.add_reader(make(xs, ys, zs if three_d else None, times, fields[nm], nm, c['proj4']))
+    for k, v in {'general:use_auto_landmask': False, 'general:coastline_action': 'none', **c['cfg']}.items():
+        o.set_config(k, v)
+    if 'environment:constant:land_binary_mask' in getattr(o, '_config', {}):
+        o.set_config('environment:constant:land_binary_mask', 0)
+    if c['model'] == 'Leeway':
+        o.seed_elements(lon=lon0, lat=lat0, time=times[0], object_type=1)
+    else:
+        kw = dict(lon=lon0, lat=lat0, z=z0, time=times[0])
+        kw.update(c.get('seed', {}))
+        o.seed_elements(**kw)
+    o.run(steps=c['steps'], time_step=c['dt'], time_step_output=c['dt'])
+    return o
+
+
+def run_product_proj(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.models.leeway import Leeway
+    from opendrift_b200.readers import reader_regular_grid
+    return run_proj_case(case, {'OceanDrift': OceanDrift, 'Leeway': Leeway},
+                         lambda x, y, z, t, f, name, proj4: reader_regular_grid.Reader(x, y, z, t, f, name=name, proj4=proj4), **model_kw)
+
+
+def check_proj(o, case):
+    ref = np.load(GOLDEN)
+    g = lambda k: ref['proj_%s__%s' % (case, k)]                 # noqa: E731
+    e = max(common.max_err_deg(np.asarray(o.elements.lon), np.asarray(o.elements.lat), g('lon'), g('lat')))
+    dz = float(np.abs(np.asarray(o.elements.z, dtype=np.float64) - g('z')).max())
+    moved = float(np.abs(g('lon') - g('lon0')).max())
+    return e, dz, moved
+
+
 if __name__ == '__main__':
     from oracle import refrun
     fx = common.Fixture('rk4_3d')
     out = {}
     refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as _RefODp
+    from opendrift.models.leeway import Leeway as _RefLWp
+    for case in PROJ_CASES:
+        ro = run_proj_case(case, {'OceanDrift': _RefODp, 'Leeway': _RefLWp},
+                           lambda x, y, z, t, f, name, proj4: refrun.make_grid_reader(x, y, z, t, f, name=name, proj4=proj4), logfile='/tmp/od_bk.log')
+        lon0 = proj_setup(case)[6]
+        out.update({'proj_%s__lon' % case: np.asarray(ro.elements.lon, dtype=np.float64), 'proj_%s__lat' % case: np.asarray(ro.elements.lat, dtype=np.float64),
+                    'proj_%s__z' % case: np.asarray(ro.elements.z, dtype=np.float64), 'proj_%s__lon0' % case: lon0.astype(np.float64)})
+        print('proj', case, len(ro.elements.lon), 'moved', float(np.abs(np.asarray(ro.elements.lon) - lon0).max()))
     from opendrift.models.oceandrift import OceanDrift as _RefOD0
     for which in HOOK_CASES:
         ro = run_hook_case(which, _RefOD0, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name), logfile='/tmp/od_bk.log')

@@ -195,12 +195,16 @@ def run_port(fx):
 
 
 # ---- host-compiled device math ---------------------------------------------------------------
+from opendrift_b200._lib import ProjDesc as _lib_ProjDesc      # noqa: E402
+
+
 class HsGroup(C.Structure):
     _fields_ = [('ncomp', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
                 ('lon_mode', C.c_int32), ('wrap_x', C.c_int32), ('global_x', C.c_int32), ('pad_', C.c_int32),
                 ('x0', C.c_double), ('xspan', C.c_double), ('y0', C.c_double), ('yspan', C.c_double),
                 ('xmin', C.c_double), ('xmax', C.c_double), ('ymin', C.c_double), ('ymax', C.c_double),
-                ('fallback', C.c_float * 2), ('z_levels', C.c_void_p)]
+                ('fallback', C.c_float * 2), ('z_levels', C.c_void_p), ('proj', _lib_ProjDesc), ('rotate_vectors', C.c_int32),
+                ('pad2_', C.c_int32)]
 
 
 class HsPair(C.Structure):

@@ -43,6 +43,7 @@ class _HostGroup:
         g.x0, g.xspan, g.y0, g.yspan = d.x0, d.xspan, d.y0, d.yspan
         g.xmin, g.xmax, g.ymin, g.ymax = d.xmin, d.xmax, d.ymin, d.ymax
         g.fallback[0], g.fallback[1] = d.fallback[0], d.fallback[1]
+        g.proj, g.rotate_vectors = d.proj, d.rotate_vectors
         g.z_levels = None if self.levels is None else self.levels.ctypes.data
         self.hs = g
 

@@ -22,6 +22,8 @@ struct hs_group {
     double x0, xspan, y0, yspan, xmin, xmax, ymin, ymax;
     float fallback[2];
     const double* z_levels;   // as the reader gives them
+    od_proj_desc proj;        // kind 0: geographic
+    int32_t rotate_vectors, pad2_;
 };
 
 struct hs_pair {
@@ -55,6 +57,11 @@ static GroupGeom make_geom(const hs_group& d, hs_levels& lv) {
         }
         q.zmin = lv.zs[0]; q.zmax = lv.zs[d.nz - 1];
         q.zs = lv.zs.data(); q.zy = lv.zy.data();
+    }
+    if (d.proj.kind != 0 && proj_from_desc(&d.proj, &q.proj) == 0) {
+        q.proj_kind = d.proj.kind;
+        q.rotate = d.rotate_vectors ? 1 : 0;
+        q.rot_delta = 10.0;
     }
     return q;
 }
@@ -395,6 +402,7 @@ int hs2_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lo
     hs_levels lv;
     GroupGeom q = make_geom(*g, lv);
     if (flags & OD_INTERP_NO_FALLBACK) q.fallback[0] = q.fallback[1] = NAN;
+    if (flags & OD_INTERP_NO_ROTATE) q.rotate = 0;
     const PairRef p = make_pair(*pr);
     const bool z64 = (flags & OD_INTERP_Z_F64) != 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -402,11 +410,11 @@ int hs2_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lo
         const VertW vw = vert_weights(q, q.zs, q.zy, zz, !z64);
         if (q.ncomp == 2) {
             float u, v;
-            sample2(q, p, vw, lon[i], lat[i], u, v, (flags & OD_INTERP_POS_F32) != 0);
+            sample2_any(q, p, vw, lon[i], lat[i], u, v, (flags & OD_INTERP_POS_F32) != 0);
             if (out0) out0[i] = u;
             if (out1) out1[i] = v;
         } else {
-            const float r = sample1(q, p, vw, lon[i], lat[i], (flags & OD_INTERP_POS_F32) != 0);
+            const float r = sample1_any(q, p, vw, lon[i], lat[i], (flags & OD_INTERP_POS_F32) != 0);
             if (out0) out0[i] = r;
         }
     }
@@ -471,7 +479,8 @@ static void run2c(const StepParams& p, int mode) {          // step_chain_kernel
 
 template <int S, bool F, int E>
 static void run2(const StepParams& p, int mode) {
-    if (p.n_chain > 0) { run2c<S, F, (E == 0 ? 0 : 1)>(p, mode); return; }
+    const bool general = p.n_chain > 0 || p.cs.g.proj_kind != 0 || (E != 0 && ((p.wind_on && p.gwind.proj_kind != 0) || (p.w_on && p.gw.proj_kind != 0)));
+    if (general) { run2c<S, F, (E == 0 ? 0 : 1)>(p, mode); return; }
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
     if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
     else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
@@ -559,7 +568,8 @@ int hs2_mix(const od_mix_args* a, const hs_group* g, const hs_pair* pr) {
     p.iter0 = a->iter0; p.skip_surface_stick = a->skip_surface_stick;
     unsigned cnt = 0;
     p.counter = &cnt;
-    for (int64_t i = 0; i < a->n; ++i) mix_particle(p, i, p.xs, p.xy);
+    if (p.g.proj_kind) for (int64_t i = 0; i < a->n; ++i) mix_particle<true>(p, i, p.xs, p.xy);
+    else for (int64_t i = 0; i < a->n; ++i) mix_particle<false>(p, i, p.xs, p.xy);
     if (a->h_n_deactivated) *a->h_n_deactivated = cnt;
     return 0;
 }
@@ -582,7 +592,8 @@ int hs2_leeway(const od_leeway_args* a, const hs_group* g_wind, const hs_pair* t
     p.noise_cur = a->d_noise_cur; p.noise_wind = a->d_noise_wind; p.noise_kinds = a->noise_kinds;
     if (a->capsize_on && !a->d_capsized) return -3;
     p.missing_code = a->missing_code;
-    for (int64_t i = 0; i < a->n; ++i) leeway_particle(p, i);
+    if (p.gwind.proj_kind || p.gcur.proj_kind) for (int64_t i = 0; i < a->n; ++i) leeway_particle<true>(p, i);
+    else for (int64_t i = 0; i < a->n; ++i) leeway_particle<false>(p, i);
     return 0;
 }
 

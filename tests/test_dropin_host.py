@@ -426,3 +426,37 @@ def test_per_iteration_mixing_launches_continue_the_device_generator(host_engine
     assert host_engine.lib.calls.count('od_vertical_mixing') == 30 + 3
     assert np.array_equal(np.asarray(hooked.elements.z), np.asarray(plain.elements.z))
     assert np.array_equal(np.asarray(hooked.elements.lon), np.asarray(plain.elements.lon))
+
+
+@pytest.mark.parametrize('case', list(__import__('bookkeeping').PROJ_CASES))
+def test_readers_on_a_projected_plane_match_reference(case, host_engine):
+    """Gridded readers whose grid lies on a stereographic plane (polar and oblique aspects): positions are projected before the
+    index arithmetic and the current / wind components rotated from the grid's axes to east / north afterwards, inside the
+    launches -- fused OceanDrift step (RK4 3-D with w, RK2 with a wind reader), vertical mixing, Leeway -- against the unmodified
+    reference running readers of the same projection (pyproj stood in for by oracle/proj_stere.py + oracle/geod_karney.py)."""
+    import bookkeeping as bk
+    o = bk.run_product_proj(case)
+    e, dz, moved = bk.check_proj(o, case)
+    assert moved > 0.01 and e < 5e-8 and dz <= 1e-9, (e, dz)
+    step = 'od_leeway_step' if case.endswith('leeway') else 'od_step_oceandrift'
+    assert step in host_engine.lib.calls                          # the fused launches, not the staged recipe
+
+
+def test_projected_reader_interpolation_with_and_without_rotation(host_engine):
+    """get_variables_interpolated of a projected reader: components along the grid's axes unless rotate_to_proj names a
+    geographic CRS (variables.py:799-837); the rotated pair has the same speed, turned by the local grid azimuth."""
+    import bookkeeping as bk
+    from opendrift_b200.readers import reader_regular_grid
+    c, xs, ys, zs, times, fields, lon0, lat0, z0 = bk.proj_setup('stere_polar_rk4_3d_w')
+    rd = reader_regular_grid.Reader(xs, ys, zs, times, fields['cur3d'], name='cur', proj4=c['proj4'])
+    lon, lat, z = lon0.astype(np.float64), lat0.astype(np.float64), z0
+    raw, _ = rd.get_variables_interpolated(list(common.CUR), time=times[1], lon=lon, lat=lat, z=z)
+    rot, _ = rd.get_variables_interpolated(list(common.CUR), time=times[1], lon=lon, lat=lat, z=z, rotate_to_proj='+proj=latlong')
+    u0, v0, u1, v1 = (np.asarray(a, dtype=np.float64) for a in (raw[common.CUR[0]], raw[common.CUR[1]], rot[common.CUR[0]], rot[common.CUR[1]]))
+    assert np.allclose(np.hypot(u0, v0), np.hypot(u1, v1), rtol=2e-6)
+    turn = np.degrees(np.arctan2(u1, v1) - np.arctan2(u0, v0))
+    turn = (turn + 180) % 360 - 180
+    # polar stereographic with lon_0 = 10: the grid's y axis points along the meridian 10 E + 180, so east of it the grid is turned
+    # clockwise by (lon - 10) degrees
+    assert np.abs(turn - (-(lon - 10.0))).max() < 0.2 or np.abs(turn - (lon - 10.0)).max() < 0.2
+    assert np.abs(turn).max() > 1.0

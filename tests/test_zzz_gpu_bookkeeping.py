@@ -103,3 +103,9 @@ def test_subblock_rewindow_on_gpu():
 @pytest.mark.parametrize('which', bk.HOOK_CASES)
 def test_mixing_loop_hooks_on_gpu(which):
     assert bk.check_hooks(bk.run_product_hooks(which), which) <= 1e-9
+
+
+@pytest.mark.parametrize('case', list(bk.PROJ_CASES))
+def test_readers_on_a_projected_plane_on_gpu(case):
+    e, dz, moved = bk.check_proj(bk.run_product_proj(case), case)
+    assert moved > 0.01 and e < 5e-8 and dz <= 1e-9, (e, dz)
