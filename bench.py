@@ -47,7 +47,7 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (one `-lms 100` process, started before the
+    """nvidia-smi clocks / throttle reasons during the timed region (one `-lms 10` process, started before the
     warm-up so that the GPU never idles between warm-up and the timed steps; samples are filtered by timestamp)."""
     Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '10'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             time.sleep(0.35)          # let the first samples arrive before the timed region starts
         except Exception:
