@@ -258,10 +258,18 @@ class PhysicsMethods:
         """Start-of-step samples the Stokes move needs (device float32 tensors) + the reference's collective
         decisions (:799-812, :893-906).  Returns None when the reference would return early."""
         eng = self.engine
-        env = self.environment
         sx, sy = 'sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity'
-        if sx not in env or sy not in env:
-            return None
+        wanted = [sx, sy, 'sea_surface_wave_significant_height', 'x_wind', 'y_wind']
+        if getattr(self, '_env_view', None) is not None or any(x > 0 for x in self._uncertainty()):
+            env = self.environment            # already materialised (helper recipes), or it must carry its uncertainty draws
+        else:
+            # the fused step never materialises the whole start-of-step environment: sample only what the Stokes move reads
+            el, torch = self.elements, self.engine.torch
+            names = [v for v in wanted if v in self._env_variables]
+            d_env, _ = self.env.device_environment(names, self.time, el.dev('lon', torch.float64), el.dev('lat', torch.float64),
+                                                   self._z_truncated(), pos_f32=el.positions_f32)
+            from .basemodel import EnvironmentView
+            env = EnvironmentView(d_env)
         us, vs = env.dev(sx, eng), env.dev(sy, eng)
         if eng.minmax(us, vs)[1] == 0:
             return None                                   # 'No Stokes drift velocity available'
