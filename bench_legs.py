@@ -97,7 +97,10 @@ class StepTimer:
         self.orig = getattr(eng, method)
 
     def __enter__(self):
+        self.stamps = []
+
         def wrapped(*a, **k):
+            self.stamps.append(time.perf_counter())
             if self.calls == self.first:
                 self.e0.record()
             if self.calls == self.total - 1:
@@ -116,6 +119,11 @@ class StepTimer:
 
     def ms_per_step(self):
         return self.e0.elapsed_time(self.e1) / max(1, self.total - 1 - self.first)
+
+    def host_ms(self):
+        """(median, 95th percentile) of the host time between two step launches, steady steps only."""
+        d = np.diff(np.array(self.stamps[self.first:])) * 1e3
+        return (float(np.median(d)), float(np.percentile(d, 95))) if len(d) else (0.0, 0.0)
 
     def tail_s(self):
         """Wall time from the launch of the last step to the return of run(): last step + final state + read-back."""
@@ -171,7 +179,8 @@ def leg_api(eng, torch, n, steps, dev_fields, grid, peak):
         out[name] = {'steps': k, 'ms_per_step_steady': ms, 'particle_steps_per_s_steady': n / (ms * 1e-3),
                      'run_wall_s': wall, 'seed_elements_s': w1 - w0, 'after_last_step_s': st.tail_s(),
                      'particle_steps_per_s_whole_run': n * k / wall,
-                     'output_columns': len(o.history['time']), 'gpu_launches_per_step': (eng.launches() - l0) / k}
+                     'output_columns': len(o.history['time']), 'gpu_launches_per_step': (eng.launches() - l0) / k,
+                     'host_ms_between_launches_p50_p95': st.host_ms()}
         assert o.num_elements_active() == n and st.calls == k
         del o
     out['note'] = ('steady = CUDA events from the launch of step 3 to the launch of the last step inside run(): per step the housekeeping '
@@ -248,7 +257,7 @@ def leg_cfg4(eng, torch, n, steps, peak):
                         '(dt 60 s, 10 inner iterations) + RK4 + wind drift + Stokes drift (Phillips) + vertical advection, dt=600 s, through '
                         'OceanDrift.run() (BASELINE configs[3])' % n,
             'value': n / (ms * 1e-3), 'unit': 'particle-steps/s', 'ms_per_step': ms, 'steps': steps, 'rng': 'philox (device, keyed by element ID)',
-            'gpu_launches_per_step': launches / steps,
+            'gpu_launches_per_step': launches / steps, 'host_ms_between_launches_p50_p95': st.host_ms(),
             'mix_kernel': {'kernel_ms': mix_ms, 'algorithmic_bytes_per_launch': mix_bytes, 'achieved_GBps': mix_bytes / (mix_ms * 1e-3) / 1e9,
                            'frac_of_hbm_peak': mix_bytes / (mix_ms * 1e-3) / 1e9 / peak,
                            'bound': 'instruction issue / latency of the 10 dependent random-walk iterations per particle (each: level '
@@ -317,6 +326,7 @@ def leg_cfg5(eng, torch, n, steps, peak):
                         'Leeway.run() (BASELINE configs[4] on one GPU)' % n,
             'value': n / (ms * 1e-3), 'unit': 'particle-steps/s', 'ms_per_step': ms, 'steps': steps, 'seed_elements_s': seed_s,
             'rng': 'philox (device, keyed by element ID)', 'gpu_launches_per_step': launches / steps,
+            'host_ms_between_launches_p50_p95': st.host_ms(),
             'leeway_kernel': {'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': kbytes, 'achieved_GBps': kbytes / (k_ms * 1e-3) / 1e9,
                               'frac_of_hbm_peak': kbytes / (k_ms * 1e-3) / 1e9 / peak,
                               'bound': 'FP64 issue (two full geodesic moves per element: leeway, then current) over 72 B of state'},
