@@ -519,6 +519,18 @@ def run_b200(args):
             for _ in range(args.parity_extra):
                 step()
 
+    # ---- the same through OceanDrift.run() on every rank (N > 1) ---------------------------------------------------------------
+    api_dist = None
+    if world > 1 and not args.no_legs:
+        import bench_legs as bl
+        try:
+            fields = {'current': {CUR[0]: [d[0] for d in dev_slabs], CUR[1]: [d[1] for d in dev_slabs],
+                                  'upward_sea_water_velocity': [d_w] * PERIOD}} if rank == 0 else None
+            api_dist = bl.leg_api_distributed(eng, torch, dist, n, args.api_steps, fields, grid, rank, world)
+        except Exception as ex:
+            import traceback
+            api_dist = {'error': repr(ex)[:300], 'where': traceback.format_exc()[-500:]}
+
     # ---- end-to-end: HOST buffers through Engine.advect_current_host, copies inside the timed region -----
     resident['on'] = False
     torch.cuda.synchronize()
@@ -663,7 +675,7 @@ def run_b200(args):
                              'particle-step; see DESIGN.md and profiles/'},
         'cpu_baseline': cpu,
         'parity': parity,
-        'api': extra.get('api'),
+        'api': extra.get('api') if world == 1 else api_dist,
         'cfg4_mixing_wind_stokes': extra.get('cfg4_mixing_wind_stokes'),
         'cfg5_leeway': extra.get('cfg5_leeway'),
         'configs0_double_gyre': gyre,

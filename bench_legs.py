@@ -191,6 +191,31 @@ def leg_api(eng, torch, n, steps, dev_fields, grid, peak):
     return out
 
 
+def leg_api_distributed(eng, torch, dist, n, steps, dev_fields, grid, rank, world):
+    """configs[2]: OceanDrift.run() under the torch.distributed job -- every rank seeds its own n elements (gpu:shard = none), only
+    rank 0's readers hold data, every new slab reaches the other ranks by the broadcast the field group issues on the copy stream.
+    Steady-state time per step from CUDA events inside run(), max over ranks."""
+    cfg = {'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': True, 'drift:stokes_drift': False, 'gpu:shard': 'none'}
+    if dev_fields is None:           # a rank that never reads: one zero slab stands in for the geometry probe of bind()
+        z3 = torch.zeros((grid.nz, grid.ny, grid.nx), dtype=torch.float32, device=eng.device)
+        dev_fields = {'current': {CUR[0]: [z3] * PERIOD, CUR[1]: [z3] * PERIOD, 'upward_sea_water_velocity': [z3] * PERIOD}}
+    lon0, lat0, z0 = syn.particle_cloud(n, seed=5000 + rank)
+    n_times = syn.n_slabs_for(steps + 2, DT) + 1
+    o = _oceandrift(eng, product_readers(grid, dev_fields, n_times), cfg)
+    o.seed_elements(lon=lon0, lat=lat0, z=z0, time=syn.T0)
+    b0 = eng.dist.slabs_broadcast
+    with StepTimer(eng, torch, 'step_oceandrift', min(3, steps - 2), steps) as st:
+        o.run(steps=steps, time_step=DT, time_step_output=steps * DT)
+    assert o.num_elements_active() == n
+    t = torch.tensor([st.ms_per_step()], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {'steps': steps, 'ms_per_step_steady_max_over_ranks': ms, 'particle_steps_per_s_steady': n * world / (ms * 1e-3),
+            'slab_broadcasts_inside_run': eng.dist.slabs_broadcast - b0, 'elements_per_rank': n,
+            'note': 'OceanDrift.run() on every rank of the torch.distributed job (gpu:shard = none: each rank seeded its own elements); forcing '
+                    'read by rank 0 only and broadcast into the other ranks\' device ring one slab ahead on the copy stream'}
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def parity_port_oceandrift(eng, torch, kind, host, grid, n, steps, cfg, port_kw):
     """A small run of the same model / configuration with the reference's draws (gpu:rng numpy) against the CPU oracle."""

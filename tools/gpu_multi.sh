@@ -7,7 +7,7 @@ cat gpurun_out/multi_n${N}_tiles.jsonl | cut -c1-700
 tail -c 600 gpurun_out/multi_n${N}_tiles.err
 run_bench () {   # tag, env...
   tag=$1; shift
-  env OD_BENCH_DEBUG=1 OD_BENCH_TAG=_$tag "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 60 --warmup 5 --no-cpu --no-parity > gpurun_out/multi_n${N}_bench_$tag.json 2> gpurun_out/multi_n${N}_bench_$tag.err
+  env OD_BENCH_DEBUG=1 OD_BENCH_TAG=_$tag "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 60 --warmup 5 --no-cpu --no-parity --no-legs > gpurun_out/multi_n${N}_bench_$tag.json 2> gpurun_out/multi_n${N}_bench_$tag.err
   tail -c 300 gpurun_out/multi_n${N}_bench_$tag.err
   python - <<PY
 import json
