@@ -71,8 +71,11 @@ int od_set_stream(od_ctx* ctx, void* cuda_stream);
 int od_sync(od_ctx* ctx);                        /* blocks until the stream is idle */
 /* OD_OPT_TILE: od_advect_current (RK schemes) stages a box of pair texels per thread block in shared memory with one
  * TMA load (cp.async.bulk.tensor.4d) and serves the bilinear corners of all stages from it; pays off for cell-sorted
- * particle arrays, results are bit-identical either way. */
-enum od_option { OD_OPT_TILE = 1 };
+ * particle arrays, results are bit-identical either way.
+ * OD_OPT_SPEC (default 1): RK4 launches of the default arithmetic on a geographic, non-periodic 3-D current group between
+ * two reader times take the specialised step kernel (csrc/od_spec.cuh); 0 keeps the general kernel.  Results are
+ * bit-identical either way (tests/test_zz_gpu_spec.py). */
+enum od_option { OD_OPT_TILE = 1, OD_OPT_SPEC = 2 };
 int od_set_option(od_ctx* ctx, int option, int value);
 int od_device_sm_count(od_ctx* ctx);
 

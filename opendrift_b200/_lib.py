@@ -13,6 +13,7 @@ OD_EULER, OD_RK2, OD_RK4 = 0, 1, 2
 OD_T_LERP, OD_T_FIRST, OD_T_SECOND, OD_T_MISSING = 0, 1, 2, 3
 OD_LON_0_360, OD_LON_PM180 = 0, 1
 OD_OPT_TILE = 1
+OD_OPT_SPEC = 2
 OD_MATH_EXACT, OD_MATH_FAST, OD_MATH_SERIES = 0, 1, 2
 OD_MIX_ENVIRONMENT, OD_MIX_LARGE1994, OD_MIX_SUNDBY1983, OD_MIX_CONSTANT = 0, 1, 2, 3
 OD_MAX_LEVELS = 128

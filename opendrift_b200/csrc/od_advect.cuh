@@ -546,8 +546,9 @@ template <> struct HotPolicy<FastMath> { typedef FastHot type; };
 #endif
 
 template <int SCHEME, bool F64, int EXTRAS, class MATH, bool CHAIN>
-OD_NOINLINE void step_particle_redo(const StepParams* p, int64_t i, const double* zs, const double* zy, const double* zsw, const double* zyw) {
-    step_particle<SCHEME, F64, EXTRAS, MATH, CHAIN>(*p, i, zs, zy, zsw, zyw, TileView(), true);
+OD_NOINLINE void step_particle_redo(const StepParams* p, int64_t i, const double* zs, const double* zy, const double* zsw, const double* zyw,
+                                    bool depth_done = true) {
+    step_particle<SCHEME, F64, EXTRAS, MATH, CHAIN>(*p, i, zs, zy, zsw, zyw, TileView(), depth_done);
 }
 
 template <int SCHEME, bool F64, int EXTRAS, class MATH = ExactMath, bool CHAIN = false>

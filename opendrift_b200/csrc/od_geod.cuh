@@ -445,10 +445,12 @@ OD_HD bool series_move(const SeriesStart& p, double lon1, double xn, double ye, 
 #endif
 constexpr double kSeries3MaxR = OD_SERIES3_MAX_R;
 
-OD_HD bool series_move3(const SeriesStart& p, double lon1, double xn, double ye, double& lon2, double& lat2) {
+// The third-order move without the longitude normalisation: lon1n = ang_normalize(lon1) is the caller's (the Runge-Kutta loop
+// of the specialised step kernel normalises the start longitude once, od_spec.cuh); lonraw = lon1n + dlon is not wrapped.
+// Always evaluates; returns whether the move was inside the series' range (lonraw / lat2 are meaningless otherwise).
+OD_HD bool series_move3_raw(const SeriesStart& p, double lon1n, double xn, double ye, double& lonraw, double& lat2) {
     const double X = xn * p.vc, Y = ye * p.vc;
     const double r = (fabs(X) + fabs(Y)) * fmax(1.0, fabs(p.t));
-    if (!(r <= kSeries3MaxR)) return false;
     const double t = p.t, T = t * t, W = p.W;
     const double p20 = 1.5 - 1.5 * W;                                               // times t  (p02 = -1/2)
     const double p12 = -2.0 * T + W * (1.5 * T - 1.0 / 6.0);
@@ -459,7 +461,18 @@ OD_HD bool series_move3(const SeriesStart& p, double lon1, double xn, double ye,
     const double P = X + (X * (p12 * Y2 + p30 * X2) + t * (p20 * X2 - 0.5 * Y2));
     const double Q = Y + Y * ((q03 * Y2 + q21 * X2) + t * X);
     lat2 = p.lat1 + (W * P) * OD_GK.rad2deg;
-    lon2 = ang_normalize(ang_normalize(lon1) + Q * p.icd);
+    lonraw = lon1n + Q * p.icd;
+    return r <= kSeries3MaxR;
+}
+
+OD_HD bool series_move3(const SeriesStart& p, double lon1, double xn, double ye, double& lon2, double& lat2) {
+    const double X = xn * p.vc, Y = ye * p.vc;
+    const double r = (fabs(X) + fabs(Y)) * fmax(1.0, fabs(p.t));
+    if (!(r <= kSeries3MaxR)) return false;
+    double lonraw, la;
+    series_move3_raw(p, ang_normalize(lon1), xn, ye, lonraw, la);
+    lat2 = la;
+    lon2 = ang_normalize(lonraw);
     return true;
 }
 

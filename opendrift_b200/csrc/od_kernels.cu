@@ -22,7 +22,9 @@
 #include "od_leeway.cuh"
 #include "od_analytic.cuh"
 #include "od_history.cuh"
+#include <type_traits>
 #include "od_bookkeep.cuh"
+#include "od_spec.cuh"
 
 using namespace od;
 
@@ -34,6 +36,9 @@ using namespace od;
 #endif
 #ifndef OD_STEP_MINB
 #define OD_STEP_MINB 8
+#endif
+#ifndef OD_SPEC_MINB
+#define OD_SPEC_MINB OD_STEP_MINB
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +100,7 @@ struct od_ctx {
     int coop_fill_blocks = -1;          // co-resident grid of fill_nan_coop_kernel (0: no cooperative launch)
     int64_t fill_cap = 0;
     int tile = 0;                       // OD_OPT_TILE: stage field boxes in shared memory with TMA
+    int spec = 1;                       // OD_OPT_SPEC: launches that qualify take the specialised step kernel (od_spec.cuh)
     // host-array pipeline (od_advect_current_host): three streams, three staging buffers
     cudaStream_t hstream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t hready = nullptr;
@@ -185,6 +191,7 @@ extern "C" int od_set_stream(od_ctx* ctx, void* s) {
 extern "C" int od_set_option(od_ctx* ctx, int option, int value) {
     if (!ctx) return OD_ERR_ARG;
     if (option == OD_OPT_TILE) { ctx->tile = value ? 1 : 0; return OD_OK; }
+    if (option == OD_OPT_SPEC) { ctx->spec = value ? 1 : 0; return OD_OK; }
     return fail(ctx, OD_ERR_ARG, "od_set_option: unknown option");
 }
 
@@ -782,6 +789,21 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const __gr
     step_particle_full<SCHEME, F64, EXTRAS, MATH>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
 }
 
+// The step specialised for the common launch (od_spec.cuh): straight-line sampler, rare cases flagged and redone by the
+// general step.  Same results as step_kernel<SCHEME, F64, EXTRAS, SeriesMath>, bit for bit.
+template <int SCHEME, bool F64, int EXTRAS>
+__global__ void __launch_bounds__(OD_BLOCK, OD_SPEC_MINB) step_spec_kernel(const __grid_constant__ StepParams p) {
+    __shared__ LevelsSmem lv;
+    __shared__ LevelsSmem lvw;
+    load_levels(lv, p.cs.g);
+    if (EXTRAS && p.w_on && p.gw.nz > 1) load_levels(lvw, p.gw);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const int rc = step_particle_spec<SCHEME, F64, EXTRAS>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+    if (rc) step_particle_redo<SCHEME, F64, EXTRAS, SeriesMath, false>(&p, i, lv.zs, lv.zy, lvw.zs, lvw.zy, rc == 2);
+}
+
 // The same step with a reader priority list for the current (StepParams::cg): a separate kernel so that the default one is
 // not touched by it.  EXTRAS is 0 or 1 here (1 also serves vertical advection only).
 template <int SCHEME, bool F64, int EXTRAS, class MATH>
@@ -1365,6 +1387,13 @@ template <int EXTRAS, class MATH>
 static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     const int grid = grid_for(p.n);
     cudaStream_t s = ctx->stream;
+    if (std::is_same<MATH, SeriesMath>::value && ctx->spec && f64 && spec_eligible(p, scheme) &&
+        !(EXTRAS != 0 && ((p.wind_on && p.gwind.proj_kind != 0) || (p.w_on && p.gw.proj_kind != 0)))) {
+        step_spec_kernel<2, true, EXTRAS><<<grid, OD_BLOCK, 0, s>>>(p);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return OD_OK;
+    }
 #ifdef OD_SLIM
     // tuning builds: only the bench's instantiations (RK4, float64 factor, no reader chain) are compiled
     if (p.n_chain > 0 || scheme != OD_RK4 || !f64) return fail(ctx, OD_ERR_ARG, "tuning build (OD_SLIM): kernel variant not compiled");

@@ -435,6 +435,11 @@ class Engine:
         """TMA-staged field boxes in shared memory for the RK kernels (cell-sorted particle arrays)."""
         self._check(self.lib.od_set_option(self.ctx, _lib.OD_OPT_TILE, 1 if on else 0))
 
+    def set_spec(self, on):
+        """The specialised RK4 step kernel for launches that qualify (csrc/od_spec.cuh; on by default, results are
+        bit-identical either way)."""
+        self._check(self.lib.od_set_option(self.ctx, _lib.OD_OPT_SPEC, 1 if on else 0))
+
     def sync(self):
         self._check(self.lib.od_sync(self.ctx))
 

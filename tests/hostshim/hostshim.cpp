@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "../../opendrift_b200/csrc/od_advect.cuh"
+#include "../../opendrift_b200/csrc/od_spec.cuh"
 #include "../../opendrift_b200/csrc/od_mix.cuh"
 #include "../../opendrift_b200/csrc/od_stokes.cuh"
 #include "../../opendrift_b200/csrc/od_leeway.cuh"
@@ -477,11 +478,24 @@ static void run2c(const StepParams& p, int mode) {          // step_chain_kernel
     else for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, ExactMath, true>(p, i, zs, zy, p.gw.zs, p.gw.zy);
 }
 
+// the specialised step (od_spec.cuh) as launch_step of od_kernels.cu selects it; hs_spec_mode(0) keeps the general step,
+// hs_spec_counts() tells how many particles took it and how many of those were flagged and redone
+static int g_spec_on = 1;
+static int64_t g_spec_n = 0, g_spec_redo = 0;
+
 template <int S, bool F, int E>
 static void run2(const StepParams& p, int mode) {
     const bool general = p.n_chain > 0 || p.cs.g.proj_kind != 0 || (E != 0 && ((p.wind_on && p.gwind.proj_kind != 0) || (p.w_on && p.gw.proj_kind != 0)));
     if (general) { run2c<S, F, (E == 0 ? 0 : 1)>(p, mode); return; }
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
+    if (S == 2 && F && mode == OD_MATH_SERIES && g_spec_on && spec_eligible(p, S)) {
+        for (int64_t i = 0; i < p.n; ++i) {
+            const int rc = step_particle_spec<2, true, E>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+            if (rc) { step_particle_redo<2, true, E, SeriesMath, false>(&p, i, zs, zy, p.gw.zs, p.gw.zy, rc == 2); ++g_spec_redo; }
+        }
+        g_spec_n += p.n;
+        return;
+    }
     if (mode == OD_MATH_SERIES) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, SeriesMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
     else if (mode == OD_MATH_FAST) for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, FastMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
     else for (int64_t i = 0; i < p.n; ++i) step_particle_full<S, F, E, ExactMath>(p, i, zs, zy, p.gw.zs, p.gw.zy);
@@ -498,6 +512,13 @@ static int launch2(const StepParams& p, int scheme, bool f, int mode) {
 }
 
 extern "C" {
+
+void hs_spec_mode(int on) { g_spec_on = on; }
+void hs_spec_counts(int64_t* n, int64_t* redo, int reset) {
+    if (n) *n = g_spec_n;
+    if (redo) *redo = g_spec_redo;
+    if (reset) g_spec_n = g_spec_redo = 0;
+}
 
 int hs2_advect(const od_advect_args* a, const hs_group* g, const hs_pair* t3, const hs_chain* chain) {
     hs_levels lv, lc[OD_MAX_CHAIN];

@@ -59,10 +59,24 @@ for _ in range(300):
     eng.step_oceandrift(grp, 'runge-kutta4', t, dt, lon.clone(), lat.clone(), z.clone(), w_group=wgrp)
 torch.cuda.synchronize()
 res = {'lib': os.environ.get('ODCUDA_LIB', 'default'), 'n': n}
-for name, fn in (
-        ('fused', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp)),
-        ('cur', lambda a, b, c: eng.advect_current(grp, 'runge-kutta4', t, dt, a, b, c)),
-        ('fast', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp, fast=1))):
+def spec(on):
+    if hasattr(eng, 'set_spec'):
+        try:
+            eng.set_spec(on)
+        except Exception:
+            pass
+
+
+t1 = times[1]                      # a step that starts on a reader time (time mode 1 at the first stage)
+for name, fn, sp in (
+        ('fused', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp), True),
+        ('fused_gen', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp), False),
+        ('fused_t1', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t1, dt, a, b, c, w_group=wgrp), True),
+        ('fused_t1_gen', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t1, dt, a, b, c, w_group=wgrp), False),
+        ('cur', lambda a, b, c: eng.advect_current(grp, 'runge-kutta4', t, dt, a, b, c), True),
+        ('cur_gen', lambda a, b, c: eng.advect_current(grp, 'runge-kutta4', t, dt, a, b, c), False),
+        ('fast', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp, fast=1), True)):
+    spec(sp)
     try:
         med, mn, dg = timeit(fn)
         res[name + '_ms'], res[name + '_min_ms'], res[name + '_sha'] = round(med, 4), round(mn, 4), dg
