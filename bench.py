@@ -487,7 +487,18 @@ def run_b200(args):
         return float(np.median(out))
 
     t_now = st['t']
-    kernel_ms = kernel_alone(lambda tl, ta, tz: eng.step_oceandrift(grp, 'runge-kutta4', t_now, dt, tl, ta, tz, w_group=wgrp))
+    # The launch is one of two instantiations of the specialised step kernel (csrc/od_spec.cuh): all three time samples between
+    # two reader times (4 of the 6 steps of a reader hour), or one of them on a reader time (the step that starts on the hour and
+    # the one that ends on it).  kernel_ms is the mean over the six alignments of the hour the timed loop ended in -- the launch
+    # mix of the timed loop; the general kernel (OD_OPT_SPEC off, same bits) is timed on the same alignments beside it.
+    hour0 = syn.T0 + timedelta(seconds=3600 * int((t_now - syn.T0).total_seconds() // 3600))
+    phases = [hour0 + timedelta(seconds=600 * k) for k in range(6)]
+    phase_ms = [kernel_alone(lambda tl, ta, tz, tp=tp: eng.step_oceandrift(grp, 'runge-kutta4', tp, dt, tl, ta, tz, w_group=wgrp)) for tp in phases]
+    kernel_ms = float(np.mean(phase_ms))
+    eng.set_spec(False)
+    general_phase_ms = [kernel_alone(lambda tl, ta, tz, tp=tp: eng.step_oceandrift(grp, 'runge-kutta4', tp, dt, tl, ta, tz, w_group=wgrp)) for tp in phases]
+    eng.set_spec(True)
+    t_now = phases[2]                   # (the variants below: an alignment with all samples between two reader times)
     sort_ms = None
     if args.sort_every:
         sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -666,7 +677,9 @@ def run_b200(args):
                 'pcie_probe': pcie},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_kernel<RK4, extras> (current advection + vertical advection in one launch)', 'kernel_ms': kernel_ms, 'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
+                     'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_spec_kernel<RK4, F64, EXTRAS=2> (current advection + vertical advection in one launch; csrc/od_spec.cuh)', 'kernel_ms': kernel_ms,
+                     'kernel_ms_by_alignment': phase_ms, 'general_kernel_ms_by_alignment': general_phase_ms, 'general_kernel_ms': float(np.mean(general_phase_ms)),
+                     'kernel_ms_mean_in_timed_loop': loop_kernel_ms,
                      'loop_ms_p50': float(np.median(per_step)), 'loop_ms_p95': float(np.percentile(per_step, 95)),
                      'loop_ms_first20_mean': float(per_step[:20].mean()), 'host_us_per_launch_median': float(np.median(host_us)), 'host_us_per_launch_max': float(np.max(host_us)),
                      'algorithmic_bytes_per_launch': b_alg,

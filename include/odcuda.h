@@ -55,7 +55,11 @@ enum od_time_mode {
 enum od_lon_mode { OD_LON_0_360 = 0, OD_LON_PM180 = 1 };
 
 enum od_interp_flags { OD_INTERP_POS_F32 = 1, OD_INTERP_NO_FALLBACK = 2, OD_INTERP_Z_F64 = 4,
-                       OD_INTERP_NO_ROTATE = 8 /* projected vector pairs stay along the grid's axes (rotate_to_proj=None) */ };
+                       OD_INTERP_NO_ROTATE = 8 /* projected vector pairs stay along the grid's axes (rotate_to_proj=None) */,
+                       OD_INTERP_OUT_F64 = 16 /* d_out are float64 arrays holding what the READER returns: the unrounded float64 vertical /
+                                                 time lerp of a 3-D block (interpolation/structured.py:139-140), the float32 value of a 2-D one */,
+                       OD_INTERP_NEAREST = 32 /* nearest grid point, as the reference samples land_binary_mask (Nearest2DInterpolator,
+                                                 interpolators.py:26-40); 2-D one-component geographic groups */ };
 
 #define OD_MAX_LEVELS 128
 #define OD_ABI_VERSION 1
@@ -170,7 +174,7 @@ typedef struct od_time_sample {
  * float32; the kernel reproduces that. */
 int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n,
               const double* d_lon, const double* d_lat, const void* d_z, int flags,
-              float* d_out0, float* d_out1);
+              void* d_out0, void* d_out1);     /* float32[n], or float64[n] with OD_INTERP_OUT_F64 */
 
 /* ---- geodesic --------------------------------------------------------------------------- */
 /* in place: (lon, lat) <- WGS84 direct(lon, lat, az_deg, dist_m); lon normalised to [-180, 180] */
@@ -547,6 +551,38 @@ typedef struct od_bookkeep_args {
 } od_bookkeep_args;
 
 int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a);
+
+/* OpenDriftSimulation.interact_with_coastline (basemodel/__init__.py:671-746) for a land_binary_mask that a gridded reader
+ * provides (sampled with od_interp + OD_INTERP_NEAREST), general:coastline_approximation_precision = None: 'stranding'
+ * deactivates the elements on land that are not in the air; 'previous' deactivates elements released on land
+ * ('seeded_on_land') and moves every element on land back to its position of the previous step.  Elements the mask does not
+ * cover (NaN) become 'missing_data' (report_missing_variables, :2501-2515) when missing_code != 0.  The previous positions
+ * are float32 arrays keyed by ID - id_base, as the reference holds them (a copy of its float32 result block, :2164-2165);
+ * od_store_previous is update_previous_state (:642-669) for lon / lat.  h_counts[4]: newly stranded, seeded_on_land,
+ * missing_data, moved back (synchronises). */
+typedef struct od_coast_args {
+    int64_t n;
+    const float* d_mask;
+    double* d_lon;
+    double* d_lat;
+    const void* d_z;              /* float32 / float64 (z_f64), NULL = 0 */
+    const void* d_age;            /* age_seconds, float32 / float64 (age_f64) */
+    int32_t* d_status;
+    int32_t* d_moving;
+    const int32_t* d_ids;
+    float* d_prev_lon;
+    float* d_prev_lat;
+    int64_t n_total;
+    int32_t id_base;
+    int32_t action;               /* 1 stranding, 2 previous */
+    int32_t stranded_code, seeded_code, missing_code;
+    int32_t check_seeded;
+    int32_t z_f64, age_f64;
+    int64_t* h_counts;            /* [4] or NULL */
+} od_coast_args;
+int od_coastline(od_ctx* ctx, const od_coast_args* a);
+int od_store_previous(od_ctx* ctx, int64_t n, const double* d_lon, const double* d_lat, const int32_t* d_ids, int32_t id_base,
+                      int64_t n_total, float* d_prev_lon, float* d_prev_lat);
 
 /* ---- particle exchange of the spatial-tile mode --------------------------------------------------------------
  * BASELINE configs[2]: every rank owns one longitude strip of the domain (and holds only that part of the forcing, plus a halo);

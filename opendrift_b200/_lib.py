@@ -144,6 +144,15 @@ class BookkeepArgs(C.Structure):
                 ('h_counts', C.POINTER(C.c_int64))]
 
 
+class CoastArgs(C.Structure):
+    _fields_ = [('n', C.c_int64), ('d_mask', C.c_void_p), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
+                ('d_age', C.c_void_p), ('d_status', C.c_void_p), ('d_moving', C.c_void_p), ('d_ids', C.c_void_p),
+                ('d_prev_lon', C.c_void_p), ('d_prev_lat', C.c_void_p), ('n_total', C.c_int64), ('id_base', C.c_int32),
+                ('action', C.c_int32), ('stranded_code', C.c_int32), ('seeded_code', C.c_int32), ('missing_code', C.c_int32),
+                ('check_seeded', C.c_int32), ('z_f64', C.c_int32), ('age_f64', C.c_int32), ('h_counts', C.POINTER(C.c_int64))]
+
+
+OD_INTERP_POS_F32, OD_INTERP_NO_FALLBACK, OD_INTERP_Z_F64, OD_INTERP_NO_ROTATE, OD_INTERP_OUT_F64, OD_INTERP_NEAREST = 1, 2, 4, 8, 16, 32
 OD_PACK_MAX_COLS, OD_PACK_MAX_WORLD = 16, 64
 
 
@@ -192,6 +201,8 @@ SYMBOLS = {
     'od_vertical_mixing': (C.c_int, [_P, C.POINTER(MixArgs)]),
     'od_vertical_buoyancy': (C.c_int, [_P, C.POINTER(BuoyancyArgs)]),
     'od_bookkeeping': (C.c_int, [_P, C.POINTER(BookkeepArgs)]),
+    'od_coastline': (C.c_int, [_P, C.POINTER(CoastArgs)]),
+    'od_store_previous': (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
     'od_pack_by_owner': (C.c_int, [_P, C.POINTER(PackArgs)]),
     'od_unpack_records': (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32]),
     'od_sort_by_cell': (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P]),

@@ -7,7 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'od_kernels.cu')
 OUT = os.path.join(HERE, 'libodcuda.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-shared', '-Xcompiler', '-fPIC', '-split-compile', '0']     # (ptxas of the ~250 kernel instantiations on all cores)
+              '-shared', '-Xcompiler', '-fPIC']
+# (-split-compile was tried: the build is bound by the single-threaded front end, not by ptxas, and the split changes the
+#  generated code -- the time-mode instantiation of step_spec_kernel came out 10 % slower on the B200)
 
 
 def sources():

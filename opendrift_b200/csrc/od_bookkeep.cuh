@@ -18,6 +18,17 @@
 //                     and counts, per launch, the elements it put into 'outside' / 'retired' and those whose status is
 //                     non-zero after the pass (one atomic per warp and counter): the host numbers new categories in the
 //                     reference's order and skips the compaction when nothing left.
+//   coast_one         OpenDriftSimulation.interact_with_coastline (basemodel/__init__.py:671-746) with
+//                     general:coastline_approximation_precision = None (the bisection towards the coastline, coastline_crossing
+//                     :81-134, queries the GSHHG landmask of the roaring_landmask package: IO-backed, not on this path):
+//                       'stranding': deactivate_elements((land_binary_mask == 1) & (z <= 0), 'stranded')
+//                       'previous':  elements of age 0 on land -> 'seeded_on_land' (while elements are being released), then every
+//                                    element on land goes back to its position of the previous step
+//                     and, for both, elements the mask reader does not cover -> 'missing_data' (report_missing_variables,
+//                     :2501-2515: land_binary_mask has no fallback value).
+//                     The previous positions are float32: the reference keeps them in a copy of its float32 result block
+//                     (:2164-2165, default_dtype :2094), so an element that is moved back lands on float32-rounded coordinates.
+//   store_previous    update_previous_state (:642-669) for lon / lat: previous[ID] = present position of every active element.
 // NumPy dtype rules are kept: the dtypes of z / terminal_velocity / age_seconds are whatever the reference's arrays have
 // (float32 as seeded arrays, float64 once a scalar property was broadcast on release, elements/elements.py:213-216).
 #pragma once
@@ -177,6 +188,77 @@ OD_BK_HD int bookkeep_one(const BookkeepParams& p, int64_t i) {
         p.moving[i] = 0;
     }
     return flags | (st != 0 ? 4 : 0);
+}
+
+struct CoastParams {
+    int64_t n;
+    const float* mask;           // land_binary_mask at the elements (float32 environment value; NaN = not covered)
+    double* lon;
+    double* lat;
+    const void* z;               // float32 / float64 (z_f64)
+    const void* age;             // age_seconds float32 / float64 (age_f64)
+    int32_t* status;
+    int32_t* moving;
+    const int32_t* ids;
+    float* prev_lon;             // [n_total] keyed by ID - id_base
+    float* prev_lat;
+    unsigned* counters;          // [0] += stranded, [1] += seeded_on_land, [2] += missing_data, [3] += moved back
+    int64_t n_total;
+    int32_t id_base;
+    int32_t action;              // 1 'stranding', 2 'previous'
+    int32_t stranded_code, seeded_code, missing_code;
+    int32_t check_seeded;        // elements were released this step (newly_seeded_IDs is not None)
+    int32_t z_f64, age_f64;
+};
+
+// returns bit 0: newly 'stranded', bit 1: newly 'seeded_on_land', bit 2: newly 'missing_data', bit 3: moved back
+OD_BK_HD int coast_one(const CoastParams& p, int64_t i) {
+    const float m = p.mask[i];
+    int flags = 0;
+    int st = p.status[i];
+    bool off = false;
+    if (!(m == m) || !(fabsf(m) <= 3.4028234663852886e38f)) {        // report_missing_variables comes first in the loop (:2247)
+        if (p.missing_code) {
+            if (st == 0) { st = p.missing_code; flags |= 4; }
+            off = true;
+        }
+    } else if (m == 1.0f) {
+        if (p.action == 1) {
+            const double z = p.z ? (p.z_f64 ? ((const double*)p.z)[i] : (double)((const float*)p.z)[i]) : 0.0;
+            if (z <= 0.0) {
+                if (st == 0) { st = p.stranded_code; flags |= 1; }
+                off = true;
+            }
+        } else if (p.action == 2) {
+            if (p.check_seeded) {
+                const bool age0 = p.age_f64 ? ((const double*)p.age)[i] == 0.0 : ((const float*)p.age)[i] == 0.0f;
+                if (age0) {
+                    if (st == 0) { st = p.seeded_code; flags |= 2; }
+                    off = true;
+                }
+            }
+            const int64_t k = (int64_t)p.ids[i] - p.id_base;
+            if (k >= 0 && k < p.n_total) {
+                p.lon[i] = (double)p.prev_lon[k];
+                p.lat[i] = (double)p.prev_lat[k];
+                flags |= 8;
+            }
+        }
+    }
+    if (off) {
+        p.status[i] = st;
+        p.moving[i] = 0;
+    }
+    return flags;
+}
+
+OD_BK_HD void store_previous_one(int64_t i, const double* lon, const double* lat, const int32_t* ids, int32_t id_base, int64_t n_total,
+                                 float* prev_lon, float* prev_lat) {
+    const int64_t k = (int64_t)ids[i] - id_base;
+    if (k >= 0 && k < n_total) {
+        prev_lon[k] = (float)lon[i];
+        prev_lat[k] = (float)lat[i];
+    }
 }
 
 }  // namespace od

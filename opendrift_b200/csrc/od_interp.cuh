@@ -525,6 +525,108 @@ OD_HD void sample2_any(const GroupGeom& g, const PairRef& pr, const VertW& vw, d
     v = rv;
 }
 
+// ---- the reader's own output precision (Reader.get_variables_interpolated, variables.py:860-920) ----------------------------------
+// What a reader hands back before Environment casts it to float32: float64 for 3-D blocks (the vertical lerp and the time
+// lerp run in float64, interpolation/structured.py:139-140, basereader/structured.py:353-364), the float32 value for 2-D
+// blocks; a projected vector pair rotated in float64.  NaN where the reader has no data (the caller applies no fallback).
+OD_HD void sample2_any_d(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, double& u, double& v, bool pos_f32) {
+    const HorizWP hp = horiz_weights_any(g, lon, lat, pos_f32);
+    const HorizW& h = hp.h;
+    double ru = NAN, rv = NAN;
+    if (h.valid && pr.mode != 3) {
+        const TexelSource ts = texel_source(pr.tex, TileView(), g.nx, g.ny, h.ix, h.ix1, h.iy, h.iy1, vw.ia, vw.ib);
+        const int r0 = 4 * h.iy * ts.lx, r1 = 4 * h.iy1 * ts.lx;
+        const int o00 = r0 + 4 * h.ix, o01 = r0 + 4 * h.ix1, o10 = r1 + 4 * h.ix, o11 = r1 + 4 * h.ix1;
+        const LayerVals A = layer_bilin(h, layer_ptr(ts, vw.ia), o00, o01, o10, o11, pr.mode);
+        LayerVals B = A;
+        if (g.nz > 1) B = layer_bilin(h, layer_ptr(ts, vw.ib), o00, o01, o10, o11, pr.mode);
+        const double du = combine_d(g, pr, vw, A.uA, B.uA, A.uB, B.uB);
+        const double dv = combine_d(g, pr, vw, A.vA, B.vA, A.vB, B.vB);
+        if (g.proj_kind && g.rotate) {
+            double sr, cr;
+            sincos(rotation_to_geographic(g.proj, hp.px, hp.py, g.rot_delta), &sr, &cr);
+            ru = OD_DSUB(OD_DMUL(du, cr), OD_DMUL(dv, sr));
+            rv = OD_DADD(OD_DMUL(du, sr), OD_DMUL(dv, cr));
+        } else {
+            ru = du;
+            rv = dv;
+        }
+    }
+    u = ru;
+    v = rv;
+}
+
+OD_HD double sample1_any_d(const GroupGeom& g, const PairRef& pr, const VertW& vw, double lon, double lat, bool pos_f32) {
+    const HorizW h = horiz_weights_any(g, lon, lat, pos_f32).h;
+    double r = NAN;
+    if (h.valid && pr.mode != 3) {
+        const long long layer = (long long)g.nx * g.ny;
+        const float* ta = pr.tex + ((long long)vw.ia * layer) * 2;
+        const Tex2 a00 = ld_tex2(ta + 2ll * h.i00), a01 = ld_tex2(ta + 2ll * h.i01);
+        const Tex2 a10 = ld_tex2(ta + 2ll * h.i10), a11 = ld_tex2(ta + 2ll * h.i11);
+        Tex2 b00 = a00, b01 = a01, b10 = a10, b11 = a11;
+        if (g.nz > 1) {
+            const float* tb = pr.tex + ((long long)vw.ib * layer) * 2;
+            b00 = ld_tex2(tb + 2ll * h.i00); b01 = ld_tex2(tb + 2ll * h.i01);
+            b10 = ld_tex2(tb + 2ll * h.i10); b11 = ld_tex2(tb + 2ll * h.i11);
+        }
+        float aA = 0.f, bA = 0.f, aB = 0.f, bB = 0.f;
+        if (pr.mode != 2) {
+            aA = bilin(h, a00.x, a01.x, a10.x, a11.x);
+            if (g.nz > 1) bA = bilin(h, b00.x, b01.x, b10.x, b11.x);
+        }
+        if (pr.mode != 1) {
+            aB = bilin(h, a00.y, a01.y, a10.y, a11.y);
+            if (g.nz > 1) bB = bilin(h, b00.y, b01.y, b10.y, b11.y);
+        }
+        r = combine_d(g, pr, vw, aA, bA, aB, bB);
+    }
+    return r;
+}
+
+// ---- nearest grid point (land_binary_mask) ------------------------------------------------------------------------------------
+// Nearest2DInterpolator (readers/interpolation/interpolators.py:26-40), which ReaderBlock.interpolate uses for land_binary_mask
+// (interpolation/structured.py:117-119): index = np.round((x - xgrid.min()) / (xgrid.max() - xgrid.min()) * len(xgrid)) -- scaled
+// by the NUMBER of grid points, not by the number of intervals, as the reference writes it --, rounded half to even, cast to
+// uint32 (a negative value wraps and lands on the last point) and clamped to len - 1; in float32 while the positions are
+// float32.  2-D one-component groups on increasing geographic axes without a virtual column (the library refuses others).
+OD_HD int nearest_index(double d, double span, double rspan, int n, bool f32) {
+    double r;
+    if (f32) r = (double)rintf(OD_FMUL((float)d / (float)span, (float)n));       // (d is the float32 difference here)
+    else r = rint(OD_DMUL(div_rn(d, span, rspan), (double)n));
+    if (!(r >= 0.0) || r >= (double)n) return n - 1;
+    return (int)r;
+}
+
+OD_HD float sample1_nearest(const GroupGeom& g, const PairRef& pr, double lon, double lat, bool pos_f32) {
+    float r = NAN;
+    double x, dx, dy;
+    if (pos_f32) {
+        const float xf = (g.lon_mode == 0) ? np_mod360f((float)lon) : OD_FADD(np_mod360f(OD_FADD((float)lon, 180.0f)), -180.0f);
+        x = (double)xf;
+        dx = (double)OD_FADD(xf, -(float)g.x0);
+        dy = (double)OD_FADD((float)lat, -(float)g.y0);
+    } else {
+        x = (g.lon_mode == 0) ? np_mod360(lon) : OD_DSUB(np_mod360(OD_DADD(lon, 180.0)), 180.0);
+        dx = OD_DSUB(x, g.x0);
+        dy = OD_DSUB(lat, g.y0);
+    }
+    const bool covered = (g.glob != 0 || ((x >= g.xmin) && (x <= g.xmax))) && (lat >= g.ymin) && (lat <= g.ymax) && (dx == dx) && (dy == dy);
+    if (covered && pr.mode != 3) {
+        const int ix = nearest_index(dx, g.xspan, g.rxspan, g.nx, pos_f32);
+        const int iy = nearest_index(dy, g.yspan, g.ryspan, g.ny, pos_f32);
+        const Tex2 a = ld_tex2(pr.tex + 2ll * ((long long)iy * g.nx + ix));
+        if (pr.mode == 1) r = a.x;
+        else if (pr.mode == 2) r = a.y;
+        else {                       // (a mask the reader does not serve as a static variable: the float32 time lerp of 2-D variables)
+            const float w1 = (float)pr.w, w0 = (float)OD_DSUB(1.0, pr.w);
+            r = OD_FADD(OD_FMUL(a.x, w0), OD_FMUL(a.y, w1));
+        }
+    }
+    if (!finite_f(r)) r = g.fallback[0];
+    return r;
+}
+
 // horizontal weights only (scalar groups: the mixing column, the sort key, vertical velocity)
 OD_HD HorizW horiz_weights_h(const GroupGeom& g, double lon, double lat, bool pos_f32) {
     return horiz_weights_any(g, lon, lat, pos_f32).h;

@@ -725,9 +725,10 @@ struct InterpParams {
     const double* lon;
     const double* lat;
     const void* z;
-    float* out0;
-    float* out1;
+    void* out0;                  // float32, or float64 with out_f64
+    void* out1;
     int pos_f32, z_f64;
+    int out_f64, nearest;
 };
 
 template <bool PROJ>
@@ -739,16 +740,48 @@ __global__ void __launch_bounds__(OD_BLOCK) interp_kernel(const InterpParams p) 
     if (i >= p.n) return;
     const double z = (p.z && p.g.nz > 1) ? (p.z_f64 ? ((const double*)p.z)[i] : (double)((const float*)p.z)[i]) : 0.0;
     const VertW vw = vert_weights(p.g, (const double*)lv.zs, (const double*)lv.zy, z, p.z_f64 == 0);
+    if (p.nearest) {             // land_binary_mask (2-D, one component, geographic: od_interp checks)
+        const float r = sample1_nearest(p.g, p.pr, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        if (p.out0) { if (p.out_f64) ((double*)p.out0)[i] = (double)r; else ((float*)p.out0)[i] = r; }
+        return;
+    }
+    if (p.out_f64) {             // the reader's own precision (no fallback: od_interp requires OD_INTERP_NO_FALLBACK with it)
+        if (p.g.ncomp == 2) {
+            double u, v;
+            sample2_any_d(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
+            if (p.out0) ((double*)p.out0)[i] = u;
+            if (p.out1) ((double*)p.out1)[i] = v;
+        } else if (p.out0) {
+            ((double*)p.out0)[i] = sample1_any_d(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0);
+        }
+        return;
+    }
     if (p.g.ncomp == 2) {
         float u, v;
         if (PROJ) sample2_any(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
         else sample2(p.g, p.pr, vw, p.lon[i], p.lat[i], u, v, p.pos_f32 != 0);
-        if (p.out0) p.out0[i] = u;
-        if (p.out1) p.out1[i] = v;
+        if (p.out0) ((float*)p.out0)[i] = u;
+        if (p.out1) ((float*)p.out1)[i] = v;
     } else {
         const float r = PROJ ? sample1_any(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0) : sample1(p.g, p.pr, vw, p.lon[i], p.lat[i], p.pos_f32 != 0);
-        if (p.out0) p.out0[i] = r;
+        if (p.out0) ((float*)p.out0)[i] = r;
     }
+}
+
+__global__ void __launch_bounds__(256) coast_kernel(const CoastParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = i < p.n ? coast_one(p, i) : 0;
+    for (int b = 0; b < 4; ++b) {
+        const unsigned m = __ballot_sync(0xffffffffu, (f >> b) & 1);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(p.counters + b, (unsigned)__popc(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) store_previous_kernel(int64_t n, const double* __restrict__ lon, const double* __restrict__ lat,
+                                                             const int32_t* __restrict__ ids, int32_t id_base, int64_t n_total,
+                                                             float* __restrict__ prev_lon, float* __restrict__ prev_lat) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_previous_one(i, lon, lat, ids, id_base, n_total, prev_lon, prev_lat);
 }
 
 __global__ void __launch_bounds__(OD_BLOCK) geod_fwd_kernel(int64_t n, double* __restrict__ lon, double* __restrict__ lat,
@@ -791,7 +824,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_STEP_MINB) step_kernel(const __gr
 
 // The step specialised for the common launch (od_spec.cuh): straight-line sampler, rare cases flagged and redone by the
 // general step.  Same results as step_kernel<SCHEME, F64, EXTRAS, SeriesMath>, bit for bit.
-template <int SCHEME, bool F64, int EXTRAS>
+template <int SCHEME, bool F64, int EXTRAS, bool LERP>
 __global__ void __launch_bounds__(OD_BLOCK, OD_SPEC_MINB) step_spec_kernel(const __grid_constant__ StepParams p) {
     __shared__ LevelsSmem lv;
     __shared__ LevelsSmem lvw;
@@ -800,7 +833,7 @@ __global__ void __launch_bounds__(OD_BLOCK, OD_SPEC_MINB) step_spec_kernel(const
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const int rc = step_particle_spec<SCHEME, F64, EXTRAS>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
+    const int rc = step_particle_spec<SCHEME, F64, EXTRAS, LERP>(p, i, lv.zs, lv.zy, lvw.zs, lvw.zy);
     if (rc) step_particle_redo<SCHEME, F64, EXTRAS, SeriesMath, false>(&p, i, lv.zs, lv.zy, lvw.zs, lvw.zy, rc == 2);
 }
 
@@ -1163,7 +1196,7 @@ static int need_group(od_ctx* ctx, int group, int ncomp) {
 }
 
 extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64_t n, const double* lon, const double* lat,
-                         const void* z, int flags, float* out0, float* out1) {
+                         const void* z, int flags, void* out0, void* out1) {
     int rc = need_group(ctx, group, 0);
     if (rc) return rc;
     if (!ts || n < 0 || (n > 0 && (!lon || !lat))) return fail(ctx, OD_ERR_ARG, "od_interp: bad arguments");
@@ -1175,6 +1208,12 @@ extern "C" int od_interp(od_ctx* ctx, int group, const od_time_sample* ts, int64
     if (rc) return rc;
     p.n = n; p.lon = lon; p.lat = lat; p.z = z; p.out0 = out0; p.out1 = out1; p.pos_f32 = flags & OD_INTERP_POS_F32;
     p.z_f64 = (flags & OD_INTERP_Z_F64) ? 1 : 0;
+    p.out_f64 = (flags & OD_INTERP_OUT_F64) ? 1 : 0;
+    p.nearest = (flags & OD_INTERP_NEAREST) ? 1 : 0;
+    if (p.out_f64 && !p.nearest && !(flags & OD_INTERP_NO_FALLBACK))
+        return fail(ctx, OD_ERR_ARG, "od_interp: OD_INTERP_OUT_F64 is the reader's output (use it with OD_INTERP_NO_FALLBACK)");
+    if (p.nearest && (p.g.ncomp != 1 || p.g.nz > 1 || p.g.proj_kind != 0 || p.g.wrap != 0 || !(p.g.xspan > 0.0) || !(p.g.yspan > 0.0)))
+        return fail(ctx, OD_ERR_ARG, "od_interp: OD_INTERP_NEAREST serves 2-D one-component geographic groups on increasing, non-periodic axes");
     if (flags & OD_INTERP_NO_FALLBACK) p.g.fallback[0] = p.g.fallback[1] = NAN;
     if (flags & OD_INTERP_NO_ROTATE) p.g.rotate = 0;
     if (p.g.proj_kind) interp_kernel<true><<<grid_for(n), OD_BLOCK, 0, ctx->stream>>>(p);
@@ -1389,7 +1428,8 @@ static int launch_step(od_ctx* ctx, int scheme, bool f64, const StepParams& p) {
     cudaStream_t s = ctx->stream;
     if (std::is_same<MATH, SeriesMath>::value && ctx->spec && f64 && spec_eligible(p, scheme) &&
         !(EXTRAS != 0 && ((p.wind_on && p.gwind.proj_kind != 0) || (p.w_on && p.gw.proj_kind != 0)))) {
-        step_spec_kernel<2, true, EXTRAS><<<grid, OD_BLOCK, 0, s>>>(p);
+        if (spec_all_lerp(p)) step_spec_kernel<2, true, EXTRAS, true><<<grid, OD_BLOCK, 0, s>>>(p);
+        else step_spec_kernel<2, true, EXTRAS, false><<<grid, OD_BLOCK, 0, s>>>(p);
         CK(cudaGetLastError());
         ctx->launches++;
         return OD_OK;
@@ -1872,6 +1912,46 @@ extern "C" int od_bookkeeping(od_ctx* ctx, const od_bookkeep_args* a) {
         CK(cudaStreamSynchronize(ctx->stream));
         for (int k = 0; k < 3; ++k) a->h_counts[k] = c[k];
     }
+    return OD_OK;
+}
+
+extern "C" int od_coastline(od_ctx* ctx, const od_coast_args* a) {
+    if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_coastline: null argument");
+    if (a->n < 0 || (a->n > 0 && (!a->d_mask || !a->d_lon || !a->d_lat || !a->d_status || !a->d_moving)))
+        return fail(ctx, OD_ERR_ARG, "od_coastline: bad arguments");
+    if (a->action != 1 && a->action != 2) return fail(ctx, OD_ERR_ARG, "od_coastline: action is 1 (stranding) or 2 (previous)");
+    if (a->action == 2 && a->n > 0 && (!a->d_ids || !a->d_prev_lon || !a->d_prev_lat || (a->check_seeded && !a->d_age)))
+        return fail(ctx, OD_ERR_ARG, "od_coastline: 'previous' needs IDs, previous positions (and ages while elements are released)");
+    if (a->h_counts) a->h_counts[0] = a->h_counts[1] = a->h_counts[2] = a->h_counts[3] = 0;
+    if (a->n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = counters(ctx);
+    if (rc) return rc;
+    CoastParams p;
+    p.n = a->n; p.mask = a->d_mask; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status;
+    p.moving = a->d_moving; p.ids = a->d_ids; p.prev_lon = a->d_prev_lon; p.prev_lat = a->d_prev_lat; p.counters = ctx->d_cnt;
+    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.stranded_code = a->stranded_code;
+    p.seeded_code = a->seeded_code; p.missing_code = a->missing_code; p.check_seeded = a->check_seeded; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
+    coast_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (a->h_counts) {
+        unsigned c[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(c, ctx->d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 4; ++k) a->h_counts[k] = c[k];
+    }
+    return OD_OK;
+}
+
+extern "C" int od_store_previous(od_ctx* ctx, int64_t n, const double* lon, const double* lat, const int32_t* ids, int32_t id_base,
+                                 int64_t n_total, float* prev_lon, float* prev_lat) {
+    if (!ctx || n < 0 || (n > 0 && (!lon || !lat || !ids || !prev_lon || !prev_lat))) return fail(ctx, OD_ERR_ARG, "od_store_previous: bad arguments");
+    if (n == 0) return OD_OK;
+    CK(cudaSetDevice(ctx->device));
+    store_previous_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, lon, lat, ids, id_base, n_total, prev_lon, prev_lat);
+    CK(cudaGetLastError());
+    ctx->launches++;
     return OD_OK;
 }
 

@@ -512,16 +512,42 @@ class Engine:
         return self.torch.as_tensor(_W(), device=self.device)
 
     # -- kernels --------------------------------------------------------------------------
-    def interp(self, group, t, lon, lat, z=None, pos_f32=False, raw=False, rotate=True):
-        """get_variables_interpolated fast path on device tensors -> list of float32 tensors."""
+    def interp(self, group, t, lon, lat, z=None, pos_f32=False, raw=False, rotate=True, out_f64=False, nearest=False):
+        """get_variables_interpolated fast path on device tensors -> list of float32 tensors (float64 with out_f64: the reader's
+        own precision, raw only).  nearest: the nearest grid point, as the reference samples land_binary_mask."""
         n = lon.numel()
         ts, _ = group.sample(t)
-        outs = [self.empty(n, self.torch.float32) for _ in range(group.ncomp)]
+        outs = [self.empty(n, self.torch.float64 if out_f64 else self.torch.float32) for _ in range(group.ncomp)]
         self._check(self.lib.od_interp(self.ctx, group.gid, C.byref(ts), n, _ptr(lon), _ptr(lat), _ptr(z),
                                        (1 if pos_f32 else 0) | (2 if raw else 0) | (4 if (z is not None and z.dtype == self.torch.float64) else 0)
-                                       | (0 if rotate else 8),
+                                       | (0 if rotate else 8) | (_lib.OD_INTERP_OUT_F64 if out_f64 else 0) | (_lib.OD_INTERP_NEAREST if nearest else 0),
                                        _ptr(outs[0]), _ptr(outs[1]) if group.ncomp == 2 else None))
         return outs
+
+    def coastline(self, mask, lon, lat, z, age, status, moving, ids, prev_lon, prev_lat, id_base, action, stranded_code=0,
+                  seeded_code=0, missing_code=0, check_seeded=False):
+        """interact_with_coastline (basemodel/__init__.py:671-746) for a sampled land_binary_mask; returns the counts
+        (stranded, seeded_on_land, missing_data, moved back)."""
+        a = _lib.CoastArgs()
+        a.n = lon.numel()
+        a.d_mask, a.d_lon, a.d_lat, a.d_z, a.d_age = _ptr(mask), _ptr(lon), _ptr(lat), _ptr(z), _ptr(age)
+        a.d_status, a.d_moving, a.d_ids = _ptr(status), _ptr(moving), _ptr(ids)
+        a.d_prev_lon, a.d_prev_lat = _ptr(prev_lon), _ptr(prev_lat)
+        a.n_total = 0 if prev_lon is None else prev_lon.numel()
+        a.id_base, a.action = int(id_base), {'stranding': 1, 'previous': 2}[action]
+        a.stranded_code, a.seeded_code, a.missing_code = int(stranded_code), int(seeded_code), int(missing_code)
+        a.check_seeded = 1 if check_seeded else 0
+        a.z_f64 = 1 if (z is not None and z.dtype == self.torch.float64) else 0
+        a.age_f64 = 1 if (age is not None and age.dtype == self.torch.float64) else 0
+        counts = (C.c_int64 * 4)()
+        a.h_counts = C.cast(counts, C.POINTER(C.c_int64))
+        self._check(self.lib.od_coastline(self.ctx, C.byref(a)))
+        return tuple(int(c) for c in counts)
+
+    def store_previous(self, lon, lat, ids, id_base, prev_lon, prev_lat):
+        """update_previous_state (:642-669) for lon / lat: previous[ID - id_base] = the present position (float32)."""
+        self._check(self.lib.od_store_previous(self.ctx, lon.numel(), _ptr(lon), _ptr(lat), _ptr(ids), int(id_base), prev_lon.numel(),
+                                               _ptr(prev_lon), _ptr(prev_lat)))
 
     def geod_fwd(self, lon, lat, az, dist):
         self._check(self.lib.od_geod_fwd(self.ctx, lon.numel(), _ptr(lon), _ptr(lat), _ptr(az), _ptr(dist)))

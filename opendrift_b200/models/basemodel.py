@@ -151,7 +151,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             'general:use_auto_landmask': {'type': 'bool', 'default': True, 'level': CONFIG_LEVEL_ADVANCED,
                                           'description': 'Accepted for script compatibility; no landmask on the GPU path.'},
             'general:coastline_action': {'type': 'enum', 'enum': ['none', 'stranding', 'previous'], 'default': 'none',
-                                         'level': CONFIG_LEVEL_BASIC, 'description': 'Only "none" is implemented.'},
+                                         'level': CONFIG_LEVEL_BASIC,
+                                         'description': 'None, or stranding / previous against the land_binary_mask of a gridded reader '
+                                                        '(with general:coastline_approximation_precision = None).'},
             'seed:number': {'type': 'int', 'default': 1, 'min': 1, 'max': 100000000, 'units': 1,
                             'level': CONFIG_LEVEL_BASIC, 'description': 'The number of elements for the simulation.'},
             # keys the reference's scripts set that concern subsystems outside the GPU path: accepted with the reference's
@@ -160,7 +162,8 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                                         'description': 'Name of simulation'},
             'general:coastline_approximation_precision': {'type': 'float', 'default': 0.001, 'min': 0.0001, 'max': 0.005, 'units': 'degrees',
                                                           'level': CONFIG_LEVEL_ADVANCED,
-                                                          'description': 'Accepted for script compatibility (no coastline interaction on the GPU path).'},
+                                                          'description': 'The bisection towards the GSHHG coastline is IO-backed (roaring_landmask) and not on the GPU path: '
+                                                                         'set to None when general:coastline_action is not none.'},
             'general:seafloor_action': {'type': 'enum', 'enum': ['none', 'lift_to_seafloor', 'deactivate', 'previous'],
                                         'default': 'lift_to_seafloor', 'level': CONFIG_LEVEL_ADVANCED,
                                         'description': 'Accepted for script compatibility: seafloor interaction needs a bathymetry reader '
@@ -354,7 +357,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
     def release_elements(self):
         """:909-934 -- scheduled elements whose time falls inside this step move to the device arrays."""
         if len(self.elements_scheduled) == 0:
+            self._newly_seeded = False                         # newly_seeded_IDs = None (:916-918)
             return
+        self._newly_seeded = True                              # (an array, possibly empty: 'is not None' in interact_with_coastline)
         t, dt = self.time, self.time_step
         st = self.elements_scheduled_time
         idx = (st >= t) & (st < t + dt) if dt.days >= 0 else (st <= t) & (st > t + dt)
@@ -362,6 +367,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         first_release = len(self.elements) == 0
         ids = np.asarray(self.elements_scheduled.ID)[idx].astype(np.int64)
+        if getattr(self, '_coast', None) is not None:
+            # _elements_previous.lon[newly_seeded_IDs] = elements_scheduled.lon[indices] (:928-931): float32 like the result block
+            k = self.engine.to_device(ids - self._id_base)
+            self._prev_lon[k] = self.engine.to_device(np.asarray(self.elements_scheduled.lon)[idx].astype(np.float32))
+            self._prev_lat[k] = self.engine.to_device(np.asarray(self.elements_scheduled.lat)[idx].astype(np.float32))
         self._release_rank[ids - self._id_base] = np.arange(self._released, self._released + len(ids))     # the reference's array order
         self._released += len(ids)
         self.elements.append_host(self.elements_scheduled, idx)
@@ -467,6 +477,91 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         """:2358-2386"""
         if self.validity_domain is not None:
             self._bookkeep(outside=True, age=False)
+
+    def _setup_coastline(self):
+        """general:coastline_action against a land_binary_mask that a gridded reader provides.  The reference's default -- the GSHHG
+        landmask of roaring_landmask, loaded when general:use_auto_landmask is on, and the bisection of coastline_crossing
+        against it -- is IO-backed and not on this path."""
+        self._coast = None
+        action = self.get_config('general:coastline_action')
+        if action == 'none' or 'land_binary_mask' not in self.required_variables:
+            return
+        if self.env.constant('land_binary_mask') is not None and not self.env.priority_list.get('land_binary_mask'):
+            if float(self.env.constant('land_binary_mask')) == 0:
+                return                                        # no land anywhere
+            raise NotImplementedError('environment:constant:land_binary_mask = 1 (land everywhere) is not a case for the GPU path')
+        if not self.env.priority_list.get('land_binary_mask'):
+            raise NotImplementedError("general:coastline_action = '%s' needs a reader that provides land_binary_mask; the GSHHG landmask "
+                                      "(general:use_auto_landmask) is host-side IO, out of scope of the GPU hot path" % action)
+        if self.get_config('seed:ocean_only'):
+            raise NotImplementedError('seed:ocean_only = True moves the seeds off the land before the run (closest_ocean_points, a host-side '
+                                      'nearest-neighbour search, basemodel/__init__.py:936-1030): not on the GPU path; set it to False')
+        if self.get_config('general:coastline_approximation_precision') is not None:
+            raise NotImplementedError('general:coastline_approximation_precision must be None on the GPU path: the bisection towards '
+                                      'the coastline queries the GSHHG landmask (basemodel/__init__.py:81-134)')
+        if action == 'previous' and not getattr(self, '_coast_previous_supported', False):
+            # an element that is moved back keeps, for this step, the environment sampled where it was on land (the reference samples
+            # before interact_with_coastline, :2238-2253): only models whose update() can run from a materialised environment do that
+            raise NotImplementedError("general:coastline_action = 'previous' is not on the GPU path of %s" % type(self).__name__)
+        torch = self.engine.torch
+        n = len(self._release_rank)
+        self._coast = action
+        self._prev_lon = torch.full((n,), float('nan'), dtype=torch.float32, device=self.engine.device)
+        self._prev_lat = torch.full((n,), float('nan'), dtype=torch.float32, device=self.engine.device)
+
+    def interact_with_coastline(self, final=False):
+        """:671-746 -- 'stranding': elements on land (and not in the air) are deactivated; 'previous': elements released on land are
+        deactivated ('seeded_on_land'), every element on land goes back to its position of the previous step.  One sampling launch
+        (nearest grid point of the mask) and one launch for the action; elements the mask reader does not cover become
+        'missing_data' (report_missing_variables, :2501-2515; not at the final call)."""
+        if getattr(self, '_coast', None) is None or self.num_elements_active() == 0:
+            return
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        cats = self.status_categories
+        mask = self._start_of_step_sample('land_binary_mask')
+        self._coast_moved = False
+        if self._coast == 'previous' and not final and bool((mask == 1).any()):
+            # Elements on land go back to where they were, but update() still sees the environment sampled where they are now
+            # (the reference samples the step's environment before this method, :2238-2253, and does not sample again): materialise
+            # it before the move; this step then runs from it (the fused step would sample at the restored positions).
+            _ = self.environment
+            self._coast_moved = True
+        names = ['missing_data'] + (['stranded'] if self._coast == 'stranding' else ['seeded_on_land'])
+        prov, nxt = {}, len(cats)
+        for nm in names:
+            if nm in cats:
+                prov[nm] = cats.index(nm)
+            else:
+                prov[nm], nxt = nxt, nxt + 1
+        age = el.dev('age_seconds')
+        if age.dtype not in (torch.float32, torch.float64):
+            age = age.to(torch.float64)
+        lon, lat = el.dev('lon', torch.float64), el.dev('lat', torch.float64)
+        n_str, n_seed, n_miss, n_back = eng.coastline(
+            mask, lon, lat, self._z_for_sampling(), age, el.dev('status', torch.int32), el.dev('moving', torch.int32),
+            el.dev('ID', torch.int32), self._prev_lon, self._prev_lat, self._id_base, self._coast,
+            stranded_code=prov.get('stranded', 0), seeded_code=prov.get('seeded_on_land', 0),
+            missing_code=0 if final else prov['missing_data'], check_seeded=getattr(self, '_newly_seeded', False))
+        el.set_dev('lon', lon)
+        el.set_dev('lat', lat)
+        # categories are numbered when they first occur, missing_data (reported at the top of the loop) before the coastline's
+        for nm, cnt in (('missing_data', n_miss), (names[1], n_str + n_seed)):
+            if cnt > 0 and nm not in cats:
+                cats.append(nm)
+                real = cats.index(nm)
+                if real != prov[nm]:
+                    st = el.dev('status')
+                    el.set_dev('status', torch.where(st == prov[nm], torch.full_like(st, real), st))
+        if n_str + n_seed + n_miss > 0:
+            self._maybe_deactivated = True
+
+    def update_previous_state(self):
+        """:642-669 for lon / lat (the element properties the reference stores when a coastline action may move elements back)."""
+        if getattr(self, '_coast', None) is None or self.num_elements_active() == 0:
+            return
+        el, torch = self.elements, self.engine.torch
+        self.engine.store_previous(el.dev('lon', torch.float64), el.dev('lat', torch.float64), el.dev('ID', torch.int32), self._id_base,
+                                   self._prev_lon, self._prev_lat)
 
     def interact_with_seafloor(self):
         """:748-783 -- elements below the sea floor (sea_floor_depth_below_sea_level from a reader + sea_surface_height) are lifted
@@ -797,6 +892,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self._released = 0
         self.steps_calculation = 0
         self._maybe_deactivated = False
+        self._setup_coastline()
         out_every = int(round(ratio))
         n_total = len(self._release_rank)
         self._n_total = n_total
@@ -822,7 +918,16 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             self._predraw_step_uncertainty()
             # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
             col, only_deact = self._column_of_step(i)
-            if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            if self._coast is not None:
+                # deactivate_outside -> interact_with_coastline -> interact_with_seafloor -> state_to_buffer -> ... (:2249-2260)
+                if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                    _ = self.environment                   # sampled before the lift, as the reference does (:2238-2256)
+                self._bookkeep(outside=True, age=False)
+                self.interact_with_coastline()
+                if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                    self.interact_with_seafloor()
+                self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
+            elif self.env.priority_list.get('sea_floor_depth_below_sea_level'):
                 _ = self.environment                       # sampled before the lift, as the reference does (:2238-2256)
                 self._bookkeep(outside=True, age=False)
                 self.interact_with_seafloor()
@@ -830,6 +935,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             else:
                 self._bookkeep(outside=True, buffer_col=col, only_deactivated=only_deact, age=True)
             self.remove_deactivated_elements()
+            self.update_previous_state()                   # (:2262: positions elements may be moved back to)
             if self.num_elements_active() > 0:
                 self._maybe_sort()
                 self.update_and_diffuse()
@@ -838,6 +944,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             self.time = self.time + self.time_step
             self.steps_calculation += 1
         self._env_view = None
+        self.interact_with_coastline(final=True)           # (:2310)
         self._restore_id_order()
         self.state_to_buffer(final=True)
         self.remove_deactivated_elements()

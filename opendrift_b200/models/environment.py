@@ -13,7 +13,12 @@ import logging
 
 import numpy as np
 
+from ..engine import bracket
+
 logger = logging.getLogger('opendrift_b200')
+
+# variables a StructuredReader serves without time interpolation (readers/basereader/structured.py:224-229)
+STATIC_VARIABLES = ('sea_floor_depth_below_sea_level', 'land_binary_mask')
 
 
 class Environment:
@@ -166,7 +171,15 @@ class Environment:
                 if not r.covers_time(time) or not hasattr(r, 'group_of'):
                     continue
                 g, comp = r.group_of(v)
-                outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True)
+                t_s, nearest = time, False
+                if all(nm in STATIC_VARIABLES for nm, (gg, _) in r._groups.items() if gg is g):
+                    # variables that do not depend on time are taken from the block before `time`, without the time lerp
+                    # (structured.py:224-229); land_binary_mask from the nearest grid point (interpolation/structured.py:117-119)
+                    br = bracket(g.times, time)
+                    if br is not None:
+                        t_s = g.times[br[0]]
+                    nearest = v == 'land_binary_mask' and not getattr(r, 'always_valid', False)   # (a constant reader has one value everywhere)
+                outs = eng.interp(g, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, nearest=nearest)
                 if res is None:
                     res = {nm: outs[cc] for nm, (gg, cc) in r._groups.items() if gg is g}
                 else:                                   # next reader fills what is still missing

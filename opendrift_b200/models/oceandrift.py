@@ -28,6 +28,7 @@ class Lagrangian3DArray(LagrangianArray):
 
 class OceanDrift(OpenDriftSimulation):
     ElementType = Lagrangian3DArray
+    _coast_previous_supported = True      # update() can run from the materialised start-of-step environment (helper recipe)
 
     # oceandrift.py:70-92
     required_variables = {
@@ -366,6 +367,8 @@ class OceanDrift(OpenDriftSimulation):
         g = self._current_group(self.time)
         if g is None:
             return False
+        if getattr(self, '_coast_moved', False):
+            return False        # elements were moved back from land: they keep the environment sampled where they were (helper recipe)
         if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
             # A reader for the sea floor: elements below it are lifted at the top of the loop, AFTER the step's environment was
             # sampled (basemodel/__init__.py:2238-2256) -- the first Runge-Kutta stage and w see the depth before the lift, the

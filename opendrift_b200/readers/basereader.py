@@ -311,7 +311,12 @@ class StructuredReader:
         ind, _, _ = self.covers_positions(lon_in, lat_in)
         if len(ind) == 0:
             raise OutsideSpatialCoverageError('All %s particles are outside domain of %s' % (n, self.name))
-        zz = np.zeros(n, dtype=np.float32) if z is None else np.asarray(z, dtype=np.float32) * np.ones(n, dtype=np.float32)
+        # (the depths keep their dtype: the reference clips and interpolates a float64 z in float64, interpolators.py:174-197)
+        if z is None:
+            zz = np.zeros(n, dtype=np.float32)
+        else:
+            zz = np.atleast_1d(np.asarray(z))
+            zz = (zz.astype(np.float64) if zz.dtype == np.float64 else zz.astype(np.float32)) * np.ones(n, dtype=zz.dtype if zz.dtype == np.float64 else np.float32)
         d_lon = eng.to_device(lon_in.astype(np.float64))
         d_lat = eng.to_device(lat_in.astype(np.float64))
         d_z = eng.to_device(zz)
@@ -323,12 +328,26 @@ class StructuredReader:
             # no fallback here: uncovered / missing samples are NaN-masked like the reference's reader output
             # (a projected reader's vector pairs are rotated to east / north when the caller names the target CRS, as
             # Environment does with rotate_to_proj = '+proj=latlong'; without it the components stay along the grid's axes)
-            outs = eng.interp(g, time, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None)
+            # the reference returns float64 for 3-D blocks -- the unrounded vertical and time lerp (interpolation/structured.py:139-140,
+            # basereader/structured.py:353-364) -- and float32 for 2-D blocks; land_binary_mask comes from the nearest grid point and,
+            # like the sea floor depth, from the block before `time` without a time lerp (structured.py:224-229)
+            three_d = g.desc.nz > 1
+            names = [nme for nme, (gg, _) in self._groups.items() if gg is g]
+            t_s, nearest = time, False
+            if all(nme in ('sea_floor_depth_below_sea_level', 'land_binary_mask') for nme in names):
+                from ..engine import bracket
+                br = bracket(g.times, time)
+                if br is not None:
+                    t_s = g.times[br[0]]
+                nearest = v == 'land_binary_mask' and not getattr(self, 'always_valid', False)   # (a constant reader has one value everywhere)
+            outs = eng.interp(g, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None, out_f64=three_d,
+                              nearest=nearest)
             for nme, (gg, cc) in self._groups.items():
                 if gg is g and nme in variables:
                     a = outs[cc].cpu().numpy()
-                    # the reference returns float64 for 3-D blocks (vertical lerp in float64) and float32 for 2-D blocks
-                    env[nme] = np.ma.masked_invalid(a.astype(np.float64) if g.desc.nz > 1 else a)
+                    if len(ind) != n:          # some positions are not covered: the reference pads into a float64 array (variables.py:841-846)
+                        a = a.astype(np.float64)
+                    env[nme] = np.ma.masked_invalid(a)
         return env, None
 
     def __repr__(self):

@@ -109,6 +109,79 @@ def _fake_pyproj():
     return m
 
 
+def _fake_xarray():
+    """xarray stand-in: everything is a MagicMock except Dataset, which holds the variables of the reference's result block as
+    plain NumPy arrays -- enough for what run() does with it outside state_to_buffer: the float32 copies of the first output
+    column that serve as `_elements_previous` / `_environment_previous` (basemodel/__init__.py:2164-2165; read and written by
+    release_elements :928-931, update_previous_state :642-669 and interact_with_coastline :671-746)."""
+    class Var(np.ndarray):
+        def assign_attrs(self, *a, **k):
+            return self
+
+    class Dataset:
+        def __init__(self, coords=None, data_vars=None, attrs=None):
+            self._vars = {}
+            for k, v in (data_vars or {}).items():
+                self._vars[k] = (np.array(v[1]) if isinstance(v, tuple) else np.array(v)).view(Var)
+            self.attrs = dict(attrs or {})
+            self.coords = coords or {}
+
+        @property
+        def data_vars(self):
+            return self._vars
+
+        @property
+        def sizes(self):
+            a = next(iter(self._vars.values()), np.zeros((0, 0)))
+            return {'trajectory': a.shape[0], 'time': a.shape[1] if a.ndim > 1 else 1}
+
+        def _sub(self, d):
+            o = Dataset(attrs=self.attrs)
+            o._vars = d
+            o.coords = self.coords
+            return o
+
+        def __getitem__(self, k):
+            if isinstance(k, (list, tuple)):
+                return self._sub({n: self._vars[n] for n in k})
+            return self._vars[k]
+
+        def __setitem__(self, k, v):
+            self._vars[k] = v
+
+        def __getattr__(self, k):
+            v = self.__dict__.get('_vars', {})
+            if k in v:
+                return v[k]
+            c = self.__dict__.get('coords', {})
+            if k in c:
+                return c[k][1] if isinstance(c[k], tuple) else c[k]
+            raise AttributeError(k)
+
+        def __iter__(self):
+            return iter(self._vars)
+
+        def __contains__(self, k):
+            return k in self._vars
+
+        def isel(self, time=None, trajectory=None, drop=False):
+            d = {}
+            for n, a in self._vars.items():
+                if time is not None and a.ndim > 1:
+                    a = a[:, time]
+                if trajectory is not None:
+                    a = a[np.asarray(trajectory)]
+                d[n] = a
+            return self._sub(d)
+
+        def copy(self, deep=True):
+            return self._sub({n: (np.array(a, copy=True) if deep else a) for n, a in self._vars.items()})
+
+    m = MagicMock()
+    m.Dataset = Dataset
+    return m
+
+
 _ready = False
 
 
@@ -130,6 +203,7 @@ def setup():
         if name not in sys.modules:
             sys.modules[name] = MagicMock()
     sys.modules['pyproj'] = _fake_pyproj()
+    sys.modules['xarray'] = _fake_xarray()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import opendrift.readers.basereader  # noqa: F401  (must precede interpolation.structured)

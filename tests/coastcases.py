@@ -1,0 +1,121 @@
+"""Coastline interaction (general:coastline_action = 'stranding' / 'previous' against the land_binary_mask of a gridded reader,
+general:coastline_approximation_precision = None) -- cases shared by the CPU (host engine) and GPU tests.
+The expected results come from the UNMODIFIED reference: tests/golden/coast_ref.npz, written by `python tests/coastcases.py` in
+the build container (oracle/refrun.py; its xarray stand-in keeps the reference's float32 `_elements_previous` block)."""
+import os
+from datetime import timedelta
+
+import numpy as np
+
+import common
+
+GOLDEN = os.path.join(common.GOLDEN, 'coast_ref.npz')
+N, STEPS = 500, 10
+
+# name -> (fixture, config, release over steps, mask covers the domain, speed-up of the currents)
+CASES = {
+    'stranding_euler_2d': ('rk4_2d', {'general:coastline_action': 'stranding', 'drift:advection_scheme': 'euler'}, 0, True, 6.0),
+    'stranding_rk4_3d_release': ('rk4_3d', {'general:coastline_action': 'stranding', 'drift:advection_scheme': 'runge-kutta4'}, 4, True, 6.0),
+    'previous_rk4_3d': ('rk4_3d', {'general:coastline_action': 'previous', 'drift:advection_scheme': 'runge-kutta4'}, 0, True, 6.0),
+    'previous_rk2_release': ('rk4_3d', {'general:coastline_action': 'previous', 'drift:advection_scheme': 'runge-kutta'}, 5, True, 6.0),
+    'previous_euler_2d_wind': ('rk4_2d', {'general:coastline_action': 'previous', 'drift:advection_scheme': 'euler',
+                                          'environment:constant:x_wind': 9.0, 'environment:constant:y_wind': -4.0}, 3, True, 6.0),
+    'stranding_partial_mask': ('rk4_2d', {'general:coastline_action': 'stranding', 'drift:advection_scheme': 'runge-kutta'}, 0, False, 6.0),
+}
+
+
+def mask_grid(fx, full):
+    """A land mask on a grid of its own (coarser than the current's, offset by a fraction of a cell): an island in the middle of the
+    particle cloud, a strip of coast in the east, a few single land points."""
+    lon0, lon1 = float(fx.grid_lon[0]), float(fx.grid_lon[-1])
+    lat0, lat1 = float(fx.grid_lat[0]), float(fx.grid_lat[-1])
+    if not full:                       # covers the western half only: elements east of it have no mask ('missing_data')
+        lon1 = lon0 + 0.5 * (lon1 - lon0)
+    nx, ny = 31, 27
+    lon = np.linspace(lon0 + 0.003, lon1 - 0.002, nx)
+    lat = np.linspace(lat0 + 0.002, lat1 - 0.003, ny)
+    cl, ca = float(np.median(fx.lon0[:N])), float(np.median(fx.lat0[:N]))
+    X, Y = np.meshgrid(lon, lat)
+    sx, sy = 0.5 * float(np.std(fx.lon0[:N])), 0.5 * float(np.std(fx.lat0[:N]))
+    m = (((X - cl) / sx) ** 2 + ((Y - ca) / sy) ** 2 < 1.0).astype(np.float32)
+    m[:, -3:] = 1.0
+    m[3, 5] = m[ny - 4, 9] = 1.0
+    return lon, lat, m
+
+
+def case_inputs(case):
+    fxname, cfg, release, full, speed = CASES[case]
+    fx = common.Fixture(fxname)
+    mlon, mlat, mask = mask_grid(fx, full)
+    u, v = (speed * fx.u).astype(np.float32), (speed * fx.v).astype(np.float32)
+    t = fx.start if not release else [fx.start, fx.start + timedelta(seconds=release * fx.dt)]
+    config = {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': None,
+              'general:coastline_approximation_precision': None, 'drift:vertical_advection': False,
+              'seed:ocean_only': False}      # (True: closest_ocean_points moves the seeds off the land before the run, host-side, :936-1030)
+    config.update(cfg)
+    z = fx.z0[:N] if fx.grid_z is not None else np.zeros(N, dtype=np.float32)
+    return fx, u, v, (mlon, mlat, mask), t, config, z
+
+
+def run_case(case, Model, make_reader, **model_kw):
+    """The same script on the reference's classes (generator) and on the product's."""
+    fx, u, v, (mlon, mlat, mask), t, config, z = case_inputs(case)
+    o = Model(loglevel=50, **model_kw)
+    o.add_reader(make_reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: u, common.CUR[1]: v}, 'current'))
+    o.add_reader(make_reader(mlon, mlat, None, fx.times, {'land_binary_mask': np.repeat(mask[None], len(fx.times), axis=0)}, 'mask'))
+    for k, val in config.items():
+        o.set_config(k, val)
+    o.seed_elements(lon=fx.lon0[:N], lat=fx.lat0[:N], z=z, time=t)
+    o.run(steps=STEPS, time_step=fx.dt, time_step_output=fx.dt)
+    return o
+
+
+def run_product(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+    return run_case(case, OceanDrift, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name), **model_kw)
+
+
+def summary(o):
+    el, de = o.elements, o.elements_deactivated
+    nd = o.num_elements_deactivated()
+    cats = list(o.status_categories)
+    out = {'id': np.asarray(el.ID, dtype=np.int64), 'lon': np.asarray(el.lon, dtype=np.float64), 'lat': np.asarray(el.lat, dtype=np.float64),
+           'cats': np.array(cats)}
+    if nd:
+        out.update({'d_id': np.asarray(de.ID, dtype=np.int64), 'd_lon': np.asarray(de.lon, dtype=np.float64),
+                    'd_lat': np.asarray(de.lat, dtype=np.float64), 'd_status': np.asarray(de.status, dtype=np.int64)})
+    else:
+        out.update({'d_id': np.zeros(0, np.int64), 'd_lon': np.zeros(0), 'd_lat': np.zeros(0), 'd_status': np.zeros(0, np.int64)})
+    return out
+
+
+def check(o, case):
+    ref = np.load(GOLDEN)
+    got = summary(o)
+    g = lambda k: ref['%s__%s' % (case, k)]                      # noqa: E731
+    assert list(got['cats']) == list(g('cats')), (list(got['cats']), list(g('cats')))
+    assert np.array_equal(got['id'], g('id'))
+    assert np.array_equal(got['d_id'], g('d_id'))                # same elements, same (concatenation) order
+    assert np.array_equal(got['d_status'], g('d_status'))
+    if len(got['id']):
+        assert max(common.max_err_deg(got['lon'], got['lat'], g('lon'), g('lat'))) < 5e-8
+    if len(got['d_id']):
+        assert max(common.max_err_deg(got['d_lon'], got['d_lat'], g('d_lon'), g('d_lat'))) < 5e-8
+    return len(got['id']), len(got['d_id']), list(got['cats'])
+
+
+if __name__ == '__main__':
+    from oracle import refrun
+    refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as RefOD
+    out = {}
+    for case in CASES:
+        ro = run_case(case, RefOD, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name), logfile='/tmp/od_coast.log')
+        s = summary(ro)
+        for k, v in s.items():
+            out['%s__%s' % (case, k)] = v
+        codes = {c: int((s['d_status'] == i).sum()) for i, c in enumerate(s['cats'])}
+        print(case, 'active', len(s['id']), 'deactivated', len(s['d_id']), codes)
+    np.savez_compressed(GOLDEN, **out)
+    print('wrote', GOLDEN)

@@ -299,6 +299,14 @@ class _HostLib:
         self.calls.append('od_vertical_buoyancy')
         return self.shim.hs_vertical_buoyancy(args)
 
+    def od_coastline(self, ctx, args):
+        self.calls.append('od_coastline')
+        return self.shim.hs2_coastline(args)
+
+    def od_store_previous(self, ctx, n, lon, lat, ids, id_base, n_total, prev_lon, prev_lat):
+        self.shim.hs2_store_previous.argtypes = [C.c_int64, _P, _P, _P, C.c_int32, C.c_int64, _P, _P]
+        return self.shim.hs2_store_previous(n, lon, lat, ids, id_base, n_total, prev_lon, prev_lat)
+
     def od_last_error(self, ctx):
         return b'hostshim call failed'
 
@@ -353,6 +361,8 @@ class HostEngine:
     bookkeeping = Engine.bookkeeping
     bbox = Engine.bbox
     vertical_buoyancy = Engine.vertical_buoyancy
+    coastline = Engine.coastline
+    store_previous = Engine.store_previous
     # gridded readers: Engine's own group management and call wrappers
     add_group = Engine.add_group
     free_group = Engine.free_group

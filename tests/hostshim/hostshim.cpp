@@ -399,26 +399,63 @@ int hs_analytic_advect(const od_analytic_desc* r, const od_analytic_advect_args*
 extern "C" {
 
 int hs2_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lon, const double* lat, const void* z, int flags,
-               float* out0, float* out1) {
+               void* out0, void* out1) {
     hs_levels lv;
     GroupGeom q = make_geom(*g, lv);
+    const bool f64 = (flags & OD_INTERP_OUT_F64) != 0, nearest = (flags & OD_INTERP_NEAREST) != 0;
+    if (f64 && !nearest && !(flags & OD_INTERP_NO_FALLBACK)) return -7;
+    if (nearest && (q.ncomp != 1 || q.nz > 1 || q.proj_kind != 0 || q.wrap != 0 || !(q.xspan > 0.0) || !(q.yspan > 0.0))) return -8;
     if (flags & OD_INTERP_NO_FALLBACK) q.fallback[0] = q.fallback[1] = NAN;
     if (flags & OD_INTERP_NO_ROTATE) q.rotate = 0;
     const PairRef p = make_pair(*pr);
-    const bool z64 = (flags & OD_INTERP_Z_F64) != 0;
+    const bool z64 = (flags & OD_INTERP_Z_F64) != 0, p32 = (flags & OD_INTERP_POS_F32) != 0;
     for (int64_t i = 0; i < n; ++i) {
         const double zz = (z && q.nz > 1) ? (z64 ? ((const double*)z)[i] : (double)((const float*)z)[i]) : 0.0;
         const VertW vw = vert_weights(q, q.zs, q.zy, zz, !z64);
-        if (q.ncomp == 2) {
+        if (nearest) {
+            const float r = sample1_nearest(q, p, lon[i], lat[i], p32);
+            if (out0) { if (f64) ((double*)out0)[i] = (double)r; else ((float*)out0)[i] = r; }
+        } else if (f64) {
+            if (q.ncomp == 2) {
+                double u, v;
+                sample2_any_d(q, p, vw, lon[i], lat[i], u, v, p32);
+                if (out0) ((double*)out0)[i] = u;
+                if (out1) ((double*)out1)[i] = v;
+            } else if (out0) {
+                ((double*)out0)[i] = sample1_any_d(q, p, vw, lon[i], lat[i], p32);
+            }
+        } else if (q.ncomp == 2) {
             float u, v;
-            sample2_any(q, p, vw, lon[i], lat[i], u, v, (flags & OD_INTERP_POS_F32) != 0);
-            if (out0) out0[i] = u;
-            if (out1) out1[i] = v;
+            sample2_any(q, p, vw, lon[i], lat[i], u, v, p32);
+            if (out0) ((float*)out0)[i] = u;
+            if (out1) ((float*)out1)[i] = v;
         } else {
-            const float r = sample1_any(q, p, vw, lon[i], lat[i], (flags & OD_INTERP_POS_F32) != 0);
-            if (out0) out0[i] = r;
+            const float r = sample1_any(q, p, vw, lon[i], lat[i], p32);
+            if (out0) ((float*)out0)[i] = r;
         }
     }
+    return 0;
+}
+
+int hs2_coastline(const od_coast_args* a) {
+    if (a->action != 1 && a->action != 2) return -2;
+    unsigned c[4] = {0, 0, 0, 0};
+    CoastParams p;
+    p.n = a->n; p.mask = a->d_mask; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status;
+    p.moving = a->d_moving; p.ids = a->d_ids; p.prev_lon = a->d_prev_lon; p.prev_lat = a->d_prev_lat; p.counters = c;
+    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.stranded_code = a->stranded_code;
+    p.seeded_code = a->seeded_code; p.missing_code = a->missing_code; p.check_seeded = a->check_seeded; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
+    for (int64_t i = 0; i < a->n; ++i) {
+        const int f = coast_one(p, i);
+        for (int b = 0; b < 4; ++b) c[b] += (f >> b) & 1;
+    }
+    if (a->h_counts) for (int b = 0; b < 4; ++b) a->h_counts[b] = c[b];
+    return 0;
+}
+
+int hs2_store_previous(int64_t n, const double* lon, const double* lat, const int32_t* ids, int32_t id_base, int64_t n_total,
+                       float* prev_lon, float* prev_lat) {
+    for (int64_t i = 0; i < n; ++i) store_previous_one(i, lon, lat, ids, id_base, n_total, prev_lon, prev_lat);
     return 0;
 }
 
@@ -490,7 +527,8 @@ static void run2(const StepParams& p, int mode) {
     const double* zs = p.cs.g.zs; const double* zy = p.cs.g.zy;
     if (S == 2 && F && mode == OD_MATH_SERIES && g_spec_on && spec_eligible(p, S)) {
         for (int64_t i = 0; i < p.n; ++i) {
-            const int rc = step_particle_spec<2, true, E>(p, i, zs, zy, p.gw.zs, p.gw.zy);
+            const int rc = spec_all_lerp(p) ? step_particle_spec<2, true, E, true>(p, i, zs, zy, p.gw.zs, p.gw.zy)
+                                            : step_particle_spec<2, true, E, false>(p, i, zs, zy, p.gw.zs, p.gw.zy);
             if (rc) { step_particle_redo<2, true, E, SeriesMath, false>(&p, i, zs, zy, p.gw.zs, p.gw.zy, rc == 2); ++g_spec_redo; }
         }
         g_spec_n += p.n;

@@ -41,7 +41,8 @@ def test_struct_layouts_match_header():
 STRUCTS = {'od_time_sample': 'TimeSample', 'od_group_desc': 'GroupDesc', 'od_host_io': 'HostIO', 'od_advect_args': 'AdvectArgs',
            'od_step_args': 'StepArgs', 'od_mix_args': 'MixArgs', 'od_leeway_args': 'LeewayArgs', 'od_stokes_args': 'StokesArgs',
            'od_proj_desc': 'ProjDesc', 'od_analytic_desc': 'AnalyticDesc', 'od_analytic_advect_args': 'AnalyticAdvectArgs',
-           'od_history_args': 'HistoryArgs', 'od_buoyancy_args': 'BuoyancyArgs', 'od_bookkeep_args': 'BookkeepArgs', 'od_pack_args': 'PackArgs'}
+           'od_history_args': 'HistoryArgs', 'od_buoyancy_args': 'BuoyancyArgs', 'od_bookkeep_args': 'BookkeepArgs', 'od_pack_args': 'PackArgs',
+           'od_coast_args': 'CoastArgs'}
 
 
 def test_every_struct_field_has_the_offset_the_c_compiler_gives_it(tmp_path):

@@ -67,12 +67,15 @@ def spec(on):
             pass
 
 
-t1 = times[1]                      # a step that starts on a reader time (time mode 1 at the first stage)
+t1 = times[1]                      # a step that starts on a reader time (single-slab time mode at the first stage)
+t5 = times[0] + timedelta(seconds=3000)      # a step that ends on a reader time (single-slab mode at the last stage)
 for name, fn, sp in (
         ('fused', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp), True),
         ('fused_gen', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp), False),
         ('fused_t1', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t1, dt, a, b, c, w_group=wgrp), True),
         ('fused_t1_gen', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t1, dt, a, b, c, w_group=wgrp), False),
+        ('fused_t5', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t5, dt, a, b, c, w_group=wgrp), True),
+        ('fused_t5_gen', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t5, dt, a, b, c, w_group=wgrp), False),
         ('cur', lambda a, b, c: eng.advect_current(grp, 'runge-kutta4', t, dt, a, b, c), True),
         ('cur_gen', lambda a, b, c: eng.advect_current(grp, 'runge-kutta4', t, dt, a, b, c), False),
         ('fast', lambda a, b, c: eng.step_oceandrift(grp, 'runge-kutta4', t, dt, a, b, c, w_group=wgrp, fast=1), True)):
