@@ -290,7 +290,7 @@ def leg_cfg4(eng, torch, n, steps, peak):
             'step_kernel_all_extras': {'kernel_ms': step_ms, 'algorithmic_bytes_per_launch': step_bytes,
                                        'achieved_GBps': step_bytes / (step_ms * 1e-3) / 1e9,
                                        'frac_of_hbm_peak': step_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                                       'kernel': 'step_kernel<RK4, F64, EXTRAS=1, SeriesMath> (current + wind move + vertical advection)'},
+                                       'kernel': 'step_spec_kernel<RK4, F64, EXTRAS=1> (current + wind move + vertical advection; csrc/od_spec.cuh)'},
             'parity': par}
 
 

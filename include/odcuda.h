@@ -574,7 +574,9 @@ typedef struct od_coast_args {
     float* d_prev_lat;
     int64_t n_total;
     int32_t id_base;
-    int32_t action;               /* 1 stranding, 2 previous */
+    int32_t action;               /* 1 stranding, 2 previous; 3: general:seafloor_action = 'previous' (interact_with_seafloor :775-783):
+                                     d_mask holds sea_floor_depth_below_sea_level, elements below the floor go back to their previous position */
+    float ssh;                    /* action 3: sea_surface_height */
     int32_t stranded_code, seeded_code, missing_code;
     int32_t check_seeded;
     int32_t z_f64, age_f64;

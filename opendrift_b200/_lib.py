@@ -148,7 +148,7 @@ class CoastArgs(C.Structure):
     _fields_ = [('n', C.c_int64), ('d_mask', C.c_void_p), ('d_lon', C.c_void_p), ('d_lat', C.c_void_p), ('d_z', C.c_void_p),
                 ('d_age', C.c_void_p), ('d_status', C.c_void_p), ('d_moving', C.c_void_p), ('d_ids', C.c_void_p),
                 ('d_prev_lon', C.c_void_p), ('d_prev_lat', C.c_void_p), ('n_total', C.c_int64), ('id_base', C.c_int32),
-                ('action', C.c_int32), ('stranded_code', C.c_int32), ('seeded_code', C.c_int32), ('missing_code', C.c_int32),
+                ('action', C.c_int32), ('ssh', C.c_float), ('stranded_code', C.c_int32), ('seeded_code', C.c_int32), ('missing_code', C.c_int32),
                 ('check_seeded', C.c_int32), ('z_f64', C.c_int32), ('age_f64', C.c_int32), ('h_counts', C.POINTER(C.c_int64))]
 
 

@@ -24,6 +24,7 @@
 //                       'stranding': deactivate_elements((land_binary_mask == 1) & (z <= 0), 'stranded')
 //                       'previous':  elements of age 0 on land -> 'seeded_on_land' (while elements are being released), then every
 //                                    element on land goes back to its position of the previous step
+//                     and the 'previous' branch of interact_with_seafloor (:775-783): elements below the sea floor go back likewise
 //                     and, for both, elements the mask reader does not cover -> 'missing_data' (report_missing_variables,
 //                     :2501-2515: land_binary_mask has no fallback value).
 //                     The previous positions are float32: the reference keeps them in a copy of its float32 result block
@@ -205,7 +206,8 @@ struct CoastParams {
     unsigned* counters;          // [0] += stranded, [1] += seeded_on_land, [2] += missing_data, [3] += moved back
     int64_t n_total;
     int32_t id_base;
-    int32_t action;              // 1 'stranding', 2 'previous'
+    int32_t action;              // 1 'stranding', 2 'previous'; 3: general:seafloor_action = 'previous' (mask = sea floor depth)
+    float ssh;                   // action 3: sea_surface_height (the water column is sea floor depth + sea surface height)
     int32_t stranded_code, seeded_code, missing_code;
     int32_t check_seeded;        // elements were released this step (newly_seeded_IDs is not None)
     int32_t z_f64, age_f64;
@@ -217,6 +219,21 @@ OD_BK_HD int coast_one(const CoastParams& p, int64_t i) {
     int flags = 0;
     int st = p.status[i];
     bool off = false;
+    if (p.action == 3) {
+        // interact_with_seafloor, 'previous' (:775-783): an element below the sea floor goes back to the horizontal position of the
+        // previous step; its depth stays.  -(sea_floor_depth + sea_surface_height) is float32 environment arithmetic.
+        const float zmin = -(m + p.ssh);
+        const bool below = p.z_f64 ? ((const double*)p.z)[i] < (double)zmin : ((const float*)p.z)[i] < zmin;
+        if (below) {
+            const int64_t k = (int64_t)p.ids[i] - p.id_base;
+            if (k >= 0 && k < p.n_total) {
+                p.lon[i] = (double)p.prev_lon[k];
+                p.lat[i] = (double)p.prev_lat[k];
+                flags |= 8;
+            }
+        }
+        return flags;
+    }
     if (!(m == m) || !(fabsf(m) <= 3.4028234663852886e38f)) {        // report_missing_variables comes first in the loop (:2247)
         if (p.missing_code) {
             if (st == 0) { st = p.missing_code; flags |= 4; }

@@ -1919,8 +1919,9 @@ extern "C" int od_coastline(od_ctx* ctx, const od_coast_args* a) {
     if (!ctx || !a) return fail(ctx, OD_ERR_ARG, "od_coastline: null argument");
     if (a->n < 0 || (a->n > 0 && (!a->d_mask || !a->d_lon || !a->d_lat || !a->d_status || !a->d_moving)))
         return fail(ctx, OD_ERR_ARG, "od_coastline: bad arguments");
-    if (a->action != 1 && a->action != 2) return fail(ctx, OD_ERR_ARG, "od_coastline: action is 1 (stranding) or 2 (previous)");
-    if (a->action == 2 && a->n > 0 && (!a->d_ids || !a->d_prev_lon || !a->d_prev_lat || (a->check_seeded && !a->d_age)))
+    if (a->action < 1 || a->action > 3) return fail(ctx, OD_ERR_ARG, "od_coastline: action is 1 (stranding), 2 (previous) or 3 (sea floor: previous)");
+    if (a->action == 3 && a->n > 0 && !a->d_z) return fail(ctx, OD_ERR_ARG, "od_coastline: the sea-floor action needs the depths");
+    if (a->action >= 2 && a->n > 0 && (!a->d_ids || !a->d_prev_lon || !a->d_prev_lat || (a->check_seeded && !a->d_age)))
         return fail(ctx, OD_ERR_ARG, "od_coastline: 'previous' needs IDs, previous positions (and ages while elements are released)");
     if (a->h_counts) a->h_counts[0] = a->h_counts[1] = a->h_counts[2] = a->h_counts[3] = 0;
     if (a->n == 0) return OD_OK;
@@ -1930,7 +1931,7 @@ extern "C" int od_coastline(od_ctx* ctx, const od_coast_args* a) {
     CoastParams p;
     p.n = a->n; p.mask = a->d_mask; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status;
     p.moving = a->d_moving; p.ids = a->d_ids; p.prev_lon = a->d_prev_lon; p.prev_lat = a->d_prev_lat; p.counters = ctx->d_cnt;
-    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.stranded_code = a->stranded_code;
+    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.ssh = a->ssh; p.stranded_code = a->stranded_code;
     p.seeded_code = a->seeded_code; p.missing_code = a->missing_code; p.check_seeded = a->check_seeded; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
     coast_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());

@@ -525,7 +525,7 @@ class Engine:
         return outs
 
     def coastline(self, mask, lon, lat, z, age, status, moving, ids, prev_lon, prev_lat, id_base, action, stranded_code=0,
-                  seeded_code=0, missing_code=0, check_seeded=False):
+                  seeded_code=0, missing_code=0, check_seeded=False, ssh=0.0):
         """interact_with_coastline (basemodel/__init__.py:671-746) for a sampled land_binary_mask; returns the counts
         (stranded, seeded_on_land, missing_data, moved back)."""
         a = _lib.CoastArgs()
@@ -534,7 +534,8 @@ class Engine:
         a.d_status, a.d_moving, a.d_ids = _ptr(status), _ptr(moving), _ptr(ids)
         a.d_prev_lon, a.d_prev_lat = _ptr(prev_lon), _ptr(prev_lat)
         a.n_total = 0 if prev_lon is None else prev_lon.numel()
-        a.id_base, a.action = int(id_base), {'stranding': 1, 'previous': 2}[action]
+        a.id_base, a.action = int(id_base), {'stranding': 1, 'previous': 2, 'seafloor_previous': 3}[action]
+        a.ssh = float(ssh)
         a.stranded_code, a.seeded_code, a.missing_code = int(stranded_code), int(seeded_code), int(missing_code)
         a.check_seeded = 1 if check_seeded else 0
         a.z_f64 = 1 if (z is not None and z.dtype == self.torch.float64) else 0

@@ -367,7 +367,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             return
         first_release = len(self.elements) == 0
         ids = np.asarray(self.elements_scheduled.ID)[idx].astype(np.int64)
-        if getattr(self, '_coast', None) is not None:
+        if getattr(self, '_store_previous', False):
             # _elements_previous.lon[newly_seeded_IDs] = elements_scheduled.lon[indices] (:928-931): float32 like the result block
             k = self.engine.to_device(ids - self._id_base)
             self._prev_lon[k] = self.engine.to_device(np.asarray(self.elements_scheduled.lon)[idx].astype(np.float32))
@@ -483,6 +483,9 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         landmask of roaring_landmask, loaded when general:use_auto_landmask is on, and the bisection of coastline_crossing
         against it -- is IO-backed and not on this path."""
         self._coast = None
+        self._store_previous = False
+        if self.get_config('general:seafloor_action') == 'previous' and self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            self._alloc_previous()
         action = self.get_config('general:coastline_action')
         if action == 'none' or 'land_binary_mask' not in self.required_variables:
             return
@@ -494,8 +497,10 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             raise NotImplementedError("general:coastline_action = '%s' needs a reader that provides land_binary_mask; the GSHHG landmask "
                                       "(general:use_auto_landmask) is host-side IO, out of scope of the GPU hot path" % action)
         if self.get_config('seed:ocean_only'):
-            raise NotImplementedError('seed:ocean_only = True moves the seeds off the land before the run (closest_ocean_points, a host-side '
-                                      'nearest-neighbour search, basemodel/__init__.py:936-1030): not on the GPU path; set it to False')
+            # "Move point seeded on land to ocean" (:2148-2155), once, before the run, on the scheduled (float32) positions
+            lon, lat = np.asarray(self.elements_scheduled.lon), np.asarray(self.elements_scheduled.lat)
+            lon, lat, _ = self.closest_ocean_points(lon, lat)
+            self.elements_scheduled.lon, self.elements_scheduled.lat = lon, lat
         if self.get_config('general:coastline_approximation_precision') is not None:
             raise NotImplementedError('general:coastline_approximation_precision must be None on the GPU path: the bisection towards '
                                       'the coastline queries the GSHHG landmask (basemodel/__init__.py:81-134)')
@@ -503,9 +508,57 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
             # an element that is moved back keeps, for this step, the environment sampled where it was on land (the reference samples
             # before interact_with_coastline, :2238-2253): only models whose update() can run from a materialised environment do that
             raise NotImplementedError("general:coastline_action = 'previous' is not on the GPU path of %s" % type(self).__name__)
+        self._coast = action
+        self._alloc_previous()
+
+    def closest_ocean_points(self, lon, lat):
+        """:936-1030 for a gridded land_binary_mask reader: the seeds on land (mask != 0, which includes 'no data') move to the
+        nearest ocean point of a 0.01 degree grid around the seeds (<= 1000 points per axis), as sampled from the same reader at its
+        start time; a k-d tree search on the host, once per run (scipy, like the reference).  Positions keep their dtype."""
+        from scipy.spatial import cKDTree
+        name = self.env.priority_list['land_binary_mask'][0]
+        land_reader = self.env.readers[name]
+        lon, lat = np.array(lon, copy=True), np.array(lat, copy=True)
+        deltalon = deltalat = 0.01
+        numbuffer = 10
+        lonmin, lonmax = lon.min() - deltalon * numbuffer, lon.max() + deltalon * numbuffer
+        latmin, latmax = lat.min() - deltalat * numbuffer, lat.max() + deltalat * numbuffer
+        sample = lambda x, y: self.env.get_environment(['land_binary_mask'], lon=x, lat=y, z=0 * x,            # noqa: E731
+                                                       time=land_reader.start_time)[0]['land_binary_mask']
+        land = sample(lon, lat)
+        if land.max() == 0:
+            return lon, lat, None
+        land_indices = np.where(land != 0)[0]
+        longrid = np.arange(lonmin, lonmax, deltalon)
+        latgrid = np.arange(latmin, latmax, deltalat)
+        if len(longrid) > 1000 or len(latgrid) > 1000:
+            longrid = np.linspace(lonmin, lonmax, 1000)
+            latgrid = np.linspace(latmin, latmax, 1000)
+        longrid, latgrid = np.meshgrid(longrid, latgrid)
+        longrid, latgrid = longrid.ravel(), latgrid.ravel()
+        covered = land_reader.covers_positions(longrid, latgrid)[0]
+        longrid, latgrid = longrid[covered], latgrid[covered]
+        if longrid.size == 0:
+            return lon, lat, land_indices
+        landgrid = sample(longrid, latgrid)
+        if landgrid.size == 0 or landgrid.min() == 1 or np.isnan(landgrid.min()):
+            return lon, lat, land_indices                      # 'No ocean pixels nearby, cannot move elements.'
+        olon, olat = longrid[landgrid == 0], latgrid[landgrid == 0]
+        tree = cKDTree(np.dstack([olon, olat])[0])
+        _dist, idx = tree.query(np.dstack([lon[land_indices], lat[land_indices]]))
+        idx = idx.ravel()
+        lon[land_indices] = olon[idx]
+        lat[land_indices] = olat[idx]
+        return lon, lat, land_indices
+
+    def _alloc_previous(self):
+        """lon / lat of the previous step, float32, one row per trajectory: the reference's `_elements_previous` (a copy of its
+        float32 result block, :2164-2165; kept when a coastline or sea-floor action may move elements back, elements.py:76-88)."""
+        if self._store_previous:
+            return
         torch = self.engine.torch
         n = len(self._release_rank)
-        self._coast = action
+        self._store_previous = True
         self._prev_lon = torch.full((n,), float('nan'), dtype=torch.float32, device=self.engine.device)
         self._prev_lat = torch.full((n,), float('nan'), dtype=torch.float32, device=self.engine.device)
 
@@ -557,7 +610,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
 
     def update_previous_state(self):
         """:642-669 for lon / lat (the element properties the reference stores when a coastline action may move elements back)."""
-        if getattr(self, '_coast', None) is None or self.num_elements_active() == 0:
+        if not getattr(self, '_store_previous', False) or self.num_elements_active() == 0:
             return
         el, torch = self.elements, self.engine.torch
         self.engine.store_previous(el.dev('lon', torch.float64), el.dev('lat', torch.float64), el.dev('ID', torch.int32), self._id_base,
@@ -571,12 +624,18 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         action = self.get_config('general:seafloor_action')
         if action == 'none':
             return
-        if action == 'previous':
-            raise NotImplementedError("general:seafloor_action = 'previous' (positions of the previous step) is not on the GPU path")
         eng, el, torch = self.engine, self.elements, self.engine.torch
         floor = self._start_of_step_sample('sea_floor_depth_below_sea_level')
         ssh = float(self.env.constant('sea_surface_height') or self.env.fallback('sea_surface_height') or 0.0) \
             if 'sea_surface_height' in self.required_variables else 0.0
+        if action == 'previous':
+            # elements below the floor go back to the horizontal position of the previous step, their depth stays (:775-783)
+            lon, lat = el.dev('lon', torch.float64), el.dev('lat', torch.float64)
+            eng.coastline(floor, lon, lat, self._z_for_sampling(), None, el.dev('status', torch.int32), el.dev('moving', torch.int32),
+                          el.dev('ID', torch.int32), self._prev_lon, self._prev_lat, self._id_base, 'seafloor_previous', ssh=ssh)
+            el.set_dev('lon', lon)
+            el.set_dev('lat', lat)
+            return
         z = self._z_for_sampling()
         code = 0
         if action == 'deactivate':
@@ -903,46 +962,58 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         i = 0
         dist_run = self._dist is not None
         self._has_subblock_readers = bool(self.env.subblock_readers())
-        for i in range(self.expected_steps_calculation):
-            self.release_elements()
-            if dist_run:
-                # the slab collectives of this step, on every rank alike (also one that holds no elements right now)
-                self.env.touch_slabs(self._stage_times(self.time))
-            if self.num_elements_active() == 0 and (self.num_elements_scheduled() > 0 or dist_run):
-                self.steps_calculation += 1                # (state_to_buffer with no elements: the column keeps its fill values)
-                self.time = self.time + self.time_step
-                continue
-            self._env_view = None
-            if self._has_subblock_readers:
-                self._cover_elements_with_blocks()
-            self._predraw_step_uncertainty()
-            # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
-            col, only_deact = self._column_of_step(i)
-            if self._coast is not None:
-                # deactivate_outside -> interact_with_coastline -> interact_with_seafloor -> state_to_buffer -> ... (:2249-2260)
-                if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
-                    _ = self.environment                   # sampled before the lift, as the reference does (:2238-2256)
-                self._bookkeep(outside=True, age=False)
-                self.interact_with_coastline()
-                if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+        # The step loop allocates small Python objects (argument structs, tensor handles) at a steady rate; a full collection of the
+        # interpreter's cyclic garbage collector over everything the process has imported takes 50-150 ms -- the time of fifty
+        # steps -- whenever it triggers.  The objects alive now are moved out of the collector's reach for the duration of the
+        # loop (they stay reference-counted); what the loop allocates is still collected, in microseconds.
+        import gc
+        frozen = gc.isenabled()
+        if frozen:
+            gc.freeze()
+        try:
+            for i in range(self.expected_steps_calculation):
+                self.release_elements()
+                if dist_run:
+                    # the slab collectives of this step, on every rank alike (also one that holds no elements right now)
+                    self.env.touch_slabs(self._stage_times(self.time))
+                if self.num_elements_active() == 0 and (self.num_elements_scheduled() > 0 or dist_run):
+                    self.steps_calculation += 1                # (state_to_buffer with no elements: the column keeps its fill values)
+                    self.time = self.time + self.time_step
+                    continue
+                self._env_view = None
+                if self._has_subblock_readers:
+                    self._cover_elements_with_blocks()
+                self._predraw_step_uncertainty()
+                # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
+                col, only_deact = self._column_of_step(i)
+                if self._coast is not None:
+                    # deactivate_outside -> interact_with_coastline -> interact_with_seafloor -> state_to_buffer -> ... (:2249-2260)
+                    if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                        _ = self.environment                   # sampled before the lift, as the reference does (:2238-2256)
+                    self._bookkeep(outside=True, age=False)
+                    self.interact_with_coastline()
+                    if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                        self.interact_with_seafloor()
+                    self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
+                elif self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+                    _ = self.environment                       # sampled before the lift, as the reference does (:2238-2256)
+                    self._bookkeep(outside=True, age=False)
                     self.interact_with_seafloor()
-                self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
-            elif self.env.priority_list.get('sea_floor_depth_below_sea_level'):
-                _ = self.environment                       # sampled before the lift, as the reference does (:2238-2256)
-                self._bookkeep(outside=True, age=False)
-                self.interact_with_seafloor()
-                self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
-            else:
-                self._bookkeep(outside=True, buffer_col=col, only_deactivated=only_deact, age=True)
-            self.remove_deactivated_elements()
-            self.update_previous_state()                   # (:2262: positions elements may be moved back to)
-            if self.num_elements_active() > 0:
-                self._maybe_sort()
-                self.update_and_diffuse()
-            elif self.num_elements_scheduled() == 0 and not dist_run:
-                break                                      # 'No more active or scheduled elements' (:2276-2278): time is not advanced
-            self.time = self.time + self.time_step
-            self.steps_calculation += 1
+                    self._bookkeep(outside=False, buffer_col=col, only_deactivated=only_deact, age=True)
+                else:
+                    self._bookkeep(outside=True, buffer_col=col, only_deactivated=only_deact, age=True)
+                self.remove_deactivated_elements()
+                self.update_previous_state()                   # (:2262: positions elements may be moved back to)
+                if self.num_elements_active() > 0:
+                    self._maybe_sort()
+                    self.update_and_diffuse()
+                elif self.num_elements_scheduled() == 0 and not dist_run:
+                    break                                      # 'No more active or scheduled elements' (:2276-2278): time is not advanced
+                self.time = self.time + self.time_step
+                self.steps_calculation += 1
+        finally:
+            if frozen:
+                gc.unfreeze()
         self._env_view = None
         self.interact_with_coastline(final=True)           # (:2310)
         self._restore_id_order()

@@ -146,7 +146,7 @@ class OceanDrift(OpenDriftSimulation):
         if action == 'none':
             return None, 0.0, 0
         if action == 'previous':
-            raise NotImplementedError("general:seafloor_action = 'previous' is not on the GPU path")
+            return None, 0.0, 0        # no lift: vertical_buoyancy() moves the elements below the floor back afterwards
         floor = self._start_of_step_sample('sea_floor_depth_below_sea_level')
         ssh = float(self.env.constant('sea_surface_height') or self.env.fallback('sea_surface_height') or 0.0)
         code = 0
@@ -174,6 +174,8 @@ class OceanDrift(OpenDriftSimulation):
     def vertical_buoyancy(self):
         """oceandrift.py:352-367: z[z < 0] = min(0, z + terminal_velocity * dt), then the sea floor."""
         self.elements.set_dev('z', self._buoyancy(self._z_for_sampling()))
+        if self.get_config('general:seafloor_action') == 'previous' and self.env.priority_list.get('sea_floor_depth_below_sea_level'):
+            self.interact_with_seafloor()          # (:363-366: elements that sank below the floor go back to their previous position)
 
     def vertical_advection(self):
         """oceandrift.py:315-350: z = min(0, z + moving*w*dt) below (or at) the surface."""

@@ -21,7 +21,15 @@ CASES = {
     'previous_euler_2d_wind': ('rk4_2d', {'general:coastline_action': 'previous', 'drift:advection_scheme': 'euler',
                                           'environment:constant:x_wind': 9.0, 'environment:constant:y_wind': -4.0}, 3, True, 6.0),
     'stranding_partial_mask': ('rk4_2d', {'general:coastline_action': 'stranding', 'drift:advection_scheme': 'runge-kutta'}, 0, False, 6.0),
+    # seed:ocean_only = True (the reference's default): closest_ocean_points moves the seeds on land to the nearest ocean point first
+    'previous_ocean_only': ('rk4_3d', {'general:coastline_action': 'previous', 'drift:advection_scheme': 'runge-kutta4',
+                                       'seed:ocean_only': True}, 2, True, 6.0),
+    # general:seafloor_action = 'previous' (interact_with_seafloor :775-783): sinking elements that end up below a shoaling sea floor go
+    # back to the horizontal position of the previous step; no land mask in this one
+    'seafloor_previous': ('rk4_3d', {'general:coastline_action': 'none', 'general:seafloor_action': 'previous',
+                                     'environment:constant:land_binary_mask': 0, 'drift:advection_scheme': 'runge-kutta'}, 3, None, 6.0),
 }
+SINK = -0.03          # terminal velocity of the sea-floor case, m/s
 
 
 def mask_grid(fx, full):
@@ -46,7 +54,7 @@ def mask_grid(fx, full):
 def case_inputs(case):
     fxname, cfg, release, full, speed = CASES[case]
     fx = common.Fixture(fxname)
-    mlon, mlat, mask = mask_grid(fx, full)
+    mlon, mlat, mask = mask_grid(fx, full is not False)
     u, v = (speed * fx.u).astype(np.float32), (speed * fx.v).astype(np.float32)
     t = fx.start if not release else [fx.start, fx.start + timedelta(seconds=release * fx.dt)]
     config = {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': None,
@@ -62,10 +70,17 @@ def run_case(case, Model, make_reader, **model_kw):
     fx, u, v, (mlon, mlat, mask), t, config, z = case_inputs(case)
     o = Model(loglevel=50, **model_kw)
     o.add_reader(make_reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: u, common.CUR[1]: v}, 'current'))
-    o.add_reader(make_reader(mlon, mlat, None, fx.times, {'land_binary_mask': np.repeat(mask[None], len(fx.times), axis=0)}, 'mask'))
+    kw = {}
+    if CASES[case][3] is None:         # a sea floor instead of a land mask: shoaling towards the east, 10 .. 70 m
+        X, Y = np.meshgrid(mlon, mlat)
+        floor = (70.0 - 60.0 * (X - mlon[0]) / (mlon[-1] - mlon[0]) + 5.0 * np.sin(9.0 * Y)).astype(np.float32)
+        o.add_reader(make_reader(mlon, mlat, None, fx.times, {'sea_floor_depth_below_sea_level': np.repeat(floor[None], len(fx.times), axis=0)}, 'floor'))
+        kw['terminal_velocity'] = SINK
+    else:
+        o.add_reader(make_reader(mlon, mlat, None, fx.times, {'land_binary_mask': np.repeat(mask[None], len(fx.times), axis=0)}, 'mask'))
     for k, val in config.items():
         o.set_config(k, val)
-    o.seed_elements(lon=fx.lon0[:N], lat=fx.lat0[:N], z=z, time=t)
+    o.seed_elements(lon=fx.lon0[:N], lat=fx.lat0[:N], z=z, time=t, **kw)
     o.run(steps=STEPS, time_step=fx.dt, time_step_output=fx.dt)
     return o
 
@@ -81,7 +96,7 @@ def summary(o):
     nd = o.num_elements_deactivated()
     cats = list(o.status_categories)
     out = {'id': np.asarray(el.ID, dtype=np.int64), 'lon': np.asarray(el.lon, dtype=np.float64), 'lat': np.asarray(el.lat, dtype=np.float64),
-           'cats': np.array(cats)}
+           'z': np.asarray(el.z, dtype=np.float64), 'cats': np.array(cats)}
     if nd:
         out.update({'d_id': np.asarray(de.ID, dtype=np.int64), 'd_lon': np.asarray(de.lon, dtype=np.float64),
                     'd_lat': np.asarray(de.lat, dtype=np.float64), 'd_status': np.asarray(de.status, dtype=np.int64)})
@@ -100,6 +115,7 @@ def check(o, case):
     assert np.array_equal(got['d_status'], g('d_status'))
     if len(got['id']):
         assert max(common.max_err_deg(got['lon'], got['lat'], g('lon'), g('lat'))) < 5e-8
+        assert np.max(np.abs(got['z'] - g('z'))) <= 1e-5
     if len(got['d_id']):
         assert max(common.max_err_deg(got['d_lon'], got['d_lat'], g('d_lon'), g('d_lat'))) < 5e-8
     return len(got['id']), len(got['d_id']), list(got['cats'])

@@ -438,12 +438,12 @@ int hs2_interp(const hs_group* g, const hs_pair* pr, int64_t n, const double* lo
 }
 
 int hs2_coastline(const od_coast_args* a) {
-    if (a->action != 1 && a->action != 2) return -2;
+    if (a->action < 1 || a->action > 3) return -2;
     unsigned c[4] = {0, 0, 0, 0};
     CoastParams p;
     p.n = a->n; p.mask = a->d_mask; p.lon = a->d_lon; p.lat = a->d_lat; p.z = a->d_z; p.age = a->d_age; p.status = a->d_status;
     p.moving = a->d_moving; p.ids = a->d_ids; p.prev_lon = a->d_prev_lon; p.prev_lat = a->d_prev_lat; p.counters = c;
-    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.stranded_code = a->stranded_code;
+    p.n_total = a->n_total; p.id_base = a->id_base; p.action = a->action; p.ssh = a->ssh; p.stranded_code = a->stranded_code;
     p.seeded_code = a->seeded_code; p.missing_code = a->missing_code; p.check_seeded = a->check_seeded; p.z_f64 = a->z_f64; p.age_f64 = a->age_f64;
     for (int64_t i = 0; i < a->n; ++i) {
         const int f = coast_one(p, i);
