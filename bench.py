@@ -670,7 +670,8 @@ def run_b200(args):
                                   if world > 1 else 'single GPU',
                    'l2': 'inputs larger than L2 (state %.0f MB + forcing %.0f MB per step)' % (n * 20 / 1e6, field_bytes / 1e6)},
         'clocks': clocks,
-        'comm': {'slab_broadcasts_in_timed_region': slabs_bcast, 'broadcast': bcast, 'numa': numa} if world > 1 else {'numa': numa},
+        'comm': {'slab_broadcasts_in_timed_region': slabs_bcast, 'broadcast': bcast, 'numa': numa,
+                 'slab_broadcast_communicator_max_ctas': getattr(eng.dist, 'bcast_ctas', None)} if world > 1 else {'numa': numa},
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 20,
                 'steps': e2e_steps, 'api': 'od_step_oceandrift_host through Engine.step_oceandrift_host (pinned host lon/lat/z in and out, %d-chunk '
                        'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
