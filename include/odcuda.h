@@ -102,12 +102,17 @@ int od_device_sm_count(od_ctx* ctx);
  * rotated from the plane's axes to east / north after the interpolation (rotate_vectors, :59-109, :799-837).  Sampled by the
  * general kernels (od_interp, the reader-chain family of step kernels, mixing, Leeway); kind 0 = geographic (+proj=latlong). */
 #define OD_PROJ_STERE_SPHERE 1
+#define OD_PROJ_MERC 2
+#define OD_PROJ_LCC 3
 typedef struct od_proj_desc {
-    int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0) */
-    int32_t has_lat_ts;           /* +lat_ts given (polar aspects only) */
-    double a;                     /* sphere radius, m */
+    int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0);
+                                     OD_PROJ_MERC: +proj=merc; OD_PROJ_LCC: +proj=lcc (+lat_1 [+lat_2]); sphere or ellipsoid (es) */
+    int32_t has_lat_ts;           /* +lat_ts given (stere: polar aspects only; merc: the latitude of true scale replaces k_0) */
+    double a;                     /* sphere radius / semi-major axis, m */
     double lat_0, lon_0, lat_ts;  /* degrees */
     double k_0, x_0, y_0;
+    double es;                    /* squared eccentricity of the ellipsoid, 0 = sphere (merc, lcc) */
+    double lat_1, lat_2;          /* standard parallels of the cone, degrees (lat_2 = lat_1: one parallel) */
 } od_proj_desc;
 
 typedef struct od_group_desc {

@@ -24,7 +24,8 @@ SCHEMES = {'euler': OD_EULER, 'runge-kutta': OD_RK2, 'runge-kutta4': OD_RK4}
 
 class ProjDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('has_lat_ts', C.c_int32), ('a', C.c_double), ('lat_0', C.c_double),
-                ('lon_0', C.c_double), ('lat_ts', C.c_double), ('k_0', C.c_double), ('x_0', C.c_double), ('y_0', C.c_double)]
+                ('lon_0', C.c_double), ('lat_ts', C.c_double), ('k_0', C.c_double), ('x_0', C.c_double), ('y_0', C.c_double),
+                ('es', C.c_double), ('lat_1', C.c_double), ('lat_2', C.c_double)]
 
 
 class GroupDesc(C.Structure):
@@ -163,6 +164,7 @@ class PackArgs(C.Structure):
 
 
 OD_PROJ_STERE_SPHERE = 1
+OD_PROJ_MERC, OD_PROJ_LCC = 2, 3
 OD_ANALYTIC_DOUBLE_GYRE = 1
 
 # every symbol include/odcuda.h declares: (restype, argtypes)

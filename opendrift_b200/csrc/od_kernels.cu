@@ -215,7 +215,7 @@ extern "C" int od_group_define(od_ctx* ctx, int group, const od_group_desc* d, c
     if (d->nz > 1 && !h_z) return fail(ctx, OD_ERR_ARG, "od_group_define: z levels missing");
     if (d->proj.kind != 0) {
         ProjStere tmp;
-        if (proj_from_desc(&d->proj, &tmp) != 0) return fail(ctx, OD_ERR_ARG, "od_group_define: unsupported projection (spherical +proj=stere)");
+        if (proj_from_desc(&d->proj, &tmp) != 0) return fail(ctx, OD_ERR_ARG, "od_group_define: unsupported projection (spherical +proj=stere, +proj=merc, +proj=lcc) or bad projection parameters");
         if (d->wrap_x || d->global_x) return fail(ctx, OD_ERR_ARG, "od_group_define: a projected group cannot be periodic / global in x");
     }
     if ((size_t)d->nx * d->ny * d->nz >= (1ull << 31)) return fail(ctx, OD_ERR_ARG, "od_group_define: block too large");

@@ -5,8 +5,10 @@
 // (rotate_vectors, :59-109: inverse projection of (x, y) and (x, y + 10 m), Geod.inv azimuth of that line, rotation by minus
 // that azimuth).  Both run per particle inside the kernels here.
 //
-// Projection: spherical stereographic, the four aspects PROJ's stere.cpp distinguishes (Snyder 1987, eqs. 21-2..21-4,
-// 20-14, 20-15, 20-18, 21-15), wrapped in PROJ's generic steps (lam = lon - lon_0 reduced to [-pi, pi], x = a x' + x_0).
+// Projections: spherical stereographic, the four aspects PROJ's stere.cpp distinguishes (Snyder 1987, eqs. 21-2..21-4,
+// 20-14, 20-15, 20-18, 21-15); Mercator (7-1, 7-2 / 7-6 .. 7-9) and Lambert conformal conic with one or two standard
+// parallels (15-1 .. 15-5 / 15-7 .. 15-11, 14-15, 15-9) on a sphere or an ellipsoid, organised like PROJ's merc.cpp / lcc.cpp
+// (msfn, tsfn, phi2); all wrapped in PROJ's generic steps (lam = lon - lon_0 reduced to [-pi, pi], x = a x' + x_0).
 // Geod.inv: only the forward azimuth of a short line is needed; it is obtained by inverting the direct solution
 // (mid-latitude first guess, one correction with the miss of the direct series move) -- the miss shrinks by
 // (s/a)^2 ~ 2e-12 per pass for the 10 m line.
@@ -18,9 +20,13 @@ namespace od {
 
 enum { PROJ_EQUIT = 0, PROJ_OBLIQ = 1, PROJ_N_POLE = 2, PROJ_S_POLE = 3 };
 
-struct ProjStere {
-    int mode;
+struct ProjStere {               // (the name is historical: kind selects the projection)
+    int mode;                    // aspect of the stereographic projection
+    int kind;                    // OD_PROJ_STERE_SPHERE, OD_PROJ_MERC, OD_PROJ_LCC
     double a, ra, akm1, sinX1, cosX1, phi0, lam0, x0, y0;
+    double e, es;                // eccentricity of the ellipsoid (0: sphere)
+    double k0;                   // scale factor (Mercator: from +lat_ts or +k_0; cone: +k_0)
+    double n, c, rho0;           // cone constant, F of Snyder 15-10, radius of the parallel of origin
 };
 
 constexpr double kPi = 3.14159265358979323846;
@@ -34,10 +40,47 @@ OD_HD double adjlon(double lam) {
     return t - kPi;
 }
 
-// lon, lat in degrees -> x, y in metres; returns false where the projection is undefined (antipode)
+// PROJ's pj_msfn (Snyder 14-15), pj_tsfn (15-9) and pj_phi2 (7-9)
+OD_HD double proj_msfn(double sinphi, double cosphi, double es) { return cosphi / sqrt(1.0 - es * sinphi * sinphi); }
+OD_HD double proj_tsfn(double phi, double sinphi, double e) {
+    return tan(0.5 * (kHalfPi - phi)) / pow((1.0 - e * sinphi) / (1.0 + e * sinphi), 0.5 * e);
+}
+OD_HD double proj_phi2(double ts, double e) {
+    double phi = kHalfPi - 2.0 * atan(ts);
+    for (int i = 0; i < 20; ++i) {
+        const double con = e * sin(phi);
+        const double nw = kHalfPi - 2.0 * atan(ts * pow((1.0 - con) / (1.0 + con), 0.5 * e));
+        const double d = fabs(nw - phi);
+        phi = nw;
+        if (d < 1e-14) break;
+    }
+    return phi;
+}
+
+// lon, lat in degrees -> x, y in metres; returns false where the projection is undefined (antipode, pole of a cylinder / cone)
 OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, double& y) {
     const double lam = adjlon(lon * kDeg - P.lam0);
     double phi = lat * kDeg;
+    if (P.kind == OD_PROJ_MERC) {
+        if (!(fabs(phi) < kHalfPi - 1e-10)) return false;
+        const double py = asinh(tan(phi)) - P.e * atanh(P.e * sin(phi));
+        x = P.a * (P.k0 * lam) + P.x0;
+        y = P.a * (P.k0 * py) + P.y0;
+        return true;
+    }
+    if (P.kind == OD_PROJ_LCC) {
+        double rho;
+        if (fabs(fabs(phi) - kHalfPi) < 1e-10) {
+            if (!(phi * P.n > 0.0)) return false;
+            rho = 0.0;
+        } else {
+            rho = P.es != 0.0 ? P.c * pow(proj_tsfn(phi, sin(phi), P.e), P.n) : P.c * pow(tan(kPio4 + 0.5 * phi), -P.n);
+        }
+        const double ln = lam * P.n;
+        x = P.a * (P.k0 * rho * sin(ln)) + P.x0;
+        y = P.a * (P.k0 * (P.rho0 - rho * cos(ln))) + P.y0;
+        return x == x && y == y;
+    }
     double sinphi, cosphi, sinlam, coslam;
     sincos(phi, &sinphi, &cosphi);
     sincos(lam, &sinlam, &coslam);
@@ -67,6 +110,30 @@ OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, 
 OD_HD void stere_inverse(const ProjStere& P, double x, double y, double& lon, double& lat) {
     x = (x - P.x0) * P.ra;
     y = (y - P.y0) * P.ra;
+    if (P.kind == OD_PROJ_MERC) {
+        const double ts = exp(-y / P.k0);
+        const double ph = P.es != 0.0 ? proj_phi2(ts, P.e) : kHalfPi - 2.0 * atan(ts);
+        lon = adjlon(x / P.k0 + P.lam0) * kRad2Deg;
+        lat = ph * kRad2Deg;
+        return;
+    }
+    if (P.kind == OD_PROJ_LCC) {
+        x = x / P.k0;
+        y = P.rho0 - y / P.k0;
+        double rho = hypot(x, y);
+        double ph, lm;
+        if (rho != 0.0) {
+            if (P.n < 0.0) { rho = -rho; x = -x; y = -y; }
+            ph = P.es != 0.0 ? proj_phi2(pow(rho / P.c, 1.0 / P.n), P.e) : 2.0 * atan(pow(P.c / rho, 1.0 / P.n)) - kHalfPi;
+            lm = atan2(x, y) / P.n;
+        } else {
+            lm = 0.0;
+            ph = P.n > 0.0 ? kHalfPi : -kHalfPi;
+        }
+        lon = adjlon(lm + P.lam0) * kRad2Deg;
+        lat = ph * kRad2Deg;
+        return;
+    }
     const double rh = hypot(x, y);
     const double c = 2.0 * atan(rh / P.akm1);
     double sinc, cosc;
@@ -121,15 +188,54 @@ OD_HD double inverse_azimuth_short(double lon1, double lat1, double lon2, double
 // od_proj_desc (include/odcuda.h) -> the per-launch constants; the aspect and scale constant are chosen as PROJ's stere
 // setup does for a sphere.  Returns 0, or 2 unknown projection, 3 bad radius / scale.
 static inline int proj_from_desc(const od_proj_desc* d, ProjStere* Pp) {
-    if (d->kind != OD_PROJ_STERE_SPHERE) return 2;
+    if (d->kind != OD_PROJ_STERE_SPHERE && d->kind != OD_PROJ_MERC && d->kind != OD_PROJ_LCC) return 2;
     if (!(d->a > 0.0) || !(d->k_0 > 0.0)) return 3;
     ProjStere& P = *Pp;
+    P.kind = d->kind;
     P.a = d->a;
     P.ra = 1.0 / d->a;
     P.phi0 = d->lat_0 * kDeg;
     P.lam0 = d->lon_0 * kDeg;
     P.x0 = d->x_0;
     P.y0 = d->y_0;
+    P.es = d->kind == OD_PROJ_STERE_SPHERE ? 0.0 : d->es;
+    if (!(P.es >= 0.0 && P.es < 1.0)) return 3;
+    P.e = sqrt(P.es);
+    P.k0 = d->k_0;
+    P.n = P.c = P.rho0 = 0.0;
+    P.mode = 0;
+    P.akm1 = P.sinX1 = P.cosX1 = 0.0;
+    if (d->kind == OD_PROJ_MERC) {                     // merc.cpp: +lat_ts replaces +k_0
+        if (d->has_lat_ts) {
+            const double phits = fabs(d->lat_ts * kDeg);
+            if (!(phits < kHalfPi)) return 3;
+            P.k0 = proj_msfn(sin(phits), cos(phits), P.es);
+        }
+        return 0;
+    }
+    if (d->kind == OD_PROJ_LCC) {                      // lcc.cpp setup
+        const double phi1 = d->lat_1 * kDeg, phi2 = d->lat_2 * kDeg;
+        if (fabs(phi1 + phi2) < 1e-10) return 3;
+        const double sinphi = sin(phi1), cosphi = cos(phi1);
+        const bool secant = fabs(phi1 - phi2) >= 1e-10;
+        double n = sinphi;
+        if (P.es != 0.0) {
+            const double m1 = proj_msfn(sinphi, cosphi, P.es), ml1 = proj_tsfn(phi1, sinphi, P.e);
+            if (secant) {
+                const double s2 = sin(phi2);
+                n = log(m1 / proj_msfn(s2, cos(phi2), P.es)) / log(ml1 / proj_tsfn(phi2, s2, P.e));
+            }
+            P.c = m1 * pow(ml1, -n) / n;
+            P.rho0 = fabs(fabs(P.phi0) - kHalfPi) < 1e-10 ? 0.0 : P.c * pow(proj_tsfn(P.phi0, sin(P.phi0), P.e), n);
+        } else {
+            if (secant) n = log(cosphi / cos(phi2)) / log(tan(kPio4 + 0.5 * phi2) / tan(kPio4 + 0.5 * phi1));
+            P.c = cosphi * pow(tan(kPio4 + 0.5 * phi1), n) / n;
+            P.rho0 = fabs(fabs(P.phi0) - kHalfPi) < 1e-10 ? 0.0 : P.c * pow(tan(kPio4 + 0.5 * P.phi0), -n);
+        }
+        P.n = n;
+        if (!(n == n) || n == 0.0) return 3;
+        return 0;
+    }
     const double t = fabs(P.phi0);
     if (fabs(t - kHalfPi) < 1e-10) P.mode = P.phi0 < 0 ? PROJ_S_POLE : PROJ_N_POLE;
     else P.mode = t > 1e-10 ? PROJ_OBLIQ : PROJ_EQUIT;

@@ -72,10 +72,10 @@ class StructuredReader:
 
     def __init__(self):
         p = str(getattr(self, 'proj4', '+proj=latlong'))
-        self.proj = None               # a projected plane (spherical +proj=stere): x / y axes and xmin .. ymax are metres in it
+        self.proj = None               # a projected plane (+proj=stere on a sphere, +proj=merc, +proj=lcc): x / y axes and xmin .. ymax are metres in it
         if not any(k in p for k in ('latlong', 'longlat', 'lonlat', 'latlon')):      # PROJ's aliases of the geographic CRS
-            from .projection import SphericalStereographic
-            self.proj = SphericalStereographic(p)      # raises for what the device code does not project
+            from .projection import make_projection
+            self.proj = make_projection(p)             # raises for what the device code does not project
             if self.subblocks:
                 raise NotImplementedError('sub-block readers on a projected plane are not on the GPU path')
             # modulate_longitude (variables.py:259-280): the longitude convention follows the corner longitudes

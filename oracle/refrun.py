@@ -71,8 +71,12 @@ def _fake_pyproj():
                 from oracle.proj_stere import Stere
                 self.impl = Stere(s)
                 self.crs = _CRS(False, s)
+            elif '+proj=merc' in s or '+proj=lcc' in s:
+                from oracle.proj_conformal import make
+                self.impl = make(s)
+                self.crs = _CRS(False, s)
             else:
-                raise NotImplementedError('fake pyproj supports latlong and spherical stere only: ' + s)
+                raise NotImplementedError('fake pyproj supports latlong, spherical stere, merc and lcc only: ' + s)
 
         def __call__(self, x, y, inverse=False):
             if self.impl is None:

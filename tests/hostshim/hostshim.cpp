@@ -278,6 +278,18 @@ int hs_analytic_interp(const od_analytic_desc* r, double t, int64_t n, const dou
     return 0;
 }
 
+// any od_proj_desc: forward (degrees -> metres; INFINITY where undefined) or inverse (metres -> degrees); returns proj_from_desc's status
+int hs_proj(const od_proj_desc* d, int inverse, int64_t n, const double* a, const double* b, double* oa, double* ob) {
+    ProjStere P;
+    const int rc = proj_from_desc(d, &P);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        if (inverse) stere_inverse(P, a[i], b[i], oa[i], ob[i]);
+        else if (!stere_forward(P, a[i], b[i], oa[i], ob[i])) oa[i] = ob[i] = INFINITY;
+    }
+    return 0;
+}
+
 void hs_stere(const od_analytic_desc* r, int inverse, int64_t n, const double* a, const double* b, double* oa, double* ob) {
     AnalyticReader R;
     if (analytic_from_desc(r, &R)) return;

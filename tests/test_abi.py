@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     # sizes the header implies (64-bit): guards against ctypes / C drift
     assert C.sizeof(_lib.TimeSample) == 24
     assert C.sizeof(_lib.HostIO) == 5 * 8 + 8 + 8
-    assert C.sizeof(_lib.GroupDesc) == 32 + 64 + 8 + (8 + 7 * 8) + 8
+    assert C.sizeof(_lib.GroupDesc) == 32 + 64 + 8 + (8 + 10 * 8) + 8
     assert C.sizeof(_lib.AdvectArgs) == 8 + 3 * 24 + 16 + 4 * 8 + 8 + 3 * 8 + 8 + 2 * 8 + 8 + 16 + 16 + 6 * 24
     assert C.sizeof(_lib.StepArgs) == C.sizeof(_lib.AdvectArgs) + 8 + 24 + 16 + 8 + 24 + 8 + 24 + 8 + 8
     assert C.sizeof(_lib.MixArgs) == 8 + 24 + 8 + 9 * 8 + 2 * 8 + 8 + 8 * 4 + 2 * 8 + 3 * 8 + 2 * 8 + 8 + 8 + 8
