@@ -104,9 +104,11 @@ int od_device_sm_count(od_ctx* ctx);
 #define OD_PROJ_STERE_SPHERE 1
 #define OD_PROJ_MERC 2
 #define OD_PROJ_LCC 3
+#define OD_PROJ_STERE_ELLPS 4
 typedef struct od_proj_desc {
     int32_t kind;                 /* OD_PROJ_STERE_SPHERE: +proj=stere on a sphere (+R, or +a with +e=0 / +es=0);
-                                     OD_PROJ_MERC: +proj=merc; OD_PROJ_LCC: +proj=lcc (+lat_1 [+lat_2]); sphere or ellipsoid (es) */
+                                     OD_PROJ_MERC: +proj=merc; OD_PROJ_LCC: +proj=lcc (+lat_1 [+lat_2]); sphere or ellipsoid (es);
+                                     OD_PROJ_STERE_ELLPS: +proj=stere on an ellipsoid (es > 0), all four aspects */
     int32_t has_lat_ts;           /* +lat_ts given (stere: polar aspects only; merc: the latitude of true scale replaces k_0) */
     double a;                     /* sphere radius / semi-major axis, m */
     double lat_0, lon_0, lat_ts;  /* degrees */

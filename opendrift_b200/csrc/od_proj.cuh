@@ -45,6 +45,11 @@ OD_HD double proj_msfn(double sinphi, double cosphi, double es) { return cosphi 
 OD_HD double proj_tsfn(double phi, double sinphi, double e) {
     return tan(0.5 * (kHalfPi - phi)) / pow((1.0 - e * sinphi) / (1.0 + e * sinphi), 0.5 * e);
 }
+// stere.cpp's ssfn_: tan(pi/4 + phi/2) ((1 - e sin phi) / (1 + e sin phi))^(e/2); chi = 2 atan(ssfn) - pi/2 is the conformal latitude
+OD_HD double proj_ssfn(double phi, double e) {
+    const double s = e * sin(phi);
+    return tan(0.5 * (kHalfPi + phi)) * pow((1.0 - s) / (1.0 + s), 0.5 * e);
+}
 OD_HD double proj_phi2(double ts, double e) {
     double phi = kHalfPi - 2.0 * atan(ts);
     for (int i = 0; i < 20; ++i) {
@@ -79,6 +84,30 @@ OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, 
         const double ln = lam * P.n;
         x = P.a * (P.k0 * rho * sin(ln)) + P.x0;
         y = P.a * (P.k0 * (P.rho0 - rho * cos(ln))) + P.y0;
+        return x == x && y == y;
+    }
+    if (P.kind == OD_PROJ_STERE_ELLPS) {               // Snyder 21-24 .. 21-40 through the conformal latitude (stere.cpp: e_forward)
+        double sl, cl;
+        sincos(lam, &sl, &cl);
+        double px, py;
+        if (P.mode == PROJ_OBLIQ || P.mode == PROJ_EQUIT) {
+            const double X = 2.0 * atan(proj_ssfn(phi, P.e)) - kHalfPi;
+            double sX, cX;
+            sincos(X, &sX, &cX);
+            const double d = P.mode == PROJ_OBLIQ ? P.cosX1 * (1.0 + P.sinX1 * sX + P.cosX1 * cX * cl) : 1.0 + cX * cl;
+            if (!(d > 1e-10)) return false;
+            const double A = P.akm1 / d;
+            px = A * cX * sl;
+            py = P.mode == PROJ_OBLIQ ? A * (P.cosX1 * sX - P.sinX1 * cX * cl) : A * sX;
+        } else {
+            if (P.mode == PROJ_S_POLE) { phi = -phi; cl = -cl; }
+            if (fabs(phi + kHalfPi) < 1e-8) return false;                  // the opposite pole
+            const double rho = P.akm1 * proj_tsfn(phi, sin(phi), P.e);
+            px = rho * sl;
+            py = -rho * cl;
+        }
+        x = P.a * px + P.x0;
+        y = P.a * py + P.y0;
         return x == x && y == y;
     }
     double sinphi, cosphi, sinlam, coslam;
@@ -130,6 +159,42 @@ OD_HD void stere_inverse(const ProjStere& P, double x, double y, double& lon, do
             lm = 0.0;
             ph = P.n > 0.0 ? kHalfPi : -kHalfPi;
         }
+        lon = adjlon(lm + P.lam0) * kRad2Deg;
+        lat = ph * kRad2Deg;
+        return;
+    }
+    if (P.kind == OD_PROJ_STERE_ELLPS) {               // stere.cpp: e_inverse (Snyder 21-36 .. 21-38, latitude by the iteration 3-4 / 7-9)
+        const double rho = hypot(x, y);
+        double tp, phi_l, xx, yy, halfpi, halfe;
+        if (P.mode == PROJ_OBLIQ || P.mode == PROJ_EQUIT) {
+            tp = 2.0 * atan2(rho * P.cosX1, P.akm1);
+            double st, ct;
+            sincos(tp, &st, &ct);
+            phi_l = rho == 0.0 ? asin(ct * P.sinX1) : asin(fmin(1.0, fmax(-1.0, ct * P.sinX1 + y * st * P.cosX1 / rho)));
+            tp = tan(0.5 * (kHalfPi + phi_l));
+            xx = x * st;
+            yy = rho * P.cosX1 * ct - y * P.sinX1 * st;
+            halfpi = kHalfPi;
+            halfe = 0.5 * P.e;
+        } else {
+            if (P.mode == PROJ_N_POLE) y = -y;
+            tp = -rho / P.akm1;
+            phi_l = kHalfPi - 2.0 * atan(-tp);
+            xx = x;
+            yy = y;
+            halfpi = -kHalfPi;
+            halfe = -0.5 * P.e;
+        }
+        double ph = phi_l;
+        for (int i = 0; i < 20; ++i) {
+            const double sp = P.e * sin(phi_l);
+            ph = 2.0 * atan(tp * pow((1.0 + sp) / (1.0 - sp), halfe)) - halfpi;
+            const double dd = fabs(phi_l - ph);
+            phi_l = ph;
+            if (dd < 1e-14) break;
+        }
+        if (P.mode == PROJ_S_POLE) ph = -ph;
+        const double lm = (xx == 0.0 && yy == 0.0) ? 0.0 : atan2(xx, yy);
         lon = adjlon(lm + P.lam0) * kRad2Deg;
         lat = ph * kRad2Deg;
         return;
@@ -188,7 +253,7 @@ OD_HD double inverse_azimuth_short(double lon1, double lat1, double lon2, double
 // od_proj_desc (include/odcuda.h) -> the per-launch constants; the aspect and scale constant are chosen as PROJ's stere
 // setup does for a sphere.  Returns 0, or 2 unknown projection, 3 bad radius / scale.
 static inline int proj_from_desc(const od_proj_desc* d, ProjStere* Pp) {
-    if (d->kind != OD_PROJ_STERE_SPHERE && d->kind != OD_PROJ_MERC && d->kind != OD_PROJ_LCC) return 2;
+    if (d->kind != OD_PROJ_STERE_SPHERE && d->kind != OD_PROJ_MERC && d->kind != OD_PROJ_LCC && d->kind != OD_PROJ_STERE_ELLPS) return 2;
     if (!(d->a > 0.0) || !(d->k_0 > 0.0)) return 3;
     ProjStere& P = *Pp;
     P.kind = d->kind;
@@ -198,7 +263,7 @@ static inline int proj_from_desc(const od_proj_desc* d, ProjStere* Pp) {
     P.lam0 = d->lon_0 * kDeg;
     P.x0 = d->x_0;
     P.y0 = d->y_0;
-    P.es = d->kind == OD_PROJ_STERE_SPHERE ? 0.0 : d->es;
+    P.es = d->kind == OD_PROJ_STERE_SPHERE ? 0.0 : d->es;           // (the sphere ignores the field)
     if (!(P.es >= 0.0 && P.es < 1.0)) return 3;
     P.e = sqrt(P.es);
     P.k0 = d->k_0;
@@ -239,6 +304,24 @@ static inline int proj_from_desc(const od_proj_desc* d, ProjStere* Pp) {
     const double t = fabs(P.phi0);
     if (fabs(t - kHalfPi) < 1e-10) P.mode = P.phi0 < 0 ? PROJ_S_POLE : PROJ_N_POLE;
     else P.mode = t > 1e-10 ? PROJ_OBLIQ : PROJ_EQUIT;
+    if (d->kind == OD_PROJ_STERE_ELLPS) {              // stere.cpp setup, ellipsoidal half
+        P.es = d->es;
+        if (!(P.es > 0.0 && P.es < 1.0)) return 3;
+        P.e = sqrt(P.es);
+        const double phits = fabs(d->has_lat_ts ? d->lat_ts * kDeg : kHalfPi);
+        if (P.mode == PROJ_N_POLE || P.mode == PROJ_S_POLE) {
+            if (fabs(phits - kHalfPi) < 1e-10) P.akm1 = 2.0 * d->k_0 / sqrt(pow(1.0 + P.e, 1.0 + P.e) * pow(1.0 - P.e, 1.0 - P.e));
+            else P.akm1 = proj_msfn(sin(phits), cos(phits), P.es) / proj_tsfn(phits, sin(phits), P.e);
+            P.sinX1 = P.cosX1 = 0.0;
+        } else {
+            const double sp = sin(P.phi0);
+            const double X = 2.0 * atan(proj_ssfn(P.phi0, P.e)) - kHalfPi;
+            P.akm1 = 2.0 * d->k_0 * cos(P.phi0) / sqrt(1.0 - P.es * sp * sp);
+            P.sinX1 = sin(X);
+            P.cosX1 = cos(X);
+        }
+        return 0;
+    }
     P.sinX1 = sin(P.phi0);
     P.cosX1 = cos(P.phi0);
     const double phits = fabs(d->has_lat_ts ? d->lat_ts * kDeg : kHalfPi);

@@ -4,8 +4,9 @@ lonlat2xy, opendrift/readers/basereader/variables.py:114-143, which wrap pyproj.
 the hot path runs on the device (csrc/od_analytic.cuh: stere_forward / stere_inverse); this module only parses the
 proj4 string into the library's od_proj_desc and mirrors the same closed forms in NumPy for those few host points.
 
-Supported: '+proj=stere' on a sphere ('+R=...' or '+a=... +e=0'), all four aspects (Snyder 1987, ch. 21); '+proj=merc' and
-'+proj=lcc' (one or two standard parallels) on a sphere or an ellipsoid (Snyder ch. 7 and 15; PROJ's merc.cpp / lcc.cpp).
+Supported: '+proj=stere' on a sphere ('+R=...' or '+a=... +e=0') or an ellipsoid, all four aspects (Snyder 1987, ch. 21);
+'+proj=merc' and '+proj=lcc' (one or two standard parallels) on a sphere or an ellipsoid (Snyder ch. 7 and 15; PROJ's merc.cpp /
+lcc.cpp).
 """
 import re
 
@@ -307,15 +308,104 @@ class LambertConformalConic(_Conformal):
         return np.where(rho != 0, lam, 0.0), np.where(rho != 0, phi, 0.5 * np.pi if self.n > 0 else -0.5 * np.pi)
 
 
+class StereographicEllipsoid(_Conformal):
+    """+proj=stere on an ellipsoid (Snyder eqs. 21-24 .. 21-40 through the conformal latitude; PROJ's stere.cpp, ellipsoidal half)."""
+    kind = _lib.OD_PROJ_STERE_ELLPS
+
+    def __init__(self, proj4):
+        super().__init__(proj4, 'stere')
+        p = self.p
+        self.has_lat_ts = 'lat_ts' in p
+        self.lat_ts = float(p.get('lat_ts', 90.0))
+        phits = abs(self.lat_ts) * _DEG if self.has_lat_ts else 0.5 * np.pi
+        phi0 = self.lat_0 * _DEG
+        t = abs(phi0)
+        if abs(t - 0.5 * np.pi) < 1e-10:
+            self.mode = 'S_POLE' if phi0 < 0 else 'N_POLE'
+        else:
+            self.mode = 'OBLIQ' if t > 1e-10 else 'EQUIT'
+        e = self.e
+        if self.mode in ('N_POLE', 'S_POLE'):
+            if abs(phits - 0.5 * np.pi) < 1e-10:
+                self.akm1 = 2.0 * self.k_0 / np.sqrt(np.power(1 + e, 1 + e) * np.power(1 - e, 1 - e))
+            else:
+                self.akm1 = float(self._msfn(np.sin(phits), np.cos(phits)) / self._tsfn(phits))
+            self.sinX1 = self.cosX1 = 0.0
+        else:
+            sp = np.sin(phi0)
+            X = 2.0 * np.arctan(self._ssfn(phi0)) - 0.5 * np.pi
+            self.akm1 = 2.0 * self.k_0 * np.cos(phi0) / np.sqrt(1.0 - self.es * sp * sp)
+            self.sinX1, self.cosX1 = float(np.sin(X)), float(np.cos(X))
+
+    def _ssfn(self, phi):
+        s = self.e * np.sin(phi)
+        return np.tan(0.5 * (0.5 * np.pi + phi)) * np.power((1.0 - s) / (1.0 + s), 0.5 * self.e)
+
+    def _fwd(self, lam, phi):
+        sl, cl = np.sin(lam), np.cos(lam)
+        if self.mode in ('OBLIQ', 'EQUIT'):
+            X = 2.0 * np.arctan(self._ssfn(phi)) - 0.5 * np.pi
+            sX, cX = np.sin(X), np.cos(X)
+            if self.mode == 'OBLIQ':
+                A = self.akm1 / (self.cosX1 * (1.0 + self.sinX1 * sX + self.cosX1 * cX * cl))
+                return A * cX * sl, A * (self.cosX1 * sX - self.sinX1 * cX * cl)
+            A = self.akm1 / (1.0 + cX * cl)
+            return A * cX * sl, A * sX
+        if self.mode == 'S_POLE':
+            phi, cl = -phi, -cl
+        rho = self.akm1 * self._tsfn(phi)
+        return rho * sl, -rho * cl
+
+    def _inv(self, x, y):
+        rho = np.hypot(x, y)
+        e = self.e
+        if self.mode in ('OBLIQ', 'EQUIT'):
+            tp = 2.0 * np.arctan2(rho * self.cosX1, self.akm1)
+            ct, st = np.cos(tp), np.sin(tp)
+            safe = np.where(rho != 0, rho, 1.0)
+            phi_l = np.where(rho == 0.0, np.arcsin(ct * self.sinX1), np.arcsin(np.clip(ct * self.sinX1 + y * st * self.cosX1 / safe, -1, 1)))
+            tp = np.tan(0.5 * (0.5 * np.pi + phi_l))
+            xx, yy = x * st, rho * self.cosX1 * ct - y * self.sinX1 * st
+            halfpi, halfe = 0.5 * np.pi, 0.5 * e
+        else:
+            if self.mode == 'N_POLE':
+                y = -y
+            tp = -rho / self.akm1
+            phi_l = 0.5 * np.pi - 2.0 * np.arctan(-tp)
+            xx, yy = x, y
+            halfpi, halfe = -0.5 * np.pi, -0.5 * e
+        phi = phi_l
+        for _ in range(20):
+            sp = e * np.sin(phi_l)
+            phi = 2.0 * np.arctan(tp * np.power((1.0 + sp) / (1.0 - sp), halfe)) - halfpi
+            d = np.max(np.abs(phi_l - phi)) if np.size(phi) else 0.0
+            phi_l = phi
+            if d < 1e-14:
+                break
+        if self.mode == 'S_POLE':
+            phi = -phi
+        return np.where((xx == 0.0) & (yy == 0.0), 0.0, np.arctan2(xx, yy)), phi
+
+
+def _is_sphere(proj4):
+    p = parse_proj4(proj4)
+    if 'R' in p:
+        return True
+    if any(k in p for k in ('ellps', 'datum', 'rf', 'f', 'b')):
+        return _ellipsoid(p, proj4)[1] == 0.0
+    es = float(p['e']) ** 2 if 'e' in p else float(p.get('es', 0.0))
+    return es == 0.0
+
+
 def make_projection(proj4):
     """The projection object of a reader's proj4 string (None for a geographic reader)."""
     if is_geographic(proj4):
         return None
     name = parse_proj4(proj4).get('proj')
     if name == 'stere':
-        return SphericalStereographic(proj4)
+        return SphericalStereographic(proj4) if _is_sphere(proj4) else StereographicEllipsoid(proj4)
     if name == 'merc':
         return Mercator(proj4)
     if name == 'lcc':
         return LambertConformalConic(proj4)
-    raise NotImplementedError('projected readers on the GPU path: +proj=stere (sphere), +proj=merc, +proj=lcc; got %s' % proj4)
+    raise NotImplementedError('projected readers on the GPU path: +proj=stere, +proj=merc, +proj=lcc; got %s' % proj4)

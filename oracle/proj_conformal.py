@@ -200,10 +200,100 @@ class Lcc(_Base):
         return np.where(rho != 0, lam, 0.0), np.where(rho != 0, phi, pole)
 
 
+class StereEllipsoid(_Base):
+    """Stereographic projection of the ELLIPSOID (Snyder eqs. 21-24 .. 21-40, inverse 21-15, 21-36 .. 21-38, 20-14 .. 20-16 and the
+    iteration 3-4 / 7-9), organised like the ellipsoidal half of PROJ's stere.cpp: conformal latitude chi through
+    ssfn(phi) = tan(pi/4 + phi/2) ((1 - e sin phi) / (1 + e sin phi))^(e/2); oblique / equatorial aspects with
+    akm1 = 2 k_0 cos(phi_0) / sqrt(1 - e^2 sin^2 phi_0); polar aspects with akm1 = 2 k_0 / sqrt((1+e)^(1+e) (1-e)^(1-e)), or, with a
+    latitude of true scale, akm1 = m(lat_ts) / t(lat_ts)."""
+
+    def __init__(self, proj4):
+        super().__init__(proj4, 'stere')
+        p = self.p
+        if self.es == 0.0:
+            raise NotImplementedError('sphere: oracle/proj_stere.py')
+        self.lat_0 = float(p.get('lat_0', 0.0))
+        self.has_lat_ts = 'lat_ts' in p
+        phits = abs(float(p['lat_ts'])) * _DEG if self.has_lat_ts else _HALFPI
+        phi0 = self.lat_0 * _DEG
+        self.phi0 = phi0
+        t = abs(phi0)
+        if abs(t - _HALFPI) < _EPS10:
+            self.mode = 'S_POLE' if phi0 < 0 else 'N_POLE'
+        else:
+            self.mode = 'OBLIQ' if t > _EPS10 else 'EQUIT'
+        e = self.e
+        if self.mode in ('N_POLE', 'S_POLE'):
+            if abs(phits - _HALFPI) < _EPS10:
+                self.akm1 = 2.0 * self.k_0 / np.sqrt(np.power(1 + e, 1 + e) * np.power(1 - e, 1 - e))
+            else:
+                sp = np.sin(phits)
+                self.akm1 = float(msfn(sp, np.cos(phits), self.es) / tsfn(phits, sp, e))
+            self.sinX1 = self.cosX1 = 0.0
+        else:
+            sp = np.sin(phi0)
+            X = 2.0 * np.arctan(self._ssfn(phi0)) - _HALFPI
+            self.akm1 = 2.0 * self.k_0 * np.cos(phi0) / np.sqrt(1.0 - self.es * sp * sp)
+            self.sinX1, self.cosX1 = float(np.sin(X)), float(np.cos(X))
+
+    def _ssfn(self, phi):
+        s = self.e * np.sin(phi)
+        return np.tan(0.5 * (_HALFPI + phi)) * np.power((1.0 - s) / (1.0 + s), 0.5 * self.e)
+
+    def _fwd(self, lam, phi):
+        sl, cl = np.sin(lam), np.cos(lam)
+        if self.mode in ('OBLIQ', 'EQUIT'):
+            X = 2.0 * np.arctan(self._ssfn(phi)) - _HALFPI
+            sX, cX = np.sin(X), np.cos(X)
+            if self.mode == 'OBLIQ':
+                A = self.akm1 / (self.cosX1 * (1.0 + self.sinX1 * sX + self.cosX1 * cX * cl))
+                return A * cX * sl, A * (self.cosX1 * sX - self.sinX1 * cX * cl)
+            A = self.akm1 / (1.0 + cX * cl)
+            return A * cX * sl, A * sX
+        if self.mode == 'S_POLE':
+            phi, cl = -phi, -cl
+        rho = self.akm1 * tsfn(phi, np.sin(phi), self.e)
+        return rho * sl, -rho * cl
+
+    def _inv(self, x, y):
+        rho = np.hypot(x, y)
+        e = self.e
+        if self.mode in ('OBLIQ', 'EQUIT'):
+            tp = 2.0 * np.arctan2(rho * self.cosX1, self.akm1)
+            ct, st = np.cos(tp), np.sin(tp)
+            safe = np.where(rho != 0, rho, 1.0)
+            phi_l = np.where(rho == 0.0, np.arcsin(ct * self.sinX1), np.arcsin(ct * self.sinX1 + y * st * self.cosX1 / safe))
+            tp = np.tan(0.5 * (_HALFPI + phi_l))
+            xx = x * st
+            yy = rho * self.cosX1 * ct - y * self.sinX1 * st
+            halfpi, halfe = _HALFPI, 0.5 * e
+        else:
+            if self.mode == 'N_POLE':
+                y = -y
+            tp = -rho / self.akm1
+            phi_l = _HALFPI - 2.0 * np.arctan(-tp)
+            xx, yy = x, y
+            halfpi, halfe = -_HALFPI, -0.5 * e
+        phi = phi_l
+        for _ in range(20):
+            sp = e * np.sin(phi_l)
+            phi = 2.0 * np.arctan(tp * np.power((1.0 + sp) / (1.0 - sp), halfe)) - halfpi
+            d = np.max(np.abs(phi_l - phi)) if np.size(phi) else 0.0
+            phi_l = phi
+            if d < 1e-14:
+                break
+        if self.mode == 'S_POLE':
+            phi = -phi
+        lam = np.where((xx == 0.0) & (yy == 0.0), 0.0, np.arctan2(xx, yy))
+        return lam, phi
+
+
 def make(proj4):
     p = parse_proj4(str(proj4))
     if p.get('proj') == 'merc':
         return Merc(proj4)
     if p.get('proj') == 'lcc':
         return Lcc(proj4)
+    if p.get('proj') == 'stere':
+        return StereEllipsoid(proj4)
     raise NotImplementedError(proj4)

@@ -68,8 +68,14 @@ def _fake_pyproj():
                 self.impl = None
                 self.crs = _CRS(True, s)
             elif '+proj=stere' in s:
-                from oracle.proj_stere import Stere
-                self.impl = Stere(s)
+                from oracle.proj_stere import Stere, parse_proj4
+                pp = parse_proj4(s)
+                sphere = 'R' in pp or not any(k in pp for k in ('ellps', 'datum', 'rf', 'f', 'b', 'es')) and float(pp.get('e', 0.0)) == 0.0
+                if sphere:
+                    self.impl = Stere(s)
+                else:
+                    from oracle.proj_conformal import StereEllipsoid
+                    self.impl = StereEllipsoid(s)
                 self.crs = _CRS(False, s)
             elif '+proj=merc' in s or '+proj=lcc' in s:
                 from oracle.proj_conformal import make

@@ -15,7 +15,12 @@ MERC_WGS84 = '+proj=merc +lon_0=0 +lat_ts=60 +ellps=WGS84 +units=m +no_defs'
 MERC_SPHERE = '+proj=merc +lon_0=10 +k_0=0.9 +x_0=100000 +y_0=-50000 +R=6371000 +units=m +no_defs'
 LCC_SPHERE = '+proj=lcc +lat_0=63.3 +lon_0=15 +lat_1=63.3 +lat_2=63.3 +R=6371000 +units=m +no_defs'           # (the MetCoOp / MEPS grid)
 LCC_WGS84 = '+proj=lcc +lat_1=52 +lat_2=68 +lat_0=60 +lon_0=8 +x_0=400000 +y_0=200000 +ellps=WGS84 +units=m +no_defs'
+STERE_WGS84_POLAR = '+proj=stere +lat_0=90 +lon_0=-10 +lat_ts=70 +x_0=1000000 +y_0=2500000 +ellps=WGS84 +units=m +no_defs'
+STERE_GRS80_OBLIQUE = '+proj=stere +lat_0=61 +lon_0=4.5 +k_0=0.9999 +ellps=GRS80 +units=m +no_defs'
 CASES = {
+    'stere_wgs84_polar_rk4_3d_w': dict(proj4=STERE_WGS84_POLAR, model='OceanDrift', readers=('cur3d',), steps=8, dt=600,
+                                       cfg={'drift:advection_scheme': 'runge-kutta4'}),
+    'stere_grs80_oblique_leeway': dict(proj4=STERE_GRS80_OBLIQUE, model='Leeway', readers=('cur2d', 'wind'), steps=6, dt=600, cfg={}),
     'merc_wgs84_rk4_3d_w': dict(proj4=MERC_WGS84, model='OceanDrift', readers=('cur3d',), steps=8, dt=600,
                                 cfg={'drift:advection_scheme': 'runge-kutta4'}),
     'lcc_sphere_rk2_wind': dict(proj4=LCC_SPHERE, model='OceanDrift', readers=('cur2d', 'wind'), steps=6, dt=900,

@@ -9,7 +9,7 @@ import pytest
 import common
 import projcases as pc
 from hostengine import HostEngine
-from test_oracle_proj_conformal import MERC, LCC
+from test_oracle_proj_conformal import MERC, LCC, STERE_E
 
 
 @pytest.fixture()
@@ -30,7 +30,7 @@ def test_projected_reader_case_equals_the_reference(case, host_engine):
     assert e < 5e-8 and dz <= (1e-9 if 'mixing' in case else 1e-5), (e, dz)
 
 
-@pytest.mark.parametrize('proj4', MERC + LCC)
+@pytest.mark.parametrize('proj4', MERC + LCC + STERE_E)
 def test_device_projection_equals_the_oracle(proj4):
     from opendrift_b200.readers.projection import make_projection
     from oracle.proj_conformal import make
@@ -41,6 +41,8 @@ def test_device_projection_equals_the_oracle(proj4):
     n = 20000
     lon = O.lon_0 + rng.uniform(-60, 60, n)
     lat = np.clip(getattr(O, 'lat_0', 0.0) + rng.uniform(-40, 40, n), -85, 85)
+    if abs(getattr(O, 'lat_0', 0.0)) == 90:
+        lat = np.sign(O.lat_0) * rng.uniform(35, 89.5, n)
     ox, oy = O.forward(lon, lat)
     px, py = P(lon, lat)
     assert np.array_equal(px, ox) and np.array_equal(py, oy)      # the product's host-side projection (seeding helper)
