@@ -593,6 +593,32 @@ def run_b200(args):
     barrier()
     e2e_ms = g0.elapsed_time(g1)
 
+    # the same call with PAGEABLE NumPy arrays -- what a caller who holds the reference's element arrays would pass; the driver
+    # stages pageable memory itself, so the copies neither overlap each other nor the kernel (reported beside the pinned number)
+    e2e_pageable = None
+    if rank == 0 and not os.environ.get('OD_BENCH_NO_PAGEABLE'):
+        try:
+            pa = [np.array(h_lon.numpy(), copy=True), np.array(h_lat.numpy(), copy=True), np.array(h_z.numpy(), copy=True)]
+            pb = [np.empty_like(a) for a in pa]
+            pbufs = [pa, pb]
+            tp = t_e2e
+            psteps = 3
+            for i in range(1 + psteps):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    w0 = time.perf_counter()
+                src, dst = pbufs[i % 2], pbufs[(i + 1) % 2]
+                eng.step_oceandrift_host(grp, 'runge-kutta4', tp, dt, src[0], src[1], src[2], dst[0], dst[1], dst[2], w_group=wgrp,
+                                         chunks=args.e2e_chunks)
+                tp += dt
+            torch.cuda.synchronize()
+            pms = (time.perf_counter() - w0) * 1e3 / psteps
+            e2e_pageable = {'value': n / (pms * 1e-3), 'unit': 'particle-steps/s', 'ms_per_step': pms, 'steps': psteps,
+                            'note': 'pageable NumPy lon / lat / z in and out (rank 0, wall clock around the blocking calls)'}
+            del pa, pb
+        except Exception as exc:
+            e2e_pageable = {'error': repr(exc)[:200]}
+
     # the link the end-to-end number lives on: this step's bytes (20 B in, 20 B out per particle) as two plain pinned
     # copies running concurrently on two streams
     pcie = None
@@ -699,7 +725,7 @@ def run_b200(args):
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': n * 20, 'd2h_bytes_per_step': n * 20,
                 'steps': e2e_steps, 'api': 'od_step_oceandrift_host through Engine.step_oceandrift_host (pinned host lon/lat/z in and out, %d-chunk '
                        'three-stream copy/compute pipeline inside the C-ABI call)' % args.e2e_chunks,
-                'pcie_probe': pcie},
+                'pcie_probe': pcie, 'pageable_numpy': e2e_pageable},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'kernel': 'step_spec_kernel<RK4, F64, EXTRAS=2> (current advection + vertical advection in one launch; csrc/od_spec.cuh)', 'kernel_ms': kernel_ms,

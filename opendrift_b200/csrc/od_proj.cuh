@@ -62,50 +62,149 @@ OD_HD double proj_phi2(double ts, double e) {
     return phi;
 }
 
+// The projections other than the spherical stereographic one run out of line: their code is compiled once per translation unit
+// instead of once per kernel instantiation (the general step kernels alone are 36), and the kernels that only ever meet
+// geographic or spherical-stereographic groups keep the size they had.  Arguments by value: no address of a kernel parameter.
+struct ProjOther {
+    int kind, mode;
+    double e, es, k0, n, c, rho0, akm1, sinX1, cosX1;
+};
+
+OD_HD ProjOther proj_other(const ProjStere& P) {
+    ProjOther q;
+    q.kind = P.kind; q.mode = P.mode; q.e = P.e; q.es = P.es; q.k0 = P.k0; q.n = P.n; q.c = P.c; q.rho0 = P.rho0;
+    q.akm1 = P.akm1; q.sinX1 = P.sinX1; q.cosX1 = P.cosX1;
+    return q;
+}
+
+#if defined(__CUDACC__)
+#define OD_PROJ_NOINLINE static __host__ __device__ __noinline__
+#else
+#define OD_PROJ_NOINLINE static
+#endif
+
+// lam (reduced, radians), phi (radians) -> x', y' on the unit sphere / ellipsoid (the caller applies a, x_0, y_0)
+OD_PROJ_NOINLINE bool proj_forward_other(ProjOther q, double lam, double phi, double* ox, double* oy) {
+    if (q.kind == OD_PROJ_MERC) {
+        if (!(fabs(phi) < kHalfPi - 1e-10)) return false;
+        const double py = asinh(tan(phi)) - q.e * atanh(q.e * sin(phi));
+        *ox = q.k0 * lam;
+        *oy = q.k0 * py;
+        return true;
+    }
+    if (q.kind == OD_PROJ_LCC) {
+        double rho;
+        if (fabs(fabs(phi) - kHalfPi) < 1e-10) {
+            if (!(phi * q.n > 0.0)) return false;
+            rho = 0.0;
+        } else {
+            rho = q.es != 0.0 ? q.c * pow(proj_tsfn(phi, sin(phi), q.e), q.n) : q.c * pow(tan(kPio4 + 0.5 * phi), -q.n);
+        }
+        const double ln = lam * q.n;
+        *ox = q.k0 * rho * sin(ln);
+        *oy = q.k0 * (q.rho0 - rho * cos(ln));
+        return true;
+    }
+    if (q.kind == OD_PROJ_STERE_ELLPS) {               // Snyder 21-24 .. 21-40 through the conformal latitude (stere.cpp: e_forward)
+        double sl, cl;
+        sincos(lam, &sl, &cl);
+        double px, py;
+        if (q.mode == PROJ_OBLIQ || q.mode == PROJ_EQUIT) {
+            const double X = 2.0 * atan(proj_ssfn(phi, q.e)) - kHalfPi;
+            double sX, cX;
+            sincos(X, &sX, &cX);
+            const double d = q.mode == PROJ_OBLIQ ? q.cosX1 * (1.0 + q.sinX1 * sX + q.cosX1 * cX * cl) : 1.0 + cX * cl;
+            if (!(d > 1e-10)) return false;
+            const double A = q.akm1 / d;
+            px = A * cX * sl;
+            py = q.mode == PROJ_OBLIQ ? A * (q.cosX1 * sX - q.sinX1 * cX * cl) : A * sX;
+        } else {
+            if (q.mode == PROJ_S_POLE) { phi = -phi; cl = -cl; }
+            if (fabs(phi + kHalfPi) < 1e-8) return false;                  // the opposite pole
+            const double rho = q.akm1 * proj_tsfn(phi, sin(phi), q.e);
+            px = rho * sl;
+            py = -rho * cl;
+        }
+        *ox = px;
+        *oy = py;
+        return true;
+    }
+    return false;
+}
+
+// x', y' -> lam (relative to lon_0, radians), phi (radians)
+OD_PROJ_NOINLINE void proj_inverse_other(ProjOther q, double x, double y, double* olam, double* ophi) {
+    if (q.kind == OD_PROJ_MERC) {
+        const double ts = exp(-y / q.k0);
+        const double ph = q.es != 0.0 ? proj_phi2(ts, q.e) : kHalfPi - 2.0 * atan(ts);
+        *olam = x / q.k0;
+        *ophi = ph;
+        return;
+    }
+    if (q.kind == OD_PROJ_LCC) {
+        x = x / q.k0;
+        y = q.rho0 - y / q.k0;
+        double rho = hypot(x, y);
+        double ph, lm;
+        if (rho != 0.0) {
+            if (q.n < 0.0) { rho = -rho; x = -x; y = -y; }
+            ph = q.es != 0.0 ? proj_phi2(pow(rho / q.c, 1.0 / q.n), q.e) : 2.0 * atan(pow(q.c / rho, 1.0 / q.n)) - kHalfPi;
+            lm = atan2(x, y) / q.n;
+        } else {
+            lm = 0.0;
+            ph = q.n > 0.0 ? kHalfPi : -kHalfPi;
+        }
+        *olam = lm;
+        *ophi = ph;
+        return;
+    }
+    if (q.kind == OD_PROJ_STERE_ELLPS) {               // stere.cpp: e_inverse (Snyder 21-36 .. 21-38, latitude by the iteration 3-4 / 7-9)
+        const double rho = hypot(x, y);
+        double tp, phi_l, xx, yy, halfpi, halfe;
+        if (q.mode == PROJ_OBLIQ || q.mode == PROJ_EQUIT) {
+            tp = 2.0 * atan2(rho * q.cosX1, q.akm1);
+            double st, ct;
+            sincos(tp, &st, &ct);
+            phi_l = rho == 0.0 ? asin(ct * q.sinX1) : asin(fmin(1.0, fmax(-1.0, ct * q.sinX1 + y * st * q.cosX1 / rho)));
+            tp = tan(0.5 * (kHalfPi + phi_l));
+            xx = x * st;
+            yy = rho * q.cosX1 * ct - y * q.sinX1 * st;
+            halfpi = kHalfPi;
+            halfe = 0.5 * q.e;
+        } else {
+            if (q.mode == PROJ_N_POLE) y = -y;
+            tp = -rho / q.akm1;
+            phi_l = kHalfPi - 2.0 * atan(-tp);
+            xx = x;
+            yy = y;
+            halfpi = -kHalfPi;
+            halfe = -0.5 * q.e;
+        }
+        double ph = phi_l;
+        for (int i = 0; i < 20; ++i) {
+            const double sp = q.e * sin(phi_l);
+            ph = 2.0 * atan(tp * pow((1.0 + sp) / (1.0 - sp), halfe)) - halfpi;
+            const double dd = fabs(phi_l - ph);
+            phi_l = ph;
+            if (dd < 1e-14) break;
+        }
+        if (q.mode == PROJ_S_POLE) ph = -ph;
+        const double lm = (xx == 0.0 && yy == 0.0) ? 0.0 : atan2(xx, yy);
+        *olam = lm;
+        *ophi = ph;
+        return;
+    }
+    *olam = 0.0;
+    *ophi = 0.0;
+}
+
 // lon, lat in degrees -> x, y in metres; returns false where the projection is undefined (antipode, pole of a cylinder / cone)
 OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, double& y) {
     const double lam = adjlon(lon * kDeg - P.lam0);
     double phi = lat * kDeg;
-    if (P.kind == OD_PROJ_MERC) {
-        if (!(fabs(phi) < kHalfPi - 1e-10)) return false;
-        const double py = asinh(tan(phi)) - P.e * atanh(P.e * sin(phi));
-        x = P.a * (P.k0 * lam) + P.x0;
-        y = P.a * (P.k0 * py) + P.y0;
-        return true;
-    }
-    if (P.kind == OD_PROJ_LCC) {
-        double rho;
-        if (fabs(fabs(phi) - kHalfPi) < 1e-10) {
-            if (!(phi * P.n > 0.0)) return false;
-            rho = 0.0;
-        } else {
-            rho = P.es != 0.0 ? P.c * pow(proj_tsfn(phi, sin(phi), P.e), P.n) : P.c * pow(tan(kPio4 + 0.5 * phi), -P.n);
-        }
-        const double ln = lam * P.n;
-        x = P.a * (P.k0 * rho * sin(ln)) + P.x0;
-        y = P.a * (P.k0 * (P.rho0 - rho * cos(ln))) + P.y0;
-        return x == x && y == y;
-    }
-    if (P.kind == OD_PROJ_STERE_ELLPS) {               // Snyder 21-24 .. 21-40 through the conformal latitude (stere.cpp: e_forward)
-        double sl, cl;
-        sincos(lam, &sl, &cl);
+    if (P.kind != OD_PROJ_STERE_SPHERE) {
         double px, py;
-        if (P.mode == PROJ_OBLIQ || P.mode == PROJ_EQUIT) {
-            const double X = 2.0 * atan(proj_ssfn(phi, P.e)) - kHalfPi;
-            double sX, cX;
-            sincos(X, &sX, &cX);
-            const double d = P.mode == PROJ_OBLIQ ? P.cosX1 * (1.0 + P.sinX1 * sX + P.cosX1 * cX * cl) : 1.0 + cX * cl;
-            if (!(d > 1e-10)) return false;
-            const double A = P.akm1 / d;
-            px = A * cX * sl;
-            py = P.mode == PROJ_OBLIQ ? A * (P.cosX1 * sX - P.sinX1 * cX * cl) : A * sX;
-        } else {
-            if (P.mode == PROJ_S_POLE) { phi = -phi; cl = -cl; }
-            if (fabs(phi + kHalfPi) < 1e-8) return false;                  // the opposite pole
-            const double rho = P.akm1 * proj_tsfn(phi, sin(phi), P.e);
-            px = rho * sl;
-            py = -rho * cl;
-        }
+        if (!proj_forward_other(proj_other(P), lam, phi, &px, &py)) return false;
         x = P.a * px + P.x0;
         y = P.a * py + P.y0;
         return x == x && y == y;
@@ -139,62 +238,9 @@ OD_HD bool stere_forward(const ProjStere& P, double lon, double lat, double& x, 
 OD_HD void stere_inverse(const ProjStere& P, double x, double y, double& lon, double& lat) {
     x = (x - P.x0) * P.ra;
     y = (y - P.y0) * P.ra;
-    if (P.kind == OD_PROJ_MERC) {
-        const double ts = exp(-y / P.k0);
-        const double ph = P.es != 0.0 ? proj_phi2(ts, P.e) : kHalfPi - 2.0 * atan(ts);
-        lon = adjlon(x / P.k0 + P.lam0) * kRad2Deg;
-        lat = ph * kRad2Deg;
-        return;
-    }
-    if (P.kind == OD_PROJ_LCC) {
-        x = x / P.k0;
-        y = P.rho0 - y / P.k0;
-        double rho = hypot(x, y);
-        double ph, lm;
-        if (rho != 0.0) {
-            if (P.n < 0.0) { rho = -rho; x = -x; y = -y; }
-            ph = P.es != 0.0 ? proj_phi2(pow(rho / P.c, 1.0 / P.n), P.e) : 2.0 * atan(pow(P.c / rho, 1.0 / P.n)) - kHalfPi;
-            lm = atan2(x, y) / P.n;
-        } else {
-            lm = 0.0;
-            ph = P.n > 0.0 ? kHalfPi : -kHalfPi;
-        }
-        lon = adjlon(lm + P.lam0) * kRad2Deg;
-        lat = ph * kRad2Deg;
-        return;
-    }
-    if (P.kind == OD_PROJ_STERE_ELLPS) {               // stere.cpp: e_inverse (Snyder 21-36 .. 21-38, latitude by the iteration 3-4 / 7-9)
-        const double rho = hypot(x, y);
-        double tp, phi_l, xx, yy, halfpi, halfe;
-        if (P.mode == PROJ_OBLIQ || P.mode == PROJ_EQUIT) {
-            tp = 2.0 * atan2(rho * P.cosX1, P.akm1);
-            double st, ct;
-            sincos(tp, &st, &ct);
-            phi_l = rho == 0.0 ? asin(ct * P.sinX1) : asin(fmin(1.0, fmax(-1.0, ct * P.sinX1 + y * st * P.cosX1 / rho)));
-            tp = tan(0.5 * (kHalfPi + phi_l));
-            xx = x * st;
-            yy = rho * P.cosX1 * ct - y * P.sinX1 * st;
-            halfpi = kHalfPi;
-            halfe = 0.5 * P.e;
-        } else {
-            if (P.mode == PROJ_N_POLE) y = -y;
-            tp = -rho / P.akm1;
-            phi_l = kHalfPi - 2.0 * atan(-tp);
-            xx = x;
-            yy = y;
-            halfpi = -kHalfPi;
-            halfe = -0.5 * P.e;
-        }
-        double ph = phi_l;
-        for (int i = 0; i < 20; ++i) {
-            const double sp = P.e * sin(phi_l);
-            ph = 2.0 * atan(tp * pow((1.0 + sp) / (1.0 - sp), halfe)) - halfpi;
-            const double dd = fabs(phi_l - ph);
-            phi_l = ph;
-            if (dd < 1e-14) break;
-        }
-        if (P.mode == PROJ_S_POLE) ph = -ph;
-        const double lm = (xx == 0.0 && yy == 0.0) ? 0.0 : atan2(xx, yy);
+    if (P.kind != OD_PROJ_STERE_SPHERE) {
+        double lm, ph;
+        proj_inverse_other(proj_other(P), x, y, &lm, &ph);
         lon = adjlon(lm + P.lam0) * kRad2Deg;
         lat = ph * kRad2Deg;
         return;

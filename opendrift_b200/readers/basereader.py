@@ -296,8 +296,8 @@ class StructuredReader:
         if isinstance(variables, str):
             variables = [variables]
         assert set(variables).issubset(self.variables), f'{variables} is not subset of {self.variables}'
-        if profiles is not None:
-            raise NotImplementedError('vertical profiles are served by the vertical-mixing kernel, not by this call')
+        if profiles is not None and isinstance(profiles, str):
+            profiles = [profiles]
         if not self.covers_time(time):
             raise OutsideTemporalCoverageError('%s is outside time coverage (%s - %s) of %s'
                                                % (time, self.start_time, self.end_time, self.name))
@@ -348,7 +348,26 @@ class StructuredReader:
                     if len(ind) != n:          # some positions are not covered: the reference pads into a float64 array (variables.py:841-846)
                         a = a.astype(np.float64)
                     env[nme] = np.ma.masked_invalid(a)
-        return env, None
+        env_profiles = None
+        if profiles:
+            # Vertical profiles (interpolation/structured.py:137-138, basereader/structured.py:365-384): for every requested variable
+            # the horizontally interpolated value of EVERY layer of the block, (nz, N), float64, lerped in time like the values --
+            # one sampling launch per layer at the layer's own depth (the vertical lerp then has weight 1 on that layer).  The run
+            # loop does not use this call (the mixing kernel walks the columns itself); it serves user code.
+            env_profiles = {}
+            for v in profiles:
+                g, c = self._groups[v]
+                if g.desc.nz <= 1:
+                    raise NotImplementedError('profiles of a 2-D variable (%s)' % v)
+                zl = np.asarray(g.z, dtype=np.float64)          # the levels as the reader gave them
+                env_profiles.setdefault('z', zl)
+                rows = []
+                for zk in zl:
+                    d_zk = eng.to_device(np.full(n, zk, dtype=np.float64))
+                    outs = eng.interp(g, time, d_lon, d_lat, d_zk, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None, out_f64=True)
+                    rows.append(outs[c].cpu().numpy())
+                env_profiles[v] = np.ma.masked_invalid(np.stack(rows))
+        return env, env_profiles
 
     def __repr__(self):
         return 'Reader: %s  [%s..%s] x [%s..%s], %s - %s, variables %s' % (

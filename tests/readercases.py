@@ -43,6 +43,12 @@ def evaluate(r3, r2):
             for v in variables:
                 a = np.ma.masked_invalid(env[v])
                 out['%s__%d__%s' % (name, ti, v)] = np.ma.filled(a, np.nan)
+    # vertical profiles (profiles=[...]): every layer of the block at the elements, lerped in time
+    for ti, t in enumerate(times):
+        env, prof = r3.get_variables_interpolated([common.CUR[0], common.CUR[1]], profiles=[common.CUR[0]], profiles_depth=50.0,
+                                                  time=t, lon=lon[:300], lat=lat[:300], z=z[:300])
+        out['prof__%d__z' % ti] = np.asarray(prof['z'], dtype=np.float64)
+        out['prof__%d__%s' % (ti, common.CUR[0])] = np.ma.filled(np.ma.masked_invalid(prof[common.CUR[0]]), np.nan)
     return out
 
 

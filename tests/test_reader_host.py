@@ -5,4 +5,4 @@ from hostengine import HostEngine
 
 
 def test_reader_output_equals_the_reference_reader_bit_for_bit():
-    assert rc.check(HostEngine()) == 21
+    assert rc.check(HostEngine()) == 27

@@ -19,4 +19,4 @@ def test_coastline_case_equals_the_reference(case):
 
 def test_reader_output_equals_the_reference_reader_bit_for_bit():
     from opendrift_b200.engine import default_engine
-    assert rc.check(default_engine()) == 21
+    assert rc.check(default_engine()) == 27
