@@ -128,7 +128,7 @@ def test_regular_grid_reader_contract():
         class P(reader_regular_grid.Reader):
             pass
         p = P.__new__(P)
-        p.proj4 = '+proj=lcc +lat_0=63 +lon_0=15 +lat_1=63 +lat_2=63 +R=6371000'       # (spherical +proj=stere is the projection on the GPU path)
+        p.proj4 = '+proj=tmerc +lat_0=0 +lon_0=15 +k_0=0.9996 +ellps=WGS84'            # (stere / merc / lcc are the projections on the GPU path)
         from opendrift_b200.readers.basereader import StructuredReader
         StructuredReader.__init__(p)
 
