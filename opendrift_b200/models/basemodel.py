@@ -952,6 +952,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         self.steps_calculation = 0
         self._maybe_deactivated = False
         self._setup_coastline()
+        if self.env.has_ensembles():
+            ok = getattr(self, '_ensemble_variables', ())
+            bad = [v for v in self.env.priority_list if self.env.has_ensembles([v]) and v not in ok]
+            if bad:
+                raise NotImplementedError('ensemble blocks for %s are not on the GPU path of %s' % (bad, type(self).__name__))
         out_every = int(round(ratio))
         n_total = len(self._release_rank)
         self._n_total = n_total

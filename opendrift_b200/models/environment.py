@@ -140,6 +140,17 @@ class Environment:
                 if any(self.readers[name].covers_time(t) for t in times)]
 
     # -- device face ---------------------------------------------------------------------------------
+    def has_ensembles(self, variables=None):
+        """True when a gridded reader in the priority lists (of `variables`, or of all) serves ensemble blocks."""
+        for v, names in self.priority_list.items():
+            if variables is not None and v not in variables:
+                continue
+            for nm in names:
+                r = self.readers.get(nm)
+                if r is not None and hasattr(r, 'has_ensembles') and r.has_ensembles(v):
+                    return True
+        return False
+
     def device_environment(self, variables, time, d_lon, d_lat, d_z, pos_f32=False):
         """dict var -> float32 device tensor, with constants / fallbacks applied, + missing mask tensor."""
         eng = self._engine
@@ -179,7 +190,8 @@ class Environment:
                     if br is not None:
                         t_s = g.times[br[0]]
                     nearest = v == 'land_binary_mask' and not getattr(r, 'always_valid', False)   # (a constant reader has one value everywhere)
-                outs = eng.interp(g, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, nearest=nearest)
+                need = None if res is None or v not in res else ~torch.isfinite(res[v])     # the elements this reader is asked for
+                outs = r.sample_groups(eng, v, t_s, d_lon, d_lat, d_z, need=need, pos_f32=pos_f32, raw=True, nearest=nearest)
                 if res is None:
                     res = {nm: outs[cc] for nm, (gg, cc) in r._groups.items() if gg is g}
                 else:                                   # next reader fills what is still missing

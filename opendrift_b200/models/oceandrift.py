@@ -29,6 +29,10 @@ class Lagrangian3DArray(LagrangianArray):
 class OceanDrift(OpenDriftSimulation):
     ElementType = Lagrangian3DArray
     _coast_previous_supported = True      # update() can run from the materialised start-of-step environment (helper recipe)
+    # variables whose reader may serve ensemble blocks (member = i % n_members): sampled through Reader.sample_groups by the helper recipes
+    _ensemble_variables = ('x_sea_water_velocity', 'y_sea_water_velocity', 'x_wind', 'y_wind', 'upward_sea_water_velocity',
+                           'sea_surface_wave_stokes_drift_x_velocity', 'sea_surface_wave_stokes_drift_y_velocity',
+                           'sea_surface_wave_significant_height', 'horizontal_diffusivity')
 
     # oceandrift.py:70-92
     required_variables = {
@@ -371,6 +375,8 @@ class OceanDrift(OpenDriftSimulation):
             return False
         if getattr(self, '_coast_moved', False):
             return False        # elements were moved back from land: they keep the environment sampled where they were (helper recipe)
+        if self.env.has_ensembles():
+            return False        # ensemble blocks: every sample goes through Reader.sample_groups (helper / staged recipes)
         if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
             # A reader for the sea floor: elements below it are lifted at the top of the loop, AFTER the step's environment was
             # sampled (basemodel/__init__.py:2238-2256) -- the first Runge-Kutta stage and w see the depth before the lift, the

@@ -38,6 +38,8 @@ class PhysicsMethods:
         rx, ry = self._current_readers(t)
         if len(rx) < 2 or len(rx) != len(ry) or any(a is not b for a, b in zip(rx, ry)) or len(rx) > 1 + _lib.OD_MAX_CHAIN:
             return None
+        if any(hasattr(r, 'has_ensembles') and r.has_ensembles() for r in rx):
+            return None
         groups = []
         for r in rx:
             if not hasattr(r, 'group_of'):
@@ -55,6 +57,8 @@ class PhysicsMethods:
         rx, ry = self._current_readers(t)
         if len(rx) > 1 or len(ry) > 1:
             return True
+        if any(hasattr(r, 'has_ensembles') and r.has_ensembles('x_sea_water_velocity') for r in rx):
+            return True                  # ensemble blocks: the member of an element depends on which elements a call serves (staged recipe)
         return len(rx) + len(ry) > 0 and (len(rx) != len(ry) or rx[0] is not ry[0])
 
     def _device_factor(self, factor, name):

@@ -240,46 +240,65 @@ class StructuredReader:
                 plan.append((a, b))
                 done |= {a, b}
         plan += [(v,) for v in self.variables if v not in done]
+        self._ens = {}
         for names in plan:
-            three_d = np.ndim(probe[names[0]]) == 3
+            # Ensemble blocks: get_variables() returns a LIST of arrays for a variable, one per ensemble member, and element i of
+            # a call is served by member i % n_members (ReaderBlock.interpolate, interpolation/structured.py:120-134).  Every member
+            # becomes a field group of its own; Reader.sample_groups() picks the member per element.  (Not filled towards the sea
+            # floor: 'Ensemble data currently not extrapolated towards seafloor', interpolation/structured.py:62-63.)
+            ens = isinstance(probe[names[0]], (list, tuple))
+            n_ens = len(probe[names[0]]) if ens else 1
+            first = probe[names[0]][0] if ens else probe[names[0]]
+            three_d = np.ndim(first) == 3
             z = np.asarray(probe['z'], dtype=np.float64) if three_d else None
-            cache = {}
-            self._block_caches.append(cache)
+            raw = {}                         # the reader's block of the time index in use, shared by the members
+            groups = []
+            for m in range(n_ens):
+                cache = {}
+                self._block_caches.append(cache)
+                if m == 0:
+                    self._block_caches.append(raw)
 
-            def supplier(ti, c, names=names, cache=cache):
-                if ti not in cache:
-                    cache.clear()
-                    blk = self._fetch_block(names, ti)
-                    arrs = []
-                    for nme in names:
-                        a = blk[nme]
-                        if hasattr(a, 'is_cuda'):           # already a device tensor: trusted, no host pass
+                def supplier(ti, c, names=names, cache=cache, raw=raw, m=m, ens=ens):
+                    if ti not in cache:
+                        cache.clear()
+                        if ti not in raw:
+                            raw.clear()
+                            raw[ti] = self._fetch_block(names, ti)
+                        blk = raw[ti]
+                        arrs = []
+                        for nme in names:
+                            a = blk[nme][m] if ens else blk[nme]
+                            if hasattr(a, 'is_cuda'):           # already a device tensor: trusted, no host pass
+                                arrs.append(a)
+                                continue
+                            a = check_variable_array(nme, a)
+                            if a.ndim == 3 and not ens:
+                                fill_nan_towards_seafloor(a)
                             arrs.append(a)
-                            continue
-                        a = check_variable_array(nme, a)
-                        if a.ndim == 3:
-                            fill_nan_towards_seafloor(a)
-                        arrs.append(a)
-                    cache[ti] = arrs
-                return cache[ti][c]
-            fb = [fallback.get(nme) for nme in names]
-            pk = {}
-            if self.proj is not None:       # the block's axes are metres in the reader's plane; vector pairs get rotated
-                pk = dict(proj=self.proj.desc(), lon_0to360=self._lon_0to360, rotate=len(names) == 2)
-            g = engine.add_group(x, y, z, len(names), self.times, supplier, fb, n_slots=n_slots, names=names, **pk)
+                        cache[ti] = arrs
+                    return cache[ti][c]
+                fb = [fallback.get(nme) for nme in names]
+                pk = {}
+                if self.proj is not None:       # the block's axes are metres in the reader's plane; vector pairs get rotated
+                    pk = dict(proj=self.proj.desc(), lon_0to360=self._lon_0to360, rotate=len(names) == 2)
+                groups.append(engine.add_group(x, y, z, len(names), self.times, supplier, fb, n_slots=n_slots, names=names, **pk))
             for c, nme in enumerate(names):
-                self._groups[nme] = (g, c)
+                self._groups[nme] = (groups[0], c)
+                if ens:
+                    self._ens[nme] = groups
 
     def unbind(self):
         """Release the device slabs of this reader."""
         eng = self._engine
         if eng is not None:
-            for g in {id(g): g for g, _ in self._groups.values()}.values():
+            allg = [g for g, _ in self._groups.values()] + [g for gs in getattr(self, '_ens', {}).values() for g in gs]
+            for g in {id(g): g for g in allg}.values():
                 try:
                     eng.free_group(g)
                 except Exception:
                     pass
-        self._engine, self._groups = None, {}
+        self._engine, self._groups, self._ens = None, {}, {}
 
     def __del__(self):
         try:
@@ -289,6 +308,36 @@ class StructuredReader:
 
     def group_of(self, variable):
         return self._groups[variable]
+
+    def has_ensembles(self, variable=None):
+        e = getattr(self, '_ens', {})
+        return bool(e) if variable is None else variable in e
+
+    def sample_groups(self, eng, v, t, d_lon, d_lat, d_z, need=None, **kw):
+        """eng.interp for the field group of variable v.  Ensemble readers: every member group is sampled and element i of the
+        positions THIS CALL SERVES -- those flagged in `need` (device bool tensor; None = all) that the reader covers -- takes
+        member i % n_members (ReaderBlock.interpolate is handed exactly those positions, interpolation/structured.py:120-134;
+        variables.py:709-858 passes the covered ones, environment.py:613-780 the still missing ones)."""
+        g, _ = self._groups[v]
+        members = getattr(self, '_ens', {}).get(v)
+        if not members:
+            return eng.interp(g, t, d_lon, d_lat, d_z, **kw)
+        torch = eng.torch
+        n = d_lon.numel()
+        ind, _, _ = self.covers_positions(d_lon.cpu().numpy(), d_lat.cpu().numpy())
+        served = torch.zeros(n, dtype=torch.bool, device=d_lon.device)
+        served[eng.to_device(np.asarray(ind, dtype=np.int64))] = True
+        if need is not None:
+            served &= need
+        member = (torch.cumsum(served.to(torch.int64), 0) - 1) % len(members)
+        outs = None
+        for m, gm in enumerate(members):
+            om = eng.interp(gm, t, d_lon, d_lat, d_z, **kw)
+            if outs is None:
+                outs = [torch.full_like(o, float('nan')) for o in om]
+            sel = served & (member == m)
+            outs = [torch.where(sel, o, acc) for o, acc in zip(om, outs)]
+        return outs
 
     # -- the reference's public entry point (variables.py:860-920) -----------------------------------
     def get_variables_interpolated(self, variables, profiles=None, profiles_depth=None, time=None,
@@ -340,8 +389,8 @@ class StructuredReader:
                 if br is not None:
                     t_s = g.times[br[0]]
                 nearest = v == 'land_binary_mask' and not getattr(self, 'always_valid', False)   # (a constant reader has one value everywhere)
-            outs = eng.interp(g, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None, out_f64=three_d,
-                              nearest=nearest)
+            outs = self.sample_groups(eng, v, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None,
+                                      out_f64=three_d, nearest=nearest)
             for nme, (gg, cc) in self._groups.items():
                 if gg is g and nme in variables:
                     a = outs[cc].cpu().numpy()
