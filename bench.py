@@ -596,7 +596,8 @@ def run_b200(args):
     # the same call with PAGEABLE NumPy arrays -- what a caller who holds the reference's element arrays would pass; the driver
     # stages pageable memory itself, so the copies neither overlap each other nor the kernel (reported beside the pinned number)
     e2e_pageable = None
-    if rank == 0 and not os.environ.get('OD_BENCH_NO_PAGEABLE'):
+    if world == 1 and not os.environ.get('OD_BENCH_NO_PAGEABLE'):      # (single process only: further steps mean further slab loads,
+                                                                          #  which are collectives in a distributed run)
         try:
             pa = [np.array(h_lon.numpy(), copy=True), np.array(h_lat.numpy(), copy=True), np.array(h_z.numpy(), copy=True)]
             pb = [np.empty_like(a) for a in pa]

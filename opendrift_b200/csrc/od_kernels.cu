@@ -325,7 +325,11 @@ extern "C" int od_group_fill_nan(od_ctx* ctx, int group, int slot, int comp, int
         int per_sm = 0, coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_nan_coop_kernel, 256, 0) == cudaSuccess && per_sm > 0)
-            ctx->coop_fill_blocks = per_sm * ctx->sm_count;
+            // (not the whole device: a cooperative grid starts only when ALL its blocks fit at once, and a collective's kernel may
+            //  be resident on the copy stream, spinning on a peer that is itself waiting to start this launch -- seen as stalls of
+            //  2-10 ms at slab changes on 2 and 4 GPUs; the grid is sized as if 16 SMs were taken: it then fits beside any
+            //  collective kernel -- NCCL uses at most 32 thread blocks -- and still fills the rest of the device)
+            ctx->coop_fill_blocks = per_sm * (ctx->sm_count > 32 ? ctx->sm_count - 16 : (ctx->sm_count > 1 ? ctx->sm_count / 2 : 1));
         else
             ctx->coop_fill_blocks = 0;
         cudaGetLastError();
