@@ -991,6 +991,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                 self._predraw_step_uncertainty()
                 # deactivate_outside -> interact_with_seafloor -> state_to_buffer -> increase_age_and_retire (:2249-2260)
                 col, only_deact = self._column_of_step(i)
+                pm = getattr(self, '_pending_missing_code', None)
+                if pm is not None:               # (Leeway with a coastline action: was the provisional 'missing_data' number used?)
+                    self._pending_missing_code = None
+                    if 'missing_data' not in self.status_categories and bool((self.elements.dev('status') == pm).any()):
+                        self.status_categories.append('missing_data')
                 if self._coast is not None:
                     # deactivate_outside -> interact_with_coastline -> interact_with_seafloor -> state_to_buffer -> ... (:2249-2260)
                     if self.env.priority_list.get('sea_floor_depth_below_sea_level'):

@@ -219,14 +219,23 @@ class Leeway(OpenDriftSimulation):
         d['jibe_probability'] = el.dev('jibe_probability')
         if d['jibe_probability'].dtype not in (torch.float32, torch.float64):
             d['jibe_probability'] = d['jibe_probability'].to(torch.float64)
-        if 'missing_data' not in self.status_categories:
-            self.status_categories.append('missing_data')
+        cats = self.status_categories
+        if 'missing_data' in cats:
+            missing_code = cats.index('missing_data')
+        elif getattr(self, '_coast', None) is None:
+            cats.append('missing_data')
+            missing_code = cats.index('missing_data')
+        else:
+            # a coastline action numbers its own categories ('stranded') when they first occur: 'missing_data' must not take a
+            # number before an element is really missing -- provisional number, named at the top of the next step if it was used
+            missing_code = len(cats)
+            self._pending_missing_code = missing_code
         eng.leeway_step(gw, gc, t, self.time_step,
                         el.dev('lon', torch.float64), el.dev('lat', torch.float64), d,
                         moving=el.dev('moving', torch.int32), status=el.dev('status', torch.int32),
                         ids=el.dev('ID', torch.int32), rand=rand, seed=self._seed, step_index=self.steps_calculation,
                         capsize_fraction=self.get_config('capsizing:leeway_fraction'),
-                        missing_code=self.status_categories.index('missing_data'), pos_f32=el.positions_f32, **caps_kw, **noise_kw)
+                        missing_code=missing_code, pos_f32=el.positions_f32, **caps_kw, **noise_kw)
         el.positions_f32 = False
         self._maybe_deactivated = True           # the kernel may have flagged elements with missing forcing
         self.stokes_drift()
