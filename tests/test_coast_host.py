@@ -57,3 +57,45 @@ def test_nearest_sampling_equals_the_reference_interpolator(host_engine):
         cov = (xx >= xg.min()) & (xx <= xg.max()) & (yy >= yg.min()) & (yy <= yg.max())
         want = np.where(cov, mask[yi, xi], np.nan)
         assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize('action,scheme,sign,out_every,release', [('stranding', 'runge-kutta4', -1, 1, 3), ('previous', 'euler', -1, 1, 0),
+                                                                  ('previous', 'runge-kutta4', 1, 3, 4), ('stranding', 'runge-kutta', 1, 3, 2)])
+def test_coastline_variants_against_the_live_reference(action, scheme, sign, out_every, release, host_engine):
+    """Backward runs, output every third step, release over several steps: the drop-in class beside the unmodified reference
+    (skipped where /root/reference is absent)."""
+    from datetime import timedelta
+    import common
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip('reference tree not present (GPU box)')
+    refrun.setup()
+    from opendrift.models.oceandrift import OceanDrift as RefOD
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_regular_grid
+
+    def run(Model, make, **kw):
+        fx = common.Fixture('rk4_3d')
+        mlon, mlat, mask = cc.mask_grid(fx, True)
+        u, v = (6 * fx.u).astype(np.float32), (6 * fx.v).astype(np.float32)
+        o = Model(loglevel=50, **kw)
+        o.add_reader(make(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, {common.CUR[0]: u, common.CUR[1]: v}, 'current'))
+        o.add_reader(make(mlon, mlat, None, fx.times, {'land_binary_mask': np.repeat(mask[None], len(fx.times), axis=0)}, 'mask'))
+        for k, val in {'general:use_auto_landmask': False, 'environment:constant:land_binary_mask': None,
+                       'general:coastline_approximation_precision': None, 'drift:vertical_advection': False, 'seed:ocean_only': False,
+                       'general:coastline_action': action, 'drift:advection_scheme': scheme}.items():
+            o.set_config(k, val)
+        if sign > 0:
+            t = fx.start if not release else [fx.start, fx.start + timedelta(seconds=release * fx.dt)]
+        else:
+            t = fx.times[-1] if not release else [fx.times[-1] - timedelta(seconds=release * fx.dt), fx.times[-1]]
+        o.seed_elements(lon=fx.lon0[:400], lat=fx.lat0[:400], z=fx.z0[:400], time=t)
+        o.run(steps=9, time_step=sign * fx.dt, time_step_output=sign * out_every * fx.dt)
+        return cc.summary(o)
+
+    r = run(RefOD, lambda lon, lat, z, t, f, name: refrun.make_grid_reader(lon, lat, z, t, f, name=name), logfile='/tmp/od_coast_live.log')
+    p = run(OceanDrift, lambda lon, lat, z, t, f, name: reader_regular_grid.Reader(lon, lat, z, t, f, name=name))
+    assert list(r['cats']) == list(p['cats']) and np.array_equal(r['id'], p['id'])
+    assert np.array_equal(r['d_id'], p['d_id']) and np.array_equal(r['d_status'], p['d_status']) and len(r['d_id']) > 0
+    assert max(common.max_err_deg(p['lon'], p['lat'], r['lon'], r['lat'])) < 5e-8
+    assert max(common.max_err_deg(p['d_lon'], p['d_lat'], r['d_lon'], r['d_lat'])) < 5e-8
