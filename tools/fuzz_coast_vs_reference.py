@@ -98,7 +98,10 @@ if __name__ == '__main__':
                 e = max(e, float(np.max(np.abs(p['z'] - r['z']))) * 1e-3)
             if ok and len(r['d_id']):
                 e = max(e, max(common.max_err_deg(p['d_lon'], p['d_lat'], r['d_lon'], r['d_lat'])))
-            tol = 1e-6 if c['leeway'] else 5e-8
+            # 'previous': an element that is moved back lands on the float32 value of its earlier position (the reference keeps the
+            # previous positions in float32); where the two float64 positions, 1e-10 deg apart, straddle a float32 rounding boundary
+            # the restored positions differ by one float32 ulp (2.4e-7 deg at these longitudes) -- seed 59
+            tol = 1e-6 if c['leeway'] else (5e-7 if 'previous' in (c['action'], c['floor']) else 5e-8)
             good = ok and e < tol
             bad += not good
             print(seed, 'OK ' if good else 'BAD', 'err %.1e' % e, 'active', len(r['id']), 'deact', len(r['d_id']), list(r['cats']), '' if good else (c, list(p['cats'])))
