@@ -135,6 +135,11 @@ def check(o, case):
     # non-reproducible last bit of NumPy's float32 arctan2 reaches 1e-7 deg over the ten steps; the
     # bar stays far below the 1e-6 deg of the north star
     tol = 1e-6 if case.startswith('leeway') else 5e-8          # (the north star's tolerance; measured 9.5e-8 on the host build)
+    # 'previous': an element that is moved back lands on the FLOAT32 value of its earlier position (the reference keeps previous
+    # positions in float32); two float64 positions 1e-10 deg apart can straddle a float32 rounding boundary, and the restored
+    # positions then differ by one float32 ulp, 2.4e-7 deg at these longitudes (tools/fuzz_coast_vs_reference.py, seed 59)
+    if 'previous' in case:
+        tol = 5e-7
     if len(got['id']):
         assert max(common.max_err_deg(got['lon'], got['lat'], g('lon'), g('lat'))) < tol
         assert np.max(np.abs(got['z'] - g('z'))) <= 1e-5
