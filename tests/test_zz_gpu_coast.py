@@ -9,7 +9,8 @@ import readercases as rc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('case', list(cc.CASES))
+# (the Leeway case was added after the round's GPU minutes were spent: it runs last, in tests/test_zzzz_gpu_leeway_coast.py)
+@pytest.mark.parametrize('case', [c for c in cc.CASES if not c.startswith('leeway')])
 def test_coastline_case_equals_the_reference(case):
     o = cc.run_product(case)
     n_act, n_deact, cats = cc.check(o, case)
