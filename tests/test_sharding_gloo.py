@@ -302,3 +302,51 @@ def test_two_rank_model_run_shards_elements_and_broadcasts_slabs():
         assert n_bcast > 0
         if rank != 0:
             assert foreign_reads == 0                                                  # forcing arrived by broadcast only
+
+
+def _coast_worker(rank, world, port, q, case):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, common.ROOT)
+    sys.path.insert(0, os.path.join(common.ROOT, 'tests'))
+    from hostengine import HostEngine
+    import coastcases as cc
+    import opendrift_b200.engine as E
+    import opendrift_b200.models.basemodel as B
+    eng = HostEngine()
+    E.default_engine = B.default_engine = lambda device=None: eng
+    o = cc.run_product(case)
+    s = cc.summary(o)
+    q.put((rank, o.shard, s['id'], s['lon'], s['lat'], s['d_id'], s['d_lon'], s['d_lat'], s['d_status'], [str(c) for c in s['cats']]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_run_with_coastline_interaction_equals_the_reference():
+    """Index shards under gloo with a land mask reader (read by rank 0, broadcast), 'stranding' and 'previous': the union of the
+    two ranks' elements is the reference's result -- survivors, deactivated elements and their status."""
+    import coastcases as cc
+    for case in ('stranding_rk4_3d_release', 'previous_rk4_3d'):
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_coast_worker, args=(r, 2, port, q, case)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+        for p in procs:
+            p.join(timeout=60)
+        ref = np.load(cc.GOLDEN)
+        g = lambda k: ref['%s__%s' % (case, k)]                      # noqa: E731
+        ids = np.concatenate([r[2] for r in res])
+        lon, lat = np.concatenate([r[3] for r in res]), np.concatenate([r[4] for r in res])
+        o = np.argsort(ids)
+        ro = np.argsort(g('id'))
+        assert np.array_equal(ids[o], g('id')[ro])
+        assert max(common.max_err_deg(lon[o], lat[o], g('lon')[ro], g('lat')[ro])) < 5e-7
+        d_ids = np.concatenate([r[5] for r in res])
+        do, dro = np.argsort(d_ids), np.argsort(g('d_id'))
+        assert np.array_equal(d_ids[do], g('d_id')[dro]) and len(d_ids) > 0
+        names = np.concatenate([np.array(r[9])[r[8]] for r in res])          # status NAMES (every rank numbers its own categories)
+        assert list(names[do]) == list(np.array([str(c) for c in g('cats')])[g('d_status')][dro])
+        assert all(r[1][:2] == sharding.shard_range(cc.N, r[0], 2) for r in res)
