@@ -1,7 +1,8 @@
 """ORACLE (test infrastructure, never the product path).
 
-CPU restatement, in NumPy float64, of two more map projections a reader's grid may lie on -- Mercator ('+proj=merc') and
-Lambert conformal conic ('+proj=lcc', one or two standard parallels) -- on a sphere or an ellipsoid, for the fake ``pyproj`` of
+CPU restatement, in NumPy float64, of three more map projections a reader's grid may lie on -- Mercator ('+proj=merc') and
+Lambert conformal conic ('+proj=lcc', one or two standard parallels) on a sphere or an ellipsoid, and the stereographic
+projection of the ELLIPSOID ('+proj=stere' with an ellipsoid; the sphere is oracle/proj_stere.py) -- for the fake ``pyproj`` of
 oracle/refrun.py: the reference hands every position to ``pyproj.Proj`` (BaseReader.lonlat2xy / xy2lonlat,
 readers/basereader/variables.py:114-143) and rotates vector components through ``Transformer`` + ``Geod.inv``
 (rotate_vectors, variables.py:59-109).
@@ -13,8 +14,8 @@ eqs. 15-1 .. 15-5 (sphere), 15-7 .. 15-11 with 14-15 and 15-9 (ellipsoid), inver
 lcc.cpp organise them (k_0 from +lat_ts for Mercator; n, c (= F), rho_0 for the cone; lam = lon - lon_0 reduced to [-pi, pi];
 x = a k_0 x' + x_0), with PROJ's helper functions msfn (m of 14-15), tsfn (t of 15-9) and phi2 (7-9).
 
-Pinning: PARITY UNPINNED against a PROJ binary.  tests/test_oracle_proj.py checks it against the closed forms evaluated with
-mpmath at 40 digits, and round trips.
+Pinning: PARITY UNPINNED against a PROJ binary.  tests/test_oracle_proj_conformal.py checks it against the closed forms (Snyder's
+equations written independently with mpmath at 40 digits: 7-7, 15-7 .. 15-10, 21-27, 21-33 / 21-34), and round trips.
 """
 import numpy as np
 
