@@ -389,8 +389,10 @@ class StructuredReader:
                 if br is not None:
                     t_s = g.times[br[0]]
                 nearest = v == 'land_binary_mask' and not getattr(self, 'always_valid', False)   # (a constant reader has one value everywhere)
+            # (a rotated vector pair is float64 also for 2-D blocks: rotate_vectors multiplies by float64 sines and cosines)
+            rotated = self.proj is not None and rotate_to_proj is not None and len(names) == 2
             outs = self.sample_groups(eng, v, t_s, d_lon, d_lat, d_z, pos_f32=pos_f32, raw=True, rotate=rotate_to_proj is not None,
-                                      out_f64=three_d, nearest=nearest)
+                                      out_f64=three_d or rotated, nearest=nearest)
             for nme, (gg, cc) in self._groups.items():
                 if gg is g and nme in variables:
                     a = outs[cc].cpu().numpy()
