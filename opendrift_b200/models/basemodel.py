@@ -608,6 +608,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if n_str + n_seed + n_miss > 0:
             self._maybe_deactivated = True
 
+    def report_missing_variables(self):
+        """:2501-2515 -- elements without forcing leave as 'missing_data' at the top of the loop.  Nothing to do here: the variables
+        of the recipes in this class have fallback values, and a land mask without one is reported by interact_with_coastline.
+        Models whose forcing has no fallback (Leeway) override this."""
+
     def update_previous_state(self):
         """:642-669 for lon / lat (the element properties the reference stores when a coastline action may move elements back)."""
         if not getattr(self, '_store_previous', False) or self.num_elements_active() == 0:
@@ -996,6 +1001,7 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                     self._pending_missing_code = None
                     if 'missing_data' not in self.status_categories and bool((self.elements.dev('status') == pm).any()):
                         self.status_categories.append('missing_data')
+                self.report_missing_variables()                # (:2249, before deactivate_outside)
                 if self._coast is not None:
                     # deactivate_outside -> interact_with_coastline -> interact_with_seafloor -> state_to_buffer -> ... (:2249-2260)
                     if self.env.priority_list.get('sea_floor_depth_below_sea_level'):

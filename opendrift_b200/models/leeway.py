@@ -175,6 +175,29 @@ class Leeway(OpenDriftSimulation):
             if substr is None or substr.lower() in (p['Description'] + p['OBJKEY']).lower():
                 print('%i %s %s' % (i, p['OBJKEY'], p['Description']))
 
+    def report_missing_variables(self):
+        """basemodel/__init__.py:2249, 2501-2515: elements whose wind or current is missing leave as 'missing_data' at the top of the
+        loop -- before update() draws np.random.random(n) for the jibing (and the capsizing draws), so n and with it the legacy
+        generator's stream are the reference's from the step on which an element leaves the readers' coverage.  With the
+        reference's draws (gpu:rng = numpy) the two vector pairs are therefore sampled here as well (two launches); the device
+        generator is keyed by element ID and does not depend on n: there the step launch flags the elements itself and they leave
+        one output step later."""
+        self._missing_reported = False
+        if type(self).update is not Leeway.update or self.get_config('gpu:rng') != 'numpy' or self.num_elements_active() == 0:
+            return
+        eng, el, torch = self.engine, self.elements, self.engine.torch
+        lon, lat = el.dev('lon', torch.float64), el.dev('lat', torch.float64)
+        missing = None
+        for xname, yname in (('x_wind', 'y_wind'), ('x_sea_water_velocity', 'y_sea_water_velocity')):
+            if self.env.reader_for(xname, self.time) is None:
+                continue                                       # constants / fallback values: never missing
+            for a in eng.interp(self._pair_group(xname, yname, self.time), self.time, lon, lat, pos_f32=el.positions_f32):
+                m = ~torch.isfinite(a)
+                missing = m if missing is None else (missing | m)
+        self._missing_reported = True
+        if missing is not None:
+            self.deactivate_elements(missing, reason='missing_data')
+
     def update(self):
         """leeway.py:430-494 as one launch."""
         eng, el, torch = self.engine, self.elements, self.engine.torch
@@ -222,12 +245,13 @@ class Leeway(OpenDriftSimulation):
         cats = self.status_categories
         if 'missing_data' in cats:
             missing_code = cats.index('missing_data')
-        elif getattr(self, '_coast', None) is None:
+        elif getattr(self, '_coast', None) is None and not getattr(self, '_missing_reported', False):
             cats.append('missing_data')
             missing_code = cats.index('missing_data')
         else:
             # a coastline action numbers its own categories ('stranded') when they first occur: 'missing_data' must not take a
             # number before an element is really missing -- provisional number, named at the top of the next step if it was used
+            # (likewise when report_missing_variables has already taken out the elements without forcing: nothing is left to flag)
             missing_code = len(cats)
             self._pending_missing_code = missing_code
         eng.leeway_step(gw, gc, t, self.time_step,
