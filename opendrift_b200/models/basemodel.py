@@ -608,10 +608,25 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if n_str + n_seed + n_miss > 0:
             self._maybe_deactivated = True
 
+    def _variables_that_may_miss(self):
+        """Variables a reader provides and for which neither a constant nor a fallback value is configured
+        (`environment:fallback:<variable>` = None): outside the readers' coverage they are missing."""
+        return [v for v in getattr(self, '_env_variables', ())
+                if self.env.priority_list.get(v) and self.env.constant(v) is None and self.env.fallback(v) is None
+                and not (v == 'land_binary_mask' and getattr(self, '_coast', None) is not None)]    # (interact_with_coastline reports it)
+
     def report_missing_variables(self):
-        """:2501-2515 -- elements without forcing leave as 'missing_data' at the top of the loop.  Nothing to do here: the variables
-        of the recipes in this class have fallback values, and a land mask without one is reported by interact_with_coastline.
-        Models whose forcing has no fallback (Leeway) override this."""
+        """:2249, 2501-2515 -- elements for which a variable without fallback value is missing (outside the readers' coverage, no data
+        there, or a position that an earlier Runge-Kutta stage without forcing has left undefined) leave as 'missing_data' at the
+        top of the loop.  Costs nothing with the default configuration (every variable of the stock recipes has a fallback value);
+        otherwise those variables are sampled here, before deactivate_outside as in the reference."""
+        may_miss = self._variables_that_may_miss()
+        if not may_miss or self.num_elements_active() == 0:
+            return
+        el, torch = self.elements, self.engine.torch
+        _, missing = self.env.device_environment(may_miss, self.time, el.dev('lon', torch.float64), el.dev('lat', torch.float64),
+                                                 self._z_truncated(), pos_f32=el.positions_f32)
+        self.deactivate_elements(missing, reason='missing_data')
 
     def update_previous_state(self):
         """:642-669 for lon / lat (the element properties the reference stores when a coastline action may move elements back)."""
@@ -1048,6 +1063,11 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         lo, hi, ao, ai = float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max())
         # (NaN compares False with everything: test for the valid range, not for the invalid one)
         if not (lo >= -180 and hi <= 360 and ao >= -90 and ai <= 90):
+            if self._variables_that_may_miss() and not (lo < -180 or hi > 360 or ao < -90 or ai > 90):
+                # Undefined positions are the reference's own outcome when a variable has no fallback value: a Runge-Kutta stage
+                # outside the readers' coverage gives an undefined velocity, the element is taken out as 'missing_data' at the top of
+                # the next step (the reference's check compares minima and maxima, which NaN passes, :4661-4669)
+                return
             raise ValueError('Invalid new coordinates')
 
     def _restore_id_order(self):
