@@ -626,7 +626,26 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         el, torch = self.elements, self.engine.torch
         _, missing = self.env.device_environment(may_miss, self.time, el.dev('lon', torch.float64), el.dev('lat', torch.float64),
                                                  self._z_truncated(), pos_f32=el.positions_f32)
+        self._deactivate_missing(missing)
+
+    def _deactivate_missing(self, missing):
+        """deactivate_elements(missing, 'missing_data') as the first of the step's deactivations.  The reference's deactivate_outside
+        that follows names its category as soon as ANY element lies beyond a drift:deactivate_*_of limit (:1774-1781), also when
+        all of them have just been labelled 'missing_data' and keep that label; the housekeeping launch only looks at active
+        elements, so that case is numbered here."""
+        torch = self.engine.torch
         self.deactivate_elements(missing, reason='missing_data')
+        if self.validity_domain is not None and 'outside' not in self.status_categories and bool(missing.any()):
+            W, E, S, N = self.validity_domain
+            lon, lat = self.elements.dev('lon', torch.float64), self.elements.dev('lat', torch.float64)
+            if E is not None and E > 180 and bool((lon < 0).any()):
+                lon = torch.where(lon < 0, lon + 360, lon)          # (:2359-2373)
+            out = torch.zeros_like(missing)
+            for lim, cmp_ in ((W, lambda a: lon < a), (E, lambda a: lon > a), (S, lambda a: lat < a), (N, lambda a: lat > a)):
+                if lim is not None:
+                    out |= cmp_(lim)
+            if bool((out & missing).any()):
+                self.status_categories.append('outside')
 
     def update_previous_state(self):
         """:642-669 for lon / lat (the element properties the reference stores when a coastline action may move elements back)."""

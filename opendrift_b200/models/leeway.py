@@ -196,7 +196,7 @@ class Leeway(OpenDriftSimulation):
                 missing = m if missing is None else (missing | m)
         self._missing_reported = True
         if missing is not None:
-            self.deactivate_elements(missing, reason='missing_data')
+            self._deactivate_missing(missing)
 
     def update(self):
         """leeway.py:430-494 as one launch."""

@@ -21,6 +21,8 @@ CASES = {
     'rk4_2d': ('rk4_2d', dict(NONE_CUR, **{'drift:advection_scheme': 'runge-kutta4'}), 0, 0.6, None),
     'rk2_diffusion_release': ('rk4_2d', dict(NONE_CUR, **{'drift:advection_scheme': 'runge-kutta', 'environment:constant:horizontal_diffusivity': 10.0}), 4, 0.6, None),
     'rk4_3d_w': ('rk4_3d', dict(NONE_CUR, **{'drift:advection_scheme': 'runge-kutta4', 'drift:vertical_advection': True}), 3, 0.62, None),
+    # a drift:deactivate_east_of limit just inside the edge of the coverage: elements can be beyond it and without data on the same step
+    'east_limit_rk2': ('rk4_2d', dict(NONE_CUR, **{'drift:advection_scheme': 'runge-kutta', 'drift:deactivate_east_of': 3.147}), 0, 0.6, None),
     'wind_leaves_euler': ('rk4_2d', dict(NONE_WIND, **{'drift:advection_scheme': 'euler'}), 0, 1.0, 0.55),
     'wind_and_current_rk4': ('rk4_2d', dict(NONE_WIND, **dict(NONE_CUR, **{'drift:advection_scheme': 'runge-kutta4', 'drift:current_uncertainty': 0.05})), 3, 0.7, 0.6),
 }
