@@ -140,6 +140,16 @@ class Environment:
                 if any(self.readers[name].covers_time(t) for t in times)]
 
     # -- device face ---------------------------------------------------------------------------------
+    def has_host_readers(self, variables=None):
+        """True when a reader in the priority lists (of `variables`, or of all) computes its values on the host
+        (readers/continuous.py): such a reader is sampled through device_sample(), never inside a fused launch."""
+        for v, names in self.priority_list.items():
+            if variables is not None and v not in variables:
+                continue
+            if any(getattr(self.readers.get(nm), 'host_callback', False) for nm in names):
+                return True
+        return False
+
     def has_ensembles(self, variables=None):
         """True when a gridded reader in the priority lists (of `variables`, or of all) serves ensemble blocks."""
         for v, names in self.priority_list.items():
@@ -169,7 +179,8 @@ class Environment:
             for name in self.priority_list.get(v, []):
                 r = self.readers[name]
                 if r.covers_time(time) and hasattr(r, 'device_sample'):      # analytical reader (no field group)
-                    smp = r.device_sample(eng, time, d_lon, d_lat, pos_f32)
+                    smp = r.device_sample(eng, time, d_lon, d_lat, pos_f32, d_z=d_z) if getattr(r, 'host_callback', False) \
+                        else r.device_sample(eng, time, d_lon, d_lat, pos_f32)
                     if res is None:
                         res = dict(smp)
                     else:

@@ -377,6 +377,8 @@ class OceanDrift(OpenDriftSimulation):
             return False        # elements were moved back from land: they keep the environment sampled where they were (helper recipe)
         if self.env.has_ensembles():
             return False        # ensemble blocks: every sample goes through Reader.sample_groups (helper / staged recipes)
+        if self.env.has_host_readers():
+            return False        # a reader that computes its values on the host (readers/continuous.py): helper / staged recipes
         if self.env.priority_list.get('sea_floor_depth_below_sea_level'):
             # A reader for the sea floor: elements below it are lifted at the top of the loop, AFTER the step's environment was
             # sampled (basemodel/__init__.py:2238-2256) -- the first Runge-Kutta stage and w see the depth before the lift, the

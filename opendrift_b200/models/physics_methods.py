@@ -57,6 +57,8 @@ class PhysicsMethods:
         rx, ry = self._current_readers(t)
         if len(rx) > 1 or len(ry) > 1:
             return True
+        if any(getattr(r, 'host_callback', False) for r in rx + ry):
+            return True                  # values computed on the host (readers/continuous.py): stage by stage through device_sample()
         if any(hasattr(r, 'has_ensembles') and r.has_ensembles('x_sea_water_velocity') for r in rx):
             return True                  # ensemble blocks: the member of an element depends on which elements a call serves (staged recipe)
         return len(rx) + len(ry) > 0 and (len(rx) != len(ry) or rx[0] is not ry[0])
