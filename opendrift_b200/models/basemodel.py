@@ -487,6 +487,15 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
         if self.get_config('general:seafloor_action') == 'previous' and self.env.priority_list.get('sea_floor_depth_below_sea_level'):
             self._alloc_previous()
         action = self.get_config('general:coastline_action')
+        if action == 'none' and self.env.priority_list.get('land_binary_mask') \
+                and self._config['general:coastline_action'].get('value') == self._config['general:coastline_action'].get('default') \
+                and not getattr(self, '_coast_default_warned', False):
+            # The reference's default is 'stranding' (against the GSHHG landmask, which is not on this path); the default here is
+            # 'none'.  A script that adds a land_binary_mask reader and leaves the action alone would strand under the reference.
+            self._coast_default_warned = True
+            logger.warning("a reader provides land_binary_mask but general:coastline_action is 'none' (the default of the GPU classes; the "
+                           "reference's default is 'stranding'): set general:coastline_action = 'stranding' and "
+                           "general:coastline_approximation_precision = None to strand elements on that mask")
         if action == 'none' or 'land_binary_mask' not in self.required_variables:
             return
         if self.env.constant('land_binary_mask') is not None and not self.env.priority_list.get('land_binary_mask'):
