@@ -1,4 +1,4 @@
-"""ContinuousReader subclasses (the reference's extension point for analytical readers, basereader/continuous.py: `get_variables`
+"""reader_constant_2d (static arrays on a grid) and ContinuousReader subclasses (the reference's extension point for analytical readers, basereader/continuous.py: `get_variables`
 returns exact values at the positions it is given) -- reader_oscillating and a user-written reader, the same scripts on the
 reference's classes and on the product's.  Expected results from the UNMODIFIED reference: tests/golden/cont_ref.npz, written by
 `python tests/contcases.py` in the build container."""
@@ -81,6 +81,54 @@ def run_product(case, **model_kw):
                     reader_oscillating, ContinuousReader, **model_kw)
 
 
+# reader_constant_2d (static 2-D arrays): the current AND the land mask of a run -> (scheme, coastline action)
+C2D_CASES = {'constant_2d_stranding_euler': ('euler', 'stranding'), 'constant_2d_previous_rk4': ('runge-kutta4', 'previous')}
+
+
+def run_c2d(case, Model, constant_2d, **model_kw):
+    import coastcases
+    scheme, action = C2D_CASES[case]
+    fx = common.Fixture('rk4_2d')
+    mlon, mlat, mask = coastcases.mask_grid(fx, True)
+    o = Model(loglevel=50, **model_kw)
+    o.add_reader(constant_2d.Reader(fx.grid_lon.astype(np.float64), fx.grid_lat.astype(np.float64),
+                                    {common.CUR[0]: 5 * fx.u[1], common.CUR[1]: 5 * fx.v[1]}))
+    o.add_reader(constant_2d.Reader(mlon, mlat, {'land_binary_mask': mask}))
+    for key, val in {'general:use_auto_landmask': False, 'general:coastline_action': action, 'general:coastline_approximation_precision': None,
+                     'drift:advection_scheme': scheme, 'seed:ocean_only': False, 'drift:vertical_advection': False}.items():
+        o.set_config(key, val)
+    np.random.seed(3)
+    o.seed_elements(lon=fx.lon0[:300], lat=fx.lat0[:300], time=[fx.start, fx.start + timedelta(seconds=1800)])
+    o.run(steps=8, time_step=fx.dt, time_step_output=fx.dt)
+    return o
+
+
+def run_c2d_product(case, **model_kw):
+    from opendrift_b200.models.oceandrift import OceanDrift
+    from opendrift_b200.readers import reader_constant_2d
+    return run_c2d(case, OceanDrift, reader_constant_2d, **model_kw)
+
+
+def summary_c2d(o):
+    out = summary(o)
+    de = o.elements_deactivated
+    out.update({'d_id': np.asarray(de.ID, dtype=np.int64), 'd_status': np.asarray(de.status, dtype=np.int64),
+                'd_lon': np.asarray(de.lon, dtype=np.float64), 'd_lat': np.asarray(de.lat, dtype=np.float64),
+                'cats': np.array(list(o.status_categories))})
+    return out
+
+
+def check_c2d(o, case):
+    ref = np.load(GOLDEN)
+    got = summary_c2d(o)
+    g = lambda k: ref['%s__%s' % (case, k)]                      # noqa: E731
+    assert list(got['cats']) == list(g('cats'))
+    assert np.array_equal(got['id'], g('id')) and np.array_equal(got['d_id'], g('d_id')) and np.array_equal(got['d_status'], g('d_status'))
+    assert max(common.max_err_deg(got['lon'], got['lat'], g('lon'), g('lat'))) < 5e-8
+    assert max(common.max_err_deg(got['d_lon'], got['d_lat'], g('d_lon'), g('d_lat'))) < 5e-7      # ('previous': float32 positions, coastcases.py)
+    return len(got['id']), len(got['d_id'])
+
+
 def reader_queries(oscillating, ContinuousBase):
     """get_variables_interpolated of the two reader kinds at a handful of positions and times."""
     fx = common.Fixture('rk4_2d')
@@ -131,6 +179,12 @@ if __name__ == '__main__':
         for k, v in summary(ro).items():
             out['%s__%s' % (case, k)] = v
         print(case, 'active', ro.num_elements_active(), 'lon', float(np.min(ro.elements.lon)), float(np.max(ro.elements.lon)))
+    from opendrift.readers import reader_constant_2d as ref_c2d
+    for case in C2D_CASES:
+        ro = run_c2d(case, RefOD, ref_c2d, logfile='/tmp/od_cont.log')
+        for k, v in summary_c2d(ro).items():
+            out['%s__%s' % (case, k)] = v
+        print(case, 'active', ro.num_elements_active(), 'deactivated', ro.num_elements_deactivated(), list(ro.status_categories))
     for k, v in reader_queries(ref_osc, RefCont).items():
         out['query__' + k] = v
     np.savez_compressed(GOLDEN, **out)

@@ -16,6 +16,13 @@ def test_continuous_readers_equal_the_reference(case):
     cc.check(o, case)
 
 
+@pytest.mark.parametrize('case', list(cc.C2D_CASES))
+def test_constant_2d_reader_equals_the_reference(case):
+    o = cc.run_c2d_product(case, engine=HostEngine())
+    n_act, n_deact = cc.check_c2d(o, case)
+    assert n_deact >= 20
+
+
 def test_reader_queries_equal_the_reference():
     from opendrift_b200.readers import reader_oscillating
     from opendrift_b200.readers.continuous import ContinuousReader

@@ -12,3 +12,9 @@ pytestmark = pytest.mark.gpu
 def test_continuous_readers_equal_the_reference(case):
     o = cc.run_product(case)
     print(case, cc.check(o, case))
+
+
+@pytest.mark.parametrize('case', list(cc.C2D_CASES))
+def test_constant_2d_reader_equals_the_reference(case):
+    o = cc.run_c2d_product(case)
+    print(case, cc.check_c2d(o, case))
