@@ -242,4 +242,53 @@ class Environment:
         env = np.zeros(n, dtype=[(v, np.float32) for v in variables])
         for v in variables:
             env[v] = d_env[v].cpu().numpy()
-        return env.view(np.recarray), None, d_missing.cpu().numpy()
+        env_profiles = None
+        if profiles:
+            if profiles_depth is None:
+                profiles_depth = np.abs(np.asarray(z)).max()       # (:552-553)
+            if trunc is not None:
+                profiles_depth = np.minimum(profiles_depth, trunc)
+            env_profiles = self._host_profiles(list(profiles), profiles_depth, time, lon, lat, zz, env)
+        return env.view(np.recarray), env_profiles, d_missing.cpu().numpy()
+
+    def _host_profiles(self, profiles, profiles_depth, time, lon, lat, z, env):
+        """The `profiles` part of get_environment (:627-640, 697-724, 793-822) for callers outside the step kernels (the vertical
+        mixing launch reads the field column itself): per variable the layers of the first reader that provides it, down to the
+        first level below profiles_depth; fallback values where that reader has nothing; `[value, value]` at `z = [0, -depth]` for
+        a constant or a variable no reader provides.  Several readers filling one another's gaps layer by layer are refused."""
+        from ..errors import NotCoveredError
+        n = len(lon)
+        out = {}
+        for var in profiles:
+            fb = self.fallback(var)
+            readers = [self.readers[nm] for nm in self.priority_list.get(var, []) if self.readers[nm].covers_time(time)] \
+                if self.constant(var) is None else []
+            got = None
+            for r in readers:
+                try:
+                    _, prof = r.get_variables_interpolated([var], profiles=[var], profiles_depth=profiles_depth, time=time, lon=lon, lat=lat, z=z)
+                except NotCoveredError:
+                    continue
+                if got is not None:
+                    raise NotImplementedError('profiles of %s from several readers that cover parts of the elements are not on the GPU path' % var)
+                a = np.ma.masked_invalid(np.ma.atleast_2d(prof[var]))
+                if np.ma.getmaskarray(a).any() and len(readers) > 1:
+                    raise NotImplementedError('profiles of %s from several readers that cover parts of the elements are not on the GPU path' % var)
+                got = (np.asarray(prof['z']), a)
+            if got is None:
+                zs = np.array([0, -profiles_depth])
+                val = env[var] if (var in env.dtype.names and (self.constant(var) is not None or readers)) else (np.nan if fb is None else fb)
+                a = np.ma.masked_invalid(np.ma.array([val * np.ones(n), val * np.ones(n)]))
+                got = (zs, a)
+            zs, a = got
+            if 'z' in out and (len(out['z']) != len(zs) or not np.allclose(out['z'], zs)):
+                raise NotImplementedError('profiles on different vertical levels (%s) are not on the GPU path' % var)
+            out['z'] = zs
+            data = np.array(np.ma.getdata(a), dtype=np.float64, copy=True)
+            # (:699-718: the first reader's profile is stored and then written onto itself through float32, all layers but the last)
+            data[:-1] = data[:-1].astype(np.float32)
+            mask = np.ma.getmaskarray(a)
+            if mask.any():
+                data[mask] = np.nan if fb is None else fb
+            out[var] = data
+        return out
