@@ -31,6 +31,22 @@ class Configurable:
         levels = list(level) if isinstance(level, (list, tuple)) else [level]
         return {k: v for k, v in self._config.items() if k.startswith(prefix) and v['level'] in levels}
 
+    def list_configspec(self, prefix=''):
+        """config.py:34-52 -- one printed line per setting: name, value, type, range, start of the description."""
+        for c, i in self._config.items():
+            if not c.startswith(prefix):
+                continue
+            val = i.get('value')
+            if i['type'] in ('bool',):
+                rang = ''
+            elif i['type'] == 'str':
+                rang = 'min length %s, max length %s' % (i['min_length'], i['max_length'])
+            elif i['type'] in ('float', 'int'):
+                rang = 'min: %s, max: %s [%s]' % (i['min'], i['max'], i.get('units'))
+            else:
+                rang = i['enum']
+            print('%-35s [%s] %-5s %s %s...' % (c, val, i['type'], rang, i['description'][0:20]))
+
     def list_config(self, prefix=''):
         lines = ['%s [%s]' % (k, v['value']) for k, v in self._config.items() if k.startswith(prefix)]
         logger.info('\n'.join(lines))

@@ -1269,6 +1269,42 @@ class OpenDriftSimulation(PhysicsMethods, Configurable):
                 self.engine.order_after_copies()
                 self._hist_other = None
 
+    # -- small services model subclasses written for the reference call from update() -----------------------------------------
+    def timer_start(self, category):
+        """timer.py:26-34 (Timeable): wall-clock time per named category, e.g. 'main loop:updating elements:vertical mixing'.
+        The launches are asynchronous: a category holds the time its host code took, not the time of the kernels it started."""
+        from datetime import datetime as _dt
+        self.__dict__.setdefault('timing', {}).setdefault(category, timedelta(0))
+        self.__dict__.setdefault('timers', {})[category] = _dt.now()
+
+    def timer_end(self, category):
+        from datetime import datetime as _dt
+        t0 = self.__dict__.setdefault('timers', {}).get(category)
+        if t0 is not None:
+            self.__dict__.setdefault('timing', {})[category] = self.__dict__['timing'].get(category, timedelta(0)) + (_dt.now() - t0)
+        self.timers[category] = None
+
+    def performance(self):
+        """basemodel/__init__.py:809-836: the categories of timer_start / timer_end, indented by their ':' levels."""
+        out = '--------------------\nPerformance:\n'
+        for category, t in self.__dict__.get('timing', {}).items():
+            parts = category.split(':')
+            out += '%s%7.1f %s\n' % ('  ' * (len(parts) - 1), t.total_seconds(), parts[-1].replace('<colon>', ':'))
+        return out + '--------------------\n'
+
+    def store_message(self, message):
+        """:4736-4740"""
+        self.__dict__.setdefault('messages', []).append(message)
+
+    def get_messages(self):
+        return ''.join('%s\n' % m for m in self.__dict__.get('messages', []))
+
+    def water_column_stretching(self):
+        """oceandrift.py:299-313: a no-op unless drift:water_column_stretching is on -- which needs the previous sea surface height and
+        is refused when the run starts; here so that an update() written for the reference can call it."""
+        if 'drift:water_column_stretching' in self._config and self.get_config('drift:water_column_stretching'):
+            raise NotImplementedError('drift:water_column_stretching = True is not on the GPU path')
+
     def get_lonlats(self):
         return np.array(self.history['lon']).T, np.array(self.history['lat']).T
 

@@ -460,3 +460,28 @@ def test_projected_reader_interpolation_with_and_without_rotation(host_engine):
     # clockwise by (lon - 10) degrees
     assert np.abs(turn - (-(lon - 10.0))).max() < 0.2 or np.abs(turn - (lon - 10.0)).max() < 0.2
     assert np.abs(turn).max() > 1.0
+
+
+def test_services_a_reference_style_update_calls(host_engine):
+    """timer_start / timer_end (timer.py:26-34), store_message (:4736-4740), water_column_stretching (oceandrift.py:299-313) and
+    list_configspec (config.py:34-52): an update() written for the reference calls them; they exist with the reference's meaning."""
+    from datetime import datetime
+    from opendrift_b200.models.oceandrift import OceanDrift
+
+    class Model(OceanDrift):
+        def update(self):
+            self.timer_start('main loop:updating elements:my physics')
+            self.water_column_stretching()
+            self.advect_ocean_current()
+            self.timer_end('main loop:updating elements:my physics')
+            self.store_message('step %d' % self.steps_calculation)
+
+    o = Model(loglevel=50)
+    o.set_config('environment:constant:x_sea_water_velocity', 1)
+    o.set_config('environment:constant:land_binary_mask', 0)
+    o.seed_elements(lon=3, lat=60, time=datetime(2024, 1, 1))
+    o.run(steps=2)
+    assert abs(float(o.elements.lon[0]) - 3.129) < 1e-3
+    assert 'my physics' in o.performance() and o.timing['main loop:updating elements:my physics'].total_seconds() >= 0
+    assert o.get_messages() == 'step 0\nstep 1\n'
+    o.list_configspec('drift:advection')
