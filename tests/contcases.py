@@ -25,6 +25,8 @@ def user_reader_class(Base):
             super().__init__()
 
         def get_variables(self, variables, time=None, x=None, y=None, z=None):
+            variables, time, x, y, z, outside = self.check_arguments(variables, time, x, y, z)     # (as the reference's readers do)
+            assert len(outside) == 0
             s = (time - common.syn.T0).total_seconds()
             x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
             depth = np.exp(np.asarray(z, dtype=np.float64) / 40.0)
