@@ -57,6 +57,39 @@ def fill_nan_towards_seafloor(a):
     return a
 
 
+def check_arguments(self, variables, time, x, y, z):
+    """variables.py:321-390 -- what reader classes written for the reference call first thing in get_variables: the variable
+    list, the time (the reader's first when None), x / y as arrays, and the indices of positions outside the reader's domain;
+    raises for unknown variables, times outside the coverage, and when every position is outside."""
+    from ..errors import VariableNotCoveredError, OutsideTemporalCoverageError, OutsideSpatialCoverageError
+    if time is None:
+        time = self.start_time
+    if isinstance(variables, str):
+        variables = [variables]
+    no_positions = x is None or y is None        # (a whole-grid request of this package: nothing to check in space)
+    if not no_positions:
+        x, y = np.atleast_1d(x), np.atleast_1d(y)
+    if z is not None:
+        z = np.asarray(z)
+    for v in variables:
+        if v not in self.variables:
+            raise VariableNotCoveredError('Variable not available: ' + v + '\nAvailable parameters are: ' + str(self.variables))
+    if self.start_time is not None and time < self.start_time and self.always_valid is False:
+        raise OutsideTemporalCoverageError('Requested time (%s) is before first available time (%s) of %s' % (time, self.start_time, self.name))
+    if self.end_time is not None and time > self.end_time and self.always_valid is False:
+        raise OutsideTemporalCoverageError('Requested time (%s) is after last available time (%s) of %s' % (time, self.end_time, self.name))
+    if no_positions:
+        return variables, time, x, y, z, np.zeros(0, dtype=np.int64)
+    bad = ~np.isfinite(x + y) | (y < self.ymin) | (y > self.ymax)
+    if not self.global_coverage():
+        bad |= (x < self.xmin) | (x > self.xmax)
+    outside = np.where(bad)[0]
+    if np.size(outside) == np.size(x):
+        raise OutsideSpatialCoverageError('Argcheck: all %s particles (%.2f-%.2fE, %.2f-%.2fN) are outside domain of %s'
+                                          % (np.size(x), x.min(), x.max(), y.min(), y.max(), self.name))
+    return variables, time, x, y, z, outside
+
+
 class StructuredReader:
     """Regular lon/lat(/z) grid reader whose interpolation runs on the GPU."""
 
@@ -141,6 +174,9 @@ class StructuredReader:
         else:
             ind = np.where((x >= self.xmin) & (x <= self.xmax) & (y >= self.ymin) & (y <= self.ymax))[0]
         return ind, x[ind], y[ind]
+
+    def check_arguments(self, variables, time, x, y, z):
+        return check_arguments(self, variables, time, x, y, z)
 
     def nearest_time(self, time):
         from ..engine import bracket
@@ -357,9 +393,13 @@ class StructuredReader:
         lon_in, lat_in = np.atleast_1d(lon), np.atleast_1d(lat)
         n = len(lon_in)
         pos_f32 = lon_in.dtype == np.float32 and lat_in.dtype == np.float32
-        ind, _, _ = self.covers_positions(lon_in, lat_in)
+        ind, xc, yc = self.covers_positions(lon_in, lat_in)
         if len(ind) == 0:
             raise OutsideSpatialCoverageError('All %s particles are outside domain of %s' % (n, self.name))
+        if self.subblocks:
+            # the block around the positions this call is about (structured.py:275-318 asks its reader for exactly that); a model
+            # run has done this for the elements' bounding box already (_cover_elements_with_blocks) and the window then holds
+            self.ensure_window((float(np.min(xc)), float(np.max(xc)), float(np.min(yc)), float(np.max(yc))), 0.0)
         # (the depths keep their dtype: the reference clips and interpolates a float64 z in float64, interpolators.py:174-197)
         if z is None:
             zz = np.zeros(n, dtype=np.float32)

@@ -56,32 +56,8 @@ class ContinuousReader:
         return ind, x[ind], y[ind]
 
     def check_arguments(self, variables, time, x, y, z):
-        """variables.py:321-390 -- what reader classes written for the reference call first thing in get_variables: the variable
-        list, the time (the reader's first when None), x / y as arrays, and the indices of positions outside the reader's domain;
-        raises for unknown variables, times outside the coverage, and when every position is outside."""
-        from ..errors import VariableNotCoveredError, OutsideTemporalCoverageError
-        if time is None:
-            time = self.start_time
-        if isinstance(variables, str):
-            variables = [variables]
-        x, y = np.atleast_1d(x), np.atleast_1d(y)
-        if z is not None:
-            z = np.asarray(z)
-        for v in variables:
-            if v not in self.variables:
-                raise VariableNotCoveredError('Variable not available: ' + v + '\nAvailable parameters are: ' + str(self.variables))
-        if self.start_time is not None and time < self.start_time and self.always_valid is False:
-            raise OutsideTemporalCoverageError('Requested time (%s) is before first available time (%s) of %s' % (time, self.start_time, self.name))
-        if self.end_time is not None and time > self.end_time and self.always_valid is False:
-            raise OutsideTemporalCoverageError('Requested time (%s) is after last available time (%s) of %s' % (time, self.end_time, self.name))
-        bad = ~np.isfinite(x + y) | (y < self.ymin) | (y > self.ymax)
-        if not self.global_coverage():
-            bad |= (x < self.xmin) | (x > self.xmax)
-        outside = np.where(bad)[0]
-        if np.size(outside) == np.size(x):
-            raise OutsideSpatialCoverageError('Argcheck: all %s particles (%.2f-%.2fE, %.2f-%.2fN) are outside domain of %s'
-                                              % (np.size(x), x.min(), x.max(), y.min(), y.max(), self.name))
-        return variables, time, x, y, z, outside
+        from .basereader import check_arguments
+        return check_arguments(self, variables, time, x, y, z)
 
     # -- device binding ----------------------------------------------------------------------------------------
     def bind(self, engine, fallback=None):

@@ -42,3 +42,49 @@ def test_projected_reader_output_beside_the_live_reference():
                     assert np.array_equal(x, y, equal_nan=True)
                 else:
                     assert np.nanmax(np.abs(x - y)) < 1e-9
+
+
+def test_check_arguments_as_reference_style_readers_call_it():
+    """variables.py:321-390: get_variables of the reference's gridded readers starts with check_arguments and nearest_time
+    (reader_netCDF_CF_generic.py:408-412); a reader written that way runs unchanged on the product's base class, with whole-grid
+    and with sub-block requests, and gives what the plain reader gives."""
+    import numpy as np
+    import pytest
+    import common
+    from opendrift_b200.readers import reader_regular_grid
+    from opendrift_b200.errors import VariableNotCoveredError, OutsideTemporalCoverageError, OutsideSpatialCoverageError
+    from datetime import timedelta
+    fx = common.Fixture('rk4_2d')
+    calls = []
+
+    class Checked(reader_regular_grid.Reader):
+        def get_variables(self, requested_variables, time=None, x=None, y=None, z=None):
+            requested_variables, time, x, y, z, outside = self.check_arguments(requested_variables, time, x, y, z)
+            nearest, *_rest = self.nearest_time(time)
+            calls.append((x is None, len(outside)))
+            return super().get_variables(requested_variables, nearest, x, y, z)
+
+    fields = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
+    t = fx.times[1] + timedelta(seconds=700)
+    lon, lat = fx.lon0[:200].astype(np.float64), fx.lat0[:200].astype(np.float64)
+    ref = {}
+    for cls, sub in ((reader_regular_grid.Reader, False), (reader_regular_grid.Reader, True), (Checked, False), (Checked, True)):
+        r = cls(fx.grid_lon, fx.grid_lat, None, fx.times, fields, name='r', subblocks=sub)
+        r.buffer = 3                     # (cells around the requested positions, as set_buffer_size would set it)
+        r.bind(HostEngine())
+        env, _ = r.get_variables_interpolated(list(fields), time=t, lon=lon, lat=lat, z=np.zeros(200))
+        got = {k: np.ma.filled(np.ma.masked_invalid(env[k]), np.nan) for k in fields}
+        assert all(np.isfinite(got[k]).all() for k in fields)
+        # (a sub-block carries its own float32 axes, so its index arithmetic differs from the whole grid's in the last bits)
+        assert all(np.array_equal(got[k], ref.setdefault(sub, got)[k]) for k in fields)
+    assert all(np.abs(ref[True][k] - ref[False][k]).max() < 1e-5 for k in fields)
+    assert calls and any(c[0] for c in calls) and any(not c[0] for c in calls)
+    r = Checked(fx.grid_lon, fx.grid_lat, None, fx.times, fields, name='r')
+    with pytest.raises(VariableNotCoveredError):
+        r.check_arguments(['x_wind'], fx.times[0], 3.0, 60.0, 0)
+    with pytest.raises(OutsideTemporalCoverageError):
+        r.check_arguments(list(fields), fx.times[-1] + timedelta(hours=1), 3.0, 60.0, 0)
+    with pytest.raises(OutsideSpatialCoverageError):
+        r.check_arguments(list(fields), fx.times[0], [50.0, 51.0], [10.0, 11.0], 0)
+    v, tt, x, y, z, outside = r.check_arguments(common.CUR[0], None, [float(fx.grid_lon[3]), 99.0], [float(fx.grid_lat[3]), 60.0], None)
+    assert v == [common.CUR[0]] and tt == fx.times[0] and list(outside) == [1] and z is None
