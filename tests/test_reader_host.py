@@ -88,3 +88,33 @@ def test_check_arguments_as_reference_style_readers_call_it():
         r.check_arguments(list(fields), fx.times[0], [50.0, 51.0], [10.0, 11.0], 0)
     v, tt, x, y, z, outside = r.check_arguments(common.CUR[0], None, [float(fx.grid_lon[3]), 99.0], [float(fx.grid_lat[3]), 60.0], None)
     assert v == [common.CUR[0]] and tt == fx.times[0] and list(outside) == [1] and z is None
+
+
+def test_sub_block_reader_queries_beside_the_live_reference():
+    """Reader-level queries on readers that hand out sub-blocks: the block around the positions of the call, the block's own index
+    geometry -- bit-equal to the reference's StructuredReader on a reader of the same kind (2-D float32, 3-D float64)."""
+    import numpy as np
+    import pytest
+    from datetime import timedelta
+    import common
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip('reference tree not present (GPU box)')
+    refrun.setup()
+    from opendrift_b200.readers import reader_regular_grid
+    for fxn in ('rk4_2d', 'rk4_3d'):
+        fx = common.Fixture(fxn)
+        fields = {common.CUR[0]: fx.u, common.CUR[1]: fx.v}
+        t = fx.times[1] + timedelta(seconds=700)
+        for sl in (slice(0, 200), slice(200, 230), slice(0, 1500)):
+            lon, lat = fx.lon0[sl].astype(np.float64), fx.lat0[sl].astype(np.float64)
+            z = np.zeros(len(lon)) if fx.grid_z is None else fx.z0[sl].astype(np.float64)
+            rr = refrun.make_grid_reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, fields, name='r', subblocks=True)
+            rp = reader_regular_grid.Reader(fx.grid_lon, fx.grid_lat, fx.grid_z, fx.times, fields, name='r', subblocks=True)
+            rr.buffer = rp.buffer = 3
+            rp.bind(HostEngine())
+            a, _ = rr.get_variables_interpolated(list(fields), time=t, lon=lon, lat=lat, z=z)
+            b, _ = rp.get_variables_interpolated(list(fields), time=t, lon=lon, lat=lat, z=z)
+            for k in fields:
+                x, y = np.ma.filled(np.ma.masked_invalid(a[k]), np.nan), np.ma.filled(np.ma.masked_invalid(b[k]), np.nan)
+                assert x.dtype == y.dtype and np.array_equal(x, y, equal_nan=True), (fxn, sl, k)
